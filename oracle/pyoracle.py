@@ -1,0 +1,195 @@
+"""ctypes driver for the CPU oracle (oracle/_build/liborb_oracle.so).
+
+TEST INFRASTRUCTURE: only tests/, bench.py's cpu_baseline / --impl reference leg and
+__graft_entry__.smoke() may import this module.  The product package never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liborb_oracle.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h", ".inc"))]
+    if (not force and os.path.exists(_SO)
+            and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs)):
+        return _SO
+    subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        L = _lib
+        L.orc_extractor_create.restype = C.c_void_p
+        L.orc_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orc_extractor_destroy.argtypes = [C.c_void_p]
+        L.orc_extract.restype = C.c_int
+        L.orc_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.orc_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        L.orc_level_size.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_level_pyramid.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_level_blurred.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_level_cands.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.orc_level_kps.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.orc_timings.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_resize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.orc_blur.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orc_fast_cell.restype = C.c_int
+        L.orc_fast_cell.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orc_atan2.restype = C.c_float
+        L.orc_atan2.argtypes = [C.c_float, C.c_float]
+        L.orc_ic_angle.restype = C.c_float
+        L.orc_ic_angle.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orc_descriptor.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]
+        L.orc_hamming.restype = C.c_int
+        L.orc_hamming.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_pattern.restype = C.POINTER(C.c_int8)
+        L.orc_distribute.restype = C.c_int
+        L.orc_distribute.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_int]
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class OracleExtractor:
+    """CPU restatement of ORB_SLAM3::ORBextractor (reference src/ORBextractor.cc)."""
+
+    def __init__(self, nfeatures=1200, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.L = lib()
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+        self.h = C.c_void_p(self.L.orc_extractor_create(nfeatures, scale_factor, nlevels, ini_th, min_th))
+        sc, isc, s2, is2 = (np.zeros(nlevels, np.float32) for _ in range(4))
+        q = np.zeros(nlevels, np.int32)
+        um = np.zeros(16, np.int32)
+        self.L.orc_tables(self.h, _p(sc), _p(isc), _p(s2), _p(is2), _p(q), _p(um))
+        self.scale_factors, self.inv_scale_factors, self.level_sigma2, self.inv_level_sigma2 = sc, isc, s2, is2
+        self.features_per_level, self.umax = q, um
+
+    def __del__(self):
+        try:
+            self.L.orc_extractor_destroy(self.h)
+        except Exception:
+            pass
+
+    def __call__(self, img, lapping=(0, 0)):
+        img = np.ascontiguousarray(img, np.uint8)
+        H, W = img.shape
+        cap = max(4 * self.nfeatures, 4096)
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        mono = self.L.orc_extract(self.h, _p(img), W, H, W, int(lapping[0]), int(lapping[1]), _p(kps), _p(desc),
+                                  cap, C.byref(n))
+        assert n.value <= cap
+        return mono, kps[:n.value].copy(), desc[:n.value].copy()
+
+    def level_size(self, l):
+        w, h = C.c_int(), C.c_int()
+        self.L.orc_level_size(self.h, l, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def level_pyramid(self, l):
+        w, h = self.level_size(l)
+        a = np.zeros((h, w), np.uint8)
+        self.L.orc_level_pyramid(self.h, l, _p(a))
+        return a
+
+    def level_blurred(self, l):
+        w, h = self.level_size(l)
+        a = np.zeros((h, w), np.uint8)
+        return a if self.L.orc_level_blurred(self.h, l, _p(a)) else None
+
+    def level_cands(self, l):
+        cap = 1 << 17
+        a = np.zeros((cap, 3), np.int32)
+        n = self.L.orc_level_cands(self.h, l, _p(a), cap)
+        assert n <= cap
+        return a[:n].copy()
+
+    def level_kps(self, l):
+        cap = 1 << 14
+        a = np.zeros(cap, KP_DTYPE)
+        n = self.L.orc_level_kps(self.h, l, _p(a), cap)
+        return a[:n].copy()
+
+    def timings(self):
+        t = np.zeros(6, np.float64)
+        self.L.orc_timings(self.h, _p(t))
+        return dict(zip(["pyramid", "fast", "quadtree", "angle", "blur", "descriptor"], t.tolist()))
+
+
+def resize(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    d = np.zeros((dh, dw), np.uint8)
+    lib().orc_resize(_p(src), src.shape[1], src.shape[0], _p(d), dw, dh)
+    return d
+
+
+def blur(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    d = np.zeros_like(src)
+    lib().orc_blur(_p(src), src.shape[1], src.shape[0], _p(d))
+    return d
+
+
+def fast_cell(win, thr):
+    """cv::FAST(win, thr, nonmax=True) restated: returns (n,3) int32 rows (x, y, score)."""
+    assert win.dtype == np.uint8 and win.strides[1] == 1
+    cap = win.size
+    out = np.zeros((max(cap, 1), 3), np.int32)
+    n = lib().orc_fast_cell(C.c_void_p(win.ctypes.data), win.shape[1], win.shape[0], win.strides[0], thr, _p(out), cap)
+    return out[:n].copy()
+
+
+def atan2_deg(y, x):
+    return float(lib().orc_atan2(float(y), float(x)))
+
+
+def ic_angle(img, x, y, umax):
+    img = np.ascontiguousarray(img, np.uint8)
+    um = np.ascontiguousarray(umax, np.int32)
+    return float(lib().orc_ic_angle(_p(img), img.shape[1], img.shape[0], int(x), int(y), _p(um)))
+
+
+def descriptor(img, x, y, angle):
+    img = np.ascontiguousarray(img, np.uint8)
+    d = np.zeros(32, np.uint8)
+    lib().orc_descriptor(_p(img), img.shape[1], img.shape[0], int(x), int(y), float(angle), _p(d))
+    return d
+
+
+def hamming(a, b):
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return int(lib().orc_hamming(_p(a), _p(b)))
+
+
+def pattern():
+    return np.ctypeslib.as_array(lib().orc_pattern(), shape=(1024,)).copy()
+
+
+def distribute(cands, minX, maxX, minY, maxY, N):
+    cands = np.ascontiguousarray(cands, np.int32)
+    out = np.zeros(max(len(cands), 1), np.int32)
+    n = lib().orc_distribute(_p(cands), len(cands), minX, maxX, minY, maxY, N, _p(out), len(out))
+    return out[:n].copy()

@@ -1,0 +1,112 @@
+// tests/host_emul/emul.cpp -- compiles the kernels' per-element math (csrc/devmath.cuh) for the HOST so
+// the CPU-only test tier can check it against the oracle / glibc / libstdc++ before any GPU run.
+// Build: g++ -O2 -ffp-contract=off -shared -fPIC (see tests/test_host_emul.py).
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../orb_slam3_detailed_comments_b200/csrc/devmath.cuh"
+
+using namespace orbdev;
+
+extern "C" {
+
+// scores of pixels (x, x+1) at row y of img (pitch w); returns packed biased lanes
+uint32_t emul_fast_x2(const uint8_t* img, int w, int x, int y) {
+    static const int RX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+    static const int RY[16] = {-3, -3, -2, -1, 0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3};
+    uint32_t r[16];
+    for (int k = 0; k < 16; ++k) {
+        const uint8_t* p = img + (size_t)(y + RY[k]) * w + x + RX[k];
+        r[k] = (uint32_t)p[0] | ((uint32_t)p[1] << 16);
+    }
+    const uint8_t* c = img + (size_t)y * w + x;
+    return fast_score_x2((uint32_t)c[0] | ((uint32_t)c[1] << 16), r);
+}
+
+float emul_atan2(float y, float x) { return fast_atan2_deg(y, x); }
+
+// number of floats in [lo_bits, hi_bits] whose emulated sin or cos differs from glibc's
+long emul_sincos_mismatch(uint32_t lo_bits, uint32_t hi_bits, int nthreads) {
+    std::atomic<long> bad(0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t)
+        th.emplace_back([&, t] {
+            long b = 0;
+            for (uint64_t i = (uint64_t)lo_bits + t; i <= hi_bits; i += nthreads) {
+                uint32_t u = (uint32_t)i;
+                float f, s, c;
+                memcpy(&f, &u, 4);
+                glibc_sincosf(f, &s, &c);
+                float rs = sinf(f), rc = cosf(f);
+                if (memcmp(&s, &rs, 4) || memcmp(&c, &rc, 4)) ++b;
+            }
+            bad += b;
+        });
+    for (auto& x : th) x.join();
+    return bad.load();
+}
+
+void emul_sincos(float a, float* s, float* c) { glibc_sincosf(a, s, c); }
+
+// sorts (key,val) with the transcribed introsort; caller compares against std::sort
+void emul_std_sort(uint32_t* keys, uint32_t* vals, int n) {
+    std::vector<SortItem> v(n);
+    for (int i = 0; i < n; ++i) v[i] = {keys[i], vals[i]};
+    std_sort(v.data(), n);
+    for (int i = 0; i < n; ++i) { keys[i] = v[i].key; vals[i] = v[i].val; }
+}
+void emul_heap_sort(uint32_t* keys, uint32_t* vals, int n) {
+    std::vector<SortItem> v(n);
+    for (int i = 0; i < n; ++i) v[i] = {keys[i], vals[i]};
+    std_heap_sort(v.data(), n);
+    for (int i = 0; i < n; ++i) { keys[i] = v[i].key; vals[i] = v[i].val; }
+}
+static bool ref_less(std::pair<uint32_t, uint32_t>& a, std::pair<uint32_t, uint32_t>& b) { return a.first < b.first; }
+void ref_std_sort(uint32_t* keys, uint32_t* vals, int n) {
+    std::vector<std::pair<uint32_t, uint32_t>> v(n);
+    for (int i = 0; i < n; ++i) v[i] = {keys[i], vals[i]};
+    std::sort(v.begin(), v.end(), ref_less);
+    for (int i = 0; i < n; ++i) { keys[i] = v[i].first; vals[i] = v[i].second; }
+}
+void ref_heap_sort(uint32_t* keys, uint32_t* vals, int n) {
+    std::vector<std::pair<uint32_t, uint32_t>> v(n);
+    for (int i = 0; i < n; ++i) v[i] = {keys[i], vals[i]};
+    std::partial_sort(v.begin(), v.end(), v.end(), ref_less);
+    for (int i = 0; i < n; ++i) { keys[i] = v[i].first; vals[i] = v[i].second; }
+}
+
+uint32_t emul_path_key(int x, int y, float hX, int regionH) { return qt_path_key(x, y, hX, regionH); }
+}
+
+// ---- quadtree (csrc/quadtree_core.cuh compiled as sequential host code) -----------------------
+#include "../../orb_slam3_detailed_comments_b200/csrc/quadtree_core.cuh"
+extern "C" int emul_distribute(const int32_t* cand3, int n, int regionW, int regionH, int N, int wCell, int hCell,
+                               int nCols, int32_t* out3, int cap_out) {
+    QtGeom g;
+    g.regionW = regionW; g.regionH = regionH;
+    g.nIni = (int)std::round((float)regionW / (float)regionH);
+    if (g.nIni < 1 || g.nIni > 4) return -2;
+    g.hX = (float)regionW / (float)g.nIni;
+    g.N = N; g.wCell = wCell; g.hCell = hCell; g.nCols = nCols;
+    int npow = 2;
+    while (npow < n) npow <<= 1;
+    std::vector<uint32_t> arr(npow, 0xffffffffu);
+    for (int i = 0; i < n; ++i) arr[i] = qt_element(qt_pack_cand(cand3[3 * i], cand3[3 * i + 1], cand3[3 * i + 2]), g);
+    qt_bitonic_sort(arr.data(), npow);
+    const int cap = 4 * N + 16;
+    std::vector<char> ws(qt_work_bytes(cap));
+    QtWork w;
+    qt_work_carve(w, ws.data(), cap);
+    std::vector<uint32_t> out(cap);
+    const int S = qt_distribute(arr.data(), n, g, w, out.data());
+    for (int i = 0; i < S && i < cap_out; ++i) {
+        out3[3 * i] = out[i] & 0xfff;
+        out3[3 * i + 1] = (out[i] >> 12) & 0xfff;
+        out3[3 * i + 2] = out[i] >> 24;
+    }
+    return S;
+}
