@@ -1,0 +1,124 @@
+/* orbslam3_b200.h -- C ABI of liborbslam3_b200.so: the B200 (sm_100a) implementation of ORB-SLAM3's
+ * per-frame data-parallel hot path.  Plain pointers and sizes only; every function returns an
+ * orb_status (0 = ok, <0 = error) and never throws.  The caller owns all host buffers; the library owns
+ * device memory per handle; one CUDA stream per handle; thread-safe across handles, not within one.
+ *
+ * The reference has no FFI layer: its boundary is the C++ member functions cited below.  The C++
+ * shims in orb_slam3_detailed_comments_b200/host/ keep those signatures and marshal onto this ABI
+ * (see INTEGRATION.md).
+ */
+#ifndef ORBSLAM3_B200_H
+#define ORBSLAM3_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    ORB_OK = 0,
+    ORB_ERR_INVALID = -1,      /* bad argument (null pointer, size out of range) */
+    ORB_ERR_EMPTY = -2,        /* empty image: ORBextractor::operator() returns -1 (ORBextractor.cc:1561) */
+    ORB_ERR_CUDA = -3,         /* CUDA runtime error; orb_last_error() has the text */
+    ORB_ERR_CAPACITY = -4,     /* output or internal capacity exceeded */
+    ORB_ERR_UNSUPPORTED = -5,  /* geometry the reference cannot process either (nIni == 0) or > 2048 px */
+    ORB_ERR_NO_DEVICE = -6     /* no CUDA device: there is NO CPU fallback */
+} orb_status;
+
+const char* orb_last_error(void);
+int orb_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * ORBextractor  (include/ORBextractor.h:43-109, src/ORBextractor.cc)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* bit-compatible with cv::KeyPoint (28 bytes) */
+typedef struct {
+    float x, y;      /* pt, level-0 pixel coordinates (pt *= scale[octave], ORBextractor.cc:1662) */
+    float size;      /* (int)(31 * scale[octave]) */
+    float angle;     /* IC_Angle, degrees [0,360) */
+    float response;  /* FAST score */
+    int32_t octave;
+    int32_t class_id; /* -1 */
+} orbx_keypoint;
+
+typedef struct {
+    int32_t n_features;    /* ORBextractor ctor args, ORBextractor.h:49-50 */
+    float scale_factor;
+    int32_t n_levels;
+    int32_t ini_th_fast;
+    int32_t min_th_fast;
+    int32_t max_width;     /* largest image this handle will see */
+    int32_t max_height;
+    int32_t max_batch;     /* images per orbx_extract_batch call (a stereo pair is 2 images) */
+    int32_t device;        /* CUDA ordinal */
+} orbx_config;
+
+typedef struct orbx_handle orbx_handle;
+
+/* replaces ORBextractor::ORBextractor (src/ORBextractor.cc:468-571) */
+orb_status orbx_create(const orbx_config* cfg, orbx_handle** out);
+void orbx_destroy(orbx_handle* h);
+
+/* GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares and
+ * mnFeaturesPerLevel / umax (ORBextractor.h:61-81,97-108).  Each array holds n_levels entries
+ * (umax: 16).  Any pointer may be NULL. */
+orb_status orbx_get_tables(const orbx_handle* h, float* scale, float* inv_scale, float* sigma2,
+                           float* inv_sigma2, int32_t* features_per_level, int32_t* umax16);
+
+/* replaces ORBextractor::operator() (src/ORBextractor.cc:1557-1682) for ONE host image.
+ * lap0/lap1 = vLappingArea.  Writes min(n, cap) keypoints + 32-byte descriptors; *n_out = n;
+ * *mono_index = the reference's return value.  Returns ORB_ERR_EMPTY for an empty image. */
+orb_status orbx_extract(orbx_handle* h, const uint8_t* img, int32_t width, int32_t height, int32_t stride,
+                        int32_t lap0, int32_t lap1, orbx_keypoint* kps, uint8_t* desc, int32_t cap,
+                        int32_t* n_out, int32_t* mono_index);
+
+/* Batched form: `batch` images of identical size, image b at imgs + b*image_stride_bytes (host memory,
+ * pinned preferred).  Results stay ON THE DEVICE inside the handle (keypoints, descriptors, the
+ * pyramids and blurred pyramids of every image) for the stereo matcher / search kernels; fetch them
+ * with orbx_download.  n_out / mono_index (host, `batch` entries) may be NULL. */
+orb_status orbx_extract_batch(orbx_handle* h, const uint8_t* imgs, int32_t batch, int32_t width,
+                              int32_t height, int32_t stride, size_t image_stride_bytes, int32_t lap0,
+                              int32_t lap1, int32_t* n_out, int32_t* mono_index);
+
+/* Same, images already resident in device memory (no H2D inside): the `value` leg of bench.py. */
+orb_status orbx_extract_batch_device(orbx_handle* h, const uint8_t* d_imgs, int32_t batch, int32_t width,
+                                     int32_t height, int32_t stride, size_t image_stride_bytes,
+                                     int32_t lap0, int32_t lap1);
+
+/* Counts of the last batch: n[b] keypoints, mono_index[b]; offsets[b] = first row of image b in the
+ * compact result arrays (offsets has batch+1 entries).  Synchronises the handle's stream. */
+orb_status orbx_counts(orbx_handle* h, int32_t* n, int32_t* mono_index, int32_t* offsets);
+
+/* Copies the compact results of the last batch to the host: kps/desc hold offsets[batch] rows. */
+orb_status orbx_download(orbx_handle* h, orbx_keypoint* kps, uint8_t* desc, int32_t cap_rows);
+
+/* mvImagePyramid[level] of image b (ORBextractor.h:83): copies the ROI (no border) into dst with
+ * row stride dst_stride; blurred != 0 returns the GaussianBlur'ed working copy (ORBextractor.cc:1632). */
+orb_status orbx_level_size(const orbx_handle* h, int32_t level, int32_t* width, int32_t* height);
+orb_status orbx_download_level(orbx_handle* h, int32_t b, int32_t level, int32_t blurred, uint8_t* dst,
+                               int32_t dst_stride);
+
+/* Stage outputs of the last batch, for stage-wise parity tests.
+ * candidates: FAST keypoints entering DistributeOctTree (ORBextractor.cc:1159-1165), sorted in the
+ * reference order; each row = x, y (relative to minBorder), score.  level keypoints: the output of
+ * DistributeOctTree in list order; each row = x, y (level pixel coords), score. */
+orb_status orbx_download_candidates(orbx_handle* h, int32_t b, int32_t level, int32_t* xys, int32_t cap,
+                                    int32_t* n_out);
+orb_status orbx_download_level_keypoints(orbx_handle* h, int32_t b, int32_t level, int32_t* xys,
+                                         int32_t cap, int32_t* n_out);
+
+/* Timing of the last batch with CUDA events on the handle's stream (milliseconds):
+ * [0] total, [1] pyramid, [2] FAST, [3] quadtree, [4] blur, [5] orientation+descriptors, [6] H2D.
+ * Only valid after orbx_set_profiling(h, 1). */
+orb_status orbx_set_profiling(orbx_handle* h, int32_t on);
+orb_status orbx_last_timings(orbx_handle* h, float* ms7);
+/* kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t orb_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBSLAM3_B200_H */

@@ -1,0 +1,95 @@
+"""ctypes binding of liborbslam3_b200.so (the C ABI declared in include/orbslam3_b200.h).
+
+There is no CPU fallback: importing this module without the built library, or creating a handle without
+a CUDA device, raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_PKG, "csrc")
+LIB_PATH = os.path.join(_PKG, "lib", "liborbslam3_b200.so")
+SOURCES = ["extractor.cu"]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+
+
+class OrbError(RuntimeError):
+    pass
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source for sm_100a into lib/liborbslam3_b200.so (nvcc cross-compiles on CPU)."""
+    srcs = [os.path.join(_CSRC, s) for s in SOURCES]
+    deps = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)] + [os.path.join(_PKG, "..", "include", "orbslam3_b200.h")]
+    if (not force and os.path.exists(LIB_PATH)
+            and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps)):
+        return LIB_PATH
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+class orbx_config(C.Structure):
+    _fields_ = [("n_features", C.c_int32), ("scale_factor", C.c_float), ("n_levels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32), ("max_width", C.c_int32),
+                ("max_height", C.c_int32), ("max_batch", C.c_int32), ("device", C.c_int32)]
+
+
+_lib = None
+_VP, _I, _F = C.c_void_p, C.c_int32, C.c_float
+_IP = C.POINTER(C.c_int32)
+
+# name -> (restype, argtypes); tests check that every symbol of include/orbslam3_b200.h is exported
+SIGNATURES = {
+    "orb_last_error": (C.c_char_p, []),
+    "orb_device_count": (C.c_int, []),
+    "orb_kernel_launches": (C.c_int64, []),
+    "orbx_create": (_I, [C.POINTER(orbx_config), C.POINTER(_VP)]),
+    "orbx_destroy": (None, [_VP]),
+    "orbx_get_tables": (_I, [_VP] + [_VP] * 6),
+    "orbx_extract": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP, _VP, _I, _IP, _IP]),
+    "orbx_extract_batch": (_I, [_VP, _VP, _I, _I, _I, _I, C.c_size_t, _I, _I, _VP, _VP]),
+    "orbx_extract_batch_device": (_I, [_VP, _VP, _I, _I, _I, _I, C.c_size_t, _I, _I]),
+    "orbx_counts": (_I, [_VP, _VP, _VP, _VP]),
+    "orbx_download": (_I, [_VP, _VP, _VP, _I]),
+    "orbx_level_size": (_I, [_VP, _I, _IP, _IP]),
+    "orbx_download_level": (_I, [_VP, _I, _I, _I, _VP, _I]),
+    "orbx_download_candidates": (_I, [_VP, _I, _I, _VP, _I, _IP]),
+    "orbx_download_level_keypoints": (_I, [_VP, _I, _I, _VP, _I, _IP]),
+    "orbx_set_profiling": (_I, [_VP, _I]),
+    "orbx_last_timings": (_I, [_VP, _VP]),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise OrbError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise OrbError(f"orb_status {status}: {lib().orb_last_error().decode(errors='replace')}")
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)

@@ -1,0 +1,45 @@
+// extractor.h -- the extractor handle (device workspace of one ORBextractor object)
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+struct orbx_handle {
+    orbx_config cfg{};
+    orb::ExtractGeom geom{};
+    int cur_w = -1, cur_h = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    bool profiling = false;
+    // ORBextractor.h:97-108 tables
+    std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
+    std::vector<int> quota, umax;
+    std::vector<int2> taps_host;
+    // device workspace (sized for max_width x max_height x max_batch)
+    uint8_t* d_pyr = nullptr;      // level-major pyramids (mvImagePyramid)
+    uint8_t* d_blur = nullptr;     // blurred pyramids
+    size_t pyr_bytes = 0;
+    uint32_t* d_cand = nullptr;    // FAST candidates, packed x|y<<12|score<<24
+    uint32_t* d_sort = nullptr;    // global fallback for the quadtree sort
+    uint32_t* d_lvl_kp = nullptr;  // DistributeOctTree output per level
+    int* d_slot = nullptr;         // output row of every emitted keypoint
+    int* d_cand_cnt = nullptr;
+    int* d_lvl_cnt = nullptr;
+    int* d_nkp = nullptr;          // [max_batch] n, [max_batch] mono, [max_batch+1] offsets
+    int* d_mono = nullptr;
+    int* d_offsets = nullptr;
+    int* d_err = nullptr;
+    int2* d_taps = nullptr;
+    orbx_keypoint* d_kps = nullptr;  // compact results of the last batch
+    uint8_t* d_desc = nullptr;
+    void* d_node_scratch = nullptr;
+    uint8_t* d_stage = nullptr;
+    size_t node_scratch_bytes = 0;
+    size_t cand_slots = 0, kp_slots = 0, sort_slots = 0, taps_slots = 0, out_rows = 0;
+    int* h_counts = nullptr;       // pinned
+    bool counts_valid = false;
+    int last_batch = 0;
+    // quadtree launch plan
+    int qt_node_cap = 0, qt_nodes_in_smem = 1, qt_sort_cap_smem = 4096;
+    size_t qt_smem_bytes = 0, qt_node_stride = 0, order_smem_bytes = 0;
+};

@@ -1,0 +1,483 @@
+// extractor_kernels.cuh -- sm_100a kernels of ORBextractor::operator()
+// (/root/reference/src/ORBextractor.cc:1557-1682).  All kernels are batched: blockIdx.{y|z} or a
+// division of blockIdx.x selects the image, so one launch covers a whole batch of frames.
+#pragma once
+#include "common.cuh"
+#include "devmath.cuh"
+#include "quadtree_core.cuh"
+
+namespace orb {
+using namespace orbdev;
+
+__device__ __constant__ int8_t c_pattern[1024] = {
+#include "orb_pattern.inc"
+};
+// umax of the radius-15 disc (ORBextractor.cc:542-570), verified against the constructor's
+// arithmetic on the host at handle creation.
+__device__ __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+// ---------------------------------------------------------------------------------------------
+// K1  ComputePyramid (ORBextractor.cc:1687-1738): level l from level l-1, cv::resize INTER_LINEAR
+// fixed-point model.  One thread = 4 destination pixels = one 32-bit store.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resize(const __grid_constant__ ExtractGeom g, int l, const int2* __restrict__ taps) {
+    const LevelGeom& D = g.lv[l];
+    const LevelGeom& S = g.lv[l - 1];
+    const int dx4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int dy = blockIdx.y * 8 + threadIdx.y;
+    if (dx4 >= D.w || dy >= D.h) return;
+    const uint8_t* src = S.base + (int64_t)blockIdx.z * S.img_stride;
+    uint8_t* dst = D.base + (int64_t)blockIdx.z * D.img_stride;
+    uint32_t packed = 0;
+    if (D.area2x) {
+        const uint8_t* a = src + (int64_t)(2 * dy) * S.pitch;
+        const uint8_t* b = a + S.pitch;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int x = dx4 + i;
+            if (x < D.w) {
+                const int v = (a[2 * x] + a[2 * x + 1] + b[2 * x] + b[2 * x + 1] + 2) >> 2;
+                packed |= (uint32_t)v << (8 * i);
+            }
+        }
+    } else {
+        const int2 ty = __ldg(&taps[D.tapOff + D.w + dy]);
+        const int sy0 = ty.x, sy1 = min(sy0 + 1, S.h - 1);
+        const int b0 = ty.y & 0xffff, b1 = (int)((uint32_t)ty.y >> 16);
+        const uint8_t* a = src + (int64_t)sy0 * S.pitch;
+        const uint8_t* b = src + (int64_t)sy1 * S.pitch;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int x = dx4 + i;
+            if (x < D.w) {
+                const int2 tx = __ldg(&taps[D.tapOff + x]);
+                const int x0 = tx.x, x1 = min(x0 + 1, S.w - 1);
+                const int c0 = tx.y & 0xffff, c1 = (int)((uint32_t)tx.y >> 16);
+                const int r0 = (int)__ldg(a + x0) * c0 + (int)__ldg(a + x1) * c1;
+                const int r1 = (int)__ldg(b + x0) * c0 + (int)__ldg(b + x1) * c1;
+                const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+                packed |= (uint32_t)v << (8 * i);
+            }
+        }
+    }
+    *reinterpret_cast<uint32_t*>(dst + (int64_t)dy * D.pitch + dx4) = packed;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2  per-cell FAST-9/16 + NMS + 20->7 fallback (ORBextractor.cc:1069-1166).
+// One CTA = one 35-px cell of one level of one image.  The cell window (+ alignment slack) is
+// staged in shared memory as 32-bit words; each thread scores 4 adjacent pixels per task with the
+// packed 16x2 DPX form (VIMNMX3.U16x2), NMS runs on the byte-packed score map, survivors are
+// appended to the level's candidate list (order-free: the quadtree re-derives the reference order
+// from the coordinates).
+// ---------------------------------------------------------------------------------------------
+#define FAST_ROWS 76
+#define FAST_TW 22
+#define FAST_THREADS 128
+
+__device__ __forceinline__ uint32_t shift_word(uint32_t L, uint32_t C, uint32_t R, int dx) {
+    switch (dx) {
+        case 1: return __byte_perm(C, R, 0x4321);
+        case 2: return __byte_perm(C, R, 0x5432);
+        case 3: return __byte_perm(C, R, 0x6543);
+        case -1: return __byte_perm(L, C, 0x6543);
+        case -2: return __byte_perm(L, C, 0x5432);
+        case -3: return __byte_perm(L, C, 0x4321);
+        default: return C;
+    }
+}
+
+__global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_constant__ ExtractGeom g, uint32_t* __restrict__ cand,
+                                                            int* __restrict__ candCnt, int* __restrict__ err) {
+    __shared__ uint32_t tile[FAST_ROWS][FAST_TW];
+    __shared__ uint32_t sc[FAST_ROWS][FAST_TW];
+    __shared__ int s_warp[FAST_THREADS / 32 + 1];
+    __shared__ int s_base;
+
+    const int cell = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
+    int l = 0;
+    while (l + 1 < g.nlevels && cell >= g.lv[l + 1].cellBase) ++l;
+    const LevelGeom& G = g.lv[l];
+    const int local = cell - G.cellBase;
+    const int ci = local / G.nCols, cj = local - ci * G.nCols;
+    const int x0 = 16 + cj * G.wCell, y0 = 16 + ci * G.hCell;
+    if (x0 >= G.maxBX - 6 || y0 >= G.maxBY - 3) return;  // ORBextractor.cc:1105,1120
+    const int x1 = min(x0 + G.wCell + 6, G.maxBX), y1 = min(y0 + G.hCell + 6, G.maxBY);
+    const int cw = x1 - x0, ch = y1 - y0;
+    if (cw < 7 || ch < 7) return;  // cv::FAST tests nothing
+    const int tx0 = x0 + 3, tx1 = x1 - 3, ty0 = y0 + 3, ty1 = y1 - 3;
+    const int gx0 = (tx0 & ~3) - 4;
+    const int ngrp = ((tx1 - 1) >> 2) - (tx0 >> 2) + 1;
+    const int nW = ngrp + 2;
+    const uint8_t* src = G.base + (int64_t)img * G.img_stride + (int64_t)y0 * G.pitch + gx0;
+
+    for (int i = tid; i < ch * nW; i += FAST_THREADS) {
+        const int r = i / nW, c = i - r * nW;
+        tile[r][c] = __ldg(reinterpret_cast<const uint32_t*>(src + (int64_t)r * G.pitch) + c);
+        sc[r][c] = 0u;
+    }
+    __syncthreads();
+
+    const int ntask = (ty1 - ty0) * ngrp;
+    const int minTh = g.minTh, iniTh = g.iniTh;
+    for (int t = tid; t < ntask; t += FAST_THREADS) {
+        const int row = t / ngrp, grp = t - row * ngrp;
+        const int r = row + 3, wd = grp + 1;
+        uint32_t W[16];
+        {
+            const uint32_t* p;
+            p = &tile[r - 3][wd - 1]; W[15] = shift_word(p[0], p[1], p[2], -1); W[0] = p[1]; W[1] = shift_word(p[0], p[1], p[2], 1);
+            p = &tile[r - 2][wd - 1]; W[14] = shift_word(p[0], p[1], p[2], -2); W[2] = shift_word(p[0], p[1], p[2], 2);
+            p = &tile[r - 1][wd - 1]; W[13] = shift_word(p[0], p[1], p[2], -3); W[3] = shift_word(p[0], p[1], p[2], 3);
+            p = &tile[r + 1][wd - 1]; W[11] = shift_word(p[0], p[1], p[2], -3); W[5] = shift_word(p[0], p[1], p[2], 3);
+            p = &tile[r + 2][wd - 1]; W[10] = shift_word(p[0], p[1], p[2], -2); W[6] = shift_word(p[0], p[1], p[2], 2);
+            p = &tile[r + 3][wd - 1]; W[9] = shift_word(p[0], p[1], p[2], -1); W[8] = p[1]; W[7] = shift_word(p[0], p[1], p[2], 1);
+        }
+        const uint32_t* pc = &tile[r][wd - 1];
+        W[12] = shift_word(pc[0], pc[1], pc[2], -3);
+        W[4] = shift_word(pc[0], pc[1], pc[2], 3);
+        const uint32_t C = pc[1];
+        uint32_t rl[16], rh[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            rl[k] = __byte_perm(W[k], 0u, 0x4140);
+            rh[k] = __byte_perm(W[k], 0u, 0x4342);
+        }
+        const uint32_t s01 = fast_score_x2(__byte_perm(C, 0u, 0x4140), rl);
+        const uint32_t s23 = fast_score_x2(__byte_perm(C, 0u, 0x4342), rh);
+        const int xb = gx0 + 4 * wd;
+        int s[4] = {(int)(s01 & 0xffffu) - 256, (int)(s01 >> 16) - 256, (int)(s23 & 0xffffu) - 256, (int)(s23 >> 16) - 256};
+        uint32_t packed = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int x = xb + k;
+            if (s[k] >= minTh && x >= tx0 && x < tx1) packed |= (uint32_t)s[k] << (8 * k);
+        }
+        sc[r][wd] = packed;
+    }
+    __syncthreads();
+
+    // NMS on the byte-packed score map; result overwrites tile[][] (the pixels are no longer needed)
+    int has_ini = 0;
+    for (int t = tid; t < ntask; t += FAST_THREADS) {
+        const int row = t / ngrp, grp = t - row * ngrp;
+        const int r = row + 3, wd = grp + 1;
+        const uint32_t* u = &sc[r - 1][wd - 1];
+        const uint32_t* m = &sc[r][wd - 1];
+        const uint32_t* d = &sc[r + 1][wd - 1];
+        const uint32_t c = m[1];
+        uint32_t res = 0u;
+        if (c != 0u) {
+            uint32_t mx = __vmaxu4(__byte_perm(u[0], u[1], 0x6543), u[1]);
+            mx = __vmaxu4(mx, __byte_perm(u[1], u[2], 0x4321));
+            mx = __vmaxu4(mx, __byte_perm(m[0], m[1], 0x6543));
+            mx = __vmaxu4(mx, __byte_perm(m[1], m[2], 0x4321));
+            mx = __vmaxu4(mx, __byte_perm(d[0], d[1], 0x6543));
+            mx = __vmaxu4(mx, d[1]);
+            mx = __vmaxu4(mx, __byte_perm(d[1], d[2], 0x4321));
+            res = c & __vcmpgtu4(c, mx);
+            const uint32_t ini4 = (uint32_t)iniTh * 0x01010101u;
+            has_ini |= (__vcmpgeu4(res, ini4) != 0u);
+        }
+        tile[r][wd] = res;
+    }
+    const int cell_has_ini = __syncthreads_or(has_ini);  // also orders the tile[] writes
+    const uint32_t thr = (uint32_t)(cell_has_ini ? iniTh : minTh);
+    const uint32_t thr4 = thr * 0x01010101u;
+
+    int cnt = 0;
+    for (int t = tid; t < ntask; t += FAST_THREADS) {
+        const int row = t / ngrp, grp = t - row * ngrp;
+        const uint32_t v = tile[row + 3][grp + 1];
+        if (v) cnt += __popc(__vcmpgeu4(v, thr4) & 0x01010101u);
+    }
+    // CTA exclusive scan of cnt
+    const int lane = tid & 31, wid = tid >> 5;
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int w = 0; w < FAST_THREADS / 32; ++w) {
+            const int v = s_warp[w];
+            s_warp[w] = run;
+            run += v;
+        }
+        s_base = run ? atomicAdd(&candCnt[img * g.nlevels + l], run) : 0;
+        s_warp[FAST_THREADS / 32] = run;
+    }
+    __syncthreads();
+    const int total = s_warp[FAST_THREADS / 32];
+    if (total == 0) return;
+    int off = s_base + s_warp[wid] + inc - cnt;
+    if (s_base + total > G.candCap) {
+        if (tid == 0) atomicExch(&err[0], 1);
+        return;
+    }
+    uint32_t* out = cand + (int64_t)img * g.candTotal + G.candOff;
+    for (int t = tid; t < ntask; t += FAST_THREADS) {
+        const int row = t / ngrp, grp = t - row * ngrp;
+        const uint32_t v = tile[row + 3][grp + 1];
+        if (!v) continue;
+        const int xb = gx0 + 4 * (grp + 1) - 16, yb = ty0 + row - 16;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t s = (v >> (8 * k)) & 0xffu;
+            if (s >= thr) out[off++] = qt_pack_cand(xb + k, yb, (int)s);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3  DistributeOctTree, one CTA per (level, image); see quadtree_core.cuh.
+// ---------------------------------------------------------------------------------------------
+#define QT_THREADS 256
+
+__global__ void __launch_bounds__(QT_THREADS) k_quadtree(const __grid_constant__ ExtractGeom g, int batch, const uint32_t* __restrict__ cand,
+                                                        const int* __restrict__ candCnt, uint32_t* __restrict__ sortScratch,
+                                                        char* __restrict__ nodeScratch, int64_t nodeScratchStride,
+                                                        int sortCapSmem, int nodesInSmem, int nodeCapMax,
+                                                        uint32_t* __restrict__ lvlKp, int* __restrict__ lvlCnt,
+                                                        int* __restrict__ err) {
+    extern __shared__ __align__(16) unsigned char qt_smem[];
+    const int l = blockIdx.x / batch, img = blockIdx.x - l * batch;  // big levels are scheduled first
+    const LevelGeom& G = g.lv[l];
+    int n = candCnt[img * g.nlevels + l];
+    if (n > G.candCap) n = G.candCap;
+    QtGeom q;
+    q.regionW = G.maxBX - 16; q.regionH = G.maxBY - 16;
+    q.nIni = G.nIni; q.hX = G.hX; q.N = G.quota;
+    q.wCell = G.wCell; q.hCell = G.hCell; q.nCols = G.nCols;
+
+    int npow = 2;
+    while (npow < n) npow <<= 1;
+    uint32_t* arr = (npow <= sortCapSmem) ? reinterpret_cast<uint32_t*>(qt_smem)
+                                          : sortScratch + (int64_t)img * g.sortTotal + G.sortOff;
+    const uint32_t* src = cand + (int64_t)img * g.candTotal + G.candOff;
+    for (int i = threadIdx.x; i < npow; i += QT_THREADS) arr[i] = (i < n) ? qt_element(src[i], q) : 0xffffffffu;
+    __syncthreads();
+    qt_bitonic_sort(arr, npow);
+
+    QtWork w;
+    const int cap = 4 * G.quota + 16;
+    void* ws = nodesInSmem ? (void*)(qt_smem + (size_t)sortCapSmem * 4)
+                           : (void*)(nodeScratch + (int64_t)blockIdx.x * nodeScratchStride);
+    qt_work_carve(w, ws, cap < nodeCapMax ? cap : nodeCapMax);
+    uint32_t* out = lvlKp + (int64_t)img * g.kpTotal + G.kpOff;
+    int S = qt_distribute(arr, n, q, w, out);
+    if (threadIdx.x == 0) {
+        if (S < 0 || S > G.kpCap) {
+            atomicExch(&err[1], 1);
+            S = 0;
+        }
+        lvlCnt[img * g.nlevels + l] = S;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3b  output slot of every keypoint (ORBextractor.cc:1656-1678): emission order is level-major;
+// keypoints whose scaled x lies in [lap0, lap1] fill the output from the back, the others from the
+// front.  One CTA per image.  Also per-image totals.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_order(const __grid_constant__ ExtractGeom g, const uint32_t* __restrict__ lvlKp,
+                                              const int* __restrict__ lvlCnt, int lap0, int lap1,
+                                              int* __restrict__ slot, int* __restrict__ nkp, int* __restrict__ mono) {
+    extern __shared__ int ord_flags[];  // kpTotal ints + 40
+    __shared__ int s_off[ORB_MAX_LEVELS + 1];
+    const int img = blockIdx.x;
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int l = 0; l < g.nlevels; ++l) {
+            s_off[l] = run;
+            run += lvlCnt[img * g.nlevels + l];
+        }
+        s_off[g.nlevels] = run;
+    }
+    __syncthreads();
+    const int total = s_off[g.nlevels];
+    const uint32_t* kp = lvlKp + (int64_t)img * g.kpTotal;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        int l = 0;
+        while (e >= s_off[l + 1]) ++l;
+        const uint32_t c = kp[g.lv[l].kpOff + (e - s_off[l])];
+        float x = (float)((int)(c & 0xfffu) + 16);
+        if (l != 0) x = fmul(x, g.lv[l].scale);
+        const bool lapping = (x >= (float)lap0) && (x <= (float)lap1);
+        ord_flags[e] = lapping ? 0 : 1;
+    }
+    __syncthreads();
+    int* tmp = ord_flags + g.kpTotal;
+    // keep the raw flag: after the scan flag[e] = (scan[e+1] - scan[e])
+    const int nmono = qt_exscan(ord_flags, total, tmp);
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const int before = ord_flags[e];
+        const int nxt = (e + 1 < total) ? ord_flags[e + 1] : nmono;
+        const bool is_mono = nxt != before;
+        slot[(int64_t)img * g.kpTotal + e] = is_mono ? before : (total - 1 - (e - before));
+    }
+    if (threadIdx.x == 0) {
+        nkp[img] = total;
+        mono[img] = nmono;
+    }
+}
+
+// exclusive scan of the per-image keypoint counts -> first compact output row of every image
+__global__ void k_offsets(const int* __restrict__ nkp, int batch, int* __restrict__ offsets) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int run = 0;
+        for (int b = 0; b < batch; ++b) {
+            offsets[b] = run;
+            run += nkp[b];
+        }
+        offsets[batch] = run;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5  GaussianBlur 7x7 sigma=2 BORDER_REFLECT_101, OpenCV's fixed-point path (SURVEY App. A.2;
+// ORBextractor.cc:1629-1637).  Tile 64x32 output pixels per CTA, all levels in one launch.
+// ---------------------------------------------------------------------------------------------
+#define BLUR_TW 64
+#define BLUR_TH 32
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return i;  // valid for n >= 4 and |overshoot| <= 3 (every pyramid level is far larger)
+}
+
+__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ ExtractGeom g) {
+    __shared__ uint8_t raw[BLUR_TH + 6][BLUR_TW + 8];
+    __shared__ uint16_t hor[BLUR_TH + 6][BLUR_TW];
+    const int tileId = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
+    int l = 0;
+    while (l + 1 < g.nlevels && tileId >= g.lv[l + 1].tileBase) ++l;
+    const LevelGeom& G = g.lv[l];
+    const int local = tileId - G.tileBase;
+    const int ty = local / G.tilesX, tx = local - ty * G.tilesX;
+    const int ox = tx * BLUR_TW, oy = ty * BLUR_TH;
+    const uint8_t* src = G.base + (int64_t)img * G.img_stride;
+    for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
+        const int r = i / (BLUR_TW + 6), c = i - r * (BLUR_TW + 6);
+        const int y = reflect101(min(oy + r - 3, G.h + 2), G.h), x = reflect101(min(ox + c - 3, G.w + 2), G.w);
+        raw[r][c] = __ldg(src + (int64_t)y * G.pitch + x);
+    }
+    __syncthreads();
+    for (int i = tid; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
+        const int r = i / BLUR_TW, c = i - r * BLUR_TW;
+        const uint8_t* p = &raw[r][c];
+        hor[r][c] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+    }
+    __syncthreads();
+    uint8_t* dst = G.blur + (int64_t)img * G.blur_stride;
+    for (int i = tid; i < BLUR_TH * BLUR_TW / 4; i += 256) {
+        const int r = i / (BLUR_TW / 4), c4 = (i - r * (BLUR_TW / 4)) * 4;
+        const int y = oy + r, x = ox + c4;
+        if (y >= G.h || x >= G.w) continue;
+        uint32_t packed = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = c4 + k;
+            const uint32_t acc = 18u * (hor[r][c] + hor[r + 6][c]) + 34u * (hor[r + 1][c] + hor[r + 5][c]) +
+                                 48u * (hor[r + 2][c] + hor[r + 4][c]) + 56u * hor[r + 3][c];
+            packed |= ((acc + 32768u) >> 16) << (8 * k);
+        }
+        *reinterpret_cast<uint32_t*>(dst + (int64_t)y * G.blur_pitch + x) = packed;  // pitch padding absorbs the tail
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4+K6  IC_Angle (ORBextractor.cc:91-138) + computeOrbDescriptor (:150-203), one warp per keypoint.
+// Writes the final cv::KeyPoint record and the 32 descriptor bytes at the compact output row.
+// ---------------------------------------------------------------------------------------------
+#define OD_WARPS 8
+
+__global__ void __launch_bounds__(OD_WARPS * 32) k_orient_describe(const __grid_constant__ ExtractGeom g, const uint32_t* __restrict__ lvlKp,
+                                                                  const int* __restrict__ lvlCnt, const int* __restrict__ slot,
+                                                                  const int* __restrict__ offsets,
+                                                                  orbx_keypoint* __restrict__ kps, uint8_t* __restrict__ desc) {
+    __shared__ int8_t s_pat[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_pat[i] = c_pattern[i];
+    __syncthreads();
+    const int img = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * OD_WARPS + (threadIdx.x >> 5);
+    int l = 0, first = 0;
+    {
+        int run = 0;
+        bool found = false;
+        for (int k = 0; k < g.nlevels; ++k) {
+            const int c = lvlCnt[img * g.nlevels + k];
+            if (!found && e < run + c) { l = k; first = run; found = true; }
+            run += c;
+        }
+        if (!found) return;  // warp-uniform
+    }
+    const LevelGeom& G = g.lv[l];
+    const uint32_t c = lvlKp[(int64_t)img * g.kpTotal + G.kpOff + (e - first)];
+    const int x = (int)(c & 0xfffu) + 16, y = (int)((c >> 12) & 0xfffu) + 16, score = (int)(c >> 24);
+
+    // intensity centroid over the radius-15 disc: lane v handles row v-15
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int v = lane - 15;
+        const int d = c_umax[v < 0 ? -v : v];
+        const uint8_t* p = G.base + (int64_t)img * G.img_stride + (int64_t)(y + v) * G.pitch + x;
+        int rs = 0;
+        for (int u = -d; u <= d; ++u) {
+            const int val = __ldg(p + u);
+            m10 += u * val;
+            rs += val;
+        }
+        m01 = v * rs;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // steered BRIEF: lane = descriptor byte
+    const float factorPI = (float)(3.14159265358979323846 / 180.f);
+    float sa, ca;
+    glibc_sincosf(fmul(angle, factorPI), &sa, &ca);
+    const uint8_t* cb = G.blur + (int64_t)img * G.blur_stride + (int64_t)y * G.blur_pitch + x;
+    const int8_t* pp = s_pat + lane * 32;
+    uint32_t val = 0u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float xa = (float)pp[4 * k], ya = (float)pp[4 * k + 1], xb = (float)pp[4 * k + 2], yb = (float)pp[4 * k + 3];
+        const int ra = round_half_even(fadd(fmul(xa, sa), fmul(ya, ca))), ca_ = round_half_even(fsub(fmul(xa, ca), fmul(ya, sa)));
+        const int rb = round_half_even(fadd(fmul(xb, sa), fmul(yb, ca))), cb_ = round_half_even(fsub(fmul(xb, ca), fmul(yb, sa)));
+        const int t0 = __ldg(cb + (int64_t)ra * G.blur_pitch + ca_);
+        const int t1 = __ldg(cb + (int64_t)rb * G.blur_pitch + cb_);
+        val |= (uint32_t)(t0 < t1) << k;
+    }
+    const int row = offsets[img] + slot[(int64_t)img * g.kpTotal + e];
+    // gather 4 descriptor bytes per word; lanes 0..7 store
+    uint32_t w = val & 0xffu;
+    w |= (__shfl_down_sync(0xffffffffu, val, 1) & 0xffu) << 8;
+    w |= (__shfl_down_sync(0xffffffffu, val, 2) & 0xffu) << 16;
+    w |= (__shfl_down_sync(0xffffffffu, val, 3) & 0xffu) << 24;
+    const uint32_t w4 = __shfl_sync(0xffffffffu, w, (lane & 7) * 4);
+    if (lane < 8) reinterpret_cast<uint32_t*>(desc + (int64_t)row * 32)[lane] = w4;
+    if (lane == 8) {
+        orbx_keypoint kp;
+        float fx = (float)x, fy = (float)y;
+        if (l != 0) {
+            fx = fmul(fx, G.scale);
+            fy = fmul(fy, G.scale);
+        }
+        kp.x = fx; kp.y = fy; kp.size = G.patch; kp.angle = angle; kp.response = (float)score;
+        kp.octave = l; kp.class_id = -1;
+        kps[row] = kp;
+    }
+}
+
+}  // namespace orb

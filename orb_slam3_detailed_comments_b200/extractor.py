@@ -1,0 +1,141 @@
+"""ORBextractor -- host-side mirror of ORB_SLAM3::ORBextractor (reference include/ORBextractor.h:43-109)
+on top of the C ABI.  Same constructor arguments, same getters, `__call__` = operator()."""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+
+class ORBextractor:
+    """ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)  (ORBextractor.h:49-50).
+
+    `extractor(image, lapping=(0, 0))` returns (monoIndex, keypoints, descriptors) exactly like
+    `operator()(image, mask, keypoints, descriptors, vLappingArea)` (ORBextractor.cc:1557-1682); an empty
+    image returns (-1, empty, empty).  `extract_batch` is the batched form used for sequence replay.
+    """
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_width=1280, max_height=720,
+                 max_batch=1, device=0):
+        self._L = N.lib()
+        self._h = C.c_void_p()
+        cfg = N.orbx_config(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_width, max_height,
+                            max_batch, device)
+        N.check(self._L.orbx_create(C.byref(cfg), C.byref(self._h)))
+        self.nfeatures, self.scaleFactor, self.nlevels = nfeatures, scaleFactor, nlevels
+        self.iniThFAST, self.minThFAST = iniThFAST, minThFAST
+        self.max_batch = max_batch
+        sc, isc, s2, is2 = (np.zeros(nlevels, np.float32) for _ in range(4))
+        q, um = np.zeros(nlevels, np.int32), np.zeros(16, np.int32)
+        N.check(self._L.orbx_get_tables(self._h, N.ptr(sc), N.ptr(isc), N.ptr(s2), N.ptr(is2), N.ptr(q), N.ptr(um)))
+        self._sc, self._isc, self._s2, self._is2 = sc, isc, s2, is2
+        self.mnFeaturesPerLevel, self.umax = q, um
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.orbx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # getters, ORBextractor.h:61-81
+    def GetLevels(self):
+        return self.nlevels
+
+    def GetScaleFactor(self):
+        return self.scaleFactor
+
+    def GetScaleFactors(self):
+        return self._sc.copy()
+
+    def GetInverseScaleFactors(self):
+        return self._isc.copy()
+
+    def GetScaleSigmaSquares(self):
+        return self._s2.copy()
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._is2.copy()
+
+    def __call__(self, image, lapping=(0, 0)):
+        if image is None or image.size == 0:
+            return -1, np.zeros(0, N.KP_DTYPE), np.zeros((0, 32), np.uint8)
+        assert image.dtype == np.uint8 and image.ndim == 2, "CV_8UC1 expected (ORBextractor.cc:1567)"
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        h, w = image.shape
+        cap = 4 * self.nfeatures + 16 * self.nlevels
+        kps = np.zeros(cap, N.KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n, mono = C.c_int32(0), C.c_int32(0)
+        N.check(self._L.orbx_extract(self._h, C.c_void_p(image.ctypes.data), w, h, image.strides[0], int(lapping[0]),
+                                     int(lapping[1]), N.ptr(kps), N.ptr(desc), cap, C.byref(n), C.byref(mono)))
+        return mono.value, kps[:n.value].copy(), desc[:n.value].copy()
+
+    # ---- batched API ---------------------------------------------------------------------------
+    def extract_batch(self, images, lapping=(0, 0)):
+        """images: (B, H, W) uint8 host array.  Returns (n[B], mono[B]); results stay on the device."""
+        images = np.ascontiguousarray(images, np.uint8)
+        b, h, w = images.shape
+        n = np.zeros(b, np.int32)
+        mono = np.zeros(b, np.int32)
+        N.check(self._L.orbx_extract_batch(self._h, N.ptr(images), b, w, h, w, h * w, int(lapping[0]), int(lapping[1]),
+                                           N.ptr(n), N.ptr(mono)))
+        return n, mono
+
+    def extract_batch_device(self, dptr, batch, width, height, stride=None, image_stride=None, lapping=(0, 0)):
+        stride = stride or width
+        image_stride = image_stride or stride * height
+        N.check(self._L.orbx_extract_batch_device(self._h, C.c_void_p(dptr), batch, width, height, stride, image_stride,
+                                                  int(lapping[0]), int(lapping[1])))
+
+    def counts(self, batch):
+        n, mono, off = np.zeros(batch, np.int32), np.zeros(batch, np.int32), np.zeros(batch + 1, np.int32)
+        N.check(self._L.orbx_counts(self._h, N.ptr(n), N.ptr(mono), N.ptr(off)))
+        return n, mono, off
+
+    def download(self, batch):
+        n, mono, off = self.counts(batch)
+        rows = int(off[batch])
+        kps = np.zeros(max(rows, 1), N.KP_DTYPE)
+        desc = np.zeros((max(rows, 1), 32), np.uint8)
+        N.check(self._L.orbx_download(self._h, N.ptr(kps), N.ptr(desc), max(rows, 1)))
+        return n, mono, off, kps[:rows], desc[:rows]
+
+    # ---- stage outputs (parity tests; mvImagePyramid is a public member of the reference class) ---
+    def level_size(self, level):
+        w, h = C.c_int32(), C.c_int32()
+        N.check(self._L.orbx_level_size(self._h, level, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def image_pyramid(self, b, level, blurred=False):
+        w, h = self.level_size(level)
+        out = np.zeros((h, w), np.uint8)
+        N.check(self._L.orbx_download_level(self._h, b, level, 1 if blurred else 0, N.ptr(out), w))
+        return out
+
+    def candidates(self, b, level):
+        cap = 1 << 18
+        out = np.zeros((cap, 3), np.int32)
+        n = C.c_int32()
+        N.check(self._L.orbx_download_candidates(self._h, b, level, N.ptr(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def level_keypoints(self, b, level):
+        cap = 1 << 16
+        out = np.zeros((cap, 3), np.int32)
+        n = C.c_int32()
+        N.check(self._L.orbx_download_level_keypoints(self._h, b, level, N.ptr(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def set_profiling(self, on=True):
+        N.check(self._L.orbx_set_profiling(self._h, 1 if on else 0))
+
+    def last_timings(self):
+        t = np.zeros(7, np.float32)
+        N.check(self._L.orbx_last_timings(self._h, N.ptr(t)))
+        return dict(zip(["total", "pyramid", "fast", "quadtree", "blur", "orient_desc", "h2d"], t.tolist()))
