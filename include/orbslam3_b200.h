@@ -112,9 +112,11 @@ orb_status orbx_download_level_keypoints(orbx_handle* h, int32_t b, int32_t leve
 
 /* Timing of the last batch with CUDA events on the handle's stream (milliseconds):
  * [0] total, [1] pyramid, [2] FAST, [3] quadtree, [4] blur, [5] orientation+descriptors, [6] H2D.
- * Only valid after orbx_set_profiling(h, 1). */
+ * Averages over the batches run since orbx_set_profiling(h, 1) (ring of the last 32). */
 orb_status orbx_set_profiling(orbx_handle* h, int32_t on);
 orb_status orbx_last_timings(orbx_handle* h, float* ms7);
+/* the handle's cudaStream_t (for CUDA-event timing on the launching stream) */
+void* orbx_cuda_stream(orbx_handle* h);
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t orb_kernel_launches(void);
 

@@ -90,22 +90,28 @@ static inline int reflect101(int i, int n) {
 }
 
 void gaussian_blur7_u8(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride) {
-    static const int k[7] = {18, 34, 48, 56, 48, 34, 18};  // Q0.8, sums to 256
+    // Q0.8 kernel {18,34,48,56,48,34,18} (sums to 256); horizontal pass keeps Q8.8, vertical pass
+    // accumulates Q16.16 and rounds with +32768 >> 16.
     std::vector<uint16_t> hbuf((size_t)w * h);
+    std::vector<uint8_t> row((size_t)w + 6);
     for (int y = 0; y < h; ++y) {
         const uint8_t* r = src + (size_t)y * sstride;
+        for (int x = -3; x < w + 3; ++x) row[x + 3] = r[reflect101(x, w)];
+        uint16_t* o = &hbuf[(size_t)y * w];
+        const uint8_t* p = row.data();
+        for (int x = 0; x < w; ++x)
+            o[x] = (uint16_t)(18 * (p[x] + p[x + 6]) + 34 * (p[x + 1] + p[x + 5]) + 48 * (p[x + 2] + p[x + 4]) + 56 * p[x + 3]);
+    }
+    for (int y = 0; y < h; ++y) {
+        const uint16_t* r[7];
+        for (int t = -3; t <= 3; ++t) r[t + 3] = &hbuf[(size_t)reflect101(y + t, h) * w];
+        uint8_t* o = dst + (size_t)y * dstride;
         for (int x = 0; x < w; ++x) {
-            int acc = 0;
-            for (int t = -3; t <= 3; ++t) acc += k[t + 3] * r[reflect101(x + t, w)];
-            hbuf[(size_t)y * w + x] = (uint16_t)acc;  // Q8.8, <= 255*256
+            const uint32_t acc = 18u * ((uint32_t)r[0][x] + r[6][x]) + 34u * ((uint32_t)r[1][x] + r[5][x]) +
+                                 48u * ((uint32_t)r[2][x] + r[4][x]) + 56u * (uint32_t)r[3][x];
+            o[x] = (uint8_t)((acc + 32768u) >> 16);
         }
     }
-    for (int y = 0; y < h; ++y)
-        for (int x = 0; x < w; ++x) {
-            uint32_t acc = 0;
-            for (int t = -3; t <= 3; ++t) acc += (uint32_t)k[t + 3] * hbuf[(size_t)reflect101(y + t, h) * w + x];
-            dst[(size_t)y * dstride + x] = (uint8_t)((acc + 32768u) >> 16);
-        }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -115,31 +121,59 @@ static const int kRingX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2
 static const int kRingY[16] = {-3, -3, -2, -1, 0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3};
 
 int fast_score16(const uint8_t* p, int stride) {
-    int d[16];
+    int d[16 + 9];
     const int c = p[0];
     for (int k = 0; k < 16; ++k) d[k] = c - p[kRingY[k] * stride + kRingX[k]];
+    for (int k = 0; k < 9; ++k) d[16 + k] = d[k];
+    // min / max over every window of 9 consecutive ring pixels via windows of 3
+    int lo3[16 + 6], hi3[16 + 6];
+    for (int k = 0; k < 22; ++k) {
+        lo3[k] = std::min(d[k], std::min(d[k + 1], d[k + 2]));
+        hi3[k] = std::max(d[k], std::max(d[k + 1], d[k + 2]));
+    }
     int best = -256;
     for (int s = 0; s < 16; ++s) {
-        int mn = 255, mx = -255;
-        for (int j = 0; j < 9; ++j) {
-            const int v = d[(s + j) & 15];
-            mn = std::min(mn, v);
-            mx = std::max(mx, v);
-        }
+        const int mn = std::min(lo3[s], std::min(lo3[s + 3], lo3[s + 6]));
+        const int mx = std::max(hi3[s], std::max(hi3[s + 3], hi3[s + 6]));
         best = std::max(best, std::max(mn, -mx));
     }
     return best - 1;
 }
 
+// 9 contiguous set bits in a circular 16-bit mask
+static inline bool arc9(uint32_t m) {
+    m |= m << 16;
+    uint32_t t = m & (m >> 1);
+    t &= t >> 2;
+    t &= t >> 4;
+    t &= m >> 8;
+    return (t & 0xffffu) != 0;
+}
+
 // One cv::FAST call on a cell window (cw x ch, top-left at win): appends row-major keypoints
 // (window coords) whose score >= thr and that are strict 3x3 local maxima among tested pixels.
+// A pixel is a corner at threshold thr iff 9 contiguous ring pixels are all > c+thr or all < c-thr
+// (cheap bit test first, like OpenCV's own pre-test); only corners get the exact score.
 void fast_cell(const uint8_t* win, int cw, int ch, int stride, int thr, std::vector<Cand>& out) {
     if (cw < 7 || ch < 7) return;
     std::vector<int> sc((size_t)cw * ch, 0);
+    int off[16];
+    for (int k = 0; k < 16; ++k) off[k] = kRingY[k] * stride + kRingX[k];
     for (int y = 3; y < ch - 3; ++y)
         for (int x = 3; x < cw - 3; ++x) {
-            const int s = fast_score16(win + (size_t)y * stride + x, stride);
-            sc[(size_t)y * cw + x] = (s >= thr) ? s : 0;
+            const uint8_t* p = win + (size_t)y * stride + x;
+            const int c = p[0], hi = c + thr, lo = c - thr;
+            // antipodal pre-test: an arc of 9 contains pixel k or pixel k+8 for every k
+            const int a = p[off[0]], b = p[off[8]];
+            if (!((a > hi) | (b > hi) | (a < lo) | (b < lo))) continue;
+            uint32_t mb = 0, md = 0;
+            for (int k = 0; k < 16; ++k) {
+                const int v = p[off[k]];
+                mb |= (uint32_t)(v > hi) << k;
+                md |= (uint32_t)(v < lo) << k;
+            }
+            if (!arc9(mb) && !arc9(md)) continue;
+            sc[(size_t)y * cw + x] = fast_score16(p, stride);  // >= thr by construction
         }
     for (int y = 3; y < ch - 3; ++y)
         for (int x = 3; x < cw - 3; ++x) {

@@ -68,6 +68,7 @@ SIGNATURES = {
     "orbx_download_level_keypoints": (_I, [_VP, _I, _I, _VP, _I, _IP]),
     "orbx_set_profiling": (_I, [_VP, _I]),
     "orbx_last_timings": (_I, [_VP, _VP]),
+    "orbx_cuda_stream": (_VP, [_VP]),
 }
 
 

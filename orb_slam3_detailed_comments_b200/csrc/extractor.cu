@@ -270,7 +270,8 @@ extern "C" orb_status orbx_create(const orbx_config* cfg, orbx_handle** out) {
     };
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
         return fail(set_error(ORB_ERR_CUDA, "cudaStreamCreate failed"));
-    for (int i = 0; i < 8; ++i) cudaEventCreate(&h->ev[i]);
+    for (int r = 0; r < orbx_handle::kProfRing; ++r)
+        for (int i = 0; i < 8; ++i) cudaEventCreate(&h->evr[r][i]);
     // size every buffer for the largest image
     h->pyr_bytes = level_bytes_total(h, cfg->max_width, cfg->max_height) + 4096;
     h->cur_w = h->cur_h = -1;
@@ -324,8 +325,9 @@ extern "C" void orbx_destroy(orbx_handle* h) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_counts) cudaFreeHost(h->h_counts);
-    for (int i = 0; i < 8; ++i)
-        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int r = 0; r < orbx_handle::kProfRing; ++r)
+        for (int i = 0; i < 8; ++i)
+            if (h->evr[r][i]) cudaEventDestroy(h->evr[r][i]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -399,7 +401,11 @@ extern "C" orb_status orbx_extract_batch_device(orbx_handle* h, const uint8_t* d
     orb_status s = check_batch_args(h, d_imgs, batch, w, hh, stride);
     if (s != ORB_OK) return s;
     LevelGeom& L0 = h->geom.lv[0];
-    if (h->profiling) cudaEventRecord(h->ev[0], h->stream);
+    if (h->profiling) {
+        h->ev = h->evr[h->prof_count % orbx_handle::kProfRing];
+        ++h->prof_count;
+        cudaEventRecord(h->ev[0], h->stream);
+    }
     const bool aligned = ((uintptr_t)d_imgs % 16 == 0) && (stride % 4 == 0) && (image_stride_bytes % 4 == 0);
     uint8_t* own = h->d_pyr;  // level 0 block of the handle
     if (aligned) {
@@ -426,7 +432,11 @@ extern "C" orb_status orbx_extract_batch(orbx_handle* h, const uint8_t* imgs, in
     L0.base = h->d_pyr;
     L0.pitch = round_up(w, 16);
     L0.img_stride = (int64_t)L0.pitch * hh;
-    if (h->profiling) cudaEventRecord(h->ev[0], h->stream);
+    if (h->profiling) {
+        h->ev = h->evr[h->prof_count % orbx_handle::kProfRing];
+        ++h->prof_count;
+        cudaEventRecord(h->ev[0], h->stream);
+    }
     if (image_stride_bytes == (size_t)stride * hh) {
         // the whole batch is one pitched 2-D copy: rows = batch * height
         ORB_CUDA(cudaMemcpy2DAsync(L0.base, L0.pitch, imgs, stride, w, (size_t)hh * batch, cudaMemcpyHostToDevice, h->stream));
@@ -565,19 +575,24 @@ extern "C" orb_status orbx_download_level_keypoints(orbx_handle* h, int32_t b, i
 extern "C" orb_status orbx_set_profiling(orbx_handle* h, int32_t on) {
     if (!h) return set_error(ORB_ERR_INVALID, "null handle");
     h->profiling = on != 0;
+    h->prof_count = 0;
     return ORB_OK;
 }
 
+// averages over the batches recorded since orbx_set_profiling (at most the last kProfRing)
 extern "C" orb_status orbx_last_timings(orbx_handle* h, float* ms7) {
-    if (!h || !ms7 || !h->profiling) return set_error(ORB_ERR_INVALID, "profiling is off");
+    if (!h || !ms7 || !h->profiling || h->prof_count < 1) return set_error(ORB_ERR_INVALID, "profiling is off or no batch ran");
     ORB_CUDA(cudaStreamSynchronize(h->stream));
-    float t = 0;
-    cudaEventElapsedTime(&t, h->ev[0], h->ev[6]); ms7[0] = t;
-    cudaEventElapsedTime(&t, h->ev[1], h->ev[2]); ms7[1] = t;
-    cudaEventElapsedTime(&t, h->ev[2], h->ev[3]); ms7[2] = t;
-    cudaEventElapsedTime(&t, h->ev[3], h->ev[4]); ms7[3] = t;
-    cudaEventElapsedTime(&t, h->ev[4], h->ev[5]); ms7[4] = t;
-    cudaEventElapsedTime(&t, h->ev[5], h->ev[6]); ms7[5] = t;
-    cudaEventElapsedTime(&t, h->ev[0], h->ev[1]); ms7[6] = t;
+    const int n = std::min(h->prof_count, (int)orbx_handle::kProfRing);
+    static const int a[7] = {0, 1, 2, 3, 4, 5, 0}, b[7] = {6, 2, 3, 4, 5, 6, 1};
+    for (int k = 0; k < 7; ++k) ms7[k] = 0.f;
+    for (int r = 0; r < n; ++r)
+        for (int k = 0; k < 7; ++k) {
+            float t = 0;
+            cudaEventElapsedTime(&t, h->evr[r][a[k]], h->evr[r][b[k]]);
+            ms7[k] += t / n;
+        }
     return ORB_OK;
 }
+
+extern "C" void* orbx_cuda_stream(orbx_handle* h) { return h ? (void*)h->stream : nullptr; }

@@ -9,7 +9,10 @@ struct orbx_handle {
     orb::ExtractGeom geom{};
     int cur_w = -1, cur_h = -1;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[8] = {};
+    static const int kProfRing = 32;
+    cudaEvent_t evr[kProfRing][8] = {};   // ring of per-batch stage events
+    cudaEvent_t* ev = evr[0];
+    int prof_count = 0;
     bool profiling = false;
     // ORBextractor.h:97-108 tables
     std::vector<float> scale, inv_scale, sigma2, inv_sigma2;

@@ -132,6 +132,9 @@ class ORBextractor:
         N.check(self._L.orbx_download_level_keypoints(self._h, b, level, N.ptr(out), cap, C.byref(n)))
         return out[:n.value].copy()
 
+    def cuda_stream(self):
+        return self._L.orbx_cuda_stream(self._h)
+
     def set_profiling(self, on=True):
         N.check(self._L.orbx_set_profiling(self._h, 1 if on else 0))
 
