@@ -120,6 +120,21 @@ void* orbx_cuda_stream(orbx_handle* h);
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t orb_kernel_launches(void);
 
+/* ------------------------------------------------------------------------------------------------
+ * Frame::ComputeStereoMatches  (src/Frame.cc:1102-1358)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Stereo matching of the last extracted batch of ONE handle holding interleaved eyes: left = image 2p,
+ * right = image 2p+1, p < n_pairs.  bf = Frame::mbf, b = Frame::mb.  Results (mvuRight / mvDepth, -1 =
+ * no match) stay on the device, row-aligned with the compact keypoint rows; right-eye rows are unused. */
+orb_status orbm_stereo_batch(orbx_handle* h, int32_t n_pairs, float bf, float b);
+orb_status orbm_stereo_download(orbx_handle* h, float* uright, float* depth, int32_t cap_rows);
+
+/* The reference's own arrangement: two extractor objects (mpORBextractorLeft / Right, Frame.cc:136-141),
+ * image 0 of each.  Writes mvuRight / mvDepth of the N left keypoints to host arrays. */
+orb_status orbm_stereo_pair(orbx_handle* left, orbx_handle* right, float bf, float b, float* uright,
+                            float* depth, int32_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -193,3 +193,18 @@ def distribute(cands, minX, maxX, minY, maxY, N):
     out = np.zeros(max(len(cands), 1), np.int32)
     n = lib().orc_distribute(_p(cands), len(cands), minX, maxX, minY, maxY, N, _p(out), len(out))
     return out[:n].copy()
+
+
+def stereo_matches(exL, exR, kpsL, descL, kpsR, descR, bf, b):
+    """Frame::ComputeStereoMatches restated (reference src/Frame.cc:1102-1358).  exL/exR are the
+    OracleExtractor objects that just produced (kpsL, descL)/(kpsR, descR) (their pyramids are read)."""
+    L = lib()
+    L.orc_stereo.restype = C.c_int
+    L.orc_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                             C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    kpsL, kpsR = np.ascontiguousarray(kpsL), np.ascontiguousarray(kpsR)
+    descL, descR = np.ascontiguousarray(descL), np.ascontiguousarray(descR)
+    uR = np.zeros(len(kpsL), np.float32)
+    dep = np.zeros(len(kpsL), np.float32)
+    kept = L.orc_stereo(exL.h, exR.h, _p(kpsL), _p(descL), len(kpsL), _p(kpsR), _p(descR), len(kpsR), bf, b, _p(uR), _p(dep))
+    return uR, dep, kept

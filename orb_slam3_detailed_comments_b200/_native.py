@@ -12,7 +12,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "lib", "liborbslam3_b200.so")
-SOURCES = ["extractor.cu"]
+SOURCES = ["extractor.cu", "stereo.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -69,6 +69,9 @@ SIGNATURES = {
     "orbx_set_profiling": (_I, [_VP, _I]),
     "orbx_last_timings": (_I, [_VP, _VP]),
     "orbx_cuda_stream": (_VP, [_VP]),
+    "orbm_stereo_batch": (_I, [_VP, _I, _F, _F]),
+    "orbm_stereo_download": (_I, [_VP, _VP, _VP, _I]),
+    "orbm_stereo_pair": (_I, [_VP, _VP, _F, _F, _VP, _VP, _I]),
 }
 
 

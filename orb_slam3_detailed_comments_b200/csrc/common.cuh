@@ -54,6 +54,7 @@ struct LevelGeom {
     int tapOff;
     int area2x;             // cv::resize INTER_AREA fast path (exact 2x decimation)
     float scale;            // mvScaleFactor[level]
+    float inv_scale;        // mvInvScaleFactor[level]
     float patch;            // (float)(int)(31 * scale)
 };
 

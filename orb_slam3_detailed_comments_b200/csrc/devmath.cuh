@@ -70,14 +70,21 @@ ORB_HD uint32_t fast_score_x2(uint32_t c2, const uint32_t r[16]) {
         lo3[k] = min3_u16x2(D[k], D[(k + 1) & 15], D[(k + 2) & 15]);
         hi3[k] = max3_u16x2(D[k], D[(k + 1) & 15], D[(k + 2) & 15]);
     }
-    uint32_t best_min = 0u, best_max = 0xffffffffu;  // max over arcs of min D; min over arcs of max D
+    // min / max over each of the 16 arcs of 9, then max-of-min / min-of-max over the arcs (3-input ops)
+    uint32_t mn9[16], mx9[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        const uint32_t mn9 = min3_u16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
-        const uint32_t mx9 = max3_u16x2(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
-        best_min = max_u16x2(best_min, mn9);
-        best_max = min_u16x2(best_max, mx9);
+        mn9[k] = min3_u16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
+        mx9[k] = max3_u16x2(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
     }
+    uint32_t a0 = max3_u16x2(mn9[0], mn9[1], mn9[2]), a1 = max3_u16x2(mn9[3], mn9[4], mn9[5]);
+    uint32_t a2 = max3_u16x2(mn9[6], mn9[7], mn9[8]), a3 = max3_u16x2(mn9[9], mn9[10], mn9[11]);
+    uint32_t a4 = max3_u16x2(mn9[12], mn9[13], mn9[14]);
+    const uint32_t best_min = max3_u16x2(max3_u16x2(a0, a1, a2), max3_u16x2(a3, a4, mn9[15]), 0u);
+    uint32_t b0 = min3_u16x2(mx9[0], mx9[1], mx9[2]), b1 = min3_u16x2(mx9[3], mx9[4], mx9[5]);
+    uint32_t b2 = min3_u16x2(mx9[6], mx9[7], mx9[8]), b3 = min3_u16x2(mx9[9], mx9[10], mx9[11]);
+    uint32_t b4 = min3_u16x2(mx9[12], mx9[13], mx9[14]);
+    const uint32_t best_max = min3_u16x2(min3_u16x2(b0, b1, b2), min3_u16x2(b3, b4, mx9[15]), 0xffffffffu);
     // bright = best_min - 256 ; dark = 256 - best_max ; score = max(bright, dark) - 1 ; return +256
     // => lane = max(best_min, 512 - best_max) - 1
     const uint32_t dark = 0x02000200u - best_max;  // per lane in [1, 511], no borrow

@@ -86,7 +86,6 @@ static orb_status plan_geometry(orbx_handle* h, int w, int hh) {
     g.minTh = h->cfg.min_th_fast;
     std::vector<int2> taps;
     int cells = 0, tiles = 0, cand = 0, kp = 0, sortOff = 0;
-    const int B = h->cfg.max_batch;
     for (int l = 0; l < nl; ++l) {
         LevelGeom& L = g.lv[l];
         L.w = (int)lrintf((float)w * h->inv_scale[l]);   // ORBextractor.cc:1691-1692
@@ -137,12 +136,13 @@ static orb_status plan_geometry(orbx_handle* h, int w, int hh) {
         L.candCap = round_up(std::max(cap, 4), 4);
         L.candOff = cand;
         cand += L.candCap;
-        L.kpCap = 4 * L.quota + 16;
+        L.kpCap = qt_node_cap(L.quota);   // the node list never exceeds N + 3 (quadtree_core.cuh)
         L.kpOff = kp;
         kp += L.kpCap;
         L.sortOff = sortOff;
         sortOff += pow2_ceil(L.candCap);
         L.scale = h->scale[l];
+        L.inv_scale = h->inv_scale[l];
         L.patch = (float)(int)(31 * h->scale[l]);   // ORBextractor.cc:1184
         L.tapOff = (int)taps.size();
         L.area2x = 0;
@@ -209,23 +209,12 @@ static orb_status apply_geometry(orbx_handle* h, int w, int hh) {
     ORB_CUDA(cudaMemcpyAsync(h->d_taps, h->taps_host.data(), h->taps_host.size() * sizeof(int2), cudaMemcpyHostToDevice,
                              h->stream));
     ORB_CUDA(cudaStreamSynchronize(h->stream));
-    // quadtree shared-memory plan
+    // quadtree launch plan.  Node workspace: qt_node_cap(N) nodes (N + 20, see quadtree_core.cuh).
     int capMax = 0;
-    for (int l = 0; l < h->cfg.n_levels; ++l) capMax = std::max(capMax, 4 * h->geom.lv[l].quota + 16);
+    for (int l = 0; l < h->cfg.n_levels; ++l) capMax = std::max(capMax, qt_node_cap(h->geom.lv[l].quota));
     h->qt_node_cap = capMax;
-    const size_t nodeBytes = qt_work_bytes(capMax);
-    const size_t budget = 200 * 1024;
-    if (nodeBytes <= 120 * 1024) {
-        h->qt_nodes_in_smem = 1;
-        int sc = 4096;
-        while ((size_t)sc * 2 * 4 + nodeBytes <= budget && sc < 32768) sc *= 2;
-        h->qt_sort_cap_smem = sc;
-        h->qt_smem_bytes = (size_t)sc * 4 + nodeBytes;
-    } else {
-        h->qt_nodes_in_smem = 0;
-        h->qt_sort_cap_smem = 32768;
-        h->qt_smem_bytes = (size_t)32768 * 4;
-    }
+    const size_t nodeBytes = (qt_work_bytes(capMax) + 15) / 16 * 16;
+    h->qt_nodes_in_smem = nodeBytes <= 96 * 1024 ? 1 : 0;
     h->qt_node_stride = (nodeBytes + 255) / 256 * 256;
     if (!h->qt_nodes_in_smem) {
         const size_t need = h->qt_node_stride * (size_t)h->cfg.max_batch * h->cfg.n_levels;
@@ -236,7 +225,42 @@ static orb_status apply_geometry(orbx_handle* h, int w, int hh) {
             h->node_scratch_bytes = need;
         }
     }
-    ORB_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qt_smem_bytes));
+    // Sort capacity in shared memory per level: a texture-rich level yields about one FAST candidate
+    // per 37 tested pixels; provision area/24 and fall back to the global scratch beyond that.
+    // Consecutive levels with the same capacity form a group (<= 3 groups, one launch each).
+    {
+        int capOf[ORB_MAX_LEVELS];
+        for (int l = 0; l < h->cfg.n_levels; ++l) {
+            const LevelGeom& L = h->geom.lv[l];
+            const int est = (int)((int64_t)(L.maxBX - 16) * (L.maxBY - 16) / 24);
+            int c = pow2_ceil(std::max(est, 1024));
+            c = std::min(c, 32768);
+            if (c > 8192) c = std::max(c, 16384);
+            else if (c > 2048) c = 8192;
+            else c = 2048;
+            while ((size_t)c * 4 + (h->qt_nodes_in_smem ? nodeBytes : 0) > 200 * 1024 && c > 2048) c >>= 1;
+            capOf[l] = c;
+        }
+        for (int l = 1; l < h->cfg.n_levels; ++l) capOf[l] = std::min(capOf[l], capOf[l - 1]);  // monotone
+        h->qt_ngroups = 0;
+        for (int l = 0; l < h->cfg.n_levels; ++l) {
+            if (h->qt_ngroups > 0 && (capOf[l] == h->qt_groups[h->qt_ngroups - 1].sort_cap || h->qt_ngroups == 3)) {
+                h->qt_groups[h->qt_ngroups - 1].level_end = l + 1;
+            } else {
+                orbx_handle::QtGroup& G = h->qt_groups[h->qt_ngroups++];
+                G.level_begin = l;
+                G.level_end = l + 1;
+                G.sort_cap = capOf[l];
+            }
+        }
+        size_t maxSmem = 0;
+        for (int i = 0; i < h->qt_ngroups; ++i) {
+            // a group that absorbed smaller levels keeps its (larger) capacity: always sufficient
+            h->qt_groups[i].smem = (size_t)h->qt_groups[i].sort_cap * 4 + (h->qt_nodes_in_smem ? nodeBytes : 0);
+            maxSmem = std::max(maxSmem, h->qt_groups[i].smem);
+        }
+        ORB_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem));
+    }
     const size_t ordBytes = ((size_t)h->geom.kpTotal + 64) * 4;
     ORB_CUDA(cudaFuncSetAttribute(k_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(ordBytes, (size_t)1024)));
     h->order_smem_bytes = ordBytes;
@@ -272,6 +296,11 @@ extern "C" orb_status orbx_create(const orbx_config* cfg, orbx_handle** out) {
         return fail(set_error(ORB_ERR_CUDA, "cudaStreamCreate failed"));
     for (int r = 0; r < orbx_handle::kProfRing; ++r)
         for (int i = 0; i < 8; ++i) cudaEventCreate(&h->evr[r][i]);
+    for (int i = 0; i < 2; ++i) {
+        cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     // size every buffer for the largest image
     h->pyr_bytes = level_bytes_total(h, cfg->max_width, cfg->max_height) + 4096;
     h->cur_w = h->cur_h = -1;
@@ -302,6 +331,9 @@ extern "C" orb_status orbx_create(const orbx_config* cfg, orbx_handle** out) {
     ALLOC(h->d_taps, h->taps_slots * sizeof(int2));
     ALLOC(h->d_kps, h->out_rows * sizeof(orbx_keypoint));
     ALLOC(h->d_desc, h->out_rows * 32);
+    ALLOC(h->d_uright, h->out_rows * sizeof(float));
+    ALLOC(h->d_depth, h->out_rows * sizeof(float));
+    ALLOC(h->d_sad, h->out_rows * sizeof(int));
 #undef ALLOC
     h->d_mono = h->d_nkp + B;
     h->d_offsets = h->d_nkp + 2 * B;
@@ -321,13 +353,19 @@ extern "C" void orbx_destroy(orbx_handle* h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->d_pyr, h->d_blur, h->d_cand, h->d_sort, h->d_lvl_kp, h->d_slot, h->d_cand_cnt, h->d_lvl_cnt,
-                    h->d_nkp, h->d_err, h->d_taps, h->d_kps, h->d_desc, h->d_node_scratch, h->d_stage};
+                    h->d_nkp, h->d_err, h->d_taps, h->d_kps, h->d_desc, h->d_node_scratch, h->d_stage,
+                    h->d_uright, h->d_depth, h->d_sad};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_counts) cudaFreeHost(h->h_counts);
     for (int r = 0; r < orbx_handle::kProfRing; ++r)
         for (int i = 0; i < 8; ++i)
             if (h->evr[r][i]) cudaEventDestroy(h->evr[r][i]);
+    for (int i = 0; i < 2; ++i) {
+        if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]);
+        if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -364,10 +402,21 @@ static orb_status run_pipeline(orbx_handle* h, int batch, int lap0, int lap1) {
     k_fast_cells<<<dim3(g.totalCells, batch), FAST_THREADS, 0, st>>>(g, h->d_cand, h->d_cand_cnt, h->d_err);
     ORB_LAUNCHED();
     if (prof) cudaEventRecord(h->ev[3], st);
-    k_quadtree<<<batch * g.nlevels, QT_THREADS, h->qt_smem_bytes, st>>>(
-        g, batch, h->d_cand, h->d_cand_cnt, h->d_sort, (char*)h->d_node_scratch, (int64_t)h->qt_node_stride,
-        h->qt_sort_cap_smem, h->qt_nodes_in_smem, h->qt_node_cap, h->d_lvl_kp, h->d_lvl_cnt, h->d_err);
-    ORB_LAUNCHED();
+    // DistributeOctTree: level groups on parallel streams (fork from / join into the handle's stream)
+    cudaEventRecord(h->ev_fork, st);
+    for (int gi = 0; gi < h->qt_ngroups; ++gi) {
+        const orbx_handle::QtGroup& Q = h->qt_groups[gi];
+        cudaStream_t qs = gi == 0 ? st : h->aux_stream[gi - 1];
+        if (gi > 0) cudaStreamWaitEvent(qs, h->ev_fork, 0);
+        k_quadtree<<<batch * (Q.level_end - Q.level_begin), QT_THREADS, Q.smem, qs>>>(
+            g, batch, Q.level_begin, h->d_cand, h->d_cand_cnt, h->d_sort, (char*)h->d_node_scratch,
+            (int64_t)h->qt_node_stride, Q.sort_cap, h->qt_nodes_in_smem, h->qt_node_cap, h->d_lvl_kp, h->d_lvl_cnt, h->d_err);
+        ORB_LAUNCHED();
+        if (gi > 0) {
+            cudaEventRecord(h->ev_join[gi - 1], qs);
+            cudaStreamWaitEvent(st, h->ev_join[gi - 1], 0);
+        }
+    }
     k_order<<<batch, 256, h->order_smem_bytes, st>>>(g, h->d_lvl_kp, h->d_lvl_cnt, lap0, lap1, h->d_slot, h->d_nkp,
                                                      h->d_mono);
     ORB_LAUNCHED();

@@ -35,6 +35,9 @@ struct orbx_handle {
     int2* d_taps = nullptr;
     orbx_keypoint* d_kps = nullptr;  // compact results of the last batch
     uint8_t* d_desc = nullptr;
+    float* d_uright = nullptr;       // Frame::mvuRight / mvDepth of the last stereo batch (row-aligned with d_kps)
+    float* d_depth = nullptr;
+    int* d_sad = nullptr;
     void* d_node_scratch = nullptr;
     uint8_t* d_stage = nullptr;
     size_t node_scratch_bytes = 0;
@@ -42,7 +45,13 @@ struct orbx_handle {
     int* h_counts = nullptr;       // pinned
     bool counts_valid = false;
     int last_batch = 0;
-    // quadtree launch plan
-    int qt_node_cap = 0, qt_nodes_in_smem = 1, qt_sort_cap_smem = 4096;
-    size_t qt_smem_bytes = 0, qt_node_stride = 0, order_smem_bytes = 0;
+    // quadtree launch plan: up to 3 level groups with their own shared-memory size, run on parallel
+    // streams (forked from / joined into `stream`)
+    struct QtGroup { int level_begin, level_end, sort_cap; size_t smem; };
+    QtGroup qt_groups[3] = {};
+    int qt_ngroups = 0;
+    cudaStream_t aux_stream[2] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {};
+    int qt_node_cap = 0, qt_nodes_in_smem = 1;
+    size_t qt_node_stride = 0, order_smem_bytes = 0;
 };

@@ -238,14 +238,27 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
 // ---------------------------------------------------------------------------------------------
 #define QT_THREADS 256
 
-__global__ void __launch_bounds__(QT_THREADS) k_quadtree(const __grid_constant__ ExtractGeom g, int batch, const uint32_t* __restrict__ cand,
-                                                        const int* __restrict__ candCnt, uint32_t* __restrict__ sortScratch,
-                                                        char* __restrict__ nodeScratch, int64_t nodeScratchStride,
-                                                        int sortCapSmem, int nodesInSmem, int nodeCapMax,
-                                                        uint32_t* __restrict__ lvlKp, int* __restrict__ lvlCnt,
+// arr / ws are passed from branch-specific call sites so that the shared-memory instance is compiled
+// with LDS/STS instead of generic loads.
+__device__ __forceinline__ int qt_run(uint32_t* arr, void* ws, int cap, int n, int npow, const uint32_t* __restrict__ src,
+                                      const QtGeom& q, uint32_t* out) {
+    for (int i = threadIdx.x; i < npow; i += QT_THREADS) arr[i] = (i < n) ? qt_element(src[i], q) : 0xffffffffu;
+    __syncthreads();
+    qt_bitonic_sort(arr, npow);
+    QtWork w;
+    qt_work_carve(w, ws, cap);
+    return qt_distribute(arr, n, q, w, out);
+}
+
+// levels [levelBegin, levelEnd) of every image; blockIdx.x = (level - levelBegin) * batch + image
+__global__ void __launch_bounds__(QT_THREADS) k_quadtree(const __grid_constant__ ExtractGeom g, int batch, int levelBegin,
+                                                        const uint32_t* __restrict__ cand, const int* __restrict__ candCnt,
+                                                        uint32_t* __restrict__ sortScratch, char* __restrict__ nodeScratch,
+                                                        int64_t nodeScratchStride, int sortCapSmem, int nodesInSmem,
+                                                        int nodeCapMax, uint32_t* __restrict__ lvlKp, int* __restrict__ lvlCnt,
                                                         int* __restrict__ err) {
     extern __shared__ __align__(16) unsigned char qt_smem[];
-    const int l = blockIdx.x / batch, img = blockIdx.x - l * batch;  // big levels are scheduled first
+    const int l = levelBegin + blockIdx.x / batch, img = blockIdx.x % batch;
     const LevelGeom& G = g.lv[l];
     int n = candCnt[img * g.nlevels + l];
     if (n > G.candCap) n = G.candCap;
@@ -253,23 +266,23 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const __grid_constant__
     q.regionW = G.maxBX - 16; q.regionH = G.maxBY - 16;
     q.nIni = G.nIni; q.hX = G.hX; q.N = G.quota;
     q.wCell = G.wCell; q.hCell = G.hCell; q.nCols = G.nCols;
-
     int npow = 2;
     while (npow < n) npow <<= 1;
-    uint32_t* arr = (npow <= sortCapSmem) ? reinterpret_cast<uint32_t*>(qt_smem)
-                                          : sortScratch + (int64_t)img * g.sortTotal + G.sortOff;
     const uint32_t* src = cand + (int64_t)img * g.candTotal + G.candOff;
-    for (int i = threadIdx.x; i < npow; i += QT_THREADS) arr[i] = (i < n) ? qt_element(src[i], q) : 0xffffffffu;
-    __syncthreads();
-    qt_bitonic_sort(arr, npow);
-
-    QtWork w;
-    const int cap = 4 * G.quota + 16;
-    void* ws = nodesInSmem ? (void*)(qt_smem + (size_t)sortCapSmem * 4)
-                           : (void*)(nodeScratch + (int64_t)blockIdx.x * nodeScratchStride);
-    qt_work_carve(w, ws, cap < nodeCapMax ? cap : nodeCapMax);
     uint32_t* out = lvlKp + (int64_t)img * g.kpTotal + G.kpOff;
-    int S = qt_distribute(arr, n, q, w, out);
+    int cap = qt_node_cap(G.quota);
+    if (cap > nodeCapMax) cap = nodeCapMax;
+    uint32_t* garr = sortScratch + (int64_t)img * g.sortTotal + G.sortOff;
+    void* gws = nodeScratch + ((int64_t)l * batch + img) * nodeScratchStride;
+    int S;
+    if (npow <= sortCapSmem) {
+        uint32_t* sarr = reinterpret_cast<uint32_t*>(qt_smem);
+        if (nodesInSmem) S = qt_run(sarr, qt_smem + (size_t)sortCapSmem * 4, cap, n, npow, src, q, out);
+        else S = qt_run(sarr, gws, cap, n, npow, src, q, out);
+    } else {
+        if (nodesInSmem) S = qt_run(garr, qt_smem + (size_t)sortCapSmem * 4, cap, n, npow, src, q, out);
+        else S = qt_run(garr, gws, cap, n, npow, src, q, out);
+    }
     if (threadIdx.x == 0) {
         if (S < 0 || S > G.kpCap) {
             atomicExch(&err[1], 1);

@@ -11,6 +11,11 @@
 //     phase are reproduced exactly -- SURVEY App. B items 2-6);
 //   * each surviving leaf picks its best candidate (max score, ties -> reference candidate order).
 //
+// Capacity: the list never exceeds max(N + 3, 4 * nIni).  A sweep only starts when the previous one
+// ended with S + 3 * nToExpand <= N (otherwise the ordered phase takes over) and a sweep replaces
+// each of the nToExpand multi-point nodes by at most 4 children, so it ends with at most
+// S + 3 * nToExpand <= N nodes; the ordered phase breaks as soon as N is reached (<= N + 3).
+//
 // The code is written as barrier-separated SPMD phases (QT_PAR_FOR / QT_SYNC) so the identical source
 // also compiles as sequential host code for tests/host_emul (no GPU in the build container).
 #pragma once
@@ -63,6 +68,8 @@ struct QtWork {
     int* scan_tmp;   // 40 ints
     int cap;
 };
+
+ORB_HD int qt_node_cap(int N) { return N + 20; }
 
 ORB_HD size_t qt_work_bytes(int cap) {
     return (size_t)cap * (2 * sizeof(QtNode) + 3 * 4 + 3 * 4 + 2 * sizeof(QtItem)) + 40 * 4 + 64;

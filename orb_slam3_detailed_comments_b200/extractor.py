@@ -132,6 +132,24 @@ class ORBextractor:
         N.check(self._L.orbx_download_level_keypoints(self._h, b, level, N.ptr(out), cap, C.byref(n)))
         return out[:n.value].copy()
 
+    # ---- Frame::ComputeStereoMatches (Frame.cc:1102-1358) --------------------------------------
+    def stereo_batch(self, n_pairs, bf, b):
+        """Stereo-match the last batch (left = image 2p, right = image 2p+1); results stay on the device."""
+        N.check(self._L.orbm_stereo_batch(self._h, n_pairs, float(bf), float(b)))
+
+    def stereo_download(self, rows):
+        uR = np.zeros(max(rows, 1), np.float32)
+        dep = np.zeros(max(rows, 1), np.float32)
+        N.check(self._L.orbm_stereo_download(self._h, N.ptr(uR), N.ptr(dep), max(rows, 1)))
+        return uR[:rows], dep[:rows]
+
+    def stereo_pair(self, right, n_left, bf, b):
+        """mvuRight, mvDepth for image 0 of `self` (left eye) against image 0 of `right`."""
+        uR = np.zeros(max(n_left, 1), np.float32)
+        dep = np.zeros(max(n_left, 1), np.float32)
+        N.check(self._L.orbm_stereo_pair(self._h, right._h, float(bf), float(b), N.ptr(uR), N.ptr(dep), max(n_left, 1)))
+        return uR[:n_left], dep[:n_left]
+
     def cuda_stream(self):
         return self._L.orbx_cuda_stream(self._h)
 

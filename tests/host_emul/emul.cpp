@@ -97,11 +97,11 @@ extern "C" int emul_distribute(const int32_t* cand3, int n, int regionW, int reg
     std::vector<uint32_t> arr(npow, 0xffffffffu);
     for (int i = 0; i < n; ++i) arr[i] = qt_element(qt_pack_cand(cand3[3 * i], cand3[3 * i + 1], cand3[3 * i + 2]), g);
     qt_bitonic_sort(arr.data(), npow);
-    const int cap = 4 * N + 16;
+    const int cap = N + 20;
     std::vector<char> ws(qt_work_bytes(cap));
     QtWork w;
     qt_work_carve(w, ws.data(), cap);
-    std::vector<uint32_t> out(cap);
+    std::vector<uint32_t> out(cap + 4);
     const int S = qt_distribute(arr.data(), n, g, w, out.data());
     for (int i = 0; i < S && i < cap_out; ++i) {
         out3[3 * i] = out[i] & 0xfff;

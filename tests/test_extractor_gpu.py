@@ -117,7 +117,7 @@ def test_handle_reuse_across_sizes():
 
 def test_other_pyramid_parameters():
     # scaleFactor 2.0 takes cv::resize's INTER_AREA fast path; 4 levels; different thresholds
-    for (nf, sf, nl, ini, mn, w, h) in [(600, 2.0, 4, 20, 7, 640, 480), (900, 1.5, 5, 30, 10, 640, 480),
+    for (nf, sf, nl, ini, mn, w, h) in [(600, 2.0, 3, 20, 7, 640, 480), (900, 1.5, 5, 30, 10, 640, 480),
                                         (5000, 1.2, 8, 20, 7, 752, 480)]:
         img = synth.frame(w, h, 31)
         ex = ORBextractor(nf, sf, nl, ini, mn, max_width=w, max_height=h)
