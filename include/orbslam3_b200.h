@@ -135,6 +135,70 @@ orb_status orbm_stereo_download(orbx_handle* h, float* uright, float* depth, int
 orb_status orbm_stereo_pair(orbx_handle* left, orbx_handle* right, float bf, float b, float* uright,
                             float* depth, int32_t cap);
 
+/* ------------------------------------------------------------------------------------------------
+ * ORBmatcher::SearchByProjection family  (include/ORBmatcher.h:40-87, src/ORBmatcher.cc), Nleft == -1
+ *
+ * The frame whose features are searched is an image of the extractor handle's last batch (for a stereo
+ * batch: the LEFT image 2p; its mvuRight comes from orbm_stereo_batch when that ran, else -1).  Several
+ * frames are processed per call; frame f uses queries [query_offset[f], query_offset[f+1]).
+ * on_device != 0: every array pointer of the query struct and the output pointers are DEVICE memory and
+ * the call does not synchronise (except for reading the two small offset tables).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    float fx, fy, cx, cy, bf, b;          /* Frame::fx.., mbf, mb */
+    float min_x, max_x, min_y, max_y;     /* Frame::mnMinX, mnMaxX, mnMinY, mnMaxY (image bounds when rectified) */
+} orbm_camera;
+
+/* SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints)  ORBmatcher.cc:45-239.
+ * One entry per map point with mbTrackInView, in vpMapPoints order, carrying the fields Frame::isInFrustum
+ * wrote into it (MapPoint.h: mTrackProjX, mTrackProjY, mTrackProjXR, mnTrackScaleLevel, mTrackViewCos,
+ * mTrackDepth) and MapPoint::GetDescriptor().  Local map points always have Observations() > 0. */
+typedef struct {
+    int32_t n_frames;
+    int32_t on_device;
+    const int32_t* frame_image;   /* [n_frames] image index in the last batch */
+    const int32_t* query_offset;  /* [n_frames + 1] */
+    const float* proj_x;
+    const float* proj_y;
+    const float* proj_xr;
+    const int32_t* level;
+    const float* view_cos;
+    const float* track_depth;     /* may be NULL unless far_points */
+    const uint8_t* desc;          /* 32 bytes per query */
+    const uint8_t* feature_claimed; /* per compact keypoint row of the batch: F.mvpMapPoints[idx] already holds a
+                                       map point with Observations() > 0; NULL = none */
+} orbm_local_queries;
+
+/* match_out[q] = feature index inside its frame (F.mvpMapPoints[bestIdx] = pMP) or -1;
+ * nmatches_out[f] = the reference's return value for frame f (may be NULL). */
+orb_status orbm_search_local_points(orbx_handle* h, const orbm_camera* cam, const orbm_local_queries* q, float th,
+                                    float nnratio, int32_t far_points, float th_far, int32_t* match_out,
+                                    int32_t* nmatches_out);
+
+/* SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)  ORBmatcher.cc:1950-2184.
+ * One entry per LastFrame feature that has a map point and is not an outlier, in LastFrame order.
+ * direction[f]: 0 = neither, 1 = bForward, 2 = bBackward (tlc.z vs mb, ORBmatcher.cc:1967-1971; computed
+ * by the caller from the two poses exactly as the reference does).  Tcw: qx qy qz qw tx ty tz (Sophus::SE3f).
+ * CurrentFrame.mvpMapPoints must be all-NULL on entry (Tracking.cc:3367). */
+typedef struct {
+    int32_t n_frames;
+    int32_t on_device;
+    const int32_t* frame_image;
+    const int32_t* query_offset;
+    const float* Tcw;             /* [n_frames][7] */
+    const int32_t* direction;     /* [n_frames] */
+    const float* world_pos;       /* [nq][3] MapPoint::GetWorldPos */
+    const int32_t* last_octave;   /* LastFrame.mvKeys[i].octave */
+    const float* last_angle;      /* LastFrame.mvKeysUn[i].angle */
+    const uint8_t* desc;          /* MapPoint::GetDescriptor */
+    const uint8_t* obs_positive;  /* pMP->Observations() > 0 */
+} orbm_last_queries;
+
+/* feature_match_out: one entry per compact keypoint row of the whole batch: the query index now held by
+ * CurrentFrame.mvpMapPoints[idx], or -1.  nmatches_out[f] = the reference's return value. */
+orb_status orbm_search_last_frame(orbx_handle* h, const orbm_camera* cam, const orbm_last_queries* q, float th,
+                                  int32_t check_orientation, int32_t* feature_match_out, int32_t* nmatches_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,211 @@
+// oracle/matcher_oracle.cpp -- TEST INFRASTRUCTURE (see oracle.h).
+// CPU restatement of the projection-search matchers for the non-fisheye case (Frame::Nleft == -1):
+//   * Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea   (src/Frame.cc:469-504, 962-978, 859-951)
+//   * ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>, th, bFar, thFar)   (src/ORBmatcher.cc:45-239)
+//   * ORBmatcher::SearchByProjection(Frame& cur, const Frame& last, th, bMono)     (src/ORBmatcher.cc:1950-2184)
+//   * ORBmatcher::ComputeThreeMaxima                                               (src/ORBmatcher.cc:2335-2377)
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "oracle.h"
+
+namespace orb_oracle {
+
+static const int GRID_COLS = 64, GRID_ROWS = 48;  // include/Frame.h:46-47
+
+struct FrameView {
+    const KeyPoint* kps;      // mvKeysUn (== mvKeys for rectified stereo)
+    const uint8_t* desc;
+    const float* uright;      // mvuRight (may be null: monocular => -1)
+    int N;
+    float minX, maxX, minY, maxY;
+    float invW, invH;         // mfGridElementWidthInv/HeightInv
+    const float* scaleFactors;
+    std::vector<size_t> grid[64][48];
+
+    void build() {  // AssignFeaturesToGrid
+        invW = (float)GRID_COLS / (maxX - minX);
+        invH = (float)GRID_ROWS / (maxY - minY);
+        for (int i = 0; i < N; ++i) {
+            const int px = (int)std::round((kps[i].x - minX) * invW);
+            const int py = (int)std::round((kps[i].y - minY) * invH);
+            if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) continue;
+            grid[px][py].push_back(i);
+        }
+    }
+
+    std::vector<size_t> area(float x, float y, float r, int minLevel, int maxLevel) const {  // GetFeaturesInArea
+        std::vector<size_t> out;
+        const int c0 = std::max(0, (int)std::floor((x - minX - r) * invW));
+        if (c0 >= GRID_COLS) return out;
+        const int c1 = std::min(GRID_COLS - 1, (int)std::ceil((x - minX + r) * invW));
+        if (c1 < 0) return out;
+        const int r0 = std::max(0, (int)std::floor((y - minY - r) * invH));
+        if (r0 >= GRID_ROWS) return out;
+        const int r1 = std::min(GRID_ROWS - 1, (int)std::ceil((y - minY + r) * invH));
+        if (r1 < 0) return out;
+        const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
+        for (int ix = c0; ix <= c1; ++ix)
+            for (int iy = r0; iy <= r1; ++iy)
+                for (size_t id : grid[ix][iy]) {
+                    const KeyPoint& k = kps[id];
+                    if (checkLevels) {
+                        if (k.octave < minLevel) continue;
+                        if (maxLevel >= 0 && k.octave > maxLevel) continue;
+                    }
+                    const float dx = k.x - x, dy = k.y - y;
+                    if (std::fabs(dx) < r && std::fabs(dy) < r) out.push_back(id);
+                }
+        return out;
+    }
+};
+
+}  // namespace orb_oracle
+
+using namespace orb_oracle;
+
+extern "C" {
+
+// SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints).  claimed[idx] != 0 <=> F.mvpMapPoints[idx]
+// already holds a map point with Observations() > 0 (updated as matches are made: local map points have
+// observations).  match[q] = feature index or -1.  Returns nmatches.
+int orc_search_local(const KeyPoint* kps, const uint8_t* desc, const float* uright, int N, const float* bounds4,
+                     const float* scaleFactors, int nq, const float* projx, const float* projy, const float* projxr,
+                     const int* level, const float* viewcos, const float* trackdepth, const uint8_t* qdesc,
+                     uint8_t* claimed, float th, float nnratio, int bFar, float thFar, int* match) {
+    FrameView F;
+    F.kps = kps; F.desc = desc; F.uright = uright; F.N = N;
+    F.minX = bounds4[0]; F.maxX = bounds4[1]; F.minY = bounds4[2]; F.maxY = bounds4[3];
+    F.scaleFactors = scaleFactors;
+    F.build();
+    int nmatches = 0;
+    const bool bFactor = th != 1.0;
+    for (int q = 0; q < nq; ++q) {
+        match[q] = -1;
+        if (bFar && trackdepth[q] > thFar) continue;
+        const int lvl = level[q];
+        float r = (viewcos[q] > 0.998) ? 2.5f : 4.0f;   // RadiusByViewingCos: literal 0.998 is a double
+        if (bFactor) r *= th;
+        const std::vector<size_t> ind = F.area(projx[q], projy[q], r * scaleFactors[lvl], lvl - 1, lvl);
+        if (ind.empty()) continue;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (size_t idx : ind) {
+            if (claimed[idx]) continue;
+            if (uright && uright[idx] > 0) {
+                const float er = std::fabs(projxr[q] - uright[idx]);
+                if (er > r * scaleFactors[lvl]) continue;
+            }
+            const int dist = descriptor_distance(qdesc + 32 * (size_t)q, desc + 32 * idx);
+            if (dist < bestDist) {
+                bestDist2 = bestDist;
+                bestDist = dist;
+                bestLevel2 = bestLevel;
+                bestLevel = kps[idx].octave;
+                bestIdx = (int)idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = kps[idx].octave;
+                bestDist2 = dist;
+            }
+        }
+        if (bestDist <= 100) {  // TH_HIGH
+            if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+            if (bestLevel != bestLevel2 || bestDist <= nnratio * bestDist2) {
+                match[q] = bestIdx;
+                claimed[bestIdx] = 1;
+                ++nmatches;
+            }
+        }
+    }
+    return nmatches;
+}
+
+// Sophus::SE3f * Vector3f (so3.hpp:358-367, se3.hpp:321-324), float32, non-contracted
+static void se3_act(const float* q /*x y z w*/, const float* t, const float* p, float* out) {
+    const float uvx = q[1] * p[2] - q[2] * p[1], uvy = q[2] * p[0] - q[0] * p[2], uvz = q[0] * p[1] - q[1] * p[0];
+    const float ux = uvx + uvx, uy = uvy + uvy, uz = uvz + uvz;
+    const float cx = q[1] * uz - q[2] * uy, cy = q[2] * ux - q[0] * uz, cz = q[0] * uy - q[1] * ux;
+    out[0] = ((p[0] + q[3] * ux) + cx) + t[0];
+    out[1] = ((p[1] + q[3] * uy) + cy) + t[1];
+    out[2] = ((p[2] + q[3] * uz) + cz) + t[2];
+}
+
+// SearchByProjection(CurrentFrame, LastFrame, th, bMono), Nleft == -1.  Queries = LastFrame features with a
+// map point that is not an outlier, in LastFrame order.  direction: 0 none, 1 forward, 2 backward.
+// obs_pos[q] != 0 <=> pMP->Observations() > 0.  feat_match[idx] = query index holding the feature or -1
+// (CurrentFrame.mvpMapPoints is all-NULL on entry, Tracking.cc:3367).  Returns nmatches.
+int orc_search_last(const KeyPoint* kps, const uint8_t* desc, const float* uright, int N, const float* bounds4,
+                    const float* scaleFactors, const float* cam6 /*fx fy cx cy bf b*/, const float* Tcw7, int direction,
+                    int nq, const float* xw, const int* lastOctave, const float* lastAngle, const uint8_t* qdesc,
+                    const uint8_t* obs_pos, float th, int checkOri, int* feat_match) {
+    FrameView F;
+    F.kps = kps; F.desc = desc; F.uright = uright; F.N = N;
+    F.minX = bounds4[0]; F.maxX = bounds4[1]; F.minY = bounds4[2]; F.maxY = bounds4[3];
+    F.scaleFactors = scaleFactors;
+    F.build();
+    for (int i = 0; i < N; ++i) feat_match[i] = -1;
+    int nmatches = 0;
+    std::vector<int> rotHist[30];
+    const float factor = 1.0f / 30;
+    const bool fwd = direction == 1, bwd = direction == 2;
+    for (int q = 0; q < nq; ++q) {
+        float pc[3];
+        se3_act(Tcw7, Tcw7 + 4, xw + 3 * q, pc);
+        const float invzc = (float)(1.0 / pc[2]);
+        if (invzc < 0) continue;
+        const float u = cam6[0] * pc[0] / pc[2] + cam6[2], v = cam6[1] * pc[1] / pc[2] + cam6[3];
+        if (u < F.minX || u > F.maxX) continue;
+        if (v < F.minY || v > F.maxY) continue;
+        const int oct = lastOctave[q];
+        const float radius = th * scaleFactors[oct];
+        std::vector<size_t> ind;
+        if (fwd) ind = F.area(u, v, radius, oct, -1);
+        else if (bwd) ind = F.area(u, v, radius, 0, oct);
+        else ind = F.area(u, v, radius, oct - 1, oct + 1);
+        if (ind.empty()) continue;
+        int bestDist = 256, bestIdx2 = -1;
+        for (size_t i2 : ind) {
+            if (feat_match[i2] >= 0 && obs_pos[feat_match[i2]]) continue;
+            if (uright && uright[i2] > 0) {
+                const float ur = u - cam6[4] * invzc;
+                const float er = std::fabs(ur - uright[i2]);
+                if (er > radius) continue;
+            }
+            const int dist = descriptor_distance(qdesc + 32 * (size_t)q, desc + 32 * i2);
+            if (dist < bestDist) {
+                bestDist = dist;
+                bestIdx2 = (int)i2;
+            }
+        }
+        if (bestDist <= 100) {
+            feat_match[bestIdx2] = q;
+            ++nmatches;
+            if (checkOri) {
+                float rot = lastAngle[q] - kps[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)std::round(rot * factor);
+                if (bin == 30) bin = 0;
+                rotHist[bin].push_back(bestIdx2);
+            }
+        }
+    }
+    if (checkOri) {
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < 30; ++i) {
+            const int s = (int)rotHist[i].size();
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < 30; ++i)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int idx : rotHist[i]) {
+                    feat_match[idx] = -1;
+                    --nmatches;
+                }
+    }
+    return nmatches;
+}
+}

@@ -208,3 +208,45 @@ def stereo_matches(exL, exR, kpsL, descL, kpsR, descR, bf, b):
     dep = np.zeros(len(kpsL), np.float32)
     kept = L.orc_stereo(exL.h, exR.h, _p(kpsL), _p(descL), len(kpsL), _p(kpsR), _p(descR), len(kpsR), bf, b, _p(uR), _p(dep))
     return uR, dep, kept
+
+
+def search_local(kps, desc, uright, bounds, scale_factors, projx, projy, projxr, level, viewcos, qdesc, th, nnratio,
+                 claimed=None, trackdepth=None, far=False, th_far=0.0):
+    """ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFar, thFar) restated (ORBmatcher.cc:45-239)."""
+    L = lib()
+    L.orc_search_local.restype = C.c_int
+    L.orc_search_local.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 8 + \
+        [C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p]
+    f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+    kps, desc, uright = np.ascontiguousarray(kps), np.ascontiguousarray(desc), f32(uright)
+    b4, sf = f32(bounds), f32(scale_factors)
+    px, py, pxr, vc, td = f32(projx), f32(projy), f32(projxr), f32(viewcos), f32(trackdepth)
+    lv = np.ascontiguousarray(level, np.int32)
+    qd = np.ascontiguousarray(qdesc, np.uint8)
+    cl = np.zeros(len(kps), np.uint8) if claimed is None else np.ascontiguousarray(claimed, np.uint8).copy()
+    nq = len(px)
+    match = np.full(max(nq, 1), -1, np.int32)
+    P = lambda a: None if a is None else _p(a)
+    nm = L.orc_search_local(_p(kps), _p(desc), P(uright), len(kps), _p(b4), _p(sf), nq, _p(px), _p(py), _p(pxr), _p(lv),
+                            _p(vc), P(td), _p(qd), _p(cl), th, nnratio, 1 if far else 0, th_far, _p(match))
+    return match[:nq], nm
+
+
+def search_last(kps, desc, uright, bounds, scale_factors, cam6, Tcw7, direction, xw, last_octave, last_angle, qdesc,
+                obs_pos, th, check_ori=True):
+    """ORBmatcher::SearchByProjection(cur, last, th, bMono) restated (ORBmatcher.cc:1950-2184)."""
+    L = lib()
+    L.orc_search_last.restype = C.c_int
+    L.orc_search_last.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_int] + [C.c_void_p] * 5 + \
+        [C.c_float, C.c_int, C.c_void_p]
+    f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+    kps, desc, uright = np.ascontiguousarray(kps), np.ascontiguousarray(desc), f32(uright)
+    b4, sf, c6, T7 = f32(bounds), f32(scale_factors), f32(cam6), f32(Tcw7)
+    xw, ang = f32(xw), f32(last_angle)
+    lo = np.ascontiguousarray(last_octave, np.int32)
+    qd, ob = np.ascontiguousarray(qdesc, np.uint8), np.ascontiguousarray(obs_pos, np.uint8)
+    fm = np.full(max(len(kps), 1), -1, np.int32)
+    P = lambda a: None if a is None else _p(a)
+    nm = L.orc_search_last(_p(kps), _p(desc), P(uright), len(kps), _p(b4), _p(sf), _p(c6), _p(T7), int(direction), len(lo),
+                           _p(xw), _p(lo), _p(ang), _p(qd), _p(ob), th, 1 if check_ori else 0, _p(fm))
+    return fm[:len(kps)], nm

@@ -12,7 +12,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "lib", "liborbslam3_b200.so")
-SOURCES = ["extractor.cu", "stereo.cu"]
+SOURCES = ["extractor.cu", "stereo.cu", "matcher.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -45,6 +45,22 @@ class orbx_config(C.Structure):
                 ("max_height", C.c_int32), ("max_batch", C.c_int32), ("device", C.c_int32)]
 
 
+class orbm_camera(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("fx", "fy", "cx", "cy", "bf", "b", "min_x", "max_x", "min_y", "max_y")]
+
+
+class orbm_local_queries(C.Structure):
+    _fields_ = [("n_frames", C.c_int32), ("on_device", C.c_int32)] + [
+        (n, C.c_void_p) for n in ("frame_image", "query_offset", "proj_x", "proj_y", "proj_xr", "level", "view_cos",
+                                  "track_depth", "desc", "feature_claimed")]
+
+
+class orbm_last_queries(C.Structure):
+    _fields_ = [("n_frames", C.c_int32), ("on_device", C.c_int32)] + [
+        (n, C.c_void_p) for n in ("frame_image", "query_offset", "Tcw", "direction", "world_pos", "last_octave",
+                                  "last_angle", "desc", "obs_positive")]
+
+
 _lib = None
 _VP, _I, _F = C.c_void_p, C.c_int32, C.c_float
 _IP = C.POINTER(C.c_int32)
@@ -72,6 +88,8 @@ SIGNATURES = {
     "orbm_stereo_batch": (_I, [_VP, _I, _F, _F]),
     "orbm_stereo_download": (_I, [_VP, _VP, _VP, _I]),
     "orbm_stereo_pair": (_I, [_VP, _VP, _F, _F, _VP, _VP, _I]),
+    "orbm_search_local_points": (_I, [_VP, C.POINTER(orbm_camera), C.POINTER(orbm_local_queries), _F, _F, _I, _F, _VP, _VP]),
+    "orbm_search_last_frame": (_I, [_VP, C.POINTER(orbm_camera), C.POINTER(orbm_last_queries), _F, _I, _VP, _VP]),
 }
 
 

@@ -433,6 +433,7 @@ static orb_status run_pipeline(orbx_handle* h, int batch, int lap0, int lap1) {
     ORB_CUDA(cudaGetLastError());
     h->last_batch = batch;
     h->counts_valid = false;
+    h->stereo_valid = false;
     return ORB_OK;
 }
 

@@ -1,0 +1,602 @@
+// matcher.cu -- ORBmatcher::SearchByProjection family on the device, for Frame::Nleft == -1
+// (pinhole / rectified stereo, the configurations of BASELINE.json):
+//   * SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints)
+//       /root/reference/src/ORBmatcher.cc:45-239      (TrackLocalMap, Tracking.cc:4062)
+//   * SearchByProjection(Frame& cur, const Frame& last, th, bMono)
+//       /root/reference/src/ORBmatcher.cc:1950-2184   (TrackWithMotionModel, Tracking.cc:3389)
+// with Frame::GetFeaturesInArea / PosInGrid (src/Frame.cc:859-951, 962-978) folded in.
+//
+// The reference is greedy: a feature claimed by query i is skipped by every later query.  Here the
+// expensive part is order-free -- one warp per query scans the frame's features (staged in shared
+// memory), applies the window / level / stereo gates, takes 256-bit Hamming distances with __popc
+// and keeps the K smallest (distance, reference-candidate-order) keys -- and a per-frame resolve pass
+// (one warp) replays the queries in order against the claim mask.  If claims eat into a query's
+// stored list so that its best / second best can no longer be known, the resolve warp rescans that
+// query with the mask applied (exact slow path).
+#include <algorithm>
+#include <vector>
+
+#include "extractor.h"
+#include "devmath.cuh"
+
+using namespace orb;
+using namespace orbdev;
+
+namespace orb {
+
+#define PM_K 4            // stored candidates per query
+#define PM_WARPS 8
+#define PM_QPB 64         // queries per CTA in the candidate kernel
+#define GRID_COLS 64      // include/Frame.h:46-47
+#define GRID_ROWS 48
+
+struct FrameFeat {   // shared-memory staging of one frame's features
+    float* x;
+    float* y;
+    float* ur;
+    uint16_t* cell;   // ix * 48 + iy, 0xffff = not in the grid (PosInGrid false)
+    uint8_t* oct;
+};
+
+struct ProjParams {
+    // frame side (an extractor handle's last batch)
+    const orbx_keypoint* kps;
+    const uint8_t* desc;
+    const float* uright;      // null => monocular (mvuRight = -1)
+    const int* offsets;
+    const int* nkp;
+    int maxFeat;
+    float minX, maxX, minY, maxY, invW, invH;
+    float fx, fy, cx, cy, bf;
+    float scale[ORB_MAX_LEVELS];
+    // query side
+    int mode;                 // 0 = local map points, 1 = last frame
+    const int* frame_image;   // [n_frames]
+    const int* qoff;          // [n_frames + 1]
+    const float* a0;          // mode 0: projX      mode 1: world pos (3 per query)
+    const float* a1;          // mode 0: projY
+    const float* a2;          // mode 0: projXR
+    const int* level;         // mode 0: predicted level   mode 1: last octave
+    const float* f0;          // mode 0: viewCos    mode 1: last angle
+    const float* f1;          // mode 0: trackDepth or null
+    const uint8_t* qdesc;
+    const uint8_t* flag;      // mode 0: initial claim mask per compact feature row (or null); mode 1: obs>0 per query
+    const float* Tcw;         // mode 1: [n_frames][7] qx qy qz qw tx ty tz
+    const int* direction;     // mode 1: [n_frames] 0 none, 1 forward, 2 backward
+    float th, nnratio, thFar;
+    int bFar, checkOri;
+    // scratch + outputs
+    unsigned long long* topk;  // [nq][PM_K]
+    int* cnt;                  // [nq] candidates passing the order-free gates
+    float* quv;                // mode 1: [nq][4] u, v, radius, invzc
+    int* match;                // mode 0: [nq] feature index or -1;  mode 1: per compact feature row: query or -1
+    int* nmatches;             // [n_frames]
+};
+
+__device__ __forceinline__ void stage_frame(const ProjParams& P, int img, unsigned char* smem, FrameFeat& F, int& N, int& row0) {
+    N = min(P.nkp[img], P.maxFeat);
+    row0 = P.offsets[img];
+    const size_t M = (size_t)P.maxFeat;
+    F.x = reinterpret_cast<float*>(smem);
+    F.y = F.x + M;
+    F.ur = F.y + M;
+    F.cell = reinterpret_cast<uint16_t*>(F.ur + M);
+    F.oct = reinterpret_cast<uint8_t*>(F.cell + M);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const orbx_keypoint k = P.kps[row0 + i];
+        F.x[i] = k.x;
+        F.y[i] = k.y;
+        F.ur[i] = P.uright ? P.uright[row0 + i] : -1.0f;
+        // Frame::PosInGrid, Frame.cc:962-978 (C round(): half away from zero)
+        const int px = (int)roundf(fmul(fsub(k.x, P.minX), P.invW)), py = (int)roundf(fmul(fsub(k.y, P.minY), P.invH));
+        F.cell[i] = (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) ? (uint16_t)0xffff : (uint16_t)(px * GRID_ROWS + py);
+        F.oct[i] = (uint8_t)k.octave;
+    }
+}
+
+__device__ __forceinline__ size_t frame_smem_bytes(int maxFeat) { return (size_t)maxFeat * 15 + 16; }
+
+struct Window {   // Frame::GetFeaturesInArea arguments resolved to cell ranges
+    float x, y, r;
+    int c0, c1, r0, r1, minLevel, maxLevel;
+    bool empty;
+};
+
+__device__ __forceinline__ Window make_window(const ProjParams& P, float x, float y, float r, int minLevel, int maxLevel) {
+    Window w;
+    w.x = x; w.y = y; w.r = r; w.minLevel = minLevel; w.maxLevel = maxLevel;
+    w.c0 = max(0, (int)floorf(fmul(fsub(fsub(x, P.minX), r), P.invW)));
+    w.c1 = min(GRID_COLS - 1, (int)ceilf(fmul(fadd(fsub(x, P.minX), r), P.invW)));
+    w.r0 = max(0, (int)floorf(fmul(fsub(fsub(y, P.minY), r), P.invH)));
+    w.r1 = min(GRID_ROWS - 1, (int)ceilf(fmul(fadd(fsub(y, P.minY), r), P.invH)));
+    w.empty = (w.c0 >= GRID_COLS) || (w.c1 < 0) || (w.r0 >= GRID_ROWS) || (w.r1 < 0);
+    return w;
+}
+
+// is feature i a candidate of the window (all gates of GetFeaturesInArea)?
+__device__ __forceinline__ bool in_window(const FrameFeat& F, const Window& w, int i) {
+    const int cell = F.cell[i];
+    if (cell == 0xffff) return false;
+    const int ix = cell / GRID_ROWS, iy = cell - ix * GRID_ROWS;
+    if (ix < w.c0 || ix > w.c1 || iy < w.r0 || iy > w.r1) return false;
+    const int oc = F.oct[i];
+    if ((w.minLevel > 0) || (w.maxLevel >= 0)) {
+        if (oc < w.minLevel) return false;
+        if (w.maxLevel >= 0 && oc > w.maxLevel) return false;
+    }
+    const float dx = fsub(F.x[i], w.x), dy = fsub(F.y[i], w.y);
+    return fabsf(dx) < w.r && fabsf(dy) < w.r;
+}
+
+__device__ __forceinline__ uint32_t hamming256(const uint4& a0, const uint4& a1, const uint8_t* d) {
+    const uint4* p = reinterpret_cast<const uint4*>(d);
+    const uint4 b0 = __ldg(p), b1 = __ldg(p + 1);
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long u = __shfl_xor_sync(0xffffffffu, v, o);
+        v = u < v ? u : v;
+    }
+    return v;
+}
+
+// Warp scan of one query: K smallest (dist << 32 | cell << 16 | id) keys among the features that pass
+// the window, the optional claim mask and the stereo gate.  Returns the number of such features.
+// stereo gate: |ur_pred - mvuRight[i]| > er_max rejects (only when mvuRight[i] > 0).
+__device__ __forceinline__ int warp_scan_query(const ProjParams& P, const FrameFeat& F, int N, int row0, const Window& w,
+                                               const uint8_t* qd, float ur_pred, float er_max, const uint8_t* claimed,
+                                               unsigned long long out[PM_K]) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long loc[PM_K];
+#pragma unroll
+    for (int k = 0; k < PM_K; ++k) loc[k] = ~0ull;
+    int count = 0;
+    if (!w.empty) {
+        const uint4* q4 = reinterpret_cast<const uint4*>(qd);
+        const uint4 a0 = __ldg(q4), a1 = __ldg(q4 + 1);
+        for (int i = lane; i < N; i += 32) {
+            if (!in_window(F, w, i)) continue;
+            if (claimed && claimed[i]) continue;
+            const float ur = F.ur[i];
+            if (ur > 0) {
+                const float er = fabsf(fsub(ur_pred, ur));
+                if (er > er_max) continue;
+            }
+            ++count;
+            const uint32_t d = hamming256(a0, a1, P.desc + (size_t)(row0 + i) * 32);
+            unsigned long long key = ((unsigned long long)d << 32) | ((unsigned long long)F.cell[i] << 16) | (unsigned long long)i;
+#pragma unroll
+            for (int k = 0; k < PM_K; ++k)   // sorted insert
+                if (key < loc[k]) {
+                    const unsigned long long t = loc[k];
+                    loc[k] = key;
+                    key = t;
+                }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+#pragma unroll
+    for (int k = 0; k < PM_K; ++k) {   // K-way merge: pop the global minimum K times
+        const unsigned long long m = warp_min_u64(loc[0]);
+        out[k] = m;
+        if (loc[0] == m && m != ~0ull) {   // keys are unique (feature id in the low bits)
+#pragma unroll
+            for (int j = 0; j + 1 < PM_K; ++j) loc[j] = loc[j + 1];
+            loc[PM_K - 1] = ~0ull;
+        }
+    }
+    return count;
+}
+
+// mode 1 per-query geometry (ORBmatcher.cc:1985-2023): returns false when the query is skipped
+__device__ __forceinline__ bool last_frame_window(const ProjParams& P, int frame, int q, Window& w, float& u, float& invzc,
+                                                  float& radius) {
+    const float* T = P.Tcw + 7 * frame;
+    const float* p = P.a0 + 3 * (size_t)q;
+    // Sophus::SE3f * Vector3f (so3.hpp:358-367): uv = qv x p; uv += uv; p' = p + w uv + qv x uv; + t
+    const float qx = T[0], qy = T[1], qz = T[2], qw = T[3];
+    const float uvx = fsub(fmul(qy, p[2]), fmul(qz, p[1])), uvy = fsub(fmul(qz, p[0]), fmul(qx, p[2])),
+                uvz = fsub(fmul(qx, p[1]), fmul(qy, p[0]));
+    const float ux = fadd(uvx, uvx), uy = fadd(uvy, uvy), uz = fadd(uvz, uvz);
+    const float c0 = fsub(fmul(qy, uz), fmul(qz, uy)), c1 = fsub(fmul(qz, ux), fmul(qx, uz)), c2 = fsub(fmul(qx, uy), fmul(qy, ux));
+    const float xc = fadd(fadd(fadd(p[0], fmul(qw, ux)), c0), T[4]);
+    const float yc = fadd(fadd(fadd(p[1], fmul(qw, uy)), c1), T[5]);
+    const float zc = fadd(fadd(fadd(p[2], fmul(qw, uz)), c2), T[6]);
+    invzc = (float)(1.0 / (double)zc);
+    if (invzc < 0) return false;
+    u = fadd(fdiv(fmul(P.fx, xc), zc), P.cx);                 // Pinhole::project, Pinhole.cpp:61-68
+    const float v = fadd(fdiv(fmul(P.fy, yc), zc), P.cy);
+    if (u < P.minX || u > P.maxX) return false;
+    if (v < P.minY || v > P.maxY) return false;
+    const int oct = P.level[q];
+    radius = fmul(P.th, P.scale[oct]);
+    const int dir = P.direction[frame];
+    if (dir == 1) w = make_window(P, u, v, radius, oct, -1);
+    else if (dir == 2) w = make_window(P, u, v, radius, 0, oct);
+    else w = make_window(P, u, v, radius, oct - 1, oct + 1);
+    return true;
+}
+
+__device__ __forceinline__ bool local_window(const ProjParams& P, int q, Window& w, float& er_max) {
+    if (P.bFar && P.f1 && P.f1[q] > P.thFar) return false;
+    const int lvl = P.level[q];
+    float r = ((double)P.f0[q] > 0.998) ? 2.5f : 4.0f;        // RadiusByViewingCos, ORBmatcher.cc:242-248
+    if (P.th != 1.0f) r = fmul(r, P.th);
+    er_max = fmul(r, P.scale[lvl]);
+    w = make_window(P, P.a0[q], P.a1[q], er_max, lvl - 1, lvl);
+    return true;
+}
+
+// ---- kernel A: order-free candidate scan ----------------------------------------------------------
+__global__ void __launch_bounds__(PM_WARPS * 32) k_proj_candidates(const __grid_constant__ ProjParams P) {
+    extern __shared__ __align__(16) unsigned char pm_smem[];
+    const int frame = blockIdx.y;
+    const int q0 = P.qoff[frame], q1 = P.qoff[frame + 1];
+    const int qbase = q0 + blockIdx.x * PM_QPB;
+    if (qbase >= q1) return;
+    FrameFeat F;
+    int N, row0;
+    stage_frame(P, P.frame_image[frame], pm_smem, F, N, row0);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int q = qbase + warp; q < min(qbase + PM_QPB, q1); q += PM_WARPS) {
+        Window w;
+        float ur_pred = 0.f, er_max = 0.f, u = 0.f, invzc = 0.f, radius = 0.f;
+        bool ok;
+        if (P.mode == 0) {
+            ok = local_window(P, q, w, er_max);
+            ur_pred = P.a2[q];
+        } else {
+            ok = last_frame_window(P, frame, q, w, u, invzc, radius);
+            ur_pred = fsub(u, fmul(P.bf, invzc));
+            er_max = radius;
+        }
+        unsigned long long top[PM_K];
+        int count = 0;
+        if (ok) count = warp_scan_query(P, F, N, row0, w, P.qdesc + 32 * (size_t)q, ur_pred, er_max, nullptr, top);
+        if (lane == 0) {
+            P.cnt[q] = ok ? count : -1;
+#pragma unroll
+            for (int k = 0; k < PM_K; ++k) P.topk[(size_t)q * PM_K + k] = ok ? top[k] : ~0ull;
+        }
+    }
+}
+
+// ---- kernel B: ordered resolve, one CTA per frame, warp 0 walks the queries ------------------------
+#define PM_CHUNK 1024
+
+__global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ ProjParams P) {
+    extern __shared__ __align__(16) unsigned char pm_smem[];
+    const int frame = blockIdx.x;
+    const int q0 = P.qoff[frame], q1 = P.qoff[frame + 1];
+    FrameFeat F;
+    int N, row0;
+    stage_frame(P, P.frame_image[frame], pm_smem, F, N, row0);
+    unsigned char* extra = pm_smem + ((frame_smem_bytes(P.maxFeat) + 15) / 16) * 16;
+    unsigned long long* s_top = reinterpret_cast<unsigned long long*>(extra);           // PM_CHUNK * PM_K
+    int* s_cnt = reinterpret_cast<int*>(s_top + PM_CHUNK * PM_K);                        // PM_CHUNK
+    int* s_holder = s_cnt + PM_CHUNK;                                                    // maxFeat: mode 1 holder query, mode 0 unused
+    uint8_t* s_claimed = reinterpret_cast<uint8_t*>(s_holder + P.maxFeat);               // maxFeat
+    __shared__ int s_hist[30];
+    __shared__ int s_nm;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        s_claimed[i] = (P.mode == 0 && P.flag) ? P.flag[row0 + i] : 0;
+        s_holder[i] = -1;
+    }
+    if (threadIdx.x < 30) s_hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_nm = 0;
+    if (P.mode == 1 && P.checkOri)
+        for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) P.quv[q] = __int_as_float(-1);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int nmatches = 0;
+    for (int base = q0; base < q1; base += PM_CHUNK) {
+        const int nchunk = min(PM_CHUNK, q1 - base);
+        for (int i = threadIdx.x; i < nchunk * PM_K; i += blockDim.x) s_top[i] = P.topk[(size_t)base * PM_K + i];
+        for (int i = threadIdx.x; i < nchunk; i += blockDim.x) s_cnt[i] = P.cnt[base + i];
+        __syncthreads();
+        if (warp == 0) {
+            for (int qi = 0; qi < nchunk; ++qi) {
+                const int q = base + qi;
+                const int count = s_cnt[qi];
+                if (P.mode == 0 && lane == 0) P.match[q] = -1;
+                if (count <= 0) continue;
+                // first two stored candidates that are still free
+                unsigned long long b1 = ~0ull, b2 = ~0ull;
+                int stored = min(count, PM_K), live = 0;
+                for (int k = 0; k < stored; ++k) {
+                    const unsigned long long key = s_top[qi * PM_K + k];
+                    const int id = (int)(key & 0xffffu);
+                    if (s_claimed[id]) continue;
+                    if (live == 0) b1 = key; else if (live == 1) b2 = key;
+                    ++live;
+                }
+                const int need = (P.mode == 0) ? 2 : 1;
+                if (live < need && count > PM_K) {
+                    // claims consumed the stored list: exact rescan with the mask applied (warp-cooperative)
+                    Window w;
+                    float ur_pred = 0.f, er_max = 0.f, u = 0.f, invzc = 0.f, radius = 0.f;
+                    if (P.mode == 0) {
+                        local_window(P, q, w, er_max);
+                        ur_pred = P.a2[q];
+                    } else {
+                        last_frame_window(P, frame, q, w, u, invzc, radius);
+                        ur_pred = fsub(u, fmul(P.bf, invzc));
+                        er_max = radius;
+                    }
+                    unsigned long long top[PM_K];
+                    warp_scan_query(P, F, N, row0, w, P.qdesc + 32 * (size_t)q, ur_pred, er_max, s_claimed, top);
+                    b1 = top[0];
+                    b2 = top[1];
+                }
+                if (b1 == ~0ull) continue;
+                const int bestDist = (int)(b1 >> 32), bestIdx = (int)(b1 & 0xffffu);
+                if (P.mode == 0) {
+                    const int bestDist2 = (b2 == ~0ull) ? 256 : (int)(b2 >> 32);
+                    const int bestLevel = F.oct[bestIdx], bestLevel2 = (b2 == ~0ull) ? -1 : (int)F.oct[(int)(b2 & 0xffffu)];
+                    if (bestDist <= 100) {   // TH_HIGH
+                        const float lim = fmul(P.nnratio, (float)bestDist2);
+                        if (bestLevel == bestLevel2 && (float)bestDist > lim) continue;
+                        if (bestLevel != bestLevel2 || (float)bestDist <= lim) {
+                            if (lane == 0) {
+                                P.match[q] = bestIdx;
+                                s_claimed[bestIdx] = 1;
+                            }
+                            ++nmatches;
+                            __syncwarp();
+                        }
+                    }
+                } else {
+                    if (bestDist <= 100) {
+                        if (lane == 0) {
+                            s_holder[bestIdx] = q;
+                            s_claimed[bestIdx] = P.flag[q] ? 1 : 0;   // only map points with observations block later queries
+                            if (P.checkOri) {
+                                float rot = fsub(P.f0[q], P.kps[row0 + bestIdx].angle);
+                                if (rot < 0.0f) rot = fadd(rot, 360.0f);
+                                int bin = (int)roundf(fmul(rot, 1.0f / 30));
+                                if (bin == 30) bin = 0;
+                                s_hist[bin] += 1;
+                                P.quv[q] = __int_as_float((bin << 16) | bestIdx);   // rotHist entry of this query
+                            }
+                        }
+                        ++nmatches;
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (P.mode == 0) {
+        if (threadIdx.x == 0) P.nmatches[frame] = nmatches;
+        return;
+    }
+    // ---- mode 1: rotation-histogram filter (ORBmatcher.cc:2160-2181, ComputeThreeMaxima :2335-2377) ----
+    __shared__ int s_keep[30];
+    if (threadIdx.x == 0) {
+        s_nm = nmatches;
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < 30; ++i) {
+            const int s = s_hist[i];
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if ((float)max2 < fmul(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+        else if ((float)max3 < fmul(0.1f, (float)max1)) { ind3 = -1; }
+        for (int i = 0; i < 30; ++i) s_keep[i] = (i == ind1 || i == ind2 || i == ind3) ? 1 : 0;
+    }
+    __syncthreads();
+    if (P.checkOri) {
+        int removed = 0;
+        for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+            if (P.cnt[q] <= 0) continue;
+            const int e = __float_as_int(P.quv[q]);
+            if (e < 0) continue;
+            const int bin = e >> 16, idx = e & 0xffff;
+            if (!s_keep[bin]) {
+                s_holder[idx] = -1;   // every entry of a rejected bin clears its feature (duplicates included)
+                ++removed;
+            }
+        }
+        if (removed) atomicSub(&s_nm, removed);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) P.match[row0 + i] = s_holder[i];
+    if (threadIdx.x == 0) P.nmatches[frame] = s_nm;
+}
+
+}  // namespace orb
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static orb_status ensure_stage(orbx_handle* h, size_t bytes) {
+    if (bytes <= h->stage_bytes) return ORB_OK;
+    if (h->d_stage) cudaFree(h->d_stage);
+    h->d_stage = nullptr;
+    h->stage_bytes = 0;
+    const size_t want = (bytes + (1 << 20)) / (1 << 20) * (1 << 20);
+    ORB_CUDA(cudaMalloc((void**)&h->d_stage, want));
+    h->stage_bytes = want;
+    return ORB_OK;
+}
+
+struct StageCursor {
+    uint8_t* base;
+    size_t off = 0;
+    template <typename T>
+    T* take(size_t n) {
+        off = (off + 255) / 256 * 256;
+        T* p = reinterpret_cast<T*>(base + off);
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+static orb_status launch_proj(orbx_handle* h, ProjParams& P, int n_frames, int max_q_per_frame) {
+    cudaStream_t st = h->stream;
+    const size_t fsm = ((size_t)P.maxFeat * 15 + 16 + 15) / 16 * 16;
+    ORB_CUDA(cudaFuncSetAttribute(k_proj_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(fsm, (size_t)1024)));
+    dim3 grid((max_q_per_frame + PM_QPB - 1) / PM_QPB, n_frames);
+    if (grid.x > 0) {
+        k_proj_candidates<<<grid, PM_WARPS * 32, fsm, st>>>(P);
+        ORB_LAUNCHED();
+    }
+    const size_t rsm = fsm + (size_t)PM_CHUNK * PM_K * 8 + (size_t)PM_CHUNK * 4 + (size_t)P.maxFeat * 5 + 64;
+    ORB_CUDA(cudaFuncSetAttribute(k_proj_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
+    k_proj_resolve<<<n_frames, 256, rsm, st>>>(P);
+    ORB_LAUNCHED();
+    ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
+}
+
+static void fill_frame_side(orbx_handle* h, const orbm_camera* cam, ProjParams& P) {
+    P.kps = h->d_kps;
+    P.desc = h->d_desc;
+    P.uright = h->stereo_valid ? h->d_uright : nullptr;
+    P.offsets = h->d_offsets;
+    P.nkp = h->d_nkp;
+    P.maxFeat = h->geom.kpTotal;
+    P.minX = cam->min_x; P.maxX = cam->max_x; P.minY = cam->min_y; P.maxY = cam->max_y;
+    P.invW = (float)GRID_COLS / (cam->max_x - cam->min_x);   // Frame.cc:187-188
+    P.invH = (float)GRID_ROWS / (cam->max_y - cam->min_y);
+    P.fx = cam->fx; P.fy = cam->fy; P.cx = cam->cx; P.cy = cam->cy; P.bf = cam->bf;
+    for (int l = 0; l < ORB_MAX_LEVELS; ++l) P.scale[l] = l < h->cfg.n_levels ? h->scale[l] : 1.f;
+}
+
+template <typename T>
+static orb_status upload(orbx_handle* h, T*& dst, const T* src, size_t n, StageCursor& cur, bool on_device) {
+    if (!src) { dst = nullptr; return ORB_OK; }
+    if (on_device) { dst = const_cast<T*>(src); return ORB_OK; }
+    dst = cur.take<T>(n);
+    ORB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    return ORB_OK;
+}
+
+extern "C" orb_status orbm_search_local_points(orbx_handle* h, const orbm_camera* cam, const orbm_local_queries* Q,
+                                               float th, float nnratio, int32_t far_points, float th_far,
+                                               int32_t* match_out, int32_t* nmatches_out) {
+    if (!h || !cam || !Q || !match_out || Q->n_frames < 1 || !Q->frame_image || !Q->query_offset)
+        return set_error(ORB_ERR_INVALID, "bad arguments");
+    ORB_CUDA(cudaSetDevice(h->cfg.device));
+    orb_status s = orbx_counts(h, nullptr, nullptr, nullptr);   // total compact rows of the batch
+    if (s != ORB_OK) return s;
+    const size_t rows = (size_t)h->h_counts[2 * h->cfg.max_batch + h->last_batch];
+    const bool dev = Q->on_device != 0;
+    const int nf = Q->n_frames;
+    std::vector<int> qoff_h(nf + 1), fimg_h(nf);
+    if (dev) {
+        ORB_CUDA(cudaMemcpyAsync(qoff_h.data(), Q->query_offset, sizeof(int) * (nf + 1), cudaMemcpyDeviceToHost, h->stream));
+        ORB_CUDA(cudaMemcpyAsync(fimg_h.data(), Q->frame_image, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->stream));
+        ORB_CUDA(cudaStreamSynchronize(h->stream));
+    } else {
+        std::copy(Q->query_offset, Q->query_offset + nf + 1, qoff_h.begin());
+        std::copy(Q->frame_image, Q->frame_image + nf, fimg_h.begin());
+    }
+    const int nq = qoff_h[nf];
+    int maxq = 0;
+    for (int f = 0; f < nf; ++f) {
+        maxq = std::max(maxq, qoff_h[f + 1] - qoff_h[f]);
+        if (fimg_h[f] < 0 || fimg_h[f] >= h->last_batch || qoff_h[f + 1] < qoff_h[f]) return set_error(ORB_ERR_INVALID, "bad frame table");
+    }
+    const size_t need = (size_t)nq * (PM_K * 8 + 4 + 4 * 6 + 32 + 8) + rows + (size_t)nf * 16 + 65536;
+    if ((s = ensure_stage(h, need)) != ORB_OK) return s;
+    StageCursor cur{h->d_stage};
+    ProjParams P{};
+    fill_frame_side(h, cam, P);
+    P.mode = 0;
+    int* d_fimg; int* d_qoff;
+    if ((s = upload(h, d_fimg, (const int*)Q->frame_image, nf, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, d_qoff, (const int*)Q->query_offset, nf + 1, cur, dev)) != ORB_OK) return s;
+    P.frame_image = d_fimg; P.qoff = d_qoff;
+    float *a0, *a1, *a2, *f0, *f1; int* lvl; uint8_t *qd, *fl;
+    if ((s = upload(h, a0, Q->proj_x, nq, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, a1, Q->proj_y, nq, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, a2, Q->proj_xr, nq, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, lvl, (const int*)Q->level, nq, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, f0, Q->view_cos, nq, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, f1, Q->track_depth, nq, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, qd, Q->desc, (size_t)nq * 32, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, fl, Q->feature_claimed, rows, cur, dev)) != ORB_OK) return s;
+    P.a0 = a0; P.a1 = a1; P.a2 = a2; P.level = lvl; P.f0 = f0; P.f1 = f1; P.qdesc = qd; P.flag = fl;
+    P.th = th; P.nnratio = nnratio; P.bFar = far_points; P.thFar = th_far;
+    P.topk = cur.take<unsigned long long>((size_t)nq * PM_K);
+    P.cnt = cur.take<int>(nq);
+    P.match = dev ? match_out : cur.take<int>(nq);
+    P.nmatches = (dev && nmatches_out) ? nmatches_out : cur.take<int>(nf);
+    if (nq > 0 && (s = launch_proj(h, P, nf, maxq)) != ORB_OK) return s;
+    if (!dev) {
+        if (nq > 0) ORB_CUDA(cudaMemcpyAsync(match_out, P.match, sizeof(int) * (size_t)nq, cudaMemcpyDeviceToHost, h->stream));
+        if (nmatches_out && nq > 0) ORB_CUDA(cudaMemcpyAsync(nmatches_out, P.nmatches, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->stream));
+        ORB_CUDA(cudaStreamSynchronize(h->stream));
+        if (nmatches_out && nq == 0) std::fill(nmatches_out, nmatches_out + nf, 0);
+    }
+    return ORB_OK;
+}
+
+extern "C" orb_status orbm_search_last_frame(orbx_handle* h, const orbm_camera* cam, const orbm_last_queries* Q, float th,
+                                             int32_t check_orientation, int32_t* feature_match_out, int32_t* nmatches_out) {
+    if (!h || !cam || !Q || !feature_match_out || Q->n_frames < 1 || !Q->frame_image || !Q->query_offset || !Q->Tcw ||
+        !Q->direction)
+        return set_error(ORB_ERR_INVALID, "bad arguments");
+    ORB_CUDA(cudaSetDevice(h->cfg.device));
+    orb_status s = orbx_counts(h, nullptr, nullptr, nullptr);   // total compact rows of the batch
+    if (s != ORB_OK) return s;
+    const int total_rows = h->h_counts[2 * h->cfg.max_batch + h->last_batch];
+    const bool dev = Q->on_device != 0;
+    const int nf = Q->n_frames;
+    std::vector<int> qoff_h(nf + 1), fimg_h(nf);
+    if (dev) {
+        ORB_CUDA(cudaMemcpyAsync(qoff_h.data(), Q->query_offset, sizeof(int) * (nf + 1), cudaMemcpyDeviceToHost, h->stream));
+        ORB_CUDA(cudaMemcpyAsync(fimg_h.data(), Q->frame_image, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->stream));
+        ORB_CUDA(cudaStreamSynchronize(h->stream));
+    } else {
+        std::copy(Q->query_offset, Q->query_offset + nf + 1, qoff_h.begin());
+        std::copy(Q->frame_image, Q->frame_image + nf, fimg_h.begin());
+    }
+    const int nq = qoff_h[nf];
+    int maxq = 0;
+    for (int f = 0; f < nf; ++f) {
+        maxq = std::max(maxq, qoff_h[f + 1] - qoff_h[f]);
+        if (fimg_h[f] < 0 || fimg_h[f] >= h->last_batch || qoff_h[f + 1] < qoff_h[f]) return set_error(ORB_ERR_INVALID, "bad frame table");
+    }
+    const size_t need = (size_t)nq * (PM_K * 8 + 4 + 4 + 12 + 4 + 4 + 32 + 1 + 16) + (size_t)total_rows * 4 + (size_t)nf * 64 + 65536;
+    if ((s = ensure_stage(h, need)) != ORB_OK) return s;
+    StageCursor cur{h->d_stage};
+    ProjParams P{};
+    fill_frame_side(h, cam, P);
+    P.mode = 1;
+    int *d_fimg, *d_qoff, *d_dir, *lvl; float *xw, *ang, *tcw; uint8_t *qd, *ob;
+    if ((s = upload(h, d_fimg, (const int*)Q->frame_image, nf, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, d_qoff, (const int*)Q->query_offset, nf + 1, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, tcw, Q->Tcw, (size_t)nf * 7, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, d_dir, (const int*)Q->direction, nf, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, xw, Q->world_pos, (size_t)nq * 3, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, lvl, (const int*)Q->last_octave, nq, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, ang, Q->last_angle, nq, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, qd, Q->desc, (size_t)nq * 32, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, ob, Q->obs_positive, nq, cur, dev)) != ORB_OK) return s;
+    P.frame_image = d_fimg; P.qoff = d_qoff; P.Tcw = tcw; P.direction = d_dir;
+    P.a0 = xw; P.level = lvl; P.f0 = ang; P.qdesc = qd; P.flag = ob;
+    P.th = th; P.checkOri = check_orientation;
+    P.topk = cur.take<unsigned long long>((size_t)nq * PM_K);
+    P.cnt = cur.take<int>(nq);
+    P.quv = cur.take<float>(nq);
+    P.match = dev ? feature_match_out : cur.take<int>(total_rows);
+    P.nmatches = (dev && nmatches_out) ? nmatches_out : cur.take<int>(nf);
+    ORB_CUDA(cudaMemsetAsync(P.match, 0xff, sizeof(int) * (size_t)total_rows, h->stream));
+    if ((s = launch_proj(h, P, nf, maxq)) != ORB_OK) return s;
+    if (!dev) {
+        ORB_CUDA(cudaMemcpyAsync(feature_match_out, P.match, sizeof(int) * (size_t)total_rows, cudaMemcpyDeviceToHost, h->stream));
+        if (nmatches_out) ORB_CUDA(cudaMemcpyAsync(nmatches_out, P.nmatches, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->stream));
+        ORB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return ORB_OK;
+}

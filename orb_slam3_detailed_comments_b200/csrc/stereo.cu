@@ -229,6 +229,7 @@ static orb_status run_stereo(orbx_handle* hl, orbx_handle* hr, int n_pairs, int 
     k_stereo_median<<<n_pairs, 256, smem2, st>>>(P);
     ORB_LAUNCHED();
     ORB_CUDA(cudaGetLastError());
+    hl->stereo_valid = true;
     return ORB_OK;
 }
 

@@ -1,0 +1,139 @@
+"""GPU tier: SearchByProjection (local map points / last frame) on the device against the CPU oracle.
+Bar: identical match pairs (bit-exact integer arrays) and identical nmatches."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from orb_slam3_detailed_comments_b200 import ORBextractor, ORBmatcher, camera, synth
+
+pytestmark = pytest.mark.gpu
+
+W, H = 640, 480
+FX, FY, CX, CY, BF, B = 435.2, 435.2, 320.0, 240.0, 47.9, 0.11
+CAM6 = np.array([FX, FY, CX, CY, BF, B], np.float32)
+BOUNDS = np.array([0, W, 0, H], np.float32)
+
+
+def quat_pose(yaw_deg, t):
+    a = np.deg2rad(yaw_deg) / 2
+    return np.array([0, np.sin(a), 0, np.cos(a), *t], np.float32)   # qx qy qz qw tx ty tz
+
+
+def make_scene(P, seed):
+    """P stereo frames: 'last' = pair seed, 'cur' = the same pair shifted by a few pixels + noise.
+    Returns the interleaved image batch for the CURRENT frames and, per frame, the last frame's oracle features."""
+    rng = np.random.default_rng(seed)
+    imgs = np.zeros((2 * P, H, W), np.uint8)
+    lasts = []
+    for p in range(P):
+        l, r, _ = synth.stereo_pair(W, H, seed=seed + 10 * p)
+        eL, eR = po.OracleExtractor(1200, 1.2, 8, 20, 7), po.OracleExtractor(1200, 1.2, 8, 20, 7)
+        _, kL, dL = eL(l)
+        _, kR, dR = eR(r)
+        uR, dep, _ = po.stereo_matches(eL, eR, kL, dL, kR, dR, BF, B)
+        lasts.append((kL, dL, uR, dep))
+        sh = (3 + p, 1)
+        noise = rng.integers(-3, 4, (H, W))
+        imgs[2 * p] = np.clip(np.roll(l, sh, (1, 0)).astype(int) + noise, 0, 255)
+        imgs[2 * p + 1] = np.clip(np.roll(r, sh, (1, 0)).astype(int) + noise, 0, 255)
+    return imgs, lasts
+
+
+def unproject(k, depth):
+    z = depth
+    return np.stack([(k["x"] - CX) * z / FX, (k["y"] - CY) * z / FY, z], 1).astype(np.float32)
+
+
+@pytest.fixture(scope="module")
+def scene():
+    P = 3
+    imgs, lasts = make_scene(P, 500)
+    ex = ORBextractor(1200, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=2 * P)
+    ex.extract_batch(imgs)
+    ex.stereo_batch(P, BF, B)
+    n, mono, off, kps, desc = ex.download(2 * P)
+    uR, dep = ex.stereo_download(int(off[-1]))
+    yield dict(P=P, ex=ex, lasts=lasts, off=off, kps=kps, desc=desc, uR=uR)
+    ex.close()
+
+
+def test_search_local_points_matches_oracle(scene):
+    P, ex, off = scene["P"], scene["ex"], scene["off"]
+    rng = np.random.default_rng(7)
+    sf = ex.GetScaleFactors()
+    for th, nnratio in [(1.0, 0.8), (3.0, 0.8), (5.0, 0.7)]:
+        qoff, px, py, pxr, lv, vc, qd = [0], [], [], [], [], [], []
+        claimed = np.zeros(int(off[-1]), np.uint8)
+        for p in range(P):
+            kL, dL, luR, ldep = scene["lasts"][p]
+            sel = np.nonzero(ldep > 0)[0]
+            # the local map: last frame's stereo points + a few thousand repeats with jitter (several map
+            # points competing for the same feature exercises the greedy claims)
+            sel = np.concatenate([sel, rng.choice(sel, 3 * len(sel))])
+            jit = rng.normal(0, 1.5, (len(sel), 2)).astype(np.float32)
+            x = (kL["x"][sel] + 3 + p + jit[:, 0]).astype(np.float32)
+            y = (kL["y"][sel] + 1 + jit[:, 1]).astype(np.float32)
+            px.append(x); py.append(y)
+            pxr.append((x - BF / ldep[sel]).astype(np.float32))
+            lv.append(np.clip(kL["octave"][sel] + rng.integers(-1, 2, len(sel)), 0, 7).astype(np.int32))
+            vc.append(rng.uniform(0.99, 1.0, len(sel)).astype(np.float32))
+            qd.append(dL[sel])
+            qoff.append(qoff[-1] + len(sel))
+            a, b = off[2 * p], off[2 * p + 1]
+            claimed[a:b] = rng.random(b - a) < 0.15     # features already matched by the motion model
+        px, py, pxr, lv, vc, qd = map(np.concatenate, (px, py, pxr, lv, vc, qd))
+        m = ORBmatcher(nnratio, True)
+        match, nm = m.SearchByProjection(ex, camera(FX, FY, CX, CY, BF, B, W, H), [2 * p for p in range(P)], qoff,
+                                         px, py, pxr, lv, vc, qd, th=th, feature_claimed=claimed)
+        for p in range(P):
+            a, b = off[2 * p], off[2 * p + 1]
+            s = slice(qoff[p], qoff[p + 1])
+            rmatch, rnm = po.search_local(scene["kps"][a:b], scene["desc"][a:b], scene["uR"][a:b], BOUNDS, sf, px[s], py[s],
+                                          pxr[s], lv[s], vc[s], qd[s], th, nnratio, claimed=claimed[a:b])
+            assert rnm == nm[p], (th, p, rnm, nm[p])
+            assert (match[s] == rmatch).all(), (th, p)
+            assert rnm > 50
+
+
+def test_search_last_frame_matches_oracle(scene):
+    P, ex, off = scene["P"], scene["ex"], scene["off"]
+    rng = np.random.default_rng(11)
+    sf = ex.GetScaleFactors()
+    total = int(off[-1])
+    for th, direction_all, check in [(15.0, 0, True), (7.0, 1, True), (7.0, 2, False)]:
+        qoff, xw, lo, la, qd, ob, Tcw, dirs = [0], [], [], [], [], [], [], []
+        for p in range(P):
+            kL, dL, luR, ldep = scene["lasts"][p]
+            sel = np.nonzero(ldep > 0)[0]
+            sel = np.concatenate([sel, sel[: len(sel) // 3]])          # duplicated map points: zero-observation overwrite path
+            pts = unproject(kL[sel], ldep[sel])
+            # camera moved so that the points shift ~ (3+p, 1) px at mid depth
+            zmid = float(np.median(ldep[sel]))
+            T = quat_pose(0.05 * p, [(3 + p) * zmid / FX, 1 * zmid / FY, 0.0])
+            xw.append(pts); lo.append(kL["octave"][sel].astype(np.int32)); la.append(kL["angle"][sel].astype(np.float32))
+            qd.append(dL[sel]); ob.append((rng.random(len(sel)) < 0.7).astype(np.uint8))
+            Tcw.append(T); dirs.append(direction_all)
+            qoff.append(qoff[-1] + len(sel))
+        xw, lo, la, qd, ob = map(np.concatenate, (xw, lo, la, qd, ob))
+        m = ORBmatcher(0.9, check)
+        fm, nm = m.SearchByProjectionLastFrame(ex, camera(FX, FY, CX, CY, BF, B, W, H), [2 * p for p in range(P)], qoff,
+                                               np.stack(Tcw), dirs, xw, lo, la, qd, ob, th, total)
+        for p in range(P):
+            a, b = off[2 * p], off[2 * p + 1]
+            s = slice(qoff[p], qoff[p + 1])
+            rfm, rnm = po.search_last(scene["kps"][a:b], scene["desc"][a:b], scene["uR"][a:b], BOUNDS, sf, CAM6, Tcw[p],
+                                      dirs[p], xw[s], lo[s], la[s], qd[s], ob[s], th, check)
+            got = fm[a:b].copy()
+            got[got >= 0] -= qoff[p]
+            assert rnm == nm[p], (th, p, rnm, nm[p])
+            assert (got == rfm).all(), (th, p)
+            assert rnm > 50
+            assert (fm[off[2 * p + 1]:off[2 * p + 2]] == -1).all()      # right-eye rows untouched
+
+
+def test_search_with_no_queries_and_monocular(scene):
+    ex, off = scene["ex"], scene["off"]
+    m = ORBmatcher(0.8, True)
+    match, nm = m.SearchByProjection(ex, camera(FX, FY, CX, CY, BF, B, W, H), [0], [0, 0], np.zeros(0), np.zeros(0),
+                                     np.zeros(0), np.zeros(0, np.int32), np.zeros(0), np.zeros((0, 32), np.uint8))
+    assert len(match) == 0 and nm[0] == 0
