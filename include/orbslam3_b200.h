@@ -199,6 +199,47 @@ typedef struct {
 orb_status orbm_search_last_frame(orbx_handle* h, const orbm_camera* cam, const orbm_last_queries* q, float th,
                                   int32_t check_orientation, int32_t* feature_match_out, int32_t* nmatches_out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer::LocalBundleAdjustment  (include/Optimizer.h:59, src/Optimizer.cc:1740-2188)
+ *
+ * The C++ shim walks the covisibility graph exactly as the reference does (Optimizer.cc:1744-1855), flattens
+ * the local window into this structure, and applies the result (outlier erasure, pose / point write-back,
+ * Optimizer.cc:2102-2187).  The device runs what `optimizer.optimize(10)` runs: g2o Levenberg-Marquardt over
+ * BlockSolver_6_3 with Huber kernels, all in fp64.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n_kf, n_mp, n_edges;
+    const double* pose;        /* [n_kf][7]  qx qy qz qw tx ty tz  (g2o::SE3Quat of Tcw), local + fixed keyframes */
+    const uint8_t* fixed;      /* [n_kf]     1 = setFixed(true) (lFixedCameras and the map's initial keyframe) */
+    const double* point;       /* [n_mp][3]  MapPoint::GetWorldPos */
+    const int32_t* edge_kf;    /* [n_edges]  index into pose[] */
+    const int32_t* edge_mp;    /* [n_edges]  index into point[] */
+    const double* obs;         /* [n_edges][3] kpUn.pt.x, kpUn.pt.y, mvuRight (< 0 => monocular EdgeSE3ProjectXYZ) */
+    const double* inv_sigma2;  /* [n_edges]  mvInvLevelSigma2[octave]: information = inv_sigma2 * I */
+    double fx, fy, cx, cy, bf; /* float members of KeyFrame promoted to double (Optimizer.cc:2038-2042) */
+    double lambda_init;        /* 100 when pMap->IsInertial() (Optimizer.cc:1867-1868), else 0 = auto */
+    int32_t max_iters;         /* 10 */
+} lba_problem;
+
+typedef struct {
+    double* pose;                  /* [n_kf][7] optimised (fixed ones unchanged) */
+    double* point;                 /* [n_mp][3] */
+    double* edge_chi2;             /* [n_edges] e->chi2() as left by the LAST computeActiveErrors (may be NULL) */
+    uint8_t* edge_depth_positive;  /* [n_edges] e->isDepthPositive() at the final estimate (may be NULL) */
+    int32_t iterations;            /* outer Levenberg iterations run */
+    int32_t trials;                /* inner trials (solve calls) */
+    double lambda, chi2, chi2_initial;
+} lba_result;
+
+typedef struct lba_handle lba_handle;
+orb_status lba_create(int32_t device, lba_handle** out);
+void lba_destroy(lba_handle* h);
+/* stop_flag mirrors `bool* pbStopFlag` (polled between LM trials; may be NULL). */
+orb_status lba_solve(lba_handle* h, const lba_problem* in, lba_result* out, const volatile int32_t* stop_flag);
+/* independent problems, one CTA each (sequence-sharded replay: one local BA per sequence) */
+orb_status lba_solve_batch(lba_handle* h, int32_t n_problems, const lba_problem* in, lba_result* out,
+                           const volatile int32_t* stop_flag);
+
 #ifdef __cplusplus
 }
 #endif

@@ -250,3 +250,25 @@ def search_last(kps, desc, uright, bounds, scale_factors, cam6, Tcw7, direction,
     nm = L.orc_search_last(_p(kps), _p(desc), P(uright), len(kps), _p(b4), _p(sf), _p(c6), _p(T7), int(direction), len(lo),
                            _p(xw), _p(lo), _p(ang), _p(qd), _p(ob), th, 1 if check_ori else 0, _p(fm))
     return fm[:len(kps)], nm
+
+
+def lba(pose, fixed, point, edge_kf, edge_mp, obs, inv_sigma2, cam5, lambda_init=0.0, max_iters=10):
+    """Optimizer::LocalBundleAdjustment's g2o Levenberg core restated (Optimizer.cc:1859-2150).
+    Returns dict(pose, point, edge_chi2, edge_depth_pos, iterations, lambda_, chi2, trials, chi2_init)."""
+    L = lib()
+    L.orc_lba.restype = C.c_int
+    L.orc_lba.argtypes = [C.c_int] * 3 + [C.c_void_p] * 8 + [C.c_double, C.c_int] + [C.c_void_p] * 4
+    pose = np.ascontiguousarray(pose, np.float64).copy()
+    point = np.ascontiguousarray(point, np.float64).copy()
+    fixed = np.ascontiguousarray(fixed, np.uint8)
+    ekf, emp = np.ascontiguousarray(edge_kf, np.int32), np.ascontiguousarray(edge_mp, np.int32)
+    obs, w = np.ascontiguousarray(obs, np.float64), np.ascontiguousarray(inv_sigma2, np.float64)
+    cam5 = np.ascontiguousarray(cam5, np.float64)
+    nE = len(ekf)
+    chi = np.zeros(nE, np.float64)
+    dpos = np.zeros(nE, np.uint8)
+    stats = np.zeros(8, np.float64)
+    it = L.orc_lba(len(pose), len(point), nE, _p(pose), _p(fixed), _p(point), _p(ekf), _p(emp), _p(obs), _p(w), _p(cam5),
+                   float(lambda_init), int(max_iters), None, _p(chi), _p(dpos), _p(stats))
+    return dict(pose=pose, point=point, edge_chi2=chi, edge_depth_pos=dpos, iterations=it, lambda_=stats[1],
+                chi2=stats[2], trials=int(stats[3]), chi2_init=stats[4])

@@ -12,7 +12,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "lib", "liborbslam3_b200.so")
-SOURCES = ["extractor.cu", "stereo.cu", "matcher.cu"]
+SOURCES = ["extractor.cu", "stereo.cu", "matcher.cu", "lba.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -61,6 +61,18 @@ class orbm_last_queries(C.Structure):
                                   "last_angle", "desc", "obs_positive")]
 
 
+class lba_problem(C.Structure):
+    _fields_ = [("n_kf", C.c_int32), ("n_mp", C.c_int32), ("n_edges", C.c_int32)] + [
+        (n, C.c_void_p) for n in ("pose", "fixed", "point", "edge_kf", "edge_mp", "obs", "inv_sigma2")] + [
+        (n, C.c_double) for n in ("fx", "fy", "cx", "cy", "bf", "lambda_init")] + [("max_iters", C.c_int32)]
+
+
+class lba_result(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("pose", "point", "edge_chi2", "edge_depth_positive")] + [
+        ("iterations", C.c_int32), ("trials", C.c_int32), ("lambda_", C.c_double), ("chi2", C.c_double),
+        ("chi2_initial", C.c_double)]
+
+
 _lib = None
 _VP, _I, _F = C.c_void_p, C.c_int32, C.c_float
 _IP = C.POINTER(C.c_int32)
@@ -89,6 +101,10 @@ SIGNATURES = {
     "orbm_stereo_download": (_I, [_VP, _VP, _VP, _I]),
     "orbm_stereo_pair": (_I, [_VP, _VP, _F, _F, _VP, _VP, _I]),
     "orbm_search_local_points": (_I, [_VP, C.POINTER(orbm_camera), C.POINTER(orbm_local_queries), _F, _F, _I, _F, _VP, _VP]),
+    "lba_create": (_I, [_I, C.POINTER(_VP)]),
+    "lba_destroy": (None, [_VP]),
+    "lba_solve": (_I, [_VP, C.POINTER(lba_problem), C.POINTER(lba_result), _VP]),
+    "lba_solve_batch": (_I, [_VP, _I, C.POINTER(lba_problem), C.POINTER(lba_result), _VP]),
     "orbm_search_last_frame": (_I, [_VP, C.POINTER(orbm_camera), C.POINTER(orbm_last_queries), _F, _I, _VP, _VP]),
 }
 
