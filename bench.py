@@ -1,8 +1,10 @@
 #!/usr/bin/env python3
 """bench.py -- tracking-thread frames/s on synthetic 640x480 stereo, 1200 features (BASELINE.json metric).
 
-One "step" = one batch of B synthetic stereo frames through the hot path (both eyes through
-ORBextractor, then -- when the matcher stages are built -- ComputeStereoMatches and SearchByProjection).
+One "step" = one batch of B synthetic stereo frames through the tracking-thread hot path: both eyes
+through ORBextractor, Frame::ComputeStereoMatches, ORBmatcher::SearchByProjection(cur, last) (motion model)
+and ORBmatcher::SearchByProjection(F, local map points) (TrackLocalMap).  The local-BA kernel (config 4, a
+LocalMapping-thread job, not per frame) is timed separately and reported under "lba".
 `value` is measured with the frames resident in HBM; `e2e` goes through the host-buffer C ABI (H2D of the
 images and D2H of keypoints/descriptors inside the timed region).
 
@@ -73,7 +75,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -81,13 +83,21 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def wait_first(self, timeout=5.0):
+        t0 = time.time()
+        while not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
+    def stop(self, t_begin=None, t_end=None):
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = [r for (t, r) in self.rows if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end + 0.05)]
+        if not rows:
+            rows = [r for (_, r) in self.rows][-3:]
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -103,35 +113,64 @@ class ClockSampler:
 
 
 def cpu_oracle_frames(pairs, threads):
-    """Reference arm: the CPU oracle on `threads` host threads, one stereo frame per task with the two eyes
-    extracted on two threads like Frame.cc:136-141 when threads >= 2.  Returns (frames/s, seconds)."""
+    """Reference arm: the CPU oracle on `threads` host threads.  Per stereo frame: both eyes through the
+    extractor (on two threads like Frame.cc:136-141 when threads >= 2), ComputeStereoMatches, then the two
+    projection searches against a map made of the frame's own stereo points (same shape as the GPU arm).
+    Returns (frames/s, seconds)."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import pyoracle as po
+    FX, FY, CX, CY, BF, BL = 435.2, 435.2, 320.0, 240.0, 47.9, 0.11
     nthr = max(1, threads)
-    exs = [po.OracleExtractor(NFEAT, 1.2, 8, 20, 7) for _ in range(nthr)]
+    nworkers = max(1, nthr // 2)
+    bounds = np.array([0, W, 0, H], np.float32)
+    cam6 = np.array([FX, FY, CX, CY, BF, BL], np.float32)
+    T = np.array([0, 0, 0, 1, 0.002, 0.001, 0], np.float32)
 
-    def one(args):
-        slot, img = args
-        exs[slot](img)          # ctypes releases the GIL during the call
+    def frame(args):
+        l, r, eL, eR, pool2 = args
+        if pool2 is not None:
+            fr = pool2.submit(eR, r)
+            _, kL, dL = eL(l)
+            _, kR, dR = fr.result()
+        else:
+            _, kL, dL = eL(l)
+            _, kR, dR = eR(r)
+        uR, dep, _ = po.stereo_matches(eL, eR, kL, dL, kR, dR, BF, BL)
+        sel = np.nonzero(dep > 0)[0]
+        if len(sel) == 0:
+            return 0
+        z = dep[sel]
+        pts = np.stack([(kL["x"][sel] - CX) * z / FX, (kL["y"][sel] - CY) * z / FY, z], 1).astype(np.float32)
+        sf = eL.scale_factors
+        po.search_last(kL, dL, uR, bounds, sf, cam6, T, 0, pts, kL["octave"][sel], kL["angle"][sel], dL[sel],
+                       np.ones(len(sel), np.uint8), 15.0, True)
+        sel4 = np.concatenate([sel, sel, sel, sel])
+        x, y = kL["x"][sel4], kL["y"][sel4]
+        po.search_local(kL, dL, uR, bounds, sf, x, y, x - BF / dep[sel4], kL["octave"][sel4],
+                        np.full(len(sel4), 0.995, np.float32), dL[sel4], 3.0, 0.8)
         return 0
-    imgs = [(i % nthr, pairs[i // 2, i % 2]) for i in range(2 * len(pairs))]
+    exs = [(po.OracleExtractor(NFEAT, 1.2, 8, 20, 7), po.OracleExtractor(NFEAT, 1.2, 8, 20, 7)) for _ in range(nworkers)]
+    pools2 = [ThreadPoolExecutor(1) if nthr >= 2 else None for _ in range(nworkers)]
     t0 = time.perf_counter()
-    if nthr == 1:
-        for a in imgs:
-            one(a)
+    chunks = [[(pairs[i, 0], pairs[i, 1], exs[wk][0], exs[wk][1], pools2[wk]) for i in range(wk, len(pairs), nworkers)]
+              for wk in range(nworkers)]
+    if nworkers == 1:
+        for a in chunks[0]:
+            frame(a)
     else:
-        # static slot assignment keeps each oracle object on one thread at a time
-        chunks = [[a for a in imgs if a[0] == s] for s in range(nthr)]
-        with ThreadPoolExecutor(nthr) as pool:
-            list(pool.map(lambda ch: [one(a) for a in ch], chunks))
+        with ThreadPoolExecutor(nworkers) as pool:
+            list(pool.map(lambda ch: [frame(a) for a in ch], chunks))
     dt = time.perf_counter() - t0
+    for p2 in pools2:
+        if p2 is not None:
+            p2.shutdown()
     return len(pairs) / dt, dt
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
     n_pairs = max(cores // 2, 1) * 2
     pairs = make_pairs(n_pairs, base=4)
     for _ in range(args.warmup):
@@ -146,8 +185,10 @@ def run_reference(args, rank, world):
     line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "stereo 640x480, 1200 features: ORBextractor L+R (CPU oracle port; the reference "
-                                   "needs OpenCV/Eigen and cannot be built here)", "frames_per_step": len(pairs)},
+            "config": {"workload": "config 3: stereo 640x480, 1200 features per eye; per frame: ORBextractor L+R, "
+                                   "ComputeStereoMatches, SearchByProjection(cur,last), SearchByProjection(F,local map) -- "
+                                   "CPU oracle port (the reference needs OpenCV/Eigen and cannot be built here)",
+                       "frames_per_step": len(pairs)},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{len(pairs)} stereo frames per step on {cores} threads"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -157,7 +198,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64, help="stereo frames per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -180,8 +221,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.batch
     nimg = 2 * B
+    dev = torch.device("cuda", local)
+    FX, FY, CX, CY, BF, BL = 435.2, 435.2, 320.0, 240.0, 47.9, 0.11
+    from orb_slam3_detailed_comments_b200 import ORBmatcher, camera, Optimizer, synth
+    cam = camera(FX, FY, CX, CY, BF, BL, W, H)
     ex = ORBextractor(NFEAT, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=nimg, device=local)
-    stream = torch.cuda.ExternalStream(ex.cuda_stream(), device=torch.device("cuda", local))
+    stream = torch.cuda.ExternalStream(ex.cuda_stream(), device=dev)
+    m_last, m_local = ORBmatcher(0.9, True), ORBmatcher(0.8, True)
 
     # input pool larger than L2 (126 MB): POOL batches of 2B images, cycled through the timed steps
     pool_batches = max(2, int(np.ceil(140e6 / (nimg * W * H))))
@@ -189,9 +235,56 @@ def main():
     host_pool = torch.from_numpy(pairs.reshape(pool_batches, nimg, H, W)).pin_memory()
     dev_pool = host_pool.cuda(non_blocking=False)
 
+    # ---- map state for the matchers: the "last frame" of every sequence is the frame itself one step earlier
+    # (its stereo points, unprojected), the local map is that set four times over with jitter --------------
+    ex.extract_batch_device(dev_pool[0].data_ptr(), nimg, W, H)
+    ex.stereo_batch(B, BF, BL)
+    n0, _, off0, kps0, desc0 = ex.download(nimg)
+    uR0, dep0 = ex.stereo_download(int(off0[-1]))
+    rng = np.random.default_rng(1234 + rank)
+    q_last = dict(off=[0], xw=[], oct=[], ang=[], desc=[], obs=[])
+    q_loc = dict(off=[0], px=[], py=[], pxr=[], lvl=[], vc=[], desc=[])
+    for p in range(B):
+        a, b = int(off0[2 * p]), int(off0[2 * p + 1])
+        k, d, z = kps0[a:b], desc0[a:b], dep0[a:b]
+        sel = np.nonzero(z > 0)[0]
+        pts = np.stack([(k["x"][sel] - CX) * z[sel] / FX, (k["y"][sel] - CY) * z[sel] / FY, z[sel]], 1).astype(np.float32)
+        q_last["xw"].append(pts); q_last["oct"].append(k["octave"][sel].astype(np.int32))
+        q_last["ang"].append(k["angle"][sel].astype(np.float32)); q_last["desc"].append(d[sel])
+        q_last["obs"].append(np.ones(len(sel), np.uint8)); q_last["off"].append(q_last["off"][-1] + len(sel))
+        sel4 = np.concatenate([sel, rng.choice(sel, 3 * len(sel))]) if len(sel) else sel
+        jit = rng.normal(0, 1.5, (len(sel4), 2)).astype(np.float32)
+        x, y = k["x"][sel4] + jit[:, 0], k["y"][sel4] + jit[:, 1]
+        q_loc["px"].append(x.astype(np.float32)); q_loc["py"].append(y.astype(np.float32))
+        q_loc["pxr"].append((x - BF / z[sel4]).astype(np.float32)); q_loc["lvl"].append(k["octave"][sel4].astype(np.int32))
+        q_loc["vc"].append(rng.uniform(0.99, 1.0, len(sel4)).astype(np.float32)); q_loc["desc"].append(d[sel4])
+        q_loc["off"].append(q_loc["off"][-1] + len(sel4))
+    cat = lambda xs, dt, shape=None: np.concatenate(xs).astype(dt) if len(xs) else np.zeros(0, dt)
+    h_last = dict(fimg=np.arange(0, nimg, 2, dtype=np.int32), off=np.array(q_last["off"], np.int32),
+                  Tcw=np.tile(np.array([0, 0, 0, 1, 0.002, 0.001, 0], np.float32), (B, 1)), dir=np.zeros(B, np.int32),
+                  xw=cat(q_last["xw"], np.float32), oct=cat(q_last["oct"], np.int32), ang=cat(q_last["ang"], np.float32),
+                  desc=cat(q_last["desc"], np.uint8), obs=cat(q_last["obs"], np.uint8))
+    h_loc = dict(fimg=h_last["fimg"], off=np.array(q_loc["off"], np.int32), px=cat(q_loc["px"], np.float32),
+                 py=cat(q_loc["py"], np.float32), pxr=cat(q_loc["pxr"], np.float32), lvl=cat(q_loc["lvl"], np.int32),
+                 vc=cat(q_loc["vc"], np.float32), desc=cat(q_loc["desc"], np.uint8))
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_last = {k: T(v) for k, v in h_last.items()}
+    d_loc = {k: T(v) for k, v in h_loc.items()}
+    rows_cap = nimg * 1500
+    d_fm = torch.full((rows_cap,), -1, dtype=torch.int32, device=dev)
+    d_nm = torch.zeros(2 * B, dtype=torch.int32, device=dev)
+    d_match = torch.full((max(int(h_loc["off"][-1]), 1),), -1, dtype=torch.int32, device=dev)
+    nq_last, nq_loc = int(h_last["off"][-1]), int(h_loc["off"][-1])
+
     def step_device(i):
         d = dev_pool[i % pool_batches]
         ex.extract_batch_device(d.data_ptr(), nimg, W, H)
+        ex.stereo_batch(B, BF, BL)
+        m_last.SearchByProjectionLastFrameDevice(ex, cam, B, d_last["fimg"], d_last["off"], d_last["Tcw"], d_last["dir"],
+                                                 d_last["xw"], d_last["oct"], d_last["ang"], d_last["desc"], d_last["obs"],
+                                                 15.0, d_fm, d_nm[:B])
+        m_local.SearchByProjectionDevice(ex, cam, B, d_loc["fimg"], d_loc["off"], d_loc["px"], d_loc["py"], d_loc["pxr"],
+                                         d_loc["lvl"], d_loc["vc"], d_loc["desc"], d_match, d_nm[B:], th=3.0)
 
     def barrier():
         torch.cuda.synchronize()
@@ -200,26 +293,30 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: inputs resident in HBM -------------------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
     for i in range(args.warmup):
         step_device(i)
     barrier()
+    sampler.wait_first()
     ex.set_profiling(True)
     launches0 = _native.lib().orb_kernel_launches()
-    sampler = ClockSampler(local)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = time.time()
     e0.record(stream)
     for i in range(args.steps):
         step_device(args.warmup + i)
     e1.record(stream)
     barrier()
+    t_end = time.time()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, t_end)
     launches = _native.lib().orb_kernel_launches() - launches0
     stage_ms = ex.last_timings()
     ex.set_profiling(False)
     n, mono, off = ex.counts(nimg)
+    nm_host = d_nm.cpu().numpy()
     t = torch.tensor([ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -229,22 +326,32 @@ def main():
     # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ----------------------
     def step_host(i):
         hb = host_pool[i % pool_batches]
-        nn, _ = ex.extract_batch(hb.numpy())
-        return ex.download(nimg)
+        ex.extract_batch(hb.numpy())
+        ex.stereo_batch(B, BF, BL)
+        nn, mm, oo, kk, dd = ex.download(nimg)
+        rows = int(oo[-1])
+        ur, dp = ex.stereo_download(rows)
+        fm, nm1 = m_last.SearchByProjectionLastFrame(ex, cam, h_last["fimg"], h_last["off"], h_last["Tcw"], h_last["dir"],
+                                                     h_last["xw"], h_last["oct"], h_last["ang"], h_last["desc"], h_last["obs"],
+                                                     15.0, rows)
+        mt, nm2 = m_local.SearchByProjection(ex, cam, h_loc["fimg"], h_loc["off"], h_loc["px"], h_loc["py"], h_loc["pxr"],
+                                             h_loc["lvl"], h_loc["vc"], h_loc["desc"], th=3.0)
+        return rows
     for i in range(args.warmup):
-        res = step_host(i)
+        step_host(i)
     barrier()
     t0 = time.perf_counter()
     d2h = 0
     for i in range(args.steps):
-        res = step_host(args.warmup + i)
-        d2h += int(res[2][-1]) * 60 + 12 * nimg
+        rows = step_host(args.warmup + i)
+        d2h += rows * (60 + 8 + 4) + 12 * nimg + 4 * nq_loc + 8 * B
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(t.item())
+    h2d_step = nimg * W * H + sum(v.nbytes for v in h_last.values()) + sum(v.nbytes for v in h_loc.values())
 
     if rank == 0:
         # roofline of the dominant kernel, live from the stage events recorded over the timed steps
@@ -253,38 +360,71 @@ def main():
         n_cand = float(np.mean([sum(len(ex.candidates(b, l)) for l in range(8)) for b in range(2)]))
         ab = algorithmic_bytes(W, H, n_kp, n_cand, level_px)
         stages = {k: stage_ms[k] for k in ["pyramid", "fast", "quadtree", "blur", "orient_desc"]}
-        top = max(stages, key=stages.get)
+        stages["stereo+search"] = max(ms_max / args.steps - stage_ms["total"], 0.0)
+        ext = {k: stages[k] for k in ["pyramid", "fast", "quadtree", "blur", "orient_desc"]}
+        top = max(ext, key=ext.get)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = ab[top] * nimg / (stages[top] * 1e-3) / 1e9
+        achieved = ab[top] * nimg / (ext[top] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None,
-                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
+                    "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                     "stage_ms_per_step": stages,
-                    "stage_gbs": {k: ab[k] * nimg / (stages[k] * 1e-3) / 1e9 for k in stages},
-                    "algorithmic_bytes_per_image": ab}
+                    "stage_gbs": {k: ab[k] * nimg / (ext[k] * 1e-3) / 1e9 for k in ext},
+                    "algorithmic_bytes_per_image": ab,
+                    "note": "FAST is ALU-pipe bound (profiles/), not HBM bound; see DESIGN.md"}
         cpu = None
         if not args.no_cpu_baseline:
             # faithful threading (Frame.cc:136-141): the two eyes on two threads, bounded sample
             v, secs = cpu_oracle_frames(pairs[:8], 2)
             cpu = {"value": v, "unit": UNIT, "cores": 2, "kind": "port",
-                   "sample": f"8 stereo frames, L/R eyes on 2 threads (Frame.cc:136-141), {secs:.1f} s"}
+                   "sample": f"8 stereo frames (extraction + stereo matching + both projection searches), "
+                             f"L/R eyes on 2 threads (Frame.cc:136-141), {secs:.1f} s"}
+        # ---- local BA (config 4): 20 KF / 3000 MP, one problem and a batch of 8 -------------------------
+        lba = None
+        try:
+            from oracle import pyoracle as po
+            opt = Optimizer(local)
+            prs = [synth.lba_problem(seed=s) for s in range(8)]
+            for _ in range(2):
+                opt.LocalBundleAdjustment(prs[0], lambda_init=100.0)
+            t0 = time.perf_counter()
+            for s in range(5):
+                g = opt.LocalBundleAdjustment(prs[s], lambda_init=100.0)
+            t_one = (time.perf_counter() - t0) / 5
+            t0 = time.perf_counter()
+            opt.LocalBundleAdjustmentBatch(prs, lambda_init=100.0)
+            t_batch = (time.perf_counter() - t0) / 8
+            t0 = time.perf_counter()
+            for s in range(3):
+                r = po.lba(prs[s]["pose"], prs[s]["fixed"], prs[s]["point"], prs[s]["edge_kf"], prs[s]["edge_mp"], prs[s]["obs"],
+                           prs[s]["inv_sigma2"], prs[s]["cam5"], 100.0, 10)
+            t_cpu = (time.perf_counter() - t0) / 3
+            lba = {"workload": "config 4: LocalBundleAdjustment 20 KF (2 fixed) / 3000 MP / ~18k edges, lambda_init 100",
+                   "ms_per_solve_e2e": 1e3 * t_one, "ms_per_solve_batch8_e2e": 1e3 * t_batch, "cpu_oracle_ms": 1e3 * t_cpu,
+                   "cpu_cores": 1, "iterations": int(g["iterations"]), "edges": int(len(prs[0]["edge_kf"]))}
+            opt.close()
+        except Exception as exc:   # never lose the headline line because the side benchmark failed
+            lba = {"error": repr(exc)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": "config 3 stage 1: stereo 640x480, 1200 features, ORBextractor L+R per frame "
-                                       "(batched); stereo matching / SearchByProjection stages join as they land",
+                "config": {"workload": "config 3: stereo 640x480, 1200 features per eye; per frame: ORBextractor L+R, "
+                                       "ComputeStereoMatches, SearchByProjection(cur,last,th=15), SearchByProjection(F,"
+                                       "local map points,th=3)",
                            "frames_per_step_per_gpu": B, "images_per_step_per_gpu": nimg,
+                           "queries_per_frame": {"last_frame": nq_last / B, "local_map": nq_loc / B},
+                           "matches_per_frame": {"last_frame": float(nm_host[:B].mean()), "local_map": float(nm_host[B:].mean())},
                            "l2": f"input pool of {pool_batches} batches = {pool_batches * nimg * W * H / 1e6:.0f} MB > 126 MB L2, "
                                  "intermediates rewritten every step",
                            "keypoints_per_image": n_kp, "fast_candidates_per_image": n_cand},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nimg * W * H,
-                        "d2h_bytes_per_step": d2h // args.steps},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_step),
+                        "d2h_bytes_per_step": int(d2h // args.steps)},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "lba": lba}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

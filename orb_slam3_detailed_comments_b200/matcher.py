@@ -26,8 +26,20 @@ def _u8(a):
     return None if a is None else np.ascontiguousarray(a, np.uint8)
 
 
+def _is_dev(a):
+    return hasattr(a, "data_ptr") and getattr(a, "is_cuda", False)
+
+
+def _dptr(a):
+    return None if a is None else C.c_void_p(a.data_ptr())
+
+
 class ORBmatcher:
-    """ORBmatcher(nnratio=0.6, checkOri=True)  (ORBmatcher.h:42)."""
+    """ORBmatcher(nnratio=0.6, checkOri=True)  (ORBmatcher.h:42).
+
+    Array arguments are host numpy arrays (the call uploads them and returns numpy results) or, all of them,
+    CUDA torch tensors of the right dtype (device-resident replay: nothing is copied, outputs are written to
+    the `out_*` tensors and the call does not synchronise)."""
 
     def __init__(self, nnratio=0.6, checkOri=True):
         self.mfNNratio = float(nnratio)
@@ -38,6 +50,8 @@ class ORBmatcher:
                            desc, th=1.0, bFarPoints=False, thFarPoints=50.0, track_depth=None, feature_claimed=None):
         """SearchByProjection(Frame&, vector<MapPoint*>, th, bFarPoints, thFarPoints) (ORBmatcher.cc:45-239) for
         several frames of `extractor`'s last batch.  Returns (match[nq] feature index or -1, nmatches[n_frames])."""
+        if _is_dev(proj_x):
+            raise TypeError("use SearchByProjectionDevice for CUDA tensors")
         fi, qo = _i32(frame_image), _i32(query_offset)
         arrs = [_f32(proj_x), _f32(proj_y), _f32(proj_xr), _i32(level), _f32(view_cos), _f32(track_depth), _u8(desc),
                 _u8(feature_claimed)]
@@ -62,3 +76,20 @@ class ORBmatcher:
         N.check(self._L.orbm_search_last_frame(extractor._h, C.byref(cam), C.byref(q), float(th),
                                                1 if self.mbCheckOrientation else 0, N.ptr(fm), N.ptr(nm)))
         return fm[:total_rows], nm
+
+    # ---- device-resident forms (CUDA torch tensors; see the class docstring) -----------------------
+    def SearchByProjectionDevice(self, extractor, cam, n_frames, frame_image, query_offset, proj_x, proj_y, proj_xr, level,
+                                 view_cos, desc, out_match, out_nmatches, th=1.0, feature_claimed=None):
+        q = N.orbm_local_queries(n_frames, 1, _dptr(frame_image), _dptr(query_offset), _dptr(proj_x), _dptr(proj_y),
+                                 _dptr(proj_xr), _dptr(level), _dptr(view_cos), None, _dptr(desc), _dptr(feature_claimed))
+        N.check(self._L.orbm_search_local_points(extractor._h, C.byref(cam), C.byref(q), float(th), self.mfNNratio, 0, 0.0,
+                                                 _dptr(out_match), _dptr(out_nmatches)))
+
+    def SearchByProjectionLastFrameDevice(self, extractor, cam, n_frames, frame_image, query_offset, Tcw, direction,
+                                          world_pos, last_octave, last_angle, desc, obs_positive, th, out_feature_match,
+                                          out_nmatches):
+        q = N.orbm_last_queries(n_frames, 1, _dptr(frame_image), _dptr(query_offset), _dptr(Tcw), _dptr(direction),
+                                _dptr(world_pos), _dptr(last_octave), _dptr(last_angle), _dptr(desc), _dptr(obs_positive))
+        N.check(self._L.orbm_search_last_frame(extractor._h, C.byref(cam), C.byref(q), float(th),
+                                               1 if self.mbCheckOrientation else 0, _dptr(out_feature_match),
+                                               _dptr(out_nmatches)))

@@ -58,14 +58,24 @@ def test_more_keyframes_than_shared_memory_system(opt):
     _compare(opt.LocalBundleAdjustment(pr), _oracle(pr, 0.0), pr)
 
 
-def test_rejected_steps_and_lambda_growth(opt):
-    # tiny initial lambda on a heavily perturbed problem: the first trials are rejected (lambda *= ni path)
+def test_rejected_steps_and_early_termination(opt):
+    # heavily perturbed points + tiny initial lambda: several trials are rejected (lambda *= ni, pop())
     pr = synth.lba_problem(n_kf=10, n_fixed=2, n_mp=800, seed=8, outlier_frac=0.2)
     rng = np.random.default_rng(0)
-    pr["point"] = pr["point"] + rng.normal(0, 0.5, pr["point"].shape)
+    pr["point"] = pr["point"] + rng.normal(0, 2.0, pr["point"].shape)
     g = opt.LocalBundleAdjustment(pr, lambda_init=1e-9)
     r = _oracle(pr, 1e-9)
-    assert r["trials"] > r["iterations"]      # at least one rejected trial happened
+    assert r["trials"] > r["iterations"]
+    assert (g["iterations"], g["trials"]) == (r["iterations"], r["trials"])
+    assert abs(g["chi2"] - r["chi2"]) <= 1e-6 * abs(r["chi2"])
+    assert np.abs(g["pose"] - r["pose"]).max() < 1e-3 and np.abs(g["point"] - r["point"]).max() < 1e-2   # 2 m perturbation
+    # perturbed poses only: converges and stops after 3 iterations without progress (the _nBad rule), < 10 iterations
+    pr = synth.lba_problem(n_kf=10, n_fixed=2, n_mp=800, seed=9, outlier_frac=0.2)
+    rng = np.random.default_rng(0)
+    rng.normal(0, 1.0, pr["point"].shape)
+    pr["pose"][2:, 4:] += rng.normal(0, 0.05, pr["pose"][2:, 4:].shape)
+    g, r = opt.LocalBundleAdjustment(pr, lambda_init=1e-9), _oracle(pr, 1e-9)
+    assert r["iterations"] < 10
     _compare(g, r, pr)
 
 
