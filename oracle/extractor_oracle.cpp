@@ -272,7 +272,7 @@ Extractor::Extractor(int nf, float sf, int nl, int ini, int mn)
     mvScaleFactor.assign(nl, 1.f);
     mvLevelSigma2.assign(nl, 1.f);
     for (int i = 1; i < nl; ++i) {
-        mvScaleFactor[i] = mvScaleFactor[i - 1] * sf;
+        mvScaleFactor[i] = (float)(mvScaleFactor[i - 1] * (double)sf);  // `double scaleFactor` member (ORBextractor.h:99)
         mvLevelSigma2[i] = mvScaleFactor[i] * mvScaleFactor[i];
     }
     mvInvScaleFactor.resize(nl);
@@ -282,7 +282,7 @@ Extractor::Extractor(int nf, float sf, int nl, int ini, int mn)
         mvInvLevelSigma2[i] = 1.0f / mvLevelSigma2[i];
     }
     mnFeaturesPerLevel.resize(nl);
-    const float factor = 1.0f / sf;
+    const float factor = (float)(1.0f / (double)sf);
     float per = nf * (1 - factor) / (1 - (float)std::pow((double)factor, (double)nl));
     int sum = 0;
     for (int l = 0; l < nl - 1; ++l) {

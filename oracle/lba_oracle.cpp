@@ -135,6 +135,35 @@ inline double huber_rho(double e, double delta, double dsqr, double* w) {
     return 2 * s * delta - dsqr;
 }
 
+// analytic Jacobians of one edge: A = d r / d X (D x 3), B = d r / d (omega, upsilon) (D x 6), row-major with
+// 3 / 6 columns.  types_six_dof_expmap.cpp:228-275 (stereo), OptimizableTypes.cpp:175-197 + Pinhole.cpp:119-130 (mono)
+inline void edge_jacobians(const Cam& cam, int D, const double R[9], const double Xc[3], double A[9], double B[18]) {
+    const double fx = cam.fx, fy = cam.fy, bf = cam.bf;
+    const double xx = Xc[0], yy = Xc[1], zz = Xc[2], z2 = zz * zz;
+    if (D == 3) {
+        for (int c = 0; c < 3; ++c) {
+            A[c] = -fx * R[c] / zz + fx * xx * R[6 + c] / z2;
+            A[3 + c] = -fy * R[3 + c] / zz + fy * yy * R[6 + c] / z2;
+            A[6 + c] = A[c] - bf * R[6 + c] / z2;
+        }
+        B[0] = xx * yy / z2 * fx; B[1] = -(1 + (xx * xx / z2)) * fx; B[2] = yy / zz * fx; B[3] = -1. / zz * fx; B[4] = 0; B[5] = xx / z2 * fx;
+        B[6] = (1 + yy * yy / z2) * fy; B[7] = -xx * yy / z2 * fy; B[8] = -xx / zz * fy; B[9] = 0; B[10] = -1. / zz * fy; B[11] = yy / z2 * fy;
+        B[12] = B[0] - bf * yy / z2; B[13] = B[1] + bf * xx / z2; B[14] = B[2]; B[15] = B[3]; B[16] = 0; B[17] = B[5] - bf / z2;
+    } else {
+        // projectJac = -Pinhole::projectJac(Xc);  A = projectJac * R;  B = projectJac * SE3deriv
+        const double J[6] = {-(fx / zz), -0.0, fx * xx / z2, -0.0, -(fy / zz), fy * yy / z2};
+        for (int c = 0; c < 3; ++c) {
+            A[c] = J[0] * R[c] + J[1] * R[3 + c] + J[2] * R[6 + c];
+            A[3 + c] = J[3] * R[c] + J[4] * R[3 + c] + J[5] * R[6 + c];
+        }
+        const double S[18] = {0, zz, -yy, 1, 0, 0, -zz, 0, xx, 0, 1, 0, yy, -xx, 0, 0, 0, 1};
+        for (int c = 0; c < 6; ++c) {
+            B[c] = J[0] * S[c] + J[1] * S[6 + c] + J[2] * S[12 + c];
+            B[6 + c] = J[3] * S[c] + J[4] * S[6 + c] + J[5] * S[12 + c];
+        }
+    }
+}
+
 // dense LDL^T (no pivoting) of an n x n symmetric matrix given by its upper triangle (row-major full
 // storage, lower part ignored).  Returns false on a zero / non-finite pivot (LinearSolverEigen fails).
 bool ldlt_solve(std::vector<double>& A, int n, const double* b, double* x) {
@@ -226,33 +255,10 @@ int orc_lba(int nKF, int nMP, int nE, double* pose, const uint8_t* fixed, double
         for (int e = 0; e < nE; ++e) {
             double r[3], Xc[3];
             const int D = edge_error(P, e, r, Xc);
-            const double xx = Xc[0], yy = Xc[1], zz = Xc[2], z2 = zz * zz;
             double R[9];
             quat_to_R(&P.pose[7 * ekf[e]], R);
             double A[9] = {0}, B[18] = {0};
-            const double fx = P.cam.fx, fy = P.cam.fy, bf = P.cam.bf;
-            if (D == 3) {
-                for (int c = 0; c < 3; ++c) {
-                    A[c] = -fx * R[c] / zz + fx * xx * R[6 + c] / z2;
-                    A[3 + c] = -fy * R[3 + c] / zz + fy * yy * R[6 + c] / z2;
-                    A[6 + c] = A[c] - bf * R[6 + c] / z2;
-                }
-                B[0] = xx * yy / z2 * fx; B[1] = -(1 + (xx * xx / z2)) * fx; B[2] = yy / zz * fx; B[3] = -1. / zz * fx; B[4] = 0; B[5] = xx / z2 * fx;
-                B[6] = (1 + yy * yy / z2) * fy; B[7] = -xx * yy / z2 * fy; B[8] = -xx / zz * fy; B[9] = 0; B[10] = -1. / zz * fy; B[11] = yy / z2 * fy;
-                B[12] = B[0] - bf * yy / z2; B[13] = B[1] + bf * xx / z2; B[14] = B[2]; B[15] = B[3]; B[16] = 0; B[17] = B[5] - bf / z2;
-            } else {
-                // projectJac = -Pinhole::projectJac(Xc);  A = projectJac * R;  B = projectJac * SE3deriv
-                const double J[6] = {-(fx / zz), -0.0, fx * xx / z2, -0.0, -(fy / zz), fy * yy / z2};
-                for (int c = 0; c < 3; ++c) {
-                    A[c] = J[0] * R[c] + J[1] * R[3 + c] + J[2] * R[6 + c];
-                    A[3 + c] = J[3] * R[c] + J[4] * R[3 + c] + J[5] * R[6 + c];
-                }
-                const double S[18] = {0, zz, -yy, 1, 0, 0, -zz, 0, xx, 0, 1, 0, yy, -xx, 0, 0, 0, 1};
-                for (int c = 0; c < 6; ++c) {
-                    B[c] = J[0] * S[c] + J[1] * S[6 + c] + J[2] * S[12 + c];
-                    B[6 + c] = J[3] * S[c] + J[4] * S[6 + c] + J[5] * S[12 + c];
-                }
-            }
+            edge_jacobians(P.cam, D, R, Xc, A, B);
             const double c2 = invs2[e] * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
             double w;
             huber_rho(c2, D == 2 ? P.deltaMono : P.deltaStereo, D == 2 ? P.dsqrMono : P.dsqrStereo, &w);
@@ -412,5 +418,30 @@ int orc_lba(int nKF, int nMP, int nE, double* pose, const uint8_t* fixed, double
         stats[0] = iters; stats[1] = lambda; stats[2] = currentChi; stats[3] = trials; stats[4] = iniChi0;
     }
     return iters;
+}
+}
+
+// ---- small exports for the finite-difference Jacobian test (tests/test_oracle_golden.py) -------------------
+extern "C" {
+// residual r (3, third = 0 for mono) of one edge
+int orc_edge_residual(const double* pose7, const double* X, const double* obs3, const double* cam5, double* r) {
+    Problem P;
+    P.pose.assign(pose7, pose7 + 7);
+    P.point.assign(X, X + 3);
+    static const int zero = 0;
+    P.ekf = &zero; P.emp = &zero; P.obs = obs3;
+    P.cam = {cam5[0], cam5[1], cam5[2], cam5[3], cam5[4]};
+    double Xc[3];
+    return edge_error(P, 0, r, Xc);
+}
+void orc_pose_oplus(double* pose7, const double* upd6) { pose_oplus(pose7, upd6); }
+void orc_edge_jacobians(const double* pose7, const double* X, int D, const double* cam5, double* A9, double* B18) {
+    Cam cam = {cam5[0], cam5[1], cam5[2], cam5[3], cam5[4]};
+    double R[9], Xc[3];
+    quat_to_R(pose7, R);
+    se3_map(pose7, X, Xc);
+    for (int i = 0; i < 9; ++i) A9[i] = 0;
+    for (int i = 0; i < 18; ++i) B18[i] = 0;
+    edge_jacobians(cam, D, R, Xc, A9, B18);
 }
 }

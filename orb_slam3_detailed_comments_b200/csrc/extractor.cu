@@ -33,7 +33,7 @@ static void build_tables(orbx_handle* h) {
     h->scale.assign(nl, 1.f);
     h->sigma2.assign(nl, 1.f);
     for (int i = 1; i < nl; ++i) {
-        h->scale[i] = h->scale[i - 1] * sf;
+        h->scale[i] = (float)(h->scale[i - 1] * (double)sf);   // the member is `double scaleFactor` (ORBextractor.h:99)
         h->sigma2[i] = h->scale[i] * h->scale[i];
     }
     h->inv_scale.resize(nl);
@@ -43,7 +43,7 @@ static void build_tables(orbx_handle* h) {
         h->inv_sigma2[i] = 1.0f / h->sigma2[i];
     }
     h->quota.resize(nl);
-    const float factor = 1.0f / sf;
+    const float factor = (float)(1.0f / (double)sf);
     float per = h->cfg.n_features * (1 - factor) / (1 - (float)pow((double)factor, (double)nl));
     int sum = 0;
     for (int l = 0; l < nl - 1; ++l) {
