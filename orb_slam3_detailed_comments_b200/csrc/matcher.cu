@@ -24,7 +24,7 @@ using namespace orbdev;
 
 namespace orb {
 
-#define PM_K 4            // stored candidates per query
+#define PM_K 8            // stored candidates per query
 #define PM_WARPS 8
 #define PM_QPB 64         // queries per CTA in the candidate kernel
 #define GRID_COLS 64      // include/Frame.h:46-47

@@ -173,18 +173,28 @@ __global__ void __launch_bounds__(256) k_stereo_median(const __grid_constant__ S
     __syncthreads();
     const int cnt = s_cnt;
     if (cnt == 0) return;
-    const int target = cnt / 2;   // vDistIdx[vDistIdx.size() / 2] of the (SAD, iL)-sorted pairs
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        const int v = md_sad[i];
-        if (v < 0) continue;
-        int rank = 0;
-        for (int j = 0; j < N; ++j) {
-            const int u = md_sad[j];
-            rank += (u >= 0) && (u < v || (u == v && j < i));
+    const int target = cnt / 2;   // vDistIdx[vDistIdx.size() / 2] of the (SAD, iL)-sorted pairs: only its SAD matters
+    // two-pass radix select on the 16-bit SAD (<= 121 * 255): high byte, then low byte
+    __shared__ int s_hist[256];
+    __shared__ int s_hi, s_rem;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            const int v = md_sad[i];
+            if (v < 0) continue;
+            if (pass == 0) atomicAdd(&s_hist[(v >> 8) & 0xff], 1);
+            else if ((v >> 8) == s_hi) atomicAdd(&s_hist[v & 0xff], 1);
         }
-        if (rank == target) s_median = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int rem = pass == 0 ? target : s_rem, b = 0;
+            while (b < 255 && rem >= s_hist[b]) { rem -= s_hist[b]; ++b; }
+            if (pass == 0) { s_hi = b; s_rem = rem; }
+            else s_median = (s_hi << 8) | b;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     const float thDist = fmul(1.5f * 1.4f, (float)s_median);
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         const int v = md_sad[i];
