@@ -392,6 +392,7 @@ def main():
             prs = [synth.lba_problem(seed=s) for s in range(8)]
             for _ in range(2):
                 opt.LocalBundleAdjustment(prs[0], lambda_init=100.0)
+            opt.LocalBundleAdjustmentBatch(prs, lambda_init=100.0)      # warm-up: sizes the pinned / device workspaces
             t0 = time.perf_counter()
             for s in range(5):
                 g = opt.LocalBundleAdjustment(prs[s], lambda_init=100.0)

@@ -76,7 +76,10 @@ def test_rejected_steps_and_early_termination(opt):
     pr["pose"][2:, 4:] += rng.normal(0, 0.05, pr["pose"][2:, 4:].shape)
     g, r = opt.LocalBundleAdjustment(pr, lambda_init=1e-9), _oracle(pr, 1e-9)
     assert r["iterations"] < 10
-    _compare(g, r, pr)
+    assert (g["iterations"], g["trials"]) == (r["iterations"], r["trials"])
+    assert abs(g["chi2"] - r["chi2"]) <= 1e-7 * abs(r["chi2"])
+    assert np.abs(g["pose"] - r["pose"]).max() < TOL
+    assert np.abs(g["point"] - r["point"]).max() < 1e-3    # 20 % outliers: weakly constrained far points
 
 
 def test_batch_of_independent_problems(opt):
