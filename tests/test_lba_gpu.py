@@ -79,7 +79,10 @@ def test_rejected_steps_and_early_termination(opt):
     assert (g["iterations"], g["trials"]) == (r["iterations"], r["trials"])
     assert abs(g["chi2"] - r["chi2"]) <= 1e-7 * abs(r["chi2"])
     assert np.abs(g["pose"] - r["pose"]).max() < TOL
-    assert np.abs(g["point"] - r["point"]).max() < 1e-3    # 20 % outliers: weakly constrained far points
+    # lambda 1e-9 leaves far two-view points almost unconstrained along the ray: compare them through what the
+    # optimiser sees (per-edge chi2), and the well-conditioned majority by coordinates
+    assert np.allclose(g["edge_chi2"], r["edge_chi2"], rtol=1e-4, atol=1e-6)
+    assert np.median(np.abs(g["point"] - r["point"])) < 1e-6
 
 
 def test_batch_of_independent_problems(opt):
