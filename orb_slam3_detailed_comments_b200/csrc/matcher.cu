@@ -34,6 +34,7 @@ struct FrameFeat {   // shared-memory staging of one frame's features
     float* x;
     float* y;
     float* ur;
+    float* ang;
     uint16_t* cell;   // ix * 48 + iy, 0xffff = not in the grid (PosInGrid false)
     uint8_t* oct;
 };
@@ -80,13 +81,15 @@ __device__ __forceinline__ void stage_frame(const ProjParams& P, int img, unsign
     F.x = reinterpret_cast<float*>(smem);
     F.y = F.x + M;
     F.ur = F.y + M;
-    F.cell = reinterpret_cast<uint16_t*>(F.ur + M);
+    F.ang = F.ur + M;
+    F.cell = reinterpret_cast<uint16_t*>(F.ang + M);
     F.oct = reinterpret_cast<uint8_t*>(F.cell + M);
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         const orbx_keypoint k = P.kps[row0 + i];
         F.x[i] = k.x;
         F.y[i] = k.y;
         F.ur[i] = P.uright ? P.uright[row0 + i] : -1.0f;
+        F.ang[i] = k.angle;
         // Frame::PosInGrid, Frame.cc:962-978 (C round(): half away from zero)
         const int px = (int)roundf(fmul(fsub(k.x, P.minX), P.invW)), py = (int)roundf(fmul(fsub(k.y, P.minY), P.invH));
         F.cell[i] = (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) ? (uint16_t)0xffff : (uint16_t)(px * GRID_ROWS + py);
@@ -94,7 +97,7 @@ __device__ __forceinline__ void stage_frame(const ProjParams& P, int img, unsign
     }
 }
 
-__device__ __forceinline__ size_t frame_smem_bytes(int maxFeat) { return (size_t)maxFeat * 15 + 16; }
+__device__ __forceinline__ size_t frame_smem_bytes(int maxFeat) { return (size_t)maxFeat * 19 + 16; }
 
 struct Window {   // Frame::GetFeaturesInArea arguments resolved to cell ranges
     float x, y, r;
@@ -295,28 +298,31 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int nmatches = 0;
+    float* s_qf = reinterpret_cast<float*>(s_claimed + ((P.maxFeat + 15) / 16) * 16);   // PM_CHUNK: mode 1 last angle
+    uint8_t* s_qflag = reinterpret_cast<uint8_t*>(s_qf + PM_CHUNK);                      // PM_CHUNK: mode 1 obs > 0
     for (int base = q0; base < q1; base += PM_CHUNK) {
         const int nchunk = min(PM_CHUNK, q1 - base);
         for (int i = threadIdx.x; i < nchunk * PM_K; i += blockDim.x) s_top[i] = P.topk[(size_t)base * PM_K + i];
-        for (int i = threadIdx.x; i < nchunk; i += blockDim.x) s_cnt[i] = P.cnt[base + i];
+        for (int i = threadIdx.x; i < nchunk; i += blockDim.x) {
+            s_cnt[i] = P.cnt[base + i];
+            if (P.mode == 0) P.match[base + i] = -1;
+            else { s_qf[i] = P.f0[base + i]; s_qflag[i] = P.flag[base + i]; }
+        }
         __syncthreads();
         if (warp == 0) {
             for (int qi = 0; qi < nchunk; ++qi) {
                 const int q = base + qi;
                 const int count = s_cnt[qi];
-                if (P.mode == 0 && lane == 0) P.match[q] = -1;
                 if (count <= 0) continue;
-                // first two stored candidates that are still free
-                unsigned long long b1 = ~0ull, b2 = ~0ull;
-                int stored = min(count, PM_K), live = 0;
-                for (int k = 0; k < stored; ++k) {
-                    const unsigned long long key = s_top[qi * PM_K + k];
-                    const int id = (int)(key & 0xffffu);
-                    if (s_claimed[id]) continue;
-                    if (live == 0) b1 = key; else if (live == 1) b2 = key;
-                    ++live;
-                }
+                // the stored candidates are sorted by (distance, reference order): lane k looks at entry k, the first
+                // (two) still-free ones are the best / second best of the reference's sequential scan
+                const int stored = min(count, PM_K);
+                const unsigned long long key = (lane < stored) ? s_top[qi * PM_K + lane] : ~0ull;
+                const bool is_free = (lane < stored) && !s_claimed[(int)(key & 0xffffu)];
+                const unsigned fm = __ballot_sync(0xffffffffu, is_free);
+                const int live = __popc(fm);
                 const int need = (P.mode == 0) ? 2 : 1;
+                unsigned long long b1 = ~0ull, b2 = ~0ull;
                 if (live < need && count > PM_K) {
                     // claims consumed the stored list: exact rescan with the mask applied (warp-cooperative)
                     Window w;
@@ -333,6 +339,13 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
                     warp_scan_query(P, F, N, row0, w, P.qdesc + 32 * (size_t)q, ur_pred, er_max, s_claimed, top);
                     b1 = top[0];
                     b2 = top[1];
+                } else {
+                    if (fm) {
+                        const int i1 = __ffs(fm) - 1;
+                        b1 = __shfl_sync(0xffffffffu, key, i1);
+                        const unsigned fm2 = fm & (fm - 1);
+                        if (fm2) b2 = __shfl_sync(0xffffffffu, key, __ffs(fm2) - 1);
+                    }
                 }
                 if (b1 == ~0ull) continue;
                 const int bestDist = (int)(b1 >> 32), bestIdx = (int)(b1 & 0xffffu);
@@ -355,9 +368,9 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
                     if (bestDist <= 100) {
                         if (lane == 0) {
                             s_holder[bestIdx] = q;
-                            s_claimed[bestIdx] = P.flag[q] ? 1 : 0;   // only map points with observations block later queries
+                            s_claimed[bestIdx] = s_qflag[qi] ? 1 : 0;   // only map points with observations block later queries
                             if (P.checkOri) {
-                                float rot = fsub(P.f0[q], P.kps[row0 + bestIdx].angle);
+                                float rot = fsub(s_qf[qi], F.ang[bestIdx]);
                                 if (rot < 0.0f) rot = fadd(rot, 360.0f);
                                 int bin = (int)roundf(fmul(rot, 1.0f / 30));
                                 if (bin == 30) bin = 0;
@@ -442,14 +455,14 @@ struct StageCursor {
 
 static orb_status launch_proj(orbx_handle* h, ProjParams& P, int n_frames, int max_q_per_frame) {
     cudaStream_t st = h->stream;
-    const size_t fsm = ((size_t)P.maxFeat * 15 + 16 + 15) / 16 * 16;
+    const size_t fsm = ((size_t)P.maxFeat * 19 + 16 + 15) / 16 * 16;
     ORB_CUDA(cudaFuncSetAttribute(k_proj_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(fsm, (size_t)1024)));
     dim3 grid((max_q_per_frame + PM_QPB - 1) / PM_QPB, n_frames);
     if (grid.x > 0) {
         k_proj_candidates<<<grid, PM_WARPS * 32, fsm, st>>>(P);
         ORB_LAUNCHED();
     }
-    const size_t rsm = fsm + (size_t)PM_CHUNK * PM_K * 8 + (size_t)PM_CHUNK * 4 + (size_t)P.maxFeat * 5 + 64;
+    const size_t rsm = fsm + (size_t)PM_CHUNK * PM_K * 8 + (size_t)PM_CHUNK * 4 + (size_t)P.maxFeat * 5 + (size_t)PM_CHUNK * 5 + 128;
     ORB_CUDA(cudaFuncSetAttribute(k_proj_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
     k_proj_resolve<<<n_frames, 256, rsm, st>>>(P);
     ORB_LAUNCHED();
