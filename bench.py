@@ -324,26 +324,42 @@ def main():
     value = world * B * args.steps / (ms_max * 1e-3)
 
     # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ----------------------
-    def step_host(i):
-        hb = host_pool[i % pool_batches]
-        ex.extract_batch(hb.numpy())
-        ex.stereo_batch(B, BF, BL)
-        nn, mm, oo, kk, dd = ex.download(nimg)
+    # Two extractor handles (two CUDA streams) alternate: the H2D + extraction + stereo of batch i+1 are queued
+    # before the blocking result reads of batch i, so PCIe traffic overlaps compute (the usage INTEGRATION.md
+    # recommends for sequence replay).  Every step still moves its own images in and its own results out.
+    ex2 = ORBextractor(NFEAT, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=nimg, device=local)
+    exs = [ex, ex2]
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    p_last = {k: pin(v) for k, v in h_last.items()}
+    p_loc = {k: pin(v) for k, v in h_loc.items()}
+
+    def submit(i):
+        e = exs[i % 2]
+        e.extract_batch_async(host_pool[i % pool_batches].numpy())
+        e.stereo_batch(B, BF, BL)
+
+    def finish(i):
+        e = exs[i % 2]
+        nn, mm, oo, kk, dd = e.download(nimg)
         rows = int(oo[-1])
-        ur, dp = ex.stereo_download(rows)
-        fm, nm1 = m_last.SearchByProjectionLastFrame(ex, cam, h_last["fimg"], h_last["off"], h_last["Tcw"], h_last["dir"],
-                                                     h_last["xw"], h_last["oct"], h_last["ang"], h_last["desc"], h_last["obs"],
+        ur, dp = e.stereo_download(rows)
+        fm, nm1 = m_last.SearchByProjectionLastFrame(e, cam, p_last["fimg"], p_last["off"], p_last["Tcw"], p_last["dir"],
+                                                     p_last["xw"], p_last["oct"], p_last["ang"], p_last["desc"], p_last["obs"],
                                                      15.0, rows)
-        mt, nm2 = m_local.SearchByProjection(ex, cam, h_loc["fimg"], h_loc["off"], h_loc["px"], h_loc["py"], h_loc["pxr"],
-                                             h_loc["lvl"], h_loc["vc"], h_loc["desc"], th=3.0)
+        mt, nm2 = m_local.SearchByProjection(e, cam, p_loc["fimg"], p_loc["off"], p_loc["px"], p_loc["py"], p_loc["pxr"],
+                                             p_loc["lvl"], p_loc["vc"], p_loc["desc"], th=3.0)
         return rows
     for i in range(args.warmup):
-        step_host(i)
+        submit(i)
+        finish(i)
     barrier()
     t0 = time.perf_counter()
     d2h = 0
+    submit(args.warmup)
     for i in range(args.steps):
-        rows = step_host(args.warmup + i)
+        if i + 1 < args.steps:
+            submit(args.warmup + i + 1)
+        rows = finish(args.warmup + i)
         d2h += rows * (60 + 8 + 4) + 12 * nimg + 4 * nq_loc + 8 * B
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0

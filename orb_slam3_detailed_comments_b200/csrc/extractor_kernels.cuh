@@ -353,10 +353,15 @@ __global__ void k_offsets(const int* __restrict__ nkp, int batch, int* __restric
 
 // ---------------------------------------------------------------------------------------------
 // K5  GaussianBlur 7x7 sigma=2 BORDER_REFLECT_101, OpenCV's fixed-point path (SURVEY App. A.2;
-// ORBextractor.cc:1629-1637).  Tile 64x32 output pixels per CTA, all levels in one launch.
+// ORBextractor.cc:1629-1637): Q0.8 kernel {18,34,48,56,48,34,18}, horizontal pass Q8.8 (u16), vertical pass
+// Q16.16, (acc + 32768) >> 16.
+// No shared memory: a thread owns 4 adjacent columns and marches down BLUR_ROWS rows with the last 7 horizontal
+// results in registers.  The horizontal pass runs on packed u16x2 lanes: with pixel sums <= 510 and an
+// accumulator <= 65280 a plain 32-bit IMAD multiplies both lanes at once without a carry between them.
 // ---------------------------------------------------------------------------------------------
-#define BLUR_TW 64
-#define BLUR_TH 32
+#define BLUR_TW 256     // columns per CTA (64 threads x 4 px)
+#define BLUR_TH 128     // rows per CTA (4 thread rows x BLUR_ROWS)
+#define BLUR_ROWS 32
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (i < 0) i = -i;
@@ -364,43 +369,73 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;  // valid for n >= 4 and |overshoot| <= 3 (every pyramid level is far larger)
 }
 
+// horizontal 7-tap of 4 adjacent pixels at columns x0..x0+3 of row `p`; returns packed Q8.8 results:
+// lo = (px0 | px2 << 16), hi = (px1 | px3 << 16)
+__device__ __forceinline__ void blur_h4(const uint8_t* __restrict__ p, int x0, int w, bool interior, uint32_t& lo, uint32_t& hi) {
+    uint32_t w0, w1, w2;   // bytes x0-4 .. x0+7
+    if (interior) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(p + x0 - 4);
+        w0 = __ldg(q); w1 = __ldg(q + 1); w2 = __ldg(q + 2);
+    } else {
+        uint32_t b[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) b[k] = (k >= 1 && k <= 10) ? (uint32_t)__ldg(p + reflect101(min(x0 - 4 + k, w + 2), w)) : 0u;
+        w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+        w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+        w2 = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
+    }
+    // S_k = the 4 pixels shifted by k-3 (bytes 1+k .. 4+k of the 12-byte window), split into even / odd lanes
+    uint32_t e[7], o[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const int off = 1 + k;   // first byte of S_k inside (w0,w1,w2)
+        uint32_t sk;
+        if (off < 4) sk = __byte_perm(w0, w1, 0x3210 + 0x1111 * off);
+        else if (off == 4) sk = w1;
+        else sk = __byte_perm(w1, w2, 0x3210 + 0x1111 * (off - 4));
+        e[k] = __byte_perm(sk, 0u, 0x4240);
+        o[k] = __byte_perm(sk, 0u, 0x4341);
+    }
+    lo = 18u * (e[0] + e[6]) + 34u * (e[1] + e[5]) + 48u * (e[2] + e[4]) + 56u * e[3];
+    hi = 18u * (o[0] + o[6]) + 34u * (o[1] + o[5]) + 48u * (o[2] + o[4]) + 56u * o[3];
+}
+
 __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ ExtractGeom g) {
-    __shared__ uint8_t raw[BLUR_TH + 6][BLUR_TW + 8];
-    __shared__ uint16_t hor[BLUR_TH + 6][BLUR_TW];
-    const int tileId = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
+    const int tileId = blockIdx.x, img = blockIdx.y;
     int l = 0;
     while (l + 1 < g.nlevels && tileId >= g.lv[l + 1].tileBase) ++l;
     const LevelGeom& G = g.lv[l];
     const int local = tileId - G.tileBase;
     const int ty = local / G.tilesX, tx = local - ty * G.tilesX;
-    const int ox = tx * BLUR_TW, oy = ty * BLUR_TH;
-    const uint8_t* src = G.base + (int64_t)img * G.img_stride;
-    for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
-        const int r = i / (BLUR_TW + 6), c = i - r * (BLUR_TW + 6);
-        const int y = reflect101(min(oy + r - 3, G.h + 2), G.h), x = reflect101(min(ox + c - 3, G.w + 2), G.w);
-        raw[r][c] = __ldg(src + (int64_t)y * G.pitch + x);
-    }
-    __syncthreads();
-    for (int i = tid; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
-        const int r = i / BLUR_TW, c = i - r * BLUR_TW;
-        const uint8_t* p = &raw[r][c];
-        hor[r][c] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
-    }
-    __syncthreads();
-    uint8_t* dst = G.blur + (int64_t)img * G.blur_stride;
-    for (int i = tid; i < BLUR_TH * BLUR_TW / 4; i += 256) {
-        const int r = i / (BLUR_TW / 4), c4 = (i - r * (BLUR_TW / 4)) * 4;
-        const int y = oy + r, x = ox + c4;
-        if (y >= G.h || x >= G.w) continue;
-        uint32_t packed = 0u;
+    const int x0 = tx * BLUR_TW + 4 * (threadIdx.x & 63);
+    const int y0 = ty * BLUR_TH + BLUR_ROWS * (threadIdx.x >> 6);
+    if (x0 >= G.w || y0 >= G.h) return;
+    const uint8_t* __restrict__ src = G.base + (int64_t)img * G.img_stride;
+    uint8_t* __restrict__ dst = G.blur + (int64_t)img * G.blur_stride;
+    const bool interior = (x0 >= 4) && (x0 + 8 <= G.w);
+    // horizontal results of the last 7 rows, unpacked to one 32-bit value per pixel (Q8.8 <= 65280)
+    uint32_t hwin[7][4];
+    const int rows = min(BLUR_ROWS, G.h - y0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int c = c4 + k;
-            const uint32_t acc = 18u * (hor[r][c] + hor[r + 6][c]) + 34u * (hor[r + 1][c] + hor[r + 5][c]) +
-                                 48u * (hor[r + 2][c] + hor[r + 4][c]) + 56u * hor[r + 3][c];
-            packed |= ((acc + 32768u) >> 16) << (8 * k);
+    for (int r = 0; r < BLUR_ROWS + 6; ++r) {
+        if (r < rows + 6) {
+            const int y = reflect101(y0 + r - 3, G.h);
+            uint32_t lo, hi;
+            blur_h4(src + (int64_t)y * G.pitch, x0, G.w, interior, lo, hi);
+            uint32_t* hrow = hwin[r % 7];
+            hrow[0] = lo & 0xffffu; hrow[2] = lo >> 16; hrow[1] = hi & 0xffffu; hrow[3] = hi >> 16;
+            if (r >= 6) {
+                // rows r-6 .. r are in the window; output row y0 + r - 6
+                uint32_t packed = 0u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t acc = 18u * (hwin[(r - 6) % 7][k] + hwin[r % 7][k]) + 34u * (hwin[(r - 5) % 7][k] + hwin[(r - 1) % 7][k]) +
+                                         48u * (hwin[(r - 4) % 7][k] + hwin[(r - 2) % 7][k]) + 56u * hwin[(r - 3) % 7][k];
+                    packed |= ((acc + 32768u) >> 16) << (8 * k);
+                }
+                *reinterpret_cast<uint32_t*>(dst + (int64_t)(y0 + r - 6) * G.blur_pitch + x0) = packed;   // pitch padding absorbs the tail
+            }
         }
-        *reinterpret_cast<uint32_t*>(dst + (int64_t)y * G.blur_pitch + x) = packed;  // pitch padding absorbs the tail
     }
 }
 

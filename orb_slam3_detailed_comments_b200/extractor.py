@@ -87,6 +87,14 @@ class ORBextractor:
                                            N.ptr(n), N.ptr(mono)))
         return n, mono
 
+    def extract_batch_async(self, images, lapping=(0, 0)):
+        """Like extract_batch but returns immediately (H2D + kernels are queued on the handle's stream); `images` must
+        stay alive (pinned memory makes the copy truly asynchronous).  Pair with counts()/download()."""
+        assert images.dtype == np.uint8 and images.flags["C_CONTIGUOUS"]
+        b, h, w = images.shape
+        N.check(self._L.orbx_extract_batch(self._h, N.ptr(images), b, w, h, w, h * w, int(lapping[0]), int(lapping[1]),
+                                           None, None))
+
     def extract_batch_device(self, dptr, batch, width, height, stride=None, image_stride=None, lapping=(0, 0)):
         stride = stride or width
         image_stride = image_stride or stride * height
