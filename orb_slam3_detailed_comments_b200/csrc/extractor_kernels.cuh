@@ -359,8 +359,8 @@ __global__ void k_offsets(const int* __restrict__ nkp, int batch, int* __restric
 // results in registers.  The horizontal pass runs on packed u16x2 lanes: with pixel sums <= 510 and an
 // accumulator <= 65280 a plain 32-bit IMAD multiplies both lanes at once without a carry between them.
 // ---------------------------------------------------------------------------------------------
-#define BLUR_TW 256     // columns per CTA (64 threads x 4 px)
-#define BLUR_TH 128     // rows per CTA (4 thread rows x BLUR_ROWS)
+#define BLUR_TW 128     // columns per CTA (32 threads x 4 px)
+#define BLUR_TH 256     // rows per CTA (8 thread rows x BLUR_ROWS); idle thread rows exit at once
 #define BLUR_ROWS 32
 
 __device__ __forceinline__ int reflect101(int i, int n) {
@@ -407,8 +407,8 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ ExtractGeo
     const LevelGeom& G = g.lv[l];
     const int local = tileId - G.tileBase;
     const int ty = local / G.tilesX, tx = local - ty * G.tilesX;
-    const int x0 = tx * BLUR_TW + 4 * (threadIdx.x & 63);
-    const int y0 = ty * BLUR_TH + BLUR_ROWS * (threadIdx.x >> 6);
+    const int x0 = tx * BLUR_TW + 4 * (threadIdx.x & 31);
+    const int y0 = ty * BLUR_TH + BLUR_ROWS * (threadIdx.x >> 5);
     if (x0 >= G.w || y0 >= G.h) return;
     const uint8_t* __restrict__ src = G.base + (int64_t)img * G.img_stride;
     uint8_t* __restrict__ dst = G.blur + (int64_t)img * G.blur_stride;
@@ -477,8 +477,10 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_describe(const __grid_
         const int d = c_umax[v < 0 ? -v : v];
         const uint8_t* p = G.base + (int64_t)img * G.img_stride + (int64_t)(y + v) * G.pitch + x;
         int rs = 0;
-        for (int u = -d; u <= d; ++u) {
-            const int val = __ldg(p + u);
+#pragma unroll
+        for (int u = -15; u <= 15; ++u) {   // fixed trip count: the loads are independent and issue back to back
+            const int au = u < 0 ? -u : u;
+            const int val = (au <= d) ? (int)__ldg(p + u) : 0;
             m10 += u * val;
             rs += val;
         }
