@@ -470,21 +470,20 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_describe(const __grid_
     const uint32_t c = lvlKp[(int64_t)img * g.kpTotal + G.kpOff + (e - first)];
     const int x = (int)(c & 0xfffu) + 16, y = (int)((c >> 12) & 0xfffu) + 16, score = (int)(c >> 24);
 
-    // intensity centroid over the radius-15 disc: lane v handles row v-15
+    // intensity centroid over the radius-15 disc: lane u+15 owns COLUMN u and walks the 31 rows, so every load
+    // instruction of the warp touches one 31-byte segment (one cache line) and the 31 loads are independent
     int m10 = 0, m01 = 0;
     if (lane < 31) {
-        const int v = lane - 15;
-        const int d = c_umax[v < 0 ? -v : v];
-        const uint8_t* p = G.base + (int64_t)img * G.img_stride + (int64_t)(y + v) * G.pitch + x;
-        int rs = 0;
+        const int u = lane - 15, au = u < 0 ? -u : u;
+        const uint8_t* p = G.base + (int64_t)img * G.img_stride + (int64_t)y * G.pitch + x + u;
+        int cs = 0;
 #pragma unroll
-        for (int u = -15; u <= 15; ++u) {   // fixed trip count: the loads are independent and issue back to back
-            const int au = u < 0 ? -u : u;
-            const int val = (au <= d) ? (int)__ldg(p + u) : 0;
-            m10 += u * val;
-            rs += val;
+        for (int v = -15; v <= 15; ++v) {
+            const int val = (au <= c_umax[v < 0 ? -v : v]) ? (int)__ldg(p + (int64_t)v * G.pitch) : 0;
+            cs += val;
+            m01 += v * val;
         }
-        m01 = v * rs;
+        m10 = u * cs;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

@@ -106,12 +106,18 @@ class ORBextractor:
         N.check(self._L.orbx_counts(self._h, N.ptr(n), N.ptr(mono), N.ptr(off)))
         return n, mono, off
 
-    def download(self, batch):
+    def download(self, batch, out=None):
+        """Compact results of the last batch.  `out` = (kps, desc) preallocated host arrays (pinned memory makes the
+        D2H a DMA instead of a staged copy); returns (n, mono, offsets, kps[:rows], desc[:rows])."""
         n, mono, off = self.counts(batch)
         rows = int(off[batch])
-        kps = np.zeros(max(rows, 1), N.KP_DTYPE)
-        desc = np.zeros((max(rows, 1), 32), np.uint8)
-        N.check(self._L.orbx_download(self._h, N.ptr(kps), N.ptr(desc), max(rows, 1)))
+        if out is None:
+            kps = np.zeros(max(rows, 1), N.KP_DTYPE)
+            desc = np.zeros((max(rows, 1), 32), np.uint8)
+        else:
+            kps, desc = out
+            assert len(kps) >= rows and len(desc) >= rows
+        N.check(self._L.orbx_download(self._h, N.ptr(kps), N.ptr(desc), max(len(kps), 1)))
         return n, mono, off, kps[:rows], desc[:rows]
 
     # ---- stage outputs (parity tests; mvImagePyramid is a public member of the reference class) ---
@@ -145,10 +151,13 @@ class ORBextractor:
         """Stereo-match the last batch (left = image 2p, right = image 2p+1); results stay on the device."""
         N.check(self._L.orbm_stereo_batch(self._h, n_pairs, float(bf), float(b)))
 
-    def stereo_download(self, rows):
-        uR = np.zeros(max(rows, 1), np.float32)
-        dep = np.zeros(max(rows, 1), np.float32)
-        N.check(self._L.orbm_stereo_download(self._h, N.ptr(uR), N.ptr(dep), max(rows, 1)))
+    def stereo_download(self, rows, out=None):
+        if out is None:
+            uR = np.zeros(max(rows, 1), np.float32)
+            dep = np.zeros(max(rows, 1), np.float32)
+        else:
+            uR, dep = out
+        N.check(self._L.orbm_stereo_download(self._h, N.ptr(uR), N.ptr(dep), max(len(uR), 1)))
         return uR[:rows], dep[:rows]
 
     def stereo_pair(self, right, n_left, bf, b):

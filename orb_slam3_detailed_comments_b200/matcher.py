@@ -47,7 +47,7 @@ class ORBmatcher:
         self._L = N.lib()
 
     def SearchByProjection(self, extractor, cam, frame_image, query_offset, proj_x, proj_y, proj_xr, level, view_cos,
-                           desc, th=1.0, bFarPoints=False, thFarPoints=50.0, track_depth=None, feature_claimed=None):
+                           desc, th=1.0, bFarPoints=False, thFarPoints=50.0, track_depth=None, feature_claimed=None, out=None):
         """SearchByProjection(Frame&, vector<MapPoint*>, th, bFarPoints, thFarPoints) (ORBmatcher.cc:45-239) for
         several frames of `extractor`'s last batch.  Returns (match[nq] feature index or -1, nmatches[n_frames])."""
         if _is_dev(proj_x):
@@ -57,22 +57,20 @@ class ORBmatcher:
                 _u8(feature_claimed)]
         q = N.orbm_local_queries(len(fi), 0, N.ptr(fi), N.ptr(qo), *[N.ptr(a) for a in arrs])
         nq = int(qo[-1])
-        match = np.full(max(nq, 1), -1, np.int32)
-        nm = np.zeros(len(fi), np.int32)
+        match, nm = out if out is not None else (np.full(max(nq, 1), -1, np.int32), np.zeros(len(fi), np.int32))
         N.check(self._L.orbm_search_local_points(extractor._h, C.byref(cam), C.byref(q), float(th), self.mfNNratio,
                                                  1 if bFarPoints else 0, float(thFarPoints), N.ptr(match), N.ptr(nm)))
         return match[:nq], nm
 
     def SearchByProjectionLastFrame(self, extractor, cam, frame_image, query_offset, Tcw, direction, world_pos,
-                                    last_octave, last_angle, desc, obs_positive, th, total_rows):
+                                    last_octave, last_angle, desc, obs_positive, th, total_rows, out=None):
         """SearchByProjection(Frame& cur, const Frame& last, th, bMono) (ORBmatcher.cc:1950-2184).
         Returns (feature_match[total_rows] query index or -1, nmatches[n_frames])."""
         fi, qo = _i32(frame_image), _i32(query_offset)
         arrs = [_f32(Tcw), _i32(direction), _f32(world_pos), _i32(last_octave), _f32(last_angle), _u8(desc),
                 _u8(obs_positive)]
         q = N.orbm_last_queries(len(fi), 0, N.ptr(fi), N.ptr(qo), *[N.ptr(a) for a in arrs])
-        fm = np.full(max(total_rows, 1), -1, np.int32)
-        nm = np.zeros(len(fi), np.int32)
+        fm, nm = out if out is not None else (np.full(max(total_rows, 1), -1, np.int32), np.zeros(len(fi), np.int32))
         N.check(self._L.orbm_search_last_frame(extractor._h, C.byref(cam), C.byref(q), float(th),
                                                1 if self.mbCheckOrientation else 0, N.ptr(fm), N.ptr(nm)))
         return fm[:total_rows], nm
