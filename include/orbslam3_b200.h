@@ -199,6 +199,25 @@ typedef struct {
 orb_status orbm_search_last_frame(orbx_handle* h, const orbm_camera* cam, const orbm_last_queries* q, float th,
                                   int32_t check_orientation, int32_t* feature_match_out, int32_t* nmatches_out);
 
+/* SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches)  ORBmatcher.cc:259-493, Nleft == -1.
+ * One entry per keyframe feature that holds a good map point, in the order of the FeatureVector merge join
+ * (ascending vocabulary node id, ascending keyframe feature index inside a node).  feature_node: vocabulary node
+ * of every frame feature (F.mFeatVec from Frame::ComputeBoW, the level-4 ancestor), one entry per compact keypoint
+ * row of the batch, -1 = none.  Output as orbm_search_last_frame (query index per feature row, or -1). */
+typedef struct {
+    int32_t n_frames;
+    int32_t on_device;
+    const int32_t* frame_image;
+    const int32_t* query_offset;
+    const int32_t* query_node;    /* vocabulary node of the keyframe feature */
+    const float* query_angle;     /* pKF->mvKeysUn[idx].angle */
+    const uint8_t* desc;          /* pKF->mDescriptors.row(idx) */
+    const int32_t* feature_node;
+} orbm_bow_queries;
+
+orb_status orbm_search_bow(orbx_handle* h, const orbm_bow_queries* q, float nnratio, int32_t check_orientation,
+                           int32_t* feature_match_out, int32_t* nmatches_out);
+
 /* ------------------------------------------------------------------------------------------------
  * Optimizer::LocalBundleAdjustment  (include/Optimizer.h:59, src/Optimizer.cc:1740-2188)
  *

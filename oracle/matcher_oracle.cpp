@@ -209,3 +209,55 @@ int orc_search_last(const KeyPoint* kps, const uint8_t* desc, const float* urigh
     return nmatches;
 }
 }
+
+// ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches), Nleft == -1
+// (src/ORBmatcher.cc:259-493).  Queries = the keyframe's features that hold a good map point, in the order of the
+// FeatureVector merge join (ascending vocabulary node id, ascending keyframe feature index inside a node) -- the
+// caller provides them in that order with their node id.  feat_node[i] = node of frame feature i (F.mFeatVec), -1 if
+// none.  feat_match[i] = query index now stored in vpMapPointMatches[i], or -1.  Returns nmatches.
+extern "C" int orc_search_bow(const KeyPoint* kps, const uint8_t* desc, const int* feat_node, int N, int nq,
+                              const int* qnode, const float* qangle, const uint8_t* qdesc, float nnratio, int checkOri,
+                              int* feat_match) {
+    for (int i = 0; i < N; ++i) feat_match[i] = -1;
+    int nmatches = 0;
+    std::vector<int> rotHist[30];
+    const float factor = 1.0f / 30;
+    for (int q = 0; q < nq; ++q) {
+        int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+        for (int i = 0; i < N; ++i) {            // vIndicesF: features of the same node, ascending index
+            if (feat_node[i] != qnode[q] || feat_node[i] < 0) continue;
+            if (feat_match[i] >= 0) continue;    // :331
+            const int dist = descriptor_distance(qdesc + 32 * (size_t)q, desc + 32 * (size_t)i);
+            if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = i; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist1 <= 50) {                   // TH_LOW
+            if ((float)bestDist1 < nnratio * (float)bestDist2) {
+                feat_match[bestIdxF] = q;
+                if (checkOri) {
+                    float rot = qangle[q] - kps[bestIdxF].angle;
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = (int)std::round(rot * factor);
+                    if (bin == 30) bin = 0;
+                    rotHist[bin].push_back(bestIdxF);
+                }
+                ++nmatches;
+            }
+        }
+    }
+    if (checkOri) {
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < 30; ++i) {
+            const int s = (int)rotHist[i].size();
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < 30; ++i)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int idx : rotHist[i]) { feat_match[idx] = -1; --nmatches; }
+    }
+    return nmatches;
+}

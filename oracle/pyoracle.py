@@ -272,3 +272,16 @@ def lba(pose, fixed, point, edge_kf, edge_mp, obs, inv_sigma2, cam5, lambda_init
                    float(lambda_init), int(max_iters), None, _p(chi), _p(dpos), _p(stats))
     return dict(pose=pose, point=point, edge_chi2=chi, edge_depth_pos=dpos, iterations=it, lambda_=stats[1],
                 chi2=stats[2], trials=int(stats[3]), chi2_init=stats[4])
+
+
+def search_bow(kps, desc, feat_node, qnode, qangle, qdesc, nnratio, check_ori=True):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) restated (ORBmatcher.cc:259-493), Nleft == -1."""
+    L = lib()
+    L.orc_search_bow.restype = C.c_int
+    L.orc_search_bow.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_float, C.c_int, C.c_void_p]
+    kps, desc = np.ascontiguousarray(kps), np.ascontiguousarray(desc)
+    fn, qn = np.ascontiguousarray(feat_node, np.int32), np.ascontiguousarray(qnode, np.int32)
+    qa, qd = np.ascontiguousarray(qangle, np.float32), np.ascontiguousarray(qdesc, np.uint8)
+    fm = np.full(max(len(kps), 1), -1, np.int32)
+    nm = L.orc_search_bow(_p(kps), _p(desc), _p(fn), len(kps), len(qn), _p(qn), _p(qa), _p(qd), nnratio, 1 if check_ori else 0, _p(fm))
+    return fm[:len(kps)], nm

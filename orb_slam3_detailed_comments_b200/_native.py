@@ -61,6 +61,11 @@ class orbm_last_queries(C.Structure):
                                   "last_angle", "desc", "obs_positive")]
 
 
+class orbm_bow_queries(C.Structure):
+    _fields_ = [("n_frames", C.c_int32), ("on_device", C.c_int32)] + [
+        (n, C.c_void_p) for n in ("frame_image", "query_offset", "query_node", "query_angle", "desc", "feature_node")]
+
+
 class lba_problem(C.Structure):
     _fields_ = [("n_kf", C.c_int32), ("n_mp", C.c_int32), ("n_edges", C.c_int32)] + [
         (n, C.c_void_p) for n in ("pose", "fixed", "point", "edge_kf", "edge_mp", "obs", "inv_sigma2")] + [
@@ -101,6 +106,7 @@ SIGNATURES = {
     "orbm_stereo_download": (_I, [_VP, _VP, _VP, _I]),
     "orbm_stereo_pair": (_I, [_VP, _VP, _F, _F, _VP, _VP, _I]),
     "orbm_search_local_points": (_I, [_VP, C.POINTER(orbm_camera), C.POINTER(orbm_local_queries), _F, _F, _I, _F, _VP, _VP]),
+    "orbm_search_bow": (_I, [_VP, C.POINTER(orbm_bow_queries), _F, _I, _VP, _VP]),
     "lba_create": (_I, [_I, C.POINTER(_VP)]),
     "lba_destroy": (None, [_VP]),
     "lba_solve": (_I, [_VP, C.POINTER(lba_problem), C.POINTER(lba_result), _VP]),

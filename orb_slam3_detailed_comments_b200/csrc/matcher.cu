@@ -4,6 +4,8 @@
 //       /root/reference/src/ORBmatcher.cc:45-239      (TrackLocalMap, Tracking.cc:4062)
 //   * SearchByProjection(Frame& cur, const Frame& last, th, bMono)
 //       /root/reference/src/ORBmatcher.cc:1950-2184   (TrackWithMotionModel, Tracking.cc:3389)
+//   * SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>&)
+//       /root/reference/src/ORBmatcher.cc:259-493     (TrackReferenceKeyFrame, Tracking.cc:3183)
 // with Frame::GetFeaturesInArea / PosInGrid (src/Frame.cc:859-951, 962-978) folded in.
 //
 // The reference is greedy: a feature claimed by query i is skipped by every later query.  Here the
@@ -37,6 +39,7 @@ struct FrameFeat {   // shared-memory staging of one frame's features
     float* ang;
     uint16_t* cell;   // ix * 48 + iy, 0xffff = not in the grid (PosInGrid false)
     uint8_t* oct;
+    int* node;        // mode 2: vocabulary node of the feature (F.mFeatVec), -1 = none
 };
 
 struct ProjParams {
@@ -51,7 +54,8 @@ struct ProjParams {
     float fx, fy, cx, cy, bf;
     float scale[ORB_MAX_LEVELS];
     // query side
-    int mode;                 // 0 = local map points, 1 = last frame
+    int mode;                 // 0 = local map points, 1 = last frame, 2 = bag of words (same vocabulary node)
+    const int* feat_node;     // mode 2: per compact feature row
     const int* frame_image;   // [n_frames]
     const int* qoff;          // [n_frames + 1]
     const float* a0;          // mode 0: projX      mode 1: world pos (3 per query)
@@ -82,7 +86,8 @@ __device__ __forceinline__ void stage_frame(const ProjParams& P, int img, unsign
     F.y = F.x + M;
     F.ur = F.y + M;
     F.ang = F.ur + M;
-    F.cell = reinterpret_cast<uint16_t*>(F.ang + M);
+    F.node = reinterpret_cast<int*>(F.ang + M);
+    F.cell = reinterpret_cast<uint16_t*>(F.node + M);
     F.oct = reinterpret_cast<uint8_t*>(F.cell + M);
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         const orbx_keypoint k = P.kps[row0 + i];
@@ -90,6 +95,7 @@ __device__ __forceinline__ void stage_frame(const ProjParams& P, int img, unsign
         F.y[i] = k.y;
         F.ur[i] = P.uright ? P.uright[row0 + i] : -1.0f;
         F.ang[i] = k.angle;
+        F.node[i] = P.feat_node ? P.feat_node[row0 + i] : -1;
         // Frame::PosInGrid, Frame.cc:962-978 (C round(): half away from zero)
         const int px = (int)roundf(fmul(fsub(k.x, P.minX), P.invW)), py = (int)roundf(fmul(fsub(k.y, P.minY), P.invH));
         F.cell[i] = (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) ? (uint16_t)0xffff : (uint16_t)(px * GRID_ROWS + py);
@@ -97,9 +103,10 @@ __device__ __forceinline__ void stage_frame(const ProjParams& P, int img, unsign
     }
 }
 
-__device__ __forceinline__ size_t frame_smem_bytes(int maxFeat) { return (size_t)maxFeat * 19 + 16; }
+__device__ __forceinline__ size_t frame_smem_bytes(int maxFeat) { return (size_t)maxFeat * 23 + 16; }
 
 struct Window {   // Frame::GetFeaturesInArea arguments resolved to cell ranges
+    int node;         // >= 0: bag-of-words query, candidates = features of this vocabulary node (no window)
     float x, y, r;
     int c0, c1, r0, r1, minLevel, maxLevel;
     bool empty;
@@ -107,6 +114,7 @@ struct Window {   // Frame::GetFeaturesInArea arguments resolved to cell ranges
 
 __device__ __forceinline__ Window make_window(const ProjParams& P, float x, float y, float r, int minLevel, int maxLevel) {
     Window w;
+    w.node = -1;
     w.x = x; w.y = y; w.r = r; w.minLevel = minLevel; w.maxLevel = maxLevel;
     w.c0 = max(0, (int)floorf(fmul(fsub(fsub(x, P.minX), r), P.invW)));
     w.c1 = min(GRID_COLS - 1, (int)ceilf(fmul(fadd(fsub(x, P.minX), r), P.invW)));
@@ -118,6 +126,7 @@ __device__ __forceinline__ Window make_window(const ProjParams& P, float x, floa
 
 // is feature i a candidate of the window (all gates of GetFeaturesInArea)?
 __device__ __forceinline__ bool in_window(const FrameFeat& F, const Window& w, int i) {
+    if (w.node >= 0) return F.node[i] == w.node;
     const int cell = F.cell[i];
     if (cell == 0xffff) return false;
     const int ix = cell / GRID_ROWS, iy = cell - ix * GRID_ROWS;
@@ -171,7 +180,7 @@ __device__ __forceinline__ int warp_scan_query(const ProjParams& P, const FrameF
             }
             ++count;
             const uint32_t d = hamming256(a0, a1, P.desc + (size_t)(row0 + i) * 32);
-            unsigned long long key = ((unsigned long long)d << 32) | ((unsigned long long)F.cell[i] << 16) | (unsigned long long)i;
+            unsigned long long key = ((unsigned long long)d << 32) | ((w.node >= 0 ? 0ull : (unsigned long long)F.cell[i]) << 16) | (unsigned long long)i;
 #pragma unroll
             for (int k = 0; k < PM_K; ++k)   // sorted insert
                 if (key < loc[k]) {
@@ -254,10 +263,15 @@ __global__ void __launch_bounds__(PM_WARPS * 32) k_proj_candidates(const __grid_
         if (P.mode == 0) {
             ok = local_window(P, q, w, er_max);
             ur_pred = P.a2[q];
-        } else {
+        } else if (P.mode == 1) {
             ok = last_frame_window(P, frame, q, w, u, invzc, radius);
             ur_pred = fsub(u, fmul(P.bf, invzc));
             er_max = radius;
+        } else {
+            w.node = P.level[q];       // query's vocabulary node
+            w.empty = w.node < 0;
+            ok = true;
+            er_max = 3.0e38f;          // no stereo gate in SearchByBoW
         }
         unsigned long long top[PM_K];
         int count = 0;
@@ -293,7 +307,7 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
     }
     if (threadIdx.x < 30) s_hist[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_nm = 0;
-    if (P.mode == 1 && P.checkOri)
+    if (P.mode != 0 && P.checkOri)
         for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) P.quv[q] = __int_as_float(-1);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -306,7 +320,7 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
         for (int i = threadIdx.x; i < nchunk; i += blockDim.x) {
             s_cnt[i] = P.cnt[base + i];
             if (P.mode == 0) P.match[base + i] = -1;
-            else { s_qf[i] = P.f0[base + i]; s_qflag[i] = P.flag[base + i]; }
+            else { s_qf[i] = P.f0[base + i]; s_qflag[i] = (P.mode == 1) ? P.flag[base + i] : (uint8_t)1; }
         }
         __syncthreads();
         if (warp == 0) {
@@ -321,7 +335,7 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
                 const bool is_free = (lane < stored) && !s_claimed[(int)(key & 0xffffu)];
                 const unsigned fm = __ballot_sync(0xffffffffu, is_free);
                 const int live = __popc(fm);
-                const int need = (P.mode == 0) ? 2 : 1;
+                const int need = (P.mode == 1) ? 1 : 2;
                 unsigned long long b1 = ~0ull, b2 = ~0ull;
                 if (live < need && count > PM_K) {
                     // claims consumed the stored list: exact rescan with the mask applied (warp-cooperative)
@@ -330,10 +344,14 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
                     if (P.mode == 0) {
                         local_window(P, q, w, er_max);
                         ur_pred = P.a2[q];
-                    } else {
+                    } else if (P.mode == 1) {
                         last_frame_window(P, frame, q, w, u, invzc, radius);
                         ur_pred = fsub(u, fmul(P.bf, invzc));
                         er_max = radius;
+                    } else {
+                        w.node = P.level[q];
+                        w.empty = w.node < 0;
+                        er_max = 3.0e38f;
                     }
                     unsigned long long top[PM_K];
                     warp_scan_query(P, F, N, row0, w, P.qdesc + 32 * (size_t)q, ur_pred, er_max, s_claimed, top);
@@ -365,10 +383,15 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
                         }
                     }
                 } else {
-                    if (bestDist <= 100) {
+                    bool accept = bestDist <= 100;
+                    if (P.mode == 2) {   // SearchByBoW: TH_LOW and the ratio test in float (ORBmatcher.cc:384-387)
+                        const int bestDist2 = (b2 == ~0ull) ? 256 : (int)(b2 >> 32);
+                        accept = bestDist <= 50 && (float)bestDist < fmul(P.nnratio, (float)bestDist2);
+                    }
+                    if (accept) {
                         if (lane == 0) {
                             s_holder[bestIdx] = q;
-                            s_claimed[bestIdx] = s_qflag[qi] ? 1 : 0;   // only map points with observations block later queries
+                            s_claimed[bestIdx] = (P.mode == 2 || s_qflag[qi]) ? 1 : 0;   // mode 1: only map points with observations block
                             if (P.checkOri) {
                                 float rot = fsub(s_qf[qi], F.ang[bestIdx]);
                                 if (rot < 0.0f) rot = fadd(rot, 360.0f);
@@ -455,7 +478,7 @@ struct StageCursor {
 
 static orb_status launch_proj(orbx_handle* h, ProjParams& P, int n_frames, int max_q_per_frame) {
     cudaStream_t st = h->stream;
-    const size_t fsm = ((size_t)P.maxFeat * 19 + 16 + 15) / 16 * 16;
+    const size_t fsm = ((size_t)P.maxFeat * 23 + 16 + 15) / 16 * 16;
     ORB_CUDA(cudaFuncSetAttribute(k_proj_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(fsm, (size_t)1024)));
     dim3 grid((max_q_per_frame + PM_QPB - 1) / PM_QPB, n_frames);
     if (grid.x > 0) {
@@ -603,6 +626,63 @@ extern "C" orb_status orbm_search_last_frame(orbx_handle* h, const orbm_camera* 
     P.cnt = cur.take<int>(nq);
     P.quv = cur.take<float>(nq);
     P.match = dev ? feature_match_out : cur.take<int>(total_rows);
+    P.nmatches = (dev && nmatches_out) ? nmatches_out : cur.take<int>(nf);
+    ORB_CUDA(cudaMemsetAsync(P.match, 0xff, sizeof(int) * (size_t)total_rows, h->stream));
+    if ((s = launch_proj(h, P, nf, maxq)) != ORB_OK) return s;
+    if (!dev) {
+        ORB_CUDA(cudaMemcpyAsync(feature_match_out, P.match, sizeof(int) * (size_t)total_rows, cudaMemcpyDeviceToHost, h->stream));
+        if (nmatches_out) ORB_CUDA(cudaMemcpyAsync(nmatches_out, P.nmatches, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->stream));
+        ORB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return ORB_OK;
+}
+
+extern "C" orb_status orbm_search_bow(orbx_handle* h, const orbm_bow_queries* Q, float nnratio, int32_t check_orientation,
+                                      int32_t* feature_match_out, int32_t* nmatches_out) {
+    if (!h || !Q || !feature_match_out || Q->n_frames < 1 || !Q->frame_image || !Q->query_offset || !Q->feature_node)
+        return set_error(ORB_ERR_INVALID, "bad arguments");
+    ORB_CUDA(cudaSetDevice(h->cfg.device));
+    orb_status s = orbx_counts(h, nullptr, nullptr, nullptr);
+    if (s != ORB_OK) return s;
+    const int total_rows = h->h_counts[2 * h->cfg.max_batch + h->last_batch];
+    const bool dev = Q->on_device != 0;
+    const int nf = Q->n_frames;
+    std::vector<int> qoff_h(nf + 1), fimg_h(nf);
+    if (dev) {
+        ORB_CUDA(cudaMemcpyAsync(qoff_h.data(), Q->query_offset, sizeof(int) * (nf + 1), cudaMemcpyDeviceToHost, h->stream));
+        ORB_CUDA(cudaMemcpyAsync(fimg_h.data(), Q->frame_image, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->stream));
+        ORB_CUDA(cudaStreamSynchronize(h->stream));
+    } else {
+        std::copy(Q->query_offset, Q->query_offset + nf + 1, qoff_h.begin());
+        std::copy(Q->frame_image, Q->frame_image + nf, fimg_h.begin());
+    }
+    const int nq = qoff_h[nf];
+    int maxq = 0;
+    for (int f = 0; f < nf; ++f) {
+        maxq = std::max(maxq, qoff_h[f + 1] - qoff_h[f]);
+        if (fimg_h[f] < 0 || fimg_h[f] >= h->last_batch || qoff_h[f + 1] < qoff_h[f]) return set_error(ORB_ERR_INVALID, "bad frame table");
+    }
+    const size_t need = (size_t)nq * (PM_K * 8 + 4 + 4 + 4 + 4 + 32 + 16) + (size_t)total_rows * 8 + (size_t)nf * 64 + 65536;
+    if ((s = ensure_stage(h, need)) != ORB_OK) return s;
+    StageCursor cur{h->d_stage};
+    ProjParams P{};
+    orbm_camera cam{1, 1, 0, 0, 0, 1, 0, (float)h->cur_w, 0, (float)h->cur_h};   // the grid is not used by this search
+    fill_frame_side(h, &cam, P);
+    P.uright = nullptr;
+    P.mode = 2;
+    int *d_fimg, *d_qoff, *qnode, *fnode; float* ang; uint8_t* qd;
+    if ((s = upload(h, d_fimg, (const int*)Q->frame_image, nf, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, d_qoff, (const int*)Q->query_offset, nf + 1, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, qnode, (const int*)Q->query_node, nq, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, ang, Q->query_angle, nq, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, qd, Q->desc, (size_t)nq * 32, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, fnode, (const int*)Q->feature_node, (size_t)total_rows, cur, dev)) != ORB_OK) return s;
+    P.frame_image = d_fimg; P.qoff = d_qoff; P.level = qnode; P.f0 = ang; P.qdesc = qd; P.feat_node = fnode;
+    P.nnratio = nnratio; P.checkOri = check_orientation;
+    P.topk = cur.take<unsigned long long>((size_t)nq * PM_K);
+    P.cnt = cur.take<int>(std::max(nq, 1));
+    P.quv = cur.take<float>(std::max(nq, 1));
+    P.match = dev ? feature_match_out : cur.take<int>(std::max(total_rows, 1));
     P.nmatches = (dev && nmatches_out) ? nmatches_out : cur.take<int>(nf);
     ORB_CUDA(cudaMemsetAsync(P.match, 0xff, sizeof(int) * (size_t)total_rows, h->stream));
     if ((s = launch_proj(h, P, nf, maxq)) != ORB_OK) return s;

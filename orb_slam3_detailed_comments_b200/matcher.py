@@ -75,6 +75,18 @@ class ORBmatcher:
                                                1 if self.mbCheckOrientation else 0, N.ptr(fm), N.ptr(nm)))
         return fm[:total_rows], nm
 
+    def SearchByBoW(self, extractor, frame_image, query_offset, query_node, query_angle, desc, feature_node, total_rows):
+        """SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (ORBmatcher.cc:259-493) for several frames.
+        Returns (feature_match[total_rows] query index or -1, nmatches[n_frames])."""
+        fi, qo = _i32(frame_image), _i32(query_offset)
+        arrs = [_i32(query_node), _f32(query_angle), _u8(desc), _i32(feature_node)]
+        q = N.orbm_bow_queries(len(fi), 0, N.ptr(fi), N.ptr(qo), *[N.ptr(a) for a in arrs])
+        fm = np.full(max(total_rows, 1), -1, np.int32)
+        nm = np.zeros(len(fi), np.int32)
+        N.check(self._L.orbm_search_bow(extractor._h, C.byref(q), self.mfNNratio, 1 if self.mbCheckOrientation else 0,
+                                        N.ptr(fm), N.ptr(nm)))
+        return fm[:total_rows], nm
+
     # ---- device-resident forms (CUDA torch tensors; see the class docstring) -----------------------
     def SearchByProjectionDevice(self, extractor, cam, n_frames, frame_image, query_offset, proj_x, proj_y, proj_xr, level,
                                  view_cos, desc, out_match, out_nmatches, th=1.0, feature_claimed=None):

@@ -137,3 +137,39 @@ def test_search_with_no_queries_and_monocular(scene):
     match, nm = m.SearchByProjection(ex, camera(FX, FY, CX, CY, BF, B, W, H), [0], [0, 0], np.zeros(0), np.zeros(0),
                                      np.zeros(0), np.zeros(0, np.int32), np.zeros(0), np.zeros((0, 32), np.uint8))
     assert len(match) == 0 and nm[0] == 0
+
+
+def test_search_by_bow_matches_oracle(scene):
+    P, ex, off = scene["P"], scene["ex"], scene["off"]
+    total = int(off[-1])
+    # a stand-in vocabulary: node = a hash of three descriptor bytes into 97 buckets (what matters to the matcher is only
+    # the partition into nodes; the real ids come from DBoW2's tree, out of scope)
+    def node_of(d):
+        return ((d[:, 0].astype(np.int32) >> 3) * 7 + (d[:, 5].astype(np.int32) >> 4) * 3 + (d[:, 17].astype(np.int32) >> 5)) % 97
+    feat_node = np.full(total, -1, np.int32)
+    for p in range(P):
+        a, b = off[2 * p], off[2 * p + 1]
+        feat_node[a:b] = node_of(scene["desc"][a:b])
+        feat_node[a:b][::17] = -1                       # a few features without a BoW entry
+    for nnratio, check in [(0.7, True), (0.9, False)]:
+        qoff, qn, qa, qd = [0], [], [], []
+        for p in range(P):
+            kL, dL, luR, ldep = scene["lasts"][p]
+            sel = np.nonzero(ldep > 0)[0]                # keyframe features holding a map point
+            nd = node_of(dL[sel])
+            order = np.lexsort((sel, nd))               # FeatureVector merge order: node, then feature index
+            sel, nd = sel[order], nd[order]
+            qn.append(nd.astype(np.int32)); qa.append(kL["angle"][sel].astype(np.float32)); qd.append(dL[sel])
+            qoff.append(qoff[-1] + len(sel))
+        qn, qa, qd = map(np.concatenate, (qn, qa, qd))
+        m = ORBmatcher(nnratio, check)
+        fm, nm = m.SearchByBoW(ex, [2 * p for p in range(P)], qoff, qn, qa, qd, feat_node, total)
+        for p in range(P):
+            a, b = off[2 * p], off[2 * p + 1]
+            s = slice(qoff[p], qoff[p + 1])
+            rfm, rnm = po.search_bow(scene["kps"][a:b], scene["desc"][a:b], feat_node[a:b], qn[s], qa[s], qd[s], nnratio, check)
+            got = fm[a:b].copy()
+            got[got >= 0] -= qoff[p]
+            assert rnm == nm[p], (nnratio, p, rnm, nm[p])
+            assert (got == rfm).all(), (nnratio, p)
+            assert rnm > 20
