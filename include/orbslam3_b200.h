@@ -218,6 +218,33 @@ typedef struct {
 orb_status orbm_search_bow(orbx_handle* h, const orbm_bow_queries* q, float nnratio, int32_t check_orientation,
                            int32_t* feature_match_out, int32_t* nmatches_out);
 
+/* SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, vMatchedPairs, bOnlyStereo, bCoarse)  ORBmatcher.cc:1045-1323,
+ * keyframes without a second camera.  Both keyframes are map state (host memory): queries = the KF1 features WITHOUT
+ * a map point (and stereo when bOnlyStereo), in FeatureVector merge order; side 2 = all features of KF2 with
+ * valid2[i] = no map point (and stereo when bOnlyStereo).  F12 = K1^-T [t12]x R12 K2^-1 (row-major, float) and the
+ * epipole of camera 1 in image 2 are computed by the caller exactly as the reference does (ORBmatcher.cc:1056-1073,
+ * Pinhole.cpp:190-193).  The handle only lends its stream, staging memory and scale tables.
+ * match12_out[q] = KF2 feature index or -1 (the caller emits the (idx1, idx2) pairs in ascending idx1). */
+typedef struct {
+    int32_t n_queries, n2;
+    const orbx_keypoint* kp1;     /* mvKeysUn of the query features */
+    const uint8_t* desc1;
+    const int32_t* node1;
+    const uint8_t* stereo1;       /* mvuRight[idx1] >= 0 */
+    const orbx_keypoint* kp2;
+    const uint8_t* desc2;
+    const int32_t* node2;         /* -1 = not in mFeatVec */
+    const uint8_t* valid2;
+    const uint8_t* stereo2;
+    float F12[9];
+    float epipole2[2];
+    int32_t coarse;               /* bCoarse: skip the epipolar-line test */
+    int32_t check_orientation;
+} orbm_triangulation;
+
+orb_status orbm_search_triangulation(orbx_handle* h, const orbm_triangulation* t, int32_t* match12_out,
+                                     int32_t* nmatches_out);
+
 /* ------------------------------------------------------------------------------------------------
  * Optimizer::LocalBundleAdjustment  (include/Optimizer.h:59, src/Optimizer.cc:1740-2188)
  *

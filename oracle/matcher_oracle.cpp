@@ -261,3 +261,71 @@ extern "C" int orc_search_bow(const KeyPoint* kps, const uint8_t* desc, const in
     }
     return nmatches;
 }
+
+// ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse), no second camera
+// (src/ORBmatcher.cc:1045-1323; Pinhole::epipolarConstrain src/CameraModels/Pinhole.cpp:186-209).
+// Queries = KF1 features WITHOUT a map point (and stereo when bOnlyStereo), in FeatureVector merge order, with their
+// node.  KF2 candidates: features of the same node without a map point (valid2 != 0), ascending index.
+// F12 = K1^-T [t12]x R12 K2^-1 is computed by the caller exactly as the reference does (Eigen, float).
+// match12[q] = KF2 feature index or -1.  Returns nmatches.
+extern "C" int orc_search_triangulation(int nq, const KeyPoint* kp1, const uint8_t* desc1, const int* node1, const uint8_t* stereo1,
+                                        int N2, const KeyPoint* kp2, const uint8_t* desc2, const int* node2, const uint8_t* valid2,
+                                        const uint8_t* stereo2, const float* F12, const float* ep2, const float* scaleFactors,
+                                        const float* sigma2, int bCoarse, int checkOri, int* match12) {
+    int nmatches = 0;
+    std::vector<int> rotHist[30];
+    const float factor = 1.0f / 30;
+    for (int q = 0; q < nq; ++q) {
+        match12[q] = -1;
+        int bestDist = 50, bestIdx2 = -1;   // TH_LOW
+        for (int i2 = 0; i2 < N2; ++i2) {
+            if (node2[i2] != node1[q] || node2[i2] < 0) continue;
+            if (!valid2[i2]) continue;
+            const int dist = descriptor_distance(desc1 + 32 * (size_t)q, desc2 + 32 * (size_t)i2);
+            if (dist > 50 || dist > bestDist) continue;
+            if (!stereo1[q] && !stereo2[i2]) {
+                const float distex = ep2[0] - kp2[i2].x, distey = ep2[1] - kp2[i2].y;
+                if (distex * distex + distey * distey < 100 * scaleFactors[kp2[i2].octave]) continue;
+            }
+            bool ok = bCoarse != 0;
+            if (!ok) {   // Pinhole::epipolarConstrain(pCamera2, kp1, kp2, R12, t12, sigmaLevel, unc = sigma2[kp2.octave])
+                const float a = kp1[q].x * F12[0] + kp1[q].y * F12[3] + F12[6];
+                const float b = kp1[q].x * F12[1] + kp1[q].y * F12[4] + F12[7];
+                const float c = kp1[q].x * F12[2] + kp1[q].y * F12[5] + F12[8];
+                const float num = a * kp2[i2].x + b * kp2[i2].y + c;
+                const float den = a * a + b * b;
+                if (den != 0) {
+                    const float dsqr = num * num / den;
+                    ok = dsqr < 3.84 * sigma2[kp2[i2].octave];
+                }
+            }
+            if (ok) { bestIdx2 = i2; bestDist = dist; }
+        }
+        if (bestIdx2 >= 0) {
+            match12[q] = bestIdx2;
+            ++nmatches;
+            if (checkOri) {
+                float rot = kp1[q].angle - kp2[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)std::round(rot * factor);
+                if (bin == 30) bin = 0;
+                rotHist[bin].push_back(q);
+            }
+        }
+    }
+    if (checkOri) {
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < 30; ++i) {
+            const int s = (int)rotHist[i].size();
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < 30; ++i)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int q : rotHist[i]) { match12[q] = -1; --nmatches; }
+    }
+    return nmatches;
+}

@@ -285,3 +285,20 @@ def search_bow(kps, desc, feat_node, qnode, qangle, qdesc, nnratio, check_ori=Tr
     fm = np.full(max(len(kps), 1), -1, np.int32)
     nm = L.orc_search_bow(_p(kps), _p(desc), _p(fn), len(kps), len(qn), _p(qn), _p(qa), _p(qd), nnratio, 1 if check_ori else 0, _p(fm))
     return fm[:len(kps)], nm
+
+
+def search_triangulation(kp1, desc1, node1, stereo1, kp2, desc2, node2, valid2, stereo2, F12, ep2, scale_factors, sigma2,
+                         coarse=False, check_ori=True):
+    """ORBmatcher::SearchForTriangulation restated (ORBmatcher.cc:1045-1323), single-camera keyframes."""
+    L = lib()
+    L.orc_search_triangulation.restype = C.c_int
+    L.orc_search_triangulation.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 9 + [C.c_int, C.c_int, C.c_void_p]
+    c = np.ascontiguousarray
+    kp1, kp2 = c(kp1), c(kp2)
+    a = [c(desc1, np.uint8), c(node1, np.int32), c(stereo1, np.uint8)]
+    b = [c(desc2, np.uint8), c(node2, np.int32), c(valid2, np.uint8), c(stereo2, np.uint8), c(F12, np.float32), c(ep2, np.float32),
+         c(scale_factors, np.float32), c(sigma2, np.float32)]
+    m = np.full(max(len(kp1), 1), -1, np.int32)
+    nm = L.orc_search_triangulation(len(kp1), _p(kp1), *[_p(x) for x in a], len(kp2), _p(kp2), *[_p(x) for x in b],
+                                    1 if coarse else 0, 1 if check_ori else 0, _p(m))
+    return m[:len(kp1)], nm

@@ -87,6 +87,22 @@ class ORBmatcher:
                                         N.ptr(fm), N.ptr(nm)))
         return fm[:total_rows], nm
 
+    def SearchForTriangulation(self, extractor, kp1, desc1, node1, stereo1, kp2, desc2, node2, valid2, stereo2, F12, epipole2,
+                               bCoarse=False):
+        """SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse) (ORBmatcher.cc:1045-1323), single camera.
+        Returns (match12[nq] KF2 index or -1, nmatches)."""
+        kp1, kp2 = np.ascontiguousarray(kp1), np.ascontiguousarray(kp2)
+        a = [_u8(desc1), _i32(node1), _u8(stereo1)]
+        b = [_u8(desc2), _i32(node2), _u8(valid2), _u8(stereo2)]
+        t = N.orbm_triangulation(len(kp1), len(kp2), N.ptr(kp1), *[N.ptr(x) for x in a], N.ptr(kp2), *[N.ptr(x) for x in b],
+                                 (C.c_float * 9)(*np.asarray(F12, np.float32).reshape(-1).tolist()),
+                                 (C.c_float * 2)(*np.asarray(epipole2, np.float32).tolist()), 1 if bCoarse else 0,
+                                 1 if self.mbCheckOrientation else 0)
+        m = np.full(max(len(kp1), 1), -1, np.int32)
+        nm = C.c_int32(0)
+        N.check(self._L.orbm_search_triangulation(extractor._h, C.byref(t), N.ptr(m), C.byref(nm)))
+        return m[:len(kp1)], nm.value
+
     # ---- device-resident forms (CUDA torch tensors; see the class docstring) -----------------------
     def SearchByProjectionDevice(self, extractor, cam, n_frames, frame_image, query_offset, proj_x, proj_y, proj_xr, level,
                                  view_cos, desc, out_match, out_nmatches, th=1.0, feature_claimed=None):

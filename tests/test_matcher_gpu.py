@@ -173,3 +173,36 @@ def test_search_by_bow_matches_oracle(scene):
             assert rnm == nm[p], (nnratio, p, rnm, nm[p])
             assert (got == rfm).all(), (nnratio, p)
             assert rnm > 20
+
+
+def test_search_for_triangulation_matches_oracle(scene):
+    # KF1 = the last frame of sequence 0 (oracle features), KF2 = the current left image of the same sequence
+    ex, off = scene["ex"], scene["off"]
+    rng = np.random.default_rng(5)
+    kL, dL, luR, ldep = scene["lasts"][0]
+    a, b = off[0], off[1]
+    k2, d2, ur2 = scene["kps"][a:b], scene["desc"][a:b], scene["uR"][a:b]
+    node_of = lambda d: ((d[:, 0].astype(np.int32) >> 3) * 7 + (d[:, 5].astype(np.int32) >> 4) * 3 + (d[:, 17].astype(np.int32) >> 5)) % 61
+    sel = np.nonzero(rng.random(len(kL)) < 0.6)[0]                 # KF1 features without a map point
+    nd = node_of(dL[sel])
+    order = np.lexsort((sel, nd))
+    sel, nd = sel[order], nd[order]
+    node2 = node_of(d2).astype(np.int32)
+    node2[::13] = -1
+    valid2 = (rng.random(len(k2)) < 0.7).astype(np.uint8)
+    # fundamental matrix of a small sideways + forward motion (float32, as the shim would compute it with Eigen)
+    K = np.array([[FX, 0, CX], [0, FY, CY], [0, 0, 1]], np.float32)
+    t = np.array([0.03, 0.002, 0.01], np.float32)
+    tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]], np.float32)
+    R = np.eye(3, dtype=np.float32)
+    F12 = (np.linalg.inv(K.T).astype(np.float32) @ tx @ R @ np.linalg.inv(K).astype(np.float32)).astype(np.float32)
+    ep = np.array([310.0, 236.0], np.float32)
+    sf, s2 = ex.GetScaleFactors(), ex.GetScaleSigmaSquares()
+    for coarse, check, mono_all in [(False, True, False), (True, True, False), (False, False, True)]:
+        st1 = (np.zeros(len(sel), np.uint8) if mono_all else (luR[sel] >= 0).astype(np.uint8))
+        st2 = (np.zeros(len(k2), np.uint8) if mono_all else (ur2 >= 0).astype(np.uint8))
+        m = ORBmatcher(0.6, check)
+        got, nm = m.SearchForTriangulation(ex, kL[sel], dL[sel], nd, st1, k2, d2, node2, valid2, st2, F12, ep, bCoarse=coarse)
+        ref, rnm = po.search_triangulation(kL[sel], dL[sel], nd, st1, k2, d2, node2, valid2, st2, F12, ep, sf, s2, coarse, check)
+        assert rnm == nm and (got == ref).all(), (coarse, check, mono_all, rnm, nm)
+        assert coarse is False or rnm > 20
