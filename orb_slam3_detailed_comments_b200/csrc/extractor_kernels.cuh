@@ -87,9 +87,16 @@ __device__ __forceinline__ uint32_t shift_word(uint32_t L, uint32_t C, uint32_t 
     }
 }
 
+#define FAST_PW 46   // 16x2-packed pixel pairs per staged row (tile width <= 88 px)
+
 __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_constant__ ExtractGeom g, uint32_t* __restrict__ cand,
                                                             int* __restrict__ candCnt, int* __restrict__ err) {
-    __shared__ uint32_t tile[FAST_ROWS][FAST_TW];
+    // The window is staged twice as 16x2-packed pixel pairs: pe[r][i] = (px 2i, px 2i+1), po[r][i] = (px 2i+1, px 2i+2).
+    // Every ring sample of a pixel pair is then ONE 32-bit shared-memory load already in the layout the packed DPX
+    // min/max instructions want (no per-sample byte permutes).
+    __shared__ uint32_t pe[FAST_ROWS][FAST_PW];
+    __shared__ uint32_t po[FAST_ROWS][FAST_PW];
+    __shared__ uint32_t tile[FAST_ROWS][FAST_TW];   // raw bytes during staging, NMS result afterwards
     __shared__ uint32_t sc[FAST_ROWS][FAST_TW];
     __shared__ int s_warp[FAST_THREADS / 32 + 1];
     __shared__ int s_base;
@@ -109,42 +116,43 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     const int gx0 = (tx0 & ~3) - 4;
     const int ngrp = ((tx1 - 1) >> 2) - (tx0 >> 2) + 1;
     const int nW = ngrp + 2;
+    // (t * magic) >> 20 == t / n exactly for t < 2048, n <= 32 (checked exhaustively); ch * nW <= 1596, ntask <= 1330
+    const uint32_t magicW = (1u << 20) / (uint32_t)nW + 1u, magicG = (1u << 20) / (uint32_t)ngrp + 1u;
     const uint8_t* src = G.base + (int64_t)img * G.img_stride + (int64_t)y0 * G.pitch + gx0;
 
     for (int i = tid; i < ch * nW; i += FAST_THREADS) {
-        const int r = i / nW, c = i - r * nW;
+        const int r = (int)(((uint32_t)i * magicW) >> 20), c = i - r * nW;
         tile[r][c] = __ldg(reinterpret_cast<const uint32_t*>(src + (int64_t)r * G.pitch) + c);
         sc[r][c] = 0u;
+    }
+    __syncthreads();
+    for (int i = tid; i < ch * nW; i += FAST_THREADS) {
+        const int r = (int)(((uint32_t)i * magicW) >> 20), c = i - r * nW;
+        const uint32_t w = tile[r][c], wn = (c + 1 < nW) ? tile[r][c + 1] : 0u;
+        pe[r][2 * c] = __byte_perm(w, 0u, 0x4140);
+        pe[r][2 * c + 1] = __byte_perm(w, 0u, 0x4342);
+        po[r][2 * c] = __byte_perm(w, 0u, 0x4241);
+        po[r][2 * c + 1] = (w >> 24) | ((wn & 0xffu) << 16);
     }
     __syncthreads();
 
     const int ntask = (ty1 - ty0) * ngrp;
     const int minTh = g.minTh, iniTh = g.iniTh;
     for (int t = tid; t < ntask; t += FAST_THREADS) {
-        const int row = t / ngrp, grp = t - row * ngrp;
-        const int r = row + 3, wd = grp + 1;
-        uint32_t W[16];
-        {
-            const uint32_t* p;
-            p = &tile[r - 3][wd - 1]; W[15] = shift_word(p[0], p[1], p[2], -1); W[0] = p[1]; W[1] = shift_word(p[0], p[1], p[2], 1);
-            p = &tile[r - 2][wd - 1]; W[14] = shift_word(p[0], p[1], p[2], -2); W[2] = shift_word(p[0], p[1], p[2], 2);
-            p = &tile[r - 1][wd - 1]; W[13] = shift_word(p[0], p[1], p[2], -3); W[3] = shift_word(p[0], p[1], p[2], 3);
-            p = &tile[r + 1][wd - 1]; W[11] = shift_word(p[0], p[1], p[2], -3); W[5] = shift_word(p[0], p[1], p[2], 3);
-            p = &tile[r + 2][wd - 1]; W[10] = shift_word(p[0], p[1], p[2], -2); W[6] = shift_word(p[0], p[1], p[2], 2);
-            p = &tile[r + 3][wd - 1]; W[9] = shift_word(p[0], p[1], p[2], -1); W[8] = p[1]; W[7] = shift_word(p[0], p[1], p[2], 1);
-        }
-        const uint32_t* pc = &tile[r][wd - 1];
-        W[12] = shift_word(pc[0], pc[1], pc[2], -3);
-        W[4] = shift_word(pc[0], pc[1], pc[2], 3);
-        const uint32_t C = pc[1];
+        const int row = (int)(((uint32_t)t * magicG) >> 20), grp = t - row * ngrp;
+        const int r = row + 3, wd = grp + 1, pA = 2 * wd;
         uint32_t rl[16], rh[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            rl[k] = __byte_perm(W[k], 0u, 0x4140);
-            rh[k] = __byte_perm(W[k], 0u, 0x4342);
-        }
-        const uint32_t s01 = fast_score_x2(__byte_perm(C, 0u, 0x4140), rl);
-        const uint32_t s23 = fast_score_x2(__byte_perm(C, 0u, 0x4342), rh);
+        // ring offsets (dx,dy) clockwise from the top: even dx -> pe at pA + dx/2, odd dx -> po at pA + (dx-1)/2
+#define RING_E(k, dy, h) { const uint32_t* q = &pe[r + (dy)][pA + (h)]; rl[k] = q[0]; rh[k] = q[1]; }
+#define RING_O(k, dy, h) { const uint32_t* q = &po[r + (dy)][pA + (h)]; rl[k] = q[0]; rh[k] = q[1]; }
+        RING_E(0, -3, 0)  RING_O(1, -3, 0)  RING_E(2, -2, 1)  RING_O(3, -1, 1)
+        RING_O(4, 0, 1)   RING_O(5, 1, 1)   RING_E(6, 2, 1)   RING_O(7, 3, 0)
+        RING_E(8, 3, 0)   RING_O(9, 3, -1)  RING_E(10, 2, -1) RING_O(11, 1, -2)
+        RING_O(12, 0, -2) RING_O(13, -1, -2) RING_E(14, -2, -1) RING_O(15, -3, -1)
+#undef RING_E
+#undef RING_O
+        const uint32_t s01 = fast_score_x2(pe[r][pA], rl);
+        const uint32_t s23 = fast_score_x2(pe[r][pA + 1], rh);
         const int xb = gx0 + 4 * wd;
         int s[4] = {(int)(s01 & 0xffffu) - 256, (int)(s01 >> 16) - 256, (int)(s23 & 0xffffu) - 256, (int)(s23 >> 16) - 256};
         uint32_t packed = 0u;
@@ -160,7 +168,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     // NMS on the byte-packed score map; result overwrites tile[][] (the pixels are no longer needed)
     int has_ini = 0;
     for (int t = tid; t < ntask; t += FAST_THREADS) {
-        const int row = t / ngrp, grp = t - row * ngrp;
+        const int row = (int)(((uint32_t)t * magicG) >> 20), grp = t - row * ngrp;
         const int r = row + 3, wd = grp + 1;
         const uint32_t* u = &sc[r - 1][wd - 1];
         const uint32_t* m = &sc[r][wd - 1];
@@ -187,7 +195,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
 
     int cnt = 0;
     for (int t = tid; t < ntask; t += FAST_THREADS) {
-        const int row = t / ngrp, grp = t - row * ngrp;
+        const int row = (int)(((uint32_t)t * magicG) >> 20), grp = t - row * ngrp;
         const uint32_t v = tile[row + 3][grp + 1];
         if (v) cnt += __popc(__vcmpgeu4(v, thr4) & 0x01010101u);
     }
@@ -221,7 +229,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     }
     uint32_t* out = cand + (int64_t)img * g.candTotal + G.candOff;
     for (int t = tid; t < ntask; t += FAST_THREADS) {
-        const int row = t / ngrp, grp = t - row * ngrp;
+        const int row = (int)(((uint32_t)t * magicG) >> 20), grp = t - row * ngrp;
         const uint32_t v = tile[row + 3][grp + 1];
         if (!v) continue;
         const int xb = gx0 + 4 * (grp + 1) - 16, yb = ty0 + row - 16;
