@@ -94,10 +94,11 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     // The window is staged twice as 16x2-packed pixel pairs: pe[r][i] = (px 2i, px 2i+1), po[r][i] = (px 2i+1, px 2i+2).
     // Every ring sample of a pixel pair is then ONE 32-bit shared-memory load already in the layout the packed DPX
     // min/max instructions want (no per-sample byte permutes).
-    __shared__ uint32_t pe[FAST_ROWS][FAST_PW];
-    __shared__ uint32_t po[FAST_ROWS][FAST_PW];
-    __shared__ uint32_t tile[FAST_ROWS][FAST_TW];   // raw bytes during staging, NMS result afterwards
-    __shared__ uint32_t sc[FAST_ROWS][FAST_TW];
+    __shared__ __align__(16) uint32_t pe[FAST_ROWS][FAST_PW];
+    __shared__ __align__(16) uint32_t po[FAST_ROWS][FAST_PW];
+    __shared__ __align__(16) uint32_t se[FAST_ROWS][FAST_PW];   // scores >= minTh (else 0) of the even-aligned pairs, 16x2
+    // NMS result, one byte per pixel: aliases pe[][] (dead once the scores are computed)
+    uint32_t (*tile)[FAST_TW] = reinterpret_cast<uint32_t (*)[FAST_TW]>(&pe[0][0]);
     __shared__ int s_warp[FAST_THREADS / 32 + 1];
     __shared__ int s_base;
 
@@ -115,24 +116,24 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     const int tx0 = x0 + 3, tx1 = x1 - 3, ty0 = y0 + 3, ty1 = y1 - 3;
     const int gx0 = (tx0 & ~3) - 4;
     const int ngrp = ((tx1 - 1) >> 2) - (tx0 >> 2) + 1;
-    const int nW = ngrp + 2;
-    // (t * magic) >> 20 == t / n exactly for t < 2048, n <= 32 (checked exhaustively); ch * nW <= 1596, ntask <= 1330
-    const uint32_t magicW = (1u << 20) / (uint32_t)nW + 1u, magicG = (1u << 20) / (uint32_t)ngrp + 1u;
+    const int nW = ngrp + 2;   // <= 21 words per staged row
+    // (t * magic) >> 20 == t / n exactly for t < 2048, n <= 32 (checked exhaustively); ntask <= 1330
+    const uint32_t magicG = (1u << 20) / (uint32_t)ngrp + 1u;
     const uint8_t* src = G.base + (int64_t)img * G.img_stride + (int64_t)y0 * G.pitch + gx0;
 
-    for (int i = tid; i < ch * nW; i += FAST_THREADS) {
-        const int r = (int)(((uint32_t)i * magicW) >> 20), c = i - r * nW;
-        tile[r][c] = __ldg(reinterpret_cast<const uint32_t*>(src + (int64_t)r * G.pitch) + c);
-        sc[r][c] = 0u;
-    }
-    __syncthreads();
-    for (int i = tid; i < ch * nW; i += FAST_THREADS) {
-        const int r = (int)(((uint32_t)i * magicW) >> 20), c = i - r * nW;
-        const uint32_t w = tile[r][c], wn = (c + 1 < nW) ? tile[r][c + 1] : 0u;
-        pe[r][2 * c] = __byte_perm(w, 0u, 0x4140);
-        pe[r][2 * c + 1] = __byte_perm(w, 0u, 0x4342);
-        po[r][2 * c] = __byte_perm(w, 0u, 0x4241);
-        po[r][2 * c + 1] = (w >> 24) | ((wn & 0xffu) << 16);
+    {   // staging: a warp per row, a lane per 32-bit word; the next word comes from the neighbour lane
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int r = warp; r < ch; r += FAST_THREADS / 32) {
+            uint32_t w = 0u;
+            if (lane < nW) w = __ldg(reinterpret_cast<const uint32_t*>(src + (int64_t)r * G.pitch) + lane);
+            const uint32_t wn = __shfl_down_sync(0xffffffffu, w, 1);
+            if (lane < nW) {
+                const uint32_t nx = (lane + 1 < nW) ? wn : 0u;
+                *reinterpret_cast<uint2*>(&pe[r][2 * lane]) = make_uint2(__byte_perm(w, 0u, 0x4140), __byte_perm(w, 0u, 0x4342));
+                *reinterpret_cast<uint2*>(&po[r][2 * lane]) = make_uint2(__byte_perm(w, 0u, 0x4241), (w >> 24) | ((nx & 0xffu) << 16));
+                *reinterpret_cast<uint2*>(&se[r][2 * lane]) = make_uint2(0u, 0u);
+            }
+        }
     }
     __syncthreads();
 
@@ -154,36 +155,40 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
         const uint32_t s01 = fast_score_x2(pe[r][pA], rl);
         const uint32_t s23 = fast_score_x2(pe[r][pA + 1], rh);
         const int xb = gx0 + 4 * wd;
-        int s[4] = {(int)(s01 & 0xffffu) - 256, (int)(s01 >> 16) - 256, (int)(s23 & 0xffffu) - 256, (int)(s23 >> 16) - 256};
-        uint32_t packed = 0u;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int x = xb + k;
-            if (s[k] >= minTh && x >= tx0 && x < tx1) packed |= (uint32_t)s[k] << (8 * k);
-        }
-        sc[r][wd] = packed;
+        const int s0 = (int)(s01 & 0xffffu) - 256, s1 = (int)(s01 >> 16) - 256, s2 = (int)(s23 & 0xffffu) - 256, s3 = (int)(s23 >> 16) - 256;
+        const uint32_t k0 = (s0 >= minTh && xb >= tx0 && xb < tx1) ? (uint32_t)s0 : 0u;
+        const uint32_t k1 = (s1 >= minTh && xb + 1 >= tx0 && xb + 1 < tx1) ? (uint32_t)s1 : 0u;
+        const uint32_t k2 = (s2 >= minTh && xb + 2 >= tx0 && xb + 2 < tx1) ? (uint32_t)s2 : 0u;
+        const uint32_t k3 = (s3 >= minTh && xb + 3 >= tx0 && xb + 3 < tx1) ? (uint32_t)s3 : 0u;
+        *reinterpret_cast<uint2*>(&se[r][pA]) = make_uint2(k0 | (k1 << 16), k2 | (k3 << 16));
     }
     __syncthreads();
 
-    // NMS on the byte-packed score map; result overwrites tile[][] (the pixels are no longer needed)
+    // NMS on the 16x2 score map with packed 3-input max; the result is byte-packed per 4 pixels into tile[][]
     int has_ini = 0;
     for (int t = tid; t < ntask; t += FAST_THREADS) {
         const int row = (int)(((uint32_t)t * magicG) >> 20), grp = t - row * ngrp;
-        const int r = row + 3, wd = grp + 1;
-        const uint32_t* u = &sc[r - 1][wd - 1];
-        const uint32_t* m = &sc[r][wd - 1];
-        const uint32_t* d = &sc[r + 1][wd - 1];
-        const uint32_t c = m[1];
+        const int r = row + 3, wd = grp + 1, pA = 2 * wd;
+        const uint32_t cA = se[r][pA], cB = se[r][pA + 1];
         uint32_t res = 0u;
-        if (c != 0u) {
-            uint32_t mx = __vmaxu4(__byte_perm(u[0], u[1], 0x6543), u[1]);
-            mx = __vmaxu4(mx, __byte_perm(u[1], u[2], 0x4321));
-            mx = __vmaxu4(mx, __byte_perm(m[0], m[1], 0x6543));
-            mx = __vmaxu4(mx, __byte_perm(m[1], m[2], 0x4321));
-            mx = __vmaxu4(mx, __byte_perm(d[0], d[1], 0x6543));
-            mx = __vmaxu4(mx, d[1]);
-            mx = __vmaxu4(mx, __byte_perm(d[1], d[2], 0x4321));
-            res = c & __vcmpgtu4(c, mx);
+        if ((cA | cB) != 0u) {
+            const uint32_t* u = &se[r - 1][pA - 1];
+            const uint32_t* m = &se[r][pA - 1];
+            const uint32_t* d = &se[r + 1][pA - 1];
+            const uint32_t u0 = u[0], u1 = u[1], u2 = u[2], u3 = u[3], m0 = m[0], m3 = m[3], d0 = d[0], d1 = d[1], d2 = d[2], d3 = d[3];
+            // odd-aligned pairs (px 2i-1, 2i) / (px 2i+1, 2i+2) from two even pairs
+            const uint32_t uA = max3_u16x2(__byte_perm(u0, u1, 0x5432), u1, __byte_perm(u1, u2, 0x5432));
+            const uint32_t dA = max3_u16x2(__byte_perm(d0, d1, 0x5432), d1, __byte_perm(d1, d2, 0x5432));
+            const uint32_t mA = max_u16x2(__byte_perm(m0, cA, 0x5432), __byte_perm(cA, cB, 0x5432));
+            const uint32_t uB = max3_u16x2(__byte_perm(u1, u2, 0x5432), u2, __byte_perm(u2, u3, 0x5432));
+            const uint32_t dB = max3_u16x2(__byte_perm(d1, d2, 0x5432), d2, __byte_perm(d2, d3, 0x5432));
+            const uint32_t mB = max_u16x2(__byte_perm(cA, cB, 0x5432), __byte_perm(cB, m3, 0x5432));
+            const uint32_t mxA = max3_u16x2(uA, dA, mA), mxB = max3_u16x2(uB, dB, mB);
+            // strictly greater than all 8 neighbours: c >= mx + 1  <=>  max(c, mx + 1) == c   (scores <= 254)
+            const uint32_t gA = max_u16x2(cA, mxA + 0x00010001u) ^ cA, gB = max_u16x2(cB, mxB + 0x00010001u) ^ cB;
+            const uint32_t r0 = (gA & 0xffffu) ? 0u : (cA & 0xffffu), r1 = (gA >> 16) ? 0u : (cA >> 16);
+            const uint32_t r2 = (gB & 0xffffu) ? 0u : (cB & 0xffffu), r3 = (gB >> 16) ? 0u : (cB >> 16);
+            res = r0 | (r1 << 8) | (r2 << 16) | (r3 << 24);
             const uint32_t ini4 = (uint32_t)iniTh * 0x01010101u;
             has_ini |= (__vcmpgeu4(res, ini4) != 0u);
         }
