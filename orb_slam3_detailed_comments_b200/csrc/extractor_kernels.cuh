@@ -121,18 +121,17 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     const uint32_t magicG = (1u << 20) / (uint32_t)ngrp + 1u;
     const uint8_t* src = G.base + (int64_t)img * G.img_stride + (int64_t)y0 * G.pitch + gx0;
 
-    {   // staging: a warp per row, a lane per 32-bit word; the next word comes from the neighbour lane
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int r = warp; r < ch; r += FAST_THREADS / 32) {
-            uint32_t w = 0u;
-            if (lane < nW) w = __ldg(reinterpret_cast<const uint32_t*>(src + (int64_t)r * G.pitch) + lane);
-            const uint32_t wn = __shfl_down_sync(0xffffffffu, w, 1);
-            if (lane < nW) {
-                const uint32_t nx = (lane + 1 < nW) ? wn : 0u;
-                *reinterpret_cast<uint2*>(&pe[r][2 * lane]) = make_uint2(__byte_perm(w, 0u, 0x4140), __byte_perm(w, 0u, 0x4342));
-                *reinterpret_cast<uint2*>(&po[r][2 * lane]) = make_uint2(__byte_perm(w, 0u, 0x4241), (w >> 24) | ((nx & 0xffu) << 16));
-                *reinterpret_cast<uint2*>(&se[r][2 * lane]) = make_uint2(0u, 0u);
-            }
+    {   // staging: one thread per 32-bit word of the window (flat index => every thread has several independent
+        // global loads in flight); the following word is re-read through L1 instead of a second shared-memory pass
+        const uint32_t magicW = (1u << 20) / (uint32_t)nW + 1u;   // exact for i < 2048 (ch * nW <= 1596)
+        for (int i = tid; i < ch * nW; i += FAST_THREADS) {
+            const int r = (int)(((uint32_t)i * magicW) >> 20), c = i - r * nW;
+            const uint32_t* rowp = reinterpret_cast<const uint32_t*>(src + (int64_t)r * G.pitch);
+            const uint32_t w = __ldg(rowp + c);
+            const uint32_t nx = (c + 1 < nW) ? __ldg(rowp + c + 1) : 0u;
+            *reinterpret_cast<uint2*>(&pe[r][2 * c]) = make_uint2(__byte_perm(w, 0u, 0x4140), __byte_perm(w, 0u, 0x4342));
+            *reinterpret_cast<uint2*>(&po[r][2 * c]) = make_uint2(__byte_perm(w, 0u, 0x4241), (w >> 24) | ((nx & 0xffu) << 16));
+            *reinterpret_cast<uint2*>(&se[r][2 * c]) = make_uint2(0u, 0u);
         }
     }
     __syncthreads();
