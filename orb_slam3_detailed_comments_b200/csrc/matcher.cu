@@ -70,6 +70,9 @@ struct ProjParams {
     const int* direction;     // mode 1: [n_frames] 0 none, 1 forward, 2 backward
     float th, nnratio, thFar;
     int bFar, checkOri;
+    // per-frame feature grid (Frame::mGrid as CSR), built by k_frame_grid for modes 0 / 1
+    uint16_t* gridOrder;       // [n_frames][maxFeat] feature ids sorted by (cell, id)
+    uint16_t* gridStart;       // [n_frames][GRID_COLS * GRID_ROWS + 1]
     // scratch + outputs
     unsigned long long* topk;  // [nq][PM_K]
     int* cnt;                  // [nq] candidates passing the order-free gates
@@ -244,6 +247,145 @@ __device__ __forceinline__ bool local_window(const ProjParams& P, int q, Window&
     return true;
 }
 
+// ---- Frame::AssignFeaturesToGrid (Frame.cc:469-504) as a CSR table: feature ids sorted by (cell, id) -------------
+#define PM_NCELL (GRID_COLS * GRID_ROWS)
+__global__ void __launch_bounds__(256) k_frame_grid(const __grid_constant__ ProjParams P) {
+    extern __shared__ __align__(16) unsigned char pm_smem[];
+    uint32_t* keys = reinterpret_cast<uint32_t*>(pm_smem);   // npow
+    const int frame = blockIdx.x, img = P.frame_image[frame];
+    const int N = min(P.nkp[img], P.maxFeat), row0 = P.offsets[img];
+    int npow = 2;
+    while (npow < N) npow <<= 1;
+    for (int i = threadIdx.x; i < npow; i += blockDim.x) {
+        uint32_t key = 0xffffffffu;
+        if (i < N) {
+            const orbx_keypoint k = P.kps[row0 + i];
+            const int px = (int)roundf(fmul(fsub(k.x, P.minX), P.invW)), py = (int)roundf(fmul(fsub(k.y, P.minY), P.invH));
+            const uint32_t cell = (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) ? 0xffffu : (uint32_t)(px * GRID_ROWS + py);
+            key = (cell << 16) | (uint32_t)i;
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    for (int k = 2; k <= npow; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < (npow >> 1); i += blockDim.x) {
+                const int l = ((i & ~(j - 1)) << 1) | (i & (j - 1)), r = l | j;
+                const uint32_t a = keys[l], b = keys[r];
+                if ((a > b) == ((l & k) == 0)) { keys[l] = b; keys[r] = a; }
+            }
+            __syncthreads();
+        }
+    uint16_t* order = P.gridOrder + (size_t)frame * P.maxFeat;
+    uint16_t* start = P.gridStart + (size_t)frame * (PM_NCELL + 1);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) order[i] = (uint16_t)(keys[i] & 0xffffu);
+    for (int c = threadIdx.x; c <= PM_NCELL; c += blockDim.x) {   // first sorted position whose cell >= c
+        int lo = 0, hi = N;
+        const uint32_t v = (uint32_t)c << 16;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (keys[mid] < v) lo = mid + 1; else hi = mid;
+        }
+        start[c] = (uint16_t)lo;
+    }
+}
+
+struct GridFeat {   // a frame's features in (cell, id) order + the CSR cell table, in shared memory
+    float* x;
+    float* y;
+    float* ur;
+    uint16_t* cell;
+    uint16_t* id;
+    uint16_t* start;   // PM_NCELL + 1
+    uint8_t* oct;
+};
+
+__device__ __forceinline__ size_t grid_smem_bytes(int maxFeat) { return (size_t)maxFeat * 17 + (PM_NCELL + 1) * 2 + 32; }
+
+__device__ __forceinline__ void stage_grid(const ProjParams& P, int frame, unsigned char* smem, GridFeat& F, int& N, int& row0) {
+    const int img = P.frame_image[frame];
+    N = min(P.nkp[img], P.maxFeat);
+    row0 = P.offsets[img];
+    const size_t M = (size_t)P.maxFeat;
+    F.x = reinterpret_cast<float*>(smem);
+    F.y = F.x + M;
+    F.ur = F.y + M;
+    F.cell = reinterpret_cast<uint16_t*>(F.ur + M);
+    F.id = F.cell + M;
+    F.start = F.id + M;
+    F.oct = reinterpret_cast<uint8_t*>(F.start + PM_NCELL + 2);
+    const uint16_t* order = P.gridOrder + (size_t)frame * P.maxFeat;
+    const uint16_t* start = P.gridStart + (size_t)frame * (PM_NCELL + 1);
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        const int i = order[j];
+        const orbx_keypoint k = P.kps[row0 + i];
+        F.x[j] = k.x;
+        F.y[j] = k.y;
+        F.ur[j] = P.uright ? P.uright[row0 + i] : -1.0f;
+        const int px = (int)roundf(fmul(fsub(k.x, P.minX), P.invW)), py = (int)roundf(fmul(fsub(k.y, P.minY), P.invH));
+        F.cell[j] = (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) ? (uint16_t)0xffff : (uint16_t)(px * GRID_ROWS + py);
+        F.id[j] = (uint16_t)i;
+        F.oct[j] = (uint8_t)k.octave;
+    }
+    for (int c = threadIdx.x; c <= PM_NCELL; c += blockDim.x) F.start[c] = start[c];
+}
+
+// GetFeaturesInArea over the CSR grid: only the cells of the window are visited (Frame.cc:905-947)
+__device__ __forceinline__ int warp_scan_query_grid(const ProjParams& P, const GridFeat& F, int row0, const Window& w, const uint8_t* qd,
+                                                    float ur_pred, float er_max, unsigned long long out[PM_K]) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long loc[PM_K];
+#pragma unroll
+    for (int k = 0; k < PM_K; ++k) loc[k] = ~0ull;
+    int count = 0;
+    if (!w.empty) {
+        const uint4* q4 = reinterpret_cast<const uint4*>(qd);
+        const uint4 a0 = __ldg(q4), a1 = __ldg(q4 + 1);
+        const bool checkLevels = (w.minLevel > 0) || (w.maxLevel >= 0);
+        for (int ix = w.c0; ix <= w.c1; ++ix) {
+            const int jb = F.start[ix * GRID_ROWS + w.r0], je = F.start[ix * GRID_ROWS + w.r1 + 1];
+            for (int j = jb + lane; j < je; j += 32) {
+                const int oc = F.oct[j];
+                if (checkLevels) {
+                    if (oc < w.minLevel) continue;
+                    if (w.maxLevel >= 0 && oc > w.maxLevel) continue;
+                }
+                const float dx = fsub(F.x[j], w.x), dy = fsub(F.y[j], w.y);
+                if (!(fabsf(dx) < w.r && fabsf(dy) < w.r)) continue;
+                const float ur = F.ur[j];
+                if (ur > 0) {
+                    const float er = fabsf(fsub(ur_pred, ur));
+                    if (er > er_max) continue;
+                }
+                ++count;
+                const int i = F.id[j];
+                const uint32_t d = hamming256(a0, a1, P.desc + (size_t)(row0 + i) * 32);
+                unsigned long long key = ((unsigned long long)d << 32) | ((unsigned long long)F.cell[j] << 16) | (unsigned long long)i;
+#pragma unroll
+                for (int k = 0; k < PM_K; ++k)
+                    if (key < loc[k]) {
+                        const unsigned long long t = loc[k];
+                        loc[k] = key;
+                        key = t;
+                    }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+#pragma unroll
+    for (int k = 0; k < PM_K; ++k) {
+        const unsigned long long m = warp_min_u64(loc[0]);
+        out[k] = m;
+        if (loc[0] == m && m != ~0ull) {
+#pragma unroll
+            for (int j = 0; j + 1 < PM_K; ++j) loc[j] = loc[j + 1];
+            loc[PM_K - 1] = ~0ull;
+        }
+    }
+    return count;
+}
+
 // ---- kernel A: order-free candidate scan ----------------------------------------------------------
 __global__ void __launch_bounds__(PM_WARPS * 32) k_proj_candidates(const __grid_constant__ ProjParams P) {
     extern __shared__ __align__(16) unsigned char pm_smem[];
@@ -252,8 +394,11 @@ __global__ void __launch_bounds__(PM_WARPS * 32) k_proj_candidates(const __grid_
     const int qbase = q0 + blockIdx.x * PM_QPB;
     if (qbase >= q1) return;
     FrameFeat F;
+    GridFeat GF;
     int N, row0;
-    stage_frame(P, P.frame_image[frame], pm_smem, F, N, row0);
+    const bool use_grid = P.mode != 2;
+    if (use_grid) stage_grid(P, frame, pm_smem, GF, N, row0);
+    else stage_frame(P, P.frame_image[frame], pm_smem, F, N, row0);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int q = qbase + warp; q < min(qbase + PM_QPB, q1); q += PM_WARPS) {
@@ -275,7 +420,8 @@ __global__ void __launch_bounds__(PM_WARPS * 32) k_proj_candidates(const __grid_
         }
         unsigned long long top[PM_K];
         int count = 0;
-        if (ok) count = warp_scan_query(P, F, N, row0, w, P.qdesc + 32 * (size_t)q, ur_pred, er_max, nullptr, top);
+        if (ok) count = use_grid ? warp_scan_query_grid(P, GF, row0, w, P.qdesc + 32 * (size_t)q, ur_pred, er_max, top)
+                                 : warp_scan_query(P, F, N, row0, w, P.qdesc + 32 * (size_t)q, ur_pred, er_max, nullptr, top);
         if (lane == 0) {
             P.cnt[q] = ok ? count : -1;
 #pragma unroll
@@ -479,10 +625,19 @@ struct StageCursor {
 static orb_status launch_proj(orbx_handle* h, ProjParams& P, int n_frames, int max_q_per_frame) {
     cudaStream_t st = h->stream;
     const size_t fsm = ((size_t)P.maxFeat * 23 + 16 + 15) / 16 * 16;
-    ORB_CUDA(cudaFuncSetAttribute(k_proj_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(fsm, (size_t)1024)));
+    const size_t gsm = ((size_t)P.maxFeat * 17 + (PM_NCELL + 1) * 2 + 32 + 15) / 16 * 16;
+    const size_t csm = std::max(fsm, gsm);
+    if (P.mode != 2) {
+        int npow = 2;
+        while (npow < P.maxFeat) npow <<= 1;
+        ORB_CUDA(cudaFuncSetAttribute(k_frame_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(npow * 4, 1024)));
+        k_frame_grid<<<n_frames, 256, (size_t)npow * 4, st>>>(P);
+        ORB_LAUNCHED();
+    }
+    ORB_CUDA(cudaFuncSetAttribute(k_proj_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(csm, (size_t)1024)));
     dim3 grid((max_q_per_frame + PM_QPB - 1) / PM_QPB, n_frames);
     if (grid.x > 0) {
-        k_proj_candidates<<<grid, PM_WARPS * 32, fsm, st>>>(P);
+        k_proj_candidates<<<grid, PM_WARPS * 32, csm, st>>>(P);
         ORB_LAUNCHED();
     }
     const size_t rsm = fsm + (size_t)PM_CHUNK * PM_K * 8 + (size_t)PM_CHUNK * 4 + (size_t)P.maxFeat * 5 + (size_t)PM_CHUNK * 5 + 128;
@@ -542,7 +697,7 @@ extern "C" orb_status orbm_search_local_points(orbx_handle* h, const orbm_camera
         maxq = std::max(maxq, qoff_h[f + 1] - qoff_h[f]);
         if (fimg_h[f] < 0 || fimg_h[f] >= h->last_batch || qoff_h[f + 1] < qoff_h[f]) return set_error(ORB_ERR_INVALID, "bad frame table");
     }
-    const size_t need = (size_t)nq * (PM_K * 8 + 4 + 4 * 6 + 32 + 8) + rows + (size_t)nf * 16 + 65536;
+    const size_t need = (size_t)nq * (PM_K * 8 + 4 + 4 * 6 + 32 + 8) + rows + (size_t)nf * (16 + 2 * (size_t)h->geom.kpTotal + 2 * 3073 + 512) + 65536;
     if ((s = ensure_stage(h, need)) != ORB_OK) return s;
     StageCursor cur{h->d_stage};
     ProjParams P{};
@@ -563,6 +718,8 @@ extern "C" orb_status orbm_search_local_points(orbx_handle* h, const orbm_camera
     if ((s = upload(h, fl, Q->feature_claimed, rows, cur, dev)) != ORB_OK) return s;
     P.a0 = a0; P.a1 = a1; P.a2 = a2; P.level = lvl; P.f0 = f0; P.f1 = f1; P.qdesc = qd; P.flag = fl;
     P.th = th; P.nnratio = nnratio; P.bFar = far_points; P.thFar = th_far;
+    P.gridOrder = cur.take<uint16_t>((size_t)nf * P.maxFeat);
+    P.gridStart = cur.take<uint16_t>((size_t)nf * (GRID_COLS * GRID_ROWS + 1));
     P.topk = cur.take<unsigned long long>((size_t)nq * PM_K);
     P.cnt = cur.take<int>(nq);
     P.match = dev ? match_out : cur.take<int>(nq);
@@ -603,7 +760,7 @@ extern "C" orb_status orbm_search_last_frame(orbx_handle* h, const orbm_camera* 
         maxq = std::max(maxq, qoff_h[f + 1] - qoff_h[f]);
         if (fimg_h[f] < 0 || fimg_h[f] >= h->last_batch || qoff_h[f + 1] < qoff_h[f]) return set_error(ORB_ERR_INVALID, "bad frame table");
     }
-    const size_t need = (size_t)nq * (PM_K * 8 + 4 + 4 + 12 + 4 + 4 + 32 + 1 + 16) + (size_t)total_rows * 4 + (size_t)nf * 64 + 65536;
+    const size_t need = (size_t)nq * (PM_K * 8 + 4 + 4 + 12 + 4 + 4 + 32 + 1 + 16) + (size_t)total_rows * 4 + (size_t)nf * (64 + 2 * (size_t)h->geom.kpTotal + 2 * 3073 + 512) + 65536;
     if ((s = ensure_stage(h, need)) != ORB_OK) return s;
     StageCursor cur{h->d_stage};
     ProjParams P{};
@@ -622,6 +779,8 @@ extern "C" orb_status orbm_search_last_frame(orbx_handle* h, const orbm_camera* 
     P.frame_image = d_fimg; P.qoff = d_qoff; P.Tcw = tcw; P.direction = d_dir;
     P.a0 = xw; P.level = lvl; P.f0 = ang; P.qdesc = qd; P.flag = ob;
     P.th = th; P.checkOri = check_orientation;
+    P.gridOrder = cur.take<uint16_t>((size_t)nf * P.maxFeat);
+    P.gridStart = cur.take<uint16_t>((size_t)nf * (GRID_COLS * GRID_ROWS + 1));
     P.topk = cur.take<unsigned long long>((size_t)nq * PM_K);
     P.cnt = cur.take<int>(nq);
     P.quv = cur.take<float>(nq);
