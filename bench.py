@@ -63,6 +63,22 @@ def make_pairs(n_pairs, base=8):
     return out
 
 
+def local_map_queries(k, d, z, rng, bf):
+    """Local-map query set of one frame (SearchLocalPoints shape): one map point per feature of the frame (its own
+    descriptor, projection jittered by 1.5 px, stereo coordinate from its depth or 5 m) plus as many unrelated points
+    (random positions, random descriptors) -- roughly the matched / unmatched mix of a real local map."""
+    n = len(k)
+    jit = rng.normal(0, 1.5, (n, 2)).astype(np.float32)
+    zz = np.where(z > 0, z, 5.0).astype(np.float32)
+    x = np.concatenate([k["x"] + jit[:, 0], rng.uniform(20, W - 20, n)]).astype(np.float32)
+    y = np.concatenate([k["y"] + jit[:, 1], rng.uniform(20, H - 20, n)]).astype(np.float32)
+    zq = np.concatenate([zz, rng.uniform(2, 15, n)]).astype(np.float32)
+    lvl = np.concatenate([k["octave"], rng.integers(0, 8, n)]).astype(np.int32)
+    vc = rng.uniform(0.99, 1.0, 2 * n).astype(np.float32)
+    desc = np.concatenate([d, rng.integers(0, 256, (n, 32), dtype=np.uint8)])
+    return x, y, (x - bf / zq).astype(np.float32), lvl, vc, desc
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
 
@@ -144,10 +160,8 @@ def cpu_oracle_frames(pairs, threads):
         sf = eL.scale_factors
         po.search_last(kL, dL, uR, bounds, sf, cam6, T, 0, pts, kL["octave"][sel], kL["angle"][sel], dL[sel],
                        np.ones(len(sel), np.uint8), 15.0, True)
-        sel4 = np.concatenate([sel, sel, sel, sel])
-        x, y = kL["x"][sel4], kL["y"][sel4]
-        po.search_local(kL, dL, uR, bounds, sf, x, y, x - BF / dep[sel4], kL["octave"][sel4],
-                        np.full(len(sel4), 0.995, np.float32), dL[sel4], 3.0, 0.8)
+        x, y, xr, lvl, vc, dq = local_map_queries(kL, dL, dep, np.random.default_rng(7), BF)
+        po.search_local(kL, dL, uR, bounds, sf, x, y, xr, lvl, vc, dq, 3.0, 0.8)
         return 0
     exs = [(po.OracleExtractor(NFEAT, 1.2, 8, 20, 7), po.OracleExtractor(NFEAT, 1.2, 8, 20, 7)) for _ in range(nworkers)]
     pools2 = [ThreadPoolExecutor(1) if nthr >= 2 else None for _ in range(nworkers)]
@@ -255,12 +269,10 @@ def main():
         q_last["xw"].append(pts); q_last["oct"].append(k["octave"][sel].astype(np.int32))
         q_last["ang"].append(k["angle"][sel].astype(np.float32)); q_last["desc"].append(d[sel])
         q_last["obs"].append(np.ones(len(sel), np.uint8)); q_last["off"].append(q_last["off"][-1] + len(sel))
-        sel4 = np.concatenate([sel, rng.choice(sel, 3 * len(sel))]) if len(sel) else sel
-        jit = rng.normal(0, 1.5, (len(sel4), 2)).astype(np.float32)
-        x, y = k["x"][sel4] + jit[:, 0], k["y"][sel4] + jit[:, 1]
-        q_loc["px"].append(x.astype(np.float32)); q_loc["py"].append(y.astype(np.float32))
-        q_loc["pxr"].append((x - BF / z[sel4]).astype(np.float32)); q_loc["lvl"].append(k["octave"][sel4].astype(np.int32))
-        q_loc["vc"].append(rng.uniform(0.99, 1.0, len(sel4)).astype(np.float32)); q_loc["desc"].append(d[sel4])
+        x, y, xr, lvl, vc, dq = local_map_queries(k, d, z, rng, BF)
+        q_loc["px"].append(x); q_loc["py"].append(y); q_loc["pxr"].append(xr); q_loc["lvl"].append(lvl)
+        q_loc["vc"].append(vc); q_loc["desc"].append(dq)
+        sel4 = x
         q_loc["off"].append(q_loc["off"][-1] + len(sel4))
     cat = lambda xs, dt, shape=None: np.concatenate(xs).astype(dt) if len(xs) else np.zeros(0, dt)
     h_last = dict(fimg=np.arange(0, nimg, 2, dtype=np.int32), off=np.array(q_last["off"], np.int32),

@@ -330,13 +330,16 @@ __device__ __forceinline__ void stage_grid(const ProjParams& P, int frame, unsig
     for (int c = threadIdx.x; c <= PM_NCELL; c += blockDim.x) F.start[c] = start[c];
 }
 
-// GetFeaturesInArea over the CSR grid: only the cells of the window are visited (Frame.cc:905-947)
+// GetFeaturesInArea over the CSR grid: only the cells of the window are visited (Frame.cc:905-947).
+// Keys are 32 bits here -- distance << 16 | position in the (cell, id)-sorted feature order, which is the
+// reference's candidate order -- so the warp-wide minimum is ONE instruction (REDUX.MIN) instead of a 64-bit
+// shuffle tree; they are widened to the (distance, cell, id) form of the resolve pass when stored.
 __device__ __forceinline__ int warp_scan_query_grid(const ProjParams& P, const GridFeat& F, int row0, const Window& w, const uint8_t* qd,
                                                     float ur_pred, float er_max, unsigned long long out[PM_K]) {
     const int lane = threadIdx.x & 31;
-    unsigned long long loc[PM_K];
+    uint32_t loc[PM_K];
 #pragma unroll
-    for (int k = 0; k < PM_K; ++k) loc[k] = ~0ull;
+    for (int k = 0; k < PM_K; ++k) loc[k] = 0xffffffffu;
     int count = 0;
     if (!w.empty) {
         const uint4* q4 = reinterpret_cast<const uint4*>(qd);
@@ -358,29 +361,31 @@ __device__ __forceinline__ int warp_scan_query_grid(const ProjParams& P, const G
                     if (er > er_max) continue;
                 }
                 ++count;
-                const int i = F.id[j];
-                const uint32_t d = hamming256(a0, a1, P.desc + (size_t)(row0 + i) * 32);
-                unsigned long long key = ((unsigned long long)d << 32) | ((unsigned long long)F.cell[j] << 16) | (unsigned long long)i;
+                const uint32_t d = hamming256(a0, a1, P.desc + (size_t)(row0 + F.id[j]) * 32);
+                uint32_t key = (d << 16) | (uint32_t)j;
 #pragma unroll
                 for (int k = 0; k < PM_K; ++k)
                     if (key < loc[k]) {
-                        const unsigned long long t = loc[k];
+                        const uint32_t t = loc[k];
                         loc[k] = key;
                         key = t;
                     }
             }
         }
     }
+    count = __reduce_add_sync(0xffffffffu, count);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+    for (int k = 0; k < PM_K; ++k) out[k] = ~0ull;
 #pragma unroll
     for (int k = 0; k < PM_K; ++k) {
-        const unsigned long long m = warp_min_u64(loc[0]);
-        out[k] = m;
-        if (loc[0] == m && m != ~0ull) {
+        const uint32_t m = __reduce_min_sync(0xffffffffu, loc[0]);
+        if (m == 0xffffffffu) break;   // warp-uniform
+        const int j = (int)(m & 0xffffu);
+        out[k] = ((unsigned long long)(m >> 16) << 32) | ((unsigned long long)F.cell[j] << 16) | (unsigned long long)F.id[j];
+        if (loc[0] == m) {             // sorted positions are unique => exactly one owner
 #pragma unroll
-            for (int j = 0; j + 1 < PM_K; ++j) loc[j] = loc[j + 1];
-            loc[PM_K - 1] = ~0ull;
+            for (int q = 0; q + 1 < PM_K; ++q) loc[q] = loc[q + 1];
+            loc[PM_K - 1] = 0xffffffffu;
         }
     }
     return count;
