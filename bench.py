@@ -252,44 +252,47 @@ def main():
     host_pool = torch.from_numpy(pairs.reshape(pool_batches, nimg, H, W)).pin_memory()
     dev_pool = host_pool.cuda(non_blocking=False)
 
-    # ---- map state for the matchers: the "last frame" of every sequence is the frame itself one step earlier
-    # (its stereo points, unprojected), the local map is that set four times over with jitter --------------
-    ex.extract_batch_device(dev_pool[0].data_ptr(), nimg, W, H)
-    ex.stereo_batch(B, BF, BL)
-    n0, _, off0, kps0, desc0 = ex.download(nimg)
-    uR0, dep0 = ex.stereo_download(int(off0[-1]))
+    # ---- map state for the matchers, one query set per pool batch: the "last frame" of every sequence is the frame
+    # itself one step earlier (its stereo points, unprojected), the local map holds one map point per feature plus as
+    # many unrelated points (local_map_queries) ----------------------------------------------------------------
     rng = np.random.default_rng(1234 + rank)
-    q_last = dict(off=[0], xw=[], oct=[], ang=[], desc=[], obs=[])
-    q_loc = dict(off=[0], px=[], py=[], pxr=[], lvl=[], vc=[], desc=[])
-    for p in range(B):
-        a, b = int(off0[2 * p]), int(off0[2 * p + 1])
-        k, d, z = kps0[a:b], desc0[a:b], dep0[a:b]
-        sel = np.nonzero(z > 0)[0]
-        pts = np.stack([(k["x"][sel] - CX) * z[sel] / FX, (k["y"][sel] - CY) * z[sel] / FY, z[sel]], 1).astype(np.float32)
-        q_last["xw"].append(pts); q_last["oct"].append(k["octave"][sel].astype(np.int32))
-        q_last["ang"].append(k["angle"][sel].astype(np.float32)); q_last["desc"].append(d[sel])
-        q_last["obs"].append(np.ones(len(sel), np.uint8)); q_last["off"].append(q_last["off"][-1] + len(sel))
-        x, y, xr, lvl, vc, dq = local_map_queries(k, d, z, rng, BF)
-        q_loc["px"].append(x); q_loc["py"].append(y); q_loc["pxr"].append(xr); q_loc["lvl"].append(lvl)
-        q_loc["vc"].append(vc); q_loc["desc"].append(dq)
-        sel4 = x
-        q_loc["off"].append(q_loc["off"][-1] + len(sel4))
-    cat = lambda xs, dt, shape=None: np.concatenate(xs).astype(dt) if len(xs) else np.zeros(0, dt)
-    h_last = dict(fimg=np.arange(0, nimg, 2, dtype=np.int32), off=np.array(q_last["off"], np.int32),
-                  Tcw=np.tile(np.array([0, 0, 0, 1, 0.002, 0.001, 0], np.float32), (B, 1)), dir=np.zeros(B, np.int32),
-                  xw=cat(q_last["xw"], np.float32), oct=cat(q_last["oct"], np.int32), ang=cat(q_last["ang"], np.float32),
-                  desc=cat(q_last["desc"], np.uint8), obs=cat(q_last["obs"], np.uint8))
-    h_loc = dict(fimg=h_last["fimg"], off=np.array(q_loc["off"], np.int32), px=cat(q_loc["px"], np.float32),
-                 py=cat(q_loc["py"], np.float32), pxr=cat(q_loc["pxr"], np.float32), lvl=cat(q_loc["lvl"], np.int32),
-                 vc=cat(q_loc["vc"], np.float32), desc=cat(q_loc["desc"], np.uint8))
     T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    d_last = {k: T(v) for k, v in h_last.items()}
-    d_loc = {k: T(v) for k, v in h_loc.items()}
+    cat = lambda xs, dt: np.concatenate(xs).astype(dt) if len(xs) else np.zeros(0, dt)
+    H_LAST, H_LOC, D_LAST, D_LOC = [], [], [], []
+    for pb in range(pool_batches):
+        ex.extract_batch_device(dev_pool[pb].data_ptr(), nimg, W, H)
+        ex.stereo_batch(B, BF, BL)
+        n0, _, off0, kps0, desc0 = ex.download(nimg)
+        uR0, dep0 = ex.stereo_download(int(off0[-1]))
+        q_last = dict(off=[0], xw=[], oct=[], ang=[], desc=[], obs=[])
+        q_loc = dict(off=[0], px=[], py=[], pxr=[], lvl=[], vc=[], desc=[])
+        for p in range(B):
+            a, b = int(off0[2 * p]), int(off0[2 * p + 1])
+            k, d, z = kps0[a:b], desc0[a:b], dep0[a:b]
+            sel = np.nonzero(z > 0)[0]
+            pts = np.stack([(k["x"][sel] - CX) * z[sel] / FX, (k["y"][sel] - CY) * z[sel] / FY, z[sel]], 1).astype(np.float32)
+            q_last["xw"].append(pts); q_last["oct"].append(k["octave"][sel].astype(np.int32))
+            q_last["ang"].append(k["angle"][sel].astype(np.float32)); q_last["desc"].append(d[sel])
+            q_last["obs"].append(np.ones(len(sel), np.uint8)); q_last["off"].append(q_last["off"][-1] + len(sel))
+            x, y, xr, lvl, vc, dq = local_map_queries(k, d, z, rng, BF)
+            q_loc["px"].append(x); q_loc["py"].append(y); q_loc["pxr"].append(xr); q_loc["lvl"].append(lvl)
+            q_loc["vc"].append(vc); q_loc["desc"].append(dq)
+            q_loc["off"].append(q_loc["off"][-1] + len(x))
+        h_last = dict(fimg=np.arange(0, nimg, 2, dtype=np.int32), off=np.array(q_last["off"], np.int32),
+                      Tcw=np.tile(np.array([0, 0, 0, 1, 0.002, 0.001, 0], np.float32), (B, 1)), dir=np.zeros(B, np.int32),
+                      xw=cat(q_last["xw"], np.float32), oct=cat(q_last["oct"], np.int32), ang=cat(q_last["ang"], np.float32),
+                      desc=cat(q_last["desc"], np.uint8), obs=cat(q_last["obs"], np.uint8))
+        h_loc = dict(fimg=h_last["fimg"], off=np.array(q_loc["off"], np.int32), px=cat(q_loc["px"], np.float32),
+                     py=cat(q_loc["py"], np.float32), pxr=cat(q_loc["pxr"], np.float32), lvl=cat(q_loc["lvl"], np.int32),
+                     vc=cat(q_loc["vc"], np.float32), desc=cat(q_loc["desc"], np.uint8))
+        H_LAST.append(h_last); H_LOC.append(h_loc)
+        D_LAST.append({k: T(v) for k, v in h_last.items()}); D_LOC.append({k: T(v) for k, v in h_loc.items()})
     rows_cap = nimg * 1500
     d_fm = [torch.full((rows_cap,), -1, dtype=torch.int32, device=dev) for _ in range(2)]
     d_nm = [torch.zeros(2 * B, dtype=torch.int32, device=dev) for _ in range(2)]
-    d_match = [torch.full((max(int(h_loc["off"][-1]), 1),), -1, dtype=torch.int32, device=dev) for _ in range(2)]
-    nq_last, nq_loc = int(h_last["off"][-1]), int(h_loc["off"][-1])
+    max_loc = max(int(hl["off"][-1]) for hl in H_LOC)
+    d_match = [torch.full((max(max_loc, 1),), -1, dtype=torch.int32, device=dev) for _ in range(2)]
+    nq_last = float(np.mean([int(hl["off"][-1]) for hl in H_LAST])); nq_loc = float(np.mean([int(hl["off"][-1]) for hl in H_LOC]))
 
     def submit_device(i):
         e = exs[i % 2]
@@ -299,6 +302,7 @@ def main():
     def finish_device(i):
         k = i % 2
         e = exs[k]
+        d_last, d_loc = D_LAST[i % pool_batches], D_LOC[i % pool_batches]
         m_last.SearchByProjectionLastFrameDevice(e, cam, B, d_last["fimg"], d_last["off"], d_last["Tcw"], d_last["dir"],
                                                  d_last["xw"], d_last["oct"], d_last["ang"], d_last["desc"], d_last["obs"],
                                                  15.0, d_fm[k], d_nm[k][:B])
@@ -366,13 +370,13 @@ def main():
     # before the blocking result reads of batch i, so PCIe traffic overlaps compute (the usage INTEGRATION.md
     # recommends for sequence replay).  Every step still moves its own images in and its own results out.
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
-    p_last = {k: pin(v) for k, v in h_last.items()}
-    p_loc = {k: pin(v) for k, v in h_loc.items()}
+    P_LAST = [{k: pin(v) for k, v in hl.items()} for hl in H_LAST]
+    P_LOC = [{k: pin(v) for k, v in hl.items()} for hl in H_LOC]
     pz = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory().numpy()
     from orb_slam3_detailed_comments_b200._native import KP_DTYPE
     o_kps = torch.zeros(rows_cap * 28, dtype=torch.uint8).pin_memory().numpy().view(KP_DTYPE)
     o_desc, o_ur, o_dep = pz((rows_cap, 32), torch.uint8), pz(rows_cap, torch.float32), pz(rows_cap, torch.float32)
-    o_fm, o_nm1, o_mt, o_nm2 = pz(rows_cap, torch.int32), pz(B, torch.int32), pz(max(nq_loc, 1), torch.int32), pz(B, torch.int32)
+    o_fm, o_nm1, o_mt, o_nm2 = pz(rows_cap, torch.int32), pz(B, torch.int32), pz(max(max_loc, 1), torch.int32), pz(B, torch.int32)
 
     def submit(i):
         e = exs[i % 2]
@@ -381,6 +385,7 @@ def main():
 
     def finish(i):
         e = exs[i % 2]
+        p_last, p_loc = P_LAST[i % pool_batches], P_LOC[i % pool_batches]
         nn, mm, oo, kk, dd = e.download(nimg, out=(o_kps, o_desc))
         rows = int(oo[-1])
         ur, dp = e.stereo_download(rows, out=(o_ur, o_dep))
@@ -401,14 +406,14 @@ def main():
         if i + 1 < args.steps:
             submit(args.warmup + i + 1)
         rows = finish(args.warmup + i)
-        d2h += rows * (60 + 8 + 4) + 12 * nimg + 4 * nq_loc + 8 * B
+        d2h += rows * (60 + 8 + 4) + 12 * nimg + 4 * int(nq_loc) + 8 * B
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(t.item())
-    h2d_step = nimg * W * H + sum(v.nbytes for v in h_last.values()) + sum(v.nbytes for v in h_loc.values())
+    h2d_step = nimg * W * H + sum(v.nbytes for v in H_LAST[0].values()) + sum(v.nbytes for v in H_LOC[0].values())
 
     if rank == 0:
         # roofline of the dominant kernel, live from the stage events recorded over the timed steps

@@ -206,3 +206,35 @@ def test_search_for_triangulation_matches_oracle(scene):
         ref, rnm = po.search_triangulation(kL[sel], dL[sel], nd, st1, k2, d2, node2, valid2, st2, F12, ep, sf, s2, coarse, check)
         assert rnm == nm and (got == ref).all(), (coarse, check, mono_all, rnm, nm)
         assert coarse is False or rnm > 20
+
+
+def test_search_local_points_one_map_point_per_feature(scene):
+    # the benchmark's query shape: every feature is the projection of its own map point (+ unrelated points)
+    P, ex, off = scene["P"], scene["ex"], scene["off"]
+    sf = ex.GetScaleFactors()
+    rng = np.random.default_rng(3)
+    qoff, parts = [0], []
+    for p in range(P):
+        a, b = off[2 * p], off[2 * p + 1]
+        k, d, ur = scene["kps"][a:b], scene["desc"][a:b], scene["uR"][a:b]
+        n = len(k)
+        z = np.where(ur > 0, BF / np.maximum(k["x"] - ur, 0.01), 5.0).astype(np.float32)
+        jit = rng.normal(0, 1.5, (n, 2)).astype(np.float32)
+        x = np.concatenate([k["x"] + jit[:, 0], rng.uniform(20, W - 20, n)]).astype(np.float32)
+        y = np.concatenate([k["y"] + jit[:, 1], rng.uniform(20, H - 20, n)]).astype(np.float32)
+        zq = np.concatenate([z, rng.uniform(2, 15, n)]).astype(np.float32)
+        lvl = np.concatenate([k["octave"], rng.integers(0, 8, n)]).astype(np.int32)
+        vc = rng.uniform(0.99, 1.0, 2 * n).astype(np.float32)
+        dq = np.concatenate([d, rng.integers(0, 256, (n, 32), dtype=np.uint8)])
+        parts.append((x, y, (x - BF / zq).astype(np.float32), lvl, vc, dq))
+        qoff.append(qoff[-1] + 2 * n)
+    px, py, pxr, lv, vc, qd = (np.concatenate([pt[i] for pt in parts]) for i in range(6))
+    m = ORBmatcher(0.8, True)
+    match, nm = m.SearchByProjection(ex, camera(FX, FY, CX, CY, BF, B, W, H), [2 * p for p in range(P)], qoff, px, py, pxr, lv, vc, qd, th=3.0)
+    for p in range(P):
+        a, b = off[2 * p], off[2 * p + 1]
+        s = slice(qoff[p], qoff[p + 1])
+        rmatch, rnm = po.search_local(scene["kps"][a:b], scene["desc"][a:b], scene["uR"][a:b], BOUNDS, sf, px[s], py[s], pxr[s], lv[s],
+                                      vc[s], qd[s], 3.0, 0.8)
+        assert rnm == nm[p] and (match[s] == rmatch).all(), (p, rnm, nm[p])
+        assert rnm > 0.9 * (b - a)
