@@ -218,6 +218,49 @@ typedef struct {
 orb_status orbm_search_bow(orbx_handle* h, const orbm_bow_queries* q, float nnratio, int32_t check_orientation,
                            int32_t* feature_match_out, int32_t* nmatches_out);
 
+/* Projection searches into a KeyFrame from a pose (Nleft == -1, pinhole):
+ *   ORBM_KF_FUSE_POSE   Fuse(pKF, vpMapPoints, th, bRight=false)                           ORBmatcher.cc:1325-1544
+ *   ORBM_KF_FUSE_SIM3   Fuse(pKF, Scw, vpPoints, th, vpReplacePoint)                       ORBmatcher.cc:1546-1687
+ *   ORBM_KF_PROJ_SIM3   SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) ORBmatcher.cc:495-618 and the
+ *                       vpPointsKFs / vpMatchedKF overload :620-732 (same search; the caller records the extra array)
+ *   ORBM_KF_PROJ_RELOC  SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist)   ORBmatcher.cc:2196-2330
+ * Several targets per call (LocalMapping::SearchInNeighbors fuses the same points into ~20 keyframes): target t
+ * searches features [feat_offset[t], feat_offset[t+1]) with queries [query_offset[t], query_offset[t+1]).
+ * Targets are map state in HOST memory (kp != NULL), or -- kp == NULL -- images target_image[t] of the handle's
+ * last batch (the frame being relocalised is still on the device).
+ * Queries = the map points that survive the caller-side skips (NULL, isBad(), IsInKeyFrame / spAlreadyFound /
+ * sAlreadyFound), in the reference's order.  Tcw: qx qy qz qw tx ty tz of the SE3f the function uses (for the Sim3
+ * variants SE3f(Scw.rotationMatrix(), Scw.translation()/Scw.scale())); Ow = pKF->GetCameraCenter() /
+ * Tcw.inverse().translation().  The level tables (mvScaleFactors, mvInvLevelSigma2, mnScaleLevels,
+ * mfLogScaleFactor = logf(scaleFactor)) are the handle's.
+ * match_out[q] = feature index inside its target (bestIdx) or -1; the caller applies the side effects in query
+ * order (Replace / AddObservation / vpReplacePoint / vpMatched[bestIdx] = pMP).  nmatches_out[t] = return value. */
+enum { ORBM_KF_FUSE_POSE = 0, ORBM_KF_FUSE_SIM3 = 1, ORBM_KF_PROJ_SIM3 = 2, ORBM_KF_PROJ_RELOC = 3 };
+typedef struct {
+    int32_t n_targets;
+    const int32_t* target_image;  /* [n_targets] when kp == NULL, else ignored */
+    const int32_t* feat_offset;   /* [n_targets + 1] when kp != NULL */
+    const orbx_keypoint* kp;      /* mvKeysUn */
+    const uint8_t* desc;          /* mDescriptors */
+    const float* uright;          /* mvuRight (FUSE_POSE reads it; NULL = monocular) */
+    const uint8_t* feat_claimed;  /* PROJ_SIM3: vpMatched[idx] != NULL, PROJ_RELOC: mvpMapPoints[i2] != NULL on entry
+                                     (per feature row, host targets: same indexing as kp; device targets: compact rows); NULL = none */
+    const float* Tcw;             /* [n_targets][7] */
+    const float* Ow;              /* [n_targets][3] */
+    const int32_t* query_offset;  /* [n_targets + 1] */
+    const float* world_pos;       /* [nq][3] MapPoint::GetWorldPos */
+    const float* normal;          /* [nq][3] MapPoint::GetNormal (unused by PROJ_RELOC, may be NULL there) */
+    const float* max_dist;        /* GetMaxDistanceInvariance */
+    const float* min_dist;        /* GetMinDistanceInvariance */
+    const uint8_t* desc_q;        /* MapPoint::GetDescriptor */
+    const float* angle;           /* PROJ_RELOC: pKF->mvKeysUn[i].angle of the query's keyframe feature; else NULL */
+} orbm_kf_queries;
+
+/* hamming_max: TH_LOW (50), TH_LOW * ratioHamming, or ORBdist. */
+orb_status orbm_search_keyframe(orbx_handle* h, const orbm_camera* cam, const orbm_kf_queries* q, int32_t variant,
+                                float th, float hamming_max, int32_t check_orientation, int32_t* match_out,
+                                int32_t* nmatches_out);
+
 /* SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, vMatchedPairs, bOnlyStereo, bCoarse)  ORBmatcher.cc:1045-1323,
  * keyframes without a second camera.  Both keyframes are map state (host memory): queries = the KF1 features WITHOUT
  * a map point (and stereo when bOnlyStereo), in FeatureVector merge order; side 2 = all features of KF2 with

@@ -329,3 +329,119 @@ extern "C" int orc_search_triangulation(int nq, const KeyPoint* kp1, const uint8
     }
     return nmatches;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Projection searches into a KeyFrame (or, variant 3, a Frame) from a pose, Nleft == -1, pinhole:
+//   variant 0  Fuse(pKF, vpMapPoints, th, bRight=false)                         src/ORBmatcher.cc:1325-1544
+//   variant 1  Fuse(pKF, Scw, vpPoints, th, vpReplacePoint)                     src/ORBmatcher.cc:1546-1687
+//   variant 2  SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratio)     src/ORBmatcher.cc:495-618
+//              (and the vpPointsKFs overload :620-732, which only records one more array per match)
+//   variant 3  SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) src/ORBmatcher.cc:2196-2330
+// Queries = the map points that pass the caller-side skips (NULL, isBad, IsInKeyFrame / spAlreadyFound), in order.
+// Tcw7: qx qy qz qw tx ty tz of the SE3f the function builds (for Scw: SE3f(Scw.rotationMatrix(),
+// Scw.translation()/Scw.scale())); Ow = Tcw.inverse().translation() / pKF->GetCameraCenter().
+// claimed[idx] (variants 2, 3): vpMatched[idx] / CurrentFrame.mvpMapPoints[i2] non-NULL on entry; updated.
+// thr: 50 (TH_LOW), TH_LOW * ratioHamming (float product) or ORBdist.  match[q] = feature index or -1.
+// Vector3f norm / dot follow Eigen's unrolled reduction x + (y + z) (Eigen/src/Core/Redux.h, not in the tree).
+// MapPoint::PredictScale  src/MapPoint.cc:688-721 with std::log(float) == logf.
+extern "C" int orc_search_keyframe(int variant, const KeyPoint* kps, const uint8_t* desc, const float* uright, int N,
+                                   const float* bounds4, const float* scaleFactors, const float* invLevelSigma2, int nLevels,
+                                   float logScaleFactor, const float* cam6, const float* Tcw7, const float* Ow, int nq,
+                                   const float* xw, const float* normal, const float* maxDist, const float* minDist,
+                                   const uint8_t* qdesc, const float* qangle, uint8_t* claimed, float th, float thr,
+                                   int checkOri, int* match) {
+    FrameView F;
+    F.kps = kps; F.desc = desc; F.uright = uright; F.N = N;
+    F.minX = bounds4[0]; F.maxX = bounds4[1]; F.minY = bounds4[2]; F.maxY = bounds4[3];
+    F.scaleFactors = scaleFactors;
+    F.build();
+    int nmatches = 0;
+    std::vector<int> rotHist[30];
+    std::vector<int> rotQuery[30];
+    const float factor = 1.0f / 30;
+    const float fx = cam6[0], fy = cam6[1], cx = cam6[2], cy = cam6[3], bf = cam6[4];
+    for (int q = 0; q < nq; ++q) {
+        match[q] = -1;
+        const float* p3Dw = xw + 3 * q;
+        float pc[3];
+        se3_act(Tcw7, Tcw7 + 4, p3Dw, pc);
+        if (variant != 3 && pc[2] < 0.0f) continue;
+        const float invz = 1 / pc[2];
+        const float u = fx * pc[0] / pc[2] + cx, v = fy * pc[1] / pc[2] + cy;       // Pinhole::project
+        if (variant == 3) {
+            if (u < F.minX || u > F.maxX) continue;
+            if (v < F.minY || v > F.maxY) continue;
+        } else if (!(u >= F.minX && u < F.maxX && v >= F.minY && v < F.maxY)) continue;   // KeyFrame::IsInImage
+        const float ur = u - bf * invz;
+        const float PO[3] = {p3Dw[0] - Ow[0], p3Dw[1] - Ow[1], p3Dw[2] - Ow[2]};
+        const float dist3D = std::sqrt(PO[0] * PO[0] + (PO[1] * PO[1] + PO[2] * PO[2]));
+        if (dist3D < minDist[q] || dist3D > maxDist[q]) continue;
+        if (variant != 3) {
+            const float* Pn = normal + 3 * q;
+            const float d = PO[0] * Pn[0] + (PO[1] * Pn[1] + PO[2] * Pn[2]);
+            if (d < 0.5 * dist3D) continue;
+        }
+        const float ratio = maxDist[q] / dist3D;
+        int nPredictedLevel = (int)std::ceil(logf(ratio) / logScaleFactor);
+        if (nPredictedLevel < 0) nPredictedLevel = 0;
+        else if (nPredictedLevel >= nLevels) nPredictedLevel = nLevels - 1;
+        const float radius = th * scaleFactors[nPredictedLevel];
+        const std::vector<size_t> ind = variant == 3 ? F.area(u, v, radius, nPredictedLevel - 1, nPredictedLevel + 1)
+                                                     : F.area(u, v, radius, -1, -1);
+        if (ind.empty()) continue;
+        int bestDist = variant == 0 || variant == 2 || variant == 3 ? 256 : 0x7fffffff, bestIdx = -1;
+        for (size_t idx : ind) {
+            if (variant >= 2 && claimed[idx]) continue;
+            const int kpLevel = kps[idx].octave;
+            if (variant != 3 && (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel)) continue;
+            if (variant == 0) {
+                if (uright && uright[idx] >= 0) {
+                    const float ex = u - kps[idx].x, ey = v - kps[idx].y, er = ur - uright[idx];
+                    const float e2 = ex * ex + ey * ey + er * er;
+                    if (e2 * invLevelSigma2[kpLevel] > 7.8) continue;
+                } else {
+                    const float ex = u - kps[idx].x, ey = v - kps[idx].y;
+                    const float e2 = ex * ex + ey * ey;
+                    if (e2 * invLevelSigma2[kpLevel] > 5.99) continue;
+                }
+            }
+            const int dist = descriptor_distance(qdesc + 32 * (size_t)q, desc + 32 * idx);
+            if (dist < bestDist) {
+                bestDist = dist;
+                bestIdx = (int)idx;
+            }
+        }
+        if ((float)bestDist <= thr) {
+            match[q] = bestIdx;
+            if (variant >= 2) claimed[bestIdx] = 1;
+            ++nmatches;
+            if (variant == 3 && checkOri) {
+                float rot = qangle[q] - kps[bestIdx].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)std::round(rot * factor);
+                if (bin == 30) bin = 0;
+                rotHist[bin].push_back(bestIdx);
+                rotQuery[bin].push_back(q);
+            }
+        }
+    }
+    if (variant == 3 && checkOri) {
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < 30; ++i) {
+            const int s = (int)rotHist[i].size();
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < 30; ++i)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (size_t j = 0; j < rotHist[i].size(); ++j) {
+                    claimed[rotHist[i][j]] = 0;       // CurrentFrame.mvpMapPoints[..] = NULL
+                    match[rotQuery[i][j]] = -1;
+                    --nmatches;
+                }
+    }
+    return nmatches;
+}

@@ -66,6 +66,12 @@ class orbm_bow_queries(C.Structure):
         (n, C.c_void_p) for n in ("frame_image", "query_offset", "query_node", "query_angle", "desc", "feature_node")]
 
 
+class orbm_kf_queries(C.Structure):
+    _fields_ = [("n_targets", C.c_int32)] + [
+        (n, C.c_void_p) for n in ("target_image", "feat_offset", "kp", "desc", "uright", "feat_claimed", "Tcw", "Ow",
+                                  "query_offset", "world_pos", "normal", "max_dist", "min_dist", "desc_q", "angle")]
+
+
 class orbm_triangulation(C.Structure):
     _fields_ = [("n_queries", C.c_int32), ("n2", C.c_int32)] + [
         (n, C.c_void_p) for n in ("kp1", "desc1", "node1", "stereo1", "kp2", "desc2", "node2", "valid2", "stereo2")] + [
@@ -113,6 +119,7 @@ SIGNATURES = {
     "orbm_stereo_pair": (_I, [_VP, _VP, _F, _F, _VP, _VP, _I]),
     "orbm_search_local_points": (_I, [_VP, C.POINTER(orbm_camera), C.POINTER(orbm_local_queries), _F, _F, _I, _F, _VP, _VP]),
     "orbm_search_bow": (_I, [_VP, C.POINTER(orbm_bow_queries), _F, _I, _VP, _VP]),
+    "orbm_search_keyframe": (_I, [_VP, C.POINTER(orbm_camera), C.POINTER(orbm_kf_queries), _I, C.c_float, C.c_float, _I, _VP, _VP]),
     "orbm_search_triangulation": (_I, [_VP, C.POINTER(orbm_triangulation), _VP, _VP]),
     "lba_create": (_I, [_I, C.POINTER(_VP)]),
     "lba_destroy": (None, [_VP]),

@@ -115,6 +115,7 @@ ORB_D float fmul(float a, float b) { return __fmul_rn(a, b); }
 ORB_D float fadd(float a, float b) { return __fadd_rn(a, b); }
 ORB_D float fsub(float a, float b) { return __fsub_rn(a, b); }
 ORB_D float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+ORB_D float fsqrt(float a) { return __fsqrt_rn(a); }
 ORB_D double dmul(double a, double b) { return __dmul_rn(a, b); }
 ORB_D double dadd(double a, double b) { return __dadd_rn(a, b); }
 ORB_D int round_half_even(float v) { return __float2int_rn(v); }
@@ -124,6 +125,7 @@ inline float fmul(float a, float b) { return a * b; }
 inline float fadd(float a, float b) { return a + b; }
 inline float fsub(float a, float b) { return a - b; }
 inline float fdiv(float a, float b) { return a / b; }
+inline float fsqrt(float a) { return sqrtf(a); }
 inline double dmul(double a, double b) { return a * b; }
 inline double dadd(double a, double b) { return a + b; }
 inline int round_half_even(float v) { return (int)lrintf(v); }
@@ -151,6 +153,63 @@ ORB_HD float fast_atan2_deg(float y, float x) {
     if (y < 0) a = fsub(360.f, a);
     return a;
 }
+
+// ---- glibc 2.39 logf (sysdeps/ieee754/flt-32/e_logf.c + e_logf_data.c, the ARM optimized-routines logf):
+// x = 2^k z with z in [OFF, 2 OFF), 16-entry table of (1/c, log c), degree-3 polynomial in fp64, one rounding
+// to float.  Validated against the host's logf over EVERY positive normal float (2 130 706 432 values, 0
+// mismatches, with and without FMA contraction) and sampled in tests/test_host_emul.py.  MapPoint::PredictScale
+// (/root/reference/src/MapPoint.cc:688-721) calls std::log(float) == logf.
+ORB_HD float glibc_logf(float x) {
+    const double T[16][2] = {
+        {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2},
+        {0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2},  {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3},
+        {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3},
+        {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4},
+        {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5}, {0x1p+0, 0x0p+0},
+        {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5},  {0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4},
+        {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3},
+        {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
+    const double Ln2 = 0x1.62e42fefa39efp-1;
+    const double A0 = -0x1.00ea348b88334p-2, A1 = 0x1.5575b0be00b6ap-2, A2 = -0x1.ffffef20a4123p-2;
+    uint32_t ix;
+#if defined(__CUDA_ARCH__)
+    ix = __float_as_uint(x);
+#else
+    memcpy(&ix, &x, 4);
+#endif
+    if (ix == 0x3f800000u) return 0.0f;
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {   // x < 2^-126, inf or nan
+        if (ix * 2 == 0) return -INFINITY;
+        if (ix == 0x7f800000u) return x;
+        if ((ix & 0x80000000u) || ix * 2 >= 0xff000000u) return NAN;
+        const float xs = x * 0x1p23f;                       // subnormal: normalise (exact)
+#if defined(__CUDA_ARCH__)
+        ix = __float_as_uint(xs);
+#else
+        memcpy(&ix, &xs, 4);
+#endif
+        ix -= 23u << 23;
+    }
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (int)((tmp >> 19) & 15u);
+    const int k = (int32_t)tmp >> 23;
+    const uint32_t iz = ix - (tmp & (0x1ffu << 23));
+    float zf;
+#if defined(__CUDA_ARCH__)
+    zf = __uint_as_float(iz);
+#else
+    memcpy(&zf, &iz, 4);
+#endif
+    const double z = (double)zf;
+    const double r = dadd(dmul(z, T[i][0]), -1.0);
+    const double y0 = dadd(T[i][1], dmul((double)k, Ln2));
+    const double r2 = dmul(r, r);
+    double y = dadd(dmul(A1, r), A2);
+    y = dadd(dmul(A0, r2), y);
+    y = dadd(dmul(y, r2), dadd(y0, r));
+    return (float)y;
+}
+
 
 // glibc 2.39 sinf/cosf for x in [0, 2*pi] (sysdeps/ieee754/flt-32/s_sincosf.h algorithm: double
 // range reduction by pi/2 and degree-7/8 double polynomials).  Validated exhaustively against the

@@ -6,6 +6,8 @@
 //       /root/reference/src/ORBmatcher.cc:1950-2184   (TrackWithMotionModel, Tracking.cc:3389)
 //   * SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>&)
 //       /root/reference/src/ORBmatcher.cc:259-493     (TrackReferenceKeyFrame, Tracking.cc:3183)
+//   * the projection searches into a KeyFrame (mode 3): Fuse x2 (:1325-1687), SearchByProjection(KF, Scw, ...) x2
+//       (:495-732), SearchByProjection(CurrentFrame, KeyFrame, sAlreadyFound, th, ORBdist) (:2196-2330)
 // with Frame::GetFeaturesInArea / PosInGrid (src/Frame.cc:859-951, 962-978) folded in.
 //
 // The reference is greedy: a feature claimed by query i is skipped by every later query.  Here the
@@ -70,6 +72,15 @@ struct ProjParams {
     const int* direction;     // mode 1: [n_frames] 0 none, 1 forward, 2 backward
     float th, nnratio, thFar;
     int bFar, checkOri;
+    // mode 3 (projection into a keyframe): a0 = world pos, f0 = query angle (variant 3), Tcw per target
+    int variant;              // 0 Fuse(pose), 1 Fuse(Scw), 2 SearchByProjection(KF, Scw), 3 SearchByProjection(F, KF, set)
+    const float* Ow;          // [n_frames][3]
+    const float* normal;      // [nq][3] MapPoint::GetNormal (variants 0-2)
+    const float* maxD;        // GetMaxDistanceInvariance
+    const float* minD;
+    float logScale, thr;
+    int nLevels;
+    float invSigma2[ORB_MAX_LEVELS];
     // per-frame feature grid (Frame::mGrid as CSR), built by k_frame_grid for modes 0 / 1
     uint16_t* gridOrder;       // [n_frames][maxFeat] feature ids sorted by (cell, id)
     uint16_t* gridStart;       // [n_frames][GRID_COLS * GRID_ROWS + 1]
@@ -159,12 +170,24 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
     return v;
 }
 
+// Fuse's reprojection gate (ORBmatcher.cc:1465-1500): stereo keypoints 3-dof chi2 > 7.8, monocular 2-dof > 5.99
+__device__ __forceinline__ bool fuse_chi2_ok(const ProjParams& P, float u, float v, float ur_pred, float kx, float ky, float kur, int oc) {
+    const float ex = fsub(u, kx), ey = fsub(v, ky);
+    if (kur >= 0) {
+        const float er = fsub(ur_pred, kur);
+        const float e2 = fadd(fadd(fmul(ex, ex), fmul(ey, ey)), fmul(er, er));
+        return !((double)fmul(e2, P.invSigma2[oc]) > 7.8);
+    }
+    const float e2 = fadd(fmul(ex, ex), fmul(ey, ey));
+    return !((double)fmul(e2, P.invSigma2[oc]) > 5.99);
+}
+
 // Warp scan of one query: K smallest (dist << 32 | cell << 16 | id) keys among the features that pass
 // the window, the optional claim mask and the stereo gate.  Returns the number of such features.
 // stereo gate: |ur_pred - mvuRight[i]| > er_max rejects (only when mvuRight[i] > 0).
 __device__ __forceinline__ int warp_scan_query(const ProjParams& P, const FrameFeat& F, int N, int row0, const Window& w,
                                                const uint8_t* qd, float ur_pred, float er_max, const uint8_t* claimed,
-                                               unsigned long long out[PM_K]) {
+                                               unsigned long long out[PM_K], int gate = 0) {
     const int lane = threadIdx.x & 31;
     unsigned long long loc[PM_K];
 #pragma unroll
@@ -177,9 +200,13 @@ __device__ __forceinline__ int warp_scan_query(const ProjParams& P, const FrameF
             if (!in_window(F, w, i)) continue;
             if (claimed && claimed[i]) continue;
             const float ur = F.ur[i];
-            if (ur > 0) {
-                const float er = fabsf(fsub(ur_pred, ur));
-                if (er > er_max) continue;
+            if (gate == 0) {
+                if (ur > 0) {
+                    const float er = fabsf(fsub(ur_pred, ur));
+                    if (er > er_max) continue;
+                }
+            } else if (gate == 2) {
+                if (!fuse_chi2_ok(P, w.x, w.y, ur_pred, F.x[i], F.y[i], ur, F.oct[i])) continue;
             }
             ++count;
             const uint32_t d = hamming256(a0, a1, P.desc + (size_t)(row0 + i) * 32);
@@ -234,6 +261,47 @@ __device__ __forceinline__ bool last_frame_window(const ProjParams& P, int frame
     if (dir == 1) w = make_window(P, u, v, radius, oct, -1);
     else if (dir == 2) w = make_window(P, u, v, radius, 0, oct);
     else w = make_window(P, u, v, radius, oct - 1, oct + 1);
+    return true;
+}
+
+// mode 3 per-query geometry: projection of a map point into a keyframe from a pose, frustum / distance / viewing
+// angle gates and MapPoint::PredictScale (MapPoint.cc:688-721, logf).  Vector3f norm and dot in Eigen's unrolled
+// order x + (y + z).  ur_pred = u - bf / z (Fuse only).
+__device__ __forceinline__ bool kf_window(const ProjParams& P, int frame, int q, Window& w, float& ur_pred) {
+    const float* T = P.Tcw + 7 * frame;
+    const float* p = P.a0 + 3 * (size_t)q;
+    const float qx = T[0], qy = T[1], qz = T[2], qw = T[3];
+    const float uvx = fsub(fmul(qy, p[2]), fmul(qz, p[1])), uvy = fsub(fmul(qz, p[0]), fmul(qx, p[2])),
+                uvz = fsub(fmul(qx, p[1]), fmul(qy, p[0]));
+    const float ux = fadd(uvx, uvx), uy = fadd(uvy, uvy), uz = fadd(uvz, uvz);
+    const float c0 = fsub(fmul(qy, uz), fmul(qz, uy)), c1 = fsub(fmul(qz, ux), fmul(qx, uz)), c2 = fsub(fmul(qx, uy), fmul(qy, ux));
+    const float xc = fadd(fadd(fadd(p[0], fmul(qw, ux)), c0), T[4]);
+    const float yc = fadd(fadd(fadd(p[1], fmul(qw, uy)), c1), T[5]);
+    const float zc = fadd(fadd(fadd(p[2], fmul(qw, uz)), c2), T[6]);
+    if (P.variant != 3 && zc < 0.0f) return false;
+    const float invz = fdiv(1.0f, zc);
+    const float u = fadd(fdiv(fmul(P.fx, xc), zc), P.cx);
+    const float v = fadd(fdiv(fmul(P.fy, yc), zc), P.cy);
+    if (P.variant == 3) {
+        if (u < P.minX || u > P.maxX) return false;
+        if (v < P.minY || v > P.maxY) return false;
+    } else if (!(u >= P.minX && u < P.maxX && v >= P.minY && v < P.maxY)) return false;
+    ur_pred = fsub(u, fmul(P.bf, invz));
+    const float* O = P.Ow + 3 * frame;
+    const float px = fsub(p[0], O[0]), py = fsub(p[1], O[1]), pz = fsub(p[2], O[2]);
+    const float dist = fsqrt(fadd(fmul(px, px), fadd(fmul(py, py), fmul(pz, pz))));
+    if (dist < P.minD[q] || dist > P.maxD[q]) return false;
+    if (P.variant != 3) {
+        const float* n = P.normal + 3 * (size_t)q;
+        const float d = fadd(fmul(px, n[0]), fadd(fmul(py, n[1]), fmul(pz, n[2])));
+        if ((double)d < 0.5 * (double)dist) return false;
+    }
+    const float ratio = fdiv(P.maxD[q], dist);
+    int lvl = (int)ceilf(fdiv(glibc_logf(ratio), P.logScale));
+    if (lvl < 0) lvl = 0;
+    else if (lvl >= P.nLevels) lvl = P.nLevels - 1;
+    const float radius = fmul(P.th, P.scale[lvl]);
+    w = make_window(P, u, v, radius, lvl - 1, P.variant == 3 ? lvl + 1 : lvl);
     return true;
 }
 
@@ -335,7 +403,7 @@ __device__ __forceinline__ void stage_grid(const ProjParams& P, int frame, unsig
 // reference's candidate order -- so the warp-wide minimum is ONE instruction (REDUX.MIN) instead of a 64-bit
 // shuffle tree; they are widened to the (distance, cell, id) form of the resolve pass when stored.
 __device__ __forceinline__ int warp_scan_query_grid(const ProjParams& P, const GridFeat& F, int row0, const Window& w, const uint8_t* qd,
-                                                    float ur_pred, float er_max, unsigned long long out[PM_K]) {
+                                                    float ur_pred, float er_max, unsigned long long out[PM_K], int gate = 0) {
     const int lane = threadIdx.x & 31;
     uint32_t loc[PM_K];
 #pragma unroll
@@ -356,9 +424,13 @@ __device__ __forceinline__ int warp_scan_query_grid(const ProjParams& P, const G
                 const float dx = fsub(F.x[j], w.x), dy = fsub(F.y[j], w.y);
                 if (!(fabsf(dx) < w.r && fabsf(dy) < w.r)) continue;
                 const float ur = F.ur[j];
-                if (ur > 0) {
-                    const float er = fabsf(fsub(ur_pred, ur));
-                    if (er > er_max) continue;
+                if (gate == 0) {
+                    if (ur > 0) {
+                        const float er = fabsf(fsub(ur_pred, ur));
+                        if (er > er_max) continue;
+                    }
+                } else if (gate == 2) {
+                    if (!fuse_chi2_ok(P, w.x, w.y, ur_pred, F.x[j], F.y[j], ur, oc)) continue;
                 }
                 ++count;
                 const uint32_t d = hamming256(a0, a1, P.desc + (size_t)(row0 + F.id[j]) * 32);
@@ -410,6 +482,7 @@ __global__ void __launch_bounds__(PM_WARPS * 32) k_proj_candidates(const __grid_
         Window w;
         float ur_pred = 0.f, er_max = 0.f, u = 0.f, invzc = 0.f, radius = 0.f;
         bool ok;
+        int gate = 0;
         if (P.mode == 0) {
             ok = local_window(P, q, w, er_max);
             ur_pred = P.a2[q];
@@ -417,6 +490,9 @@ __global__ void __launch_bounds__(PM_WARPS * 32) k_proj_candidates(const __grid_
             ok = last_frame_window(P, frame, q, w, u, invzc, radius);
             ur_pred = fsub(u, fmul(P.bf, invzc));
             er_max = radius;
+        } else if (P.mode == 3) {
+            ok = kf_window(P, frame, q, w, ur_pred);
+            gate = P.variant == 0 ? 2 : 1;
         } else {
             w.node = P.level[q];       // query's vocabulary node
             w.empty = w.node < 0;
@@ -425,8 +501,8 @@ __global__ void __launch_bounds__(PM_WARPS * 32) k_proj_candidates(const __grid_
         }
         unsigned long long top[PM_K];
         int count = 0;
-        if (ok) count = use_grid ? warp_scan_query_grid(P, GF, row0, w, P.qdesc + 32 * (size_t)q, ur_pred, er_max, top)
-                                 : warp_scan_query(P, F, N, row0, w, P.qdesc + 32 * (size_t)q, ur_pred, er_max, nullptr, top);
+        if (ok) count = use_grid ? warp_scan_query_grid(P, GF, row0, w, P.qdesc + 32 * (size_t)q, ur_pred, er_max, top, gate)
+                                 : warp_scan_query(P, F, N, row0, w, P.qdesc + 32 * (size_t)q, ur_pred, er_max, nullptr, top, gate);
         if (lane == 0) {
             P.cnt[q] = ok ? count : -1;
 #pragma unroll
@@ -453,12 +529,12 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
     __shared__ int s_hist[30];
     __shared__ int s_nm;
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        s_claimed[i] = (P.mode == 0 && P.flag) ? P.flag[row0 + i] : 0;
+        s_claimed[i] = ((P.mode == 0 || (P.mode == 3 && P.variant >= 2)) && P.flag) ? P.flag[row0 + i] : 0;
         s_holder[i] = -1;
     }
     if (threadIdx.x < 30) s_hist[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_nm = 0;
-    if (P.mode != 0 && P.checkOri)
+    if (P.mode != 0 && P.checkOri && P.quv)
         for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) P.quv[q] = __int_as_float(-1);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -470,8 +546,9 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
         for (int i = threadIdx.x; i < nchunk * PM_K; i += blockDim.x) s_top[i] = P.topk[(size_t)base * PM_K + i];
         for (int i = threadIdx.x; i < nchunk; i += blockDim.x) {
             s_cnt[i] = P.cnt[base + i];
-            if (P.mode == 0) P.match[base + i] = -1;
-            else { s_qf[i] = P.f0[base + i]; s_qflag[i] = (P.mode == 1) ? P.flag[base + i] : (uint8_t)1; }
+            if (P.mode == 0 || P.mode == 3) P.match[base + i] = -1;
+            if (P.mode == 3) { s_qf[i] = P.f0 ? P.f0[base + i] : 0.f; s_qflag[i] = 1; }
+            else if (P.mode != 0) { s_qf[i] = P.f0[base + i]; s_qflag[i] = (P.mode == 1) ? P.flag[base + i] : (uint8_t)1; }
         }
         __syncthreads();
         if (warp == 0) {
@@ -486,12 +563,13 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
                 const bool is_free = (lane < stored) && !s_claimed[(int)(key & 0xffffu)];
                 const unsigned fm = __ballot_sync(0xffffffffu, is_free);
                 const int live = __popc(fm);
-                const int need = (P.mode == 1) ? 1 : 2;
+                const int need = (P.mode == 1 || P.mode == 3) ? 1 : 2;
                 unsigned long long b1 = ~0ull, b2 = ~0ull;
                 if (live < need && count > PM_K) {
                     // claims consumed the stored list: exact rescan with the mask applied (warp-cooperative)
                     Window w;
                     float ur_pred = 0.f, er_max = 0.f, u = 0.f, invzc = 0.f, radius = 0.f;
+                    int gate = 0;
                     if (P.mode == 0) {
                         local_window(P, q, w, er_max);
                         ur_pred = P.a2[q];
@@ -499,13 +577,16 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
                         last_frame_window(P, frame, q, w, u, invzc, radius);
                         ur_pred = fsub(u, fmul(P.bf, invzc));
                         er_max = radius;
+                    } else if (P.mode == 3) {
+                        kf_window(P, frame, q, w, ur_pred);
+                        gate = P.variant == 0 ? 2 : 1;
                     } else {
                         w.node = P.level[q];
                         w.empty = w.node < 0;
                         er_max = 3.0e38f;
                     }
                     unsigned long long top[PM_K];
-                    warp_scan_query(P, F, N, row0, w, P.qdesc + 32 * (size_t)q, ur_pred, er_max, s_claimed, top);
+                    warp_scan_query(P, F, N, row0, w, P.qdesc + 32 * (size_t)q, ur_pred, er_max, s_claimed, top, gate);
                     b1 = top[0];
                     b2 = top[1];
                 } else {
@@ -532,6 +613,23 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
                             ++nmatches;
                             __syncwarp();
                         }
+                    }
+                } else if (P.mode == 3) {
+                    if ((float)bestDist <= P.thr) {
+                        if (lane == 0) {
+                            P.match[q] = bestIdx;
+                            if (P.variant >= 2) s_claimed[bestIdx] = 1;
+                            if (P.variant == 3 && P.checkOri) {
+                                float rot = fsub(s_qf[qi], F.ang[bestIdx]);
+                                if (rot < 0.0f) rot = fadd(rot, 360.0f);
+                                int bin = (int)roundf(fmul(rot, 1.0f / 30));
+                                if (bin == 30) bin = 0;
+                                s_hist[bin] += 1;
+                                P.quv[q] = __int_as_float((bin << 16) | bestIdx);
+                            }
+                        }
+                        ++nmatches;
+                        __syncwarp();
                     }
                 } else {
                     bool accept = bestDist <= 100;
@@ -560,7 +658,7 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
         }
         __syncthreads();
     }
-    if (P.mode == 0) {
+    if (P.mode == 0 || (P.mode == 3 && !(P.variant == 3 && P.checkOri))) {
         if (threadIdx.x == 0) P.nmatches[frame] = nmatches;
         return;
     }
@@ -588,14 +686,16 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
             if (e < 0) continue;
             const int bin = e >> 16, idx = e & 0xffff;
             if (!s_keep[bin]) {
-                s_holder[idx] = -1;   // every entry of a rejected bin clears its feature (duplicates included)
+                if (P.mode == 3) P.match[q] = -1;
+                else s_holder[idx] = -1;   // every entry of a rejected bin clears its feature (duplicates included)
                 ++removed;
             }
         }
         if (removed) atomicSub(&s_nm, removed);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < N; i += blockDim.x) P.match[row0 + i] = s_holder[i];
+    if (P.mode != 3)
+        for (int i = threadIdx.x; i < N; i += blockDim.x) P.match[row0 + i] = s_holder[i];
     if (threadIdx.x == 0) P.nmatches[frame] = s_nm;
 }
 
@@ -632,7 +732,7 @@ static orb_status launch_proj(orbx_handle* h, ProjParams& P, int n_frames, int m
     const size_t fsm = ((size_t)P.maxFeat * 23 + 16 + 15) / 16 * 16;
     const size_t gsm = ((size_t)P.maxFeat * 17 + (PM_NCELL + 1) * 2 + 32 + 15) / 16 * 16;
     const size_t csm = std::max(fsm, gsm);
-    if (P.mode != 2) {
+    if (P.mode != 2) {   // modes 0, 1, 3 search a window of the feature grid
         int npow = 2;
         while (npow < P.maxFeat) npow <<= 1;
         ORB_CUDA(cudaFuncSetAttribute(k_frame_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(npow * 4, 1024)));
@@ -855,5 +955,98 @@ extern "C" orb_status orbm_search_bow(orbx_handle* h, const orbm_bow_queries* Q,
         if (nmatches_out) ORB_CUDA(cudaMemcpyAsync(nmatches_out, P.nmatches, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->stream));
         ORB_CUDA(cudaStreamSynchronize(h->stream));
     }
+    return ORB_OK;
+}
+
+extern "C" orb_status orbm_search_keyframe(orbx_handle* h, const orbm_camera* cam, const orbm_kf_queries* Q, int32_t variant,
+                                           float th, float hamming_max, int32_t check_orientation, int32_t* match_out,
+                                           int32_t* nmatches_out) {
+    if (!h || !cam || !Q || !match_out || Q->n_targets < 1 || !Q->query_offset || !Q->Tcw || !Q->Ow || variant < 0 || variant > 3)
+        return set_error(ORB_ERR_INVALID, "bad arguments");
+    if (Q->kp ? (!Q->feat_offset || !Q->desc) : !Q->target_image) return set_error(ORB_ERR_INVALID, "bad target description");
+    ORB_CUDA(cudaSetDevice(h->cfg.device));
+    const int nt = Q->n_targets;
+    const int nq = Q->query_offset[nt];
+    if (nq > 0 && (!Q->world_pos || !Q->max_dist || !Q->min_dist || !Q->desc_q || (variant != 3 && !Q->normal) ||
+                   (variant == 3 && check_orientation && !Q->angle)))
+        return set_error(ORB_ERR_INVALID, "missing query arrays");
+    int maxq = 0;
+    for (int t = 0; t < nt; ++t) {
+        if (Q->query_offset[t + 1] < Q->query_offset[t]) return set_error(ORB_ERR_INVALID, "bad query table");
+        maxq = std::max(maxq, Q->query_offset[t + 1] - Q->query_offset[t]);
+    }
+    ProjParams P{};
+    size_t rows = 0;
+    int maxFeat = 1;
+    std::vector<int> img(nt), nkp(nt);
+    orb_status s;
+    if (Q->kp) {
+        for (int t = 0; t < nt; ++t) {
+            const int n = Q->feat_offset[t + 1] - Q->feat_offset[t];
+            if (n < 0 || n > 5400) return set_error(ORB_ERR_UNSUPPORTED, "keyframe with more than 5400 features");
+            img[t] = t;
+            nkp[t] = n;
+            maxFeat = std::max(maxFeat, n);
+        }
+        rows = (size_t)Q->feat_offset[nt];
+    } else {
+        if ((s = orbx_counts(h, nullptr, nullptr, nullptr)) != ORB_OK) return s;
+        rows = (size_t)h->h_counts[2 * h->cfg.max_batch + h->last_batch];
+        for (int t = 0; t < nt; ++t) {
+            img[t] = Q->target_image[t];
+            if (img[t] < 0 || img[t] >= h->last_batch) return set_error(ORB_ERR_INVALID, "bad target image");
+        }
+        maxFeat = h->geom.kpTotal;
+    }
+    const size_t need = (size_t)nq * (PM_K * 8 + 4 + 4 + 12 + 12 + 8 + 32 + 4 + 4 + 64) + rows * (sizeof(orbx_keypoint) + 32 + 4 + 1) +
+                        (size_t)nt * (128 + 2 * (size_t)maxFeat + 2 * 3073 + 512) + 65536;
+    if ((s = ensure_stage(h, need)) != ORB_OK) return s;
+    StageCursor cur{h->d_stage};
+    fill_frame_side(h, cam, P);
+    P.mode = 3;
+    P.variant = variant;
+    int *d_img, *d_qoff;
+    if ((s = upload(h, d_img, (const int*)img.data(), nt, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, d_qoff, (const int*)Q->query_offset, nt + 1, cur, false)) != ORB_OK) return s;
+    P.frame_image = d_img; P.qoff = d_qoff;
+    uint8_t* fl = nullptr;
+    if (Q->kp) {
+        orbx_keypoint* kp; uint8_t* de; float* ur; int *off, *nk;
+        if ((s = upload(h, kp, Q->kp, rows, cur, false)) != ORB_OK) return s;
+        if ((s = upload(h, de, Q->desc, rows * 32, cur, false)) != ORB_OK) return s;
+        if ((s = upload(h, ur, Q->uright, rows, cur, false)) != ORB_OK) return s;
+        if ((s = upload(h, off, (const int*)Q->feat_offset, nt, cur, false)) != ORB_OK) return s;
+        if ((s = upload(h, nk, (const int*)nkp.data(), nt, cur, false)) != ORB_OK) return s;
+        P.kps = kp; P.desc = de; P.uright = ur; P.offsets = off; P.nkp = nk; P.maxFeat = maxFeat;
+    }
+    if ((s = upload(h, fl, Q->feat_claimed, rows, cur, false)) != ORB_OK) return s;
+    float *tcw, *ow, *xw, *nr, *mx, *mn, *ang; uint8_t* qd;
+    if ((s = upload(h, tcw, Q->Tcw, (size_t)nt * 7, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, ow, Q->Ow, (size_t)nt * 3, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, xw, Q->world_pos, (size_t)nq * 3, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, nr, Q->normal, (size_t)nq * 3, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, mx, Q->max_dist, nq, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, mn, Q->min_dist, nq, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, ang, Q->angle, nq, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, qd, Q->desc_q, (size_t)nq * 32, cur, false)) != ORB_OK) return s;
+    P.Tcw = tcw; P.Ow = ow; P.a0 = xw; P.normal = nr; P.maxD = mx; P.minD = mn; P.f0 = ang; P.qdesc = qd; P.flag = fl;
+    P.th = th; P.thr = hamming_max; P.checkOri = (variant == 3) ? check_orientation : 0;
+    P.nLevels = h->cfg.n_levels;
+    P.logScale = logf((float)h->cfg.scale_factor);                       // Frame.cc:121 mfLogScaleFactor = log(mfScaleFactor)
+    for (int l = 0; l < ORB_MAX_LEVELS; ++l) P.invSigma2[l] = l < h->cfg.n_levels ? h->inv_sigma2[l] : 1.f;
+    P.gridOrder = cur.take<uint16_t>((size_t)nt * P.maxFeat);
+    P.gridStart = cur.take<uint16_t>((size_t)nt * (GRID_COLS * GRID_ROWS + 1));
+    P.topk = cur.take<unsigned long long>((size_t)std::max(nq, 1) * PM_K);
+    P.cnt = cur.take<int>(std::max(nq, 1));
+    P.quv = cur.take<float>(std::max(nq, 1));
+    P.match = cur.take<int>(std::max(nq, 1));
+    P.nmatches = cur.take<int>(nt);
+    if (nq > 0) {
+        if ((s = launch_proj(h, P, nt, maxq)) != ORB_OK) return s;
+        ORB_CUDA(cudaMemcpyAsync(match_out, P.match, sizeof(int) * (size_t)nq, cudaMemcpyDeviceToHost, h->stream));
+        if (nmatches_out) ORB_CUDA(cudaMemcpyAsync(nmatches_out, P.nmatches, sizeof(int) * nt, cudaMemcpyDeviceToHost, h->stream));
+    }
+    ORB_CUDA(cudaStreamSynchronize(h->stream));   // also keeps the host vectors alive until the uploads are done
+    if (nmatches_out && nq == 0) std::fill(nmatches_out, nmatches_out + nt, 0);
     return ORB_OK;
 }

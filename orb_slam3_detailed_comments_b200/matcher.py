@@ -103,6 +103,69 @@ class ORBmatcher:
         N.check(self._L.orbm_search_triangulation(extractor._h, C.byref(t), N.ptr(m), C.byref(nm)))
         return m[:len(kp1)], nm.value
 
+    # ---- projection searches into keyframes (map state in host memory) --------------------------------------------
+    FUSE_POSE, FUSE_SIM3, PROJ_SIM3, PROJ_RELOC = 0, 1, 2, 3
+
+    def _search_keyframe(self, extractor, cam, variant, targets, queries, th, hamming_max, target_images=None):
+        """targets: list of dicts(kp, desc, uright|None, claimed|None, Tcw[7], Ow[3]) -- or, with target_images, dicts
+        (claimed|None, Tcw, Ow) for images of the extractor's last batch; queries: list (one per target) of dicts
+        (world_pos, normal|None, max_dist, min_dist, desc, angle|None).  Returns ([match per target], [nmatches])."""
+        nt = len(targets)
+        qoff = np.zeros(nt + 1, np.int32)
+        qoff[1:] = np.cumsum([len(q["world_pos"]) for q in queries])
+        cat = lambda key, dt, width: (np.ascontiguousarray(np.concatenate([np.asarray(q[key], dt).reshape(-1, width) for q in queries]))
+                                      if all(q.get(key) is not None for q in queries) else None)
+        xw, nr = cat("world_pos", np.float32, 3), cat("normal", np.float32, 3)
+        mx, mn, ang = cat("max_dist", np.float32, 1), cat("min_dist", np.float32, 1), cat("angle", np.float32, 1)
+        qd = cat("desc", np.uint8, 32)
+        tcw = np.ascontiguousarray(np.stack([np.asarray(t["Tcw"], np.float32) for t in targets]))
+        ow = np.ascontiguousarray(np.stack([np.asarray(t["Ow"], np.float32) for t in targets]))
+        keep = [qoff, xw, nr, mx, mn, ang, qd, tcw, ow]
+        if target_images is None:
+            foff = np.zeros(nt + 1, np.int32)
+            foff[1:] = np.cumsum([len(t["kp"]) for t in targets])
+            kp = np.ascontiguousarray(np.concatenate([t["kp"] for t in targets]))
+            de = np.ascontiguousarray(np.concatenate([np.asarray(t["desc"], np.uint8).reshape(-1, 32) for t in targets]))
+            ur = (np.ascontiguousarray(np.concatenate([np.asarray(t["uright"], np.float32) for t in targets]))
+                  if all(t.get("uright") is not None for t in targets) else None)
+            cl = (np.ascontiguousarray(np.concatenate([np.asarray(t["claimed"], np.uint8) for t in targets]))
+                  if all(t.get("claimed") is not None for t in targets) else None)
+            timg = None
+        else:
+            foff = kp = de = ur = None
+            timg = _i32(target_images)
+            cl = targets[0].get("claimed_rows")
+            cl = None if cl is None else _u8(cl)
+        keep += [foff, kp, de, ur, cl, timg]
+        P = lambda a: None if a is None else N.ptr(a)
+        q = N.orbm_kf_queries(nt, P(timg), P(foff), P(kp), P(de), P(ur), P(cl), P(tcw), P(ow), P(qoff), P(xw), P(nr), P(mx), P(mn),
+                              P(qd), P(ang))
+        nq = int(qoff[-1])
+        m = np.full(max(nq, 1), -1, np.int32)
+        nm = np.zeros(nt, np.int32)
+        N.check(self._L.orbm_search_keyframe(extractor._h, C.byref(cam), C.byref(q), int(variant), float(th), float(hamming_max),
+                                             1 if self.mbCheckOrientation else 0, N.ptr(m), N.ptr(nm)))
+        return [m[qoff[t]:qoff[t + 1]] for t in range(nt)], nm
+
+    def Fuse(self, extractor, cam, targets, queries, th=3.0):
+        """Fuse(pKF, vpMapPoints, th, bRight=false) (ORBmatcher.cc:1325-1544) for several keyframes at once: the search
+        part; the caller applies Replace / AddObservation in query order from bestIdx."""
+        return self._search_keyframe(extractor, cam, self.FUSE_POSE, targets, queries, th, 50.0)
+
+    def FuseSim3(self, extractor, cam, targets, queries, th):
+        """Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (ORBmatcher.cc:1546-1687)."""
+        return self._search_keyframe(extractor, cam, self.FUSE_SIM3, targets, queries, th, 50.0)
+
+    def SearchByProjectionSim3(self, extractor, cam, targets, queries, th, ratioHamming=1.0):
+        """SearchByProjection(pKF, Scw, vpPoints, [vpPointsKFs,] vpMatched, [vpMatchedKF,] th, ratioHamming)
+        (ORBmatcher.cc:495-732)."""
+        return self._search_keyframe(extractor, cam, self.PROJ_SIM3, targets, queries, th, float(np.float32(50) * np.float32(ratioHamming)))
+
+    def SearchByProjectionReloc(self, extractor, cam, targets, queries, th, ORBdist, target_images=None):
+        """SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:2196-2330); the frame is given
+        as host arrays or (target_images) as an image of the extractor's last batch."""
+        return self._search_keyframe(extractor, cam, self.PROJ_RELOC, targets, queries, th, float(ORBdist), target_images)
+
     # ---- device-resident forms (CUDA torch tensors; see the class docstring) -----------------------
     def SearchByProjectionDevice(self, extractor, cam, n_frames, frame_image, query_offset, proj_x, proj_y, proj_xr, level,
                                  view_cos, desc, out_match, out_nmatches, th=1.0, feature_claimed=None):

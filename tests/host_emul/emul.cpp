@@ -52,6 +52,26 @@ long emul_sincos_mismatch(uint32_t lo_bits, uint32_t hi_bits, int nthreads) {
 
 void emul_sincos(float a, float* s, float* c) { glibc_sincosf(a, s, c); }
 
+// number of floats in [lo_bits, hi_bits] (stride `step`) whose emulated logf differs from glibc's
+long emul_logf_mismatch(uint32_t lo_bits, uint32_t hi_bits, uint32_t step, int nthreads) {
+    std::atomic<long> bad(0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t)
+        th.emplace_back([&, t] {
+            long b = 0;
+            for (uint64_t i = (uint64_t)lo_bits + (uint64_t)t * step; i <= hi_bits; i += (uint64_t)nthreads * step) {
+                uint32_t u = (uint32_t)i;
+                float f;
+                memcpy(&f, &u, 4);
+                const float a = glibc_logf(f), r = logf(f);
+                if (memcmp(&a, &r, 4)) ++b;
+            }
+            bad += b;
+        });
+    for (auto& x : th) x.join();
+    return bad.load();
+}
+
 // sorts (key,val) with the transcribed introsort; caller compares against std::sort
 void emul_std_sort(uint32_t* keys, uint32_t* vals, int n) {
     std::vector<SortItem> v(n);

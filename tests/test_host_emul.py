@@ -29,6 +29,8 @@ def emul():
     L.emul_atan2.argtypes = [C.c_float, C.c_float]
     L.emul_sincos_mismatch.restype = C.c_long
     L.emul_sincos_mismatch.argtypes = [C.c_uint32, C.c_uint32, C.c_int]
+    L.emul_logf_mismatch.restype = C.c_long
+    L.emul_logf_mismatch.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
     for f in ("emul_std_sort", "emul_heap_sort", "ref_std_sort", "ref_heap_sort"):
         getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.emul_path_key.restype = C.c_uint32
@@ -87,6 +89,14 @@ def test_sincos_sampled_matches_glibc(emul):
     for a in range(lo, hi, step):
         bad += emul.emul_sincos_mismatch(a, min(a + step // 97, hi), 4)
     assert bad == 0
+
+
+def test_logf_matches_glibc(emul):
+    """MapPoint::PredictScale's logf: every float of [2^-6, 2^10] (the range of mfMaxDistance / dist) and a
+    stride-211 sweep of all positive floats incl. subnormals, inf."""
+    lo, hi = int(np.float32(2.0 ** -6).view(np.uint32)), int(np.float32(2.0 ** 10).view(np.uint32))
+    assert emul.emul_logf_mismatch(lo, hi, 1, os.cpu_count() or 4) == 0
+    assert emul.emul_logf_mismatch(1, 0x7f800000, 211, os.cpu_count() or 4) == 0
 
 
 @pytest.mark.slow

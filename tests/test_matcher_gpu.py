@@ -238,3 +238,88 @@ def test_search_local_points_one_map_point_per_feature(scene):
                                       vc[s], qd[s], 3.0, 0.8)
         assert rnm == nm[p] and (match[s] == rmatch).all(), (p, rnm, nm[p])
         assert rnm > 0.9 * (b - a)
+
+
+# ---- projection searches into keyframes: Fuse x2, SearchByProjection(KF, Scw), SearchByProjection(F, KF, set) -------------------
+def _camera_center(T):
+    q, t = T[:4].astype(np.float64), T[4:].astype(np.float64)
+    x, y, z, w = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    return (-R.T @ t).astype(np.float32)
+
+
+def _kf_queries(scene, p, rng, sf, dup):
+    """Map points seen by the 'last' frame of pair p, expressed in that frame (= world), with the MapPoint fields the
+    searches read: normal, scale-invariance distances (MapPoint::UpdateNormalAndDepth, MapPoint.cc:600-660), descriptor."""
+    kL, dL, luR, ldep = scene["lasts"][p]
+    sel = np.nonzero(ldep > 0)[0]
+    sel = np.concatenate([sel, rng.choice(sel, int(dup * len(sel)))])   # competing map points: greedy claims
+    pts = unproject(kL[sel], ldep[sel]) + rng.normal(0, 0.002, (len(sel), 3)).astype(np.float32)
+    dist = np.linalg.norm(pts, axis=1).astype(np.float32)
+    nrm = pts / dist[:, None] + rng.normal(0, 0.2, pts.shape).astype(np.float32)
+    nrm = (nrm / np.linalg.norm(nrm, axis=1)[:, None]).astype(np.float32)
+    nrm[rng.random(len(sel)) < 0.05] *= -1                               # a few points seen from behind: viewing-angle gate
+    maxd = (dist * sf[kL["octave"][sel]]).astype(np.float32)
+    mind = (maxd / sf[7]).astype(np.float32)
+    return dict(world_pos=pts, normal=nrm, max_dist=np.float32(1.2) * maxd, min_dist=np.float32(0.8) * mind, desc=dL[sel],
+                angle=kL["angle"][sel].astype(np.float32))
+
+
+@pytest.mark.parametrize("variant,th,thr", [(0, 3.0, 50.0), (0, 8.0, 50.0), (1, 4.0, 50.0), (2, 6.0, 50.0), (2, 10.0, 37.5), (3, 10.0, 100.0),
+                                            (3, 3.0, 64.0)])
+def test_search_keyframe_matches_oracle(scene, variant, th, thr):
+    P, ex, off = scene["P"], scene["ex"], scene["off"]
+    rng = np.random.default_rng(100 + variant)
+    sf = ex.GetScaleFactors()
+    isg = ex.GetInverseScaleSigmaSquares()
+    logsf = po.logf(1.2)
+    cam = camera(FX, FY, CX, CY, BF, B, W, H)
+    targets, queries = [], []
+    for p in range(P):
+        a, b = off[2 * p], off[2 * p + 1]
+        zmid = float(np.median(scene["lasts"][p][3][scene["lasts"][p][3] > 0]))
+        T = quat_pose(0.05 * p, [(3 + p) * zmid / FX, 1 * zmid / FY, 0.0])
+        cl = (rng.random(b - a) < 0.2).astype(np.uint8) if variant >= 2 else None
+        targets.append(dict(kp=scene["kps"][a:b], desc=scene["desc"][a:b], uright=scene["uR"][a:b], claimed=cl, Tcw=T,
+                            Ow=_camera_center(T)))
+        queries.append(_kf_queries(scene, p, rng, sf, dup=1.0 if variant >= 2 else 0.3))
+    m = ORBmatcher(0.9, True)
+    got, nm = m._search_keyframe(ex, cam, variant, targets, queries, th, thr)
+    total = 0
+    for p in range(P):
+        t, q = targets[p], queries[p]
+        rm, rnm, _ = po.search_keyframe(variant, t["kp"], t["desc"], t["uright"], BOUNDS, sf, isg, logsf, CAM6, t["Tcw"], t["Ow"],
+                                        q["world_pos"], q["normal"], q["max_dist"], q["min_dist"], q["desc"], q["angle"], t["claimed"],
+                                        th, thr)
+        assert rnm == nm[p], (variant, p, rnm, nm[p])
+        assert (got[p] == rm).all(), (variant, p, int((got[p] != rm).sum()))
+        total += rnm
+    assert total > 100, total
+
+
+def test_search_keyframe_reloc_on_device_frame(scene):
+    """SearchByProjection(CurrentFrame, pKF, ...) with the frame still on the device (image 2p of the last batch)."""
+    P, ex, off = scene["P"], scene["ex"], scene["off"]
+    rng = np.random.default_rng(5)
+    sf, isg, logsf = ex.GetScaleFactors(), ex.GetInverseScaleSigmaSquares(), po.logf(1.2)
+    cam = camera(FX, FY, CX, CY, BF, B, W, H)
+    claimed_rows = (rng.random(int(off[-1])) < 0.1).astype(np.uint8)
+    targets, queries = [], []
+    for p in range(P):
+        zmid = float(np.median(scene["lasts"][p][3][scene["lasts"][p][3] > 0]))
+        T = quat_pose(0.05 * p, [(3 + p) * zmid / FX, 1 * zmid / FY, 0.0])
+        targets.append(dict(Tcw=T, Ow=_camera_center(T), claimed_rows=claimed_rows))
+        queries.append(_kf_queries(scene, p, rng, sf, dup=0.5))
+    for check in (True, False):
+        m = ORBmatcher(0.9, check)
+        got, nm = m.SearchByProjectionReloc(ex, cam, targets, queries, 10.0, 100, target_images=[2 * p for p in range(P)])
+        for p in range(P):
+            a, b = off[2 * p], off[2 * p + 1]
+            t, q = targets[p], queries[p]
+            rm, rnm, _ = po.search_keyframe(3, scene["kps"][a:b], scene["desc"][a:b], scene["uR"][a:b], BOUNDS, sf, isg, logsf, CAM6,
+                                            t["Tcw"], t["Ow"], q["world_pos"], None, q["max_dist"], q["min_dist"], q["desc"], q["angle"],
+                                            claimed_rows[a:b], 10.0, 100.0, check_ori=check)
+            assert rnm == nm[p] and (got[p] == rm).all(), (check, p, rnm, nm[p])
+            assert rnm > 50
