@@ -224,6 +224,10 @@ orb_status orbm_search_bow(orbx_handle* h, const orbm_bow_queries* q, float nnra
  *   ORBM_KF_PROJ_SIM3   SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) ORBmatcher.cc:495-618 and the
  *                       vpPointsKFs / vpMatchedKF overload :620-732 (same search; the caller records the extra array)
  *   ORBM_KF_PROJ_RELOC  SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist)   ORBmatcher.cc:2196-2330
+ *   ORBM_KF_SIM3_ONEWAY one direction of SearchBySim3(pKF1, pKF2, vpMatches12, S12, th)     ORBmatcher.cc:1689-1948:
+ *                       the map points of keyframe A (good, not already matched) into keyframe B through
+ *                       p_B = S_BA * (T_Aw * p_w); the caller runs both directions (two targets of one call) and keeps
+ *                       the pairs that agree (:1930-1945).  Tcw = T_Aw, Sim3 = S_BA, Ow unused.
  * Several targets per call (LocalMapping::SearchInNeighbors fuses the same points into ~20 keyframes): target t
  * searches features [feat_offset[t], feat_offset[t+1]) with queries [query_offset[t], query_offset[t+1]).
  * Targets are map state in HOST memory (kp != NULL), or -- kp == NULL -- images target_image[t] of the handle's
@@ -235,7 +239,7 @@ orb_status orbm_search_bow(orbx_handle* h, const orbm_bow_queries* q, float nnra
  * mfLogScaleFactor = logf(scaleFactor)) are the handle's.
  * match_out[q] = feature index inside its target (bestIdx) or -1; the caller applies the side effects in query
  * order (Replace / AddObservation / vpReplacePoint / vpMatched[bestIdx] = pMP).  nmatches_out[t] = return value. */
-enum { ORBM_KF_FUSE_POSE = 0, ORBM_KF_FUSE_SIM3 = 1, ORBM_KF_PROJ_SIM3 = 2, ORBM_KF_PROJ_RELOC = 3 };
+enum { ORBM_KF_FUSE_POSE = 0, ORBM_KF_FUSE_SIM3 = 1, ORBM_KF_PROJ_SIM3 = 2, ORBM_KF_PROJ_RELOC = 3, ORBM_KF_SIM3_ONEWAY = 4 };
 typedef struct {
     int32_t n_targets;
     const int32_t* target_image;  /* [n_targets] when kp == NULL, else ignored */
@@ -247,6 +251,8 @@ typedef struct {
                                      (per feature row, host targets: same indexing as kp; device targets: compact rows); NULL = none */
     const float* Tcw;             /* [n_targets][7] */
     const float* Ow;              /* [n_targets][3] */
+    const float* Sim3;            /* SIM3_ONEWAY: [n_targets][8] quaternion x y z w (non-unit, RxSO3), translation, and
+                                     scale = rxso3().quaternion().squaredNorm() as the caller's Eigen evaluates it; else NULL */
     const int32_t* query_offset;  /* [n_targets + 1] */
     const float* world_pos;       /* [nq][3] MapPoint::GetWorldPos */
     const float* normal;          /* [nq][3] MapPoint::GetNormal (unused by PROJ_RELOC, may be NULL there) */
@@ -256,7 +262,7 @@ typedef struct {
     const float* angle;           /* PROJ_RELOC: pKF->mvKeysUn[i].angle of the query's keyframe feature; else NULL */
 } orbm_kf_queries;
 
-/* hamming_max: TH_LOW (50), TH_LOW * ratioHamming, or ORBdist. */
+/* hamming_max: TH_LOW (50), TH_LOW * ratioHamming, ORBdist, or TH_HIGH (100) for SIM3_ONEWAY. */
 orb_status orbm_search_keyframe(orbx_handle* h, const orbm_camera* cam, const orbm_kf_queries* q, int32_t variant,
                                 float th, float hamming_max, int32_t check_orientation, int32_t* match_out,
                                 int32_t* nmatches_out);

@@ -337,6 +337,10 @@ extern "C" int orc_search_triangulation(int nq, const KeyPoint* kp1, const uint8
 //   variant 2  SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratio)     src/ORBmatcher.cc:495-618
 //              (and the vpPointsKFs overload :620-732, which only records one more array per match)
 //   variant 3  SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) src/ORBmatcher.cc:2196-2330
+//   variant 4  one direction of SearchBySim3(pKF1, pKF2, vpMatches12, S12, th)  src/ORBmatcher.cc:1689-1948:
+//              p_c = S * (Tcw * p_w) with S = (non-unit quaternion x y z w, translation, scale = quaternion().squaredNorm()
+//              as the caller's Eigen computes it) -- Sophus rxso3.hpp:265-273, sim3.hpp:227-230; queries = the map points
+//              of the other keyframe that are good and not already matched; no claims; TH_HIGH.
 // Queries = the map points that pass the caller-side skips (NULL, isBad, IsInKeyFrame / spAlreadyFound), in order.
 // Tcw7: qx qy qz qw tx ty tz of the SE3f the function builds (for Scw: SE3f(Scw.rotationMatrix(),
 // Scw.translation()/Scw.scale())); Ow = Tcw.inverse().translation() / pKF->GetCameraCenter().
@@ -346,7 +350,8 @@ extern "C" int orc_search_triangulation(int nq, const KeyPoint* kp1, const uint8
 // MapPoint::PredictScale  src/MapPoint.cc:688-721 with std::log(float) == logf.
 extern "C" int orc_search_keyframe(int variant, const KeyPoint* kps, const uint8_t* desc, const float* uright, int N,
                                    const float* bounds4, const float* scaleFactors, const float* invLevelSigma2, int nLevels,
-                                   float logScaleFactor, const float* cam6, const float* Tcw7, const float* Ow, int nq,
+                                   float logScaleFactor, const float* cam6, const float* Tcw7, const float* Ow,
+                                   const float* S8, int nq,
                                    const float* xw, const float* normal, const float* maxDist, const float* minDist,
                                    const uint8_t* qdesc, const float* qangle, uint8_t* claimed, float th, float thr,
                                    int checkOri, int* match) {
@@ -365,18 +370,37 @@ extern "C" int orc_search_keyframe(int variant, const KeyPoint* kps, const uint8
         const float* p3Dw = xw + 3 * q;
         float pc[3];
         se3_act(Tcw7, Tcw7 + 4, p3Dw, pc);
-        if (variant != 3 && pc[2] < 0.0f) continue;
-        const float invz = 1 / pc[2];
-        const float u = fx * pc[0] / pc[2] + cx, v = fy * pc[1] / pc[2] + cy;       // Pinhole::project
+        float u, v, invz;
+        if (variant == 4) {
+            const float* sq = S8;          // x y z w
+            const float* p = pc;
+            const float uvx = sq[1] * p[2] - sq[2] * p[1], uvy = sq[2] * p[0] - sq[0] * p[2], uvz = sq[0] * p[1] - sq[1] * p[0];
+            const float ux = uvx + uvx, uy = uvy + uvy, uz = uvz + uvz;
+            const float c0 = sq[1] * uz - sq[2] * uy, c1 = sq[2] * ux - sq[0] * uz, c2 = sq[0] * uy - sq[1] * ux;
+            const float p2[3] = {(S8[7] * p[0] + (sq[3] * ux + c0)) + S8[4], (S8[7] * p[1] + (sq[3] * uy + c1)) + S8[5],
+                                 (S8[7] * p[2] + (sq[3] * uz + c2)) + S8[6]};
+            pc[0] = p2[0]; pc[1] = p2[1]; pc[2] = p2[2];
+            if (pc[2] < 0.0) continue;
+            invz = (float)(1.0 / pc[2]);
+            const float x = pc[0] * invz, y = pc[1] * invz;
+            u = fx * x + cx;
+            v = fy * y + cy;
+        } else {
+            if (variant != 3 && pc[2] < 0.0f) continue;
+            invz = 1 / pc[2];
+            u = fx * pc[0] / pc[2] + cx;       // Pinhole::project
+            v = fy * pc[1] / pc[2] + cy;
+        }
         if (variant == 3) {
             if (u < F.minX || u > F.maxX) continue;
             if (v < F.minY || v > F.maxY) continue;
         } else if (!(u >= F.minX && u < F.maxX && v >= F.minY && v < F.maxY)) continue;   // KeyFrame::IsInImage
         const float ur = u - bf * invz;
-        const float PO[3] = {p3Dw[0] - Ow[0], p3Dw[1] - Ow[1], p3Dw[2] - Ow[2]};
+        float PO[3] = {p3Dw[0] - Ow[0], p3Dw[1] - Ow[1], p3Dw[2] - Ow[2]};
+        if (variant == 4) { PO[0] = pc[0]; PO[1] = pc[1]; PO[2] = pc[2]; }      // dist3D = p3Dc2.norm()
         const float dist3D = std::sqrt(PO[0] * PO[0] + (PO[1] * PO[1] + PO[2] * PO[2]));
         if (dist3D < minDist[q] || dist3D > maxDist[q]) continue;
-        if (variant != 3) {
+        if (variant < 3) {
             const float* Pn = normal + 3 * q;
             const float d = PO[0] * Pn[0] + (PO[1] * Pn[1] + PO[2] * Pn[2]);
             if (d < 0.5 * dist3D) continue;
@@ -391,7 +415,7 @@ extern "C" int orc_search_keyframe(int variant, const KeyPoint* kps, const uint8
         if (ind.empty()) continue;
         int bestDist = variant == 0 || variant == 2 || variant == 3 ? 256 : 0x7fffffff, bestIdx = -1;
         for (size_t idx : ind) {
-            if (variant >= 2 && claimed[idx]) continue;
+            if ((variant == 2 || variant == 3) && claimed[idx]) continue;
             const int kpLevel = kps[idx].octave;
             if (variant != 3 && (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel)) continue;
             if (variant == 0) {
@@ -413,7 +437,7 @@ extern "C" int orc_search_keyframe(int variant, const KeyPoint* kps, const uint8
         }
         if ((float)bestDist <= thr) {
             match[q] = bestIdx;
-            if (variant >= 2) claimed[bestIdx] = 1;
+            if (variant == 2 || variant == 3) claimed[bestIdx] = 1;
             ++nmatches;
             if (variant == 3 && checkOri) {
                 float rot = qangle[q] - kps[bestIdx].angle;

@@ -305,15 +305,16 @@ def search_triangulation(kp1, desc1, node1, stereo1, kp2, desc2, node2, valid2, 
 
 
 def search_keyframe(variant, kps, desc, uright, bounds, scale_factors, inv_sigma2, log_scale_factor, cam6, Tcw7, Ow, xw, normal,
-                    max_dist, min_dist, qdesc, qangle, claimed, th, thr, check_ori=True):
+                    max_dist, min_dist, qdesc, qangle, claimed, th, thr, check_ori=True, sim3=None):
     """Fuse x2 / SearchByProjection(KF, Scw) / SearchByProjection(F, KF, set) restated (ORBmatcher.cc:1325-1687, 495-732,
     2196-2330).  Returns (match[nq], nmatches, claimed_after)."""
     L = lib()
     L.orc_search_keyframe.restype = C.c_int
     L.orc_search_keyframe.argtypes = [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_float] + \
-        [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 7 + [C.c_float, C.c_float, C.c_int, C.c_void_p]
+        [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 7 + [C.c_float, C.c_float, C.c_int, C.c_void_p]
     f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
     P = lambda a: None if a is None else _p(a)
+    s8 = f32(sim3)
     kps, desc, uright = np.ascontiguousarray(kps), np.ascontiguousarray(desc), f32(uright)
     b4, sf, isg, c6, T7, ow = f32(bounds), f32(scale_factors), f32(inv_sigma2), f32(cam6), f32(Tcw7), f32(Ow)
     xw, nr, mx, mn, ang = f32(xw), f32(normal), f32(max_dist), f32(min_dist), f32(qangle)
@@ -322,7 +323,7 @@ def search_keyframe(variant, kps, desc, uright, bounds, scale_factors, inv_sigma
     nq = len(xw)
     m = np.full(max(nq, 1), -1, np.int32)
     nm = L.orc_search_keyframe(int(variant), _p(kps), _p(desc), P(uright), len(kps), _p(b4), _p(sf), _p(isg), len(sf),
-                               float(log_scale_factor), _p(c6), _p(T7), _p(ow), nq, _p(xw), P(nr), _p(mx), _p(mn), _p(qd), P(ang),
+                               float(log_scale_factor), _p(c6), _p(T7), _p(ow), P(s8), nq, _p(xw), P(nr), _p(mx), _p(mn), _p(qd), P(ang),
                                _p(cl), float(th), float(thr), 1 if check_ori else 0, _p(m))
     return m[:nq], nm, cl[:len(kps)]
 

@@ -69,7 +69,7 @@ class orbm_bow_queries(C.Structure):
 class orbm_kf_queries(C.Structure):
     _fields_ = [("n_targets", C.c_int32)] + [
         (n, C.c_void_p) for n in ("target_image", "feat_offset", "kp", "desc", "uright", "feat_claimed", "Tcw", "Ow",
-                                  "query_offset", "world_pos", "normal", "max_dist", "min_dist", "desc_q", "angle")]
+                                  "Sim3", "query_offset", "world_pos", "normal", "max_dist", "min_dist", "desc_q", "angle")]
 
 
 class orbm_triangulation(C.Structure):

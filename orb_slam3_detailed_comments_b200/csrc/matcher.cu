@@ -73,8 +73,10 @@ struct ProjParams {
     float th, nnratio, thFar;
     int bFar, checkOri;
     // mode 3 (projection into a keyframe): a0 = world pos, f0 = query angle (variant 3), Tcw per target
-    int variant;              // 0 Fuse(pose), 1 Fuse(Scw), 2 SearchByProjection(KF, Scw), 3 SearchByProjection(F, KF, set)
+    int variant;              // 0 Fuse(pose), 1 Fuse(Scw), 2 SearchByProjection(KF, Scw), 3 SearchByProjection(F, KF, set),
+                              // 4 one direction of SearchBySim3
     const float* Ow;          // [n_frames][3]
+    const float* S;           // variant 4: [n_frames][8] Sim3 quaternion (non-unit) x y z w, translation, scale
     const float* normal;      // [nq][3] MapPoint::GetNormal (variants 0-2)
     const float* maxD;        // GetMaxDistanceInvariance
     const float* minD;
@@ -182,57 +184,92 @@ __device__ __forceinline__ bool fuse_chi2_ok(const ProjParams& P, float u, float
     return !((double)fmul(e2, P.invSigma2[oc]) > 5.99);
 }
 
-// Warp scan of one query: K smallest (dist << 32 | cell << 16 | id) keys among the features that pass
-// the window, the optional claim mask and the stereo gate.  Returns the number of such features.
-// stereo gate: |ur_pred - mvuRight[i]| > er_max rejects (only when mvuRight[i] > 0).
+// Candidate test shared by the two scans below: window / vocabulary node, optional claim mask, then the gate --
+// gate 0: stereo window |ur_pred - mvuRight[i]| <= er_max when mvuRight[i] > 0 (modes 0 / 1); gate 1: none;
+// gate 2: Fuse's reprojection chi2.
+__device__ __forceinline__ bool scan_accepts(const ProjParams& P, const FrameFeat& F, const Window& w, int i, float ur_pred,
+                                             float er_max, const uint8_t* claimed, int gate) {
+    if (!in_window(F, w, i)) return false;
+    if (claimed && claimed[i]) return false;
+    const float ur = F.ur[i];
+    if (gate == 0) {
+        if (ur > 0) {
+            const float er = fabsf(fsub(ur_pred, ur));
+            if (er > er_max) return false;
+        }
+    } else if (gate == 2) {
+        if (!fuse_chi2_ok(P, w.x, w.y, ur_pred, F.x[i], F.y[i], ur, F.oct[i])) return false;
+    }
+    return true;
+}
+
+// Bag-of-words scan of one query (mode 2): the candidates are the frame features of the query's vocabulary node in
+// feature order, so (distance << 16 | id) in 32 bits is the reference order and the K smallest come out of K REDUX.MIN.
+// Returns the number of candidates; out[k] = distance << 32 | id.
 __device__ __forceinline__ int warp_scan_query(const ProjParams& P, const FrameFeat& F, int N, int row0, const Window& w,
-                                               const uint8_t* qd, float ur_pred, float er_max, const uint8_t* claimed,
-                                               unsigned long long out[PM_K], int gate = 0) {
+                                               const uint8_t* qd, unsigned long long out[PM_K]) {
     const int lane = threadIdx.x & 31;
-    unsigned long long loc[PM_K];
+    uint32_t loc[PM_K];
 #pragma unroll
-    for (int k = 0; k < PM_K; ++k) loc[k] = ~0ull;
+    for (int k = 0; k < PM_K; ++k) loc[k] = 0xffffffffu;
     int count = 0;
     if (!w.empty) {
         const uint4* q4 = reinterpret_cast<const uint4*>(qd);
         const uint4 a0 = __ldg(q4), a1 = __ldg(q4 + 1);
-        for (int i = lane; i < N; i += 32) {
-            if (!in_window(F, w, i)) continue;
-            if (claimed && claimed[i]) continue;
-            const float ur = F.ur[i];
-            if (gate == 0) {
-                if (ur > 0) {
-                    const float er = fabsf(fsub(ur_pred, ur));
-                    if (er > er_max) continue;
-                }
-            } else if (gate == 2) {
-                if (!fuse_chi2_ok(P, w.x, w.y, ur_pred, F.x[i], F.y[i], ur, F.oct[i])) continue;
-            }
+        for (int base = 0; base < N; base += 32) {
+            const int i = base + lane;
+            if (i >= N || !scan_accepts(P, F, w, i, 0.f, 3.0e38f, nullptr, 1)) continue;
             ++count;
-            const uint32_t d = hamming256(a0, a1, P.desc + (size_t)(row0 + i) * 32);
-            unsigned long long key = ((unsigned long long)d << 32) | ((w.node >= 0 ? 0ull : (unsigned long long)F.cell[i]) << 16) | (unsigned long long)i;
+            uint32_t key = (hamming256(a0, a1, P.desc + (size_t)(row0 + i) * 32) << 16) | (uint32_t)i;
 #pragma unroll
             for (int k = 0; k < PM_K; ++k)   // sorted insert
                 if (key < loc[k]) {
-                    const unsigned long long t = loc[k];
+                    const uint32_t t = loc[k];
                     loc[k] = key;
                     key = t;
                 }
         }
     }
+    count = __reduce_add_sync(0xffffffffu, count);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+    for (int k = 0; k < PM_K; ++k) out[k] = ~0ull;
 #pragma unroll
-    for (int k = 0; k < PM_K; ++k) {   // K-way merge: pop the global minimum K times
-        const unsigned long long m = warp_min_u64(loc[0]);
-        out[k] = m;
-        if (loc[0] == m && m != ~0ull) {   // keys are unique (feature id in the low bits)
+    for (int k = 0; k < PM_K; ++k) {
+        const uint32_t m = __reduce_min_sync(0xffffffffu, loc[0]);
+        if (m == 0xffffffffu) break;   // warp-uniform
+        out[k] = ((unsigned long long)(m >> 16) << 32) | (unsigned long long)(m & 0xffffu);
+        if (loc[0] == m) {             // ids are unique => exactly one owner
 #pragma unroll
-            for (int j = 0; j + 1 < PM_K; ++j) loc[j] = loc[j + 1];
-            loc[PM_K - 1] = ~0ull;
+            for (int q = 0; q + 1 < PM_K; ++q) loc[q] = loc[q + 1];
+            loc[PM_K - 1] = 0xffffffffu;
         }
     }
     return count;
+}
+
+// Exact rescan of one query with the claim mask applied (resolve slow path): only the best and the second best
+// (distance, reference candidate order = cell, id) keys are needed.  Each lane keeps its own two smallest keys; the
+// warp minimum is b1, the minimum of what remains is b2.
+__device__ __forceinline__ void warp_rescan_best2(const ProjParams& P, const FrameFeat& F, int N, int row0, const Window& w,
+                                                  const uint8_t* qd, float ur_pred, float er_max, const uint8_t* claimed, int gate,
+                                                  unsigned long long& b1, unsigned long long& b2) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long l1 = ~0ull, l2 = ~0ull;
+    if (!w.empty) {
+        const uint4* q4 = reinterpret_cast<const uint4*>(qd);
+        const uint4 a0 = __ldg(q4), a1 = __ldg(q4 + 1);
+        for (int base = 0; base < N; base += 32) {
+            const int i = base + lane;
+            if (i >= N || !scan_accepts(P, F, w, i, ur_pred, er_max, claimed, gate)) continue;
+            const unsigned long long d = hamming256(a0, a1, P.desc + (size_t)(row0 + i) * 32);
+            const unsigned long long cell = w.node >= 0 ? 0ull : (unsigned long long)F.cell[i];
+            const unsigned long long key = (d << 32) | (cell << 16) | (unsigned long long)i;
+            if (key < l1) { l2 = l1; l1 = key; }
+            else if (key < l2) l2 = key;
+        }
+    }
+    b1 = warp_min_u64(l1);
+    b2 = warp_min_u64(l1 == b1 ? l2 : l1);   // keys are unique (feature id in the low bits)
 }
 
 // mode 1 per-query geometry (ORBmatcher.cc:1985-2023): returns false when the query is skipped
@@ -277,21 +314,38 @@ __device__ __forceinline__ bool kf_window(const ProjParams& P, int frame, int q,
     const float c0 = fsub(fmul(qy, uz), fmul(qz, uy)), c1 = fsub(fmul(qz, ux), fmul(qx, uz)), c2 = fsub(fmul(qx, uy), fmul(qy, ux));
     const float xc = fadd(fadd(fadd(p[0], fmul(qw, ux)), c0), T[4]);
     const float yc = fadd(fadd(fadd(p[1], fmul(qw, uy)), c1), T[5]);
-    const float zc = fadd(fadd(fadd(p[2], fmul(qw, uz)), c2), T[6]);
-    if (P.variant != 3 && zc < 0.0f) return false;
-    const float invz = fdiv(1.0f, zc);
-    const float u = fadd(fdiv(fmul(P.fx, xc), zc), P.cx);
-    const float v = fadd(fdiv(fmul(P.fy, yc), zc), P.cy);
+    float zc = fadd(fadd(fadd(p[2], fmul(qw, uz)), c2), T[6]);
+    float u, v, invz, px, py, pz;
+    if (P.variant == 4) {
+        // p2 = S * p1 (Sophus rxso3.hpp:265-273, sim3.hpp:227-230): scale p + (w 2(v x p) + v x 2(v x p)) + t
+        const float* S = P.S + 8 * frame;
+        const float sx = S[0], sy = S[1], sz = S[2], sw = S[3], sc = S[7];
+        const float ax = fsub(fmul(sy, zc), fmul(sz, yc)), ay = fsub(fmul(sz, xc), fmul(sx, zc)), az = fsub(fmul(sx, yc), fmul(sy, xc));
+        const float bx = fadd(ax, ax), by = fadd(ay, ay), bz = fadd(az, az);
+        const float d0 = fsub(fmul(sy, bz), fmul(sz, by)), d1 = fsub(fmul(sz, bx), fmul(sx, bz)), d2 = fsub(fmul(sx, by), fmul(sy, bx));
+        px = fadd(fadd(fmul(sc, xc), fadd(fmul(sw, bx), d0)), S[4]);
+        py = fadd(fadd(fmul(sc, yc), fadd(fmul(sw, by), d1)), S[5]);
+        pz = fadd(fadd(fmul(sc, zc), fadd(fmul(sw, bz), d2)), S[6]);
+        if ((double)pz < 0.0) return false;
+        invz = (float)(1.0 / (double)pz);
+        u = fadd(fmul(P.fx, fmul(px, invz)), P.cx);
+        v = fadd(fmul(P.fy, fmul(py, invz)), P.cy);
+    } else {
+        if (P.variant != 3 && zc < 0.0f) return false;
+        invz = fdiv(1.0f, zc);
+        u = fadd(fdiv(fmul(P.fx, xc), zc), P.cx);
+        v = fadd(fdiv(fmul(P.fy, yc), zc), P.cy);
+        const float* O = P.Ow + 3 * frame;
+        px = fsub(p[0], O[0]); py = fsub(p[1], O[1]); pz = fsub(p[2], O[2]);
+    }
     if (P.variant == 3) {
         if (u < P.minX || u > P.maxX) return false;
         if (v < P.minY || v > P.maxY) return false;
     } else if (!(u >= P.minX && u < P.maxX && v >= P.minY && v < P.maxY)) return false;
     ur_pred = fsub(u, fmul(P.bf, invz));
-    const float* O = P.Ow + 3 * frame;
-    const float px = fsub(p[0], O[0]), py = fsub(p[1], O[1]), pz = fsub(p[2], O[2]);
     const float dist = fsqrt(fadd(fmul(px, px), fadd(fmul(py, py), fmul(pz, pz))));
     if (dist < P.minD[q] || dist > P.maxD[q]) return false;
-    if (P.variant != 3) {
+    if (P.variant < 3) {
         const float* n = P.normal + 3 * (size_t)q;
         const float d = fadd(fmul(px, n[0]), fadd(fmul(py, n[1]), fmul(pz, n[2])));
         if ((double)d < 0.5 * (double)dist) return false;
@@ -502,7 +556,7 @@ __global__ void __launch_bounds__(PM_WARPS * 32) k_proj_candidates(const __grid_
         unsigned long long top[PM_K];
         int count = 0;
         if (ok) count = use_grid ? warp_scan_query_grid(P, GF, row0, w, P.qdesc + 32 * (size_t)q, ur_pred, er_max, top, gate)
-                                 : warp_scan_query(P, F, N, row0, w, P.qdesc + 32 * (size_t)q, ur_pred, er_max, nullptr, top, gate);
+                                 : warp_scan_query(P, F, N, row0, w, P.qdesc + 32 * (size_t)q, top);
         if (lane == 0) {
             P.cnt[q] = ok ? count : -1;
 #pragma unroll
@@ -510,6 +564,7 @@ __global__ void __launch_bounds__(PM_WARPS * 32) k_proj_candidates(const __grid_
         }
     }
 }
+
 
 // ---- kernel B: ordered resolve, one CTA per frame, warp 0 walks the queries ------------------------
 #define PM_CHUNK 1024
@@ -529,7 +584,7 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
     __shared__ int s_hist[30];
     __shared__ int s_nm;
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        s_claimed[i] = ((P.mode == 0 || (P.mode == 3 && P.variant >= 2)) && P.flag) ? P.flag[row0 + i] : 0;
+        s_claimed[i] = ((P.mode == 0 || (P.mode == 3 && (P.variant == 2 || P.variant == 3))) && P.flag) ? P.flag[row0 + i] : 0;
         s_holder[i] = -1;
     }
     if (threadIdx.x < 30) s_hist[threadIdx.x] = 0;
@@ -560,7 +615,8 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
                 // (two) still-free ones are the best / second best of the reference's sequential scan
                 const int stored = min(count, PM_K);
                 const unsigned long long key = (lane < stored) ? s_top[qi * PM_K + lane] : ~0ull;
-                const bool is_free = (lane < stored) && !s_claimed[(int)(key & 0xffffu)];
+                const int kidx = (lane < stored) ? (int)(key & 0xffffu) : 0;   // in range even if the load is speculated
+                const bool is_free = (lane < stored) && !s_claimed[kidx];
                 const unsigned fm = __ballot_sync(0xffffffffu, is_free);
                 const int live = __popc(fm);
                 const int need = (P.mode == 1 || P.mode == 3) ? 1 : 2;
@@ -585,10 +641,7 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
                         w.empty = w.node < 0;
                         er_max = 3.0e38f;
                     }
-                    unsigned long long top[PM_K];
-                    warp_scan_query(P, F, N, row0, w, P.qdesc + 32 * (size_t)q, ur_pred, er_max, s_claimed, top, gate);
-                    b1 = top[0];
-                    b2 = top[1];
+                    warp_rescan_best2(P, F, N, row0, w, P.qdesc + 32 * (size_t)q, ur_pred, er_max, s_claimed, gate, b1, b2);
                 } else {
                     if (fm) {
                         const int i1 = __ffs(fm) - 1;
@@ -601,7 +654,8 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
                 const int bestDist = (int)(b1 >> 32), bestIdx = (int)(b1 & 0xffffu);
                 if (P.mode == 0) {
                     const int bestDist2 = (b2 == ~0ull) ? 256 : (int)(b2 >> 32);
-                    const int bestLevel = F.oct[bestIdx], bestLevel2 = (b2 == ~0ull) ? -1 : (int)F.oct[(int)(b2 & 0xffffu)];
+                    const int idx2 = (b2 == ~0ull) ? 0 : (int)(b2 & 0xffffu);   // in range even if the load is speculated
+                    const int bestLevel = F.oct[bestIdx], bestLevel2 = (b2 == ~0ull) ? -1 : (int)F.oct[idx2];
                     if (bestDist <= 100) {   // TH_HIGH
                         const float lim = fmul(P.nnratio, (float)bestDist2);
                         if (bestLevel == bestLevel2 && (float)bestDist > lim) continue;
@@ -618,7 +672,7 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
                     if ((float)bestDist <= P.thr) {
                         if (lane == 0) {
                             P.match[q] = bestIdx;
-                            if (P.variant >= 2) s_claimed[bestIdx] = 1;
+                            if (P.variant == 2 || P.variant == 3) s_claimed[bestIdx] = 1;
                             if (P.variant == 3 && P.checkOri) {
                                 float rot = fsub(s_qf[qi], F.ang[bestIdx]);
                                 if (rot < 0.0f) rot = fadd(rot, 360.0f);
@@ -961,13 +1015,14 @@ extern "C" orb_status orbm_search_bow(orbx_handle* h, const orbm_bow_queries* Q,
 extern "C" orb_status orbm_search_keyframe(orbx_handle* h, const orbm_camera* cam, const orbm_kf_queries* Q, int32_t variant,
                                            float th, float hamming_max, int32_t check_orientation, int32_t* match_out,
                                            int32_t* nmatches_out) {
-    if (!h || !cam || !Q || !match_out || Q->n_targets < 1 || !Q->query_offset || !Q->Tcw || !Q->Ow || variant < 0 || variant > 3)
+    if (!h || !cam || !Q || !match_out || Q->n_targets < 1 || !Q->query_offset || !Q->Tcw || !Q->Ow || variant < 0 || variant > 4 ||
+        (variant == 4 && !Q->Sim3))
         return set_error(ORB_ERR_INVALID, "bad arguments");
     if (Q->kp ? (!Q->feat_offset || !Q->desc) : !Q->target_image) return set_error(ORB_ERR_INVALID, "bad target description");
     ORB_CUDA(cudaSetDevice(h->cfg.device));
     const int nt = Q->n_targets;
     const int nq = Q->query_offset[nt];
-    if (nq > 0 && (!Q->world_pos || !Q->max_dist || !Q->min_dist || !Q->desc_q || (variant != 3 && !Q->normal) ||
+    if (nq > 0 && (!Q->world_pos || !Q->max_dist || !Q->min_dist || !Q->desc_q || (variant < 3 && !Q->normal) ||
                    (variant == 3 && check_orientation && !Q->angle)))
         return set_error(ORB_ERR_INVALID, "missing query arrays");
     int maxq = 0;
@@ -1020,7 +1075,9 @@ extern "C" orb_status orbm_search_keyframe(orbx_handle* h, const orbm_camera* ca
         P.kps = kp; P.desc = de; P.uright = ur; P.offsets = off; P.nkp = nk; P.maxFeat = maxFeat;
     }
     if ((s = upload(h, fl, Q->feat_claimed, rows, cur, false)) != ORB_OK) return s;
-    float *tcw, *ow, *xw, *nr, *mx, *mn, *ang; uint8_t* qd;
+    float *tcw, *ow, *xw, *nr, *mx, *mn, *ang, *s8; uint8_t* qd;
+    if ((s = upload(h, s8, Q->Sim3, (size_t)nt * 8, cur, false)) != ORB_OK) return s;
+    P.S = s8;
     if ((s = upload(h, tcw, Q->Tcw, (size_t)nt * 7, cur, false)) != ORB_OK) return s;
     if ((s = upload(h, ow, Q->Ow, (size_t)nt * 3, cur, false)) != ORB_OK) return s;
     if ((s = upload(h, xw, Q->world_pos, (size_t)nq * 3, cur, false)) != ORB_OK) return s;

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) k_tri_rotation(const __grid_constant__ Tr
     if (P.checkOri) {
         int removed = 0;
         for (int q = threadIdx.x; q < P.nq; q += blockDim.x)
-            if (P.match[q] >= 0 && !s_keep[P.bins[q]]) {
+            if (P.match[q] >= 0 && !s_keep[min(max(P.bins[q], 0), 29)]) {
                 P.match[q] = -1;
                 ++removed;
             }

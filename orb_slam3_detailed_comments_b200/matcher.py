@@ -104,7 +104,7 @@ class ORBmatcher:
         return m[:len(kp1)], nm.value
 
     # ---- projection searches into keyframes (map state in host memory) --------------------------------------------
-    FUSE_POSE, FUSE_SIM3, PROJ_SIM3, PROJ_RELOC = 0, 1, 2, 3
+    FUSE_POSE, FUSE_SIM3, PROJ_SIM3, PROJ_RELOC, SIM3_ONEWAY = 0, 1, 2, 3, 4
 
     def _search_keyframe(self, extractor, cam, variant, targets, queries, th, hamming_max, target_images=None):
         """targets: list of dicts(kp, desc, uright|None, claimed|None, Tcw[7], Ow[3]) -- or, with target_images, dicts
@@ -120,7 +120,9 @@ class ORBmatcher:
         qd = cat("desc", np.uint8, 32)
         tcw = np.ascontiguousarray(np.stack([np.asarray(t["Tcw"], np.float32) for t in targets]))
         ow = np.ascontiguousarray(np.stack([np.asarray(t["Ow"], np.float32) for t in targets]))
-        keep = [qoff, xw, nr, mx, mn, ang, qd, tcw, ow]
+        s8 = (np.ascontiguousarray(np.stack([np.asarray(t["Sim3"], np.float32) for t in targets]))
+              if all(t.get("Sim3") is not None for t in targets) else None)
+        keep = [qoff, xw, nr, mx, mn, ang, qd, tcw, ow, s8]
         if target_images is None:
             foff = np.zeros(nt + 1, np.int32)
             foff[1:] = np.cumsum([len(t["kp"]) for t in targets])
@@ -138,7 +140,7 @@ class ORBmatcher:
             cl = None if cl is None else _u8(cl)
         keep += [foff, kp, de, ur, cl, timg]
         P = lambda a: None if a is None else N.ptr(a)
-        q = N.orbm_kf_queries(nt, P(timg), P(foff), P(kp), P(de), P(ur), P(cl), P(tcw), P(ow), P(qoff), P(xw), P(nr), P(mx), P(mn),
+        q = N.orbm_kf_queries(nt, P(timg), P(foff), P(kp), P(de), P(ur), P(cl), P(tcw), P(ow), P(s8), P(qoff), P(xw), P(nr), P(mx), P(mn),
                               P(qd), P(ang))
         nq = int(qoff[-1])
         m = np.full(max(nq, 1), -1, np.int32)
@@ -160,6 +162,20 @@ class ORBmatcher:
         """SearchByProjection(pKF, Scw, vpPoints, [vpPointsKFs,] vpMatched, [vpMatchedKF,] th, ratioHamming)
         (ORBmatcher.cc:495-732)."""
         return self._search_keyframe(extractor, cam, self.PROJ_SIM3, targets, queries, th, float(np.float32(50) * np.float32(ratioHamming)))
+
+    def SearchBySim3(self, extractor, cam, kf1, kf2, S12, S21, mp1, mp2, th):
+        """SearchBySim3(pKF1, pKF2, vpMatches12, S12, th) (ORBmatcher.cc:1689-1948).  kf1 / kf2: dicts(kp, desc, Tcw[7]);
+        S12 / S21: 8 floats (quaternion x y z w, translation, scale) -- S21 = S12.inverse() from the caller's Sophus;
+        mp1 / mp2: dicts(index: keyframe feature index of every good, not-yet-matched map point, world_pos, max_dist,
+        min_dist, desc).  Returns (vnMatch12 dict {i1: i2} of the mutually consistent pairs, nFound)."""
+        zero = np.zeros(3, np.float32)
+        targets = [dict(kp=kf2["kp"], desc=kf2["desc"], Tcw=kf1["Tcw"], Ow=zero, Sim3=S21),      # KF1's points into KF2
+                   dict(kp=kf1["kp"], desc=kf1["desc"], Tcw=kf2["Tcw"], Ow=zero, Sim3=S12)]      # KF2's points into KF1
+        (m12, m21), _ = self._search_keyframe(extractor, cam, self.SIM3_ONEWAY, targets, [mp1, mp2], th, 100.0)
+        vn1 = {int(i1): int(i2) for i1, i2 in zip(mp1["index"], m12) if i2 >= 0}
+        vn2 = {int(i2): int(i1) for i2, i1 in zip(mp2["index"], m21) if i1 >= 0}
+        found = {i1: i2 for i1, i2 in sorted(vn1.items()) if vn2.get(i2, -1) == i1}
+        return found, len(found)
 
     def SearchByProjectionReloc(self, extractor, cam, targets, queries, th, ORBdist, target_images=None):
         """SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:2196-2330); the frame is given

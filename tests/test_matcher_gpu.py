@@ -323,3 +323,64 @@ def test_search_keyframe_reloc_on_device_frame(scene):
                                             claimed_rows[a:b], 10.0, 100.0, check_ori=check)
             assert rnm == nm[p] and (got[p] == rm).all(), (check, p, rnm, nm[p])
             assert rnm > 50
+
+
+def _quat_to_R(q):
+    x, y, z, w = [float(v) for v in q]
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def _sim3(q_unit, t, s):
+    """8 floats of a Sophus::Sim3f: RxSO3 quaternion (norm^2 = scale), translation, scale = squaredNorm in float32."""
+    q = (np.asarray(q_unit, np.float64) * np.sqrt(s)).astype(np.float32)
+    sc = np.float32(np.float32(q[0] * q[0] + q[1] * q[1]) + np.float32(q[2] * q[2] + q[3] * q[3]))
+    return np.concatenate([q, np.asarray(t, np.float32), [sc]]).astype(np.float32)
+
+
+def test_search_by_sim3_matches_oracle(scene):
+    P, ex, off = scene["P"], scene["ex"], scene["off"]
+    rng = np.random.default_rng(21)
+    sf, isg, logsf = ex.GetScaleFactors(), ex.GetInverseScaleSigmaSquares(), po.logf(1.2)
+    cam = camera(FX, FY, CX, CY, BF, B, W, H)
+    for p in range(P):
+        kL, dL, luR, ldep = scene["lasts"][p]                       # keyframe 1: world frame = its camera frame
+        a, b = off[2 * p], off[2 * p + 1]
+        k2, d2, u2 = scene["kps"][a:b], scene["desc"][a:b], scene["uR"][a:b]
+        dep2 = np.where(u2 > 0, BF / np.maximum(k2["x"] - u2, 1e-3), -1).astype(np.float32)
+        zmid = float(np.median(ldep[ldep > 0]))
+        T1 = np.array([0, 0, 0, 1, 0, 0, 0], np.float32)
+        T2 = quat_pose(0.05 * p, [(3 + p) * zmid / FX, 1 * zmid / FY, 0.0])
+        R2, t2 = _quat_to_R(T2[:4]), T2[4:].astype(np.float64)
+        s = 1.0 + 0.01 * p
+        q12 = np.array([-T2[0], -T2[1], -T2[2], T2[3]], np.float64)  # R12 = R2^T
+        t12 = -(R2.T @ t2) * s
+        S12 = _sim3(q12, t12, s)
+        S21 = _sim3(T2[:4], t2 / s * 1.0, 1.0 / s)                   # p2 = (1/s) R2 (p1 - t12) ~= R2 p1/s + t2/s
+
+        def points(k, d, dep, Tcw, frac):
+            sel = np.nonzero(dep > 0)[0]
+            sel = sel[rng.random(len(sel)) < frac]                    # the rest: no map point / already matched
+            pc = unproject(k[sel], dep[sel]).astype(np.float64)
+            R, t = _quat_to_R(Tcw[:4]), Tcw[4:].astype(np.float64)
+            pw = ((pc - t) @ R).astype(np.float32)
+            dist = np.linalg.norm(pc, axis=1).astype(np.float32)
+            maxd = (dist * sf[k["octave"][sel]]).astype(np.float32)
+            return dict(index=sel, world_pos=pw, max_dist=np.float32(1.2) * maxd, min_dist=np.float32(0.8) * (maxd / sf[7]).astype(np.float32),
+                        desc=d[sel])
+
+        mp1, mp2 = points(kL, dL, ldep, T1, 0.8), points(k2, d2, dep2, T2, 0.8)
+        kf1, kf2 = dict(kp=kL, desc=dL, Tcw=T1), dict(kp=k2, desc=d2, Tcw=T2)
+        m = ORBmatcher(0.9, True)
+        found, nfound = m.SearchBySim3(ex, cam, kf1, kf2, S12, S21, mp1, mp2, 7.5)
+        zero = np.zeros(3, np.float32)
+        r12, _, _ = po.search_keyframe(4, k2, d2, None, BOUNDS, sf, isg, logsf, CAM6, T1, zero, mp1["world_pos"], None, mp1["max_dist"],
+                                       mp1["min_dist"], mp1["desc"], None, None, 7.5, 100.0, sim3=S21)
+        r21, _, _ = po.search_keyframe(4, kL, dL, None, BOUNDS, sf, isg, logsf, CAM6, T2, zero, mp2["world_pos"], None, mp2["max_dist"],
+                                       mp2["min_dist"], mp2["desc"], None, None, 7.5, 100.0, sim3=S12)
+        vn1 = {int(i1): int(i2) for i1, i2 in zip(mp1["index"], r12) if i2 >= 0}
+        vn2 = {int(i2): int(i1) for i2, i1 in zip(mp2["index"], r21) if i1 >= 0}
+        ref = {i1: i2 for i1, i2 in vn1.items() if vn2.get(i2, -1) == i1}
+        assert found == ref and nfound == len(ref)
+        assert len(vn1) > 100 and len(vn2) > 100 and nfound > 20, (len(vn1), len(vn2), nfound)
