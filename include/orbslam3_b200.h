@@ -218,6 +218,47 @@ typedef struct {
 orb_status orbm_search_bow(orbx_handle* h, const orbm_bow_queries* q, float nnratio, int32_t check_orientation,
                            int32_t* feature_match_out, int32_t* nmatches_out);
 
+/* SearchForInitialization(Frame& F1, Frame& F2, vector<cv::Point2f>& vbPrevMatched, vector<int>& vnMatches12, int windowSize)
+ * ORBmatcher.cc:734-890 (monocular initialisation, Tracking.cc:2588).  F1 (the reference frame) is host memory: all its
+ * mvKeysUn / descriptors (features with octave > 0 are skipped by the search itself); F2 is host memory (kp2 != NULL) or
+ * image target_image of the handle's last batch.  prev_matched = vbPrevMatched (x, y per F1 feature).
+ * matches12_out[i1] = F2 feature index or -1 (vnMatches12); the caller refreshes vbPrevMatched from it (:880-884). */
+typedef struct {
+    int32_t n1;
+    const orbx_keypoint* kp1;
+    const uint8_t* desc1;
+    const float* prev_matched;    /* [n1][2] */
+    int32_t n2;                   /* host F2 */
+    const orbx_keypoint* kp2;
+    const uint8_t* desc2;
+    int32_t target_image;         /* device F2 when kp2 == NULL */
+} orbm_init_queries;
+
+orb_status orbm_search_initialization(orbx_handle* h, const orbm_camera* cam, const orbm_init_queries* q, int32_t window_size,
+                                      float nnratio, int32_t check_orientation, int32_t* matches12_out, int32_t* nmatches_out);
+
+/* SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12)  ORBmatcher.cc:892-1043, single-camera
+ * keyframes (loop closing / place recognition).  Both keyframes are map state in host memory; several (pKF1, pKF2) pairs
+ * per call.  Queries = the KF1 features that hold a good map point, in FeatureVector merge order (ascending node,
+ * ascending feature index inside a node); side 2 = all features of KF2 with node2[i] = vocabulary node (-1 = not in
+ * mFeatVec) and valid2[i] = holds a good map point.  match12_out[q] = KF2 feature index (vpMatches12[idx1] =
+ * vpMapPoints2[idx2]) or -1; nmatches_out[pair] = the reference's return value. */
+typedef struct {
+    int32_t n_pairs;
+    const int32_t* feat_offset;   /* [n_pairs + 1] keyframe-2 features of every pair back to back */
+    const orbx_keypoint* kp2;     /* mvKeysUn (angle is read) */
+    const uint8_t* desc2;
+    const int32_t* node2;
+    const uint8_t* valid2;        /* NULL = all */
+    const int32_t* query_offset;  /* [n_pairs + 1] */
+    const int32_t* query_node;
+    const float* query_angle;     /* pKF1->mvKeysUn[idx1].angle */
+    const uint8_t* desc1;
+} orbm_bow_kf_queries;
+
+orb_status orbm_search_bow_keyframes(orbx_handle* h, const orbm_bow_kf_queries* q, float nnratio, int32_t check_orientation,
+                                     int32_t* match12_out, int32_t* nmatches_out);
+
 /* Projection searches into a KeyFrame from a pose (Nleft == -1, pinhole):
  *   ORBM_KF_FUSE_POSE   Fuse(pKF, vpMapPoints, th, bRight=false)                           ORBmatcher.cc:1325-1544
  *   ORBM_KF_FUSE_SIM3   Fuse(pKF, Scw, vpPoints, th, vpReplacePoint)                       ORBmatcher.cc:1546-1687

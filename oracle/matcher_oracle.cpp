@@ -469,3 +469,127 @@ extern "C" int orc_search_keyframe(int variant, const KeyPoint* kps, const uint8
     }
     return nmatches;
 }
+
+// ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12)  src/ORBmatcher.cc:892-1043,
+// single-camera keyframes.  Queries = KF1 features with a good map point in FeatureVector merge order; node2[i] = node of
+// KF2 feature i (-1 none), valid2[i] = holds a good map point.  match12[q] = idx2 or -1.  Returns nmatches.
+extern "C" int orc_search_bow_kf(const KeyPoint* kp2, const uint8_t* desc2, const int* node2, const uint8_t* valid2, int n2, int nq,
+                                 const int* qnode, const float* qangle, const uint8_t* desc1, float nnratio, int checkOri,
+                                 int* match12) {
+    std::vector<char> vbMatched2(n2, 0);
+    std::vector<int> rotHist[30];
+    const float factor = 1.0f / 30;
+    int nmatches = 0;
+    for (int q = 0; q < nq; ++q) {
+        match12[q] = -1;
+        if (qnode[q] < 0) continue;
+        int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+        for (int idx2 = 0; idx2 < n2; ++idx2) {          // f2it->second: ascending feature index inside the node
+            if (node2[idx2] != qnode[q]) continue;
+            if (vbMatched2[idx2] || !(valid2 ? valid2[idx2] : 1)) continue;
+            const int dist = descriptor_distance(desc1 + 32 * (size_t)q, desc2 + 32 * (size_t)idx2);
+            if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist1 < 50) {
+            if ((float)bestDist1 < nnratio * (float)bestDist2) {
+                match12[q] = bestIdx2;
+                vbMatched2[bestIdx2] = 1;
+                if (checkOri) {
+                    float rot = qangle[q] - kp2[bestIdx2].angle;
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = (int)std::round(rot * factor);
+                    if (bin == 30) bin = 0;
+                    rotHist[bin].push_back(q);
+                }
+                ++nmatches;
+            }
+        }
+    }
+    if (checkOri) {
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < 30; ++i) {
+            const int s = (int)rotHist[i].size();
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < 30; ++i)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int q : rotHist[i]) {
+                    match12[q] = -1;
+                    --nmatches;
+                }
+    }
+    return nmatches;
+}
+
+// ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)  src/ORBmatcher.cc:734-890.
+// matches12[i1] = i2 or -1.  Returns nmatches.  (The caller refreshes vbPrevMatched, :880-884.)
+extern "C" int orc_search_initialization(const KeyPoint* kp1, const uint8_t* desc1, int n1, const float* prevMatched,
+                                         const KeyPoint* kp2, const uint8_t* desc2, int n2, const float* bounds4, int windowSize,
+                                         float nnratio, int checkOri, int* matches12) {
+    FrameView F;
+    F.kps = kp2; F.desc = desc2; F.uright = nullptr; F.N = n2;
+    F.minX = bounds4[0]; F.maxX = bounds4[1]; F.minY = bounds4[2]; F.maxY = bounds4[3];
+    F.scaleFactors = nullptr;
+    F.build();
+    int nmatches = 0;
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    std::vector<int> rotHist[30];
+    const float factor = 1.0f / 30;
+    std::vector<int> vMatchedDistance(n2, 0x7fffffff), vnMatches21(n2, -1);
+    for (int i1 = 0; i1 < n1; ++i1) {
+        const int level1 = kp1[i1].octave;
+        if (level1 > 0) continue;
+        const std::vector<size_t> ind = F.area(prevMatched[2 * i1], prevMatched[2 * i1 + 1], (float)windowSize, level1, level1);
+        if (ind.empty()) continue;
+        int bestDist = 0x7fffffff, bestDist2 = 0x7fffffff, bestIdx2 = -1;
+        for (size_t i2 : ind) {
+            const int dist = descriptor_distance(desc1 + 32 * (size_t)i1, desc2 + 32 * i2);
+            if (vMatchedDistance[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = (int)i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= 50) {
+            if (bestDist < (float)bestDist2 * nnratio) {
+                if (vnMatches21[bestIdx2] >= 0) {
+                    matches12[vnMatches21[bestIdx2]] = -1;
+                    --nmatches;
+                }
+                matches12[i1] = bestIdx2;
+                vnMatches21[bestIdx2] = i1;
+                vMatchedDistance[bestIdx2] = bestDist;
+                ++nmatches;
+                if (checkOri) {
+                    float rot = kp1[i1].angle - kp2[bestIdx2].angle;
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = (int)std::round(rot * factor);
+                    if (bin == 30) bin = 0;
+                    rotHist[bin].push_back(i1);
+                }
+            }
+        }
+    }
+    if (checkOri) {
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < 30; ++i) {
+            const int s = (int)rotHist[i].size();
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < 30; ++i)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int idx1 : rotHist[i])
+                    if (matches12[idx1] >= 0) {
+                        matches12[idx1] = -1;
+                        --nmatches;
+                    }
+    }
+    return nmatches;
+}

@@ -335,3 +335,32 @@ def logf(x):
     m.logf.restype = C.c_float
     m.logf.argtypes = [C.c_float]
     return m.logf(float(np.float32(x)))
+
+
+def search_bow_kf(kp2, desc2, node2, valid2, qnode, qangle, desc1, nnratio, check_ori=True):
+    """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) restated (ORBmatcher.cc:892-1043)."""
+    L = lib()
+    L.orc_search_bow_kf.restype = C.c_int
+    L.orc_search_bow_kf.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_float, C.c_int, C.c_void_p]
+    c = np.ascontiguousarray
+    kp2 = c(kp2)
+    a = [c(desc2, np.uint8), c(node2, np.int32), c(valid2, np.uint8)]
+    b = [c(qnode, np.int32), c(qangle, np.float32), c(desc1, np.uint8)]
+    m = np.full(max(len(b[0]), 1), -1, np.int32)
+    nm = L.orc_search_bow_kf(_p(kp2), *[_p(x) for x in a], len(kp2), len(b[0]), *[_p(x) for x in b], nnratio, 1 if check_ori else 0, _p(m))
+    return m[:len(b[0])], nm
+
+
+def search_initialization(kp1, desc1, prev_matched, kp2, desc2, bounds, window_size, nnratio, check_ori=True):
+    """ORBmatcher::SearchForInitialization restated (ORBmatcher.cc:734-890)."""
+    L = lib()
+    L.orc_search_initialization.restype = C.c_int
+    L.orc_search_initialization.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                            C.c_float, C.c_int, C.c_void_p]
+    c = np.ascontiguousarray
+    kp1, kp2, d1, d2 = c(kp1), c(kp2), c(desc1, np.uint8), c(desc2, np.uint8)
+    pm, b4 = c(prev_matched, np.float32), c(bounds, np.float32)
+    m = np.full(max(len(kp1), 1), -1, np.int32)
+    nm = L.orc_search_initialization(_p(kp1), _p(d1), len(kp1), _p(pm), _p(kp2), _p(d2), len(kp2), _p(b4), int(window_size), nnratio,
+                                     1 if check_ori else 0, _p(m))
+    return m[:len(kp1)], nm

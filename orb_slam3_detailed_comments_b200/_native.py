@@ -72,6 +72,16 @@ class orbm_kf_queries(C.Structure):
                                   "Sim3", "query_offset", "world_pos", "normal", "max_dist", "min_dist", "desc_q", "angle")]
 
 
+class orbm_init_queries(C.Structure):
+    _fields_ = [("n1", C.c_int32), ("kp1", C.c_void_p), ("desc1", C.c_void_p), ("prev_matched", C.c_void_p), ("n2", C.c_int32),
+                ("kp2", C.c_void_p), ("desc2", C.c_void_p), ("target_image", C.c_int32)]
+
+
+class orbm_bow_kf_queries(C.Structure):
+    _fields_ = [("n_pairs", C.c_int32)] + [
+        (n, C.c_void_p) for n in ("feat_offset", "kp2", "desc2", "node2", "valid2", "query_offset", "query_node", "query_angle", "desc1")]
+
+
 class orbm_triangulation(C.Structure):
     _fields_ = [("n_queries", C.c_int32), ("n2", C.c_int32)] + [
         (n, C.c_void_p) for n in ("kp1", "desc1", "node1", "stereo1", "kp2", "desc2", "node2", "valid2", "stereo2")] + [
@@ -119,6 +129,8 @@ SIGNATURES = {
     "orbm_stereo_pair": (_I, [_VP, _VP, _F, _F, _VP, _VP, _I]),
     "orbm_search_local_points": (_I, [_VP, C.POINTER(orbm_camera), C.POINTER(orbm_local_queries), _F, _F, _I, _F, _VP, _VP]),
     "orbm_search_bow": (_I, [_VP, C.POINTER(orbm_bow_queries), _F, _I, _VP, _VP]),
+    "orbm_search_initialization": (_I, [_VP, C.POINTER(orbm_camera), C.POINTER(orbm_init_queries), _I, C.c_float, _I, _VP, _VP]),
+    "orbm_search_bow_keyframes": (_I, [_VP, C.POINTER(orbm_bow_kf_queries), C.c_float, _I, _VP, _VP]),
     "orbm_search_keyframe": (_I, [_VP, C.POINTER(orbm_camera), C.POINTER(orbm_kf_queries), _I, C.c_float, C.c_float, _I, _VP, _VP]),
     "orbm_search_triangulation": (_I, [_VP, C.POINTER(orbm_triangulation), _VP, _VP]),
     "lba_create": (_I, [_I, C.POINTER(_VP)]),

@@ -8,6 +8,7 @@
 //       /root/reference/src/ORBmatcher.cc:259-493     (TrackReferenceKeyFrame, Tracking.cc:3183)
 //   * the projection searches into a KeyFrame (mode 3): Fuse x2 (:1325-1687), SearchByProjection(KF, Scw, ...) x2
 //       (:495-732), SearchByProjection(CurrentFrame, KeyFrame, sAlreadyFound, th, ORBdist) (:2196-2330)
+//   * SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (mode 4, :734-890)
 // with Frame::GetFeaturesInArea / PosInGrid (src/Frame.cc:859-951, 962-978) folded in.
 //
 // The reference is greedy: a feature claimed by query i is skipped by every later query.  Here the
@@ -56,7 +57,8 @@ struct ProjParams {
     float fx, fy, cx, cy, bf;
     float scale[ORB_MAX_LEVELS];
     // query side
-    int mode;                 // 0 = local map points, 1 = last frame, 2 = bag of words (same vocabulary node)
+    int mode;                 // 0 = local map points, 1 = last frame, 2 = bag of words (same vocabulary node),
+                              // 3 = projection into a keyframe, 4 = monocular initialisation (a0/a1 = vbPrevMatched, level = octave)
     const int* feat_node;     // mode 2: per compact feature row
     const int* frame_image;   // [n_frames]
     const int* qoff;          // [n_frames + 1]
@@ -252,7 +254,7 @@ __device__ __forceinline__ int warp_scan_query(const ProjParams& P, const FrameF
 // warp minimum is b1, the minimum of what remains is b2.
 __device__ __forceinline__ void warp_rescan_best2(const ProjParams& P, const FrameFeat& F, int N, int row0, const Window& w,
                                                   const uint8_t* qd, float ur_pred, float er_max, const uint8_t* claimed, int gate,
-                                                  unsigned long long& b1, unsigned long long& b2) {
+                                                  unsigned long long& b1, unsigned long long& b2, const int* md = nullptr) {
     const int lane = threadIdx.x & 31;
     unsigned long long l1 = ~0ull, l2 = ~0ull;
     if (!w.empty) {
@@ -262,6 +264,7 @@ __device__ __forceinline__ void warp_rescan_best2(const ProjParams& P, const Fra
             const int i = base + lane;
             if (i >= N || !scan_accepts(P, F, w, i, ur_pred, er_max, claimed, gate)) continue;
             const unsigned long long d = hamming256(a0, a1, P.desc + (size_t)(row0 + i) * 32);
+            if (md && md[i] <= (int)d) continue;   // SearchForInitialization: vMatchedDistance[i2] <= dist
             const unsigned long long cell = w.node >= 0 ? 0ull : (unsigned long long)F.cell[i];
             const unsigned long long key = (d << 32) | (cell << 16) | (unsigned long long)i;
             if (key < l1) { l2 = l1; l1 = key; }
@@ -547,6 +550,10 @@ __global__ void __launch_bounds__(PM_WARPS * 32) k_proj_candidates(const __grid_
         } else if (P.mode == 3) {
             ok = kf_window(P, frame, q, w, ur_pred);
             gate = P.variant == 0 ? 2 : 1;
+        } else if (P.mode == 4) {
+            ok = P.level[q] <= 0;      // level1 > 0: continue (ORBmatcher.cc:758-760)
+            if (ok) w = make_window(P, P.a0[q], P.a1[q], P.th, 0, 0);
+            gate = 1;
         } else {
             w.node = P.level[q];       // query's vocabulary node
             w.empty = w.node < 0;
@@ -583,27 +590,36 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
     uint8_t* s_claimed = reinterpret_cast<uint8_t*>(s_holder + P.maxFeat);               // maxFeat
     __shared__ int s_hist[30];
     __shared__ int s_nm;
+    const bool bowKF = P.mode == 2 && P.variant == 1;          // SearchByBoW(KF, KF): per-query output, strict TH_LOW
+    const bool init = P.mode == 4;                              // SearchForInitialization: distance-dependent claims
+    const bool perQuery = P.mode == 0 || P.mode == 3 || bowKF || init;  // match[q] = feature  (else: match[feature row] = query)
+    const bool claims = P.mode == 0 || bowKF || (P.mode == 3 && (P.variant == 2 || P.variant == 3));
+    const bool oriHist = P.checkOri && (P.mode == 1 || P.mode == 2 || init || (P.mode == 3 && P.variant == 3));
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        s_claimed[i] = ((P.mode == 0 || (P.mode == 3 && (P.variant == 2 || P.variant == 3))) && P.flag) ? P.flag[row0 + i] : 0;
+        s_claimed[i] = (claims && P.flag) ? P.flag[row0 + i] : 0;
         s_holder[i] = -1;
     }
     if (threadIdx.x < 30) s_hist[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_nm = 0;
-    if (P.mode != 0 && P.checkOri && P.quv)
+    if (oriHist)
         for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) P.quv[q] = __int_as_float(-1);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int nmatches = 0;
     float* s_qf = reinterpret_cast<float*>(s_claimed + ((P.maxFeat + 15) / 16) * 16);   // PM_CHUNK: mode 1 last angle
     uint8_t* s_qflag = reinterpret_cast<uint8_t*>(s_qf + PM_CHUNK);                      // PM_CHUNK: mode 1 obs > 0
+    int* s_md = reinterpret_cast<int*>(s_qflag + PM_CHUNK);                              // maxFeat (mode 4): vMatchedDistance
+    if (init) {
+        for (int i = threadIdx.x; i < N; i += blockDim.x) s_md[i] = 0x7fffffff;
+        __syncthreads();
+    }
     for (int base = q0; base < q1; base += PM_CHUNK) {
         const int nchunk = min(PM_CHUNK, q1 - base);
         for (int i = threadIdx.x; i < nchunk * PM_K; i += blockDim.x) s_top[i] = P.topk[(size_t)base * PM_K + i];
         for (int i = threadIdx.x; i < nchunk; i += blockDim.x) {
             s_cnt[i] = P.cnt[base + i];
-            if (P.mode == 0 || P.mode == 3) P.match[base + i] = -1;
-            if (P.mode == 3) { s_qf[i] = P.f0 ? P.f0[base + i] : 0.f; s_qflag[i] = 1; }
-            else if (P.mode != 0) { s_qf[i] = P.f0[base + i]; s_qflag[i] = (P.mode == 1) ? P.flag[base + i] : (uint8_t)1; }
+            if (perQuery) P.match[base + i] = -1;
+            if (P.mode != 0) { s_qf[i] = P.f0 ? P.f0[base + i] : 0.f; s_qflag[i] = (P.mode == 1) ? P.flag[base + i] : (uint8_t)1; }
         }
         __syncthreads();
         if (warp == 0) {
@@ -616,10 +632,10 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
                 const int stored = min(count, PM_K);
                 const unsigned long long key = (lane < stored) ? s_top[qi * PM_K + lane] : ~0ull;
                 const int kidx = (lane < stored) ? (int)(key & 0xffffu) : 0;   // in range even if the load is speculated
-                const bool is_free = (lane < stored) && !s_claimed[kidx];
+                const bool is_free = (lane < stored) && (init ? s_md[kidx] > (int)(key >> 32) : !s_claimed[kidx]);
                 const unsigned fm = __ballot_sync(0xffffffffu, is_free);
                 const int live = __popc(fm);
-                const int need = (P.mode == 1 || P.mode == 3) ? 1 : 2;
+                const int need = (P.mode == 1 || P.mode == 3) ? 1 : 2;   // modes 0, 2, 4 use the second best
                 unsigned long long b1 = ~0ull, b2 = ~0ull;
                 if (live < need && count > PM_K) {
                     // claims consumed the stored list: exact rescan with the mask applied (warp-cooperative)
@@ -636,12 +652,16 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
                     } else if (P.mode == 3) {
                         kf_window(P, frame, q, w, ur_pred);
                         gate = P.variant == 0 ? 2 : 1;
+                    } else if (init) {
+                        w = make_window(P, P.a0[q], P.a1[q], P.th, 0, 0);
+                        gate = 1;
                     } else {
                         w.node = P.level[q];
                         w.empty = w.node < 0;
                         er_max = 3.0e38f;
                     }
-                    warp_rescan_best2(P, F, N, row0, w, P.qdesc + 32 * (size_t)q, ur_pred, er_max, s_claimed, gate, b1, b2);
+                    warp_rescan_best2(P, F, N, row0, w, P.qdesc + 32 * (size_t)q, ur_pred, er_max, init ? nullptr : s_claimed, gate, b1, b2,
+                                      init ? s_md : nullptr);
                 } else {
                     if (fm) {
                         const int i1 = __ffs(fm) - 1;
@@ -668,12 +688,39 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
                             __syncwarp();
                         }
                     }
-                } else if (P.mode == 3) {
-                    if ((float)bestDist <= P.thr) {
+                } else if (init) {
+                    // ORBmatcher.cc:800-835: TH_LOW, ratio against the second best, a better match steals the feature
+                    const float d2f = (b2 == ~0ull) ? 2147483648.0f : (float)(int)(b2 >> 32);
+                    if (bestDist <= 50 && (float)bestDist < fmul(d2f, P.nnratio)) {
+                        const int old = s_holder[bestIdx];
+                        if (lane == 0) {
+                            if (old >= 0) P.match[old] = -1;
+                            P.match[q] = bestIdx;
+                            s_holder[bestIdx] = q;
+                            s_md[bestIdx] = bestDist;
+                            if (oriHist) {
+                                float rot = fsub(s_qf[qi], F.ang[bestIdx]);
+                                if (rot < 0.0f) rot = fadd(rot, 360.0f);
+                                int bin = (int)roundf(fmul(rot, 1.0f / 30));
+                                if (bin == 30) bin = 0;
+                                s_hist[bin] += 1;
+                                P.quv[q] = __int_as_float((bin << 16) | bestIdx);
+                            }
+                        }
+                        if (old < 0) ++nmatches;
+                        __syncwarp();
+                    }
+                } else if (perQuery) {
+                    bool accept = (float)bestDist <= P.thr;
+                    if (bowKF) {   // ORBmatcher.cc:978-982: bestDist1 < TH_LOW and the ratio test in float
+                        const int bestDist2 = (b2 == ~0ull) ? 256 : (int)(b2 >> 32);
+                        accept = bestDist < 50 && (float)bestDist < fmul(P.nnratio, (float)bestDist2);
+                    }
+                    if (accept) {
                         if (lane == 0) {
                             P.match[q] = bestIdx;
-                            if (P.variant == 2 || P.variant == 3) s_claimed[bestIdx] = 1;
-                            if (P.variant == 3 && P.checkOri) {
+                            if (claims) s_claimed[bestIdx] = 1;
+                            if (oriHist) {
                                 float rot = fsub(s_qf[qi], F.ang[bestIdx]);
                                 if (rot < 0.0f) rot = fadd(rot, 360.0f);
                                 int bin = (int)roundf(fmul(rot, 1.0f / 30));
@@ -695,7 +742,7 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
                         if (lane == 0) {
                             s_holder[bestIdx] = q;
                             s_claimed[bestIdx] = (P.mode == 2 || s_qflag[qi]) ? 1 : 0;   // mode 1: only map points with observations block
-                            if (P.checkOri) {
+                            if (oriHist) {
                                 float rot = fsub(s_qf[qi], F.ang[bestIdx]);
                                 if (rot < 0.0f) rot = fadd(rot, 360.0f);
                                 int bin = (int)roundf(fmul(rot, 1.0f / 30));
@@ -712,7 +759,7 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
         }
         __syncthreads();
     }
-    if (P.mode == 0 || (P.mode == 3 && !(P.variant == 3 && P.checkOri))) {
+    if (perQuery && !oriHist) {
         if (threadIdx.x == 0) P.nmatches[frame] = nmatches;
         return;
     }
@@ -732,7 +779,7 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
         for (int i = 0; i < 30; ++i) s_keep[i] = (i == ind1 || i == ind2 || i == ind3) ? 1 : 0;
     }
     __syncthreads();
-    if (P.checkOri) {
+    if (oriHist) {
         int removed = 0;
         for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
             if (P.cnt[q] <= 0) continue;
@@ -740,7 +787,11 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
             if (e < 0) continue;
             const int bin = e >> 16, idx = e & 0xffff;
             if (!s_keep[bin]) {
-                if (P.mode == 3) P.match[q] = -1;
+                if (init) {                 // ORBmatcher.cc:870-876: only matches that are still alive count
+                    if (P.match[q] >= 0) { P.match[q] = -1; ++removed; }
+                    continue;
+                }
+                if (perQuery) P.match[q] = -1;
                 else s_holder[idx] = -1;   // every entry of a rejected bin clears its feature (duplicates included)
                 ++removed;
             }
@@ -748,7 +799,7 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
         if (removed) atomicSub(&s_nm, removed);
     }
     __syncthreads();
-    if (P.mode != 3)
+    if (!perQuery)
         for (int i = threadIdx.x; i < N; i += blockDim.x) P.match[row0 + i] = s_holder[i];
     if (threadIdx.x == 0) P.nmatches[frame] = s_nm;
 }
@@ -799,7 +850,7 @@ static orb_status launch_proj(orbx_handle* h, ProjParams& P, int n_frames, int m
         k_proj_candidates<<<grid, PM_WARPS * 32, csm, st>>>(P);
         ORB_LAUNCHED();
     }
-    const size_t rsm = fsm + (size_t)PM_CHUNK * PM_K * 8 + (size_t)PM_CHUNK * 4 + (size_t)P.maxFeat * 5 + (size_t)PM_CHUNK * 5 + 128;
+    const size_t rsm = fsm + (size_t)PM_CHUNK * PM_K * 8 + (size_t)PM_CHUNK * 4 + (size_t)P.maxFeat * (P.mode == 4 ? 9 : 5) + (size_t)PM_CHUNK * 5 + 256;
     ORB_CUDA(cudaFuncSetAttribute(k_proj_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
     k_proj_resolve<<<n_frames, 256, rsm, st>>>(P);
     ORB_LAUNCHED();
@@ -1105,5 +1156,140 @@ extern "C" orb_status orbm_search_keyframe(orbx_handle* h, const orbm_camera* ca
     }
     ORB_CUDA(cudaStreamSynchronize(h->stream));   // also keeps the host vectors alive until the uploads are done
     if (nmatches_out && nq == 0) std::fill(nmatches_out, nmatches_out + nt, 0);
+    return ORB_OK;
+}
+
+extern "C" orb_status orbm_search_bow_keyframes(orbx_handle* h, const orbm_bow_kf_queries* Q, float nnratio, int32_t check_orientation,
+                                                int32_t* match12_out, int32_t* nmatches_out) {
+    if (!h || !Q || !match12_out || Q->n_pairs < 1 || !Q->feat_offset || !Q->query_offset || !Q->kp2 || !Q->desc2 || !Q->node2)
+        return set_error(ORB_ERR_INVALID, "bad arguments");
+    ORB_CUDA(cudaSetDevice(h->cfg.device));
+    const int nt = Q->n_pairs;
+    const int nq = Q->query_offset[nt];
+    const size_t rows = (size_t)Q->feat_offset[nt];
+    if (nq > 0 && (!Q->query_node || !Q->query_angle || !Q->desc1)) return set_error(ORB_ERR_INVALID, "missing query arrays");
+    int maxq = 0, maxFeat = 1;
+    std::vector<int> img(nt), nkp(nt);
+    for (int t = 0; t < nt; ++t) {
+        const int n = Q->feat_offset[t + 1] - Q->feat_offset[t];
+        if (n < 0 || n > 5400) return set_error(ORB_ERR_UNSUPPORTED, "keyframe with more than 5400 features");
+        if (Q->query_offset[t + 1] < Q->query_offset[t]) return set_error(ORB_ERR_INVALID, "bad query table");
+        img[t] = t;
+        nkp[t] = n;
+        maxFeat = std::max(maxFeat, n);
+        maxq = std::max(maxq, Q->query_offset[t + 1] - Q->query_offset[t]);
+    }
+    std::vector<uint8_t> invalid(std::max<size_t>(rows, 1), 0);   // vbMatched2 starts false; features without a good map point never match
+    if (Q->valid2)
+        for (size_t i = 0; i < rows; ++i) invalid[i] = Q->valid2[i] ? 0 : 1;
+    const size_t need = (size_t)nq * (PM_K * 8 + 4 + 4 + 4 + 4 + 32 + 64) + rows * (sizeof(orbx_keypoint) + 32 + 4 + 1) + (size_t)nt * 128 + 65536;
+    orb_status s;
+    if ((s = ensure_stage(h, need)) != ORB_OK) return s;
+    StageCursor cur{h->d_stage};
+    ProjParams P{};
+    orbm_camera cam{1, 1, 0, 0, 0, 1, 0, 1, 0, 1};   // the grid is not used by this search
+    fill_frame_side(h, &cam, P);
+    P.mode = 2;
+    P.variant = 1;
+    int *d_img, *d_qoff, *off, *nk, *qnode, *fnode; orbx_keypoint* kp; uint8_t *de, *fl, *qd; float* ang;
+    if ((s = upload(h, d_img, (const int*)img.data(), nt, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, d_qoff, (const int*)Q->query_offset, nt + 1, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, kp, Q->kp2, rows, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, de, Q->desc2, rows * 32, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, off, (const int*)Q->feat_offset, nt, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, nk, (const int*)nkp.data(), nt, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, fnode, (const int*)Q->node2, rows, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, fl, (const uint8_t*)invalid.data(), rows, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, qnode, (const int*)Q->query_node, nq, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, ang, Q->query_angle, nq, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, qd, Q->desc1, (size_t)nq * 32, cur, false)) != ORB_OK) return s;
+    P.frame_image = d_img; P.qoff = d_qoff;
+    P.kps = kp; P.desc = de; P.uright = nullptr; P.offsets = off; P.nkp = nk; P.maxFeat = maxFeat;
+    P.feat_node = fnode; P.flag = fl; P.level = qnode; P.f0 = ang; P.qdesc = qd;
+    P.nnratio = nnratio; P.checkOri = check_orientation;
+    P.topk = cur.take<unsigned long long>((size_t)std::max(nq, 1) * PM_K);
+    P.cnt = cur.take<int>(std::max(nq, 1));
+    P.quv = cur.take<float>(std::max(nq, 1));
+    P.match = cur.take<int>(std::max(nq, 1));
+    P.nmatches = cur.take<int>(nt);
+    if (nq > 0) {
+        if ((s = launch_proj(h, P, nt, maxq)) != ORB_OK) return s;
+        ORB_CUDA(cudaMemcpyAsync(match12_out, P.match, sizeof(int) * (size_t)nq, cudaMemcpyDeviceToHost, h->stream));
+        if (nmatches_out) ORB_CUDA(cudaMemcpyAsync(nmatches_out, P.nmatches, sizeof(int) * nt, cudaMemcpyDeviceToHost, h->stream));
+    }
+    ORB_CUDA(cudaStreamSynchronize(h->stream));
+    if (nmatches_out && nq == 0) std::fill(nmatches_out, nmatches_out + nt, 0);
+    return ORB_OK;
+}
+
+extern "C" orb_status orbm_search_initialization(orbx_handle* h, const orbm_camera* cam, const orbm_init_queries* Q, int32_t window_size,
+                                                 float nnratio, int32_t check_orientation, int32_t* matches12_out, int32_t* nmatches_out) {
+    if (!h || !cam || !Q || !matches12_out || Q->n1 < 0 || (Q->kp2 ? (!Q->desc2 || Q->n2 < 0) : Q->target_image < 0))
+        return set_error(ORB_ERR_INVALID, "bad arguments");
+    if (Q->n1 > 0 && (!Q->kp1 || !Q->desc1 || !Q->prev_matched)) return set_error(ORB_ERR_INVALID, "missing query arrays");
+    ORB_CUDA(cudaSetDevice(h->cfg.device));
+    const int nq = Q->n1;
+    orb_status s;
+    size_t rows = 0;
+    int img = 0, nkp_h = 0, off_h = 0;
+    if (Q->kp2) {
+        if (Q->n2 > 4700) return set_error(ORB_ERR_UNSUPPORTED, "frame with more than 4700 features");
+        rows = (size_t)Q->n2;
+        nkp_h = Q->n2;
+    } else {
+        if ((s = orbx_counts(h, nullptr, nullptr, nullptr)) != ORB_OK) return s;
+        if (Q->target_image >= h->last_batch) return set_error(ORB_ERR_INVALID, "bad target image");
+        img = Q->target_image;
+    }
+    std::vector<float> px(std::max(nq, 1)), py(std::max(nq, 1)), ang(std::max(nq, 1));
+    std::vector<int> lvl(std::max(nq, 1));
+    for (int i = 0; i < nq; ++i) {
+        px[i] = Q->prev_matched[2 * i];
+        py[i] = Q->prev_matched[2 * i + 1];
+        ang[i] = Q->kp1[i].angle;
+        lvl[i] = Q->kp1[i].octave;
+    }
+    const int qoff_h[2] = {0, nq};
+    const size_t need = (size_t)nq * (PM_K * 8 + 4 * 8 + 32 + 64) + rows * (sizeof(orbx_keypoint) + 32 + 8) +
+                        2 * (size_t)std::max(h->geom.kpTotal, (int)rows) + 2 * 3073 + 65536;
+    if ((s = ensure_stage(h, need)) != ORB_OK) return s;
+    StageCursor cur{h->d_stage};
+    ProjParams P{};
+    fill_frame_side(h, cam, P);
+    P.uright = nullptr;
+    P.mode = 4;
+    int *d_img, *d_qoff, *d_lvl; float *d_px, *d_py, *d_ang; uint8_t* qd;
+    if ((s = upload(h, d_img, (const int*)&img, 1, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, d_qoff, (const int*)qoff_h, 2, cur, false)) != ORB_OK) return s;
+    if (Q->kp2) {
+        orbx_keypoint* kp; uint8_t* de; int *off, *nk;
+        if ((s = upload(h, kp, Q->kp2, rows, cur, false)) != ORB_OK) return s;
+        if ((s = upload(h, de, Q->desc2, rows * 32, cur, false)) != ORB_OK) return s;
+        if ((s = upload(h, off, (const int*)&off_h, 1, cur, false)) != ORB_OK) return s;
+        if ((s = upload(h, nk, (const int*)&nkp_h, 1, cur, false)) != ORB_OK) return s;
+        P.kps = kp; P.desc = de; P.offsets = off; P.nkp = nk; P.maxFeat = std::max(Q->n2, 1);
+    }
+    if ((s = upload(h, d_px, (const float*)px.data(), nq, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, d_py, (const float*)py.data(), nq, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, d_ang, (const float*)ang.data(), nq, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, d_lvl, (const int*)lvl.data(), nq, cur, false)) != ORB_OK) return s;
+    if ((s = upload(h, qd, Q->desc1, (size_t)nq * 32, cur, false)) != ORB_OK) return s;
+    P.frame_image = d_img; P.qoff = d_qoff; P.a0 = d_px; P.a1 = d_py; P.f0 = d_ang; P.level = d_lvl; P.qdesc = qd;
+    P.th = (float)window_size;     // GetFeaturesInArea(x, y, windowSize, ...): int -> const float& r
+    P.nnratio = nnratio; P.checkOri = check_orientation;
+    P.gridOrder = cur.take<uint16_t>((size_t)P.maxFeat);
+    P.gridStart = cur.take<uint16_t>((size_t)(GRID_COLS * GRID_ROWS + 1));
+    P.topk = cur.take<unsigned long long>((size_t)std::max(nq, 1) * PM_K);
+    P.cnt = cur.take<int>(std::max(nq, 1));
+    P.quv = cur.take<float>(std::max(nq, 1));
+    P.match = cur.take<int>(std::max(nq, 1));
+    P.nmatches = cur.take<int>(1);
+    if (nq > 0) {
+        if ((s = launch_proj(h, P, 1, nq)) != ORB_OK) return s;
+        ORB_CUDA(cudaMemcpyAsync(matches12_out, P.match, sizeof(int) * (size_t)nq, cudaMemcpyDeviceToHost, h->stream));
+        if (nmatches_out) ORB_CUDA(cudaMemcpyAsync(nmatches_out, P.nmatches, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    }
+    ORB_CUDA(cudaStreamSynchronize(h->stream));
+    if (nmatches_out && nq == 0) *nmatches_out = 0;
     return ORB_OK;
 }

@@ -87,6 +87,41 @@ class ORBmatcher:
                                         N.ptr(fm), N.ptr(nm)))
         return fm[:total_rows], nm
 
+    def SearchForInitialization(self, extractor, cam, kp1, desc1, vbPrevMatched, windowSize=10, kp2=None, desc2=None, target_image=0):
+        """SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (ORBmatcher.cc:734-890).  F2 = host arrays
+        (kp2, desc2) or image target_image of the extractor's last batch.  Returns (vnMatches12[n1], nmatches)."""
+        kp1, d1 = np.ascontiguousarray(kp1), _u8(desc1)
+        pm = np.ascontiguousarray(vbPrevMatched, np.float32).reshape(-1, 2)
+        if kp2 is not None:
+            kp2, d2 = np.ascontiguousarray(kp2), _u8(desc2)
+            q = N.orbm_init_queries(len(kp1), N.ptr(kp1), N.ptr(d1), N.ptr(pm), len(kp2), N.ptr(kp2), N.ptr(d2), -1)
+        else:
+            q = N.orbm_init_queries(len(kp1), N.ptr(kp1), N.ptr(d1), N.ptr(pm), 0, None, None, int(target_image))
+        m = np.full(max(len(kp1), 1), -1, np.int32)
+        nm = C.c_int32(0)
+        N.check(self._L.orbm_search_initialization(extractor._h, C.byref(cam), C.byref(q), int(windowSize), self.mfNNratio,
+                                                   1 if self.mbCheckOrientation else 0, N.ptr(m), C.byref(nm)))
+        return m[:len(kp1)], nm.value
+
+    def SearchByBoWKeyFrames(self, extractor, pairs):
+        """SearchByBoW(pKF1, pKF2, vpMatches12) (ORBmatcher.cc:892-1043) for several keyframe pairs.  pairs: list of dicts
+        (kp2, desc2, node2, valid2, query_node, query_angle, desc1) -- queries in FeatureVector merge order.
+        Returns ([match12 per pair], nmatches[n_pairs])."""
+        nt = len(pairs)
+        foff, qoff = np.zeros(nt + 1, np.int32), np.zeros(nt + 1, np.int32)
+        foff[1:] = np.cumsum([len(p["kp2"]) for p in pairs])
+        qoff[1:] = np.cumsum([len(p["query_node"]) for p in pairs])
+        cat = lambda key, dt: np.ascontiguousarray(np.concatenate([np.asarray(p[key], dt) for p in pairs]))
+        kp2 = np.ascontiguousarray(np.concatenate([p["kp2"] for p in pairs]))
+        a = [cat("desc2", np.uint8), cat("node2", np.int32), cat("valid2", np.uint8)]
+        b = [cat("query_node", np.int32), cat("query_angle", np.float32), cat("desc1", np.uint8)]
+        q = N.orbm_bow_kf_queries(nt, N.ptr(foff), N.ptr(kp2), *[N.ptr(x) for x in a], N.ptr(qoff), *[N.ptr(x) for x in b])
+        m = np.full(max(int(qoff[-1]), 1), -1, np.int32)
+        nm = np.zeros(nt, np.int32)
+        N.check(self._L.orbm_search_bow_keyframes(extractor._h, C.byref(q), self.mfNNratio, 1 if self.mbCheckOrientation else 0,
+                                                  N.ptr(m), N.ptr(nm)))
+        return [m[qoff[t]:qoff[t + 1]] for t in range(nt)], nm
+
     def SearchForTriangulation(self, extractor, kp1, desc1, node1, stereo1, kp2, desc2, node2, valid2, stereo2, F12, epipole2,
                                bCoarse=False):
         """SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse) (ORBmatcher.cc:1045-1323), single camera.

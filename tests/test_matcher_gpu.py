@@ -384,3 +384,64 @@ def test_search_by_sim3_matches_oracle(scene):
         ref = {i1: i2 for i1, i2 in vn1.items() if vn2.get(i2, -1) == i1}
         assert found == ref and nfound == len(ref)
         assert len(vn1) > 100 and len(vn2) > 100 and nfound > 20, (len(vn1), len(vn2), nfound)
+
+
+def test_search_by_bow_keyframes_matches_oracle(scene):
+    """SearchByBoW(pKF1, pKF2): KF1 = the last frame of each pair (oracle features), KF2 = the current left image."""
+    P, ex, off = scene["P"], scene["ex"], scene["off"]
+    rng = np.random.default_rng(31)
+    node_of = lambda d: ((d[:, 0].astype(np.int32) >> 3) * 7 + (d[:, 5].astype(np.int32) >> 4) * 3 + (d[:, 17].astype(np.int32) >> 5)) % 97
+    pairs = []
+    for p in range(P):
+        kL, dL, luR, ldep = scene["lasts"][p]
+        a, b = off[2 * p], off[2 * p + 1]
+        k2, d2 = scene["kps"][a:b], scene["desc"][a:b]
+        node2 = node_of(d2)
+        node2[::19] = -1
+        valid2 = (rng.random(len(k2)) < 0.7).astype(np.uint8)
+        sel = np.nonzero(rng.random(len(kL)) < 0.75)[0]             # KF1 features with a good map point
+        sel = np.concatenate([sel, sel[:: 5]])                      # duplicates: the vbMatched2 claims matter
+        nd = node_of(dL[sel])
+        order = np.lexsort((sel, nd))
+        sel, nd = sel[order], nd[order]
+        pairs.append(dict(kp2=k2, desc2=d2, node2=node2, valid2=valid2, query_node=nd.astype(np.int32),
+                          query_angle=kL["angle"][sel].astype(np.float32), desc1=dL[sel]))
+    for nnratio, check in [(0.75, True), (0.9, False)]:
+        m = ORBmatcher(nnratio, check)
+        got, nm = m.SearchByBoWKeyFrames(ex, pairs)
+        for p, pr in enumerate(pairs):
+            rm, rnm = po.search_bow_kf(pr["kp2"], pr["desc2"], pr["node2"], pr["valid2"], pr["query_node"], pr["query_angle"], pr["desc1"],
+                                       nnratio, check)
+            assert rnm == nm[p] and (got[p] == rm).all(), (nnratio, p, rnm, nm[p])
+            assert rnm > 50
+
+
+def test_search_for_initialization_matches_oracle(scene):
+    """SearchForInitialization(F1, F2, vbPrevMatched, ...): F1 = the last frame (oracle features), F2 = the current left image,
+    on the device and as host arrays; duplicated F1 features make later, better matches steal a feature (:812-817)."""
+    P, ex, off = scene["P"], scene["ex"], scene["off"]
+    cam = camera(FX, FY, CX, CY, BF, B, W, H)
+    rng = np.random.default_rng(41)
+    for p in range(P):
+        kL, dL, _, _ = scene["lasts"][p]
+        a, b = off[2 * p], off[2 * p + 1]
+        k2, d2 = scene["kps"][a:b], scene["desc"][a:b]
+        # F1: the last frame plus noisy copies of a third of its level-0 features (their descriptors get a few flipped bits, so the
+        # copy or the original can be the closer one)
+        l0 = np.nonzero(kL["octave"] == 0)[0]
+        dup = rng.choice(l0, len(l0) // 3, replace=False)
+        kp1 = np.concatenate([kL[dup], kL])
+        dd = dL[dup].copy()
+        flips = rng.integers(0, 256, (len(dup), 3))
+        for j in range(3):
+            dd[np.arange(len(dup)), flips[:, j] // 8] ^= (1 << (flips[:, j] % 8)).astype(np.uint8)
+        d1 = np.concatenate([dd, dL])
+        prev = np.stack([kp1["x"], kp1["y"]], 1).astype(np.float32)        # vbPrevMatched = F1 keypoint positions (Tracking.cc:2560)
+        for win, nnratio, check in [(100, 0.9, True), (30, 0.8, False)]:
+            m = ORBmatcher(nnratio, check)
+            g_dev, n_dev = m.SearchForInitialization(ex, cam, kp1, d1, prev, win, target_image=2 * p)
+            g_host, n_host = m.SearchForInitialization(ex, cam, kp1, d1, prev, win, kp2=k2, desc2=d2)
+            rm, rnm = po.search_initialization(kp1, d1, prev, k2, d2, BOUNDS, win, nnratio, check)
+            assert n_dev == rnm and (g_dev == rm).all(), (p, win, n_dev, rnm, int((g_dev != rm).sum()))
+            assert n_host == rnm and (g_host == rm).all(), (p, win)
+            assert rnm > 50, rnm
