@@ -217,6 +217,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="stereo frames per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--handles", type=int, default=4, help="extractor handles (CUDA streams) the steps are pipelined over")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -240,8 +241,9 @@ def main():
     from orb_slam3_detailed_comments_b200 import ORBmatcher, camera, Optimizer, synth
     cam = camera(FX, FY, CX, CY, BF, BL, W, H)
     ex = ORBextractor(NFEAT, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=nimg, device=local)
-    ex2 = ORBextractor(NFEAT, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=nimg, device=local)
-    exs = [ex, ex2]     # two handles = two CUDA streams: batch i+1 is queued while batch i's ordered passes drain
+    NH = max(2, args.handles)
+    # NH handles = NH CUDA streams: batches i+1 .. i+NH-1 are queued while batch i's ordered passes drain
+    exs = [ex] + [ORBextractor(NFEAT, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=nimg, device=local) for _ in range(NH - 1)]
     streams = [torch.cuda.ExternalStream(e.cuda_stream(), device=dev) for e in exs]
     stream = streams[0]
     m_last, m_local = ORBmatcher(0.9, True), ORBmatcher(0.8, True)
@@ -288,19 +290,19 @@ def main():
         H_LAST.append(h_last); H_LOC.append(h_loc)
         D_LAST.append({k: T(v) for k, v in h_last.items()}); D_LOC.append({k: T(v) for k, v in h_loc.items()})
     rows_cap = nimg * 1500
-    d_fm = [torch.full((rows_cap,), -1, dtype=torch.int32, device=dev) for _ in range(2)]
-    d_nm = [torch.zeros(2 * B, dtype=torch.int32, device=dev) for _ in range(2)]
+    d_fm = [torch.full((rows_cap,), -1, dtype=torch.int32, device=dev) for _ in range(NH)]
+    d_nm = [torch.zeros(2 * B, dtype=torch.int32, device=dev) for _ in range(NH)]
     max_loc = max(int(hl["off"][-1]) for hl in H_LOC)
-    d_match = [torch.full((max(max_loc, 1),), -1, dtype=torch.int32, device=dev) for _ in range(2)]
+    d_match = [torch.full((max(max_loc, 1),), -1, dtype=torch.int32, device=dev) for _ in range(NH)]
     nq_last = float(np.mean([int(hl["off"][-1]) for hl in H_LAST])); nq_loc = float(np.mean([int(hl["off"][-1]) for hl in H_LOC]))
 
     def submit_device(i):
-        e = exs[i % 2]
+        e = exs[i % NH]
         e.extract_batch_device(dev_pool[i % pool_batches].data_ptr(), nimg, W, H)
         e.stereo_batch(B, BF, BL)
 
     def finish_device(i):
-        k = i % 2
+        k = i % NH
         e = exs[k]
         d_last, d_loc = D_LAST[i % pool_batches], D_LOC[i % pool_batches]
         m_last.SearchByProjectionLastFrameDevice(e, cam, B, d_last["fimg"], d_last["off"], d_last["Tcw"], d_last["dir"],
@@ -319,10 +321,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: inputs resident in HBM; software-pipelined over the two handles ------------------------
+    # ---- value: inputs resident in HBM; software-pipelined over the NH handles ------------------------
     sampler = ClockSampler(local)
     sampler.start()
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, NH)):
         step_device(i)
     barrier()
     sampler.wait_first()
@@ -331,14 +333,18 @@ def main():
     barrier()
     t_begin = time.time()
     e0.record(streams[0])
-    streams[1].wait_event(e0)
-    submit_device(args.warmup)
+    for st in streams[1:]:
+        st.wait_event(e0)
+    for j in range(min(NH - 1, args.steps)):
+        submit_device(args.warmup + j)
     for i in range(args.steps):
-        if i + 1 < args.steps:
-            submit_device(args.warmup + i + 1)
+        if i + NH - 1 < args.steps:
+            submit_device(args.warmup + i + NH - 1)
         finish_device(args.warmup + i)
-    eb.record(streams[1])
-    streams[0].wait_event(eb)
+    for st in streams[1:]:
+        ev = torch.cuda.Event()
+        ev.record(st)
+        streams[0].wait_event(ev)
     e1.record(streams[0])
     barrier()
     t_end = time.time()
@@ -351,7 +357,7 @@ def main():
     nser = min(args.steps, 32) // 2 * 2
     ser0.record(streams[0])
     for i in range(0, nser, 2):
-        step_device(2 * (args.warmup + i))  # even index => handle 0, the profiled one
+        step_device(NH * (args.warmup + i))  # multiple of NH => handle 0, the profiled one
     ser1.record(streams[0])
     barrier()
     serial_ms_per_step = ser0.elapsed_time(ser1) / max(nser // 2, 1)
@@ -374,41 +380,47 @@ def main():
     P_LOC = [{k: pin(v) for k, v in hl.items()} for hl in H_LOC]
     pz = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory().numpy()
     from orb_slam3_detailed_comments_b200._native import KP_DTYPE
-    o_kps = torch.zeros(rows_cap * 28, dtype=torch.uint8).pin_memory().numpy().view(KP_DTYPE)
-    o_desc, o_ur, o_dep = pz((rows_cap, 32), torch.uint8), pz(rows_cap, torch.float32), pz(rows_cap, torch.float32)
-    o_fm, o_nm1, o_mt, o_nm2 = pz(rows_cap, torch.int32), pz(B, torch.int32), pz(max(max_loc, 1), torch.int32), pz(B, torch.int32)
+    def out_buffers():
+        return dict(kps=torch.zeros(rows_cap * 28, dtype=torch.uint8).pin_memory().numpy().view(KP_DTYPE), desc=pz((rows_cap, 32), torch.uint8),
+                    ur=pz(rows_cap, torch.float32), dep=pz(rows_cap, torch.float32), fm=pz(rows_cap, torch.int32), nm1=pz(B, torch.int32),
+                    mt=pz(max(max_loc, 1), torch.int32), nm2=pz(B, torch.int32))
+    OUT = [out_buffers() for _ in range(NH)]
 
-    def submit(i):
-        e = exs[i % 2]
+    def step_e2e(i, k):
+        """One step through the host-pointer C ABI on handle k: images in (pinned host -> device), extraction, stereo,
+        both searches, every result back in pinned host buffers.  Each call blocks until its results are on the host."""
+        e, o = exs[k], OUT[k]
+        p_last, p_loc = P_LAST[i % pool_batches], P_LOC[i % pool_batches]
         e.extract_batch_async(host_pool[i % pool_batches].numpy())
         e.stereo_batch(B, BF, BL)
-
-    def finish(i):
-        e = exs[i % 2]
-        p_last, p_loc = P_LAST[i % pool_batches], P_LOC[i % pool_batches]
-        nn, mm, oo, kk, dd = e.download(nimg, out=(o_kps, o_desc))
+        nn, mm, oo, kk, dd = e.download(nimg, out=(o["kps"], o["desc"]))
         rows = int(oo[-1])
-        ur, dp = e.stereo_download(rows, out=(o_ur, o_dep))
-        fm, nm1 = m_last.SearchByProjectionLastFrame(e, cam, p_last["fimg"], p_last["off"], p_last["Tcw"], p_last["dir"],
-                                                     p_last["xw"], p_last["oct"], p_last["ang"], p_last["desc"], p_last["obs"],
-                                                     15.0, rows, out=(o_fm, o_nm1))
-        mt, nm2 = m_local.SearchByProjection(e, cam, p_loc["fimg"], p_loc["off"], p_loc["px"], p_loc["py"], p_loc["pxr"],
-                                             p_loc["lvl"], p_loc["vc"], p_loc["desc"], th=3.0, out=(o_mt, o_nm2))
-        return rows
-    for i in range(args.warmup):
-        submit(i)
-        finish(i)
+        e.stereo_download(rows, out=(o["ur"], o["dep"]))
+        m_last.SearchByProjectionLastFrame(e, cam, p_last["fimg"], p_last["off"], p_last["Tcw"], p_last["dir"], p_last["xw"], p_last["oct"],
+                                           p_last["ang"], p_last["desc"], p_last["obs"], 15.0, rows, out=(o["fm"], o["nm1"]))
+        m_local.SearchByProjection(e, cam, p_loc["fimg"], p_loc["off"], p_loc["px"], p_loc["py"], p_loc["pxr"], p_loc["lvl"], p_loc["vc"],
+                                   p_loc["desc"], th=3.0, out=(o["mt"], o["nm2"]))
+        return rows * (60 + 8 + 4) + 12 * nimg + 4 * int(nq_loc) + 8 * B
+
+    # One host thread per handle, the deployment shape of sequence-sharded replay (INTEGRATION.md section 6): every thread
+    # drives its own handle / CUDA stream through the blocking C ABI, so one thread's result reads overlap the others'
+    # uploads and kernels.  ctypes releases the GIL inside the calls.
+    import concurrent.futures as cf
+    pool = cf.ThreadPoolExecutor(max_workers=NH)
+
+    def worker(k, first, count):
+        tot = 0
+        for i in range(first + k, first + count, NH):
+            tot += step_e2e(i, k)
+        return tot
+
+    list(pool.map(lambda k: worker(k, 0, max(args.warmup, NH)), range(NH)))
     barrier()
     t0 = time.perf_counter()
-    d2h = 0
-    submit(args.warmup)
-    for i in range(args.steps):
-        if i + 1 < args.steps:
-            submit(args.warmup + i + 1)
-        rows = finish(args.warmup + i)
-        d2h += rows * (60 + 8 + 4) + 12 * nimg + 4 * int(nq_loc) + 8 * B
+    d2h = sum(pool.map(lambda k: worker(k, max(args.warmup, NH), args.steps), range(NH)))
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    pool.shutdown()
     t = torch.tensor([dt], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -440,7 +452,7 @@ def main():
                     "stage_gbs": {k: ab[k] * nimg / (ext[k] * 1e-3) / 1e9 for k in ext},
                     "algorithmic_bytes_per_image": ab,
                     "note": "stage times from a serial pass (one stream) right after the timed region; the timed region itself is "
-                            "software-pipelined over two streams.  FAST is ALU-pipe bound (profiles/), not HBM bound; see DESIGN.md"}
+                            "software-pipelined over the handles' streams.  FAST is ALU-pipe bound (profiles/), not HBM bound; see DESIGN.md"}
         cpu = None
         if not args.no_cpu_baseline:
             # faithful threading (Frame.cc:136-141): the two eyes on two threads, bounded sample
@@ -482,6 +494,7 @@ def main():
                                        "ComputeStereoMatches, SearchByProjection(cur,last,th=15), SearchByProjection(F,"
                                        "local map points,th=3)",
                            "frames_per_step_per_gpu": B, "images_per_step_per_gpu": nimg,
+                           "pipeline": f"{NH} extractor handles / CUDA streams; value: one host thread; e2e: one host thread per handle",
                            "queries_per_frame": {"last_frame": nq_last / B, "local_map": nq_loc / B},
                            "matches_per_frame": {"last_frame": float(nm_host[:B].mean()), "local_map": float(nm_host[B:].mean())},
                            "l2": f"input pool of {pool_batches} batches = {pool_batches * nimg * W * H / 1e6:.0f} MB > 126 MB L2, "
