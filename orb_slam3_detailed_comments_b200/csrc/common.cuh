@@ -62,6 +62,7 @@ struct ExtractGeom {
     int nlevels, totalCells, totalTiles;
     int candTotal, kpTotal, sortTotal;  // per-image block sizes (uint32 slots)
     int iniTh, minTh;
+    int fastRows;                       // max over the levels of hCell + 6: rows of the FAST cell staging arrays
     LevelGeom lv[ORB_MAX_LEVELS];
 };
 

@@ -110,6 +110,7 @@ static orb_status plan_geometry(orbx_handle* h, int w, int hh) {
         L.hCell = (int)ceilf(height / L.nRows);
         L.cellBase = cells;
         cells += L.nCols * L.nRows;
+        g.fastRows = std::max(g.fastRows, L.hCell + 6);
         L.tilesX = (L.w + BLUR_TW - 1) / BLUR_TW;
         L.tilesY = (L.h + BLUR_TH - 1) / BLUR_TH;
         L.tileBase = tiles;
@@ -154,6 +155,7 @@ static orb_status plan_geometry(orbx_handle* h, int w, int hh) {
             linear_taps(P.h, L.h, taps.data() + L.tapOff + L.w);
         }
     }
+    if (g.fastRows > FAST_ROWS) return set_error(ORB_ERR_UNSUPPORTED, "FAST cell taller than the staging arrays");
     g.totalCells = cells;
     g.totalTiles = tiles;
     g.candTotal = cand;
@@ -399,7 +401,11 @@ static orb_status run_pipeline(orbx_handle* h, int batch, int lap0, int lap1) {
         ORB_LAUNCHED();
     }
     if (prof) cudaEventRecord(h->ev[2], st);
-    k_fast_cells<<<dim3(g.totalCells, batch), FAST_THREADS, 0, st>>>(g, h->d_cand, h->d_cand_cnt, h->d_err);
+    {   // pe / po / se rows + the NMS tile (which also holds the list of pixel pairs that pass the high-speed test)
+        const size_t fsm = (size_t)g.fastRows * (3 * FAST_PW + FAST_TW) * 4;
+        ORB_CUDA(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+        k_fast_cells<<<dim3(g.totalCells, batch), FAST_THREADS, fsm, st>>>(g, h->d_cand, h->d_cand_cnt, h->d_err);
+    }
     ORB_LAUNCHED();
     if (prof) cudaEventRecord(h->ev[3], st);
     // DistributeOctTree: level groups on parallel streams (fork from / join into the handle's stream)

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ ExtractG
 // appended to the level's candidate list (order-free: the quadtree re-derives the reference order
 // from the coordinates).
 // ---------------------------------------------------------------------------------------------
-#define FAST_ROWS 76
+#define FAST_ROWS 76   // upper bound on the staged rows of a cell (hCell + 6); the kernel sizes its arrays from ExtractGeom::fastRows
 #define FAST_TW 22
 #define FAST_THREADS 128
 
@@ -89,18 +89,35 @@ __device__ __forceinline__ uint32_t shift_word(uint32_t L, uint32_t C, uint32_t 
 
 #define FAST_PW 46   // 16x2-packed pixel pairs per staged row (tile width <= 88 px)
 
+// cv::FAST's high-speed test in packed form: a 9-arc of the 16-ring contains at least one pixel of each antipodal pair,
+// so a pixel can only be a corner at threshold T if min over the 4 pairs (k, k+8), k = 0, 2, 4, 6, of max(r_k, r_k+8)
+// exceeds c + T (bright arc), or max over the pairs of min(r_k, r_k+8) is below c - T (dark arc).
+// hi / lo = that min-of-max / max-of-min for two adjacent pixels (16x2 lanes, raw 0..255); returns a mask with bit 15 /
+// bit 31 set for the lane(s) that pass.
+__device__ __forceinline__ uint32_t fast_pretest_x2(uint32_t c2, uint32_t hi, uint32_t lo, uint32_t T2p1) {
+    const uint32_t H = 0x80008000u;
+    const uint32_t x = (hi | H) - (c2 + T2p1);      // lane >= 0x8000  <=>  hi >= c + T + 1   (no borrow crosses the lanes)
+    const uint32_t y = (c2 | H) - (lo + T2p1);      //                 <=>  c >= lo + T + 1
+    return (x | y) & H;
+}
+
 __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_constant__ ExtractGeom g, uint32_t* __restrict__ cand,
                                                             int* __restrict__ candCnt, int* __restrict__ err) {
     // The window is staged twice as 16x2-packed pixel pairs: pe[r][i] = (px 2i, px 2i+1), po[r][i] = (px 2i+1, px 2i+2).
     // Every ring sample of a pixel pair is then ONE 32-bit shared-memory load already in the layout the packed DPX
-    // min/max instructions want (no per-sample byte permutes).
-    __shared__ __align__(16) uint32_t pe[FAST_ROWS][FAST_PW];
-    __shared__ __align__(16) uint32_t po[FAST_ROWS][FAST_PW];
-    __shared__ __align__(16) uint32_t se[FAST_ROWS][FAST_PW];   // scores >= minTh (else 0) of the even-aligned pairs, 16x2
-    // NMS result, one byte per pixel: aliases pe[][] (dead once the scores are computed)
-    uint32_t (*tile)[FAST_TW] = reinterpret_cast<uint32_t (*)[FAST_TW]>(&pe[0][0]);
+    // min/max instructions want (no per-sample byte permutes).  Rows are sized for the tallest cell of this geometry.
+    extern __shared__ __align__(16) uint32_t fast_smem[];
+    const int R = g.fastRows;
+    uint32_t (*pe)[FAST_PW] = reinterpret_cast<uint32_t (*)[FAST_PW]>(fast_smem);
+    uint32_t (*po)[FAST_PW] = pe + R;
+    uint32_t (*se)[FAST_PW] = po + R;   // scores >= T (else 0) of the even-aligned pairs, 16x2
+    // NMS result, one byte per pixel; the list of pixel pairs that pass the high-speed test lives in the same bytes
+    // (dead before the NMS writes)
+    uint32_t (*tile)[FAST_TW] = reinterpret_cast<uint32_t (*)[FAST_TW]>(se + R);
+    uint16_t* lst = reinterpret_cast<uint16_t*>(tile);
     __shared__ int s_warp[FAST_THREADS / 32 + 1];
     __shared__ int s_base;
+    __shared__ int s_nlist;
 
     const int cell = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
     int l = 0;
@@ -134,68 +151,116 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
             *reinterpret_cast<uint2*>(&se[r][2 * c]) = make_uint2(0u, 0u);
         }
     }
+    if (tid == 0) s_nlist = 0;
     __syncthreads();
 
-    const int ntask = (ty1 - ty0) * ngrp;
-    const int minTh = g.minTh, iniTh = g.iniTh;
-    for (int t = tid; t < ntask; t += FAST_THREADS) {
-        const int row = (int)(((uint32_t)t * magicG) >> 20), grp = t - row * ngrp;
-        const int r = row + 3, wd = grp + 1, pA = 2 * wd;
-        uint32_t rl[16], rh[16];
-        // ring offsets (dx,dy) clockwise from the top: even dx -> pe at pA + dx/2, odd dx -> po at pA + (dx-1)/2
-#define RING_E(k, dy, h) { const uint32_t* q = &pe[r + (dy)][pA + (h)]; rl[k] = q[0]; rh[k] = q[1]; }
-#define RING_O(k, dy, h) { const uint32_t* q = &po[r + (dy)][pA + (h)]; rl[k] = q[0]; rh[k] = q[1]; }
-        RING_E(0, -3, 0)  RING_O(1, -3, 0)  RING_E(2, -2, 1)  RING_O(3, -1, 1)
-        RING_O(4, 0, 1)   RING_O(5, 1, 1)   RING_E(6, 2, 1)   RING_O(7, 3, 0)
-        RING_E(8, 3, 0)   RING_O(9, 3, -1)  RING_E(10, 2, -1) RING_O(11, 1, -2)
-        RING_O(12, 0, -2) RING_O(13, -1, -2) RING_E(14, -2, -1) RING_O(15, -3, -1)
+    const int ntask = (ty1 - ty0) * ngrp;          // one task = 4 adjacent pixels = two 16x2 pairs
+    const int ntaskW = (ntask + 31) & ~31;         // warp-uniform trip count (ballots inside)
+    const int lane = tid & 31, wid = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    int thr = g.iniTh;
+    // Frame cells are searched at iniThFAST first and, only if that leaves the cell empty, again at minThFAST
+    // (ORBextractor.cc:1135-1148).  A corner at threshold T has score >= T, and a score below T never suppresses one
+    // at or above it, so each pass only needs the scores >= its own T.
+    for (int pass = 0; pass < 2; ++pass) {
+        thr = pass ? g.minTh : g.iniTh;
+        const uint32_t T2p1 = (uint32_t)(thr + 1) * 0x00010001u;
+        // A: high-speed test of every pixel pair; the survivors are compacted into lst[]
+        for (int t = tid; t < ntaskW; t += FAST_THREADS) {
+            uint32_t pa = 0u, pb = 0u;
+            int code = 0;
+            if (t < ntask) {
+                const int row = (int)(((uint32_t)t * magicG) >> 20), grp = t - row * ngrp;
+                const int r = row + 3, pA = 2 * (grp + 1);
+                code = r * 64 + pA;
+                // antipodal ring pairs (0,8) (2,10) (4,12) (6,14): (dx,dy) = (0,-3)/(0,3) (2,-2)/(-2,2) (3,0)/(-3,0) (2,2)/(-2,-2)
+                const uint32_t *q0 = &pe[r - 3][pA], *q8 = &pe[r + 3][pA], *q2 = &pe[r - 2][pA + 1], *q10 = &pe[r + 2][pA - 1];
+                const uint32_t *q4 = &po[r][pA + 1], *q12 = &po[r][pA - 2], *q6 = &pe[r + 2][pA + 1], *q14 = &pe[r - 2][pA - 1];
+                const uint2 c = *reinterpret_cast<const uint2*>(&pe[r][pA]);   // pA is even: 8-byte aligned
+                const uint32_t hiA = min_u16x2(min3_u16x2(max_u16x2(q0[0], q8[0]), max_u16x2(q2[0], q10[0]), max_u16x2(q4[0], q12[0])),
+                                               max_u16x2(q6[0], q14[0]));
+                const uint32_t loA = max_u16x2(max3_u16x2(min_u16x2(q0[0], q8[0]), min_u16x2(q2[0], q10[0]), min_u16x2(q4[0], q12[0])),
+                                               min_u16x2(q6[0], q14[0]));
+                const uint32_t hiB = min_u16x2(min3_u16x2(max_u16x2(q0[1], q8[1]), max_u16x2(q2[1], q10[1]), max_u16x2(q4[1], q12[1])),
+                                               max_u16x2(q6[1], q14[1]));
+                const uint32_t loB = max_u16x2(max3_u16x2(min_u16x2(q0[1], q8[1]), min_u16x2(q2[1], q10[1]), min_u16x2(q4[1], q12[1])),
+                                               min_u16x2(q6[1], q14[1]));
+                pa = fast_pretest_x2(c.x, hiA, loA, T2p1);
+                pb = fast_pretest_x2(c.y, hiB, loB, T2p1);
+            }
+            const unsigned ma = __ballot_sync(0xffffffffu, pa != 0u), mb = __ballot_sync(0xffffffffu, pb != 0u);
+            const int na = __popc(ma), n = na + __popc(mb);
+            if (n) {   // warp-uniform
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_nlist, n);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (pa) lst[base + __popc(ma & lt)] = (uint16_t)code;
+                if (pb) lst[base + na + __popc(mb & lt)] = (uint16_t)(code + 1);
+            }
+        }
+        __syncthreads();
+        // B: full score of the listed pairs only
+        const int nl = s_nlist;
+        for (int i = tid; i < nl; i += FAST_THREADS) {
+            const int code = lst[i], r = code >> 6, p = code & 63;
+            uint32_t ring[16];
+            // ring offsets (dx,dy) clockwise from the top: even dx -> pe at p + dx/2, odd dx -> po at p + (dx-1)/2
+#define RING_E(k, dy, h) ring[k] = pe[r + (dy)][p + (h)];
+#define RING_O(k, dy, h) ring[k] = po[r + (dy)][p + (h)];
+            RING_E(0, -3, 0)  RING_O(1, -3, 0)  RING_E(2, -2, 1)  RING_O(3, -1, 1)
+            RING_O(4, 0, 1)   RING_O(5, 1, 1)   RING_E(6, 2, 1)   RING_O(7, 3, 0)
+            RING_E(8, 3, 0)   RING_O(9, 3, -1)  RING_E(10, 2, -1) RING_O(11, 1, -2)
+            RING_O(12, 0, -2) RING_O(13, -1, -2) RING_E(14, -2, -1) RING_O(15, -3, -1)
 #undef RING_E
 #undef RING_O
-        const uint32_t s01 = fast_score_x2(pe[r][pA], rl);
-        const uint32_t s23 = fast_score_x2(pe[r][pA + 1], rh);
-        const int xb = gx0 + 4 * wd;
-        const int s0 = (int)(s01 & 0xffffu) - 256, s1 = (int)(s01 >> 16) - 256, s2 = (int)(s23 & 0xffffu) - 256, s3 = (int)(s23 >> 16) - 256;
-        const uint32_t k0 = (s0 >= minTh && xb >= tx0 && xb < tx1) ? (uint32_t)s0 : 0u;
-        const uint32_t k1 = (s1 >= minTh && xb + 1 >= tx0 && xb + 1 < tx1) ? (uint32_t)s1 : 0u;
-        const uint32_t k2 = (s2 >= minTh && xb + 2 >= tx0 && xb + 2 < tx1) ? (uint32_t)s2 : 0u;
-        const uint32_t k3 = (s3 >= minTh && xb + 3 >= tx0 && xb + 3 < tx1) ? (uint32_t)s3 : 0u;
-        *reinterpret_cast<uint2*>(&se[r][pA]) = make_uint2(k0 | (k1 << 16), k2 | (k3 << 16));
-    }
-    __syncthreads();
-
-    // NMS on the 16x2 score map with packed 3-input max; the result is byte-packed per 4 pixels into tile[][]
-    int has_ini = 0;
-    for (int t = tid; t < ntask; t += FAST_THREADS) {
-        const int row = (int)(((uint32_t)t * magicG) >> 20), grp = t - row * ngrp;
-        const int r = row + 3, wd = grp + 1, pA = 2 * wd;
-        const uint32_t cA = se[r][pA], cB = se[r][pA + 1];
-        uint32_t res = 0u;
-        if ((cA | cB) != 0u) {
-            const uint32_t* u = &se[r - 1][pA - 1];
-            const uint32_t* m = &se[r][pA - 1];
-            const uint32_t* d = &se[r + 1][pA - 1];
-            const uint32_t u0 = u[0], u1 = u[1], u2 = u[2], u3 = u[3], m0 = m[0], m3 = m[3], d0 = d[0], d1 = d[1], d2 = d[2], d3 = d[3];
-            // odd-aligned pairs (px 2i-1, 2i) / (px 2i+1, 2i+2) from two even pairs
-            const uint32_t uA = max3_u16x2(__byte_perm(u0, u1, 0x5432), u1, __byte_perm(u1, u2, 0x5432));
-            const uint32_t dA = max3_u16x2(__byte_perm(d0, d1, 0x5432), d1, __byte_perm(d1, d2, 0x5432));
-            const uint32_t mA = max_u16x2(__byte_perm(m0, cA, 0x5432), __byte_perm(cA, cB, 0x5432));
-            const uint32_t uB = max3_u16x2(__byte_perm(u1, u2, 0x5432), u2, __byte_perm(u2, u3, 0x5432));
-            const uint32_t dB = max3_u16x2(__byte_perm(d1, d2, 0x5432), d2, __byte_perm(d2, d3, 0x5432));
-            const uint32_t mB = max_u16x2(__byte_perm(cA, cB, 0x5432), __byte_perm(cB, m3, 0x5432));
-            const uint32_t mxA = max3_u16x2(uA, dA, mA), mxB = max3_u16x2(uB, dB, mB);
-            // strictly greater than all 8 neighbours: c >= mx + 1  <=>  max(c, mx + 1) == c   (scores <= 254)
-            const uint32_t gA = max_u16x2(cA, mxA + 0x00010001u) ^ cA, gB = max_u16x2(cB, mxB + 0x00010001u) ^ cB;
-            const uint32_t r0 = (gA & 0xffffu) ? 0u : (cA & 0xffffu), r1 = (gA >> 16) ? 0u : (cA >> 16);
-            const uint32_t r2 = (gB & 0xffffu) ? 0u : (cB & 0xffffu), r3 = (gB >> 16) ? 0u : (cB >> 16);
-            res = r0 | (r1 << 8) | (r2 << 16) | (r3 << 24);
-            const uint32_t ini4 = (uint32_t)iniTh * 0x01010101u;
-            has_ini |= (__vcmpgeu4(res, ini4) != 0u);
+            const uint32_t s01 = fast_score_x2(pe[r][p], ring);
+            const int xb = gx0 + 2 * p;
+            const int s0 = (int)(s01 & 0xffffu) - 256, s1 = (int)(s01 >> 16) - 256;
+            const uint32_t k0 = (s0 >= thr && xb >= tx0 && xb < tx1) ? (uint32_t)s0 : 0u;
+            const uint32_t k1 = (s1 >= thr && xb + 1 >= tx0 && xb + 1 < tx1) ? (uint32_t)s1 : 0u;
+            se[r][p] = k0 | (k1 << 16);
         }
-        tile[r][wd] = res;
+        __syncthreads();
+
+        // NMS on the 16x2 score map with packed 3-input max; the result is byte-packed per 4 pixels into tile[][]
+        int has = 0;
+        for (int t = tid; t < ntask; t += FAST_THREADS) {
+            const int row = (int)(((uint32_t)t * magicG) >> 20), grp = t - row * ngrp;
+            const int r = row + 3, wd = grp + 1, pA = 2 * wd;
+            const uint32_t cA = se[r][pA], cB = se[r][pA + 1];
+            uint32_t res = 0u;
+            if ((cA | cB) != 0u) {
+                const uint32_t* u = &se[r - 1][pA - 1];
+                const uint32_t* m = &se[r][pA - 1];
+                const uint32_t* d = &se[r + 1][pA - 1];
+                const uint32_t u0 = u[0], u1 = u[1], u2 = u[2], u3 = u[3], m0 = m[0], m3 = m[3], d0 = d[0], d1 = d[1], d2 = d[2], d3 = d[3];
+                // odd-aligned pairs (px 2i-1, 2i) / (px 2i+1, 2i+2) from two even pairs
+                const uint32_t uA = max3_u16x2(__byte_perm(u0, u1, 0x5432), u1, __byte_perm(u1, u2, 0x5432));
+                const uint32_t dA = max3_u16x2(__byte_perm(d0, d1, 0x5432), d1, __byte_perm(d1, d2, 0x5432));
+                const uint32_t mA = max_u16x2(__byte_perm(m0, cA, 0x5432), __byte_perm(cA, cB, 0x5432));
+                const uint32_t uB = max3_u16x2(__byte_perm(u1, u2, 0x5432), u2, __byte_perm(u2, u3, 0x5432));
+                const uint32_t dB = max3_u16x2(__byte_perm(d1, d2, 0x5432), d2, __byte_perm(d2, d3, 0x5432));
+                const uint32_t mB = max_u16x2(__byte_perm(cA, cB, 0x5432), __byte_perm(cB, m3, 0x5432));
+                const uint32_t mxA = max3_u16x2(uA, dA, mA), mxB = max3_u16x2(uB, dB, mB);
+                // strictly greater than all 8 neighbours: c >= mx + 1  <=>  max(c, mx + 1) == c   (scores <= 254)
+                const uint32_t gA = max_u16x2(cA, mxA + 0x00010001u) ^ cA, gB = max_u16x2(cB, mxB + 0x00010001u) ^ cB;
+                const uint32_t r0 = (gA & 0xffffu) ? 0u : (cA & 0xffffu), r1 = (gA >> 16) ? 0u : (cA >> 16);
+                const uint32_t r2 = (gB & 0xffffu) ? 0u : (cB & 0xffffu), r3 = (gB >> 16) ? 0u : (cB >> 16);
+                res = r0 | (r1 << 8) | (r2 << 16) | (r3 << 24);
+                has |= (res != 0u);
+            }
+            tile[r][wd] = res;
+        }
+        if (__syncthreads_or(has) || pass == 1) break;  // also orders the tile[] writes
+        // empty at iniThFAST: clear the score map and run the cell again at minThFAST
+        for (int i = tid; i < ch * nW; i += FAST_THREADS) {
+            const int r = (int)(((uint32_t)i * ((1u << 20) / (uint32_t)nW + 1u)) >> 20), c = i - r * nW;
+            *reinterpret_cast<uint2*>(&se[r][2 * c]) = make_uint2(0u, 0u);
+        }
+        if (tid == 0) s_nlist = 0;
+        __syncthreads();
     }
-    const int cell_has_ini = __syncthreads_or(has_ini);  // also orders the tile[] writes
-    const uint32_t thr = (uint32_t)(cell_has_ini ? iniTh : minTh);
-    const uint32_t thr4 = thr * 0x01010101u;
+    const uint32_t thr4 = (uint32_t)thr * 0x01010101u;
 
     int cnt = 0;
     for (int t = tid; t < ntask; t += FAST_THREADS) {
@@ -204,7 +269,6 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
         if (v) cnt += __popc(__vcmpgeu4(v, thr4) & 0x01010101u);
     }
     // CTA exclusive scan of cnt
-    const int lane = tid & 31, wid = tid >> 5;
     int inc = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -240,7 +304,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t s = (v >> (8 * k)) & 0xffu;
-            if (s >= thr) out[off++] = qt_pack_cand(xb + k, yb, (int)s);
+            if (s >= (uint32_t)thr) out[off++] = qt_pack_cand(xb + k, yb, (int)s);
         }
     }
 }
