@@ -94,6 +94,7 @@ struct ProjParams {
     float* quv;                // mode 1: [nq][4] u, v, radius, invzc
     int* match;                // mode 0: [nq] feature index or -1;  mode 1: per compact feature row: query or -1
     int* nmatches;             // [n_frames]
+    int* seqFlag;              // [n_frames] modes 0 / 1: set by the parallel resolve when a frame must take the sequential kernel; null = always sequential
 };
 
 __device__ __forceinline__ void stage_frame(const ProjParams& P, int img, unsigned char* smem, FrameFeat& F, int& N, int& row0) {
@@ -254,7 +255,8 @@ __device__ __forceinline__ int warp_scan_query(const ProjParams& P, const FrameF
 // warp minimum is b1, the minimum of what remains is b2.
 __device__ __forceinline__ void warp_rescan_best2(const ProjParams& P, const FrameFeat& F, int N, int row0, const Window& w,
                                                   const uint8_t* qd, float ur_pred, float er_max, const uint8_t* claimed, int gate,
-                                                  unsigned long long& b1, unsigned long long& b2, const int* md = nullptr) {
+                                                  unsigned long long& b1, unsigned long long& b2, const int* md = nullptr,
+                                                  const int* claimMin = nullptr, int ql = 0) {
     const int lane = threadIdx.x & 31;
     unsigned long long l1 = ~0ull, l2 = ~0ull;
     if (!w.empty) {
@@ -263,6 +265,7 @@ __device__ __forceinline__ void warp_rescan_best2(const ProjParams& P, const Fra
         for (int base = 0; base < N; base += 32) {
             const int i = base + lane;
             if (i >= N || !scan_accepts(P, F, w, i, ur_pred, er_max, claimed, gate)) continue;
+            if (claimMin && claimMin[i] < ql) continue;   // parallel resolve: claimed by an earlier query
             const unsigned long long d = hamming256(a0, a1, P.desc + (size_t)(row0 + i) * 32);
             if (md && md[i] <= (int)d) continue;   // SearchForInitialization: vMatchedDistance[i2] <= dist
             const unsigned long long cell = w.node >= 0 ? 0ull : (unsigned long long)F.cell[i];
@@ -579,6 +582,7 @@ __global__ void __launch_bounds__(PM_WARPS * 32) k_proj_candidates(const __grid_
 __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ ProjParams P) {
     extern __shared__ __align__(16) unsigned char pm_smem[];
     const int frame = blockIdx.x;
+    if (P.seqFlag && P.seqFlag[frame] == 0) return;   // resolved by k_proj_resolve_par
     const int q0 = P.qoff[frame], q1 = P.qoff[frame + 1];
     FrameFeat F;
     int N, row0;
@@ -804,6 +808,182 @@ __global__ void __launch_bounds__(256) k_proj_resolve(const __grid_constant__ Pr
     if (threadIdx.x == 0) P.nmatches[frame] = s_nm;
 }
 
+
+// ---- kernel B': the ordered resolve as a parallel fixed point (modes 0 and 1, the per-frame tracking searches) -----
+// The reference walks the queries in order and a feature taken by query i is skipped by every later query.  Here every
+// query first picks from its stored (distance, order)-sorted list as if nothing were taken; then, round after round,
+// each query re-decides seeing only the features claimed BY EARLIER QUERIES in the previous round (claim[f] = smallest
+// query index whose accepted choice is f).  Query 0 is final after one round, and a query is final one round after all
+// the earlier queries it depends on, so the loop ends in (longest dependency chain + 1) rounds -- 2 to 4 in practice --
+// and at the fixed point every choice is exactly what the sequential walk produces.  A query whose stored list is
+// exhausted by claims (count > PM_K) gets the same exact rescan as in the sequential kernel, with the claim predicate.
+#define PR_THREADS 512
+#define PR_QCAP 8192
+#define PR_LIST 512
+
+__device__ __forceinline__ int pr_decide(const ProjParams& P, const FrameFeat& F, unsigned long long b1, unsigned long long b2) {
+    if (b1 == ~0ull) return -1;
+    const int bestDist = (int)(b1 >> 32), bestIdx = (int)(b1 & 0xffffu);
+    if (bestDist > 100) return -1;   // TH_HIGH
+    if (P.mode == 0) {               // ORBmatcher.cc:203-232
+        const int bestDist2 = (b2 == ~0ull) ? 256 : (int)(b2 >> 32);
+        const int idx2 = (b2 == ~0ull) ? 0 : (int)(b2 & 0xffffu);
+        const int bestLevel = F.oct[bestIdx], bestLevel2 = (b2 == ~0ull) ? -1 : (int)F.oct[idx2];
+        if (bestLevel == bestLevel2 && (float)bestDist > fmul(P.nnratio, (float)bestDist2)) return -1;
+    }
+    return bestIdx;
+}
+
+__global__ void __launch_bounds__(PR_THREADS) k_proj_resolve_par(const __grid_constant__ ProjParams P) {
+    extern __shared__ __align__(16) unsigned char pm_smem[];
+    const int frame = blockIdx.x, tid = threadIdx.x;
+    const int q0 = P.qoff[frame], q1 = P.qoff[frame + 1], nq = q1 - q0;
+    if (nq > PR_QCAP) {
+        if (tid == 0) P.seqFlag[frame] = 1;
+        return;
+    }
+    FrameFeat F;
+    int N, row0;
+    stage_frame(P, P.frame_image[frame], pm_smem, F, N, row0);
+    unsigned char* extra = pm_smem + ((frame_smem_bytes(P.maxFeat) + 15) / 16) * 16;
+    int* s_claim = reinterpret_cast<int*>(extra);            // maxFeat
+    int* s_holder = s_claim + P.maxFeat;                       // maxFeat (mode 1: last query holding the feature)
+    int* s_choice = s_holder + P.maxFeat;                      // PR_QCAP
+    int* s_list = s_choice + PR_QCAP;                          // PR_LIST
+    uint8_t* s_static = reinterpret_cast<uint8_t*>(s_list + PR_LIST);   // maxFeat
+    __shared__ int s_hist[30], s_keep[30], s_nm, s_nlist, s_over;
+    for (int i = tid; i < N; i += PR_THREADS) {
+        s_static[i] = (P.mode == 0 && P.flag) ? P.flag[row0 + i] : 0;
+        s_holder[i] = -1;
+        s_claim[i] = 0x7fffffff;
+    }
+    for (int i = tid; i < nq; i += PR_THREADS) s_choice[i] = -1;
+    if (tid < 30) s_hist[tid] = 0;
+    if (tid == 0) { s_nm = 0; s_nlist = 0; s_over = 0; }
+    __syncthreads();
+    const int need = P.mode == 1 ? 1 : 2;
+    const int lane = tid & 31, warp = tid >> 5;
+    for (;;) {
+        int changed = 0;
+        for (int ql = tid; ql < nq; ql += PR_THREADS) {
+            const int q = q0 + ql, count = P.cnt[q];
+            int choice = -1;
+            if (count > 0) {
+                const int stored = min(count, PM_K);
+                const unsigned long long* top = P.topk + (size_t)q * PM_K;
+                unsigned long long b1 = ~0ull, b2 = ~0ull;
+                int nfree = 0;
+                for (int k = 0; k < stored && nfree < need; ++k) {
+                    const unsigned long long key = top[k];
+                    const int f = (int)(key & 0xffffu);
+                    if (s_static[f] || s_claim[f] < ql) continue;
+                    if (nfree == 0) b1 = key; else b2 = key;
+                    ++nfree;
+                }
+                if (nfree < need && count > PM_K) {   // exhausted by claims: exact rescan below
+                    const int slot = atomicAdd(&s_nlist, 1);
+                    if (slot < PR_LIST) s_list[slot] = ql; else s_over = 1;
+                    continue;
+                }
+                choice = pr_decide(P, F, b1, b2);
+            }
+            if (choice != s_choice[ql]) { s_choice[ql] = choice; changed = 1; }
+        }
+        __syncthreads();
+        const int nl = min(s_nlist, PR_LIST);
+        for (int i = warp; i < nl; i += PR_THREADS / 32) {
+            const int ql = s_list[i], q = q0 + ql;
+            Window w;
+            float ur_pred = 0.f, er_max = 0.f, u = 0.f, invzc = 0.f, radius = 0.f;
+            if (P.mode == 0) {
+                local_window(P, q, w, er_max);
+                ur_pred = P.a2[q];
+            } else {
+                last_frame_window(P, frame, q, w, u, invzc, radius);
+                ur_pred = fsub(u, fmul(P.bf, invzc));
+                er_max = radius;
+            }
+            unsigned long long b1, b2;
+            warp_rescan_best2(P, F, N, row0, w, P.qdesc + 32 * (size_t)q, ur_pred, er_max, s_static, 0, b1, b2, nullptr, s_claim, ql);
+            const int choice = pr_decide(P, F, b1, b2);
+            if (lane == 0 && choice != s_choice[ql]) { s_choice[ql] = choice; changed = 1; }
+        }
+        const int any = __syncthreads_or(changed);
+        if (s_over) {                                  // more exhausted lists than the rescan list holds: sequential kernel
+            if (tid == 0) P.seqFlag[frame] = 1;
+            return;
+        }
+        if (!any) break;
+        for (int i = tid; i < N; i += PR_THREADS) s_claim[i] = 0x7fffffff;
+        if (tid == 0) s_nlist = 0;
+        __syncthreads();
+        for (int ql = tid; ql < nq; ql += PR_THREADS) {
+            const int c = s_choice[ql];
+            if (c >= 0 && (P.mode == 0 || P.flag[q0 + ql])) atomicMin(&s_claim[c], ql);   // mode 1: only map points with observations block
+        }
+        __syncthreads();
+    }
+    // ---- outputs ---------------------------------------------------------------------------------------------------
+    int acc = 0;
+    for (int ql = tid; ql < nq; ql += PR_THREADS) {
+        const int q = q0 + ql, c = s_choice[ql];
+        if (P.mode == 0) {
+            P.match[q] = c;
+        } else {
+            int e = -1;
+            if (c >= 0) {
+                atomicMax(&s_holder[c], q);              // the last query that takes a feature holds it
+                if (P.checkOri) {
+                    float rot = fsub(P.f0[q], F.ang[c]);
+                    if (rot < 0.0f) rot = fadd(rot, 360.0f);
+                    int bin = (int)roundf(fmul(rot, 1.0f / 30));
+                    if (bin == 30) bin = 0;
+                    atomicAdd(&s_hist[bin], 1);
+                    e = (bin << 16) | c;
+                }
+            }
+            if (P.checkOri) P.quv[q] = __int_as_float(e);
+        }
+        acc += c >= 0;
+    }
+    acc = __reduce_add_sync(0xffffffffu, acc);
+    if (lane == 0 && acc) atomicAdd(&s_nm, acc);
+    __syncthreads();
+    if (P.mode == 0) {
+        if (tid == 0) P.nmatches[frame] = s_nm;
+        return;
+    }
+    // rotation-histogram filter (ORBmatcher.cc:2160-2181, ComputeThreeMaxima :2335-2377)
+    if (tid == 0) {
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < 30; ++i) {
+            const int s = s_hist[i];
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if ((float)max2 < fmul(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+        else if ((float)max3 < fmul(0.1f, (float)max1)) { ind3 = -1; }
+        for (int i = 0; i < 30; ++i) s_keep[i] = (i == ind1 || i == ind2 || i == ind3) ? 1 : 0;
+    }
+    __syncthreads();
+    if (P.checkOri) {
+        int removed = 0;
+        for (int ql = tid; ql < nq; ql += PR_THREADS) {
+            const int e = __float_as_int(P.quv[q0 + ql]);
+            if (e < 0) continue;
+            if (!s_keep[e >> 16]) {
+                s_holder[e & 0xffff] = -1;   // every entry of a rejected bin clears its feature (duplicates included)
+                ++removed;
+            }
+        }
+        if (removed) atomicSub(&s_nm, removed);
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += PR_THREADS) P.match[row0 + i] = s_holder[i];
+    if (tid == 0) P.nmatches[frame] = s_nm;
+}
+
 }  // namespace orb
 
 // ------------------------------------------------------------------------------------------------
@@ -848,6 +1028,12 @@ static orb_status launch_proj(orbx_handle* h, ProjParams& P, int n_frames, int m
     dim3 grid((max_q_per_frame + PM_QPB - 1) / PM_QPB, n_frames);
     if (grid.x > 0) {
         k_proj_candidates<<<grid, PM_WARPS * 32, csm, st>>>(P);
+        ORB_LAUNCHED();
+    }
+    if (P.seqFlag) {   // modes 0 / 1: parallel fixed-point resolve; frames it cannot finish are flagged for the sequential kernel
+        const size_t psm = fsm + (size_t)P.maxFeat * 9 + (size_t)(PR_QCAP + PR_LIST) * 4 + 64;
+        ORB_CUDA(cudaFuncSetAttribute(k_proj_resolve_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+        k_proj_resolve_par<<<n_frames, PR_THREADS, psm, st>>>(P);
         ORB_LAUNCHED();
     }
     const size_t rsm = fsm + (size_t)PM_CHUNK * PM_K * 8 + (size_t)PM_CHUNK * 4 + (size_t)P.maxFeat * (P.mode == 4 ? 9 : 5) + (size_t)PM_CHUNK * 5 + 256;
@@ -934,6 +1120,8 @@ extern "C" orb_status orbm_search_local_points(orbx_handle* h, const orbm_camera
     P.cnt = cur.take<int>(nq);
     P.match = dev ? match_out : cur.take<int>(nq);
     P.nmatches = (dev && nmatches_out) ? nmatches_out : cur.take<int>(nf);
+    P.seqFlag = cur.take<int>(nf);
+    ORB_CUDA(cudaMemsetAsync(P.seqFlag, 0, sizeof(int) * nf, h->stream));
     if (nq > 0 && (s = launch_proj(h, P, nf, maxq)) != ORB_OK) return s;
     if (!dev) {
         if (nq > 0) ORB_CUDA(cudaMemcpyAsync(match_out, P.match, sizeof(int) * (size_t)nq, cudaMemcpyDeviceToHost, h->stream));
@@ -997,6 +1185,8 @@ extern "C" orb_status orbm_search_last_frame(orbx_handle* h, const orbm_camera* 
     P.match = dev ? feature_match_out : cur.take<int>(total_rows);
     P.nmatches = (dev && nmatches_out) ? nmatches_out : cur.take<int>(nf);
     ORB_CUDA(cudaMemsetAsync(P.match, 0xff, sizeof(int) * (size_t)total_rows, h->stream));
+    P.seqFlag = cur.take<int>(nf);
+    ORB_CUDA(cudaMemsetAsync(P.seqFlag, 0, sizeof(int) * nf, h->stream));
     if ((s = launch_proj(h, P, nf, maxq)) != ORB_OK) return s;
     if (!dev) {
         ORB_CUDA(cudaMemcpyAsync(feature_match_out, P.match, sizeof(int) * (size_t)total_rows, cudaMemcpyDeviceToHost, h->stream));
