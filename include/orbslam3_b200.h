@@ -376,6 +376,32 @@ orb_status lba_solve(lba_handle* h, const lba_problem* in, lba_result* out, cons
 orb_status lba_solve_batch(lba_handle* h, int32_t n_problems, const lba_problem* in, lba_result* out,
                            const volatile int32_t* stop_flag);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer::PoseOptimization(Frame*)  (include/Optimizer.h:48, src/Optimizer.cc:55-412), Nleft == -1
+ *
+ * The tracking thread calls it after every projection search (Tracking.cc:3222, 3443, 3522).  Several frames per call
+ * (sequence-sharded replay); frame f owns edges [edge_offset[f], edge_offset[f+1]): one per feature i with
+ * pFrame->mvpMapPoints[i] != NULL, in feature order -- world_pos = pMP->GetWorldPos(), obs = kpUn.pt.x, kpUn.pt.y,
+ * mvuRight[i] (< 0 => monocular EdgeSE3ProjectXYZOnlyPose, else EdgeStereoSE3ProjectXYZOnlyPose), inv_sigma2 =
+ * mvInvLevelSigma2[kpUn.octave].  pose = pFrame->GetPose() (qx qy qz qw tx ty tz).  All arithmetic in fp64 like g2o.
+ * pose_out[f] = SE3quat_recov (the caller casts to float and calls SetPose); outlier_out[e] = pFrame->mvbOutlier of the
+ * edge's feature; inliers_out[f] = the return value nInitialCorrespondences - nBad (0 and an unchanged pose when a frame
+ * has fewer than 3 correspondences).  stats_out (may be NULL): rounds, LM iterations, LM trials, 0 per frame.
+ * on_device != 0: every array (inputs and outputs) is device memory and the call does not synchronise. */
+typedef struct {
+    int32_t n_frames;
+    int32_t on_device;
+    const int32_t* edge_offset;   /* [n_frames + 1] */
+    const float* pose;            /* [n_frames][7] */
+    const float* world_pos;       /* [ne][3] */
+    const float* obs;             /* [ne][3] */
+    const float* inv_sigma2;      /* [ne] */
+    float fx, fy, cx, cy, bf;     /* pFrame->fx .. mbf */
+} orbo_pose_problems;
+
+orb_status orbo_pose_optimization(orbx_handle* h, const orbo_pose_problems* in, double* pose_out, uint8_t* outlier_out,
+                                  int32_t* inliers_out, int32_t* stats_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -445,3 +445,152 @@ void orc_edge_jacobians(const double* pose7, const double* X, int D, const doubl
     edge_jacobians(cam, D, R, Xc, A9, B18);
 }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Optimizer::PoseOptimization(Frame*)  src/Optimizer.cc:55-412, Nleft == -1 (one camera or rectified stereo).
+// One VertexSE3Expmap, unary edges EdgeSE3ProjectXYZOnlyPose (OptimizableTypes.cpp) / EdgeStereoSE3ProjectXYZOnlyPose
+// (Thirdparty/g2o types_six_dof_expmap.cpp:339-404), Levenberg over LinearSolverDense, 4 rounds of 10 iterations that
+// restart from the frame's pose, chi2 classification (5.991 / 7.815, compared as floats) after every round, the robust
+// kernel dropped after round 2.
+//   Xw[n][3], obs[n][3] (obs[2] < 0 => monocular edge), invs2[n], cam5 = fx fy cx cy bf.
+//   pose7 in: frame pose (qx qy qz qw tx ty tz), out: SE3quat_recov.  outlier[n] out: pFrame->mvbOutlier.
+//   stats: {rounds run, total LM iterations, total LM trials, final lambda}.  Returns nInitialCorrespondences - nBad.
+extern "C" int orc_pose_optimization(int n, const double* Xw, const double* obs, const double* invs2, const double* cam5,
+                                     double* pose7, uint8_t* outlier, double* stats) {
+    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    if (n < 3) return 0;                                    // Optimizer.cc:292-293
+    Problem P;
+    P.nKF = 1; P.nMP = n; P.nE = n;
+    P.pose.assign(pose7, pose7 + 7);
+    P.point.assign(Xw, Xw + 3 * (size_t)n);
+    std::vector<int> ekf(n, 0), emp(n);
+    for (int i = 0; i < n; ++i) emp[i] = i;
+    P.fixed = nullptr; P.ekf = ekf.data(); P.emp = emp.data(); P.obs = obs; P.invs2 = invs2;
+    P.cam = {cam5[0], cam5[1], cam5[2], cam5[3], cam5[4]};
+    P.deltaMono = (double)(float)std::sqrt(5.991);          // Optimizer.cc:101-102 (const float)
+    P.deltaStereo = (double)(float)std::sqrt(7.815);
+    P.dsqrMono = (double)(float)(P.deltaMono * P.deltaMono);
+    P.dsqrStereo = (double)(float)(P.deltaStereo * P.deltaStereo);
+    std::vector<double> pose0(pose7, pose7 + 7), err(n, 0.0);
+    std::vector<uint8_t> level(n, 0);
+    bool robust = true;
+    for (int i = 0; i < n; ++i) outlier[i] = 0;
+    double H[36], b[6], x[6];
+
+    auto edge_chi2 = [&](int e) {
+        double r[3], Xc[3];
+        edge_error(P, e, r, Xc);
+        return invs2[e] * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    };
+    auto compute_errors = [&]() -> double {                  // computeActiveErrors + activeRobustChi2
+        double chi = 0;
+        for (int e = 0; e < n; ++e) {
+            if (level[e]) continue;
+            const double c = edge_chi2(e);
+            err[e] = c;
+            const bool mono = obs[3 * e + 2] < 0;
+            double w;
+            chi += robust ? huber_rho(c, mono ? P.deltaMono : P.deltaStereo, mono ? P.dsqrMono : P.dsqrStereo, &w) : c;
+        }
+        return chi;
+    };
+    auto build_system = [&]() {
+        std::fill(H, H + 36, 0.0);
+        std::fill(b, b + 6, 0.0);
+        double R[9];
+        quat_to_R(P.pose.data(), R);
+        for (int e = 0; e < n; ++e) {
+            if (level[e]) continue;
+            double r[3], Xc[3], A[9] = {0}, B[18] = {0};
+            const int D = edge_error(P, e, r, Xc);
+            edge_jacobians(P.cam, D, R, Xc, A, B);
+            const double c2 = invs2[e] * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+            double w = 1.0;
+            if (robust) huber_rho(c2, D == 2 ? P.deltaMono : P.deltaStereo, D == 2 ? P.dsqrMono : P.dsqrStereo, &w);
+            const double om = w * invs2[e];
+            for (int i = 0; i < 6; ++i) {
+                for (int j = 0; j < 6; ++j) {
+                    double s = 0;
+                    for (int d = 0; d < D; ++d) s += B[6 * d + i] * B[6 * d + j];
+                    H[6 * i + j] += om * s;
+                }
+                double s = 0;
+                for (int d = 0; d < D; ++d) s += B[6 * d + i] * r[d];
+                b[i] += -om * s;
+            }
+        }
+    };
+
+    int nBadEdges = 0, rounds = 0, totalIters = 0, totalTrials = 0;
+    double lambda = -1;
+    for (int it = 0; it < 4; ++it) {
+        P.pose = pose0;                                      // vSE3->setEstimate(pFrame->GetPose())
+        int nActive = 0;
+        for (int e = 0; e < n; ++e) nActive += level[e] == 0;
+        if (nActive > 0) {                                   // optimize(10): initializeOptimization(0) found the vertex
+            double ni = 2, currentChi = 0;
+            int nBadIt = 0;
+            bool ok = true;
+            for (int iter = 0; iter < 10 && ok; ++iter) {
+                currentChi = compute_errors();
+                double tempChi = currentChi;
+                const double iniChi = currentChi;
+                build_system();
+                if (iter == 0) {
+                    double md = 0;
+                    for (int j = 0; j < 6; ++j) md = std::max(std::fabs(H[7 * j]), md);
+                    lambda = 1e-5 * md;
+                    ni = 2;
+                    nBadIt = 0;
+                }
+                double rho = 0;
+                int qmax = 0;
+                do {
+                    const std::vector<double> saved = P.pose;    // push
+                    std::vector<double> Hl(H, H + 36);
+                    for (int j = 0; j < 6; ++j) Hl[7 * j] += lambda;
+                    const bool ok2 = ldlt_solve(Hl, 6, b, x);
+                    pose_oplus(P.pose.data(), x);
+                    tempChi = compute_errors();
+                    if (!ok2) tempChi = std::numeric_limits<double>::max();
+                    rho = currentChi - tempChi;
+                    double scale = 0;
+                    for (int j = 0; j < 6; ++j) scale += x[j] * (lambda * x[j] + b[j]);
+                    scale += 1e-3;
+                    rho /= scale;
+                    if (rho > 0 && std::isfinite(tempChi)) {
+                        double alpha = 1. - std::pow((2 * rho - 1), 3);
+                        alpha = std::min(alpha, 2. / 3.);
+                        lambda *= std::max(1. / 3., alpha);
+                        ni = 2;
+                        currentChi = tempChi;
+                    } else {
+                        lambda *= ni;
+                        ni *= 2;
+                        P.pose = saved;                          // pop
+                    }
+                    ++qmax;
+                    ++totalTrials;
+                } while (rho < 0 && qmax < 10);
+                ++totalIters;
+                if (qmax == 10 || rho == 0) { ok = false; break; }
+                if ((iniChi - currentChi) * 1e3 < iniChi) ++nBadIt; else nBadIt = 0;
+                if (nBadIt >= 3) { ok = false; break; }
+            }
+        }
+        nBadEdges = 0;
+        for (int e = 0; e < n; ++e) {
+            if (outlier[e]) err[e] = edge_chi2(e);            // e->computeError() for the edges the optimiser did not touch
+            const float chi2 = (float)err[e];
+            const float th = obs[3 * e + 2] < 0 ? 5.991f : 7.815f;
+            if (chi2 > th) { outlier[e] = 1; level[e] = 1; ++nBadEdges; }
+            else { outlier[e] = 0; level[e] = 0; }
+        }
+        if (it == 2) robust = false;
+        ++rounds;
+        if (n < 10) break;                                   // optimizer.edges().size() < 10
+    }
+    memcpy(pose7, P.pose.data(), sizeof(double) * 7);
+    if (stats) { stats[0] = rounds; stats[1] = totalIters; stats[2] = totalTrials; stats[3] = lambda; }
+    return n - nBadEdges;
+}

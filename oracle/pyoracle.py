@@ -364,3 +364,19 @@ def search_initialization(kp1, desc1, prev_matched, kp2, desc2, bounds, window_s
     nm = L.orc_search_initialization(_p(kp1), _p(d1), len(kp1), _p(pm), _p(kp2), _p(d2), len(kp2), _p(b4), int(window_size), nnratio,
                                      1 if check_ori else 0, _p(m))
     return m[:len(kp1)], nm
+
+
+def pose_optimization(pose7, Xw, obs, inv_sigma2, cam5):
+    """Optimizer::PoseOptimization restated (Optimizer.cc:55-412).  Returns dict(pose, outlier, inliers, rounds, iterations, trials)."""
+    L = lib()
+    L.orc_pose_optimization.restype = C.c_int
+    L.orc_pose_optimization.argtypes = [C.c_int] + [C.c_void_p] * 7
+    c = np.ascontiguousarray
+    pose = c(pose7, np.float64).copy()
+    Xw, obs, w, cam5 = c(Xw, np.float64), c(obs, np.float64), c(inv_sigma2, np.float64), c(cam5, np.float64)
+    n = len(Xw)
+    out = np.zeros(max(n, 1), np.uint8)
+    stats = np.zeros(4, np.float64)
+    inl = L.orc_pose_optimization(n, _p(Xw), _p(obs), _p(w), _p(cam5), _p(pose), _p(out), _p(stats))
+    return dict(pose=pose, outlier=out[:n], inliers=inl, rounds=int(stats[0]), iterations=int(stats[1]), trials=int(stats[2]),
+                lambda_=float(stats[3]))

@@ -12,7 +12,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "lib", "liborbslam3_b200.so")
-SOURCES = ["extractor.cu", "stereo.cu", "matcher.cu", "triangulation.cu", "lba.cu"]
+SOURCES = ["extractor.cu", "stereo.cu", "matcher.cu", "triangulation.cu", "lba.cu", "poseopt.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -70,6 +70,11 @@ class orbm_kf_queries(C.Structure):
     _fields_ = [("n_targets", C.c_int32)] + [
         (n, C.c_void_p) for n in ("target_image", "feat_offset", "kp", "desc", "uright", "feat_claimed", "Tcw", "Ow",
                                   "Sim3", "query_offset", "world_pos", "normal", "max_dist", "min_dist", "desc_q", "angle")]
+
+
+class orbo_pose_problems(C.Structure):
+    _fields_ = [("n_frames", C.c_int32), ("on_device", C.c_int32), ("edge_offset", C.c_void_p), ("pose", C.c_void_p),
+                ("world_pos", C.c_void_p), ("obs", C.c_void_p), ("inv_sigma2", C.c_void_p)] + [(n, C.c_float) for n in ("fx", "fy", "cx", "cy", "bf")]
 
 
 class orbm_init_queries(C.Structure):
@@ -133,6 +138,7 @@ SIGNATURES = {
     "orbm_search_bow_keyframes": (_I, [_VP, C.POINTER(orbm_bow_kf_queries), C.c_float, _I, _VP, _VP]),
     "orbm_search_keyframe": (_I, [_VP, C.POINTER(orbm_camera), C.POINTER(orbm_kf_queries), _I, C.c_float, C.c_float, _I, _VP, _VP]),
     "orbm_search_triangulation": (_I, [_VP, C.POINTER(orbm_triangulation), _VP, _VP]),
+    "orbo_pose_optimization": (_I, [_VP, C.POINTER(orbo_pose_problems), _VP, _VP, _VP, _VP]),
     "lba_create": (_I, [_I, C.POINTER(_VP)]),
     "lba_destroy": (None, [_VP]),
     "lba_solve": (_I, [_VP, C.POINTER(lba_problem), C.POINTER(lba_result), _VP]),

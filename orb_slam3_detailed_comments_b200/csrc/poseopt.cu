@@ -1,0 +1,318 @@
+// poseopt.cu -- Optimizer::PoseOptimization(Frame*) on the device, Nleft == -1
+//   /root/reference/src/Optimizer.cc:55-412 (called twice per frame by the tracking thread: Tracking.cc:3222, 3443, 3522)
+// One VertexSE3Expmap and unary edges EdgeSE3ProjectXYZOnlyPose (src/OptimizableTypes.cpp) /
+// EdgeStereoSE3ProjectXYZOnlyPose (Thirdparty/g2o/g2o/types/types_six_dof_expmap.cpp:339-404); g2o Levenberg over a dense
+// 6 x 6 system; 4 rounds of 10 iterations that restart from the frame's pose; chi2 classification after every round
+// (5.991 / 7.815 as floats); the robust kernel is dropped after round 2.
+//
+// One CTA per frame, a batch of frames per launch.  Every thread carries the pose, lambda and the whole LM control state
+// replicated in registers: the only cross-thread traffic is the two block reductions (robust chi2; the 21 + 6 entries of
+// H and b), whose butterfly + fixed-order warp sum gives every thread bit-identical values, so the accept / reject
+// decisions, the 6 x 6 LDL^T and the exponential-map update are computed redundantly without any broadcast.
+#include <algorithm>
+#include <vector>
+
+#include "extractor.h"
+#include "ba_math.cuh"
+
+using namespace orb;
+
+namespace orb {
+
+#define PO_THREADS 128
+#define PO_WARPS (PO_THREADS / 32)
+
+struct PoseOptParams {
+    const int* eoff;          // [n_frames + 1]
+    const float* pose;        // [n_frames][7]
+    const float* xw;          // [ne][3]
+    const float* obs;         // [ne][3]
+    const float* invs2;       // [ne]
+    double fx, fy, cx, cy, bf;
+    double* err;              // [ne] scratch: e->chi2() as left by the last computeActiveErrors
+    uint8_t* outlier;         // [ne] out (doubles as the edge level)
+    double* pose_out;         // [n_frames][7]
+    int* inliers;             // [n_frames]
+    int* stats;               // [n_frames][4] rounds, LM iterations, LM trials, -
+};
+
+__device__ __forceinline__ double po_block_sum(double v, double* s_red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();                               // s_red free again
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = s_red[0];
+#pragma unroll
+    for (int w = 1; w < PO_WARPS; ++w) s += s_red[w];
+    return s;
+}
+
+// residual of one edge at pose T; returns the dimension (2 mono, 3 stereo)
+__device__ __forceinline__ int po_edge_error(const PoseOptParams& P, const double* T, int e, double r[3], double Xc[3]) {
+    const double X[3] = {(double)P.xw[3 * (size_t)e], (double)P.xw[3 * (size_t)e + 1], (double)P.xw[3 * (size_t)e + 2]};
+    se3_map(T, X, Xc);
+    const double z0 = (double)P.obs[3 * (size_t)e], z1 = (double)P.obs[3 * (size_t)e + 1], z2 = (double)P.obs[3 * (size_t)e + 2];
+    if (z2 < 0) {   // EdgeSE3ProjectXYZOnlyPose::computeError + Pinhole::project(Vector3d)
+        r[0] = z0 - (P.fx * Xc[0] / Xc[2] + P.cx);
+        r[1] = z1 - (P.fy * Xc[1] / Xc[2] + P.cy);
+        r[2] = 0;
+        return 2;
+    }
+    const double invz = (double)__fdiv_rn(1.0f, (float)Xc[2]);   // cam_project: const float invz = 1.0f/trans_xyz[2]
+    const double u = Xc[0] * invz * P.fx + P.cx;
+    r[0] = z0 - u;
+    r[1] = z1 - (Xc[1] * invz * P.fy + P.cy);
+    r[2] = z2 - (u - P.bf * invz);
+    return 3;
+}
+
+__global__ void __launch_bounds__(PO_THREADS) k_pose_opt(const __grid_constant__ PoseOptParams P) {
+    __shared__ double s_red[PO_WARPS];
+    __shared__ double s_part[PO_WARPS][27];
+    const int frame = blockIdx.x, tid = threadIdx.x;
+    const int e0 = P.eoff[frame], n = P.eoff[frame + 1] - e0;
+    double pose0[7], T[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) pose0[i] = T[i] = (double)P.pose[7 * frame + i];
+    if (n < 3) {   // Optimizer.cc:292-293: return 0, the frame keeps its pose
+        if (tid == 0) {
+            for (int i = 0; i < 7; ++i) P.pose_out[7 * frame + i] = pose0[i];
+            P.inliers[frame] = 0;
+            P.stats[4 * frame] = P.stats[4 * frame + 1] = P.stats[4 * frame + 2] = 0;
+        }
+        for (int e = tid; e < n; e += PO_THREADS) P.outlier[e0 + e] = 0;
+        return;
+    }
+    const double dM = (double)(float)sqrt(5.991), dS = (double)(float)sqrt(7.815);       // const float deltaMono / deltaStereo
+    const double sqM = (double)(float)(dM * dM), sqS = (double)(float)(dS * dS);           // RobustKernelHuber::dsqr
+    for (int e = tid; e < n; e += PO_THREADS) P.outlier[e0 + e] = 0;
+    bool robust = true;
+    int nBadEdges = 0, rounds = 0, totalIters = 0, totalTrials = 0;
+
+    auto compute_errors = [&](const double* pose) -> double {   // computeActiveErrors + activeRobustChi2 (level-0 edges)
+        double chi = 0;
+        for (int e = tid; e < n; e += PO_THREADS) {
+            if (P.outlier[e0 + e]) continue;
+            double r[3], Xc[3];
+            const int D = po_edge_error(P, pose, e0 + e, r, Xc);
+            const double c = (double)P.invs2[e0 + e] * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+            P.err[e0 + e] = c;
+            double w;
+            chi += robust ? huber_rho(c, D == 2 ? dM : dS, D == 2 ? sqM : sqS, &w) : c;
+        }
+        return po_block_sum(chi, s_red);
+    };
+
+    for (int it = 0; it < 4; ++it) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) T[i] = pose0[i];             // vSE3->setEstimate(pFrame->GetPose())
+        int nActive = 0;
+        for (int e = tid; e < n; e += PO_THREADS) nActive += P.outlier[e0 + e] == 0;
+        nActive = (int)po_block_sum((double)nActive, s_red);
+        if (nActive > 0) {
+            double lambda = 0, ni = 2, currentChi = 0;
+            int nBadIt = 0;
+            for (int iter = 0; iter < 10; ++iter) {
+                currentChi = compute_errors(T);
+                double tempChi = currentChi;
+                const double iniChi = currentChi;
+                // ---- buildSystem: H (upper triangle, 21) and b (6) ------------------------------------------------
+                double acc[27];
+#pragma unroll
+                for (int i = 0; i < 27; ++i) acc[i] = 0;
+                for (int e = tid; e < n; e += PO_THREADS) {
+                    if (P.outlier[e0 + e]) continue;
+                    double r[3], Xc[3], B[18];
+                    const int D = po_edge_error(P, T, e0 + e, r, Xc);
+                    pose_jacobian(D, P.fx, P.fy, P.bf, Xc, B);
+                    const double c2 = (double)P.invs2[e0 + e] * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+                    double w = 1.0;
+                    if (robust) huber_rho(c2, D == 2 ? dM : dS, D == 2 ? sqM : sqS, &w);
+                    const double om = w * (double)P.invs2[e0 + e];
+                    int k = 0;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+                        for (int j = i; j < 6; ++j) {
+                            double s = B[i] * B[j] + B[6 + i] * B[6 + j];
+                            if (D == 3) s += B[12 + i] * B[12 + j];
+                            acc[k++] += om * s;
+                        }
+                        double s = B[i] * r[0] + B[6 + i] * r[1];
+                        if (D == 3) s += B[12 + i] * r[2];
+                        acc[21 + i] += -om * s;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 27; ++i) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+                }
+                __syncthreads();
+                if ((tid & 31) == 0)
+                    for (int i = 0; i < 27; ++i) s_part[tid >> 5][i] = acc[i];
+                __syncthreads();
+                double H[36], b[6];
+                {
+                    int k = 0;
+                    for (int i = 0; i < 6; ++i)
+                        for (int j = i; j < 6; ++j) {
+                            double s = s_part[0][k];
+                            for (int w = 1; w < PO_WARPS; ++w) s += s_part[w][k];
+                            H[6 * i + j] = H[6 * j + i] = s;
+                            ++k;
+                        }
+                    for (int i = 0; i < 6; ++i) {
+                        double s = s_part[0][21 + i];
+                        for (int w = 1; w < PO_WARPS; ++w) s += s_part[w][21 + i];
+                        b[i] = s;
+                    }
+                }
+                if (iter == 0) {   // computeLambdaInit: tau * max diagonal
+                    double md = 0;
+                    for (int j = 0; j < 6; ++j) md = fmax(fabs(H[7 * j]), md);
+                    lambda = 1e-5 * md;
+                    ni = 2;
+                    nBadIt = 0;
+                }
+                double rho = 0;
+                int qmax = 0;
+                do {
+                    double saved[7], x[6];
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) saved[i] = T[i];                 // push
+                    const bool ok2 = ldlt6_solve(H, lambda, b, x);
+                    pose_oplus(T, x);
+                    tempChi = compute_errors(T);
+                    if (!ok2) tempChi = 1.7976931348623157e308;
+                    rho = currentChi - tempChi;
+                    double scale = 0;
+                    for (int j = 0; j < 6; ++j) scale += x[j] * (lambda * x[j] + b[j]);
+                    scale += 1e-3;
+                    rho /= scale;
+                    if (rho > 0 && isfinite(tempChi)) {
+                        double alpha = 2 * rho - 1;
+                        alpha = 1. - alpha * alpha * alpha;
+                        alpha = fmin(alpha, 2. / 3.);
+                        lambda *= fmax(1. / 3., alpha);
+                        ni = 2;
+                        currentChi = tempChi;
+                    } else {
+                        lambda *= ni;
+                        ni *= 2;
+#pragma unroll
+                        for (int i = 0; i < 7; ++i) T[i] = saved[i];             // pop
+                    }
+                    ++qmax;
+                    ++totalTrials;
+                } while (rho < 0 && qmax < 10);
+                ++totalIters;
+                if (qmax == 10 || rho == 0) break;
+                if ((iniChi - currentChi) * 1e3 < iniChi) ++nBadIt; else nBadIt = 0;
+                if (nBadIt >= 3) break;
+            }
+        }
+        // ---- classification (Optimizer.cc:312-390) ------------------------------------------------------------------
+        int bad = 0;
+        for (int e = tid; e < n; e += PO_THREADS) {
+            double c = P.err[e0 + e];
+            if (P.outlier[e0 + e]) {           // e->computeError() for the edges the optimiser did not touch
+                double r[3], Xc[3];
+                po_edge_error(P, T, e0 + e, r, Xc);
+                c = (double)P.invs2[e0 + e] * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+                P.err[e0 + e] = c;
+            }
+            const float chi2 = (float)c;
+            const float th = P.obs[3 * (size_t)(e0 + e) + 2] < 0 ? 5.991f : 7.815f;
+            const bool out = chi2 > th;
+            P.outlier[e0 + e] = out ? 1 : 0;
+            bad += out;
+        }
+        nBadEdges = (int)po_block_sum((double)bad, s_red);
+        if (it == 2) robust = false;
+        ++rounds;
+        if (n < 10) break;                     // optimizer.edges().size() < 10
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 7; ++i) P.pose_out[7 * frame + i] = T[i];
+        P.inliers[frame] = n - nBadEdges;
+        P.stats[4 * frame] = rounds; P.stats[4 * frame + 1] = totalIters; P.stats[4 * frame + 2] = totalTrials; P.stats[4 * frame + 3] = 0;
+    }
+}
+
+}  // namespace orb
+
+struct PoStage {
+    uint8_t* base;
+    size_t off = 0;
+    template <typename T>
+    T* take(size_t n) {
+        off = (off + 255) / 256 * 256;
+        T* p = reinterpret_cast<T*>(base + off);
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+extern "C" orb_status orbo_pose_optimization(orbx_handle* h, const orbo_pose_problems* in, double* pose_out, uint8_t* outlier_out,
+                                             int32_t* inliers_out, int32_t* stats_out) {
+    if (!h || !in || in->n_frames < 1 || !in->edge_offset || !in->pose || !pose_out || !inliers_out)
+        return set_error(ORB_ERR_INVALID, "bad arguments");
+    ORB_CUDA(cudaSetDevice(h->cfg.device));
+    const bool dev = in->on_device != 0;
+    const int nf = in->n_frames;
+    int ne = 0;
+    if (dev) {
+        ORB_CUDA(cudaMemcpyAsync(&ne, in->edge_offset + nf, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        ORB_CUDA(cudaStreamSynchronize(h->stream));
+    } else {
+        ne = in->edge_offset[nf];
+    }
+    if (ne < 0 || (ne > 0 && (!in->world_pos || !in->obs || !in->inv_sigma2 || !outlier_out))) return set_error(ORB_ERR_INVALID, "missing edge arrays");
+    // scratch (and, for host callers, staging) comes from the handle's matcher stage buffer
+    const size_t need = (size_t)ne * (8 + 1 + (dev ? 0 : 28)) + (size_t)nf * (dev ? 16 : 128) + 65536;
+    if (need > h->stage_bytes) {
+        if (h->d_stage) cudaFree(h->d_stage);
+        h->d_stage = nullptr;
+        h->stage_bytes = 0;
+        const size_t want = (need + (1 << 20)) / (1 << 20) * (1 << 20);
+        ORB_CUDA(cudaMalloc((void**)&h->d_stage, want));
+        h->stage_bytes = want;
+    }
+    PoStage cur{h->d_stage};
+    PoseOptParams P{};
+    P.fx = in->fx; P.fy = in->fy; P.cx = in->cx; P.cy = in->cy; P.bf = in->bf;   // float members promoted (Optimizer.cc:146-150)
+    P.err = cur.take<double>(std::max(ne, 1));
+    auto up = [&](auto*& dst, const auto* src, size_t n) -> orb_status {
+        using T = std::remove_cv_t<std::remove_pointer_t<decltype(src)>>;
+        if (dev) { dst = const_cast<T*>(src); return ORB_OK; }
+        T* d = cur.take<T>(std::max<size_t>(n, 1));
+        if (n) ORB_CUDA(cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+        dst = d;
+        return ORB_OK;
+    };
+    int* eoff; float *pose, *xw, *obs, *w;
+    orb_status s;
+    if ((s = up(eoff, (const int*)in->edge_offset, nf + 1)) != ORB_OK) return s;
+    if ((s = up(pose, in->pose, (size_t)nf * 7)) != ORB_OK) return s;
+    if ((s = up(xw, in->world_pos, (size_t)ne * 3)) != ORB_OK) return s;
+    if ((s = up(obs, in->obs, (size_t)ne * 3)) != ORB_OK) return s;
+    if ((s = up(w, in->inv_sigma2, (size_t)ne)) != ORB_OK) return s;
+    P.eoff = eoff; P.pose = pose; P.xw = xw; P.obs = obs; P.invs2 = w;
+    P.outlier = dev ? outlier_out : cur.take<uint8_t>(std::max(ne, 1));
+    P.pose_out = dev ? pose_out : cur.take<double>((size_t)nf * 7);
+    P.inliers = dev ? inliers_out : cur.take<int>(nf);
+    P.stats = (dev && stats_out) ? stats_out : cur.take<int>((size_t)nf * 4);
+    k_pose_opt<<<nf, PO_THREADS, 0, h->stream>>>(P);
+    ORB_LAUNCHED();
+    ORB_CUDA(cudaGetLastError());
+    if (!dev) {
+        ORB_CUDA(cudaMemcpyAsync(pose_out, P.pose_out, sizeof(double) * 7 * (size_t)nf, cudaMemcpyDeviceToHost, h->stream));
+        if (ne > 0) ORB_CUDA(cudaMemcpyAsync(outlier_out, P.outlier, (size_t)ne, cudaMemcpyDeviceToHost, h->stream));
+        ORB_CUDA(cudaMemcpyAsync(inliers_out, P.inliers, sizeof(int) * (size_t)nf, cudaMemcpyDeviceToHost, h->stream));
+        if (stats_out) ORB_CUDA(cudaMemcpyAsync(stats_out, P.stats, sizeof(int) * 4 * (size_t)nf, cudaMemcpyDeviceToHost, h->stream));
+        ORB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return ORB_OK;
+}

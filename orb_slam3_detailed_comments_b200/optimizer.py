@@ -58,3 +58,37 @@ class Optimizer:
 
     def LocalBundleAdjustment(self, problem, lambda_init=0.0, max_iters=10, stop_flag=None):
         return self.LocalBundleAdjustmentBatch([problem], lambda_init, max_iters, stop_flag)[0]
+
+
+def PoseOptimization(extractor, frames, cam5):
+    """Optimizer::PoseOptimization(Frame*) (src/Optimizer.cc:55-412) for a batch of frames on the extractor's stream.
+    frames: list of dicts(pose[7] float32 Tcw, world_pos[n][3], obs[n][3] (obs[:, 2] < 0 => monocular), inv_sigma2[n]);
+    cam5 = fx fy cx cy bf.  Returns a list of dicts(pose float64[7], outlier uint8[n], inliers, rounds, iterations, trials)."""
+    L = N.lib()
+    nf = len(frames)
+    eoff = np.zeros(nf + 1, np.int32)
+    eoff[1:] = np.cumsum([len(f["world_pos"]) for f in frames])
+    ne = int(eoff[-1])
+    cat = lambda key, width: np.ascontiguousarray(np.concatenate([np.asarray(f[key], np.float32).reshape(-1, width) for f in frames])
+                                                  if ne else np.zeros((0, width)), np.float32)
+    pose = np.ascontiguousarray(np.stack([np.asarray(f["pose"], np.float32) for f in frames]))
+    xw, obs, w = cat("world_pos", 3), cat("obs", 3), cat("inv_sigma2", 1)
+    fx, fy, cx, cy, bf = [float(np.float32(v)) for v in cam5]
+    p = N.orbo_pose_problems(nf, 0, N.ptr(eoff), N.ptr(pose), N.ptr(xw) if ne else None, N.ptr(obs) if ne else None,
+                             N.ptr(w) if ne else None, fx, fy, cx, cy, bf)
+    pose_out = np.zeros((nf, 7), np.float64)
+    outl = np.zeros(max(ne, 1), np.uint8)
+    inl = np.zeros(nf, np.int32)
+    stats = np.zeros((nf, 4), np.int32)
+    N.check(L.orbo_pose_optimization(extractor._h, C.byref(p), N.ptr(pose_out), N.ptr(outl), N.ptr(inl), N.ptr(stats)))
+    return [dict(pose=pose_out[f], outlier=outl[eoff[f]:eoff[f + 1]], inliers=int(inl[f]), rounds=int(stats[f, 0]),
+                 iterations=int(stats[f, 1]), trials=int(stats[f, 2])) for f in range(nf)]
+
+
+def PoseOptimizationDevice(extractor, n_frames, edge_offset, pose, world_pos, obs, inv_sigma2, cam5, pose_out, outlier_out, inliers_out):
+    """Device-resident form (CUDA torch tensors, no synchronisation): see include/orbslam3_b200.h."""
+    L = N.lib()
+    fx, fy, cx, cy, bf = [float(np.float32(v)) for v in cam5]
+    dp = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    p = N.orbo_pose_problems(n_frames, 1, dp(edge_offset), dp(pose), dp(world_pos), dp(obs), dp(inv_sigma2), fx, fy, cx, cy, bf)
+    N.check(L.orbo_pose_optimization(extractor._h, C.byref(p), dp(pose_out), dp(outlier_out), dp(inliers_out), None))
