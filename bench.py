@@ -487,6 +487,63 @@ def main():
             opt.close()
         except Exception as exc:   # never lose the headline line because the side benchmark failed
             lba = {"error": repr(exc)}
+        # ---- PoseOptimization (twice per frame on the tracking thread): a batch of B frames --------------
+        pose_opt = None
+        try:
+            from oracle import pyoracle as po
+            from orb_slam3_detailed_comments_b200 import PoseOptimization, PoseOptimizationDevice
+            prng = np.random.default_rng(99)
+
+            def po_frame(n):
+                Xc = np.stack([prng.uniform(-3, 3, n), prng.uniform(-2, 2, n), prng.uniform(2, 12, n)], 1)
+                ax = prng.normal(size=3); ax /= np.linalg.norm(ax)
+                q = np.concatenate([ax * np.sin(0.015), [np.cos(0.015)]]); tt = prng.normal(0, 0.05, 3)
+                x, y, z, w = q
+                R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                              [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                              [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+                Xw = (Xc - tt) @ R
+                u, v = FX * Xc[:, 0] / Xc[:, 2] + CX, FY * Xc[:, 1] / Xc[:, 2] + CY
+                obs = np.stack([u, v, u - BF / Xc[:, 2]], 1) + prng.normal(0, 0.7, (n, 3))
+                obs[prng.random(n) < 0.2, 2] = -1
+                bad = prng.random(n) < 0.1
+                obs[bad, :2] += prng.normal(0, 30, (int(bad.sum()), 2))
+                return dict(pose=np.array([0, 0, 0, 1, 0, 0, 0], np.float32), world_pos=Xw.astype(np.float32), obs=obs.astype(np.float32),
+                            inv_sigma2=(1 / (1.2 ** prng.integers(0, 8, n)) ** 2).astype(np.float32))
+            cam5 = [FX, FY, CX, CY, BF]
+            res = {}
+            for tag, n_e in (("after_motion_model_550_edges", 550), ("after_local_map_1200_edges", 1200)):
+                frames = [po_frame(n_e) for _ in range(B)]
+                PoseOptimization(ex, frames, cam5)
+                t0 = time.perf_counter()
+                for _ in range(5):
+                    got = PoseOptimization(ex, frames, cam5)
+                t_e2e = (time.perf_counter() - t0) / 5
+                eoff = torch.tensor(np.arange(B + 1, dtype=np.int32) * n_e, device=dev)
+                d_pose = T(np.stack([f["pose"] for f in frames])); d_xw = T(np.concatenate([f["world_pos"] for f in frames]))
+                d_obs = T(np.concatenate([f["obs"] for f in frames])); d_w = T(np.concatenate([f["inv_sigma2"] for f in frames]))
+                o_pose = torch.zeros((B, 7), dtype=torch.float64, device=dev); o_out = torch.zeros(B * n_e, dtype=torch.uint8, device=dev)
+                o_inl = torch.zeros(B, dtype=torch.int32, device=dev)
+                ea, eb2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                PoseOptimizationDevice(ex, B, eoff, d_pose, d_xw, d_obs, d_w, cam5, o_pose, o_out, o_inl)
+                torch.cuda.synchronize()
+                ea.record(streams[0])
+                for _ in range(10):
+                    PoseOptimizationDevice(ex, B, eoff, d_pose, d_xw, d_obs, d_w, cam5, o_pose, o_out, o_inl)
+                eb2.record(streams[0])
+                torch.cuda.synchronize()
+                t_dev = ea.elapsed_time(eb2) / 10
+                t0 = time.perf_counter()
+                for f in frames[:8]:
+                    r = po.pose_optimization(f["pose"], f["world_pos"], f["obs"], f["inv_sigma2"], np.float32(cam5))
+                t_cpu = (time.perf_counter() - t0) / 8
+                res[tag] = {"frames_per_call": B, "ms_per_call_device_resident": t_dev, "ms_per_call_e2e": 1e3 * t_e2e,
+                            "cpu_oracle_ms_per_frame": 1e3 * t_cpu, "lm_iterations_per_frame": float(np.mean([g["iterations"] for g in got])),
+                            "inliers_per_frame": float(np.mean([g["inliers"] for g in got]))}
+            pose_opt = {"workload": "Optimizer::PoseOptimization, one CTA per frame, 80 % stereo / 20 % monocular edges, 10 % outliers",
+                        **res}
+        except Exception as exc:
+            pose_opt = {"error": repr(exc)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -502,7 +559,7 @@ def main():
                            "keypoints_per_image": n_kp, "fast_candidates_per_image": n_cand},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_step),
                         "d2h_bytes_per_step": int(d2h // args.steps)},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "lba": lba}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "lba": lba, "pose_optimization": pose_opt}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
