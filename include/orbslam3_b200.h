@@ -402,6 +402,26 @@ typedef struct {
 orb_status orbo_pose_optimization(orbx_handle* h, const orbo_pose_problems* in, double* pose_out, uint8_t* outlier_out,
                                   int32_t* inliers_out, int32_t* stats_out);
 
+/* The correspondence walk of PoseOptimization (Optimizer.cc:104-290) for frames whose features and matches are still on
+ * the device: one edge per feature that holds a map point, in feature order.  feature_match (per compact keypoint row:
+ * query index or -1) is the output of orbm_search_last_frame / orbm_search_bow; query_match (per query: feature index or
+ * -1) the output of orbm_search_local_points; exactly one of the two is given.  world_pos[q] = pMP->GetWorldPos() of
+ * query q.  ALL pointers are device memory; no synchronisation.  Outputs feed
+ * orbo_pose_optimization (on_device = 1): edge_offset_out[n_frames + 1], and per edge the feature index inside its frame
+ * (to map outlier flags back to mvbOutlier), world position, observation (x, y, mvuRight or -1) and
+ * mvInvLevelSigma2[octave]; each output must hold one entry per feature of the listed frames. */
+typedef struct {
+    int32_t n_frames;
+    const int32_t* frame_image;   /* [n_frames] image index in the handle's last batch */
+    const int32_t* feature_match; /* or NULL */
+    const int32_t* query_offset;  /* [n_frames + 1], with query_match */
+    const int32_t* query_match;   /* or NULL */
+    const float* world_pos;       /* [nq][3] */
+} orbo_edge_source;
+
+orb_status orbo_pose_edges(orbx_handle* h, const orbo_edge_source* src, int32_t* edge_offset_out, int32_t* edge_feature_out,
+                           float* world_pos_out, float* obs_out, float* inv_sigma2_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -241,6 +241,100 @@ __global__ void __launch_bounds__(PO_THREADS) k_pose_opt(const __grid_constant__
     }
 }
 
+
+// ---- edge list of PoseOptimization from the searches' device-resident outputs ----------------------------------------
+// The reference walks pFrame->mvpMapPoints in feature order (Optimizer.cc:104-290): one edge per feature that holds a map
+// point.  feature_match (per compact keypoint row: query index or -1) is what orbm_search_last_frame / orbm_search_bow
+// write; query_match (per query: feature index or -1) is what orbm_search_local_points writes and is scattered to the
+// features first.  Two launches: counts per frame, then (offset = sum of the counts before) the ordered fill.
+struct EdgeParams {
+    const orbx_keypoint* kps;
+    const float* uright;          // null => monocular
+    const int* offsets;
+    const int* nkp;
+    int maxFeat;
+    const int* frame_image;
+    const int* feature_match;     // or null
+    const int* qoff;              // with query_match
+    const int* query_match;       // or null
+    const float* xw;              // [nq][3]
+    float invSigma2[ORB_MAX_LEVELS];
+    int* cnt;                     // [n_frames]
+    int* eoff;                    // [n_frames + 1]
+    int* efeat;                   // [ne] feature index inside the frame
+    float* exw;                   // [ne][3]
+    float* eobs;                  // [ne][3]
+    float* ew;                    // [ne]
+};
+
+#define PE_THREADS 256
+
+template <bool FILL>
+__global__ void __launch_bounds__(PE_THREADS) k_pose_edges(const __grid_constant__ EdgeParams P, int n_frames) {
+    extern __shared__ int pe_holder[];   // maxFeat
+    __shared__ int s_warp[PE_THREADS / 32 + 1];
+    __shared__ int s_base, s_run;
+    const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int img = P.frame_image[frame];
+    const int N = min(P.nkp[img], P.maxFeat), row0 = P.offsets[img];
+    for (int i = tid; i < N; i += PE_THREADS) pe_holder[i] = P.feature_match ? P.feature_match[row0 + i] : -1;
+    __syncthreads();
+    if (P.query_match) {
+        const int q0 = P.qoff[frame], q1 = P.qoff[frame + 1];
+        for (int q = q0 + tid; q < q1; q += PE_THREADS) {
+            const int f = P.query_match[q];
+            if (f >= 0 && f < N) pe_holder[f] = q;   // a feature is claimed by at most one query of a search
+        }
+        __syncthreads();
+    }
+    if (!FILL) {
+        int c = 0;
+        for (int i = tid; i < N; i += PE_THREADS) c += pe_holder[i] >= 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0) s_warp[wid] = c;
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int w = 0; w < PE_THREADS / 32; ++w) t += s_warp[w];
+            P.cnt[frame] = t;
+        }
+        return;
+    }
+    if (tid == 0) {
+        int b = 0;
+        for (int f = 0; f < frame; ++f) b += P.cnt[f];
+        s_base = b;
+        s_run = 0;
+        P.eoff[frame] = b;
+        if (frame == n_frames - 1) P.eoff[n_frames] = b + P.cnt[frame];
+    }
+    __syncthreads();
+    for (int base = 0; base < N; base += PE_THREADS) {          // ordered compaction, PE_THREADS features at a time
+        const int i = base + tid;
+        const int q = i < N ? pe_holder[i] : -1;
+        const unsigned m = __ballot_sync(0xffffffffu, q >= 0);
+        if (lane == 0) s_warp[wid] = __popc(m);
+        __syncthreads();
+        int before = s_run;
+        for (int w = 0; w < wid; ++w) before += s_warp[w];
+        if (q >= 0) {
+            const int e = s_base + before + __popc(m & ((1u << lane) - 1u));
+            const orbx_keypoint k = P.kps[row0 + i];
+            P.efeat[e] = i;
+            P.exw[3 * (size_t)e] = P.xw[3 * (size_t)q]; P.exw[3 * (size_t)e + 1] = P.xw[3 * (size_t)q + 1]; P.exw[3 * (size_t)e + 2] = P.xw[3 * (size_t)q + 2];
+            P.eobs[3 * (size_t)e] = k.x; P.eobs[3 * (size_t)e + 1] = k.y; P.eobs[3 * (size_t)e + 2] = P.uright ? P.uright[row0 + i] : -1.0f;
+            P.ew[e] = P.invSigma2[k.octave];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int w = 0; w < PE_THREADS / 32; ++w) t += s_warp[w];
+            s_run += t;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace orb
 
 struct PoStage {
@@ -314,5 +408,38 @@ extern "C" orb_status orbo_pose_optimization(orbx_handle* h, const orbo_pose_pro
         if (stats_out) ORB_CUDA(cudaMemcpyAsync(stats_out, P.stats, sizeof(int) * 4 * (size_t)nf, cudaMemcpyDeviceToHost, h->stream));
         ORB_CUDA(cudaStreamSynchronize(h->stream));
     }
+    return ORB_OK;
+}
+
+extern "C" orb_status orbo_pose_edges(orbx_handle* h, const orbo_edge_source* src, int32_t* edge_offset_out, int32_t* edge_feature_out,
+                                      float* world_pos_out, float* obs_out, float* inv_sigma2_out) {
+    if (!h || !src || src->n_frames < 1 || !src->frame_image || !src->world_pos || ((src->feature_match != nullptr) == (src->query_match != nullptr)) ||
+        (src->query_match && !src->query_offset) || !edge_offset_out || !edge_feature_out || !world_pos_out || !obs_out || !inv_sigma2_out)
+        return set_error(ORB_ERR_INVALID, "bad arguments");
+    if (h->last_batch < 1) return set_error(ORB_ERR_INVALID, "no batch has been extracted");
+    ORB_CUDA(cudaSetDevice(h->cfg.device));
+    const int nf = src->n_frames;
+    const size_t need = (size_t)nf * 4 + 4096;
+    if (need > h->stage_bytes) {
+        if (h->d_stage) cudaFree(h->d_stage);
+        h->d_stage = nullptr;
+        h->stage_bytes = 0;
+        ORB_CUDA(cudaMalloc((void**)&h->d_stage, (size_t)1 << 20));
+        h->stage_bytes = (size_t)1 << 20;
+    }
+    EdgeParams P{};
+    P.kps = h->d_kps; P.uright = h->stereo_valid ? h->d_uright : nullptr; P.offsets = h->d_offsets; P.nkp = h->d_nkp;
+    P.maxFeat = h->geom.kpTotal;
+    P.frame_image = src->frame_image; P.feature_match = src->feature_match; P.qoff = src->query_offset; P.query_match = src->query_match;
+    P.xw = src->world_pos;
+    for (int l = 0; l < ORB_MAX_LEVELS; ++l) P.invSigma2[l] = l < h->cfg.n_levels ? h->inv_sigma2[l] : 1.f;
+    P.cnt = reinterpret_cast<int*>(h->d_stage);
+    P.eoff = edge_offset_out; P.efeat = edge_feature_out; P.exw = world_pos_out; P.eobs = obs_out; P.ew = inv_sigma2_out;
+    const size_t sm = (size_t)P.maxFeat * 4;
+    k_pose_edges<false><<<nf, PE_THREADS, sm, h->stream>>>(P, nf);
+    ORB_LAUNCHED();
+    k_pose_edges<true><<<nf, PE_THREADS, sm, h->stream>>>(P, nf);
+    ORB_LAUNCHED();
+    ORB_CUDA(cudaGetLastError());
     return ORB_OK;
 }

@@ -92,3 +92,13 @@ def PoseOptimizationDevice(extractor, n_frames, edge_offset, pose, world_pos, ob
     dp = lambda t: None if t is None else C.c_void_p(t.data_ptr())
     p = N.orbo_pose_problems(n_frames, 1, dp(edge_offset), dp(pose), dp(world_pos), dp(obs), dp(inv_sigma2), fx, fy, cx, cy, bf)
     N.check(L.orbo_pose_optimization(extractor._h, C.byref(p), dp(pose_out), dp(outlier_out), dp(inliers_out), None))
+
+
+def PoseEdgesDevice(extractor, n_frames, frame_image, world_pos, edge_offset_out, edge_feature_out, world_pos_out, obs_out, inv_sigma2_out,
+                    feature_match=None, query_offset=None, query_match=None):
+    """PoseOptimization's correspondence walk (Optimizer.cc:104-290) over device-resident search outputs (CUDA torch tensors)."""
+    L = N.lib()
+    dp = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    src = N.orbo_edge_source(n_frames, dp(frame_image), dp(feature_match), dp(query_offset), dp(query_match), dp(world_pos))
+    N.check(L.orbo_pose_edges(extractor._h, C.byref(src), dp(edge_offset_out), dp(edge_feature_out), dp(world_pos_out), dp(obs_out),
+                              dp(inv_sigma2_out)))
