@@ -76,7 +76,12 @@ def local_map_queries(k, d, z, rng, bf):
     lvl = np.concatenate([k["octave"], rng.integers(0, 8, n)]).astype(np.int32)
     vc = rng.uniform(0.99, 1.0, 2 * n).astype(np.float32)
     desc = np.concatenate([d, rng.integers(0, 256, (n, 32), dtype=np.uint8)])
-    return x, y, (x - bf / zq).astype(np.float32), lvl, vc, desc
+    # world position of every map point, in the frame's own camera frame (the synthetic map is anchored there): the matched
+    # half sits where the feature was triangulated, so its projection differs from the query's by the 1.5 px jitter
+    xs = np.concatenate([k["x"], x[n:]]).astype(np.float32)
+    ys = np.concatenate([k["y"], y[n:]]).astype(np.float32)
+    xw = np.stack([(xs - 320.0) * zq / 435.2, (ys - 240.0) * zq / 435.2, zq], 1).astype(np.float32)
+    return x, y, (x - bf / zq).astype(np.float32), lvl, vc, desc, xw
 
 
 class ClockSampler:
@@ -131,7 +136,8 @@ class ClockSampler:
 def cpu_oracle_frames(pairs, threads):
     """Reference arm: the CPU oracle on `threads` host threads.  Per stereo frame: both eyes through the
     extractor (on two threads like Frame.cc:136-141 when threads >= 2), ComputeStereoMatches, then the two
-    projection searches against a map made of the frame's own stereo points (same shape as the GPU arm).
+    projection searches against a map made of the frame's own stereo points, each followed by PoseOptimization over the
+    features that got a map point (same shape as the GPU arm).
     Returns (frames/s, seconds)."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import pyoracle as po
@@ -158,10 +164,21 @@ def cpu_oracle_frames(pairs, threads):
         z = dep[sel]
         pts = np.stack([(kL["x"][sel] - CX) * z / FX, (kL["y"][sel] - CY) * z / FY, z], 1).astype(np.float32)
         sf = eL.scale_factors
-        po.search_last(kL, dL, uR, bounds, sf, cam6, T, 0, pts, kL["octave"][sel], kL["angle"][sel], dL[sel],
-                       np.ones(len(sel), np.uint8), 15.0, True)
-        x, y, xr, lvl, vc, dq = local_map_queries(kL, dL, dep, np.random.default_rng(7), BF)
-        po.search_local(kL, dL, uR, bounds, sf, x, y, xr, lvl, vc, dq, 3.0, 0.8)
+        isg = (1.0 / (sf * sf)).astype(np.float32)
+        cam5 = np.float32([FX, FY, CX, CY, BF])
+
+        def pose_opt(feat, xw):        # Optimizer::PoseOptimization over the features that hold a map point (feature order)
+            obs = np.stack([kL["x"][feat], kL["y"][feat], uR[feat]], 1)
+            return po.pose_optimization(T, xw, obs, isg[kL["octave"][feat]], cam5)
+        fm, _ = po.search_last(kL, dL, uR, bounds, sf, cam6, T, 0, pts, kL["octave"][sel], kL["angle"][sel], dL[sel],
+                               np.ones(len(sel), np.uint8), 15.0, True)
+        feat = np.nonzero(fm >= 0)[0]
+        pose_opt(feat, pts[fm[feat]])
+        x, y, xr, lvl, vc, dq, xwl = local_map_queries(kL, dL, dep, np.random.default_rng(7), BF)
+        mt, _ = po.search_local(kL, dL, uR, bounds, sf, x, y, xr, lvl, vc, dq, 3.0, 0.8)
+        qs = np.nonzero(mt >= 0)[0]
+        order = np.argsort(mt[qs], kind="stable")
+        pose_opt(mt[qs][order], xwl[qs][order])
         return 0
     exs = [(po.OracleExtractor(NFEAT, 1.2, 8, 20, 7), po.OracleExtractor(NFEAT, 1.2, 8, 20, 7)) for _ in range(nworkers)]
     pools2 = [ThreadPoolExecutor(1) if nthr >= 2 else None for _ in range(nworkers)]
@@ -200,7 +217,8 @@ def run_reference(args, rank, world):
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic", "impl": "reference",
             "config": {"workload": "config 3: stereo 640x480, 1200 features per eye; per frame: ORBextractor L+R, "
-                                   "ComputeStereoMatches, SearchByProjection(cur,last), SearchByProjection(F,local map) -- "
+                                   "ComputeStereoMatches, SearchByProjection(cur,last), PoseOptimization, SearchByProjection(F,local map), "
+                                   "PoseOptimization -- "
                                    "CPU oracle port (the reference needs OpenCV/Eigen and cannot be built here)",
                        "frames_per_step": len(pairs)},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
@@ -267,7 +285,7 @@ def main():
         n0, _, off0, kps0, desc0 = ex.download(nimg)
         uR0, dep0 = ex.stereo_download(int(off0[-1]))
         q_last = dict(off=[0], xw=[], oct=[], ang=[], desc=[], obs=[])
-        q_loc = dict(off=[0], px=[], py=[], pxr=[], lvl=[], vc=[], desc=[])
+        q_loc = dict(off=[0], px=[], py=[], pxr=[], lvl=[], vc=[], desc=[], xw=[])
         for p in range(B):
             a, b = int(off0[2 * p]), int(off0[2 * p + 1])
             k, d, z = kps0[a:b], desc0[a:b], dep0[a:b]
@@ -276,9 +294,9 @@ def main():
             q_last["xw"].append(pts); q_last["oct"].append(k["octave"][sel].astype(np.int32))
             q_last["ang"].append(k["angle"][sel].astype(np.float32)); q_last["desc"].append(d[sel])
             q_last["obs"].append(np.ones(len(sel), np.uint8)); q_last["off"].append(q_last["off"][-1] + len(sel))
-            x, y, xr, lvl, vc, dq = local_map_queries(k, d, z, rng, BF)
+            x, y, xr, lvl, vc, dq, xwl = local_map_queries(k, d, z, rng, BF)
             q_loc["px"].append(x); q_loc["py"].append(y); q_loc["pxr"].append(xr); q_loc["lvl"].append(lvl)
-            q_loc["vc"].append(vc); q_loc["desc"].append(dq)
+            q_loc["vc"].append(vc); q_loc["desc"].append(dq); q_loc["xw"].append(xwl)
             q_loc["off"].append(q_loc["off"][-1] + len(x))
         h_last = dict(fimg=np.arange(0, nimg, 2, dtype=np.int32), off=np.array(q_last["off"], np.int32),
                       Tcw=np.tile(np.array([0, 0, 0, 1, 0.002, 0.001, 0], np.float32), (B, 1)), dir=np.zeros(B, np.int32),
@@ -286,7 +304,7 @@ def main():
                       desc=cat(q_last["desc"], np.uint8), obs=cat(q_last["obs"], np.uint8))
         h_loc = dict(fimg=h_last["fimg"], off=np.array(q_loc["off"], np.int32), px=cat(q_loc["px"], np.float32),
                      py=cat(q_loc["py"], np.float32), pxr=cat(q_loc["pxr"], np.float32), lvl=cat(q_loc["lvl"], np.int32),
-                     vc=cat(q_loc["vc"], np.float32), desc=cat(q_loc["desc"], np.uint8))
+                     vc=cat(q_loc["vc"], np.float32), desc=cat(q_loc["desc"], np.uint8), xw=cat(q_loc["xw"], np.float32))
         H_LAST.append(h_last); H_LOC.append(h_loc)
         D_LAST.append({k: T(v) for k, v in h_last.items()}); D_LOC.append({k: T(v) for k, v in h_loc.items()})
     rows_cap = nimg * 1500
@@ -295,6 +313,13 @@ def main():
     max_loc = max(int(hl["off"][-1]) for hl in H_LOC)
     d_match = [torch.full((max(max_loc, 1),), -1, dtype=torch.int32, device=dev) for _ in range(NH)]
     nq_last = float(np.mean([int(hl["off"][-1]) for hl in H_LAST])); nq_loc = float(np.mean([int(hl["off"][-1]) for hl in H_LOC]))
+    # PoseOptimization after each search (Tracking.cc:3443, 3522): edge lists and results, per handle
+    from orb_slam3_detailed_comments_b200 import PoseOptimization, PoseOptimizationDevice, PoseEdgesDevice
+    CAM5 = [FX, FY, CX, CY, BF]
+    zi = lambda n, dt: torch.zeros(n, dtype=dt, device=dev)
+    d_po = [dict(off=zi(B + 1, torch.int32), feat=zi(rows_cap, torch.int32), xw=zi((rows_cap, 3), torch.float32), obs=zi((rows_cap, 3), torch.float32),
+                 w=zi(rows_cap, torch.float32), pose=zi((2, B, 7), torch.float64), out=zi(rows_cap, torch.uint8), inl=zi((2, B), torch.int32))
+            for _ in range(NH)]
 
     def submit_device(i):
         e = exs[i % NH]
@@ -308,8 +333,14 @@ def main():
         m_last.SearchByProjectionLastFrameDevice(e, cam, B, d_last["fimg"], d_last["off"], d_last["Tcw"], d_last["dir"],
                                                  d_last["xw"], d_last["oct"], d_last["ang"], d_last["desc"], d_last["obs"],
                                                  15.0, d_fm[k], d_nm[k][:B])
+        po_ = d_po[k]
+        PoseEdgesDevice(e, B, d_last["fimg"], d_last["xw"], po_["off"], po_["feat"], po_["xw"], po_["obs"], po_["w"], feature_match=d_fm[k])
+        PoseOptimizationDevice(e, B, po_["off"], d_last["Tcw"], po_["xw"], po_["obs"], po_["w"], CAM5, po_["pose"][0], po_["out"], po_["inl"][0])
         m_local.SearchByProjectionDevice(e, cam, B, d_loc["fimg"], d_loc["off"], d_loc["px"], d_loc["py"], d_loc["pxr"],
                                          d_loc["lvl"], d_loc["vc"], d_loc["desc"], d_match[k], d_nm[k][B:], th=3.0)
+        PoseEdgesDevice(e, B, d_loc["fimg"], d_loc["xw"], po_["off"], po_["feat"], po_["xw"], po_["obs"], po_["w"],
+                        query_offset=d_loc["off"], query_match=d_match[k])
+        PoseOptimizationDevice(e, B, po_["off"], d_last["Tcw"], po_["xw"], po_["obs"], po_["w"], CAM5, po_["pose"][1], po_["out"], po_["inl"][1])
 
     def step_device(i):     # un-pipelined form (used for the per-stage roofline pass)
         submit_device(i)
@@ -380,6 +411,22 @@ def main():
     P_LOC = [{k: pin(v) for k, v in hl.items()} for hl in H_LOC]
     pz = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory().numpy()
     from orb_slam3_detailed_comments_b200._native import KP_DTYPE
+    ISG = ex.GetInverseScaleSigmaSquares().astype(np.float32)
+
+    def PoseOptimizationBatchHost(e, counts, Tcw, xw, obs, w, cam5):
+        """orbo_pose_optimization, host-pointer form, on flat edge arrays (frame f owns counts[f] consecutive edges)."""
+        from orb_slam3_detailed_comments_b200 import _native as NN
+        import ctypes as CC
+        nfr = len(counts)
+        eoff = np.zeros(nfr + 1, np.int32)
+        eoff[1:] = np.cumsum(counts)
+        pose = np.ascontiguousarray(Tcw, np.float32)
+        xw, obs, w = np.ascontiguousarray(xw, np.float32), np.ascontiguousarray(obs, np.float32), np.ascontiguousarray(w, np.float32)
+        prob = NN.orbo_pose_problems(nfr, 0, NN.ptr(eoff), NN.ptr(pose), NN.ptr(xw), NN.ptr(obs), NN.ptr(w), *[float(np.float32(v)) for v in cam5], 0)
+        pose_out, outl, inl = np.zeros((nfr, 7), np.float64), np.zeros(max(int(eoff[-1]), 1), np.uint8), np.zeros(nfr, np.int32)
+        NN.check(NN.lib().orbo_pose_optimization(e._h, CC.byref(prob), NN.ptr(pose_out), NN.ptr(outl), NN.ptr(inl), None))
+        return pose_out, outl, inl
+
     def out_buffers():
         return dict(kps=torch.zeros(rows_cap * 28, dtype=torch.uint8).pin_memory().numpy().view(KP_DTYPE), desc=pz((rows_cap, 32), torch.uint8),
                     ur=pz(rows_cap, torch.float32), dep=pz(rows_cap, torch.float32), fm=pz(rows_cap, torch.int32), nm1=pz(B, torch.int32),
@@ -396,11 +443,30 @@ def main():
         nn, mm, oo, kk, dd = e.download(nimg, out=(o["kps"], o["desc"]))
         rows = int(oo[-1])
         e.stereo_download(rows, out=(o["ur"], o["dep"]))
-        m_last.SearchByProjectionLastFrame(e, cam, p_last["fimg"], p_last["off"], p_last["Tcw"], p_last["dir"], p_last["xw"], p_last["oct"],
-                                           p_last["ang"], p_last["desc"], p_last["obs"], 15.0, rows, out=(o["fm"], o["nm1"]))
-        m_local.SearchByProjection(e, cam, p_loc["fimg"], p_loc["off"], p_loc["px"], p_loc["py"], p_loc["pxr"], p_loc["lvl"], p_loc["vc"],
-                                   p_loc["desc"], th=3.0, out=(o["mt"], o["nm2"]))
-        return rows * (60 + 8 + 4) + 12 * nimg + 4 * int(nq_loc) + 8 * B
+        fm, _ = m_last.SearchByProjectionLastFrame(e, cam, p_last["fimg"], p_last["off"], p_last["Tcw"], p_last["dir"], p_last["xw"], p_last["oct"],
+                                                   p_last["ang"], p_last["desc"], p_last["obs"], 15.0, rows, out=(o["fm"], o["nm1"]))
+        kps_h, ur_h = o["kps"], o["ur"]
+
+        def pose_opt(rows_sel, xw, per_frame_counts):
+            """PoseOptimization of the B frames through the host-pointer C ABI: the reference's correspondence walk
+            (Optimizer.cc:104-290) is a gather over the result arrays the previous calls returned."""
+            k = kps_h[rows_sel]
+            obs = np.stack([k["x"], k["y"], ur_h[rows_sel]], 1)
+            return PoseOptimizationBatchHost(e, per_frame_counts, p_last["Tcw"], xw, obs, ISG[k["octave"]], CAM5)
+        left_rows = np.concatenate([np.arange(oo[2 * p], oo[2 * p + 1]) for p in range(B)])
+        fml = fm[left_rows]
+        sel = fml >= 0
+        cnt1 = np.add.reduceat(sel.astype(np.int32), np.cumsum([0] + [int(oo[2 * p + 1] - oo[2 * p]) for p in range(B)])[:-1]) if B else []
+        pose_opt(left_rows[sel], p_last["xw"][fml[sel]], cnt1)
+        mt, _ = m_local.SearchByProjection(e, cam, p_loc["fimg"], p_loc["off"], p_loc["px"], p_loc["py"], p_loc["pxr"], p_loc["lvl"], p_loc["vc"],
+                                           p_loc["desc"], th=3.0, out=(o["mt"], o["nm2"]))
+        nql = int(p_loc["off"][-1])
+        mtv = mt[:nql]
+        qs = np.nonzero(mtv >= 0)[0]
+        qframe = np.searchsorted(p_loc["off"], qs, side="right") - 1
+        cnt2 = np.bincount(qframe, minlength=B)
+        pose_opt(oo[2 * qframe] + mtv[qs], p_loc["xw"][qs], cnt2)
+        return rows * (60 + 8 + 4) + 12 * nimg + 4 * int(nq_loc) + 8 * B + 2 * B * (56 + 4) + len(left_rows) // 2
 
     # One host thread per handle, the deployment shape of sequence-sharded replay (INTEGRATION.md section 6): every thread
     # drives its own handle / CUDA stream through the blocking C ABI, so one thread's result reads overlap the others'
@@ -548,8 +614,8 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": "config 3: stereo 640x480, 1200 features per eye; per frame: ORBextractor L+R, "
-                                       "ComputeStereoMatches, SearchByProjection(cur,last,th=15), SearchByProjection(F,"
-                                       "local map points,th=3)",
+                                       "ComputeStereoMatches, SearchByProjection(cur,last,th=15), PoseOptimization, "
+                                       "SearchByProjection(F,local map points,th=3), PoseOptimization",
                            "frames_per_step_per_gpu": B, "images_per_step_per_gpu": nimg,
                            "pipeline": f"{NH} extractor handles / CUDA streams; value: one host thread; e2e: one host thread per handle",
                            "queries_per_frame": {"last_frame": nq_last / B, "local_map": nq_loc / B},

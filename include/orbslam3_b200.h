@@ -397,6 +397,7 @@ typedef struct {
     const float* obs;             /* [ne][3] */
     const float* inv_sigma2;      /* [ne] */
     float fx, fy, cx, cy, bf;     /* pFrame->fx .. mbf */
+    int32_t n_edges_max;          /* on_device: an upper bound of edge_offset[n_frames] (sizes the scratch); else ignored */
 } orbo_pose_problems;
 
 orb_status orbo_pose_optimization(orbx_handle* h, const orbo_pose_problems* in, double* pose_out, uint8_t* outlier_out,

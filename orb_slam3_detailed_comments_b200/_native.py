@@ -74,7 +74,7 @@ class orbm_kf_queries(C.Structure):
 
 class orbo_pose_problems(C.Structure):
     _fields_ = [("n_frames", C.c_int32), ("on_device", C.c_int32), ("edge_offset", C.c_void_p), ("pose", C.c_void_p),
-                ("world_pos", C.c_void_p), ("obs", C.c_void_p), ("inv_sigma2", C.c_void_p)] + [(n, C.c_float) for n in ("fx", "fy", "cx", "cy", "bf")]
+                ("world_pos", C.c_void_p), ("obs", C.c_void_p), ("inv_sigma2", C.c_void_p)] + [(n, C.c_float) for n in ("fx", "fy", "cx", "cy", "bf")] + [("n_edges_max", C.c_int32)]
 
 
 class orbo_edge_source(C.Structure):

@@ -356,13 +356,8 @@ extern "C" orb_status orbo_pose_optimization(orbx_handle* h, const orbo_pose_pro
     ORB_CUDA(cudaSetDevice(h->cfg.device));
     const bool dev = in->on_device != 0;
     const int nf = in->n_frames;
-    int ne = 0;
-    if (dev) {
-        ORB_CUDA(cudaMemcpyAsync(&ne, in->edge_offset + nf, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        ORB_CUDA(cudaStreamSynchronize(h->stream));
-    } else {
-        ne = in->edge_offset[nf];
-    }
+    // device callers give an upper bound of the edge count (it sizes the scratch): no read-back, no synchronisation
+    const int ne = dev ? in->n_edges_max : in->edge_offset[nf];
     if (ne < 0 || (ne > 0 && (!in->world_pos || !in->obs || !in->inv_sigma2 || !outlier_out))) return set_error(ORB_ERR_INVALID, "missing edge arrays");
     // scratch (and, for host callers, staging) comes from the handle's matcher stage buffer
     const size_t need = (size_t)ne * (8 + 1 + (dev ? 0 : 28)) + (size_t)nf * (dev ? 16 : 128) + 65536;

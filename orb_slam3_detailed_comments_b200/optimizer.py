@@ -75,7 +75,7 @@ def PoseOptimization(extractor, frames, cam5):
     xw, obs, w = cat("world_pos", 3), cat("obs", 3), cat("inv_sigma2", 1)
     fx, fy, cx, cy, bf = [float(np.float32(v)) for v in cam5]
     p = N.orbo_pose_problems(nf, 0, N.ptr(eoff), N.ptr(pose), N.ptr(xw) if ne else None, N.ptr(obs) if ne else None,
-                             N.ptr(w) if ne else None, fx, fy, cx, cy, bf)
+                             N.ptr(w) if ne else None, fx, fy, cx, cy, bf, 0)
     pose_out = np.zeros((nf, 7), np.float64)
     outl = np.zeros(max(ne, 1), np.uint8)
     inl = np.zeros(nf, np.int32)
@@ -90,7 +90,8 @@ def PoseOptimizationDevice(extractor, n_frames, edge_offset, pose, world_pos, ob
     L = N.lib()
     fx, fy, cx, cy, bf = [float(np.float32(v)) for v in cam5]
     dp = lambda t: None if t is None else C.c_void_p(t.data_ptr())
-    p = N.orbo_pose_problems(n_frames, 1, dp(edge_offset), dp(pose), dp(world_pos), dp(obs), dp(inv_sigma2), fx, fy, cx, cy, bf)
+    p = N.orbo_pose_problems(n_frames, 1, dp(edge_offset), dp(pose), dp(world_pos), dp(obs), dp(inv_sigma2), fx, fy, cx, cy, bf,
+                             int(inv_sigma2.numel()))
     N.check(L.orbo_pose_optimization(extractor._h, C.byref(p), dp(pose_out), dp(outlier_out), dp(inliers_out), None))
 
 
