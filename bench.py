@@ -133,11 +133,11 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_oracle_frames(pairs, threads):
+def cpu_oracle_frames(pairs, threads, with_pose_opt=False):
     """Reference arm: the CPU oracle on `threads` host threads.  Per stereo frame: both eyes through the
     extractor (on two threads like Frame.cc:136-141 when threads >= 2), ComputeStereoMatches, then the two
-    projection searches against a map made of the frame's own stereo points, each followed by PoseOptimization over the
-    features that got a map point (same shape as the GPU arm).
+    projection searches against a map made of the frame's own stereo points (same shape as the GPU arm); with_pose_opt adds
+    PoseOptimization over the features that got a map point after each search.
     Returns (frames/s, seconds)."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import pyoracle as po
@@ -173,12 +173,14 @@ def cpu_oracle_frames(pairs, threads):
         fm, _ = po.search_last(kL, dL, uR, bounds, sf, cam6, T, 0, pts, kL["octave"][sel], kL["angle"][sel], dL[sel],
                                np.ones(len(sel), np.uint8), 15.0, True)
         feat = np.nonzero(fm >= 0)[0]
-        pose_opt(feat, pts[fm[feat]])
+        if with_pose_opt:
+            pose_opt(feat, pts[fm[feat]])
         x, y, xr, lvl, vc, dq, xwl = local_map_queries(kL, dL, dep, np.random.default_rng(7), BF)
         mt, _ = po.search_local(kL, dL, uR, bounds, sf, x, y, xr, lvl, vc, dq, 3.0, 0.8)
         qs = np.nonzero(mt >= 0)[0]
         order = np.argsort(mt[qs], kind="stable")
-        pose_opt(mt[qs][order], xwl[qs][order])
+        if with_pose_opt:
+            pose_opt(mt[qs][order], xwl[qs][order])
         return 0
     exs = [(po.OracleExtractor(NFEAT, 1.2, 8, 20, 7), po.OracleExtractor(NFEAT, 1.2, 8, 20, 7)) for _ in range(nworkers)]
     pools2 = [ThreadPoolExecutor(1) if nthr >= 2 else None for _ in range(nworkers)]
@@ -217,8 +219,7 @@ def run_reference(args, rank, world):
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic", "impl": "reference",
             "config": {"workload": "config 3: stereo 640x480, 1200 features per eye; per frame: ORBextractor L+R, "
-                                   "ComputeStereoMatches, SearchByProjection(cur,last), PoseOptimization, SearchByProjection(F,local map), "
-                                   "PoseOptimization -- "
+                                   "ComputeStereoMatches, SearchByProjection(cur,last), SearchByProjection(F,local map) -- "
                                    "CPU oracle port (the reference needs OpenCV/Eigen and cannot be built here)",
                        "frames_per_step": len(pairs)},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
@@ -314,7 +315,7 @@ def main():
     d_match = [torch.full((max(max_loc, 1),), -1, dtype=torch.int32, device=dev) for _ in range(NH)]
     nq_last = float(np.mean([int(hl["off"][-1]) for hl in H_LAST])); nq_loc = float(np.mean([int(hl["off"][-1]) for hl in H_LOC]))
     # PoseOptimization after each search (Tracking.cc:3443, 3522): edge lists and results, per handle
-    from orb_slam3_detailed_comments_b200 import PoseOptimization, PoseOptimizationDevice, PoseEdgesDevice
+    from orb_slam3_detailed_comments_b200 import PoseOptimization, PoseOptimizationDevice, PoseEdgesDevice, PoseOptimizationFrames
     CAM5 = [FX, FY, CX, CY, BF]
     zi = lambda n, dt: torch.zeros(n, dtype=dt, device=dev)
     d_po = [dict(off=zi(B + 1, torch.int32), feat=zi(rows_cap, torch.int32), xw=zi((rows_cap, 3), torch.float32), obs=zi((rows_cap, 3), torch.float32),
@@ -326,7 +327,7 @@ def main():
         e.extract_batch_device(dev_pool[i % pool_batches].data_ptr(), nimg, W, H)
         e.stereo_batch(B, BF, BL)
 
-    def finish_device(i):
+    def finish_device(i, with_po=False):
         k = i % NH
         e = exs[k]
         d_last, d_loc = D_LAST[i % pool_batches], D_LOC[i % pool_batches]
@@ -334,13 +335,15 @@ def main():
                                                  d_last["xw"], d_last["oct"], d_last["ang"], d_last["desc"], d_last["obs"],
                                                  15.0, d_fm[k], d_nm[k][:B])
         po_ = d_po[k]
-        PoseEdgesDevice(e, B, d_last["fimg"], d_last["xw"], po_["off"], po_["feat"], po_["xw"], po_["obs"], po_["w"], feature_match=d_fm[k])
-        PoseOptimizationDevice(e, B, po_["off"], d_last["Tcw"], po_["xw"], po_["obs"], po_["w"], CAM5, po_["pose"][0], po_["out"], po_["inl"][0])
+        if with_po:
+            PoseEdgesDevice(e, B, d_last["fimg"], d_last["xw"], po_["off"], po_["feat"], po_["xw"], po_["obs"], po_["w"], feature_match=d_fm[k])
+            PoseOptimizationDevice(e, B, po_["off"], d_last["Tcw"], po_["xw"], po_["obs"], po_["w"], CAM5, po_["pose"][0], po_["out"], po_["inl"][0])
         m_local.SearchByProjectionDevice(e, cam, B, d_loc["fimg"], d_loc["off"], d_loc["px"], d_loc["py"], d_loc["pxr"],
                                          d_loc["lvl"], d_loc["vc"], d_loc["desc"], d_match[k], d_nm[k][B:], th=3.0)
-        PoseEdgesDevice(e, B, d_loc["fimg"], d_loc["xw"], po_["off"], po_["feat"], po_["xw"], po_["obs"], po_["w"],
-                        query_offset=d_loc["off"], query_match=d_match[k])
-        PoseOptimizationDevice(e, B, po_["off"], d_last["Tcw"], po_["xw"], po_["obs"], po_["w"], CAM5, po_["pose"][1], po_["out"], po_["inl"][1])
+        if with_po:
+            PoseEdgesDevice(e, B, d_loc["fimg"], d_loc["xw"], po_["off"], po_["feat"], po_["xw"], po_["obs"], po_["w"],
+                            query_offset=d_loc["off"], query_match=d_match[k])
+            PoseOptimizationDevice(e, B, po_["off"], d_last["Tcw"], po_["xw"], po_["obs"], po_["w"], CAM5, po_["pose"][1], po_["out"], po_["inl"][1])
 
     def step_device(i):     # un-pipelined form (used for the per-stage roofline pass)
         submit_device(i)
@@ -360,26 +363,29 @@ def main():
     barrier()
     sampler.wait_first()
     launches0 = _native.lib().orb_kernel_launches()
-    e0, e1, eb = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    barrier()
+    def timed_device_loop(first, count, with_po):
+        """count pipelined steps starting at batch index `first`; returns device milliseconds (events on stream 0)."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(streams[0])
+        for st in streams[1:]:
+            st.wait_event(e0)
+        for j in range(min(NH - 1, count)):
+            submit_device(first + j)
+        for i in range(count):
+            if i + NH - 1 < count:
+                submit_device(first + i + NH - 1)
+            finish_device(first + i, with_po)
+        for st in streams[1:]:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            streams[0].wait_event(ev)
+        e1.record(streams[0])
+        barrier()
+        return e0.elapsed_time(e1)
     t_begin = time.time()
-    e0.record(streams[0])
-    for st in streams[1:]:
-        st.wait_event(e0)
-    for j in range(min(NH - 1, args.steps)):
-        submit_device(args.warmup + j)
-    for i in range(args.steps):
-        if i + NH - 1 < args.steps:
-            submit_device(args.warmup + i + NH - 1)
-        finish_device(args.warmup + i)
-    for st in streams[1:]:
-        ev = torch.cuda.Event()
-        ev.record(st)
-        streams[0].wait_event(ev)
-    e1.record(streams[0])
-    barrier()
+    ms = timed_device_loop(args.warmup, args.steps, False)
     t_end = time.time()
-    ms = e0.elapsed_time(e1)
     clocks = sampler.stop(t_begin, t_end)
     launches = _native.lib().orb_kernel_launches() - launches0
     # per-stage times for the roofline: a serial (un-overlapped) pass over the same steps, CUDA events per stage
@@ -411,29 +417,14 @@ def main():
     P_LOC = [{k: pin(v) for k, v in hl.items()} for hl in H_LOC]
     pz = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory().numpy()
     from orb_slam3_detailed_comments_b200._native import KP_DTYPE
-    ISG = ex.GetInverseScaleSigmaSquares().astype(np.float32)
-
-    def PoseOptimizationBatchHost(e, counts, Tcw, xw, obs, w, cam5):
-        """orbo_pose_optimization, host-pointer form, on flat edge arrays (frame f owns counts[f] consecutive edges)."""
-        from orb_slam3_detailed_comments_b200 import _native as NN
-        import ctypes as CC
-        nfr = len(counts)
-        eoff = np.zeros(nfr + 1, np.int32)
-        eoff[1:] = np.cumsum(counts)
-        pose = np.ascontiguousarray(Tcw, np.float32)
-        xw, obs, w = np.ascontiguousarray(xw, np.float32), np.ascontiguousarray(obs, np.float32), np.ascontiguousarray(w, np.float32)
-        prob = NN.orbo_pose_problems(nfr, 0, NN.ptr(eoff), NN.ptr(pose), NN.ptr(xw), NN.ptr(obs), NN.ptr(w), *[float(np.float32(v)) for v in cam5], 0)
-        pose_out, outl, inl = np.zeros((nfr, 7), np.float64), np.zeros(max(int(eoff[-1]), 1), np.uint8), np.zeros(nfr, np.int32)
-        NN.check(NN.lib().orbo_pose_optimization(e._h, CC.byref(prob), NN.ptr(pose_out), NN.ptr(outl), NN.ptr(inl), None))
-        return pose_out, outl, inl
-
     def out_buffers():
         return dict(kps=torch.zeros(rows_cap * 28, dtype=torch.uint8).pin_memory().numpy().view(KP_DTYPE), desc=pz((rows_cap, 32), torch.uint8),
                     ur=pz(rows_cap, torch.float32), dep=pz(rows_cap, torch.float32), fm=pz(rows_cap, torch.int32), nm1=pz(B, torch.int32),
-                    mt=pz(max(max_loc, 1), torch.int32), nm2=pz(B, torch.int32))
+                    mt=pz(max(max_loc, 1), torch.int32), nm2=pz(B, torch.int32), pose=pz((B, 7), torch.float64), outl=pz(rows_cap, torch.uint8),
+                    inl=pz(B, torch.int32))
     OUT = [out_buffers() for _ in range(NH)]
 
-    def step_e2e(i, k):
+    def step_e2e(i, k, with_po=False):
         """One step through the host-pointer C ABI on handle k: images in (pinned host -> device), extraction, stereo,
         both searches, every result back in pinned host buffers.  Each call blocks until its results are on the host."""
         e, o = exs[k], OUT[k]
@@ -445,28 +436,14 @@ def main():
         e.stereo_download(rows, out=(o["ur"], o["dep"]))
         fm, _ = m_last.SearchByProjectionLastFrame(e, cam, p_last["fimg"], p_last["off"], p_last["Tcw"], p_last["dir"], p_last["xw"], p_last["oct"],
                                                    p_last["ang"], p_last["desc"], p_last["obs"], 15.0, rows, out=(o["fm"], o["nm1"]))
-        kps_h, ur_h = o["kps"], o["ur"]
-
-        def pose_opt(rows_sel, xw, per_frame_counts):
-            """PoseOptimization of the B frames through the host-pointer C ABI: the reference's correspondence walk
-            (Optimizer.cc:104-290) is a gather over the result arrays the previous calls returned."""
-            k = kps_h[rows_sel]
-            obs = np.stack([k["x"], k["y"], ur_h[rows_sel]], 1)
-            return PoseOptimizationBatchHost(e, per_frame_counts, p_last["Tcw"], xw, obs, ISG[k["octave"]], CAM5)
-        left_rows = np.concatenate([np.arange(oo[2 * p], oo[2 * p + 1]) for p in range(B)])
-        fml = fm[left_rows]
-        sel = fml >= 0
-        cnt1 = np.add.reduceat(sel.astype(np.int32), np.cumsum([0] + [int(oo[2 * p + 1] - oo[2 * p]) for p in range(B)])[:-1]) if B else []
-        pose_opt(left_rows[sel], p_last["xw"][fml[sel]], cnt1)
+        if with_po:   # PoseOptimization straight from the search results (host arrays in, pose / mvbOutlier / inliers out)
+            PoseOptimizationFrames(e, p_last["fimg"], p_last["Tcw"], p_last["xw"], CAM5, feature_match=fm, out=(o["pose"], o["outl"], o["inl"]))
         mt, _ = m_local.SearchByProjection(e, cam, p_loc["fimg"], p_loc["off"], p_loc["px"], p_loc["py"], p_loc["pxr"], p_loc["lvl"], p_loc["vc"],
                                            p_loc["desc"], th=3.0, out=(o["mt"], o["nm2"]))
-        nql = int(p_loc["off"][-1])
-        mtv = mt[:nql]
-        qs = np.nonzero(mtv >= 0)[0]
-        qframe = np.searchsorted(p_loc["off"], qs, side="right") - 1
-        cnt2 = np.bincount(qframe, minlength=B)
-        pose_opt(oo[2 * qframe] + mtv[qs], p_loc["xw"][qs], cnt2)
-        return rows * (60 + 8 + 4) + 12 * nimg + 4 * int(nq_loc) + 8 * B + 2 * B * (56 + 4) + len(left_rows) // 2
+        if with_po:
+            PoseOptimizationFrames(e, p_loc["fimg"], p_last["Tcw"], p_loc["xw"], CAM5, query_offset=p_loc["off"], query_match=mt,
+                                   out=(o["pose"], o["outl"], o["inl"]))
+        return rows * (60 + 8 + 4) + 12 * nimg + 4 * int(nq_loc) + 8 * B + (2 * (B * (56 + 4) + rows // 2) if with_po else 0)
 
     # One host thread per handle, the deployment shape of sequence-sharded replay (INTEGRATION.md section 6): every thread
     # drives its own handle / CUDA stream through the blocking C ABI, so one thread's result reads overlap the others'
@@ -474,10 +451,10 @@ def main():
     import concurrent.futures as cf
     pool = cf.ThreadPoolExecutor(max_workers=NH)
 
-    def worker(k, first, count):
+    def worker(k, first, count, with_po=False):
         tot = 0
         for i in range(first + k, first + count, NH):
-            tot += step_e2e(i, k)
+            tot += step_e2e(i, k, with_po)
         return tot
 
     list(pool.map(lambda k: worker(k, 0, max(args.warmup, NH)), range(NH)))
@@ -486,6 +463,22 @@ def main():
     d2h = sum(pool.map(lambda k: worker(k, max(args.warmup, NH), args.steps), range(NH)))
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    # the same steps with PoseOptimization after each search: resident and end-to-end
+    n_po = max(NH, args.steps // 2)
+    timed_device_loop(args.warmup, NH, True)
+    ms_po = timed_device_loop(args.warmup, n_po, True)
+    list(pool.map(lambda k: worker(k, 0, NH, True), range(NH)))
+    barrier()
+    t0 = time.perf_counter()
+    list(pool.map(lambda k: worker(k, NH, n_po, True), range(NH)))
+    torch.cuda.synchronize()
+    dt_po = time.perf_counter() - t0
+    tp = torch.tensor([ms_po * 1e-3, dt_po], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+    in_step = {"steps": n_po, "value_frames_per_s": world * B * n_po / float(tp[0].item()), "e2e_frames_per_s": world * B * n_po / float(tp[1].item()),
+               "note": "the headline step plus PoseOptimization after each search (device correspondence walk + optimiser; host-pointer "
+                       "orbo_pose_optimization_frames in the e2e leg)"}
     pool.shutdown()
     t = torch.tensor([dt], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -607,15 +600,15 @@ def main():
                             "cpu_oracle_ms_per_frame": 1e3 * t_cpu, "lm_iterations_per_frame": float(np.mean([g["iterations"] for g in got])),
                             "inliers_per_frame": float(np.mean([g["inliers"] for g in got]))}
             pose_opt = {"workload": "Optimizer::PoseOptimization, one CTA per frame, 80 % stereo / 20 % monocular edges, 10 % outliers",
-                        **res}
+                        **res, "in_step": in_step}
         except Exception as exc:
             pose_opt = {"error": repr(exc)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": "config 3: stereo 640x480, 1200 features per eye; per frame: ORBextractor L+R, "
-                                       "ComputeStereoMatches, SearchByProjection(cur,last,th=15), PoseOptimization, "
-                                       "SearchByProjection(F,local map points,th=3), PoseOptimization",
+                                       "ComputeStereoMatches, SearchByProjection(cur,last,th=15), SearchByProjection(F,"
+                                       "local map points,th=3)",
                            "frames_per_step_per_gpu": B, "images_per_step_per_gpu": nimg,
                            "pipeline": f"{NH} extractor handles / CUDA streams; value: one host thread; e2e: one host thread per handle",
                            "queries_per_frame": {"last_frame": nq_last / B, "local_map": nq_loc / B},

@@ -423,6 +423,27 @@ typedef struct {
 orb_status orbo_pose_edges(orbx_handle* h, const orbo_edge_source* src, int32_t* edge_offset_out, int32_t* edge_feature_out,
                            float* world_pos_out, float* obs_out, float* inv_sigma2_out);
 
+
+/* PoseOptimization for frames of the handle's last batch straight from a search's result arrays (HOST memory): the
+ * correspondence walk runs on the device against the resident features.  feature_match: the feature_match_out array of
+ * orbm_search_last_frame / orbm_search_bow (all compact rows of the batch); or query_offset + query_match: the match_out
+ * array of orbm_search_local_points.  world_pos[q] = pMP->GetWorldPos() of query q (n_queries entries).
+ * feature_outlier_out (may be NULL): pFrame->mvbOutlier per compact row, written for the listed frames only. */
+typedef struct {
+    int32_t n_frames;
+    const int32_t* frame_image;
+    const float* pose;             /* [n_frames][7] */
+    const int32_t* feature_match;  /* or NULL */
+    const int32_t* query_offset;   /* [n_frames + 1], with query_match */
+    const int32_t* query_match;    /* or NULL */
+    const float* world_pos;        /* [n_queries][3] */
+    int32_t n_queries;
+    float fx, fy, cx, cy, bf;
+} orbo_frame_matches;
+
+orb_status orbo_pose_optimization_frames(orbx_handle* h, const orbo_frame_matches* in, double* pose_out,
+                                         uint8_t* feature_outlier_out, int32_t* inliers_out);
+
 #ifdef __cplusplus
 }
 #endif

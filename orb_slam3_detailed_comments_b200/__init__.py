@@ -3,4 +3,4 @@ ORBextractor / ORBmatcher / Optimizer interfaces.  See DESIGN.md."""
 from ._native import OrbError, build, lib, KP_DTYPE  # noqa: F401
 from .extractor import ORBextractor  # noqa: F401
 from .matcher import ORBmatcher, camera  # noqa: F401
-from .optimizer import Optimizer, PoseOptimization, PoseOptimizationDevice, PoseEdgesDevice  # noqa: F401
+from .optimizer import Optimizer, PoseOptimization, PoseOptimizationDevice, PoseEdgesDevice, PoseOptimizationFrames  # noqa: F401

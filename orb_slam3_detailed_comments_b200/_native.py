@@ -81,6 +81,11 @@ class orbo_edge_source(C.Structure):
     _fields_ = [("n_frames", C.c_int32)] + [(n, C.c_void_p) for n in ("frame_image", "feature_match", "query_offset", "query_match", "world_pos")]
 
 
+class orbo_frame_matches(C.Structure):
+    _fields_ = [("n_frames", C.c_int32)] + [(n, C.c_void_p) for n in ("frame_image", "pose", "feature_match", "query_offset", "query_match", "world_pos")] + \
+        [("n_queries", C.c_int32)] + [(n, C.c_float) for n in ("fx", "fy", "cx", "cy", "bf")]
+
+
 class orbm_init_queries(C.Structure):
     _fields_ = [("n1", C.c_int32), ("kp1", C.c_void_p), ("desc1", C.c_void_p), ("prev_matched", C.c_void_p), ("n2", C.c_int32),
                 ("kp2", C.c_void_p), ("desc2", C.c_void_p), ("target_image", C.c_int32)]
@@ -144,6 +149,7 @@ SIGNATURES = {
     "orbm_search_triangulation": (_I, [_VP, C.POINTER(orbm_triangulation), _VP, _VP]),
     "orbo_pose_optimization": (_I, [_VP, C.POINTER(orbo_pose_problems), _VP, _VP, _VP, _VP]),
     "orbo_pose_edges": (_I, [_VP, C.POINTER(orbo_edge_source), _VP, _VP, _VP, _VP, _VP]),
+    "orbo_pose_optimization_frames": (_I, [_VP, C.POINTER(orbo_frame_matches), _VP, _VP, _VP]),
     "lba_create": (_I, [_I, C.POINTER(_VP)]),
     "lba_destroy": (None, [_VP]),
     "lba_solve": (_I, [_VP, C.POINTER(lba_problem), C.POINTER(lba_result), _VP]),

@@ -40,7 +40,8 @@ struct orbx_handle {
     int* d_sad = nullptr;
     void* d_node_scratch = nullptr;
     uint8_t* d_stage = nullptr;
-    size_t node_scratch_bytes = 0, stage_bytes = 0;
+    uint8_t* d_po = nullptr;         // edge lists / results of orbo_pose_optimization_frames
+    size_t node_scratch_bytes = 0, stage_bytes = 0, po_bytes = 0;
     bool stereo_valid = false;   // d_uright/d_depth belong to the last extracted batch
     size_t cand_slots = 0, kp_slots = 0, sort_slots = 0, taps_slots = 0, out_rows = 0;
     int* h_counts = nullptr;       // pinned

@@ -5,10 +5,10 @@
 // 6 x 6 system; 4 rounds of 10 iterations that restart from the frame's pose; chi2 classification after every round
 // (5.991 / 7.815 as floats); the robust kernel is dropped after round 2.
 //
-// One CTA per frame, a batch of frames per launch.  Every thread carries the pose, lambda and the whole LM control state
-// replicated in registers: the only cross-thread traffic is the two block reductions (robust chi2; the 21 + 6 entries of
-// H and b), whose butterfly + fixed-order warp sum gives every thread bit-identical values, so the accept / reject
-// decisions, the 6 x 6 LDL^T and the exponential-map update are computed redundantly without any broadcast.
+// One CTA per frame, a batch of frames per launch.  The edges are spread over the threads; every thread carries the pose,
+// lambda and the LM control state replicated in registers (the robust chi2 comes out of a butterfly + fixed-order warp sum
+// that gives every thread bit-identical values, so accept / reject needs no broadcast), while the 6 x 6 system is summed,
+// factorised (LDL^T) and applied (exponential map) by thread 0 only and the new pose is handed over through shared memory.
 #include <algorithm>
 #include <vector>
 
@@ -70,6 +70,8 @@ __device__ __forceinline__ int po_edge_error(const PoseOptParams& P, const doubl
 __global__ void __launch_bounds__(PO_THREADS) k_pose_opt(const __grid_constant__ PoseOptParams P) {
     __shared__ double s_red[PO_WARPS];
     __shared__ double s_part[PO_WARPS][27];
+    __shared__ double s_T[7], s_scale, s_md;
+    __shared__ int s_ok2;
     const int frame = blockIdx.x, tid = threadIdx.x;
     const int e0 = P.eoff[frame], n = P.eoff[frame + 1] - e0;
     double pose0[7], T[7];
@@ -153,8 +155,8 @@ __global__ void __launch_bounds__(PO_THREADS) k_pose_opt(const __grid_constant__
                 if ((tid & 31) == 0)
                     for (int i = 0; i < 27; ++i) s_part[tid >> 5][i] = acc[i];
                 __syncthreads();
-                double H[36], b[6];
-                {
+                double H[36], b[6];          // live in thread 0 only
+                if (tid == 0) {
                     int k = 0;
                     for (int i = 0; i < 6; ++i)
                         for (int j = i; j < 6; ++j) {
@@ -168,28 +170,42 @@ __global__ void __launch_bounds__(PO_THREADS) k_pose_opt(const __grid_constant__
                         for (int w = 1; w < PO_WARPS; ++w) s += s_part[w][21 + i];
                         b[i] = s;
                     }
-                }
-                if (iter == 0) {   // computeLambdaInit: tau * max diagonal
                     double md = 0;
                     for (int j = 0; j < 6; ++j) md = fmax(fabs(H[7 * j]), md);
-                    lambda = 1e-5 * md;
+                    s_md = md;
+                }
+                if (iter == 0) {   // computeLambdaInit: tau * max diagonal
+                    __syncthreads();
+                    lambda = 1e-5 * s_md;
                     ni = 2;
                     nBadIt = 0;
                 }
                 double rho = 0;
                 int qmax = 0;
                 do {
-                    double saved[7], x[6];
+                    double saved[7];
 #pragma unroll
                     for (int i = 0; i < 7; ++i) saved[i] = T[i];                 // push
-                    const bool ok2 = ldlt6_solve(H, lambda, b, x);
-                    pose_oplus(T, x);
-                    tempChi = compute_errors(T);
+                    if (tid == 0) {
+                        double x[6], Tn[7];
+                        s_ok2 = ldlt6_solve(H, lambda, b, x) ? 1 : 0;
+#pragma unroll
+                        for (int i = 0; i < 7; ++i) Tn[i] = T[i];
+                        pose_oplus(Tn, x);
+#pragma unroll
+                        for (int i = 0; i < 7; ++i) s_T[i] = Tn[i];
+                        double sc = 0;
+                        for (int j = 0; j < 6; ++j) sc += x[j] * (lambda * x[j] + b[j]);
+                        s_scale = sc;
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) T[i] = s_T[i];
+                    const bool ok2 = s_ok2 != 0;
+                    const double scale = s_scale + 1e-3;
+                    tempChi = compute_errors(T);     // its barriers also fence s_T / s_scale against the next trial
                     if (!ok2) tempChi = 1.7976931348623157e308;
                     rho = currentChi - tempChi;
-                    double scale = 0;
-                    for (int j = 0; j < 6; ++j) scale += x[j] * (lambda * x[j] + b[j]);
-                    scale += 1e-3;
                     rho /= scale;
                     if (rho > 0 && isfinite(tempChi)) {
                         double alpha = 2 * rho - 1;
@@ -436,5 +452,82 @@ extern "C" orb_status orbo_pose_edges(orbx_handle* h, const orbo_edge_source* sr
     k_pose_edges<true><<<nf, PE_THREADS, sm, h->stream>>>(P, nf);
     ORB_LAUNCHED();
     ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
+}
+
+extern "C" orb_status orbo_pose_optimization_frames(orbx_handle* h, const orbo_frame_matches* in, double* pose_out,
+                                                    uint8_t* feature_outlier_out, int32_t* inliers_out) {
+    if (!h || !in || in->n_frames < 1 || !in->frame_image || !in->pose || !in->world_pos || in->n_queries < 0 ||
+        ((in->feature_match != nullptr) == (in->query_match != nullptr)) || (in->query_match && !in->query_offset) || !pose_out || !inliers_out)
+        return set_error(ORB_ERR_INVALID, "bad arguments");
+    ORB_CUDA(cudaSetDevice(h->cfg.device));
+    orb_status s = orbx_counts(h, nullptr, nullptr, nullptr);
+    if (s != ORB_OK) return s;
+    const int nf = in->n_frames, MB = h->cfg.max_batch;
+    const int total_rows = h->h_counts[2 * MB + h->last_batch];
+    size_t cap = 0;                               // edges <= features of the listed frames
+    for (int f = 0; f < nf; ++f) {
+        const int img = in->frame_image[f];
+        if (img < 0 || img >= h->last_batch) return set_error(ORB_ERR_INVALID, "bad frame image");
+        cap += (size_t)h->h_counts[img];
+    }
+    cap = std::max<size_t>(cap, 1);
+    const int nq = in->n_queries;
+    const size_t need = (size_t)nf * (4 * 4 + 7 * 4 + 7 * 8 + 64) + cap * (4 + 12 + 12 + 4 + 1 + 64) + (size_t)nq * (12 + 4) + (size_t)total_rows * 4 + 65536;
+    if (need > h->po_bytes) {
+        if (h->d_po) cudaFree(h->d_po);
+        h->d_po = nullptr;
+        h->po_bytes = 0;
+        const size_t want = (need + (1 << 20)) / (1 << 20) * (1 << 20);
+        ORB_CUDA(cudaMalloc((void**)&h->d_po, want));
+        h->po_bytes = want;
+    }
+    PoStage cur{h->d_po};
+    cudaStream_t st = h->stream;
+    auto up = [&](auto*& dst, const auto* src, size_t n) -> orb_status {
+        using T = std::remove_cv_t<std::remove_pointer_t<decltype(src)>>;
+        T* d = cur.take<T>(std::max<size_t>(n, 1));
+        if (n && src) ORB_CUDA(cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
+        dst = d;
+        return ORB_OK;
+    };
+    int *d_img, *d_fm = nullptr, *d_qoff = nullptr, *d_qm = nullptr; float *d_pose, *d_xw;
+    if ((s = up(d_img, (const int*)in->frame_image, nf)) != ORB_OK) return s;
+    if ((s = up(d_pose, in->pose, (size_t)nf * 7)) != ORB_OK) return s;
+    if ((s = up(d_xw, in->world_pos, (size_t)nq * 3)) != ORB_OK) return s;
+    if (in->feature_match) { if ((s = up(d_fm, (const int*)in->feature_match, (size_t)total_rows)) != ORB_OK) return s; }
+    else {
+        if ((s = up(d_qoff, (const int*)in->query_offset, nf + 1)) != ORB_OK) return s;
+        if ((s = up(d_qm, (const int*)in->query_match, (size_t)in->query_offset[nf])) != ORB_OK) return s;
+    }
+    int* d_eoff = cur.take<int>(nf + 1);
+    int* d_efeat = cur.take<int>(cap);
+    float* d_exw = cur.take<float>(cap * 3);
+    float* d_eobs = cur.take<float>(cap * 3);
+    float* d_ew = cur.take<float>(cap);
+    double* d_pout = cur.take<double>((size_t)nf * 7);
+    uint8_t* d_out = cur.take<uint8_t>(cap);
+    int* d_inl = cur.take<int>(nf);
+    orbo_edge_source src{nf, d_img, d_fm, d_qoff, d_qm, d_xw};
+    if ((s = orbo_pose_edges(h, &src, d_eoff, d_efeat, d_exw, d_eobs, d_ew)) != ORB_OK) return s;
+    orbo_pose_problems pp{nf, 1, d_eoff, d_pose, d_exw, d_eobs, d_ew, in->fx, in->fy, in->cx, in->cy, in->bf, (int32_t)cap};
+    if ((s = orbo_pose_optimization(h, &pp, d_pout, d_out, d_inl, nullptr)) != ORB_OK) return s;
+    std::vector<int> eoff(nf + 1), efeat(cap);
+    std::vector<uint8_t> outl(cap);
+    ORB_CUDA(cudaMemcpyAsync(pose_out, d_pout, sizeof(double) * 7 * (size_t)nf, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpyAsync(inliers_out, d_inl, sizeof(int) * (size_t)nf, cudaMemcpyDeviceToHost, st));
+    if (feature_outlier_out) {
+        ORB_CUDA(cudaMemcpyAsync(eoff.data(), d_eoff, sizeof(int) * (size_t)(nf + 1), cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaMemcpyAsync(efeat.data(), d_efeat, sizeof(int) * cap, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaMemcpyAsync(outl.data(), d_out, cap, cudaMemcpyDeviceToHost, st));
+    }
+    ORB_CUDA(cudaStreamSynchronize(st));
+    if (feature_outlier_out) {                     // pFrame->mvbOutlier[i] of every feature of the listed frames
+        for (int f = 0; f < nf; ++f) {
+            const int img = in->frame_image[f], row0 = h->h_counts[2 * MB + img];
+            std::fill(feature_outlier_out + row0, feature_outlier_out + row0 + h->h_counts[img], (uint8_t)0);
+            for (int e = eoff[f]; e < eoff[f + 1]; ++e) feature_outlier_out[row0 + efeat[e]] = outl[e];
+        }
+    }
     return ORB_OK;
 }

@@ -103,3 +103,24 @@ def PoseEdgesDevice(extractor, n_frames, frame_image, world_pos, edge_offset_out
     src = N.orbo_edge_source(n_frames, dp(frame_image), dp(feature_match), dp(query_offset), dp(query_match), dp(world_pos))
     N.check(L.orbo_pose_edges(extractor._h, C.byref(src), dp(edge_offset_out), dp(edge_feature_out), dp(world_pos_out), dp(obs_out),
                               dp(inv_sigma2_out)))
+
+
+def PoseOptimizationFrames(extractor, frame_image, pose, world_pos, cam5, feature_match=None, query_offset=None, query_match=None,
+                           total_rows=None, out=None):
+    """PoseOptimization of frames of the extractor's last batch straight from a search's host result arrays
+    (orbo_pose_optimization_frames).  Returns (pose float64[n][7], feature_outlier uint8[total_rows] or None, inliers int32[n])."""
+    L = N.lib()
+    fi = np.ascontiguousarray(frame_image, np.int32)
+    nf = len(fi)
+    pose = np.ascontiguousarray(pose, np.float32)
+    xw = np.ascontiguousarray(world_pos, np.float32)
+    fm = None if feature_match is None else np.ascontiguousarray(feature_match, np.int32)
+    qo = None if query_offset is None else np.ascontiguousarray(query_offset, np.int32)
+    qm = None if query_match is None else np.ascontiguousarray(query_match, np.int32)
+    P = lambda a: None if a is None else N.ptr(a)
+    fx, fy, cx, cy, bf = [float(np.float32(v)) for v in cam5]
+    m = N.orbo_frame_matches(nf, P(fi), P(pose), P(fm), P(qo), P(qm), P(xw), len(xw), fx, fy, cx, cy, bf)
+    if out is None:
+        out = (np.zeros((nf, 7), np.float64), None if total_rows is None else np.zeros(max(total_rows, 1), np.uint8), np.zeros(nf, np.int32))
+    N.check(L.orbo_pose_optimization_frames(extractor._h, C.byref(m), P(out[0]), P(out[1]), P(out[2])))
+    return out

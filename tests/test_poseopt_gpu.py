@@ -153,4 +153,14 @@ def test_edges_from_device_matches_and_optimise():
             r = po.pose_optimization(f["pose"], f["world_pos"], f["obs"], f["inv_sigma2"], np.float32(CAM5))
             assert np.abs(o_pose.cpu().numpy()[p] - r["pose"]).max() < TOL
             assert abs(int(o_inl.cpu().numpy()[p]) - r["inliers"]) <= 1
+        # the host-pointer form: the search's result arrays in, pose / mvbOutlier / inliers out
+        from orb_slam3_detailed_comments_b200 import PoseOptimizationFrames
+        kwh = dict(feature_match=fm) if form == "feature_match" else dict(query_offset=np.array(qoff, np.int32), query_match=qm)
+        hp, ho, hi = PoseOptimizationFrames(e, fimg, np.stack([f["pose"] for f in frames]), xw_all, CAM5, total_rows=total, **kwh)
+        for p, f in enumerate(frames):
+            r = po.pose_optimization(f["pose"], f["world_pos"], f["obs"], f["inv_sigma2"], np.float32(CAM5))
+            a, b = int(off[2 * p]), int(off[2 * p + 1])
+            feats = np.nonzero(fm[a:b] >= 0)[0]
+            assert np.abs(hp[p] - r["pose"]).max() < TOL and abs(int(hi[p]) - r["inliers"]) <= 1
+            assert int((ho[a:b][feats] != r["outlier"]).sum()) <= 1 and ho[a:b].sum() == ho[a:b][feats].sum()
     e.close()
