@@ -19,7 +19,7 @@ using namespace orb;
 
 namespace orb {
 
-#define PO_THREADS 128
+#define PO_THREADS 256
 #define PO_WARPS (PO_THREADS / 32)
 
 struct PoseOptParams {
