@@ -492,24 +492,29 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ ExtractGeo
     // horizontal results of the last 7 rows, unpacked to one 32-bit value per pixel (Q8.8 <= 65280)
     uint32_t hwin[7][4];
     const int rows = min(BLUR_ROWS, G.h - y0);
+    // 7 rows per trip: the window slot r % 7 == j is then a compile-time register index, and the body (1/5 of the fully
+    // unrolled form) stays resident in the instruction cache -- the 38-row unroll was 124 KB of code and stalled on fetch
+    for (int rb = 0; rb < BLUR_ROWS + 6; rb += 7) {
 #pragma unroll
-    for (int r = 0; r < BLUR_ROWS + 6; ++r) {
-        if (r < rows + 6) {
-            const int y = reflect101(y0 + r - 3, G.h);
-            uint32_t lo, hi;
-            blur_h4(src + (int64_t)y * G.pitch, x0, G.w, interior, lo, hi);
-            uint32_t* hrow = hwin[r % 7];
-            hrow[0] = lo & 0xffffu; hrow[2] = lo >> 16; hrow[1] = hi & 0xffffu; hrow[3] = hi >> 16;
-            if (r >= 6) {
-                // rows r-6 .. r are in the window; output row y0 + r - 6
-                uint32_t packed = 0u;
+        for (int j = 0; j < 7; ++j) {
+            const int r = rb + j;
+            if (r < rows + 6) {
+                const int y = reflect101(y0 + r - 3, G.h);
+                uint32_t lo, hi;
+                blur_h4(src + (int64_t)y * G.pitch, x0, G.w, interior, lo, hi);
+                uint32_t* hrow = hwin[j];
+                hrow[0] = lo & 0xffffu; hrow[2] = lo >> 16; hrow[1] = hi & 0xffffu; hrow[3] = hi >> 16;
+                if (r >= 6) {
+                    // rows r-6 .. r are in the window; output row y0 + r - 6
+                    uint32_t packed = 0u;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t acc = 18u * (hwin[(r - 6) % 7][k] + hwin[r % 7][k]) + 34u * (hwin[(r - 5) % 7][k] + hwin[(r - 1) % 7][k]) +
-                                         48u * (hwin[(r - 4) % 7][k] + hwin[(r - 2) % 7][k]) + 56u * hwin[(r - 3) % 7][k];
-                    packed |= ((acc + 32768u) >> 16) << (8 * k);
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t acc = 18u * (hwin[(j + 1) % 7][k] + hwin[j][k]) + 34u * (hwin[(j + 2) % 7][k] + hwin[(j + 6) % 7][k]) +
+                                             48u * (hwin[(j + 3) % 7][k] + hwin[(j + 5) % 7][k]) + 56u * hwin[(j + 4) % 7][k];
+                        packed |= ((acc + 32768u) >> 16) << (8 * k);
+                    }
+                    *reinterpret_cast<uint32_t*>(dst + (int64_t)(y0 + r - 6) * G.blur_pitch + x0) = packed;   // pitch padding absorbs the tail
                 }
-                *reinterpret_cast<uint32_t*>(dst + (int64_t)(y0 + r - 6) * G.blur_pitch + x0) = packed;   // pitch padding absorbs the tail
             }
         }
     }
@@ -572,8 +577,8 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_describe(const __grid_
     const float factorPI = (float)(3.14159265358979323846 / 180.f);
     float sa, ca;
     glibc_sincosf(fmul(angle, factorPI), &sa, &ca);
-    const uint8_t* cb = G.blur + (int64_t)img * G.blur_stride + (int64_t)y * G.blur_pitch + x;
     const int8_t* pp = s_pat + lane * 32;
+    const uint8_t* cb = G.blur + (int64_t)img * G.blur_stride + (int64_t)y * G.blur_pitch + x;
     uint32_t val = 0u;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
