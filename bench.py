@@ -506,12 +506,20 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = ab[top] * nimg / (ext[top] * 1e-3) / 1e9
+        traffic = None      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_fast_traffic.json")))
+            if top == "fast":
+                traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * nimg / tr["images_per_launch"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None,
+                    "frac": achieved / peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                     "stage_ms_per_step": stages,
                     "stage_gbs": {k: ab[k] * nimg / (ext[k] * 1e-3) / 1e9 for k in ext},
                     "algorithmic_bytes_per_image": ab,
+                    "traffic_source": "profiles/r01_fast_traffic.json (ncu --set full, bytes per launch of 128 images)",
                     "note": "stage times from a serial pass (one stream) right after the timed region; the timed region itself is "
                             "software-pipelined over the handles' streams.  FAST is ALU-pipe bound (profiles/), not HBM bound; see DESIGN.md"}
         cpu = None
