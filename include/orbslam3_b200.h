@@ -167,6 +167,8 @@ typedef struct {
     const uint8_t* desc;          /* 32 bytes per query */
     const uint8_t* feature_claimed; /* per compact keypoint row of the batch: F.mvpMapPoints[idx] already holds a
                                        map point with Observations() > 0; NULL = none */
+    const uint8_t* in_view;       /* pMP->mbTrackInView per entry (orbf_is_in_frustum output): entries with 0 are skipped
+                                     like ORBmatcher.cc:52-53 and get match -1; NULL = every entry is in view */
 } orbm_local_queries;
 
 /* match_out[q] = feature index inside its frame (F.mvpMapPoints[bestIdx] = pMP) or -1;
@@ -174,6 +176,31 @@ typedef struct {
 orb_status orbm_search_local_points(orbx_handle* h, const orbm_camera* cam, const orbm_local_queries* q, float th,
                                     float nnratio, int32_t far_points, float th_far, int32_t* match_out,
                                     int32_t* nmatches_out);
+
+/* Frame::isInFrustum(MapPoint*, viewingCosLimit)  src/Frame.cc:667-720, Nleft == -1 (Tracking::SearchLocalPoints,
+ * Tracking.cc:4022).  Frame f tests points [point_offset[f], point_offset[f+1]) -- mvpLocalMapPoints after the caller-side
+ * skips (already matched in this frame, isBad) -- against its pose members mRcw (row-major), mtcw, mOw
+ * (Frame::UpdatePoseMatrices).  Outputs per point are the MapPoint fields the search reads: mbTrackInView, mTrackProjX,
+ * mTrackProjY, mTrackProjXR, mnTrackScaleLevel, mTrackViewCos, mTrackDepth; they plug into orbm_local_queries (with
+ * in_view) without compaction.  on_device != 0: all arrays are device memory, n_points_max bounds point_offset[n_frames],
+ * no synchronisation. */
+typedef struct {
+    int32_t n_frames;
+    int32_t on_device;
+    const int32_t* point_offset;  /* [n_frames + 1] */
+    const float* Rcw;             /* [n_frames][9] */
+    const float* tcw;             /* [n_frames][3] */
+    const float* Ow;              /* [n_frames][3] */
+    const float* world_pos;       /* [np][3] */
+    const float* normal;          /* [np][3] MapPoint::GetNormal */
+    const float* max_dist;        /* GetMaxDistanceInvariance */
+    const float* min_dist;        /* GetMinDistanceInvariance */
+    int32_t n_points_max;         /* device callers: grid bound; else ignored */
+} orbf_frustum_points;
+
+orb_status orbf_is_in_frustum(orbx_handle* h, const orbm_camera* cam, const orbf_frustum_points* in, float viewing_cos_limit,
+                              uint8_t* in_view_out, float* proj_x_out, float* proj_y_out, float* proj_xr_out, int32_t* level_out,
+                              float* view_cos_out, float* track_depth_out);
 
 /* SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)  ORBmatcher.cc:1950-2184.
  * One entry per LastFrame feature that has a map point and is not an outlier, in LastFrame order.

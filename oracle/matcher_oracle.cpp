@@ -593,3 +593,48 @@ extern "C" int orc_search_initialization(const KeyPoint* kp1, const uint8_t* des
     }
     return nmatches;
 }
+
+// Frame::isInFrustum(MapPoint*, viewingCosLimit)  src/Frame.cc:667-720, Nleft == -1.  Per map point: Pc = mRcw * P + mtcw
+// (Eigen fixed-size product / norm / dot in the unrolled reduction order x + (y + z), Eigen/src/Core/Redux.h -- not in the
+// tree), depth / image-bounds / scale-invariance-distance / viewing-angle gates, MapPoint::PredictScale.
+// Outputs per point: in_view (mbTrackInView), mTrackProjX / Y / XR, mnTrackScaleLevel, mTrackViewCos, mTrackDepth.
+// Points that fail keep proj = -1 / level -1 except that mTrackProjX / Y are already set when only the distance or
+// viewing-angle gate fails (:690-691), as in the reference.
+extern "C" int orc_is_in_frustum(int n, const float* Rcw9, const float* tcw, const float* Ow, const float* bounds4, const float* cam6,
+                                 int nLevels, float logScaleFactor, float viewingCosLimit, const float* xw, const float* normal,
+                                 const float* maxDist, const float* minDist, uint8_t* in_view, float* projx, float* projy, float* projxr,
+                                 int* level, float* viewcos, float* depth) {
+    int nvis = 0;
+    for (int i = 0; i < n; ++i) {
+        in_view[i] = 0; projx[i] = -1; projy[i] = -1; projxr[i] = -1; level[i] = -1; viewcos[i] = 0; depth[i] = 0;
+        const float* P = xw + 3 * i;
+        float Pc[3];
+        for (int r = 0; r < 3; ++r) Pc[r] = (Rcw9[3 * r] * P[0] + (Rcw9[3 * r + 1] * P[1] + Rcw9[3 * r + 2] * P[2])) + tcw[r];
+        const float Pc_dist = std::sqrt(Pc[0] * Pc[0] + (Pc[1] * Pc[1] + Pc[2] * Pc[2]));
+        const float PcZ = Pc[2];
+        const float invz = 1.0f / PcZ;
+        if (PcZ < 0.0f) continue;
+        const float u = cam6[0] * Pc[0] / Pc[2] + cam6[2], v = cam6[1] * Pc[1] / Pc[2] + cam6[3];
+        if (u < bounds4[0] || u > bounds4[1]) continue;
+        if (v < bounds4[2] || v > bounds4[3]) continue;
+        projx[i] = u;
+        projy[i] = v;
+        const float PO[3] = {P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2]};
+        const float dist = std::sqrt(PO[0] * PO[0] + (PO[1] * PO[1] + PO[2] * PO[2]));
+        if (dist < minDist[i] || dist > maxDist[i]) continue;
+        const float* Pn = normal + 3 * i;
+        const float vc = (PO[0] * Pn[0] + (PO[1] * Pn[1] + PO[2] * Pn[2])) / dist;
+        if (vc < viewingCosLimit) continue;
+        const float ratio = maxDist[i] / dist;
+        int lvl = (int)std::ceil(logf(ratio) / logScaleFactor);
+        if (lvl < 0) lvl = 0;
+        else if (lvl >= nLevels) lvl = nLevels - 1;
+        in_view[i] = 1;
+        projxr[i] = u - cam6[4] * invz;
+        depth[i] = Pc_dist;
+        level[i] = lvl;
+        viewcos[i] = vc;
+        ++nvis;
+    }
+    return nvis;
+}

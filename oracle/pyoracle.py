@@ -380,3 +380,20 @@ def pose_optimization(pose7, Xw, obs, inv_sigma2, cam5):
     inl = L.orc_pose_optimization(n, _p(Xw), _p(obs), _p(w), _p(cam5), _p(pose), _p(out), _p(stats))
     return dict(pose=pose, outlier=out[:n], inliers=inl, rounds=int(stats[0]), iterations=int(stats[1]), trials=int(stats[2]),
                 lambda_=float(stats[3]))
+
+
+def is_in_frustum(Rcw, tcw, Ow, bounds, cam6, n_levels, log_scale_factor, xw, normal, max_dist, min_dist, viewing_cos_limit=0.5):
+    """Frame::isInFrustum restated (Frame.cc:667-720).  Returns dict(in_view, proj_x, proj_y, proj_xr, level, view_cos, depth)."""
+    L = lib()
+    L.orc_is_in_frustum.restype = C.c_int
+    L.orc_is_in_frustum.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_float, C.c_float] + [C.c_void_p] * 11
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    R, t, O, b4, c6 = f32(Rcw), f32(tcw), f32(Ow), f32(bounds), f32(cam6)
+    xw, nr, mx, mn = f32(xw), f32(normal), f32(max_dist), f32(min_dist)
+    n = len(xw)
+    out = dict(in_view=np.zeros(max(n, 1), np.uint8), proj_x=np.zeros(max(n, 1), np.float32), proj_y=np.zeros(max(n, 1), np.float32),
+               proj_xr=np.zeros(max(n, 1), np.float32), level=np.zeros(max(n, 1), np.int32), view_cos=np.zeros(max(n, 1), np.float32),
+               depth=np.zeros(max(n, 1), np.float32))
+    L.orc_is_in_frustum(n, _p(R), _p(t), _p(O), _p(b4), _p(c6), int(n_levels), float(log_scale_factor), float(viewing_cos_limit), _p(xw), _p(nr),
+                        _p(mx), _p(mn), *[_p(out[k]) for k in ("in_view", "proj_x", "proj_y", "proj_xr", "level", "view_cos", "depth")])
+    return {k: v[:n] for k, v in out.items()}

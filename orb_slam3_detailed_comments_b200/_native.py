@@ -52,7 +52,7 @@ class orbm_camera(C.Structure):
 class orbm_local_queries(C.Structure):
     _fields_ = [("n_frames", C.c_int32), ("on_device", C.c_int32)] + [
         (n, C.c_void_p) for n in ("frame_image", "query_offset", "proj_x", "proj_y", "proj_xr", "level", "view_cos",
-                                  "track_depth", "desc", "feature_claimed")]
+                                  "track_depth", "desc", "feature_claimed", "in_view")]
 
 
 class orbm_last_queries(C.Structure):
@@ -84,6 +84,11 @@ class orbo_edge_source(C.Structure):
 class orbo_frame_matches(C.Structure):
     _fields_ = [("n_frames", C.c_int32)] + [(n, C.c_void_p) for n in ("frame_image", "pose", "feature_match", "query_offset", "query_match", "world_pos")] + \
         [("n_queries", C.c_int32)] + [(n, C.c_float) for n in ("fx", "fy", "cx", "cy", "bf")]
+
+
+class orbf_frustum_points(C.Structure):
+    _fields_ = [("n_frames", C.c_int32), ("on_device", C.c_int32)] + [
+        (n, C.c_void_p) for n in ("point_offset", "Rcw", "tcw", "Ow", "world_pos", "normal", "max_dist", "min_dist")] + [("n_points_max", C.c_int32)]
 
 
 class orbm_init_queries(C.Structure):
@@ -150,6 +155,7 @@ SIGNATURES = {
     "orbo_pose_optimization": (_I, [_VP, C.POINTER(orbo_pose_problems), _VP, _VP, _VP, _VP]),
     "orbo_pose_edges": (_I, [_VP, C.POINTER(orbo_edge_source), _VP, _VP, _VP, _VP, _VP]),
     "orbo_pose_optimization_frames": (_I, [_VP, C.POINTER(orbo_frame_matches), _VP, _VP, _VP]),
+    "orbf_is_in_frustum": (_I, [_VP, C.POINTER(orbm_camera), C.POINTER(orbf_frustum_points), C.c_float] + [_VP] * 7),
     "lba_create": (_I, [_I, C.POINTER(_VP)]),
     "lba_destroy": (None, [_VP]),
     "lba_solve": (_I, [_VP, C.POINTER(lba_problem), C.POINTER(lba_result), _VP]),

@@ -94,6 +94,7 @@ struct ProjParams {
     float* quv;                // mode 1: [nq][4] u, v, radius, invzc
     int* match;                // mode 0: [nq] feature index or -1;  mode 1: per compact feature row: query or -1
     int* nmatches;             // [n_frames]
+    const uint8_t* qvalid;     // mode 0: mbTrackInView per query (Frame::isInFrustum), null = all
     int* seqFlag;              // [n_frames] modes 0 / 1: set by the parallel resolve when a frame must take the sequential kernel; null = always sequential
 };
 
@@ -366,6 +367,7 @@ __device__ __forceinline__ bool kf_window(const ProjParams& P, int frame, int q,
 }
 
 __device__ __forceinline__ bool local_window(const ProjParams& P, int q, Window& w, float& er_max) {
+    if (P.qvalid && !P.qvalid[q]) return false;                 // !pMP->mbTrackInView (ORBmatcher.cc:52-53)
     if (P.bFar && P.f1 && P.f1[q] > P.thFar) return false;
     const int lvl = P.level[q];
     float r = ((double)P.f0[q] > 0.998) ? 2.5f : 4.0f;        // RadiusByViewingCos, ORBmatcher.cc:242-248
@@ -984,6 +986,67 @@ __global__ void __launch_bounds__(PR_THREADS) k_proj_resolve_par(const __grid_co
     if (tid == 0) P.nmatches[frame] = s_nm;
 }
 
+
+// ---- Frame::isInFrustum (src/Frame.cc:667-720): one thread per candidate map point ------------------------------------
+struct FrustumParams {
+    const int* poff;           // [n_frames + 1]
+    const float* Rcw;          // [n_frames][9] row-major mRcw
+    const float* tcw;          // [n_frames][3] mtcw
+    const float* Ow;           // [n_frames][3] mOw
+    const float* xw;           // [np][3]
+    const float* normal;
+    const float* maxD;
+    const float* minD;
+    float fx, fy, cx, cy, bf, minX, maxX, minY, maxY, logScale, cosLimit;
+    int nLevels;
+    uint8_t* in_view;
+    float *px, *py, *pxr, *vc, *depth;
+    int* level;
+};
+
+__global__ void __launch_bounds__(256) k_in_frustum(const __grid_constant__ FrustumParams P) {
+    const int frame = blockIdx.y;
+    const int p0 = P.poff[frame], p1 = P.poff[frame + 1];
+    const int i = p0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p1) return;
+    const float* R = P.Rcw + 9 * frame;
+    const float* t = P.tcw + 3 * frame;
+    const float* O = P.Ow + 3 * frame;
+    const float X = P.xw[3 * (size_t)i], Y = P.xw[3 * (size_t)i + 1], Z = P.xw[3 * (size_t)i + 2];
+    uint8_t vis = 0;
+    float u = -1.f, v = -1.f, ur = -1.f, viewCos = 0.f, dep = 0.f;
+    int lvl = -1;
+    // Eigen's fixed-size product / norm / dot: a0 b0 + (a1 b1 + a2 b2)
+    const float xc = fadd(fadd(fmul(R[0], X), fadd(fmul(R[1], Y), fmul(R[2], Z))), t[0]);
+    const float yc = fadd(fadd(fmul(R[3], X), fadd(fmul(R[4], Y), fmul(R[5], Z))), t[1]);
+    const float zc = fadd(fadd(fmul(R[6], X), fadd(fmul(R[7], Y), fmul(R[8], Z))), t[2]);
+    const float pcDist = fsqrt(fadd(fmul(xc, xc), fadd(fmul(yc, yc), fmul(zc, zc))));
+    const float invz = fdiv(1.0f, zc);
+    do {
+        if (zc < 0.0f) break;
+        const float uu = fadd(fdiv(fmul(P.fx, xc), zc), P.cx), vv = fadd(fdiv(fmul(P.fy, yc), zc), P.cy);
+        if (uu < P.minX || uu > P.maxX) break;
+        if (vv < P.minY || vv > P.maxY) break;
+        u = uu;
+        v = vv;
+        const float ox = fsub(X, O[0]), oy = fsub(Y, O[1]), oz = fsub(Z, O[2]);
+        const float dist = fsqrt(fadd(fmul(ox, ox), fadd(fmul(oy, oy), fmul(oz, oz))));
+        if (dist < P.minD[i] || dist > P.maxD[i]) break;
+        const float* n = P.normal + 3 * (size_t)i;
+        const float c = fdiv(fadd(fmul(ox, n[0]), fadd(fmul(oy, n[1]), fmul(oz, n[2]))), dist);
+        if (c < P.cosLimit) break;
+        int l = (int)ceilf(fdiv(glibc_logf(fdiv(P.maxD[i], dist)), P.logScale));   // MapPoint::PredictScale
+        if (l < 0) l = 0;
+        else if (l >= P.nLevels) l = P.nLevels - 1;
+        vis = 1;
+        ur = fsub(uu, fmul(P.bf, invz));
+        dep = pcDist;
+        lvl = l;
+        viewCos = c;
+    } while (false);
+    P.in_view[i] = vis; P.px[i] = u; P.py[i] = v; P.pxr[i] = ur; P.level[i] = lvl; P.vc[i] = viewCos; P.depth[i] = dep;
+}
+
 }  // namespace orb
 
 // ------------------------------------------------------------------------------------------------
@@ -1112,6 +1175,9 @@ extern "C" orb_status orbm_search_local_points(orbx_handle* h, const orbm_camera
     if ((s = upload(h, f1, Q->track_depth, nq, cur, dev)) != ORB_OK) return s;
     if ((s = upload(h, qd, Q->desc, (size_t)nq * 32, cur, dev)) != ORB_OK) return s;
     if ((s = upload(h, fl, Q->feature_claimed, rows, cur, dev)) != ORB_OK) return s;
+    uint8_t* qv;
+    if ((s = upload(h, qv, Q->in_view, nq, cur, dev)) != ORB_OK) return s;
+    P.qvalid = qv;
     P.a0 = a0; P.a1 = a1; P.a2 = a2; P.level = lvl; P.f0 = f0; P.f1 = f1; P.qdesc = qd; P.flag = fl;
     P.th = th; P.nnratio = nnratio; P.bFar = far_points; P.thFar = th_far;
     P.gridOrder = cur.take<uint16_t>((size_t)nf * P.maxFeat);
@@ -1481,5 +1547,73 @@ extern "C" orb_status orbm_search_initialization(orbx_handle* h, const orbm_came
     }
     ORB_CUDA(cudaStreamSynchronize(h->stream));
     if (nmatches_out && nq == 0) *nmatches_out = 0;
+    return ORB_OK;
+}
+
+extern "C" orb_status orbf_is_in_frustum(orbx_handle* h, const orbm_camera* cam, const orbf_frustum_points* in, float viewing_cos_limit,
+                                         uint8_t* in_view_out, float* proj_x_out, float* proj_y_out, float* proj_xr_out, int32_t* level_out,
+                                         float* view_cos_out, float* track_depth_out) {
+    if (!h || !cam || !in || in->n_frames < 1 || !in->point_offset || !in->Rcw || !in->tcw || !in->Ow || !in_view_out || !proj_x_out ||
+        !proj_y_out || !proj_xr_out || !level_out || !view_cos_out || !track_depth_out)
+        return set_error(ORB_ERR_INVALID, "bad arguments");
+    ORB_CUDA(cudaSetDevice(h->cfg.device));
+    const bool dev = in->on_device != 0;
+    const int nf = in->n_frames;
+    if (dev && in->n_points_max < 0) return set_error(ORB_ERR_INVALID, "n_points_max is required for device callers");
+    const int np = dev ? in->n_points_max : in->point_offset[nf];
+    int maxp = np;                                   // grid.x covers the largest frame; device callers: the total bound
+    if (!dev) {
+        maxp = 0;
+        for (int f = 0; f < nf; ++f) {
+            if (in->point_offset[f + 1] < in->point_offset[f]) return set_error(ORB_ERR_INVALID, "bad point table");
+            maxp = std::max(maxp, in->point_offset[f + 1] - in->point_offset[f]);
+        }
+    }
+    if (np > 0 && (!in->world_pos || !in->normal || !in->max_dist || !in->min_dist)) return set_error(ORB_ERR_INVALID, "missing point arrays");
+    orb_status s;
+    const size_t need = dev ? 4096 : (size_t)np * (12 + 12 + 4 + 4 + 1 + 4 * 5 + 4 + 64) + (size_t)nf * 128 + 65536;
+    if ((s = ensure_stage(h, need)) != ORB_OK) return s;
+    StageCursor cur{h->d_stage};
+    FrustumParams P{};
+    int* poff; float *R, *t, *O, *xw, *nr, *mx, *mn;
+    if ((s = upload(h, poff, (const int*)in->point_offset, nf + 1, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, R, in->Rcw, (size_t)nf * 9, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, t, in->tcw, (size_t)nf * 3, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, O, in->Ow, (size_t)nf * 3, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, xw, in->world_pos, (size_t)np * 3, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, nr, in->normal, (size_t)np * 3, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, mx, in->max_dist, np, cur, dev)) != ORB_OK) return s;
+    if ((s = upload(h, mn, in->min_dist, np, cur, dev)) != ORB_OK) return s;
+    P.poff = poff; P.Rcw = R; P.tcw = t; P.Ow = O; P.xw = xw; P.normal = nr; P.maxD = mx; P.minD = mn;
+    P.fx = cam->fx; P.fy = cam->fy; P.cx = cam->cx; P.cy = cam->cy; P.bf = cam->bf;
+    P.minX = cam->min_x; P.maxX = cam->max_x; P.minY = cam->min_y; P.maxY = cam->max_y;
+    P.logScale = logf((float)h->cfg.scale_factor);
+    P.cosLimit = viewing_cos_limit;
+    P.nLevels = h->cfg.n_levels;
+    const int npa = std::max(np, 1);
+    P.in_view = dev ? in_view_out : cur.take<uint8_t>(npa);
+    P.px = dev ? proj_x_out : cur.take<float>(npa);
+    P.py = dev ? proj_y_out : cur.take<float>(npa);
+    P.pxr = dev ? proj_xr_out : cur.take<float>(npa);
+    P.vc = dev ? view_cos_out : cur.take<float>(npa);
+    P.depth = dev ? track_depth_out : cur.take<float>(npa);
+    P.level = dev ? level_out : cur.take<int>(npa);
+    if (maxp > 0) {
+        k_in_frustum<<<dim3((maxp + 255) / 256, nf), 256, 0, h->stream>>>(P);
+        ORB_LAUNCHED();
+        ORB_CUDA(cudaGetLastError());
+    }
+    if (!dev) {
+        if (np > 0) {
+            ORB_CUDA(cudaMemcpyAsync(in_view_out, P.in_view, (size_t)np, cudaMemcpyDeviceToHost, h->stream));
+            ORB_CUDA(cudaMemcpyAsync(proj_x_out, P.px, sizeof(float) * (size_t)np, cudaMemcpyDeviceToHost, h->stream));
+            ORB_CUDA(cudaMemcpyAsync(proj_y_out, P.py, sizeof(float) * (size_t)np, cudaMemcpyDeviceToHost, h->stream));
+            ORB_CUDA(cudaMemcpyAsync(proj_xr_out, P.pxr, sizeof(float) * (size_t)np, cudaMemcpyDeviceToHost, h->stream));
+            ORB_CUDA(cudaMemcpyAsync(level_out, P.level, sizeof(int) * (size_t)np, cudaMemcpyDeviceToHost, h->stream));
+            ORB_CUDA(cudaMemcpyAsync(view_cos_out, P.vc, sizeof(float) * (size_t)np, cudaMemcpyDeviceToHost, h->stream));
+            ORB_CUDA(cudaMemcpyAsync(track_depth_out, P.depth, sizeof(float) * (size_t)np, cudaMemcpyDeviceToHost, h->stream));
+        }
+        ORB_CUDA(cudaStreamSynchronize(h->stream));
+    }
     return ORB_OK;
 }

@@ -47,14 +47,15 @@ class ORBmatcher:
         self._L = N.lib()
 
     def SearchByProjection(self, extractor, cam, frame_image, query_offset, proj_x, proj_y, proj_xr, level, view_cos,
-                           desc, th=1.0, bFarPoints=False, thFarPoints=50.0, track_depth=None, feature_claimed=None, out=None):
+                           desc, th=1.0, bFarPoints=False, thFarPoints=50.0, track_depth=None, feature_claimed=None, out=None,
+                           in_view=None):
         """SearchByProjection(Frame&, vector<MapPoint*>, th, bFarPoints, thFarPoints) (ORBmatcher.cc:45-239) for
         several frames of `extractor`'s last batch.  Returns (match[nq] feature index or -1, nmatches[n_frames])."""
         if _is_dev(proj_x):
             raise TypeError("use SearchByProjectionDevice for CUDA tensors")
         fi, qo = _i32(frame_image), _i32(query_offset)
         arrs = [_f32(proj_x), _f32(proj_y), _f32(proj_xr), _i32(level), _f32(view_cos), _f32(track_depth), _u8(desc),
-                _u8(feature_claimed)]
+                _u8(feature_claimed), _u8(in_view)]
         q = N.orbm_local_queries(len(fi), 0, N.ptr(fi), N.ptr(qo), *[N.ptr(a) for a in arrs])
         nq = int(qo[-1])
         match, nm = out if out is not None else (np.full(max(nq, 1), -1, np.int32), np.zeros(len(fi), np.int32))
@@ -219,9 +220,9 @@ class ORBmatcher:
 
     # ---- device-resident forms (CUDA torch tensors; see the class docstring) -----------------------
     def SearchByProjectionDevice(self, extractor, cam, n_frames, frame_image, query_offset, proj_x, proj_y, proj_xr, level,
-                                 view_cos, desc, out_match, out_nmatches, th=1.0, feature_claimed=None):
+                                 view_cos, desc, out_match, out_nmatches, th=1.0, feature_claimed=None, in_view=None):
         q = N.orbm_local_queries(n_frames, 1, _dptr(frame_image), _dptr(query_offset), _dptr(proj_x), _dptr(proj_y),
-                                 _dptr(proj_xr), _dptr(level), _dptr(view_cos), None, _dptr(desc), _dptr(feature_claimed))
+                                 _dptr(proj_xr), _dptr(level), _dptr(view_cos), None, _dptr(desc), _dptr(feature_claimed), _dptr(in_view))
         N.check(self._L.orbm_search_local_points(extractor._h, C.byref(cam), C.byref(q), float(th), self.mfNNratio, 0, 0.0,
                                                  _dptr(out_match), _dptr(out_nmatches)))
 
@@ -233,3 +234,26 @@ class ORBmatcher:
         N.check(self._L.orbm_search_last_frame(extractor._h, C.byref(cam), C.byref(q), float(th),
                                                1 if self.mbCheckOrientation else 0, _dptr(out_feature_match),
                                                _dptr(out_nmatches)))
+
+
+def isInFrustum(extractor, cam, point_offset, Rcw, tcw, Ow, world_pos, normal, max_dist, min_dist, viewingCosLimit=0.5):
+    """Frame::isInFrustum (Frame.cc:667-720) for the candidate map points of several frames (host arrays).
+    Returns dict(in_view, proj_x, proj_y, proj_xr, level, view_cos, depth), one entry per candidate."""
+    po = _i32(point_offset)
+    nf, n = len(po) - 1, int(po[-1])
+    a = [_f32(Rcw), _f32(tcw), _f32(Ow), _f32(world_pos), _f32(normal), _f32(max_dist), _f32(min_dist)]
+    fp = N.orbf_frustum_points(nf, 0, N.ptr(po), *[N.ptr(x) for x in a], 0)
+    m = max(n, 1)
+    out = dict(in_view=np.zeros(m, np.uint8), proj_x=np.zeros(m, np.float32), proj_y=np.zeros(m, np.float32), proj_xr=np.zeros(m, np.float32),
+               level=np.zeros(m, np.int32), view_cos=np.zeros(m, np.float32), depth=np.zeros(m, np.float32))
+    N.check(N.lib().orbf_is_in_frustum(extractor._h, C.byref(cam), C.byref(fp), float(viewingCosLimit),
+                                       *[N.ptr(out[k]) for k in ("in_view", "proj_x", "proj_y", "proj_xr", "level", "view_cos", "depth")]))
+    return {k: v[:n] for k, v in out.items()}
+
+
+def isInFrustumDevice(extractor, cam, n_frames, point_offset, Rcw, tcw, Ow, world_pos, normal, max_dist, min_dist, out, viewingCosLimit=0.5):
+    """Device-resident form (CUDA torch tensors; `out` = dict of tensors with the keys isInFrustum returns); no synchronisation."""
+    fp = N.orbf_frustum_points(n_frames, 1, _dptr(point_offset), _dptr(Rcw), _dptr(tcw), _dptr(Ow), _dptr(world_pos), _dptr(normal),
+                               _dptr(max_dist), _dptr(min_dist), int(max_dist.numel()))
+    N.check(N.lib().orbf_is_in_frustum(extractor._h, C.byref(cam), C.byref(fp), float(viewingCosLimit),
+                                       *[_dptr(out[k]) for k in ("in_view", "proj_x", "proj_y", "proj_xr", "level", "view_cos", "depth")]))

@@ -445,3 +445,48 @@ def test_search_for_initialization_matches_oracle(scene):
             assert n_dev == rnm and (g_dev == rm).all(), (p, win, n_dev, rnm, int((g_dev != rm).sum()))
             assert n_host == rnm and (g_host == rm).all(), (p, win)
             assert rnm > 50, rnm
+
+
+def test_is_in_frustum_and_masked_local_search(scene):
+    """Frame::isInFrustum on the device (bit-exact float fields vs the oracle), then SearchByProjection(F, vpMapPoints) fed by its
+    outputs through the in_view mask == the oracle search over the compacted visible points."""
+    from orb_slam3_detailed_comments_b200 import isInFrustum
+    P, ex, off = scene["P"], scene["ex"], scene["off"]
+    rng = np.random.default_rng(61)
+    sf, logsf = ex.GetScaleFactors(), po.logf(1.2)
+    cam = camera(FX, FY, CX, CY, BF, B, W, H)
+    poff, Rs, ts, Os, qs = [0], [], [], [], []
+    for p in range(P):
+        zmid = float(np.median(scene["lasts"][p][3][scene["lasts"][p][3] > 0]))
+        T = quat_pose(0.05 * p, [(3 + p) * zmid / FX, 1 * zmid / FY, 0.0])
+        R = _quat_to_R(T[:4]).astype(np.float32)
+        t = T[4:].astype(np.float32)
+        q = _kf_queries(scene, p, rng, sf, dup=0.5)
+        # some points behind the camera / far outside the image / out of the scale-invariance range
+        n = len(q["world_pos"])
+        q["world_pos"][rng.random(n) < 0.05, 2] *= -1
+        q["world_pos"][rng.random(n) < 0.05, 0] += 30
+        q["max_dist"][rng.random(n) < 0.05] *= 0.3
+        Rs.append(R); ts.append(t); Os.append((-R.T.astype(np.float64) @ t.astype(np.float64)).astype(np.float32)); qs.append(q)
+        poff.append(poff[-1] + n)
+    cat = lambda k: np.concatenate([q[k] for q in qs])
+    got = isInFrustum(ex, cam, poff, np.stack(Rs), np.stack(ts), np.stack(Os), cat("world_pos"), cat("normal"), cat("max_dist"), cat("min_dist"))
+    for p in range(P):
+        s = slice(poff[p], poff[p + 1])
+        r = po.is_in_frustum(Rs[p], ts[p], Os[p], BOUNDS, CAM6, 8, logsf, qs[p]["world_pos"], qs[p]["normal"], qs[p]["max_dist"], qs[p]["min_dist"])
+        for k in ("in_view", "level"):
+            assert (got[k][s] == r[k]).all(), (p, k)
+        for k in ("proj_x", "proj_y", "proj_xr", "view_cos", "depth"):
+            assert (got[k][s].view(np.uint32) == r[k].view(np.uint32)).all(), (p, k)
+        assert 50 < r["in_view"].sum() < len(r["in_view"])
+    m = ORBmatcher(0.8, True)
+    match, nm = m.SearchByProjection(ex, cam, [2 * p for p in range(P)], poff, got["proj_x"], got["proj_y"], got["proj_xr"], got["level"],
+                                     got["view_cos"], cat("desc"), th=3.0, in_view=got["in_view"])
+    for p in range(P):
+        a, b = off[2 * p], off[2 * p + 1]
+        s = slice(poff[p], poff[p + 1])
+        vis = np.nonzero(got["in_view"][s])[0]
+        rmatch, rnm = po.search_local(scene["kps"][a:b], scene["desc"][a:b], scene["uR"][a:b], BOUNDS, sf, got["proj_x"][s][vis], got["proj_y"][s][vis],
+                                      got["proj_xr"][s][vis], got["level"][s][vis], got["view_cos"][s][vis], qs[p]["desc"][vis], 3.0, 0.8)
+        assert rnm == nm[p] and (match[s][vis] == rmatch).all() and (np.delete(match[s], vis) == -1).all(), (p, rnm, nm[p])
+        assert rnm > 50
