@@ -90,6 +90,8 @@ orb_status orbx_extract_batch_device(orbx_handle* h, const uint8_t* d_imgs, int3
 
 /* Counts of the last batch: n[b] keypoints, mono_index[b]; offsets[b] = first row of image b in the
  * compact result arrays (offsets has batch+1 entries).  Synchronises the handle's stream. */
+/* upper bound of the keypoints of one image (row stride of per-image outputs such as orbv_transform's BowVector) */
+int32_t orbx_max_features(const orbx_handle* h);
 orb_status orbx_counts(orbx_handle* h, int32_t* n, int32_t* mono_index, int32_t* offsets);
 
 /* Copies the compact results of the last batch to the host: kps/desc hold offsets[batch] rows. */
@@ -470,6 +472,28 @@ typedef struct {
 
 orb_status orbo_pose_optimization_frames(orbx_handle* h, const orbo_frame_matches* in, double* pose_out,
                                          uint8_t* feature_outlier_out, int32_t* inliers_out);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Frame::ComputeBoW / KeyFrame::ComputeBoW  (src/Frame.cc:984-997): mpORBvocabulary->transform(descriptors, mBowVec,
+ * mFeatVec, 4) -- DBoW2 TemplatedVocabulary::transform, Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1260, with the
+ * TF_IDF weighting and L1 scoring ORBvoc.txt is loaded with.
+ *
+ * orbv_create uploads the vocabulary tree the caller flattened from its DBoW2 object: node 0 is the root, the children of
+ * node i are child_ids[child_offset[i] .. child_offset[i+1]) in m_nodes[i].children order, node_desc = m_nodes[i].descriptor
+ * (32 bytes), node_word / node_weight = word_id / weight of the leaves (ignored for inner nodes), depth_levels = m_L.
+ * orbv_transform runs every descriptor of the extractor's last batch down the tree: word_out / weight_out per compact row
+ * (WordId, idf weight; weight 0 = stopped word), node_out = the NodeId at levelsup levels above the leaf (what
+ * mFeatVec.addFeature receives and what orbm_search_bow takes as feature_node).  Optionally the BowVector of every image:
+ * bow_count_out[img] entries of (bow_word_out, bow_weight_out)[img][max features] in ascending word order, weights summed
+ * in feature order and L1-normalised exactly like BowVector::addWeight / normalize.  on_device != 0: outputs are device
+ * memory, no synchronisation. */
+typedef struct orbv_vocabulary orbv_vocabulary;
+orb_status orbv_create(int32_t device, int32_t n_nodes, int32_t depth_levels, const int32_t* child_offset, const int32_t* child_ids,
+                       const uint8_t* node_desc, const int32_t* node_word, const double* node_weight, orbv_vocabulary** out);
+void orbv_destroy(orbv_vocabulary* v);
+orb_status orbv_transform(orbx_handle* h, const orbv_vocabulary* voc, int32_t levelsup, int32_t on_device, int32_t* word_out,
+                          int32_t* node_out, double* weight_out, int32_t* bow_count_out, int32_t* bow_word_out, double* bow_weight_out);
 
 #ifdef __cplusplus
 }

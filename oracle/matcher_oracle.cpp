@@ -638,3 +638,46 @@ extern "C" int orc_is_in_frustum(int n, const float* Rcw9, const float* tcw, con
     }
     return nvis;
 }
+
+// DBoW2 TemplatedVocabulary<FORB>::transform(features, BowVector&, FeatureVector&, levelsup) with TF_IDF + L1
+// (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1260, BowVector.cpp:34-84; Frame::ComputeBoW, src/Frame.cc:984-997).
+// Tree flattened as in include/orbslam3_b200.h (orbv_create).  Outputs per feature: word, node at levelsup, weight; and the
+// BowVector (ascending words, L1-normalised weights).  Returns the BowVector size.
+#include <map>
+extern "C" int orc_bow_transform(int n_nodes, int L, const int* child_off, const int* child, const uint8_t* ndesc, const int* nword,
+                                 const double* nweight, int levelsup, int n, const uint8_t* desc, int* word, int* node, double* weight,
+                                 int* bow_word, double* bow_weight) {
+    std::map<unsigned, double> v;
+    const int nid_level = L - levelsup;
+    for (int i = 0; i < n; ++i) {
+        int nid = 0;
+        int final_id = 0, current_level = 0;
+        while (child_off[final_id] != child_off[final_id + 1]) {
+            ++current_level;
+            const int c0 = child_off[final_id], c1 = child_off[final_id + 1];
+            int best = child[c0];
+            double best_d = (double)descriptor_distance(desc + 32 * (size_t)i, ndesc + 32 * (size_t)best);
+            for (int c = c0 + 1; c < c1; ++c) {
+                const double d = (double)descriptor_distance(desc + 32 * (size_t)i, ndesc + 32 * (size_t)child[c]);
+                if (d < best_d) { best_d = d; best = child[c]; }
+            }
+            final_id = best;
+            if (current_level == nid_level) nid = final_id;
+        }
+        word[i] = nword[final_id];
+        weight[i] = nweight[final_id];
+        node[i] = nid;
+        if (weight[i] > 0) {
+            auto it = v.lower_bound((unsigned)word[i]);
+            if (it != v.end() && !(v.key_comp()((unsigned)word[i], it->first))) it->second += weight[i];
+            else v.insert(it, std::make_pair((unsigned)word[i], weight[i]));
+        }
+    }
+    double norm = 0.0;
+    for (auto& kv : v) norm += std::fabs(kv.second);
+    if (norm > 0.0)
+        for (auto& kv : v) kv.second /= norm;
+    int k = 0;
+    for (auto& kv : v) { bow_word[k] = (int)kv.first; bow_weight[k] = kv.second; ++k; }
+    return k;
+}

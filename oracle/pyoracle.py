@@ -397,3 +397,21 @@ def is_in_frustum(Rcw, tcw, Ow, bounds, cam6, n_levels, log_scale_factor, xw, no
     L.orc_is_in_frustum(n, _p(R), _p(t), _p(O), _p(b4), _p(c6), int(n_levels), float(log_scale_factor), float(viewing_cos_limit), _p(xw), _p(nr),
                         _p(mx), _p(mn), *[_p(out[k]) for k in ("in_view", "proj_x", "proj_y", "proj_xr", "level", "view_cos", "depth")])
     return {k: v[:n] for k, v in out.items()}
+
+
+def bow_transform(voc, desc, levelsup=4):
+    """DBoW2 transform restated (TemplatedVocabulary.h:1127-1260).  voc: dict(child_offset, child_ids, node_desc, node_word, node_weight, L).
+    Returns dict(word, node, weight, bow_word, bow_weight)."""
+    L = lib()
+    L.orc_bow_transform.restype = C.c_int
+    L.orc_bow_transform.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_int] + [C.c_void_p] * 6
+    c = np.ascontiguousarray
+    co, ci = c(voc["child_offset"], np.int32), c(voc["child_ids"], np.int32)
+    nd, nw, wt = c(voc["node_desc"], np.uint8), c(voc["node_word"], np.int32), c(voc["node_weight"], np.float64)
+    desc = c(desc, np.uint8)
+    n = len(desc)
+    word, node, weight = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.float64)
+    bw, bv = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.float64)
+    k = L.orc_bow_transform(len(nw), int(voc["L"]), _p(co), _p(ci), _p(nd), _p(nw), _p(wt), int(levelsup), n, _p(desc), _p(word), _p(node), _p(weight),
+                            _p(bw), _p(bv))
+    return dict(word=word[:n], node=node[:n], weight=weight[:n], bow_word=bw[:k], bow_weight=bv[:k])

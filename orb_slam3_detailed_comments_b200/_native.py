@@ -12,7 +12,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "lib", "liborbslam3_b200.so")
-SOURCES = ["extractor.cu", "stereo.cu", "matcher.cu", "triangulation.cu", "lba.cu", "poseopt.cu"]
+SOURCES = ["extractor.cu", "stereo.cu", "matcher.cu", "triangulation.cu", "lba.cu", "poseopt.cu", "bow.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -156,6 +156,10 @@ SIGNATURES = {
     "orbo_pose_edges": (_I, [_VP, C.POINTER(orbo_edge_source), _VP, _VP, _VP, _VP, _VP]),
     "orbo_pose_optimization_frames": (_I, [_VP, C.POINTER(orbo_frame_matches), _VP, _VP, _VP]),
     "orbf_is_in_frustum": (_I, [_VP, C.POINTER(orbm_camera), C.POINTER(orbf_frustum_points), C.c_float] + [_VP] * 7),
+    "orbx_max_features": (_I, [_VP]),
+    "orbv_create": (_I, [_I, _I, _I, _VP, _VP, _VP, _VP, _VP, C.POINTER(_VP)]),
+    "orbv_destroy": (None, [_VP]),
+    "orbv_transform": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "lba_create": (_I, [_I, C.POINTER(_VP)]),
     "lba_destroy": (None, [_VP]),
     "lba_solve": (_I, [_VP, C.POINTER(lba_problem), C.POINTER(lba_result), _VP]),

@@ -185,6 +185,15 @@ extern "C" int orb_device_count(void) {
 }
 extern "C" int64_t orb_kernel_launches(void) { return (int64_t)g_launches.load(); }
 
+// upper bound of the keypoints one image can produce (sum over the levels of quota + 20): the row stride of the per-image
+// outputs of orbv_transform
+extern "C" int32_t orbx_max_features(const orbx_handle* h) {
+    if (!h) return 0;
+    int t = 0;
+    for (int l = 0; l < h->cfg.n_levels; ++l) t += qt_node_cap(h->quota[l]);
+    return t;
+}
+
 static orb_status apply_geometry(orbx_handle* h, int w, int hh) {
     if (w == h->cur_w && hh == h->cur_h) return ORB_OK;
     if (w > h->cfg.max_width || hh > h->cfg.max_height || w < 1 || hh < 1)

@@ -43,6 +43,9 @@ class ORBextractor:
             pass
 
     # getters, ORBextractor.h:61-81
+    def max_features_per_image(self):
+        return int(self._L.orbx_max_features(self._h))
+
     def GetLevels(self):
         return self.nlevels
 
