@@ -495,6 +495,25 @@ void orbv_destroy(orbv_vocabulary* v);
 orb_status orbv_transform(orbx_handle* h, const orbv_vocabulary* voc, int32_t levelsup, int32_t on_device, int32_t* word_out,
                           int32_t* node_out, double* weight_out, int32_t* bow_count_out, int32_t* bow_word_out, double* bow_weight_out);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * MapPoint maintenance either side of the searches (LocalMapping.cc:300-340, 860-875), batched over map points; the
+ * extractor handle lends its stream, scratch and level tables.  Observations of point i are rows
+ * [obs_offset[i], obs_offset[i+1]) in the order the reference walks mObservations (std::map<KeyFrame*, ...>).
+ *
+ * MapPoint::ComputeDistinctiveDescriptors  src/MapPoint.cc:438-520: best_index_out[i] = position (inside the point's
+ * observation list) of the descriptor with the smallest median Hamming distance to the set -- sort + vDists[0.5*(N-1)],
+ * first minimum -- or -1 for a point without observations (mDescriptor is then left as it is).
+ *
+ * MapPoint::UpdateNormalAndDepth  src/MapPoint.cc:567-640: obs_center = pKF->GetCameraCenter() per observation, ref_center /
+ * ref_level = camera centre of mpRefKF and the octave of the point's keypoint there.  normal_out = mNormalVector,
+ * max_dist_out / min_dist_out = mfMaxDistance / mfMinDistance (in/out: points without observations keep their values). */
+orb_status orbp_distinctive_descriptors(orbx_handle* h, int32_t n_points, const int32_t* obs_offset, const uint8_t* obs_desc,
+                                        int32_t* best_index_out);
+orb_status orbp_update_normal_and_depth(orbx_handle* h, int32_t n_points, const int32_t* obs_offset, const float* obs_center,
+                                        const float* world_pos, const float* ref_center, const int32_t* ref_level,
+                                        float* normal_out, float* max_dist_out, float* min_dist_out);
+
 #ifdef __cplusplus
 }
 #endif

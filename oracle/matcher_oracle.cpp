@@ -681,3 +681,45 @@ extern "C" int orc_bow_transform(int n_nodes, int L, const int* child_off, const
     for (auto& kv : v) { bow_word[k] = (int)kv.first; bow_weight[k] = kv.second; ++k; }
     return k;
 }
+
+// MapPoint::ComputeDistinctiveDescriptors  src/MapPoint.cc:438-520 (one map point): returns the position of the chosen
+// descriptor in the observation list, -1 when the list is empty.
+#include <algorithm>
+extern "C" int orc_distinctive_descriptor(int N, const uint8_t* descs) {
+    if (N <= 0) return -1;
+    std::vector<float> D((size_t)N * N);
+    for (int i = 0; i < N; ++i) {
+        D[(size_t)i * N + i] = 0;
+        for (int j = i + 1; j < N; ++j) {
+            const int d = descriptor_distance(descs + 32 * (size_t)i, descs + 32 * (size_t)j);
+            D[(size_t)i * N + j] = (float)d;
+            D[(size_t)j * N + i] = (float)d;
+        }
+    }
+    int BestMedian = 0x7fffffff, BestIdx = 0;
+    for (int i = 0; i < N; ++i) {
+        std::vector<int> vDists(D.begin() + (size_t)i * N, D.begin() + (size_t)i * N + N);
+        std::sort(vDists.begin(), vDists.end());
+        const int median = vDists[(size_t)(0.5 * (N - 1))];
+        if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+    }
+    return BestIdx;
+}
+
+// MapPoint::UpdateNormalAndDepth  src/MapPoint.cc:567-640 (one map point, pinhole keyframes): out3 = mNormalVector,
+// *maxd / *mind = mfMaxDistance / mfMinDistance.  Vector3f::norm in Eigen's unrolled order x^2 + (y^2 + z^2).
+extern "C" void orc_update_normal_and_depth(int N, const float* centers, const float* pos, const float* refCenter, int level,
+                                            const float* scaleFactors, int nLevels, float* out3, float* maxd, float* mind) {
+    if (N <= 0) return;
+    float normal[3] = {0, 0, 0};
+    for (int o = 0; o < N; ++o) {
+        const float v[3] = {pos[0] - centers[3 * o], pos[1] - centers[3 * o + 1], pos[2] - centers[3 * o + 2]};
+        const float nrm = std::sqrt(v[0] * v[0] + (v[1] * v[1] + v[2] * v[2]));
+        for (int c = 0; c < 3; ++c) normal[c] = normal[c] + v[c] / nrm;
+    }
+    const float PC[3] = {pos[0] - refCenter[0], pos[1] - refCenter[1], pos[2] - refCenter[2]};
+    const float dist = std::sqrt(PC[0] * PC[0] + (PC[1] * PC[1] + PC[2] * PC[2]));
+    *maxd = dist * scaleFactors[level];
+    *mind = *maxd / scaleFactors[nLevels - 1];
+    for (int c = 0; c < 3; ++c) out3[c] = normal[c] / (float)N;
+}

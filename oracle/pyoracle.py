@@ -415,3 +415,24 @@ def bow_transform(voc, desc, levelsup=4):
     k = L.orc_bow_transform(len(nw), int(voc["L"]), _p(co), _p(ci), _p(nd), _p(nw), _p(wt), int(levelsup), n, _p(desc), _p(word), _p(node), _p(weight),
                             _p(bw), _p(bv))
     return dict(word=word[:n], node=node[:n], weight=weight[:n], bow_word=bw[:k], bow_weight=bv[:k])
+
+
+def distinctive_descriptor(descs):
+    """MapPoint::ComputeDistinctiveDescriptors restated (MapPoint.cc:438-520): index of the chosen observation descriptor."""
+    L = lib()
+    L.orc_distinctive_descriptor.restype = C.c_int
+    L.orc_distinctive_descriptor.argtypes = [C.c_int, C.c_void_p]
+    d = np.ascontiguousarray(descs, np.uint8).reshape(-1, 32)
+    return L.orc_distinctive_descriptor(len(d), _p(d) if len(d) else None)
+
+
+def update_normal_and_depth(centers, pos, ref_center, level, scale_factors):
+    """MapPoint::UpdateNormalAndDepth restated (MapPoint.cc:567-640).  Returns (normal[3], max_dist, min_dist) as float32."""
+    L = lib()
+    L.orc_update_normal_and_depth.restype = None
+    L.orc_update_normal_and_depth.argtypes = [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 3
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    c, p, r, sf = f32(centers).reshape(-1, 3), f32(pos), f32(ref_center), f32(scale_factors)
+    out, mx, mn = np.zeros(3, np.float32), np.zeros(1, np.float32), np.zeros(1, np.float32)
+    L.orc_update_normal_and_depth(len(c), _p(c), _p(p), _p(r), int(level), _p(sf), len(sf), _p(out), _p(mx), _p(mn))
+    return out, mx[0], mn[0]
