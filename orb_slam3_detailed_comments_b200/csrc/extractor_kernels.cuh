@@ -530,8 +530,14 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_describe(const __grid_
                                                                   const int* __restrict__ lvlCnt, const int* __restrict__ slot,
                                                                   const int* __restrict__ offsets,
                                                                   orbx_keypoint* __restrict__ kps, uint8_t* __restrict__ desc) {
-    __shared__ int8_t s_pat[1024];
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_pat[i] = c_pattern[i];
+    // the 256 point pairs as one 32-bit word each (xa, ya, xb, yb as int8), transposed so that lane's k-th pair sits at
+    // [k][lane]: one conflict-free LDS.32 per pair instead of four byte loads
+    __shared__ uint32_t s_pat[8][32];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const uint32_t w = (uint32_t)(uint8_t)c_pattern[4 * i] | ((uint32_t)(uint8_t)c_pattern[4 * i + 1] << 8) |
+                           ((uint32_t)(uint8_t)c_pattern[4 * i + 2] << 16) | ((uint32_t)(uint8_t)c_pattern[4 * i + 3] << 24);
+        s_pat[i & 7][i >> 3] = w;      // pair i belongs to lane i / 8 (descriptor byte), bit i % 8
+    }
     __syncthreads();
     const int img = blockIdx.y;
     const int lane = threadIdx.x & 31;
@@ -577,12 +583,13 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_describe(const __grid_
     const float factorPI = (float)(3.14159265358979323846 / 180.f);
     float sa, ca;
     glibc_sincosf(fmul(angle, factorPI), &sa, &ca);
-    const int8_t* pp = s_pat + lane * 32;
     const uint8_t* cb = G.blur + (int64_t)img * G.blur_stride + (int64_t)y * G.blur_pitch + x;
     uint32_t val = 0u;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float xa = (float)pp[4 * k], ya = (float)pp[4 * k + 1], xb = (float)pp[4 * k + 2], yb = (float)pp[4 * k + 3];
+        const uint32_t pw = s_pat[k][lane];
+        const float xa = (float)(int8_t)(pw & 0xffu), ya = (float)(int8_t)((pw >> 8) & 0xffu), xb = (float)(int8_t)((pw >> 16) & 0xffu),
+                    yb = (float)(int8_t)(pw >> 24);
         const int ra = round_half_even(fadd(fmul(xa, sa), fmul(ya, ca))), ca_ = round_half_even(fsub(fmul(xa, ca), fmul(ya, sa)));
         const int rb = round_half_even(fadd(fmul(xb, sa), fmul(yb, ca))), cb_ = round_half_even(fsub(fmul(xb, ca), fmul(yb, sa)));
         const int t0 = __ldg(cb + (int64_t)ra * G.blur_pitch + ca_);
