@@ -91,6 +91,24 @@ ORB_HD uint32_t fast_score_x2(uint32_t c2, const uint32_t r[16]) {
     return max_u16x2(best_min, dark) - 0x00010001u;
 }
 
+// cv::FAST's high-speed test in packed form: a 9-arc of the 16-ring contains at least one pixel of each antipodal pair,
+// so a pixel can only be a corner at threshold T if min over the 4 pairs (k, k+8), k = 0, 2, 4, 6, of max(r_k, r_k+8)
+// exceeds c + T (bright arc), or max over the pairs of min(r_k, r_k+8) is below c - T (dark arc).
+// hi / lo = that min-of-max / max-of-min for two adjacent pixels (16x2 lanes, raw 0..255); returns a mask with bit 15 /
+// bit 31 set for the lane(s) that pass.
+ORB_HD uint32_t fast_pretest_x2(uint32_t c2, uint32_t hi, uint32_t lo, uint32_t T2p1) {
+    const uint32_t H = 0x80008000u;
+    const uint32_t x = (hi | H) - (c2 + T2p1);      // lane >= 0x8000  <=>  hi >= c + T + 1   (no borrow crosses the lanes)
+    const uint32_t y = (c2 | H) - (lo + T2p1);      //                 <=>  c >= lo + T + 1
+    return (x | y) & H;
+}
+
+// hi / lo of fast_pretest_x2 from the 8 even ring samples r[0], r[2], ..., r[14] (packed like the centre)
+ORB_HD void fast_pretest_bounds_x2(const uint32_t r[16], uint32_t* hi, uint32_t* lo) {
+    *hi = min_u16x2(min3_u16x2(max_u16x2(r[0], r[8]), max_u16x2(r[2], r[10]), max_u16x2(r[4], r[12])), max_u16x2(r[6], r[14]));
+    *lo = max_u16x2(max3_u16x2(min_u16x2(r[0], r[8]), min_u16x2(r[2], r[10]), min_u16x2(r[4], r[12])), min_u16x2(r[6], r[14]));
+}
+
 // scalar reference form of the same score (used by the emulation test and the slow paths)
 ORB_HD int fast_score_scalar(int c, const int ring[16]) {
     int best = -256;

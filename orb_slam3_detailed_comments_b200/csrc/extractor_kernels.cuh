@@ -89,18 +89,6 @@ __device__ __forceinline__ uint32_t shift_word(uint32_t L, uint32_t C, uint32_t 
 
 #define FAST_PW 46   // 16x2-packed pixel pairs per staged row (tile width <= 88 px)
 
-// cv::FAST's high-speed test in packed form: a 9-arc of the 16-ring contains at least one pixel of each antipodal pair,
-// so a pixel can only be a corner at threshold T if min over the 4 pairs (k, k+8), k = 0, 2, 4, 6, of max(r_k, r_k+8)
-// exceeds c + T (bright arc), or max over the pairs of min(r_k, r_k+8) is below c - T (dark arc).
-// hi / lo = that min-of-max / max-of-min for two adjacent pixels (16x2 lanes, raw 0..255); returns a mask with bit 15 /
-// bit 31 set for the lane(s) that pass.
-__device__ __forceinline__ uint32_t fast_pretest_x2(uint32_t c2, uint32_t hi, uint32_t lo, uint32_t T2p1) {
-    const uint32_t H = 0x80008000u;
-    const uint32_t x = (hi | H) - (c2 + T2p1);      // lane >= 0x8000  <=>  hi >= c + T + 1   (no borrow crosses the lanes)
-    const uint32_t y = (c2 | H) - (lo + T2p1);      //                 <=>  c >= lo + T + 1
-    return (x | y) & H;
-}
-
 __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_constant__ ExtractGeom g, uint32_t* __restrict__ cand,
                                                             int* __restrict__ candCnt, int* __restrict__ err) {
     // The window is staged twice as 16x2-packed pixel pairs: pe[r][i] = (px 2i, px 2i+1), po[r][i] = (px 2i+1, px 2i+2).

@@ -29,6 +29,40 @@ uint32_t emul_fast_x2(const uint8_t* img, int w, int x, int y) {
 
 float emul_atan2(float y, float x) { return fast_atan2_deg(y, x); }
 
+// FAST high-speed test vs the full score on random pixel pairs: returns the number of lanes where the score reaches T but
+// the test rejects (must be 0: the test is a necessary condition), and through *passed the lanes that pass the test.
+long emul_pretest_violations(uint32_t seed, long n, int T, int contrast, long* passed) {
+    uint64_t s = seed * 6364136223846793005ull + 1442695040888963407ull;
+    auto rnd = [&]() { s = s * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(s >> 33); };
+    long bad = 0, pass = 0;
+    for (long it = 0; it < n; ++it) {
+        const uint32_t base = rnd() & 0xff;
+        auto px = [&]() { int v = (int)base + (int)(rnd() % (2 * contrast + 1)) - contrast; v = v < 0 ? 0 : (v > 255 ? 255 : v); return (uint32_t)v; };
+        uint32_t r[16];
+        const uint32_t c2 = px() | (px() << 16);
+        for (int k = 0; k < 16; ++k) r[k] = px() | (px() << 16);
+        if ((rnd() & 3) == 0) {               // plant a bright or dark arc so that real corners occur
+            const int start = rnd() & 15, len = 9 + (rnd() % 5), sign = (rnd() & 1) ? 1 : -1;
+            for (int j = 0; j < len; ++j) {
+                const int k = (start + j) & 15;
+                int v0 = (int)(c2 & 0xff) + sign * (T + 1 + (int)(rnd() % 40)), v1 = (int)(c2 >> 16) + sign * (T + 1 + (int)(rnd() % 40));
+                v0 = v0 < 0 ? 0 : (v0 > 255 ? 255 : v0); v1 = v1 < 0 ? 0 : (v1 > 255 ? 255 : v1);
+                r[k] = (uint32_t)v0 | ((uint32_t)v1 << 16);
+            }
+        }
+        uint32_t hi, lo;
+        fast_pretest_bounds_x2(r, &hi, &lo);
+        const uint32_t m = fast_pretest_x2(c2, hi, lo, (uint32_t)(T + 1) * 0x00010001u);
+        const uint32_t sc = fast_score_x2(c2, r);
+        const int s0 = (int)(sc & 0xffff) - 256, s1 = (int)(sc >> 16) - 256;
+        if (s0 >= T && !(m & 0x8000u)) ++bad;
+        if (s1 >= T && !(m & 0x80000000u)) ++bad;
+        pass += ((m & 0x8000u) != 0) + ((m & 0x80000000u) != 0);
+    }
+    *passed = pass;
+    return bad;
+}
+
 // number of floats in [lo_bits, hi_bits] whose emulated sin or cos differs from glibc's
 long emul_sincos_mismatch(uint32_t lo_bits, uint32_t hi_bits, int nthreads) {
     std::atomic<long> bad(0);

@@ -29,6 +29,8 @@ def emul():
     L.emul_atan2.argtypes = [C.c_float, C.c_float]
     L.emul_sincos_mismatch.restype = C.c_long
     L.emul_sincos_mismatch.argtypes = [C.c_uint32, C.c_uint32, C.c_int]
+    L.emul_pretest_violations.restype = C.c_long
+    L.emul_pretest_violations.argtypes = [C.c_uint32, C.c_long, C.c_int, C.c_int, C.POINTER(C.c_long)]
     L.emul_logf_mismatch.restype = C.c_long
     L.emul_logf_mismatch.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
     for f in ("emul_std_sort", "emul_heap_sort", "ref_std_sort", "ref_heap_sort"):
@@ -89,6 +91,19 @@ def test_sincos_sampled_matches_glibc(emul):
     for a in range(lo, hi, step):
         bad += emul.emul_sincos_mismatch(a, min(a + step // 97, hi), 4)
     assert bad == 0
+
+
+def test_fast_high_speed_test_is_a_necessary_condition(emul):
+    """k_fast_cells computes the full score only for pixel pairs that pass the packed antipodal-pair test: a corner at
+    threshold T (score >= T) must never be rejected by it, at both thresholds and over flat / noisy / high-contrast pixels."""
+    total_pass = 0
+    for T in (20, 7):
+        for contrast in (3, 12, 40, 255):
+            passed = C.c_long(0)
+            assert emul.emul_pretest_violations(1000 + T + contrast, 400000, T, contrast, C.byref(passed)) == 0, (T, contrast)
+            assert 0 < passed.value < 800000           # it does reject something and does accept something
+            total_pass += passed.value
+    assert total_pass > 0
 
 
 def test_logf_matches_glibc(emul):
