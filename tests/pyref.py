@@ -1,0 +1,239 @@
+"""Plain-Python restatements of a few ORBmatcher searches, written from the reference independently of oracle/ (second pin for
+the C++ oracle; small inputs only).  float32 arithmetic is done with numpy scalars in the reference's operation order."""
+import numpy as np
+
+f32 = np.float32
+POP = np.array([bin(i).count("1") for i in range(256)], np.int32)
+
+
+def hamming(a, b):
+    return int(POP[np.bitwise_xor(a, b)].sum())
+
+
+class Grid:
+    """Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea (src/Frame.cc:469-504, 859-951, 962-978), 64 x 48 cells."""
+
+    def __init__(self, kps, bounds):
+        self.k = kps
+        self.minX, self.maxX, self.minY, self.maxY = [f32(v) for v in bounds]
+        self.invW = f32(64) / f32(self.maxX - self.minX)
+        self.invH = f32(48) / f32(self.maxY - self.minY)
+        self.cells = {}
+        for i in range(len(kps)):
+            px = int(np.floor(float(f32(f32(kps["x"][i] - self.minX) * self.invW)) + 0.5)) if f32(f32(kps["x"][i] - self.minX) * self.invW) >= 0 else \
+                -int(np.floor(-float(f32(f32(kps["x"][i] - self.minX) * self.invW)) + 0.5))          # C round(): half away from zero
+            py = int(np.floor(float(f32(f32(kps["y"][i] - self.minY) * self.invH)) + 0.5)) if f32(f32(kps["y"][i] - self.minY) * self.invH) >= 0 else \
+                -int(np.floor(-float(f32(f32(kps["y"][i] - self.minY) * self.invH)) + 0.5))
+            if 0 <= px < 64 and 0 <= py < 48:
+                self.cells.setdefault((px, py), []).append(i)
+
+    def area(self, x, y, r, min_level=-1, max_level=-1):
+        x, y, r = f32(x), f32(y), f32(r)
+        c0 = max(0, int(np.floor(f32(f32(f32(x - self.minX) - r) * self.invW))))
+        if c0 >= 64:
+            return []
+        c1 = min(63, int(np.ceil(f32(f32(f32(x - self.minX) + r) * self.invW))))
+        if c1 < 0:
+            return []
+        r0 = max(0, int(np.floor(f32(f32(f32(y - self.minY) - r) * self.invH))))
+        if r0 >= 48:
+            return []
+        r1 = min(47, int(np.ceil(f32(f32(f32(y - self.minY) + r) * self.invH))))
+        if r1 < 0:
+            return []
+        check = (min_level > 0) or (max_level >= 0)
+        out = []
+        for ix in range(c0, c1 + 1):
+            for iy in range(r0, r1 + 1):
+                for i in self.cells.get((ix, iy), []):
+                    o = int(self.k["octave"][i])
+                    if check:
+                        if o < min_level:
+                            continue
+                        if max_level >= 0 and o > max_level:
+                            continue
+                    if abs(f32(self.k["x"][i] - x)) < r and abs(f32(self.k["y"][i] - y)) < r:
+                        out.append(i)
+        return out
+
+
+def three_maxima(hist):
+    """ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:2335-2377)."""
+    max1 = max2 = max3 = 0
+    ind1 = ind2 = ind3 = -1
+    for i, h in enumerate(hist):
+        s = len(h)
+        if s > max1:
+            max3, max2, max1 = max2, max1, s
+            ind3, ind2, ind1 = ind2, ind1, i
+        elif s > max2:
+            max3, max2 = max2, s
+            ind3, ind2 = ind2, i
+        elif s > max3:
+            max3, ind3 = s, i
+    if max2 < f32(0.1) * f32(max1):
+        ind2 = ind3 = -1
+    elif max3 < f32(0.1) * f32(max1):
+        ind3 = -1
+    return ind1, ind2, ind3
+
+
+def rot_bin(a1, a2):
+    rot = f32(f32(a1) - f32(a2))
+    if rot < 0.0:
+        rot = f32(rot + f32(360.0))
+    v = float(f32(rot * f32(f32(1.0) / f32(30))))
+    b = int(np.floor(v + 0.5))
+    return 0 if b == 30 else b
+
+
+def search_for_initialization(kp1, d1, prev, kp2, d2, bounds, window, nnratio, check_ori=True):
+    """ORBmatcher::SearchForInitialization (ORBmatcher.cc:734-890)."""
+    g = Grid(kp2, bounds)
+    n1, n2 = len(kp1), len(kp2)
+    m12, m21, md = [-1] * n1, [-1] * n2, [2 ** 31 - 1] * n2
+    hist = [[] for _ in range(30)]
+    nm = 0
+    for i1 in range(n1):
+        if kp1["octave"][i1] > 0:
+            continue
+        ind = g.area(prev[i1][0], prev[i1][1], f32(window), 0, 0)
+        if not ind:
+            continue
+        best = best2 = 2 ** 31 - 1
+        bi = -1
+        for i2 in ind:
+            d = hamming(d1[i1], d2[i2])
+            if md[i2] <= d:
+                continue
+            if d < best:
+                best2, best, bi = best, d, i2
+            elif d < best2:
+                best2 = d
+        if best <= 50 and f32(best) < f32(f32(best2) * f32(nnratio)):
+            if m21[bi] >= 0:
+                m12[m21[bi]] = -1
+                nm -= 1
+            m12[i1], m21[bi], md[bi] = bi, i1, best
+            nm += 1
+            if check_ori:
+                hist[rot_bin(kp1["angle"][i1], kp2["angle"][bi])].append(i1)
+    if check_ori:
+        keep = three_maxima(hist)
+        for b in range(30):
+            if b in keep:
+                continue
+            for i1 in hist[b]:
+                if m12[i1] >= 0:
+                    m12[i1] = -1
+                    nm -= 1
+    return np.array(m12, np.int32), nm
+
+
+def search_bow_keyframes(kp2, d2, node2, valid2, qnode, qangle, d1, nnratio, check_ori=True):
+    """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...) (ORBmatcher.cc:892-1043) on flattened word groups."""
+    n2 = len(kp2)
+    matched2 = [False] * n2
+    out = [-1] * len(qnode)
+    hist = [[] for _ in range(30)]
+    nm = 0
+    by_node = {}
+    for i2 in range(n2):
+        by_node.setdefault(int(node2[i2]), []).append(i2)
+    for q in range(len(qnode)):
+        if qnode[q] < 0:
+            continue
+        b1 = b2 = 256
+        bi = -1
+        for i2 in by_node.get(int(qnode[q]), []):
+            if matched2[i2] or not valid2[i2]:
+                continue
+            d = hamming(d1[q], d2[i2])
+            if d < b1:
+                b2, b1, bi = b1, d, i2
+            elif d < b2:
+                b2 = d
+        if b1 < 50 and f32(b1) < f32(f32(nnratio) * f32(b2)):
+            out[q] = bi
+            matched2[bi] = True
+            if check_ori:
+                hist[rot_bin(qangle[q], kp2["angle"][bi])].append(q)
+            nm += 1
+    if check_ori:
+        keep = three_maxima(hist)
+        for b in range(30):
+            if b not in keep:
+                for q in hist[b]:
+                    out[q] = -1
+                    nm -= 1
+    return np.array(out, np.int32), nm
+
+
+def se3_act(T, p):
+    """Sophus::SE3f * Vector3f with Eigen's quaternion _transformVector (float32)."""
+    qx, qy, qz, qw = [f32(v) for v in T[:4]]
+    p = [f32(v) for v in p]
+    uv = [f32(f32(qy * p[2]) - f32(qz * p[1])), f32(f32(qz * p[0]) - f32(qx * p[2])), f32(f32(qx * p[1]) - f32(qy * p[0]))]
+    uv = [f32(v + v) for v in uv]
+    c = [f32(f32(qy * uv[2]) - f32(qz * uv[1])), f32(f32(qz * uv[0]) - f32(qx * uv[2])), f32(f32(qx * uv[1]) - f32(qy * uv[0]))]
+    return [f32(f32(f32(p[i] + f32(qw * uv[i])) + c[i]) + f32(T[4 + i])) for i in range(3)]
+
+
+def fuse(variant, kps, desc, uright, bounds, sf, inv_sigma2, log_sf, cam, T, Ow, xw, normal, maxd, mind, qdesc, th):
+    """ORBmatcher::Fuse(pKF, vpMapPoints, th) (variant 0, ORBmatcher.cc:1325-1544) and Fuse(pKF, Scw, ...) (variant 1, :1546-1687):
+    the search part, bestIdx per map point or -1."""
+    import math
+    import ctypes
+    import ctypes.util
+    libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    libm.logf.restype = ctypes.c_float
+    libm.logf.argtypes = [ctypes.c_float]
+    g = Grid(kps, bounds)
+    fx, fy, cx, cy, bf = [f32(v) for v in cam[:5]]
+    out = []
+    for q in range(len(xw)):
+        pc = se3_act(T, xw[q])
+        res = -1
+        while True:
+            if pc[2] < 0:
+                break
+            invz = f32(f32(1) / pc[2])
+            u = f32(f32(f32(fx * pc[0]) / pc[2]) + cx)
+            v = f32(f32(f32(fy * pc[1]) / pc[2]) + cy)
+            if not (u >= g.minX and u < g.maxX and v >= g.minY and v < g.maxY):
+                break
+            ur = f32(u - f32(bf * invz))
+            PO = [f32(f32(xw[q][i]) - f32(Ow[i])) for i in range(3)]
+            dist = f32(math.sqrt(float(f32(f32(PO[0] * PO[0]) + f32(f32(PO[1] * PO[1]) + f32(PO[2] * PO[2]))))))
+            if dist < mind[q] or dist > maxd[q]:
+                break
+            dot = f32(f32(PO[0] * f32(normal[q][0])) + f32(f32(PO[1] * f32(normal[q][1])) + f32(PO[2] * f32(normal[q][2]))))
+            if float(dot) < 0.5 * float(dist):
+                break
+            lvl = int(math.ceil(float(f32(f32(libm.logf(float(f32(f32(maxd[q]) / dist)))) / f32(log_sf)))))
+            lvl = max(0, min(lvl, len(sf) - 1))
+            radius = f32(f32(th) * f32(sf[lvl]))
+            best, bi = (256, -1) if variant == 0 else (2 ** 31 - 1, -1)
+            for i in g.area(u, v, radius):
+                o = int(kps["octave"][i])
+                if o < lvl - 1 or o > lvl:
+                    continue
+                if variant == 0:
+                    ex, ey = f32(u - kps["x"][i]), f32(v - kps["y"][i])
+                    if uright is not None and uright[i] >= 0:
+                        er = f32(ur - f32(uright[i]))
+                        e2 = f32(f32(f32(ex * ex) + f32(ey * ey)) + f32(er * er))
+                        if float(f32(e2 * f32(inv_sigma2[o]))) > 7.8:
+                            continue
+                    else:
+                        e2 = f32(f32(ex * ex) + f32(ey * ey))
+                        if float(f32(e2 * f32(inv_sigma2[o]))) > 5.99:
+                            continue
+                d = hamming(qdesc[q], desc[i])
+                if d < best:
+                    best, bi = d, i
+            if best <= 50:
+                res = bi
+            break
+        out.append(res)
+    return np.array(out, np.int32)

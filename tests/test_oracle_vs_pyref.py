@@ -1,0 +1,80 @@
+"""CPU tier: the C++ oracle against plain-Python restatements written independently from the reference (tests/pyref.py):
+SearchForInitialization, SearchByBoW(KF, KF), Fuse x2.  Small inputs (pure-Python loops)."""
+import numpy as np
+import pytest
+
+import pyref
+from oracle import pyoracle as po
+from orb_slam3_detailed_comments_b200 import synth
+
+W, H = 320, 240
+FX, FY, CX, CY, BF, B = 217.6, 217.6, 160.0, 120.0, 24.0, 0.11
+BOUNDS = [0, W, 0, H]
+
+
+@pytest.fixture(scope="module")
+def frames():
+    l, r, _ = synth.stereo_pair(W, H, seed=77)
+    eL, eR = po.OracleExtractor(500, 1.2, 8, 20, 7), po.OracleExtractor(500, 1.2, 8, 20, 7)
+    _, kL, dL = eL(l)
+    _, kR, dR = eR(r)
+    uR, dep, _ = po.stereo_matches(eL, eR, kL, dL, kR, dR, BF, B)
+    _, k2, d2 = eL(np.clip(np.roll(l, (2, 1), (1, 0)).astype(int) + np.random.default_rng(0).integers(-2, 3, (H, W)), 0, 255).astype(np.uint8))
+    return eL, kL, dL, uR, dep, k2, d2
+
+
+def test_search_for_initialization(frames):
+    eL, kL, dL, uR, dep, k2, d2 = frames
+    rng = np.random.default_rng(1)
+    l0 = np.nonzero(kL["octave"] == 0)[0]
+    dup = rng.choice(l0, len(l0) // 3, replace=False)          # duplicated queries: match stealing
+    kp1, d1 = np.concatenate([kL[dup], kL]), np.concatenate([dL[dup], dL])
+    prev = np.stack([kp1["x"], kp1["y"]], 1).astype(np.float32)
+    for win, ratio, check in [(100, 0.9, True), (20, 0.8, False)]:
+        m, nm = po.search_initialization(kp1, d1, prev, k2, d2, BOUNDS, win, ratio, check)
+        rm, rnm = pyref.search_for_initialization(kp1, d1, prev, k2, d2, BOUNDS, win, ratio, check)
+        assert nm == rnm and (m == rm).all() and nm > 20
+
+
+def test_search_by_bow_keyframes(frames):
+    eL, kL, dL, uR, dep, k2, d2 = frames
+    rng = np.random.default_rng(2)
+    node_of = lambda d: ((d[:, 0].astype(np.int32) >> 3) * 7 + (d[:, 5].astype(np.int32) >> 4) * 3 + (d[:, 17].astype(np.int32) >> 5)) % 23
+    q = np.nonzero(rng.random(len(kL)) < 0.8)[0]
+    q = np.concatenate([q, q[::4]])
+    nd = node_of(dL[q])
+    order = np.lexsort((q, nd))
+    q, nd = q[order], nd[order]
+    node2 = node_of(d2)
+    node2[::13] = -1
+    valid2 = (rng.random(len(k2)) < 0.7).astype(np.uint8)
+    for ratio, check in [(0.75, True), (0.9, False)]:
+        m, nm = po.search_bow_kf(k2, d2, node2, valid2, nd, kL["angle"][q], dL[q], ratio, check)
+        rm, rnm = pyref.search_bow_keyframes(k2, d2, node2, valid2, nd, kL["angle"][q], dL[q], ratio, check)
+        assert nm == rnm and (m == rm).all() and nm > 10
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_fuse(frames, variant):
+    eL, kL, dL, uR, dep, k2, d2 = frames
+    rng = np.random.default_rng(3 + variant)
+    sf = eL.scale_factors
+    isg = (1.0 / (sf * sf)).astype(np.float32)
+    logsf = po.logf(1.2)
+    sel = np.nonzero(dep > 0)[0]
+    z = dep[sel]
+    pts = np.stack([(kL["x"][sel] - CX) * z / FX, (kL["y"][sel] - CY) * z / FY, z], 1).astype(np.float32)
+    dist = np.linalg.norm(pts, axis=1).astype(np.float32)
+    nrm = (pts / dist[:, None] + rng.normal(0, 0.3, pts.shape)).astype(np.float32)
+    nrm = (nrm / np.linalg.norm(nrm, axis=1)[:, None]).astype(np.float32)
+    maxd = np.float32(1.2) * (dist * sf[kL["octave"][sel]]).astype(np.float32)
+    mind = np.float32(0.8) * (maxd / np.float32(1.2) / sf[7]).astype(np.float32)
+    zmid = float(np.median(z))
+    T = np.array([0, 0.001, 0, 1, 2 * zmid / FX, 1 * zmid / FY, 0], np.float32)
+    T[:4] /= np.linalg.norm(T[:4])
+    Ow = (-T[4:]).astype(np.float32)
+    ur2 = np.where(rng.random(len(k2)) < 0.6, k2["x"] - 5, -1).astype(np.float32)
+    cam6 = [FX, FY, CX, CY, BF, B]
+    m, nm, _ = po.search_keyframe(variant, k2, d2, ur2, BOUNDS, sf, isg, logsf, cam6, T, Ow, pts, nrm, maxd, mind, dL[sel], None, None, 4.0, 50.0)
+    rm = pyref.fuse(variant, k2, d2, ur2, BOUNDS, sf, isg, logsf, cam6, T, Ow, pts, nrm, maxd, mind, dL[sel], 4.0)
+    assert (m == rm).all() and nm == int((rm >= 0).sum()) and nm > 20
