@@ -237,3 +237,97 @@ def fuse(variant, kps, desc, uright, bounds, sf, inv_sigma2, log_sf, cam, T, Ow,
             break
         out.append(res)
     return np.array(out, np.int32)
+
+
+def search_local_points(kps, desc, uright, bounds, sf, projx, projy, projxr, level, viewcos, qdesc, th, nnratio, claimed=None):
+    """ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>, th, ...) (ORBmatcher.cc:45-239), Nleft == -1; every query is an
+    in-view map point with observations.  Returns (match[nq], nmatches)."""
+    g = Grid(kps, bounds)
+    holder = [bool(c) for c in claimed] if claimed is not None else [False] * len(kps)
+    out = [-1] * len(projx)
+    nm = 0
+    for q in range(len(projx)):
+        lvl = int(level[q])
+        r = f32(2.5) if float(f32(viewcos[q])) > 0.998 else f32(4.0)
+        if float(f32(th)) != 1.0:
+            r = f32(r * f32(th))
+        rr = f32(r * f32(sf[lvl]))
+        ind = g.area(projx[q], projy[q], rr, lvl - 1, lvl)
+        if not ind:
+            continue
+        b1 = b2 = 256
+        l1 = l2 = -1
+        bi = -1
+        for i in ind:
+            if holder[i]:
+                continue
+            if uright is not None and uright[i] > 0:
+                er = abs(f32(f32(projxr[q]) - f32(uright[i])))
+                if er > rr:
+                    continue
+            d = hamming(qdesc[q], desc[i])
+            if d < b1:
+                b2, b1, l2, l1, bi = b1, d, l1, int(kps["octave"][i]), i
+            elif d < b2:
+                l2, b2 = int(kps["octave"][i]), d
+        if b1 <= 100:
+            if l1 == l2 and f32(b1) > f32(f32(nnratio) * f32(b2)):
+                continue
+            if l1 != l2 or f32(b1) <= f32(f32(nnratio) * f32(b2)):
+                out[q] = bi
+                holder[bi] = True
+                nm += 1
+    return np.array(out, np.int32), nm
+
+
+def search_last_frame(kps, desc, uright, bounds, sf, cam, T, direction, xw, last_octave, last_angle, qdesc, obs_pos, th, check_ori=True):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (ORBmatcher.cc:1950-2184), Nleft == -1.
+    Returns (feature_match[N] query index or -1, nmatches)."""
+    g = Grid(kps, bounds)
+    fx, fy, cx, cy, bf = [f32(v) for v in cam[:5]]
+    fm = [-1] * len(kps)
+    hist = [[] for _ in range(30)]
+    nm = 0
+    for q in range(len(xw)):
+        pc = se3_act(T, xw[q])
+        invzc = f32(1.0 / float(pc[2]))
+        if invzc < 0:
+            continue
+        u = f32(f32(f32(fx * pc[0]) / pc[2]) + cx)
+        v = f32(f32(f32(fy * pc[1]) / pc[2]) + cy)
+        if u < g.minX or u > g.maxX or v < g.minY or v > g.maxY:
+            continue
+        o = int(last_octave[q])
+        radius = f32(f32(th) * f32(sf[o]))
+        if direction == 1:
+            ind = g.area(u, v, radius, o, -1)
+        elif direction == 2:
+            ind = g.area(u, v, radius, 0, o)
+        else:
+            ind = g.area(u, v, radius, o - 1, o + 1)
+        if not ind:
+            continue
+        best, bi = 256, -1
+        for i in ind:
+            if fm[i] >= 0 and obs_pos[fm[i]]:
+                continue
+            if uright is not None and uright[i] > 0:
+                ur = f32(u - f32(bf * invzc))
+                if abs(f32(ur - f32(uright[i]))) > radius:
+                    continue
+            d = hamming(qdesc[q], desc[i])
+            if d < best:
+                best, bi = d, i
+        if best <= 100:
+            fm[bi] = q
+            nm += 1
+            if check_ori:
+                hist[rot_bin(last_angle[q], kps["angle"][bi])].append(bi)
+    if check_ori:
+        keep = three_maxima(hist)
+        for b in range(30):
+            if b not in keep:
+                for i in hist[b]:
+                    fm[i] = -1
+                    nm -= 1
+    return np.array(fm, np.int32), nm

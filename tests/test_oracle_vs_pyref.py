@@ -78,3 +78,42 @@ def test_fuse(frames, variant):
     m, nm, _ = po.search_keyframe(variant, k2, d2, ur2, BOUNDS, sf, isg, logsf, cam6, T, Ow, pts, nrm, maxd, mind, dL[sel], None, None, 4.0, 50.0)
     rm = pyref.fuse(variant, k2, d2, ur2, BOUNDS, sf, isg, logsf, cam6, T, Ow, pts, nrm, maxd, mind, dL[sel], 4.0)
     assert (m == rm).all() and nm == int((rm >= 0).sum()) and nm > 20
+
+
+def test_search_local_points(frames):
+    """The per-frame local-map search (greedy claims, level rule, stereo gate) -- the headline matcher."""
+    eL, kL, dL, uR, dep, k2, d2 = frames
+    rng = np.random.default_rng(9)
+    sf = eL.scale_factors
+    ur2 = np.where(rng.random(len(k2)) < 0.6, k2["x"] - 4, -1).astype(np.float32)
+    sel = np.concatenate([np.arange(len(kL)), rng.integers(0, len(kL), 2 * len(kL))])     # several map points compete for a feature
+    jit = rng.normal(0, 1.5, (len(sel), 2)).astype(np.float32)
+    px, py = (kL["x"][sel] + 2 + jit[:, 0]).astype(np.float32), (kL["y"][sel] + 1 + jit[:, 1]).astype(np.float32)
+    pxr = (px - 4 + rng.normal(0, 2, len(sel))).astype(np.float32)
+    lvl = np.clip(kL["octave"][sel] + rng.integers(-1, 2, len(sel)), 0, 7).astype(np.int32)
+    vc = rng.uniform(0.99, 1.0, len(sel)).astype(np.float32)
+    claimed = (rng.random(len(k2)) < 0.1).astype(np.uint8)
+    for th, ratio in [(1.0, 0.8), (3.0, 0.8), (5.0, 0.7)]:
+        m, nm = po.search_local(k2, d2, ur2, BOUNDS, sf, px, py, pxr, lvl, vc, dL[sel], th, ratio, claimed=claimed)
+        rm, rnm = pyref.search_local_points(k2, d2, ur2, BOUNDS, sf, px, py, pxr, lvl, vc, dL[sel], th, ratio, claimed)
+        assert nm == rnm and (m == rm).all() and nm > 30, (th, nm, rnm)
+
+
+def test_search_last_frame(frames):
+    eL, kL, dL, uR, dep, k2, d2 = frames
+    rng = np.random.default_rng(10)
+    sf = eL.scale_factors
+    ur2 = np.where(rng.random(len(k2)) < 0.6, k2["x"] - 4, -1).astype(np.float32)
+    sel = np.nonzero(dep > 0)[0]
+    sel = np.concatenate([sel, sel[::3]])
+    z = dep[sel]
+    pts = np.stack([(kL["x"][sel] - CX) * z / FX, (kL["y"][sel] - CY) * z / FY, z], 1).astype(np.float32)
+    zmid = float(np.median(z))
+    T = np.array([0, 0.001, 0, 1, 2 * zmid / FX, 1 * zmid / FY, 0], np.float32)
+    T[:4] /= np.linalg.norm(T[:4])
+    obs = (rng.random(len(sel)) < 0.7).astype(np.uint8)
+    cam6 = np.float32([FX, FY, CX, CY, BF, B])
+    for th, direction, check in [(15.0, 0, True), (7.0, 1, True), (7.0, 2, False)]:
+        fm, nm = po.search_last(k2, d2, ur2, BOUNDS, sf, cam6, T, direction, pts, kL["octave"][sel], kL["angle"][sel], dL[sel], obs, th, check)
+        rfm, rnm = pyref.search_last_frame(k2, d2, ur2, BOUNDS, sf, cam6, T, direction, pts, kL["octave"][sel], kL["angle"][sel], dL[sel], obs, th, check)
+        assert nm == rnm and (fm == rfm).all() and nm > 20, (th, direction, nm, rnm)
