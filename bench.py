@@ -393,7 +393,7 @@ def main():
     # per-stage times for the roofline: a serial (un-overlapped) pass over the same steps, CUDA events per stage
     ex.set_profiling(True)
     ser0, ser1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    nser = min(args.steps, 32) // 2 * 2
+    nser = max(2, min(args.steps, 32) // 2 * 2)     # at least one profiled serial step whatever --steps is
     ser0.record(streams[0])
     for i in range(0, nser, 2):
         step_device(NH * (args.warmup + i))  # multiple of NH => handle 0, the profiled one
