@@ -331,3 +331,90 @@ def search_last_frame(kps, desc, uright, bounds, sf, cam, T, direction, xw, last
                     fm[i] = -1
                     nm -= 1
     return np.array(fm, np.int32), nm
+
+
+def c_round(v):
+    """C round() of a float32 value: half away from zero."""
+    v = float(v)
+    return np.floor(v + 0.5) if v >= 0 else -np.floor(-v + 0.5)
+
+
+def compute_stereo_matches(kL, dL, kR, dR, pyrL, pyrR, sf, inv_sf, bf, b):
+    """Frame::ComputeStereoMatches (src/Frame.cc:1102-1358).  pyrL / pyrR: lists of the 8 level images (mvImagePyramid).
+    Returns (mvuRight, mvDepth) as float32 arrays."""
+    import math
+    N = len(kL)
+    uright, depth = np.full(N, -1, np.float32), np.full(N, -1, np.float32)
+    nrows = pyrL[0].shape[0]
+    rows = [[] for _ in range(nrows)]
+    for iR in range(len(kR)):
+        r = f32(f32(2.0) * f32(sf[kR["octave"][iR]]))
+        maxr, minr = int(math.ceil(float(f32(kR["y"][iR] + r)))), int(math.floor(float(f32(kR["y"][iR] - r))))
+        for y in range(minr, maxr + 1):
+            rows[y].append(iR)
+    minZ, minD = f32(b), f32(0)
+    maxD = f32(f32(bf) / minZ)
+    dist_idx = []
+    for iL in range(N):
+        lvl, vL, uL = int(kL["octave"][iL]), f32(kL["y"][iL]), f32(kL["x"][iL])
+        cands = rows[int(vL)]
+        if not cands:
+            continue
+        minU, maxU = f32(uL - maxD), f32(uL - minD)
+        if maxU < 0:
+            continue
+        best, bestR = 100, 0
+        for iR in cands:
+            o = int(kR["octave"][iR])
+            if o < lvl - 1 or o > lvl + 1:
+                continue
+            uR = f32(kR["x"][iR])
+            if uR >= minU and uR <= maxU:
+                d = hamming(dL[iL], dR[iR])
+                if d < best:
+                    best, bestR = d, iR
+        if best >= 75:
+            continue
+        uR0 = f32(kR["x"][bestR])
+        s = f32(inv_sf[lvl])
+        suL, svL, suR0 = f32(c_round(f32(uL * s))), f32(c_round(f32(vL * s))), f32(c_round(f32(uR0 * s)))
+        w, L = 5, 5
+        IL = pyrL[lvl][int(svL) - w:int(svL) + w + 1, int(suL) - w:int(suL) + w + 1].astype(np.int32)
+        iniu, endu = f32(f32(suR0 + L) - w), f32(f32(f32(suR0 + L) + w) + 1)
+        if iniu < 0 or endu >= pyrR[lvl].shape[1]:
+            continue
+        bestDist, bestinc = 2 ** 31 - 1, 0
+        vd = [f32(0)] * (2 * L + 1)
+        for inc in range(-L, L + 1):
+            c0 = int(f32(f32(suR0 + inc) - w))
+            IR = pyrR[lvl][int(svL) - w:int(svL) + w + 1, c0:c0 + 2 * w + 1].astype(np.int32)
+            dist = f32(float(np.abs(IL - IR).sum()))
+            if dist < f32(bestDist):
+                bestDist, bestinc = int(dist), inc
+            vd[L + inc] = dist
+        if bestinc == -L or bestinc == L:
+            continue
+        d1, d2, d3 = vd[L + bestinc - 1], vd[L + bestinc], vd[L + bestinc + 1]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            delta = f32(f32(d1 - d3) / f32(f32(2.0) * f32(f32(d1 + d3) - f32(f32(2.0) * d2))))
+        if delta < -1 or delta > 1 or np.isnan(delta):
+            continue
+        bestuR = f32(f32(sf[lvl]) * f32(f32(suR0 + f32(bestinc)) + delta))
+        disp = f32(uL - bestuR)
+        if disp >= minD and disp < maxD:
+            if disp <= 0:
+                disp = f32(0.01)
+                bestuR = f32(float(uL) - 0.01)
+            depth[iL] = f32(f32(bf) / disp)
+            uright[iL] = bestuR
+            dist_idx.append((bestDist, iL))
+    dist_idx.sort()
+    if dist_idx:
+        median = f32(dist_idx[len(dist_idx) // 2][0])
+        th = f32(f32(f32(1.5) * f32(1.4)) * median)
+        for i in range(len(dist_idx) - 1, -1, -1):
+            if f32(dist_idx[i][0]) < th:
+                break
+            uright[dist_idx[i][1]] = -1
+            depth[dist_idx[i][1]] = -1
+    return uright, depth

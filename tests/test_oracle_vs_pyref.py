@@ -117,3 +117,17 @@ def test_search_last_frame(frames):
         fm, nm = po.search_last(k2, d2, ur2, BOUNDS, sf, cam6, T, direction, pts, kL["octave"][sel], kL["angle"][sel], dL[sel], obs, th, check)
         rfm, rnm = pyref.search_last_frame(k2, d2, ur2, BOUNDS, sf, cam6, T, direction, pts, kL["octave"][sel], kL["angle"][sel], dL[sel], obs, th, check)
         assert nm == rnm and (fm == rfm).all() and nm > 20, (th, direction, nm, rnm)
+
+
+def test_compute_stereo_matches():
+    """Frame::ComputeStereoMatches: row-band candidates, Hamming coarse match, 11 x 11 SAD refinement over 11 shifts, parabola,
+    median outlier filter -- bit-exact mvuRight / mvDepth."""
+    l, r, _ = synth.stereo_pair(W, H, seed=78)
+    eL, eR = po.OracleExtractor(500, 1.2, 8, 20, 7), po.OracleExtractor(500, 1.2, 8, 20, 7)
+    _, kL, dL = eL(l)
+    _, kR, dR = eR(r)
+    uR, dep, _ = po.stereo_matches(eL, eR, kL, dL, kR, dR, BF, B)
+    pyrL, pyrR = [eL.level_pyramid(i) for i in range(8)], [eR.level_pyramid(i) for i in range(8)]
+    ruR, rdep = pyref.compute_stereo_matches(kL, dL, kR, dR, pyrL, pyrR, eL.scale_factors, eL.inv_scale_factors, BF, B)
+    assert (uR.view(np.uint32) == ruR.view(np.uint32)).all() and (dep.view(np.uint32) == rdep.view(np.uint32)).all()
+    assert (dep > 0).sum() > 100
