@@ -418,3 +418,41 @@ def compute_stereo_matches(kL, dL, kR, dR, pyrL, pyrR, sf, inv_sf, bf, b):
             uright[dist_idx[i][1]] = -1
             depth[dist_idx[i][1]] = -1
     return uright, depth
+
+
+def search_bow_frame(kps, desc, feat_node, qnode, qangle, qdesc, nnratio, check_ori=True):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (ORBmatcher.cc:259-493), Nleft == -1, on flattened word
+    groups: queries = keyframe features with a good map point in merge order.  Returns (feature_match[N], nmatches)."""
+    N = len(kps)
+    fm = [-1] * N
+    by_node = {}
+    for i in range(N):
+        by_node.setdefault(int(feat_node[i]), []).append(i)
+    hist = [[] for _ in range(30)]
+    nm = 0
+    for q in range(len(qnode)):
+        if qnode[q] < 0:
+            continue
+        b1 = b2 = 256
+        bi = -1
+        for i in by_node.get(int(qnode[q]), []):
+            if fm[i] >= 0:
+                continue
+            d = hamming(qdesc[q], desc[i])
+            if d < b1:
+                b2, b1, bi = b1, d, i
+            elif d < b2:
+                b2 = d
+        if b1 <= 50 and f32(b1) < f32(f32(nnratio) * f32(b2)):
+            fm[bi] = q
+            if check_ori:
+                hist[rot_bin(qangle[q], kps["angle"][bi])].append(bi)
+            nm += 1
+    if check_ori:
+        keep = three_maxima(hist)
+        for b in range(30):
+            if b not in keep:
+                for i in hist[b]:
+                    fm[i] = -1
+                    nm -= 1
+    return np.array(fm, np.int32), nm

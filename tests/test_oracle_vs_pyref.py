@@ -131,3 +131,20 @@ def test_compute_stereo_matches():
     ruR, rdep = pyref.compute_stereo_matches(kL, dL, kR, dR, pyrL, pyrR, eL.scale_factors, eL.inv_scale_factors, BF, B)
     assert (uR.view(np.uint32) == ruR.view(np.uint32)).all() and (dep.view(np.uint32) == rdep.view(np.uint32)).all()
     assert (dep > 0).sum() > 100
+
+
+def test_search_by_bow_frame(frames):
+    eL, kL, dL, uR, dep, k2, d2 = frames
+    rng = np.random.default_rng(12)
+    node_of = lambda d: ((d[:, 0].astype(np.int32) >> 3) * 7 + (d[:, 5].astype(np.int32) >> 4) * 3 + (d[:, 17].astype(np.int32) >> 5)) % 19
+    fnode = node_of(d2)
+    fnode[::11] = -1
+    q = np.nonzero(rng.random(len(kL)) < 0.8)[0]
+    q = np.concatenate([q, q[::3]])
+    nd = node_of(dL[q])
+    order = np.lexsort((q, nd))
+    q, nd = q[order], nd[order]
+    for ratio, check in [(0.7, True), (0.9, False)]:
+        fm, nm = po.search_bow(k2, d2, fnode, nd, kL["angle"][q], dL[q], ratio, check)
+        rfm, rnm = pyref.search_bow_frame(k2, d2, fnode, nd, kL["angle"][q], dL[q], ratio, check)
+        assert nm == rnm and (fm == rfm).all() and nm > 10
