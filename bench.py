@@ -521,9 +521,9 @@ def main():
                     "algorithmic_bytes_per_image": ab,
                     "traffic_source": "profiles/r01_fast_traffic.json (ncu --set full, bytes per launch of 128 images)",
                     "note": "stage times from a serial pass (one stream) right after the timed region; the timed region itself is "
-                            "software-pipelined over the handles' streams.  FAST is ALU-pipe bound (profiles/), not HBM bound; see DESIGN.md"}
+                            "software-pipelined over the handles' streams.  FAST is bound by integer issue and barrier / shared-memory latency (profiles/), not by HBM; see DESIGN.md"}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only
             # faithful threading (Frame.cc:136-141): the two eyes on two threads, bounded sample
             v, secs = cpu_oracle_frames(pairs[:8], 2)
             cpu = {"value": v, "unit": UNIT, "cores": 2, "kind": "port",
