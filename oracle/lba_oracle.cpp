@@ -594,3 +594,509 @@ extern "C" int orc_pose_optimization(int n, const double* Xw, const double* obs,
     if (stats) { stats[0] = rounds; stats[1] = totalIters; stats[2] = totalTrials; stats[3] = lambda; }
     return n - nBadEdges;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Optimizer::LocalInertialBA numeric core  src/Optimizer.cc:2203-2812 (one camera, Nleft == -1) -- SURVEY 8(f) N2.
+// ORACLE ONLY so far: the device implementation is the next row; this restatement, its finite-difference checks and its
+// fixed-point tests (tests/test_oracle_inertial.py) are the groundwork.
+//
+// Vertices per keyframe: VertexPose (ImuCamPose: Rwb, twb; update twb += Rwb ut, Rwb = Rwb Exp(ur), G2oTypes.cc:221-244),
+// VertexVelocity, VertexGyroBias, VertexAccBias (additive); a keyframe is either optimised or fixed as a whole.  Marginalised
+// VertexSBAPointXYZ per map point.  Edges: EdgeMono / EdgeStereo (G2oTypes.h, .cc:390-490) with Huber sqrt(5.991) /
+// sqrt(7.815); EdgeInertial (G2oTypes.cc:563-687) between consecutive keyframes, optionally Huber sqrt(16.92);
+// EdgeGyroRW / EdgeAccRW (G2oTypes.h:736-800).  g2o Levenberg with a user lambda (1e0, or 1e-2 when bLarge), BlockSolverX
+// + LinearSolverEigen: dense here, landmarks eliminated by the Schur complement.
+// Inputs the caller computes exactly as the reference does: the 9 x 9 EdgeInertial information (inverse of C.block<9,9>,
+// symmetrised, eigenvalues < 1e-12 clamped, times 1e-2 for the oldest link), InfoG / InfoA (inverse 3 x 3 blocks of C), the
+// preintegrated deltas and bias Jacobians (float members of IMU::Preintegrated) and the bias they were linearised at.
+// NormalizeRotation (an SVD re-orthonormalisation of matrices that are orthonormal to rounding) is omitted: it moves values by
+// ~1e-16 (double) / ~1e-7 (the float delta rotation), far inside the 1e-4 parity bar.
+namespace {
+
+struct Mat3 { double m[9]; };
+inline Mat3 mat3_mul(const Mat3& a, const Mat3& b) {
+    Mat3 c;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) c.m[3 * i + j] = a.m[3 * i] * b.m[j] + a.m[3 * i + 1] * b.m[3 + j] + a.m[3 * i + 2] * b.m[6 + j];
+    return c;
+}
+inline Mat3 mat3_T(const Mat3& a) { return Mat3{{a.m[0], a.m[3], a.m[6], a.m[1], a.m[4], a.m[7], a.m[2], a.m[5], a.m[8]}}; }
+inline void mat3_vec(const Mat3& a, const double* v, double* o) {
+    for (int i = 0; i < 3; ++i) o[i] = a.m[3 * i] * v[0] + a.m[3 * i + 1] * v[1] + a.m[3 * i + 2] * v[2];
+}
+inline Mat3 skew(const double* w) { return Mat3{{0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0}}; }
+inline Mat3 mat3_I() { return Mat3{{1, 0, 0, 0, 1, 0, 0, 0, 1}}; }
+
+// G2oTypes.cc:908-986
+inline Mat3 exp_so3(const double* w) {
+    const double d2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], d = std::sqrt(d2);
+    const Mat3 W = skew(w), W2 = mat3_mul(W, W);
+    Mat3 r = mat3_I();
+    if (d < 1e-5) { for (int i = 0; i < 9; ++i) r.m[i] += W.m[i] + 0.5 * W2.m[i]; }
+    else { for (int i = 0; i < 9; ++i) r.m[i] += W.m[i] * std::sin(d) / d + W2.m[i] * (1.0 - std::cos(d)) / d2; }
+    return r;
+}
+inline void log_so3(const Mat3& R, double* w) {
+    const double tr = R.m[0] + R.m[4] + R.m[8];
+    w[0] = (R.m[7] - R.m[5]) / 2; w[1] = (R.m[2] - R.m[6]) / 2; w[2] = (R.m[3] - R.m[1]) / 2;
+    const double costheta = (tr - 1.0) * 0.5f;
+    if (costheta > 1 || costheta < -1) return;
+    const double theta = std::acos(costheta), s = std::sin(theta);
+    if (std::fabs(s) < 1e-5) return;
+    for (int i = 0; i < 3; ++i) w[i] = theta * w[i] / s;
+}
+inline Mat3 right_jac_so3(const double* v, bool inverse) {
+    const double d2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2], d = std::sqrt(d2);
+    Mat3 r = mat3_I();
+    if (d < 1e-5) return r;
+    const Mat3 W = skew(v), W2 = mat3_mul(W, W);
+    if (inverse) { for (int i = 0; i < 9; ++i) r.m[i] += W.m[i] / 2 + W2.m[i] * (1.0 / d2 - (1.0 + std::cos(d)) / (2.0 * d * std::sin(d))); }
+    else { for (int i = 0; i < 9; ++i) r.m[i] += -W.m[i] * (1.0 - std::cos(d)) / d2 + W2.m[i] * (d - std::sin(d)) / (d2 * d); }
+    return r;
+}
+
+struct InertialLink {   // one EdgeInertial + EdgeGyroRW + EdgeAccRW between keyframes k1 (previous) and k2
+    int k1, k2, robust;
+    double dt;
+    float dR[9], dV[3], dP[3], JRg[9], JVg[9], JVa[9], JPg[9], JPa[9], blin[6];   // blin: bax bay baz bwx bwy bwz of the preintegration
+    double info[81], infoG[9], infoA[9];
+};
+
+struct KfState { Mat3 Rwb; double twb[3], v[3], bg[3], ba[3]; };
+
+struct InertialProblem {
+    int nKF, nMP, nE, nL;
+    std::vector<KfState> kf;
+    std::vector<double> point;
+    const uint8_t* fixed;
+    const int *ekf, *emp;
+    const double *obs, *invs2;
+    const InertialLink* links;
+    Mat3 Rcb, Rbc;
+    double tcb[3], tbc[3];
+    double fx, fy, cx, cy, bf;
+};
+
+inline void cam_pose(const InertialProblem& P, const KfState& s, Mat3& Rcw, double* tcw) {   // ImuCamPose::Update, G2oTypes.cc:236-243
+    const Mat3 Rbw = mat3_T(s.Rwb);
+    double tbw[3];
+    mat3_vec(Rbw, s.twb, tbw);
+    for (int i = 0; i < 3; ++i) tbw[i] = -tbw[i];
+    Rcw = mat3_mul(P.Rcb, Rbw);
+    mat3_vec(P.Rcb, tbw, tcw);
+    for (int i = 0; i < 3; ++i) tcw[i] += P.tcb[i];
+}
+
+// reprojection residual (EdgeMono / EdgeStereo::computeError) and, optionally, Jacobians Jp (D x 3, point) and Jx (D x 6, pose)
+inline int reproj(const InertialProblem& P, int e, double* r, double* Jp, double* Jx) {
+    const KfState& s = P.kf[P.ekf[e]];
+    Mat3 Rcw;
+    double tcw[3], Xc[3];
+    cam_pose(P, s, Rcw, tcw);
+    mat3_vec(Rcw, &P.point[3 * P.emp[e]], Xc);
+    for (int i = 0; i < 3; ++i) Xc[i] += tcw[i];
+    const double* z = P.obs + 3 * e;
+    const int D = z[2] < 0 ? 2 : 3;
+    const double u = P.fx * Xc[0] / Xc[2] + P.cx, v = P.fy * Xc[1] / Xc[2] + P.cy;   // Pinhole::project(Vector3d)
+    r[0] = z[0] - u;
+    r[1] = z[1] - v;
+    r[2] = 0;
+    if (D == 3) r[2] = z[2] - (u - P.bf * (1 / Xc[2]));
+    if (Jp) {
+        double pj[9] = {P.fx / Xc[2], 0, -P.fx * Xc[0] / (Xc[2] * Xc[2]), 0, P.fy / Xc[2], -P.fy * Xc[1] / (Xc[2] * Xc[2]), 0, 0, 0};
+        if (D == 3) { pj[6] = pj[0]; pj[7] = pj[1]; pj[8] = pj[2] + P.bf * (1.0 / (Xc[2] * Xc[2])); }
+        double Xb[3];
+        mat3_vec(P.Rbc, Xc, Xb);
+        for (int i = 0; i < 3; ++i) Xb[i] += P.tbc[i];
+        const double S[18] = {0, Xb[2], -Xb[1], 1, 0, 0, -Xb[2], 0, Xb[0], 0, 1, 0, Xb[1], -Xb[0], 0, 0, 0, 1};
+        for (int d = 0; d < D; ++d) {
+            for (int c = 0; c < 3; ++c) Jp[3 * d + c] = -(pj[3 * d] * Rcw.m[c] + pj[3 * d + 1] * Rcw.m[3 + c] + pj[3 * d + 2] * Rcw.m[6 + c]);
+            double pr[3];   // proj_jac * Rcb
+            for (int c = 0; c < 3; ++c) pr[c] = pj[3 * d] * P.Rcb.m[c] + pj[3 * d + 1] * P.Rcb.m[3 + c] + pj[3 * d + 2] * P.Rcb.m[6 + c];
+            for (int c = 0; c < 6; ++c) Jx[6 * d + c] = pr[0] * S[c] + pr[1] * S[6 + c] + pr[2] * S[12 + c];
+        }
+    }
+    return D;
+}
+
+// EdgeInertial::computeError / linearizeOplus.  e9 = (er, ev, ep).  J (optional): 9 x 30 over [pose1 6 | v1 3 | bg1 3 | ba1 3 | pose2 6 | v2 3 | 6 unused]
+inline void inertial(const InertialProblem& P, const InertialLink& L, double* e9, double* J) {
+    const KfState &s1 = P.kf[L.k1], &s2 = P.kf[L.k2];
+    const double g[3] = {0, 0, -(double)9.81f};   // IMU::GRAVITY_VALUE is a float (ImuTypes.h:41)
+    // IMU::Bias holds floats; the deltas are evaluated in float (ImuTypes.cc:388-430)
+    float dbg[3], dba[3];
+    for (int i = 0; i < 3; ++i) { dba[i] = (float)s1.ba[i] - L.blin[i]; dbg[i] = (float)s1.bg[i] - L.blin[3 + i]; }
+    float wv[3];
+    for (int i = 0; i < 3; ++i) wv[i] = L.JRg[3 * i] * dbg[0] + L.JRg[3 * i + 1] * dbg[1] + L.JRg[3 * i + 2] * dbg[2];
+    const double wd[3] = {wv[0], wv[1], wv[2]};
+    const Mat3 E = exp_so3(wd);
+    Mat3 dR;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            dR.m[3 * i + j] = (double)(float)((double)L.dR[3 * i] * E.m[j] + (double)L.dR[3 * i + 1] * E.m[3 + j] + (double)L.dR[3 * i + 2] * E.m[6 + j]);
+    double dV[3], dP[3];
+    for (int i = 0; i < 3; ++i) {
+        dV[i] = (double)(float)(L.dV[i] + (L.JVg[3 * i] * dbg[0] + L.JVg[3 * i + 1] * dbg[1] + L.JVg[3 * i + 2] * dbg[2]) +
+                                (L.JVa[3 * i] * dba[0] + L.JVa[3 * i + 1] * dba[1] + L.JVa[3 * i + 2] * dba[2]));
+        dP[i] = (double)(float)(L.dP[i] + (L.JPg[3 * i] * dbg[0] + L.JPg[3 * i + 1] * dbg[1] + L.JPg[3 * i + 2] * dbg[2]) +
+                                (L.JPa[3 * i] * dba[0] + L.JPa[3 * i + 1] * dba[1] + L.JPa[3 * i + 2] * dba[2]));
+    }
+    const Mat3 Rbw1 = mat3_T(s1.Rwb);
+    const Mat3 eR = mat3_mul(mat3_mul(mat3_T(dR), Rbw1), s2.Rwb);
+    double er[3];
+    log_so3(eR, er);
+    const double dt = L.dt;
+    double a[3], b[3], ra[3], rb[3];
+    for (int i = 0; i < 3; ++i) {
+        a[i] = s2.v[i] - s1.v[i] - g[i] * dt;
+        b[i] = s2.twb[i] - s1.twb[i] - s1.v[i] * dt - g[i] * dt * dt / 2;
+    }
+    mat3_vec(Rbw1, a, ra);
+    mat3_vec(Rbw1, b, rb);
+    for (int i = 0; i < 3; ++i) { e9[i] = er[i]; e9[3 + i] = ra[i] - dV[i]; e9[6 + i] = rb[i] - dP[i]; }
+    if (!J) return;
+    std::fill(J, J + 9 * 30, 0.0);
+    auto put = [&](int row0, int col0, const Mat3& M, double sgn) {
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) J[(row0 + i) * 30 + col0 + j] = sgn * M.m[3 * i + j];
+    };
+    const Mat3 invJr = right_jac_so3(er, true);
+    put(0, 0, mat3_mul(mat3_mul(invJr, mat3_T(s2.Rwb)), s1.Rwb), -1.0);          // d er / d r1
+    put(3, 0, skew(ra), 1.0);                                                   // d ev / d r1
+    put(6, 0, skew(rb), 1.0);                                                   // d ep / d r1
+    put(6, 3, mat3_I(), -1.0);                                                  // d ep / d t1
+    put(3, 6, Rbw1, -1.0);                                                      // velocity 1
+    { Mat3 m = Rbw1; for (double& x : m.m) x *= dt; put(6, 6, m, -1.0); }
+    Mat3 JRgd, JVgd, JPgd, JVad, JPad;
+    for (int i = 0; i < 9; ++i) { JRgd.m[i] = L.JRg[i]; JVgd.m[i] = L.JVg[i]; JPgd.m[i] = L.JPg[i]; JVad.m[i] = L.JVa[i]; JPad.m[i] = L.JPa[i]; }
+    const double dbgd[3] = {dbg[0], dbg[1], dbg[2]};
+    double jw[3];
+    mat3_vec(JRgd, dbgd, jw);
+    put(0, 9, mat3_mul(mat3_mul(mat3_mul(invJr, mat3_T(eR)), right_jac_so3(jw, false)), JRgd), -1.0);   // gyro bias 1
+    put(3, 9, JVgd, -1.0);
+    put(6, 9, JPgd, -1.0);
+    put(3, 12, JVad, -1.0);                                                     // acc bias 1
+    put(6, 12, JPad, -1.0);
+    put(0, 15, invJr, 1.0);                                                     // pose 2
+    put(6, 18, mat3_mul(Rbw1, s2.Rwb), 1.0);
+    put(3, 21, Rbw1, 1.0);                                                      // velocity 2
+}
+
+inline void kf_oplus(KfState& s, const double* d15) {   // pose (6), velocity, gyro bias, acc bias
+    double dt[3];
+    mat3_vec(s.Rwb, d15 + 3, dt);
+    for (int i = 0; i < 3; ++i) s.twb[i] += dt[i];
+    s.Rwb = mat3_mul(s.Rwb, exp_so3(d15));
+    for (int i = 0; i < 3; ++i) { s.v[i] += d15[6 + i]; s.bg[i] += d15[9 + i]; s.ba[i] += d15[12 + i]; }
+}
+
+}  // namespace
+
+extern "C" {
+
+// state: nKF x 21 doubles (Rwb row-major 9, twb 3, v 3, bg 3, ba 3), in/out.  fixed[nKF].  point nMP x 3 in/out.
+// Tcb: Rcb (9) tcb (3).  cam5: fx fy cx cy bf.  links: nL records (see liba_link in pyoracle.py).  Outputs as orc_lba.
+int orc_liba(int nKF, int nMP, int nE, int nL, double* state, const uint8_t* fixed, double* point, const int* ekf, const int* emp,
+             const double* obs, const double* invs2, const double* Tcb12, const double* cam5, const void* links_raw, double lambdaInit,
+             int maxIters, double* edge_chi2, double* link_chi2, double* stats) {
+    InertialProblem P;
+    P.nKF = nKF; P.nMP = nMP; P.nE = nE; P.nL = nL;
+    P.kf.resize(nKF);
+    for (int k = 0; k < nKF; ++k) {
+        const double* s = state + 21 * k;
+        for (int i = 0; i < 9; ++i) P.kf[k].Rwb.m[i] = s[i];
+        for (int i = 0; i < 3; ++i) { P.kf[k].twb[i] = s[9 + i]; P.kf[k].v[i] = s[12 + i]; P.kf[k].bg[i] = s[15 + i]; P.kf[k].ba[i] = s[18 + i]; }
+    }
+    P.point.assign(point, point + 3 * (size_t)nMP);
+    P.fixed = fixed; P.ekf = ekf; P.emp = emp; P.obs = obs; P.invs2 = invs2;
+    P.links = static_cast<const InertialLink*>(links_raw);
+    for (int i = 0; i < 9; ++i) P.Rcb.m[i] = Tcb12[i];
+    for (int i = 0; i < 3; ++i) P.tcb[i] = Tcb12[9 + i];
+    P.Rbc = mat3_T(P.Rcb);
+    mat3_vec(P.Rbc, P.tcb, P.tbc);
+    for (int i = 0; i < 3; ++i) P.tbc[i] = -P.tbc[i];
+    P.fx = cam5[0]; P.fy = cam5[1]; P.cx = cam5[2]; P.cy = cam5[3]; P.bf = cam5[4];
+    const double dM = (double)(float)std::sqrt(5.991), dS = (double)(float)std::sqrt(7.815), dI = std::sqrt(16.92);
+    const double sqM = (double)(float)(dM * dM), sqS = (double)(float)(dS * dS), sqI = (double)(float)(dI * dI);
+
+    std::vector<int> pidx(nKF, -1);
+    int nP = 0;
+    for (int k = 0; k < nKF; ++k) if (!fixed[k]) pidx[k] = nP++;
+    const int sp = 15 * nP, sl = 3 * nMP;
+    std::vector<double> Hpp((size_t)sp * sp), Hll((size_t)nMP * 9), W((size_t)nE * 18), b(sp + sl), x(sp + sl), err(nE, 0.0), lerr(nL * 3, 0.0);
+
+    auto link_errors = [&](const InertialLink& L, double* c3) {   // chi2 of the inertial, gyro-RW and acc-RW edges
+        double e9[9];
+        inertial(P, L, e9, nullptr);
+        double c = 0;
+        for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) c += e9[i] * L.info[9 * i + j] * e9[j];
+        c3[0] = c;
+        double cg = 0, ca = 0;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                cg += (P.kf[L.k2].bg[i] - P.kf[L.k1].bg[i]) * L.infoG[3 * i + j] * (P.kf[L.k2].bg[j] - P.kf[L.k1].bg[j]);
+                ca += (P.kf[L.k2].ba[i] - P.kf[L.k1].ba[i]) * L.infoA[3 * i + j] * (P.kf[L.k2].ba[j] - P.kf[L.k1].ba[j]);
+            }
+        c3[1] = cg; c3[2] = ca;
+    };
+    auto compute_errors = [&]() -> double {
+        double chi = 0;
+        for (int e = 0; e < nE; ++e) {
+            double r[3];
+            const int D = reproj(P, e, r, nullptr, nullptr);
+            const double c = invs2[e] * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+            err[e] = c;
+            double w;
+            chi += huber_rho(c, D == 2 ? dM : dS, D == 2 ? sqM : sqS, &w);
+        }
+        for (int l = 0; l < nL; ++l) {
+            double c3[3];
+            link_errors(P.links[l], c3);
+            for (int i = 0; i < 3; ++i) lerr[3 * l + i] = c3[i];
+            double w;
+            chi += (P.links[l].robust ? huber_rho(c3[0], dI, sqI, &w) : c3[0]) + c3[1] + c3[2];
+        }
+        return chi;
+    };
+    auto add_pp = [&](int r0, int c0, int nr, int nc, const double* M, int ld) {
+        for (int i = 0; i < nr; ++i) for (int j = 0; j < nc; ++j) Hpp[(size_t)(r0 + i) * sp + c0 + j] += M[i * ld + j];
+    };
+    auto build_system = [&]() {
+        std::fill(Hpp.begin(), Hpp.end(), 0.0);
+        std::fill(Hll.begin(), Hll.end(), 0.0);
+        std::fill(W.begin(), W.end(), 0.0);
+        std::fill(b.begin(), b.end(), 0.0);
+        for (int e = 0; e < nE; ++e) {
+            double r[3], Jp[9], Jx[18];
+            const int D = reproj(P, e, r, Jp, Jx);
+            const double c2 = invs2[e] * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+            double w;
+            huber_rho(c2, D == 2 ? dM : dS, D == 2 ? sqM : sqS, &w);
+            const double om = w * invs2[e];
+            const int mp = emp[e], pi = pidx[ekf[e]];
+            for (int i = 0; i < 3; ++i) {
+                for (int j = 0; j < 3; ++j) { double s = 0; for (int d = 0; d < D; ++d) s += Jp[3 * d + i] * Jp[3 * d + j]; Hll[9 * (size_t)mp + 3 * i + j] += om * s; }
+                double s = 0; for (int d = 0; d < D; ++d) s += Jp[3 * d + i] * r[d];
+                b[sp + 3 * mp + i] += -om * s;
+            }
+            if (pi >= 0) {
+                double M[36];
+                for (int i = 0; i < 6; ++i) {
+                    for (int j = 0; j < 6; ++j) { double s = 0; for (int d = 0; d < D; ++d) s += Jx[6 * d + i] * Jx[6 * d + j]; M[6 * i + j] = om * s; }
+                    for (int j = 0; j < 3; ++j) { double s = 0; for (int d = 0; d < D; ++d) s += Jx[6 * d + i] * Jp[3 * d + j]; W[18 * (size_t)e + 3 * i + j] = om * s; }
+                    double s = 0; for (int d = 0; d < D; ++d) s += Jx[6 * d + i] * r[d];
+                    b[15 * pi + i] += -om * s;
+                }
+                add_pp(15 * pi, 15 * pi, 6, 6, M, 6);
+            }
+        }
+        for (int l = 0; l < nL; ++l) {
+            const InertialLink& L = P.links[l];
+            double e9[9], J[9 * 30];
+            inertial(P, L, e9, J);
+            double c = 0;
+            for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) c += e9[i] * L.info[9 * i + j] * e9[j];
+            double w = 1.0;
+            if (L.robust) huber_rho(c, dI, sqI, &w);
+            // columns: k1 -> [0, 15), k2 pose -> [15, 21), k2 velocity -> [21, 24)
+            const int p1 = pidx[L.k1], p2 = pidx[L.k2];
+            auto col_of = [&](int c30) -> int {
+                if (c30 < 15) return p1 >= 0 ? 15 * p1 + c30 : -1;
+                if (c30 < 21) return p2 >= 0 ? 15 * p2 + (c30 - 15) : -1;
+                if (c30 < 24) return p2 >= 0 ? 15 * p2 + 6 + (c30 - 21) : -1;
+                return -1;
+            };
+            double OJ[9 * 30], Oe[9];   // w * Info * J, w * Info * e
+            for (int i = 0; i < 9; ++i) {
+                double s = 0; for (int k = 0; k < 9; ++k) s += L.info[9 * i + k] * e9[k];
+                Oe[i] = w * s;
+                for (int cidx = 0; cidx < 24; ++cidx) { double t = 0; for (int k = 0; k < 9; ++k) t += L.info[9 * i + k] * J[k * 30 + cidx]; OJ[i * 30 + cidx] = w * t; }
+            }
+            for (int ca = 0; ca < 24; ++ca) {
+                const int ga = col_of(ca);
+                if (ga < 0) continue;
+                double s = 0; for (int k = 0; k < 9; ++k) s += J[k * 30 + ca] * Oe[k];
+                b[ga] += -s;
+                for (int cb = 0; cb < 24; ++cb) {
+                    const int gb = col_of(cb);
+                    if (gb < 0) continue;
+                    double t = 0; for (int k = 0; k < 9; ++k) t += J[k * 30 + ca] * OJ[k * 30 + cb];
+                    Hpp[(size_t)ga * sp + gb] += t;
+                }
+            }
+            // random walks: e = b2 - b1, J1 = -I, J2 = I
+            for (int which = 0; which < 2; ++which) {
+                const double* info = which == 0 ? L.infoG : L.infoA;
+                const int off = which == 0 ? 9 : 12;
+                double e3[3], Oe3[3];
+                for (int i = 0; i < 3; ++i) e3[i] = which == 0 ? P.kf[L.k2].bg[i] - P.kf[L.k1].bg[i] : P.kf[L.k2].ba[i] - P.kf[L.k1].ba[i];
+                for (int i = 0; i < 3; ++i) Oe3[i] = info[3 * i] * e3[0] + info[3 * i + 1] * e3[1] + info[3 * i + 2] * e3[2];
+                for (int i = 0; i < 3; ++i) {
+                    if (p1 >= 0) b[15 * p1 + off + i] += Oe3[i];      // -J1^T Omega e = +Omega e
+                    if (p2 >= 0) b[15 * p2 + off + i] += -Oe3[i];
+                    for (int j = 0; j < 3; ++j) {
+                        if (p1 >= 0) Hpp[(size_t)(15 * p1 + off + i) * sp + 15 * p1 + off + j] += info[3 * i + j];
+                        if (p2 >= 0) Hpp[(size_t)(15 * p2 + off + i) * sp + 15 * p2 + off + j] += info[3 * i + j];
+                        if (p1 >= 0 && p2 >= 0) {
+                            Hpp[(size_t)(15 * p1 + off + i) * sp + 15 * p2 + off + j] -= info[3 * i + j];
+                            Hpp[(size_t)(15 * p2 + off + i) * sp + 15 * p1 + off + j] -= info[3 * i + j];
+                        }
+                    }
+                }
+            }
+        }
+    };
+    std::vector<std::vector<int>> byPoint(nMP);
+    for (int e = 0; e < nE; ++e) byPoint[emp[e]].push_back(e);
+    auto solve = [&](double lambda) -> bool {
+        std::vector<double> Hs(Hpp), bs(b.begin(), b.begin() + sp), Dinv((size_t)nMP * 9);
+        for (int j = 0; j < sp; ++j) Hs[(size_t)j * sp + j] += lambda;
+        for (int l = 0; l < nMP; ++l) {
+            double D[9];
+            for (int i = 0; i < 9; ++i) D[i] = Hll[9 * (size_t)l + i];
+            D[0] += lambda; D[4] += lambda; D[8] += lambda;
+            if (!inv3(D, &Dinv[9 * (size_t)l])) return false;
+            const double* Di = &Dinv[9 * (size_t)l];
+            const double* bl = &b[sp + 3 * l];
+            double Dib[3];
+            for (int i = 0; i < 3; ++i) Dib[i] = Di[3 * i] * bl[0] + Di[3 * i + 1] * bl[1] + Di[3 * i + 2] * bl[2];
+            for (int e1 : byPoint[l]) {
+                const int p1 = pidx[ekf[e1]];
+                if (p1 < 0) continue;
+                const double* W1 = &W[18 * (size_t)e1];
+                double WD[18];   // W1 (6x3) * Dinv
+                for (int i = 0; i < 6; ++i) for (int j = 0; j < 3; ++j) WD[3 * i + j] = W1[3 * i] * Di[j] + W1[3 * i + 1] * Di[3 + j] + W1[3 * i + 2] * Di[6 + j];
+                for (int i = 0; i < 6; ++i) bs[15 * p1 + i] -= W1[3 * i] * Dib[0] + W1[3 * i + 1] * Dib[1] + W1[3 * i + 2] * Dib[2];
+                for (int e2 : byPoint[l]) {
+                    const int p2 = pidx[ekf[e2]];
+                    if (p2 < 0) continue;
+                    const double* W2 = &W[18 * (size_t)e2];
+                    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j)
+                        Hs[(size_t)(15 * p1 + i) * sp + 15 * p2 + j] -= WD[3 * i] * W2[3 * j] + WD[3 * i + 1] * W2[3 * j + 1] + WD[3 * i + 2] * W2[3 * j + 2];
+                }
+            }
+        }
+        if (sp > 0 && !ldlt_solve(Hs, sp, bs.data(), x.data())) return false;
+        for (int l = 0; l < nMP; ++l) {
+            double c[3] = {b[sp + 3 * l], b[sp + 3 * l + 1], b[sp + 3 * l + 2]};
+            for (int e : byPoint[l]) {
+                const int p = pidx[ekf[e]];
+                if (p < 0) continue;
+                const double* Wm = &W[18 * (size_t)e];
+                for (int j = 0; j < 3; ++j) for (int i = 0; i < 6; ++i) c[j] -= Wm[3 * i + j] * x[15 * p + i];
+            }
+            const double* Di = &Dinv[9 * (size_t)l];
+            for (int i = 0; i < 3; ++i) x[sp + 3 * l + i] = Di[3 * i] * c[0] + Di[3 * i + 1] * c[1] + Di[3 * i + 2] * c[2];
+        }
+        return true;
+    };
+
+    double lambda = lambdaInit, ni = 2;
+    int nBad = 0, iters = 0, trials = 0;
+    double currentChi = 0, iniChi0 = 0;
+    for (int it = 0; it < maxIters; ++it) {
+        currentChi = compute_errors();
+        if (it == 0) iniChi0 = currentChi;
+        double tempChi = currentChi;
+        const double iniChi = currentChi;
+        build_system();
+        if (it == 0) {
+            if (!(lambdaInit > 0)) {
+                double md = 0;
+                for (int j = 0; j < sp; ++j) md = std::max(std::fabs(Hpp[(size_t)j * sp + j]), md);
+                for (int l = 0; l < nMP; ++l) for (int j = 0; j < 3; ++j) md = std::max(std::fabs(Hll[9 * (size_t)l + 4 * j]), md);
+                lambda = 1e-5 * md;
+            }
+            ni = 2;
+            nBad = 0;
+        }
+        double rho = 0;
+        int qmax = 0;
+        do {
+            const std::vector<KfState> savedKf = P.kf;
+            const std::vector<double> savedPoint = P.point;
+            const bool ok2 = solve(lambda);
+            for (int k = 0; k < nKF; ++k) if (pidx[k] >= 0) kf_oplus(P.kf[k], &x[15 * pidx[k]]);
+            for (int l = 0; l < nMP; ++l) for (int i = 0; i < 3; ++i) P.point[3 * l + i] += x[sp + 3 * l + i];
+            tempChi = compute_errors();
+            if (!ok2) tempChi = std::numeric_limits<double>::max();
+            rho = currentChi - tempChi;
+            double scale = 0;
+            for (int j = 0; j < sp + sl; ++j) scale += x[j] * (lambda * x[j] + b[j]);
+            scale += 1e-3;
+            rho /= scale;
+            if (rho > 0 && std::isfinite(tempChi)) {
+                double alpha = 1. - std::pow((2 * rho - 1), 3);
+                alpha = std::min(alpha, 2. / 3.);
+                lambda *= std::max(1. / 3., alpha);
+                ni = 2;
+                currentChi = tempChi;
+            } else {
+                lambda *= ni;
+                ni *= 2;
+                P.kf = savedKf;
+                P.point = savedPoint;
+            }
+            ++qmax;
+            ++trials;
+        } while (rho < 0 && qmax < 10);
+        ++iters;
+        if (qmax == 10 || rho == 0) break;
+        if ((iniChi - currentChi) * 1e3 < iniChi) ++nBad; else nBad = 0;
+        if (nBad >= 3) break;
+    }
+    for (int e = 0; e < nE; ++e) if (edge_chi2) edge_chi2[e] = err[e];
+    for (int l = 0; l < 3 * nL; ++l) if (link_chi2) link_chi2[l] = lerr[l];
+    for (int k = 0; k < nKF; ++k) {
+        double* s = state + 21 * k;
+        for (int i = 0; i < 9; ++i) s[i] = P.kf[k].Rwb.m[i];
+        for (int i = 0; i < 3; ++i) { s[9 + i] = P.kf[k].twb[i]; s[12 + i] = P.kf[k].v[i]; s[15 + i] = P.kf[k].bg[i]; s[18 + i] = P.kf[k].ba[i]; }
+    }
+    memcpy(point, P.point.data(), sizeof(double) * 3 * (size_t)nMP);
+    if (stats) { stats[0] = iters; stats[1] = lambda; stats[2] = currentChi; stats[3] = trials; stats[4] = iniChi0; }
+    return iters;
+}
+
+// test hooks: one EdgeInertial evaluated at the given states (error 9, Jacobian 9 x 30), and the ImuCamPose update
+int orc_inertial_link_size() { return (int)sizeof(InertialLink); }
+void orc_inertial_edge(const double* state2x21, const void* link_raw, double* e9, double* J270) {
+    InertialProblem P;
+    P.kf.resize(2);
+    for (int k = 0; k < 2; ++k) {
+        const double* s = state2x21 + 21 * k;
+        for (int i = 0; i < 9; ++i) P.kf[k].Rwb.m[i] = s[i];
+        for (int i = 0; i < 3; ++i) { P.kf[k].twb[i] = s[9 + i]; P.kf[k].v[i] = s[12 + i]; P.kf[k].bg[i] = s[15 + i]; P.kf[k].ba[i] = s[18 + i]; }
+    }
+    InertialLink L = *static_cast<const InertialLink*>(link_raw);
+    L.k1 = 0; L.k2 = 1;
+    inertial(P, L, e9, J270);
+}
+void orc_kf_oplus(double* state21, const double* d15) {
+    KfState s;
+    for (int i = 0; i < 9; ++i) s.Rwb.m[i] = state21[i];
+    for (int i = 0; i < 3; ++i) { s.twb[i] = state21[9 + i]; s.v[i] = state21[12 + i]; s.bg[i] = state21[15 + i]; s.ba[i] = state21[18 + i]; }
+    kf_oplus(s, d15);
+    for (int i = 0; i < 9; ++i) state21[i] = s.Rwb.m[i];
+    for (int i = 0; i < 3; ++i) { state21[9 + i] = s.twb[i]; state21[12 + i] = s.v[i]; state21[15 + i] = s.bg[i]; state21[18 + i] = s.ba[i]; }
+}
+}
+
+// test hook: one EdgeMono / EdgeStereo (inertial parametrisation) at a keyframe state: residual (3), d r / d X (9), d r / d pose (18)
+extern "C" int orc_liba_reproj(const double* state21, const double* Xw, const double* obs3, const double* Tcb12, const double* cam5,
+                               double* r3, double* Jp9, double* Jx18) {
+    InertialProblem P;
+    P.kf.resize(1);
+    for (int i = 0; i < 9; ++i) P.kf[0].Rwb.m[i] = state21[i];
+    for (int i = 0; i < 3; ++i) { P.kf[0].twb[i] = state21[9 + i]; P.kf[0].v[i] = 0; P.kf[0].bg[i] = 0; P.kf[0].ba[i] = 0; }
+    P.point.assign(Xw, Xw + 3);
+    const int ekf = 0, emp = 0;
+    const double w = 1.0;
+    P.ekf = &ekf; P.emp = &emp; P.obs = obs3; P.invs2 = &w;
+    for (int i = 0; i < 9; ++i) P.Rcb.m[i] = Tcb12[i];
+    for (int i = 0; i < 3; ++i) P.tcb[i] = Tcb12[9 + i];
+    P.Rbc = mat3_T(P.Rcb);
+    mat3_vec(P.Rbc, P.tcb, P.tbc);
+    for (int i = 0; i < 3; ++i) P.tbc[i] = -P.tbc[i];
+    P.fx = cam5[0]; P.fy = cam5[1]; P.cx = cam5[2]; P.cy = cam5[3]; P.bf = cam5[4];
+    return reproj(P, 0, r3, Jp9, Jx18);
+}

@@ -436,3 +436,72 @@ def update_normal_and_depth(centers, pos, ref_center, level, scale_factors):
     out, mx, mn = np.zeros(3, np.float32), np.zeros(1, np.float32), np.zeros(1, np.float32)
     L.orc_update_normal_and_depth(len(c), _p(c), _p(p), _p(r), int(level), _p(sf), len(sf), _p(out), _p(mx), _p(mn))
     return out, mx[0], mn[0]
+
+
+# ---- Optimizer::LocalInertialBA (oracle only so far) ------------------------------------------------------------
+LIBA_LINK = np.dtype([("k1", np.int32), ("k2", np.int32), ("robust", np.int32), ("_pad", np.int32), ("dt", np.float64),
+                      ("dR", np.float32, 9), ("dV", np.float32, 3), ("dP", np.float32, 3), ("JRg", np.float32, 9), ("JVg", np.float32, 9),
+                      ("JVa", np.float32, 9), ("JPg", np.float32, 9), ("JPa", np.float32, 9), ("blin", np.float32, 6),
+                      ("info", np.float64, 81), ("infoG", np.float64, 9), ("infoA", np.float64, 9)], align=False)
+
+
+def _liba_lib():
+    L = lib()
+    L.orc_inertial_link_size.restype = C.c_int
+    assert L.orc_inertial_link_size() == LIBA_LINK.itemsize, (L.orc_inertial_link_size(), LIBA_LINK.itemsize)
+    return L
+
+
+def liba(state, fixed, point, edge_kf, edge_mp, obs, inv_sigma2, Tcb12, cam5, links, lambda_init=1.0, max_iters=10):
+    """Optimizer::LocalInertialBA's g2o core restated (Optimizer.cc:2203-2812).  state: [nKF][21] = Rwb(9) twb v bg ba.
+    Returns dict(state, point, edge_chi2, link_chi2[nL][3], iterations, trials, lambda_, chi2, chi2_init)."""
+    L = _liba_lib()
+    L.orc_liba.restype = C.c_int
+    L.orc_liba.argtypes = [C.c_int] * 4 + [C.c_void_p] * 10 + [C.c_double, C.c_int] + [C.c_void_p] * 3
+    c = np.ascontiguousarray
+    st, pt = c(state, np.float64).copy(), c(point, np.float64).copy()
+    fx = c(fixed, np.uint8)
+    ekf, emp = c(edge_kf, np.int32), c(edge_mp, np.int32)
+    ob, w = c(obs, np.float64), c(inv_sigma2, np.float64)
+    T, cam = c(Tcb12, np.float64), c(cam5, np.float64)
+    lk = c(links, LIBA_LINK)
+    nE, nL = len(ekf), len(lk)
+    chi, lchi, stats = np.zeros(max(nE, 1)), np.zeros(max(3 * nL, 1)), np.zeros(8)
+    P = lambda a: _p(a) if a.size else None
+    it = L.orc_liba(len(st), len(pt), nE, nL, _p(st), _p(fx), P(pt), P(ekf), P(emp), P(ob), P(w), _p(T), _p(cam), P(lk), float(lambda_init),
+                    int(max_iters), _p(chi), _p(lchi), _p(stats))
+    return dict(state=st, point=pt, edge_chi2=chi[:nE], link_chi2=lchi[:3 * nL].reshape(nL, 3), iterations=it, trials=int(stats[3]),
+                lambda_=stats[1], chi2=stats[2], chi2_init=stats[4])
+
+
+def inertial_edge(state2, link):
+    """EdgeInertial::computeError / linearizeOplus at two keyframe states: (e9, J[9][24]) with columns pose1 v1 bg1 ba1 pose2 v2."""
+    L = _liba_lib()
+    L.orc_inertial_edge.restype = None
+    L.orc_inertial_edge.argtypes = [C.c_void_p] * 4
+    st = np.ascontiguousarray(state2, np.float64)
+    lk = np.ascontiguousarray(link, LIBA_LINK).reshape(1)
+    e, J = np.zeros(9), np.zeros(270)
+    L.orc_inertial_edge(_p(st), _p(lk), _p(e), _p(J))
+    return e, J.reshape(9, 30)[:, :24]
+
+
+def kf_oplus(state21, d15):
+    L = lib()
+    L.orc_kf_oplus.restype = None
+    L.orc_kf_oplus.argtypes = [C.c_void_p, C.c_void_p]
+    s, d = np.ascontiguousarray(state21, np.float64).copy(), np.ascontiguousarray(d15, np.float64)
+    L.orc_kf_oplus(_p(s), _p(d))
+    return s
+
+
+def liba_reproj(state21, Xw, obs3, Tcb12, cam5):
+    """EdgeMono / EdgeStereo of the inertial BA at one keyframe: (D, r[3], Jpoint[D][3], Jpose[D][6])."""
+    L = lib()
+    L.orc_liba_reproj.restype = C.c_int
+    L.orc_liba_reproj.argtypes = [C.c_void_p] * 8
+    c = lambda a: np.ascontiguousarray(a, np.float64)
+    s, X, o, T, cam = c(state21), c(Xw), c(obs3), c(Tcb12), c(cam5)
+    r, Jp, Jx = np.zeros(3), np.zeros(9), np.zeros(18)
+    D = L.orc_liba_reproj(_p(s), _p(X), _p(o), _p(T), _p(cam), _p(r), _p(Jp), _p(Jx))
+    return D, r, Jp.reshape(3, 3)[:D], Jx.reshape(3, 6)[:D]

@@ -1,0 +1,159 @@
+"""CPU tier: the LocalInertialBA oracle (the device side is not built yet).  Pins available without the reference:
+finite differences of EdgeInertial's analytic Jacobians under the vertices' own update rules, the noise-free fixed point, and
+recovery of a perturbed trajectory."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+G = np.array([0, 0, -float(np.float32(9.81))])
+
+
+def expm(w):
+    w = np.asarray(w, float)
+    t = np.linalg.norm(w)
+    W = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if t < 1e-9:
+        return np.eye(3) + W
+    return np.eye(3) + np.sin(t) / t * W + (1 - np.cos(t)) / t ** 2 * W @ W
+
+
+def make_trajectory(n_kf, rng, dt=0.25):
+    """Smooth body trajectory + exact preintegrated deltas between consecutive keyframes (zero bias, no noise)."""
+    states, links = [], []
+    R, p, v = expm(rng.normal(0, 0.2, 3)), rng.normal(0, 1, 3), rng.normal(0, 0.5, 3)
+    for k in range(n_kf):
+        states.append(np.concatenate([R.reshape(-1), p, v, np.zeros(3), np.zeros(3)]))
+        if k == n_kf - 1:
+            break
+        w, a = rng.normal(0, 0.3, 3), rng.normal(0, 1.0, 3)           # constant body rates over the interval
+        dR = expm(w * dt)
+        R2 = R @ dR
+        acc_w = R @ a                                                 # crude: world acceleration constant over the interval
+        v2 = v + (acc_w + G) * dt
+        p2 = p + v * dt + 0.5 * (acc_w + G) * dt * dt
+        dV = R.T @ (v2 - v - G * dt)
+        dP = R.T @ (p2 - p - v * dt - 0.5 * G * dt * dt)
+        lk = np.zeros(1, po.LIBA_LINK)[0]
+        lk["k1"], lk["k2"], lk["robust"], lk["dt"] = k, k + 1, 0, dt
+        lk["dR"], lk["dV"], lk["dP"] = dR.reshape(-1), dV, dP
+        lk["JRg"] = (-np.eye(3) * dt).reshape(-1)                     # plausible first-order bias Jacobians
+        lk["JVg"] = (rng.normal(0, 0.05, (3, 3))).reshape(-1)
+        lk["JVa"] = (-np.eye(3) * dt).reshape(-1)
+        lk["JPg"] = (rng.normal(0, 0.01, (3, 3))).reshape(-1)
+        lk["JPa"] = (-np.eye(3) * 0.5 * dt * dt).reshape(-1)
+        lk["blin"] = 0
+        A = rng.normal(size=(9, 9))
+        lk["info"] = (A @ A.T + 9 * np.eye(9)).reshape(-1) * 50
+        lk["infoG"] = (np.eye(3) * 1e4).reshape(-1)
+        lk["infoA"] = (np.eye(3) * 1e3).reshape(-1)
+        links.append(lk)
+        R, p, v = R2, p2, v2
+    return np.array(states), np.array(links, po.LIBA_LINK)
+
+
+def test_inertial_edge_jacobians_by_finite_differences():
+    rng = np.random.default_rng(0)
+    states, links = make_trajectory(2, rng)
+    states[0, 15:21] = rng.normal(0, 0.01, 6)          # non-zero biases so that the bias columns are exercised
+    states[1, 12:15] += rng.normal(0, 0.1, 3)          # off the fixed point: non-zero residual
+    states[1, :9] = (states[1, :9].reshape(3, 3) @ expm(rng.normal(0, 0.05, 3))).reshape(-1)
+    e0, J = po.inertial_edge(states, links[0])
+    assert np.abs(e0).max() > 1e-3
+    h = 1e-6
+    Jn = np.zeros((9, 24))
+    for c in range(24):
+        d1, d2 = np.zeros(15), np.zeros(15)
+        for sgn in (+1, -1):
+            s = states.copy()
+            if c < 15:
+                d = np.zeros(15); d[c] = sgn * h
+                s[0] = po.kf_oplus(s[0], d)
+            else:
+                d = np.zeros(15); d[c - 15] = sgn * h
+                s[1] = po.kf_oplus(s[1], d)
+            e, _ = po.inertial_edge(s, links[0])
+            Jn[:, c] += sgn * e / (2 * h)
+    # the float evaluation of the preintegrated deltas (ImuTypes.cc) limits the bias columns to ~1e-2 relative
+    assert np.abs(J[:, :9] - Jn[:, :9]).max() < 1e-5            # pose 1, velocity 1
+    assert np.abs(J[:, 15:24] - Jn[:, 15:24]).max() < 1e-5      # pose 2, velocity 2
+    assert np.abs(J[:, 9:15] - Jn[:, 9:15]).max() < 5e-2 * max(1.0, np.abs(J[:, 9:15]).max())
+
+
+def scene(n_kf=8, n_mp=400, seed=1, noise=0.0):
+    rng = np.random.default_rng(seed)
+    states, links = make_trajectory(n_kf, rng)
+    FX, FY, CX, CY, BF = 435.2, 435.2, 320.0, 240.0, 47.9
+    Rcb, tcb = expm([0.01, -0.02, 0.015]), np.array([0.05, -0.01, 0.02])
+    Tcb = np.concatenate([Rcb.reshape(-1), tcb])
+    pts, ekf, emp, obs = [], [], [], []
+    for j in range(n_mp):
+        k0 = rng.integers(0, n_kf)
+        Rwb, twb = states[k0, :9].reshape(3, 3), states[k0, 9:12]
+        Xc = np.array([rng.uniform(-2, 2), rng.uniform(-1.5, 1.5), rng.uniform(3, 10)])
+        Xb = Rcb.T @ (Xc - tcb)
+        Xw = Rwb @ Xb + twb
+        seen = 0
+        for k in range(n_kf):
+            Rwb, twb = states[k, :9].reshape(3, 3), states[k, 9:12]
+            Xc = Rcb @ (Rwb.T @ (Xw - twb)) + tcb
+            if Xc[2] < 0.5:
+                continue
+            u, v = FX * Xc[0] / Xc[2] + CX, FY * Xc[1] / Xc[2] + CY
+            if not (0 <= u < 640 and 0 <= v < 480):
+                continue
+            ur = u - BF / Xc[2] if rng.random() < 0.7 else -1.0
+            ekf.append(k); emp.append(len(pts)); obs.append([u + rng.normal(0, noise), v + rng.normal(0, noise), ur if ur < 0 else ur + rng.normal(0, noise)])
+            seen += 1
+        if seen >= 2:
+            pts.append(Xw)
+        else:
+            del ekf[len(ekf) - seen:], emp[len(emp) - seen:], obs[len(obs) - seen:]
+    fixed = np.zeros(n_kf, np.uint8)
+    fixed[0] = 1
+    return dict(state=states, links=links, Tcb=Tcb, cam5=[FX, FY, CX, CY, BF], point=np.array(pts), edge_kf=np.array(ekf, np.int32),
+                edge_mp=np.array(emp, np.int32), obs=np.array(obs), inv_sigma2=np.ones(len(ekf)), fixed=fixed)
+
+
+def test_noise_free_problem_is_a_fixed_point():
+    s = scene()
+    r = po.liba(s["state"], s["fixed"], s["point"], s["edge_kf"], s["edge_mp"], s["obs"], s["inv_sigma2"], s["Tcb"], s["cam5"], s["links"], 1.0, 10)
+    assert r["chi2_init"] < 1e-3                       # float storage of the preintegrated deltas leaves ~1e-7 residuals
+    assert np.abs(r["state"] - s["state"]).max() < 1e-5 and np.abs(r["point"] - s["point"]).max() < 1e-4
+
+
+def test_recovers_a_perturbed_trajectory():
+    s = scene(seed=2)
+    rng = np.random.default_rng(3)
+    st = s["state"].copy()
+    for k in range(1, len(st)):
+        st[k] = po.kf_oplus(st[k], np.concatenate([rng.normal(0, 0.01, 3), rng.normal(0, 0.03, 3), rng.normal(0, 0.05, 3), np.zeros(6)]))
+    pt = s["point"] + rng.normal(0, 0.05, s["point"].shape)
+    r = po.liba(st, s["fixed"], pt, s["edge_kf"], s["edge_mp"], s["obs"], s["inv_sigma2"], s["Tcb"], s["cam5"], s["links"], 1.0, 25)
+    assert r["chi2"] < 1e-3 * r["chi2_init"]
+    assert np.abs(r["state"][:, 9:12] - s["state"][:, 9:12]).max() < 2e-3          # positions
+    assert np.abs(r["state"][:, :9] - s["state"][:, :9]).max() < 1e-3              # rotations
+    assert np.abs(r["state"][:, 12:15] - s["state"][:, 12:15]).max() < 2e-2        # velocities
+    assert (r["state"][0] == s["state"][0]).all()                                  # the fixed keyframe is untouched
+
+
+@pytest.mark.parametrize("stereo", [False, True])
+def test_reprojection_jacobians_by_finite_differences(stereo):
+    rng = np.random.default_rng(5)
+    s = scene(n_kf=2, n_mp=5, seed=6)
+    st = s["state"][1]
+    Xw = s["point"][0] + rng.normal(0, 0.05, 3)
+    obs = np.array([300.0, 200.0, 290.0 if stereo else -1.0])
+    D, r0, Jp, Jx = po.liba_reproj(st, Xw, obs, s["Tcb"], s["cam5"])
+    assert D == (3 if stereo else 2)
+    h = 1e-6
+    for c in range(3):
+        d = np.zeros(3); d[c] = h
+        rp = po.liba_reproj(st, Xw + d, obs, s["Tcb"], s["cam5"])[1]
+        rm = po.liba_reproj(st, Xw - d, obs, s["Tcb"], s["cam5"])[1]
+        assert np.abs((rp - rm)[:D] / (2 * h) - Jp[:, c]).max() < 1e-4
+    for c in range(6):
+        d = np.zeros(15); d[c] = h
+        rp = po.liba_reproj(po.kf_oplus(st, d), Xw, obs, s["Tcb"], s["cam5"])[1]
+        rm = po.liba_reproj(po.kf_oplus(st, -d), Xw, obs, s["Tcb"], s["cam5"])[1]
+        assert np.abs((rp - rm)[:D] / (2 * h) - Jx[:, c]).max() < 1e-4
