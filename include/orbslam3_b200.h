@@ -514,6 +514,61 @@ orb_status orbp_update_normal_and_depth(orbx_handle* h, int32_t n_points, const 
                                         const float* world_pos, const float* ref_center, const int32_t* ref_level,
                                         float* normal_out, float* max_dist_out, float* min_dist_out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer::LocalInertialBA  (include/Optimizer.h:63, src/Optimizer.cc:2203-2812), single camera -- the numeric core
+ * `optimizer.optimize(opt_it)`: g2o Levenberg (user lambda 1e0, or 1e-2 when bLarge) over BlockSolverX with
+ * VertexPose / VertexVelocity / VertexGyroBias / VertexAccBias per keyframe, marginalised VertexSBAPointXYZ, EdgeMono /
+ * EdgeStereo (Huber sqrt(5.991) / sqrt(7.815)), EdgeInertial (+ optional Huber sqrt(16.92)), EdgeGyroRW, EdgeAccRW.
+ *
+ * STATUS: host-emulation-validated against the oracle (tests/test_liba_emul.py); NOT yet run on a GPU (round-1 GPU budget
+ * was spent before this row).  The shim builds the window (Optimizer.cc:2217-2340) and fills these arrays:
+ *   state[k]   Rwb (9, row-major) twb v bg ba of keyframe k  (ImuCamPose of VertexPose + the three additive vertices)
+ *   fixed[k]   1 for the N+1-th keyframe and the covisible lFixedKeyFrames (all four vertices setFixed)
+ *   links      one per consecutive pair with mpImuPreintegrated: float members of IMU::Preintegrated (dR dV dP JRg JVg JVa
+ *              JPg JPa, the bias b it was integrated at as bax bay baz bwx bwy bwz), dT, info = EdgeInertial's 9 x 9
+ *              information (G2oTypes.cc:575-586: inverse of C.block<9,9>(0,0) symmetrised, eigenvalues < 1e-12 zeroed; x 1e-2
+ *              for the oldest link i == N-1, Optimizer.cc:2467-2479), infoG / infoA = inverses of C.block<3,3>(9,9) / (12,12)
+ *              (Optimizer.cc:2486-2494); robust = 1 where the reference installs the Huber kernel (i == N-1 || bRecInit)
+ *   edges      as lba_problem (obs z < 0 => EdgeMono)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t k1, k2, robust, pad;
+    double dt;
+    float dR[9], dV[3], dP[3], JRg[9], JVg[9], JVa[9], JPg[9], JPa[9], bias[6];
+    double info[81], infoG[9], infoA[9];
+} liba_link;                       /* 1080 bytes */
+
+typedef struct {
+    int32_t n_kf, n_mp, n_edges, n_links;
+    const double* state;           /* [n_kf][21] */
+    const uint8_t* fixed;          /* [n_kf] */
+    const double* point;           /* [n_mp][3] */
+    const int32_t* edge_kf;        /* [n_edges] */
+    const int32_t* edge_mp;        /* [n_edges] */
+    const double* obs;             /* [n_edges][3] */
+    const double* inv_sigma2;      /* [n_edges] */
+    const liba_link* links;        /* [n_links] */
+    double Tcb[12];                /* Rcb (9, row-major) tcb (3): ImuCamPose::Rcb[0] / tcb[0] */
+    double fx, fy, cx, cy, bf;
+    double lambda_init;            /* 1e0 / 1e-2 (0 = g2o's automatic tau * max diagonal) */
+    int32_t max_iters;             /* opt_it: 10, or 4 when bLarge */
+} liba_problem;
+
+typedef struct {
+    double* state;                 /* [n_kf][21] optimised */
+    double* point;                 /* [n_mp][3] */
+    double* edge_chi2;             /* [n_edges] (may be NULL) */
+    double* link_chi2;             /* [n_links][3] inertial, gyro RW, acc RW (may be NULL) */
+    int32_t iterations, trials;
+    double lambda, chi2, chi2_initial;
+} liba_result;
+
+typedef struct liba_handle liba_handle;
+orb_status liba_create(int32_t device, liba_handle** out);
+void liba_destroy(liba_handle* h);
+/* independent windows, one CTA each */
+orb_status liba_solve(liba_handle* h, int32_t n_problems, const liba_problem* in, liba_result* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "lib", "liborbslam3_b200.so")
-SOURCES = ["extractor.cu", "stereo.cu", "matcher.cu", "triangulation.cu", "lba.cu", "poseopt.cu", "bow.cu", "mappoint.cu"]
+SOURCES = ["extractor.cu", "stereo.cu", "matcher.cu", "triangulation.cu", "lba.cu", "poseopt.cu", "bow.cu", "mappoint.cu", "liba.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -119,6 +119,24 @@ class lba_result(C.Structure):
         ("chi2_initial", C.c_double)]
 
 
+# liba_link of include/orbslam3_b200.h (1080 bytes)
+LIBA_LINK = np.dtype([("k1", "<i4"), ("k2", "<i4"), ("robust", "<i4"), ("pad", "<i4"), ("dt", "<f8"), ("dR", "<f4", 9), ("dV", "<f4", 3),
+                      ("dP", "<f4", 3), ("JRg", "<f4", 9), ("JVg", "<f4", 9), ("JVa", "<f4", 9), ("JPg", "<f4", 9), ("JPa", "<f4", 9),
+                      ("bias", "<f4", 6), ("info", "<f8", 81), ("infoG", "<f8", 9), ("infoA", "<f8", 9)])
+assert LIBA_LINK.itemsize == 1080
+
+
+class liba_problem(C.Structure):
+    _fields_ = [("n_kf", C.c_int32), ("n_mp", C.c_int32), ("n_edges", C.c_int32), ("n_links", C.c_int32)] + [
+        (n, C.c_void_p) for n in ("state", "fixed", "point", "edge_kf", "edge_mp", "obs", "inv_sigma2", "links")] + [
+        ("Tcb", C.c_double * 12)] + [(n, C.c_double) for n in ("fx", "fy", "cx", "cy", "bf", "lambda_init")] + [("max_iters", C.c_int32)]
+
+
+class liba_result(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("state", "point", "edge_chi2", "link_chi2")] + [
+        ("iterations", C.c_int32), ("trials", C.c_int32), ("lambda_", C.c_double), ("chi2", C.c_double), ("chi2_initial", C.c_double)]
+
+
 _lib = None
 _VP, _I, _F = C.c_void_p, C.c_int32, C.c_float
 _IP = C.POINTER(C.c_int32)
@@ -166,6 +184,9 @@ SIGNATURES = {
     "lba_destroy": (None, [_VP]),
     "lba_solve": (_I, [_VP, C.POINTER(lba_problem), C.POINTER(lba_result), _VP]),
     "lba_solve_batch": (_I, [_VP, _I, C.POINTER(lba_problem), C.POINTER(lba_result), _VP]),
+    "liba_create": (_I, [_I, C.POINTER(_VP)]),
+    "liba_destroy": (None, [_VP]),
+    "liba_solve": (_I, [_VP, _I, C.POINTER(liba_problem), C.POINTER(liba_result)]),
     "orbm_search_last_frame": (_I, [_VP, C.POINTER(orbm_camera), C.POINTER(orbm_last_queries), _F, _I, _VP, _VP]),
 }
 

@@ -1,0 +1,113 @@
+// liba.cu -- Optimizer::LocalInertialBA's numeric core on the device (include/orbslam3_b200.h, liba_*).
+// The algorithm lives in liba_core.cuh as barrier-separated SPMD phases shared with the CPU emulation harness; this file is
+// the launch wrapper: one CTA per window, everything for a window in one blob (liba_pack.h), fp64 throughout.
+// STATUS: cross-compiles for sm_100a and is validated on the host through tests/host_emul; first GPU run is pending.
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "liba_pack.h"
+
+using namespace orb;
+
+namespace {
+
+constexpr int LIBA_THREADS = 256;
+
+__global__ void __launch_bounds__(LIBA_THREADS) k_liba(const LibaDev* __restrict__ problems) {
+    __shared__ double s_red[LIBA_THREADS / 32];
+    LibaDev P = problems[blockIdx.x];
+    P.red = s_red;
+    liba_optimize(P);
+}
+
+}  // namespace
+
+struct liba_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint8_t* d_buf = nullptr;
+    size_t d_bytes = 0;
+    uint8_t* h_buf = nullptr;
+    size_t h_bytes = 0;
+};
+
+extern "C" orb_status liba_create(int32_t device, liba_handle** out) {
+    if (!out) return set_error(ORB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+        return set_error(ORB_ERR_NO_DEVICE, "no usable CUDA device (this library has no CPU fallback)");
+    ORB_CUDA(cudaSetDevice(device));
+    liba_handle* h = new liba_handle();
+    h->device = device;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return set_error(ORB_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    *out = h;
+    return ORB_OK;
+}
+
+extern "C" void liba_destroy(liba_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->d_buf) cudaFree(h->d_buf);
+    if (h->h_buf) cudaFreeHost(h->h_buf);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" orb_status liba_solve(liba_handle* h, int32_t n_problems, const liba_problem* in, liba_result* out) {
+    if (!h || !in || !out || n_problems < 0) return set_error(ORB_ERR_INVALID, "null argument");
+    if (n_problems == 0) return ORB_OK;
+    ORB_CUDA(cudaSetDevice(h->device));
+    for (int i = 0; i < n_problems; ++i) {
+        const liba_problem& p = in[i];
+        if (p.n_kf <= 0 || p.n_mp < 0 || p.n_edges < 0 || p.n_links < 0 || !p.state || !p.fixed || !out[i].state || !out[i].point ||
+            (p.n_mp && !p.point) || (p.n_edges && (!p.edge_kf || !p.edge_mp || !p.obs || !p.inv_sigma2)) || (p.n_links && !p.links))
+            return set_error(ORB_ERR_INVALID, "liba_problem: missing array");
+        for (int e = 0; e < p.n_edges; ++e)
+            if (p.edge_kf[e] < 0 || p.edge_kf[e] >= p.n_kf || p.edge_mp[e] < 0 || p.edge_mp[e] >= p.n_mp)
+                return set_error(ORB_ERR_INVALID, "liba_problem: edge index out of range");
+        for (int l = 0; l < p.n_links; ++l)
+            if (p.links[l].k1 < 0 || p.links[l].k1 >= p.n_kf || p.links[l].k2 < 0 || p.links[l].k2 >= p.n_kf)
+                return set_error(ORB_ERR_INVALID, "liba_problem: link index out of range");
+    }
+    // blob: [LibaDev x n] then per problem io | in | work
+    std::vector<LibaLayout> lay(n_problems);
+    std::vector<size_t> base(n_problems);
+    size_t total = ((sizeof(LibaDev) * (size_t)n_problems) + 255) & ~(size_t)255;
+    for (int i = 0; i < n_problems; ++i) {
+        lay[i] = liba_pack(in[i], nullptr, nullptr, nullptr);
+        base[i] = total;
+        total += (lay[i].total + 255) & ~(size_t)255;
+    }
+    if (total > h->d_bytes) {
+        if (h->d_buf) cudaFree(h->d_buf);
+        h->d_buf = nullptr; h->d_bytes = 0;
+        ORB_CUDA(cudaMalloc((void**)&h->d_buf, total + total / 4));
+        h->d_bytes = total + total / 4;
+    }
+    if (total > h->h_bytes) {
+        if (h->h_buf) cudaFreeHost(h->h_buf);
+        h->h_buf = nullptr; h->h_bytes = 0;
+        ORB_CUDA(cudaMallocHost((void**)&h->h_buf, total + total / 4));
+        h->h_bytes = total + total / 4;
+    }
+    LibaDev* hdev = reinterpret_cast<LibaDev*>(h->h_buf);
+    ORB_CUDA(cudaMemsetAsync(h->d_buf, 0, total, h->stream));
+    for (int i = 0; i < n_problems; ++i) liba_pack(in[i], h->h_buf + base[i], h->d_buf + base[i], &hdev[i]);
+    ORB_CUDA(cudaMemcpyAsync(h->d_buf, h->h_buf, sizeof(LibaDev) * (size_t)n_problems, cudaMemcpyHostToDevice, h->stream));
+    for (int i = 0; i < n_problems; ++i)
+        ORB_CUDA(cudaMemcpyAsync(h->d_buf + base[i], h->h_buf + base[i], lay[i].io_bytes + lay[i].in_bytes, cudaMemcpyHostToDevice, h->stream));
+    k_liba<<<n_problems, LIBA_THREADS, 0, h->stream>>>(reinterpret_cast<const LibaDev*>(h->d_buf));
+    ORB_CUDA(cudaGetLastError());
+    for (int i = 0; i < n_problems; ++i)
+        ORB_CUDA(cudaMemcpyAsync(h->h_buf + base[i], h->d_buf + base[i], lay[i].io_bytes, cudaMemcpyDeviceToHost, h->stream));
+    ORB_CUDA(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n_problems; ++i) liba_unpack(in[i], h->h_buf + base[i], hdev[i], h->d_buf + base[i], &out[i]);
+    return ORB_OK;
+}

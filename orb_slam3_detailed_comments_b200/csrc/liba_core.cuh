@@ -1,0 +1,613 @@
+// liba_core.cuh -- Optimizer::LocalInertialBA's numeric core (/root/reference/src/Optimizer.cc:2203-2812) as
+// barrier-separated SPMD phases, one CTA per problem.  Like quadtree_core.cuh, the identical source compiles for the
+// device (LIBA_PAR_FOR = thread-strided loop, LIBA_SYNC = __syncthreads, block reductions, double atomics) and for the
+// host (one "thread"), so tests/host_emul can run this very algorithm against the CPU oracle without a GPU.
+//
+// g2o graph being solved (single camera, Nleft == -1):
+//   vertices  VertexPose (ImuCamPose: twb += Rwb ut, Rwb = Rwb Exp(ur); G2oTypes.cc:221-244), VertexVelocity,
+//             VertexGyroBias, VertexAccBias per keyframe (15 parameters, fixed or free as a whole), VertexSBAPointXYZ
+//             per map point (marginalised)
+//   edges     EdgeMono / EdgeStereo (G2oTypes.cc:390-490), Huber sqrt(5.991) / sqrt(7.815)
+//             EdgeInertial (G2oTypes.cc:563-687), optional Huber sqrt(16.92); EdgeGyroRW / EdgeAccRW (G2oTypes.h:736-800)
+//   solver    OptimizationAlgorithmLevenberg with a user lambda, BlockSolverX: landmarks eliminated by the Schur complement,
+//             the reduced (15 nFree)^2 system factorised densely (LDL^T), gain ratio / lambda schedule / stop rules as g2o.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define LIBA_HD __host__ __device__ inline
+#else
+#define LIBA_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define LIBA_PAR_FOR(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
+#define LIBA_SYNC() __syncthreads()
+#define LIBA_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define LIBA_LEADER() (threadIdx.x == 0)
+#define LIBA_FLAG_SET(p) (*(p) = 1)
+#elif defined(LIBA_EMUL_THREADS)
+// tests/host_emul/liba_mt.cpp: N host threads play one CTA with REAL barriers and atomics, so ThreadSanitizer reports a missing
+// LIBA_SYNC (or a plain store that should be atomic) as a data race -- the device-only hazards, checked without a device.
+namespace orb {
+extern thread_local int liba_tid;
+extern int liba_nthreads;
+void liba_barrier();
+inline void liba_atomic_add(double* p, double v) {
+    unsigned long long* u = reinterpret_cast<unsigned long long*>(p);
+    unsigned long long old = __atomic_load_n(u, __ATOMIC_RELAXED), want;
+    do {
+        double d;
+        __builtin_memcpy(&d, &old, 8);
+        d += v;
+        __builtin_memcpy(&want, &d, 8);
+    } while (!__atomic_compare_exchange_n(u, &old, want, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+}
+}
+#define LIBA_PAR_FOR(i, n) for (int i = orb::liba_tid; i < (n); i += orb::liba_nthreads)
+#define LIBA_SYNC() orb::liba_barrier()
+#define LIBA_ATOMIC_ADD(p, v) orb::liba_atomic_add((p), (v))
+#define LIBA_LEADER() (orb::liba_tid == 0)
+#define LIBA_FLAG_SET(p) __atomic_store_n((p), 1, __ATOMIC_RELAXED)
+#else
+#define LIBA_PAR_FOR(i, n) for (int i = 0; i < (n); ++i)
+#define LIBA_SYNC() ((void)0)
+#define LIBA_ATOMIC_ADD(p, v) (*(p) += (v))
+#define LIBA_LEADER() (true)
+#define LIBA_FLAG_SET(p) (*(p) = 1)
+#endif
+
+namespace orb {
+
+struct LibaLink {   // == liba_link of include/orbslam3_b200.h
+    int k1, k2, robust, pad;
+    double dt;
+    float dR[9], dV[3], dP[3], JRg[9], JVg[9], JVa[9], JPg[9], JPa[9], bias[6];
+    double info[81], infoG[9], infoA[9];
+};
+
+struct LibaDev {
+    int nKF, nMP, nE, nL, nFree, sp;   // sp = 15 nFree
+    double* state;        // [nKF][21] Rwb(9) twb v bg ba
+    double* state_saved;
+    double* point;        // [nMP][3]
+    double* point_saved;
+    const int* pidx;      // [nKF] free index or -1
+    const int* ekf;       // [nE]
+    const int* emp;
+    const double* obs;    // [nE][3]
+    const double* invs2;  // [nE]
+    const int* pt_off;    // [nMP + 1] edges by point (CSR)
+    const int* pt_edge;   // [nE]
+    const LibaLink* links;
+    double Rcb[9], tcb[3], Rbc[9], tbc[3];
+    double fx, fy, cx, cy, bf;
+    double lambda_init;
+    int max_iters;
+    // work
+    double* err;          // [nE]
+    double* lerr;         // [nL][3]
+    double* Hpp;          // [sp][sp]
+    double* Hs;           // [sp][sp]
+    double* b;            // [sp + 3 nMP]
+    double* bs;           // [sp]
+    double* x;            // [sp + 3 nMP]
+    double* y;            // [sp]
+    double* Hll;          // [nMP][9]
+    double* Dinv;         // [nMP][9]
+    double* W;            // [nE][18]  pose(6) x point(3)
+    int* flag;            // [4] solver failure flag
+    double* red;          // reduction scratch (device: shared memory, 64 doubles)
+    // results
+    double* out_scalars;  // iterations, trials, lambda, chi2, chi2_initial
+};
+
+// ---- small fixed-size linear algebra -------------------------------------------------------------------------------
+LIBA_HD void m3_mul(const double* a, const double* b, double* c) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) c[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+}
+LIBA_HD void m3_T(const double* a, double* t) {
+    t[0] = a[0]; t[1] = a[3]; t[2] = a[6]; t[3] = a[1]; t[4] = a[4]; t[5] = a[7]; t[6] = a[2]; t[7] = a[5]; t[8] = a[8];
+}
+LIBA_HD void m3_vec(const double* a, const double* v, double* o) {
+    for (int i = 0; i < 3; ++i) o[i] = a[3 * i] * v[0] + a[3 * i + 1] * v[1] + a[3 * i + 2] * v[2];
+}
+LIBA_HD void m3_skew(const double* w, double* W) {
+    W[0] = 0; W[1] = -w[2]; W[2] = w[1]; W[3] = w[2]; W[4] = 0; W[5] = -w[0]; W[6] = -w[1]; W[7] = w[0]; W[8] = 0;
+}
+LIBA_HD void so3_exp(const double* w, double* R) {   // G2oTypes.cc:908-929 (NormalizeRotation omitted: ~1e-16)
+    const double d2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], d = sqrt(d2);
+    double W[9], W2[9];
+    m3_skew(w, W);
+    m3_mul(W, W, W2);
+    const double a = d < 1e-5 ? 1.0 : sin(d) / d, c = d < 1e-5 ? 0.5 : (1.0 - cos(d)) / d2;
+    for (int i = 0; i < 9; ++i) R[i] = ((i & 3) == 0 ? 1.0 : 0.0) + a * W[i] + c * W2[i];
+}
+LIBA_HD void so3_log(const double* R, double* w) {   // G2oTypes.cc:931-945
+    const double tr = R[0] + R[4] + R[8];
+    w[0] = (R[7] - R[5]) / 2; w[1] = (R[2] - R[6]) / 2; w[2] = (R[3] - R[1]) / 2;
+    const double costheta = (tr - 1.0) * 0.5;
+    if (costheta > 1 || costheta < -1) return;
+    const double theta = acos(costheta), s = sin(theta);
+    if (fabs(s) < 1e-5) return;
+    for (int i = 0; i < 3; ++i) w[i] = theta * w[i] / s;
+}
+LIBA_HD void so3_jr(const double* v, bool inverse, double* J) {   // G2oTypes.cc:947-985
+    const double d2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2], d = sqrt(d2);
+    for (int i = 0; i < 9; ++i) J[i] = (i & 3) == 0 ? 1.0 : 0.0;
+    if (d < 1e-5) return;
+    double W[9], W2[9];
+    m3_skew(v, W);
+    m3_mul(W, W, W2);
+    if (inverse) { const double c = 1.0 / d2 - (1.0 + cos(d)) / (2.0 * d * sin(d)); for (int i = 0; i < 9; ++i) J[i] += W[i] / 2 + W2[i] * c; }
+    else { const double a = (1.0 - cos(d)) / d2, c = (d - sin(d)) / (d2 * d); for (int i = 0; i < 9; ++i) J[i] += -W[i] * a + W2[i] * c; }
+}
+LIBA_HD bool m3_inv(const double* M, double* Mi) {
+    const double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
+    const double det = M[0] * c00 + M[1] * c01 + M[2] * c02;
+    if (!(fabs(det) > 0) || !isfinite(det)) return false;
+    const double id = 1.0 / det;
+    Mi[0] = c00 * id; Mi[1] = (M[2] * M[7] - M[1] * M[8]) * id; Mi[2] = (M[1] * M[5] - M[2] * M[4]) * id;
+    Mi[3] = c01 * id; Mi[4] = (M[0] * M[8] - M[2] * M[6]) * id; Mi[5] = (M[2] * M[3] - M[0] * M[5]) * id;
+    Mi[6] = c02 * id; Mi[7] = (M[1] * M[6] - M[0] * M[7]) * id; Mi[8] = (M[0] * M[4] - M[1] * M[3]) * id;
+    return true;
+}
+LIBA_HD double liba_huber(double e, double delta, double dsqr, double* w) {
+    if (e <= dsqr) { *w = 1.0; return e; }
+    const double s = sqrt(e);
+    *w = delta / s;
+    return 2 * s * delta - dsqr;
+}
+
+// block-wide sum / max: every thread receives the result (host: identity)
+LIBA_HD double liba_sum(const LibaDev& P, double v) {
+#if defined(__CUDA_ARCH__)
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) P.red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += P.red[w];
+    return s;
+#elif defined(LIBA_EMUL_THREADS)
+    liba_barrier();
+    P.red[liba_tid] = v;
+    liba_barrier();
+    double s = 0;
+    for (int w = 0; w < liba_nthreads; ++w) s += P.red[w];
+    return s;
+#else
+    (void)P;
+    return v;
+#endif
+}
+LIBA_HD double liba_max(const LibaDev& P, double v) {
+#if defined(__CUDA_ARCH__)
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) P.red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = P.red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) s = fmax(s, P.red[w]);
+    return s;
+#elif defined(LIBA_EMUL_THREADS)
+    liba_barrier();
+    P.red[liba_tid] = v;
+    liba_barrier();
+    double s = P.red[0];
+    for (int w = 1; w < liba_nthreads; ++w) s = fmax(s, P.red[w]);
+    return s;
+#else
+    (void)P;
+    return v;
+#endif
+}
+
+// ---- edges -----------------------------------------------------------------------------------------------------------
+LIBA_HD void liba_cam_pose(const LibaDev& P, const double* s, double* Rcw, double* tcw) {   // ImuCamPose::Update tail
+    double Rbw[9], tbw[3];
+    m3_T(s, Rbw);
+    m3_vec(Rbw, s + 9, tbw);
+    for (int i = 0; i < 3; ++i) tbw[i] = -tbw[i];
+    m3_mul(P.Rcb, Rbw, Rcw);
+    m3_vec(P.Rcb, tbw, tcw);
+    for (int i = 0; i < 3; ++i) tcw[i] += P.tcb[i];
+}
+
+// EdgeMono / EdgeStereo: residual r (3), optionally Jp (D x 3, point) and Jx (D x 6, pose).  Returns D.
+LIBA_HD int liba_reproj(const LibaDev& P, int e, double* r, double* Jp, double* Jx) {
+    double Rcw[9], tcw[3], Xc[3];
+    liba_cam_pose(P, P.state + 21 * (size_t)P.ekf[e], Rcw, tcw);
+    m3_vec(Rcw, P.point + 3 * (size_t)P.emp[e], Xc);
+    for (int i = 0; i < 3; ++i) Xc[i] += tcw[i];
+    const double* z = P.obs + 3 * (size_t)e;
+    const int D = z[2] < 0 ? 2 : 3;
+    const double u = P.fx * Xc[0] / Xc[2] + P.cx, v = P.fy * Xc[1] / Xc[2] + P.cy;
+    r[0] = z[0] - u;
+    r[1] = z[1] - v;
+    r[2] = D == 3 ? z[2] - (u - P.bf * (1 / Xc[2])) : 0.0;
+    if (Jp) {
+        double pj[9] = {P.fx / Xc[2], 0, -P.fx * Xc[0] / (Xc[2] * Xc[2]), 0, P.fy / Xc[2], -P.fy * Xc[1] / (Xc[2] * Xc[2]), 0, 0, 0};
+        if (D == 3) { pj[6] = pj[0]; pj[7] = pj[1]; pj[8] = pj[2] + P.bf * (1.0 / (Xc[2] * Xc[2])); }
+        double Xb[3];
+        m3_vec(P.Rbc, Xc, Xb);
+        for (int i = 0; i < 3; ++i) Xb[i] += P.tbc[i];
+        const double S[18] = {0, Xb[2], -Xb[1], 1, 0, 0, -Xb[2], 0, Xb[0], 0, 1, 0, Xb[1], -Xb[0], 0, 0, 0, 1};
+        for (int d = 0; d < D; ++d) {
+            double pr[3];
+            for (int c = 0; c < 3; ++c) {
+                Jp[3 * d + c] = -(pj[3 * d] * Rcw[c] + pj[3 * d + 1] * Rcw[3 + c] + pj[3 * d + 2] * Rcw[6 + c]);
+                pr[c] = pj[3 * d] * P.Rcb[c] + pj[3 * d + 1] * P.Rcb[3 + c] + pj[3 * d + 2] * P.Rcb[6 + c];
+            }
+            for (int c = 0; c < 6; ++c) Jx[6 * d + c] = pr[0] * S[c] + pr[1] * S[6 + c] + pr[2] * S[12 + c];
+        }
+    }
+    return D;
+}
+
+// EdgeInertial: e9 and (optionally) J, 9 x 24 over [pose1 6 | v1 3 | bg1 3 | ba1 3 | pose2 6 | v2 3]
+LIBA_HD void liba_inertial(const LibaDev& P, const LibaLink& L, double* e9, double* J) {
+    const double* s1 = P.state + 21 * (size_t)L.k1;
+    const double* s2 = P.state + 21 * (size_t)L.k2;
+    const double g[3] = {0, 0, -(double)9.81f};
+    float dbg[3], dba[3], wv[3];
+    for (int i = 0; i < 3; ++i) { dba[i] = (float)s1[18 + i] - L.bias[i]; dbg[i] = (float)s1[15 + i] - L.bias[3 + i]; }
+    for (int i = 0; i < 3; ++i) wv[i] = L.JRg[3 * i] * dbg[0] + L.JRg[3 * i + 1] * dbg[1] + L.JRg[3 * i + 2] * dbg[2];
+    const double wd[3] = {wv[0], wv[1], wv[2]};
+    double E[9], dR[9], dV[3], dP[3];
+    so3_exp(wd, E);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            dR[3 * i + j] = (double)(float)((double)L.dR[3 * i] * E[j] + (double)L.dR[3 * i + 1] * E[3 + j] + (double)L.dR[3 * i + 2] * E[6 + j]);
+    for (int i = 0; i < 3; ++i) {
+        dV[i] = (double)(float)(L.dV[i] + (L.JVg[3 * i] * dbg[0] + L.JVg[3 * i + 1] * dbg[1] + L.JVg[3 * i + 2] * dbg[2]) +
+                                (L.JVa[3 * i] * dba[0] + L.JVa[3 * i + 1] * dba[1] + L.JVa[3 * i + 2] * dba[2]));
+        dP[i] = (double)(float)(L.dP[i] + (L.JPg[3 * i] * dbg[0] + L.JPg[3 * i + 1] * dbg[1] + L.JPg[3 * i + 2] * dbg[2]) +
+                                (L.JPa[3 * i] * dba[0] + L.JPa[3 * i + 1] * dba[1] + L.JPa[3 * i + 2] * dba[2]));
+    }
+    double Rbw1[9], dRt[9], t1[9], eR[9], er[3];
+    m3_T(s1, Rbw1);
+    m3_T(dR, dRt);
+    m3_mul(dRt, Rbw1, t1);
+    m3_mul(t1, s2, eR);
+    so3_log(eR, er);
+    const double dt = L.dt;
+    double a[3], bb[3], ra[3], rb[3];
+    for (int i = 0; i < 3; ++i) {
+        a[i] = s2[12 + i] - s1[12 + i] - g[i] * dt;
+        bb[i] = s2[9 + i] - s1[9 + i] - s1[12 + i] * dt - g[i] * dt * dt / 2;
+    }
+    m3_vec(Rbw1, a, ra);
+    m3_vec(Rbw1, bb, rb);
+    for (int i = 0; i < 3; ++i) { e9[i] = er[i]; e9[3 + i] = ra[i] - dV[i]; e9[6 + i] = rb[i] - dP[i]; }
+    if (!J) return;
+    for (int i = 0; i < 9 * 24; ++i) J[i] = 0.0;
+#define LIBA_PUT(row0, col0, M, sgn) for (int i_ = 0; i_ < 3; ++i_) for (int j_ = 0; j_ < 3; ++j_) J[((row0) + i_) * 24 + (col0) + j_] = (sgn) * (M)[3 * i_ + j_];
+    double invJr[9], R2t[9], m1[9], m2[9], sk[9], I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    so3_jr(er, true, invJr);
+    m3_T(s2, R2t);
+    m3_mul(invJr, R2t, m1);
+    m3_mul(m1, s1, m2);
+    LIBA_PUT(0, 0, m2, -1.0)
+    m3_skew(ra, sk);
+    LIBA_PUT(3, 0, sk, 1.0)
+    m3_skew(rb, sk);
+    LIBA_PUT(6, 0, sk, 1.0)
+    LIBA_PUT(6, 3, I3, -1.0)
+    LIBA_PUT(3, 6, Rbw1, -1.0)
+    for (int i = 0; i < 9; ++i) m1[i] = Rbw1[i] * dt;
+    LIBA_PUT(6, 6, m1, -1.0)
+    double JRg[9], JVg[9], JPg[9], JVa[9], JPa[9], jw[3], eRt[9], Jr[9];
+    for (int i = 0; i < 9; ++i) { JRg[i] = L.JRg[i]; JVg[i] = L.JVg[i]; JPg[i] = L.JPg[i]; JVa[i] = L.JVa[i]; JPa[i] = L.JPa[i]; }
+    const double dbgd[3] = {dbg[0], dbg[1], dbg[2]};
+    m3_vec(JRg, dbgd, jw);
+    so3_jr(jw, false, Jr);
+    m3_T(eR, eRt);
+    m3_mul(invJr, eRt, m1);
+    m3_mul(m1, Jr, m2);
+    m3_mul(m2, JRg, m1);
+    LIBA_PUT(0, 9, m1, -1.0)
+    LIBA_PUT(3, 9, JVg, -1.0)
+    LIBA_PUT(6, 9, JPg, -1.0)
+    LIBA_PUT(3, 12, JVa, -1.0)
+    LIBA_PUT(6, 12, JPa, -1.0)
+    LIBA_PUT(0, 15, invJr, 1.0)
+    m3_mul(Rbw1, s2, m1);
+    LIBA_PUT(6, 18, m1, 1.0)
+    LIBA_PUT(3, 21, Rbw1, 1.0)
+#undef LIBA_PUT
+}
+
+LIBA_HD void liba_kf_oplus(double* s, const double* d15) {
+    double dt[3], E[9], R[9];
+    m3_vec(s, d15 + 3, dt);
+    for (int i = 0; i < 3; ++i) s[9 + i] += dt[i];
+    so3_exp(d15, E);
+    m3_mul(s, E, R);
+    for (int i = 0; i < 9; ++i) s[i] = R[i];
+    for (int i = 0; i < 3; ++i) { s[12 + i] += d15[6 + i]; s[15 + i] += d15[9 + i]; s[18 + i] += d15[12 + i]; }
+}
+
+// ---- phases -----------------------------------------------------------------------------------------------------------
+struct LibaHuber { double dM, dS, dI, sqM, sqS, sqI; };
+
+LIBA_HD LibaHuber liba_huber_constants() {
+    LibaHuber h;
+    h.dM = (double)(float)sqrt(5.991); h.dS = (double)(float)sqrt(7.815); h.dI = sqrt(16.92);
+    h.sqM = (double)(float)(h.dM * h.dM); h.sqS = (double)(float)(h.dS * h.dS); h.sqI = (double)(float)(h.dI * h.dI);
+    return h;
+}
+
+LIBA_HD void liba_link_chi2(const LibaDev& P, const LibaLink& L, double* c3) {
+    double e9[9];
+    liba_inertial(P, L, e9, nullptr);
+    double c = 0;
+    for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) c += e9[i] * L.info[9 * i + j] * e9[j];
+    c3[0] = c;
+    const double* s1 = P.state + 21 * (size_t)L.k1;
+    const double* s2 = P.state + 21 * (size_t)L.k2;
+    double cg = 0, ca = 0;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            cg += (s2[15 + i] - s1[15 + i]) * L.infoG[3 * i + j] * (s2[15 + j] - s1[15 + j]);
+            ca += (s2[18 + i] - s1[18 + i]) * L.infoA[3 * i + j] * (s2[18 + j] - s1[18 + j]);
+        }
+    c3[1] = cg; c3[2] = ca;
+}
+
+LIBA_HD double liba_compute_errors(const LibaDev& P, const LibaHuber& H) {   // computeActiveErrors + activeRobustChi2
+    double chi = 0;
+    LIBA_PAR_FOR(e, P.nE) {
+        double r[3];
+        const int D = liba_reproj(P, e, r, nullptr, nullptr);
+        const double c = P.invs2[e] * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+        P.err[e] = c;
+        double w;
+        chi += liba_huber(c, D == 2 ? H.dM : H.dS, D == 2 ? H.sqM : H.sqS, &w);
+    }
+    LIBA_PAR_FOR(l, P.nL) {
+        double c3[3], w;
+        liba_link_chi2(P, P.links[l], c3);
+        for (int i = 0; i < 3; ++i) P.lerr[3 * l + i] = c3[i];
+        chi += (P.links[l].robust ? liba_huber(c3[0], H.dI, H.sqI, &w) : c3[0]) + c3[1] + c3[2];
+    }
+    return liba_sum(P, chi);
+}
+
+LIBA_HD void liba_build(const LibaDev& P, const LibaHuber& H) {   // linearizeOplus + constructQuadraticForm of every edge
+    const int sp = P.sp;
+    LIBA_PAR_FOR(i, sp * sp) P.Hpp[i] = 0.0;
+    LIBA_PAR_FOR(i, sp) P.b[i] = 0.0;
+    LIBA_SYNC();
+    LIBA_PAR_FOR(l, P.nMP) {     // a thread owns a map point: H_ll and b_l in registers, pose terms by atomics
+        double hl[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
+        for (int k = P.pt_off[l]; k < P.pt_off[l + 1]; ++k) {
+            const int e = P.pt_edge[k];
+            double r[3], Jp[9], Jx[18];
+            const int D = liba_reproj(P, e, r, Jp, Jx);
+            const double c2 = P.invs2[e] * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+            double w;
+            liba_huber(c2, D == 2 ? H.dM : H.dS, D == 2 ? H.sqM : H.sqS, &w);
+            const double om = w * P.invs2[e];
+            for (int i = 0; i < 3; ++i) {
+                for (int j = 0; j < 3; ++j) { double s = 0; for (int d = 0; d < D; ++d) s += Jp[3 * d + i] * Jp[3 * d + j]; hl[3 * i + j] += om * s; }
+                double s = 0; for (int d = 0; d < D; ++d) s += Jp[3 * d + i] * r[d];
+                bl[i] += -om * s;
+            }
+            const int pi = P.pidx[P.ekf[e]];
+            double* We = P.W + 18 * (size_t)e;
+            for (int i = 0; i < 6; ++i) {
+                for (int j = 0; j < 3; ++j) { double s = 0; for (int d = 0; d < D; ++d) s += Jx[6 * d + i] * Jp[3 * d + j]; We[3 * i + j] = pi >= 0 ? om * s : 0.0; }
+                if (pi < 0) continue;
+                for (int j = 0; j < 6; ++j) { double s = 0; for (int d = 0; d < D; ++d) s += Jx[6 * d + i] * Jx[6 * d + j]; LIBA_ATOMIC_ADD(&P.Hpp[(size_t)(15 * pi + i) * sp + 15 * pi + j], om * s); }
+                double s = 0; for (int d = 0; d < D; ++d) s += Jx[6 * d + i] * r[d];
+                LIBA_ATOMIC_ADD(&P.b[15 * pi + i], -om * s);
+            }
+        }
+        for (int i = 0; i < 9; ++i) P.Hll[9 * (size_t)l + i] = hl[i];
+        for (int i = 0; i < 3; ++i) P.b[sp + 3 * l + i] = bl[i];
+    }
+    LIBA_PAR_FOR(l, P.nL) {      // inertial link + the two random walks
+        const LibaLink& L = P.links[l];
+        double e9[9], J[9 * 24], OJ[9 * 24], Oe[9];
+        liba_inertial(P, L, e9, J);
+        double c = 0;
+        for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) c += e9[i] * L.info[9 * i + j] * e9[j];
+        double w = 1.0;
+        if (L.robust) liba_huber(c, H.dI, H.sqI, &w);
+        const int p1 = P.pidx[L.k1], p2 = P.pidx[L.k2];
+        for (int i = 0; i < 9; ++i) {
+            double s = 0; for (int k = 0; k < 9; ++k) s += L.info[9 * i + k] * e9[k];
+            Oe[i] = w * s;
+            for (int cc = 0; cc < 24; ++cc) { double t = 0; for (int k = 0; k < 9; ++k) t += L.info[9 * i + k] * J[k * 24 + cc]; OJ[i * 24 + cc] = w * t; }
+        }
+        for (int ca = 0; ca < 24; ++ca) {
+            const int ga = ca < 15 ? (p1 >= 0 ? 15 * p1 + ca : -1) : (p2 >= 0 ? 15 * p2 + (ca - 15) : -1);   // columns 15..23 = pose2 (6), v2 (3)
+            if (ga < 0) continue;
+            double s = 0; for (int k = 0; k < 9; ++k) s += J[k * 24 + ca] * Oe[k];
+            LIBA_ATOMIC_ADD(&P.b[ga], -s);
+            for (int cb = 0; cb < 24; ++cb) {
+                const int gb = cb < 15 ? (p1 >= 0 ? 15 * p1 + cb : -1) : (p2 >= 0 ? 15 * p2 + (cb - 15) : -1);
+                if (gb < 0) continue;
+                double t = 0; for (int k = 0; k < 9; ++k) t += J[k * 24 + ca] * OJ[k * 24 + cb];
+                LIBA_ATOMIC_ADD(&P.Hpp[(size_t)ga * sp + gb], t);
+            }
+        }
+        const double* s1 = P.state + 21 * (size_t)L.k1;
+        const double* s2 = P.state + 21 * (size_t)L.k2;
+        for (int which = 0; which < 2; ++which) {      // e = b2 - b1, J1 = -I, J2 = I
+            const double* info = which == 0 ? L.infoG : L.infoA;
+            const int off = which == 0 ? 9 : 12, so = which == 0 ? 15 : 18;
+            double e3[3], Oe3[3];
+            for (int i = 0; i < 3; ++i) e3[i] = s2[so + i] - s1[so + i];
+            for (int i = 0; i < 3; ++i) Oe3[i] = info[3 * i] * e3[0] + info[3 * i + 1] * e3[1] + info[3 * i + 2] * e3[2];
+            for (int i = 0; i < 3; ++i) {
+                if (p1 >= 0) LIBA_ATOMIC_ADD(&P.b[15 * p1 + off + i], Oe3[i]);
+                if (p2 >= 0) LIBA_ATOMIC_ADD(&P.b[15 * p2 + off + i], -Oe3[i]);
+                for (int j = 0; j < 3; ++j) {
+                    if (p1 >= 0) LIBA_ATOMIC_ADD(&P.Hpp[(size_t)(15 * p1 + off + i) * sp + 15 * p1 + off + j], info[3 * i + j]);
+                    if (p2 >= 0) LIBA_ATOMIC_ADD(&P.Hpp[(size_t)(15 * p2 + off + i) * sp + 15 * p2 + off + j], info[3 * i + j]);
+                    if (p1 >= 0 && p2 >= 0) {
+                        LIBA_ATOMIC_ADD(&P.Hpp[(size_t)(15 * p1 + off + i) * sp + 15 * p2 + off + j], -info[3 * i + j]);
+                        LIBA_ATOMIC_ADD(&P.Hpp[(size_t)(15 * p2 + off + i) * sp + 15 * p1 + off + j], -info[3 * i + j]);
+                    }
+                }
+            }
+        }
+    }
+    LIBA_SYNC();
+}
+
+// (H + lambda I) x = b through the Schur complement on the landmarks; false on a singular block / pivot
+LIBA_HD bool liba_solve_system(const LibaDev& P, double lambda) {
+    const int sp = P.sp;
+    LIBA_PAR_FOR(i, sp * sp) P.Hs[i] = P.Hpp[i] + ((i / sp) == (i % sp) ? lambda : 0.0);
+    LIBA_PAR_FOR(i, sp) P.bs[i] = P.b[i];
+    if (LIBA_LEADER()) P.flag[0] = 0;
+    LIBA_SYNC();
+    LIBA_PAR_FOR(l, P.nMP) {
+        double D[9], Di[9];
+        for (int i = 0; i < 9; ++i) D[i] = P.Hll[9 * (size_t)l + i];
+        D[0] += lambda; D[4] += lambda; D[8] += lambda;
+        if (!m3_inv(D, Di)) { LIBA_FLAG_SET(&P.flag[0]); continue; }
+        for (int i = 0; i < 9; ++i) P.Dinv[9 * (size_t)l + i] = Di[i];
+        const double* bl = P.b + sp + 3 * l;
+        double Dib[3];
+        for (int i = 0; i < 3; ++i) Dib[i] = Di[3 * i] * bl[0] + Di[3 * i + 1] * bl[1] + Di[3 * i + 2] * bl[2];
+        for (int k1 = P.pt_off[l]; k1 < P.pt_off[l + 1]; ++k1) {
+            const int e1 = P.pt_edge[k1], p1 = P.pidx[P.ekf[e1]];
+            if (p1 < 0) continue;
+            const double* W1 = P.W + 18 * (size_t)e1;
+            double WD[18];
+            for (int i = 0; i < 6; ++i) for (int j = 0; j < 3; ++j) WD[3 * i + j] = W1[3 * i] * Di[j] + W1[3 * i + 1] * Di[3 + j] + W1[3 * i + 2] * Di[6 + j];
+            for (int i = 0; i < 6; ++i) LIBA_ATOMIC_ADD(&P.bs[15 * p1 + i], -(W1[3 * i] * Dib[0] + W1[3 * i + 1] * Dib[1] + W1[3 * i + 2] * Dib[2]));
+            for (int k2 = P.pt_off[l]; k2 < P.pt_off[l + 1]; ++k2) {
+                const int e2 = P.pt_edge[k2], p2 = P.pidx[P.ekf[e2]];
+                if (p2 < 0) continue;
+                const double* W2 = P.W + 18 * (size_t)e2;
+                for (int i = 0; i < 6; ++i)
+                    for (int j = 0; j < 6; ++j)
+                        LIBA_ATOMIC_ADD(&P.Hs[(size_t)(15 * p1 + i) * sp + 15 * p2 + j], -(WD[3 * i] * W2[3 * j] + WD[3 * i + 1] * W2[3 * j + 1] + WD[3 * i + 2] * W2[3 * j + 2]));
+            }
+        }
+    }
+    LIBA_SYNC();
+    // dense LDL^T of Hs (upper triangle read, right-looking): after step j row j holds D_j at (j,j) and L(i,j) at (j,i), i > j
+    for (int j = 0; j < sp; ++j) {
+        const double dj = P.Hs[(size_t)j * sp + j];
+        if (!(fabs(dj) > 0) || !isfinite(dj)) { if (LIBA_LEADER()) LIBA_FLAG_SET(&P.flag[0]); break; }   // uniform: every thread reads the same dj
+        const int m = sp - j - 1;
+        LIBA_PAR_FOR(t, m * m) {        // trailing update with the not-yet-scaled row j:  A(i,k) -= A(j,i) A(j,k) / d_j, k >= i
+            const int i = j + 1 + t / m, k = j + 1 + t % m;
+            if (k >= i) P.Hs[(size_t)i * sp + k] -= P.Hs[(size_t)j * sp + i] * P.Hs[(size_t)j * sp + k] / dj;
+        }
+        LIBA_SYNC();
+        LIBA_PAR_FOR(t, m) P.Hs[(size_t)j * sp + j + 1 + t] /= dj;   // L(j+1+t, j)
+        LIBA_SYNC();
+    }
+    LIBA_SYNC();
+    const bool failed = P.flag[0] != 0;
+    if (!failed && sp > 0) {
+        // forward: y = L^-1 bs ; diagonal ; backward: x = L^-T y     (column-oriented, one column per barrier)
+        LIBA_PAR_FOR(i, sp) P.y[i] = P.bs[i];
+        LIBA_SYNC();
+        for (int j = 0; j < sp; ++j) {
+            const double yj = P.y[j];
+            LIBA_PAR_FOR(t, sp - j - 1) P.y[j + 1 + t] -= P.Hs[(size_t)j * sp + j + 1 + t] * yj;
+            LIBA_SYNC();
+        }
+        LIBA_PAR_FOR(i, sp) P.y[i] /= P.Hs[(size_t)i * sp + i];
+        LIBA_SYNC();
+        for (int j = sp - 1; j >= 0; --j) {
+            const double xj = P.y[j];
+            LIBA_PAR_FOR(t, j) P.y[t] -= P.Hs[(size_t)t * sp + j] * xj;   // L(j, t) lives at (t, j)
+            LIBA_SYNC();
+        }
+        LIBA_PAR_FOR(i, sp) P.x[i] = P.y[i];
+        LIBA_SYNC();
+        LIBA_PAR_FOR(l, P.nMP) {
+            double c[3] = {P.b[sp + 3 * l], P.b[sp + 3 * l + 1], P.b[sp + 3 * l + 2]};
+            for (int k = P.pt_off[l]; k < P.pt_off[l + 1]; ++k) {
+                const int e = P.pt_edge[k], p = P.pidx[P.ekf[e]];
+                if (p < 0) continue;
+                const double* Wm = P.W + 18 * (size_t)e;
+                for (int j = 0; j < 3; ++j) for (int i = 0; i < 6; ++i) c[j] -= Wm[3 * i + j] * P.x[15 * p + i];
+            }
+            const double* Di = P.Dinv + 9 * (size_t)l;
+            for (int i = 0; i < 3; ++i) P.x[sp + 3 * l + i] = Di[3 * i] * c[0] + Di[3 * i + 1] * c[1] + Di[3 * i + 2] * c[2];
+        }
+        LIBA_SYNC();
+    }
+    return !failed;
+}
+
+// the whole optimisation: g2o SparseOptimizer::optimize(max_iters) over OptimizationAlgorithmLevenberg
+LIBA_HD void liba_optimize(const LibaDev& P) {
+    const LibaHuber H = liba_huber_constants();
+    const int sp = P.sp, sl = 3 * P.nMP;
+    double lambda = P.lambda_init, ni = 2, currentChi = 0, iniChi0 = 0;
+    int nBad = 0, iters = 0, trials = 0;
+    for (int it = 0; it < P.max_iters; ++it) {
+        currentChi = liba_compute_errors(P, H);
+        if (it == 0) iniChi0 = currentChi;
+        double tempChi = currentChi;
+        const double iniChi = currentChi;
+        liba_build(P, H);
+        if (it == 0) {
+            if (!(P.lambda_init > 0)) {      // computeLambdaInit: tau * max diagonal over all vertices
+                double md = 0;
+                LIBA_PAR_FOR(j, sp) md = fmax(md, fabs(P.Hpp[(size_t)j * sp + j]));
+                LIBA_PAR_FOR(l, P.nMP) for (int j = 0; j < 3; ++j) md = fmax(md, fabs(P.Hll[9 * (size_t)l + 4 * j]));
+                lambda = 1e-5 * liba_max(P, md);
+            }
+            ni = 2;
+            nBad = 0;
+        }
+        double rho = 0;
+        int qmax = 0;
+        do {
+            LIBA_PAR_FOR(i, 21 * P.nKF) P.state_saved[i] = P.state[i];      // push
+            LIBA_PAR_FOR(i, sl) P.point_saved[i] = P.point[i];
+            LIBA_SYNC();
+            const bool ok2 = liba_solve_system(P, lambda);
+            LIBA_PAR_FOR(k, P.nKF) if (P.pidx[k] >= 0) liba_kf_oplus(P.state + 21 * (size_t)k, P.x + 15 * P.pidx[k]);
+            LIBA_PAR_FOR(i, sl) P.point[i] += P.x[sp + i];
+            LIBA_SYNC();
+            tempChi = liba_compute_errors(P, H);
+            if (!ok2) tempChi = 1.7976931348623157e308;
+            double sc = 0;
+            LIBA_PAR_FOR(j, sp + sl) sc += P.x[j] * (lambda * P.x[j] + P.b[j]);
+            const double scale = liba_sum(P, sc) + 1e-3;
+            rho = (currentChi - tempChi) / scale;
+            if (rho > 0 && isfinite(tempChi)) {
+                double alpha = 2 * rho - 1;
+                alpha = 1. - alpha * alpha * alpha;
+                alpha = fmin(alpha, 2. / 3.);
+                lambda *= fmax(1. / 3., alpha);
+                ni = 2;
+                currentChi = tempChi;
+            } else {
+                lambda *= ni;
+                ni *= 2;
+                LIBA_SYNC();
+                LIBA_PAR_FOR(i, 21 * P.nKF) P.state[i] = P.state_saved[i];  // pop
+                LIBA_PAR_FOR(i, sl) P.point[i] = P.point_saved[i];
+                LIBA_SYNC();
+            }
+            ++qmax;
+            ++trials;
+        } while (rho < 0 && qmax < 10);
+        ++iters;
+        if (qmax == 10 || rho == 0) break;
+        if ((iniChi - currentChi) * 1e3 < iniChi) ++nBad; else nBad = 0;
+        if (nBad >= 3) break;
+    }
+    if (LIBA_LEADER()) {
+        P.out_scalars[0] = iters; P.out_scalars[1] = trials; P.out_scalars[2] = lambda; P.out_scalars[3] = currentChi; P.out_scalars[4] = iniChi0;
+    }
+    LIBA_SYNC();
+}
+
+}  // namespace orb

@@ -124,3 +124,67 @@ def PoseOptimizationFrames(extractor, frame_image, pose, world_pos, cam5, featur
         out = (np.zeros((nf, 7), np.float64), None if total_rows is None else np.zeros(max(total_rows, 1), np.uint8), np.zeros(nf, np.int32))
     N.check(L.orbo_pose_optimization_frames(extractor._h, C.byref(m), P(out[0]), P(out[1]), P(out[2])))
     return out
+
+
+def pack_inertial_problem(pr, lambda_init, max_iters, keep):
+    """dict(state[nKF][21], fixed, point, edge_kf, edge_mp, obs, inv_sigma2, links (N.LIBA_LINK records), Tcb[12], cam5) ->
+    (liba_problem, liba_result, out dict).  `keep` receives the arrays the structs point into."""
+    c = np.ascontiguousarray
+    arrs = dict(state=c(pr["state"], np.float64), fixed=c(pr["fixed"], np.uint8), point=c(pr["point"], np.float64).reshape(-1, 3),
+                edge_kf=c(pr["edge_kf"], np.int32), edge_mp=c(pr["edge_mp"], np.int32), obs=c(pr["obs"], np.float64).reshape(-1, 3),
+                inv_sigma2=c(pr["inv_sigma2"], np.float64), links=c(np.asarray(pr["links"]).view(N.LIBA_LINK) if
+                                                                       np.asarray(pr["links"]).dtype.itemsize == N.LIBA_LINK.itemsize
+                                                                       else pr["links"], N.LIBA_LINK).reshape(-1))
+    ne, nl = len(arrs["edge_kf"]), len(arrs["links"])
+    out = dict(state=np.zeros_like(arrs["state"]), point=np.zeros_like(arrs["point"]), edge_chi2=np.zeros(max(ne, 1)),
+               link_chi2=np.zeros((max(nl, 1), 3)))
+    keep.append((arrs, out))
+    P = lambda a: N.ptr(a) if a.size else None
+    p = N.liba_problem(len(arrs["state"]), len(arrs["point"]), ne, nl, N.ptr(arrs["state"]), N.ptr(arrs["fixed"]), P(arrs["point"]),
+                       P(arrs["edge_kf"]), P(arrs["edge_mp"]), P(arrs["obs"]), P(arrs["inv_sigma2"]), P(arrs["links"]),
+                       (C.c_double * 12)(*np.asarray(pr["Tcb"], np.float64).reshape(-1).tolist()),
+                       *np.asarray(pr["cam5"], np.float64).tolist(), float(lambda_init), int(max_iters))
+    r = N.liba_result(N.ptr(out["state"]), N.ptr(out["point"]), N.ptr(out["edge_chi2"]), N.ptr(out["link_chi2"]), 0, 0, 0.0, 0.0, 0.0)
+    return p, r, out
+
+
+def finish_inertial_result(pr_arrays, out, r):
+    ne, nl = len(pr_arrays["edge_kf"]), len(pr_arrays["links"])
+    out["edge_chi2"] = out["edge_chi2"][:ne]
+    out["link_chi2"] = out["link_chi2"][:nl]
+    out.update(iterations=r.iterations, trials=r.trials, lambda_=r.lambda_, chi2=r.chi2, chi2_init=r.chi2_initial)
+    return out
+
+
+class InertialOptimizer:
+    """Optimizer::LocalInertialBA's numeric core (include/Optimizer.h:63, src/Optimizer.cc:2203-2812) over the flat liba_problem
+    layout, one CTA per window.  Host-emulation-validated; first GPU run pending."""
+
+    def __init__(self, device=0):
+        self._L = N.lib()
+        self._h = C.c_void_p()
+        N.check(self._L.liba_create(device, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.liba_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def LocalInertialBABatch(self, problems, lambda_init=1.0, max_iters=10):
+        keep, ps, rs, outs = [], [], [], []
+        for pr in problems:
+            p, r, o = pack_inertial_problem(pr, lambda_init, max_iters, keep)
+            ps.append(p); rs.append(r); outs.append(o)
+        Pa = (N.liba_problem * len(ps))(*ps)
+        Ra = (N.liba_result * len(rs))(*rs)
+        N.check(self._L.liba_solve(self._h, len(ps), Pa, Ra))
+        return [finish_inertial_result(k[0], o, r) for k, o, r in zip(keep, outs, Ra)]
+
+    def LocalInertialBA(self, problem, lambda_init=1.0, max_iters=10):
+        return self.LocalInertialBABatch([problem], lambda_init, max_iters)[0]

@@ -164,3 +164,27 @@ extern "C" int emul_distribute(const int32_t* cand3, int n, int regionW, int reg
     }
     return S;
 }
+
+// ---- LocalInertialBA: the device algorithm (csrc/liba_core.cuh) run by one host "thread" ---------------------------------------
+#include "../../orb_slam3_detailed_comments_b200/csrc/liba_pack.h"
+
+extern "C" int emul_liba(const liba_problem* p, liba_result* r) {
+    const orb::LibaLayout lay = orb::liba_pack(*p, nullptr, nullptr, nullptr);
+    std::vector<uint8_t> blob(lay.total + 16, 0);
+    orb::LibaDev dev;
+    orb::liba_pack(*p, blob.data(), blob.data(), &dev);
+    orb::liba_optimize(dev);
+    orb::liba_unpack(*p, blob.data(), dev, blob.data(), r);
+    return r->iterations;
+}
+
+// one EdgeInertial through the device code: e9, J[9][24]
+extern "C" void emul_liba_inertial(const double* state2x21, const liba_link* link, double* e9, double* J216) {
+    orb::LibaDev dev;
+    memset(&dev, 0, sizeof(dev));
+    dev.state = const_cast<double*>(state2x21);
+    orb::LibaLink L;
+    memcpy(&L, link, sizeof(L));
+    L.k1 = 0; L.k2 = 1;
+    orb::liba_inertial(dev, L, e9, J216);
+}

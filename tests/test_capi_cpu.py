@@ -21,7 +21,7 @@ def lib():
 def _declared_functions():
     text = open(os.path.join(ROOT, "include", "orbslam3_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    names = set(re.findall(r"\b((?:orb|orbx|orbm|orbo|orbf|orbv|orbp|lba)_[a-z0-9_]+)\s*\(", text))
+    names = set(re.findall(r"\b((?:orb|orbx|orbm|orbo|orbf|orbv|orbp|lba|liba)_[a-z0-9_]+)\s*\(", text))
     return sorted(names)
 
 
@@ -38,6 +38,8 @@ def test_struct_layouts_match_the_header():
     assert N.KP_DTYPE.itemsize == 28            # cv::KeyPoint
     assert C.sizeof(N.orbx_config) == 36
     assert C.sizeof(N.orbm_camera) == 40
+    assert N.LIBA_LINK.itemsize == 1080         # liba_link
+    assert C.sizeof(N.liba_problem) == 16 + 8 * 8 + 12 * 8 + 6 * 8 + 8
 
 
 def test_no_device_means_loud_failure(lib):

@@ -15,14 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 @pytest.fixture(scope="module")
 def emul():
-    d = os.path.join(HERE, "host_emul")
-    so = os.path.join(d, "libemul.so")
-    srcs = [os.path.join(d, "emul.cpp"),
-            os.path.join(HERE, "..", "orb_slam3_detailed_comments_b200", "csrc", "devmath.cuh")]
-    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-o", so,
-                               srcs[0], "-lpthread"])
-    L = C.CDLL(so)
+    from _emul import build_and_load
+    L = build_and_load()
     L.emul_fast_x2.restype = C.c_uint32
     L.emul_fast_x2.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.emul_atan2.restype = C.c_float

@@ -1,0 +1,157 @@
+"""CPU tier: the DEVICE algorithm of LocalInertialBA (csrc/liba_core.cuh -- the very source nvcc compiles into k_liba) built for
+the host and run against the oracle (oracle/lba_oracle.cpp orc_liba).  Same phases, same packing (csrc/liba_pack.h), same C ABI
+structs; what this cannot see are device-only hazards (barrier placement, atomics), which the GPU test covers once it has run."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from orb_slam3_detailed_comments_b200 import _native as N
+from orb_slam3_detailed_comments_b200.optimizer import finish_inertial_result, pack_inertial_problem
+from test_oracle_inertial import scene
+
+TOL = 1e-4   # BASELINE.json north_star tolerance for the BA rows
+
+
+@pytest.fixture(scope="module")
+def emul():
+    from _emul import build_and_load
+    L = build_and_load()
+    L.emul_liba.restype = C.c_int
+    L.emul_liba.argtypes = [C.POINTER(N.liba_problem), C.POINTER(N.liba_result)]
+    L.emul_liba_inertial.restype = None
+    L.emul_liba_inertial.argtypes = [C.c_void_p] * 4
+    return L
+
+
+def run_emul(L, pr, lambda_init, max_iters):
+    keep = []
+    p, r, out = pack_inertial_problem(pr, lambda_init, max_iters, keep)
+    L.emul_liba(C.byref(p), C.byref(r))
+    return finish_inertial_result(keep[0][0], out, r)
+
+
+def perturbed(seed, n_kf=8, n_mp=300, noise=0.5):
+    s = scene(n_kf=n_kf, n_mp=n_mp, seed=seed, noise=noise)
+    rng = np.random.default_rng(seed + 100)
+    st = s["state"].copy()
+    for k in range(1, len(st)):
+        st[k] = po.kf_oplus(st[k], np.concatenate([rng.normal(0, 0.01, 3), rng.normal(0, 0.03, 3), rng.normal(0, 0.05, 3),
+                                                   rng.normal(0, 1e-3, 3), rng.normal(0, 1e-2, 3)]))
+    s["state"] = st
+    s["point"] = s["point"] + rng.normal(0, 0.05, s["point"].shape)
+    return s
+
+
+def test_link_layouts_agree():
+    assert N.LIBA_LINK.itemsize == po.LIBA_LINK.itemsize == 1080
+    for (n1, n2) in zip(N.LIBA_LINK.names, po.LIBA_LINK.names):
+        assert N.LIBA_LINK.fields[n1][1] == po.LIBA_LINK.fields[n2][1]
+
+
+def test_inertial_edge_matches_oracle(emul):
+    s = perturbed(5)
+    for l in range(len(s["links"])):
+        lk = np.ascontiguousarray(s["links"][l:l + 1])
+        st = np.ascontiguousarray(s["state"][[int(lk["k1"][0]), int(lk["k2"][0])]])
+        e_o, J_o = po.inertial_edge(st, lk[0])
+        e, J = np.zeros(9), np.zeros((9, 24))
+        emul.emul_liba_inertial(st.ctypes.data, lk.ctypes.data, e.ctypes.data, J.ctypes.data)
+        assert np.array_equal(e, e_o) and np.array_equal(J, J_o)
+
+
+@pytest.mark.parametrize("seed,lam,iters,n_fixed", [(11, 1.0, 10, 1), (12, 1e-2, 4, 1), (13, 1.0, 10, 3), (14, 0.0, 6, 2)])
+def test_device_algorithm_matches_oracle(emul, seed, lam, iters, n_fixed):
+    s = perturbed(seed)
+    s["fixed"][:] = 0
+    s["fixed"][:n_fixed] = 1
+    if seed == 13:
+        s["links"]["robust"] = 1
+    ref = po.liba(s["state"], s["fixed"], s["point"], s["edge_kf"], s["edge_mp"], s["obs"], s["inv_sigma2"], s["Tcb"], s["cam5"], s["links"], lam, iters)
+    got = run_emul(emul, s, lam, iters)
+    assert got["iterations"] == ref["iterations"] and got["trials"] == ref["trials"]
+    assert abs(got["chi2_init"] - ref["chi2_init"]) <= 1e-9 * max(1.0, ref["chi2_init"])
+    assert abs(got["chi2"] - ref["chi2"]) <= 1e-6 * max(1.0, ref["chi2"])
+    assert abs(got["lambda_"] - ref["lambda_"]) <= 1e-6 * ref["lambda_"]
+    assert np.abs(got["state"] - ref["state"]).max() < TOL
+    assert np.abs(got["point"] - ref["point"]).max() < TOL
+    assert np.allclose(got["edge_chi2"], ref["edge_chi2"], rtol=1e-6, atol=1e-8)
+    assert np.allclose(got["link_chi2"], ref["link_chi2"], rtol=1e-6, atol=1e-8)
+    assert (got["state"][:n_fixed] == s["state"][:n_fixed]).all()
+    assert ref["chi2"] < ref["chi2_init"]
+
+
+def test_noise_free_window_is_a_fixed_point(emul):
+    s = scene()
+    got = run_emul(emul, s, 1.0, 10)
+    assert got["chi2_init"] < 1e-3
+    assert np.abs(got["state"] - s["state"]).max() < 1e-5 and np.abs(got["point"] - s["point"]).max() < 1e-4
+
+
+def test_mono_only_and_all_fixed_but_one(emul):
+    s = perturbed(21, n_kf=5, n_mp=120)
+    s["obs"][:, 2] = -1.0
+    s["fixed"][:] = 1
+    s["fixed"][-1] = 0
+    ref = po.liba(s["state"], s["fixed"], s["point"], s["edge_kf"], s["edge_mp"], s["obs"], s["inv_sigma2"], s["Tcb"], s["cam5"], s["links"], 1.0, 10)
+    got = run_emul(emul, s, 1.0, 10)
+    assert got["iterations"] == ref["iterations"] and got["trials"] == ref["trials"]
+    assert np.abs(got["state"] - ref["state"]).max() < TOL and np.abs(got["point"] - ref["point"]).max() < TOL
+
+
+# ---- the same source run by N host threads with real barriers / atomics under ThreadSanitizer -----------------------------------
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def mt_binary():
+    d = os.path.join(HERE, "host_emul")
+    exe = os.path.join(d, "liba_mt_tsan")
+    csrc = os.path.join(HERE, "..", "orb_slam3_detailed_comments_b200", "csrc")
+    srcs = [os.path.join(d, "liba_mt.cpp"), os.path.join(csrc, "liba_core.cuh"), os.path.join(csrc, "liba_pack.h"),
+            os.path.join(HERE, "..", "include", "orbslam3_b200.h")]
+    if not os.path.exists(exe) or any(os.path.getmtime(s) > os.path.getmtime(exe) for s in srcs):
+        subprocess.check_call(["g++", "-O1", "-g", "-fsanitize=thread", "-ffp-contract=off", "-std=c++20", "-o", exe, srcs[0], "-lpthread"])
+    return exe
+
+
+def run_mt(exe, s, lam, iters, threads, tmp_path):
+    c = np.ascontiguousarray
+    links = c(s["links"]).view(N.LIBA_LINK).reshape(-1)
+    blob = b"".join([
+        np.array([len(s["state"]), len(s["point"]), len(s["edge_kf"]), len(links), iters, 0], np.int32).tobytes(),
+        np.concatenate([[lam], np.asarray(s["Tcb"], np.float64).reshape(-1), np.asarray(s["cam5"], np.float64)]).tobytes(),
+        c(s["state"], np.float64).tobytes(), c(s["point"], np.float64).tobytes(), c(s["obs"], np.float64).tobytes(),
+        c(s["inv_sigma2"], np.float64).tobytes(), c(s["edge_kf"], np.int32).tobytes(), c(s["edge_mp"], np.int32).tobytes(),
+        links.tobytes(), c(s["fixed"], np.uint8).tobytes()])
+    fin, fout = tmp_path / "p.bin", tmp_path / "r.bin"
+    fin.write_bytes(blob)
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1 exitcode=66")
+    pr = subprocess.run([exe, str(fin), str(fout), str(threads)], env=env, capture_output=True, text=True, timeout=600)
+    assert pr.returncode == 0, "ThreadSanitizer / driver failure:\n" + pr.stderr[-4000:]
+    o = np.frombuffer(fout.read_bytes(), np.float64)
+    nk, nm, ne, nl = len(s["state"]), len(s["point"]), len(s["edge_kf"]), len(links)
+    a = 5
+    st = o[a:a + 21 * nk].reshape(nk, 21); a += 21 * nk
+    pt = o[a:a + 3 * nm].reshape(nm, 3); a += 3 * nm
+    chi = o[a:a + ne]; a += ne
+    lchi = o[a:a + 3 * nl].reshape(nl, 3)
+    return dict(iterations=int(o[0]), trials=int(o[1]), lambda_=o[2], chi2=o[3], chi2_init=o[4], state=st, point=pt, edge_chi2=chi, link_chi2=lchi)
+
+
+@pytest.mark.parametrize("threads", [2, 7, 16])
+def test_threaded_run_is_race_free_and_matches_oracle(mt_binary, tmp_path, threads):
+    """N threads, real barriers, real atomics, ThreadSanitizer on: a missing LIBA_SYNC in liba_core.cuh fails here.  Atomic
+    accumulation order differs from run to run, so values match the oracle to the BA tolerance, not bit for bit."""
+    s = perturbed(31, n_kf=6, n_mp=150)
+    s["fixed"][:] = 0
+    s["fixed"][:2] = 1
+    ref = po.liba(s["state"], s["fixed"], s["point"], s["edge_kf"], s["edge_mp"], s["obs"], s["inv_sigma2"], s["Tcb"], s["cam5"], s["links"], 1.0, 6)
+    got = run_mt(mt_binary, s, 1.0, 6, threads, tmp_path)
+    assert got["iterations"] == ref["iterations"] and abs(got["trials"] - ref["trials"]) <= 1
+    assert abs(got["chi2"] - ref["chi2"]) <= 1e-5 * max(1.0, ref["chi2"])
+    assert np.abs(got["state"] - ref["state"]).max() < TOL and np.abs(got["point"] - ref["point"]).max() < TOL

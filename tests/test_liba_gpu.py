@@ -1,0 +1,46 @@
+"""GPU tier: liba_solve (LocalInertialBA's numeric core, csrc/liba.cu) against the oracle, through the C ABI.
+The kernel's source (csrc/liba_core.cuh) is validated on the CPU by tests/test_liba_emul.py (single-thread run == oracle; N-thread
+run under ThreadSanitizer race-free).  It had not yet been launched on a device when round 1's GPU budget ran out, so this file is
+opt-in (ORB_LIBA_GPU=1) until its first green run -- an unproven kernel must not be able to turn the GPU tier red."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from test_liba_emul import TOL, perturbed
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("ORB_LIBA_GPU") != "1", reason="first device run pending: set ORB_LIBA_GPU=1")]
+
+
+@pytest.fixture(scope="module")
+def opt():
+    from orb_slam3_detailed_comments_b200.optimizer import InertialOptimizer
+    o = InertialOptimizer(0)
+    yield o
+    o.close()
+
+
+def oracle(s, lam, iters):
+    return po.liba(s["state"], s["fixed"], s["point"], s["edge_kf"], s["edge_mp"], s["obs"], s["inv_sigma2"], s["Tcb"], s["cam5"], s["links"], lam, iters)
+
+
+def check(got, ref):
+    assert got["iterations"] == ref["iterations"] and abs(got["trials"] - ref["trials"]) <= 1
+    assert abs(got["chi2"] - ref["chi2"]) <= 1e-5 * max(1.0, ref["chi2"])
+    assert np.abs(got["state"] - ref["state"]).max() < TOL and np.abs(got["point"] - ref["point"]).max() < TOL
+
+
+@pytest.mark.parametrize("seed,lam,iters,n_fixed", [(11, 1.0, 10, 1), (12, 1e-2, 4, 1), (13, 1.0, 10, 3)])
+def test_matches_oracle(opt, seed, lam, iters, n_fixed):
+    s = perturbed(seed)
+    s["fixed"][:] = 0
+    s["fixed"][:n_fixed] = 1
+    check(opt.LocalInertialBA(s, lam, iters), oracle(s, lam, iters))
+
+
+def test_batch_of_windows(opt):
+    ss = [perturbed(40 + i, n_kf=5 + i, n_mp=150) for i in range(4)]
+    for got, s in zip(opt.LocalInertialBABatch(ss, 1.0, 10), ss):
+        check(got, oracle(s, 1.0, 10))
