@@ -82,6 +82,7 @@ extern "C" orb_status liba_solve(liba_handle* h, int32_t n_problems, const liba_
     size_t total = ((sizeof(LibaDev) * (size_t)n_problems) + 255) & ~(size_t)255;
     for (int i = 0; i < n_problems; ++i) {
         lay[i] = liba_pack(in[i], nullptr, nullptr, nullptr);
+        if (lay[i].total == 0) return set_error(ORB_ERR_INVALID, "liba_problem: two links join the same keyframe pair (or > 65535 keyframes)");
         base[i] = total;
         total += (lay[i].total + 255) & ~(size_t)255;
     }

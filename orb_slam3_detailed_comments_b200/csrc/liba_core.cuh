@@ -1,6 +1,7 @@
 // liba_core.cuh -- Optimizer::LocalInertialBA's numeric core (/root/reference/src/Optimizer.cc:2203-2812) as
 // barrier-separated SPMD phases, one CTA per problem.  Like quadtree_core.cuh, the identical source compiles for the
-// device (LIBA_PAR_FOR = thread-strided loop, LIBA_SYNC = __syncthreads, block reductions, double atomics) and for the
+// device (LIBA_PAR_FOR = thread-strided loop, LIBA_SYNC = __syncthreads, block reductions; no atomics: every sum is a gather in a
+// fixed order, so Levenberg's accept / reject decisions do not depend on scheduling) and for the
 // host (one "thread"), so tests/host_emul can run this very algorithm against the CPU oracle without a GPU.
 //
 // g2o graph being solved (single camera, Nleft == -1):
@@ -24,7 +25,6 @@
 #if defined(__CUDA_ARCH__)
 #define LIBA_PAR_FOR(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
 #define LIBA_SYNC() __syncthreads()
-#define LIBA_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #define LIBA_LEADER() (threadIdx.x == 0)
 #define LIBA_FLAG_SET(p) (*(p) = 1)
 #elif defined(LIBA_EMUL_THREADS)
@@ -34,26 +34,14 @@ namespace orb {
 extern thread_local int liba_tid;
 extern int liba_nthreads;
 void liba_barrier();
-inline void liba_atomic_add(double* p, double v) {
-    unsigned long long* u = reinterpret_cast<unsigned long long*>(p);
-    unsigned long long old = __atomic_load_n(u, __ATOMIC_RELAXED), want;
-    do {
-        double d;
-        __builtin_memcpy(&d, &old, 8);
-        d += v;
-        __builtin_memcpy(&want, &d, 8);
-    } while (!__atomic_compare_exchange_n(u, &old, want, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
-}
 }
 #define LIBA_PAR_FOR(i, n) for (int i = orb::liba_tid; i < (n); i += orb::liba_nthreads)
 #define LIBA_SYNC() orb::liba_barrier()
-#define LIBA_ATOMIC_ADD(p, v) orb::liba_atomic_add((p), (v))
 #define LIBA_LEADER() (orb::liba_tid == 0)
 #define LIBA_FLAG_SET(p) __atomic_store_n((p), 1, __ATOMIC_RELAXED)
 #else
 #define LIBA_PAR_FOR(i, n) for (int i = 0; i < (n); ++i)
 #define LIBA_SYNC() ((void)0)
-#define LIBA_ATOMIC_ADD(p, v) (*(p) += (v))
 #define LIBA_LEADER() (true)
 #define LIBA_FLAG_SET(p) (*(p) = 1)
 #endif
@@ -78,8 +66,17 @@ struct LibaDev {
     const int* emp;
     const double* obs;    // [nE][3]
     const double* invs2;  // [nE]
-    const int* pt_off;    // [nMP + 1] edges by point (CSR)
+    const int* pt_off;    // [nMP + 1] edges by point (CSR, ascending edge index inside a point)
     const int* pt_edge;   // [nE]
+    const int* kf_off;    // [nKF + 1] edges by keyframe (CSR, ascending edge index)
+    const int* kf_edge;   // [nE]
+    const int* kl_off;    // [nKF + 1] links by keyframe; entry = 2 * link + role (0: the keyframe is k1, 1: it is k2)
+    const int* kl_ent;    // [2 nL]
+    int nPairs;           // upper block pairs (p1 <= p2) of optimisable keyframes that share at least one map point
+    const int* pair_p;    // [nPairs] p1 << 16 | p2
+    const int* pair_off;  // [nPairs + 1] into co_e1 / co_e2, entries ordered by map point
+    const int* co_e1;     // edge of p1 observing the shared point
+    const int* co_e2;     // edge of p2
     const LibaLink* links;
     double Rcb[9], tcb[3], Rbc[9], tbc[3];
     double fx, fy, cx, cy, bf;
@@ -97,6 +94,10 @@ struct LibaDev {
     double* Hll;          // [nMP][9]
     double* Dinv;         // [nMP][9]
     double* W;            // [nE][18]  pose(6) x point(3)
+    double* WD;           // [nE][18]  W D^-1 (per trial)
+    double* Wdb;          // [nE][6]   W D^-1 b_l
+    double* Epp;          // [nE][27]  upper triangle (21) of the edge's 6 x 6 pose block, then its 6 b terms
+    double* Lblk;         // [nL][930] 30 x 30 block over [k1 15 | k2 15] of the inertial + random-walk edges, then 30 b terms
     int* flag;            // [4] solver failure flag
     double* red;          // reduction scratch (device: shared memory, 64 doubles)
     // results
@@ -376,12 +377,14 @@ LIBA_HD double liba_compute_errors(const LibaDev& P, const LibaHuber& H) {   // 
     return liba_sum(P, chi);
 }
 
-LIBA_HD void liba_build(const LibaDev& P, const LibaHuber& H) {   // linearizeOplus + constructQuadraticForm of every edge
+LIBA_HD int liba_tri(int i, int j) { return i * 6 - i * (i - 1) / 2 + (j - i); }   // (i <= j) of a 6 x 6 upper triangle -> [0, 21)
+
+// linearizeOplus + constructQuadraticForm of every edge.  Phase 1 computes per-edge / per-link blocks, phase 2 gathers them into
+// H_pp and b in a fixed order (edges of a keyframe ascending, then its links ascending).
+LIBA_HD void liba_build(const LibaDev& P, const LibaHuber& H) {
     const int sp = P.sp;
     LIBA_PAR_FOR(i, sp * sp) P.Hpp[i] = 0.0;
-    LIBA_PAR_FOR(i, sp) P.b[i] = 0.0;
-    LIBA_SYNC();
-    LIBA_PAR_FOR(l, P.nMP) {     // a thread owns a map point: H_ll and b_l in registers, pose terms by atomics
+    LIBA_PAR_FOR(l, P.nMP) {     // a thread owns a map point: H_ll and b_l stay in registers
         double hl[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
         for (int k = P.pt_off[l]; k < P.pt_off[l + 1]; ++k) {
             const int e = P.pt_edge[k];
@@ -396,45 +399,39 @@ LIBA_HD void liba_build(const LibaDev& P, const LibaHuber& H) {   // linearizeOp
                 double s = 0; for (int d = 0; d < D; ++d) s += Jp[3 * d + i] * r[d];
                 bl[i] += -om * s;
             }
-            const int pi = P.pidx[P.ekf[e]];
+            const bool freeKf = P.pidx[P.ekf[e]] >= 0;
             double* We = P.W + 18 * (size_t)e;
+            double* Ee = P.Epp + 27 * (size_t)e;
             for (int i = 0; i < 6; ++i) {
-                for (int j = 0; j < 3; ++j) { double s = 0; for (int d = 0; d < D; ++d) s += Jx[6 * d + i] * Jp[3 * d + j]; We[3 * i + j] = pi >= 0 ? om * s : 0.0; }
-                if (pi < 0) continue;
-                for (int j = 0; j < 6; ++j) { double s = 0; for (int d = 0; d < D; ++d) s += Jx[6 * d + i] * Jx[6 * d + j]; LIBA_ATOMIC_ADD(&P.Hpp[(size_t)(15 * pi + i) * sp + 15 * pi + j], om * s); }
+                for (int j = 0; j < 3; ++j) { double s = 0; for (int d = 0; d < D; ++d) s += Jx[6 * d + i] * Jp[3 * d + j]; We[3 * i + j] = freeKf ? om * s : 0.0; }
+                for (int j = i; j < 6; ++j) { double s = 0; for (int d = 0; d < D; ++d) s += Jx[6 * d + i] * Jx[6 * d + j]; Ee[liba_tri(i, j)] = om * s; }
                 double s = 0; for (int d = 0; d < D; ++d) s += Jx[6 * d + i] * r[d];
-                LIBA_ATOMIC_ADD(&P.b[15 * pi + i], -om * s);
+                Ee[21 + i] = -om * s;
             }
         }
         for (int i = 0; i < 9; ++i) P.Hll[9 * (size_t)l + i] = hl[i];
         for (int i = 0; i < 3; ++i) P.b[sp + 3 * l + i] = bl[i];
     }
-    LIBA_PAR_FOR(l, P.nL) {      // inertial link + the two random walks
+    LIBA_PAR_FOR(l, P.nL) {      // inertial link + the two random walks -> one 30 x 30 block over [k1 | k2]
         const LibaLink& L = P.links[l];
-        double e9[9], J[9 * 24], OJ[9 * 24], Oe[9];
+        double* B = P.Lblk + 930 * (size_t)l;
+        double e9[9], J[9 * 24], Oe[9];
         liba_inertial(P, L, e9, J);
         double c = 0;
         for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) c += e9[i] * L.info[9 * i + j] * e9[j];
         double w = 1.0;
         if (L.robust) liba_huber(c, H.dI, H.sqI, &w);
-        const int p1 = P.pidx[L.k1], p2 = P.pidx[L.k2];
+        for (int i = 0; i < 930; ++i) B[i] = 0.0;
         for (int i = 0; i < 9; ++i) {
             double s = 0; for (int k = 0; k < 9; ++k) s += L.info[9 * i + k] * e9[k];
             Oe[i] = w * s;
-            for (int cc = 0; cc < 24; ++cc) { double t = 0; for (int k = 0; k < 9; ++k) t += L.info[9 * i + k] * J[k * 24 + cc]; OJ[i * 24 + cc] = w * t; }
         }
-        for (int ca = 0; ca < 24; ++ca) {
-            const int ga = ca < 15 ? (p1 >= 0 ? 15 * p1 + ca : -1) : (p2 >= 0 ? 15 * p2 + (ca - 15) : -1);   // columns 15..23 = pose2 (6), v2 (3)
-            if (ga < 0) continue;
-            double s = 0; for (int k = 0; k < 9; ++k) s += J[k * 24 + ca] * Oe[k];
-            LIBA_ATOMIC_ADD(&P.b[ga], -s);
-            for (int cb = 0; cb < 24; ++cb) {
-                const int gb = cb < 15 ? (p1 >= 0 ? 15 * p1 + cb : -1) : (p2 >= 0 ? 15 * p2 + (cb - 15) : -1);
-                if (gb < 0) continue;
-                double t = 0; for (int k = 0; k < 9; ++k) t += J[k * 24 + ca] * OJ[k * 24 + cb];
-                LIBA_ATOMIC_ADD(&P.Hpp[(size_t)ga * sp + gb], t);
-            }
+        for (int cb = 0; cb < 24; ++cb) {     // column cb of w Info J, then J^T times it (inertial columns 0..23 sit at block columns 0..23)
+            double oj[9];
+            for (int i = 0; i < 9; ++i) { double t = 0; for (int k = 0; k < 9; ++k) t += L.info[9 * i + k] * J[k * 24 + cb]; oj[i] = w * t; }
+            for (int ca = 0; ca < 24; ++ca) { double t = 0; for (int k = 0; k < 9; ++k) t += J[k * 24 + ca] * oj[k]; B[ca * 30 + cb] = t; }
         }
+        for (int ca = 0; ca < 24; ++ca) { double s = 0; for (int k = 0; k < 9; ++k) s += J[k * 24 + ca] * Oe[k]; B[900 + ca] = -s; }
         const double* s1 = P.state + 21 * (size_t)L.k1;
         const double* s2 = P.state + 21 * (size_t)L.k2;
         for (int which = 0; which < 2; ++which) {      // e = b2 - b1, J1 = -I, J2 = I
@@ -444,18 +441,41 @@ LIBA_HD void liba_build(const LibaDev& P, const LibaHuber& H) {   // linearizeOp
             for (int i = 0; i < 3; ++i) e3[i] = s2[so + i] - s1[so + i];
             for (int i = 0; i < 3; ++i) Oe3[i] = info[3 * i] * e3[0] + info[3 * i + 1] * e3[1] + info[3 * i + 2] * e3[2];
             for (int i = 0; i < 3; ++i) {
-                if (p1 >= 0) LIBA_ATOMIC_ADD(&P.b[15 * p1 + off + i], Oe3[i]);
-                if (p2 >= 0) LIBA_ATOMIC_ADD(&P.b[15 * p2 + off + i], -Oe3[i]);
+                B[900 + off + i] += Oe3[i];
+                B[900 + 15 + off + i] += -Oe3[i];
                 for (int j = 0; j < 3; ++j) {
-                    if (p1 >= 0) LIBA_ATOMIC_ADD(&P.Hpp[(size_t)(15 * p1 + off + i) * sp + 15 * p1 + off + j], info[3 * i + j]);
-                    if (p2 >= 0) LIBA_ATOMIC_ADD(&P.Hpp[(size_t)(15 * p2 + off + i) * sp + 15 * p2 + off + j], info[3 * i + j]);
-                    if (p1 >= 0 && p2 >= 0) {
-                        LIBA_ATOMIC_ADD(&P.Hpp[(size_t)(15 * p1 + off + i) * sp + 15 * p2 + off + j], -info[3 * i + j]);
-                        LIBA_ATOMIC_ADD(&P.Hpp[(size_t)(15 * p2 + off + i) * sp + 15 * p1 + off + j], -info[3 * i + j]);
-                    }
+                    B[(off + i) * 30 + off + j] += info[3 * i + j];
+                    B[(15 + off + i) * 30 + 15 + off + j] += info[3 * i + j];
+                    B[(off + i) * 30 + 15 + off + j] -= info[3 * i + j];
+                    B[(15 + off + i) * 30 + off + j] -= info[3 * i + j];
                 }
             }
         }
+    }
+    LIBA_SYNC();
+    LIBA_PAR_FOR(t, P.nKF * 240) {      // a thread owns one entry of a keyframe's 15 x 15 diagonal block (t % 240 < 225) or of its b
+        const int k = t / 240, q = t % 240, pi = P.pidx[k];
+        if (pi < 0) continue;
+        const bool isB = q >= 225;
+        const int r = isB ? q - 225 : q / 15, c = isB ? 0 : q % 15;
+        double acc = 0.0;
+        if (r < 6 && (isB || c < 6)) {
+            const int slot = isB ? 21 + r : (r <= c ? liba_tri(r, c) : liba_tri(c, r));
+            for (int n = P.kf_off[k]; n < P.kf_off[k + 1]; ++n) acc += P.Epp[27 * (size_t)P.kf_edge[n] + slot];
+        }
+        for (int n = P.kl_off[k]; n < P.kl_off[k + 1]; ++n) {
+            const int l = P.kl_ent[n] >> 1, o = 15 * (P.kl_ent[n] & 1);
+            acc += isB ? P.Lblk[930 * (size_t)l + 900 + o + r] : P.Lblk[930 * (size_t)l + (o + r) * 30 + o + c];
+        }
+        if (isB) P.b[15 * pi + r] = acc; else P.Hpp[(size_t)(15 * pi + r) * sp + 15 * pi + c] = acc;
+    }
+    LIBA_PAR_FOR(t, P.nL * 225) {       // the k1-k2 coupling of a link (at most one link per keyframe pair: liba_pack checks)
+        const int l = t / 225, r = (t % 225) / 15, c = t % 15;
+        const int p1 = P.pidx[P.links[l].k1], p2 = P.pidx[P.links[l].k2];
+        if (p1 < 0 || p2 < 0) continue;
+        const double* B = P.Lblk + 930 * (size_t)l;
+        P.Hpp[(size_t)(15 * p1 + r) * sp + 15 * p2 + c] = B[r * 30 + 15 + c];
+        P.Hpp[(size_t)(15 * p2 + c) * sp + 15 * p1 + r] = B[(15 + c) * 30 + r];
     }
     LIBA_SYNC();
 }
@@ -464,10 +484,9 @@ LIBA_HD void liba_build(const LibaDev& P, const LibaHuber& H) {   // linearizeOp
 LIBA_HD bool liba_solve_system(const LibaDev& P, double lambda) {
     const int sp = P.sp;
     LIBA_PAR_FOR(i, sp * sp) P.Hs[i] = P.Hpp[i] + ((i / sp) == (i % sp) ? lambda : 0.0);
-    LIBA_PAR_FOR(i, sp) P.bs[i] = P.b[i];
     if (LIBA_LEADER()) P.flag[0] = 0;
     LIBA_SYNC();
-    LIBA_PAR_FOR(l, P.nMP) {
+    LIBA_PAR_FOR(l, P.nMP) {     // D^-1 per landmark, W D^-1 and W D^-1 b_l per edge
         double D[9], Di[9];
         for (int i = 0; i < 9; ++i) D[i] = P.Hll[9 * (size_t)l + i];
         D[0] += lambda; D[4] += lambda; D[8] += lambda;
@@ -476,22 +495,35 @@ LIBA_HD bool liba_solve_system(const LibaDev& P, double lambda) {
         const double* bl = P.b + sp + 3 * l;
         double Dib[3];
         for (int i = 0; i < 3; ++i) Dib[i] = Di[3 * i] * bl[0] + Di[3 * i + 1] * bl[1] + Di[3 * i + 2] * bl[2];
-        for (int k1 = P.pt_off[l]; k1 < P.pt_off[l + 1]; ++k1) {
-            const int e1 = P.pt_edge[k1], p1 = P.pidx[P.ekf[e1]];
-            if (p1 < 0) continue;
-            const double* W1 = P.W + 18 * (size_t)e1;
-            double WD[18];
-            for (int i = 0; i < 6; ++i) for (int j = 0; j < 3; ++j) WD[3 * i + j] = W1[3 * i] * Di[j] + W1[3 * i + 1] * Di[3 + j] + W1[3 * i + 2] * Di[6 + j];
-            for (int i = 0; i < 6; ++i) LIBA_ATOMIC_ADD(&P.bs[15 * p1 + i], -(W1[3 * i] * Dib[0] + W1[3 * i + 1] * Dib[1] + W1[3 * i + 2] * Dib[2]));
-            for (int k2 = P.pt_off[l]; k2 < P.pt_off[l + 1]; ++k2) {
-                const int e2 = P.pt_edge[k2], p2 = P.pidx[P.ekf[e2]];
-                if (p2 < 0) continue;
-                const double* W2 = P.W + 18 * (size_t)e2;
-                for (int i = 0; i < 6; ++i)
-                    for (int j = 0; j < 6; ++j)
-                        LIBA_ATOMIC_ADD(&P.Hs[(size_t)(15 * p1 + i) * sp + 15 * p2 + j], -(WD[3 * i] * W2[3 * j] + WD[3 * i + 1] * W2[3 * j + 1] + WD[3 * i + 2] * W2[3 * j + 2]));
+        for (int k = P.pt_off[l]; k < P.pt_off[l + 1]; ++k) {
+            const int e = P.pt_edge[k];
+            const double* W1 = P.W + 18 * (size_t)e;
+            double* WD = P.WD + 18 * (size_t)e;
+            for (int i = 0; i < 6; ++i) {
+                for (int j = 0; j < 3; ++j) WD[3 * i + j] = W1[3 * i] * Di[j] + W1[3 * i + 1] * Di[3 + j] + W1[3 * i + 2] * Di[6 + j];
+                P.Wdb[6 * (size_t)e + i] = W1[3 * i] * Dib[0] + W1[3 * i + 1] * Dib[1] + W1[3 * i + 2] * Dib[2];
             }
         }
+    }
+    LIBA_SYNC();
+    LIBA_PAR_FOR(t, P.nKF * 15) {      // reduced right-hand side
+        const int k = t / 15, r = t % 15, pi = P.pidx[k];
+        if (pi < 0) continue;
+        double acc = P.b[15 * pi + r];
+        if (r < 6) for (int n = P.kf_off[k]; n < P.kf_off[k + 1]; ++n) acc -= P.Wdb[6 * (size_t)P.kf_edge[n] + r];
+        P.bs[15 * pi + r] = acc;
+    }
+    LIBA_PAR_FOR(t, P.nPairs * 36) {   // Schur complement: a thread owns one entry of one 6 x 6 block (upper block triangle only)
+        const int q = t / 36, i = (t % 36) / 6, j = t % 6;
+        const int p1 = P.pair_p[q] >> 16, p2 = P.pair_p[q] & 0xffff;
+        double* dst = P.Hs + (size_t)(15 * p1 + i) * sp + 15 * p2 + j;
+        double acc = *dst;
+        for (int n = P.pair_off[q]; n < P.pair_off[q + 1]; ++n) {
+            const double* WD = P.WD + 18 * (size_t)P.co_e1[n] + 3 * i;
+            const double* W2 = P.W + 18 * (size_t)P.co_e2[n] + 3 * j;
+            acc -= WD[0] * W2[0] + WD[1] * W2[1] + WD[2] * W2[2];
+        }
+        *dst = acc;
     }
     LIBA_SYNC();
     // dense LDL^T of Hs (upper triangle read, right-looking): after step j row j holds D_j at (j,j) and L(i,j) at (j,i), i > j
