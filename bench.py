@@ -556,6 +556,38 @@ def main():
             opt.close()
         except Exception as exc:   # never lose the headline line because the side benchmark failed
             lba = {"error": repr(exc)}
+        # ---- LocalInertialBA: opt-in until the kernel has had its first green device run ---------------
+        liba = {"skipped": "k_liba is CPU-validated only (tests/test_liba_emul.py); set ORB_LIBA_GPU=1 to time it"}
+        if os.environ.get("ORB_LIBA_GPU") == "1":
+            try:
+                from oracle import pyoracle as po
+                from orb_slam3_detailed_comments_b200 import InertialOptimizer
+                iopt = InertialOptimizer(local)
+                wins = [synth.inertial_window(seed=s) for s in range(8)]
+                for _ in range(2):
+                    iopt.LocalInertialBA(wins[0], 1.0, 10)
+                iopt.LocalInertialBABatch(wins, 1.0, 10)
+                t0 = time.perf_counter()
+                for s in range(5):
+                    gi = iopt.LocalInertialBA(wins[s], 1.0, 10)
+                ti_one = (time.perf_counter() - t0) / 5
+                t0 = time.perf_counter()
+                iopt.LocalInertialBABatch(wins, 1.0, 10)
+                ti_batch = (time.perf_counter() - t0) / 8
+                t0 = time.perf_counter()
+                w4 = wins[4]
+                ri = po.liba(w4["state"], w4["fixed"], w4["point"], w4["edge_kf"], w4["edge_mp"], w4["obs"], w4["inv_sigma2"], w4["Tcb"],
+                             w4["cam5"], w4["links"].view(po.LIBA_LINK), 1.0, 10)
+                ti_cpu = time.perf_counter() - t0
+                liba = {"workload": "LocalInertialBA window: 10 optimisable + 4 fixed keyframes, 10 inertial links, 2000 points, "
+                                    f"{len(w4['edge_kf'])} edges, lambda 1e0, 10 iterations",
+                        "ms_per_solve_e2e": 1e3 * ti_one, "ms_per_solve_batch8_e2e": 1e3 * ti_batch, "cpu_oracle_ms": 1e3 * ti_cpu, "cpu_cores": 1,
+                        "iterations": int(gi["iterations"]), "oracle_iterations": int(ri["iterations"]),
+                        "max_abs_state_diff_vs_oracle": float(np.abs(gi["state"] - ri["state"]).max()),
+                        "max_abs_point_diff_vs_oracle": float(np.abs(gi["point"] - ri["point"]).max())}
+                iopt.close()
+            except Exception as exc:
+                liba = {"error": repr(exc)}
         # ---- PoseOptimization (twice per frame on the tracking thread): a batch of B frames --------------
         pose_opt = None
         try:
@@ -628,7 +660,7 @@ def main():
                            "keypoints_per_image": n_kp, "fast_candidates_per_image": n_cand},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_step),
                         "d2h_bytes_per_step": int(d2h // args.steps)},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "lba": lba, "pose_optimization": pose_opt}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "lba": lba, "inertial_ba": liba, "pose_optimization": pose_opt}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

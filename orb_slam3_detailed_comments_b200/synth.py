@@ -168,3 +168,89 @@ def lba_problem(n_kf=20, n_fixed=2, n_mp=3000, seed=0, mono_frac=0.1, outlier_fr
                 inv_sigma2=np.array(inv_s2, np.float64), cam5=np.array([np.float32(fx), np.float32(fy), np.float32(cx),
                                                                          np.float32(cy), np.float32(bf)], np.float64),
                 pose_gt=np.concatenate([Tq, Tt], 1), point_gt=pts)
+
+
+def _expm(w):
+    w = np.asarray(w, float)
+    t = np.linalg.norm(w)
+    W = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if t < 1e-9:
+        return np.eye(3) + W
+    return np.eye(3) + np.sin(t) / t * W + (1 - np.cos(t)) / t ** 2 * W @ W
+
+
+def inertial_window(n_opt=10, n_cov_fixed=3, n_mp=2000, seed=0, noise=0.5, perturb=True, dt=0.25):
+    """A synthetic Optimizer::LocalInertialBA window (Optimizer.cc:2217-2340): a temporal chain of n_opt optimisable keyframes
+    plus the fixed keyframe before them (index 0), joined by inertial links, then n_cov_fixed fixed covisible keyframes without
+    links; stereo / mono observations of n_mp points.  Returns the dict orb_slam3_detailed_comments_b200.InertialOptimizer takes
+    (state [nKF][21] = Rwb twb v bg ba, fixed, point, edge_kf, edge_mp, obs, inv_sigma2, links, Tcb, cam5)."""
+    from ._native import LIBA_LINK
+    rng = np.random.default_rng(seed)
+    G = np.array([0, 0, -float(np.float32(9.81))])
+    n_chain = n_opt + 1
+    states, links = [], np.zeros(n_chain - 1, LIBA_LINK)
+    R, p, v = _expm(rng.normal(0, 0.2, 3)), rng.normal(0, 1, 3), rng.normal(0, 0.3, 3)
+    for k in range(n_chain):
+        states.append(np.concatenate([R.reshape(-1), p, v, np.zeros(6)]))
+        if k == n_chain - 1:
+            break
+        w, a = rng.normal(0, 0.15, 3), rng.normal(0, 0.5, 3) - R.T @ G * 0.97      # near-hovering body: specific force ~ -g
+        dR = _expm(w * dt)
+        acc_w = R @ a
+        v2 = v + (acc_w + G) * dt
+        p2 = p + v * dt + 0.5 * (acc_w + G) * dt * dt
+        lk = links[k]
+        lk["k1"], lk["k2"], lk["robust"], lk["dt"] = k, k + 1, int(k == 0), dt
+        lk["dR"], lk["dV"], lk["dP"] = dR.reshape(-1), R.T @ (v2 - v - G * dt), R.T @ (p2 - p - v * dt - 0.5 * G * dt * dt)
+        lk["JRg"] = (-np.eye(3) * dt).reshape(-1)
+        lk["JVg"] = rng.normal(0, 0.05, 9)
+        lk["JVa"] = (-np.eye(3) * dt).reshape(-1)
+        lk["JPg"] = rng.normal(0, 0.01, 9)
+        lk["JPa"] = (-np.eye(3) * 0.5 * dt * dt).reshape(-1)
+        A = rng.normal(size=(9, 9))
+        lk["info"] = ((A @ A.T + 9 * np.eye(9)) * 50 * (1e-2 if k == 0 else 1.0)).reshape(-1)
+        lk["infoG"] = (np.eye(3) * 1e4).reshape(-1)
+        lk["infoA"] = (np.eye(3) * 1e3).reshape(-1)
+        R, p, v = R @ dR, p2, v2
+    for _ in range(n_cov_fixed):       # covisible fixed keyframes: poses near the chain, no inertial links
+        s = states[rng.integers(0, n_chain)].copy()
+        s[:9] = (s[:9].reshape(3, 3) @ _expm(rng.normal(0, 0.05, 3))).reshape(-1)
+        s[9:12] += rng.normal(0, 0.3, 3)
+        states.append(s)
+    states = np.array(states)
+    n_kf = len(states)
+    FX, FY, CX, CY, BF = 435.2, 435.2, 320.0, 240.0, 47.9
+    Rcb, tcb = _expm([0.01, -0.02, 0.015]), np.array([0.05, -0.01, 0.02])
+    Rwb = states[:, :9].reshape(n_kf, 3, 3)
+    twb = states[:, 9:12]
+    k0 = rng.integers(0, n_kf, n_mp)
+    Xc0 = np.stack([rng.uniform(-2, 2, n_mp), rng.uniform(-1.5, 1.5, n_mp), rng.uniform(3, 10, n_mp)], 1)
+    Xw = np.einsum("nij,nj->ni", Rwb[k0], (Xc0 - tcb) @ Rcb) + twb[k0]
+    Xb = np.einsum("kji,nkj->nki", Rwb, Xw[:, None, :] - twb[None])          # [n_mp][n_kf][3]
+    Xc = Xb @ Rcb.T + tcb
+    z = Xc[..., 2]
+    zs = np.where(z > 0.5, z, 1.0)
+    u, vv = FX * Xc[..., 0] / zs + CX, FY * Xc[..., 1] / zs + CY
+    vis = (z > 0.5) & (u >= 0) & (u < 640) & (vv >= 0) & (vv < 480)
+    keep = vis.sum(1) >= 2
+    Xw, vis, u, vv, z = Xw[keep], vis[keep], u[keep], vv[keep], z[keep]
+    emp, ekf = np.nonzero(vis)
+    ur = np.where(rng.random(len(emp)) < 0.7, u[emp, ekf] - BF / z[emp, ekf] + rng.normal(0, noise, len(emp)), -1.0)
+    obs = np.stack([u[emp, ekf] + rng.normal(0, noise, len(emp)), vv[emp, ekf] + rng.normal(0, noise, len(emp)), ur], 1)
+    level = rng.integers(0, 8, len(emp))
+    inv_sigma2 = (1.0 / np.float32(1.2) ** (2 * level)).astype(np.float64)
+    fixed = np.zeros(n_kf, np.uint8)
+    fixed[0] = 1
+    fixed[n_chain:] = 1
+    point = Xw.copy()
+    if perturb:
+        for k in range(1, n_chain):
+            Rk = states[k, :9].reshape(3, 3)
+            states[k, 9:12] += Rk @ rng.normal(0, 0.02, 3)
+            states[k, :9] = (Rk @ _expm(rng.normal(0, 0.005, 3))).reshape(-1)
+            states[k, 12:15] += rng.normal(0, 0.03, 3)
+            states[k, 15:18] += rng.normal(0, 1e-3, 3)
+            states[k, 18:21] += rng.normal(0, 1e-2, 3)
+        point += rng.normal(0, 0.03, point.shape)
+    return dict(state=states, fixed=fixed, point=point, edge_kf=ekf.astype(np.int32), edge_mp=emp.astype(np.int32), obs=obs,
+                inv_sigma2=inv_sigma2, links=links, Tcb=np.concatenate([Rcb.reshape(-1), tcb]), cam5=[FX, FY, CX, CY, BF])

@@ -1,0 +1,16 @@
+#!/bin/bash
+# First device run of k_liba (LocalInertialBA).  Run through gpurun from the repo root:
+#   gpurun --timeout 900 -- 'bash scripts/liba_first_contact.sh'
+# Writes gpurun_out/liba_*.  The kernel is CPU-validated (tests/test_liba_emul.py); until this script has been green once the GPU
+# test and the bench section stay opt-in behind ORB_LIBA_GPU=1.
+set -u
+mkdir -p gpurun_out
+export ORB_LIBA_GPU=1
+timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_liba_gpu.py -x -q -k "matches_oracle and 11" > gpurun_out/liba_memcheck.log 2>&1
+echo "memcheck exit $?" | tee -a gpurun_out/liba_memcheck.log
+timeout 300 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_liba_gpu.py -x -q -k "matches_oracle and 12" > gpurun_out/liba_racecheck.log 2>&1
+echo "racecheck exit $?" | tee -a gpurun_out/liba_racecheck.log
+timeout 600 python -m pytest tests/test_liba_gpu.py -x -q 2>&1 | tee gpurun_out/liba_tests.log
+timeout 600 python bench.py --steps 5 --warmup 3 2>gpurun_out/liba_bench.err | tee gpurun_out/liba_bench.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_liba -c 20 --csv --log-file gpurun_out/liba_launches.csv \
+    python -m pytest tests/test_liba_gpu.py -x -q -k batch > gpurun_out/liba_ncu.log 2>&1

@@ -170,6 +170,7 @@ extern "C" int emul_distribute(const int32_t* cand3, int n, int regionW, int reg
 
 extern "C" int emul_liba(const liba_problem* p, liba_result* r) {
     const orb::LibaLayout lay = orb::liba_pack(*p, nullptr, nullptr, nullptr);
+    if (lay.total == 0) return -1;
     std::vector<uint8_t> blob(lay.total + 16, 0);
     orb::LibaDev dev;
     orb::liba_pack(*p, blob.data(), blob.data(), &dev);
@@ -188,3 +189,5 @@ extern "C" void emul_liba_inertial(const double* state2x21, const liba_link* lin
     L.k1 = 0; L.k2 = 1;
     orb::liba_inertial(dev, L, e9, J216);
 }
+
+extern "C" size_t emul_liba_layout_total(const liba_problem* p) { return orb::liba_pack(*p, nullptr, nullptr, nullptr).total; }

@@ -155,3 +155,33 @@ def test_threaded_run_is_race_free_and_matches_oracle(mt_binary, tmp_path, threa
     assert got["iterations"] == ref["iterations"] and abs(got["trials"] - ref["trials"]) <= 1
     assert abs(got["chi2"] - ref["chi2"]) <= 1e-5 * max(1.0, ref["chi2"])
     assert np.abs(got["state"] - ref["state"]).max() < TOL and np.abs(got["point"] - ref["point"]).max() < TOL
+
+
+def test_bench_window_matches_oracle(emul):
+    """The window bench.py times (synth.inertial_window: 10 optimisable + 4 fixed keyframes, covisible fixed ones without links,
+    level-dependent information, a robust oldest link)."""
+    from orb_slam3_detailed_comments_b200 import synth
+    s = synth.inertial_window(seed=3, n_mp=600)
+    ref = po.liba(s["state"], s["fixed"], s["point"], s["edge_kf"], s["edge_mp"], s["obs"], s["inv_sigma2"], s["Tcb"], s["cam5"],
+                  s["links"].view(po.LIBA_LINK), 1.0, 10)
+    got = run_emul(emul, s, 1.0, 10)
+    assert got["iterations"] == ref["iterations"] and got["trials"] == ref["trials"]
+    assert np.abs(got["state"] - ref["state"]).max() < TOL and np.abs(got["point"] - ref["point"]).max() < TOL
+    assert ref["chi2"] < 0.1 * ref["chi2_init"]
+    assert (got["state"][s["fixed"] == 1] == s["state"][s["fixed"] == 1]).all()
+
+
+def test_duplicate_links_are_rejected():
+    from orb_slam3_detailed_comments_b200 import synth
+    s = synth.inertial_window(seed=4, n_mp=100)
+    s["links"] = np.concatenate([s["links"], s["links"][:1]])
+    keep = []
+    p, r, _ = pack_inertial_problem(s, 1.0, 10, keep)
+    from _emul import build_and_load
+    L = build_and_load()
+    L.emul_liba_layout_total.restype = C.c_size_t
+    L.emul_liba_layout_total.argtypes = [C.POINTER(N.liba_problem)]
+    assert L.emul_liba_layout_total(C.byref(p)) == 0
+    s["links"] = s["links"][:-1]
+    p, r, _ = pack_inertial_problem(s, 1.0, 10, keep)
+    assert L.emul_liba_layout_total(C.byref(p)) > 0
