@@ -79,3 +79,43 @@ def synthetic_vocabulary(k=10, L=3, seed=0, stop_fraction=0.02):
         child_offset.append(len(child_ids))
     return dict(child_offset=np.array(child_offset, np.int32), child_ids=np.array(child_ids, np.int32), node_desc=np.stack(desc),
                 node_word=np.array(word, np.int32), node_weight=np.array(weight, np.float64), L=L)
+
+
+def load_orbvoc_text(source):
+    """ORBVocabulary::loadFromTextFile (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1338-1420) into orbv_create's flat layout.
+    `source`: a path or a binary file object holding ORBvoc.txt ("k L scoring weighting", then one line per node:
+    parent isLeaf 32 descriptor bytes weight).  Node ids are line numbers (root = 0), children keep file order
+    (children.push_back), words are numbered in leaf order (m_words).
+    One deliberate deviation: the reference's `while(!f.eof())` loop turns the file's final newline into one more, empty line,
+    i.e. a childless extra child of the root whose descriptor is uninitialised memory; that node is not reproduced."""
+    import pandas as pd
+    fh = open(source, "rb") if isinstance(source, (str, bytes)) else source
+    try:
+        header = fh.readline().split()
+        k, L, scoring, weighting = [int(v) for v in header[:4]]
+        if not (0 <= k <= 20 and 1 <= L <= 10 and 0 <= scoring <= 5 and 0 <= weighting <= 3):
+            raise ValueError("not a DBoW2 text vocabulary")
+        if scoring != 0 or weighting != 0:
+            raise ValueError("only TF_IDF weighting with L1 scoring (what ORBvoc.txt declares) is implemented on the device")
+        t = pd.read_csv(fh, sep=r"\s+", header=None, engine="c", dtype=np.float64).to_numpy()
+    finally:
+        if fh is not source:
+            fh.close()
+    if t.shape[1] != 35:
+        raise ValueError("expected parent, isLeaf, 32 descriptor bytes and a weight per line")
+    n = len(t) + 1
+    parent = t[:, 0].astype(np.int64)
+    is_leaf = t[:, 1] > 0
+    if (parent >= np.arange(1, n)).any() or (parent < 0).any():
+        raise ValueError("a node precedes its parent")
+    node_desc = np.zeros((n, 32), np.uint8)
+    node_desc[1:] = t[:, 2:34].astype(np.uint8)
+    node_weight = np.zeros(n, np.float64)
+    node_weight[1:] = t[:, 34]
+    node_word = np.full(n, -1, np.int32)
+    node_word[1:][is_leaf] = np.arange(int(is_leaf.sum()), dtype=np.int32)
+    counts = np.bincount(parent, minlength=n)
+    child_offset = np.zeros(n + 1, np.int32)
+    child_offset[1:] = np.cumsum(counts)
+    child_ids = (np.argsort(parent, kind="stable") + 1).astype(np.int32)      # stable: file order inside a parent
+    return dict(child_offset=child_offset, child_ids=child_ids, node_desc=node_desc, node_word=node_word, node_weight=node_weight, L=L, k=k)

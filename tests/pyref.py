@@ -456,3 +456,35 @@ def search_bow_frame(kps, desc, feat_node, qnode, qangle, qdesc, nnratio, check_
                     fm[i] = -1
                     nm -= 1
     return np.array(fm, np.int32), nm
+
+
+def bow_transform(voc, desc, levelsup=4):
+    """DBoW2 TemplatedVocabulary::transform (TemplatedVocabulary.h:1127-1260) in plain numpy over the flat tree of
+    orb_slam3_detailed_comments_b200.vocabulary (TF_IDF + L1).  Returns word, node, weight per feature, and the BowVector
+    (ascending words, weights) plus the FeatureVector as {node: [features]} -- features of stopped words (weight 0) enter neither."""
+    co, ch, nd, nw, wt, L = voc["child_offset"], voc["child_ids"], voc["node_desc"], voc["node_word"], voc["node_weight"], voc["L"]
+    nid_level = L - levelsup
+    n = len(desc)
+    word, node, weight = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.float64)
+    bow, feat = {}, {}
+    for i in range(n):
+        fid, level, nid = 0, 0, 0
+        while True:
+            level += 1
+            kids = ch[co[fid]:co[fid + 1]]
+            d = POP[nd[kids] ^ desc[i][None, :]].sum(1)
+            fid = int(kids[int(np.argmin(d))])          # first minimum: `if(d < best_d)`
+            if level == nid_level:
+                nid = fid
+            if co[fid] == co[fid + 1]:
+                break
+        word[i], node[i], weight[i] = nw[fid], nid, wt[fid]
+        if weight[i] > 0:
+            bow[int(word[i])] = bow.get(int(word[i]), 0.0) + float(weight[i])      # addWeight in feature order
+            feat.setdefault(nid, []).append(i)
+    ws = sorted(bow)
+    norm = 0.0
+    for w in ws:                                        # BowVector::normalize(L1): ascending word order
+        norm += abs(bow[w])
+    vals = [bow[w] / norm for w in ws] if norm > 0 else [bow[w] for w in ws]
+    return dict(word=word, node=node, weight=weight, bow_word=np.array(ws, np.int32), bow_weight=np.array(vals, np.float64), feat=feat)
