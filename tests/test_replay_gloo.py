@@ -41,7 +41,7 @@ def _worker(rank, world, port, ret):
 
 def test_two_rank_gloo_sharding_and_gather():
     world = 2
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()
     ret = mgr.dict()
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
