@@ -568,6 +568,11 @@ orb_status liba_create(int32_t device, liba_handle** out);
 void liba_destroy(liba_handle* h);
 /* independent windows, one CTA each */
 orb_status liba_solve(liba_handle* h, int32_t n_problems, const liba_problem* in, liba_result* out);
+/* Host helper (no device work): liba_link::info / infoG / infoA from IMU::Preintegrated::C (15 x 15 floats, row-major), as
+ * EdgeInertial's constructor (G2oTypes.cc:575-586: inverse of the top-left 9 x 9 block, symmetrised, eigenvalues < 1e-12 zeroed)
+ * and Optimizer.cc:2486-2494 (inverses of C.block<3,3>(9,9) and (12,12)) compute them; oldest != 0 applies the 1e-2 of
+ * Optimizer.cc:2477-2478 (i == N - 1). */
+orb_status liba_link_information(const float* C15x15, int32_t oldest, double* info81, double* infoG9, double* infoA9);
 
 #ifdef __cplusplus
 }

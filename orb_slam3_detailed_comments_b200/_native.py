@@ -187,6 +187,7 @@ SIGNATURES = {
     "liba_create": (_I, [_I, C.POINTER(_VP)]),
     "liba_destroy": (None, [_VP]),
     "liba_solve": (_I, [_VP, _I, C.POINTER(liba_problem), C.POINTER(liba_result)]),
+    "liba_link_information": (_I, [_VP, _I, _VP, _VP, _VP]),
     "orbm_search_last_frame": (_I, [_VP, C.POINTER(orbm_camera), C.POINTER(orbm_last_queries), _F, _I, _VP, _VP]),
 }
 

@@ -112,3 +112,72 @@ extern "C" orb_status liba_solve(liba_handle* h, int32_t n_problems, const liba_
     for (int i = 0; i < n_problems; ++i) liba_unpack(in[i], h->h_buf + base[i], hdev[i], h->d_buf + base[i], &out[i]);
     return ORB_OK;
 }
+
+// ---- host helper: the information matrices of one link from IMU::Preintegrated::C ---------------------------------------------
+namespace {
+
+bool invert_n(const double* A, int n, double* out) {      // Gauss-Jordan with partial pivoting (Eigen's inverse() is PartialPivLU)
+    std::vector<double> a(A, A + n * n);
+    for (int i = 0; i < n * n; ++i) out[i] = (i / n == i % n) ? 1.0 : 0.0;
+    for (int c = 0; c < n; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < n; ++r) if (fabs(a[r * n + c]) > fabs(a[piv * n + c])) piv = r;
+        if (!(fabs(a[piv * n + c]) > 0)) return false;
+        if (piv != c) for (int k = 0; k < n; ++k) { std::swap(a[c * n + k], a[piv * n + k]); std::swap(out[c * n + k], out[piv * n + k]); }
+        const double d = 1.0 / a[c * n + c];
+        for (int k = 0; k < n; ++k) { a[c * n + k] *= d; out[c * n + k] *= d; }
+        for (int r = 0; r < n; ++r) {
+            if (r == c) continue;
+            const double f = a[r * n + c];
+            if (f == 0.0) continue;
+            for (int k = 0; k < n; ++k) { a[r * n + k] -= f * a[c * n + k]; out[r * n + k] -= f * out[c * n + k]; }
+        }
+    }
+    return true;
+}
+
+void jacobi_eigen(double* A, int n, double* V) {          // cyclic Jacobi: A (symmetric) -> diagonal, V = eigenvectors (columns)
+    for (int i = 0; i < n * n; ++i) V[i] = (i / n == i % n) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        double off = 0, diag = 0;
+        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) (i == j ? diag : off) += A[i * n + j] * A[i * n + j];
+        if (off <= 1e-32 * diag) break;
+        for (int p = 0; p < n; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                if (A[p * n + q] == 0.0) continue;
+                const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * A[p * n + q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < n; ++k) { const double akp = A[k * n + p], akq = A[k * n + q]; A[k * n + p] = c * akp - s * akq; A[k * n + q] = s * akp + c * akq; }
+                for (int k = 0; k < n; ++k) { const double apk = A[p * n + k], aqk = A[q * n + k]; A[p * n + k] = c * apk - s * aqk; A[q * n + k] = s * apk + c * aqk; }
+                for (int k = 0; k < n; ++k) { const double vkp = V[k * n + p], vkq = V[k * n + q]; V[k * n + p] = c * vkp - s * vkq; V[k * n + q] = s * vkp + c * vkq; }
+            }
+    }
+}
+
+}  // namespace
+
+extern "C" orb_status liba_link_information(const float* C15, int32_t oldest, double* info81, double* infoG9, double* infoA9) {
+    if (!C15 || !info81 || !infoG9 || !infoA9) return set_error(ORB_ERR_INVALID, "null argument");
+    double M[81], Mi[81], V[81];
+    for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) M[9 * i + j] = (double)C15[15 * i + j];
+    if (!invert_n(M, 9, Mi)) return set_error(ORB_ERR_INVALID, "liba_link_information: singular covariance block");
+    for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) M[9 * i + j] = (Mi[9 * i + j] + Mi[9 * j + i]) / 2;      // G2oTypes.cc:577
+    jacobi_eigen(M, 9, V);
+    double eig[9];
+    for (int i = 0; i < 9; ++i) eig[i] = M[9 * i + i] < 1e-12 ? 0.0 : M[9 * i + i];                                    // G2oTypes.cc:580-583
+    const double scale = oldest ? 1e-2 : 1.0;                                                                         // Optimizer.cc:2477-2478
+    for (int i = 0; i < 9; ++i)
+        for (int j = 0; j < 9; ++j) {
+            double s = 0;
+            for (int k = 0; k < 9; ++k) s += V[9 * i + k] * eig[k] * V[9 * j + k];
+            info81[9 * i + j] = s * scale;
+        }
+    for (int b = 0; b < 2; ++b) {
+        double B[9];
+        const int o = 9 + 3 * b;
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) B[3 * i + j] = (double)C15[15 * (o + i) + o + j];
+        if (!invert_n(B, 3, b == 0 ? infoG9 : infoA9)) return set_error(ORB_ERR_INVALID, "liba_link_information: singular random-walk covariance");
+    }
+    return ORB_OK;
+}

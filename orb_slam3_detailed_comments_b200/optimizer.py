@@ -188,3 +188,11 @@ class InertialOptimizer:
 
     def LocalInertialBA(self, problem, lambda_init=1.0, max_iters=10):
         return self.LocalInertialBABatch([problem], lambda_init, max_iters)[0]
+
+
+def link_information(C15, oldest=False):
+    """EdgeInertial / EdgeGyroRW / EdgeAccRW information matrices from IMU::Preintegrated::C (liba_link_information; host-only)."""
+    Cm = np.ascontiguousarray(C15, np.float32).reshape(15, 15)
+    info, ig, ia = np.zeros(81), np.zeros(9), np.zeros(9)
+    N.check(N.lib().liba_link_information(N.ptr(Cm), int(bool(oldest)), N.ptr(info), N.ptr(ig), N.ptr(ia)))
+    return info.reshape(9, 9), ig.reshape(3, 3), ia.reshape(3, 3)

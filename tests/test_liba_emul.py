@@ -185,3 +185,24 @@ def test_duplicate_links_are_rejected():
     s["links"] = s["links"][:-1]
     p, r, _ = pack_inertial_problem(s, 1.0, 10, keep)
     assert L.emul_liba_layout_total(C.byref(p)) > 0
+
+
+def test_link_information_helper_matches_numpy():
+    """liba_link_information (host-only entry of the C ABI): EdgeInertial's information from IMU::Preintegrated::C."""
+    from orb_slam3_detailed_comments_b200.optimizer import link_information
+    rng = np.random.default_rng(0)
+    for trial in range(12):
+        A = rng.normal(size=(15, 15))
+        Cm = (A @ A.T * 1e-4 + np.diag(rng.uniform(1e-6, 1e-3, 15))).astype(np.float32)
+        if trial % 4 == 0:
+            Cm[:9, :9] *= 1e8            # information eigenvalues around 1e-6..1e-12: some fall under the 1e-12 clamp
+        info, ig, ia = link_information(Cm, oldest=(trial % 2 == 0))
+        M = np.linalg.inv(Cm[:9, :9].astype(np.float64))
+        w, V = np.linalg.eigh((M + M.T) / 2)
+        w[w < 1e-12] = 0
+        ref = V @ np.diag(w) @ V.T * (1e-2 if trial % 2 == 0 else 1.0)
+        assert np.abs(info - ref).max() <= 1e-9 * np.abs(ref).max()
+        assert np.allclose(ig, np.linalg.inv(Cm[9:12, 9:12].astype(np.float64)), rtol=1e-12)
+        assert np.allclose(ia, np.linalg.inv(Cm[12:15, 12:15].astype(np.float64)), rtol=1e-12)
+    with pytest.raises(Exception):
+        link_information(np.zeros((15, 15), np.float32))
