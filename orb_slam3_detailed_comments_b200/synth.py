@@ -179,12 +179,66 @@ def _expm(w):
     return np.eye(3) + np.sin(t) / t * W + (1 - np.cos(t)) / t ** 2 * W @ W
 
 
+def _hat32(v):
+    return np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]], np.float32)
+
+
+def preintegrate(acc, gyr, dt, bias6=None, ng=1.7e-4, na=2.0e-3, ngw=1.9393e-5, naw=3.0e-3, freq=200.0):
+    """IMU::Preintegrated::IntegrateNewMeasurement over a run of samples (src/ImuTypes.cc:247-320, IntegratedRotation :125-152,
+    Calib::Set :565-580 with Tracking's sqrt(freq) scaling of the EuRoC.yaml noise densities), in float32 like the reference.
+    acc / gyr: [n][3]; bias6 = bax bay baz bwx bwy bwz.  Returns the members a liba_link needs (dR dV dP JRg JVg JVa JPg JPa, C
+    15 x 15, dT, bias).  NormalizeRotation (an SVD re-orthonormalisation) is replaced by nothing: n <= a few hundred steps."""
+    f = np.float32
+    b = np.zeros(6, f) if bias6 is None else np.asarray(bias6, f)
+    sf = np.sqrt(freq)
+    Nga = np.diag(np.array([(ng * sf) ** 2] * 3 + [(na * sf) ** 2] * 3, f))
+    NgaWalk = np.diag(np.array([(ngw / sf) ** 2] * 3 + [(naw / sf) ** 2] * 3, f))
+    dR, dV, dP = np.eye(3, dtype=f), np.zeros(3, f), np.zeros(3, f)
+    JRg, JVg, JVa, JPg, JPa = (np.zeros((3, 3), f) for _ in range(5))
+    C = np.zeros((15, 15), f)
+    dT = f(0)
+    dt = f(dt)
+    for a_m, w_m in zip(np.asarray(acc, f), np.asarray(gyr, f)):
+        A, B = np.eye(9, dtype=f), np.zeros((9, 6), f)
+        a = a_m - b[:3]
+        dP = dP + dV * dt + f(0.5) * (dR @ a) * dt * dt
+        dV = dV + (dR @ a) * dt
+        Wacc = _hat32(a)
+        A[3:6, 0:3] = -dR * dt @ Wacc
+        A[6:9, 0:3] = f(-0.5) * dR * dt * dt @ Wacc
+        A[6:9, 3:6] = np.eye(3, dtype=f) * dt
+        B[3:6, 3:6] = dR * dt
+        B[6:9, 3:6] = f(0.5) * dR * dt * dt
+        JPa = JPa + JVa * dt - f(0.5) * dR * dt * dt
+        JPg = JPg + JVg * dt - f(0.5) * dR * dt * dt @ Wacc @ JRg
+        JVa = JVa - dR * dt
+        JVg = JVg - dR * dt @ Wacc @ JRg
+        v = (w_m - b[3:]) * dt
+        d2 = f(v @ v)
+        d = np.sqrt(d2)
+        W = _hat32(v)
+        if d < 1e-4:
+            dRi, rJ = np.eye(3, dtype=f) + W, np.eye(3, dtype=f)
+        else:
+            dRi = np.eye(3, dtype=f) + W * (np.sin(d) / d) + W @ W * ((f(1) - np.cos(d)) / d2)
+            rJ = np.eye(3, dtype=f) - W * ((f(1) - np.cos(d)) / d2) + W @ W * ((d - np.sin(d)) / (d2 * d))
+        dR = (dR @ dRi).astype(f)
+        A[0:3, 0:3] = dRi.T
+        B[0:3, 0:3] = rJ * dt
+        C[0:9, 0:9] = A @ C[0:9, 0:9] @ A.T + B @ Nga @ B.T
+        C[9:15, 9:15] += NgaWalk
+        JRg = dRi.T @ JRg - rJ * dt
+        dT = dT + dt
+    return dict(dR=dR, dV=dV, dP=dP, JRg=JRg, JVg=JVg, JVa=JVa, JPg=JPg, JPa=JPa, C=C, dT=float(dT), bias=b)
+
+
 def inertial_window(n_opt=10, n_cov_fixed=3, n_mp=2000, seed=0, noise=0.5, perturb=True, dt=0.25):
     """A synthetic Optimizer::LocalInertialBA window (Optimizer.cc:2217-2340): a temporal chain of n_opt optimisable keyframes
-    plus the fixed keyframe before them (index 0), joined by inertial links, then n_cov_fixed fixed covisible keyframes without
-    links; stereo / mono observations of n_mp points.  Returns the dict orb_slam3_detailed_comments_b200.InertialOptimizer takes
+    plus the fixed keyframe before them (index 0), joined by inertial links preintegrated from synthetic 200 Hz IMU samples
+    (preintegrate(), information matrices through liba_link_information), then n_cov_fixed fixed covisible keyframes without links; stereo / mono observations of n_mp points.  Returns the dict orb_slam3_detailed_comments_b200.InertialOptimizer takes
     (state [nKF][21] = Rwb twb v bg ba, fixed, point, edge_kf, edge_mp, obs, inv_sigma2, links, Tcb, cam5)."""
     from ._native import LIBA_LINK
+    from .optimizer import link_information
     rng = np.random.default_rng(seed)
     G = np.array([0, 0, -float(np.float32(9.81))])
     n_chain = n_opt + 1
@@ -194,23 +248,26 @@ def inertial_window(n_opt=10, n_cov_fixed=3, n_mp=2000, seed=0, noise=0.5, pertu
         states.append(np.concatenate([R.reshape(-1), p, v, np.zeros(6)]))
         if k == n_chain - 1:
             break
-        w, a = rng.normal(0, 0.15, 3), rng.normal(0, 0.5, 3) - R.T @ G * 0.97      # near-hovering body: specific force ~ -g
-        dR = _expm(w * dt)
-        acc_w = R @ a
-        v2 = v + (acc_w + G) * dt
-        p2 = p + v * dt + 0.5 * (acc_w + G) * dt * dt
+        # 200 Hz IMU samples over the interval: slowly varying body rates and a specific force near -g (a hovering platform),
+        # preintegrated exactly as the reference does; the next keyframe state is the one these deltas predict
+        n_s = int(round(dt * 200))
+        tt = np.linspace(0, 1, n_s)[:, None]
+        w0, w1 = rng.normal(0, 0.15, 3), rng.normal(0, 0.15, 3)
+        a0, a1 = rng.normal(0, 0.5, 3), rng.normal(0, 0.5, 3)
+        gyr = w0 * (1 - tt) + w1 * tt
+        acc = a0 * (1 - tt) + a1 * tt - (R.T @ G) * 0.97
+        pre = preintegrate(acc, gyr, dt / n_s)
+        dT = pre["dT"]
+        dR = pre["dR"].astype(np.float64)
+        v2 = v + G * dT + R @ pre["dV"].astype(np.float64)
+        p2 = p + v * dT + 0.5 * G * dT * dT + R @ pre["dP"].astype(np.float64)
         lk = links[k]
-        lk["k1"], lk["k2"], lk["robust"], lk["dt"] = k, k + 1, int(k == 0), dt
-        lk["dR"], lk["dV"], lk["dP"] = dR.reshape(-1), R.T @ (v2 - v - G * dt), R.T @ (p2 - p - v * dt - 0.5 * G * dt * dt)
-        lk["JRg"] = (-np.eye(3) * dt).reshape(-1)
-        lk["JVg"] = rng.normal(0, 0.05, 9)
-        lk["JVa"] = (-np.eye(3) * dt).reshape(-1)
-        lk["JPg"] = rng.normal(0, 0.01, 9)
-        lk["JPa"] = (-np.eye(3) * 0.5 * dt * dt).reshape(-1)
-        A = rng.normal(size=(9, 9))
-        lk["info"] = ((A @ A.T + 9 * np.eye(9)) * 50 * (1e-2 if k == 0 else 1.0)).reshape(-1)
-        lk["infoG"] = (np.eye(3) * 1e4).reshape(-1)
-        lk["infoA"] = (np.eye(3) * 1e3).reshape(-1)
+        lk["k1"], lk["k2"], lk["robust"], lk["dt"] = k, k + 1, int(k == 0), dT
+        for name in ("dR", "dV", "dP", "JRg", "JVg", "JVa", "JPg", "JPa"):
+            lk[name] = pre[name].reshape(-1)
+        lk["bias"] = pre["bias"]
+        info, ig, ia = link_information(pre["C"], oldest=(k == 0))
+        lk["info"], lk["infoG"], lk["infoA"] = info.reshape(-1), ig.reshape(-1), ia.reshape(-1)
         R, p, v = R @ dR, p2, v2
     for _ in range(n_cov_fixed):       # covisible fixed keyframes: poses near the chain, no inertial links
         s = states[rng.integers(0, n_chain)].copy()

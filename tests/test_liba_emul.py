@@ -206,3 +206,41 @@ def test_link_information_helper_matches_numpy():
         assert np.allclose(ia, np.linalg.inv(Cm[12:15, 12:15].astype(np.float64)), rtol=1e-12)
     with pytest.raises(Exception):
         link_information(np.zeros((15, 15), np.float32))
+
+
+def test_threaded_run_on_the_bench_window(mt_binary, tmp_path):
+    """Realistic conditioning (preintegrated links: information ~1e8 on rotation, 1e10 on the gyro random walk) under a different
+    reduction order (8 threads): same Levenberg path, values inside the BA tolerance, and no data race."""
+    from orb_slam3_detailed_comments_b200 import synth
+    s = synth.inertial_window(seed=5, n_mp=500)
+    ref = po.liba(s["state"], s["fixed"], s["point"], s["edge_kf"], s["edge_mp"], s["obs"], s["inv_sigma2"], s["Tcb"], s["cam5"],
+                  s["links"].view(po.LIBA_LINK), 1.0, 10)
+    got = run_mt(mt_binary, s, 1.0, 10, 8, tmp_path)
+    assert got["iterations"] == ref["iterations"] and abs(got["trials"] - ref["trials"]) <= 1
+    assert np.abs(got["state"] - ref["state"]).max() < TOL and np.abs(got["point"] - ref["point"]).max() < TOL
+
+
+def test_preintegration_generator_is_self_consistent():
+    """synth.preintegrate (the float32 restatement of IMU::Preintegrated::IntegrateNewMeasurement that feeds the synthetic windows):
+    constant rates -> closed forms; bias Jacobians -> finite differences of the deltas with respect to the bias."""
+    from orb_slam3_detailed_comments_b200 import synth
+    n, dt = 50, 0.005
+    w, a = np.array([0.2, -0.1, 0.3]), np.array([0.5, -0.3, 9.6])
+    pre = synth.preintegrate(np.tile(a, (n, 1)), np.tile(w, (n, 1)), dt)
+    assert np.abs(pre["dR"] - synth._expm(w * n * dt)).max() < 2e-5
+    assert abs(pre["dT"] - n * dt) < 1e-6
+    eps = 1e-3
+    for axis in range(3):
+        for kind, sl in (("a", 0), ("g", 3)):
+            b = np.zeros(6)
+            b[sl + axis] = eps
+            p2 = synth.preintegrate(np.tile(a, (n, 1)), np.tile(w, (n, 1)), dt, b)
+            JV, JP = pre["JVa" if kind == "a" else "JVg"], pre["JPa" if kind == "a" else "JPg"]
+            assert np.abs((p2["dV"] - pre["dV"]) / eps - JV[:, axis]).max() < 5e-3
+            assert np.abs((p2["dP"] - pre["dP"]) / eps - JP[:, axis]).max() < 5e-3
+            if kind == "g":
+                dphi = (pre["dR"].astype(np.float64).T @ p2["dR"].astype(np.float64))
+                rot = np.array([dphi[2, 1] - dphi[1, 2], dphi[0, 2] - dphi[2, 0], dphi[1, 0] - dphi[0, 1]]) / 2
+                assert np.abs(rot / eps - pre["JRg"][:, axis]).max() < 5e-3
+    Cm = pre["C"].astype(np.float64)
+    assert np.allclose(Cm, Cm.T, atol=1e-9) and (np.linalg.eigvalsh(Cm[:9, :9]) > 0).all()
