@@ -597,8 +597,8 @@ extern "C" int orc_pose_optimization(int n, const double* Xw, const double* obs,
 
 // ------------------------------------------------------------------------------------------------
 // Optimizer::LocalInertialBA numeric core  src/Optimizer.cc:2203-2812 (one camera, Nleft == -1) -- SURVEY 8(f) N2.
-// ORACLE ONLY so far: the device implementation is the next row; this restatement, its finite-difference checks and its
-// fixed-point tests (tests/test_oracle_inertial.py) are the groundwork.
+// The device implementation is csrc/liba_core.cuh (checked against this restatement by tests/test_liba_emul.py and, on a GPU,
+// tests/test_liba_gpu.py); this restatement is pinned by finite-difference checks and fixed-point tests (tests/test_oracle_inertial.py).
 //
 // Vertices per keyframe: VertexPose (ImuCamPose: Rwb, twb; update twb += Rwb ut, Rwb = Rwb Exp(ur), G2oTypes.cc:221-244),
 // VertexVelocity, VertexGyroBias, VertexAccBias (additive); a keyframe is either optimised or fixed as a whole.  Marginalised

@@ -1,4 +1,4 @@
-"""CPU tier: the LocalInertialBA oracle (the device side is not built yet).  Pins available without the reference:
+"""CPU tier: the LocalInertialBA oracle (the device side is csrc/liba_core.cuh, checked against this oracle by tests/test_liba_emul.py).  Pins available without the reference:
 finite differences of EdgeInertial's analytic Jacobians under the vertices' own update rules, the noise-free fixed point, and
 recovery of a perturbed trajectory."""
 import numpy as np
