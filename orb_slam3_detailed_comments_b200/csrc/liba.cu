@@ -1,8 +1,10 @@
 // liba.cu -- Optimizer::LocalInertialBA's numeric core on the device (include/orbslam3_b200.h, liba_*).
 // The algorithm lives in liba_core.cuh as barrier-separated SPMD phases shared with the CPU emulation harness; this file is
-// the launch wrapper: one CTA per window, everything for a window in one blob (liba_pack.h), fp64 throughout.
+// the launch wrapper: one thread-block cluster (or one CTA) per window, everything for a window in one blob (liba_pack.h),
+// fp64 throughout.
 // STATUS: cross-compiles for sm_100a and is validated on the host through tests/host_emul; first GPU run is pending.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -14,11 +16,19 @@ using namespace orb;
 namespace {
 
 constexpr int LIBA_THREADS = 256;
+constexpr int LIBA_CS_MAX = 8;       // CTAs (SMs) per window: a portable-size thread-block cluster
 
-__global__ void __launch_bounds__(LIBA_THREADS) k_liba(const LibaDev* __restrict__ problems) {
+// One team (a cluster of `cs` CTAs, or one CTA) per window; blocks of a cluster are consecutive in x.
+__global__ void __launch_bounds__(LIBA_THREADS) k_liba(const LibaDev* __restrict__ problems, int cs) {
     __shared__ double s_red[LIBA_THREADS / 32];
-    LibaDev P = problems[blockIdx.x];
+    LibaDev P = problems[blockIdx.x / cs];
     P.red = s_red;
+    P.cs = cs;
+    P.rank = blockIdx.x % cs;
+    P.l_id = threadIdx.x;
+    P.l_stride = blockDim.x;
+    P.t_id = P.rank * blockDim.x + threadIdx.x;
+    P.t_stride = cs * blockDim.x;
     liba_optimize(P);
 }
 
@@ -104,7 +114,28 @@ extern "C" orb_status liba_solve(liba_handle* h, int32_t n_problems, const liba_
     ORB_CUDA(cudaMemcpyAsync(h->d_buf, h->h_buf, sizeof(LibaDev) * (size_t)n_problems, cudaMemcpyHostToDevice, h->stream));
     for (int i = 0; i < n_problems; ++i)
         ORB_CUDA(cudaMemcpyAsync(h->d_buf + base[i], h->h_buf + base[i], lay[i].io_bytes + lay[i].in_bytes, cudaMemcpyHostToDevice, h->stream));
-    k_liba<<<n_problems, LIBA_THREADS, 0, h->stream>>>(reinterpret_cast<const LibaDev*>(h->d_buf));
+    // small batches get a cluster of 8 SMs per window, large ones fewer (ORB_LIBA_CLUSTER = 1 | 2 | 4 | 8 overrides: a tuning knob)
+    int cs = (n_problems * LIBA_CS_MAX <= 148) ? LIBA_CS_MAX : (n_problems * 4 <= 148 ? 4 : (n_problems * 2 <= 148 ? 2 : 1));
+    if (const char* e = getenv("ORB_LIBA_CLUSTER")) {
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) cs = v;
+    }
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(n_problems * cs);
+        cfg.blockDim = dim3(LIBA_THREADS);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = h->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        ORB_CUDA(cudaLaunchKernelEx(&cfg, k_liba, reinterpret_cast<const LibaDev*>(h->d_buf), cs));
+    }
+    ORB_LAUNCHED();
     ORB_CUDA(cudaGetLastError());
     for (int i = 0; i < n_problems; ++i)
         ORB_CUDA(cudaMemcpyAsync(h->h_buf + base[i], h->d_buf + base[i], lay[i].io_bytes, cudaMemcpyDeviceToHost, h->stream));

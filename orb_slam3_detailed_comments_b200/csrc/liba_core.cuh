@@ -22,27 +22,34 @@
 #define LIBA_HD inline
 #endif
 
+// Execution model.  A TEAM works on one window: on the device a thread-block cluster of `cs` CTAs (cs = 1: one CTA); in
+// tests/host_emul/liba_mt.cpp `cs` groups of host threads; in tests/host_emul/emul.cpp a single thread.  Every thread holds its own
+// copy of the descriptor `P` with its place in the team (t_id / t_stride over the whole team, l_id / l_stride inside its CTA, rank).
+//   LIBA_PAR_FOR / LIBA_SYNC      team-wide strided loop / team-wide barrier (cluster barrier: orders global memory across the CTAs)
+//   LIBA_LOCAL_FOR / LIBA_LOCAL_SYNC   the same inside one CTA; used by the dense factorisation, which runs on rank 0 only because
+//                                      it needs two barriers per column and a CTA barrier is an order of magnitude cheaper
+#define LIBA_PAR_FOR(i, n) for (int i = P.t_id; i < (n); i += P.t_stride)
+#define LIBA_LOCAL_FOR(i, n) for (int i = P.l_id; i < (n); i += P.l_stride)
+#define LIBA_LEADER() (P.t_id == 0)
+#define LIBA_RANK0() (P.rank == 0)
 #if defined(__CUDA_ARCH__)
-#define LIBA_PAR_FOR(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
-#define LIBA_SYNC() __syncthreads()
-#define LIBA_LEADER() (threadIdx.x == 0)
+#include <cooperative_groups.h>
+#define LIBA_SYNC() do { if (P.cs > 1) cooperative_groups::this_cluster().sync(); else __syncthreads(); } while (0)
+#define LIBA_LOCAL_SYNC() __syncthreads()
 #define LIBA_FLAG_SET(p) (*(p) = 1)
 #elif defined(LIBA_EMUL_THREADS)
-// tests/host_emul/liba_mt.cpp: N host threads play one CTA with REAL barriers and atomics, so ThreadSanitizer reports a missing
-// LIBA_SYNC (or a plain store that should be atomic) as a data race -- the device-only hazards, checked without a device.
+// tests/host_emul/liba_mt.cpp: host threads play the team with REAL barriers, so ThreadSanitizer reports a missing LIBA_SYNC, a
+// LIBA_LOCAL_SYNC where a team barrier is needed, or two threads accumulating into one location, as a data race.
 namespace orb {
-extern thread_local int liba_tid;
-extern int liba_nthreads;
-void liba_barrier();
+void liba_barrier_team();
+void liba_barrier_cta(int rank);
 }
-#define LIBA_PAR_FOR(i, n) for (int i = orb::liba_tid; i < (n); i += orb::liba_nthreads)
-#define LIBA_SYNC() orb::liba_barrier()
-#define LIBA_LEADER() (orb::liba_tid == 0)
+#define LIBA_SYNC() orb::liba_barrier_team()
+#define LIBA_LOCAL_SYNC() orb::liba_barrier_cta(P.rank)
 #define LIBA_FLAG_SET(p) __atomic_store_n((p), 1, __ATOMIC_RELAXED)
 #else
-#define LIBA_PAR_FOR(i, n) for (int i = 0; i < (n); ++i)
 #define LIBA_SYNC() ((void)0)
-#define LIBA_LEADER() (true)
+#define LIBA_LOCAL_SYNC() ((void)0)
 #define LIBA_FLAG_SET(p) (*(p) = 1)
 #endif
 
@@ -99,7 +106,11 @@ struct LibaDev {
     double* Epp;          // [nE][27]  upper triangle (21) of the edge's 6 x 6 pose block, then its 6 b terms
     double* Lblk;         // [nL][930] 30 x 30 block over [k1 15 | k2 15] of the inertial + random-walk edges, then 30 b terms
     int* flag;            // [4] solver failure flag
-    double* red;          // reduction scratch (device: shared memory, 64 doubles)
+    double* red;          // reduction scratch of this CTA (device: shared memory, one double per warp; emulation: per thread)
+    double* partials;     // [8] per-CTA partial results of a team reduction (global memory)
+    int t_id, t_stride;   // this thread's place in the team ...
+    int l_id, l_stride;   // ... and inside its CTA
+    int rank, cs;         // CTA rank in the team, CTAs per team
     // results
     double* out_scalars;  // iterations, trials, lambda, chi2, chi2_initial
 };
@@ -162,7 +173,7 @@ LIBA_HD double liba_huber(double e, double delta, double dsqr, double* w) {
     return 2 * s * delta - dsqr;
 }
 
-// block-wide sum / max: every thread receives the result (host: identity)
+// team-wide sum / max in a fixed order (warp tree, warps in order, CTAs in rank order): every thread receives the same value
 LIBA_HD double liba_sum(const LibaDev& P, double v) {
 #if defined(__CUDA_ARCH__)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -171,13 +182,20 @@ LIBA_HD double liba_sum(const LibaDev& P, double v) {
     __syncthreads();
     double s = 0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += P.red[w];
+    if (P.cs > 1) {
+        if (threadIdx.x == 0) P.partials[P.rank] = s;
+        cooperative_groups::this_cluster().sync();
+        s = 0;
+        for (int r = 0; r < P.cs; ++r) s += P.partials[r];
+        cooperative_groups::this_cluster().sync();      // partials are rewritten by the next reduction
+    }
     return s;
 #elif defined(LIBA_EMUL_THREADS)
-    liba_barrier();
-    P.red[liba_tid] = v;
-    liba_barrier();
+    liba_barrier_team();
+    P.red[P.t_id] = v;
+    liba_barrier_team();
     double s = 0;
-    for (int w = 0; w < liba_nthreads; ++w) s += P.red[w];
+    for (int w = 0; w < P.t_stride; ++w) s += P.red[w];
     return s;
 #else
     (void)P;
@@ -192,13 +210,20 @@ LIBA_HD double liba_max(const LibaDev& P, double v) {
     __syncthreads();
     double s = P.red[0];
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w) s = fmax(s, P.red[w]);
+    if (P.cs > 1) {
+        if (threadIdx.x == 0) P.partials[P.rank] = s;
+        cooperative_groups::this_cluster().sync();
+        s = P.partials[0];
+        for (int r = 1; r < P.cs; ++r) s = fmax(s, P.partials[r]);
+        cooperative_groups::this_cluster().sync();
+    }
     return s;
 #elif defined(LIBA_EMUL_THREADS)
-    liba_barrier();
-    P.red[liba_tid] = v;
-    liba_barrier();
+    liba_barrier_team();
+    P.red[P.t_id] = v;
+    liba_barrier_team();
     double s = P.red[0];
-    for (int w = 1; w < liba_nthreads; ++w) s = fmax(s, P.red[w]);
+    for (int w = 1; w < P.t_stride; ++w) s = fmax(s, P.red[w]);
     return s;
 #else
     (void)P;
@@ -526,39 +551,47 @@ LIBA_HD bool liba_solve_system(const LibaDev& P, double lambda) {
         *dst = acc;
     }
     LIBA_SYNC();
-    // dense LDL^T of Hs (upper triangle read, right-looking): after step j row j holds D_j at (j,j) and L(i,j) at (j,i), i > j
-    for (int j = 0; j < sp; ++j) {
-        const double dj = P.Hs[(size_t)j * sp + j];
-        if (!(fabs(dj) > 0) || !isfinite(dj)) { if (LIBA_LEADER()) LIBA_FLAG_SET(&P.flag[0]); break; }   // uniform: every thread reads the same dj
-        const int m = sp - j - 1;
-        LIBA_PAR_FOR(t, m * m) {        // trailing update with the not-yet-scaled row j:  A(i,k) -= A(j,i) A(j,k) / d_j, k >= i
-            const int i = j + 1 + t / m, k = j + 1 + t % m;
-            if (k >= i) P.Hs[(size_t)i * sp + k] -= P.Hs[(size_t)j * sp + i] * P.Hs[(size_t)j * sp + k] / dj;
+    // dense LDL^T of Hs (upper triangle read, right-looking) and the triangular solves, on the team's first CTA only.  After step j
+    // row j holds D_j at (j,j) and L(i,j) at (j,i), i > j.
+    if (LIBA_RANK0()) {
+        bool bad = P.flag[0] != 0;            // a singular landmark block (set before the team barrier above)
+        for (int j = 0; j < sp && !bad; ++j) {
+            const double dj = P.Hs[(size_t)j * sp + j];
+            if (!(fabs(dj) > 0) || !isfinite(dj)) { bad = true; break; }   // uniform: every thread reads the same dj
+            const int m = sp - j - 1;
+            LIBA_LOCAL_FOR(t, m * m) {        // trailing update with the not-yet-scaled row j:  A(i,k) -= A(j,i) A(j,k) / d_j, k >= i
+                const int i = j + 1 + t / m, k = j + 1 + t % m;
+                if (k >= i) P.Hs[(size_t)i * sp + k] -= P.Hs[(size_t)j * sp + i] * P.Hs[(size_t)j * sp + k] / dj;
+            }
+            LIBA_LOCAL_SYNC();
+            LIBA_LOCAL_FOR(t, m) P.Hs[(size_t)j * sp + j + 1 + t] /= dj;   // L(j+1+t, j)
+            LIBA_LOCAL_SYNC();
         }
-        LIBA_SYNC();
-        LIBA_PAR_FOR(t, m) P.Hs[(size_t)j * sp + j + 1 + t] /= dj;   // L(j+1+t, j)
-        LIBA_SYNC();
+        if (bad) {
+            LIBA_LOCAL_SYNC();                // every thread has read the flag / the pivot before it is (re)written
+            if (P.l_id == 0) LIBA_FLAG_SET(&P.flag[0]);
+        } else {
+            // forward: y = L^-1 bs ; diagonal ; backward: x = L^-T y     (column-oriented, one column per barrier)
+            LIBA_LOCAL_FOR(i, sp) P.y[i] = P.bs[i];
+            LIBA_LOCAL_SYNC();
+            for (int j = 0; j < sp; ++j) {
+                const double yj = P.y[j];
+                LIBA_LOCAL_FOR(t, sp - j - 1) P.y[j + 1 + t] -= P.Hs[(size_t)j * sp + j + 1 + t] * yj;
+                LIBA_LOCAL_SYNC();
+            }
+            LIBA_LOCAL_FOR(i, sp) P.y[i] /= P.Hs[(size_t)i * sp + i];
+            LIBA_LOCAL_SYNC();
+            for (int j = sp - 1; j >= 0; --j) {
+                const double xj = P.y[j];
+                LIBA_LOCAL_FOR(t, j) P.y[t] -= P.Hs[(size_t)t * sp + j] * xj;   // L(j, t) lives at (t, j)
+                LIBA_LOCAL_SYNC();
+            }
+            LIBA_LOCAL_FOR(i, sp) P.x[i] = P.y[i];
+        }
     }
-    LIBA_SYNC();
+    LIBA_SYNC();      // x (keyframe part) and the failure flag reach the whole team
     const bool failed = P.flag[0] != 0;
-    if (!failed && sp > 0) {
-        // forward: y = L^-1 bs ; diagonal ; backward: x = L^-T y     (column-oriented, one column per barrier)
-        LIBA_PAR_FOR(i, sp) P.y[i] = P.bs[i];
-        LIBA_SYNC();
-        for (int j = 0; j < sp; ++j) {
-            const double yj = P.y[j];
-            LIBA_PAR_FOR(t, sp - j - 1) P.y[j + 1 + t] -= P.Hs[(size_t)j * sp + j + 1 + t] * yj;
-            LIBA_SYNC();
-        }
-        LIBA_PAR_FOR(i, sp) P.y[i] /= P.Hs[(size_t)i * sp + i];
-        LIBA_SYNC();
-        for (int j = sp - 1; j >= 0; --j) {
-            const double xj = P.y[j];
-            LIBA_PAR_FOR(t, j) P.y[t] -= P.Hs[(size_t)t * sp + j] * xj;   // L(j, t) lives at (t, j)
-            LIBA_SYNC();
-        }
-        LIBA_PAR_FOR(i, sp) P.x[i] = P.y[i];
-        LIBA_SYNC();
+    if (!failed) {
         LIBA_PAR_FOR(l, P.nMP) {
             double c[3] = {P.b[sp + 3 * l], P.b[sp + 3 * l + 1], P.b[sp + 3 * l + 2]};
             for (int k = P.pt_off[l]; k < P.pt_off[l + 1]; ++k) {

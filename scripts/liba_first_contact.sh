@@ -6,9 +6,9 @@
 set -u
 mkdir -p gpurun_out
 export ORB_LIBA_GPU=1
-timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_liba_gpu.py -x -q -k "matches_oracle and 11" > gpurun_out/liba_memcheck.log 2>&1
+timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_liba_gpu.py -x -q -k "matches_oracle and 11-1.0" > gpurun_out/liba_memcheck.log 2>&1
 echo "memcheck exit $?" | tee -a gpurun_out/liba_memcheck.log
-timeout 300 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_liba_gpu.py -x -q -k "matches_oracle and 12" > gpurun_out/liba_racecheck.log 2>&1
+timeout 300 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_liba_gpu.py -x -q -k "matches_oracle and 12-0.01" > gpurun_out/liba_racecheck.log 2>&1
 echo "racecheck exit $?" | tee -a gpurun_out/liba_racecheck.log
 timeout 600 python -m pytest tests/test_liba_gpu.py -x -q 2>&1 | tee gpurun_out/liba_tests.log
 timeout 600 python bench.py --steps 5 --warmup 3 2>gpurun_out/liba_bench.err | tee gpurun_out/liba_bench.json

@@ -1,21 +1,22 @@
-// tests/host_emul/liba_mt.cpp -- csrc/liba_core.cuh (the source of the k_liba kernel) executed by N host threads that play one
-// CTA: LIBA_PAR_FOR strides by thread id, LIBA_SYNC is a real barrier, LIBA_ATOMIC_ADD a real atomic.  Built with
+// tests/host_emul/liba_mt.cpp -- csrc/liba_core.cuh (the source of the k_liba kernel) executed by host threads that play a
+// team of CTAs: LIBA_PAR_FOR strides by team thread id, LIBA_SYNC is a real team barrier, LIBA_LOCAL_SYNC a real per-CTA barrier.  Built with
 // -fsanitize=thread, a missing barrier or a non-atomic shared update in the device algorithm shows up as a reported data race
-// (exit code 66) on the CPU.  Usage: liba_mt <problem.bin> <result.bin> <threads>
+// (exit code 66) on the CPU.  Usage: liba_mt <problem.bin> <result.bin> <threads per CTA> [CTAs]
 #define LIBA_EMUL_THREADS 1
 #include <barrier>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 #include <thread>
 #include <vector>
 
 #include "../../orb_slam3_detailed_comments_b200/csrc/liba_pack.h"
 
 namespace orb {
-thread_local int liba_tid = 0;
-int liba_nthreads = 1;
-static std::barrier<>* g_barrier = nullptr;
-void liba_barrier() { g_barrier->arrive_and_wait(); }
+static std::barrier<>* g_team = nullptr;
+static std::vector<std::barrier<>*> g_cta;
+void liba_barrier_team() { g_team->arrive_and_wait(); }
+void liba_barrier_cta(int rank) { g_cta[rank]->arrive_and_wait(); }
 }
 
 template <class T>
@@ -45,23 +46,26 @@ int main(int argc, char** argv) {
     for (int i = 0; i < 12; ++i) p.Tcb[i] = dbl[1 + i];
     p.fx = dbl[13]; p.fy = dbl[14]; p.cx = dbl[15]; p.cy = dbl[16]; p.bf = dbl[17];
 
-    const int T = atoi(argv[3]);
+    const int T = atoi(argv[3]), CS = argc > 4 ? atoi(argv[4]) : 1;     // T threads per "CTA", CS "CTAs" in the team
     const orb::LibaLayout lay = orb::liba_pack(p, nullptr, nullptr, nullptr);
+    if (lay.total == 0) return 3;
     std::vector<uint8_t> blob(lay.total + 16, 0);
     orb::LibaDev dev;
     orb::liba_pack(p, blob.data(), blob.data(), &dev);
-    std::vector<double> red(T);
+    std::vector<double> red(T * CS);
     dev.red = red.data();
-    orb::liba_nthreads = T;
-    std::barrier<> bar(T);
-    orb::g_barrier = &bar;
+    std::barrier<> team(T * CS);
+    orb::g_team = &team;
+    std::vector<std::unique_ptr<std::barrier<>>> ctas;
+    for (int r = 0; r < CS; ++r) { ctas.emplace_back(new std::barrier<>(T)); orb::g_cta.push_back(ctas.back().get()); }
     std::vector<std::thread> th;
-    for (int t = 0; t < T; ++t)
-        th.emplace_back([&, t] {
-            orb::liba_tid = t;
-            const orb::LibaDev P = dev;      // every "thread" holds its own copy of the descriptor, like the kernel
-            orb::liba_optimize(P);
-        });
+    for (int r = 0; r < CS; ++r)
+        for (int t = 0; t < T; ++t)
+            th.emplace_back([&, r, t] {
+                orb::LibaDev P = dev;            // every "thread" holds its own copy of the descriptor, like the kernel
+                P.cs = CS; P.rank = r; P.l_id = t; P.l_stride = T; P.t_id = r * T + t; P.t_stride = CS * T;
+                orb::liba_optimize(P);
+            });
     for (auto& t : th) t.join();
 
     std::vector<double> ostate(21 * (size_t)p.n_kf), opoint(3 * (size_t)p.n_mp + 1), ochi(p.n_edges + 1), olchi(3 * (size_t)p.n_links + 1);

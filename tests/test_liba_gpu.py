@@ -32,8 +32,10 @@ def check(got, ref):
     assert np.abs(got["state"] - ref["state"]).max() < TOL and np.abs(got["point"] - ref["point"]).max() < TOL
 
 
+@pytest.mark.parametrize("cluster", [1, 8, 2])
 @pytest.mark.parametrize("seed,lam,iters,n_fixed", [(11, 1.0, 10, 1), (12, 1e-2, 4, 1), (13, 1.0, 10, 3)])
-def test_matches_oracle(opt, seed, lam, iters, n_fixed):
+def test_matches_oracle(opt, monkeypatch, seed, lam, iters, n_fixed, cluster):
+    monkeypatch.setenv("ORB_LIBA_CLUSTER", str(cluster))      # CTAs per window (liba.cu reads it at every call)
     s = perturbed(seed)
     s["fixed"][:] = 0
     s["fixed"][:n_fixed] = 1
@@ -44,3 +46,12 @@ def test_batch_of_windows(opt):
     ss = [perturbed(40 + i, n_kf=5 + i, n_mp=150) for i in range(4)]
     for got, s in zip(opt.LocalInertialBABatch(ss, 1.0, 10), ss):
         check(got, oracle(s, 1.0, 10))
+
+
+def test_bench_window(opt):
+    """The window bench.py times: realistic preintegrated links (information up to 1e10), 27 k edges, a cluster of 8 CTAs."""
+    from orb_slam3_detailed_comments_b200 import synth
+    s = synth.inertial_window(seed=2)
+    ref = po.liba(s["state"], s["fixed"], s["point"], s["edge_kf"], s["edge_mp"], s["obs"], s["inv_sigma2"], s["Tcb"], s["cam5"],
+                  s["links"].view(po.LIBA_LINK), 1.0, 10)
+    check(opt.LocalInertialBA(s, 1.0, 10), ref)
