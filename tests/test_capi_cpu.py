@@ -51,6 +51,7 @@ def test_no_device_means_loud_failure(lib):
     assert b"no CPU fallback" in lib.orb_last_error()
     o = C.c_void_p()
     assert lib.lba_create(0, C.byref(o)) == -6
+    assert lib.liba_create(0, C.byref(o)) == -6 and b"no CPU fallback" in lib.orb_last_error()
 
 
 def test_bad_arguments_are_rejected_without_a_device(lib):
@@ -59,6 +60,8 @@ def test_bad_arguments_are_rejected_without_a_device(lib):
     bad = N.orbx_config(1000, 1.0, 8, 20, 7, 640, 480, 1, 0)       # scaleFactor must exceed 1
     assert lib.orbx_create(C.byref(bad), C.byref(h)) == -1
     assert lib.orbx_counts(None, None, None, None) == -1
+    assert lib.liba_create(0, None) == -1 and lib.liba_solve(None, 1, None, None) == -1
+    assert lib.liba_link_information(None, 0, None, None, None) == -1
 
 
 def test_product_sources_never_touch_the_oracle():
