@@ -4,6 +4,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -271,6 +273,7 @@ static orb_status apply_geometry(orbx_handle* h, int w, int hh) {
             maxSmem = std::max(maxSmem, h->qt_groups[i].smem);
         }
         ORB_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem));
+        ORB_CUDA(cudaFuncSetAttribute(k_quadtree_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem));
     }
     const size_t ordBytes = ((size_t)h->geom.kpTotal + 64) * 4;
     ORB_CUDA(cudaFuncSetAttribute(k_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(ordBytes, (size_t)1024)));
@@ -291,6 +294,7 @@ extern "C" orb_status orbx_create(const orbx_config* cfg, orbx_handle** out) {
     ORB_CUDA(cudaSetDevice(cfg->device));
     orbx_handle* h = new orbx_handle();
     h->cfg = *cfg;
+    if (const char* v = getenv("ORB_QT_VARIANT")) h->qt_variant = atoi(v) == 1 ? 1 : 0;   // opt-in: see k_quadtree_v1
     build_tables(h);
     static const int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
     for (int i = 0; i < 16; ++i)
@@ -423,7 +427,7 @@ static orb_status run_pipeline(orbx_handle* h, int batch, int lap0, int lap1) {
         const orbx_handle::QtGroup& Q = h->qt_groups[gi];
         cudaStream_t qs = gi == 0 ? st : h->aux_stream[gi - 1];
         if (gi > 0) cudaStreamWaitEvent(qs, h->ev_fork, 0);
-        k_quadtree<<<batch * (Q.level_end - Q.level_begin), QT_THREADS, Q.smem, qs>>>(
+        (h->qt_variant == 1 ? k_quadtree_v1 : k_quadtree)<<<batch * (Q.level_end - Q.level_begin), QT_THREADS, Q.smem, qs>>>(
             g, batch, Q.level_begin, h->d_cand, h->d_cand_cnt, h->d_sort, (char*)h->d_node_scratch,
             (int64_t)h->qt_node_stride, Q.sort_cap, h->qt_nodes_in_smem, h->qt_node_cap, h->d_lvl_kp, h->d_lvl_cnt, h->d_err);
         ORB_LAUNCHED();

@@ -30,6 +30,14 @@ namespace orbdev {
 #define QT_PAR_FOR(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
 #define QT_SYNC() __syncthreads()
 #define QT_SERIAL if (threadIdx.x == 0)
+#elif defined(QT_EMUL_THREADS)
+// tests/host_emul/qt_mt.cpp: host threads play the CTA with a real barrier (ThreadSanitizer then sees a missing QT_SYNC as a race)
+extern thread_local int qt_tid;
+extern int qt_nthreads;
+void qt_barrier();
+#define QT_PAR_FOR(i, n) for (int i = orbdev::qt_tid; i < (n); i += orbdev::qt_nthreads)
+#define QT_SYNC() orbdev::qt_barrier()
+#define QT_SERIAL if (orbdev::qt_tid == 0)
 #else
 #define QT_PAR_FOR(i, n) for (int i = 0; i < (n); ++i)
 #define QT_SYNC() ((void)0)
@@ -166,6 +174,23 @@ __device__ inline int qt_exscan(int* a, int n, int* tmp) {
         run += v;
     }
     __syncthreads();
+    return total;
+}
+#elif defined(QT_EMUL_THREADS)
+inline int qt_exscan(int* a, int n, int* tmp) {
+    qt_barrier();
+    if (qt_tid == 0) {
+        int run = 0;
+        for (int i = 0; i < n; ++i) {
+            const int v = a[i];
+            a[i] = run;
+            run += v;
+        }
+        tmp[32] = run;
+    }
+    qt_barrier();
+    const int total = tmp[32];
+    qt_barrier();
     return total;
 }
 #else
@@ -356,6 +381,10 @@ ORB_HD void qt_std_sort_items(QtItem* a, int n) {
     }
 }
 
+}  // namespace orbdev
+#include "quadtree_sort_par.cuh"
+namespace orbdev {
+
 // reference candidate order (cell row, cell col, y, x) as one comparable key
 ORB_HD uint64_t qt_order_key(int x, int y, const QtGeom& g) {
     const int ci = (y - 3) / g.hCell, cj = (x - 3) / g.wCell;
@@ -367,7 +396,10 @@ ORB_HD uint64_t qt_order_key(int x, int y, const QtGeom& g) {
 // of the t-th node of the final list.  Returns the list length (uniform across the CTA), or -1
 // when the workspace capacity would be exceeded.
 // ---------------------------------------------------------------------------------------------
-ORB_HD int qt_distribute(const uint32_t* arr, int n, const QtGeom& g, QtWork& w, uint32_t* out) {
+// VARIANT 0: the ordered phase's std::sort by one thread (GPU-validated in round 1).  VARIANT 1: the same moves spread over the
+// CTA (quadtree_sort_par.cuh; CPU-validated, opt-in until its first device run).
+template <int VARIANT>
+ORB_HD int qt_distribute_v(const uint32_t* arr, int n, const QtGeom& g, QtWork& w, uint32_t* out) {
     // roots (ORBextractor.cc:718-786): non-empty ones, in order
     int S = 0;
     QT_SERIAL {
@@ -457,8 +489,12 @@ ORB_HD int qt_distribute(const uint32_t* arr, int n, const QtGeom& g, QtWork& w,
                     finish = true;
                     break;
                 }
-                QT_SERIAL { qt_std_sort_items(w.items, nItems); }
-                QT_SYNC();
+                if (VARIANT == 0) {
+                    QT_SERIAL { qt_std_sort_items(w.items, nItems); }
+                    QT_SYNC();
+                } else {
+                    qt_std_sort_items_par(w.items, nItems, w.items2, w.m, w.bnd, w.f, w.scan_tmp);
+                }
                 // processing order p = 0.. corresponds to sorted index j = nItems-1-p
                 QT_PAR_FOR(p, nItems) {
                     const QtItem it = w.items[nItems - 1 - p];
@@ -484,6 +520,8 @@ ORB_HD int qt_distribute(const uint32_t* arr, int n, const QtGeom& g, QtWork& w,
                     }
 #if defined(__CUDA_ARCH__)
                     if (local) atomicAdd(&w.scan_tmp[37], local);
+#elif defined(QT_EMUL_THREADS)
+                    if (local) __atomic_fetch_add(&w.scan_tmp[37], local, __ATOMIC_RELAXED);
 #else
                     w.scan_tmp[37] += local;
 #endif
@@ -576,6 +614,10 @@ ORB_HD int qt_distribute(const uint32_t* arr, int n, const QtGeom& g, QtWork& w,
     }
     QT_SYNC();
     return S;
+}
+
+ORB_HD int qt_distribute(const uint32_t* arr, int n, const QtGeom& g, QtWork& w, uint32_t* out) {
+    return qt_distribute_v<0>(arr, n, g, w, out);
 }
 
 }  // namespace orbdev

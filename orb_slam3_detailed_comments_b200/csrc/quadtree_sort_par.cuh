@@ -1,0 +1,155 @@
+// quadtree_sort_par.cuh -- std::sort(vSizeAndPointerToNode.begin(), end(), compareNodes) of DistributeOctTree's ordered phase
+// (/root/reference/src/ORBextractor.cc:932-940) with libstdc++'s exact sequence of moves, but spread over the CTA.
+//
+// compareNodes orders by (point count, UL.x) only, nodes tie often, and the reference then divides the tied nodes in whatever order
+// libstdc++'s introsort left them -- so the permutation itself is part of the result.  quadtree_core.cuh's qt_std_sort_items is a
+// one-thread transcription (ncu, round 1: ~30 % of k_quadtree's stall samples are the other 255 threads waiting for it at the
+// barrier).  The same moves, restructured:
+//   * __introsort_loop recurses on the right part and iterates on the left: the segments alive at one recursion depth are
+//     disjoint, so a GENERATION of segments is processed concurrently, one thread per segment, with the transcription's own
+//     median-of-three + unguarded partition (or heap sort when the depth limit is hit); the critical path becomes
+//     n + n/2 + n/4 + ... instead of n log2(n / 16);
+//   * __final_insertion_sort only ever moves an element in front of strictly greater ones, i.e. it is a STABLE sort of whatever
+//     the partitioning left: every thread computes the stable rank of one element instead (n <= a few hundred).
+// Included by quadtree_core.cuh (uses QtItem, qt_item_less, qt_exscan and the QT_ SPMD macros).
+#pragma once
+
+namespace orbdev {
+
+// one __introsort_loop step on [first, last): pivot to a[first] (__move_median_to_first), __unguarded_partition; returns the cut
+ORB_HD int qt_sortpar_partition(QtItem* a, int first, int last) {
+    const int mid = first + (last - first) / 2;
+    const int A = first + 1, B = mid, C = last - 1;
+    int pick;
+    if (qt_item_less(a[A], a[B])) {
+        if (qt_item_less(a[B], a[C])) pick = B;
+        else if (qt_item_less(a[A], a[C])) pick = C;
+        else pick = A;
+    } else if (qt_item_less(a[A], a[C])) pick = A;
+    else if (qt_item_less(a[B], a[C])) pick = C;
+    else pick = B;
+    { const QtItem t = a[first]; a[first] = a[pick]; a[pick] = t; }
+    const QtItem pv = a[first];
+    int lo = first + 1, hi = last;
+    while (true) {
+        while (qt_item_less(a[lo], pv)) ++lo;
+        --hi;
+        while (qt_item_less(pv, a[hi])) --hi;
+        if (!(lo < hi)) break;
+        const QtItem t = a[lo]; a[lo] = a[hi]; a[hi] = t;
+        ++lo;
+    }
+    return lo;
+}
+
+// __partial_sort(first, last, last) == __make_heap + __sort_heap on h[0..len)
+ORB_HD void qt_sortpar_heapsort(QtItem* h, int len) {
+    for (int parent = (len - 2) / 2;; --parent) {
+        const QtItem v = h[parent];
+        int hole = parent, child = parent;
+        while (child < (len - 1) / 2) {
+            child = 2 * (child + 1);
+            if (qt_item_less(h[child], h[child - 1])) --child;
+            h[hole] = h[child];
+            hole = child;
+        }
+        if ((len & 1) == 0 && child == (len - 2) / 2) {
+            child = 2 * (child + 1);
+            h[hole] = h[child - 1];
+            hole = child - 1;
+        }
+        int par = (hole - 1) / 2;
+        while (hole > parent && qt_item_less(h[par], v)) {
+            h[hole] = h[par];
+            hole = par;
+            par = (hole - 1) / 2;
+        }
+        h[hole] = v;
+        if (parent == 0) break;
+    }
+    for (int end = len - 1; end > 0; --end) {
+        const QtItem v = h[end];
+        h[end] = h[0];
+        int hole = 0, child = 0;
+        while (child < (end - 1) / 2) {
+            child = 2 * (child + 1);
+            if (qt_item_less(h[child], h[child - 1])) --child;
+            h[hole] = h[child];
+            hole = child;
+        }
+        if ((end & 1) == 0 && child == (end - 2) / 2) {
+            child = 2 * (child + 1);
+            h[hole] = h[child - 1];
+            hole = child - 1;
+        }
+        int par = (hole - 1) / 2;
+        while (hole > 0 && qt_item_less(h[par], v)) {
+            h[hole] = h[par];
+            hole = par;
+            par = (hole - 1) / 2;
+        }
+        h[hole] = v;
+    }
+}
+
+// a[0..n) sorted exactly as std::sort(a, a + n, compareNodes) leaves it.  tmp: n items.  seg / nxt: 3 ints per segment slot each
+// (first, last, depth), room for n / 8 + 2 slots; flag: n / 8 + 2 ints; scan_tmp: qt_exscan's scratch.  Whole CTA; returns after a
+// barrier.  Every segment on a list is longer than 16, so a generation holds at most n / 17 of them.
+ORB_HD void qt_std_sort_items_par(QtItem* a, int n, QtItem* tmp, int* seg, int* nxt, int* flag, int* scan_tmp) {
+    if (n <= 1) return;   // uniform
+    if (n > 16) {
+        int lg = 0;
+        for (int t = n; t > 1; t >>= 1) ++lg;
+        QT_SERIAL { seg[0] = 0; seg[1] = n; seg[2] = 2 * lg; }
+        QT_SYNC();
+        int nseg = 1;
+        while (nseg > 0) {
+            QT_PAR_FOR(s, nseg) {
+                const int first = seg[3 * s], last = seg[3 * s + 1], depth = seg[3 * s + 2];
+                int cut = first;
+                if (depth == 0) qt_sortpar_heapsort(a + first, last - first);      // this segment is finished
+                else cut = qt_sortpar_partition(a, first, last);
+                // children: the left part [first, cut) and the right part [cut, last), alive while longer than 16
+                const bool l_alive = depth != 0 && cut - first > 16, r_alive = depth != 0 && last - cut > 16;
+                nxt[3 * (2 * s)] = first; nxt[3 * (2 * s) + 1] = cut; nxt[3 * (2 * s) + 2] = depth - 1;
+                nxt[3 * (2 * s + 1)] = cut; nxt[3 * (2 * s + 1) + 1] = last; nxt[3 * (2 * s + 1) + 2] = depth - 1;
+                flag[2 * s] = l_alive ? 1 : 0;
+                flag[2 * s + 1] = r_alive ? 1 : 0;
+            }
+            QT_SYNC();
+            const int nslots = 2 * nseg;
+            QT_PAR_FOR(s, nslots) seg[s] = flag[s];              // keep the flags: the scan below overwrites them with ranks
+            QT_SYNC();
+            const int alive = qt_exscan(flag, nslots, scan_tmp);
+            // seg[0..nslots) holds the flags; the compacted list is built in tmp's storage?  no: reuse nxt -> seg via a staging pass
+            QT_PAR_FOR(s, nslots) {
+                if (seg[s]) {
+                    const int d = flag[s];
+                    // staging area behind the slots of this generation (3 * nslots ints in) -- disjoint from the reads of nxt[3s..]
+                    nxt[3 * nslots + 3 * d] = nxt[3 * s];
+                    nxt[3 * nslots + 3 * d + 1] = nxt[3 * s + 1];
+                    nxt[3 * nslots + 3 * d + 2] = nxt[3 * s + 2];
+                }
+            }
+            QT_SYNC();
+            QT_PAR_FOR(s, 3 * alive) seg[s] = nxt[3 * nslots + s];
+            QT_SYNC();
+            nseg = alive;
+        }
+    }
+    // __final_insertion_sort == stable sort of the current arrangement
+    QT_PAR_FOR(i, n) {
+        const QtItem v = a[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const QtItem u = a[j];
+            rank += (qt_item_less(u, v) || (j < i && !qt_item_less(v, u))) ? 1 : 0;
+        }
+        tmp[rank] = v;
+    }
+    QT_SYNC();
+    QT_PAR_FOR(i, n) a[i] = tmp[i];
+    QT_SYNC();
+}
+
+}  // namespace orbdev

@@ -138,8 +138,8 @@ uint32_t emul_path_key(int x, int y, float hX, int regionH) { return qt_path_key
 
 // ---- quadtree (csrc/quadtree_core.cuh compiled as sequential host code) -----------------------
 #include "../../orb_slam3_detailed_comments_b200/csrc/quadtree_core.cuh"
-extern "C" int emul_distribute(const int32_t* cand3, int n, int regionW, int regionH, int N, int wCell, int hCell,
-                               int nCols, int32_t* out3, int cap_out) {
+static int emul_distribute_variant(int variant, const int32_t* cand3, int n, int regionW, int regionH, int N, int wCell, int hCell,
+                                   int nCols, int32_t* out3, int cap_out) {
     QtGeom g;
     g.regionW = regionW; g.regionH = regionH;
     g.nIni = (int)std::round((float)regionW / (float)regionH);
@@ -156,13 +156,38 @@ extern "C" int emul_distribute(const int32_t* cand3, int n, int regionW, int reg
     QtWork w;
     qt_work_carve(w, ws.data(), cap);
     std::vector<uint32_t> out(cap + 4);
-    const int S = qt_distribute(arr.data(), n, g, w, out.data());
+    const int S = variant == 0 ? qt_distribute(arr.data(), n, g, w, out.data()) : qt_distribute_v<1>(arr.data(), n, g, w, out.data());
     for (int i = 0; i < S && i < cap_out; ++i) {
         out3[3 * i] = out[i] & 0xfff;
         out3[3 * i + 1] = (out[i] >> 12) & 0xfff;
         out3[3 * i + 2] = out[i] >> 24;
     }
     return S;
+}
+
+extern "C" int emul_distribute(const int32_t* cand3, int n, int regionW, int regionH, int N, int wCell, int hCell, int nCols,
+                               int32_t* out3, int cap_out) {
+    return emul_distribute_variant(0, cand3, n, regionW, regionH, N, wCell, hCell, nCols, out3, cap_out);
+}
+extern "C" int emul_distribute_v1(const int32_t* cand3, int n, int regionW, int regionH, int N, int wCell, int hCell, int nCols,
+                                  int32_t* out3, int cap_out) {
+    return emul_distribute_variant(1, cand3, n, regionW, regionH, N, wCell, hCell, nCols, out3, cap_out);
+}
+
+// std::sort(vSizeAndPointerToNode, compareNodes) three ways: libstdc++ itself, the one-thread transcription, the CTA-parallel form.
+// items: n x (cnt, ulx, payload); which = 0 libstdc++, 1 qt_std_sort_items, 2 qt_std_sort_items_par.  out: payloads in sorted order.
+extern "C" void emul_sort_items(const uint32_t* items3, int n, int which, uint32_t* out_payload) {
+    std::vector<QtItem> a(n + 1), tmp(n + 1);
+    for (int i = 0; i < n; ++i) { a[i].cnt = items3[3 * i]; a[i].ulx_pos = (items3[3 * i + 1] << 16) | (items3[3 * i + 2] & 0xffffu); }
+    if (which == 0) {
+        std::sort(a.begin(), a.begin() + n, [](const QtItem& x, const QtItem& y) { return qt_item_less(x, y); });
+    } else if (which == 1) {
+        qt_std_sort_items(a.data(), n);
+    } else {
+        std::vector<int> seg(n + 64), nxt(3 * n + 64), flag(n + 64), st(64);
+        qt_std_sort_items_par(a.data(), n, tmp.data(), seg.data(), nxt.data(), flag.data(), st.data());
+    }
+    for (int i = 0; i < n; ++i) out_payload[i] = a[i].ulx_pos & 0xffffu;
 }
 
 // ---- LocalInertialBA: the device algorithm (csrc/liba_core.cuh) run by one host "thread" ---------------------------------------

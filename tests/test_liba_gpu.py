@@ -11,7 +11,8 @@ from oracle import pyoracle as po
 from test_liba_emul import TOL, perturbed
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ORB_LIBA_GPU") != "1", reason="first device run pending: set ORB_LIBA_GPU=1")]
+              pytest.mark.skipif(os.environ.get("ORB_LIBA_GPU") != "1" and os.environ.get("ORB_FIRST_CONTACT") != "1",
+                                 reason="first device run pending: set ORB_FIRST_CONTACT=1 (or ORB_LIBA_GPU=1)")]
 
 
 @pytest.fixture(scope="module")

@@ -1,0 +1,43 @@
+"""GPU tier, opt-in (ORB_FIRST_CONTACT=1): k_quadtree_v1 -- the ordered phase's std::sort spread over the CTA -- against the oracle.
+The kernel's algorithm is validated on the CPU (tests/test_quadtree_emul.py: libstdc++ move for move, threaded run under
+ThreadSanitizer) but has not run on a device yet; the default path (k_quadtree) keeps its round-1 machine code bit for bit."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from orb_slam3_detailed_comments_b200 import ORBextractor, synth
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("ORB_FIRST_CONTACT") != "1", reason="first device run pending: set ORB_FIRST_CONTACT=1")]
+
+CASES = [(640, 480, 1, 1.5, 60, 1200), (640, 480, 2, 6.0, 10, 1200), (752, 480, 3, 1.5, 60, 1200), (320, 240, 4, 3.0, 20, 500),
+         (1280, 720, 5, 1.5, 60, 2000), (640, 480, 7, 1.5, 60, 5000)]
+
+
+@pytest.mark.parametrize("w,h,seed,sigma,nrect,nf", CASES)
+def test_variant_1_is_bit_exact(monkeypatch, w, h, seed, sigma, nrect, nf):
+    monkeypatch.setenv("ORB_QT_VARIANT", "1")            # read by orbx_create
+    img = synth.frame(w, h, seed, sigma, nrect)
+    ex = ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=1)
+    ref = po.OracleExtractor(nf, 1.2, 8, 20, 7)
+    mono, kps, desc = ex(img)
+    rmono, rk, rd = ref(img)
+    assert mono == rmono and len(kps) == len(rk)
+    assert (kps.view(np.uint8) == rk.view(np.uint8)).all() and (desc == rd).all()
+    ex.close()
+
+
+def test_variant_1_batch(monkeypatch):
+    monkeypatch.setenv("ORB_QT_VARIANT", "1")
+    imgs = np.stack([synth.frame(640, 480, 20 + i) for i in range(6)])
+    ex = ORBextractor(1200, 1.2, 8, 20, 7, max_width=640, max_height=480, max_batch=6)
+    ex.extract_batch(imgs)
+    n, mono, off, kps, desc = ex.download(6)
+    ref = po.OracleExtractor(1200, 1.2, 8, 20, 7)
+    for i in range(6):
+        rmono, rk, rd = ref(imgs[i])
+        a, b = int(off[i]), int(off[i + 1])
+        assert b - a == len(rk) and (kps[a:b].view(np.uint8) == rk.view(np.uint8)).all() and (desc[a:b] == rd).all()
+    ex.close()
