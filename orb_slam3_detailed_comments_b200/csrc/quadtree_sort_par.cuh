@@ -152,4 +152,38 @@ ORB_HD void qt_std_sort_items_par(QtItem* a, int n, QtItem* tmp, int* seg, int* 
     QT_SYNC();
 }
 
+// Bitonic sort with two butterfly stages per pass (variant 1 of the candidate sort).  For one merge size k the stages j = k/2 ... 1
+// are taken in pairs (j, j/2): a thread loads the four elements that differ in bits j and j/2, does both compare-exchange
+// levels in registers and stores them -- half the barriers and half the shared-memory round trips of qt_bitonic_sort; an odd
+// stage count leaves one ordinary pass (j = 1).  Keys are unique per candidate pixel (root | path | score), so any correct sort
+// yields the same array.
+ORB_HD void qt_bitonic_sort_r4(uint32_t* arr, int npow) {
+    for (int k = 2; k <= npow; k <<= 1) {
+        int j = k >> 1;
+        for (; j >= 2; j >>= 2) {
+            const int h = j >> 1;
+            QT_PAR_FOR(i, npow >> 2) {
+                const int l0 = (i & (h - 1)) | ((i & ~(h - 1)) << 2);   // i spread over the index bits other than h and j = 2h
+                uint32_t a0 = arr[l0], a1 = arr[l0 | h], a2 = arr[l0 | j], a3 = arr[l0 | j | h];
+                const bool up = (l0 & k) == 0;
+                uint32_t x;
+                if ((a0 > a2) == up) { x = a0; a0 = a2; a2 = x; }
+                if ((a1 > a3) == up) { x = a1; a1 = a3; a3 = x; }
+                if ((a0 > a1) == up) { x = a0; a0 = a1; a1 = x; }
+                if ((a2 > a3) == up) { x = a2; a2 = a3; a3 = x; }
+                arr[l0] = a0; arr[l0 | h] = a1; arr[l0 | j] = a2; arr[l0 | j | h] = a3;
+            }
+            QT_SYNC();
+        }
+        if (j == 1) {
+            QT_PAR_FOR(i, npow >> 1) {
+                const int l = i << 1, r = l | 1;
+                const uint32_t a = arr[l], b = arr[r];
+                if ((a > b) == ((l & k) == 0)) { arr[l] = b; arr[r] = a; }
+            }
+            QT_SYNC();
+        }
+    }
+}
+
 }  // namespace orbdev

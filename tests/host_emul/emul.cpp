@@ -150,7 +150,7 @@ static int emul_distribute_variant(int variant, const int32_t* cand3, int n, int
     while (npow < n) npow <<= 1;
     std::vector<uint32_t> arr(npow, 0xffffffffu);
     for (int i = 0; i < n; ++i) arr[i] = qt_element(qt_pack_cand(cand3[3 * i], cand3[3 * i + 1], cand3[3 * i + 2]), g);
-    qt_bitonic_sort(arr.data(), npow);
+    if (variant == 0) qt_bitonic_sort(arr.data(), npow); else qt_bitonic_sort_r4(arr.data(), npow);
     const int cap = N + 20;
     std::vector<char> ws(qt_work_bytes(cap));
     QtWork w;
@@ -188,6 +188,10 @@ extern "C" void emul_sort_items(const uint32_t* items3, int n, int which, uint32
         qt_std_sort_items_par(a.data(), n, tmp.data(), seg.data(), nxt.data(), flag.data(), st.data());
     }
     for (int i = 0; i < n; ++i) out_payload[i] = a[i].ulx_pos & 0xffffu;
+}
+
+extern "C" void emul_bitonic(uint32_t* arr, int npow, int variant) {
+    if (variant == 0) qt_bitonic_sort(arr, npow); else qt_bitonic_sort_r4(arr, npow);
 }
 
 // ---- LocalInertialBA: the device algorithm (csrc/liba_core.cuh) run by one host "thread" ---------------------------------------

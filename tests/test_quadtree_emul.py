@@ -28,6 +28,8 @@ def emul():
     for f in (L.emul_distribute, L.emul_distribute_v1):
         f.restype = C.c_int
         f.argtypes = [C.c_void_p, C.c_int] + [C.c_int] * 6 + [C.c_void_p, C.c_int]
+    L.emul_bitonic.restype = None
+    L.emul_bitonic.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.emul_sort_items.restype = None
     L.emul_sort_items.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     return L
@@ -195,3 +197,18 @@ def test_threaded_quadtree_on_adversarial_sets(qt_mt, tmp_path, case):
         ref = po.distribute(c, 16, W - 16, 16, H - 16, N)
         got = run_mt(qt_mt, c, W, H, N, 1, 6, tmp_path)
         assert len(got) == len(ref) and (got == c[ref]).all(), (case, N)
+
+
+@pytest.mark.parametrize("npow", [2, 4, 8, 16, 32, 64, 512, 1024, 4096, 8192, 16384])
+def test_two_stage_bitonic_sorts(emul, npow):
+    rng = np.random.default_rng(npow)
+    for trial in range(3):
+        a = rng.integers(0, 1 << 32, npow, dtype=np.uint64).astype(np.uint32)
+        if trial == 1:
+            a[rng.integers(0, npow, npow // 3 + 1)] = 0xffffffff        # padding sentinels as in the kernel
+        if trial == 2:
+            a = np.sort(a)[::-1].copy()
+        b0, b1 = a.copy(), a.copy()
+        emul.emul_bitonic(b0.ctypes.data, npow, 0)
+        emul.emul_bitonic(b1.ctypes.data, npow, 1)
+        assert (b0 == np.sort(a)).all() and (b1 == b0).all()
