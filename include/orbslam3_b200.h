@@ -559,8 +559,11 @@ typedef struct {
     double* point;                 /* [n_mp][3] */
     double* edge_chi2;             /* [n_edges] (may be NULL) */
     double* link_chi2;             /* [n_links][3] inertial, gyro RW, acc RW (may be NULL) */
+    uint8_t* edge_depth_positive;  /* [n_edges] e->isDepthPositive() at the final estimate (may be NULL); Optimizer.cc:2704 */
     int32_t iterations, trials;
     double lambda, chi2, chi2_initial;
+    double chi2_last_trial;        /* optimizer.activeRobustChi2() as read right after optimize() (err_end, Optimizer.cc:2685): the
+                                      errors of the LAST Levenberg trial, accepted or not -- what edge_chi2 / link_chi2 hold too */
 } liba_result;
 
 typedef struct liba_handle liba_handle;

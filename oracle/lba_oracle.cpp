@@ -795,10 +795,12 @@ inline void kf_oplus(KfState& s, const double* d15) {   // pose (6), velocity, g
 extern "C" {
 
 // state: nKF x 21 doubles (Rwb row-major 9, twb 3, v 3, bg 3, ba 3), in/out.  fixed[nKF].  point nMP x 3 in/out.
-// Tcb: Rcb (9) tcb (3).  cam5: fx fy cx cy bf.  links: nL records (see liba_link in pyoracle.py).  Outputs as orc_lba.
+// Tcb: Rcb (9) tcb (3).  cam5: fx fy cx cy bf.  links: nL records (see liba_link in pyoracle.py).  Outputs as orc_lba; stats[5] =
+// optimizer.activeRobustChi2() as the reference reads it right after optimize() (Optimizer.cc:2685: the errors of the LAST trial, accepted
+// or not); edge_depth_positive[e] = EdgeMono / EdgeStereo::isDepthPositive() at the final estimate (G2oTypes.cc:212-215).
 int orc_liba(int nKF, int nMP, int nE, int nL, double* state, const uint8_t* fixed, double* point, const int* ekf, const int* emp,
              const double* obs, const double* invs2, const double* Tcb12, const double* cam5, const void* links_raw, double lambdaInit,
-             int maxIters, double* edge_chi2, double* link_chi2, double* stats) {
+             int maxIters, double* edge_chi2, double* link_chi2, double* stats, uint8_t* edge_depth_positive) {
     InertialProblem P;
     P.nKF = nKF; P.nMP = nMP; P.nE = nE; P.nL = nL;
     P.kf.resize(nKF);
@@ -993,9 +995,10 @@ int orc_liba(int nKF, int nMP, int nE, int nL, double* state, const uint8_t* fix
 
     double lambda = lambdaInit, ni = 2;
     int nBad = 0, iters = 0, trials = 0;
-    double currentChi = 0, iniChi0 = 0;
+    double currentChi = 0, iniChi0 = 0, lastChi = 0;
     for (int it = 0; it < maxIters; ++it) {
         currentChi = compute_errors();
+        lastChi = currentChi;
         if (it == 0) iniChi0 = currentChi;
         double tempChi = currentChi;
         const double iniChi = currentChi;
@@ -1019,6 +1022,7 @@ int orc_liba(int nKF, int nMP, int nE, int nL, double* state, const uint8_t* fix
             for (int k = 0; k < nKF; ++k) if (pidx[k] >= 0) kf_oplus(P.kf[k], &x[15 * pidx[k]]);
             for (int l = 0; l < nMP; ++l) for (int i = 0; i < 3; ++i) P.point[3 * l + i] += x[sp + 3 * l + i];
             tempChi = compute_errors();
+            lastChi = tempChi;
             if (!ok2) tempChi = std::numeric_limits<double>::max();
             rho = currentChi - tempChi;
             double scale = 0;
@@ -1053,7 +1057,15 @@ int orc_liba(int nKF, int nMP, int nE, int nL, double* state, const uint8_t* fix
         for (int i = 0; i < 3; ++i) { s[9 + i] = P.kf[k].twb[i]; s[12 + i] = P.kf[k].v[i]; s[15 + i] = P.kf[k].bg[i]; s[18 + i] = P.kf[k].ba[i]; }
     }
     memcpy(point, P.point.data(), sizeof(double) * 3 * (size_t)nMP);
-    if (stats) { stats[0] = iters; stats[1] = lambda; stats[2] = currentChi; stats[3] = trials; stats[4] = iniChi0; }
+    if (stats) { stats[0] = iters; stats[1] = lambda; stats[2] = currentChi; stats[3] = trials; stats[4] = iniChi0; stats[5] = lastChi; }
+    if (edge_depth_positive)
+        for (int e = 0; e < nE; ++e) {
+            Mat3 Rcw;
+            double tcw[3];
+            cam_pose(P, P.kf[ekf[e]], Rcw, tcw);
+            const double* X = &P.point[3 * emp[e]];
+            edge_depth_positive[e] = (Rcw.m[6] * X[0] + Rcw.m[7] * X[1] + Rcw.m[8] * X[2] + tcw[2]) > 0.0 ? 1 : 0;
+        }
     return iters;
 }
 

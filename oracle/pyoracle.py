@@ -454,10 +454,10 @@ def _liba_lib():
 
 def liba(state, fixed, point, edge_kf, edge_mp, obs, inv_sigma2, Tcb12, cam5, links, lambda_init=1.0, max_iters=10):
     """Optimizer::LocalInertialBA's g2o core restated (Optimizer.cc:2203-2812).  state: [nKF][21] = Rwb(9) twb v bg ba.
-    Returns dict(state, point, edge_chi2, link_chi2[nL][3], iterations, trials, lambda_, chi2, chi2_init)."""
+    Returns dict(state, point, edge_chi2, link_chi2[nL][3], iterations, trials, lambda_, chi2, chi2_init, chi2_last, edge_depth_pos)."""
     L = _liba_lib()
     L.orc_liba.restype = C.c_int
-    L.orc_liba.argtypes = [C.c_int] * 4 + [C.c_void_p] * 10 + [C.c_double, C.c_int] + [C.c_void_p] * 3
+    L.orc_liba.argtypes = [C.c_int] * 4 + [C.c_void_p] * 10 + [C.c_double, C.c_int] + [C.c_void_p] * 4
     c = np.ascontiguousarray
     st, pt = c(state, np.float64).copy(), c(point, np.float64).copy()
     fx = c(fixed, np.uint8)
@@ -466,12 +466,12 @@ def liba(state, fixed, point, edge_kf, edge_mp, obs, inv_sigma2, Tcb12, cam5, li
     T, cam = c(Tcb12, np.float64), c(cam5, np.float64)
     lk = c(links, LIBA_LINK)
     nE, nL = len(ekf), len(lk)
-    chi, lchi, stats = np.zeros(max(nE, 1)), np.zeros(max(3 * nL, 1)), np.zeros(8)
+    chi, lchi, stats, dpos = np.zeros(max(nE, 1)), np.zeros(max(3 * nL, 1)), np.zeros(8), np.zeros(max(nE, 1), np.uint8)
     P = lambda a: _p(a) if a.size else None
     it = L.orc_liba(len(st), len(pt), nE, nL, _p(st), _p(fx), P(pt), P(ekf), P(emp), P(ob), P(w), _p(T), _p(cam), P(lk), float(lambda_init),
-                    int(max_iters), _p(chi), _p(lchi), _p(stats))
+                    int(max_iters), _p(chi), _p(lchi), _p(stats), _p(dpos))
     return dict(state=st, point=pt, edge_chi2=chi[:nE], link_chi2=lchi[:3 * nL].reshape(nL, 3), iterations=it, trials=int(stats[3]),
-                lambda_=stats[1], chi2=stats[2], chi2_init=stats[4])
+                lambda_=stats[1], chi2=stats[2], chi2_init=stats[4], chi2_last=stats[5], edge_depth_pos=dpos[:nE])
 
 
 def inertial_edge(state2, link):

@@ -133,8 +133,9 @@ class liba_problem(C.Structure):
 
 
 class liba_result(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("state", "point", "edge_chi2", "link_chi2")] + [
-        ("iterations", C.c_int32), ("trials", C.c_int32), ("lambda_", C.c_double), ("chi2", C.c_double), ("chi2_initial", C.c_double)]
+    _fields_ = [(n, C.c_void_p) for n in ("state", "point", "edge_chi2", "link_chi2", "edge_depth_positive")] + [
+        ("iterations", C.c_int32), ("trials", C.c_int32), ("lambda_", C.c_double), ("chi2", C.c_double), ("chi2_initial", C.c_double),
+        ("chi2_last_trial", C.c_double)]
 
 
 _lib = None

@@ -13,6 +13,8 @@
 
 using namespace orb;
 
+static_assert(sizeof(liba_problem) == 232 && sizeof(liba_result) == 80, "C ABI layout (include/orbslam3_b200.h)");
+
 namespace {
 
 constexpr int LIBA_THREADS = 256;

@@ -112,7 +112,8 @@ struct LibaDev {
     int l_id, l_stride;   // ... and inside its CTA
     int rank, cs;         // CTA rank in the team, CTAs per team
     // results
-    double* out_scalars;  // iterations, trials, lambda, chi2, chi2_initial
+    double* out_scalars;  // iterations, trials, lambda, chi2, chi2_initial, chi2 of the last trial
+    unsigned char* dpos;  // [nE] isDepthPositive at the final estimate
 };
 
 // ---- small fixed-size linear algebra -------------------------------------------------------------------------------
@@ -612,10 +613,11 @@ LIBA_HD bool liba_solve_system(const LibaDev& P, double lambda) {
 LIBA_HD void liba_optimize(const LibaDev& P) {
     const LibaHuber H = liba_huber_constants();
     const int sp = P.sp, sl = 3 * P.nMP;
-    double lambda = P.lambda_init, ni = 2, currentChi = 0, iniChi0 = 0;
+    double lambda = P.lambda_init, ni = 2, currentChi = 0, iniChi0 = 0, lastChi = 0;
     int nBad = 0, iters = 0, trials = 0;
     for (int it = 0; it < P.max_iters; ++it) {
         currentChi = liba_compute_errors(P, H);
+        lastChi = currentChi;
         if (it == 0) iniChi0 = currentChi;
         double tempChi = currentChi;
         const double iniChi = currentChi;
@@ -641,6 +643,7 @@ LIBA_HD void liba_optimize(const LibaDev& P) {
             LIBA_PAR_FOR(i, sl) P.point[i] += P.x[sp + i];
             LIBA_SYNC();
             tempChi = liba_compute_errors(P, H);
+            lastChi = tempChi;
             if (!ok2) tempChi = 1.7976931348623157e308;
             double sc = 0;
             LIBA_PAR_FOR(j, sp + sl) sc += P.x[j] * (lambda * P.x[j] + P.b[j]);
@@ -669,8 +672,15 @@ LIBA_HD void liba_optimize(const LibaDev& P) {
         if ((iniChi - currentChi) * 1e3 < iniChi) ++nBad; else nBad = 0;
         if (nBad >= 3) break;
     }
+    LIBA_PAR_FOR(e, P.nE) {      // EdgeMono / EdgeStereo::isDepthPositive at the final estimate (G2oTypes.cc:212-215)
+        double Rcw[9], tcw[3];
+        liba_cam_pose(P, P.state + 21 * (size_t)P.ekf[e], Rcw, tcw);
+        const double* X = P.point + 3 * (size_t)P.emp[e];
+        P.dpos[e] = (Rcw[6] * X[0] + Rcw[7] * X[1] + Rcw[8] * X[2] + tcw[2]) > 0.0 ? 1 : 0;
+    }
     if (LIBA_LEADER()) {
         P.out_scalars[0] = iters; P.out_scalars[1] = trials; P.out_scalars[2] = lambda; P.out_scalars[3] = currentChi; P.out_scalars[4] = iniChi0;
+        P.out_scalars[5] = lastChi;
     }
     LIBA_SYNC();
 }

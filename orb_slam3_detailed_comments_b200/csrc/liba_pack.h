@@ -1,6 +1,6 @@
 // liba_pack.h -- host-side flattening of a liba_problem into one blob laid out for liba_core.cuh.  Pure host C++ so that the
 // CUDA wrapper (liba.cu) and the CPU emulation harness (tests/host_emul) share it.
-//   [io]   state, point, err, lerr, out_scalars            host -> device before, device -> host after
+//   [io]   state, point, err, lerr, out_scalars, dpos            host -> device before, device -> host after
 //   [in]   obs, invs2, links, pidx, ekf, emp, pt_off, pt_edge
 //   [work] saved state, normal equations, Schur scratch    zero-filled
 #pragma once
@@ -79,7 +79,7 @@ inline LibaLayout liba_pack(const liba_problem& p, uint8_t* host, uint8_t* devBa
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
     // io
-    const size_t oState = take(8 * 21 * (size_t)nKF), oPoint = take(8 * sl), oErr = take(8 * (size_t)nE), oLerr = take(8 * 3 * (size_t)nL), oOut = take(8 * 8);
+    const size_t oState = take(8 * 21 * (size_t)nKF), oPoint = take(8 * sl), oErr = take(8 * (size_t)nE), oLerr = take(8 * 3 * (size_t)nL), oOut = take(8 * 8), oDpos = take((size_t)nE);
     lay.io_bytes = off;
     // in
     const size_t oObs = take(8 * 3 * (size_t)nE), oInv = take(8 * (size_t)nE), oLinks = take(sizeof(LibaLink) * (size_t)nL);
@@ -135,7 +135,7 @@ inline LibaLayout liba_pack(const liba_problem& p, uint8_t* host, uint8_t* devBa
     d.max_iters = p.max_iters;
     d.err = D(oErr); d.lerr = D(oLerr); d.Hpp = D(oHpp); d.Hs = D(oHs); d.b = D(oB); d.bs = D(oBs); d.x = D(oX); d.y = D(oY);
     d.Hll = D(oHll); d.Dinv = D(oDinv); d.W = D(oW); d.WD = D(oWD); d.Wdb = D(oWdb); d.Epp = D(oEpp); d.Lblk = D(oLblk);
-    d.flag = I(oFlag); d.red = nullptr; d.partials = D(oPart); d.out_scalars = D(oOut);
+    d.flag = I(oFlag); d.red = nullptr; d.partials = D(oPart); d.out_scalars = D(oOut); d.dpos = devBase + oDpos;
     d.t_id = 0; d.t_stride = 1; d.l_id = 0; d.l_stride = 1; d.rank = 0; d.cs = 1;      // a team of one thread; the launcher overrides per thread
     return lay;
 }
@@ -147,8 +147,10 @@ inline void liba_unpack(const liba_problem& p, const uint8_t* host, const LibaDe
     memcpy(r->point, H(d.point), 8 * 3 * (size_t)p.n_mp);
     if (r->edge_chi2) memcpy(r->edge_chi2, H(d.err), 8 * (size_t)p.n_edges);
     if (r->link_chi2) memcpy(r->link_chi2, H(d.lerr), 8 * 3 * (size_t)p.n_links);
+    if (r->edge_depth_positive) memcpy(r->edge_depth_positive, host + (d.dpos - devBase), (size_t)p.n_edges);
     const double* o = H(d.out_scalars);
     r->iterations = (int32_t)o[0]; r->trials = (int32_t)o[1]; r->lambda = o[2]; r->chi2 = o[3]; r->chi2_initial = o[4];
+    r->chi2_last_trial = o[5];
 }
 
 }  // namespace orb

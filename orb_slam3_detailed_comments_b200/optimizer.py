@@ -137,14 +137,15 @@ def pack_inertial_problem(pr, lambda_init, max_iters, keep):
                                                                        else pr["links"], N.LIBA_LINK).reshape(-1))
     ne, nl = len(arrs["edge_kf"]), len(arrs["links"])
     out = dict(state=np.zeros_like(arrs["state"]), point=np.zeros_like(arrs["point"]), edge_chi2=np.zeros(max(ne, 1)),
-               link_chi2=np.zeros((max(nl, 1), 3)))
+               link_chi2=np.zeros((max(nl, 1), 3)), edge_depth_pos=np.zeros(max(ne, 1), np.uint8))
     keep.append((arrs, out))
     P = lambda a: N.ptr(a) if a.size else None
     p = N.liba_problem(len(arrs["state"]), len(arrs["point"]), ne, nl, N.ptr(arrs["state"]), N.ptr(arrs["fixed"]), P(arrs["point"]),
                        P(arrs["edge_kf"]), P(arrs["edge_mp"]), P(arrs["obs"]), P(arrs["inv_sigma2"]), P(arrs["links"]),
                        (C.c_double * 12)(*np.asarray(pr["Tcb"], np.float64).reshape(-1).tolist()),
                        *np.asarray(pr["cam5"], np.float64).tolist(), float(lambda_init), int(max_iters))
-    r = N.liba_result(N.ptr(out["state"]), N.ptr(out["point"]), N.ptr(out["edge_chi2"]), N.ptr(out["link_chi2"]), 0, 0, 0.0, 0.0, 0.0)
+    r = N.liba_result(N.ptr(out["state"]), N.ptr(out["point"]), N.ptr(out["edge_chi2"]), N.ptr(out["link_chi2"]),
+                      N.ptr(out["edge_depth_pos"]), 0, 0, 0.0, 0.0, 0.0, 0.0)
     return p, r, out
 
 
@@ -152,7 +153,8 @@ def finish_inertial_result(pr_arrays, out, r):
     ne, nl = len(pr_arrays["edge_kf"]), len(pr_arrays["links"])
     out["edge_chi2"] = out["edge_chi2"][:ne]
     out["link_chi2"] = out["link_chi2"][:nl]
-    out.update(iterations=r.iterations, trials=r.trials, lambda_=r.lambda_, chi2=r.chi2, chi2_init=r.chi2_initial)
+    out["edge_depth_pos"] = out["edge_depth_pos"][:ne]
+    out.update(iterations=r.iterations, trials=r.trials, lambda_=r.lambda_, chi2=r.chi2, chi2_init=r.chi2_initial, chi2_last=r.chi2_last_trial)
     return out
 
 

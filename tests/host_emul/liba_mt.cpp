@@ -70,7 +70,7 @@ int main(int argc, char** argv) {
 
     std::vector<double> ostate(21 * (size_t)p.n_kf), opoint(3 * (size_t)p.n_mp + 1), ochi(p.n_edges + 1), olchi(3 * (size_t)p.n_links + 1);
     liba_result r;
-    r.state = ostate.data(); r.point = opoint.data(); r.edge_chi2 = ochi.data(); r.link_chi2 = olchi.data();
+    r.state = ostate.data(); r.point = opoint.data(); r.edge_chi2 = ochi.data(); r.link_chi2 = olchi.data(); r.edge_depth_positive = nullptr;
     orb::liba_unpack(p, blob.data(), dev, blob.data(), &r);
     FILE* o = fopen(argv[2], "wb");
     if (!o) return 2;

@@ -40,6 +40,7 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(N.orbm_camera) == 40
     assert N.LIBA_LINK.itemsize == 1080         # liba_link
     assert C.sizeof(N.liba_problem) == 16 + 8 * 8 + 12 * 8 + 6 * 8 + 8
+    assert C.sizeof(N.liba_result) == 5 * 8 + 8 + 4 * 8
 
 
 def test_no_device_means_loud_failure(lib):

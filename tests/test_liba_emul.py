@@ -78,6 +78,8 @@ def test_device_algorithm_matches_oracle(emul, seed, lam, iters, n_fixed):
     assert np.abs(got["point"] - ref["point"]).max() < TOL
     assert np.allclose(got["edge_chi2"], ref["edge_chi2"], rtol=1e-6, atol=1e-8)
     assert np.allclose(got["link_chi2"], ref["link_chi2"], rtol=1e-6, atol=1e-8)
+    assert abs(got["chi2_last"] - ref["chi2_last"]) <= 1e-6 * max(1.0, ref["chi2_last"])      # err_end of Optimizer.cc:2685
+    assert (got["edge_depth_pos"] == ref["edge_depth_pos"]).all() and ref["edge_depth_pos"].all()
     assert (got["state"][:n_fixed] == s["state"][:n_fixed]).all()
     assert ref["chi2"] < ref["chi2_init"]
 
@@ -244,3 +246,20 @@ def test_preintegration_generator_is_self_consistent():
                 assert np.abs(rot / eps - pre["JRg"][:, axis]).max() < 5e-3
     Cm = pre["C"].astype(np.float64)
     assert np.allclose(Cm, Cm.T, atol=1e-9) and (np.linalg.eigvalsh(Cm[:9, :9]) > 0).all()
+
+
+def test_depth_sign_and_last_trial_chi2(emul):
+    """A point pushed behind one of its cameras: isDepthPositive() is reported per edge at the final estimate; chi2_last is the
+    robust chi2 of the last Levenberg trial (what the reference reads as err_end), not necessarily the accepted one."""
+    s = perturbed(51, n_kf=5, n_mp=80)
+    k = int(s["edge_kf"][0])
+    Rwb, twb = s["state"][k, :9].reshape(3, 3), s["state"][k, 9:12]
+    Rcb, tcb = np.asarray(s["Tcb"][:9]).reshape(3, 3), np.asarray(s["Tcb"][9:])
+    s["point"][int(s["edge_mp"][0])] = Rwb @ (Rcb.T @ (np.array([0.1, 0.1, -2.0]) - tcb)) + twb      # z = -2 in that camera
+    ref = po.liba(s["state"], s["fixed"], s["point"], s["edge_kf"], s["edge_mp"], s["obs"], s["inv_sigma2"], s["Tcb"], s["cam5"], s["links"], 1.0, 0)
+    got = run_emul(emul, s, 1.0, 0)                 # zero iterations: the estimate stays where it was put
+    assert ref["edge_depth_pos"][0] == 0 and (got["edge_depth_pos"] == ref["edge_depth_pos"]).all()
+    ref = po.liba(s["state"], s["fixed"], s["point"], s["edge_kf"], s["edge_mp"], s["obs"], s["inv_sigma2"], s["Tcb"], s["cam5"], s["links"], 1.0, 6)
+    got = run_emul(emul, s, 1.0, 6)
+    assert (got["edge_depth_pos"] == ref["edge_depth_pos"]).all()
+    assert abs(got["chi2_last"] - ref["chi2_last"]) <= 1e-6 * max(1.0, ref["chi2_last"]) and ref["chi2_last"] >= ref["chi2"] - 1e-9
