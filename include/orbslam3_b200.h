@@ -365,6 +365,18 @@ orb_status orbm_search_triangulation(orbx_handle* h, const orbm_triangulation* t
                                      int32_t* nmatches_out);
 
 /* ------------------------------------------------------------------------------------------------
+ * cv::BFMatcher(cv::NORM_HAMMING).knnMatch(query, train, matches, 2) -- the brute-force 256-bit Hamming search of
+ * Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1553; BFmatcher is a member of Frame, include/Frame.h), batched over independent
+ * (query, train) descriptor sets: pair p owns query rows [query_offset[p], query_offset[p+1]) and train rows likewise.
+ * idx_out / dist_out: [query rows][2] = trainIdx / distance of the nearest and second nearest train row of the SAME pair, ascending
+ * distance, ties by ascending trainIdx (OpenCV's order); -1 where the train set has fewer than 1 / 2 rows (knnMatch then returns a
+ * shorter list).  The caller applies the reference's ratio test `m[0].distance < m[1].distance * 0.7` (Frame.cc:1560).
+ * STATUS: CPU oracle pinned against cv2; the kernel has not had a device run yet (tests opt-in with ORB_FIRST_CONTACT=1).
+ * ---------------------------------------------------------------------------------------------- */
+orb_status orbm_hamming_knn2(orbx_handle* h, int32_t n_pairs, const int32_t* query_offset, const uint8_t* query_desc,
+                             const int32_t* train_offset, const uint8_t* train_desc, int32_t* idx_out, int32_t* dist_out);
+
+/* ------------------------------------------------------------------------------------------------
  * Optimizer::LocalBundleAdjustment  (include/Optimizer.h:59, src/Optimizer.cc:1740-2188)
  *
  * The C++ shim walks the covisibility graph exactly as the reference does (Optimizer.cc:1744-1855), flattens

@@ -723,3 +723,19 @@ extern "C" void orc_update_normal_and_depth(int N, const float* centers, const f
     *mind = *maxd / scaleFactors[nLevels - 1];
     for (int c = 0; c < 3; ++c) out3[c] = normal[c] / (float)N;
 }
+
+// cv::BFMatcher(cv::NORM_HAMMING).knnMatch(query, train, matches, 2) as Frame::ComputeStereoFishEyeMatches uses it (src/Frame.cc:1553):
+// per query the two nearest train rows, ascending distance, ties by ascending train index (what OpenCV returns; pinned against
+// cv2 4.13 by tests/test_knn_cpu.py).  idx / dist: [nq][2], -1 where the train set has fewer rows.
+extern "C" void orc_hamming_knn2(int nq, const uint8_t* q, int nt, const uint8_t* t, int* idx, int* dist) {
+    for (int i = 0; i < nq; ++i) {
+        int bi[2] = {-1, -1}, bd[2] = {-1, -1};
+        for (int j = 0; j < nt; ++j) {
+            int d = 0;
+            for (int k = 0; k < 32; ++k) d += __builtin_popcount((unsigned)(q[32 * (size_t)i + k] ^ t[32 * (size_t)j + k]));
+            if (bi[0] < 0 || d < bd[0]) { bi[1] = bi[0]; bd[1] = bd[0]; bi[0] = j; bd[0] = d; }
+            else if (bi[1] < 0 || d < bd[1]) { bi[1] = j; bd[1] = d; }
+        }
+        idx[2 * i] = bi[0]; idx[2 * i + 1] = bi[1]; dist[2 * i] = bd[0]; dist[2 * i + 1] = bd[1];
+    }
+}

@@ -438,7 +438,18 @@ def update_normal_and_depth(centers, pos, ref_center, level, scale_factors):
     return out, mx[0], mn[0]
 
 
-# ---- Optimizer::LocalInertialBA (oracle only so far) ------------------------------------------------------------
+def hamming_knn2(query, train):
+    """cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, k=2) restated (Frame.cc:1553).  Returns (idx[nq][2], dist[nq][2]), -1 = none."""
+    L = lib()
+    L.orc_hamming_knn2.restype = None
+    L.orc_hamming_knn2.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    q, t = np.ascontiguousarray(query, np.uint8).reshape(-1, 32), np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+    idx, dist = np.zeros((max(len(q), 1), 2), np.int32), np.zeros((max(len(q), 1), 2), np.int32)
+    L.orc_hamming_knn2(len(q), _p(q) if len(q) else None, len(t), _p(t) if len(t) else None, _p(idx), _p(dist))
+    return idx[:len(q)], dist[:len(q)]
+
+
+# ---- Optimizer::LocalInertialBA (SURVEY 8(f) N2) ------------------------------------------------------------
 LIBA_LINK = np.dtype([("k1", np.int32), ("k2", np.int32), ("robust", np.int32), ("_pad", np.int32), ("dt", np.float64),
                       ("dR", np.float32, 9), ("dV", np.float32, 3), ("dP", np.float32, 3), ("JRg", np.float32, 9), ("JVg", np.float32, 9),
                       ("JVa", np.float32, 9), ("JPg", np.float32, 9), ("JPa", np.float32, 9), ("blin", np.float32, 6),

@@ -257,3 +257,23 @@ def isInFrustumDevice(extractor, cam, n_frames, point_offset, Rcw, tcw, Ow, worl
                                _dptr(max_dist), _dptr(min_dist), int(max_dist.numel()))
     N.check(N.lib().orbf_is_in_frustum(extractor._h, C.byref(cam), C.byref(fp), float(viewingCosLimit),
                                        *[_dptr(out[k]) for k in ("in_view", "proj_x", "proj_y", "proj_xr", "level", "view_cos", "depth")]))
+
+
+def knnMatch2(extractor, query_sets, train_sets):
+    """cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, 2) (Frame::ComputeStereoFishEyeMatches, src/Frame.cc:1553) for a batch of
+    independent (query descriptors [nq][32], train descriptors [nt][32]) pairs on the extractor's stream.
+    Returns a list of (idx[nq][2], dist[nq][2]) int32 arrays; -1 where the train set has fewer rows."""
+    L = N.lib()
+    qs = [np.ascontiguousarray(q, np.uint8).reshape(-1, 32) for q in query_sets]
+    ts = [np.ascontiguousarray(t, np.uint8).reshape(-1, 32) for t in train_sets]
+    assert len(qs) == len(ts)
+    qo = np.zeros(len(qs) + 1, np.int32)
+    to = np.zeros(len(ts) + 1, np.int32)
+    qo[1:] = np.cumsum([len(q) for q in qs])
+    to[1:] = np.cumsum([len(t) for t in ts])
+    qd = np.ascontiguousarray(np.concatenate(qs)) if qo[-1] else np.zeros((1, 32), np.uint8)
+    td = np.ascontiguousarray(np.concatenate(ts)) if to[-1] else np.zeros((1, 32), np.uint8)
+    idx = np.zeros((max(int(qo[-1]), 1), 2), np.int32)
+    dist = np.zeros((max(int(qo[-1]), 1), 2), np.int32)
+    N.check(L.orbm_hamming_knn2(extractor._h, len(qs), N.ptr(qo), N.ptr(qd), N.ptr(to), N.ptr(td), N.ptr(idx), N.ptr(dist)))
+    return [(idx[qo[i]:qo[i + 1]], dist[qo[i]:qo[i + 1]]) for i in range(len(qs))]

@@ -18,3 +18,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k
 # k_quadtree_v1 (CTA-parallel ordered-phase sort): parity, then the per-stage effect
 timeout 600 python -m pytest tests/test_zz_quadtree_v1_gpu.py -x -q 2>&1 | tee gpurun_out/qt_v1_tests.log
 ORB_QT_VARIANT=1 timeout 600 python bench.py --steps 5 --warmup 3 2>gpurun_out/qt_v1_bench.err | tee gpurun_out/qt_v1_bench.json
+# K9 brute-force Hamming 2-NN (orbm_hamming_knn2)
+timeout 300 python -m pytest tests/test_zz_knn_gpu.py -x -q 2>&1 | tee gpurun_out/knn_tests.log
