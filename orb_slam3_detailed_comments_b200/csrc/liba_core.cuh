@@ -1,8 +1,9 @@
 // liba_core.cuh -- Optimizer::LocalInertialBA's numeric core (/root/reference/src/Optimizer.cc:2203-2812) as
-// barrier-separated SPMD phases, one CTA per problem.  Like quadtree_core.cuh, the identical source compiles for the
-// device (LIBA_PAR_FOR = thread-strided loop, LIBA_SYNC = __syncthreads, block reductions; no atomics: every sum is a gather in a
-// fixed order, so Levenberg's accept / reject decisions do not depend on scheduling) and for the
-// host (one "thread"), so tests/host_emul can run this very algorithm against the CPU oracle without a GPU.
+// barrier-separated SPMD phases run by a TEAM of threads (a thread-block cluster on the device; see "Execution model" below).
+// Like quadtree_core.cuh, the identical source compiles for the device and for the host, so tests/host_emul can run this very
+// algorithm against the CPU oracle -- by one thread, and by several threads with real barriers under ThreadSanitizer -- without a
+// GPU.  There are no atomics: every sum is a gather in a fixed order, so Levenberg's accept / reject decisions do not depend on
+// scheduling.
 //
 // g2o graph being solved (single camera, Nleft == -1):
 //   vertices  VertexPose (ImuCamPose: twb += Rwb ut, Rwb = Rwb Exp(ur); G2oTypes.cc:221-244), VertexVelocity,
