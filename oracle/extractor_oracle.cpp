@@ -163,9 +163,22 @@ void fast_cell(const uint8_t* win, int cw, int ch, int stride, int thr, std::vec
         for (int x = 3; x < cw - 3; ++x) {
             const uint8_t* p = win + (size_t)y * stride + x;
             const int c = p[0], hi = c + thr, lo = c - thr;
-            // antipodal pre-test: an arc of 9 contains pixel k or pixel k+8 for every k
-            const int a = p[off[0]], b = p[off[8]];
-            if (!((a > hi) | (b > hi) | (a < lo) | (b < lo))) continue;
+            // antipodal pre-test: an arc of 9 contains pixel k or pixel k+8 for every k, so a bright (dark) arc needs one bright
+            // (dark) pixel in EVERY antipodal pair; four pairs, tested progressively like OpenCV's own high-speed test
+            {
+                const int a0 = p[off[0]], b0 = p[off[8]];
+                int br = (a0 > hi) | (b0 > hi), dk = (a0 < lo) | (b0 < lo);
+                if (!(br | dk)) continue;
+                const int a1 = p[off[4]], b1 = p[off[12]];
+                br &= (a1 > hi) | (b1 > hi); dk &= (a1 < lo) | (b1 < lo);
+                if (!(br | dk)) continue;
+                const int a2 = p[off[2]], b2 = p[off[10]];
+                br &= (a2 > hi) | (b2 > hi); dk &= (a2 < lo) | (b2 < lo);
+                if (!(br | dk)) continue;
+                const int a3 = p[off[6]], b3 = p[off[14]];
+                br &= (a3 > hi) | (b3 > hi); dk &= (a3 < lo) | (b3 < lo);
+                if (!(br | dk)) continue;
+            }
             uint32_t mb = 0, md = 0;
             for (int k = 0; k < 16; ++k) {
                 const int v = p[off[k]];
