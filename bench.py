@@ -200,7 +200,7 @@ def cpu_oracle_frames(pairs, threads, with_pose_opt=False):
     return len(pairs) / dt, dt
 
 
-def straw_man_guard(pair):
+def _straw_man_guard(pair):
     """the oracle's OpenCV-equivalent stages are scalar restatements; cv2 (one thread) runs the same stages with
     SIMD.  Times both on one image of the workload and returns the factor by which a frame of the CPU arm gets cheaper when every
     such stage is charged at min(oracle, cv2): ratio = frame_ms_with_cv2_stages / frame_ms_oracle (<= 1).
@@ -251,6 +251,13 @@ def straw_man_guard(pair):
     return {"oracle_stage_ms_per_image": stage, "cv2_stage_ms_per_image": cv, "image_ms_oracle": t_img, "rest_of_frame_ms_oracle": t_rest, "delta_ms_per_image": delta,
             "frame_ms_oracle": f_or, "frame_ms_with_cv2_stages": f_cv, "ratio": f_cv / f_or if f_or > 0 else 1.0,
             "note": "value = oracle-measured frames/s / ratio; cv2 4.x single-threaded; FAST charged as one whole-level detect per level"}
+
+
+def straw_man_guard(pair):
+    try:
+        return _straw_man_guard(pair)
+    except Exception as exc:      # the guard must never cost the bench line
+        return {"error": repr(exc), "ratio": 1.0}
 
 
 def run_reference(args, rank, world):
