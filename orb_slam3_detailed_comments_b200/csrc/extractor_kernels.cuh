@@ -370,7 +370,7 @@ __device__ __forceinline__ int qt_run_v1(uint32_t* arr, void* ws, int cap, int n
     return qt_distribute_v<1>(arr, n, q, w, out);
 }
 
-__global__ void __launch_bounds__(QT_THREADS) k_quadtree_v1(const __grid_constant__ ExtractGeom g, int batch, int levelBegin,
+__global__ void __launch_bounds__(QT_THREADS, 4) k_quadtree_v1(const __grid_constant__ ExtractGeom g, int batch, int levelBegin,
                                                            const uint32_t* __restrict__ cand, const int* __restrict__ candCnt,
                                                            uint32_t* __restrict__ sortScratch, char* __restrict__ nodeScratch,
                                                            int64_t nodeScratchStride, int sortCapSmem, int nodesInSmem,
