@@ -263,3 +263,15 @@ def test_depth_sign_and_last_trial_chi2(emul):
     got = run_emul(emul, s, 1.0, 6)
     assert (got["edge_depth_pos"] == ref["edge_depth_pos"]).all()
     assert abs(got["chi2_last"] - ref["chi2_last"]) <= 1e-6 * max(1.0, ref["chi2_last"]) and ref["chi2_last"] >= ref["chi2"] - 1e-9
+
+
+def test_large_window_blarge_settings(emul):
+    """bLarge (Optimizer.cc:2211-2216, 2347): 25 optimisable keyframes (a 375 x 375 reduced system), lambda 1e-2, 4 iterations."""
+    from orb_slam3_detailed_comments_b200 import synth
+    s = synth.inertial_window(n_opt=25, n_cov_fixed=5, n_mp=900, seed=9)
+    ref = po.liba(s["state"], s["fixed"], s["point"], s["edge_kf"], s["edge_mp"], s["obs"], s["inv_sigma2"], s["Tcb"], s["cam5"],
+                  s["links"].view(po.LIBA_LINK), 1e-2, 4)
+    got = run_emul(emul, s, 1e-2, 4)
+    assert got["iterations"] == ref["iterations"] and got["trials"] == ref["trials"]
+    assert np.abs(got["state"] - ref["state"]).max() < TOL and np.abs(got["point"] - ref["point"]).max() < TOL
+    assert ref["chi2"] < 0.05 * ref["chi2_init"]

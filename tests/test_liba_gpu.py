@@ -56,3 +56,12 @@ def test_bench_window(opt):
     ref = po.liba(s["state"], s["fixed"], s["point"], s["edge_kf"], s["edge_mp"], s["obs"], s["inv_sigma2"], s["Tcb"], s["cam5"],
                   s["links"].view(po.LIBA_LINK), 1.0, 10)
     check(opt.LocalInertialBA(s, 1.0, 10), ref)
+
+
+def test_large_window(opt):
+    """bLarge: 25 optimisable keyframes (375 x 375 reduced system in global memory), lambda 1e-2, 4 iterations."""
+    from orb_slam3_detailed_comments_b200 import synth
+    s = synth.inertial_window(n_opt=25, n_cov_fixed=5, n_mp=900, seed=9)
+    ref = po.liba(s["state"], s["fixed"], s["point"], s["edge_kf"], s["edge_mp"], s["obs"], s["inv_sigma2"], s["Tcb"], s["cam5"],
+                  s["links"].view(po.LIBA_LINK), 1e-2, 4)
+    check(opt.LocalInertialBA(s, 1e-2, 4), ref)
