@@ -4,7 +4,6 @@ import ctypes as C
 import os
 import re
 
-import numpy as np
 import pytest
 
 from orb_slam3_detailed_comments_b200 import _native as N

@@ -2,7 +2,6 @@
 glibc and libstdc++.  This is what lets kernel arithmetic be checked in a container without a GPU."""
 import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 import pytest

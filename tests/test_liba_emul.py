@@ -2,6 +2,8 @@
 the host and run against the oracle (oracle/lba_oracle.cpp orc_liba).  Same phases, same packing (csrc/liba_pack.h), same C ABI
 structs; what this cannot see are device-only hazards (barrier placement, atomics), which the GPU test covers once it has run."""
 import ctypes as C
+import os
+import subprocess
 
 import numpy as np
 import pytest
@@ -12,6 +14,7 @@ from orb_slam3_detailed_comments_b200.optimizer import finish_inertial_result, p
 from test_oracle_inertial import scene
 
 TOL = 1e-4   # BASELINE.json north_star tolerance for the BA rows
+HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 @pytest.fixture(scope="module")
@@ -102,11 +105,7 @@ def test_mono_only_and_all_fixed_but_one(emul):
     assert np.abs(got["state"] - ref["state"]).max() < TOL and np.abs(got["point"] - ref["point"]).max() < TOL
 
 
-# ---- the same source run by N host threads with real barriers / atomics under ThreadSanitizer -----------------------------------
-import os
-import subprocess
-
-HERE = os.path.dirname(os.path.abspath(__file__))
+# ---- the same source run by N host threads with real barriers under ThreadSanitizer ---------------------------------------------
 
 
 @pytest.fixture(scope="module")

@@ -3,7 +3,6 @@ import hashlib
 import os
 
 import numpy as np
-import pytest
 
 from oracle import pyoracle as po
 from orb_slam3_detailed_comments_b200 import synth
