@@ -157,3 +157,23 @@ def test_reprojection_jacobians_by_finite_differences(stereo):
         rp = po.liba_reproj(po.kf_oplus(st, d), Xw, obs, s["Tcb"], s["cam5"])[1]
         rm = po.liba_reproj(po.kf_oplus(st, -d), Xw, obs, s["Tcb"], s["cam5"])[1]
         assert np.abs((rp - rm)[:D] / (2 * h) - Jx[:, c]).max() < 1e-4
+
+
+def test_golden_window():
+    """The committed window (tests/golden/golden_liba.npz): the oracle still produces what it produced when the fixture was made, and
+    the generator still produces the fixture's inputs."""
+    import os
+    from orb_slam3_detailed_comments_b200 import synth
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_liba.npz"))
+    links = np.frombuffer(z["in_links"].tobytes(), po.LIBA_LINK)
+    r = po.liba(z["in_state"], z["in_fixed"], z["in_point"], z["in_edge_kf"], z["in_edge_mp"], z["in_obs"], z["in_inv_sigma2"], z["in_Tcb"],
+                z["in_cam5"], links, 1.0, 10)
+    sc = z["scalars"]
+    assert r["iterations"] == int(sc[0]) and r["trials"] == int(sc[1])
+    assert np.allclose([r["lambda_"], r["chi2"], r["chi2_init"], r["chi2_last"]], sc[2:], rtol=1e-9)
+    assert np.abs(r["state"] - z["state"]).max() < 1e-9 and np.abs(r["point"] - z["point"]).max() < 1e-9
+    assert np.allclose(r["edge_chi2"], z["edge_chi2"], rtol=1e-7, atol=1e-9) and np.allclose(r["link_chi2"], z["link_chi2"], rtol=1e-7, atol=1e-9)
+    assert (r["edge_depth_pos"] == z["edge_depth_pos"]).all()
+    s = synth.inertial_window(n_opt=5, n_cov_fixed=2, n_mp=120, seed=17)
+    assert np.allclose(s["state"], z["in_state"], rtol=0, atol=1e-9) and np.allclose(s["obs"], z["in_obs"], rtol=0, atol=1e-6)
+    assert np.allclose(s["links"]["info"], links["info"], rtol=1e-6) and np.allclose(s["links"]["dP"], links["dP"], rtol=0, atol=1e-7)
