@@ -91,3 +91,56 @@ def test_hamming_matches_cv2_norm():
     a, b = rng.integers(0, 256, (50, 32), dtype=np.uint8), rng.integers(0, 256, (50, 32), dtype=np.uint8)
     for i in range(50):
         assert po.hamming(a[i], b[i]) == int(cv2.norm(a[i], b[i], cv2.NORM_HAMMING))
+
+
+def _orb(nfeatures=3000):
+    return cv2.ORB_create(nfeatures=nfeatures, scaleFactor=1.2, nlevels=1, edgeThreshold=19, firstLevel=0, WTA_K=2,
+                          scoreType=cv2.ORB_FAST_SCORE, patchSize=31, fastThreshold=20)
+
+
+@pytest.mark.parametrize("seed,sigma,nrect", [(1, 1.5, 60), (2, 6.0, 10), (9, 1.0, 120)])
+def test_ic_angle_matches_opencv_orb(seed, sigma, nrect):
+    """IC_Angle (ORBextractor.cc:91-138: intensity-centroid moments over the umax disc + cv::fastAtan2) against the orientation
+    OpenCV's own ORB assigns to the keypoints it detects on the same image (one level): bit-identical floats."""
+    img = synth.frame(640, 480, seed, sigma, nrect)
+    um = po.OracleExtractor(1000, 1.2, 8, 20, 7).umax
+    kps = _orb().detect(img, None)
+    assert len(kps) > 30
+    for p in kps:
+        x, y = int(round(p.pt[0])), int(round(p.pt[1]))
+        assert np.float32(po.ic_angle(img, x, y, um)) == np.float32(p.angle), (x, y)
+
+
+def test_descriptor_matches_opencv_orb_up_to_its_blur():
+    """computeOrbDescriptor (ORBextractor.cc:150-203: bit_pattern_31_, steering by the keypoint angle, cvRound, bit order) against
+    cv2.ORB.compute on the oracle's own level-0 keypoints and angles.  OpenCV's ORB blurs a SUB-MATRIX of its pyramid image, which takes
+    GaussianBlur's float path; ORB-SLAM3 blurs a clone (ORBextractor.cc:1629-1632), which takes the bit-exact fixed-point path the
+    oracle follows -- the blurred images differ by at most 1 grey level.  So: most descriptors are identical, and every differing bit
+    compares two samples whose (fixed-point) blurred intensities are within 2 of each other; a wrong pattern entry, rotation, rounding
+    or bit order would flip bits on well-separated samples."""
+    img = synth.frame(640, 480, 1)
+    ex = po.OracleExtractor(1000, 1.2, 1, 20, 7)          # one level: level-0 coordinates are image coordinates
+    _, k, d = ex(img)
+    kps = [cv2.KeyPoint(float(q["x"]), float(q["y"]), 31.0, float(q["angle"]), float(q["response"]), 0, -1) for q in k]
+    kp2, dcv = _orb(5000).compute(img, kps)
+    assert len(kp2) == len(k) and all(a.pt == b.pt for a, b in zip(kps, kp2))
+    same = (dcv == d).all(1)
+    assert same.mean() > 0.7
+    blur = cv2.GaussianBlur(img, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+    pat = po.pattern().reshape(-1, 2).astype(np.float32)
+    f32 = np.float32
+    nbits = 0
+    for i in np.nonzero(~same)[0]:
+        x0, y0 = int(k[i]["x"]), int(k[i]["y"])
+        ang = f32(k[i]["angle"]) * f32(f32(np.pi) / f32(180.0))
+        a, b = f32(np.cos(np.float64(ang))), f32(np.sin(np.float64(ang)))
+        diff = np.unpackbits((dcv[i] ^ d[i])[:, None], axis=1, bitorder="little")
+        for byte, bit in zip(*np.nonzero(diff)):
+            v = []
+            for p in (16 * byte + 2 * bit, 16 * byte + 2 * bit + 1):
+                px, py = pat[p]
+                xr, yr = f32(f32(px * a) - f32(py * b)), f32(f32(px * b) + f32(py * a))
+                v.append(int(blur[y0 + int(np.rint(yr)), x0 + int(np.rint(xr))]))
+            assert abs(v[0] - v[1]) <= 2, (i, byte, bit, v)
+            nbits += 1
+    assert nbits < 0.005 * d.size * 8
