@@ -214,3 +214,79 @@ def test_bias_correction_agrees_with_reintegration():
         first_order = np.abs(po.inertial_edge(st, link_of(pre0))[0] - e_true).max()  # ignoring the bias change altogether
         assert errs[-1] < 0.02 * first_order
     assert errs[1] < 0.4 * errs[0] + 2e-6        # halving the bias change quarters the discrepancy (float32 deltas: 1e-6 floor)
+
+
+def _log_so3(R):
+    c = min(1.0, max(-1.0, (np.trace(R) - 1) / 2))
+    w = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]]) / 2
+    th = np.arccos(c)
+    return w if abs(np.sin(th)) < 1e-5 else th * w / np.sin(th)
+
+
+def numpy_cost(s, state, point):
+    """The objective LocalInertialBA hands to g2o, in plain numpy from the reference's edge definitions (G2oTypes.cc:390-490, 592-611,
+    G2oTypes.h:736-800; Huber sqrt(5.991) / sqrt(7.815) / sqrt(16.92) where installed)."""
+    fx, fy, cx, cy, bf = s["cam5"]
+    Rcb, tcb = np.asarray(s["Tcb"][:9]).reshape(3, 3), np.asarray(s["Tcb"][9:])
+    hub = lambda c, d: c if c <= float(np.float32(d * d)) else 2 * np.sqrt(c) * d - float(np.float32(d * d))
+    dM, dS, dI = float(np.float32(np.sqrt(5.991))), float(np.float32(np.sqrt(7.815))), np.sqrt(16.92)
+    total = 0.0
+    for e in range(len(s["edge_kf"])):
+        st = state[s["edge_kf"][e]]
+        Rwb, twb = st[:9].reshape(3, 3), st[9:12]
+        Xc = Rcb @ (Rwb.T @ (point[s["edge_mp"][e]] - twb)) + tcb
+        u, v = fx * Xc[0] / Xc[2] + cx, fy * Xc[1] / Xc[2] + cy
+        z = s["obs"][e]
+        r = [z[0] - u, z[1] - v] + ([] if z[2] < 0 else [z[2] - (u - bf / Xc[2])])
+        total += hub(s["inv_sigma2"][e] * float(np.dot(r, r)), dM if z[2] < 0 else dS)
+    links = np.asarray(s["links"]).view(po.LIBA_LINK).reshape(-1)
+    for L in links:
+        s1, s2 = state[L["k1"]], state[L["k2"]]
+        R1, R2 = s1[:9].reshape(3, 3), s2[:9].reshape(3, 3)
+        dbg, dba = s1[15:18] - L["blin"][3:].astype(float), s1[18:21] - L["blin"][:3].astype(float)
+        m = lambda k: L[k].astype(float).reshape(3, 3)
+        dR = m("dR") @ expm(m("JRg") @ dbg)
+        dV = L["dV"].astype(float) + m("JVg") @ dbg + m("JVa") @ dba
+        dP = L["dP"].astype(float) + m("JPg") @ dbg + m("JPa") @ dba
+        dt = L["dt"]
+        e9 = np.concatenate([_log_so3(dR.T @ R1.T @ R2), R1.T @ (s2[12:15] - s1[12:15] - G * dt) - dV,
+                             R1.T @ (s2[9:12] - s1[9:12] - s1[12:15] * dt - G * dt * dt / 2) - dP])
+        c = float(e9 @ L["info"].reshape(9, 9) @ e9)
+        total += hub(c, dI) if L["robust"] else c
+        eg, ea = s2[15:18] - s1[15:18], s2[18:21] - s1[18:21]
+        total += float(eg @ L["infoG"].reshape(3, 3) @ eg) + float(ea @ L["infoA"].reshape(3, 3) @ ea)
+    return total
+
+
+def test_objective_and_stationarity_against_numpy():
+    """Independent of the oracle's Jacobians, Schur complement and LM control: (i) the chi2 the oracle reports IS the numpy objective at
+    the initial and at the final estimate; (ii) run to convergence, the final estimate is a stationary point of that objective along
+    positions, velocities, biases of the free keyframes and the coordinates of a sample of map points."""
+    from orb_slam3_detailed_comments_b200 import synth
+    s = synth.inertial_window(n_opt=4, n_cov_fixed=2, n_mp=90, seed=23)
+    r = po.liba(s["state"], s["fixed"], s["point"], s["edge_kf"], s["edge_mp"], s["obs"], s["inv_sigma2"], s["Tcb"], s["cam5"],
+                s["links"].view(po.LIBA_LINK), 1.0, 200)
+    c0, c1 = numpy_cost(s, s["state"], s["point"]), numpy_cost(s, r["state"], r["point"])
+    assert abs(r["chi2_init"] - c0) <= 2e-5 * c0 and abs(r["chi2"] - c1) <= 2e-5 * c1 + 1e-6     # float32 delta storage inside the edge
+    assert c1 < 0.01 * c0
+
+    def grad(state, point, h):
+        g = []
+        for k in np.nonzero(s["fixed"] == 0)[0]:
+            for c in range(9, 21):
+                a, b = state.copy(), state.copy()
+                a[k, c] += h[c]
+                b[k, c] -= h[c]
+                g.append((numpy_cost(s, a, point) - numpy_cost(s, b, point)) / (2 * h[c]))
+        for l in range(0, len(point), 9):
+            for c in range(3):
+                a, b = point.copy(), point.copy()
+                a[l, c] += 1e-6
+                b[l, c] -= 1e-6
+                g.append((numpy_cost(s, state, a) - numpy_cost(s, state, b)) / 2e-6)
+        return np.array(g)
+    h = np.full(21, 1e-6)
+    h[15:18] = 1e-8            # gyro bias: information ~1e10, keep the probe inside the quadratic region
+    g0, g1 = grad(s["state"], s["point"], h), grad(r["state"], r["point"], h)
+    scale = np.maximum(np.abs(g0), 1e-3 * np.abs(g0).max())
+    assert (np.abs(g1) / scale).max() < 5e-3, (np.abs(g1) / scale).max()
