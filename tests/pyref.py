@@ -179,9 +179,12 @@ def se3_act(T, p):
     return [f32(f32(f32(p[i] + f32(qw * uv[i])) + c[i]) + f32(T[4 + i])) for i in range(3)]
 
 
-def fuse(variant, kps, desc, uright, bounds, sf, inv_sigma2, log_sf, cam, T, Ow, xw, normal, maxd, mind, qdesc, th):
-    """ORBmatcher::Fuse(pKF, vpMapPoints, th) (variant 0, ORBmatcher.cc:1325-1544) and Fuse(pKF, Scw, ...) (variant 1, :1546-1687):
-    the search part, bestIdx per map point or -1."""
+def fuse(variant, kps, desc, uright, bounds, sf, inv_sigma2, log_sf, cam, T, Ow, xw, normal, maxd, mind, qdesc, th, thr=50.0, claimed=None):
+    """ORBmatcher::Fuse(pKF, vpMapPoints, th) (variant 0, ORBmatcher.cc:1325-1544), Fuse(pKF, Scw, ...) (variant 1, :1546-1687) and
+    SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (variant 2, :495-618: features that already hold a match are
+    skipped and every accepted match claims its feature; accepted when bestDist <= TH_LOW * ratioHamming = thr): the search part,
+    bestIdx per map point or -1."""
+    claimed = np.zeros(len(kps), bool) if claimed is None else np.asarray(claimed, bool).copy()
     import math
     import ctypes
     import ctypes.util
@@ -213,8 +216,10 @@ def fuse(variant, kps, desc, uright, bounds, sf, inv_sigma2, log_sf, cam, T, Ow,
             lvl = int(math.ceil(float(f32(f32(libm.logf(float(f32(f32(maxd[q]) / dist)))) / f32(log_sf)))))
             lvl = max(0, min(lvl, len(sf) - 1))
             radius = f32(f32(th) * f32(sf[lvl]))
-            best, bi = (256, -1) if variant == 0 else (2 ** 31 - 1, -1)
+            best, bi = (256, -1) if variant in (0, 2) else (2 ** 31 - 1, -1)
             for i in g.area(u, v, radius):
+                if variant == 2 and claimed[i]:
+                    continue
                 o = int(kps["octave"][i])
                 if o < lvl - 1 or o > lvl:
                     continue
@@ -232,7 +237,11 @@ def fuse(variant, kps, desc, uright, bounds, sf, inv_sigma2, log_sf, cam, T, Ow,
                 d = hamming(qdesc[q], desc[i])
                 if d < best:
                     best, bi = d, i
-            if best <= 50:
+            if variant == 2:
+                if bi >= 0 and float(best) <= float(f32(thr)):
+                    res = bi
+                    claimed[bi] = True
+            elif best <= 50:
                 res = bi
             break
         out.append(res)
@@ -488,3 +497,66 @@ def bow_transform(voc, desc, levelsup=4):
         norm += abs(bow[w])
     vals = [bow[w] / norm for w in ws] if norm > 0 else [bow[w] for w in ws]
     return dict(word=word, node=node, weight=weight, bow_word=np.array(ws, np.int32), bow_weight=np.array(vals, np.float64), feat=feat)
+
+
+def search_for_triangulation(kp1, d1, node1, stereo1, kp2, d2, node2, valid2, stereo2, F12, ep2, scale_factors, sigma2, coarse=False,
+                             check_ori=True):
+    """ORBmatcher::SearchForTriangulation (ORBmatcher.cc:1045-1323), single-camera keyframes, written as the reference walks it:
+    FeatureVector node by node (std::map order), inside a node the KF1 features without a map point in index order, for each the
+    KF2 features of the SAME node without a map point in index order.  `dist > TH_LOW || dist > bestDist` lets a later candidate at
+    the same distance replace an earlier one; vbMatched2 is read but never set in this version of the reference, so a KF2 feature can
+    be chosen by several KF1 features.  Epipolar gate as Pinhole::epipolarConstrain (Pinhole.cpp:186-216) from the caller's F12."""
+    f32 = np.float32
+    F = np.asarray(F12, f32).reshape(3, 3)
+    TH_LOW, HISTO = 50, 30
+    n1 = len(kp1)
+    m12 = np.full(n1, -1, np.int32)
+    hist = [[] for _ in range(HISTO)]
+    feat2 = {}
+    for i2 in range(len(kp2)):                                  # FeatureVector of KF2: node -> features in index order
+        if node2[i2] >= 0:
+            feat2.setdefault(int(node2[i2]), []).append(i2)
+    feat1 = {}
+    for q in range(n1):
+        feat1.setdefault(int(node1[q]), []).append(q)
+    nm = 0
+    for node in sorted(set(feat1) & set(feat2)):
+        for q in feat1[node]:
+            best, best_i = TH_LOW, -1
+            x1, y1 = f32(kp1["x"][q]), f32(kp1["y"][q])
+            for i2 in feat2[node]:
+                if not valid2[i2]:
+                    continue
+                dist = hamming(d1[q], d2[i2])
+                if dist > TH_LOW or dist > best:
+                    continue
+                x2, y2 = f32(kp2["x"][i2]), f32(kp2["y"][i2])
+                if not stereo1[q] and not stereo2[i2]:
+                    ex, ey = f32(f32(ep2[0]) - x2), f32(f32(ep2[1]) - y2)
+                    if f32(f32(ex * ex) + f32(ey * ey)) < f32(f32(100) * f32(scale_factors[kp2["octave"][i2]])):
+                        continue
+                ok = bool(coarse)
+                if not ok:
+                    a = f32(f32(f32(x1 * F[0, 0]) + f32(y1 * F[1, 0])) + F[2, 0])
+                    b = f32(f32(f32(x1 * F[0, 1]) + f32(y1 * F[1, 1])) + F[2, 1])
+                    c = f32(f32(f32(x1 * F[0, 2]) + f32(y1 * F[1, 2])) + F[2, 2])
+                    num = f32(f32(f32(a * x2) + f32(b * y2)) + c)
+                    den = f32(f32(a * a) + f32(b * b))
+                    if den != 0:
+                        dsqr = f32(f32(num * num) / den)
+                        ok = float(dsqr) < 3.84 * float(f32(sigma2[kp2["octave"][i2]]))       # float < double * float
+                if ok:
+                    best, best_i = dist, i2
+            if best_i >= 0:
+                m12[q] = best_i
+                nm += 1
+                if check_ori:
+                    hist[rot_bin(kp1["angle"][q], kp2["angle"][best_i])].append(q)
+    if check_ori:
+        keep = three_maxima(hist)
+        for i in range(HISTO):
+            if i not in keep:
+                for q in hist[i]:
+                    m12[q] = -1
+                    nm -= 1
+    return m12, nm

@@ -148,3 +148,61 @@ def test_search_by_bow_frame(frames):
         fm, nm = po.search_bow(k2, d2, fnode, nd, kL["angle"][q], dL[q], ratio, check)
         rfm, rnm = pyref.search_bow_frame(k2, d2, fnode, nd, kL["angle"][q], dL[q], ratio, check)
         assert nm == rnm and (fm == rfm).all() and nm > 10
+
+
+def test_search_for_triangulation(frames):
+    eL, kL, dL, uR, dep, k2, d2 = frames
+    rng = np.random.default_rng(8)
+    node_of = lambda d: ((d[:, 0].astype(np.int32) >> 3) * 7 + (d[:, 5].astype(np.int32) >> 4) * 3 + (d[:, 17].astype(np.int32) >> 5)) % 19
+    sel = np.nonzero(rng.random(len(kL)) < 0.7)[0]
+    nd = node_of(dL[sel])
+    node2 = node_of(d2).astype(np.int32)
+    node2[::11] = -1
+    valid2 = (rng.random(len(k2)) < 0.8).astype(np.uint8)
+    K = np.array([[FX, 0, CX], [0, FY, CY], [0, 0, 1]], np.float32)
+    t = np.array([0.03, 0.002, 0.01], np.float32)
+    tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]], np.float32)
+    F12 = (np.linalg.inv(K.T).astype(np.float32) @ tx @ np.eye(3, dtype=np.float32) @ np.linalg.inv(K).astype(np.float32)).astype(np.float32)
+    ep = np.array([150.0, 118.0], np.float32)
+    sf, s2 = eL.scale_factors, eL.level_sigma2
+    ur2 = np.where(rng.random(len(k2)) < 0.5, 1.0, -1.0)
+    total = 0
+    for coarse, check, mono_all in [(False, True, False), (True, True, False), (False, False, True), (True, False, True)]:
+        st1 = np.zeros(len(sel), np.uint8) if mono_all else (uR[sel] >= 0).astype(np.uint8)
+        st2 = np.zeros(len(k2), np.uint8) if mono_all else (ur2 >= 0).astype(np.uint8)
+        m, nm = po.search_triangulation(kL[sel], dL[sel], nd, st1, k2, d2, node2, valid2, st2, F12, ep, sf, s2, coarse, check)
+        rm, rnm = pyref.search_for_triangulation(kL[sel], dL[sel], nd, st1, k2, d2, node2, valid2, st2, F12, ep, sf, s2, coarse, check)
+        assert nm == rnm and (m == rm).all(), (coarse, check, mono_all)
+        total += nm
+    assert total > 40
+
+
+def test_search_by_projection_sim3(frames):
+    """SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (ORBmatcher.cc:495-618): claims carried from query to query,
+    some features already matched on entry."""
+    eL, kL, dL, uR, dep, k2, d2 = frames
+    rng = np.random.default_rng(12)
+    sf = eL.scale_factors
+    isg = (1.0 / (sf * sf)).astype(np.float32)
+    logsf = po.logf(1.2)
+    sel = np.nonzero(dep > 0)[0]
+    sel = np.concatenate([sel, sel[::3]])                      # duplicated map points compete for the same features
+    z = dep[sel]
+    pts = np.stack([(kL["x"][sel] - CX) * z / FX, (kL["y"][sel] - CY) * z / FY, z], 1).astype(np.float32)
+    dist = np.linalg.norm(pts, axis=1).astype(np.float32)
+    nrm = (pts / dist[:, None] + rng.normal(0, 0.3, pts.shape)).astype(np.float32)
+    nrm = (nrm / np.linalg.norm(nrm, axis=1)[:, None]).astype(np.float32)
+    maxd = np.float32(1.2) * (dist * sf[kL["octave"][sel]]).astype(np.float32)
+    mind = np.float32(0.8) * (maxd / np.float32(1.2) / sf[7]).astype(np.float32)
+    zmid = float(np.median(z))
+    T = np.array([0, 0.001, 0, 1, 2 * zmid / FX, 1 * zmid / FY, 0], np.float32)
+    T[:4] /= np.linalg.norm(T[:4])
+    Ow = (-T[4:]).astype(np.float32)
+    cam6 = [FX, FY, CX, CY, BF, B]
+    pre = (rng.random(len(k2)) < 0.15).astype(np.uint8)        # vpMatched[idx] != NULL on entry
+    for th, ratio in [(8.0, 1.5), (4.0, 1.0)]:
+        thr = float(np.float32(50) * np.float32(ratio))
+        m, nm, cl = po.search_keyframe(2, k2, d2, None, BOUNDS, sf, isg, logsf, cam6, T, Ow, pts, nrm, maxd, mind, dL[sel], None, pre, th, thr)
+        rm = pyref.fuse(2, k2, d2, None, BOUNDS, sf, isg, logsf, cam6, T, Ow, pts, nrm, maxd, mind, dL[sel], th, thr, pre)
+        assert (m == rm).all() and nm == int((rm >= 0).sum()) and nm > 20
+        assert len(set(m[m >= 0].tolist())) == nm and not pre[m[m >= 0]].any()     # one map point per feature, none on a pre-matched one
