@@ -560,3 +560,105 @@ def search_for_triangulation(kp1, d1, node1, stereo1, kp2, d2, node2, valid2, st
                     m12[q] = -1
                     nm -= 1
     return m12, nm
+
+
+def search_by_projection_reloc(kps, desc, bounds, sf, log_sf, cam, T, Ow, xw, maxd, mind, qdesc, qangle, claimed, th, orb_dist, check_ori=True):
+    """ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:2196-2330), pinhole: the keyframe's
+    map points (those not bad and not already found) projected with the frame's pose -- no depth-sign test, inclusive image bounds,
+    no viewing-angle test -- GetFeaturesInArea restricted to levels [n - 1, n + 1], features that already hold a map point skipped,
+    every accepted match claims its feature, rotation histogram over (keyframe keypoint angle - frame keypoint angle) with the
+    losers un-claimed at the end.  Returns (match per query or -1, claimed after)."""
+    import ctypes
+    import ctypes.util
+    import math
+    libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    libm.logf.restype = ctypes.c_float
+    libm.logf.argtypes = [ctypes.c_float]
+    g = Grid(kps, bounds)
+    fx, fy, cx, cy = [f32(v) for v in cam[:4]]
+    claimed = np.asarray(claimed, bool).copy()
+    match = np.full(len(xw), -1, np.int32)
+    hist = [[] for _ in range(30)]
+    for q in range(len(xw)):
+        pc = se3_act(T, xw[q])
+        u = f32(f32(f32(fx * pc[0]) / pc[2]) + cx)
+        v = f32(f32(f32(fy * pc[1]) / pc[2]) + cy)
+        if u < g.minX or u > g.maxX or v < g.minY or v > g.maxY:
+            continue
+        PO = [f32(f32(xw[q][i]) - f32(Ow[i])) for i in range(3)]
+        dist = f32(math.sqrt(float(f32(f32(PO[0] * PO[0]) + f32(f32(PO[1] * PO[1]) + f32(PO[2] * PO[2]))))))
+        if dist < mind[q] or dist > maxd[q]:
+            continue
+        lvl = int(math.ceil(float(f32(f32(libm.logf(float(f32(f32(maxd[q]) / dist)))) / f32(log_sf)))))
+        lvl = max(0, min(lvl, len(sf) - 1))
+        radius = f32(f32(th) * f32(sf[lvl]))
+        best, bi = 256, -1
+        for i in g.area(u, v, radius, lvl - 1, lvl + 1):
+            if claimed[i]:
+                continue
+            d = hamming(qdesc[q], desc[i])
+            if d < best:
+                best, bi = d, i
+        if best <= orb_dist:
+            match[q] = bi
+            claimed[bi] = True
+            if check_ori:
+                hist[rot_bin(qangle[q], kps["angle"][bi])].append((bi, q))
+    if check_ori:
+        keep = three_maxima(hist)
+        for b in range(30):
+            if b not in keep:
+                for bi, q in hist[b]:
+                    claimed[bi] = False
+                    match[q] = -1
+    return match, claimed
+
+
+def search_by_sim3_oneway(kps, desc, bounds, sf, log_sf, cam, T, S8, xw, maxd, mind, qdesc, th):
+    """One direction of ORBmatcher::SearchBySim3 (ORBmatcher.cc:1719-1790): the map points of the OTHER keyframe, taken to its camera
+    frame by its pose T (SE3f) and to this keyframe's camera frame by the similarity S = (non-unit quaternion x y z w, translation,
+    scale = |q|^2): Sophus RxSO3::operator* -- scale p + (w 2(v x p) + v x 2(v x p)) -- plus the translation (rxso3.hpp:265-273,
+    sim3.hpp:227-230).  Depth sign, KeyFrame::IsInImage, distance range on |p_c|, PredictScale, GetFeaturesInArea, octave in
+    [n - 1, n], best Hamming distance <= TH_HIGH.  No claims.  Returns the feature index per query or -1."""
+    import ctypes
+    import ctypes.util
+    import math
+    libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    libm.logf.restype = ctypes.c_float
+    libm.logf.argtypes = [ctypes.c_float]
+    g = Grid(kps, bounds)
+    fx, fy, cx, cy = [f32(v) for v in cam[:4]]
+    qx, qy, qz, qw = [f32(v) for v in S8[:4]]
+    t = [f32(v) for v in S8[4:7]]
+    scale = f32(S8[7])
+    out = np.full(len(xw), -1, np.int32)
+    for q in range(len(xw)):
+        p = se3_act(T, xw[q])
+        c = [f32(f32(qy * p[2]) - f32(qz * p[1])), f32(f32(qz * p[0]) - f32(qx * p[2])), f32(f32(qx * p[1]) - f32(qy * p[0]))]
+        u2 = [f32(v + v) for v in c]
+        cc = [f32(f32(qy * u2[2]) - f32(qz * u2[1])), f32(f32(qz * u2[0]) - f32(qx * u2[2])), f32(f32(qx * u2[1]) - f32(qy * u2[0]))]
+        pc = [f32(f32(f32(scale * p[i]) + f32(f32(qw * u2[i]) + cc[i])) + t[i]) for i in range(3)]
+        if pc[2] < 0.0:
+            continue
+        invz = f32(1.0 / float(pc[2]))                          # const float invz = 1.0 / p3Dc2(2): double division, rounded
+        u = f32(f32(fx * f32(pc[0] * invz)) + cx)
+        v = f32(f32(fy * f32(pc[1] * invz)) + cy)
+        if not (u >= g.minX and u < g.maxX and v >= g.minY and v < g.maxY):
+            continue
+        dist = f32(math.sqrt(float(f32(f32(pc[0] * pc[0]) + f32(f32(pc[1] * pc[1]) + f32(pc[2] * pc[2]))))))
+        if dist < mind[q] or dist > maxd[q]:
+            continue
+        lvl = int(math.ceil(float(f32(f32(libm.logf(float(f32(f32(maxd[q]) / dist)))) / f32(log_sf)))))
+        lvl = max(0, min(lvl, len(sf) - 1))
+        radius = f32(f32(th) * f32(sf[lvl]))
+        best, bi = 2 ** 31 - 1, -1
+        for i in g.area(u, v, radius):
+            o = int(kps["octave"][i])
+            if o < lvl - 1 or o > lvl:
+                continue
+            d = hamming(qdesc[q], desc[i])
+            if d < best:
+                best, bi = d, i
+        if best <= 100:
+            out[q] = bi
+    return out

@@ -206,3 +206,67 @@ def test_search_by_projection_sim3(frames):
         rm = pyref.fuse(2, k2, d2, None, BOUNDS, sf, isg, logsf, cam6, T, Ow, pts, nrm, maxd, mind, dL[sel], th, thr, pre)
         assert (m == rm).all() and nm == int((rm >= 0).sum()) and nm > 20
         assert len(set(m[m >= 0].tolist())) == nm and not pre[m[m >= 0]].any()     # one map point per feature, none on a pre-matched one
+
+
+def test_search_by_projection_reloc(frames):
+    """SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:2196-2330)."""
+    eL, kL, dL, uR, dep, k2, d2 = frames
+    rng = np.random.default_rng(21)
+    sf = eL.scale_factors
+    isg = (1.0 / (sf * sf)).astype(np.float32)
+    logsf = po.logf(1.2)
+    sel = np.nonzero(dep > 0)[0]
+    sel = np.concatenate([sel, sel[::4]])
+    z = dep[sel]
+    pts = np.stack([(kL["x"][sel] - CX) * z / FX, (kL["y"][sel] - CY) * z / FY, z], 1).astype(np.float32)
+    pts[::17, 2] *= -1                                           # behind the camera: this overload has no depth-sign test
+    dist = np.linalg.norm(pts, axis=1).astype(np.float32)
+    maxd = np.float32(1.2) * (dist * sf[kL["octave"][sel]]).astype(np.float32)
+    mind = np.float32(0.8) * (maxd / np.float32(1.2) / sf[7]).astype(np.float32)
+    zmid = float(np.median(np.abs(z)))
+    T = np.array([0, 0.001, 0.002, 1, 2 * zmid / FX, 1 * zmid / FY, 0], np.float32)
+    T[:4] /= np.linalg.norm(T[:4])
+    Ow = (-T[4:]).astype(np.float32)
+    cam6 = [FX, FY, CX, CY, BF, B]
+    pre = (rng.random(len(k2)) < 0.2).astype(np.uint8)          # CurrentFrame.mvpMapPoints[i2] != NULL on entry
+    ang = (kL["angle"][sel] + rng.choice([0.0, 0.0, 0.0, 90.0], len(sel))).astype(np.float32) % np.float32(360)
+    total = 0
+    for th, orb_dist, check in [(10.0, 100, True), (3.0, 64, True), (10.0, 100, False)]:
+        m, nm, cl = po.search_keyframe(3, k2, d2, None, BOUNDS, sf, isg, logsf, cam6, T, Ow, pts, None, maxd, mind, dL[sel], ang, pre, th,
+                                       float(orb_dist), check)
+        rm, rcl = pyref.search_by_projection_reloc(k2, d2, BOUNDS, sf, logsf, cam6, T, Ow, pts, maxd, mind, dL[sel], ang, pre, th, orb_dist, check)
+        assert (m == rm).all() and nm == int((rm >= 0).sum()) and (cl.astype(bool) == rcl).all(), (th, orb_dist, check)
+        total += nm
+    assert total > 60
+
+
+def test_search_by_sim3_one_direction(frames):
+    """One direction of SearchBySim3 (ORBmatcher.cc:1719-1790) with a non-trivial similarity (rotation, translation, scale 1.07)."""
+    eL, kL, dL, uR, dep, k2, d2 = frames
+    rng = np.random.default_rng(31)
+    sf = eL.scale_factors
+    isg = (1.0 / (sf * sf)).astype(np.float32)
+    logsf = po.logf(1.2)
+    sel = np.nonzero(dep > 0)[0]
+    z = dep[sel]
+    pts = np.stack([(kL["x"][sel] - CX) * z / FX, (kL["y"][sel] - CY) * z / FY, z], 1).astype(np.float32)
+    T = np.array([0, 0, 0, 1, 0, 0, 0], np.float32)             # the other keyframe's pose: identity (points are in its camera frame)
+    s = 1.07
+    q = np.array([0.004, -0.006, 0.003, 1.0])
+    q = q / np.linalg.norm(q) * np.sqrt(s)                      # RxSO3 stores sqrt(scale) * unit quaternion
+    zmid = float(np.median(z))
+    S8 = np.array([*q, 2 * zmid / FX, 1 * zmid / FY, -0.07 * zmid, 0], np.float32)
+    S8[7] = np.float32(np.dot(S8[:4], S8[:4]))                  # scale = quaternion().squaredNorm() in float
+    pc = s * pts + S8[4:7]
+    dist = np.linalg.norm(pc, axis=1).astype(np.float32)
+    maxd = np.float32(1.2) * (dist * sf[kL["octave"][sel]]).astype(np.float32)
+    mind = np.float32(0.8) * (maxd / np.float32(1.2) / sf[7]).astype(np.float32)
+    cam6 = [FX, FY, CX, CY, BF, B]
+    total = 0
+    for th in (7.5, 3.0):
+        m, nm, _ = po.search_keyframe(4, k2, d2, None, BOUNDS, sf, isg, logsf, cam6, T, np.zeros(3, np.float32), pts, None, maxd, mind,
+                                      dL[sel], None, None, th, 100.0, True, S8)
+        rm = pyref.search_by_sim3_oneway(k2, d2, BOUNDS, sf, logsf, cam6, T, S8, pts, maxd, mind, dL[sel], th)
+        assert (m == rm).all() and nm == int((rm >= 0).sum()), th
+        total += nm
+    assert total > 40
