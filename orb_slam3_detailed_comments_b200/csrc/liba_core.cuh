@@ -56,6 +56,9 @@ void liba_barrier_cta(int rank);
 
 namespace orb {
 
+#define LIBA_CHUNKS 8     // the long gathers (edges of a keyframe, co-observations of a keyframe pair) are summed in this many
+                          // contiguous chunks by different threads, then the chunk sums in order: still a fixed order
+
 struct LibaLink {   // == liba_link of include/orbslam3_b200.h
     int k1, k2, robust, pad;
     double dt;
@@ -106,6 +109,8 @@ struct LibaDev {
     double* Wdb;          // [nE][6]   W D^-1 b_l
     double* Epp;          // [nE][27]  upper triangle (21) of the edge's 6 x 6 pose block, then its 6 b terms
     double* Lblk;         // [nL][930] 30 x 30 block over [k1 15 | k2 15] of the inertial + random-walk edges, then 30 b terms
+    double* part;         // [LIBA_CHUNKS * max(27 nKF, 36 nPairs)] chunk sums of the two long gathers
+    double* part_b;       // [LIBA_CHUNKS * 6 nKF] chunk sums of the reduced right-hand side
     int* flag;            // [4] solver failure flag
     double* red;          // reduction scratch of this CTA (device: shared memory, one double per warp; emulation: per thread)
     double* partials;     // [8] per-CTA partial results of a team reduction (global memory)
@@ -480,6 +485,16 @@ LIBA_HD void liba_build(const LibaDev& P, const LibaHuber& H) {
         }
     }
     LIBA_SYNC();
+    LIBA_PAR_FOR(t, P.nKF * 27 * LIBA_CHUNKS) {     // chunk sums of the 21 + 6 per-edge pose terms over a keyframe's edges
+        const int k = t / (27 * LIBA_CHUNKS), slot = (t / LIBA_CHUNKS) % 27, ch = t % LIBA_CHUNKS;
+        if (P.pidx[k] < 0) continue;
+        const int n0 = P.kf_off[k], len = P.kf_off[k + 1] - n0;
+        const int a = n0 + (int)((long long)len * ch / LIBA_CHUNKS), b = n0 + (int)((long long)len * (ch + 1) / LIBA_CHUNKS);
+        double acc = 0.0;
+        for (int n = a; n < b; ++n) acc += P.Epp[27 * (size_t)P.kf_edge[n] + slot];
+        P.part[t] = acc;
+    }
+    LIBA_SYNC();
     LIBA_PAR_FOR(t, P.nKF * 240) {      // a thread owns one entry of a keyframe's 15 x 15 diagonal block (t % 240 < 225) or of its b
         const int k = t / 240, q = t % 240, pi = P.pidx[k];
         if (pi < 0) continue;
@@ -488,7 +503,8 @@ LIBA_HD void liba_build(const LibaDev& P, const LibaHuber& H) {
         double acc = 0.0;
         if (r < 6 && (isB || c < 6)) {
             const int slot = isB ? 21 + r : (r <= c ? liba_tri(r, c) : liba_tri(c, r));
-            for (int n = P.kf_off[k]; n < P.kf_off[k + 1]; ++n) acc += P.Epp[27 * (size_t)P.kf_edge[n] + slot];
+            const double* pp = P.part + ((size_t)k * 27 + slot) * LIBA_CHUNKS;
+            for (int ch = 0; ch < LIBA_CHUNKS; ++ch) acc += pp[ch];
         }
         for (int n = P.kl_off[k]; n < P.kl_off[k + 1]; ++n) {
             const int l = P.kl_ent[n] >> 1, o = 15 * (P.kl_ent[n] & 1);
@@ -533,24 +549,43 @@ LIBA_HD bool liba_solve_system(const LibaDev& P, double lambda) {
         }
     }
     LIBA_SYNC();
-    LIBA_PAR_FOR(t, P.nKF * 15) {      // reduced right-hand side
+    LIBA_PAR_FOR(t, P.nKF * 6 * LIBA_CHUNKS) {      // reduced right-hand side, chunk sums of W D^-1 b_l over a keyframe's edges
+        const int k = t / (6 * LIBA_CHUNKS), r = (t / LIBA_CHUNKS) % 6, ch = t % LIBA_CHUNKS;
+        if (P.pidx[k] < 0) continue;
+        const int n0 = P.kf_off[k], len = P.kf_off[k + 1] - n0;
+        const int a = n0 + (int)((long long)len * ch / LIBA_CHUNKS), b = n0 + (int)((long long)len * (ch + 1) / LIBA_CHUNKS);
+        double acc = 0.0;
+        for (int n = a; n < b; ++n) acc += P.Wdb[6 * (size_t)P.kf_edge[n] + r];
+        P.part_b[t] = acc;
+    }
+    LIBA_PAR_FOR(t, P.nPairs * 36 * LIBA_CHUNKS) {   // Schur complement, chunk sums: one entry of one 6 x 6 block, one chunk of the pair's list
+        const int q = t / (36 * LIBA_CHUNKS), ij = (t / LIBA_CHUNKS) % 36, ch = t % LIBA_CHUNKS, i = ij / 6, j = ij % 6;
+        const int n0 = P.pair_off[q], len = P.pair_off[q + 1] - n0;
+        const int a = n0 + (int)((long long)len * ch / LIBA_CHUNKS), b = n0 + (int)((long long)len * (ch + 1) / LIBA_CHUNKS);
+        double acc = 0.0;
+        for (int n = a; n < b; ++n) {
+            const double* WD = P.WD + 18 * (size_t)P.co_e1[n] + 3 * i;
+            const double* W2 = P.W + 18 * (size_t)P.co_e2[n] + 3 * j;
+            acc += WD[0] * W2[0] + WD[1] * W2[1] + WD[2] * W2[2];
+        }
+        P.part[t] = acc;
+    }
+    LIBA_SYNC();
+    LIBA_PAR_FOR(t, P.nKF * 15) {      // reduced right-hand side: chunk sums in order
         const int k = t / 15, r = t % 15, pi = P.pidx[k];
         if (pi < 0) continue;
-        double acc = P.b[15 * pi + r];
-        if (r < 6) for (int n = P.kf_off[k]; n < P.kf_off[k + 1]; ++n) acc -= P.Wdb[6 * (size_t)P.kf_edge[n] + r];
-        P.bs[15 * pi + r] = acc;
+        double acc = 0.0;
+        if (r < 6) for (int ch = 0; ch < LIBA_CHUNKS; ++ch) acc += P.part_b[((size_t)k * 6 + r) * LIBA_CHUNKS + ch];
+        P.bs[15 * pi + r] = P.b[15 * pi + r] - acc;
     }
-    LIBA_PAR_FOR(t, P.nPairs * 36) {   // Schur complement: a thread owns one entry of one 6 x 6 block (upper block triangle only)
+    LIBA_PAR_FOR(t, P.nPairs * 36) {   // a thread owns one entry of one 6 x 6 block (upper block triangle only): chunk sums in order
         const int q = t / 36, i = (t % 36) / 6, j = t % 6;
         const int p1 = P.pair_p[q] >> 16, p2 = P.pair_p[q] & 0xffff;
         double* dst = P.Hs + (size_t)(15 * p1 + i) * sp + 15 * p2 + j;
-        double acc = *dst;
-        for (int n = P.pair_off[q]; n < P.pair_off[q + 1]; ++n) {
-            const double* WD = P.WD + 18 * (size_t)P.co_e1[n] + 3 * i;
-            const double* W2 = P.W + 18 * (size_t)P.co_e2[n] + 3 * j;
-            acc -= WD[0] * W2[0] + WD[1] * W2[1] + WD[2] * W2[2];
-        }
-        *dst = acc;
+        const double* pp = P.part + (size_t)t * LIBA_CHUNKS;
+        double acc = 0.0;
+        for (int ch = 0; ch < LIBA_CHUNKS; ++ch) acc += pp[ch];
+        *dst -= acc;
     }
     LIBA_SYNC();
     // dense LDL^T of Hs (upper triangle read, right-looking) and the triangular solves, on the team's first CTA only.  After step j
