@@ -444,29 +444,45 @@ LIBA_HD void liba_build(const LibaDev& P, const LibaHuber& H) {
         for (int i = 0; i < 9; ++i) P.Hll[9 * (size_t)l + i] = hl[i];
         for (int i = 0; i < 3; ++i) P.b[sp + 3 * l + i] = bl[i];
     }
-    LIBA_PAR_FOR(l, P.nL) {      // inertial link + the two random walks -> one 30 x 30 block over [k1 | k2]
+    LIBA_PAR_FOR(t, P.nL * 25) {   // inertial links -> one 30 x 30 block over [k1 15 | k2 15] each; a thread owns one column (24: the tail)
+        const int l = t / 25, cb = t % 25;
         const LibaLink& L = P.links[l];
         double* B = P.Lblk + 930 * (size_t)l;
-        double e9[9], J[9 * 24], Oe[9];
+        double e9[9], J[9 * 24];
         liba_inertial(P, L, e9, J);
         double c = 0;
         for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) c += e9[i] * L.info[9 * i + j] * e9[j];
         double w = 1.0;
         if (L.robust) liba_huber(c, H.dI, H.sqI, &w);
-        for (int i = 0; i < 930; ++i) B[i] = 0.0;
-        for (int i = 0; i < 9; ++i) {
-            double s = 0; for (int k = 0; k < 9; ++k) s += L.info[9 * i + k] * e9[k];
-            Oe[i] = w * s;
-        }
-        for (int cb = 0; cb < 24; ++cb) {     // column cb of w Info J, then J^T times it (inertial columns 0..23 sit at block columns 0..23)
+        if (cb < 24) {        // column cb of w Info J, then J^T times it (inertial columns 0..23 sit at block columns 0..23)
             double oj[9];
-            for (int i = 0; i < 9; ++i) { double t = 0; for (int k = 0; k < 9; ++k) t += L.info[9 * i + k] * J[k * 24 + cb]; oj[i] = w * t; }
-            for (int ca = 0; ca < 24; ++ca) { double t = 0; for (int k = 0; k < 9; ++k) t += J[k * 24 + ca] * oj[k]; B[ca * 30 + cb] = t; }
+            for (int i = 0; i < 9; ++i) { double s2 = 0; for (int k = 0; k < 9; ++k) s2 += L.info[9 * i + k] * J[k * 24 + cb]; oj[i] = w * s2; }
+            for (int ca = 0; ca < 24; ++ca) { double s2 = 0; for (int k = 0; k < 9; ++k) s2 += J[k * 24 + ca] * oj[k]; B[ca * 30 + cb] = s2; }
+            for (int ca = 24; ca < 30; ++ca) B[ca * 30 + cb] = 0.0;
+        } else {              // columns 24..29 (bias of k2: random walks only, added below) and the right-hand side
+            double Oe[9];
+            for (int i = 0; i < 9; ++i) { double s2 = 0; for (int k = 0; k < 9; ++k) s2 += L.info[9 * i + k] * e9[k]; Oe[i] = w * s2; }
+            for (int ca = 0; ca < 30; ++ca) for (int cc = 24; cc < 30; ++cc) B[ca * 30 + cc] = 0.0;
+            for (int ca = 0; ca < 24; ++ca) { double s2 = 0; for (int k = 0; k < 9; ++k) s2 += J[k * 24 + ca] * Oe[k]; B[900 + ca] = -s2; }
+            for (int ca = 24; ca < 30; ++ca) B[900 + ca] = 0.0;
         }
-        for (int ca = 0; ca < 24; ++ca) { double s = 0; for (int k = 0; k < 9; ++k) s += J[k * 24 + ca] * Oe[k]; B[900 + ca] = -s; }
+    }
+    LIBA_SYNC();
+    LIBA_PAR_FOR(t, P.nKF * 27 * LIBA_CHUNKS) {     // chunk sums of the 21 + 6 per-edge pose terms over a keyframe's edges
+        const int k = t / (27 * LIBA_CHUNKS), slot = (t / LIBA_CHUNKS) % 27, ch = t % LIBA_CHUNKS;
+        if (P.pidx[k] < 0) continue;
+        const int n0 = P.kf_off[k], len = P.kf_off[k + 1] - n0;
+        const int a = n0 + (int)((long long)len * ch / LIBA_CHUNKS), b = n0 + (int)((long long)len * (ch + 1) / LIBA_CHUNKS);
+        double acc = 0.0;
+        for (int n = a; n < b; ++n) acc += P.Epp[27 * (size_t)P.kf_edge[n] + slot];
+        P.part[t] = acc;
+    }
+    LIBA_PAR_FOR(l, P.nL) {      // the two bias random walks of a link (e = b2 - b1, J1 = -I, J2 = I) go into the same block
+        const LibaLink& L = P.links[l];
+        double* B = P.Lblk + 930 * (size_t)l;
         const double* s1 = P.state + 21 * (size_t)L.k1;
         const double* s2 = P.state + 21 * (size_t)L.k2;
-        for (int which = 0; which < 2; ++which) {      // e = b2 - b1, J1 = -I, J2 = I
+        for (int which = 0; which < 2; ++which) {
             const double* info = which == 0 ? L.infoG : L.infoA;
             const int off = which == 0 ? 9 : 12, so = which == 0 ? 15 : 18;
             double e3[3], Oe3[3];
@@ -483,16 +499,6 @@ LIBA_HD void liba_build(const LibaDev& P, const LibaHuber& H) {
                 }
             }
         }
-    }
-    LIBA_SYNC();
-    LIBA_PAR_FOR(t, P.nKF * 27 * LIBA_CHUNKS) {     // chunk sums of the 21 + 6 per-edge pose terms over a keyframe's edges
-        const int k = t / (27 * LIBA_CHUNKS), slot = (t / LIBA_CHUNKS) % 27, ch = t % LIBA_CHUNKS;
-        if (P.pidx[k] < 0) continue;
-        const int n0 = P.kf_off[k], len = P.kf_off[k + 1] - n0;
-        const int a = n0 + (int)((long long)len * ch / LIBA_CHUNKS), b = n0 + (int)((long long)len * (ch + 1) / LIBA_CHUNKS);
-        double acc = 0.0;
-        for (int n = a; n < b; ++n) acc += P.Epp[27 * (size_t)P.kf_edge[n] + slot];
-        P.part[t] = acc;
     }
     LIBA_SYNC();
     LIBA_PAR_FOR(t, P.nKF * 240) {      // a thread owns one entry of a keyframe's 15 x 15 diagonal block (t % 240 < 225) or of its b
