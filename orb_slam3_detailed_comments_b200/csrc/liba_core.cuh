@@ -111,6 +111,7 @@ struct LibaDev {
     double* Lblk;         // [nL][930] 30 x 30 block over [k1 15 | k2 15] of the inertial + random-walk edges, then 30 b terms
     double* part;         // [LIBA_CHUNKS * max(27 nKF, 36 nPairs)] chunk sums of the two long gathers
     double* part_b;       // [LIBA_CHUNKS * 6 nKF] chunk sums of the reduced right-hand side
+    double* Ypan;         // [15][sp] panel D1 L21^T of the blocked factorisation
     int* flag;            // [4] solver failure flag
     double* red;          // reduction scratch of this CTA (device: shared memory, one double per warp; emulation: per thread)
     double* partials;     // [8] per-CTA partial results of a team reduction (global memory)
@@ -533,7 +534,7 @@ LIBA_HD void liba_build(const LibaDev& P, const LibaHuber& H) {
 LIBA_HD bool liba_solve_system(const LibaDev& P, double lambda) {
     const int sp = P.sp;
     LIBA_PAR_FOR(i, sp * sp) P.Hs[i] = P.Hpp[i] + ((i / sp) == (i % sp) ? lambda : 0.0);
-    if (LIBA_LEADER()) P.flag[0] = 0;
+    if (LIBA_LEADER()) { P.flag[0] = 0; P.flag[1] = 0; }
     LIBA_SYNC();
     LIBA_PAR_FOR(l, P.nMP) {     // D^-1 per landmark, W D^-1 and W D^-1 b_l per edge
         double D[9], Di[9];
@@ -594,42 +595,99 @@ LIBA_HD bool liba_solve_system(const LibaDev& P, double lambda) {
         *dst -= acc;
     }
     LIBA_SYNC();
-    // dense LDL^T of Hs (upper triangle read, right-looking) and the triangular solves, on the team's first CTA only.  After step j
-    // row j holds D_j at (j,j) and L(i,j) at (j,i), i > j.
+    // Dense LDL^T of Hs (upper triangle) and the triangular solves, on the team's first CTA only, BLOCKED by keyframe (15 x 15 pivots):
+    // per block column (a) one thread factorises the diagonal block, (b) a thread per remaining column solves the 15 x 15 unit
+    // lower system for the panel (Y = L11^-1 A12 = D1 L21^T, kept in Ypan; L21^T = D1^-1 Y stored in place), (c) the trailing
+    // update A22 -= Y^T (D1^-1 Y).  Afterwards row j holds D_j at (j,j) and L(i,j) at (j,i), i > j.  Seven CTA barriers per block
+    // column over the whole solve instead of six per scalar column.
     if (LIBA_RANK0()) {
         bool bad = P.flag[0] != 0;            // a singular landmark block (set before the team barrier above)
-        for (int j = 0; j < sp && !bad; ++j) {
-            const double dj = P.Hs[(size_t)j * sp + j];
-            if (!(fabs(dj) > 0) || !isfinite(dj)) { bad = true; break; }   // uniform: every thread reads the same dj
-            const int m = sp - j - 1;
-            LIBA_LOCAL_FOR(t, m * m) {        // trailing update with the not-yet-scaled row j:  A(i,k) -= A(j,i) A(j,k) / d_j, k >= i
-                const int i = j + 1 + t / m, k = j + 1 + t % m;
-                if (k >= i) P.Hs[(size_t)i * sp + k] -= P.Hs[(size_t)j * sp + i] * P.Hs[(size_t)j * sp + k] / dj;
+        const int nb = sp / 15;
+        for (int J = 0; J < nb && !bad; ++J) {
+            const int j0 = 15 * J, j1 = j0 + 15, m = sp - j1;
+            if (P.l_id == 0) {
+                bool ok = true;
+                for (int jj = j0; jj < j1 && ok; ++jj) {
+                    const double dj = P.Hs[(size_t)jj * sp + jj];
+                    if (!(fabs(dj) > 0) || !isfinite(dj)) { ok = false; break; }
+                    for (int ii = jj + 1; ii < j1; ++ii) {
+                        const double f = P.Hs[(size_t)jj * sp + ii] / dj;
+                        for (int kk = ii; kk < j1; ++kk) P.Hs[(size_t)ii * sp + kk] -= f * P.Hs[(size_t)jj * sp + kk];
+                    }
+                    for (int ii = jj + 1; ii < j1; ++ii) P.Hs[(size_t)jj * sp + ii] /= dj;
+                }
+                if (!ok) LIBA_FLAG_SET(&P.flag[1]);
             }
             LIBA_LOCAL_SYNC();
-            LIBA_LOCAL_FOR(t, m) P.Hs[(size_t)j * sp + j + 1 + t] /= dj;   // L(j+1+t, j)
+            bad = P.flag[1] != 0;             // uniform: written before the barrier, by one thread
+            if (bad) break;
+            LIBA_LOCAL_FOR(t, m) {
+                const int c = j1 + t;
+                double yv[15];
+                for (int a = 0; a < 15; ++a) {
+                    double sacc = P.Hs[(size_t)(j0 + a) * sp + c];
+                    for (int b2 = 0; b2 < a; ++b2) sacc -= P.Hs[(size_t)(j0 + b2) * sp + j0 + a] * yv[b2];
+                    yv[a] = sacc;
+                }
+                for (int a = 0; a < 15; ++a) {
+                    P.Ypan[(size_t)a * sp + c] = yv[a];
+                    P.Hs[(size_t)(j0 + a) * sp + c] = yv[a] / P.Hs[(size_t)(j0 + a) * sp + j0 + a];
+                }
+            }
+            LIBA_LOCAL_SYNC();
+            LIBA_LOCAL_FOR(t, m * m) {
+                const int ii = j1 + t / m, kk = j1 + t % m;
+                if (kk >= ii) {
+                    double sacc = 0.0;
+                    for (int a = 0; a < 15; ++a) sacc += P.Ypan[(size_t)a * sp + ii] * P.Hs[(size_t)(j0 + a) * sp + kk];
+                    P.Hs[(size_t)ii * sp + kk] -= sacc;
+                }
+            }
             LIBA_LOCAL_SYNC();
         }
         if (bad) {
-            LIBA_LOCAL_SYNC();                // every thread has read the flag / the pivot before it is (re)written
+            LIBA_LOCAL_SYNC();                // every thread has read the flags before flag[0] is (re)written
             if (P.l_id == 0) LIBA_FLAG_SET(&P.flag[0]);
         } else {
-            // forward: y = L^-1 bs ; diagonal ; backward: x = L^-T y     (column-oriented, one column per barrier)
-            LIBA_LOCAL_FOR(i, sp) P.y[i] = P.bs[i];
+            // forward L y = bs, diagonal, backward L^T x = y, block by block
+            LIBA_LOCAL_FOR(i2, sp) P.y[i2] = P.bs[i2];
             LIBA_LOCAL_SYNC();
-            for (int j = 0; j < sp; ++j) {
-                const double yj = P.y[j];
-                LIBA_LOCAL_FOR(t, sp - j - 1) P.y[j + 1 + t] -= P.Hs[(size_t)j * sp + j + 1 + t] * yj;
+            for (int J = 0; J < nb; ++J) {
+                const int j0 = 15 * J, j1 = j0 + 15, m = sp - j1;
+                if (P.l_id == 0)
+                    for (int a = 1; a < 15; ++a) {
+                        double sacc = P.y[j0 + a];
+                        for (int b2 = 0; b2 < a; ++b2) sacc -= P.Hs[(size_t)(j0 + b2) * sp + j0 + a] * P.y[j0 + b2];
+                        P.y[j0 + a] = sacc;
+                    }
+                LIBA_LOCAL_SYNC();
+                LIBA_LOCAL_FOR(t, m) {
+                    const int c = j1 + t;
+                    double sacc = 0.0;
+                    for (int a = 0; a < 15; ++a) sacc += P.Hs[(size_t)(j0 + a) * sp + c] * P.y[j0 + a];
+                    P.y[c] -= sacc;
+                }
                 LIBA_LOCAL_SYNC();
             }
-            LIBA_LOCAL_FOR(i, sp) P.y[i] /= P.Hs[(size_t)i * sp + i];
+            LIBA_LOCAL_FOR(i2, sp) P.y[i2] /= P.Hs[(size_t)i2 * sp + i2];
             LIBA_LOCAL_SYNC();
-            for (int j = sp - 1; j >= 0; --j) {
-                const double xj = P.y[j];
-                LIBA_LOCAL_FOR(t, j) P.y[t] -= P.Hs[(size_t)t * sp + j] * xj;   // L(j, t) lives at (t, j)
+            for (int J = nb - 1; J >= 0; --J) {
+                const int j0 = 15 * J, j1 = j0 + 15;
+                LIBA_LOCAL_FOR(a, 15) {
+                    double sacc = 0.0;
+                    for (int c = j1; c < sp; ++c) sacc += P.Hs[(size_t)(j0 + a) * sp + c] * P.y[c];
+                    P.y[j0 + a] -= sacc;
+                }
+                LIBA_LOCAL_SYNC();
+                if (P.l_id == 0)
+                    for (int a = 13; a >= 0; --a) {
+                        double sacc = P.y[j0 + a];
+                        for (int b2 = a + 1; b2 < 15; ++b2) sacc -= P.Hs[(size_t)(j0 + a) * sp + j0 + b2] * P.y[j0 + b2];
+                        P.y[j0 + a] = sacc;
+                    }
                 LIBA_LOCAL_SYNC();
             }
-            LIBA_LOCAL_FOR(i, sp) P.x[i] = P.y[i];
+            LIBA_LOCAL_FOR(i2, sp) P.x[i2] = P.y[i2];
         }
     }
     LIBA_SYNC();      // x (keyframe part) and the failure flag reach the whole team

@@ -92,7 +92,7 @@ inline LibaLayout liba_pack(const liba_problem& p, uint8_t* host, uint8_t* devBa
     const size_t oStateS = take(8 * 21 * (size_t)nKF), oPointS = take(8 * sl), oHpp = take(8 * sp * sp), oHs = take(8 * sp * sp), oB = take(8 * (sp + sl)), oBs = take(8 * sp),
                  oX = take(8 * (sp + sl)), oY = take(8 * sp), oHll = take(8 * 9 * (size_t)nMP), oDinv = take(8 * 9 * (size_t)nMP), oW = take(8 * 18 * (size_t)nE),
                  oWD = take(8 * 18 * (size_t)nE), oWdb = take(8 * 6 * (size_t)nE), oEpp = take(8 * 27 * (size_t)nE), oLblk = take(8 * 930 * (size_t)nL), oFlag = take(16), oPart = take(8 * 8),
-                 oChunk = take(8 * (size_t)LIBA_CHUNKS * std::max((size_t)27 * nKF, (size_t)36 * nPairs)), oChunkB = take(8 * (size_t)LIBA_CHUNKS * 6 * nKF);
+                 oChunk = take(8 * (size_t)LIBA_CHUNKS * std::max((size_t)27 * nKF, (size_t)36 * nPairs)), oChunkB = take(8 * (size_t)LIBA_CHUNKS * 6 * nKF), oYpan = take(8 * 15 * sp);
     lay.work_bytes = off - lay.io_bytes - lay.in_bytes;
     lay.total = off;
     if (!host) return lay;
@@ -136,7 +136,7 @@ inline LibaLayout liba_pack(const liba_problem& p, uint8_t* host, uint8_t* devBa
     d.lambda_init = p.lambda_init;
     d.max_iters = p.max_iters;
     d.err = D(oErr); d.lerr = D(oLerr); d.Hpp = D(oHpp); d.Hs = D(oHs); d.b = D(oB); d.bs = D(oBs); d.x = D(oX); d.y = D(oY);
-    d.Hll = D(oHll); d.Dinv = D(oDinv); d.W = D(oW); d.WD = D(oWD); d.Wdb = D(oWdb); d.Epp = D(oEpp); d.Lblk = D(oLblk); d.part = D(oChunk); d.part_b = D(oChunkB);
+    d.Hll = D(oHll); d.Dinv = D(oDinv); d.W = D(oW); d.WD = D(oWD); d.Wdb = D(oWdb); d.Epp = D(oEpp); d.Lblk = D(oLblk); d.part = D(oChunk); d.part_b = D(oChunkB); d.Ypan = D(oYpan);
     d.flag = I(oFlag); d.red = nullptr; d.partials = D(oPart); d.out_scalars = D(oOut); d.dpos = devBase + oDpos;
     d.t_id = 0; d.t_stride = 1; d.l_id = 0; d.l_stride = 1; d.rank = 0; d.cs = 1;      // a team of one thread; the launcher overrides per thread
     return lay;
