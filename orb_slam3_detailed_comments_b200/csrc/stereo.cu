@@ -5,8 +5,11 @@
 // level, parabola refinement.  A second kernel applies the 2.1 * median SAD filter per frame.
 #include <algorithm>
 
+#include <stdlib.h>
+
 #include "extractor.h"
 #include "devmath.cuh"
+#include "stereo_core.cuh"
 
 using namespace orb;
 using namespace orbdev;
@@ -158,6 +161,86 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(const __grid_con
     }
 }
 
+// Variant 1 (ORB_STEREO_VARIANT=1; CPU-validated through tests/host_emul, first device run pending): one THREAD per left keypoint,
+// the right keypoints bucketed by image row once per CTA -- see stereo_core.cuh.  k_stereo_match above keeps its round-1 machine code.
+#define ST1_THREADS 128
+
+__global__ void __launch_bounds__(ST1_THREADS) k_stereo_match_v1(const __grid_constant__ StereoParams P,
+                                                               const __grid_constant__ ExtractGeom gL,
+                                                               const __grid_constant__ ExtractGeom gR) {
+    extern __shared__ __align__(16) unsigned char st_smem[];
+    __shared__ StLevel s_lv[ORB_MAX_LEVELS];
+    const int pair = blockIdx.y;
+    const int imgL = pair * P.strideL + P.baseL, imgR = pair * P.strideR + P.baseR;
+    const int N = P.L.nkp[imgL], Nr = min(P.R.nkp[imgR], P.maxRight);
+    const int rowL0 = P.L.offsets[imgL], rowR0 = P.R.offsets[imgR];
+    if ((int)(blockIdx.x * ST1_THREADS) >= N) return;     // uniform per CTA
+    const int H = gR.lv[0].h;
+    float* s_x = reinterpret_cast<float*>(st_smem);
+    int* s_band = reinterpret_cast<int*>(st_smem + 4 * (size_t)P.maxRight);
+    int* s_ent = reinterpret_cast<int*>(st_smem + 8 * (size_t)P.maxRight);
+    int* s_off = reinterpret_cast<int*>(st_smem + 12 * (size_t)P.maxRight);          // H + 1 offsets
+    int* s_cur = s_off + (H + 1);                                                     // H fill cursors
+    signed char* s_oct = reinterpret_cast<signed char*>(s_cur + H);
+    for (int i = threadIdx.x; i <= H; i += blockDim.x) s_off[i] = 0;
+    if (threadIdx.x < gL.nlevels) {
+        const int l = threadIdx.x;
+        StLevel v;
+        v.L = gL.lv[l].base + (int64_t)imgL * gL.lv[l].img_stride;
+        v.R = gR.lv[l].base + (int64_t)imgR * gR.lv[l].img_stride;
+        v.pitchL = gL.lv[l].pitch; v.pitchR = gR.lv[l].pitch; v.wR = gR.lv[l].w;
+        v.scale = gL.lv[l].scale; v.inv_scale = gL.lv[l].inv_scale;
+        s_lv[l] = v;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < Nr; j += blockDim.x) {   // stage + count: x, (minr | maxr << 16), octave   (Frame.cc:1134-1156)
+        const orbx_keypoint k = P.R.kps[rowR0 + j];
+        const float r = fmul(2.0f, gR.lv[k.octave].scale);
+        const int maxr = (int)ceilf(fadd(k.y, r)), minr = (int)floorf(fsub(k.y, r));
+        s_x[j] = k.x;
+        s_band[j] = (minr & 0xffff) | (maxr << 16);
+        s_oct[j] = (signed char)k.octave;
+        atomicAdd(&s_off[st_row_bucket(k.y, H) + 1], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {                                 // inclusive scan of the H bucket counts by one warp
+        int carry = 0;
+        for (int base = 1; base <= H; base += 32) {
+            const int i = base + (int)threadIdx.x;
+            int v = i <= H ? s_off[i] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, v, o);
+                if ((int)threadIdx.x >= o) v += u;
+            }
+            if (i <= H) s_off[i] = v + carry;
+            carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < H; i += blockDim.x) s_cur[i] = s_off[i];
+    __syncthreads();
+    for (int j = threadIdx.x; j < Nr; j += blockDim.x) {
+        const int bkt = st_row_bucket(P.R.kps[rowR0 + j].y, H);
+        s_ent[atomicAdd(&s_cur[bkt], 1)] = j;
+    }
+    __syncthreads();
+    const int iL = blockIdx.x * ST1_THREADS + threadIdx.x;
+    if (iL >= N) return;
+    StRight R;
+    R.x = s_x; R.band = s_band; R.oct = s_oct; R.row_off = s_off; R.row_ent = s_ent;
+    R.H = H; R.W = st_scan_window(gR.lv[gR.nlevels - 1].scale);
+    const int rowL = rowL0 + iL;
+    const orbx_keypoint kpL = P.L.kps[rowL];
+    float u, d;
+    int sad;
+    stereo_match_one(kpL.x, kpL.y, kpL.octave, reinterpret_cast<const uint32_t*>(P.L.desc + (size_t)rowL * 32), R,
+                     P.R.desc + (size_t)rowR0 * 32, s_lv, P.bf, P.b, &u, &d, &sad);
+    P.uright[rowL] = u;
+    P.depth[rowL] = d;
+    P.sad[rowL] = sad;
+}
+
 // Frame.cc:1338-1357: drop matches whose SAD >= 1.5 * 1.4 * median SAD.  One CTA per frame.
 __global__ void __launch_bounds__(256) k_stereo_median(const __grid_constant__ StereoParams P) {
     extern __shared__ int md_sad[];
@@ -229,10 +312,20 @@ static orb_status run_stereo(orbx_handle* hl, orbx_handle* hr, int n_pairs, int 
     P.bf = bf; P.b = b;
     P.uright = hl->d_uright; P.depth = hl->d_depth; P.sad = hl->d_sad;
     P.maxRight = hr->geom.kpTotal;
-    const size_t smem = 9 * (size_t)P.maxRight + 16;
-    ORB_CUDA(cudaFuncSetAttribute(k_stereo_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)1024)));
-    dim3 grid((hl->geom.kpTotal + ST_WARPS - 1) / ST_WARPS, n_pairs);
-    k_stereo_match<<<grid, ST_WARPS * 32, smem, st>>>(P, hl->geom, hr->geom);
+    const char* venv = getenv("ORB_STEREO_VARIANT");      // read at every call: a test can switch variants inside one process
+    const int variant = venv && atoi(venv) == 1 ? 1 : 0;
+    if (variant == 1) {
+        const int H = hr->geom.lv[0].h;
+        const size_t smem1 = 13 * (size_t)P.maxRight + 4 * (2 * (size_t)H + 2) + 64;
+        ORB_CUDA(cudaFuncSetAttribute(k_stereo_match_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem1, (size_t)1024)));
+        dim3 grid1((hl->geom.kpTotal + ST1_THREADS - 1) / ST1_THREADS, n_pairs);
+        k_stereo_match_v1<<<grid1, ST1_THREADS, smem1, st>>>(P, hl->geom, hr->geom);
+    } else {
+        const size_t smem = 9 * (size_t)P.maxRight + 16;
+        ORB_CUDA(cudaFuncSetAttribute(k_stereo_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)1024)));
+        dim3 grid((hl->geom.kpTotal + ST_WARPS - 1) / ST_WARPS, n_pairs);
+        k_stereo_match<<<grid, ST_WARPS * 32, smem, st>>>(P, hl->geom, hr->geom);
+    }
     ORB_LAUNCHED();
     const size_t smem2 = 4 * (size_t)hl->geom.kpTotal + 16;
     ORB_CUDA(cudaFuncSetAttribute(k_stereo_median, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem2, (size_t)1024)));

@@ -10,6 +10,9 @@ export ORB_FIRST_CONTACT=1
 # 1. k_quadtree_v1 (two-stage bitonic passes + CTA-parallel ordered-phase sort): parity, then the per-stage effect on the headline step
 timeout 600 python -m pytest tests/test_zz_quadtree_v1_gpu.py -x -q 2>&1 | tee gpurun_out/qt_v1_tests.log
 ORB_QT_VARIANT=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>gpurun_out/qt_v1_bench.err | tee gpurun_out/qt_v1_bench.json
+# 1b. k_stereo_match_v1 (thread per left keypoint, row buckets): parity, then the bench with both variants on
+timeout 600 python -m pytest tests/test_zz_stereo_v1_gpu.py -x -q 2>&1 | tee gpurun_out/stereo_v1_tests.log
+ORB_QT_VARIANT=1 ORB_STEREO_VARIANT=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>gpurun_out/v1_bench.err | tee gpurun_out/v1_bench.json
 # 2. K9 brute-force Hamming 2-NN (orbm_hamming_knn2)
 timeout 300 python -m pytest tests/test_zz_knn_gpu.py -x -q 2>&1 | tee gpurun_out/knn_tests.log
 # 3. k_liba (LocalInertialBA): sanitizers on one small window, parity at 1 / 2 / 8 CTAs per window, timing, launch list

@@ -220,3 +220,42 @@ extern "C" void emul_liba_inertial(const double* state2x21, const liba_link* lin
 }
 
 extern "C" size_t emul_liba_layout_total(const liba_problem* p) { return orb::liba_pack(*p, nullptr, nullptr, nullptr).total; }
+
+// ---- Frame::ComputeStereoMatches, variant 1: csrc/stereo_core.cuh (the body of k_stereo_match_v1's threads) on the host ----------------
+#include "../../orb_slam3_detailed_comments_b200/csrc/stereo_core.cuh"
+
+// levelsL / levelsR: nlevels pointers to the raw pyramid levels (tightly packed, pitch = width); wl / wr: their widths.
+// Outputs per left keypoint BEFORE the median-SAD filter (Frame.cc:1338-1357): uright, depth, sad (-1 = none).
+extern "C" void emul_stereo_v1(const orbx_keypoint* kL, const uint8_t* dL, int nL, const orbx_keypoint* kR, const uint8_t* dR, int nR,
+                               int nlevels, const uint8_t* const* levelsL, const uint8_t* const* levelsR, const int* wl, const int* wr,
+                               const float* scale, const float* inv_scale, int H, float bf, float b, float* out_u, float* out_d,
+                               int* out_sad) {
+    std::vector<float> x(nR + 1);
+    std::vector<int> band(nR + 1), off(H + 2, 0), ent(nR + 1);
+    std::vector<signed char> oct(nR + 1);
+    for (int j = 0; j < nR; ++j) {
+        const float r = fmul(2.0f, scale[kR[j].octave]);
+        const int maxr = (int)ceilf(fadd(kR[j].y, r)), minr = (int)floorf(fsub(kR[j].y, r));
+        x[j] = kR[j].x;
+        band[j] = (minr & 0xffff) | (maxr << 16);
+        oct[j] = (signed char)kR[j].octave;
+        ++off[st_row_bucket(kR[j].y, H) + 1];
+    }
+    for (int i = 0; i < H; ++i) off[i + 1] += off[i];
+    {
+        std::vector<int> cur(off.begin(), off.begin() + H);
+        for (int j = nR - 1; j >= 0; --j) ent[cur[st_row_bucket(kR[j].y, H)]++] = j;     // reversed on purpose: bucket order must not matter
+    }
+    std::vector<StLevel> lv(nlevels);
+    for (int l = 0; l < nlevels; ++l) {
+        lv[l].L = levelsL[l]; lv[l].R = levelsR[l];
+        lv[l].pitchL = wl[l]; lv[l].pitchR = wr[l]; lv[l].wR = wr[l];
+        lv[l].scale = scale[l]; lv[l].inv_scale = inv_scale[l];
+    }
+    StRight R;
+    R.x = x.data(); R.band = band.data(); R.oct = oct.data(); R.row_off = off.data(); R.row_ent = ent.data();
+    R.H = H; R.W = st_scan_window(scale[nlevels - 1]);
+    for (int i = 0; i < nL; ++i)
+        stereo_match_one(kL[i].x, kL[i].y, kL[i].octave, reinterpret_cast<const uint32_t*>(dL + 32 * (size_t)i), R, dR, lv.data(), bf, b,
+                         &out_u[i], &out_d[i], &out_sad[i]);
+}

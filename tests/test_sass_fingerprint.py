@@ -1,6 +1,6 @@
 """CPU tier: the machine code of every kernel that ran green on a B200 in round 1 is still what the library ships.
 profiles/r01_sass_fingerprints.json was taken (scripts/sass_fingerprint.py) from the build whose sources were last validated on the
-GPU box; kernels added afterwards without a device run (k_liba, k_quadtree_v1, k_hamming_knn2) are listed as such and are opt-in at run time.
+GPU box; kernels added afterwards without a device run (k_liba, k_quadtree_v1, k_hamming_knn2, k_stereo_match_v1) are listed as such and are opt-in at run time.
 An intentional kernel change must come with a GPU run and a refreshed fingerprint file."""
 import importlib.util
 import json
@@ -10,7 +10,7 @@ import shutil
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-UNPROVEN = ("k_liba", "k_quadtree_v1", "k_hamming_knn2")
+UNPROVEN = ("k_liba", "k_quadtree_v1", "k_hamming_knn2", "k_stereo_match_v1")
 
 
 @pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not available")
