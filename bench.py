@@ -723,7 +723,9 @@ def main():
                            "matches_per_frame": {"last_frame": float(nm_host[:B].mean()), "local_map": float(nm_host[B:].mean())},
                            "l2": f"input pool of {pool_batches} batches = {pool_batches * nimg * W * H / 1e6:.0f} MB > 126 MB L2, "
                                  "intermediates rewritten every step",
-                           "keypoints_per_image": n_kp, "fast_candidates_per_image": n_cand},
+                           "keypoints_per_image": n_kp, "fast_candidates_per_image": n_cand,
+                           "kernel_variants": {"quadtree": int(os.environ.get("ORB_QT_VARIANT", "0") == "1"),
+                                               "stereo": int(os.environ.get("ORB_STEREO_VARIANT", "0") == "1")}},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_step),
                         "d2h_bytes_per_step": int(d2h // args.steps)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "lba": lba, "inertial_ba": liba, "pose_optimization": pose_opt}
