@@ -5,9 +5,10 @@ import importlib.util
 import os
 
 import numpy as np
+import pytest
 
 from oracle import pyoracle as po
-from orb_slam3_detailed_comments_b200 import synthetic_vocabulary
+from orb_slam3_detailed_comments_b200 import synth, synthetic_vocabulary
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 G = np.load(os.path.join(HERE, "golden", "golden_v2.npz"))
@@ -119,3 +120,34 @@ def test_pose_optimization_recovers_a_known_pose_and_flags_the_planted_outliers(
     assert (r["outlier"].astype(bool) == bad).all() and r["inliers"] == n - bad.sum() and r["rounds"] == 4
     few = po.pose_optimization([0, 0, 0, 1, 0, 0, 0], Xw[:2], obs[:2], np.ones(2), [435.2, 435.2, 320, 240, 47.9])
     assert few["inliers"] == 0 and few["rounds"] == 0 and (few["pose"] == [0, 0, 0, 1, 0, 0, 0]).all()
+
+
+@pytest.mark.parametrize("lap", [(0, 0), (0, 1000), (100, 300), (250, 251)])       # std::vector<int> vLappingArea
+def test_emission_order_and_lapping_area_against_numpy(lap):
+    """ORBextractor::operator() (ORBextractor.cc:1646-1681): level by level, a keypoint whose scaled x lies in [vLappingArea[0],
+    vLappingArea[1]] is written from the BACK of the output (stereoIndex--), the others from the front (monoIndex++); the return value
+    is monoIndex.  Restated in numpy from the oracle's own per-level lists (level_kps, in the order DistributeOctTree + the per-level
+    loop produce them) and compared with what the oracle's operator() returns."""
+    img = synth.frame(320, 240, 6)
+    ex = po.OracleExtractor(500, 1.2, 8, 20, 7)
+    mono, kps, desc = ex(img, lapping=lap)
+    lv = [ex.level_kps(l) for l in range(8)]
+    n = sum(len(a) for a in lv)
+    assert n == len(kps) and n > 100
+    out = np.zeros(n, kps.dtype)
+    mi, si = 0, n - 1
+    for l in range(8):
+        sc = np.float32(ex.scale_factors[l])
+        for k in lv[l]:
+            k = k.copy()
+            if l != 0:
+                k["x"], k["y"] = np.float32(k["x"]) * sc, np.float32(k["y"]) * sc
+            if k["x"] >= np.float32(lap[0]) and k["x"] <= np.float32(lap[1]):
+                out[si] = k
+                si -= 1
+            else:
+                out[mi] = k
+                mi += 1
+    assert mono == mi
+    for f in ("x", "y", "octave", "response"):
+        assert (out[f] == kps[f]).all(), f
