@@ -273,7 +273,8 @@ static orb_status apply_geometry(orbx_handle* h, int w, int hh) {
             maxSmem = std::max(maxSmem, h->qt_groups[i].smem);
         }
         ORB_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem));
-        ORB_CUDA(cudaFuncSetAttribute(k_quadtree_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem));
+        ORB_CUDA(cudaFuncSetAttribute(k_quadtree_v1<QT_THREADS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem));
+        ORB_CUDA(cudaFuncSetAttribute(k_quadtree_v1<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem));
     }
     const size_t ordBytes = ((size_t)h->geom.kpTotal + 64) * 4;
     ORB_CUDA(cudaFuncSetAttribute(k_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(ordBytes, (size_t)1024)));
@@ -427,7 +428,9 @@ static orb_status run_pipeline(orbx_handle* h, int batch, int lap0, int lap1) {
         const orbx_handle::QtGroup& Q = h->qt_groups[gi];
         cudaStream_t qs = gi == 0 ? st : h->aux_stream[gi - 1];
         if (gi > 0) cudaStreamWaitEvent(qs, h->ev_fork, 0);
-        (h->qt_variant == 1 ? k_quadtree_v1 : k_quadtree)<<<batch * (Q.level_end - Q.level_begin), QT_THREADS, Q.smem, qs>>>(
+        const bool wide = h->qt_variant == 1 && Q.level_begin == 0;      // the group with level 0: 1024 threads per CTA
+        (h->qt_variant == 0 ? k_quadtree : wide ? k_quadtree_v1<1024, 1> : k_quadtree_v1<QT_THREADS, 4>)
+            <<<batch * (Q.level_end - Q.level_begin), wide ? 1024 : QT_THREADS, Q.smem, qs>>>(
             g, batch, Q.level_begin, h->d_cand, h->d_cand_cnt, h->d_sort, (char*)h->d_node_scratch,
             (int64_t)h->qt_node_stride, Q.sort_cap, h->qt_nodes_in_smem, h->qt_node_cap, h->d_lvl_kp, h->d_lvl_cnt, h->d_err);
         ORB_LAUNCHED();

@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const __grid_constant__
 // selected with ORB_QT_VARIANT=1 at orbx_create until it has had its own device run.
 __device__ __forceinline__ int qt_run_v1(uint32_t* arr, void* ws, int cap, int n, int npow, const uint32_t* __restrict__ src,
                                          const QtGeom& q, uint32_t* out) {
-    for (int i = threadIdx.x; i < npow; i += QT_THREADS) arr[i] = (i < n) ? qt_element(src[i], q) : 0xffffffffu;
+    for (int i = threadIdx.x; i < npow; i += blockDim.x) arr[i] = (i < n) ? qt_element(src[i], q) : 0xffffffffu;
     __syncthreads();
     qt_bitonic_sort_r4(arr, npow);
     QtWork w;
@@ -370,7 +370,11 @@ __device__ __forceinline__ int qt_run_v1(uint32_t* arr, void* ws, int cap, int n
     return qt_distribute_v<1>(arr, n, q, w, out);
 }
 
-__global__ void __launch_bounds__(QT_THREADS, 4) k_quadtree_v1(const __grid_constant__ ExtractGeom g, int batch, int levelBegin,
+// MAXT = 256 (four CTAs per SM) for the small levels; MAXT = 1024 for the group that holds level 0, whose 128-per-batch CTAs each sort
+// 4-8 k candidates: one CTA per SM either way, so four times the threads shorten the longest kernel of the stage.  The body only uses
+// blockDim.x (QT_PAR_FOR, qt_exscan), never QT_THREADS.
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_quadtree_v1(const __grid_constant__ ExtractGeom g, int batch, int levelBegin,
                                                            const uint32_t* __restrict__ cand, const int* __restrict__ candCnt,
                                                            uint32_t* __restrict__ sortScratch, char* __restrict__ nodeScratch,
                                                            int64_t nodeScratchStride, int sortCapSmem, int nodesInSmem,
