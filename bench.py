@@ -654,6 +654,36 @@ def main():
                 iopt.close()
             except Exception as exc:
                 liba = {"error": repr(exc)}
+        # ---- K9 brute-force Hamming 2-NN (BFMatcher.knnMatch of ComputeStereoFishEyeMatches): opt-in until its first device run ----
+        knn = {"skipped": "k_hamming_knn2 has not had a device run yet; set ORB_FIRST_CONTACT=1 to time it"}
+        if os.environ.get("ORB_FIRST_CONTACT") == "1":
+            try:
+                from orb_slam3_detailed_comments_b200 import knnMatch2
+                krng = np.random.default_rng(5)
+                qs = [krng.integers(0, 256, (1200, 32), dtype=np.uint8) for _ in range(64)]
+                ts = [krng.integers(0, 256, (1200, 32), dtype=np.uint8) for _ in range(64)]
+                for _ in range(3):
+                    knnMatch2(exs[0], qs, ts)
+                t0 = time.perf_counter()
+                for _ in range(5):
+                    got = knnMatch2(exs[0], qs, ts)
+                t_knn = (time.perf_counter() - t0) / 5
+                t_cv = None
+                try:
+                    import cv2
+                    cv2.setNumThreads(1)
+                    bfm = cv2.BFMatcher(cv2.NORM_HAMMING)
+                    t0 = time.perf_counter()
+                    ref = bfm.knnMatch(qs[0], ts[0], 2)
+                    t_cv = time.perf_counter() - t0
+                    same = all(got[0][0][i, 0] == m[0].trainIdx and got[0][0][i, 1] == m[1].trainIdx for i, m in enumerate(ref))
+                except ImportError:
+                    same = None
+                knn = {"workload": "64 pairs of 1200 x 1200 descriptors, knnMatch k = 2, host pointers", "ms_per_call_e2e": 1e3 * t_knn,
+                       "pairs_per_s": 64 / t_knn, "cv2_bfmatcher_ms_per_pair_1_thread": None if t_cv is None else 1e3 * t_cv,
+                       "first_pair_equals_cv2": same}
+            except Exception as exc:
+                knn = {"error": repr(exc)}
         # ---- PoseOptimization (twice per frame on the tracking thread): a batch of B frames --------------
         pose_opt = None
         try:
@@ -728,7 +758,7 @@ def main():
                                                "stereo": int(os.environ.get("ORB_STEREO_VARIANT", "0") == "1")}},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_step),
                         "d2h_bytes_per_step": int(d2h // args.steps)},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "lba": lba, "inertial_ba": liba, "pose_optimization": pose_opt}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "lba": lba, "inertial_ba": liba, "hamming_knn": knn, "pose_optimization": pose_opt}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
