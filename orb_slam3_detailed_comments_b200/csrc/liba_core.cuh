@@ -167,8 +167,8 @@ LIBA_HD void so3_jr(const double* v, bool inverse, double* J) {   // G2oTypes.cc
 LIBA_HD bool m3_inv(const double* M, double* Mi) {
     const double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
     const double det = M[0] * c00 + M[1] * c01 + M[2] * c02;
-    if (!(fabs(det) > 0) || !isfinite(det)) return false;
     const double id = 1.0 / det;
+    if (!isfinite(id)) return false;          // det == 0, subnormal, or not finite: the block solver reports failure
     Mi[0] = c00 * id; Mi[1] = (M[2] * M[7] - M[1] * M[8]) * id; Mi[2] = (M[1] * M[5] - M[2] * M[4]) * id;
     Mi[3] = c01 * id; Mi[4] = (M[0] * M[8] - M[2] * M[6]) * id; Mi[5] = (M[2] * M[3] - M[0] * M[5]) * id;
     Mi[6] = c02 * id; Mi[7] = (M[1] * M[6] - M[0] * M[7]) * id; Mi[8] = (M[0] * M[4] - M[1] * M[3]) * id;

@@ -274,3 +274,22 @@ def test_large_window_blarge_settings(emul):
     assert got["iterations"] == ref["iterations"] and got["trials"] == ref["trials"]
     assert np.abs(got["state"] - ref["state"]).max() < TOL and np.abs(got["point"] - ref["point"]).max() < TOL
     assert ref["chi2"] < 0.05 * ref["chi2_init"]
+
+
+def test_solver_failure_path(emul):
+    """A landmark whose only edge carries zero information, with a lambda so small that det(H_ll + lambda I) underflows to 0: the
+    block solver fails, g2o's Levenberg raises lambda and retries (optimization_algorithm_levenberg.cpp:96-128).  The device algorithm
+    must take the same path as the oracle (failure flag, restored estimate, same trial count) and recover once lambda is large enough."""
+    s = perturbed(61, n_kf=5, n_mp=80)
+    s["point"] = np.concatenate([s["point"], [[0.3, -0.2, 6.0]]])
+    s["edge_kf"] = np.concatenate([s["edge_kf"], [1]]).astype(np.int32)
+    s["edge_mp"] = np.concatenate([s["edge_mp"], [len(s["point"]) - 1]]).astype(np.int32)
+    s["obs"] = np.concatenate([s["obs"], [[300.0, 200.0, -1.0]]])
+    s["inv_sigma2"] = np.concatenate([s["inv_sigma2"], [0.0]])
+    for lam in (1e-200, 1e-120):
+        ref = po.liba(s["state"], s["fixed"], s["point"], s["edge_kf"], s["edge_mp"], s["obs"], s["inv_sigma2"], s["Tcb"], s["cam5"], s["links"], lam, 6)
+        got = run_emul(emul, s, lam, 6)
+        assert got["iterations"] == ref["iterations"] and got["trials"] == ref["trials"], lam
+        assert np.array_equal(np.isfinite(got["state"]), np.isfinite(ref["state"])) and np.isfinite(ref["state"]).all()
+        assert np.abs(got["state"] - ref["state"]).max() < TOL and np.abs(got["point"] - ref["point"]).max() < TOL
+        assert ref["trials"] > ref["iterations"]          # at least one failed / rejected trial happened
