@@ -293,3 +293,17 @@ def test_solver_failure_path(emul):
         assert np.array_equal(np.isfinite(got["state"]), np.isfinite(ref["state"])) and np.isfinite(ref["state"]).all()
         assert np.abs(got["state"] - ref["state"]).max() < TOL and np.abs(got["point"] - ref["point"]).max() < TOL
         assert ref["trials"] > ref["iterations"]          # at least one failed / rejected trial happened
+
+
+def test_solver_failure_path_threaded(mt_binary, tmp_path):
+    """The failure flags (set by several threads, read by all after a barrier) under ThreadSanitizer, two "CTAs"."""
+    s = perturbed(61, n_kf=5, n_mp=80)
+    s["point"] = np.concatenate([s["point"], [[0.3, -0.2, 6.0]]])
+    s["edge_kf"] = np.concatenate([s["edge_kf"], [1]]).astype(np.int32)
+    s["edge_mp"] = np.concatenate([s["edge_mp"], [len(s["point"]) - 1]]).astype(np.int32)
+    s["obs"] = np.concatenate([s["obs"], [[300.0, 200.0, -1.0]]])
+    s["inv_sigma2"] = np.concatenate([s["inv_sigma2"], [0.0]])
+    ref = po.liba(s["state"], s["fixed"], s["point"], s["edge_kf"], s["edge_mp"], s["obs"], s["inv_sigma2"], s["Tcb"], s["cam5"], s["links"], 1e-200, 3)
+    got = run_mt(mt_binary, s, 1e-200, 3, 4, tmp_path, 2)
+    assert got["iterations"] == ref["iterations"] and got["trials"] == ref["trials"] == 10
+    assert np.abs(got["state"] - ref["state"]).max() < 1e-12
