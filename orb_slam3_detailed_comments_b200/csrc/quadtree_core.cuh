@@ -38,6 +38,12 @@ void qt_barrier();
 #define QT_PAR_FOR(i, n) for (int i = orbdev::qt_tid; i < (n); i += orbdev::qt_nthreads)
 #define QT_SYNC() orbdev::qt_barrier()
 #define QT_SERIAL if (orbdev::qt_tid == 0)
+#elif defined(QT_HOST_COUNT_SYNCS)
+// host, one thread, counting the barriers a CTA would execute (tests/host_emul: the barrier budget of the two variants)
+extern long qt_sync_count;
+#define QT_PAR_FOR(i, n) for (int i = 0; i < (n); ++i)
+#define QT_SYNC() ((void)++orbdev::qt_sync_count)
+#define QT_SERIAL
 #else
 #define QT_PAR_FOR(i, n) for (int i = 0; i < (n); ++i)
 #define QT_SYNC() ((void)0)
