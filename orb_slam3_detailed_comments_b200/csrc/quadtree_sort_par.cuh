@@ -93,7 +93,7 @@ ORB_HD void qt_sortpar_heapsort(QtItem* h, int len) {
 }
 
 // a[0..n) sorted exactly as std::sort(a, a + n, compareNodes) leaves it.  tmp: n items.  seg / nxt: 3 ints per segment slot each
-// (first, last, depth), room for n / 8 + 2 slots; flag: n / 8 + 2 ints; scan_tmp: qt_exscan's scratch.  Whole CTA; returns after a
+// (first, last, depth), room for n / 8 + 2 slots; flag: 2 * (n / 8 + 2) ints; scan_tmp: qt_exscan's scratch.  Whole CTA; returns after a
 // barrier.  Every segment on a list is longer than 16, so a generation holds at most n / 17 of them.
 ORB_HD void qt_std_sort_items_par(QtItem* a, int n, QtItem* tmp, int* seg, int* nxt, int* flag, int* scan_tmp) {
     if (n <= 1) return;   // uniform
@@ -103,6 +103,7 @@ ORB_HD void qt_std_sort_items_par(QtItem* a, int n, QtItem* tmp, int* seg, int* 
         QT_SERIAL { seg[0] = 0; seg[1] = n; seg[2] = 2 * lg; }
         QT_SYNC();
         int nseg = 1;
+        const int nslots_max = n / 8 + 2;     // 2 * (n / 17) slots at most
         while (nseg > 0) {
             QT_PAR_FOR(s, nseg) {
                 const int first = seg[3 * s], last = seg[3 * s + 1], depth = seg[3 * s + 2];
@@ -113,26 +114,22 @@ ORB_HD void qt_std_sort_items_par(QtItem* a, int n, QtItem* tmp, int* seg, int* 
                 const bool l_alive = depth != 0 && cut - first > 16, r_alive = depth != 0 && last - cut > 16;
                 nxt[3 * (2 * s)] = first; nxt[3 * (2 * s) + 1] = cut; nxt[3 * (2 * s) + 2] = depth - 1;
                 nxt[3 * (2 * s + 1)] = cut; nxt[3 * (2 * s + 1) + 1] = last; nxt[3 * (2 * s + 1) + 2] = depth - 1;
-                flag[2 * s] = l_alive ? 1 : 0;
-                flag[2 * s + 1] = r_alive ? 1 : 0;
+                flag[2 * s] = flag[nslots_max + 2 * s] = l_alive ? 1 : 0;
+                flag[2 * s + 1] = flag[nslots_max + 2 * s + 1] = r_alive ? 1 : 0;
             }
             QT_SYNC();
+            // compact the alive children into the next generation's list: the flags live twice (the scan turns one copy into ranks);
+            // `seg` is dead once the partitions are done, so the survivors are scattered straight into it
             const int nslots = 2 * nseg;
-            QT_PAR_FOR(s, nslots) seg[s] = flag[s];              // keep the flags: the scan below overwrites them with ranks
-            QT_SYNC();
             const int alive = qt_exscan(flag, nslots, scan_tmp);
-            // seg[0..nslots) holds the flags; the compacted list is built in tmp's storage?  no: reuse nxt -> seg via a staging pass
             QT_PAR_FOR(s, nslots) {
-                if (seg[s]) {
+                if (flag[nslots_max + s]) {
                     const int d = flag[s];
-                    // staging area behind the slots of this generation (3 * nslots ints in) -- disjoint from the reads of nxt[3s..]
-                    nxt[3 * nslots + 3 * d] = nxt[3 * s];
-                    nxt[3 * nslots + 3 * d + 1] = nxt[3 * s + 1];
-                    nxt[3 * nslots + 3 * d + 2] = nxt[3 * s + 2];
+                    seg[3 * d] = nxt[3 * s];
+                    seg[3 * d + 1] = nxt[3 * s + 1];
+                    seg[3 * d + 2] = nxt[3 * s + 2];
                 }
             }
-            QT_SYNC();
-            QT_PAR_FOR(s, 3 * alive) seg[s] = nxt[3 * nslots + s];
             QT_SYNC();
             nseg = alive;
         }
