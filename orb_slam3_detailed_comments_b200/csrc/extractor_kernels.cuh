@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const __grid_constant__
     }
 }
 
-// K3 variant 1: the candidate sort takes two butterfly stages per pass, and the ordered phase's std::sort is spread over the CTA
+// K3 variant 1: the candidate sort takes up to three butterfly stages per pass, and the ordered phase's std::sort is spread over the CTA
 // instead of run by thread 0 (both in quadtree_sort_par.cuh).  A separate
 // kernel so that k_quadtree -- green on a B200 in round 1 -- keeps its machine code bit for bit (scripts/sass_fingerprint.py);
 // selected with ORB_QT_VARIANT=1 at orbx_create until it has had its own device run.
@@ -364,7 +364,7 @@ __device__ __forceinline__ int qt_run_v1(uint32_t* arr, void* ws, int cap, int n
                                          const QtGeom& q, uint32_t* out) {
     for (int i = threadIdx.x; i < npow; i += blockDim.x) arr[i] = (i < n) ? qt_element(src[i], q) : 0xffffffffu;
     __syncthreads();
-    qt_bitonic_sort_r4(arr, npow);
+    qt_bitonic_sort_r8(arr, npow);
     QtWork w;
     qt_work_carve(w, ws, cap);
     return qt_distribute_v<1>(arr, n, q, w, out);

@@ -7,7 +7,7 @@
 set -u
 mkdir -p gpurun_out
 export ORB_FIRST_CONTACT=1
-# 1. k_quadtree_v1 (two-stage bitonic passes + CTA-parallel ordered-phase sort): parity, then the per-stage effect on the headline step
+# 1. k_quadtree_v1 (multi-stage bitonic passes + CTA-parallel ordered-phase sort): parity, then the per-stage effect on the headline step
 timeout 600 python -m pytest tests/test_zz_quadtree_v1_gpu.py -x -q 2>&1 | tee gpurun_out/qt_v1_tests.log
 ORB_QT_VARIANT=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>gpurun_out/qt_v1_bench.err | tee gpurun_out/qt_v1_bench.json
 # 1b. k_stereo_match_v1 (thread per left keypoint, row buckets): parity, then the bench with both variants on

@@ -150,7 +150,7 @@ static int emul_distribute_variant(int variant, const int32_t* cand3, int n, int
     while (npow < n) npow <<= 1;
     std::vector<uint32_t> arr(npow, 0xffffffffu);
     for (int i = 0; i < n; ++i) arr[i] = qt_element(qt_pack_cand(cand3[3 * i], cand3[3 * i + 1], cand3[3 * i + 2]), g);
-    if (variant == 0) qt_bitonic_sort(arr.data(), npow); else qt_bitonic_sort_r4(arr.data(), npow);
+    if (variant == 0) qt_bitonic_sort(arr.data(), npow); else qt_bitonic_sort_r8(arr.data(), npow);
     const int cap = N + 20;
     std::vector<char> ws(qt_work_bytes(cap));
     QtWork w;
@@ -191,7 +191,7 @@ extern "C" void emul_sort_items(const uint32_t* items3, int n, int which, uint32
 }
 
 extern "C" void emul_bitonic(uint32_t* arr, int npow, int variant) {
-    if (variant == 0) qt_bitonic_sort(arr, npow); else qt_bitonic_sort_r4(arr, npow);
+    if (variant == 0) qt_bitonic_sort(arr, npow); else if (variant == 1) qt_bitonic_sort_r4(arr, npow); else qt_bitonic_sort_r8(arr, npow);
 }
 
 // ---- LocalInertialBA: the device algorithm (csrc/liba_core.cuh) run by one host "thread" ---------------------------------------

@@ -36,7 +36,7 @@ int main(int argc, char** argv) {
         QtWork w;
         qt_work_carve(w, ws.data(), cap);
         qt_sync_count = 0;
-        if (variant == 0) qt_bitonic_sort(arr.data(), npow); else qt_bitonic_sort_r4(arr.data(), npow);
+        if (variant == 0) qt_bitonic_sort(arr.data(), npow); else qt_bitonic_sort_r8(arr.data(), npow);
         const long s_sort = qt_sync_count;
         const int S = variant == 0 ? qt_distribute_v<0>(arr.data(), n, g, w, out.data()) : qt_distribute_v<1>(arr.data(), n, g, w, out.data());
         printf("%d %ld %ld %d %d\n", variant, s_sort, qt_sync_count, npow, S);

@@ -52,7 +52,7 @@ int main(int argc, char** argv) {
     for (int t = 0; t < T; ++t)
         th.emplace_back([&, t] {
             qt_tid = t;
-            if (variant == 0) qt_bitonic_sort(arr.data(), npow); else qt_bitonic_sort_r4(arr.data(), npow);
+            if (variant == 0) qt_bitonic_sort(arr.data(), npow); else qt_bitonic_sort_r8(arr.data(), npow);
             QtWork w;                             // per-thread copy of the workspace descriptor, like the kernel's registers
             qt_work_carve(w, ws.data(), cap);
             S[t] = variant == 0 ? qt_distribute_v<0>(arr.data(), n, g, w, out.data()) : qt_distribute_v<1>(arr.data(), n, g, w, out.data());

@@ -199,7 +199,7 @@ def test_threaded_quadtree_on_adversarial_sets(qt_mt, tmp_path, case):
 
 
 @pytest.mark.parametrize("npow", [2, 4, 8, 16, 32, 64, 512, 1024, 4096, 8192, 16384])
-def test_two_stage_bitonic_sorts(emul, npow):
+def test_multi_stage_bitonic_sorts(emul, npow):
     rng = np.random.default_rng(npow)
     for trial in range(3):
         a = rng.integers(0, 1 << 32, npow, dtype=np.uint64).astype(np.uint32)
@@ -207,7 +207,8 @@ def test_two_stage_bitonic_sorts(emul, npow):
             a[rng.integers(0, npow, npow // 3 + 1)] = 0xffffffff        # padding sentinels as in the kernel
         if trial == 2:
             a = np.sort(a)[::-1].copy()
-        b0, b1 = a.copy(), a.copy()
+        b0, b1, b2 = a.copy(), a.copy(), a.copy()
         emul.emul_bitonic(b0.ctypes.data, npow, 0)
-        emul.emul_bitonic(b1.ctypes.data, npow, 1)
-        assert (b0 == np.sort(a)).all() and (b1 == b0).all()
+        emul.emul_bitonic(b1.ctypes.data, npow, 1)      # two stages per pass
+        emul.emul_bitonic(b2.ctypes.data, npow, 2)      # three stages per pass (the one k_quadtree_v1 uses)
+        assert (b0 == np.sort(a)).all() and (b1 == b0).all() and (b2 == b0).all()
