@@ -86,6 +86,9 @@ int orc_fast_cell(const uint8_t* win, int cw, int ch, int stride, int thr, int32
     return (int)c.size();
 }
 float orc_atan2(float y, float x) { return fast_atan2_deg(y, x); }
+void orc_set_fast_simd(int on) { set_fast_simd(on); }
+// both score routines on a 7 x 7 patch (row-major, centre at [3][3]): out2 = {SSE2, scalar}
+void orc_fast_scores(const uint8_t* patch49, int* out2) { out2[0] = fast_score16(patch49 + 3 * 7 + 3, 7); out2[1] = fast_score16_scalar(patch49 + 3 * 7 + 3, 7); }
 float orc_ic_angle(const uint8_t* img, int w, int h, int x, int y, const int* umax16) {
     Plane P; P.w = w; P.h = h; P.px.assign(img, img + (size_t)w * h);
     std::vector<int> u(umax16, umax16 + 16);

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <list>
 #include <utility>
+#include <emmintrin.h>
 
 namespace orb_oracle {
 
@@ -120,7 +121,37 @@ void gaussian_blur7_u8(const uint8_t* src, int w, int h, int sstride, uint8_t* d
 static const int kRingX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
 static const int kRingY[16] = {-3, -3, -2, -1, 0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3};
 
+// score = max over the 16 arcs of 9 of max(min d, -max d) - 1, eight arcs at a time (SSE2, int16), the way OpenCV's cornerScore<16>
+// arranges it: with a = min(d[k+1 .. k+8]) the arcs starting at k and at k + 1 are min(a, d[k]) and min(a, d[k+9]).  Integer min / max
+// only, so the value is exactly fast_score16_scalar's (tests compare them on random rings).
 int fast_score16(const uint8_t* p, int stride) {
+    alignas(16) short d[32];
+    const int c = p[0];
+    for (int k = 0; k < 25; ++k) d[k] = (short)(c - p[kRingY[k & 15] * stride + kRingX[k & 15]]);
+    __m128i q0 = _mm_set1_epi16(-1000), q1 = _mm_set1_epi16(1000);
+    for (int k = 0; k < 16; k += 8) {
+        __m128i v0 = _mm_loadu_si128((const __m128i*)(d + k + 1)), v1 = _mm_loadu_si128((const __m128i*)(d + k + 2));
+        __m128i a = _mm_min_epi16(v0, v1), b = _mm_max_epi16(v0, v1);
+        for (int j = 3; j <= 8; ++j) {
+            v0 = _mm_loadu_si128((const __m128i*)(d + k + j));
+            a = _mm_min_epi16(a, v0);
+            b = _mm_max_epi16(b, v0);
+        }
+        v0 = _mm_loadu_si128((const __m128i*)(d + k));
+        q0 = _mm_max_epi16(q0, _mm_min_epi16(a, v0));
+        q1 = _mm_min_epi16(q1, _mm_max_epi16(b, v0));
+        v0 = _mm_loadu_si128((const __m128i*)(d + k + 9));
+        q0 = _mm_max_epi16(q0, _mm_min_epi16(a, v0));
+        q1 = _mm_min_epi16(q1, _mm_max_epi16(b, v0));
+    }
+    q0 = _mm_max_epi16(q0, _mm_sub_epi16(_mm_setzero_si128(), q1));
+    q0 = _mm_max_epi16(q0, _mm_srli_si128(q0, 8));
+    q0 = _mm_max_epi16(q0, _mm_srli_si128(q0, 4));
+    q0 = _mm_max_epi16(q0, _mm_srli_si128(q0, 2));
+    return (short)_mm_cvtsi128_si32(q0) - 1;
+}
+
+int fast_score16_scalar(const uint8_t* p, int stride) {
     int d[16 + 9];
     const int c = p[0];
     for (int k = 0; k < 16; ++k) d[k] = c - p[kRingY[k] * stride + kRingX[k]];
@@ -338,6 +369,64 @@ void Extractor::compute_pyramid(const uint8_t* img, int w, int h, int stride) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The corner TEST of cv::FAST for 16 pixels at a time (SSE2), the way OpenCV's own FAST_t<16> does it: a pixel is a corner at
+// threshold T iff 9 consecutive ring pixels are all > c + T or all < c - T.  Run once over the part of a level that the cells'
+// tested areas tile, it gives a score map -- exact score where the pixel is a corner at T, 0 elsewhere -- from
+// which every cell's cv::FAST(T, nms = true) result follows (a cell's NMS ignores pixels outside its own tested area).  Purely a
+// faster route to the same numbers: detect_level(simd = false) keeps the cell-by-cell scalar path and tests/ compares the two; it
+// also makes the timed CPU baseline a fairer stand-in for OpenCV's SIMD FAST.
+// ---------------------------------------------------------------------------------------------
+static int g_fast_simd = 1;
+void set_fast_simd(int on) { g_fast_simd = on; }
+
+static void fast_score_map(const Plane& P, int x0, int x1, int y0, int y1, int thr, std::vector<uint8_t>& S) {   // tested pixels [x0, x1) x [y0, y1)
+    S.assign((size_t)P.w * P.h, 0);
+    int off[25];
+    for (int k = 0; k < 25; ++k) off[k] = kRingY[k & 15] * P.w + kRingX[k & 15];
+    const __m128i delta = _mm_set1_epi8((char)-128), t = _mm_set1_epi8((char)thr), K8 = _mm_set1_epi8(8);
+    for (int y = y0; y < y1; ++y) {
+        const uint8_t* row = &P.px[(size_t)y * P.w];
+        for (int xb = x0; xb < x1; xb += 16) {
+            const int x = std::min(xb, x1 - 16);                 // the last block overlaps the previous one
+            const uint8_t* p = row + x;
+            __m128i c = _mm_loadu_si128((const __m128i*)p);
+            const __m128i v0 = _mm_xor_si128(_mm_adds_epu8(c, t), delta);   // c + T  (saturating), signed domain
+            const __m128i v1 = _mm_xor_si128(_mm_subs_epu8(c, t), delta);   // c - T
+            const __m128i a0 = _mm_xor_si128(_mm_loadu_si128((const __m128i*)(p + off[0])), delta);
+            const __m128i a4 = _mm_xor_si128(_mm_loadu_si128((const __m128i*)(p + off[4])), delta);
+            const __m128i a8 = _mm_xor_si128(_mm_loadu_si128((const __m128i*)(p + off[8])), delta);
+            const __m128i a12 = _mm_xor_si128(_mm_loadu_si128((const __m128i*)(p + off[12])), delta);
+            // an arc of 9 contains two neighbouring compass points
+            __m128i m0 = _mm_and_si128(_mm_cmpgt_epi8(a0, v0), _mm_cmpgt_epi8(a4, v0));
+            __m128i m1 = _mm_and_si128(_mm_cmpgt_epi8(v1, a0), _mm_cmpgt_epi8(v1, a4));
+            m0 = _mm_or_si128(m0, _mm_and_si128(_mm_cmpgt_epi8(a4, v0), _mm_cmpgt_epi8(a8, v0)));
+            m1 = _mm_or_si128(m1, _mm_and_si128(_mm_cmpgt_epi8(v1, a4), _mm_cmpgt_epi8(v1, a8)));
+            m0 = _mm_or_si128(m0, _mm_and_si128(_mm_cmpgt_epi8(a8, v0), _mm_cmpgt_epi8(a12, v0)));
+            m1 = _mm_or_si128(m1, _mm_and_si128(_mm_cmpgt_epi8(v1, a8), _mm_cmpgt_epi8(v1, a12)));
+            m0 = _mm_or_si128(m0, _mm_and_si128(_mm_cmpgt_epi8(a12, v0), _mm_cmpgt_epi8(a0, v0)));
+            m1 = _mm_or_si128(m1, _mm_and_si128(_mm_cmpgt_epi8(v1, a12), _mm_cmpgt_epi8(v1, a0)));
+            if (_mm_movemask_epi8(_mm_or_si128(m0, m1)) == 0) continue;
+            __m128i c0 = _mm_setzero_si128(), c1 = c0, max0 = c0, max1 = c0;
+            for (int k = 0; k < 25; ++k) {
+                const __m128i r = _mm_xor_si128(_mm_loadu_si128((const __m128i*)(p + off[k])), delta);
+                m0 = _mm_cmpgt_epi8(r, v0);
+                m1 = _mm_cmpgt_epi8(v1, r);
+                c0 = _mm_and_si128(_mm_sub_epi8(c0, m0), m0);    // run length of "brighter", reset where the test fails
+                c1 = _mm_and_si128(_mm_sub_epi8(c1, m1), m1);
+                max0 = _mm_max_epu8(max0, c0);
+                max1 = _mm_max_epu8(max1, c1);
+            }
+            int mask = _mm_movemask_epi8(_mm_cmpgt_epi8(_mm_max_epu8(max0, max1), K8));     // a run of 9 or more
+            while (mask) {
+                const int b = __builtin_ctz(mask);
+                mask &= mask - 1;
+                S[(size_t)y * P.w + x + b] = (uint8_t)fast_score16(p + b, P.w);              // >= thr by construction, <= 254
+            }
+        }
+    }
+}
+
 // per-level cell loop, ORBextractor.cc:1069-1166.  Output coords are relative to minBorder.
 void Extractor::detect_level(int level, std::vector<Cand>& out) const {
     const Plane& P = pyramid[level];
@@ -349,6 +438,10 @@ void Extractor::detect_level(int level, std::vector<Cand>& out) const {
     if (nCols < 1 || nRows < 1) return;
     const int wCell = (int)std::ceil(width / nCols), hCell = (int)std::ceil(height / nRows);
     std::vector<Cand> cell;
+    // tested pixels of all cells tile [minBX + 3, maxBX - 3) x [minBY + 3, maxBY - 3)
+    const bool simd = g_fast_simd && (maxBX - minBX - 6) >= 16;
+    std::vector<uint8_t> S;
+    if (simd) fast_score_map(P, minBX + 3, maxBX - 3, minBY + 3, maxBY - 3, iniThFAST, S);
     for (int i = 0; i < nRows; ++i) {
         const float iniY = (float)(minBY + i * hCell);
         float maxY = iniY + hCell + 6;
@@ -362,7 +455,27 @@ void Extractor::detect_level(int level, std::vector<Cand>& out) const {
             const int x0 = (int)iniX, y0 = (int)iniY, cw = (int)maxX - x0, ch = (int)maxY - y0;
             const uint8_t* win = &P.px[(size_t)y0 * P.w + x0];
             cell.clear();
-            fast_cell(win, cw, ch, P.w, iniThFAST, cell);
+            if (simd && cw >= 7 && ch >= 7) {
+                // cv::FAST(iniThFAST, nms) of this window from the level's score map: strict 3 x 3 maximum among the window's own
+                // tested pixels (columns [3, cw - 3), rows [3, ch - 3)); everything outside counts as 0
+                const uint8_t* sm = &S[(size_t)y0 * P.w + x0];
+                for (int y = 3; y < ch - 3; ++y)
+                    for (int x = 3; x < cw - 3; ++x) {
+                        const int sc0 = sm[(size_t)y * P.w + x];
+                        if (sc0 == 0) continue;
+                        bool mx = true;
+                        for (int dy = -1; dy <= 1 && mx; ++dy)
+                            for (int dx = -1; dx <= 1; ++dx) {
+                                if (!dx && !dy) continue;
+                                const int yy = y + dy, xx = x + dx;
+                                const int nb = (yy >= 3 && yy < ch - 3 && xx >= 3 && xx < cw - 3) ? sm[(size_t)yy * P.w + xx] : 0;
+                                if (sc0 <= nb) { mx = false; break; }
+                            }
+                        if (mx) cell.push_back({x, y, sc0});
+                    }
+            } else {
+                fast_cell(win, cw, ch, P.w, iniThFAST, cell);
+            }
             if (cell.empty()) fast_cell(win, cw, ch, P.w, minThFAST, cell);
             for (const Cand& c : cell) out.push_back({c.x + j * wCell, c.y + i * hCell, c.score});
         }

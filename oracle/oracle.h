@@ -71,9 +71,11 @@ class Extractor {
 void resize_linear_u8(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh,
                       int dstride);
 void gaussian_blur7_u8(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride);
-int fast_score16(const uint8_t* p, int stride);  // max T such that p is a FAST-9/16 corner, i.e. cv response
+int fast_score16(const uint8_t* p, int stride);
+int fast_score16_scalar(const uint8_t* p, int stride);   // the same value without SIMD (tests)  // max T such that p is a FAST-9/16 corner, i.e. cv response
 void fast_cell(const uint8_t* win, int cw, int ch, int stride, int thr, std::vector<Cand>& out);
 float fast_atan2_deg(float y, float x);
+void set_fast_simd(int on);   // 1 (default): level-wide SSE2 corner test; 0: cell-by-cell scalar path (tests compare the two)
 float ic_angle(const Plane& im, int x, int y, const std::vector<int>& umax);
 void orb_descriptor(const Plane& blurred, int x, int y, float angle_deg, uint8_t* desc32);
 int descriptor_distance(const uint8_t* a, const uint8_t* b);
