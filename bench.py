@@ -588,11 +588,13 @@ def main():
         cpu = None
         if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only
             # faithful threading (Frame.cc:136-141): the two eyes on two threads, bounded sample
-            v_oracle, secs = cpu_oracle_frames(pairs[:8], 2)
+            n_cpu = min(len(pairs), 128)        # a few seconds of CPU work: stable to a few percent
+            cpu_oracle_frames(pairs[:2], 2)     # warm-up (page-in, thread pools)
+            v_oracle, secs = cpu_oracle_frames(pairs[:n_cpu], 2)
             guard = straw_man_guard(pairs[0])
             v = v_oracle / guard["ratio"] if guard else v_oracle
             cpu = {"value": v, "unit": UNIT, "cores": 2, "kind": "port",
-                   "sample": f"8 stereo frames (extraction + stereo matching + both projection searches), "
+                   "sample": f"{n_cpu} stereo frames (extraction + stereo matching + both projection searches), "
                              f"L/R eyes on 2 threads (Frame.cc:136-141), {secs:.1f} s",
                    "value_oracle_only": v_oracle, "straw_man_guard": guard}
         # ---- local BA (config 4): 20 KF / 3000 MP, one problem and a batch of 8 -------------------------
