@@ -50,3 +50,21 @@ def test_ratio_test_on_extracted_descriptors():
     assert (i0 == i1).all() and (d0 == d1).all()
     good = d0[:, 0] < d0[:, 1] * np.float32(0.7)
     assert good.sum() > 50
+
+
+def test_fuzz_against_opencv():
+    """Random shapes and bit densities (hypothesis): the oracle equals cv2.BFMatcher.knnMatch on every draw."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(0, 70), st.integers(0, 70), st.integers(1, 8), st.integers(0, 2 ** 31 - 1))
+    def run(nq, nt, bits, seed):
+        rng = np.random.default_rng(seed)
+        q = rng.integers(0, 1 << bits, (nq, 32)).astype(np.uint8)
+        t = rng.integers(0, 1 << bits, (nt, 32)).astype(np.uint8)
+        if nq and nt > 3:
+            t[rng.integers(0, nt, 3)] = q[rng.integers(0, nq)]
+        i0, d0 = po.hamming_knn2(q, t)
+        i1, d1 = cv_knn2(q, t)
+        assert (i0 == i1).all() and (d0 == d1).all()
+    run()
