@@ -212,3 +212,23 @@ def test_multi_stage_bitonic_sorts(emul, npow):
         emul.emul_bitonic(b1.ctypes.data, npow, 1)      # two stages per pass
         emul.emul_bitonic(b2.ctypes.data, npow, 2)      # three stages per pass (the one k_quadtree_v1 uses)
         assert (b0 == np.sort(a)).all() and (b1 == b0).all() and (b2 == b0).all()
+
+
+def test_parallel_std_sort_fuzz(emul):
+    """hypothesis: random lengths and key ranges (dense ties to distinct keys) -- libstdc++ std::sort, the one-thread transcription and
+    the CTA-parallel form agree on the full payload order every time."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.integers(0, 700), st.integers(1, 40), st.integers(1, 300), st.integers(0, 2 ** 31 - 1), st.booleans())
+    def run(n, kc, kx, seed, presorted):
+        rng = np.random.default_rng(seed)
+        c = np.stack([rng.integers(2, 2 + kc, n), rng.integers(0, kx, n), np.arange(n)], 1).astype(np.uint32).reshape(n, 3)
+        if presorted and n:
+            c = c[np.lexsort((c[:, 1], c[:, 0]))]
+            c[:, 2] = np.arange(n)
+        if n == 0:
+            return
+        ref, one, par = _sort_three_ways(emul, c)
+        assert (one == ref).all() and (par == ref).all()
+    run()
