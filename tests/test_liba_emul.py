@@ -307,3 +307,54 @@ def test_solver_failure_path_threaded(mt_binary, tmp_path):
     got = run_mt(mt_binary, s, 1e-200, 3, 4, tmp_path, 2)
     assert got["iterations"] == ref["iterations"] and got["trials"] == ref["trials"] == 10
     assert np.abs(got["state"] - ref["state"]).max() < 1e-12
+
+
+def test_window_shape_fuzz(emul):
+    """hypothesis: window sizes, which keyframes are fixed (incl. both ends of a link, or all but one), robust flags, mono / stereo mixes,
+    dropped links -- the device algorithm follows the oracle's Levenberg path on every draw."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(2, 8), st.integers(12, 90), st.integers(0, 2 ** 31 - 1), st.sampled_from([1.0, 1e-2, 0.0, 100.0]), st.integers(1, 6))
+    def run(n_kf, n_mp, seed, lam, iters):
+        rng = np.random.default_rng(seed)
+        s = perturbed(int(rng.integers(0, 1000)), n_kf=n_kf, n_mp=n_mp)
+        if len(s["edge_kf"]) == 0:
+            return
+        fx = (rng.random(n_kf) < 0.4).astype(np.uint8)
+        if fx.all():
+            fx[rng.integers(0, n_kf)] = 0
+        s["fixed"] = fx
+        s["links"] = s["links"].copy()
+        s["links"]["robust"] = rng.integers(0, 2, len(s["links"]))
+        if len(s["links"]) > 1 and rng.random() < 0.5:
+            s["links"] = np.delete(s["links"], rng.integers(0, len(s["links"])))
+        s["obs"] = s["obs"].copy()
+        s["obs"][rng.random(len(s["obs"])) < 0.3, 2] = -1.0
+        ref = po.liba(s["state"], s["fixed"], s["point"], s["edge_kf"], s["edge_mp"], s["obs"], s["inv_sigma2"], s["Tcb"], s["cam5"], s["links"], lam, iters)
+        got = run_emul(emul, s, lam, iters)
+        assert got["iterations"] == ref["iterations"] and abs(got["trials"] - ref["trials"]) <= 1
+        if got["trials"] == ref["trials"]:
+            assert np.abs(got["state"] - ref["state"]).max() < TOL and np.abs(got["point"] - ref["point"]).max() < TOL
+        assert (got["state"][fx == 1] == s["state"][fx == 1]).all()
+    run()
+
+
+def test_threaded_window_shape_fuzz(mt_binary, tmp_path):
+    """The same kind of draws run by T threads x C "CTAs" under ThreadSanitizer: no race on any window shape."""
+    rng = np.random.default_rng(123)
+    for trial in range(10):
+        n_kf, n_mp = int(rng.integers(2, 8)), int(rng.integers(12, 80))
+        s = perturbed(int(rng.integers(0, 1000)), n_kf=n_kf, n_mp=n_mp)
+        if len(s["edge_kf"]) == 0:
+            continue
+        fx = (rng.random(n_kf) < 0.4).astype(np.uint8)
+        if fx.all():
+            fx[rng.integers(0, n_kf)] = 0
+        s["fixed"] = fx
+        lam = [1.0, 0.0, 1e-2][trial % 3]
+        ref = po.liba(s["state"], s["fixed"], s["point"], s["edge_kf"], s["edge_mp"], s["obs"], s["inv_sigma2"], s["Tcb"], s["cam5"], s["links"], lam, 4)
+        got = run_mt(mt_binary, s, lam, 4, int(rng.integers(1, 6)), tmp_path, int(rng.choice([1, 2, 4, 8])))
+        assert got["iterations"] == ref["iterations"] and abs(got["trials"] - ref["trials"]) <= 1
+        if got["trials"] == ref["trials"]:
+            assert np.abs(got["state"] - ref["state"]).max() < TOL
