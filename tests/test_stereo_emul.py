@@ -68,3 +68,30 @@ def test_v1_edge_cases(emul):
     uR, dep, _ = po.stereo_matches(eL, eR, kL, dL, kR2, dR2, BF, B)
     u, d = run_v1(emul, eL, eR, kL, dL, kR2, dR2, 240, BF, B)
     assert (u.view(np.uint32) == uR.view(np.uint32)).all() and (d.view(np.uint32) == dep.view(np.uint32)).all()
+
+
+def test_v1_on_synthetic_right_keypoint_sets(emul):
+    """Right keypoint sets built to stress the candidate gates rather than coming from an extraction: every left keypoint gets several
+    right twins at random disparities, rows up to +-9 px away, octaves +-2 and a few flipped descriptor bits (many equal distances:
+    the lowest right index must win), plus unrelated keypoints; coordinates at the image border included."""
+    l, r, _ = synth.stereo_pair(640, 480, 12)
+    eL, eR = po.OracleExtractor(800, 1.2, 8, 20, 7), po.OracleExtractor(800, 1.2, 8, 20, 7)
+    _, kL, dL = eL(l)
+    eR(r)                                                   # only its pyramid is used
+    for seed in range(6):
+        rng = np.random.default_rng(seed)
+        reps = int(rng.integers(1, 4))
+        kR = np.concatenate([kL] * reps).copy()
+        dR = np.concatenate([dL] * reps).copy()
+        kR["x"] = np.clip(kR["x"] - rng.uniform(-5, 70, len(kR)).astype(np.float32), 0, 639)
+        kR["y"] = np.clip(kR["y"] + rng.integers(-9, 10, len(kR)).astype(np.float32), 0, 479)
+        kR["octave"] = np.clip(kR["octave"] + rng.integers(-2, 3, len(kR)), 0, 7)
+        flips = rng.integers(0, 256, (len(kR), 3))
+        for c in range(3):
+            m = rng.random(len(kR)) < 0.5
+            dR[m, flips[m, c] // 8] ^= (1 << (flips[m, c] % 8)).astype(np.uint8)
+        perm = rng.permutation(len(kR))
+        kR, dR = np.ascontiguousarray(kR[perm]), np.ascontiguousarray(dR[perm])
+        uR, dep, _ = po.stereo_matches(eL, eR, kL, dL, kR, dR, BF, B)
+        u, d = run_v1(emul, eL, eR, kL, dL, kR, dR, 480, BF, B)
+        assert (u.view(np.uint32) == uR.view(np.uint32)).all() and (d.view(np.uint32) == dep.view(np.uint32)).all(), seed
