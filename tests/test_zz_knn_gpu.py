@@ -12,7 +12,9 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("ORB_FIRST_CONTACT") != "1", reason="first device run pending: set ORB_FIRST_CONTACT=1")]
 
 
-def test_batched_sets_match_oracle():
+@pytest.mark.parametrize("tma", ["0", "1"])
+def test_batched_sets_match_oracle(monkeypatch, tma):
+    monkeypatch.setenv("ORB_KNN_TMA", tma)      # 1: train tiles by cp.async.bulk + mbarrier (read at every call)
     rng = np.random.default_rng(7)
     shapes = [(300, 500, 2), (257, 129, 8), (40, 1, 8), (5, 2, 1), (1200, 1200, 8), (3, 0, 8), (0, 7, 8), (513, 385, 3)]
     qs = [rng.integers(0, 1 << b, (nq, 32)).astype(np.uint8) for nq, nt, b in shapes]
