@@ -11,6 +11,7 @@
 // a restatement whose only pin is self-consistency + the committed golden vectors => "parity
 // unpinned by the reference" for those stages.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <vector>
 

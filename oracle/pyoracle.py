@@ -516,3 +516,114 @@ def liba_reproj(state21, Xw, obs3, Tcb12, cam5):
     r, Jp, Jx = np.zeros(3), np.zeros(9), np.zeros(18)
     D = L.orc_liba_reproj(_p(s), _p(X), _p(o), _p(T), _p(cam), _p(r), _p(Jp), _p(Jx))
     return D, r, Jp.reshape(3, 3)[:D], Jx.reshape(3, 6)[:D]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# oracle/_ref: the reference's OWN src/ORBextractor.cc, compiled unmodified against ref_shim/opencv2 (oracle/Makefile,
+# target `ref`).  Buildable only where /root/reference exists (the build container); the built .so travels.
+# ----------------------------------------------------------------------------------------------------------------
+_REF_SO = os.path.join(_HERE, "_ref", "liborb_ref.so")
+REFERENCE_ROOT = os.environ.get("ORB_REFERENCE_ROOT", "/root/reference")
+_ref_lib = None
+
+
+def build_ref(force=False):
+    """Returns the path of oracle/_ref/liborb_ref.so, building it when the reference checkout is present; None when it is
+    neither built nor buildable."""
+    if os.path.exists(os.path.join(REFERENCE_ROOT, "src", "ORBextractor.cc")):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref", f"REF={REFERENCE_ROOT}"] + (["-B"] if force else []))
+    return _REF_SO if os.path.exists(_REF_SO) else None
+
+
+def ref_lib():
+    global _ref_lib
+    if _ref_lib is None:
+        if build_ref() is None:
+            raise RuntimeError("oracle/_ref/liborb_ref.so is not built and /root/reference is not present")
+        L = _ref_lib = C.CDLL(_REF_SO)
+        L.ref_extractor_create.restype = C.c_void_p
+        L.ref_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.ref_extractor_destroy.argtypes = [C.c_void_p]
+        L.ref_extract.restype = C.c_int
+        L.ref_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                  C.c_int, C.POINTER(C.c_int)]
+        L.ref_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        L.ref_level_size.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.ref_level_pyramid.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_keypoints_octtree.restype = C.c_int
+        L.ref_keypoints_octtree.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_distribute.restype = C.c_int
+        L.ref_distribute.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_int]
+    return _ref_lib
+
+
+class RefExtractor:
+    """ORB_SLAM3::ORBextractor itself (reference src/ORBextractor.cc compiled as it lies) behind a C wrapper."""
+
+    def __init__(self, nfeatures=1200, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.L = ref_lib()
+        self.nlevels, self.nfeatures = nlevels, nfeatures
+        self.h = C.c_void_p(self.L.ref_extractor_create(nfeatures, scale_factor, nlevels, ini_th, min_th))
+        sc, isc, s2, is2 = (np.zeros(nlevels, np.float32) for _ in range(4))
+        q = np.zeros(nlevels, np.int32)
+        um = np.zeros(16, np.int32)
+        self.L.ref_tables(self.h, _p(sc), _p(isc), _p(s2), _p(is2), _p(q), _p(um))
+        self.scale_factors, self.inv_scale_factors, self.level_sigma2, self.inv_level_sigma2 = sc, isc, s2, is2
+        self.features_per_level, self.umax = q, um
+
+    def __del__(self):
+        try:
+            self.L.ref_extractor_destroy(self.h)
+        except Exception:
+            pass
+
+    def __call__(self, img, lapping=(0, 0)):
+        img = np.ascontiguousarray(img, np.uint8)
+        H, W = img.shape
+        cap = max(4 * self.nfeatures, 4096)
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        mono = self.L.ref_extract(self.h, _p(img), W, H, W, int(lapping[0]), int(lapping[1]), _p(kps), _p(desc), cap, C.byref(n))
+        assert mono != -100 and n.value <= cap
+        return mono, kps[:n.value].copy(), desc[:n.value].copy()
+
+    def level_size(self, l):
+        w, h = C.c_int(), C.c_int()
+        self.L.ref_level_size(self.h, l, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def level_pyramid(self, l):
+        w, h = self.level_size(l)
+        a = np.zeros((h, w), np.uint8)
+        self.L.ref_level_pyramid(self.h, l, _p(a))
+        return a
+
+    def keypoints_octtree(self, img):
+        """ComputePyramid + ComputeKeyPointsOctTree: list of per-level keypoint arrays (level coordinates, angles set)."""
+        img = np.ascontiguousarray(img, np.uint8)
+        H, W = img.shape
+        cap = max(8 * self.nfeatures, 8192)
+        kps = np.zeros(cap, KP_DTYPE)
+        off = np.zeros(self.nlevels + 1, np.int32)
+        n = self.L.ref_keypoints_octtree(self.h, _p(img), W, H, W, _p(kps), cap, _p(off))
+        assert n >= 0
+        return [kps[off[l]:off[l + 1]].copy() for l in range(self.nlevels)]
+
+    def distribute(self, cand, minX, maxX, minY, maxY, N, level=0):
+        """DistributeOctTree on an (n, 3) int32 candidate array (x, y, response): (k, 4) rows (x, y, response, input index)."""
+        cand = np.ascontiguousarray(cand, np.int32)
+        cap = len(cand) + 8
+        out = np.zeros((cap, 4), np.int32)
+        k = self.L.ref_distribute(self.h, _p(cand), len(cand), minX, maxX, minY, maxY, N, level, _p(out), cap)
+        assert k >= 0
+        return out[:k].copy()
+
+
+def oracle_distribute(cand, minX, maxX, minY, maxY, N):
+    """The restatement's DistributeOctTree on the same input: indices into cand in output order."""
+    cand = np.ascontiguousarray(cand, np.int32)
+    out = np.zeros(len(cand) + 8, np.int32)
+    k = lib().orc_distribute(_p(cand), len(cand), minX, maxX, minY, maxY, N, _p(out), len(out))
+    return out[:k].copy()
