@@ -624,9 +624,9 @@ def main():
             opt.close()
         except Exception as exc:   # never lose the headline line because the side benchmark failed
             lba = {"error": repr(exc)}
-        # ---- LocalInertialBA: opt-in until the kernel has had its first green device run ---------------
-        liba = {"skipped": "k_liba is CPU-validated only (tests/test_liba_emul.py); set ORB_LIBA_GPU=1 to time it"}
-        if os.environ.get("ORB_LIBA_GPU") == "1":
+        # ---- LocalInertialBA ---------------------------------------------------------------------------
+        liba = None
+        if True:
             try:
                 from oracle import pyoracle as po
                 from orb_slam3_detailed_comments_b200 import InertialOptimizer
@@ -656,9 +656,9 @@ def main():
                 iopt.close()
             except Exception as exc:
                 liba = {"error": repr(exc)}
-        # ---- K9 brute-force Hamming 2-NN (BFMatcher.knnMatch of ComputeStereoFishEyeMatches): opt-in until its first device run ----
-        knn = {"skipped": "k_hamming_knn2 has not had a device run yet; set ORB_FIRST_CONTACT=1 to time it"}
-        if os.environ.get("ORB_FIRST_CONTACT") == "1":
+        # ---- K9 brute-force Hamming 2-NN (BFMatcher.knnMatch of ComputeStereoFishEyeMatches) ----------------------------------
+        knn = None
+        if True:
             try:
                 from orb_slam3_detailed_comments_b200 import knnMatch2
                 krng = np.random.default_rng(5)
@@ -756,8 +756,8 @@ def main():
                            "l2": f"input pool of {pool_batches} batches = {pool_batches * nimg * W * H / 1e6:.0f} MB > 126 MB L2, "
                                  "intermediates rewritten every step",
                            "keypoints_per_image": n_kp, "fast_candidates_per_image": n_cand,
-                           "kernel_variants": {"quadtree": int(os.environ.get("ORB_QT_VARIANT", "0") == "1"),
-                                               "stereo": int(os.environ.get("ORB_STEREO_VARIANT", "0") == "1")}},
+                           "kernel_variants": {"quadtree": int(os.environ.get("ORB_QT_VARIANT", "1") != "0"),
+                                               "stereo": int(os.environ.get("ORB_STEREO_VARIANT", "1") != "0")}},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_step),
                         "d2h_bytes_per_step": int(d2h // args.steps)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "lba": lba, "inertial_ba": liba, "hamming_knn": knn, "pose_optimization": pose_opt}

@@ -295,7 +295,7 @@ extern "C" orb_status orbx_create(const orbx_config* cfg, orbx_handle** out) {
     ORB_CUDA(cudaSetDevice(cfg->device));
     orbx_handle* h = new orbx_handle();
     h->cfg = *cfg;
-    if (const char* v = getenv("ORB_QT_VARIANT")) h->qt_variant = atoi(v) == 1 ? 1 : 0;   // opt-in: see k_quadtree_v1
+    if (const char* v = getenv("ORB_QT_VARIANT")) h->qt_variant = atoi(v) == 0 ? 0 : 1;   // 0 selects the round-1 kernel (k_quadtree)
     build_tables(h);
     static const int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
     for (int i = 0; i < 16; ++i)

@@ -8,7 +8,7 @@ struct orbx_handle {
     orbx_config cfg{};
     orb::ExtractGeom geom{};
     int cur_w = -1, cur_h = -1;
-    int qt_variant = 0;   // 0: k_quadtree; 1: k_quadtree_v1 (ORB_QT_VARIANT=1 at orbx_create)
+    int qt_variant = 1;   // 1 (default): k_quadtree_v1; 0: k_quadtree (ORB_QT_VARIANT=0 at orbx_create)
     cudaStream_t stream = nullptr;
     static const int kProfRing = 32;
     cudaEvent_t evr[kProfRing][8] = {};   // ring of per-batch stage events

@@ -313,7 +313,7 @@ static orb_status run_stereo(orbx_handle* hl, orbx_handle* hr, int n_pairs, int 
     P.uright = hl->d_uright; P.depth = hl->d_depth; P.sad = hl->d_sad;
     P.maxRight = hr->geom.kpTotal;
     const char* venv = getenv("ORB_STEREO_VARIANT");      // read at every call: a test can switch variants inside one process
-    const int variant = venv && atoi(venv) == 1 ? 1 : 0;
+    const int variant = venv && atoi(venv) == 0 ? 0 : 1;   // default 1 (k_stereo_match_v1) since its round-2 device run
     if (variant == 1) {
         const int H = hr->geom.lv[0].h;
         const size_t smem1 = 13 * (size_t)P.maxRight + 4 * (2 * (size_t)H + 2) + 64;

@@ -1,7 +1,6 @@
 """GPU tier: liba_solve (LocalInertialBA's numeric core, csrc/liba.cu) against the oracle, through the C ABI.
 The kernel's source (csrc/liba_core.cuh) is validated on the CPU by tests/test_liba_emul.py (single-thread run == oracle; N-thread
-run under ThreadSanitizer race-free).  It had not yet been launched on a device when round 1's GPU budget ran out, so this file is
-opt-in (ORB_LIBA_GPU=1) until its first green run -- an unproven kernel must not be able to turn the GPU tier red."""
+run under ThreadSanitizer race-free).  First device run: round 2 (compute-sanitizer memcheck + racecheck clean, all cases green)."""
 import os
 
 import numpy as np
@@ -10,9 +9,7 @@ import pytest
 from oracle import pyoracle as po
 from test_liba_emul import TOL, perturbed
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ORB_LIBA_GPU") != "1" and os.environ.get("ORB_FIRST_CONTACT") != "1",
-                                 reason="first device run pending: set ORB_FIRST_CONTACT=1 (or ORB_LIBA_GPU=1)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")

@@ -1,4 +1,4 @@
-"""GPU tier, opt-in (ORB_FIRST_CONTACT=1): orbm_hamming_knn2 (csrc/knn.cu, K9 brute-force Hamming 2-NN) against the oracle, which
+"""GPU tier: orbm_hamming_knn2 (csrc/knn.cu, K9 brute-force Hamming 2-NN) against the oracle, which
 tests/test_knn_cpu.py pins to cv2.BFMatcher.  Written after round 1's last GPU run: opt-in until its first green device run."""
 import os
 
@@ -8,8 +8,7 @@ import pytest
 from oracle import pyoracle as po
 from orb_slam3_detailed_comments_b200 import ORBextractor, knnMatch2
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ORB_FIRST_CONTACT") != "1", reason="first device run pending: set ORB_FIRST_CONTACT=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("tma", ["0", "1"])

@@ -1,6 +1,6 @@
-"""GPU tier, opt-in (ORB_FIRST_CONTACT=1): k_quadtree_v1 -- the ordered phase's std::sort spread over the CTA -- against the oracle.
-The kernel's algorithm is validated on the CPU (tests/test_quadtree_emul.py: libstdc++ move for move, threaded run under
-ThreadSanitizer) but has not run on a device yet; the default path (k_quadtree) keeps its round-1 machine code bit for bit."""
+"""GPU tier: both DistributeOctTree kernels against the oracle: k_quadtree_v1 (default since its first device run in round 2: multi-stage
+bitonic passes, the ordered phase's std::sort spread over the CTA; CPU-validated by tests/test_quadtree_emul.py) and the round-1
+k_quadtree (ORB_QT_VARIANT=0), which keeps its machine code bit for bit."""
 import os
 
 import numpy as np
@@ -9,16 +9,16 @@ import pytest
 from oracle import pyoracle as po
 from orb_slam3_detailed_comments_b200 import ORBextractor, synth
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ORB_FIRST_CONTACT") != "1", reason="first device run pending: set ORB_FIRST_CONTACT=1")]
+pytestmark = pytest.mark.gpu
 
 CASES = [(640, 480, 1, 1.5, 60, 1200), (640, 480, 2, 6.0, 10, 1200), (752, 480, 3, 1.5, 60, 1200), (320, 240, 4, 3.0, 20, 500),
          (1280, 720, 5, 1.5, 60, 2000), (640, 480, 7, 1.5, 60, 5000)]
 
 
+@pytest.mark.parametrize("variant", ["1", "0"])
 @pytest.mark.parametrize("w,h,seed,sigma,nrect,nf", CASES)
-def test_variant_1_is_bit_exact(monkeypatch, w, h, seed, sigma, nrect, nf):
-    monkeypatch.setenv("ORB_QT_VARIANT", "1")            # read by orbx_create
+def test_variant_is_bit_exact(monkeypatch, variant, w, h, seed, sigma, nrect, nf):
+    monkeypatch.setenv("ORB_QT_VARIANT", variant)        # read by orbx_create; 1 is the default since round 2
     img = synth.frame(w, h, seed, sigma, nrect)
     ex = ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=1)
     ref = po.OracleExtractor(nf, 1.2, 8, 20, 7)
@@ -33,8 +33,9 @@ def test_variant_1_is_bit_exact(monkeypatch, w, h, seed, sigma, nrect, nf):
     ex.close()
 
 
-def test_variant_1_batch(monkeypatch):
-    monkeypatch.setenv("ORB_QT_VARIANT", "1")
+@pytest.mark.parametrize("variant", ["1", "0"])
+def test_variant_batch(monkeypatch, variant):
+    monkeypatch.setenv("ORB_QT_VARIANT", variant)
     imgs = np.stack([synth.frame(640, 480, 20 + i) for i in range(6)])
     ex = ORBextractor(1200, 1.2, 8, 20, 7, max_width=640, max_height=480, max_batch=6)
     ex.extract_batch(imgs)
