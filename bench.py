@@ -299,6 +299,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="stereo frames per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extract-only", action="store_true", help="headline step only: skip the LBA / inertial / knn / PoseOptimization sections")
     ap.add_argument("--handles", type=int, default=4, help="extractor handles (CUDA streams) the steps are pipelined over")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -600,6 +601,8 @@ def main():
         # ---- local BA (config 4): 20 KF / 3000 MP, one problem and a batch of 8 -------------------------
         lba = None
         try:
+            if args.extract_only:
+                raise RuntimeError("skipped (--extract-only)")
             from oracle import pyoracle as po
             opt = Optimizer(local)
             prs = [synth.lba_problem(seed=s) for s in range(8)]
@@ -628,6 +631,8 @@ def main():
         liba = None
         if True:
             try:
+                if args.extract_only:
+                    raise RuntimeError("skipped (--extract-only)")
                 from oracle import pyoracle as po
                 from orb_slam3_detailed_comments_b200 import InertialOptimizer
                 iopt = InertialOptimizer(local)
@@ -660,6 +665,8 @@ def main():
         knn = None
         if True:
             try:
+                if args.extract_only:
+                    raise RuntimeError("skipped (--extract-only)")
                 from orb_slam3_detailed_comments_b200 import knnMatch2
                 krng = np.random.default_rng(5)
                 qs = [krng.integers(0, 256, (1200, 32), dtype=np.uint8) for _ in range(64)]
@@ -689,6 +696,8 @@ def main():
         # ---- PoseOptimization (twice per frame on the tracking thread): a batch of B frames --------------
         pose_opt = None
         try:
+            if args.extract_only:
+                raise RuntimeError("skipped (--extract-only)")
             from oracle import pyoracle as po
             from orb_slam3_detailed_comments_b200 import PoseOptimization, PoseOptimizationDevice
             prng = np.random.default_rng(99)
@@ -757,7 +766,8 @@ def main():
                                  "intermediates rewritten every step",
                            "keypoints_per_image": n_kp, "fast_candidates_per_image": n_cand,
                            "kernel_variants": {"quadtree": int(os.environ.get("ORB_QT_VARIANT", "1") != "0"),
-                                               "stereo": int(os.environ.get("ORB_STEREO_VARIANT", "1") != "0")}},
+                                               "stereo": int(os.environ.get("ORB_STEREO_VARIANT", "1") != "0"),
+                                               "fast": int(os.environ.get("ORB_FAST_VARIANT", "1") != "0")}},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_step),
                         "d2h_bytes_per_step": int(d2h // args.steps)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "lba": lba, "inertial_ba": liba, "hamming_knn": knn, "pose_optimization": pose_opt}

@@ -91,6 +91,34 @@ ORB_HD uint32_t fast_score_x2(uint32_t c2, const uint32_t r[16]) {
     return max_u16x2(best_min, dark) - 0x00010001u;
 }
 
+// The same score from the RAW ring values (no per-sample subtraction): with A = max over the arcs of (min of the arc) and
+// B = min over the arcs of (max of the arc), score = max(A - c, c - B) - 1.  Returns the same +256-biased lanes as fast_score_x2.
+ORB_HD uint32_t fast_score_raw_x2(uint32_t c2, const uint32_t r[16]) {
+    uint32_t lo3[16], hi3[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        lo3[k] = min3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+        hi3[k] = max3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+    }
+    uint32_t mn9[16], mx9[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        mn9[k] = min3_u16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
+        mx9[k] = max3_u16x2(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
+    }
+    const uint32_t a0 = max3_u16x2(mn9[0], mn9[1], mn9[2]), a1 = max3_u16x2(mn9[3], mn9[4], mn9[5]);
+    const uint32_t a2 = max3_u16x2(mn9[6], mn9[7], mn9[8]), a3 = max3_u16x2(mn9[9], mn9[10], mn9[11]);
+    const uint32_t a4 = max3_u16x2(mn9[12], mn9[13], mn9[14]);
+    const uint32_t A = max_u16x2(max3_u16x2(a0, a1, a2), max3_u16x2(a3, a4, mn9[15]));
+    const uint32_t b0 = min3_u16x2(mx9[0], mx9[1], mx9[2]), b1 = min3_u16x2(mx9[3], mx9[4], mx9[5]);
+    const uint32_t b2 = min3_u16x2(mx9[6], mx9[7], mx9[8]), b3 = min3_u16x2(mx9[9], mx9[10], mx9[11]);
+    const uint32_t b4 = min3_u16x2(mx9[12], mx9[13], mx9[14]);
+    const uint32_t B = min_u16x2(min3_u16x2(b0, b1, b2), min3_u16x2(b3, b4, mx9[15]));
+    const uint32_t t1 = (A + 0x01000100u) - c2;   // ring brighter than the centre: A - c + 256 per lane, in [1, 511]
+    const uint32_t t2 = (c2 + 0x01000100u) - B;   // ring darker:                   c - B + 256
+    return max_u16x2(t1, t2) - 0x00010001u;
+}
+
 // cv::FAST's high-speed test in packed form: a 9-arc of the 16-ring contains at least one pixel of each antipodal pair,
 // so a pixel can only be a corner at threshold T if min over the 4 pairs (k, k+8), k = 0, 2, 4, 6, of max(r_k, r_k+8)
 // exceeds c + T (bright arc), or max over the pairs of min(r_k, r_k+8) is below c - T (dark arc).

@@ -158,6 +158,32 @@ static orb_status plan_geometry(orbx_handle* h, int w, int hh) {
         }
     }
     if (g.fastRows > FAST_ROWS) return set_error(ORB_ERR_UNSUPPORTED, "FAST cell taller than the staging arrays");
+    {   // k_fast_cells_v2: table of the cells cv::FAST actually tests (ORBextractor.cc:1098-1126), staging sizes from the geometry
+        h->cells_host.clear();
+        int maxCh = 7, maxPairs = 8, maxTask = 1;
+        for (int l = 0; l < nl; ++l) {
+            const LevelGeom& L = g.lv[l];
+            for (int i = 0; i < L.nRows; ++i)
+                for (int j = 0; j < L.nCols; ++j) {
+                    const int x0 = 16 + j * L.wCell, y0 = 16 + i * L.hCell;
+                    if (x0 >= L.maxBX - 6 || y0 >= L.maxBY - 3) continue;
+                    const int cw = std::min(x0 + L.wCell + 6, L.maxBX) - x0, ch = std::min(y0 + L.hCell + 6, L.maxBY) - y0;
+                    if (cw < 7 || ch < 7) continue;
+                    if (cw > 255 || ch > 255) return set_error(ORB_ERR_UNSUPPORTED, "FAST cell wider than 255 px");
+                    h->cells_host.push_back(make_uint2((uint32_t)x0 | ((uint32_t)y0 << 12) | ((uint32_t)l << 24), (uint32_t)cw | ((uint32_t)ch << 8)));
+                    const int tx0 = x0 + 3, tx1 = x0 + cw - 3;
+                    const int gx0 = ((tx0 & ~3) - 4) & ~7, wd0 = ((tx0 & ~3) - gx0) >> 2, ngrp = ((tx1 - 1) >> 2) - (tx0 >> 2) + 1;
+                    const int nC8 = (wd0 + ngrp + 2) >> 1;
+                    maxCh = std::max(maxCh, ch);
+                    maxPairs = std::max(maxPairs, 4 * nC8);
+                    maxTask = std::max(maxTask, (ch - 6) * ngrp);
+                }
+        }
+        h->fast_R = maxCh;
+        h->fast_PW = maxPairs | 1;   // odd row stride: the lanes of a warp work on consecutive rows (bank-conflict-free)
+        h->fast_LW = 64 * ((round_up(maxTask, 32) + FAST2_THREADS - 1) / FAST2_THREADS);   // per warp: both pairs of every task it tests
+        if (h->fast_PW > 64) return set_error(ORB_ERR_UNSUPPORTED, "FAST cell wider than the pair index of k_fast_cells_v2");
+    }
     g.totalCells = cells;
     g.totalTiles = tiles;
     g.candTotal = cand;
@@ -221,6 +247,13 @@ static orb_status apply_geometry(orbx_handle* h, int w, int hh) {
         return set_error(ORB_ERR_CAPACITY, "workspace sized for max image is too small for this size");
     ORB_CUDA(cudaMemcpyAsync(h->d_taps, h->taps_host.data(), h->taps_host.size() * sizeof(int2), cudaMemcpyHostToDevice,
                              h->stream));
+    if (h->cells_host.size() > h->cells_slots) {
+        if (h->d_cells) cudaFree(h->d_cells);
+        h->d_cells = nullptr;
+        h->cells_slots = h->cells_host.size() + 64;
+        ORB_CUDA(cudaMalloc(&h->d_cells, h->cells_slots * sizeof(uint2)));
+    }
+    ORB_CUDA(cudaMemcpyAsync(h->d_cells, h->cells_host.data(), h->cells_host.size() * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
     ORB_CUDA(cudaStreamSynchronize(h->stream));
     // quadtree launch plan.  Node workspace: qt_node_cap(N) nodes (N + 20, see quadtree_core.cuh).
     int capMax = 0;
@@ -295,6 +328,7 @@ extern "C" orb_status orbx_create(const orbx_config* cfg, orbx_handle** out) {
     ORB_CUDA(cudaSetDevice(cfg->device));
     orbx_handle* h = new orbx_handle();
     h->cfg = *cfg;
+    if (const char* v = getenv("ORB_FAST_VARIANT")) h->fast_variant = atoi(v) == 0 ? 0 : 1;   // 0 selects the round-1 kernel
     if (const char* v = getenv("ORB_QT_VARIANT")) h->qt_variant = atoi(v) == 0 ? 0 : 1;   // 0 selects the round-1 kernel (k_quadtree)
     build_tables(h);
     static const int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
@@ -370,7 +404,7 @@ extern "C" void orbx_destroy(orbx_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->d_pyr, h->d_blur, h->d_cand, h->d_sort, h->d_lvl_kp, h->d_slot, h->d_cand_cnt, h->d_lvl_cnt,
                     h->d_nkp, h->d_err, h->d_taps, h->d_kps, h->d_desc, h->d_node_scratch, h->d_stage, h->d_po,
-                    h->d_uright, h->d_depth, h->d_sad};
+                    h->d_uright, h->d_depth, h->d_sad, h->d_cells};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_counts) cudaFreeHost(h->h_counts);
@@ -415,7 +449,15 @@ static orb_status run_pipeline(orbx_handle* h, int batch, int lap0, int lap1) {
         ORB_LAUNCHED();
     }
     if (prof) cudaEventRecord(h->ev[2], st);
-    {   // pe / po / se rows + the NMS tile (which also holds the list of pixel pairs that pass the high-speed test)
+    if (h->fast_variant == 1) {   // pe / po rows, the byte score map, one list of pixel pairs per warp
+        FastPlan fp;
+        fp.cells = h->d_cells; fp.nCells = (int)h->cells_host.size(); fp.R = h->fast_R; fp.PW = h->fast_PW; fp.LW = h->fast_LW;
+        const int ws = ((fp.PW - 1) >> 1) | 1;
+        const size_t fsm = (size_t)round_up(fp.R * fp.PW, 4) * 8 + (size_t)round_up(fp.R * ws * 4, 16) + (size_t)2 * (FAST2_THREADS / 32) * fp.LW * 2;
+        auto kern = fp.PW == 29 ? k_fast_cells_v2<29> : k_fast_cells_v2<0>;
+        ORB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+        if (fp.nCells > 0) kern<<<dim3(fp.nCells, batch), FAST2_THREADS, fsm, st>>>(g, fp, h->d_cand, h->d_cand_cnt, h->d_err);
+    } else {   // pe / po / se rows + the NMS tile (which also holds the list of pixel pairs that pass the high-speed test)
         const size_t fsm = (size_t)g.fastRows * (3 * FAST_PW + FAST_TW) * 4;
         ORB_CUDA(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
         k_fast_cells<<<dim3(g.totalCells, batch), FAST_THREADS, fsm, st>>>(g, h->d_cand, h->d_cand_cnt, h->d_err);
@@ -478,7 +520,7 @@ extern "C" orb_status orbx_extract_batch_device(orbx_handle* h, const uint8_t* d
         ++h->prof_count;
         cudaEventRecord(h->ev[0], h->stream);
     }
-    const bool aligned = ((uintptr_t)d_imgs % 16 == 0) && (stride % 4 == 0) && (image_stride_bytes % 4 == 0);
+    const bool aligned = ((uintptr_t)d_imgs % 16 == 0) && (stride % 8 == 0) && (image_stride_bytes % 8 == 0);   // k_fast_cells_v2 stages with 64-bit loads
     uint8_t* own = h->d_pyr;  // level 0 block of the handle
     if (aligned) {
         L0.base = const_cast<uint8_t*>(d_imgs);
@@ -534,11 +576,11 @@ extern "C" orb_status orbx_counts(orbx_handle* h, int32_t* n, int32_t* mono_inde
         ORB_CUDA(cudaStreamSynchronize(h->stream));
         h->counts_valid = true;
         const int* e = h->h_counts + 3 * MB + 4;
-        if (e[0] || e[1]) {
-            cudaMemsetAsync(h->d_err, 0, sizeof(int) * 8, h->stream);
-            return set_error(ORB_ERR_CAPACITY, e[0] ? "FAST candidate capacity exceeded" : "quadtree node capacity exceeded");
-        }
+        h->batch_status = (e[0] || e[1]) ? (e[0] ? 1 : 2) : 0;   // latched until the next extract: every accessor keeps reporting it
+        if (h->batch_status) cudaMemsetAsync(h->d_err, 0, sizeof(int) * 8, h->stream);
     }
+    if (h->batch_status)
+        return set_error(ORB_ERR_CAPACITY, h->batch_status == 1 ? "FAST candidate capacity exceeded" : "quadtree node capacity exceeded");
     for (int b = 0; b < B; ++b) {
         if (n) n[b] = h->h_counts[b];
         if (mono_index) mono_index[b] = h->h_counts[MB + b];

@@ -8,6 +8,11 @@ struct orbx_handle {
     orbx_config cfg{};
     orb::ExtractGeom geom{};
     int cur_w = -1, cur_h = -1;
+    int fast_variant = 1; // 1 (default): k_fast_cells_v2; 0: the round-1 k_fast_cells (ORB_FAST_VARIANT=0 at orbx_create)
+    std::vector<uint2> cells_host;   // k_fast_cells_v2: one record per non-empty FAST cell
+    uint2* d_cells = nullptr;
+    size_t cells_slots = 0;
+    int fast_R = 0, fast_PW = 0, fast_LW = 0;
     int qt_variant = 1;   // 1 (default): k_quadtree_v1; 0: k_quadtree (ORB_QT_VARIANT=0 at orbx_create)
     cudaStream_t stream = nullptr;
     static const int kProfRing = 32;
@@ -47,6 +52,7 @@ struct orbx_handle {
     size_t cand_slots = 0, kp_slots = 0, sort_slots = 0, taps_slots = 0, out_rows = 0;
     int* h_counts = nullptr;       // pinned
     bool counts_valid = false;
+    int batch_status = 0;   // 0 ok; 1 FAST candidate overflow, 2 quadtree node overflow of the last batch (truncated results are never served)
     int last_batch = 0;
     // quadtree launch plan: up to 3 level groups with their own shared-memory size, run on parallel
     // streams (forked from / joined into `stream`)

@@ -665,3 +665,5 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_describe(const __grid_
 }
 
 }  // namespace orb
+
+#include "fast_cells_v2.cuh"

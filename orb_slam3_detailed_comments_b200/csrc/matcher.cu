@@ -1189,6 +1189,7 @@ extern "C" orb_status orbm_search_local_points(orbx_handle* h, const orbm_camera
     P.seqFlag = cur.take<int>(nf);
     ORB_CUDA(cudaMemsetAsync(P.seqFlag, 0, sizeof(int) * nf, h->stream));
     if (nq > 0 && (s = launch_proj(h, P, nf, maxq)) != ORB_OK) return s;
+    if (dev && nq == 0 && nmatches_out) ORB_CUDA(cudaMemsetAsync(nmatches_out, 0, sizeof(int) * nf, h->stream));   // no kernel ran: a consumer must not see the previous step's counts
     if (!dev) {
         if (nq > 0) ORB_CUDA(cudaMemcpyAsync(match_out, P.match, sizeof(int) * (size_t)nq, cudaMemcpyDeviceToHost, h->stream));
         if (nmatches_out && nq > 0) ORB_CUDA(cudaMemcpyAsync(nmatches_out, P.nmatches, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->stream));

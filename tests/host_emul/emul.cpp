@@ -27,6 +27,28 @@ uint32_t emul_fast_x2(const uint8_t* img, int w, int x, int y) {
     return fast_score_x2((uint32_t)c[0] | ((uint32_t)c[1] << 16), r);
 }
 
+// fast_score_raw_x2 (k_fast_cells_v2) against fast_score_x2 on n random centre / ring sets (extremes and planted arcs included):
+// returns the number of sets on which they differ.
+long emul_fast_raw_mismatch(uint32_t seed, long n) {
+    uint64_t s = seed * 6364136223846793005ull + 1442695040888963407ull;
+    auto rnd = [&]() { s = s * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(s >> 33); };
+    long bad = 0;
+    for (long it = 0; it < n; ++it) {
+        const int mode = rnd() % 4;
+        const uint32_t base = rnd() & 0xff, contrast = mode == 0 ? 255 : (mode == 1 ? 40 : 8);
+        auto px = [&]() {
+            if (mode == 3) return (uint32_t)((rnd() & 1) ? 255 : 0);
+            int v = (int)base + (int)(rnd() % (2 * contrast + 1)) - (int)contrast;
+            return (uint32_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+        };
+        uint32_t r[16];
+        const uint32_t c2 = px() | (px() << 16);
+        for (int k = 0; k < 16; ++k) r[k] = px() | (px() << 16);
+        if (fast_score_raw_x2(c2, r) != fast_score_x2(c2, r)) ++bad;
+    }
+    return bad;
+}
+
 float emul_atan2(float y, float x) { return fast_atan2_deg(y, x); }
 
 // FAST high-speed test vs the full score on random pixel pairs: returns the number of lanes where the score reaches T but

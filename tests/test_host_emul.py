@@ -66,6 +66,13 @@ def test_fast_score_x2_matches_oracle(emul):
     assert len(cands) > 0
 
 
+def test_fast_score_raw_form_equals_subtracted_form(emul):
+    """k_fast_cells_v2 scores from the raw ring values (max-of-min / min-of-max, centre subtracted once at the end)."""
+    emul.emul_fast_raw_mismatch.restype = C.c_long
+    emul.emul_fast_raw_mismatch.argtypes = [C.c_uint32, C.c_long]
+    assert emul.emul_fast_raw_mismatch(7, 2_000_000) == 0
+
+
 def test_atan2_matches_oracle(emul):
     rng = np.random.default_rng(1)
     for _ in range(20000):

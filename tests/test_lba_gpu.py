@@ -94,6 +94,16 @@ def test_batch_of_independent_problems(opt):
         _compare(g, _oracle(pr, 100.0), pr)
 
 
+def test_batch_of_mixed_sizes(opt):
+    """A batch whose largest problem keeps its reduced system in global memory (> 24 free keyframes) next to ones that keep it in shared
+    memory: the launch's shared-memory size must follow the largest SHARED-memory problem (lba.cu)."""
+    prs = [synth.lba_problem(n_kf=12, n_fixed=2, n_mp=500, seed=40), synth.lba_problem(n_kf=32, n_fixed=2, n_mp=900, seed=41),
+           synth.lba_problem(n_kf=20, n_fixed=2, n_mp=700, seed=42)]
+    gs = opt.LocalBundleAdjustmentBatch(prs, lambda_init=100.0)
+    for pr, g in zip(prs, gs):
+        _compare(g, _oracle(pr, 100.0), pr)
+
+
 def test_stop_flag_set_returns_input(opt):
     pr = synth.lba_problem(n_kf=6, n_fixed=1, n_mp=200, seed=9)
     flag = np.ones(1, np.int32)

@@ -1,7 +1,7 @@
-"""CPU tier: the machine code of every kernel that ran green on a B200 in round 1 is still what the library ships.
-profiles/r01_sass_fingerprints.json was taken (scripts/sass_fingerprint.py) from the build whose sources were last validated on the
-GPU box; kernels added afterwards without a device run (k_liba, k_quadtree_v1, k_hamming_knn2, k_stereo_match_v1) are listed as such and are opt-in at run time.
-An intentional kernel change must come with a GPU run and a refreshed fingerprint file."""
+"""CPU tier: the machine code the library ships is the machine code whose `pytest -m gpu` run was green on a B200.
+profiles/r02_sass_fingerprints.json is taken (scripts/sass_fingerprint.py) from the build that last passed the whole GPU tier
+(every kernel has had a device run since round 2: UNPROVEN is empty).  An intentional kernel change must come with a GPU run and a
+refreshed fingerprint file; an unintentional one (a shared header edit that changes another kernel's code) fails here first."""
 import importlib.util
 import json
 import os
@@ -10,7 +10,7 @@ import shutil
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-UNPROVEN = ("k_liba", "k_quadtree_v1", "k_hamming_knn2", "k_stereo_match_v1")
+UNPROVEN = ()
 
 
 @pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not available")
@@ -21,7 +21,7 @@ def test_validated_kernels_are_bit_identical():
     from orb_slam3_detailed_comments_b200 import _native as N
     N.build()
     now = mod.fingerprints()
-    ref = json.load(open(os.path.join(ROOT, "profiles", "r01_sass_fingerprints.json")))
+    ref = json.load(open(os.path.join(ROOT, "profiles", "r02_sass_fingerprints.json")))
     proven = {k: v for k, v in ref.items() if not any(u in k for u in UNPROVEN)}
     assert len(proven) >= 24
     for k, v in proven.items():
