@@ -102,6 +102,9 @@ orb_status orbx_download(orbx_handle* h, orbx_keypoint* kps, uint8_t* desc, int3
 orb_status orbx_level_size(const orbx_handle* h, int32_t level, int32_t* width, int32_t* height);
 orb_status orbx_download_level(orbx_handle* h, int32_t b, int32_t level, int32_t blurred, uint8_t* dst,
                                int32_t dst_stride);
+/* All n_levels of image b at once (what a host-side mvImagePyramid needs after operator()): dst[l] / dst_stride[l] per
+ * level, every copy queued on the handle's stream and ONE synchronisation at the end (orbx_download_level syncs per call). */
+orb_status orbx_download_pyramid(orbx_handle* h, int32_t b, int32_t blurred, uint8_t* const* dst, const int32_t* dst_stride);
 
 /* Stage outputs of the last batch, for stage-wise parity tests.
  * candidates: FAST keypoints entering DistributeOctTree (ORBextractor.cc:1159-1165), sorted in the
@@ -413,6 +416,9 @@ orb_status lba_create(int32_t device, lba_handle** out);
 void lba_destroy(lba_handle* h);
 /* stop_flag mirrors `bool* pbStopFlag` (polled between LM trials; may be NULL). */
 orb_status lba_solve(lba_handle* h, const lba_problem* in, lba_result* out, const volatile int32_t* stop_flag);
+/* The same with the reference's own flag type: stop_flag points at the one-byte C++ `bool` that LocalMapping::InterruptBA sets
+ * (Optimizer.h:59 `bool* pbStopFlag`). */
+orb_status lba_solve_bool(lba_handle* h, const lba_problem* in, lba_result* out, const volatile uint8_t* stop_flag);
 /* independent problems, one CTA each (sequence-sharded replay: one local BA per sequence) */
 orb_status lba_solve_batch(lba_handle* h, int32_t n_problems, const lba_problem* in, lba_result* out,
                            const volatile int32_t* stop_flag);

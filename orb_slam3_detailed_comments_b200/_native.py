@@ -157,6 +157,7 @@ SIGNATURES = {
     "orbx_download": (_I, [_VP, _VP, _VP, _I]),
     "orbx_level_size": (_I, [_VP, _I, _IP, _IP]),
     "orbx_download_level": (_I, [_VP, _I, _I, _I, _VP, _I]),
+    "orbx_download_pyramid": (_I, [_VP, _I, _I, _VP, _VP]),
     "orbx_download_candidates": (_I, [_VP, _I, _I, _VP, _I, _IP]),
     "orbx_download_level_keypoints": (_I, [_VP, _I, _I, _VP, _I, _IP]),
     "orbx_set_profiling": (_I, [_VP, _I]),
@@ -184,6 +185,7 @@ SIGNATURES = {
     "lba_create": (_I, [_I, C.POINTER(_VP)]),
     "lba_destroy": (None, [_VP]),
     "lba_solve": (_I, [_VP, C.POINTER(lba_problem), C.POINTER(lba_result), _VP]),
+    "lba_solve_bool": (_I, [_VP, C.POINTER(lba_problem), C.POINTER(lba_result), _VP]),
     "lba_solve_batch": (_I, [_VP, _I, C.POINTER(lba_problem), C.POINTER(lba_result), _VP]),
     "orbm_hamming_knn2": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "liba_create": (_I, [_I, C.POINTER(_VP)]),

@@ -635,6 +635,18 @@ extern "C" orb_status orbx_download_level(orbx_handle* h, int32_t b, int32_t lev
     return ORB_OK;
 }
 
+extern "C" orb_status orbx_download_pyramid(orbx_handle* h, int32_t b, int32_t blurred, uint8_t* const* dst, const int32_t* dst_stride) {
+    if (!h || !dst || !dst_stride || b < 0 || b >= h->last_batch) return set_error(ORB_ERR_INVALID, "bad batch index / null arrays");
+    for (int l = 0; l < h->cfg.n_levels; ++l) {
+        const LevelGeom& L = h->geom.lv[l];
+        if (!dst[l] || dst_stride[l] < L.w) return set_error(ORB_ERR_INVALID, "bad destination for a pyramid level");
+        const uint8_t* src = blurred ? L.blur + (int64_t)b * L.blur_stride : L.base + (int64_t)b * L.img_stride;
+        ORB_CUDA(cudaMemcpy2DAsync(dst[l], dst_stride[l], src, blurred ? L.blur_pitch : L.pitch, L.w, L.h, cudaMemcpyDeviceToHost, h->stream));
+    }
+    ORB_CUDA(cudaStreamSynchronize(h->stream));
+    return ORB_OK;
+}
+
 extern "C" orb_status orbx_download_candidates(orbx_handle* h, int32_t b, int32_t level, int32_t* xys, int32_t cap,
                                                int32_t* n_out) {
     if (!h || !n_out || level < 0 || level >= h->cfg.n_levels || b < 0 || b >= h->last_batch)

@@ -1,7 +1,7 @@
-// cvshim/opencv2/opencv.hpp -- a stand-in for the handful of OpenCV types that the reference's
-// include/ORBextractor.h mentions, so that host/ORBextractor_b200.cc can be COMPILE-CHECKED against the
-// reference's real header in an image without OpenCV (tests/test_host_shim.py).  A real integration uses the
-// real <opencv2/opencv.hpp>; nothing here is linked into liborbslam3_b200.so.
+// refshim/opencv2/opencv.hpp -- a stand-in for the handful of OpenCV types that the reference's include/ORBextractor.h,
+// ORBmatcher.h and the skeleton classes mention, so that the host translation units can be COMPILE-CHECKED against the
+// reference's real class declarations and their marshaling RUN (tests/host/) in an image without OpenCV C++.  A real
+// integration uses the real <opencv2/opencv.hpp>; nothing here is linked into liborbslam3_b200.so.
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -50,6 +50,10 @@ class Mat {
     bool isContinuous() const { return step == (size_t)cols; }
     uint8_t* ptr(int r = 0) { return data + (size_t)r * step; }
     const uint8_t* ptr(int r = 0) const { return data + (size_t)r * step; }
+    template <typename T> T* ptr(int r = 0) { return reinterpret_cast<T*>(data + (size_t)r * step); }
+    template <typename T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(data + (size_t)r * step); }
+    Mat row(int r) const { Mat m; m.rows = 1; m.cols = cols; m.step = step; m.data = data + (size_t)r * step; m.store_ = store_; return m; }
+    Mat clone() const { Mat m; if (!empty()) { m.create(rows, cols, 0); for (int r = 0; r < rows; ++r) std::memcpy(m.ptr(r), ptr(r), (size_t)cols); } return m; }
 
    private:
     std::shared_ptr<std::vector<uint8_t>> store_;

@@ -1,0 +1,169 @@
+// refshim/ref_skeleton.h -- SKELETONS of the reference's Frame / KeyFrame / MapPoint / Map classes for the compile check and the
+// marshaling tests of the host translation units (host/ORBmatcher_b200.cc, Frame_stereo_b200.cc, Optimizer_lba_b200.cc).
+//
+// The reference's own include/Frame.h, KeyFrame.h, MapPoint.h, Map.h pull in the whole system (Sophus, g2o, DBoW2, boost
+// serialization, Pangolin through Tracking.h); none of that exists in this image.  This header is pre-included (g++ -include) and
+// defines those headers' include guards, so that the reference's UNMODIFIED include/ORBmatcher.h and include/Optimizer.h -- the
+// class declarations our translation units implement -- are parsed against these skeletons instead.
+//
+// Every member between "//@ref <header>" and "//@end" is declared EXACTLY as in that reference header; tests/test_host_shim.py
+// checks each such line against the header's text.  Only members our translation units touch are listed.  Bodies (a mock map for
+// tests/host/) are in ref_skeleton_impl.h.  A real integration does not use this file: it compiles the same translation units
+// against the real headers.
+#pragma once
+#define FRAME_H
+#define KEYFRAME_H
+#define MAPPOINT_H
+#define MAP_H
+#define LOOPCLOSING_H
+
+#include <list>
+#include <map>
+#include <mutex>
+#include <set>
+#include <tuple>
+#include <vector>
+
+#include "Eigen/Core"
+#include "opencv2/opencv.hpp"
+#include "sophus/se3.hpp"
+#include "sophus/sim3.hpp"
+#include "ORBextractor.h"   // the reference's own header (it needs nothing but <opencv2/opencv.hpp>)
+
+namespace g2o { class Sim3; }
+
+using namespace std;   // the reference headers rely on it (ORBmatcher.h:64 `vector<pair<size_t, size_t> >`, Optimizer.h:64 `map<...>`)
+
+namespace ORB_SLAM3 {
+
+class KeyFrame;
+class MapPoint;
+class Map;
+class Frame;
+class GeometricCamera;
+
+class LoopClosing {
+   public:
+    typedef std::map<KeyFrame*, g2o::Sim3*> KeyFrameAndPose;   // placeholder: Optimizer.h names the type in signatures we do not implement
+};
+
+class Map {
+   public:
+//@ref Map.h
+    long unsigned int GetInitKFid();
+    void IncreaseChangeIndex();
+    bool IsInertial();
+    std::mutex mMutexMapUpdate;
+    std::set<long unsigned int> msOptKFs;
+    std::set<long unsigned int> msFixedKFs;
+//@end
+    // mock state (tests/host only)
+    long unsigned int mock_init_kf_id = 0;
+    bool mock_inertial = false;
+    int mock_change_index = 0;
+};
+
+class MapPoint {
+   public:
+//@ref MapPoint.h
+    void SetWorldPos(const Eigen::Vector3f &Pos);
+    Eigen::Vector3f GetWorldPos();
+    Eigen::Vector3f GetNormal();
+    std::map<KeyFrame*,std::tuple<int,int>> GetObservations();
+    int Observations();
+    void EraseObservation(KeyFrame* pKF, bool erase = true);
+    bool isBad();
+    cv::Mat GetDescriptor();
+    void UpdateNormalAndDepth();
+    Map* GetMap();
+    long unsigned int mnId;
+    float mTrackProjX;
+    float mTrackProjY;
+    float mTrackDepth;
+    float mTrackProjXR;
+    bool mbTrackInView, mbTrackInViewR;
+    int mnTrackScaleLevel, mnTrackScaleLevelR;
+    float mTrackViewCos, mTrackViewCosR;
+    long unsigned int mnBALocalForKF;
+//@end
+    // mock state (tests/host only)
+    Eigen::Vector3f mock_pos, mock_normal;
+    std::map<KeyFrame*, std::tuple<int, int>> mock_obs;
+    cv::Mat mock_desc;
+    Map* mock_map = nullptr;
+    bool mock_bad = false;
+    int mock_normal_updates = 0;
+    MapPoint() : mnId(0), mTrackProjX(0), mTrackProjY(0), mTrackDepth(0), mTrackProjXR(0), mbTrackInView(false), mbTrackInViewR(false),
+                 mnTrackScaleLevel(0), mnTrackScaleLevelR(0), mTrackViewCos(0), mTrackViewCosR(0), mnBALocalForKF(0) {}
+};
+
+class KeyFrame {
+   public:
+//@ref KeyFrame.h
+    void SetPose(const Sophus::SE3f &Tcw);
+    Sophus::SE3f GetPose();
+    std::vector<KeyFrame* > GetVectorCovisibleKeyFrames();
+    void EraseMapPointMatch(MapPoint* pMP);
+    std::vector<MapPoint*> GetMapPointMatches();
+    bool isBad();
+    Map* GetMap();
+    long unsigned int mnId;
+    long unsigned int mnBALocalForKF;
+    long unsigned int mnBAFixedForKF;
+    const float fx, fy, cx, cy, invfx, invfy, mbf, mb, mThDepth;
+    const std::vector<cv::KeyPoint> mvKeys;
+    const std::vector<cv::KeyPoint> mvKeysUn;
+    const std::vector<float> mvuRight; // negative value for monocular points
+    const cv::Mat mDescriptors;
+    const std::vector<float> mvInvLevelSigma2;
+    GeometricCamera* mpCamera, *mpCamera2;
+    const int NLeft, NRight;
+//@end
+    // mock state (tests/host only)
+    Sophus::SE3f mock_Tcw;
+    std::vector<KeyFrame*> mock_covisible;
+    std::vector<MapPoint*> mock_matches;
+    Map* mock_map = nullptr;
+    bool mock_bad = false;
+    int mock_pose_sets = 0;
+    KeyFrame(long unsigned int id, float fx_, float fy_, float cx_, float cy_, float bf_, float b_, const std::vector<cv::KeyPoint>& keysUn,
+             const std::vector<float>& uRight, const std::vector<float>& invSigma2)
+        : mnId(id), mnBALocalForKF(0), mnBAFixedForKF(0), fx(fx_), fy(fy_), cx(cx_), cy(cy_), invfx(1.f / fx_), invfy(1.f / fy_), mbf(bf_),
+          mb(b_), mThDepth(0), mvKeys(keysUn), mvKeysUn(keysUn), mvuRight(uRight), mDescriptors(), mvInvLevelSigma2(invSigma2),
+          mpCamera(nullptr), mpCamera2(nullptr), NLeft(-1), NRight(-1) {}
+};
+
+class Frame {
+   public:
+//@ref Frame.h
+    void ComputeStereoMatches();
+    inline Sophus::SE3<float> GetPose() const {
+        return mTcw;
+    }
+    ORBextractor* mpORBextractorLeft, *mpORBextractorRight;
+    static float fx;
+    static float fy;
+    static float cx;
+    static float cy;
+    float mbf;
+    float mb;
+    int N;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysRight;
+    std::vector<cv::KeyPoint> mvKeysUn;
+    std::vector<MapPoint*> mvpMapPoints;
+    std::vector<float> mvuRight;
+    std::vector<float> mvDepth;
+    cv::Mat mDescriptors, mDescriptorsRight;
+    std::vector<bool> mvbOutlier;
+    static float mnMinX;
+    static float mnMaxX;
+    static float mnMinY;
+    static float mnMaxY;
+    GeometricCamera* mpCamera, *mpCamera2;
+    int Nleft, Nright;
+    Sophus::SE3<float> mTcw;
+//@end
+    Frame() : mpORBextractorLeft(nullptr), mpORBextractorRight(nullptr), mbf(0), mb(0), N(0), mpCamera(nullptr), mpCamera2(nullptr), Nleft(-1), Nright(-1) {}
+};
+
+}  // namespace ORB_SLAM3

@@ -1,0 +1,36 @@
+// refshim/ref_skeleton_impl.h -- bodies of the skeleton classes: a minimal in-memory map for the marshaling tests (tests/host/).
+// Include in exactly one translation unit of a test binary.
+#pragma once
+#include "ref_skeleton.h"
+
+namespace ORB_SLAM3 {
+
+float Frame::fx = 0, Frame::fy = 0, Frame::cx = 0, Frame::cy = 0, Frame::mnMinX = 0, Frame::mnMaxX = 0, Frame::mnMinY = 0, Frame::mnMaxY = 0;
+
+long unsigned int Map::GetInitKFid() { return mock_init_kf_id; }
+void Map::IncreaseChangeIndex() { ++mock_change_index; }
+bool Map::IsInertial() { return mock_inertial; }
+
+void MapPoint::SetWorldPos(const Eigen::Vector3f& Pos) { mock_pos = Pos; }
+Eigen::Vector3f MapPoint::GetWorldPos() { return mock_pos; }
+Eigen::Vector3f MapPoint::GetNormal() { return mock_normal; }
+std::map<KeyFrame*, std::tuple<int, int>> MapPoint::GetObservations() { return mock_obs; }
+int MapPoint::Observations() { return (int)mock_obs.size(); }
+void MapPoint::EraseObservation(KeyFrame* pKF, bool) { mock_obs.erase(pKF); }
+bool MapPoint::isBad() { return mock_bad; }
+cv::Mat MapPoint::GetDescriptor() { return mock_desc; }
+void MapPoint::UpdateNormalAndDepth() { ++mock_normal_updates; }
+Map* MapPoint::GetMap() { return mock_map; }
+
+void KeyFrame::SetPose(const Sophus::SE3f& Tcw) { mock_Tcw = Tcw; ++mock_pose_sets; }
+Sophus::SE3f KeyFrame::GetPose() { return mock_Tcw; }
+std::vector<KeyFrame*> KeyFrame::GetVectorCovisibleKeyFrames() { return mock_covisible; }
+void KeyFrame::EraseMapPointMatch(MapPoint* pMP) {
+    for (auto& m : mock_matches)
+        if (m == pMP) m = nullptr;
+}
+std::vector<MapPoint*> KeyFrame::GetMapPointMatches() { return mock_matches; }
+bool KeyFrame::isBad() { return mock_bad; }
+Map* KeyFrame::GetMap() { return mock_map; }
+
+}  // namespace ORB_SLAM3

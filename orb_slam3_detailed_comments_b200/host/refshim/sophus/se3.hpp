@@ -1,0 +1,40 @@
+// refshim/sophus/se3.hpp -- stand-in for Sophus::SE3<T> (Thirdparty/Sophus/sophus/se3.hpp): the members the host translation
+// units call, over refshim/Eigen.  Compile-check / marshaling tests only; a real integration uses the vendored Sophus.
+#pragma once
+#include "Eigen/Core"
+
+namespace Sophus {
+
+template <typename T>
+class SE3 {
+   public:
+    SE3() {}
+    SE3(const Eigen::Quaternion<T>& q, const Eigen::Matrix<T, 3, 1>& t) : q_(q), t_(t) { q_.normalize(); }   // SO3(quat) normalises
+    const Eigen::Quaternion<T>& unit_quaternion() const { return q_; }
+    const Eigen::Matrix<T, 3, 1>& translation() const { return t_; }
+    Eigen::Matrix<T, 3, 1>& translation() { return t_; }
+    Eigen::Matrix<T, 3, 3> rotationMatrix() const { return q_.toRotationMatrix(); }
+    SE3 inverse() const {
+        SE3 o;
+        o.q_ = q_.conjugate();
+        o.t_ = -(o.q_.toRotationMatrix() * t_);
+        return o;
+    }
+    Eigen::Matrix<T, 3, 1> operator*(const Eigen::Matrix<T, 3, 1>& p) const { return q_.toRotationMatrix() * p + t_; }
+    SE3 operator*(const SE3& b) const {
+        SE3 o;
+        o.q_ = q_ * b.q_;
+        o.t_ = q_.toRotationMatrix() * b.t_ + t_;
+        return o;
+    }
+    template <typename U>
+    SE3<U> cast() const { SE3<U> o(q_.template cast<U>(), t_.template cast<U>()); return o; }
+
+   private:
+    Eigen::Quaternion<T> q_;
+    Eigen::Matrix<T, 3, 1> t_;
+};
+typedef SE3<float> SE3f;
+typedef SE3<double> SE3d;
+
+}  // namespace Sophus
