@@ -122,6 +122,18 @@ orb_status orbx_set_profiling(orbx_handle* h, int32_t on);
 orb_status orbx_last_timings(orbx_handle* h, float* ms7);
 /* the handle's cudaStream_t (for CUDA-event timing on the launching stream) */
 void* orbx_cuda_stream(orbx_handle* h);
+
+/* CUDA-graph replay of a step.  Everything the caller queues on the handle's stream between begin and end -- the device-pointer
+ * entry points: orbx_extract_batch_device, orbm_stereo_batch, the on_device searches under orbm_set_device_query_bounds,
+ * orbo_pose_* with on_device -- is captured instead of executed; orbx_graph_launch replays it with one launch.  Captured calls
+ * must not synchronise or allocate: run the same step once eagerly first (it sizes every scratch buffer).  Pointers are baked
+ * in: a replay reads the same input buffers and writes the same outputs, with whatever contents they hold then. */
+typedef struct orbx_graph orbx_graph;
+orb_status orbx_graph_begin(orbx_handle* h);
+orb_status orbx_graph_end(orbx_handle* h, orbx_graph** out);
+orb_status orbx_graph_launch(orbx_handle* h, orbx_graph* g);
+int32_t orbx_graph_kernels(const orbx_graph* g);   /* kernel nodes per replay */
+void orbx_graph_destroy(orbx_graph* g);
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t orb_kernel_launches(void);
 
@@ -153,6 +165,13 @@ typedef struct {
     float fx, fy, cx, cy, bf, b;          /* Frame::fx.., mbf, mb */
     float min_x, max_x, min_y, max_y;     /* Frame::mnMinX, mnMaxX, mnMinY, mnMaxY (image bounds when rectified) */
 } orbm_camera;
+
+/* Device-pointer searches (on_device != 0) normally read the two small offset tables and the batch's row count back to size
+ * their launches -- two synchronisations per call.  With bounds set (> 0) they read nothing back: total_queries bounds
+ * query_offset[n_frames], max_queries_per_frame every frame's query count, total_rows the batch's compact keypoint rows (the
+ * length of the caller's per-row output arrays; clamped to max_batch * orbx_max_features).  The kernels take the real counts from the device tables, so
+ * results are unchanged; the calls become pure kernel launches (capturable, orbx_graph_begin).  0, 0, 0 restores the default. */
+orb_status orbm_set_device_query_bounds(orbx_handle* h, int32_t total_queries, int32_t max_queries_per_frame, int32_t total_rows);
 
 /* SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints)  ORBmatcher.cc:45-239.
  * One entry per map point with mbTrackInView, in vpMapPoints order, carrying the fields Frame::isInFrustum

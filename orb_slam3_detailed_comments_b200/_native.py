@@ -158,6 +158,12 @@ SIGNATURES = {
     "orbx_level_size": (_I, [_VP, _I, _IP, _IP]),
     "orbx_download_level": (_I, [_VP, _I, _I, _I, _VP, _I]),
     "orbx_download_pyramid": (_I, [_VP, _I, _I, _VP, _VP]),
+    "orbx_graph_begin": (_I, [_VP]),
+    "orbx_graph_end": (_I, [_VP, C.POINTER(C.c_void_p)]),
+    "orbx_graph_launch": (_I, [_VP, _VP]),
+    "orbx_graph_kernels": (_I, [_VP]),
+    "orbx_graph_destroy": (None, [_VP]),
+    "orbm_set_device_query_bounds": (_I, [_VP, _I, _I, _I]),
     "orbx_download_candidates": (_I, [_VP, _I, _I, _VP, _I, _IP]),
     "orbx_download_level_keypoints": (_I, [_VP, _I, _I, _VP, _I, _IP]),
     "orbx_set_profiling": (_I, [_VP, _I]),

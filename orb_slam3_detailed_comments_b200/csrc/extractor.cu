@@ -635,6 +635,67 @@ extern "C" orb_status orbx_download_level(orbx_handle* h, int32_t b, int32_t lev
     return ORB_OK;
 }
 
+// ---- CUDA-graph capture of whatever the caller queues on the handle's stream between begin and end ----------------------
+struct orbx_graph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int kernels = 0;
+};
+
+extern "C" orb_status orbx_graph_begin(orbx_handle* h) {
+    if (!h || h->capturing) return set_error(ORB_ERR_INVALID, "null handle or capture already open");
+    ORB_CUDA(cudaSetDevice(h->cfg.device));
+    if (h->profiling) return set_error(ORB_ERR_INVALID, "switch profiling off before capturing");
+    ORB_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    h->capturing = true;
+    return ORB_OK;
+}
+
+extern "C" orb_status orbx_graph_end(orbx_handle* h, orbx_graph** out) {
+    if (!h || !out || !h->capturing) return set_error(ORB_ERR_INVALID, "no capture is open on this handle");
+    h->capturing = false;
+    orbx_graph* g = new orbx_graph();
+    cudaError_t e = cudaStreamEndCapture(h->stream, &g->graph);
+    if (e != cudaSuccess || !g->graph) {
+        delete g;
+        cudaGetLastError();
+        return set_error(ORB_ERR_CUDA, "cudaStreamEndCapture failed (a captured call synchronised or allocated)");
+    }
+    size_t n = 0;
+    cudaGraphGetNodes(g->graph, nullptr, &n);
+    std::vector<cudaGraphNode_t> nodes(n);
+    if (n) cudaGraphGetNodes(g->graph, nodes.data(), &n);
+    for (size_t i = 0; i < n; ++i) {
+        cudaGraphNodeType t;
+        if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) ++g->kernels;
+    }
+    e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+    if (e != cudaSuccess) {
+        cudaGraphDestroy(g->graph);
+        delete g;
+        return set_error(ORB_ERR_CUDA, "cudaGraphInstantiate failed");
+    }
+    *out = g;
+    return ORB_OK;
+}
+
+extern "C" orb_status orbx_graph_launch(orbx_handle* h, orbx_graph* g) {
+    if (!h || !g || !g->exec) return set_error(ORB_ERR_INVALID, "null handle or graph");
+    ORB_CUDA(cudaGraphLaunch(g->exec, h->stream));
+    g_launches += g->kernels;
+    h->counts_valid = false;    // a replay produces new results
+    return ORB_OK;
+}
+
+extern "C" int32_t orbx_graph_kernels(const orbx_graph* g) { return g ? g->kernels : 0; }
+
+extern "C" void orbx_graph_destroy(orbx_graph* g) {
+    if (!g) return;
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+}
+
 extern "C" orb_status orbx_download_pyramid(orbx_handle* h, int32_t b, int32_t blurred, uint8_t* const* dst, const int32_t* dst_stride) {
     if (!h || !dst || !dst_stride || b < 0 || b >= h->last_batch) return set_error(ORB_ERR_INVALID, "bad batch index / null arrays");
     for (int l = 0; l < h->cfg.n_levels; ++l) {

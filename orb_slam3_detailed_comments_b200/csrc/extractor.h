@@ -52,6 +52,8 @@ struct orbx_handle {
     size_t cand_slots = 0, kp_slots = 0, sort_slots = 0, taps_slots = 0, out_rows = 0;
     int* h_counts = nullptr;       // pinned
     bool counts_valid = false;
+    int q_total_bound = 0, q_frame_bound = 0, rows_bound = 0;   // orbm_set_device_query_bounds: sync-free device-pointer searches
+    bool capturing = false;   // between orbx_graph_begin and orbx_graph_end
     int batch_status = 0;   // 0 ok; 1 FAST candidate overflow, 2 quadtree node overflow of the last batch (truncated results are never served)
     int last_batch = 0;
     // quadtree launch plan: up to 3 level groups with their own shared-memory size, run on parallel

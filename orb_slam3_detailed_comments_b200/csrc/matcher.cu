@@ -1054,6 +1054,7 @@ __global__ void __launch_bounds__(256) k_in_frustum(const __grid_constant__ Frus
 // ------------------------------------------------------------------------------------------------
 static orb_status ensure_stage(orbx_handle* h, size_t bytes) {
     if (bytes <= h->stage_bytes) return ORB_OK;
+    if (h->capturing) return set_error(ORB_ERR_INVALID, "scratch must be sized by one eager call with the same bounds before a graph capture");
     if (h->d_stage) cudaFree(h->d_stage);
     h->d_stage = nullptr;
     h->stage_bytes = 0;
@@ -1130,19 +1131,34 @@ static orb_status upload(orbx_handle* h, T*& dst, const T* src, size_t n, StageC
     return ORB_OK;
 }
 
+extern "C" orb_status orbm_set_device_query_bounds(orbx_handle* h, int32_t total_queries, int32_t max_queries_per_frame, int32_t total_rows) {
+    if (!h || total_queries < 0 || max_queries_per_frame < 0 || total_rows < 0) return set_error(ORB_ERR_INVALID, "bad bounds");
+    h->q_total_bound = total_queries; h->q_frame_bound = max_queries_per_frame;
+    h->rows_bound = std::min(total_rows, (int)h->out_rows);   // a batch never has more rows than the handle's result capacity
+    return ORB_OK;
+}
+
 extern "C" orb_status orbm_search_local_points(orbx_handle* h, const orbm_camera* cam, const orbm_local_queries* Q,
                                                float th, float nnratio, int32_t far_points, float th_far,
                                                int32_t* match_out, int32_t* nmatches_out) {
     if (!h || !cam || !Q || !match_out || Q->n_frames < 1 || !Q->frame_image || !Q->query_offset)
         return set_error(ORB_ERR_INVALID, "bad arguments");
     ORB_CUDA(cudaSetDevice(h->cfg.device));
-    orb_status s = orbx_counts(h, nullptr, nullptr, nullptr);   // total compact rows of the batch
-    if (s != ORB_OK) return s;
-    const size_t rows = (size_t)h->h_counts[2 * h->cfg.max_batch + h->last_batch];
     const bool dev = Q->on_device != 0;
+    const bool bounded = dev && h->q_total_bound > 0;   // orbm_set_device_query_bounds: nothing is read back, no synchronisation
+    orb_status s = ORB_OK;
+    size_t rows = (size_t)(h->rows_bound > 0 ? h->rows_bound : (int)h->out_rows);
+    if (!bounded) {
+        s = orbx_counts(h, nullptr, nullptr, nullptr);   // total compact rows of the batch
+        if (s != ORB_OK) return s;
+        rows = (size_t)h->h_counts[2 * h->cfg.max_batch + h->last_batch];
+    }
     const int nf = Q->n_frames;
     std::vector<int> qoff_h(nf + 1), fimg_h(nf);
-    if (dev) {
+    if (bounded) {
+        for (int f = 0; f <= nf; ++f) qoff_h[f] = 0;
+        for (int f = 0; f < nf; ++f) fimg_h[f] = 0;
+    } else if (dev) {
         ORB_CUDA(cudaMemcpyAsync(qoff_h.data(), Q->query_offset, sizeof(int) * (nf + 1), cudaMemcpyDeviceToHost, h->stream));
         ORB_CUDA(cudaMemcpyAsync(fimg_h.data(), Q->frame_image, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->stream));
         ORB_CUDA(cudaStreamSynchronize(h->stream));
@@ -1150,12 +1166,13 @@ extern "C" orb_status orbm_search_local_points(orbx_handle* h, const orbm_camera
         std::copy(Q->query_offset, Q->query_offset + nf + 1, qoff_h.begin());
         std::copy(Q->frame_image, Q->frame_image + nf, fimg_h.begin());
     }
-    const int nq = qoff_h[nf];
+    int nq = qoff_h[nf];
     int maxq = 0;
     for (int f = 0; f < nf; ++f) {
         maxq = std::max(maxq, qoff_h[f + 1] - qoff_h[f]);
         if (fimg_h[f] < 0 || fimg_h[f] >= h->last_batch || qoff_h[f + 1] < qoff_h[f]) return set_error(ORB_ERR_INVALID, "bad frame table");
     }
+    if (bounded) { nq = h->q_total_bound; maxq = h->q_frame_bound; }   // upper bounds: the kernels take the real counts from the device tables
     const size_t need = (size_t)nq * (PM_K * 8 + 4 + 4 * 6 + 32 + 8) + rows + (size_t)nf * (16 + 2 * (size_t)h->geom.kpTotal + 2 * 3073 + 512) + 65536;
     if ((s = ensure_stage(h, need)) != ORB_OK) return s;
     StageCursor cur{h->d_stage};
@@ -1205,13 +1222,21 @@ extern "C" orb_status orbm_search_last_frame(orbx_handle* h, const orbm_camera* 
         !Q->direction)
         return set_error(ORB_ERR_INVALID, "bad arguments");
     ORB_CUDA(cudaSetDevice(h->cfg.device));
-    orb_status s = orbx_counts(h, nullptr, nullptr, nullptr);   // total compact rows of the batch
-    if (s != ORB_OK) return s;
-    const int total_rows = h->h_counts[2 * h->cfg.max_batch + h->last_batch];
     const bool dev = Q->on_device != 0;
+    const bool bounded = dev && h->q_total_bound > 0;   // orbm_set_device_query_bounds: nothing is read back, no synchronisation
+    orb_status s = ORB_OK;
+    int total_rows = h->rows_bound > 0 ? h->rows_bound : (int)h->out_rows;
+    if (!bounded) {
+        s = orbx_counts(h, nullptr, nullptr, nullptr);   // total compact rows of the batch
+        if (s != ORB_OK) return s;
+        total_rows = h->h_counts[2 * h->cfg.max_batch + h->last_batch];
+    }
     const int nf = Q->n_frames;
     std::vector<int> qoff_h(nf + 1), fimg_h(nf);
-    if (dev) {
+    if (bounded) {
+        for (int f = 0; f <= nf; ++f) qoff_h[f] = 0;
+        for (int f = 0; f < nf; ++f) fimg_h[f] = 0;
+    } else if (dev) {
         ORB_CUDA(cudaMemcpyAsync(qoff_h.data(), Q->query_offset, sizeof(int) * (nf + 1), cudaMemcpyDeviceToHost, h->stream));
         ORB_CUDA(cudaMemcpyAsync(fimg_h.data(), Q->frame_image, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->stream));
         ORB_CUDA(cudaStreamSynchronize(h->stream));
@@ -1219,12 +1244,13 @@ extern "C" orb_status orbm_search_last_frame(orbx_handle* h, const orbm_camera* 
         std::copy(Q->query_offset, Q->query_offset + nf + 1, qoff_h.begin());
         std::copy(Q->frame_image, Q->frame_image + nf, fimg_h.begin());
     }
-    const int nq = qoff_h[nf];
+    int nq = qoff_h[nf];
     int maxq = 0;
     for (int f = 0; f < nf; ++f) {
         maxq = std::max(maxq, qoff_h[f + 1] - qoff_h[f]);
         if (fimg_h[f] < 0 || fimg_h[f] >= h->last_batch || qoff_h[f + 1] < qoff_h[f]) return set_error(ORB_ERR_INVALID, "bad frame table");
     }
+    if (bounded) { nq = h->q_total_bound; maxq = h->q_frame_bound; }
     const size_t need = (size_t)nq * (PM_K * 8 + 4 + 4 + 12 + 4 + 4 + 32 + 1 + 16) + (size_t)total_rows * 4 + (size_t)nf * (64 + 2 * (size_t)h->geom.kpTotal + 2 * 3073 + 512) + 65536;
     if ((s = ensure_stage(h, need)) != ORB_OK) return s;
     StageCursor cur{h->d_stage};

@@ -173,6 +173,32 @@ class ORBextractor:
     def cuda_stream(self):
         return self._L.orbx_cuda_stream(self._h)
 
+    # ---- CUDA-graph replay (include/orbslam3_b200.h: orbx_graph_*) ----
+    def set_device_query_bounds(self, total_queries, max_queries_per_frame, total_rows):
+        """Bounds for the device-pointer searches: with them set they read nothing back and do not synchronise."""
+        N.check(self._L.orbm_set_device_query_bounds(self._h, int(total_queries), int(max_queries_per_frame), int(total_rows)))
+
+    def graph_capture(self, step):
+        """Runs step() -- device-pointer entry points on this handle only -- under stream capture; returns an opaque graph.
+        The same step must have run once eagerly before (it sizes the scratch buffers)."""
+        N.check(self._L.orbx_graph_begin(self._h))
+        try:
+            step()
+        finally:
+            g = C.c_void_p()
+            status = self._L.orbx_graph_end(self._h, C.byref(g))
+        N.check(status)
+        return g
+
+    def graph_launch(self, g):
+        N.check(self._L.orbx_graph_launch(self._h, g))
+
+    def graph_kernels(self, g):
+        return int(self._L.orbx_graph_kernels(g))
+
+    def graph_destroy(self, g):
+        self._L.orbx_graph_destroy(g)
+
     def set_profiling(self, on=True):
         N.check(self._L.orbx_set_profiling(self._h, 1 if on else 0))
 
