@@ -393,7 +393,7 @@ orb_status orbm_search_triangulation(orbx_handle* h, const orbm_triangulation* t
  * idx_out / dist_out: [query rows][2] = trainIdx / distance of the nearest and second nearest train row of the SAME pair, ascending
  * distance, ties by ascending trainIdx (OpenCV's order); -1 where the train set has fewer than 1 / 2 rows (knnMatch then returns a
  * shorter list).  The caller applies the reference's ratio test `m[0].distance < m[1].distance * 0.7` (Frame.cc:1560).
- * STATUS: CPU oracle pinned against cv2; the kernel has not had a device run yet (tests opt-in with ORB_FIRST_CONTACT=1).
+ * Oracle pinned against cv2's BFMatcher; GPU parity in tests/test_zz_knn_gpu.py.
  * ---------------------------------------------------------------------------------------------- */
 orb_status orbm_hamming_knn2(orbx_handle* h, int32_t n_pairs, const int32_t* query_offset, const uint8_t* query_desc,
                              const int32_t* train_offset, const uint8_t* train_desc, int32_t* idx_out, int32_t* dist_out);
@@ -613,6 +613,68 @@ orb_status liba_solve(liba_handle* h, int32_t n_problems, const liba_problem* in
  * and Optimizer.cc:2486-2494 (inverses of C.block<3,3>(9,9) and (12,12)) compute them; oldest != 0 applies the 1e-2 of
  * Optimizer.cc:2477-2478 (i == N - 1). */
 orb_status liba_link_information(const float* C15x15, int32_t oldest, double* info81, double* infoG9, double* infoA9);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched sequence replay: the tracking-thread step of n_frames stereo frames, HOST buffers in, HOST buffers out.
+ *
+ * What Tracking does per frame -- Frame::Frame (both eyes through ORBextractor::operator(), Frame.cc:136-141, and
+ * ComputeStereoMatches, Frame.cc:1102), TrackWithMotionModel (ORBmatcher::SearchByProjection(cur, last) then
+ * Optimizer::PoseOptimization, Tracking.cc:3389-3443), TrackLocalMap (SearchByProjection(F, local map points) then
+ * PoseOptimization, Tracking.cc:4052, 3522) -- queued for a batch of frames (one per replayed sequence) on the handle's
+ * stream.  orbr_submit copies the images and the query arrays in, queues every kernel and returns without waiting;
+ * orbr_collect waits for the batch's count tables, copies back exactly the rows it produced and waits once more.  Pinned
+ * host memory makes the copies asynchronous; a host thread that keeps several handles in flight (submit on handles
+ * k+1 .. k+H-1 before collecting handle k) overlaps uploads, kernels and downloads without further threads.
+ * One step per handle may be in flight.  Images: 2 * n_frames, left eye of frame p = image 2p, right eye = image 2p + 1.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n_frames;
+    const uint8_t* images;               /* HOST: 2 * n_frames images */
+    int32_t width, height, stride;       /* stride in bytes between rows */
+    size_t image_stride_bytes;           /* between consecutive images */
+    float bf, b;                         /* Frame::mbf, Frame::mb */
+    const orbm_last_queries* last;       /* HOST arrays (on_device is ignored); NULL = no motion-model search */
+    float th_last;
+    int32_t check_orientation_last;      /* ORBmatcher::mbCheckOrientation */
+    const orbm_local_queries* local;     /* HOST arrays; feature_claimed must be NULL; NULL = no local-map search */
+    float th_local, nnratio_local;
+    int32_t far_points;
+    float th_far;
+    int32_t pose_optimization;           /* != 0: Optimizer::PoseOptimization after each search */
+    const float* pose;                   /* [n_frames][7] pFrame->GetPose() on entry of PoseOptimization (with pose_optimization) */
+    const float* local_world_pos;        /* [nq_local][3] GetWorldPos() of the local-map entries (with pose_optimization) */
+} orbr_step;
+
+typedef struct {                         /* HOST result buffers; any pointer may be NULL (that result is not copied back) */
+    int32_t cap_rows;                    /* capacity, in rows, of every per-row / per-edge array below */
+    orbx_keypoint* keypoints;            /* compact rows of the whole batch, image after image (mvKeys) */
+    uint8_t* descriptors;                /* [rows][32] (mDescriptors) */
+    float* uright;                       /* [rows] mvuRight (left-eye rows) */
+    float* depth;                        /* [rows] mvDepth */
+    int32_t* n;                          /* [2 n_frames] keypoints per image */
+    int32_t* offsets;                    /* [2 n_frames + 1] first row of every image */
+    int32_t* last_feature_match;         /* [rows] as orbm_search_last_frame */
+    int32_t* last_nmatches;              /* [n_frames] */
+    int32_t* local_match;                /* [nq_local] as orbm_search_local_points */
+    int32_t* local_nmatches;             /* [n_frames] */
+    /* PoseOptimization after the motion-model search [0] and after the local-map search [1] */
+    double* pose[2];                     /* [n_frames][7] */
+    int32_t* inliers[2];                 /* [n_frames] */
+    int32_t* edge_offset[2];             /* [n_frames + 1] */
+    int32_t* edge_feature[2];            /* [edges] feature index inside its frame */
+    uint8_t* edge_outlier[2];            /* [edges] pFrame->mvbOutlier of that feature */
+} orbr_results;
+
+orb_status orbr_submit(orbx_handle* h, const orbm_camera* cam, const orbr_step* step);
+orb_status orbr_collect(orbx_handle* h, const orbr_results* out, int32_t* total_rows_out);
+
+/* Keyframe state of image `image` of the last batch (the pose the caller passes, mvKeysUn positions and octaves, mvuRight,
+ * mDescriptors: what KeyFrame::KeyFrame(Frame&) keeps, KeyFrame.cc:45-90) as ONE block in device memory:
+ * [int32 n][7 x f32 pose][n x (x, y) f32][n x int32 octave][n x f32 uright][n x 32 B descriptors], at most
+ * orbx_keyframe_block_bytes(h) bytes.  Replicas that share a map all-gather these fixed-capacity blocks (NCCL) when a rank
+ * inserts a keyframe.  d_pose7 and d_block (16-byte aligned) are device memory; no synchronisation. */
+size_t orbx_keyframe_block_bytes(const orbx_handle* h);
+orb_status orbx_pack_keyframe_device(orbx_handle* h, int32_t image, const float* d_pose7, uint8_t* d_block, size_t block_bytes);
 
 #ifdef __cplusplus
 }

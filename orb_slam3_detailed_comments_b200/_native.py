@@ -12,7 +12,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "lib", "liborbslam3_b200.so")
-SOURCES = ["extractor.cu", "stereo.cu", "matcher.cu", "triangulation.cu", "lba.cu", "poseopt.cu", "bow.cu", "mappoint.cu", "liba.cu", "knn.cu"]
+SOURCES = ["extractor.cu", "stereo.cu", "matcher.cu", "triangulation.cu", "lba.cu", "poseopt.cu", "bow.cu", "mappoint.cu", "liba.cu", "knn.cu", "replay.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -84,6 +84,20 @@ class orbo_edge_source(C.Structure):
 class orbo_frame_matches(C.Structure):
     _fields_ = [("n_frames", C.c_int32)] + [(n, C.c_void_p) for n in ("frame_image", "pose", "feature_match", "query_offset", "query_match", "world_pos")] + \
         [("n_queries", C.c_int32)] + [(n, C.c_float) for n in ("fx", "fy", "cx", "cy", "bf")]
+
+
+class orbr_step(C.Structure):
+    _fields_ = [("n_frames", C.c_int32), ("images", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("stride", C.c_int32),
+                ("image_stride_bytes", C.c_size_t), ("bf", C.c_float), ("b", C.c_float), ("last", C.POINTER(orbm_last_queries)),
+                ("th_last", C.c_float), ("check_orientation_last", C.c_int32), ("local", C.POINTER(orbm_local_queries)),
+                ("th_local", C.c_float), ("nnratio_local", C.c_float), ("far_points", C.c_int32), ("th_far", C.c_float),
+                ("pose_optimization", C.c_int32), ("pose", C.c_void_p), ("local_world_pos", C.c_void_p)]
+
+
+class orbr_results(C.Structure):
+    _fields_ = [("cap_rows", C.c_int32)] + [(n, C.c_void_p) for n in ("keypoints", "descriptors", "uright", "depth", "n", "offsets",
+                                                                     "last_feature_match", "last_nmatches", "local_match", "local_nmatches")] + \
+        [(n, C.c_void_p * 2) for n in ("pose", "inliers", "edge_offset", "edge_feature", "edge_outlier")]
 
 
 class orbf_frustum_points(C.Structure):
@@ -198,6 +212,10 @@ SIGNATURES = {
     "liba_destroy": (None, [_VP]),
     "liba_solve": (_I, [_VP, _I, C.POINTER(liba_problem), C.POINTER(liba_result)]),
     "liba_link_information": (_I, [_VP, _I, _VP, _VP, _VP]),
+    "orbx_keyframe_block_bytes": (C.c_size_t, [_VP]),
+    "orbx_pack_keyframe_device": (_I, [_VP, _I, _VP, _VP, C.c_size_t]),
+    "orbr_submit": (_I, [_VP, C.POINTER(orbm_camera), C.POINTER(orbr_step)]),
+    "orbr_collect": (_I, [_VP, C.POINTER(orbr_results), _IP]),
     "orbm_search_last_frame": (_I, [_VP, C.POINTER(orbm_camera), C.POINTER(orbm_last_queries), _F, _I, _VP, _VP]),
 }
 

@@ -402,6 +402,7 @@ extern "C" void orbx_destroy(orbx_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    orbr_release(h);
     void* ptrs[] = {h->d_pyr, h->d_blur, h->d_cand, h->d_sort, h->d_lvl_kp, h->d_slot, h->d_cand_cnt, h->d_lvl_cnt,
                     h->d_nkp, h->d_err, h->d_taps, h->d_kps, h->d_desc, h->d_node_scratch, h->d_stage, h->d_po,
                     h->d_uright, h->d_depth, h->d_sad, h->d_cells};

@@ -4,6 +4,9 @@
 
 #include "common.cuh"
 
+struct orbr_state;
+void orbr_release(struct orbx_handle* h);   // replay.cu
+
 struct orbx_handle {
     orbx_config cfg{};
     orb::ExtractGeom geom{};
@@ -65,4 +68,5 @@ struct orbx_handle {
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {};
     int qt_node_cap = 0, qt_nodes_in_smem = 1;
     size_t qt_node_stride = 0, order_smem_bytes = 0;
+    orbr_state* replay = nullptr;   // orbr_submit / orbr_collect state (replay.cu)
 };

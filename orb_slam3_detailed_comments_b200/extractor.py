@@ -199,6 +199,14 @@ class ORBextractor:
     def graph_destroy(self, g):
         self._L.orbx_graph_destroy(g)
 
+    def keyframe_block_bytes(self):
+        return int(self._L.orbx_keyframe_block_bytes(self._h))
+
+    def pack_keyframe_device(self, image, d_pose7, d_block):
+        """Keyframe state of one image of the last batch into a device block (CUDA torch tensors; replay.unpack_keyframe reads it)."""
+        N.check(self._L.orbx_pack_keyframe_device(self._h, int(image), C.c_void_p(d_pose7.data_ptr()), C.c_void_p(d_block.data_ptr()),
+                                                  d_block.numel() * d_block.element_size()))
+
     def set_profiling(self, on=True):
         N.check(self._L.orbx_set_profiling(self._h, 1 if on else 0))
 

@@ -68,3 +68,62 @@ def max_over_ranks(ms, device):
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+# ---- native replay step (include/orbslam3_b200.h: orbr_submit / orbr_collect) -----------------------------------------------
+class TrackingStep:
+    """The tracking-thread step of a batch of stereo frames on one extractor handle, host buffers in / host buffers out:
+    `submit` queues the image upload, both eyes' extraction, ComputeStereoMatches, SearchByProjection(cur, last),
+    SearchByProjection(F, local map points) and (optionally) PoseOptimization after each search, and returns at once;
+    `collect` waits and copies the results into the caller's (ideally pinned) arrays.  Keep several handles in flight from
+    one host thread: submit on handles k+1 .. k+H-1 before collecting handle k."""
+
+    def __init__(self, extractor, cam, bf, b, th_last=15.0, th_local=3.0, nnratio_local=0.8, check_orientation=True, far_points=False,
+                 th_far=50.0):
+        import ctypes as C
+        from . import _native as N
+        self._C, self._N, self._L = C, N, N.lib()
+        self.ex, self.cam = extractor, cam
+        self.args = (float(bf), float(b), float(th_last), 1 if check_orientation else 0, float(th_local), float(nnratio_local),
+                     1 if far_points else 0, float(th_far))
+        self._keep = None
+
+    def submit(self, images, last=None, local=None, pose=None, local_world_pos=None):
+        """images: (2 * n_frames, H, W) uint8 host array; last / local: dicts of host arrays with the field names of
+        orbm_last_queries / orbm_local_queries (fimg, off, Tcw, dir, xw, oct, ang, desc, obs / fimg, off, px, py, pxr, lvl, vc, desc
+        [, td, in_view]); pose + local_world_pos switch PoseOptimization on."""
+        C, N = self._C, self._N
+        assert images.dtype == np.uint8 and images.flags["C_CONTIGUOUS"] and images.ndim == 3
+        nimg, h, w = images.shape
+        nf = nimg // 2
+        bf, b, thl, ori, thc, nnr, far, thfar = self.args
+        ql = qc = None
+        if last is not None:
+            ql = N.orbm_last_queries(nf, 0, *[N.ptr(last[k]) if last.get(k) is not None else None
+                                              for k in ("fimg", "off", "Tcw", "dir", "xw", "oct", "ang", "desc", "obs")])
+        if local is not None:
+            qc = N.orbm_local_queries(nf, 0, *[N.ptr(local[k]) if local.get(k) is not None else None
+                                               for k in ("fimg", "off", "px", "py", "pxr", "lvl", "vc", "td", "desc", "claimed", "in_view")])
+        po = pose is not None
+        st = N.orbr_step(nf, N.ptr(images), w, h, w, w * h, bf, b, C.pointer(ql) if ql is not None else None, thl, ori,
+                         C.pointer(qc) if qc is not None else None, thc, nnr, far, thfar, 1 if po else 0,
+                         N.ptr(pose) if po else None, N.ptr(local_world_pos) if (po and local_world_pos is not None) else None)
+        self._keep = (images, last, local, pose, local_world_pos, ql, qc)      # the arrays must outlive the asynchronous copies
+        N.check(self._L.orbr_submit(self.ex._h, C.byref(self.cam), C.byref(st)))
+
+    def collect(self, out):
+        """out: dict of preallocated host arrays -- kps, desc, ur, dep (cap_rows rows), n, offsets, fm, nm1, mt, nm2 and, with
+        PoseOptimization, pose (2, nf, 7) f64, inl (2, nf) i32, eoff (2, nf + 1) i32, efeat (2, cap) i32, outl (2, cap) u8.
+        Missing keys are not copied back.  Returns the number of compact rows of the batch."""
+        C, N = self._C, self._N
+        g = lambda k: N.ptr(out[k]) if out.get(k) is not None else None
+        two = lambda k: (C.c_void_p * 2)(*[C.c_void_p(out[k][i].ctypes.data) if out.get(k) is not None else None for i in range(2)])
+        cap = min(len(out[k]) for k in ("kps", "desc", "ur", "dep", "fm") if out.get(k) is not None)
+        if out.get("efeat") is not None:
+            cap = min(cap, out["efeat"].shape[1])
+        res = N.orbr_results(int(cap), g("kps"), g("desc"), g("ur"), g("dep"), g("n"), g("offsets"), g("fm"), g("nm1"), g("mt"), g("nm2"),
+                             two("pose"), two("inl"), two("eoff"), two("efeat"), two("outl"))
+        rows = C.c_int32(0)
+        N.check(self._L.orbr_collect(self.ex._h, C.byref(res), C.byref(rows)))
+        self._keep = None
+        return rows.value

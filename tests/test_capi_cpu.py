@@ -20,7 +20,7 @@ def lib():
 def _declared_functions():
     text = open(os.path.join(ROOT, "include", "orbslam3_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    names = set(re.findall(r"\b((?:orb|orbx|orbm|orbo|orbf|orbv|orbp|lba|liba)_[a-z0-9_]+)\s*\(", text))
+    names = set(re.findall(r"\b((?:orb|orbx|orbm|orbo|orbf|orbv|orbp|orbr|lba|liba)_[a-z0-9_]+)\s*\(", text))
     return sorted(names)
 
 
