@@ -217,8 +217,9 @@ typedef struct {
     const float* Ow;              /* [n_frames][3] */
     const float* world_pos;       /* [np][3] */
     const float* normal;          /* [np][3] MapPoint::GetNormal */
-    const float* max_dist;        /* GetMaxDistanceInvariance */
-    const float* min_dist;        /* GetMinDistanceInvariance */
+    const float* max_dist;        /* MapPoint::mfMaxDistance, the RAW member (orbp_update_normal_and_depth's output): the distance gate applies
+                                     GetMaxDistanceInvariance's 1.2f itself, PredictScale divides the raw value (MapPoint.cc:658-721) */
+    const float* min_dist;        /* MapPoint::mfMinDistance, raw (the gate applies 0.8f) */
     int32_t n_points_max;         /* device callers: grid bound; else ignored */
 } orbf_frustum_points;
 
@@ -348,8 +349,9 @@ typedef struct {
     const int32_t* query_offset;  /* [n_targets + 1] */
     const float* world_pos;       /* [nq][3] MapPoint::GetWorldPos */
     const float* normal;          /* [nq][3] MapPoint::GetNormal (unused by PROJ_RELOC, may be NULL there) */
-    const float* max_dist;        /* GetMaxDistanceInvariance */
-    const float* min_dist;        /* GetMinDistanceInvariance */
+    const float* max_dist;        /* MapPoint::mfMaxDistance, the RAW member (orbp_update_normal_and_depth's output): the distance gate applies
+                                     GetMaxDistanceInvariance's 1.2f itself, PredictScale divides the raw value (MapPoint.cc:658-721) */
+    const float* min_dist;        /* MapPoint::mfMinDistance, raw (the gate applies 0.8f) */
     const uint8_t* desc_q;        /* MapPoint::GetDescriptor */
     const float* angle;           /* PROJ_RELOC: pKF->mvKeysUn[i].angle of the query's keyframe feature; else NULL */
 } orbm_kf_queries;

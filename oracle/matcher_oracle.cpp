@@ -399,7 +399,7 @@ extern "C" int orc_search_keyframe(int variant, const KeyPoint* kps, const uint8
         float PO[3] = {p3Dw[0] - Ow[0], p3Dw[1] - Ow[1], p3Dw[2] - Ow[2]};
         if (variant == 4) { PO[0] = pc[0]; PO[1] = pc[1]; PO[2] = pc[2]; }      // dist3D = p3Dc2.norm()
         const float dist3D = std::sqrt(PO[0] * PO[0] + (PO[1] * PO[1] + PO[2] * PO[2]));
-        if (dist3D < minDist[q] || dist3D > maxDist[q]) continue;
+        if (dist3D < 0.8f * minDist[q] || dist3D > 1.2f * maxDist[q]) continue;   // Get{Min,Max}DistanceInvariance (MapPoint.cc:658-672); minDist / maxDist = mfMinDistance / mfMaxDistance
         if (variant < 3) {
             const float* Pn = normal + 3 * q;
             const float d = PO[0] * Pn[0] + (PO[1] * Pn[1] + PO[2] * Pn[2]);
@@ -621,7 +621,7 @@ extern "C" int orc_is_in_frustum(int n, const float* Rcw9, const float* tcw, con
         projy[i] = v;
         const float PO[3] = {P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2]};
         const float dist = std::sqrt(PO[0] * PO[0] + (PO[1] * PO[1] + PO[2] * PO[2]));
-        if (dist < minDist[i] || dist > maxDist[i]) continue;
+        if (dist < 0.8f * minDist[i] || dist > 1.2f * maxDist[i]) continue;   // Get{Min,Max}DistanceInvariance; PredictScale below takes the raw mfMaxDistance
         const float* Pn = normal + 3 * i;
         const float vc = (PO[0] * Pn[0] + (PO[1] * Pn[1] + PO[2] * Pn[2])) / dist;
         if (vc < viewingCosLimit) continue;

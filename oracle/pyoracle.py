@@ -627,3 +627,123 @@ def oracle_distribute(cand, minX, maxX, minY, maxY, N):
     out = np.zeros(len(cand) + 8, np.int32)
     k = lib().orc_distribute(_p(cand), len(cand), minX, maxX, minY, maxY, N, _p(out), len(out))
     return out[:k].copy()
+
+
+# ---- oracle/_ref part 2: member functions of the reference's ORBmatcher.cc / Frame.cc / MapPoint.cc / Pinhole.cpp compiled verbatim
+# over skeleton classes (oracle/Makefile target ref2; ref_shim/ref_capi2.cpp) ------------------------------------------------------
+_REF2_SO = os.path.join(_HERE, "_ref", "liborb_ref2.so")
+_ref2_lib = None
+
+
+def build_ref2(force=False):
+    if os.path.exists(os.path.join(REFERENCE_ROOT, "src", "ORBmatcher.cc")):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref2", f"REF={REFERENCE_ROOT}"] + (["-B"] if force else []))
+    return _REF2_SO if os.path.exists(_REF2_SO) else None
+
+
+def ref2_lib():
+    global _ref2_lib
+    if _ref2_lib is None:
+        if build_ref2() is None:
+            raise RuntimeError("oracle/_ref/liborb_ref2.so is not built and /root/reference is not present")
+        ref_lib()
+        L = _ref2_lib = C.CDLL(_REF2_SO)
+        VP, I, F = C.c_void_p, C.c_int, C.c_float
+        L.ref2_frame_create.restype = VP
+        L.ref2_frame_create.argtypes = [VP, VP, VP, I, VP, VP, I, VP, VP]
+        L.ref2_frame_destroy.argtypes = [VP]
+        L.ref2_descriptor_distance.restype = I
+        L.ref2_descriptor_distance.argtypes = [VP, VP]
+        L.ref2_three_maxima.argtypes = [VP, I, VP]
+        L.ref2_constants.argtypes = [VP, VP]
+        L.ref2_get_features_in_area.restype = I
+        L.ref2_get_features_in_area.argtypes = [VP, F, F, F, I, I, VP, I]
+        L.ref2_search_local.restype = I
+        L.ref2_search_local.argtypes = [VP, I] + [VP] * 8 + [F, F, I, F, VP]
+        L.ref2_search_last.restype = I
+        L.ref2_search_last.argtypes = [VP, VP, VP, I] + [VP] * 5 + [F, I, I, VP, VP]
+        L.ref2_is_in_frustum.restype = I
+        L.ref2_is_in_frustum.argtypes = [VP, VP, VP, VP, I, VP, VP, VP, VP, F] + [VP] * 7
+        L.ref2_stereo_matches.argtypes = [VP, VP, VP, VP, VP, I, VP, VP]
+    return _ref2_lib
+
+
+class RefFrame:
+    """A reference Frame (Nleft == -1) skeleton filled from flat arrays; methods run the reference's own member functions."""
+
+    def __init__(self, kps, desc, uright, bounds, scale_factors, cam6, Tcw7=None):
+        self.L = ref2_lib()
+        f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+        self._keep = (np.ascontiguousarray(kps), np.ascontiguousarray(desc, np.uint8), f32(uright), f32(bounds), f32(scale_factors), f32(cam6), f32(Tcw7))
+        k, d, u, b, s, c, t = self._keep
+        P = lambda a: None if a is None else _p(a)
+        self.N = len(k)
+        self.h = C.c_void_p(self.L.ref2_frame_create(_p(k), _p(d), P(u), len(k), _p(b), _p(s), len(s), _p(c), P(t)))
+
+    def __del__(self):
+        try:
+            self.L.ref2_frame_destroy(self.h)
+        except Exception:
+            pass
+
+    def features_in_area(self, x, y, r, min_level=-1, max_level=-1):
+        out = np.zeros(max(self.N, 1), np.int32)
+        n = self.L.ref2_get_features_in_area(self.h, x, y, r, min_level, max_level, _p(out), len(out))
+        return out[:n].copy()
+
+    def search_local(self, projx, projy, projxr, level, viewcos, qdesc, th, nnratio, claimed=None, trackdepth=None, far=False, th_far=0.0):
+        f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+        px, py, pxr, vc, td = f32(projx), f32(projy), f32(projxr), f32(viewcos), f32(trackdepth)
+        lv, qd = np.ascontiguousarray(level, np.int32), np.ascontiguousarray(qdesc, np.uint8)
+        cl = None if claimed is None else np.ascontiguousarray(claimed, np.uint8)
+        nq = len(px)
+        match = np.full(max(nq, 1), -1, np.int32)
+        P = lambda a: None if a is None else _p(a)
+        nm = self.L.ref2_search_local(self.h, nq, _p(px), _p(py), _p(pxr), _p(lv), _p(vc), P(td), _p(qd), P(cl), th, nnratio, 1 if far else 0, th_far, _p(match))
+        return match[:nq], nm
+
+    def search_last(self, Tcw7, Tlw7, xw, last_octave, last_angle, qdesc, obs_pos, th, check_ori=True, mono=False):
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)
+        Tc, Tl, xw, ang = f32(Tcw7), f32(Tlw7), f32(xw), f32(last_angle)
+        lo, qd, ob = np.ascontiguousarray(last_octave, np.int32), np.ascontiguousarray(qdesc, np.uint8), np.ascontiguousarray(obs_pos, np.uint8)
+        fm = np.full(max(self.N, 1), -1, np.int32)
+        direction = C.c_int(0)
+        nm = self.L.ref2_search_last(self.h, _p(Tc), _p(Tl), len(lo), _p(xw), _p(lo), _p(ang), _p(qd), _p(ob), th, 1 if check_ori else 0, 1 if mono else 0,
+                                     _p(fm), C.byref(direction))
+        return fm[:self.N], nm, direction.value
+
+    def is_in_frustum(self, Rcw, tcw, Ow, xw, normal, max_dist, min_dist, limit=0.5):
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)
+        R, t, O, xw, nr, mx, mn = f32(Rcw), f32(tcw), f32(Ow), f32(xw), f32(normal), f32(max_dist), f32(min_dist)
+        n = len(xw)
+        out = dict(in_view=np.zeros(max(n, 1), np.uint8), proj_x=np.zeros(max(n, 1), np.float32), proj_y=np.zeros(max(n, 1), np.float32),
+                   proj_xr=np.zeros(max(n, 1), np.float32), level=np.zeros(max(n, 1), np.int32), view_cos=np.zeros(max(n, 1), np.float32),
+                   depth=np.zeros(max(n, 1), np.float32))
+        self.L.ref2_is_in_frustum(self.h, _p(R), _p(t), _p(O), n, _p(xw), _p(nr), _p(mx), _p(mn), limit,
+                                  *[_p(out[k]) for k in ("in_view", "proj_x", "proj_y", "proj_xr", "level", "view_cos", "depth")])
+        return {k: v[:n] for k, v in out.items()}
+
+    def stereo_matches(self, ref_ex_left, ref_ex_right, kpsR, descR):
+        """Frame::ComputeStereoMatches; the two RefExtractor objects must just have extracted the left / right image."""
+        kR, dR = np.ascontiguousarray(kpsR), np.ascontiguousarray(descR, np.uint8)
+        uR, dep = np.zeros(max(self.N, 1), np.float32), np.zeros(max(self.N, 1), np.float32)
+        self.L.ref2_stereo_matches(self.h, ref_ex_left.h, ref_ex_right.h, _p(kR), _p(dR), len(kR), _p(uR), _p(dep))
+        return uR[:self.N], dep[:self.N]
+
+
+def ref2_descriptor_distance(a, b):
+    a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
+    return ref2_lib().ref2_descriptor_distance(_p(a), _p(b))
+
+
+def ref2_three_maxima(sizes):
+    s = np.ascontiguousarray(sizes, np.int32)
+    out = np.zeros(3, np.int32)
+    ref2_lib().ref2_three_maxima(_p(s), len(s), _p(out))
+    return tuple(int(v) for v in out)
+
+
+def ref2_constants():
+    c, r = np.zeros(3, np.int32), np.zeros(2, np.float32)
+    ref2_lib().ref2_constants(_p(c), _p(r))
+    return dict(TH_LOW=int(c[0]), TH_HIGH=int(c[1]), HISTO_LENGTH=int(c[2]), radius_close=float(r[0]), radius_far=float(r[1]))

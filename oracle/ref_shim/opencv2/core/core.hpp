@@ -110,6 +110,8 @@ class Mat {
 
     uchar* ptr(int r = 0) { return data + (size_t)r * step; }
     const uchar* ptr(int r = 0) const { return data + (size_t)r * step; }
+    template <typename T> T* ptr(int r = 0) { return (T*)(data + (size_t)r * step); }
+    template <typename T> const T* ptr(int r = 0) const { return (const T*)(data + (size_t)r * step); }
     template <typename T> T& at(int r, int c) { return ((T*)(data + (size_t)r * step))[c]; }
     template <typename T> const T& at(int r, int c) const { return ((const T*)(data + (size_t)r * step))[c]; }
 
@@ -179,6 +181,19 @@ struct Scalar {
     double v[4];
     Scalar(double a = 0, double b = 0, double c = 0, double d = 0) : v{a, b, c, d} {}
 };
+
+enum NormTypes { NORM_INF = 1, NORM_L1 = 2, NORM_L2 = 4, NORM_HAMMING = 6 };
+// cv::norm(a, b, NORM_L1) of two u8 matrices of the same size (Frame::ComputeStereoMatches' SAD): an exact integer sum
+static inline double norm(const Mat& a, const Mat& b, int normType) {
+    assert(normType == NORM_L1 && a.rows == b.rows && a.cols == b.cols);
+    (void)normType;
+    long s = 0;
+    for (int r = 0; r < a.rows; ++r) {
+        const uchar *pa = a.ptr(r), *pb = b.ptr(r);
+        for (int c = 0; c < a.cols; ++c) s += pa[c] > pb[c] ? pa[c] - pb[c] : pb[c] - pa[c];
+    }
+    return (double)s;
+}
 
 // --- the five OpenCV routines ORBextractor.cc calls (ref_shim/cv_models.cpp) ---
 void resize(InputArray src, OutputArray dst, Size dsize, double fx = 0, double fy = 0, int interpolation = INTER_LINEAR);

@@ -1,0 +1,186 @@
+// oracle/ref_shim/skel/ref_frame_skel.h -- TEST INFRASTRUCTURE.
+//
+// Skeleton of the reference's Frame / MapPoint / camera classes, holding exactly the members that the member functions
+// oracle/Makefile extracts from the reference sources at build time touch:
+//     ORBmatcher.cc : ORBmatcher::ORBmatcher, SearchByProjection(Frame&, vector<MapPoint*>&, ...), SearchByProjection(Frame&, const
+//                     Frame&, th, bMono), RadiusByViewingCos, ComputeThreeMaxima, DescriptorDistance, TH_LOW / TH_HIGH / HISTO_LENGTH
+//     Frame.cc      : AssignFeaturesToGrid, PosInGrid, GetFeaturesInArea, isInFrustum(MapPoint*, float), ComputeStereoMatches
+//     MapPoint.cc   : PredictScale(const float&, Frame*)
+//     Pinhole.cpp   : project(const Eigen::Vector3f&)
+// Those functions are compiled VERBATIM (oracle/tools/extract_functions.py writes them into oracle/_ref/gen/, a build directory)
+// against the reference's own include/ORBmatcher.h and include/ORBextractor.h; this header defines the include guards of
+// Frame.h / KeyFrame.h / MapPoint.h (which pull in DBoW2, g2o, boost, Pangolin: none exist in this image) and supplies the class
+// members with the reference's names and types.  So oracle/_ref/liborb_ref2.so = (reference control flow of the matchers, the
+// grid, the stereo matcher and isInFrustum, verbatim) x (the arithmetic models below).
+//
+// Arithmetic that is NOT the reference's own code and therefore pins nothing: the miniature Eigen (fixed-size float vectors /
+// 3x3 matrix; matrix * vector and dot / norm in the summation order DESIGN.md section 2 states for Eigen's unrolled kernels) and the
+// miniature Sophus::SE3f (quaternion action as Thirdparty/Sophus so3.hpp:358-367) -- the same orders the oracle restates.
+#pragma once
+#define FRAME_H
+#define KEYFRAME_H
+#define MAPPOINT_H
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <list>
+#include <map>
+#include <mutex>
+#include <set>
+#include <vector>
+
+#include <opencv2/core/core.hpp>   // oracle/ref_shim/opencv2: the miniature cv::
+#include "ORBextractor.h"          // the reference's own header
+
+#define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+
+namespace Eigen {
+template <typename T, int R, int C>
+struct Matrix {
+    T v[R * C];
+    Matrix() { for (int i = 0; i < R * C; ++i) v[i] = T(0); }
+    Matrix(T a, T b) { static_assert(R * C == 2, "2-vector"); v[0] = a; v[1] = b; }
+    Matrix(T a, T b, T c) { static_assert(R * C == 3, "3-vector"); v[0] = a; v[1] = b; v[2] = c; }
+    T& operator()(int i) { return v[i]; }
+    const T& operator()(int i) const { return v[i]; }
+    T& operator[](int i) { return v[i]; }
+    const T& operator[](int i) const { return v[i]; }
+    T& operator()(int r, int c) { return v[r * C + c]; }
+    const T& operator()(int r, int c) const { return v[r * C + c]; }
+    Matrix operator+(const Matrix& b) const { Matrix o; for (int i = 0; i < R * C; ++i) o.v[i] = v[i] + b.v[i]; return o; }
+    Matrix operator-(const Matrix& b) const { Matrix o; for (int i = 0; i < R * C; ++i) o.v[i] = v[i] - b.v[i]; return o; }
+    Matrix operator-() const { Matrix o; for (int i = 0; i < R * C; ++i) o.v[i] = -v[i]; return o; }
+    // 3-term sums in the order x + (y + z) (Eigen 3.3+'s unrolled fixed-size reduction)
+    T dot(const Matrix& b) const { static_assert(R * C == 3, "3-vector"); return v[0] * b.v[0] + (v[1] * b.v[1] + v[2] * b.v[2]); }
+    T norm() const { return std::sqrt(dot(*this)); }
+    Matrix<T, R, 1> operator*(const Matrix<T, C, 1>& b) const {
+        static_assert(R == 3 && C == 3, "3x3 * 3x1");
+        Matrix<T, R, 1> o;
+        for (int r = 0; r < 3; ++r) o.v[r] = (*this)(r, 0) * b.v[0] + ((*this)(r, 1) * b.v[1] + (*this)(r, 2) * b.v[2]);
+        return o;
+    }
+};
+typedef Matrix<float, 2, 1> Vector2f;
+typedef Matrix<float, 3, 1> Vector3f;
+typedef Matrix<float, 3, 3> Matrix3f;
+}  // namespace Eigen
+
+namespace Sophus {
+template <typename T>
+class SE3 {   // unit quaternion (x y z w) + translation; point action as so3.hpp:358-367 (Eigen's _transformVector), then + t
+   public:
+    T q[4], t[3];
+    SE3() : q{0, 0, 0, 1}, t{0, 0, 0} {}
+    Eigen::Matrix<T, 3, 1> translation() const { return Eigen::Matrix<T, 3, 1>(t[0], t[1], t[2]); }
+    static void rot(const T* q, const T* p, T* o) {
+        const T uvx = q[1] * p[2] - q[2] * p[1], uvy = q[2] * p[0] - q[0] * p[2], uvz = q[0] * p[1] - q[1] * p[0];
+        const T ux = uvx + uvx, uy = uvy + uvy, uz = uvz + uvz;
+        const T cx = q[1] * uz - q[2] * uy, cy = q[2] * ux - q[0] * uz, cz = q[0] * uy - q[1] * ux;
+        o[0] = (p[0] + q[3] * ux) + cx; o[1] = (p[1] + q[3] * uy) + cy; o[2] = (p[2] + q[3] * uz) + cz;
+    }
+    Eigen::Matrix<T, 3, 1> operator*(const Eigen::Matrix<T, 3, 1>& p) const {
+        T o[3];
+        rot(q, p.v, o);
+        return Eigen::Matrix<T, 3, 1>(o[0] + t[0], o[1] + t[1], o[2] + t[2]);
+    }
+    SE3 inverse() const {   // se3.hpp: SE3(so3().inverse(), so3().inverse() * (translation() * -1))
+        SE3 r;
+        r.q[0] = -q[0]; r.q[1] = -q[1]; r.q[2] = -q[2]; r.q[3] = q[3];
+        const T nt[3] = {t[0] * T(-1), t[1] * T(-1), t[2] * T(-1)};
+        rot(r.q, nt, r.t);
+        return r;
+    }
+};
+typedef SE3<float> SE3f;
+template <typename T>
+class Sim3 {};
+typedef Sim3<float> Sim3f;
+}  // namespace Sophus
+
+using namespace std;   // the reference headers and sources rely on it
+
+namespace ORB_SLAM3 {
+
+#define FRAME_GRID_ROWS 48
+#define FRAME_GRID_COLS 64
+
+class Frame;
+class KeyFrame;   // named in ORBmatcher.h signatures only
+
+class GeometricCamera {
+   public:
+    virtual ~GeometricCamera() {}
+    virtual Eigen::Vector2f project(const Eigen::Vector3f& v3D) = 0;
+};
+class Pinhole : public GeometricCamera {
+   public:
+    Eigen::Vector2f project(const Eigen::Vector3f& v3D);   // body extracted from src/CameraModels/Pinhole.cpp
+    std::vector<float> mvParameters;
+};
+
+class MapPoint {
+   public:
+    MapPoint() : mTrackProjX(0), mTrackProjY(0), mTrackDepth(0), mTrackDepthR(0), mTrackProjXR(0), mTrackProjYR(0), mbTrackInView(false),
+                 mbTrackInViewR(false), mnTrackScaleLevel(0), mnTrackScaleLevelR(0), mTrackViewCos(0), mTrackViewCosR(0), nObs(1),
+                 mfMinDistance(0), mfMaxDistance(0) {}
+    Eigen::Vector3f GetWorldPos() { return mWorldPos; }
+    Eigen::Vector3f GetNormal() { return mNormalVector; }
+    cv::Mat GetDescriptor() { return mDescriptor.clone(); }
+    int Observations() { return nObs; }
+    bool isBad() { return false; }
+    float GetMinDistanceInvariance() { return 0.8f * mfMinDistance; }   // MapPoint.cc:658-672
+    float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }
+    int PredictScale(const float& currentDist, Frame* pF);             // body extracted from src/MapPoint.cc
+    float mTrackProjX, mTrackProjY, mTrackDepth, mTrackDepthR, mTrackProjXR, mTrackProjYR;
+    bool mbTrackInView, mbTrackInViewR;
+    int mnTrackScaleLevel, mnTrackScaleLevelR;
+    float mTrackViewCos, mTrackViewCosR;
+    // state
+    int nObs;
+    Eigen::Vector3f mWorldPos, mNormalVector;
+    cv::Mat mDescriptor;
+    float mfMinDistance, mfMaxDistance;
+    std::mutex mMutexPos;
+    int query_index = -1;   // not in the reference: which query of the flat test arrays this object is
+};
+
+class Frame {
+   public:
+    Frame() : mpORBextractorLeft(nullptr), mpORBextractorRight(nullptr), mbf(0), mb(0), N(0), mnScaleLevels(8), mfLogScaleFactor(0),
+              mpCamera(nullptr), Nleft(-1), Nright(-1) {}
+    // extracted from src/Frame.cc
+    void AssignFeaturesToGrid();
+    bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
+    vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1, const int maxLevel = -1,
+                                     const bool bRight = false) const;
+    bool isInFrustum(MapPoint* pMP, float viewingCosLimit);
+    bool isInFrustumChecks(MapPoint*, float, bool = false) { return false; }   // fisheye branch (Nleft != -1): not exercised
+    void ComputeStereoMatches();
+    inline Sophus::SE3<float> GetPose() const { return mTcw; }
+    Sophus::SE3<float> GetRelativePoseTrl() const { return Sophus::SE3<float>(); }   // fisheye branch: not exercised
+    ORBextractor *mpORBextractorLeft, *mpORBextractorRight;
+    float mbf, mb;
+    int N;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysRight, mvKeysUn;
+    std::vector<MapPoint*> mvpMapPoints;
+    std::vector<float> mvuRight, mvDepth;
+    cv::Mat mDescriptors, mDescriptorsRight;
+    std::vector<bool> mvbOutlier;
+    static float mfGridElementWidthInv, mfGridElementHeightInv;
+    std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+    std::vector<std::size_t> mGridRight[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+    int mnScaleLevels;
+    float mfLogScaleFactor;
+    vector<float> mvScaleFactors, mvInvScaleFactors;
+    static float mnMinX, mnMaxX, mnMinY, mnMaxY;
+    GeometricCamera* mpCamera;
+    int Nleft, Nright;
+    std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;   // fisheye branch (Nleft != -1): not exercised
+    Sophus::SE3<float> mTcw;
+    Eigen::Matrix<float, 3, 3> mRcw;
+    Eigen::Matrix<float, 3, 1> mtcw, mOw;
+};
+
+}  // namespace ORB_SLAM3

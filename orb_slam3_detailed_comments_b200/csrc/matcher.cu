@@ -80,7 +80,7 @@ struct ProjParams {
     const float* Ow;          // [n_frames][3]
     const float* S;           // variant 4: [n_frames][8] Sim3 quaternion (non-unit) x y z w, translation, scale
     const float* normal;      // [nq][3] MapPoint::GetNormal (variants 0-2)
-    const float* maxD;        // GetMaxDistanceInvariance
+    const float* maxD;        // mfMaxDistance (raw member)
     const float* minD;
     float logScale, thr;
     int nLevels;
@@ -351,7 +351,9 @@ __device__ __forceinline__ bool kf_window(const ProjParams& P, int frame, int q,
     } else if (!(u >= P.minX && u < P.maxX && v >= P.minY && v < P.maxY)) return false;
     ur_pred = fsub(u, fmul(P.bf, invz));
     const float dist = fsqrt(fadd(fmul(px, px), fadd(fmul(py, py), fmul(pz, pz))));
-    if (dist < P.minD[q] || dist > P.maxD[q]) return false;
+    // GetMinDistanceInvariance / GetMaxDistanceInvariance (MapPoint.cc:658-672): 0.8f * mfMinDistance, 1.2f * mfMaxDistance; PredictScale
+    // (MapPoint.cc:688-721) takes the RAW mfMaxDistance
+    if (dist < fmul(0.8f, P.minD[q]) || dist > fmul(1.2f, P.maxD[q])) return false;
     if (P.variant < 3) {
         const float* n = P.normal + 3 * (size_t)q;
         const float d = fadd(fmul(px, n[0]), fadd(fmul(py, n[1]), fmul(pz, n[2])));
@@ -1031,7 +1033,7 @@ __global__ void __launch_bounds__(256) k_in_frustum(const __grid_constant__ Frus
         v = vv;
         const float ox = fsub(X, O[0]), oy = fsub(Y, O[1]), oz = fsub(Z, O[2]);
         const float dist = fsqrt(fadd(fmul(ox, ox), fadd(fmul(oy, oy), fmul(oz, oz))));
-        if (dist < P.minD[i] || dist > P.maxD[i]) break;
+        if (dist < fmul(0.8f, P.minD[i]) || dist > fmul(1.2f, P.maxD[i])) break;   // Get{Min,Max}DistanceInvariance, MapPoint.cc:658-672
         const float* n = P.normal + 3 * (size_t)i;
         const float c = fdiv(fadd(fmul(ox, n[0]), fadd(fmul(oy, n[1]), fmul(oz, n[2]))), dist);
         if (c < P.cosLimit) break;

@@ -44,8 +44,8 @@ def cases():
     dist = np.linalg.norm(pts, axis=1).astype(np.float32)
     nrm = (pts / dist[:, None] + rng.normal(0, 0.2, pts.shape)).astype(np.float32)
     nrm = (nrm / np.linalg.norm(nrm, axis=1)[:, None]).astype(np.float32)
-    maxd = np.float32(1.2) * (dist * sf[kL["octave"][sel]]).astype(np.float32)
-    mind = np.float32(0.8) * (maxd / np.float32(1.2) / sf[7]).astype(np.float32)
+    maxd = (dist * sf[kL["octave"][sel]]).astype(np.float32)          # raw mfMaxDistance / mfMinDistance (the gates apply 1.2f / 0.8f)
+    mind = (maxd / sf[7]).astype(np.float32)
     zmid = float(np.median(z))
     T = np.array([0, 0.0004, 0, 1, 3 * zmid / FX, 1 * zmid / FY, 0], np.float32)
     T[:4] /= np.linalg.norm(T[:4])

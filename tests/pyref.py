@@ -208,7 +208,7 @@ def fuse(variant, kps, desc, uright, bounds, sf, inv_sigma2, log_sf, cam, T, Ow,
             ur = f32(u - f32(bf * invz))
             PO = [f32(f32(xw[q][i]) - f32(Ow[i])) for i in range(3)]
             dist = f32(math.sqrt(float(f32(f32(PO[0] * PO[0]) + f32(f32(PO[1] * PO[1]) + f32(PO[2] * PO[2]))))))
-            if dist < mind[q] or dist > maxd[q]:
+            if dist < f32(f32(0.8) * f32(mind[q])) or dist > f32(f32(1.2) * f32(maxd[q])):   # Get{Min,Max}DistanceInvariance; mind / maxd are the raw members
                 break
             dot = f32(f32(PO[0] * f32(normal[q][0])) + f32(f32(PO[1] * f32(normal[q][1])) + f32(PO[2] * f32(normal[q][2]))))
             if float(dot) < 0.5 * float(dist):
@@ -587,7 +587,7 @@ def search_by_projection_reloc(kps, desc, bounds, sf, log_sf, cam, T, Ow, xw, ma
             continue
         PO = [f32(f32(xw[q][i]) - f32(Ow[i])) for i in range(3)]
         dist = f32(math.sqrt(float(f32(f32(PO[0] * PO[0]) + f32(f32(PO[1] * PO[1]) + f32(PO[2] * PO[2]))))))
-        if dist < mind[q] or dist > maxd[q]:
+        if dist < f32(f32(0.8) * f32(mind[q])) or dist > f32(f32(1.2) * f32(maxd[q])):   # Get{Min,Max}DistanceInvariance; mind / maxd are the raw members
             continue
         lvl = int(math.ceil(float(f32(f32(libm.logf(float(f32(f32(maxd[q]) / dist)))) / f32(log_sf)))))
         lvl = max(0, min(lvl, len(sf) - 1))
@@ -646,7 +646,7 @@ def search_by_sim3_oneway(kps, desc, bounds, sf, log_sf, cam, T, S8, xw, maxd, m
         if not (u >= g.minX and u < g.maxX and v >= g.minY and v < g.maxY):
             continue
         dist = f32(math.sqrt(float(f32(f32(pc[0] * pc[0]) + f32(f32(pc[1] * pc[1]) + f32(pc[2] * pc[2]))))))
-        if dist < mind[q] or dist > maxd[q]:
+        if dist < f32(f32(0.8) * f32(mind[q])) or dist > f32(f32(1.2) * f32(maxd[q])):   # Get{Min,Max}DistanceInvariance; mind / maxd are the raw members
             continue
         lvl = int(math.ceil(float(f32(f32(libm.logf(float(f32(f32(maxd[q]) / dist)))) / f32(log_sf)))))
         lvl = max(0, min(lvl, len(sf) - 1))

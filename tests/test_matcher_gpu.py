@@ -263,7 +263,8 @@ def _kf_queries(scene, p, rng, sf, dup):
     nrm[rng.random(len(sel)) < 0.05] *= -1                               # a few points seen from behind: viewing-angle gate
     maxd = (dist * sf[kL["octave"][sel]]).astype(np.float32)
     mind = (maxd / sf[7]).astype(np.float32)
-    return dict(world_pos=pts, normal=nrm, max_dist=np.float32(1.2) * maxd, min_dist=np.float32(0.8) * mind, desc=dL[sel],
+    return dict(world_pos=pts, normal=nrm, max_dist=maxd, min_dist=mind,   # raw mfMaxDistance / mfMinDistance
+                desc=dL[sel],
                 angle=kL["angle"][sel].astype(np.float32))
 
 
@@ -367,7 +368,7 @@ def test_search_by_sim3_matches_oracle(scene):
             pw = ((pc - t) @ R).astype(np.float32)
             dist = np.linalg.norm(pc, axis=1).astype(np.float32)
             maxd = (dist * sf[k["octave"][sel]]).astype(np.float32)
-            return dict(index=sel, world_pos=pw, max_dist=np.float32(1.2) * maxd, min_dist=np.float32(0.8) * (maxd / sf[7]).astype(np.float32),
+            return dict(index=sel, world_pos=pw, max_dist=maxd, min_dist=(maxd / sf[7]).astype(np.float32),
                         desc=d[sel])
 
         mp1, mp2 = points(kL, dL, ldep, T1, 0.8), points(k2, d2, dep2, T2, 0.8)

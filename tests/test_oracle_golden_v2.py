@@ -40,7 +40,7 @@ def test_is_in_frustum_against_numpy_float32():
     PO = (pts - Ow).astype(f32)
     dist = np.sqrt((PO[:, 0] * PO[:, 0] + (PO[:, 1] * PO[:, 1] + PO[:, 2] * PO[:, 2])).astype(f32)).astype(f32)
     vc = ((PO[:, 0] * nrm[:, 0] + (PO[:, 1] * nrm[:, 1] + PO[:, 2] * nrm[:, 2])).astype(f32) / dist).astype(f32)
-    vis = (Pc[:, 2] >= 0) & (u >= 0) & (u <= 640) & (v >= 0) & (v <= 480) & (dist >= mind) & (dist <= maxd) & (vc >= f32(0.5))
+    vis = (Pc[:, 2] >= 0) & (u >= 0) & (u <= 640) & (v >= 0) & (v <= 480) & (dist >= (f32(0.8) * mind).astype(f32)) & (dist <= (f32(1.2) * maxd).astype(f32)) & (vc >= f32(0.5))   # Get{Min,Max}DistanceInvariance
     assert (G["fr_in_view"].astype(bool) == vis).all()
     assert (G["fr_proj_x"][vis] == u[vis]).all() and (G["fr_proj_y"][vis] == v[vis]).all() and (G["fr_view_cos"][vis] == vc[vis]).all()
     lvl = np.ceil((np.log((maxd / dist).astype(np.float64)) / np.log(1.2))).astype(int).clip(0, 7)   # double log: may differ at exact powers only
