@@ -948,7 +948,7 @@ def main():
                            "keypoints_per_image": n_kp, "fast_candidates_per_image": n_cand,
                            "kernel_variants": {"quadtree": int(os.environ.get("ORB_QT_VARIANT", "1") != "0"),
                                                "stereo": int(os.environ.get("ORB_STEREO_VARIANT", "1") != "0"),
-                                               "fast": int(os.environ.get("ORB_FAST_VARIANT", "1") != "0")}},
+                                               "fast": int(os.environ.get("ORB_FAST_VARIANT", "1"))}},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(wl.h2d_bytes_per_batch() * BPS),
                         "d2h_bytes_per_step": int(d2h_tot // args.steps),
                         "repeats_frames_per_s": e2e_rates, "spread": (max(e2e_rates) - min(e2e_rates)) / e2e_value if e2e_value else None,

@@ -783,4 +783,16 @@ extern "C" orb_status orbx_last_timings(orbx_handle* h, float* ms7) {
     return ORB_OK;
 }
 
+#if defined(QT_PROFILE)
+// profile build only (tools/qt_phases.py): the quadtree phase clocks, summed over the CTAs since the last reset
+extern "C" void orbx_debug_qt_profile(long long* out32, int reset) {
+    cudaDeviceSynchronize();
+    if (out32) cudaMemcpyFromSymbol(out32, orbdev::g_qt_prof, sizeof(long long) * 32);
+    if (reset) {
+        long long z[32] = {};
+        cudaMemcpyToSymbol(orbdev::g_qt_prof, z, sizeof(z));
+    }
+}
+#endif
+
 extern "C" void* orbx_cuda_stream(orbx_handle* h) { return h ? (void*)h->stream : nullptr; }

@@ -330,6 +330,9 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const __grid_constant__
     q.regionW = G.maxBX - 16; q.regionH = G.maxBY - 16;
     q.nIni = G.nIni; q.hX = G.hX; q.N = G.quota;
     q.wCell = G.wCell; q.hCell = G.hCell; q.nCols = G.nCols;
+#if defined(QT_PROFILE)
+    q.prof_base = l == 0 ? 0 : 16;
+#endif
     int npow = 2;
     while (npow < n) npow <<= 1;
     const uint32_t* src = cand + (int64_t)img * g.candTotal + G.candOff;
@@ -362,9 +365,13 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const __grid_constant__
 // selected with ORB_QT_VARIANT=1 at orbx_create until it has had its own device run.
 __device__ __forceinline__ int qt_run_v1(uint32_t* arr, void* ws, int cap, int n, int npow, const uint32_t* __restrict__ src,
                                          const QtGeom& q, uint32_t* out) {
+    QT_PROF_BEGIN();
+    if (npow < 256) npow = 256;     // qt_bitonic_sort_w sorts whole 256-element warp blocks (every sort buffer holds >= 2048 elements)
     for (int i = threadIdx.x; i < npow; i += blockDim.x) arr[i] = (i < n) ? qt_element(src[i], q) : 0xffffffffu;
     __syncthreads();
-    qt_bitonic_sort_r8(arr, npow);
+    QT_TICK(q, 0)
+    qt_bitonic_sort_w(arr, npow);
+    QT_TICK(q, 1)
     QtWork w;
     qt_work_carve(w, ws, cap);
     return qt_distribute_v<1>(arr, n, q, w, out);
@@ -389,6 +396,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_quadtree_v1(const __grid_constan
     q.regionW = G.maxBX - 16; q.regionH = G.maxBY - 16;
     q.nIni = G.nIni; q.hX = G.hX; q.N = G.quota;
     q.wCell = G.wCell; q.hCell = G.hCell; q.nCols = G.nCols;
+#if defined(QT_PROFILE)
+    q.prof_base = l == 0 ? 0 : 16;
+#endif
     int npow = 2;
     while (npow < n) npow <<= 1;
     const uint32_t* src = cand + (int64_t)img * g.candTotal + G.candOff;

@@ -30,6 +30,7 @@ namespace orbdev {
 #define QT_PAR_FOR(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
 #define QT_SYNC() __syncthreads()
 #define QT_SERIAL if (threadIdx.x == 0)
+#define QT_NTHREADS ((int)blockDim.x)
 #elif defined(QT_EMUL_THREADS)
 // tests/host_emul/qt_mt.cpp: host threads play the CTA with a real barrier (ThreadSanitizer then sees a missing QT_SYNC as a race)
 extern thread_local int qt_tid;
@@ -38,16 +39,32 @@ void qt_barrier();
 #define QT_PAR_FOR(i, n) for (int i = orbdev::qt_tid; i < (n); i += orbdev::qt_nthreads)
 #define QT_SYNC() orbdev::qt_barrier()
 #define QT_SERIAL if (orbdev::qt_tid == 0)
+#define QT_NTHREADS (orbdev::qt_nthreads)
 #elif defined(QT_HOST_COUNT_SYNCS)
 // host, one thread, counting the barriers a CTA would execute (tests/host_emul: the barrier budget of the two variants)
 extern long qt_sync_count;
 #define QT_PAR_FOR(i, n) for (int i = 0; i < (n); ++i)
 #define QT_SYNC() ((void)++orbdev::qt_sync_count)
 #define QT_SERIAL
+#define QT_NTHREADS 1
 #else
 #define QT_PAR_FOR(i, n) for (int i = 0; i < (n); ++i)
 #define QT_SYNC() ((void)0)
 #define QT_SERIAL
+#define QT_NTHREADS 1
+#endif
+
+// Phase clocks of the device build (-DQT_PROFILE only: tools/qt_phases.py): thread 0 of every CTA adds the cycles between ticks to
+// g_qt_prof[slot]; slot = 16 * (level-0 CTA ? 0 : 1) + phase.  Compiled out of the product library.
+#if defined(__CUDACC__) && defined(QT_PROFILE)
+__device__ long long g_qt_prof[32];
+#endif
+#if defined(__CUDA_ARCH__) && defined(QT_PROFILE)
+#define QT_PROF_BEGIN() long long qt_tl_ = clock64()
+#define QT_TICK(g, k) { const long long t_ = clock64(); if (threadIdx.x == 0) atomicAdd((unsigned long long*)&g_qt_prof[(g).prof_base + (k)], (unsigned long long)(t_ - qt_tl_)); qt_tl_ = t_; }
+#else
+#define QT_PROF_BEGIN() ((void)0)
+#define QT_TICK(g, k) {}
 #endif
 
 struct QtNode {      // 20 bytes
@@ -67,6 +84,9 @@ struct QtGeom {
     float hX;
     int N;                 // features wanted at this level
     int wCell, hCell, nCols;  // FAST cell grid (defines the reference's candidate order)
+#if defined(QT_PROFILE)
+    int prof_base;
+#endif
 };
 
 // workspace layout for `cap` nodes; all pointers may be shared or global memory
@@ -263,11 +283,9 @@ ORB_HD QtNode qt_child(const QtNode& nd, const int* b3, int q) {
 
 ORB_HD bool qt_expandable(const QtNode& nd) { return (nd.hi - nd.lo) > 1 && (int)(nd.pd >> 24) < QT_LEVELS; }
 
-ORB_HD bool qt_item_less(const QtItem& a, const QtItem& b) {  // compareNodes, ORBextractor.cc:676-697
-    if (a.cnt < b.cnt) return true;
-    if (a.cnt > b.cnt) return false;
-    return (a.ulx_pos >> 16) < (b.ulx_pos >> 16);
-}
+// compareNodes (ORBextractor.cc:676-697) orders by (point count, UL.x): one 48-bit key, compared without branches
+ORB_HD uint64_t qt_item_key(const QtItem& a) { return ((uint64_t)a.cnt << 16) | (uint64_t)(a.ulx_pos >> 16); }
+ORB_HD bool qt_item_less(const QtItem& a, const QtItem& b) { return qt_item_key(a) < qt_item_key(b); }
 
 // std::sort on QtItem with the libstdc++ sequence of moves (devmath.cuh std_sort, specialised)
 ORB_HD void qt_std_sort_items(QtItem* a, int n) {
@@ -407,6 +425,7 @@ ORB_HD uint64_t qt_order_key(int x, int y, const QtGeom& g) {
 template <int VARIANT>
 ORB_HD int qt_distribute_v(const uint32_t* arr, int n, const QtGeom& g, QtWork& w, uint32_t* out) {
     // roots (ORBextractor.cc:718-786): non-empty ones, in order
+    QT_PROF_BEGIN();
     int S = 0;
     QT_SERIAL {
         int lo = 0, cnt = 0;
@@ -428,6 +447,7 @@ ORB_HD int qt_distribute_v(const uint32_t* arr, int n, const QtGeom& g, QtWork& 
     QT_SYNC();
 
     bool finish = (S == 0);
+    QT_TICK(g, 2)
     while (!finish) {
         const int prevS = S;
         // ---- one sweep over the list (ORBextractor.cc:814-906) --------------------------------
@@ -485,6 +505,7 @@ ORB_HD int qt_distribute_v(const uint32_t* arr, int n, const QtGeom& g, QtWork& 
         S = E + NM;
         { QtNode* t = w.cur; w.cur = w.nxt; w.nxt = t; }
         int nItems = X;
+        QT_TICK(g, 3)
         if (S >= g.N || S == prevS) {
             finish = true;
         } else if (S + 3 * nItems > g.N) {
@@ -499,8 +520,9 @@ ORB_HD int qt_distribute_v(const uint32_t* arr, int n, const QtGeom& g, QtWork& 
                     QT_SERIAL { qt_std_sort_items(w.items, nItems); }
                     QT_SYNC();
                 } else {
-                    qt_std_sort_items_par(w.items, nItems, w.items2, w.m, w.bnd, w.f, w.scan_tmp);
+                    qt_std_sort_items_par(w.items, nItems, w.items2, w.m, w.bnd, w.f, w.scan_tmp, 6 * w.cap);   // bnd | m | x | f are contiguous: 6 * cap ints from w.bnd
                 }
+                QT_TICK(g, 4)
                 // processing order p = 0.. corresponds to sorted index j = nItems-1-p
                 QT_PAR_FOR(p, nItems) {
                     const QtItem it = w.items[nItems - 1 - p];
@@ -554,6 +576,7 @@ ORB_HD int qt_distribute_v(const uint32_t* arr, int n, const QtGeom& g, QtWork& 
                 }
                 if (Ek + kept > w.cap) return -1;
                 const int Xk = qt_exscan(w.x, K, w.scan_tmp);  // x[p] = items created before p
+                QT_TICK(g, 5)
                 QT_PAR_FOR(t, S) {
                     // kept nodes keep their relative order behind all new children
                     const QtNode nd = w.cur[t];
@@ -594,6 +617,7 @@ ORB_HD int qt_distribute_v(const uint32_t* arr, int n, const QtGeom& g, QtWork& 
                 nItems = Xk;
                 { QtNode* t = w.cur; w.cur = w.nxt; w.nxt = t; }
                 { QtItem* t = w.items; w.items = w.items2; w.items2 = t; }
+                QT_TICK(g, 6)
                 if (S >= g.N || S == prev2) finish = true;
             }
         }
@@ -619,6 +643,7 @@ ORB_HD int qt_distribute_v(const uint32_t* arr, int n, const QtGeom& g, QtWork& 
         out[t] = qt_pack_cand(bx, by, (int)(best & 0xffu));
     }
     QT_SYNC();
+    QT_TICK(g, 7)
     return S;
 }
 

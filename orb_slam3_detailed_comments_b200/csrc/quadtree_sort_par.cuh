@@ -29,16 +29,53 @@ ORB_HD int qt_sortpar_partition(QtItem* a, int first, int last) {
     else if (qt_item_less(a[B], a[C])) pick = C;
     else pick = B;
     { const QtItem t = a[first]; a[first] = a[pick]; a[pick] = t; }
-    const QtItem pv = a[first];
+    const uint64_t pv = qt_item_key(a[first]);
     int lo = first + 1, hi = last;
+    // The two scans of __unguarded_partition read four items per round trip (the loads are independent, the tests sequential): the
+    // chain of one shared-memory latency per element was the critical path of the whole ordered phase (phase clocks, round 2).
+    // Reads run at most three items past a scan's stopping point: inside the workspace on the device, inside the padding the host
+    // harnesses allocate (tests/host_emul).
+#if defined(QT_EMUL_THREADS)
+    // threaded host emulation (ThreadSanitizer): one item per read -- a speculative read may land in a segment another thread is
+    // partitioning, which is harmless (the value is never used) but is a data race by the letter
     while (true) {
-        while (qt_item_less(a[lo], pv)) ++lo;
+        while (qt_item_key(a[lo]) < pv) ++lo;
         --hi;
-        while (qt_item_less(pv, a[hi])) --hi;
+        while (pv < qt_item_key(a[hi])) --hi;
         if (!(lo < hi)) break;
         const QtItem t = a[lo]; a[lo] = a[hi]; a[hi] = t;
         ++lo;
     }
+#else
+    while (true) {
+        while (true) {
+            const uint64_t k0 = qt_item_key(a[lo]), k1 = qt_item_key(a[lo + 1]), k2 = qt_item_key(a[lo + 2]), k3 = qt_item_key(a[lo + 3]);
+            if (!(k0 < pv)) break;
+            ++lo;
+            if (!(k1 < pv)) break;
+            ++lo;
+            if (!(k2 < pv)) break;
+            ++lo;
+            if (!(k3 < pv)) break;
+            ++lo;
+        }
+        --hi;
+        while (true) {
+            const uint64_t k0 = qt_item_key(a[hi]), k1 = qt_item_key(a[hi - 1]), k2 = qt_item_key(a[hi - 2]), k3 = qt_item_key(a[hi - 3]);
+            if (!(pv < k0)) break;
+            --hi;
+            if (!(pv < k1)) break;
+            --hi;
+            if (!(pv < k2)) break;
+            --hi;
+            if (!(pv < k3)) break;
+            --hi;
+        }
+        if (!(lo < hi)) break;
+        const QtItem t = a[lo]; a[lo] = a[hi]; a[hi] = t;
+        ++lo;
+    }
+#endif
     return lo;
 }
 
@@ -95,11 +132,49 @@ ORB_HD void qt_sortpar_heapsort(QtItem* h, int len) {
 // a[0..n) sorted exactly as std::sort(a, a + n, compareNodes) leaves it.  tmp: n items.  seg / nxt: 3 ints per segment slot each
 // (first, last, depth), room for n / 8 + 2 slots; flag: 2 * (n / 8 + 2) ints; scan_tmp: qt_exscan's scratch.  Whole CTA; returns after a
 // barrier.  Every segment on a list is longer than 16, so a generation holds at most n / 17 of them.
-ORB_HD void qt_std_sort_items_par(QtItem* a, int n, QtItem* tmp, int* seg, int* nxt, int* flag, int* scan_tmp) {
+ORB_HD void qt_std_sort_items_par(QtItem* a, int n, QtItem* tmp, int* seg, int* nxt, int* flag, int* scan_tmp, int nxt_ints) {
     if (n <= 1) return;   // uniform
     if (n > 16) {
         int lg = 0;
         for (int t = n; t > 1; t >>= 1) ++lg;
+#if defined(__CUDA_ARCH__)
+        // device: the generations are run by warp 0 alone -- a generation has at most n / 17 segments (one lane each), and its five
+        // CTA barriers (partition | scan x 3 | scatter) become __syncwarp; the other warps wait at the one barrier below
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            const unsigned lt = (1u << lane) - 1u;
+            int* cur = seg;      // 3 ints per segment: first, last, depth
+            int* oth = nxt;
+            if (lane == 0) { cur[0] = 0; cur[1] = n; cur[2] = 2 * lg; }
+            __syncwarp();
+            int nseg = 1;
+            while (nseg > 0) {
+                int off = 0;
+                for (int base = 0; base < nseg; base += 32) {
+                    const int sI = base + lane;
+                    int first = 0, cut = 0, last = 0, depth = 0;
+                    bool l_alive = false, r_alive = false;
+                    if (sI < nseg) {
+                        first = cur[3 * sI]; last = cur[3 * sI + 1]; depth = cur[3 * sI + 2];
+                        cut = first;
+                        if (depth == 0) qt_sortpar_heapsort(a + first, last - first);
+                        else cut = qt_sortpar_partition(a, first, last);
+                        l_alive = depth != 0 && cut - first > 16;
+                        r_alive = depth != 0 && last - cut > 16;
+                    }
+                    const unsigned ml = __ballot_sync(0xffffffffu, l_alive), mr = __ballot_sync(0xffffffffu, r_alive);
+                    const int pos = off + __popc(ml & lt) + __popc(mr & lt);
+                    if (l_alive) { oth[3 * pos] = first; oth[3 * pos + 1] = cut; oth[3 * pos + 2] = depth - 1; }
+                    if (r_alive) { const int pr = pos + (l_alive ? 1 : 0); oth[3 * pr] = cut; oth[3 * pr + 1] = last; oth[3 * pr + 2] = depth - 1; }
+                    off += __popc(ml) + __popc(mr);
+                }
+                __syncwarp();
+                nseg = off;
+                { int* t_ = cur; cur = oth; oth = t_; }
+            }
+        }
+        QT_SYNC();
+#else
         QT_SERIAL { seg[0] = 0; seg[1] = n; seg[2] = 2 * lg; }
         QT_SYNC();
         int nseg = 1;
@@ -133,16 +208,29 @@ ORB_HD void qt_std_sort_items_par(QtItem* a, int n, QtItem* tmp, int* seg, int* 
             QT_SYNC();
             nseg = alive;
         }
+#endif
     }
-    // __final_insertion_sort == stable sort of the current arrangement
-    QT_PAR_FOR(i, n) {
-        const QtItem v = a[i];
+    // __final_insertion_sort == stable sort of the current arrangement: rank(i) = #{j : key_j < key_i} + #{j < i : key_j == key_i}.
+    // G threads share an item (each counts over a slice of j; nxt is free by now and holds the partial counts).
+    int G = 1;
+    while (G < 4 && 2 * G * n <= QT_NTHREADS && 2 * G * n <= nxt_ints) G <<= 1;
+    const int slice = (n + G - 1) / G;
+    QT_PAR_FOR(t, n * G) {
+        const int i = t / G, part = t - i * G;
+        const uint64_t kv = qt_item_key(a[i]);
+        const int j0 = part * slice, j1 = (j0 + slice < n) ? j0 + slice : n;
         int rank = 0;
-        for (int j = 0; j < n; ++j) {
-            const QtItem u = a[j];
-            rank += (qt_item_less(u, v) || (j < i && !qt_item_less(v, u))) ? 1 : 0;
+        for (int j = j0; j < j1; ++j) {
+            const uint64_t ku = qt_item_key(a[j]);
+            rank += (ku < kv ? 1 : 0) + ((ku == kv) & (j < i) ? 1 : 0);
         }
-        tmp[rank] = v;
+        nxt[t] = rank;
+    }
+    QT_SYNC();
+    QT_PAR_FOR(i, n) {
+        int rank = 0;
+        for (int k = 0; k < G; ++k) rank += nxt[i * G + k];
+        tmp[rank] = a[i];
     }
     QT_SYNC();
     QT_PAR_FOR(i, n) a[i] = tmp[i];
@@ -227,5 +315,108 @@ ORB_HD void qt_bitonic_sort_r8(uint32_t* arr, int npow) {
     }
 #undef QT_CX
 }
+
+#if defined(__CUDACC__)
+// ---- device only: bitonic sort whose strides <= 128 never touch shared memory -----------------------------------------------
+// ncu (round 2, profiles/r02_source_lines.md): qt_bitonic_sort_r8 spent 26 % (level 0) / 43 % (levels 1-7) of k_quadtree_v1 and four
+// times the ideal shared-memory wavefronts -- in the passes with strides < 32 a thread's eight elements are 8 / 4 / 2 words apart
+// from its neighbour's, an 8- / 4- / 2-way bank conflict on all sixteen accesses.  Here a warp owns 256 consecutive elements: lane
+// i holds arr[base + 4 i .. + 3] and arr[base + 128 + 4 i .. + 3] (two conflict-free 128-bit accesses), so strides 128, 2 and 1 are
+// compare-exchanges between a lane's own registers and strides 64 .. 4 are one shuffle each with lane ^ 16 .. lane ^ 1.  All merges
+// up to 256 run in one such pass; a larger merge takes shared-memory passes (three / two / one stage each, strides >= 256 only:
+// conflict-free) followed by one warp pass.  8192 elements: 13 barriers (35 before, 91 with one stage per pass).  Keys are unique,
+// so any correct sort gives the same array.
+__device__ __forceinline__ void qt_warp_stages(uint32_t (&v)[8], int idx0, int k, int jstart, int lane) {
+#define QT_IDX(e) (idx0 + ((e) & 3) + (((e) >> 2) << 7))
+#define QT_CXU(x, y, up) { const uint32_t lo_ = min((x), (y)), hi_ = max((x), (y)); (x) = (up) ? lo_ : hi_; (y) = (up) ? hi_ : lo_; }
+#pragma unroll
+    for (int s = 7; s >= 0; --s) {
+        const int j = 1 << s;
+        if (j > jstart) continue;
+        if (s == 7) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) QT_CXU(v[e], v[e + 4], (QT_IDX(e) & k) == 0)
+        } else if (s >= 2) {
+            const int m = j >> 2;
+            const bool lower = (lane & m) == 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const bool up = (QT_IDX(e) & k) == 0;
+                const uint32_t other = __shfl_xor_sync(0xffffffffu, v[e], m);
+                v[e] = (lower == up) ? min(v[e], other) : max(v[e], other);
+            }
+        } else if (s == 1) {
+            QT_CXU(v[0], v[2], (QT_IDX(0) & k) == 0) QT_CXU(v[1], v[3], (QT_IDX(1) & k) == 0)
+            QT_CXU(v[4], v[6], (QT_IDX(4) & k) == 0) QT_CXU(v[5], v[7], (QT_IDX(5) & k) == 0)
+        } else {
+            QT_CXU(v[0], v[1], (QT_IDX(0) & k) == 0) QT_CXU(v[2], v[3], (QT_IDX(2) & k) == 0)
+            QT_CXU(v[4], v[5], (QT_IDX(4) & k) == 0) QT_CXU(v[6], v[7], (QT_IDX(6) & k) == 0)
+        }
+    }
+#undef QT_IDX
+#undef QT_CXU
+}
+
+// npow: a power of two >= 256; arr 16-byte aligned; whole CTA (blockDim a multiple of 32); returns after a barrier
+__device__ inline void qt_bitonic_sort_w(uint32_t* arr, int npow) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, nblk = npow >> 8;
+#define QT_CX(x, y) { if (((x) > (y)) == up) { const uint32_t t_ = (x); (x) = (y); (y) = t_; } }
+    for (int kk = 256; kk <= npow; kk <<= 1) {
+        // shared-memory passes for the strides >= 256 of merge size kk (none for kk == 256)
+        int j = kk >> 1;
+        for (; j >= 1024; j >>= 3) {
+            const int h = j >> 1, q = j >> 2;
+            for (int i = threadIdx.x; i < (npow >> 3); i += blockDim.x) {
+                const int l0 = (i & (q - 1)) | ((i & ~(q - 1)) << 3);
+                uint32_t a0 = arr[l0], a1 = arr[l0 | q], a2 = arr[l0 | h], a3 = arr[l0 | h | q];
+                uint32_t a4 = arr[l0 | j], a5 = arr[l0 | j | q], a6 = arr[l0 | j | h], a7 = arr[l0 | j | h | q];
+                const bool up = (l0 & kk) == 0;
+                QT_CX(a0, a4) QT_CX(a1, a5) QT_CX(a2, a6) QT_CX(a3, a7)
+                QT_CX(a0, a2) QT_CX(a1, a3) QT_CX(a4, a6) QT_CX(a5, a7)
+                QT_CX(a0, a1) QT_CX(a2, a3) QT_CX(a4, a5) QT_CX(a6, a7)
+                arr[l0] = a0; arr[l0 | q] = a1; arr[l0 | h] = a2; arr[l0 | h | q] = a3;
+                arr[l0 | j] = a4; arr[l0 | j | q] = a5; arr[l0 | j | h] = a6; arr[l0 | j | h | q] = a7;
+            }
+            __syncthreads();
+        }
+        if (j == 512) {          // strides 512 and 256
+            for (int i = threadIdx.x; i < (npow >> 2); i += blockDim.x) {
+                const int l0 = (i & 255) | ((i & ~255) << 2);
+                uint32_t a0 = arr[l0], a1 = arr[l0 | 256], a2 = arr[l0 | 512], a3 = arr[l0 | 768];
+                const bool up = (l0 & kk) == 0;
+                QT_CX(a0, a2) QT_CX(a1, a3) QT_CX(a0, a1) QT_CX(a2, a3)
+                arr[l0] = a0; arr[l0 | 256] = a1; arr[l0 | 512] = a2; arr[l0 | 768] = a3;
+            }
+            __syncthreads();
+        } else if (j == 256) {   // stride 256 alone
+            for (int i = threadIdx.x; i < (npow >> 1); i += blockDim.x) {
+                const int l0 = (i & 255) | ((i & ~255) << 1);
+                uint32_t a0 = arr[l0], a1 = arr[l0 | 256];
+                const bool up = (l0 & kk) == 0;
+                QT_CX(a0, a1)
+                arr[l0] = a0; arr[l0 | 256] = a1;
+            }
+            __syncthreads();
+        }
+        // warp pass: strides 128 .. 1 of merge size kk; for kk == 256 every merge from 2 up to 256
+        for (int b = warp; b < nblk; b += nwarps) {
+            const int base = b << 8, idx0 = base + 4 * lane;
+            uint4* p0 = reinterpret_cast<uint4*>(arr + idx0);
+            uint4* p1 = reinterpret_cast<uint4*>(arr + idx0 + 128);
+            const uint4 x0 = *p0, x1 = *p1;
+            uint32_t v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            if (kk == 256) {
+                for (int k = 2; k <= 256; k <<= 1) qt_warp_stages(v, idx0, k, k >> 1, lane);
+            } else {
+                qt_warp_stages(v, idx0, kk, 128, lane);
+            }
+            *p0 = make_uint4(v[0], v[1], v[2], v[3]);
+            *p1 = make_uint4(v[4], v[5], v[6], v[7]);
+        }
+        __syncthreads();
+    }
+#undef QT_CX
+}
+#endif  // __CUDACC__
 
 }  // namespace orbdev

@@ -199,15 +199,16 @@ extern "C" int emul_distribute_v1(const int32_t* cand3, int n, int regionW, int 
 // std::sort(vSizeAndPointerToNode, compareNodes) three ways: libstdc++ itself, the one-thread transcription, the CTA-parallel form.
 // items: n x (cnt, ulx, payload); which = 0 libstdc++, 1 qt_std_sort_items, 2 qt_std_sort_items_par.  out: payloads in sorted order.
 extern "C" void emul_sort_items(const uint32_t* items3, int n, int which, uint32_t* out_payload) {
-    std::vector<QtItem> a(n + 1), tmp(n + 1);
+    std::vector<QtItem> abuf(n + 9), tmp(n + 1);      // four items of padding either side: the partition's scans read ahead
+    QtItem* a = abuf.data() + 4;
     for (int i = 0; i < n; ++i) { a[i].cnt = items3[3 * i]; a[i].ulx_pos = (items3[3 * i + 1] << 16) | (items3[3 * i + 2] & 0xffffu); }
     if (which == 0) {
-        std::sort(a.begin(), a.begin() + n, [](const QtItem& x, const QtItem& y) { return qt_item_less(x, y); });
+        std::sort(a, a + n, [](const QtItem& x, const QtItem& y) { return qt_item_less(x, y); });
     } else if (which == 1) {
-        qt_std_sort_items(a.data(), n);
+        qt_std_sort_items(a, n);
     } else {
-        std::vector<int> seg(n + 64), nxt(3 * n + 64), flag(n + 64), st(64);
-        qt_std_sort_items_par(a.data(), n, tmp.data(), seg.data(), nxt.data(), flag.data(), st.data());
+        std::vector<int> seg(n + 64), nxt(4 * n + 64), flag(n + 64), st(64);
+        qt_std_sort_items_par(a, n, tmp.data(), seg.data(), nxt.data(), flag.data(), st.data(), 4 * n + 64);
     }
     for (int i = 0; i < n; ++i) out_payload[i] = a[i].ulx_pos & 0xffffu;
 }
