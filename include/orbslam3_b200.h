@@ -474,7 +474,7 @@ orb_status orbo_pose_optimization(orbx_handle* h, const orbo_pose_problems* in, 
 /* The correspondence walk of PoseOptimization (Optimizer.cc:104-290) for frames whose features and matches are still on
  * the device: one edge per feature that holds a map point, in feature order.  feature_match (per compact keypoint row:
  * query index or -1) is the output of orbm_search_last_frame / orbm_search_bow; query_match (per query: feature index or
- * -1) the output of orbm_search_local_points; exactly one of the two is given.  world_pos[q] = pMP->GetWorldPos() of
+ * -1) the output of orbm_search_local_points; one of the two is given, or both together with query_world_pos.  world_pos[q] = pMP->GetWorldPos() of
  * query q.  ALL pointers are device memory; no synchronisation.  Outputs feed
  * orbo_pose_optimization (on_device = 1): edge_offset_out[n_frames + 1], and per edge the feature index inside its frame
  * (to map outlier flags back to mvbOutlier), world position, observation (x, y, mvuRight or -1) and
@@ -486,6 +486,10 @@ typedef struct {
     const int32_t* query_offset;  /* [n_frames + 1], with query_match */
     const int32_t* query_match;   /* or NULL */
     const float* world_pos;       /* [nq][3] */
+    const float* query_world_pos; /* NULL, or -- with BOTH feature_match and query_match given (TrackLocalMap: the map points the motion-model
+                                     search left in the frame plus the local-map matches; a feature both hold goes to the local-map one, as
+                                     ORBmatcher.cc:116-118 only lets the second search take features whose map point has no observations) --
+                                     GetWorldPos() of the query_match entries; world_pos then belongs to the feature_match entries */
 } orbo_edge_source;
 
 orb_status orbo_pose_edges(orbx_handle* h, const orbo_edge_source* src, int32_t* edge_offset_out, int32_t* edge_feature_out,
@@ -629,6 +633,23 @@ orb_status liba_link_information(const float* C15x15, int32_t oldest, double* in
  * k+1 .. k+H-1 before collecting handle k) overlaps uploads, kernels and downloads without further threads.
  * One step per handle may be in flight.  Images: 2 * n_frames, left eye of frame p = image 2p, right eye = image 2p + 1.
  * ---------------------------------------------------------------------------------------------- */
+/* The chained data flow of one tracked frame (Tracking.cc:3389-3522, 4010-4062) instead of two independent searches with precomputed
+ * projections: the motion-model search and its PoseOptimization run first; the features whose map point came out an outlier are released
+ * (Tracking.cc:3447-3470); the optimised pose goes through Sophus::SE3f (Optimizer.cc:406-410, Frame::UpdatePoseMatrices) into
+ * Frame::isInFrustum for every local map point that the motion-model search did not already put into the frame (mnLastFrameSeen,
+ * Tracking.cc:3997-4000); SearchByProjection(F, local map points) sees the features that still hold a map point with observations
+ * (ORBmatcher.cc:116-118); the second PoseOptimization starts from the first one's pose over ALL map points the frame holds. */
+typedef struct {
+    const int32_t* point_offset;         /* [n_frames + 1] local map points of every frame (mvpLocalMapPoints, isBad ones removed) */
+    const float* world_pos;              /* [np][3] GetWorldPos */
+    const float* normal;                 /* [np][3] GetNormal */
+    const float* max_dist;               /* [np] mfMaxDistance (raw) */
+    const float* min_dist;               /* [np] mfMinDistance (raw) */
+    const uint8_t* desc;                 /* [np][32] GetDescriptor */
+    const int32_t* last_query;           /* [np] this map point's index in the frame's OWN `last` query list (0-based inside the frame), or -1 */
+    float viewing_cos_limit;             /* 0.5 (Tracking.cc:4022) */
+} orbr_chain;
+
 typedef struct {
     int32_t n_frames;
     const uint8_t* images;               /* HOST: 2 * n_frames images */
@@ -645,6 +666,8 @@ typedef struct {
     int32_t pose_optimization;           /* != 0: Optimizer::PoseOptimization after each search */
     const float* pose;                   /* [n_frames][7] pFrame->GetPose() on entry of PoseOptimization (with pose_optimization) */
     const float* local_world_pos;        /* [nq_local][3] GetWorldPos() of the local-map entries (with pose_optimization) */
+    const orbr_chain* chain;             /* NULL, or the chained flow: needs `last` and `pose`, `local` must be NULL; PoseOptimization runs after both
+                                            searches whatever pose_optimization says; local_* results are indexed by the chain's map points */
 } orbr_step;
 
 typedef struct {                         /* HOST result buffers; any pointer may be NULL (that result is not copied back) */
@@ -665,6 +688,14 @@ typedef struct {                         /* HOST result buffers; any pointer may
     int32_t* edge_offset[2];             /* [n_frames + 1] */
     int32_t* edge_feature[2];            /* [edges] feature index inside its frame */
     uint8_t* edge_outlier[2];            /* [edges] pFrame->mvbOutlier of that feature */
+    /* chained flow only: what Frame::isInFrustum wrote into every local map point (0 / -1 where it was skipped or not in view) */
+    uint8_t* chain_in_view;              /* [np] mbTrackInView */
+    float* chain_proj_x;                 /* [np] mTrackProjX */
+    float* chain_proj_y;
+    float* chain_proj_xr;
+    int32_t* chain_level;                /* [np] mnTrackScaleLevel */
+    float* chain_view_cos;               /* [np] mTrackViewCos */
+    float* chain_pose_f;                 /* [n_frames][7] the Sophus::SE3f the frame holds after the first PoseOptimization (qx qy qz qw tx ty tz) */
 } orbr_results;
 
 orb_status orbr_submit(orbx_handle* h, const orbm_camera* cam, const orbr_step* step);

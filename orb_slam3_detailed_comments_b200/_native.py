@@ -80,7 +80,7 @@ class orbo_pose_problems(C.Structure):
 
 
 class orbo_edge_source(C.Structure):
-    _fields_ = [("n_frames", C.c_int32)] + [(n, C.c_void_p) for n in ("frame_image", "feature_match", "query_offset", "query_match", "world_pos")]
+    _fields_ = [("n_frames", C.c_int32)] + [(n, C.c_void_p) for n in ("frame_image", "feature_match", "query_offset", "query_match", "world_pos", "query_world_pos")]
 
 
 class orbo_frame_matches(C.Structure):
@@ -88,18 +88,23 @@ class orbo_frame_matches(C.Structure):
         [("n_queries", C.c_int32)] + [(n, C.c_float) for n in ("fx", "fy", "cx", "cy", "bf")]
 
 
+class orbr_chain(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("point_offset", "world_pos", "normal", "max_dist", "min_dist", "desc", "last_query")] + [("viewing_cos_limit", C.c_float)]
+
+
 class orbr_step(C.Structure):
     _fields_ = [("n_frames", C.c_int32), ("images", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("stride", C.c_int32),
                 ("image_stride_bytes", C.c_size_t), ("bf", C.c_float), ("b", C.c_float), ("last", C.POINTER(orbm_last_queries)),
                 ("th_last", C.c_float), ("check_orientation_last", C.c_int32), ("local", C.POINTER(orbm_local_queries)),
                 ("th_local", C.c_float), ("nnratio_local", C.c_float), ("far_points", C.c_int32), ("th_far", C.c_float),
-                ("pose_optimization", C.c_int32), ("pose", C.c_void_p), ("local_world_pos", C.c_void_p)]
+                ("pose_optimization", C.c_int32), ("pose", C.c_void_p), ("local_world_pos", C.c_void_p), ("chain", C.POINTER(orbr_chain))]
 
 
 class orbr_results(C.Structure):
     _fields_ = [("cap_rows", C.c_int32)] + [(n, C.c_void_p) for n in ("keypoints", "descriptors", "uright", "depth", "n", "offsets",
                                                                      "last_feature_match", "last_nmatches", "local_match", "local_nmatches")] + \
-        [(n, C.c_void_p * 2) for n in ("pose", "inliers", "edge_offset", "edge_feature", "edge_outlier")]
+        [(n, C.c_void_p * 2) for n in ("pose", "inliers", "edge_offset", "edge_feature", "edge_outlier")] + \
+        [(n, C.c_void_p) for n in ("chain_in_view", "chain_proj_x", "chain_proj_y", "chain_proj_xr", "chain_level", "chain_view_cos", "chain_pose_f")]
 
 
 class orbf_frustum_points(C.Structure):

@@ -274,6 +274,7 @@ struct EdgeParams {
     const int* qoff;              // with query_match
     const int* query_match;       // or null
     const float* xw;              // [nq][3]
+    const float* xw2;             // with BOTH sources: world positions of the query_match entries (xw then belongs to feature_match)
     float invSigma2[ORB_MAX_LEVELS];
     int* cnt;                     // [n_frames]
     int* eoff;                    // [n_frames + 1]
@@ -297,9 +298,10 @@ __global__ void __launch_bounds__(PE_THREADS) k_pose_edges(const __grid_constant
     __syncthreads();
     if (P.query_match) {
         const int q0 = P.qoff[frame], q1 = P.qoff[frame + 1];
+        const int tag = P.xw2 ? 0x40000000 : 0;      // both sources: entries of the second one carry a tag (their positions come from xw2)
         for (int q = q0 + tid; q < q1; q += PE_THREADS) {
             const int f = P.query_match[q];
-            if (f >= 0 && f < N) pe_holder[f] = q;   // a feature is claimed by at most one query of a search
+            if (f >= 0 && f < N) pe_holder[f] = q | tag;   // a feature is claimed by at most one query of a search
         }
         __syncthreads();
     }
@@ -337,7 +339,8 @@ __global__ void __launch_bounds__(PE_THREADS) k_pose_edges(const __grid_constant
             const int e = s_base + before + __popc(m & ((1u << lane) - 1u));
             const orbx_keypoint k = P.kps[row0 + i];
             P.efeat[e] = i;
-            P.exw[3 * (size_t)e] = P.xw[3 * (size_t)q]; P.exw[3 * (size_t)e + 1] = P.xw[3 * (size_t)q + 1]; P.exw[3 * (size_t)e + 2] = P.xw[3 * (size_t)q + 2];
+            const float* wp = (q & 0x40000000) ? P.xw2 + 3 * (size_t)(q & 0x3fffffff) : P.xw + 3 * (size_t)q;
+            P.exw[3 * (size_t)e] = wp[0]; P.exw[3 * (size_t)e + 1] = wp[1]; P.exw[3 * (size_t)e + 2] = wp[2];
             P.eobs[3 * (size_t)e] = k.x; P.eobs[3 * (size_t)e + 1] = k.y; P.eobs[3 * (size_t)e + 2] = P.uright ? P.uright[row0 + i] : -1.0f;
             P.ew[e] = P.invSigma2[k.octave];
         }
@@ -424,8 +427,9 @@ extern "C" orb_status orbo_pose_optimization(orbx_handle* h, const orbo_pose_pro
 
 extern "C" orb_status orbo_pose_edges(orbx_handle* h, const orbo_edge_source* src, int32_t* edge_offset_out, int32_t* edge_feature_out,
                                       float* world_pos_out, float* obs_out, float* inv_sigma2_out) {
-    if (!h || !src || src->n_frames < 1 || !src->frame_image || !src->world_pos || ((src->feature_match != nullptr) == (src->query_match != nullptr)) ||
-        (src->query_match && !src->query_offset) || !edge_offset_out || !edge_feature_out || !world_pos_out || !obs_out || !inv_sigma2_out)
+    const bool both = src && src->feature_match && src->query_match;
+    if (!h || !src || src->n_frames < 1 || !src->frame_image || !src->world_pos || (!src->feature_match && !src->query_match) ||
+        (both && !src->query_world_pos) || (!both && src->query_world_pos) || (src->query_match && !src->query_offset) || !edge_offset_out || !edge_feature_out || !world_pos_out || !obs_out || !inv_sigma2_out)
         return set_error(ORB_ERR_INVALID, "bad arguments");
     if (h->last_batch < 1) return set_error(ORB_ERR_INVALID, "no batch has been extracted");
     ORB_CUDA(cudaSetDevice(h->cfg.device));
@@ -443,6 +447,7 @@ extern "C" orb_status orbo_pose_edges(orbx_handle* h, const orbo_edge_source* sr
     P.maxFeat = h->geom.kpTotal;
     P.frame_image = src->frame_image; P.feature_match = src->feature_match; P.qoff = src->query_offset; P.query_match = src->query_match;
     P.xw = src->world_pos;
+    P.xw2 = src->query_world_pos;
     for (int l = 0; l < ORB_MAX_LEVELS; ++l) P.invSigma2[l] = l < h->cfg.n_levels ? h->inv_sigma2[l] : 1.f;
     P.cnt = reinterpret_cast<int*>(h->d_stage);
     P.eoff = edge_offset_out; P.efeat = edge_feature_out; P.exw = world_pos_out; P.eobs = obs_out; P.ew = inv_sigma2_out;
@@ -508,7 +513,7 @@ extern "C" orb_status orbo_pose_optimization_frames(orbx_handle* h, const orbo_f
     double* d_pout = cur.take<double>((size_t)nf * 7);
     uint8_t* d_out = cur.take<uint8_t>(cap);
     int* d_inl = cur.take<int>(nf);
-    orbo_edge_source src{nf, d_img, d_fm, d_qoff, d_qm, d_xw};
+    orbo_edge_source src{nf, d_img, d_fm, d_qoff, d_qm, d_xw, nullptr};
     if ((s = orbo_pose_edges(h, &src, d_eoff, d_efeat, d_exw, d_eobs, d_ew)) != ORB_OK) return s;
     orbo_pose_problems pp{nf, 1, d_eoff, d_pose, d_exw, d_eobs, d_ew, in->fx, in->fy, in->cx, in->cy, in->bf, (int32_t)cap};
     if ((s = orbo_pose_optimization(h, &pp, d_pout, d_out, d_inl, nullptr)) != ORB_OK) return s;

@@ -96,11 +96,11 @@ def PoseOptimizationDevice(extractor, n_frames, edge_offset, pose, world_pos, ob
 
 
 def PoseEdgesDevice(extractor, n_frames, frame_image, world_pos, edge_offset_out, edge_feature_out, world_pos_out, obs_out, inv_sigma2_out,
-                    feature_match=None, query_offset=None, query_match=None):
+                    feature_match=None, query_offset=None, query_match=None, query_world_pos=None):
     """PoseOptimization's correspondence walk (Optimizer.cc:104-290) over device-resident search outputs (CUDA torch tensors)."""
     L = N.lib()
     dp = lambda t: None if t is None else C.c_void_p(t.data_ptr())
-    src = N.orbo_edge_source(n_frames, dp(frame_image), dp(feature_match), dp(query_offset), dp(query_match), dp(world_pos))
+    src = N.orbo_edge_source(n_frames, dp(frame_image), dp(feature_match), dp(query_offset), dp(query_match), dp(world_pos), dp(query_world_pos))
     N.check(L.orbo_pose_edges(extractor._h, C.byref(src), dp(edge_offset_out), dp(edge_feature_out), dp(world_pos_out), dp(obs_out),
                               dp(inv_sigma2_out)))
 
@@ -160,7 +160,7 @@ def finish_inertial_result(pr_arrays, out, r):
 
 class InertialOptimizer:
     """Optimizer::LocalInertialBA's numeric core (include/Optimizer.h:63, src/Optimizer.cc:2203-2812) over the flat liba_problem
-    layout, one CTA per window.  Host-emulation-validated; first GPU run pending."""
+    layout, one CTA per window.  GPU parity: tests/test_liba_gpu.py."""
 
     def __init__(self, device=0):
         self._L = N.lib()

@@ -88,10 +88,11 @@ class TrackingStep:
                      1 if far_points else 0, float(th_far))
         self._keep = None
 
-    def submit(self, images, last=None, local=None, pose=None, local_world_pos=None):
+    def submit(self, images, last=None, local=None, pose=None, local_world_pos=None, chain=None):
         """images: (2 * n_frames, H, W) uint8 host array; last / local: dicts of host arrays with the field names of
         orbm_last_queries / orbm_local_queries (fimg, off, Tcw, dir, xw, oct, ang, desc, obs / fimg, off, px, py, pxr, lvl, vc, desc
-        [, td, in_view]); pose + local_world_pos switch PoseOptimization on."""
+        [, td, in_view]); pose + local_world_pos switch PoseOptimization on.  chain: dict(off, xw, normal, max_dist, min_dist, desc,
+        last_query[, cos_limit]) of the frames' local map points selects the chained flow (orbr_chain): needs last and pose, no local."""
         C, N = self._C, self._N
         assert images.dtype == np.uint8 and images.flags["C_CONTIGUOUS"] and images.ndim == 3
         nimg, h, w = images.shape
@@ -105,15 +106,21 @@ class TrackingStep:
             qc = N.orbm_local_queries(nf, 0, *[N.ptr(local[k]) if local.get(k) is not None else None
                                                for k in ("fimg", "off", "px", "py", "pxr", "lvl", "vc", "td", "desc", "claimed", "in_view")])
         po = pose is not None
+        ch = None
+        if chain is not None:
+            ch = N.orbr_chain(*[N.ptr(chain[k]) for k in ("off", "xw", "normal", "max_dist", "min_dist", "desc", "last_query")],
+                              float(chain.get("cos_limit", 0.5)))
         st = N.orbr_step(nf, N.ptr(images), w, h, w, w * h, bf, b, C.pointer(ql) if ql is not None else None, thl, ori,
                          C.pointer(qc) if qc is not None else None, thc, nnr, far, thfar, 1 if po else 0,
-                         N.ptr(pose) if po else None, N.ptr(local_world_pos) if (po and local_world_pos is not None) else None)
-        self._keep = (images, last, local, pose, local_world_pos, ql, qc)      # the arrays must outlive the asynchronous copies
+                         N.ptr(pose) if po else None, N.ptr(local_world_pos) if (po and local_world_pos is not None) else None,
+                         C.pointer(ch) if ch is not None else None)
+        self._keep = (images, last, local, pose, local_world_pos, ql, qc, chain, ch)      # the arrays must outlive the asynchronous copies
         N.check(self._L.orbr_submit(self.ex._h, C.byref(self.cam), C.byref(st)))
 
     def collect(self, out):
         """out: dict of preallocated host arrays -- kps, desc, ur, dep (cap_rows rows), n, offsets, fm, nm1, mt, nm2 and, with
-        PoseOptimization, pose (2, nf, 7) f64, inl (2, nf) i32, eoff (2, nf + 1) i32, efeat (2, cap) i32, outl (2, cap) u8.
+        PoseOptimization, pose (2, nf, 7) f64, inl (2, nf) i32, eoff (2, nf + 1) i32, efeat (2, cap) i32, outl (2, cap) u8; chained
+        flow: c_in_view, c_px, c_py, c_pxr, c_level, c_vc (per local map point) and c_pose (nf, 7) f32.
         Missing keys are not copied back.  Returns the number of compact rows of the batch."""
         C, N = self._C, self._N
         g = lambda k: N.ptr(out[k]) if out.get(k) is not None else None
@@ -122,7 +129,8 @@ class TrackingStep:
         if out.get("efeat") is not None:
             cap = min(cap, out["efeat"].shape[1])
         res = N.orbr_results(int(cap), g("kps"), g("desc"), g("ur"), g("dep"), g("n"), g("offsets"), g("fm"), g("nm1"), g("mt"), g("nm2"),
-                             two("pose"), two("inl"), two("eoff"), two("efeat"), two("outl"))
+                             two("pose"), two("inl"), two("eoff"), two("efeat"), two("outl"),
+                             g("c_in_view"), g("c_px"), g("c_py"), g("c_pxr"), g("c_level"), g("c_vc"), g("c_pose"))
         rows = C.c_int32(0)
         N.check(self._L.orbr_collect(self.ex._h, C.byref(res), C.byref(rows)))
         self._keep = None
