@@ -379,7 +379,8 @@ class Workload:
         T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)
         cat = lambda xs, dt: np.concatenate(xs).astype(dt) if len(xs) else np.zeros(0, dt)
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
-        self.H_LAST, self.H_LOC, self.D_LAST, self.D_LOC, self.P_LAST, self.P_LOC = [], [], [], [], [], []
+        self.H_LAST, self.H_LOC, self.D_LAST, self.D_LOC, self.P_LAST, self.P_LOC, self.P_CHAIN = [], [], [], [], [], [], []
+        sfac = ex.GetScaleFactors()
         for pb in range(self.pool_batches):
             ex.extract_batch_device(self.dev_pool[pb].data_ptr(), nimg, self.W, self.H)
             ex.stereo_batch(B, BF, BL)
@@ -387,6 +388,7 @@ class Workload:
             uR0, dep0 = ex.stereo_download(int(off0[-1]))
             q_last = dict(off=[0], xw=[], oct=[], ang=[], desc=[], obs=[])
             q_loc = dict(off=[0], px=[], py=[], pxr=[], lvl=[], vc=[], desc=[], xw=[])
+            q_ch = dict(off=[0], xw=[], normal=[], max_dist=[], min_dist=[], desc=[], last_query=[])
             for p in range(B):
                 a, b = int(off0[2 * p]), int(off0[2 * p + 1])
                 k, d, z = kps0[a:b], desc0[a:b], dep0[a:b]
@@ -399,6 +401,17 @@ class Workload:
                 q_loc["px"].append(x); q_loc["py"].append(y); q_loc["pxr"].append(xr); q_loc["lvl"].append(lvl)
                 q_loc["vc"].append(vc); q_loc["desc"].append(dq); q_loc["xw"].append(xwl)
                 q_loc["off"].append(q_loc["off"][-1] + len(x))
+                # chained flow (orbr_chain): the local map = the LastFrame map points themselves + one point per remaining feature + as many
+                # unrelated ones, as world positions with normals and distance ranges (the device projects them with the optimised pose)
+                nl = len(sel)
+                lq = np.full(len(xwl), -1, np.int32)
+                lq[sel] = np.arange(nl, dtype=np.int32)
+                octs = np.concatenate([k["octave"], rng.integers(0, 8, len(k))])
+                dist = np.linalg.norm(xwl, axis=1).astype(np.float32)
+                maxd = (dist * sfac[octs]).astype(np.float32)
+                q_ch["xw"].append(xwl); q_ch["normal"].append((xwl / np.maximum(dist[:, None], 1e-6)).astype(np.float32)); q_ch["max_dist"].append(maxd)
+                q_ch["min_dist"].append((maxd / sfac[7]).astype(np.float32)); q_ch["desc"].append(dq); q_ch["last_query"].append(lq)
+                q_ch["off"].append(q_ch["off"][-1] + len(xwl))
             h_last = dict(fimg=np.arange(0, nimg, 2, dtype=np.int32), off=np.array(q_last["off"], np.int32),
                           Tcw=np.tile(np.array([0, 0, 0, 1, 0.002, 0.001, 0], np.float32), (B, 1)), dir=np.zeros(B, np.int32),
                           xw=cat(q_last["xw"], np.float32).reshape(-1, 3), oct=cat(q_last["oct"], np.int32), ang=cat(q_last["ang"], np.float32),
@@ -409,6 +422,10 @@ class Workload:
             self.H_LAST.append(h_last); self.H_LOC.append(h_loc)
             self.D_LAST.append({k: T(v) for k, v in h_last.items()}); self.D_LOC.append({k: T(v) for k, v in h_loc.items()})
             self.P_LAST.append({k: pin(v) for k, v in h_last.items()}); self.P_LOC.append({k: pin(v) for k, v in h_loc.items()})
+            self.P_CHAIN.append(dict(off=pin(np.array(q_ch["off"], np.int32)), xw=pin(cat(q_ch["xw"], np.float32).reshape(-1, 3)),
+                                     normal=pin(cat(q_ch["normal"], np.float32).reshape(-1, 3)), max_dist=pin(cat(q_ch["max_dist"], np.float32)),
+                                     min_dist=pin(cat(q_ch["min_dist"], np.float32)), desc=pin(cat(q_ch["desc"], np.uint8).reshape(-1, 32)),
+                                     last_query=pin(cat(q_ch["last_query"], np.int32))))
         dev, NH = self.dev, self.NH
         self.rows_cap = nimg * (self.ex._L.orbx_max_features(self.ex._h))
         self.max_last = max(int(h["off"][-1]) for h in self.H_LAST)
@@ -501,6 +518,9 @@ class Workload:
     def e2e_submit(self, i, with_po=False):
         k, pb = i % self.NH, i % self.pool_batches
         pl, pc = self.P_LAST[pb], self.P_LOC[pb]
+        if with_po == "chain":       # the chained flow: the local map as world points, projected on the device with the optimised pose
+            self.steps_e2e[k].submit(self.host_pool[pb].numpy(), last=pl, pose=pl["Tcw"], chain=self.P_CHAIN[pb])
+            return
         self.steps_e2e[k].submit(self.host_pool[pb].numpy(), last=pl, local=pc, pose=pl["Tcw"] if with_po else None,
                                  local_world_pos=pc["xw"] if with_po else None)
 
@@ -530,6 +550,13 @@ class Workload:
             d2h += self.e2e_collect(first + i, with_po)[1]
         dt = time.perf_counter() - t0
         return dt, d2h
+
+    def chain_stats(self):
+        """what the last chained batch on handle 0 produced (sanity numbers for the bench line)"""
+        o = self.OUT[0]
+        return {"local_matches_per_frame": float(o["nm2"].mean()), "motion_model_matches_per_frame": float(o["nm1"].mean()),
+                "inliers_after_motion_model": float(o["inl"][0].mean()), "inliers_after_local_map": float(o["inl"][1].mean()),
+                "local_map_points_per_frame": float(self.P_CHAIN[0]["off"][-1]) / self.B}
 
     def h2d_bytes_per_batch(self, with_po=False):
         skip = () if with_po else ("xw",)
@@ -841,6 +868,21 @@ def main():
                    "note": "the headline step plus PoseOptimization after each search (device correspondence walk + optimiser in the same graph; "
                            "pose_optimization = 1 in orbr_submit for the e2e leg)"}
 
+    # ---- the chained per-frame data flow (orbr_chain): pose -> isInFrustum -> search -> PoseOptimization on the device, end to end ----
+    chained = None
+    if not args.extract_only:
+        try:
+            n_ch = max(NH, (args.steps * BPS) // 4)
+            wl.e2e_loop(0, 2 * NH, "chain")
+            barrier()
+            dt_ch = max_ranks(wl.e2e_loop(NH, n_ch, "chain")[0])
+            chained = {"batches": n_ch, "e2e_frames_per_s": world * B * n_ch / dt_ch, **wl.chain_stats(),
+                       "note": "TrackWithMotionModel + TrackLocalMap as one device flow per batch (Tracking.cc:3389-3522, 4010-4062): motion-model search, "
+                               "PoseOptimization, outlier release, Sophus::SE3f, isInFrustum of the local map, local-map search against the remaining "
+                               "claims, PoseOptimization over every map point of the frame; host buffers in and out (orbr_submit with orbr_chain)"}
+        except Exception as exc:
+            chained = {"error": repr(exc)}
+
     # ---- a real-texture-like input (5-10 k FAST candidates per image) beside the corner-rich default ----
     natural = None
     if not args.extract_only and cid == 3:
@@ -954,7 +996,7 @@ def main():
                         "repeats_frames_per_s": e2e_rates, "spread": (max(e2e_rates) - min(e2e_rates)) / e2e_value if e2e_value else None,
                         "api": "orbr_submit / orbr_collect (pinned host buffers in and out), one host thread, median of the repeats"},
                 "gpu_launches": int(launches), "graph_launches": int(args.steps * BPS) if use_graph else 0, "kernels_per_batch": int(kernels_per_batch),
-                "clocks": clocks, "parity": parity, "roofline": roofline, "cpu_baseline": cpu, "latency_b1": latency, "config5": cfg5, **side}
+                "clocks": clocks, "parity": parity, "roofline": roofline, "cpu_baseline": cpu, "latency_b1": latency, "chained_flow": chained, "config5": cfg5, **side}
         print(json.dumps(line))
     wl.close()
     if world > 1:

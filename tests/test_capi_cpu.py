@@ -71,3 +71,19 @@ def test_product_sources_never_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "pyoracle" not in src and "liborb_oracle" not in src and "oracle/" not in src.replace("oracle/tools", ""), f
+
+
+def test_ctypes_structs_have_the_size_the_header_gives_them(tmp_path):
+    """Every struct that crosses the C ABI by pointer: sizeof in C (gcc on include/orbslam3_b200.h) == ctypes.sizeof of the binding."""
+    import subprocess
+    names = ["orbx_config", "orbm_camera", "orbm_local_queries", "orbm_last_queries", "orbm_bow_queries", "orbm_kf_queries", "orbo_pose_problems",
+             "orbo_edge_source", "orbo_frame_matches", "orbf_frustum_points", "orbm_init_queries", "orbm_bow_kf_queries", "orbm_triangulation",
+             "lba_problem", "lba_result", "liba_problem", "liba_result", "orbr_chain", "orbr_step", "orbr_results"]
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "orbslam3_b200.h"\nint main(void) {\n' +
+                   "".join(f'    printf("{n} %zu\\n", sizeof({n}));\n' for n in names) + "    return 0;\n}\n")
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for n in names:
+        assert int(got[n]) == C.sizeof(getattr(N, n)), (n, got[n], C.sizeof(getattr(N, n)))

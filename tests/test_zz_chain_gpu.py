@@ -77,7 +77,7 @@ def test_chained_frame_flow_matches_the_oracle_stage_by_stage():
         octs = np.concatenate([k["octave"][selL], k["octave"][selB], rng.integers(0, 8, nC)])
         dist = np.linalg.norm(xw, axis=1).astype(np.float32)
         maxd = (dist * sf[octs] * rng.uniform(0.75, 1.3, len(xw))).astype(np.float32)
-        nrm = -xw / np.maximum(dist[:, None], 1e-6) + rng.normal(0, 0.35, xw.shape)
+        nrm = xw / np.maximum(dist[:, None], 1e-6) + rng.normal(0, 0.35, xw.shape)     # MapPoint::mNormalVector: mean viewing direction, camera -> point
         nrm = (nrm / np.linalg.norm(nrm, axis=1)[:, None]).astype(np.float32)
         perm = rng.permutation(len(xw))
         ch["xw"].append(xw[perm]); ch["normal"].append(nrm[perm]); ch["max_dist"].append(maxd[perm]); ch["min_dist"].append((maxd / sf[7]).astype(np.float32)[perm])
