@@ -63,8 +63,8 @@ def test_chained_frame_flow_matches_the_oracle_stage_by_stage():
         selL, selB = st[::2], st[1::2]
         pts = lambda s: np.stack([(k["x"][s] - CX) * z[s] / FX, (k["y"][s] - CY) * z[s] / FY, z[s]], 1).astype(np.float32)
         xwL = pts(selL)
-        gross = rng.random(len(selL)) < 0.06                      # map points that moved: matched by the search, thrown out by PoseOptimization
-        xwL[gross] += rng.normal(0, 0.4, (int(gross.sum()), 3)).astype(np.float32)
+        gross = rng.random(len(selL)) < 0.06                      # map points at half their depth: same pixel, so the search matches them; the
+        xwL[gross] *= np.float32(0.5)                             # stereo residual then makes PoseOptimization throw them out
         last["xw"].append(xwL); last["oct"].append(k["octave"][selL].astype(np.int32)); last["ang"].append(k["angle"][selL].astype(np.float32))
         last["desc"].append(d[selL]); last["obs"].append((rng.random(len(selL)) < 0.9).astype(np.uint8)); last["off"].append(last["off"][-1] + len(selL))
         # local map: the LastFrame map points themselves (in a shuffled order), points seen by other features, points out of view
