@@ -273,7 +273,7 @@ static orb_status apply_geometry(orbx_handle* h, int w, int hh) {
     }
     // Sort capacity in shared memory per level: a texture-rich level yields about one FAST candidate
     // per 37 tested pixels; provision area/24 and fall back to the global scratch beyond that.
-    // Consecutive levels with the same capacity form a group (<= 3 groups, one launch each).
+    // Consecutive levels with the same capacity form a group (<= 4 groups, one launch each on its own stream).
     {
         int capOf[ORB_MAX_LEVELS];
         for (int l = 0; l < h->cfg.n_levels; ++l) {
@@ -282,7 +282,8 @@ static orb_status apply_geometry(orbx_handle* h, int w, int hh) {
             int c = pow2_ceil(std::max(est, 1024));
             c = std::min(c, 32768);
             if (c > 8192) c = std::max(c, 16384);
-            else if (c > 2048) c = 8192;
+            else if (c > 4096 || (c > 2048 && h->qt_max_groups < 4)) c = 8192;
+            else if (c > 2048) c = 4096;     // ORB_QT_GROUPS=4 only: levels 2-4 of a 640x480 pyramid sort <= 4096 keys
             else c = 2048;
             while ((size_t)c * 4 + (h->qt_nodes_in_smem ? nodeBytes : 0) > 200 * 1024 && c > 2048) c >>= 1;
             capOf[l] = c;
@@ -290,7 +291,7 @@ static orb_status apply_geometry(orbx_handle* h, int w, int hh) {
         for (int l = 1; l < h->cfg.n_levels; ++l) capOf[l] = std::min(capOf[l], capOf[l - 1]);  // monotone
         h->qt_ngroups = 0;
         for (int l = 0; l < h->cfg.n_levels; ++l) {
-            if (h->qt_ngroups > 0 && (capOf[l] == h->qt_groups[h->qt_ngroups - 1].sort_cap || h->qt_ngroups == 3)) {
+            if (h->qt_ngroups > 0 && (capOf[l] == h->qt_groups[h->qt_ngroups - 1].sort_cap || h->qt_ngroups == h->qt_max_groups)) {
                 h->qt_groups[h->qt_ngroups - 1].level_end = l + 1;
             } else {
                 orbx_handle::QtGroup& G = h->qt_groups[h->qt_ngroups++];
@@ -330,6 +331,7 @@ extern "C" orb_status orbx_create(const orbx_config* cfg, orbx_handle** out) {
     h->cfg = *cfg;
     if (const char* v = getenv("ORB_FAST_VARIANT")) h->fast_variant = atoi(v) == 0 ? 0 : 1;   // 0 selects the round-1 kernel
     if (const char* v = getenv("ORB_QT_VARIANT")) h->qt_variant = atoi(v) == 0 ? 0 : 1;   // 0 selects the round-1 kernel (k_quadtree)
+    if (const char* v = getenv("ORB_QT_GROUPS")) h->qt_max_groups = atoi(v) == 4 ? 4 : 3;
     build_tables(h);
     static const int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
     for (int i = 0; i < 16; ++i)
@@ -346,7 +348,7 @@ extern "C" orb_status orbx_create(const orbx_config* cfg, orbx_handle** out) {
         return fail(set_error(ORB_ERR_CUDA, "cudaStreamCreate failed"));
     for (int r = 0; r < orbx_handle::kProfRing; ++r)
         for (int i = 0; i < 8; ++i) cudaEventCreate(&h->evr[r][i]);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
         cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming);
     }
@@ -384,7 +386,18 @@ extern "C" orb_status orbx_create(const orbx_config* cfg, orbx_handle** out) {
     ALLOC(h->d_uright, h->out_rows * sizeof(float));
     ALLOC(h->d_depth, h->out_rows * sizeof(float));
     ALLOC(h->d_sad, h->out_rows * sizeof(int));
+    ALLOC(h->d_pat, 256 * sizeof(uint32_t));
 #undef ALLOC
+    {   // the rBRIEF pattern as 256 packed words (xa, ya, xb, yb), transposed to [pair % 8][pair / 8] for k_orient_describe
+        static const int8_t pat[1024] = {
+#include "orb_pattern.inc"
+        };
+        uint32_t w[256];
+        for (int i = 0; i < 256; ++i)
+            w[(i & 7) * 32 + (i >> 3)] = (uint32_t)(uint8_t)pat[4 * i] | ((uint32_t)(uint8_t)pat[4 * i + 1] << 8) | ((uint32_t)(uint8_t)pat[4 * i + 2] << 16) |
+                                         ((uint32_t)(uint8_t)pat[4 * i + 3] << 24);
+        if (cudaMemcpy(h->d_pat, w, sizeof(w), cudaMemcpyHostToDevice) != cudaSuccess) return fail(set_error(ORB_ERR_CUDA, "pattern upload failed"));
+    }
     h->d_mono = h->d_nkp + B;
     h->d_offsets = h->d_nkp + 2 * B;
     cudaMemset(h->d_err, 0, sizeof(int) * 8);
@@ -405,14 +418,14 @@ extern "C" void orbx_destroy(orbx_handle* h) {
     orbr_release(h);
     void* ptrs[] = {h->d_pyr, h->d_blur, h->d_cand, h->d_sort, h->d_lvl_kp, h->d_slot, h->d_cand_cnt, h->d_lvl_cnt,
                     h->d_nkp, h->d_err, h->d_taps, h->d_kps, h->d_desc, h->d_node_scratch, h->d_stage, h->d_po,
-                    h->d_uright, h->d_depth, h->d_sad, h->d_cells};
+                    h->d_uright, h->d_depth, h->d_sad, h->d_cells, h->d_pat};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_counts) cudaFreeHost(h->h_counts);
     for (int r = 0; r < orbx_handle::kProfRing; ++r)
         for (int i = 0; i < 8; ++i)
             if (h->evr[r][i]) cudaEventDestroy(h->evr[r][i]);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
         if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]);
         if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
     }
@@ -492,7 +505,7 @@ static orb_status run_pipeline(orbx_handle* h, int batch, int lap0, int lap1) {
     ORB_LAUNCHED();
     if (prof) cudaEventRecord(h->ev[5], st);
     k_orient_describe<<<dim3((g.kpTotal + OD_WARPS - 1) / OD_WARPS, batch), OD_WARPS * 32, 0, st>>>(
-        g, h->d_lvl_kp, h->d_lvl_cnt, h->d_slot, h->d_offsets, h->d_kps, h->d_desc);
+        g, h->d_lvl_kp, h->d_lvl_cnt, h->d_slot, h->d_offsets, h->d_pat, h->d_kps, h->d_desc);
     ORB_LAUNCHED();
     if (prof) cudaEventRecord(h->ev[6], st);
     ORB_CUDA(cudaGetLastError());

@@ -47,6 +47,7 @@ struct orbx_handle {
     float* d_uright = nullptr;       // Frame::mvuRight / mvDepth of the last stereo batch (row-aligned with d_kps)
     float* d_depth = nullptr;
     int* d_sad = nullptr;
+    uint32_t* d_pat = nullptr;       // rBRIEF pattern, 256 packed pairs transposed for k_orient_describe
     void* d_node_scratch = nullptr;
     uint8_t* d_stage = nullptr;
     uint8_t* d_po = nullptr;         // edge lists / results of orbo_pose_optimization_frames
@@ -59,13 +60,16 @@ struct orbx_handle {
     bool capturing = false;   // between orbx_graph_begin and orbx_graph_end
     int batch_status = 0;   // 0 ok; 1 FAST candidate overflow, 2 quadtree node overflow of the last batch (truncated results are never served)
     int last_batch = 0;
-    // quadtree launch plan: up to 3 level groups with their own shared-memory size, run on parallel
+    // quadtree launch plan: up to 4 level groups with their own shared-memory size, run on parallel
     // streams (forked from / joined into `stream`)
     struct QtGroup { int level_begin, level_end, sort_cap; size_t smem; };
-    QtGroup qt_groups[3] = {};
+    QtGroup qt_groups[4] = {};
+    int qt_max_groups = 3;   // level groups (launches) of the quadtree stage: {16384+, 8192, 2048} sort capacities; ORB_QT_GROUPS=4 adds a 4096 group
+                             // (measured in round 2: 16 KB less shared memory for levels 2-4, but 0.317 instead of 0.278 ms per batch -- more
+                             // co-resident CTAs contend for the same SMs' barrier / shared-memory latency)
     int qt_ngroups = 0;
-    cudaStream_t aux_stream[2] = {};
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {};
+    cudaStream_t aux_stream[3] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {};
     int qt_node_cap = 0, qt_nodes_in_smem = 1;
     size_t qt_node_stride = 0, order_smem_bytes = 0;
     orbr_state* replay = nullptr;   // orbr_submit / orbr_collect state (replay.cu)

@@ -9,9 +9,6 @@
 namespace orb {
 using namespace orbdev;
 
-__device__ __constant__ int8_t c_pattern[1024] = {
-#include "orb_pattern.inc"
-};
 // umax of the radius-15 disc (ORBextractor.cc:542-570), verified against the constructor's
 // arithmetic on the host at handle creation.
 __device__ __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
@@ -504,18 +501,27 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 
 // horizontal 7-tap of 4 adjacent pixels at columns x0..x0+3 of row `p`; returns packed Q8.8 results:
 // lo = (px0 | px2 << 16), hi = (px1 | px3 << 16)
-__device__ __forceinline__ void blur_h4(const uint8_t* __restrict__ p, int x0, int w, bool interior, uint32_t& lo, uint32_t& hi) {
+// mode 0: interior (three aligned word loads); mode 1: left edge, x0 == 0 (columns -3 .. -1 reflect to 3 .. 1: one PRMT of the first
+// word); mode 2: right edge: ten byte loads, window column x0 - 3 + k read at itself while k < kr and at its mirror image
+// 2w - 2 - column from there on (BORDER_REFLECT_101; columns past w + 2 only feed the pitch padding).  ncu, round 2: with the reflect
+// arithmetic inside the row loop the edge path was 35 % of k_blur's instructions -- a warp that holds one edge lane runs it for
+// every row (profiles/r02_source_lines.md).
+__device__ __forceinline__ void blur_h4(const uint8_t* __restrict__ p, int x0, int mode, int kr, int colA, int colB, uint32_t& lo, uint32_t& hi) {
     uint32_t w0, w1, w2;   // bytes x0-4 .. x0+7
-    if (interior) {
+    if (mode == 0) {
         const uint32_t* q = reinterpret_cast<const uint32_t*>(p + x0 - 4);
         w0 = __ldg(q); w1 = __ldg(q + 1); w2 = __ldg(q + 2);
+    } else if (mode == 1) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+        w1 = __ldg(q); w2 = __ldg(q + 1);
+        w0 = __byte_perm(w1, 0u, 0x1230);
     } else {
-        uint32_t b[12];
+        uint32_t b[10];
 #pragma unroll
-        for (int k = 0; k < 12; ++k) b[k] = (k >= 1 && k <= 10) ? (uint32_t)__ldg(p + reflect101(min(x0 - 4 + k, w + 2), w)) : 0u;
-        w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
-        w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
-        w2 = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
+        for (int k = 0; k < 10; ++k) b[k] = (uint32_t)__ldg(p + (k < kr ? colA + k : colB - k));
+        w0 = (b[0] << 8) | (b[1] << 16) | (b[2] << 24);
+        w1 = b[3] | (b[4] << 8) | (b[5] << 16) | (b[6] << 24);
+        w2 = b[7] | (b[8] << 8) | (b[9] << 16);
     }
     // S_k = the 4 pixels shifted by k-3 (bytes 1+k .. 4+k of the 12-byte window), split into even / odd lanes
     uint32_t e[7], o[7];
@@ -533,7 +539,7 @@ __device__ __forceinline__ void blur_h4(const uint8_t* __restrict__ p, int x0, i
     hi = 18u * (o[0] + o[6]) + 34u * (o[1] + o[5]) + 48u * (o[2] + o[4]) + 56u * o[3];
 }
 
-__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ ExtractGeom g) {
+__global__ void __launch_bounds__(256, 4) k_blur(const __grid_constant__ ExtractGeom g) {
     const int tileId = blockIdx.x, img = blockIdx.y;
     int l = 0;
     while (l + 1 < g.nlevels && tileId >= g.lv[l + 1].tileBase) ++l;
@@ -545,7 +551,8 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ ExtractGeo
     if (x0 >= G.w || y0 >= G.h) return;
     const uint8_t* __restrict__ src = G.base + (int64_t)img * G.img_stride;
     uint8_t* __restrict__ dst = G.blur + (int64_t)img * G.blur_stride;
-    const bool interior = (x0 >= 4) && (x0 + 8 <= G.w);
+    const int mode = (x0 + 8 <= G.w) ? (x0 >= 4 ? 0 : 1) : 2;
+    const int colA = x0 - 3, kr = G.w - colA, colB = 2 * G.w - 2 - colA;   // mode 2: window column colA + k, mirrored from k == kr on
     // horizontal results of the last 7 rows, unpacked to one 32-bit value per pixel (Q8.8 <= 65280)
     uint32_t hwin[7][4];
     const int rows = min(BLUR_ROWS, G.h - y0);
@@ -558,7 +565,7 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ ExtractGeo
             if (r < rows + 6) {
                 const int y = reflect101(y0 + r - 3, G.h);
                 uint32_t lo, hi;
-                blur_h4(src + (int64_t)y * G.pitch, x0, G.w, interior, lo, hi);
+                blur_h4(src + (int64_t)y * G.pitch, x0, mode, kr, colA, colB, lo, hi);
                 uint32_t* hrow = hwin[j];
                 hrow[0] = lo & 0xffffu; hrow[2] = lo >> 16; hrow[1] = hi & 0xffffu; hrow[3] = hi >> 16;
                 if (r >= 6) {
@@ -585,30 +592,27 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ ExtractGeo
 
 __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_describe(const __grid_constant__ ExtractGeom g, const uint32_t* __restrict__ lvlKp,
                                                                   const int* __restrict__ lvlCnt, const int* __restrict__ slot,
-                                                                  const int* __restrict__ offsets,
+                                                                  const int* __restrict__ offsets, const uint32_t* __restrict__ patT,
                                                                   orbx_keypoint* __restrict__ kps, uint8_t* __restrict__ desc) {
-    // the 256 point pairs as one 32-bit word each (xa, ya, xb, yb as int8), transposed so that lane's k-th pair sits at
-    // [k][lane]: one conflict-free LDS.32 per pair instead of four byte loads
-    __shared__ uint32_t s_pat[8][32];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        const uint32_t w = (uint32_t)(uint8_t)c_pattern[4 * i] | ((uint32_t)(uint8_t)c_pattern[4 * i + 1] << 8) |
-                           ((uint32_t)(uint8_t)c_pattern[4 * i + 2] << 16) | ((uint32_t)(uint8_t)c_pattern[4 * i + 3] << 24);
-        s_pat[i & 7][i >> 3] = w;      // pair i belongs to lane i / 8 (descriptor byte), bit i % 8
-    }
-    __syncthreads();
+    // patT: the 256 point pairs as one 32-bit word each (xa, ya, xb, yb as int8), transposed so that lane's k-th pair sits at
+    // [k][lane] -- built once per handle in global memory.  (Round 1 staged it per CTA from __constant__ memory: 32 different constant
+    // addresses per load serialise, and the staging + barrier were 25 % of the kernel's stall samples, profiles/r02_source_lines.md.)
     const int img = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int e = blockIdx.x * OD_WARPS + (threadIdx.x >> 5);
     int l = 0, first = 0;
-    {
-        int run = 0;
-        bool found = false;
-        for (int k = 0; k < g.nlevels; ++k) {
-            const int c = lvlCnt[img * g.nlevels + k];
-            if (!found && e < run + c) { l = k; first = run; found = true; }
-            run += c;
+    {   // level of emission index e: lanes 0 .. nlevels-1 hold the level counts, a shuffle scan gives the running totals
+        const int c = lane < g.nlevels ? lvlCnt[img * g.nlevels + lane] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
-        if (!found) return;  // warp-uniform
+        const unsigned m = __ballot_sync(0xffffffffu, lane < g.nlevels && e < incl);
+        if (m == 0u) return;  // warp-uniform
+        l = __ffs(m) - 1;
+        first = __shfl_sync(0xffffffffu, incl - c, l);
     }
     const LevelGeom& G = g.lv[l];
     const uint32_t c = lvlKp[(int64_t)img * g.kpTotal + G.kpOff + (e - first)];
@@ -644,7 +648,7 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_describe(const __grid_
     uint32_t val = 0u;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const uint32_t pw = s_pat[k][lane];
+        const uint32_t pw = __ldg(patT + 32 * k + lane);
         const float xa = (float)(int8_t)(pw & 0xffu), ya = (float)(int8_t)((pw >> 8) & 0xffu), xb = (float)(int8_t)((pw >> 16) & 0xffu),
                     yb = (float)(int8_t)(pw >> 24);
         const int ra = round_half_even(fadd(fmul(xa, sa), fmul(ya, ca))), ca_ = round_half_even(fsub(fmul(xa, ca), fmul(ya, sa)));

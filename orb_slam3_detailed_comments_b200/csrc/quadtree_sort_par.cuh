@@ -129,6 +129,84 @@ ORB_HD void qt_sortpar_heapsort(QtItem* h, int len) {
     }
 }
 
+
+#if defined(__CUDACC__)
+// One __introsort_loop step on [first, last) by a whole WARP, with exactly the result of qt_sortpar_partition.
+// __unguarded_partition alternates two scans: `lo` runs up to the next item that is NOT LESS than the pivot, `hi` down to the next
+// item that is NOT GREATER, the two are swapped, and so on until the scans meet.  Between two swaps both scans only cross items no
+// earlier swap has touched, so the k-th stop of `lo` is the k-th position L_k (ascending, from first + 1) whose ORIGINAL key is not
+// less than the pivot, the k-th stop of `hi` the k-th position R_k (descending, from last - 1; `first` itself, which holds the pivot,
+// is the final sentinel) whose original key is not greater: swap k happens while L_k < R_k, and the scans meet at
+// min(L_j, R_{j-1}) for the first j that fails (the item swapped into R_{j-1} stops `lo` if no untouched one does first).
+// So: two ballot-ranked position lists, the swaps of all k < j at once, one formula for the cut.  (Phase clocks, round 2: one
+// thread's chain of dependent swaps over ~250 items with many equal keys was the largest phase of the level-0 CTA.)
+// scratch: 2 * (last - first) ints.  All 32 lanes call with the same arguments; returns the cut in every lane.
+__device__ inline int qt_sortpar_partition_warp(QtItem* a, int first, int last, int* scratch, int lane) {
+    const unsigned lt = (1u << lane) - 1u;
+    if (lane == 0) {
+        const int mid = first + (last - first) / 2;
+        const int A = first + 1, B = mid, C = last - 1;
+        int pick;
+        if (qt_item_less(a[A], a[B])) {
+            if (qt_item_less(a[B], a[C])) pick = B;
+            else if (qt_item_less(a[A], a[C])) pick = C;
+            else pick = A;
+        } else if (qt_item_less(a[A], a[C])) pick = A;
+        else if (qt_item_less(a[B], a[C])) pick = C;
+        else pick = B;
+        const QtItem t = a[first]; a[first] = a[pick]; a[pick] = t;
+    }
+    __syncwarp();
+    const uint64_t pv = qt_item_key(a[first]);
+    const int len = last - first;
+    int* Lpos = scratch;          // ascending positions with key >= pivot
+    int* Rpos = scratch + len;    // ascending positions with key <= pivot; Rpos[0] = first (the pivot itself)
+    if (lane == 0) Rpos[0] = first;
+    int nL = 0, nR = 1;
+    for (int base = first + 1; base < last; base += 32) {
+        const int p = base + lane;
+        bool fl = false, fr = false;
+        if (p < last) {
+            const uint64_t k = qt_item_key(a[p]);
+            fl = !(k < pv);
+            fr = !(pv < k);
+        }
+        const unsigned ml = __ballot_sync(0xffffffffu, fl), mr = __ballot_sync(0xffffffffu, fr);
+        if (fl) Lpos[nL + __popc(ml & lt)] = p;
+        if (fr) Rpos[nR + __popc(mr & lt)] = p;
+        nL += __popc(ml);
+        nR += __popc(mr);
+    }
+    __syncwarp();
+    const int kmax = nL < nR ? nL : nR;
+    int j = 0;
+    for (int base = 0; base < kmax; base += 32) {
+        const int k = base + lane;
+        int lp = 0, rp = 0;
+        bool c = false;
+        if (k < kmax) {
+            lp = Lpos[k];
+            rp = Rpos[nR - 1 - k];
+            c = lp < rp;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, c);
+        if (c) { const QtItem t = a[lp]; a[lp] = a[rp]; a[rp] = t; }     // the pairs of all k < j are disjoint positions
+        j += __popc(m);
+        if (m != 0xffffffffu) break;      // warp-uniform: L_k < R_k holds for a prefix of k only
+    }
+    __syncwarp();
+    int cut;
+    if (j == 0) cut = Lpos[0];            // exists: the median-of-three leaves an item >= pivot inside (first, last)
+    else {
+        const int rprev = Rpos[nR - j];   // R_{j-1}
+        cut = (j < nL && Lpos[j] < rprev) ? Lpos[j] : rprev;
+    }
+    __syncwarp();
+    return cut;
+}
+#define QT_COOP_MIN 40    // segments longer than this are partitioned by the whole warp, shorter ones one per lane
+#endif
+
 // a[0..n) sorted exactly as std::sort(a, a + n, compareNodes) leaves it.  tmp: n items.  seg / nxt: 3 ints per segment slot each
 // (first, last, depth), room for n / 8 + 2 slots; flag: 2 * (n / 8 + 2) ints; scan_tmp: qt_exscan's scratch.  Whole CTA; returns after a
 // barrier.  Every segment on a list is longer than 16, so a generation holds at most n / 17 of them.
@@ -154,11 +232,23 @@ ORB_HD void qt_std_sort_items_par(QtItem* a, int n, QtItem* tmp, int* seg, int* 
                     const int sI = base + lane;
                     int first = 0, cut = 0, last = 0, depth = 0;
                     bool l_alive = false, r_alive = false;
-                    if (sI < nseg) {
-                        first = cur[3 * sI]; last = cur[3 * sI + 1]; depth = cur[3 * sI + 2];
-                        cut = first;
+                    const bool mine = sI < nseg;
+                    if (mine) { first = cur[3 * sI]; last = cur[3 * sI + 1]; depth = cur[3 * sI + 2]; cut = first; }
+                    // long segments first, one after the other, by the whole warp (tmp is free until the rank phase: its scratch)
+                    const bool big = mine && depth != 0 && last - first > QT_COOP_MIN;
+                    unsigned mb = __ballot_sync(0xffffffffu, big);
+                    while (mb) {
+                        const int src = __ffs(mb) - 1;
+                        mb &= mb - 1;
+                        const int f = __shfl_sync(0xffffffffu, first, src), l_ = __shfl_sync(0xffffffffu, last, src);
+                        const int c = qt_sortpar_partition_warp(a, f, l_, reinterpret_cast<int*>(tmp), lane);
+                        if (lane == src) cut = c;
+                    }
+                    if (mine && !big) {
                         if (depth == 0) qt_sortpar_heapsort(a + first, last - first);
                         else cut = qt_sortpar_partition(a, first, last);
+                    }
+                    if (mine) {
                         l_alive = depth != 0 && cut - first > 16;
                         r_alive = depth != 0 && last - cut > 16;
                     }

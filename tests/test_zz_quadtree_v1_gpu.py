@@ -46,3 +46,20 @@ def test_variant_batch(monkeypatch, variant):
         a, b = int(off[i]), int(off[i + 1])
         assert b - a == len(rk) and (kps[a:b].view(np.uint8) == rk.view(np.uint8)).all() and (desc[a:b] == rd).all()
     ex.close()
+
+
+def test_many_textures_final_keypoints(monkeypatch):
+    """The ordered phase's std::sort emulation (warp-cooperative partitions of the long segments, one lane per short one) decides the
+    order in which tied nodes are divided: 24 textures x 8 levels of different candidate densities against the oracle, final output."""
+    monkeypatch.setenv("ORB_QT_VARIANT", "1")
+    rng = np.random.default_rng(11)
+    imgs = np.stack([synth.frame(640, 480, 200 + i, float(rng.choice([1.0, 1.5, 2.5, 3.5, 5.0, 8.0])), int(rng.choice([5, 20, 60, 120]))) for i in range(24)])
+    ex = ORBextractor(1200, 1.2, 8, 20, 7, max_width=640, max_height=480, max_batch=24)
+    ex.extract_batch(imgs)
+    n, mono, off, kps, desc = ex.download(24)
+    ref = po.OracleExtractor(1200, 1.2, 8, 20, 7)
+    for i in range(24):
+        rmono, rk, rd = ref(imgs[i])
+        a, b = int(off[i]), int(off[i + 1])
+        assert b - a == len(rk) and (kps[a:b].view(np.uint8) == rk.view(np.uint8)).all() and (desc[a:b] == rd).all(), i
+    ex.close()
