@@ -58,6 +58,7 @@ extern "C" orb_status liba_create(int32_t device, liba_handle** out) {
         delete h;
         return set_error(ORB_ERR_CUDA, "cudaStreamCreate failed");
     }
+    ORB_CUDA(cudaFuncSetAttribute(k_liba, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));   // 16-CTA clusters for one or two windows
     *out = h;
     return ORB_OK;
 }
@@ -116,11 +117,12 @@ extern "C" orb_status liba_solve(liba_handle* h, int32_t n_problems, const liba_
     ORB_CUDA(cudaMemcpyAsync(h->d_buf, h->h_buf, sizeof(LibaDev) * (size_t)n_problems, cudaMemcpyHostToDevice, h->stream));
     for (int i = 0; i < n_problems; ++i)
         ORB_CUDA(cudaMemcpyAsync(h->d_buf + base[i], h->h_buf + base[i], lay[i].io_bytes + lay[i].in_bytes, cudaMemcpyHostToDevice, h->stream));
-    // small batches get a cluster of 8 SMs per window, large ones fewer (ORB_LIBA_CLUSTER = 1 | 2 | 4 | 8 overrides: a tuning knob)
-    int cs = (n_problems * LIBA_CS_MAX <= 148) ? LIBA_CS_MAX : (n_problems * 4 <= 148 ? 4 : (n_problems * 2 <= 148 ? 2 : 1));
+    // one or two windows get a cluster of 16 SMs each (the non-portable size), small batches 8, large ones fewer
+    // (ORB_LIBA_CLUSTER = 1 | 2 | 4 | 8 | 16 overrides: a tuning knob)
+    int cs = n_problems <= 2 ? 16 : ((n_problems * LIBA_CS_MAX <= 148) ? LIBA_CS_MAX : (n_problems * 4 <= 148 ? 4 : (n_problems * 2 <= 148 ? 2 : 1)));
     if (const char* e = getenv("ORB_LIBA_CLUSTER")) {
         const int v = atoi(e);
-        if (v == 1 || v == 2 || v == 4 || v == 8) cs = v;
+        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) cs = v;
     }
     {
         cudaLaunchConfig_t cfg = {};

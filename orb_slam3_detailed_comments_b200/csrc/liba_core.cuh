@@ -114,7 +114,7 @@ struct LibaDev {
     double* Ypan;         // [15][sp] panel D1 L21^T of the blocked factorisation
     int* flag;            // [4] solver failure flag
     double* red;          // reduction scratch of this CTA (device: shared memory, one double per warp; emulation: per thread)
-    double* partials;     // [8] per-CTA partial results of a team reduction (global memory)
+    double* partials;     // [16] per-CTA partial results of a team reduction (global memory)
     int t_id, t_stride;   // this thread's place in the team ...
     int l_id, l_stride;   // ... and inside its CTA
     int rank, cs;         // CTA rank in the team, CTAs per team

@@ -91,7 +91,7 @@ inline LibaLayout liba_pack(const liba_problem& p, uint8_t* host, uint8_t* devBa
     // work
     const size_t oStateS = take(8 * 21 * (size_t)nKF), oPointS = take(8 * sl), oHpp = take(8 * sp * sp), oHs = take(8 * sp * sp), oB = take(8 * (sp + sl)), oBs = take(8 * sp),
                  oX = take(8 * (sp + sl)), oY = take(8 * sp), oHll = take(8 * 9 * (size_t)nMP), oDinv = take(8 * 9 * (size_t)nMP), oW = take(8 * 18 * (size_t)nE),
-                 oWD = take(8 * 18 * (size_t)nE), oWdb = take(8 * 6 * (size_t)nE), oEpp = take(8 * 27 * (size_t)nE), oLblk = take(8 * 930 * (size_t)nL), oFlag = take(16), oPart = take(8 * 8),
+                 oWD = take(8 * 18 * (size_t)nE), oWdb = take(8 * 6 * (size_t)nE), oEpp = take(8 * 27 * (size_t)nE), oLblk = take(8 * 930 * (size_t)nL), oFlag = take(16), oPart = take(8 * 16),
                  oChunk = take(8 * (size_t)LIBA_CHUNKS * std::max((size_t)27 * nKF, (size_t)36 * nPairs)), oChunkB = take(8 * (size_t)LIBA_CHUNKS * 6 * nKF), oYpan = take(8 * 15 * sp);
     lay.work_bytes = off - lay.io_bytes - lay.in_bytes;
     lay.total = off;

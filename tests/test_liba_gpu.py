@@ -30,7 +30,7 @@ def check(got, ref):
     assert np.abs(got["state"] - ref["state"]).max() < TOL and np.abs(got["point"] - ref["point"]).max() < TOL
 
 
-@pytest.mark.parametrize("cluster", [1, 8, 2])
+@pytest.mark.parametrize("cluster", [1, 8, 2, 16])
 @pytest.mark.parametrize("seed,lam,iters,n_fixed", [(11, 1.0, 10, 1), (12, 1e-2, 4, 1), (13, 1.0, 10, 3)])
 def test_matches_oracle(opt, monkeypatch, seed, lam, iters, n_fixed, cluster):
     monkeypatch.setenv("ORB_LIBA_CLUSTER", str(cluster))      # CTAs per window (liba.cu reads it at every call)
