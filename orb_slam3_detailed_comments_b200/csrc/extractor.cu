@@ -331,6 +331,7 @@ extern "C" orb_status orbx_create(const orbx_config* cfg, orbx_handle** out) {
     h->cfg = *cfg;
     if (const char* v = getenv("ORB_FAST_VARIANT")) h->fast_variant = atoi(v) == 0 ? 0 : 1;   // 0 selects the round-1 kernel
     if (const char* v = getenv("ORB_QT_VARIANT")) h->qt_variant = atoi(v) == 0 ? 0 : 1;   // 0 selects the round-1 kernel (k_quadtree)
+    if (const char* v = getenv("ORB_FAST_TMA")) h->fast_tma = atoi(v) != 0;   // window rows of k_fast_cells_v2 staged by TMA bulk copies
     if (const char* v = getenv("ORB_QT_GROUPS")) h->qt_max_groups = atoi(v) == 4 ? 4 : 3;
     build_tables(h);
     static const int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
@@ -468,9 +469,20 @@ static orb_status run_pipeline(orbx_handle* h, int batch, int lap0, int lap1) {
         fp.cells = h->d_cells; fp.nCells = (int)h->cells_host.size(); fp.R = h->fast_R; fp.PW = h->fast_PW; fp.LW = h->fast_LW;
         const int ws = ((fp.PW - 1) >> 1) | 1;
         const size_t fsm = (size_t)round_up(fp.R * fp.PW, 4) * 8 + (size_t)round_up(fp.R * ws * 4, 16) + (size_t)2 * (FAST2_THREADS / 32) * fp.LW * 2;
-        auto kern = fp.PW == 29 ? k_fast_cells_v2<29> : k_fast_cells_v2<0>;
-        ORB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
-        if (fp.nCells > 0) kern<<<dim3(fp.nCells, batch), FAST2_THREADS, fsm, st>>>(g, fp, h->d_cand, h->d_cand_cnt, h->d_err);
+        // ORB_FAST_TMA=1: the window rows by TMA bulk copies -- needs 64-byte rows to cover the staged columns (PW == 29: the 35-37 px
+        // cells of the usual geometries) and 16-byte aligned level images (own levels always; an aliased level 0 is checked here)
+        bool tma = h->fast_tma && fp.PW == 29;
+        for (int l = 0; l < g.nlevels && tma; ++l)
+            tma = (g.lv[l].pitch % 16 == 0) && (g.lv[l].img_stride % 16 == 0) && ((uintptr_t)g.lv[l].base % 16 == 0);
+        if (tma) {
+            const size_t fsmT = fsm + (size_t)fp.R * 64;
+            ORB_CUDA(cudaFuncSetAttribute(k_fast_cells_v2<29, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmT));
+            if (fp.nCells > 0) k_fast_cells_v2<29, true><<<dim3(fp.nCells, batch), FAST2_THREADS, fsmT, st>>>(g, fp, h->d_cand, h->d_cand_cnt, h->d_err);
+        } else {
+            auto kern = fp.PW == 29 ? k_fast_cells_v2<29> : k_fast_cells_v2<0>;
+            ORB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+            if (fp.nCells > 0) kern<<<dim3(fp.nCells, batch), FAST2_THREADS, fsm, st>>>(g, fp, h->d_cand, h->d_cand_cnt, h->d_err);
+        }
     } else {   // pe / po / se rows + the NMS tile (which also holds the list of pixel pairs that pass the high-speed test)
         const size_t fsm = (size_t)g.fastRows * (3 * FAST_PW + FAST_TW) * 4;
         ORB_CUDA(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));

@@ -31,9 +31,39 @@ struct FastPlan {
 
 #define FAST2_THREADS 128
 
+// TMA (1-D bulk copy) staging of the window: ORB_FAST_TMA=1.  A window row is one 64-byte, 16-byte aligned span of the level image
+// (the staged columns start at gx0 & ~15 and end before gx0 + 64 for 35-37 px cells), so thread r arms nothing and issues ONE
+// cp.async.bulk for row r; thread 0 arms the mbarrier with the byte count of the whole window.  The raw bytes land in shared
+// memory and are expanded to the 16x2 pairs from there.  SASS: UBLKCP.S.G, SYNCS.ARRIVE.TRANS64, SYNCS.PHASECHK.TRANS64.TRYWAIT.
+__device__ __forceinline__ uint32_t fast_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fast_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fast_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fast_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fast_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fast_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(fast_smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(fast_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fast_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "FAST_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra FAST_DONE;\n"
+        "bra FAST_WAIT;\n"
+        "FAST_DONE:\n"
+        "}\n" ::"r"(fast_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 // PWC > 0: the row stride is a compile-time constant (every ring offset becomes an immediate of the shared-memory load);
 // PWC == 0: taken from the plan at run time (any geometry).
-template <int PWC>
+template <int PWC, bool TMA = false>
 __global__ void __launch_bounds__(FAST2_THREADS, 8)
 k_fast_cells_v2(const __grid_constant__ ExtractGeom g, const __grid_constant__ FastPlan fp, uint32_t* __restrict__ cand,
                 int* __restrict__ candCnt, int* __restrict__ err) {
@@ -67,6 +97,35 @@ k_fast_cells_v2(const __grid_constant__ ExtractGeom g, const __grid_constant__ F
     const int nC8 = (wd0 + ngrp + 2) >> 1;                   // 8-byte chunks per staged row (one margin word on the right)
     const uint8_t* src = G.base + (int64_t)img * G.img_stride + (int64_t)y0 * G.pitch + gx0;
 
+    if (TMA) {   // the window's rows by bulk copies into a raw byte tile, then expanded from shared memory
+        __shared__ __align__(8) uint64_t s_bar;
+        uint8_t* raw = reinterpret_cast<uint8_t*>(lst2 + 4 * fp.LW);      // R rows of 64 bytes, 16-byte aligned
+        const int gx16 = gx0 & ~15, shift = gx0 - gx16;                   // gx0 is 8-byte aligned: shift is 0 or 8
+        const uint32_t rowBytes = (uint32_t)min(64, G.pitch - gx16);      // a multiple of 16; the last cells of a row stop at the pitch
+        if (tid == 0) {
+            fast_mbar_init(&s_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) fast_mbar_expect_tx(&s_bar, (uint32_t)ch * rowBytes);
+        if (tid < ch) fast_bulk_g2s(raw + 64 * tid, src - shift + (int64_t)tid * G.pitch, rowBytes, &s_bar);
+        for (int i = tid; i < (sbBytes >> 4); i += FAST2_THREADS) reinterpret_cast<uint4*>(sb)[i] = make_uint4(0u, 0u, 0u, 0u);
+        fast_mbar_wait(&s_bar, 0u);
+        const uint32_t magicC = (1u << 20) / (uint32_t)nC8 + 1u;
+        const int total = ch * nC8;
+        for (int i = tid; i < total; i += FAST2_THREADS) {
+            const int r = (int)(((uint32_t)i * magicC) >> 20), c = i - r * nC8;
+            const uint8_t* rp = raw + 64 * r + shift + 8 * c;
+            const uint2 w = *reinterpret_cast<const uint2*>(rp);
+            const uint32_t nx = (c + 1 < nC8) ? *reinterpret_cast<const uint32_t*>(rp + 8) : 0u;
+            uint32_t* de = pe + r * PW + 4 * c;
+            uint32_t* dp = de + RP;
+            de[0] = __byte_perm(w.x, 0u, 0x4140); de[1] = __byte_perm(w.x, 0u, 0x4342);
+            de[2] = __byte_perm(w.y, 0u, 0x4140); de[3] = __byte_perm(w.y, 0u, 0x4342);
+            dp[0] = __byte_perm(w.x, 0u, 0x4241); dp[1] = __byte_perm(w.x, w.y, 0x4433) & 0x00ff00ffu;
+            dp[2] = __byte_perm(w.y, 0u, 0x4241); dp[3] = __byte_perm(w.y, nx, 0x4433) & 0x00ff00ffu;
+        }
+    } else
     {   // staging, three rows of loads in flight per thread (a cell is 2.4 rounds of 128 eight-pixel chunks at 640x480)
         const uint32_t magicC = (1u << 20) / (uint32_t)nC8 + 1u;   // (i * magic) >> 20 == i / n exactly for i < 2048, n <= 32
         const int total = ch * nC8;

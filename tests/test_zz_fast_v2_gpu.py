@@ -67,3 +67,20 @@ def test_fast_variant_batch(monkeypatch, variant):
         a, b = int(off[i]), int(off[i + 1])
         assert b - a == len(rk) and (kps[a:b].view(np.uint8) == rk.view(np.uint8)).all() and (desc[a:b] == rd).all()
     ex.close()
+
+
+@pytest.mark.parametrize("w,h,seed,sigma,nrect,nf", CASES[:4] + CASES[6:])
+def test_fast_tma_staging_is_bit_exact(monkeypatch, w, h, seed, sigma, nrect, nf):
+    """ORB_FAST_TMA=1: the window rows arrive by cp.async.bulk + mbarrier (k_fast_cells_v2<29, true>) where the cell geometry
+    allows it (64-byte rows: the 35-37 px cells of these sizes; 16-byte aligned level images), the default staging elsewhere --
+    same candidates, keypoints and descriptors either way."""
+    monkeypatch.setenv("ORB_FAST_TMA", "1")               # read by orbx_create
+    img = synth.frame(w, h, seed, sigma, nrect)
+    ex = ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=1)
+    ref = po.OracleExtractor(nf, 1.2, 8, 20, 7)
+    mono, kps, desc = ex(img)
+    rmono, rk, rd = ref(img)
+    _check_stages(ex, ref)
+    assert mono == rmono and len(kps) == len(rk)
+    assert (kps.view(np.uint8) == rk.view(np.uint8)).all() and (desc == rd).all()
+    ex.close()
