@@ -331,6 +331,8 @@ extern "C" orb_status orbx_create(const orbx_config* cfg, orbx_handle** out) {
     h->cfg = *cfg;
     if (const char* v = getenv("ORB_FAST_VARIANT")) h->fast_variant = atoi(v) == 0 ? 0 : 1;   // 0 selects the round-1 kernel
     if (const char* v = getenv("ORB_QT_VARIANT")) h->qt_variant = atoi(v) == 0 ? 0 : 1;   // 0 selects the round-1 kernel (k_quadtree)
+    if (const char* v = getenv("ORB_BLUR_VARIANT")) h->blur_variant = atoi(v);       // 0: packed 16x2 multiply-adds instead of IDP.4A
+    if (const char* v = getenv("ORB_RESIZE_VARIANT")) h->resize_variant = atoi(v);   // 0: k_resize (4 px of one row per thread)
     if (const char* v = getenv("ORB_FAST_TMA")) h->fast_tma = atoi(v) != 0;   // window rows of k_fast_cells_v2 staged by TMA bulk copies
     if (const char* v = getenv("ORB_QT_GROUPS")) h->qt_max_groups = atoi(v) == 4 ? 4 : 3;
     build_tables(h);
@@ -459,8 +461,15 @@ static orb_status run_pipeline(orbx_handle* h, int batch, int lap0, int lap1) {
     if (prof) cudaEventRecord(h->ev[1], st);
     ORB_CUDA(cudaMemsetAsync(h->d_cand_cnt, 0, sizeof(int) * batch * g.nlevels, st));
     for (int l = 1; l < g.nlevels; ++l) {
-        dim3 grid((g.lv[l].w + 127) / 128, (g.lv[l].h + 7) / 8, batch), block(32, 8);
-        k_resize<<<grid, block, 0, st>>>(g, l, h->d_taps);
+        if (h->resize_variant >= 1 && !g.lv[l].area2x) {   // 4 px x 4 (or 8) rows per thread, source-row interpolations shared between rows
+            const int rows = h->resize_variant == 2 ? 8 : 4;
+            dim3 grid((g.lv[l].w + 127) / 128, (g.lv[l].h + 8 * rows - 1) / (8 * rows), batch);
+            if (rows == 8) k_resize_v2<8><<<grid, 256, 0, st>>>(g, l, h->d_taps);
+            else k_resize_v2<4><<<grid, 256, 0, st>>>(g, l, h->d_taps);
+        } else {
+            dim3 grid((g.lv[l].w + 127) / 128, (g.lv[l].h + 7) / 8, batch), block(32, 8);
+            k_resize<<<grid, block, 0, st>>>(g, l, h->d_taps);
+        }
         ORB_LAUNCHED();
     }
     if (prof) cudaEventRecord(h->ev[2], st);
@@ -513,7 +522,8 @@ static orb_status run_pipeline(orbx_handle* h, int batch, int lap0, int lap1) {
     k_offsets<<<1, 32, 0, st>>>(h->d_nkp, batch, h->d_offsets);
     ORB_LAUNCHED();
     if (prof) cudaEventRecord(h->ev[4], st);
-    k_blur<<<dim3(g.totalTiles, batch), 256, 0, st>>>(g);
+    if (h->blur_variant == 1) k_blur<true><<<dim3(g.totalTiles, batch), 256, 0, st>>>(g);    // horizontal pass by IDP.4A
+    else k_blur<false><<<dim3(g.totalTiles, batch), 256, 0, st>>>(g);
     ORB_LAUNCHED();
     if (prof) cudaEventRecord(h->ev[5], st);
     k_orient_describe<<<dim3((g.kpTotal + OD_WARPS - 1) / OD_WARPS, batch), OD_WARPS * 32, 0, st>>>(

@@ -16,6 +16,8 @@ struct orbx_handle {
     uint2* d_cells = nullptr;
     size_t cells_slots = 0;
     int fast_R = 0, fast_PW = 0, fast_LW = 0;
+    int blur_variant = 1;    // 1: k_blur<true> (IDP.4A horizontal pass, default), 0: k_blur<false>
+    int resize_variant = 1;  // 1: k_resize_v2 (default), 0: k_resize
     bool fast_tma = false;   // ORB_FAST_TMA=1: k_fast_cells_v2<29, true> (window rows by cp.async.bulk + mbarrier)
     int qt_variant = 1;   // 1 (default): k_quadtree_v1; 0: k_quadtree (ORB_QT_VARIANT=0 at orbx_create)
     cudaStream_t stream = nullptr;

@@ -60,6 +60,63 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ ExtractG
     *reinterpret_cast<uint32_t*>(dst + (int64_t)dy * D.pitch + dx4) = packed;
 }
 
+// k_resize_v2: one thread = 4 destination pixels x RS2_ROWS (4 or 8) destination rows.  The x taps are decoded once per thread, and the
+// horizontal interpolation of a source row is computed once and shared by the two destination rows that read it (at scale 1.2 four
+// out of five destination rows start on the source row the previous one ended on), so a destination pixel costs ~1.4 source-row
+// interpolations instead of 2 and a quarter of the tap / address work.  Same arithmetic, same order: bit-exact with k_resize.
+template <int RS2_ROWS>
+__global__ void __launch_bounds__(256) k_resize_v2(const __grid_constant__ ExtractGeom g, int l, const int2* __restrict__ taps) {
+    const LevelGeom& D = g.lv[l];
+    const LevelGeom& S = g.lv[l - 1];
+    const int dx4 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
+    const int dy0 = (blockIdx.y * 8 + (threadIdx.x >> 5)) * RS2_ROWS;
+    if (dx4 >= D.w || dy0 >= D.h) return;
+    const uint8_t* __restrict__ src = S.base + (int64_t)blockIdx.z * S.img_stride;
+    uint8_t* __restrict__ dst = D.base + (int64_t)blockIdx.z * D.img_stride + dx4;
+    int xo0[4], xo1[4], c0[4], c1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int2 tx = __ldg(&taps[D.tapOff + min(dx4 + i, D.w - 1)]);   // columns past the width feed the pitch padding only
+        xo0[i] = tx.x; xo1[i] = min(tx.x + 1, S.w - 1);
+        c0[i] = tx.y & 0xffff; c1[i] = (int)((uint32_t)tx.y >> 16);
+    }
+    int have = -1;     // source row whose horizontal interpolation sits in hc[]
+    int hc[4] = {0, 0, 0, 0};
+    const int nrow = min(RS2_ROWS, D.h - dy0);
+    for (int k = 0; k < nrow; ++k) {   // warp-uniform: a warp is 32 threads of one destination row group
+        const int2 ty = __ldg(&taps[D.tapOff + D.w + dy0 + k]);
+        const int sy0 = ty.x, sy1 = min(sy0 + 1, S.h - 1);
+        const int b0 = ty.y & 0xffff, b1 = (int)((uint32_t)ty.y >> 16);
+        int h0[4], h1[4];
+        if (sy0 == have) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h0[i] = hc[i];
+        } else {
+            const uint8_t* a = src + (int64_t)sy0 * S.pitch;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h0[i] = ((int)__ldg(a + xo0[i]) * c0[i] + (int)__ldg(a + xo1[i]) * c1[i]) >> 4;
+        }
+        if (sy1 == sy0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h1[i] = h0[i];
+        } else {
+            const uint8_t* b = src + (int64_t)sy1 * S.pitch;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h1[i] = ((int)__ldg(b + xo0[i]) * c0[i] + (int)__ldg(b + xo1[i]) * c1[i]) >> 4;
+        }
+        uint32_t packed = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int v = (((b0 * h0[i]) >> 16) + ((b1 * h1[i]) >> 16) + 2) >> 2;
+            packed |= (uint32_t)v << (8 * i);
+            hc[i] = h1[i];
+        }
+        have = sy1;
+        if (dx4 + 4 > D.w) packed &= 0xffffffffu >> (8 * (dx4 + 4 - D.w));   // as k_resize: zero past the width
+        *reinterpret_cast<uint32_t*>(dst + (int64_t)(dy0 + k) * D.pitch) = packed;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K2  per-cell FAST-9/16 + NMS + 20->7 fallback (ORBextractor.cc:1069-1166).
 // One CTA = one 35-px cell of one level of one image.  The cell window (+ alignment slack) is
@@ -506,7 +563,8 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 // 2w - 2 - column from there on (BORDER_REFLECT_101; columns past w + 2 only feed the pitch padding).  ncu, round 2: with the reflect
 // arithmetic inside the row loop the edge path was 35 % of k_blur's instructions -- a warp that holds one edge lane runs it for
 // every row (profiles/r02_source_lines.md).
-__device__ __forceinline__ void blur_h4(const uint8_t* __restrict__ p, int x0, int mode, int kr, int colA, int colB, uint32_t& lo, uint32_t& hi) {
+template <bool DP4A>
+__device__ __forceinline__ void blur_h4(const uint8_t* __restrict__ p, int x0, int mode, int kr, int colA, int colB, uint32_t* __restrict__ h) {
     uint32_t w0, w1, w2;   // bytes x0-4 .. x0+7
     if (mode == 0) {
         const uint32_t* q = reinterpret_cast<const uint32_t*>(p + x0 - 4);
@@ -523,6 +581,13 @@ __device__ __forceinline__ void blur_h4(const uint8_t* __restrict__ p, int x0, i
         w1 = b[3] | (b[4] << 8) | (b[5] << 16) | (b[6] << 24);
         w2 = b[7] | (b[8] << 8) | (b[9] << 16);
     }
+    if constexpr (DP4A) {   // pixel i = bytes 1+i .. 7+i of the window: two 4-byte dot products with the Q8 kernel (IDP.4A.U8.U8)
+        const uint32_t cA = 18u | (34u << 8) | (48u << 16) | (56u << 24), cB = 48u | (34u << 8) | (18u << 16);
+        h[0] = __dp4a(__byte_perm(w0, w1, 0x4321), cA, __dp4a(__byte_perm(w1, w2, 0x4321), cB, 0u));
+        h[1] = __dp4a(__byte_perm(w0, w1, 0x5432), cA, __dp4a(__byte_perm(w1, w2, 0x5432), cB, 0u));
+        h[2] = __dp4a(__byte_perm(w0, w1, 0x6543), cA, __dp4a(__byte_perm(w1, w2, 0x6543), cB, 0u));
+        h[3] = __dp4a(w1, cA, __dp4a(w2, cB, 0u));
+    } else {
     // S_k = the 4 pixels shifted by k-3 (bytes 1+k .. 4+k of the 12-byte window), split into even / odd lanes
     uint32_t e[7], o[7];
 #pragma unroll
@@ -535,10 +600,13 @@ __device__ __forceinline__ void blur_h4(const uint8_t* __restrict__ p, int x0, i
         e[k] = __byte_perm(sk, 0u, 0x4240);
         o[k] = __byte_perm(sk, 0u, 0x4341);
     }
-    lo = 18u * (e[0] + e[6]) + 34u * (e[1] + e[5]) + 48u * (e[2] + e[4]) + 56u * e[3];
-    hi = 18u * (o[0] + o[6]) + 34u * (o[1] + o[5]) + 48u * (o[2] + o[4]) + 56u * o[3];
+    const uint32_t lo = 18u * (e[0] + e[6]) + 34u * (e[1] + e[5]) + 48u * (e[2] + e[4]) + 56u * e[3];   // px 0 | px 2 << 16, each <= 65280
+    const uint32_t hi = 18u * (o[0] + o[6]) + 34u * (o[1] + o[5]) + 48u * (o[2] + o[4]) + 56u * o[3];   // px 1 | px 3 << 16
+    h[0] = lo & 0xffffu; h[2] = lo >> 16; h[1] = hi & 0xffffu; h[3] = hi >> 16;
+    }
 }
 
+template <bool DP4A>
 __global__ void __launch_bounds__(256, 4) k_blur(const __grid_constant__ ExtractGeom g) {
     const int tileId = blockIdx.x, img = blockIdx.y;
     int l = 0;
@@ -564,10 +632,7 @@ __global__ void __launch_bounds__(256, 4) k_blur(const __grid_constant__ Extract
             const int r = rb + j;
             if (r < rows + 6) {
                 const int y = reflect101(y0 + r - 3, G.h);
-                uint32_t lo, hi;
-                blur_h4(src + (int64_t)y * G.pitch, x0, mode, kr, colA, colB, lo, hi);
-                uint32_t* hrow = hwin[j];
-                hrow[0] = lo & 0xffffu; hrow[2] = lo >> 16; hrow[1] = hi & 0xffffu; hrow[3] = hi >> 16;
+                blur_h4<DP4A>(src + (int64_t)y * G.pitch, x0, mode, kr, colA, colB, hwin[j]);
                 if (r >= 6) {
                     // rows r-6 .. r are in the window; output row y0 + r - 6
                     uint32_t packed = 0u;

@@ -96,6 +96,7 @@ struct ProjParams {
     int* nmatches;             // [n_frames]
     const uint8_t* qvalid;     // mode 0: mbTrackInView per query (Frame::isInFrustum), null = all
     int* seqFlag;              // [n_frames] modes 0 / 1: set by the parallel resolve when a frame must take the sequential kernel; null = always sequential
+    int qpb;                   // queries per CTA of k_proj_candidates_grp
 };
 
 __device__ __forceinline__ void stage_frame(const ProjParams& P, int img, unsigned char* smem, FrameFeat& F, int& N, int& row0) {
@@ -381,44 +382,69 @@ __device__ __forceinline__ bool local_window(const ProjParams& P, int q, Window&
 
 // ---- Frame::AssignFeaturesToGrid (Frame.cc:469-504) as a CSR table: feature ids sorted by (cell, id) -------------
 #define PM_NCELL (GRID_COLS * GRID_ROWS)
+// Counting sort: per-cell histogram, exclusive scan (= the CSR table), unordered scatter, then every feature finds its rank among
+// the ids of its own cell (runs are a few features long; a run of n costs n steps per feature, so the worst case stays bounded).
+// Features outside the grid (PosInGrid false) form the run after the last cell, in id order, as in the sorted-key formulation.
 __global__ void __launch_bounds__(256) k_frame_grid(const __grid_constant__ ProjParams P) {
     extern __shared__ __align__(16) unsigned char pm_smem[];
-    uint32_t* keys = reinterpret_cast<uint32_t*>(pm_smem);   // npow
+    int* cnt = reinterpret_cast<int*>(pm_smem);                         // PM_NCELL + 2: counts, then exclusive starts
+    uint16_t* cellOf = reinterpret_cast<uint16_t*>(cnt + PM_NCELL + 2);   // maxFeat
+    uint16_t* tmp = cellOf + P.maxFeat;                                  // maxFeat: ids in cell order, unordered inside a cell
+    __shared__ int s_warp[8];
     const int frame = blockIdx.x, img = P.frame_image[frame];
     const int N = min(P.nkp[img], P.maxFeat), row0 = P.offsets[img];
-    int npow = 2;
-    while (npow < N) npow <<= 1;
-    for (int i = threadIdx.x; i < npow; i += blockDim.x) {
-        uint32_t key = 0xffffffffu;
-        if (i < N) {
-            const orbx_keypoint k = P.kps[row0 + i];
-            const int px = (int)roundf(fmul(fsub(k.x, P.minX), P.invW)), py = (int)roundf(fmul(fsub(k.y, P.minY), P.invH));
-            const uint32_t cell = (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) ? 0xffffu : (uint32_t)(px * GRID_ROWS + py);
-            key = (cell << 16) | (uint32_t)i;
-        }
-        keys[i] = key;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int c = tid; c < PM_NCELL + 2; c += 256) cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < N; i += 256) {
+        const orbx_keypoint k = P.kps[row0 + i];
+        const int px = (int)roundf(fmul(fsub(k.x, P.minX), P.invW)), py = (int)roundf(fmul(fsub(k.y, P.minY), P.invH));
+        const int cell = (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) ? PM_NCELL : (px * GRID_ROWS + py);
+        cellOf[i] = (uint16_t)cell;
+        atomicAdd(&cnt[cell], 1);
     }
     __syncthreads();
-    for (int k = 2; k <= npow; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < (npow >> 1); i += blockDim.x) {
-                const int l = ((i & ~(j - 1)) << 1) | (i & (j - 1)), r = l | j;
-                const uint32_t a = keys[l], b = keys[r];
-                if ((a > b) == ((l & k) == 0)) { keys[l] = b; keys[r] = a; }
-            }
-            __syncthreads();
-        }
-    uint16_t* order = P.gridOrder + (size_t)frame * P.maxFeat;
+    // exclusive scan of cnt[0 .. PM_NCELL] (3073 entries; 13 per thread covers 3328)
+    constexpr int PER = (PM_NCELL + 1 + 255) / 256;
+    int loc[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int c = tid * PER + k;
+        loc[k] = c <= PM_NCELL ? cnt[c] : 0;
+        sum += loc[k];
+    }
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    int base = inc - sum;
+    for (int w = 0; w < wid; ++w) base += s_warp[w];
     uint16_t* start = P.gridStart + (size_t)frame * (PM_NCELL + 1);
-    for (int i = threadIdx.x; i < N; i += blockDim.x) order[i] = (uint16_t)(keys[i] & 0xffffu);
-    for (int c = threadIdx.x; c <= PM_NCELL; c += blockDim.x) {   // first sorted position whose cell >= c
-        int lo = 0, hi = N;
-        const uint32_t v = (uint32_t)c << 16;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (keys[mid] < v) lo = mid + 1; else hi = mid;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int c = tid * PER + k;
+        if (c <= PM_NCELL) {
+            cnt[c] = base;                       // start of cell c; cnt doubles as the fill cursor below
+            if (c < PM_NCELL) start[c] = (uint16_t)base;
+            else start[PM_NCELL] = (uint16_t)base;   // first position outside the grid
         }
-        start[c] = (uint16_t)lo;
+        base += loc[k];
+    }
+    if (tid == 0) cnt[PM_NCELL + 1] = N;
+    __syncthreads();
+    for (int i = tid; i < N; i += 256) tmp[atomicAdd(&cnt[cellOf[i]], 1)] = (uint16_t)i;   // cnt[c] ends at start[c + 1]
+    __syncthreads();
+    uint16_t* order = P.gridOrder + (size_t)frame * P.maxFeat;
+    for (int p = tid; p < N; p += 256) {
+        const int id = tmp[p], c = cellOf[id];
+        const int b = c > 0 ? cnt[c - 1] : 0, e = cnt[c];   // the cursors after the scatter: cnt[c] = end of cell c = start of cell c + 1
+        int rank = 0;
+        for (int q = b; q < e; ++q) rank += tmp[q] < id;
+        order[b + rank] = (uint16_t)id;
     }
 }
 
@@ -525,6 +551,99 @@ __device__ __forceinline__ int warp_scan_query_grid(const ProjParams& P, const G
         }
     }
     return count;
+}
+
+// ---- kernel A', modes 0 / 1: G lanes per query ----------------------------------------------------
+// The windows of the two per-frame searches are small (th = 3: 2-3 grid columns of 2-3 cells, ~0.4 features per cell; th = 15: 4-12
+// columns), so a whole warp per query leaves 31 lanes idle on every column run.  Here a query belongs to G adjacent lanes: lane g
+// walks the columns c0 + g, c0 + g + G, ... serially, every lane keeps its own sorted top-K and the group merges them with K
+// REDUX.MIN rounds.  The candidate SET, the keys and therefore the stored top-K are those of the warp-wide scan (keys are unique).
+template <int G>
+__device__ __forceinline__ int group_scan_query_grid(const ProjParams& P, const GridFeat& F, int row0, const Window& w, const uint8_t* qd,
+                                                     float ur_pred, float er_max, unsigned gmask, int sub, unsigned long long out[PM_K]) {
+    uint32_t loc[PM_K];
+#pragma unroll
+    for (int k = 0; k < PM_K; ++k) loc[k] = 0xffffffffu;
+    int count = 0;
+    if (!w.empty) {
+        const uint4* q4 = reinterpret_cast<const uint4*>(qd);
+        const uint4 a0 = __ldg(q4), a1 = __ldg(q4 + 1);
+        const bool checkLevels = (w.minLevel > 0) || (w.maxLevel >= 0);
+        for (int ix = w.c0 + sub; ix <= w.c1; ix += G) {
+            const int jb = F.start[ix * GRID_ROWS + w.r0], je = F.start[ix * GRID_ROWS + w.r1 + 1];
+            for (int j = jb; j < je; ++j) {   // one exit per iteration: the gates are a predicate, not branches
+                const int oc = F.oct[j];
+                const float dx = fsub(F.x[j], w.x), dy = fsub(F.y[j], w.y), ur = F.ur[j];
+                bool pass = !(checkLevels && (oc < w.minLevel || (w.maxLevel >= 0 && oc > w.maxLevel)));
+                pass = pass && (fabsf(dx) < w.r && fabsf(dy) < w.r);
+                pass = pass && !(ur > 0 && fabsf(fsub(ur_pred, ur)) > er_max);
+                if (pass) {
+                    ++count;
+                    const uint32_t d = hamming256(a0, a1, P.desc + (size_t)(row0 + F.id[j]) * 32);
+                    uint32_t key = (d << 16) | (uint32_t)j;
+#pragma unroll
+                    for (int k = 0; k < PM_K; ++k) {   // branch-free sorted insert
+                        const uint32_t lo = min(key, loc[k]);
+                        key = max(key, loc[k]);
+                        loc[k] = lo;
+                    }
+                }
+            }
+        }
+    }
+    count = __reduce_add_sync(gmask, count);
+#pragma unroll
+    for (int k = 0; k < PM_K; ++k) out[k] = ~0ull;
+#pragma unroll
+    for (int k = 0; k < PM_K; ++k) {
+        const uint32_t m = __reduce_min_sync(gmask, loc[0]);
+        if (m == 0xffffffffu) break;   // uniform over the group
+        const int j = (int)(m & 0xffffu);
+        out[k] = ((unsigned long long)(m >> 16) << 32) | ((unsigned long long)F.cell[j] << 16) | (unsigned long long)F.id[j];
+        if (loc[0] == m) {             // sorted positions are unique => exactly one owner
+#pragma unroll
+            for (int q = 0; q + 1 < PM_K; ++q) loc[q] = loc[q + 1];
+            loc[PM_K - 1] = 0xffffffffu;
+        }
+    }
+    return count;
+}
+
+template <int G>
+__global__ void __launch_bounds__(PM_WARPS * 32) k_proj_candidates_grp(const __grid_constant__ ProjParams P) {
+    extern __shared__ __align__(16) unsigned char pm_smem[];
+    const int frame = blockIdx.y;
+    const int q0 = P.qoff[frame], q1 = P.qoff[frame + 1];
+    const int qbase = q0 + blockIdx.x * P.qpb;
+    if (qbase >= q1) return;
+    GridFeat GF;
+    int N, row0;
+    stage_grid(P, frame, pm_smem, GF, N, row0);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, sub = lane & (G - 1);
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - sub));
+    const int qend = min(qbase + P.qpb, q1);
+    for (int q = qbase + (int)(threadIdx.x / G); q < qend; q += PM_WARPS * 32 / G) {   // uniform over the G lanes of a query
+        Window w;
+        float ur_pred = 0.f, er_max = 0.f, u = 0.f, invzc = 0.f, radius = 0.f;
+        bool ok;
+        if (P.mode == 0) {
+            ok = local_window(P, q, w, er_max);
+            ur_pred = P.a2[q];
+        } else {
+            ok = last_frame_window(P, frame, q, w, u, invzc, radius);
+            ur_pred = fsub(u, fmul(P.bf, invzc));
+            er_max = radius;
+        }
+        unsigned long long top[PM_K];
+        int count = 0;
+        if (ok) count = group_scan_query_grid<G>(P, GF, row0, w, P.qdesc + 32 * (size_t)q, ur_pred, er_max, gmask, sub, top);
+        if (sub == 0) {
+            P.cnt[q] = ok ? count : -1;
+#pragma unroll
+            for (int k = 0; k < PM_K; ++k) P.topk[(size_t)q * PM_K + k] = ok ? top[k] : ~0ull;
+        }
+    }
 }
 
 // ---- kernel A: order-free candidate scan ----------------------------------------------------------
@@ -1084,17 +1203,32 @@ static orb_status launch_proj(orbx_handle* h, ProjParams& P, int n_frames, int m
     const size_t gsm = ((size_t)P.maxFeat * 17 + (PM_NCELL + 1) * 2 + 32 + 15) / 16 * 16;
     const size_t csm = std::max(fsm, gsm);
     if (P.mode != 2) {   // modes 0, 1, 3 search a window of the feature grid
-        int npow = 2;
-        while (npow < P.maxFeat) npow <<= 1;
-        ORB_CUDA(cudaFuncSetAttribute(k_frame_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(npow * 4, 1024)));
-        k_frame_grid<<<n_frames, 256, (size_t)npow * 4, st>>>(P);
+        const size_t gridSm = (size_t)(PM_NCELL + 2) * 4 + (size_t)P.maxFeat * 4 + 16;
+        ORB_CUDA(cudaFuncSetAttribute(k_frame_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(gridSm, (size_t)1024)));
+        k_frame_grid<<<n_frames, 256, gridSm, st>>>(P);
         ORB_LAUNCHED();
     }
-    ORB_CUDA(cudaFuncSetAttribute(k_proj_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(csm, (size_t)1024)));
-    dim3 grid((max_q_per_frame + PM_QPB - 1) / PM_QPB, n_frames);
-    if (grid.x > 0) {
-        k_proj_candidates<<<grid, PM_WARPS * 32, csm, st>>>(P);
-        ORB_LAUNCHED();
+    // modes 0 / 1 (the two per-frame searches): G lanes per query (ORB_PROJ_LANES = 4 | 8 | 16; 32 = the warp-per-query kernel)
+    const char* vLanes = getenv("ORB_PROJ_LANES");
+    const char* vQpb = getenv("ORB_PROJ_QPB");
+    const int envLanes = vLanes ? atoi(vLanes) : 0, envQpb = vQpb ? atoi(vQpb) : 0;
+    const int lanes = P.mode > 1 ? 32 : (envLanes ? envLanes : (P.mode == 0 ? 4 : 8));
+    if (lanes == 4 || lanes == 8 || lanes == 16) {
+        P.qpb = envQpb > 0 ? envQpb : (P.mode == 0 ? 128 : 64);
+        auto kern = lanes == 4 ? k_proj_candidates_grp<4> : (lanes == 8 ? k_proj_candidates_grp<8> : k_proj_candidates_grp<16>);
+        ORB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(csm, (size_t)1024)));
+        dim3 grid((max_q_per_frame + P.qpb - 1) / P.qpb, n_frames);
+        if (grid.x > 0) {
+            kern<<<grid, PM_WARPS * 32, csm, st>>>(P);
+            ORB_LAUNCHED();
+        }
+    } else {
+        ORB_CUDA(cudaFuncSetAttribute(k_proj_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(csm, (size_t)1024)));
+        dim3 grid((max_q_per_frame + PM_QPB - 1) / PM_QPB, n_frames);
+        if (grid.x > 0) {
+            k_proj_candidates<<<grid, PM_WARPS * 32, csm, st>>>(P);
+            ORB_LAUNCHED();
+        }
     }
     if (P.seqFlag) {   // modes 0 / 1: parallel fixed-point resolve; frames it cannot finish are flagged for the sequential kernel
         const size_t psm = fsm + (size_t)P.maxFeat * 9 + (size_t)(PR_QCAP + PR_LIST) * 4 + 64;

@@ -1,0 +1,20 @@
+#!/bin/bash
+# k_resize_v2 (4 px x 4 rows per thread) and k_blur<true> (IDP.4A horizontal pass): extractor parity, then bench per variant
+set -u
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_extractor_gpu.py tests/test_zz_fast_v2_gpu.py tests/test_zz_replay_step_gpu.py tests/test_zz_host_boundary_gpu.py tests/test_zz_config5_gpu.py tests/test_stereo_gpu.py -x -q 2>&1 | tail -6 | tee gpurun_out/r02_k12_tests.log
+run() {
+  name=$1; shift
+  env "$@" timeout 600 python bench.py --no-cpu-baseline --e2e-repeats 1 --latency-frames 5 > gpurun_out/r02_k12_bench_$name.json 2> gpurun_out/r02_k12_bench_$name.err
+  python - <<PY
+import json
+d = json.load(open("gpurun_out/r02_k12_bench_$name.json"))
+s = d["roofline"]["stage_ms_per_batch"]
+print("$name: value", round(d["value"]), "e2e", round(d["e2e"]["value"]), {k: round(v, 3) for k, v in s.items()}, "parity", d["parity"]["ok"])
+PY
+}
+run default ORB_X=0
+run old ORB_RESIZE_VARIANT=0 ORB_BLUR_VARIANT=0
+run resize_only ORB_BLUR_VARIANT=0
+run blur_only ORB_RESIZE_VARIANT=0
+run default2 ORB_X=0

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Per-CUDA-line shares of a kernel's executed warp instructions and warp-stall samples from an ncu report's source page.
 
-  python tools/ncu_source_lines.py gpurun_out/r02_fq.ncu-rep k_fast_cells_v2 [min_pct] >> profiles/r02_source_lines.md
+  python tools/ncu_source_lines.py gpurun_out/r02_fq.ncu-rep k_fast_cells_v2 [min_pct [nth-matching-launch]] >> profiles/r02_source_lines.md
 """
 import csv
 import io
@@ -13,7 +13,7 @@ import sys
 def main():
     rep, kern = sys.argv[1], sys.argv[2]
     min_pct = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
-    out = subprocess.check_output(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", f"regex:{kern}"] + (["--kernel-id", sys.argv[4]] if len(sys.argv) > 4 else []),
+    out = subprocess.check_output(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", f"regex:{kern}"] + (["--launch-skip", sys.argv[4], "--launch-count", "1"] if len(sys.argv) > 4 else []),
                                   text=True, stderr=subprocess.DEVNULL)
     rows = list(csv.reader(io.StringIO(out)))
     agg, cur_file, hdr, func = {}, None, None, None
