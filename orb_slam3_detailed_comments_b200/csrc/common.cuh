@@ -1,5 +1,7 @@
 // common.cuh -- shared declarations of the sm_100a hot-path library (liborbslam3_b200.so)
 #pragma once
+#include <utility>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -30,6 +32,31 @@ inline orb_status set_error(orb_status s, const std::string& msg) {
     } while (0)
 
 #define ORB_LAUNCHED() (++orb::g_launches)
+
+// Launch with the device's highest stream priority (ORB_PRIO=1) -- for the latency-bound kernels of the step (one CTA per image or
+// per frame: quadtree, ordering, stereo, the searches).  With several batches in flight on different streams their few CTAs then
+// take the next free SM slots instead of queueing behind the hundreds of thousands of CTAs of another batch's FAST / blur launch,
+// so the dependent-latency chains run under the issue-bound kernels.  The attribute is kept by stream capture (graph kernel nodes).
+inline int launch_priority() {
+    static const int prio = [] {
+        const char* v = getenv("ORB_PRIO");
+        if (!v || atoi(v) == 0) return 0;
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        return greatest;
+    }();
+    return prio;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_p(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributePriority;
+    at[0].val.priority = launch_priority();
+    cfg.attrs = at; cfg.numAttrs = launch_priority() != 0 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 #define ORB_MAX_LEVELS 12
 

@@ -506,20 +506,19 @@ static orb_status run_pipeline(orbx_handle* h, int batch, int lap0, int lap1) {
         cudaStream_t qs = gi == 0 ? st : h->aux_stream[gi - 1];
         if (gi > 0) cudaStreamWaitEvent(qs, h->ev_fork, 0);
         const bool wide = h->qt_variant == 1 && Q.level_begin == 0;      // the group with level 0: 1024 threads per CTA
-        (h->qt_variant == 0 ? k_quadtree : wide ? k_quadtree_v1<1024, 1> : k_quadtree_v1<QT_THREADS, 4>)
-            <<<batch * (Q.level_end - Q.level_begin), wide ? 1024 : QT_THREADS, Q.smem, qs>>>(
-            g, batch, Q.level_begin, h->d_cand, h->d_cand_cnt, h->d_sort, (char*)h->d_node_scratch,
-            (int64_t)h->qt_node_stride, Q.sort_cap, h->qt_nodes_in_smem, h->qt_node_cap, h->d_lvl_kp, h->d_lvl_cnt, h->d_err);
+        launch_p(h->qt_variant == 0 ? k_quadtree : wide ? k_quadtree_v1<1024, 1> : k_quadtree_v1<QT_THREADS, 4>,
+                 dim3(batch * (Q.level_end - Q.level_begin)), dim3(wide ? 1024 : QT_THREADS), Q.smem, qs,
+                 g, batch, Q.level_begin, h->d_cand, h->d_cand_cnt, h->d_sort, (char*)h->d_node_scratch,
+                 (int64_t)h->qt_node_stride, Q.sort_cap, h->qt_nodes_in_smem, h->qt_node_cap, h->d_lvl_kp, h->d_lvl_cnt, h->d_err);
         ORB_LAUNCHED();
         if (gi > 0) {
             cudaEventRecord(h->ev_join[gi - 1], qs);
             cudaStreamWaitEvent(st, h->ev_join[gi - 1], 0);
         }
     }
-    k_order<<<batch, 256, h->order_smem_bytes, st>>>(g, h->d_lvl_kp, h->d_lvl_cnt, lap0, lap1, h->d_slot, h->d_nkp,
-                                                     h->d_mono);
+    launch_p(k_order, dim3(batch), dim3(256), h->order_smem_bytes, st, g, h->d_lvl_kp, h->d_lvl_cnt, lap0, lap1, h->d_slot, h->d_nkp, h->d_mono);
     ORB_LAUNCHED();
-    k_offsets<<<1, 32, 0, st>>>(h->d_nkp, batch, h->d_offsets);
+    launch_p(k_offsets, dim3(1), dim3(32), 0, st, h->d_nkp, batch, h->d_offsets);
     ORB_LAUNCHED();
     if (prof) cudaEventRecord(h->ev[4], st);
     if (h->blur_variant == 1) k_blur<true><<<dim3(g.totalTiles, batch), 256, 0, st>>>(g);    // horizontal pass by IDP.4A

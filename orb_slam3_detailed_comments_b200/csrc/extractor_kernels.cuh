@@ -684,15 +684,20 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_describe(const __grid_
     const int x = (int)(c & 0xfffu) + 16, y = (int)((c >> 12) & 0xfffu) + 16, score = (int)(c >> 24);
 
     // intensity centroid over the radius-15 disc: lane u+15 owns COLUMN u and walks the 31 rows, so every load
-    // instruction of the warp touches one 31-byte segment (one cache line) and the 31 loads are independent
+    // instruction of the warp touches one 31-byte segment (one cache line) and the 31 loads are independent.
+    // (Measured and dropped: lane = row with nine word loads and IDP.4A against weight tables -- 30 % fewer instructions for the
+    // kernel, but every load instruction then touches 31 cache lines: 0.225 instead of 0.184 ms.)
     int m10 = 0, m01 = 0;
     if (lane < 31) {
+        constexpr int um[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};   // == c_umax, as immediates
         const int u = lane - 15, au = u < 0 ? -u : u;
-        const uint8_t* p = G.base + (int64_t)img * G.img_stride + (int64_t)y * G.pitch + x + u;
+        const uint8_t* q = G.base + (int64_t)img * G.img_stride + (int64_t)(y - 15) * G.pitch + x + u;
+        const int64_t pitch = G.pitch;
         int cs = 0;
 #pragma unroll
         for (int v = -15; v <= 15; ++v) {
-            const int val = (au <= c_umax[v < 0 ? -v : v]) ? (int)__ldg(p + (int64_t)v * G.pitch) : 0;
+            const int val = (au <= um[v < 0 ? -v : v]) ? (int)__ldg(q) : 0;
+            q += pitch;
             cs += val;
             m01 += v * val;
         }

@@ -1205,7 +1205,7 @@ static orb_status launch_proj(orbx_handle* h, ProjParams& P, int n_frames, int m
     if (P.mode != 2) {   // modes 0, 1, 3 search a window of the feature grid
         const size_t gridSm = (size_t)(PM_NCELL + 2) * 4 + (size_t)P.maxFeat * 4 + 16;
         ORB_CUDA(cudaFuncSetAttribute(k_frame_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(gridSm, (size_t)1024)));
-        k_frame_grid<<<n_frames, 256, gridSm, st>>>(P);
+        launch_p(k_frame_grid, dim3(n_frames), dim3(256), gridSm, st, P);
         ORB_LAUNCHED();
     }
     // modes 0 / 1 (the two per-frame searches): G lanes per query (ORB_PROJ_LANES = 4 | 8 | 16; 32 = the warp-per-query kernel)
@@ -1219,7 +1219,7 @@ static orb_status launch_proj(orbx_handle* h, ProjParams& P, int n_frames, int m
         ORB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(csm, (size_t)1024)));
         dim3 grid((max_q_per_frame + P.qpb - 1) / P.qpb, n_frames);
         if (grid.x > 0) {
-            kern<<<grid, PM_WARPS * 32, csm, st>>>(P);
+            launch_p(kern, grid, dim3(PM_WARPS * 32), csm, st, P);
             ORB_LAUNCHED();
         }
     } else {
@@ -1233,12 +1233,12 @@ static orb_status launch_proj(orbx_handle* h, ProjParams& P, int n_frames, int m
     if (P.seqFlag) {   // modes 0 / 1: parallel fixed-point resolve; frames it cannot finish are flagged for the sequential kernel
         const size_t psm = fsm + (size_t)P.maxFeat * 9 + (size_t)(PR_QCAP + PR_LIST) * 4 + 64;
         ORB_CUDA(cudaFuncSetAttribute(k_proj_resolve_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-        k_proj_resolve_par<<<n_frames, PR_THREADS, psm, st>>>(P);
+        launch_p(k_proj_resolve_par, dim3(n_frames), dim3(PR_THREADS), psm, st, P);
         ORB_LAUNCHED();
     }
     const size_t rsm = fsm + (size_t)PM_CHUNK * PM_K * 8 + (size_t)PM_CHUNK * 4 + (size_t)P.maxFeat * (P.mode == 4 ? 9 : 5) + (size_t)PM_CHUNK * 5 + 256;
     ORB_CUDA(cudaFuncSetAttribute(k_proj_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
-    k_proj_resolve<<<n_frames, 256, rsm, st>>>(P);
+    launch_p(k_proj_resolve, dim3(n_frames), dim3(256), rsm, st, P);
     ORB_LAUNCHED();
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;

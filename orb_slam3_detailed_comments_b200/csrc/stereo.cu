@@ -319,7 +319,7 @@ static orb_status run_stereo(orbx_handle* hl, orbx_handle* hr, int n_pairs, int 
         const size_t smem1 = 13 * (size_t)P.maxRight + 4 * (2 * (size_t)H + 2) + 64;
         ORB_CUDA(cudaFuncSetAttribute(k_stereo_match_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem1, (size_t)1024)));
         dim3 grid1((hl->geom.kpTotal + ST1_THREADS - 1) / ST1_THREADS, n_pairs);
-        k_stereo_match_v1<<<grid1, ST1_THREADS, smem1, st>>>(P, hl->geom, hr->geom);
+        launch_p(k_stereo_match_v1, grid1, dim3(ST1_THREADS), smem1, st, P, hl->geom, hr->geom);
     } else {
         const size_t smem = 9 * (size_t)P.maxRight + 16;
         ORB_CUDA(cudaFuncSetAttribute(k_stereo_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)1024)));
@@ -329,7 +329,7 @@ static orb_status run_stereo(orbx_handle* hl, orbx_handle* hr, int n_pairs, int 
     ORB_LAUNCHED();
     const size_t smem2 = 4 * (size_t)hl->geom.kpTotal + 16;
     ORB_CUDA(cudaFuncSetAttribute(k_stereo_median, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem2, (size_t)1024)));
-    k_stereo_median<<<n_pairs, 256, smem2, st>>>(P);
+    launch_p(k_stereo_median, dim3(n_pairs), dim3(256), smem2, st, P);
     ORB_LAUNCHED();
     ORB_CUDA(cudaGetLastError());
     hl->stereo_valid = true;
