@@ -527,7 +527,9 @@ orb_status orbo_pose_optimization_frames(orbx_handle* h, const orbo_frame_matche
  * (32 bytes), node_word / node_weight = word_id / weight of the leaves (ignored for inner nodes), depth_levels = m_L.
  * orbv_transform runs every descriptor of the extractor's last batch down the tree: word_out / weight_out per compact row
  * (WordId, idf weight; weight 0 = stopped word), node_out = the NodeId at levelsup levels above the leaf (what
- * mFeatVec.addFeature receives and what orbm_search_bow takes as feature_node).  Optionally the BowVector of every image:
+ * mFeatVec.addFeature receives and what orbm_search_bow takes as feature_node).  DBoW2 adds a feature to mBowVec AND to mFeatVec
+ * only when its weight is > 0 (TemplatedVocabulary.h:1153-1157): a caller rebuilding mFeatVec lists feature i under node_out[i]
+ * iff weight_out[i] > 0 and passes feature_node = -1 for the others.  Optionally the BowVector of every image:
  * bow_count_out[img] entries of (bow_word_out, bow_weight_out)[img][max features] in ascending word order, weights summed
  * in feature order and L1-normalised exactly like BowVector::addWeight / normalize.  on_device != 0: outputs are device
  * memory, no synchronisation. */

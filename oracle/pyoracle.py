@@ -747,3 +747,79 @@ def ref2_constants():
     c, r = np.zeros(3, np.int32), np.zeros(2, np.float32)
     ref2_lib().ref2_constants(_p(c), _p(r))
     return dict(TH_LOW=int(c[0]), TH_HIGH=int(c[1]), HISTO_LENGTH=int(c[2]), radius_close=float(r[0]), radius_far=float(r[1]))
+
+
+# ---- oracle/_ref part 3: the reference's own DBoW2 (Thirdparty/DBoW2) compiled where it lies (oracle/Makefile target ref3) -----------
+_REF3_SO = os.path.join(_HERE, "_ref", "liborb_ref3.so")
+_ref3_lib = None
+
+
+def build_ref3(force=False):
+    if os.path.exists(os.path.join(REFERENCE_ROOT, "Thirdparty", "DBoW2", "DBoW2", "TemplatedVocabulary.h")):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref3", f"REF={REFERENCE_ROOT}"] + (["-B"] if force else []))
+    return _REF3_SO if os.path.exists(_REF3_SO) else None
+
+
+def ref3_lib():
+    global _ref3_lib
+    if _ref3_lib is None:
+        if build_ref3() is None:
+            raise RuntimeError("oracle/_ref/liborb_ref3.so is not built and /root/reference is not present")
+        L = _ref3_lib = C.CDLL(_REF3_SO)
+        VP, I = C.c_void_p, C.c_int
+        L.ref3_voc_load_text.restype = VP
+        L.ref3_voc_load_text.argtypes = [C.c_char_p]
+        L.ref3_voc_destroy.argtypes = [VP]
+        L.ref3_voc_info.argtypes = [VP, VP]
+        L.ref3_transform.restype = I
+        L.ref3_transform.argtypes = [VP, VP, I, I, VP, VP, VP, VP]
+        L.ref3_transform_one.restype = I
+        L.ref3_transform_one.argtypes = [VP, VP, I, VP, VP, VP]
+        L.ref3_score.restype = C.c_double
+        L.ref3_score.argtypes = [VP, I, VP, VP, I, VP, VP]
+        L.ref3_forb_distance.restype = I
+        L.ref3_forb_distance.argtypes = [VP, VP]
+    return _ref3_lib
+
+
+class RefVocabulary:
+    """The reference's ORBVocabulary (DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>) loaded with its own loadFromTextFile."""
+
+    def __init__(self, text_path):
+        self.L = ref3_lib()
+        self.h = C.c_void_p(self.L.ref3_voc_load_text(os.fsencode(text_path)))
+        if not self.h:
+            raise RuntimeError(f"loadFromTextFile({text_path}) failed")
+        info = np.zeros(6, np.int32)
+        self.L.ref3_voc_info(self.h, _p(info))
+        self.k, self.depth, self.scoring, self.weighting, self.words, self.nodes = (int(x) for x in info)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref3_voc_destroy(self.h)
+            self.h = None
+
+    def transform(self, desc, levelsup=4):
+        """Frame::ComputeBoW's call: returns dict(bow_word, bow_weight, feat_node, ascending)."""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(d)
+        bw, bv, fn, asc = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.float64), np.zeros(max(n, 1), np.int32), np.zeros(1, np.int32)
+        k = self.L.ref3_transform(self.h, _p(d), n, int(levelsup), _p(bw), _p(bv), _p(fn), _p(asc))
+        return dict(bow_word=bw[:k], bow_weight=bv[:k], feat_node=fn[:n], ascending=bool(asc[0]))
+
+    def transform_one(self, d32, levelsup=4):
+        d = np.ascontiguousarray(d32, np.uint8)
+        w, n, wt = np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1, np.float64)
+        if not self.L.ref3_transform_one(self.h, _p(d), int(levelsup), _p(w), _p(wt), _p(n)):
+            raise AssertionError("DBoW2: transform(feature) / getWordWeight disagree with transform(feature, id, weight, nid, levelsup)")
+        return int(w[0]), float(wt[0]), int(n[0])
+
+    def score(self, w1, v1, w2, v2):
+        a, b = np.ascontiguousarray(w1, np.int32), np.ascontiguousarray(w2, np.int32)
+        x, y = np.ascontiguousarray(v1, np.float64), np.ascontiguousarray(v2, np.float64)
+        return float(self.L.ref3_score(self.h, len(a), _p(a), _p(x), len(b), _p(b), _p(y)))
+
+
+def ref3_forb_distance(a, b):
+    a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
+    return int(ref3_lib().ref3_forb_distance(_p(a), _p(b)))

@@ -16,10 +16,14 @@
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <sstream>     // the real core.hpp pulls these in; Thirdparty/DBoW2's TemplatedVocabulary.h relies on it
+#include <stdexcept>
+#include <string>
 #include <vector>
 
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_32F 5
 #define CV_PI 3.1415926535897932384626433832795
 
 typedef unsigned char uchar;
@@ -93,10 +97,11 @@ class Mat {
     Mat(Size s, int type) { create(s.height, s.width, type); }
     Mat(int r, int c, int /*type*/, void* ext, size_t stp = 0) : rows(r), cols(c), data((uchar*)ext), step(stp ? stp : (size_t)c) {}
 
-    void create(int r, int c, int /*type*/) {
+    void create(int r, int c, int type) {
         if (data && r == rows && c == cols) return;   // cv::Mat::create keeps a buffer of the right shape
-        rows = r; cols = c; step = (size_t)c;
-        store_.reset(new std::vector<uchar>((size_t)r * c));
+        const size_t es = type == CV_32F ? 4 : 1;     // CV_32F: only DBoW2's FORB::toMat32F (never called) asks for it
+        rows = r; cols = c; step = (size_t)c * es;
+        store_.reset(new std::vector<uchar>((size_t)r * c * es));
         data = store_->data();
     }
     void create(Size s, int type) { create(s.height, s.width, type); }
@@ -202,6 +207,29 @@ void copyMakeBorder(InputArray src, OutputArray dst, int top, int bottom, int le
 void GaussianBlur(InputArray src, OutputArray dst, Size ksize, double sigmaX, double sigmaY = 0, int borderType = BORDER_DEFAULT);
 void FAST(InputArray image, std::vector<KeyPoint>& keypoints, int threshold, bool nonmaxSuppression = true);
 float fastAtan2(float y, float x);
+
+// cv::FileStorage / cv::FileNode: Thirdparty/DBoW2's TemplatedVocabulary has virtual save / load members over them (YAML
+// vocabularies).  ORB-SLAM3 loads its vocabulary with loadFromTextFile, so these only have to compile; using them throws.
+class FileNode {
+   public:
+    FileNode operator[](const char*) const { throw std::runtime_error("cv::FileNode is not modelled"); }
+    FileNode operator[](const std::string&) const { throw std::runtime_error("cv::FileNode is not modelled"); }
+    FileNode operator[](int) const { throw std::runtime_error("cv::FileNode is not modelled"); }
+    size_t size() const { return 0; }
+    operator int() const { return 0; }
+    operator double() const { return 0.0; }
+    operator std::string() const { return std::string(); }
+};
+class FileStorage {
+   public:
+    enum { READ = 0, WRITE = 1 };
+    FileStorage(const std::string&, int) {}
+    bool isOpened() const { return false; }
+    FileNode operator[](const std::string&) const { throw std::runtime_error("cv::FileStorage is not modelled"); }
+    FileNode operator[](const char*) const { throw std::runtime_error("cv::FileStorage is not modelled"); }
+};
+template <typename T>
+static inline FileStorage& operator<<(FileStorage& fs, const T&) { throw std::runtime_error("cv::FileStorage is not modelled"); return fs; }
 
 struct KeyPointsFilter {   // only ComputeKeyPointsOld (dead code in the reference) uses it
     static void retainBest(std::vector<KeyPoint>& keypoints, int npoints);
