@@ -665,6 +665,17 @@ def ref2_lib():
         L.ref2_is_in_frustum.restype = I
         L.ref2_is_in_frustum.argtypes = [VP, VP, VP, VP, I, VP, VP, VP, VP, F] + [VP] * 7
         L.ref2_stereo_matches.argtypes = [VP, VP, VP, VP, VP, I, VP, VP]
+        L.ref2_kf_create.restype = VP
+        L.ref2_kf_create.argtypes = [VP, VP, VP, I, VP, VP, VP, VP, VP, I, VP, VP]
+        L.ref2_kf_destroy.argtypes = [VP]
+        L.ref2_search_bow.restype = I
+        L.ref2_search_bow.argtypes = [VP, VP, VP, F, I, VP]
+        L.ref2_search_bow_kf.restype = I
+        L.ref2_search_bow_kf.argtypes = [VP, VP, F, I, VP]
+        L.ref2_search_initialization.restype = I
+        L.ref2_search_initialization.argtypes = [VP, VP, VP, I, F, I, VP]
+        L.ref2_search_triangulation.restype = I
+        L.ref2_search_triangulation.argtypes = [VP, VP, I, I, I, VP, VP, VP]
     return _ref2_lib
 
 
@@ -747,6 +758,54 @@ def ref2_constants():
     c, r = np.zeros(3, np.int32), np.zeros(2, np.float32)
     ref2_lib().ref2_constants(_p(c), _p(r))
     return dict(TH_LOW=int(c[0]), TH_HIGH=int(c[1]), HISTO_LENGTH=int(c[2]), radius_close=float(r[0]), radius_far=float(r[1]))
+
+
+class RefKeyFrame:
+    """A reference KeyFrame skeleton (single camera) filled from flat arrays, for the KeyFrame-typed matchers of ORBmatcher.cc."""
+
+    def __init__(self, kps, desc, uright=None, node=None, has_mp=None, bad=None, scale_factors=None, level_sigma2=None, cam4=(1, 1, 0, 0), Tcw7=None):
+        self.L = ref2_lib()
+        f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+        u8 = lambda a: None if a is None else np.ascontiguousarray(a, np.uint8)
+        i32 = lambda a: None if a is None else np.ascontiguousarray(a, np.int32)
+        self._keep = (np.ascontiguousarray(kps), u8(desc), f32(uright), i32(node), u8(has_mp), u8(bad), f32(scale_factors), f32(level_sigma2), f32(cam4), f32(Tcw7))
+        k, d, u, n, m, b, s, l2, c, t = self._keep
+        P = lambda a: None if a is None else _p(a)
+        self.N = len(k)
+        self.h = C.c_void_p(self.L.ref2_kf_create(_p(k), _p(d), P(u), len(k), P(n), P(m), P(b), P(s), P(l2), 0 if s is None else len(s), _p(c), P(t)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref2_kf_destroy(self.h)
+            self.h = None
+
+
+def ref2_search_bow(frame, feat_node, kf, nnratio, check_ori=True):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) of the reference: (feat_match[N] = KF feature index or -1, nmatches)."""
+    fn = np.ascontiguousarray(feat_node, np.int32)
+    fm = np.full(max(frame.N, 1), -1, np.int32)
+    n = frame.L.ref2_search_bow(frame.h, _p(fn), kf.h, nnratio, 1 if check_ori else 0, _p(fm))
+    return fm[:frame.N], n
+
+
+def ref2_search_bow_kf(kf1, kf2, nnratio, check_ori=True):
+    m = np.full(max(kf1.N, 1), -1, np.int32)
+    n = kf1.L.ref2_search_bow_kf(kf1.h, kf2.h, nnratio, 1 if check_ori else 0, _p(m))
+    return m[:kf1.N], n
+
+
+def ref2_search_initialization(f1, f2, prev_matched, window_size, nnratio, check_ori=True):
+    pm = np.ascontiguousarray(prev_matched, np.float32).copy()
+    m = np.full(max(f1.N, 1), -1, np.int32)
+    n = f1.L.ref2_search_initialization(f1.h, f2.h, _p(pm), int(window_size), nnratio, 1 if check_ori else 0, _p(m))
+    return m[:f1.N], n, pm
+
+
+def ref2_search_triangulation(kf1, kf2, only_stereo=False, coarse=False, check_ori=True):
+    m = np.full(max(kf1.N, 1), -1, np.int32)
+    F12, ep = np.zeros(9, np.float32), np.zeros(2, np.float32)
+    n = kf1.L.ref2_search_triangulation(kf1.h, kf2.h, 1 if only_stereo else 0, 1 if coarse else 0, 1 if check_ori else 0, _p(m), _p(F12), _p(ep))
+    return m[:kf1.N], n, F12.reshape(3, 3), ep
 
 
 # ---- oracle/_ref part 3: the reference's own DBoW2 (Thirdparty/DBoW2) compiled where it lies (oracle/Makefile target ref3) -----------

@@ -9,6 +9,7 @@
 #include "ORBmatcher.h"   // the reference's own header (its MapPoint.h / KeyFrame.h / Frame.h includes are guarded out by the skeleton)
 
 #include <cstring>
+#include <memory>
 
 namespace ORB_SLAM3 {
 float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
@@ -222,6 +223,128 @@ void ref2_stereo_matches(void* h, void* exL, void* exR, const void* kpsR, const 
     F.mDescriptorsRight = desc_mat(descR, NR);
     F.ComputeStereoMatches();
     for (int i = 0; i < F.N; ++i) { uright[i] = F.mvuRight[i]; depth[i] = F.mvDepth[i]; }
+}
+
+}  // extern "C"
+
+// ---- part 2b: the KeyFrame-typed matchers ------------------------------------------------------------------------------------
+namespace {
+struct KFHolder {
+    KeyFrame K;
+    Pinhole cam;
+    std::unique_ptr<MapPoint[]> mps;   // one per feature; mvpMapPoints[i] points here when the feature holds a map point
+};
+void fill_featvec(DBoW2::FeatureVector& fv, const int* node, int n) {
+    fv.clear();
+    if (!node) return;
+    for (int i = 0; i < n; ++i)
+        if (node[i] >= 0) fv.addFeature((DBoW2::NodeId)node[i], (unsigned)i);   // ascending i, as TemplatedVocabulary::transform adds them
+}
+}  // namespace
+
+extern "C" {
+
+// A single-camera KeyFrame (NLeft == -1, mpCamera2 == NULL) from flat arrays.  node[i] = mFeatVec node of feature i or -1;
+// has_mp[i] != 0: feature i holds a map point (bad[i] != 0: MapPoint::isBad()); the map point of feature i carries query_index = i.
+void* ref2_kf_create(const void* kps, const unsigned char* desc, const float* uright, int N, const int* node, const unsigned char* has_mp,
+                     const unsigned char* bad, const float* scaleFactors, const float* levelSigma2, int nlevels, const float* cam4, const float* Tcw7) {
+    KFHolder* H = new KFHolder();
+    KeyFrame& K = H->K;
+    const Kp28* k = (const Kp28*)kps;
+    K.N = N;
+    K.mvKeys.resize(N);
+    for (int i = 0; i < N; ++i) {
+        cv::KeyPoint& o = K.mvKeys[i];
+        o.pt.x = k[i].x; o.pt.y = k[i].y; o.size = k[i].size; o.angle = k[i].angle; o.response = k[i].response; o.octave = k[i].octave; o.class_id = k[i].class_id;
+    }
+    K.mvKeysUn = K.mvKeys;
+    K.mDescriptors = desc_mat(desc, N);
+    K.mvuRight.assign(N, -1.0f);
+    if (uright) for (int i = 0; i < N; ++i) K.mvuRight[i] = uright[i];
+    fill_featvec(K.mFeatVec, node, N);
+    H->mps.reset(new MapPoint[std::max(N, 1)]);
+    K.mvpMapPoints.assign(N, static_cast<MapPoint*>(NULL));
+    for (int i = 0; i < N; ++i) {
+        H->mps[i].query_index = i;
+        H->mps[i].mbBad = bad && bad[i];
+        if (has_mp && has_mp[i]) K.mvpMapPoints[i] = &H->mps[i];
+    }
+    if (scaleFactors) K.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    if (levelSigma2) K.mvLevelSigma2.assign(levelSigma2, levelSigma2 + nlevels);
+    H->cam.mvParameters = {cam4[0], cam4[1], cam4[2], cam4[3]};
+    K.mpCamera = &H->cam;
+    if (Tcw7) {
+        for (int i = 0; i < 4; ++i) K.mTcw.q[i] = Tcw7[i];
+        for (int i = 0; i < 3; ++i) K.mTcw.t[i] = Tcw7[4 + i];
+    }
+    return H;
+}
+void ref2_kf_destroy(void* h) { delete (KFHolder*)h; }
+
+// ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches): feat_node = F.mFeatVec;
+// feat_match[idxF] = the KF feature whose map point F's feature idxF now holds, or -1
+int ref2_search_bow(void* hF, const int* feat_node, void* hKF, float nnratio, int checkOri, int* feat_match) {
+    Frame& F = ((Holder*)hF)->F;
+    KeyFrame& K = ((KFHolder*)hKF)->K;
+    fill_featvec(F.mFeatVec, feat_node, F.N);
+    std::vector<MapPoint*> vp;
+    ORBmatcher matcher(nnratio, checkOri != 0);
+    const int n = matcher.SearchByBoW(&K, F, vp);
+    for (int i = 0; i < F.N; ++i) feat_match[i] = vp[i] ? vp[i]->query_index : -1;
+    return n;
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12): match12[idx1] = the KF2 feature, or -1
+int ref2_search_bow_kf(void* hKF1, void* hKF2, float nnratio, int checkOri, int* match12) {
+    KeyFrame& K1 = ((KFHolder*)hKF1)->K;
+    KeyFrame& K2 = ((KFHolder*)hKF2)->K;
+    std::vector<MapPoint*> vp;
+    ORBmatcher matcher(nnratio, checkOri != 0);
+    const int n = matcher.SearchByBoW(&K1, &K2, vp);
+    for (int i = 0; i < K1.N; ++i) match12[i] = vp[i] ? vp[i]->query_index : -1;
+    return n;
+}
+
+// ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize): prevMatched = 2 floats per F1 feature, in / out
+int ref2_search_initialization(void* hF1, void* hF2, float* prevMatched, int windowSize, float nnratio, int checkOri, int* matches12) {
+    Frame& F1 = ((Holder*)hF1)->F;
+    Frame& F2 = ((Holder*)hF2)->F;
+    std::vector<cv::Point2f> prev(F1.N);
+    for (int i = 0; i < F1.N; ++i) prev[i] = cv::Point2f(prevMatched[2 * i], prevMatched[2 * i + 1]);
+    std::vector<int> m12;
+    ORBmatcher matcher(nnratio, checkOri != 0);
+    const int n = matcher.SearchForInitialization(F1, F2, prev, m12, windowSize);
+    for (int i = 0; i < F1.N; ++i) { matches12[i] = m12[i]; prevMatched[2 * i] = prev[i].x; prevMatched[2 * i + 1] = prev[i].y; }
+    return n;
+}
+
+// ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse): match12[idx1] = idx2 or -1.  F12 / ep = the
+// fundamental matrix Pinhole::epipolarConstrain builds and the epipole, recomputed here with the same (miniature) Eigen / Sophus calls
+// so that the test can hand the oracle the values its caller would.
+int ref2_search_triangulation(void* hKF1, void* hKF2, int bOnlyStereo, int bCoarse, int checkOri, int* match12, float* F12_9, float* ep2) {
+    KeyFrame& K1 = ((KFHolder*)hKF1)->K;
+    KeyFrame& K2 = ((KFHolder*)hKF2)->K;
+    std::vector<std::pair<size_t, size_t> > pairs;
+    ORBmatcher matcher(0.6f, checkOri != 0);
+    const int n = matcher.SearchForTriangulation(&K1, &K2, pairs, bOnlyStereo != 0, bCoarse != 0);
+    for (int i = 0; i < K1.N; ++i) match12[i] = -1;
+    for (size_t i = 0; i < pairs.size(); ++i) match12[pairs[i].first] = (int)pairs[i].second;
+    {   // ORBmatcher.cc:1052-1070 and Pinhole.cpp:191-194
+        Sophus::SE3f T1w = K1.GetPose(), T2w = K2.GetPose(), Tw2 = K2.GetPoseInverse();
+        Eigen::Vector3f Cw = K1.GetCameraCenter();
+        Eigen::Vector3f C2 = T2w * Cw;
+        Eigen::Vector2f ep = K2.mpCamera->project(C2);
+        Sophus::SE3f T12 = T1w * Tw2;
+        Eigen::Matrix3f R12 = T12.rotationMatrix();
+        Eigen::Vector3f t12 = T12.translation();
+        Eigen::Matrix3f t12x = Sophus::SO3f::hat(t12);
+        Eigen::Matrix3f Ka = K1.mpCamera->toK_(), Kb = K2.mpCamera->toK_();
+        Eigen::Matrix3f F12 = Ka.transpose().inverse() * t12x * R12 * Kb.inverse();
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) F12_9[3 * r + c] = F12(r, c);
+        ep2[0] = ep(0); ep2[1] = ep(1);
+    }
+    return n;
 }
 
 }  // extern "C"

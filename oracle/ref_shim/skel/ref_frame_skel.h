@@ -5,8 +5,10 @@
 //     ORBmatcher.cc : ORBmatcher::ORBmatcher, SearchByProjection(Frame&, vector<MapPoint*>&, ...), SearchByProjection(Frame&, const
 //                     Frame&, th, bMono), RadiusByViewingCos, ComputeThreeMaxima, DescriptorDistance, TH_LOW / TH_HIGH / HISTO_LENGTH
 //     Frame.cc      : AssignFeaturesToGrid, PosInGrid, GetFeaturesInArea, isInFrustum(MapPoint*, float), ComputeStereoMatches
+//                     SearchByBoW(KeyFrame*, Frame&, ...), SearchByBoW(KeyFrame*, KeyFrame*, ...), SearchForInitialization,
+//                     SearchForTriangulation
 //     MapPoint.cc   : PredictScale(const float&, Frame*)
-//     Pinhole.cpp   : project(const Eigen::Vector3f&)
+//     Pinhole.cpp   : project(const Eigen::Vector3f&), toK_(), epipolarConstrain(...)
 // Those functions are compiled VERBATIM (oracle/tools/extract_functions.py writes them into oracle/_ref/gen/, a build directory)
 // against the reference's own include/ORBmatcher.h and include/ORBextractor.h; this header defines the include guards of
 // Frame.h / KeyFrame.h / MapPoint.h (which pull in DBoW2, g2o, boost, Pangolin: none exist in this image) and supplies the class
@@ -33,6 +35,8 @@
 
 #include <opencv2/core/core.hpp>   // oracle/ref_shim/opencv2: the miniature cv::
 #include "ORBextractor.h"          // the reference's own header
+#include "DBoW2/BowVector.h"       // the reference's own Thirdparty/DBoW2 headers (std::map subclasses); boost stubs: ref_shim/dbow
+#include "DBoW2/FeatureVector.h"
 
 #define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
 
@@ -61,6 +65,43 @@ struct Matrix {
         for (int r = 0; r < 3; ++r) o.v[r] = (*this)(r, 0) * b.v[0] + ((*this)(r, 1) * b.v[1] + (*this)(r, 2) * b.v[2]);
         return o;
     }
+    // --- only Pinhole::epipolarConstrain's F12 = K1^-T [t]x R12 K2^-1 needs what follows; its value is handed to the oracle as an
+    // input by the test (the oracle takes F12 from its caller), so these models decide nothing that is compared
+    template <int C2>
+    Matrix<T, R, C2> operator*(const Matrix<T, C, C2>& b) const {
+        static_assert(C2 > 1, "matrix * matrix");
+        Matrix<T, R, C2> o;
+        for (int r = 0; r < R; ++r)
+            for (int c = 0; c < C2; ++c) {
+                T a = T(0);
+                for (int k = 0; k < C; ++k) a += (*this)(r, k) * b(k, c);
+                o(r, c) = a;
+            }
+        return o;
+    }
+    Matrix<T, C, R> transpose() const {
+        Matrix<T, C, R> o;
+        for (int r = 0; r < R; ++r)
+            for (int c = 0; c < C; ++c) o(c, r) = (*this)(r, c);
+        return o;
+    }
+    Matrix inverse() const {   // cofactors / determinant
+        static_assert(R == 3 && C == 3, "3x3");
+        const Matrix& m = *this;
+        Matrix o;
+        const T det = m(0, 0) * (m(1, 1) * m(2, 2) - m(1, 2) * m(2, 1)) - m(0, 1) * (m(1, 0) * m(2, 2) - m(1, 2) * m(2, 0)) +
+                      m(0, 2) * (m(1, 0) * m(2, 1) - m(1, 1) * m(2, 0));
+        const T id = T(1) / det;
+        o(0, 0) = (m(1, 1) * m(2, 2) - m(1, 2) * m(2, 1)) * id; o(0, 1) = (m(0, 2) * m(2, 1) - m(0, 1) * m(2, 2)) * id; o(0, 2) = (m(0, 1) * m(1, 2) - m(0, 2) * m(1, 1)) * id;
+        o(1, 0) = (m(1, 2) * m(2, 0) - m(1, 0) * m(2, 2)) * id; o(1, 1) = (m(0, 0) * m(2, 2) - m(0, 2) * m(2, 0)) * id; o(1, 2) = (m(0, 2) * m(1, 0) - m(0, 0) * m(1, 2)) * id;
+        o(2, 0) = (m(1, 0) * m(2, 1) - m(1, 1) * m(2, 0)) * id; o(2, 1) = (m(0, 1) * m(2, 0) - m(0, 0) * m(2, 1)) * id; o(2, 2) = (m(0, 0) * m(1, 1) - m(0, 1) * m(1, 0)) * id;
+        return o;
+    }
+    struct CommaInit {   // `K << a, b, c, ...;` row-major
+        Matrix* m; int i;
+        CommaInit& operator,(T x) { m->v[i++] = x; return *this; }
+    };
+    CommaInit operator<<(T x) { v[0] = x; return CommaInit{this, 1}; }
 };
 typedef Matrix<float, 2, 1> Vector2f;
 typedef Matrix<float, 3, 1> Vector3f;
@@ -85,6 +126,26 @@ class SE3 {   // unit quaternion (x y z w) + translation; point action as so3.hp
         rot(q, p.v, o);
         return Eigen::Matrix<T, 3, 1>(o[0] + t[0], o[1] + t[1], o[2] + t[2]);
     }
+    Eigen::Matrix<T, 3, 3> rotationMatrix() const {   // Eigen::Quaternion::toRotationMatrix (values handed to the oracle by the test)
+        Eigen::Matrix<T, 3, 3> m;
+        const T tx = T(2) * q[0], ty = T(2) * q[1], tz = T(2) * q[2];
+        const T twx = tx * q[3], twy = ty * q[3], twz = tz * q[3], txx = tx * q[0], txy = ty * q[0], txz = tz * q[0], tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+        m(0, 0) = T(1) - (tyy + tzz); m(0, 1) = txy - twz; m(0, 2) = txz + twy;
+        m(1, 0) = txy + twz; m(1, 1) = T(1) - (txx + tzz); m(1, 2) = tyz - twx;
+        m(2, 0) = txz - twy; m(2, 1) = tyz + twx; m(2, 2) = T(1) - (txx + tyy);
+        return m;
+    }
+    SE3 operator*(const SE3& b) const {   // se3.hpp: rotation = q * b.q (renormalised by Sophus; inputs here are unit), t = t + q * b.t
+        SE3 r;
+        r.q[3] = q[3] * b.q[3] - q[0] * b.q[0] - q[1] * b.q[1] - q[2] * b.q[2];
+        r.q[0] = q[3] * b.q[0] + q[0] * b.q[3] + q[1] * b.q[2] - q[2] * b.q[1];
+        r.q[1] = q[3] * b.q[1] + q[1] * b.q[3] + q[2] * b.q[0] - q[0] * b.q[2];
+        r.q[2] = q[3] * b.q[2] + q[2] * b.q[3] + q[0] * b.q[1] - q[1] * b.q[0];
+        T o[3];
+        rot(q, b.t, o);
+        r.t[0] = o[0] + t[0]; r.t[1] = o[1] + t[1]; r.t[2] = o[2] + t[2];
+        return r;
+    }
     SE3 inverse() const {   // se3.hpp: SE3(so3().inverse(), so3().inverse() * (translation() * -1))
         SE3 r;
         r.q[0] = -q[0]; r.q[1] = -q[1]; r.q[2] = -q[2]; r.q[3] = q[3];
@@ -94,6 +155,15 @@ class SE3 {   // unit quaternion (x y z w) + translation; point action as so3.hp
     }
 };
 typedef SE3<float> SE3f;
+template <typename T>
+struct SO3 {
+    static Eigen::Matrix<T, 3, 3> hat(const Eigen::Matrix<T, 3, 1>& w) {   // so3.hpp: [0 -c b; c 0 -a; -b a 0]
+        Eigen::Matrix<T, 3, 3> m;
+        m(0, 1) = -w(2); m(0, 2) = w(1); m(1, 0) = w(2); m(1, 2) = -w(0); m(2, 0) = -w(1); m(2, 1) = w(0);
+        return m;
+    }
+};
+typedef SO3<float> SO3f;
 template <typename T>
 class Sim3 {};
 typedef Sim3<float> Sim3f;
@@ -107,16 +177,23 @@ namespace ORB_SLAM3 {
 #define FRAME_GRID_COLS 64
 
 class Frame;
-class KeyFrame;   // named in ORBmatcher.h signatures only
+class KeyFrame;
 
 class GeometricCamera {
    public:
     virtual ~GeometricCamera() {}
     virtual Eigen::Vector2f project(const Eigen::Vector3f& v3D) = 0;
+    virtual Eigen::Matrix3f toK_() = 0;
+    virtual bool epipolarConstrain(GeometricCamera* otherCamera, const cv::KeyPoint& kp1, const cv::KeyPoint& kp2, const Eigen::Matrix3f& R12,
+                                   const Eigen::Vector3f& t12, const float sigmaLevel, const float unc) = 0;
 };
 class Pinhole : public GeometricCamera {
    public:
-    Eigen::Vector2f project(const Eigen::Vector3f& v3D);   // body extracted from src/CameraModels/Pinhole.cpp
+    // bodies extracted from src/CameraModels/Pinhole.cpp
+    Eigen::Vector2f project(const Eigen::Vector3f& v3D);
+    Eigen::Matrix3f toK_();
+    bool epipolarConstrain(GeometricCamera* pCamera2, const cv::KeyPoint& kp1, const cv::KeyPoint& kp2, const Eigen::Matrix3f& R12,
+                           const Eigen::Vector3f& t12, const float sigmaLevel, const float unc);
     std::vector<float> mvParameters;
 };
 
@@ -129,7 +206,8 @@ class MapPoint {
     Eigen::Vector3f GetNormal() { return mNormalVector; }
     cv::Mat GetDescriptor() { return mDescriptor.clone(); }
     int Observations() { return nObs; }
-    bool isBad() { return false; }
+    bool isBad() { return mbBad; }
+    bool mbBad = false;
     float GetMinDistanceInvariance() { return 0.8f * mfMinDistance; }   // MapPoint.cc:658-672
     float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }
     int PredictScale(const float& currentDist, Frame* pF);             // body extracted from src/MapPoint.cc
@@ -176,11 +254,36 @@ class Frame {
     vector<float> mvScaleFactors, mvInvScaleFactors;
     static float mnMinX, mnMaxX, mnMinY, mnMaxY;
     GeometricCamera* mpCamera;
+    GeometricCamera* mpCamera2 = nullptr;
+    DBoW2::BowVector mBowVec;
+    DBoW2::FeatureVector mFeatVec;
     int Nleft, Nright;
     std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;   // fisheye branch (Nleft != -1): not exercised
     Sophus::SE3<float> mTcw;
     Eigen::Matrix<float, 3, 3> mRcw;
     Eigen::Matrix<float, 3, 1> mtcw, mOw;
+};
+
+class KeyFrame {   // the members the extracted KeyFrame-typed matchers read (single camera: NLeft == -1, mpCamera2 == nullptr)
+   public:
+    KeyFrame() : N(0), NLeft(-1), NRight(-1), mpCamera(nullptr), mpCamera2(nullptr) {}
+    vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
+    Sophus::SE3f GetPose() { return mTcw; }
+    Sophus::SE3f GetPoseInverse() { return mTcw.inverse(); }
+    Eigen::Vector3f GetCameraCenter() { return mTcw.inverse().translation(); }
+    Sophus::SE3f GetRightPose() { return Sophus::SE3f(); }          // two-camera rigs (mpCamera2): not exercised
+    Sophus::SE3f GetRightPoseInverse() { return Sophus::SE3f(); }
+    int N, NLeft, NRight;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysUn, mvKeysRight;
+    std::vector<float> mvuRight, mvDepth;
+    cv::Mat mDescriptors;
+    DBoW2::BowVector mBowVec;
+    DBoW2::FeatureVector mFeatVec;
+    std::vector<float> mvScaleFactors, mvLevelSigma2, mvInvLevelSigma2;
+    GeometricCamera *mpCamera, *mpCamera2;
+    std::vector<MapPoint*> mvpMapPoints;
+    Sophus::SE3f mTcw;
 };
 
 }  // namespace ORB_SLAM3
