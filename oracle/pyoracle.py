@@ -665,6 +665,9 @@ def ref2_lib():
         L.ref2_is_in_frustum.restype = I
         L.ref2_is_in_frustum.argtypes = [VP, VP, VP, VP, I, VP, VP, VP, VP, F] + [VP] * 7
         L.ref2_stereo_matches.argtypes = [VP, VP, VP, VP, VP, I, VP, VP]
+        L.ref2_distinctive_descriptor.restype = I
+        L.ref2_distinctive_descriptor.argtypes = [I, VP, VP, VP]
+        L.ref2_update_normal_and_depth.argtypes = [I, VP, VP, I, I, VP, I, VP, VP]
         L.ref2_kf_create.restype = VP
         L.ref2_kf_create.argtypes = [VP, VP, VP, I, VP, VP, VP, VP, VP, I, VP, VP]
         L.ref2_kf_destroy.argtypes = [VP]
@@ -806,6 +809,24 @@ def ref2_search_triangulation(kf1, kf2, only_stereo=False, coarse=False, check_o
     F12, ep = np.zeros(9, np.float32), np.zeros(2, np.float32)
     n = kf1.L.ref2_search_triangulation(kf1.h, kf2.h, 1 if only_stereo else 0, 1 if coarse else 0, 1 if check_ori else 0, _p(m), _p(F12), _p(ep))
     return m[:kf1.N], n, F12.reshape(3, 3), ep
+
+
+def ref2_distinctive_descriptor(descs, kf_bad=None):
+    """MapPoint::ComputeDistinctiveDescriptors of the reference over one observation per keyframe: the chosen 32 bytes, or None."""
+    d = np.ascontiguousarray(descs, np.uint8).reshape(-1, 32)
+    b = None if kf_bad is None else np.ascontiguousarray(kf_bad, np.uint8)
+    out = np.zeros(32, np.uint8)
+    ok = ref2_lib().ref2_distinctive_descriptor(len(d), _p(d) if len(d) else None, None if b is None else _p(b), _p(out))
+    return out if ok else None
+
+
+def ref2_update_normal_and_depth(centers, pos, ref, level, scale_factors):
+    """MapPoint::UpdateNormalAndDepth of the reference: (normal[3], mfMaxDistance, mfMinDistance)."""
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    c, p, sf = f32(centers).reshape(-1, 3), f32(pos), f32(scale_factors)
+    n, mm = np.zeros(3, np.float32), np.zeros(2, np.float32)
+    ref2_lib().ref2_update_normal_and_depth(len(c), _p(c), _p(p), int(ref), int(level), _p(sf), len(sf), _p(n), _p(mm))
+    return n, mm[0], mm[1]
 
 
 # ---- oracle/_ref part 3: the reference's own DBoW2 (Thirdparty/DBoW2) compiled where it lies (oracle/Makefile target ref3) -----------

@@ -348,3 +348,48 @@ int ref2_search_triangulation(void* hKF1, void* hKF2, int bOnlyStereo, int bCoar
 }
 
 }  // extern "C"
+
+// ---- part 2c: MapPoint maintenance ------------------------------------------------------------------------------------------------
+extern "C" {
+
+// MapPoint::ComputeDistinctiveDescriptors: observation i = feature 0 of keyframe i (descriptor descs[i], KeyFrame::isBad() = kf_bad[i]);
+// the keyframes live in one array, so std::map<KeyFrame*, ...> walks them in index order.  Writes mDescriptor; returns 0 when the
+// function returned before choosing (no observation / all keyframes bad), else 1.
+int ref2_distinctive_descriptor(int nObs, const unsigned char* descs, const unsigned char* kf_bad, unsigned char* out32) {
+    std::unique_ptr<KeyFrame[]> kfs(new KeyFrame[std::max(nObs, 1)]);
+    MapPoint mp;
+    for (int i = 0; i < nObs; ++i) {
+        kfs[i].mDescriptors = desc_mat(descs + 32 * (size_t)i, 1);
+        kfs[i].mbBad = kf_bad && kf_bad[i];
+        mp.mObservations[&kfs[i]] = std::make_tuple(0, -1);
+    }
+    mp.mDescriptor = cv::Mat();
+    mp.ComputeDistinctiveDescriptors();
+    if (mp.mDescriptor.empty()) return 0;
+    std::memcpy(out32, mp.mDescriptor.data, 32);
+    return 1;
+}
+
+// MapPoint::UpdateNormalAndDepth: observation i is seen from camera centre centers[3 i ..] (a keyframe with identity rotation and
+// translation -centre); the reference keyframe is observation ref, its feature's octave = level.
+void ref2_update_normal_and_depth(int nObs, const float* centers, const float* pos, int ref, int level, const float* scaleFactors, int nlevels,
+                                  float* normal3, float* maxmin2) {
+    std::unique_ptr<KeyFrame[]> kfs(new KeyFrame[std::max(nObs, 1)]);
+    MapPoint mp;
+    for (int i = 0; i < nObs; ++i) {
+        KeyFrame& K = kfs[i];
+        for (int k = 0; k < 3; ++k) K.mTcw.t[k] = -centers[3 * i + k];
+        K.mvKeysUn.resize(1);
+        K.mvKeysUn[0].octave = level;
+        K.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+        K.mnScaleLevels = nlevels;
+        mp.mObservations[&K] = std::make_tuple(0, -1);
+    }
+    mp.mpRefKF = &kfs[ref];
+    mp.mWorldPos = Eigen::Vector3f(pos[0], pos[1], pos[2]);
+    mp.UpdateNormalAndDepth();
+    for (int k = 0; k < 3; ++k) normal3[k] = mp.mNormalVector(k);
+    maxmin2[0] = mp.mfMaxDistance; maxmin2[1] = mp.mfMinDistance;
+}
+
+}  // extern "C"

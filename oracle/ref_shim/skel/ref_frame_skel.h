@@ -7,7 +7,7 @@
 //     Frame.cc      : AssignFeaturesToGrid, PosInGrid, GetFeaturesInArea, isInFrustum(MapPoint*, float), ComputeStereoMatches
 //                     SearchByBoW(KeyFrame*, Frame&, ...), SearchByBoW(KeyFrame*, KeyFrame*, ...), SearchForInitialization,
 //                     SearchForTriangulation
-//     MapPoint.cc   : PredictScale(const float&, Frame*)
+//     MapPoint.cc   : PredictScale(const float&, Frame*), ComputeDistinctiveDescriptors(), UpdateNormalAndDepth()
 //     Pinhole.cpp   : project(const Eigen::Vector3f&), toK_(), epipolarConstrain(...)
 // Those functions are compiled VERBATIM (oracle/tools/extract_functions.py writes them into oracle/_ref/gen/, a build directory)
 // against the reference's own include/ORBmatcher.h and include/ORBextractor.h; this header defines the include guards of
@@ -31,6 +31,7 @@
 #include <map>
 #include <mutex>
 #include <set>
+#include <tuple>
 #include <vector>
 
 #include <opencv2/core/core.hpp>   // oracle/ref_shim/opencv2: the miniature cv::
@@ -56,6 +57,8 @@ struct Matrix {
     Matrix operator+(const Matrix& b) const { Matrix o; for (int i = 0; i < R * C; ++i) o.v[i] = v[i] + b.v[i]; return o; }
     Matrix operator-(const Matrix& b) const { Matrix o; for (int i = 0; i < R * C; ++i) o.v[i] = v[i] - b.v[i]; return o; }
     Matrix operator-() const { Matrix o; for (int i = 0; i < R * C; ++i) o.v[i] = -v[i]; return o; }
+    Matrix operator/(T s) const { Matrix o; for (int i = 0; i < R * C; ++i) o.v[i] = v[i] / s; return o; }   // scalar_quotient_op: a division per coefficient
+    void setZero() { for (int i = 0; i < R * C; ++i) v[i] = T(0); }
     // 3-term sums in the order x + (y + z) (Eigen 3.3+'s unrolled fixed-size reduction)
     T dot(const Matrix& b) const { static_assert(R * C == 3, "3-vector"); return v[0] * b.v[0] + (v[1] * b.v[1] + v[2] * b.v[2]); }
     T norm() const { return std::sqrt(dot(*this)); }
@@ -210,7 +213,9 @@ class MapPoint {
     bool mbBad = false;
     float GetMinDistanceInvariance() { return 0.8f * mfMinDistance; }   // MapPoint.cc:658-672
     float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }
-    int PredictScale(const float& currentDist, Frame* pF);             // body extracted from src/MapPoint.cc
+    int PredictScale(const float& currentDist, Frame* pF);             // bodies extracted from src/MapPoint.cc
+    void ComputeDistinctiveDescriptors();
+    void UpdateNormalAndDepth();
     float mTrackProjX, mTrackProjY, mTrackDepth, mTrackDepthR, mTrackProjXR, mTrackProjYR;
     bool mbTrackInView, mbTrackInViewR;
     int mnTrackScaleLevel, mnTrackScaleLevelR;
@@ -220,7 +225,9 @@ class MapPoint {
     Eigen::Vector3f mWorldPos, mNormalVector;
     cv::Mat mDescriptor;
     float mfMinDistance, mfMaxDistance;
-    std::mutex mMutexPos;
+    std::mutex mMutexPos, mMutexFeatures;
+    std::map<KeyFrame*, std::tuple<int, int> > mObservations;
+    KeyFrame* mpRefKF = nullptr;
     int query_index = -1;   // not in the reference: which query of the flat test arrays this object is
 };
 
@@ -274,6 +281,10 @@ class KeyFrame {   // the members the extracted KeyFrame-typed matchers read (si
     Eigen::Vector3f GetCameraCenter() { return mTcw.inverse().translation(); }
     Sophus::SE3f GetRightPose() { return Sophus::SE3f(); }          // two-camera rigs (mpCamera2): not exercised
     Sophus::SE3f GetRightPoseInverse() { return Sophus::SE3f(); }
+    Eigen::Vector3f GetRightCameraCenter() { return Eigen::Vector3f(); }
+    bool isBad() { return mbBad; }
+    bool mbBad = false;
+    int mnScaleLevels = 8;
     int N, NLeft, NRight;
     std::vector<cv::KeyPoint> mvKeys, mvKeysUn, mvKeysRight;
     std::vector<float> mvuRight, mvDepth;

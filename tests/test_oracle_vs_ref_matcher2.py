@@ -125,3 +125,41 @@ def test_search_for_triangulation(two_frames, only_stereo, coarse, check, mono):
     got[q] = om
     assert on == rn and (got == rm).all()
     assert rn > (5 if not coarse else 40)
+
+
+def test_compute_distinctive_descriptors():
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:438-529): least median Hamming distance to the other observations; ties keep
+    the first; bad keyframes are left out."""
+    rng = np.random.default_rng(8)
+    base = rng.integers(0, 256, 32, dtype=np.uint8)
+    for n in (1, 2, 3, 4, 7, 12, 30):
+        for rep in range(6):
+            d = np.repeat(base[None], n, 0).copy()
+            for r in range(n):
+                for b in rng.integers(0, 256, int(rng.integers(0, 60))):
+                    d[r, b // 8] ^= np.uint8(1 << (b % 8))
+            if rep == 5 and n > 2:
+                d[1] = d[0]                                       # exact ties
+            bad = (rng.random(n) < 0.25).astype(np.uint8) if rep % 2 else np.zeros(n, np.uint8)
+            good = d[bad == 0]
+            want = po.distinctive_descriptor(good)
+            got = po.ref2_distinctive_descriptor(d, bad)
+            if len(good) == 0:
+                assert got is None and want == -1
+            else:
+                assert (got == good[want]).all(), (n, rep)
+
+
+def test_update_normal_and_depth():
+    """MapPoint::UpdateNormalAndDepth (MapPoint.cc:567-643): float bits of the mean viewing direction and of the two distance bounds."""
+    rng = np.random.default_rng(4)
+    sf = np.array([1.2 ** i for i in range(8)], np.float32)
+    for n in (1, 2, 5, 17):
+        for _ in range(8):
+            centers = rng.normal(0, 2.0, (n, 3)).astype(np.float32)
+            pos = (rng.normal(0, 1.0, 3) + np.array([0, 0, 8.0])).astype(np.float32)
+            ref, level = int(rng.integers(0, n)), int(rng.integers(0, 8))
+            a = po.update_normal_and_depth(centers, pos, centers[ref], level, sf)
+            b = po.ref2_update_normal_and_depth(centers, pos, ref, level, sf)
+            assert (a[0].view(np.uint32) == b[0].view(np.uint32)).all()
+            assert np.float32(a[1]).view(np.uint32) == np.float32(b[1]).view(np.uint32) and np.float32(a[2]).view(np.uint32) == np.float32(b[2]).view(np.uint32)
