@@ -668,6 +668,18 @@ def ref2_lib():
         L.ref2_distinctive_descriptor.restype = I
         L.ref2_distinctive_descriptor.argtypes = [I, VP, VP, VP]
         L.ref2_update_normal_and_depth.argtypes = [I, VP, VP, I, I, VP, I, VP, VP]
+        L.ref2_kf_set_geometry.argtypes = [VP, VP, VP, F]
+        L.ref2_kf_set_mappoints.argtypes = [VP, VP, VP, VP, VP]
+        L.ref2_fuse.restype = I
+        L.ref2_fuse.argtypes = [VP, I] + [VP] * 7 + [F, VP]
+        L.ref2_fuse_sim3.restype = I
+        L.ref2_fuse_sim3.argtypes = [VP, VP, I] + [VP] * 6 + [F, VP, VP, VP]
+        L.ref2_search_kf_sim3.restype = I
+        L.ref2_search_kf_sim3.argtypes = [VP, VP, I] + [VP] * 7 + [F, F, I, VP, VP, VP]
+        L.ref2_search_frame_kf.restype = I
+        L.ref2_search_frame_kf.argtypes = [VP, VP, VP, VP, VP, F, I, I, VP]
+        L.ref2_search_by_sim3.restype = I
+        L.ref2_search_by_sim3.argtypes = [VP, VP, VP, VP, F, VP]
         L.ref2_kf_create.restype = VP
         L.ref2_kf_create.argtypes = [VP, VP, VP, I, VP, VP, VP, VP, VP, I, VP, VP]
         L.ref2_kf_destroy.argtypes = [VP]
@@ -781,6 +793,71 @@ class RefKeyFrame:
         if getattr(self, "h", None):
             self.L.ref2_kf_destroy(self.h)
             self.h = None
+
+
+def _qarrays(q):
+    f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: None if a is None else np.ascontiguousarray(a, np.uint8)
+    return f32(q["world_pos"]), f32(q.get("normal")), f32(q["max_dist"]), f32(q["min_dist"]), u8(q["desc"]), u8(q.get("bad"))
+
+
+def ref2_kf_set_geometry(kf, frame, inv_level_sigma2, bf):
+    a = np.ascontiguousarray(inv_level_sigma2, np.float32)
+    kf.L.ref2_kf_set_geometry(kf.h, frame.h, _p(a), float(bf))
+    kf._geom_frame = frame
+
+
+def ref2_kf_set_mappoints(kf, world_pos, max_dist, min_dist, desc):
+    a = [np.ascontiguousarray(world_pos, np.float32), np.ascontiguousarray(max_dist, np.float32), np.ascontiguousarray(min_dist, np.float32),
+         np.ascontiguousarray(desc, np.uint8)]
+    kf.L.ref2_kf_set_mappoints(kf.h, *[_p(x) for x in a])
+
+
+def ref2_fuse(kf, q, th, in_kf=None):
+    """ORBmatcher::Fuse(pKF, vpMapPoints, th) of the reference: (fused[nq] = keyframe feature or -1, nFused)."""
+    P = lambda a: None if a is None else _p(a)
+    xw, nr, mx, mn, d, bad = _qarrays(q)
+    ik = None if in_kf is None else np.ascontiguousarray(in_kf, np.uint8)
+    out = np.full(max(len(xw), 1), -1, np.int32)
+    n = kf.L.ref2_fuse(kf.h, len(xw), _p(xw), P(nr), _p(mx), _p(mn), _p(d), P(bad), P(ik), float(th), _p(out))
+    return out[:len(xw)], n
+
+
+def ref2_fuse_sim3(kf, S8, q, th):
+    P = lambda a: None if a is None else _p(a)
+    xw, nr, mx, mn, d, bad = _qarrays(q)
+    s = np.ascontiguousarray(S8, np.float32)
+    out, T, Ow = np.full(max(len(xw), 1), -1, np.int32), np.zeros(7, np.float32), np.zeros(3, np.float32)
+    n = kf.L.ref2_fuse_sim3(kf.h, _p(s), len(xw), _p(xw), P(nr), _p(mx), _p(mn), _p(d), P(bad), float(th), _p(out), _p(T), _p(Ow))
+    return out[:len(xw)], n, T, Ow
+
+
+def ref2_search_kf_sim3(kf, S8, q, matched_in, th, ratio_hamming, with_kfs=False):
+    P = lambda a: None if a is None else _p(a)
+    xw, nr, mx, mn, d, bad = _qarrays(q)
+    s = np.ascontiguousarray(S8, np.float32)
+    mi = None if matched_in is None else np.ascontiguousarray(matched_in, np.uint8)
+    out, T, Ow = np.full(max(len(xw), 1), -1, np.int32), np.zeros(7, np.float32), np.zeros(3, np.float32)
+    n = kf.L.ref2_search_kf_sim3(kf.h, _p(s), len(xw), _p(xw), P(nr), _p(mx), _p(mn), _p(d), P(bad), P(mi), float(th), float(ratio_hamming),
+                                 1 if with_kfs else 0, _p(out), _p(T), _p(Ow))
+    return out[:len(xw)], n, T, Ow
+
+
+def ref2_search_frame_kf(frame, Tcw7, kf, already, claimed, th, orb_dist, check_ori=True):
+    P = lambda a: None if a is None else _p(a)
+    T = np.ascontiguousarray(Tcw7, np.float32)
+    al = None if already is None else np.ascontiguousarray(already, np.uint8)
+    cl = None if claimed is None else np.ascontiguousarray(claimed, np.uint8)
+    out = np.full(max(frame.N, 1), -1, np.int32)
+    n = frame.L.ref2_search_frame_kf(frame.h, _p(T), kf.h, P(al), P(cl), float(th), int(orb_dist), 1 if check_ori else 0, _p(out))
+    return out[:frame.N], n
+
+
+def ref2_search_by_sim3(kf1, kf2, S12, S21, th, matches12=None):
+    a, b = np.ascontiguousarray(S12, np.float32), np.ascontiguousarray(S21, np.float32)
+    m = np.full(max(kf1.N, 1), -1, np.int32) if matches12 is None else np.ascontiguousarray(matches12, np.int32).copy()
+    n = kf1.L.ref2_search_by_sim3(kf1.h, kf2.h, _p(a), _p(b), float(th), _p(m))
+    return m[:kf1.N], n
 
 
 def ref2_search_bow(frame, feat_node, kf, nnratio, check_ori=True):

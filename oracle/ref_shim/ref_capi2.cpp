@@ -13,6 +13,7 @@
 
 namespace ORB_SLAM3 {
 float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
+MapPoint* MapPoint::g_last_asked = nullptr;
 #include "../_ref/gen/ref2_gen.inc"
 }  // namespace ORB_SLAM3
 
@@ -390,6 +391,182 @@ void ref2_update_normal_and_depth(int nObs, const float* centers, const float* p
     mp.UpdateNormalAndDepth();
     for (int k = 0; k < 3; ++k) normal3[k] = mp.mNormalVector(k);
     maxmin2[0] = mp.mfMaxDistance; maxmin2[1] = mp.mfMinDistance;
+}
+
+}  // extern "C"
+
+// ---- part 2d: projections into a keyframe ---------------------------------------------------------------------------------------------
+namespace {
+struct QuerySet {   // the map points handed to a search: world position, normal, distance members, descriptor
+    std::unique_ptr<MapPoint[]> mp;
+    std::vector<MapPoint*> ptr;
+    QuerySet(int n, const float* xw, const float* normal, const float* maxD, const float* minD, const unsigned char* desc, const unsigned char* bad) : mp(new MapPoint[std::max(n, 1)]), ptr(n) {
+        for (int q = 0; q < n; ++q) {
+            MapPoint& m = mp[q];
+            m.mWorldPos = Eigen::Vector3f(xw[3 * q], xw[3 * q + 1], xw[3 * q + 2]);
+            if (normal) m.mNormalVector = Eigen::Vector3f(normal[3 * q], normal[3 * q + 1], normal[3 * q + 2]);
+            m.mfMaxDistance = maxD[q]; m.mfMinDistance = minD[q];
+            m.mDescriptor = desc_mat(desc + 32 * (size_t)q, 1);
+            m.mbBad = bad && bad[q];
+            m.query_index = q;
+            ptr[q] = &m;
+        }
+    }
+};
+void set_sim3(Sophus::Sim3f& S, const float* s8) {
+    for (int i = 0; i < 4; ++i) S.q[i] = s8[i];
+    for (int i = 0; i < 3; ++i) S.t[i] = s8[4 + i];
+}
+void export_scw(const Sophus::Sim3f& Scw, float* Tcw7, float* Ow3) {   // ORBmatcher.cc:503-504 / 1554-1555
+    Sophus::SE3f Tcw = Sophus::SE3f(Scw.rotationMatrix(), Scw.translation() / Scw.scale());
+    Eigen::Vector3f Ow = Tcw.inverse().translation();
+    for (int i = 0; i < 4; ++i) Tcw7[i] = Tcw.q[i];
+    for (int i = 0; i < 3; ++i) { Tcw7[4 + i] = Tcw.t[i]; Ow3[i] = Ow(i); }
+}
+}  // namespace
+
+extern "C" {
+
+// what the KeyFrame constructor copies from its Frame (KeyFrame.cc:60-100): the grid, the image bounds (as int), the cell sizes, the
+// scale tables, the intrinsics
+void ref2_kf_set_geometry(void* hKF, void* hF, const float* invLevelSigma2, float bf) {
+    KeyFrame& K = ((KFHolder*)hKF)->K;
+    Frame& F = ((Holder*)hF)->F;
+    K.mGrid.assign(FRAME_GRID_COLS, std::vector<std::vector<size_t> >(FRAME_GRID_ROWS));
+    for (int i = 0; i < FRAME_GRID_COLS; ++i)
+        for (int j = 0; j < FRAME_GRID_ROWS; ++j) K.mGrid[i][j] = F.mGrid[i][j];
+    K.mnMinX = (int)Frame::mnMinX; K.mnMinY = (int)Frame::mnMinY; K.mnMaxX = (int)Frame::mnMaxX; K.mnMaxY = (int)Frame::mnMaxY;
+    K.mfGridElementWidthInv = Frame::mfGridElementWidthInv; K.mfGridElementHeightInv = Frame::mfGridElementHeightInv;
+    K.mfLogScaleFactor = F.mfLogScaleFactor; K.mnScaleLevels = F.mnScaleLevels;
+    K.mvScaleFactors = F.mvScaleFactors;
+    K.mvInvLevelSigma2.assign(invLevelSigma2, invLevelSigma2 + F.mnScaleLevels);
+    const std::vector<float>& c = ((KFHolder*)hKF)->cam.mvParameters;
+    K.fx = c[0]; K.fy = c[1]; K.cx = c[2]; K.cy = c[3]; K.mbf = bf;
+}
+
+// the keyframe's own map points (features with has_mp): world position, distance members, descriptor
+void ref2_kf_set_mappoints(void* hKF, const float* xw, const float* maxD, const float* minD, const unsigned char* desc) {
+    KFHolder* H = (KFHolder*)hKF;
+    for (int i = 0; i < H->K.N; ++i) {
+        MapPoint& m = H->mps[i];
+        m.mWorldPos = Eigen::Vector3f(xw[3 * i], xw[3 * i + 1], xw[3 * i + 2]);
+        m.mfMaxDistance = maxD[i]; m.mfMinDistance = minD[i];
+        m.mDescriptor = desc_mat(desc + 32 * (size_t)i, 1);
+    }
+}
+
+// ORBmatcher::Fuse(pKF, vpMapPoints, th, bRight = false): fused[q] = the keyframe feature query q was fused into, or -1.
+// in_kf[q] != 0: MapPoint::IsInKeyFrame(pKF).  Features with has_mp hold a map point on entry (Replace branch), the others are filled
+// by AddMapPoint as the function goes.
+int ref2_fuse(void* hKF, int nq, const float* xw, const float* normal, const float* maxD, const float* minD, const unsigned char* qdesc,
+              const unsigned char* bad, const unsigned char* in_kf, float th, int* fused) {
+    KeyFrame& K = ((KFHolder*)hKF)->K;
+    QuerySet Q(nq, xw, normal, maxD, minD, qdesc, bad);
+    for (int q = 0; q < nq; ++q)
+        if (in_kf && in_kf[q]) Q.mp[q].mObservations[&K] = std::make_tuple(0, -1);
+    std::vector<std::pair<int, int> > log;
+    K.log_get = &log;
+    std::vector<MapPoint*> saved = K.mvpMapPoints;
+    ORBmatcher matcher(0.6f, true);
+    const int n = matcher.Fuse(&K, Q.ptr, th, false);
+    K.log_get = nullptr;
+    K.mvpMapPoints = saved;
+    for (int q = 0; q < nq; ++q) fused[q] = -1;
+    for (size_t i = 0; i < log.size(); ++i) fused[log[i].first] = log[i].second;
+    return n;
+}
+
+// ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint): S8 = Scw as (non-unit quaternion x y z w, translation, -); already[q] != 0:
+// the point is one of pKF->GetMapPoints().  Tcw7 / Ow3: the SE3f and camera centre the function builds, for the oracle's caller-side inputs.
+int ref2_fuse_sim3(void* hKF, const float* S8, int nq, const float* xw, const float* normal, const float* maxD, const float* minD,
+                   const unsigned char* qdesc, const unsigned char* bad, float th, int* fused, float* Tcw7, float* Ow3) {
+    KeyFrame& K = ((KFHolder*)hKF)->K;
+    QuerySet Q(nq, xw, normal, maxD, minD, qdesc, bad);
+    Sophus::Sim3f Scw;
+    set_sim3(Scw, S8);
+    export_scw(Scw, Tcw7, Ow3);
+    std::vector<std::pair<int, int> > log;
+    K.log_get = &log;
+    std::vector<MapPoint*> saved = K.mvpMapPoints;
+    std::vector<MapPoint*> repl(nq, static_cast<MapPoint*>(NULL));
+    ORBmatcher matcher(0.6f, true);
+    const int n = matcher.Fuse(&K, Scw, Q.ptr, th, repl);
+    K.log_get = nullptr;
+    K.mvpMapPoints = saved;
+    for (int q = 0; q < nq; ++q) fused[q] = -1;
+    for (size_t i = 0; i < log.size(); ++i) fused[log[i].first] = log[i].second;
+    return n;
+}
+
+// ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (with_kfs == 0) and the overload with
+// vpPointsKFs / vpMatchedKF (with_kfs != 0).  matched_in[idx] != 0: vpMatched[idx] is non-NULL on entry.  match[q] = feature or -1.
+int ref2_search_kf_sim3(void* hKF, const float* S8, int nq, const float* xw, const float* normal, const float* maxD, const float* minD,
+                        const unsigned char* qdesc, const unsigned char* bad, const unsigned char* matched_in, float th, float ratioHamming,
+                        int with_kfs, int* match, float* Tcw7, float* Ow3) {
+    KeyFrame& K = ((KFHolder*)hKF)->K;
+    QuerySet Q(nq, xw, normal, maxD, minD, qdesc, bad);
+    Sophus::Sim3f Scw;
+    set_sim3(Scw, S8);
+    export_scw(Scw, Tcw7, Ow3);
+    MapPoint occupied;
+    occupied.query_index = -1;
+    std::vector<MapPoint*> vpMatched(K.N, static_cast<MapPoint*>(NULL));
+    for (int i = 0; i < K.N; ++i)
+        if (matched_in && matched_in[i]) vpMatched[i] = &occupied;
+    ORBmatcher matcher(0.75f, true);
+    int n;
+    if (with_kfs) {
+        std::vector<KeyFrame*> kfs(nq, &K), mkf(K.N, static_cast<KeyFrame*>(NULL));
+        n = matcher.SearchByProjection(&K, Scw, Q.ptr, kfs, vpMatched, mkf, th, ratioHamming);
+    } else {
+        n = matcher.SearchByProjection(&K, Scw, Q.ptr, vpMatched, th, ratioHamming);
+    }
+    for (int q = 0; q < nq; ++q) match[q] = -1;
+    for (int i = 0; i < K.N; ++i)
+        if (vpMatched[i] && vpMatched[i] != &occupied) match[vpMatched[i]->query_index] = i;
+    return n;
+}
+
+// ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist): the keyframe's map points (ref2_kf_set_mappoints) are
+// the queries; already[i] != 0: the point of KF feature i is in sAlreadyFound; claimed[idx]: CurrentFrame.mvpMapPoints[idx] non-NULL on
+// entry.  feat_match[idx] = the KF feature whose point the frame feature now holds, or -1.
+int ref2_search_frame_kf(void* hF, const float* Tcw7, void* hKF, const unsigned char* already, const unsigned char* claimed, float th, int ORBdist,
+                         int checkOri, int* feat_match) {
+    Frame& F = ((Holder*)hF)->F;
+    KFHolder* KH = (KFHolder*)hKF;
+    set_pose(F, Tcw7);
+    MapPoint occupied;
+    for (int i = 0; i < F.N; ++i) F.mvpMapPoints[i] = (claimed && claimed[i]) ? &occupied : static_cast<MapPoint*>(NULL);
+    std::set<MapPoint*> found;
+    for (int i = 0; i < KH->K.N; ++i)
+        if (already && already[i] && KH->K.mvpMapPoints[i]) found.insert(KH->K.mvpMapPoints[i]);
+    ORBmatcher matcher(0.9f, checkOri != 0);
+    const int n = matcher.SearchByProjection(F, &KH->K, found, th, ORBdist);
+    for (int i = 0; i < F.N; ++i) {
+        feat_match[i] = (F.mvpMapPoints[i] && F.mvpMapPoints[i] != &occupied) ? F.mvpMapPoints[i]->query_index : -1;
+        F.mvpMapPoints[i] = NULL;
+    }
+    return n;
+}
+
+// ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, S12, th): S21_8 = S12.inverse() as the caller's Sophus computes it (the oracle takes
+// both directions from its caller).  matches12[i1] = KF2 feature or -1, in (pre-existing matches) / out (with the new ones).
+int ref2_search_by_sim3(void* hKF1, void* hKF2, const float* S12_8, const float* S21_8, float th, int* matches12) {
+    KFHolder* H1 = (KFHolder*)hKF1;
+    KFHolder* H2 = (KFHolder*)hKF2;
+    KeyFrame &K1 = H1->K, &K2 = H2->K;
+    Sophus::Sim3f S12, S21;
+    set_sim3(S12, S12_8);
+    set_sim3(S21, S21_8);
+    S12.inv = &S21; S21.inv = &S12;
+    for (int i = 0; i < K2.N; ++i) H2->mps[i].mObservations[&K2] = std::make_tuple(i, -1);   // GetIndexInKeyFrame(pKF2)
+    std::vector<MapPoint*> vp(K1.N, static_cast<MapPoint*>(NULL));
+    for (int i = 0; i < K1.N; ++i)
+        if (matches12[i] >= 0) vp[i] = &H2->mps[matches12[i]];
+    ORBmatcher matcher(0.75f, true);
+    const int n = matcher.SearchBySim3(&K1, &K2, vp, S12, th);
+    for (int i = 0; i < K1.N; ++i) matches12[i] = vp[i] ? vp[i]->query_index : -1;
+    return n;
 }
 
 }  // extern "C"

@@ -6,8 +6,10 @@
 //                     Frame&, th, bMono), RadiusByViewingCos, ComputeThreeMaxima, DescriptorDistance, TH_LOW / TH_HIGH / HISTO_LENGTH
 //     Frame.cc      : AssignFeaturesToGrid, PosInGrid, GetFeaturesInArea, isInFrustum(MapPoint*, float), ComputeStereoMatches
 //                     SearchByBoW(KeyFrame*, Frame&, ...), SearchByBoW(KeyFrame*, KeyFrame*, ...), SearchForInitialization,
-//                     SearchForTriangulation
-//     MapPoint.cc   : PredictScale(const float&, Frame*), ComputeDistinctiveDescriptors(), UpdateNormalAndDepth()
+//                     SearchForTriangulation, Fuse (both overloads), SearchByProjection(KeyFrame*, Sim3f&, ...) (both overloads),
+//                     SearchByProjection(Frame&, KeyFrame*, set<MapPoint*>&, ...), SearchBySim3
+//     KeyFrame.cc   : GetFeaturesInArea, IsInImage
+//     MapPoint.cc   : PredictScale(const float&, Frame*), PredictScale(const float&, KeyFrame*), ComputeDistinctiveDescriptors(), UpdateNormalAndDepth()
 //     Pinhole.cpp   : project(const Eigen::Vector3f&), toK_(), epipolarConstrain(...)
 // Those functions are compiled VERBATIM (oracle/tools/extract_functions.py writes them into oracle/_ref/gen/, a build directory)
 // against the reference's own include/ORBmatcher.h and include/ORBextractor.h; this header defines the include guards of
@@ -117,6 +119,29 @@ class SE3 {   // unit quaternion (x y z w) + translation; point action as so3.hp
    public:
     T q[4], t[3];
     SE3() : q{0, 0, 0, 1}, t{0, 0, 0} {}
+    // SE3(rotation matrix, translation): Eigen's matrix -> quaternion conversion (Quaternion.h, quaternionbase_assign_impl<..., 3, 3>);
+    // the test hands the resulting quaternion to the oracle, whose caller would have built it with the real Eigen
+    SE3(const Eigen::Matrix<T, 3, 3>& m, const Eigen::Matrix<T, 3, 1>& tr) {
+        T tq = m(0, 0) + m(1, 1) + m(2, 2);
+        if (tq > T(0)) {
+            tq = std::sqrt(tq + T(1.0));
+            q[3] = T(0.5) * tq;
+            tq = T(0.5) / tq;
+            q[0] = (m(2, 1) - m(1, 2)) * tq; q[1] = (m(0, 2) - m(2, 0)) * tq; q[2] = (m(1, 0) - m(0, 1)) * tq;
+        } else {
+            int i = 0;
+            if (m(1, 1) > m(0, 0)) i = 1;
+            if (m(2, 2) > m(i, i)) i = 2;
+            const int j = (i + 1) % 3, k = (j + 1) % 3;
+            tq = std::sqrt(m(i, i) - m(j, j) - m(k, k) + T(1.0));
+            q[i] = T(0.5) * tq;
+            tq = T(0.5) / tq;
+            q[3] = (m(k, j) - m(j, k)) * tq; q[j] = (m(j, i) + m(i, j)) * tq; q[k] = (m(k, i) + m(i, k)) * tq;
+        }
+        const T n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);   // Sophus normalises in SO3(Matrix) -> setQuaternion
+        for (int a = 0; a < 4; ++a) q[a] /= n;
+        for (int a = 0; a < 3; ++a) t[a] = tr(a);
+    }
     Eigen::Matrix<T, 3, 1> translation() const { return Eigen::Matrix<T, 3, 1>(t[0], t[1], t[2]); }
     static void rot(const T* q, const T* p, T* o) {
         const T uvx = q[1] * p[2] - q[2] * p[1], uvy = q[2] * p[0] - q[0] * p[2], uvz = q[0] * p[1] - q[1] * p[0];
@@ -168,7 +193,30 @@ struct SO3 {
 };
 typedef SO3<float> SO3f;
 template <typename T>
-class Sim3 {};
+class Sim3 {   // RxSO3 as a NON-unit quaternion (rotation * sqrt(scale)) + translation; point action p' = q p q* + t (rxso3.hpp:265-273,
+   public:     // sim3.hpp:227-230 -- the same statement the oracle restates).  inverse() returns what the test stored: the oracle takes both
+    T q[4], t[3];   // directions from its caller.
+    const Sim3* inv = nullptr;
+    Sim3() : q{0, 0, 0, 1}, t{0, 0, 0} {}
+    T scale() const { return q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]; }   // quaternion().squaredNorm()
+    Eigen::Matrix<T, 3, 1> translation() const { return Eigen::Matrix<T, 3, 1>(t[0], t[1], t[2]); }
+    Eigen::Matrix<T, 3, 3> rotationMatrix() const {   // rxso3.hpp: the unit quaternion's matrix
+        SE3<T> u;
+        const T n = std::sqrt(scale());
+        for (int a = 0; a < 4; ++a) u.q[a] = q[a] / n;
+        return u.rotationMatrix();
+    }
+    Sim3 inverse() const { return *inv; }
+    Eigen::Matrix<T, 3, 1> operator*(const Eigen::Matrix<T, 3, 1>& p) const {
+        // q p q*: Eigen's Quaternion * Quaternion products with p as a pure quaternion (rxso3.hpp:268-272)
+        const T px = p(0), py = p(1), pz = p(2);
+        const T aw = -q[0] * px - q[1] * py - q[2] * pz, ax = q[3] * px + q[1] * pz - q[2] * py, ay = q[3] * py + q[2] * px - q[0] * pz,
+                az = q[3] * pz + q[0] * py - q[1] * px;   // a = q * (0, p)
+        const T bx = -aw * q[0] + ax * q[3] - ay * q[2] + az * q[1], by = -aw * q[1] + ay * q[3] - az * q[0] + ax * q[2],
+                bz = -aw * q[2] + az * q[3] - ax * q[1] + ay * q[0];   // vec(a * conj(q))
+        return Eigen::Matrix<T, 3, 1>(bx + t[0], by + t[1], bz + t[2]);
+    }
+};
 typedef Sim3<float> Sim3f;
 }  // namespace Sophus
 
@@ -209,8 +257,14 @@ class MapPoint {
     Eigen::Vector3f GetNormal() { return mNormalVector; }
     cv::Mat GetDescriptor() { return mDescriptor.clone(); }
     int Observations() { return nObs; }
-    bool isBad() { return mbBad; }
+    bool isBad() { g_last_asked = this; return mbBad; }     // the matchers ask every query point first: who is being processed
     bool mbBad = false;
+    static MapPoint* g_last_asked;
+    bool IsInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) != 0; }
+    std::tuple<int, int> GetIndexInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) ? mObservations[pKF] : std::tuple<int, int>(-1, -1); }
+    void AddObservation(KeyFrame* pKF, int idx) { mObservations[pKF] = std::tuple<int, int>(idx, -1); }
+    void Replace(MapPoint*) {}                              // Fuse's map surgery: not part of what is compared
+    int PredictScale(const float& currentDist, KeyFrame* pKF);
     float GetMinDistanceInvariance() { return 0.8f * mfMinDistance; }   // MapPoint.cc:658-672
     float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }
     int PredictScale(const float& currentDist, Frame* pF);             // bodies extracted from src/MapPoint.cc
@@ -275,7 +329,26 @@ class KeyFrame {   // the members the extracted KeyFrame-typed matchers read (si
    public:
     KeyFrame() : N(0), NLeft(-1), NRight(-1), mpCamera(nullptr), mpCamera2(nullptr) {}
     vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
-    MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
+    MapPoint* GetMapPoint(const size_t& idx) {   // Fuse asks for the map point at bestIdx once per fused query: log (query, feature)
+        if (log_get && MapPoint::g_last_asked) log_get->push_back(std::make_pair(MapPoint::g_last_asked->query_index, (int)idx));
+        return mvpMapPoints[idx];
+    }
+    std::vector<std::pair<int, int> >* log_get = nullptr;
+    void AddMapPoint(MapPoint* pMP, const size_t& idx) { mvpMapPoints[idx] = pMP; }
+    std::set<MapPoint*> GetMapPoints() {
+        std::set<MapPoint*> s;
+        for (size_t i = 0; i < mvpMapPoints.size(); ++i)
+            if (mvpMapPoints[i] && !mvpMapPoints[i]->mbBad) s.insert(mvpMapPoints[i]);
+        return s;
+    }
+    // bodies extracted from src/KeyFrame.cc
+    vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const bool bRight = false) const;
+    bool IsInImage(const float& x, const float& y) const;
+    int mnGridCols = FRAME_GRID_COLS, mnGridRows = FRAME_GRID_ROWS;
+    float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+    int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;
+    std::vector<std::vector<std::vector<size_t> > > mGrid, mGridRight;
+    float fx = 0, fy = 0, cx = 0, cy = 0, mbf = 0, mfLogScaleFactor = 0;
     Sophus::SE3f GetPose() { return mTcw; }
     Sophus::SE3f GetPoseInverse() { return mTcw.inverse(); }
     Eigen::Vector3f GetCameraCenter() { return mTcw.inverse().translation(); }
