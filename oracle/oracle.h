@@ -4,12 +4,14 @@
 // cpu_baseline / --impl reference leg and __graft_entry__.smoke() may load this library; the product
 // library (liborbslam3_b200.so) never links, loads or calls it.
 //
-// Parity pin status: the reference (electech6/ORB_SLAM3_detailed_comments) ships no tests and cannot
-// be compiled in this image (no OpenCV C++/Eigen).  The OpenCV-backed stages are pinned against the
-// real cv2 4.13 build in tests/test_oracle_vs_cv2.py (resize, GaussianBlur, FAST, fastAtan2) and
-// glibc sinf/cosf exhaustively; the ORB-SLAM3-specific control flow (quadtree, matchers, g2o LM) is
-// a restatement whose only pin is self-consistency + the committed golden vectors => "parity
-// unpinned by the reference" for those stages.
+// Parity pin status: the reference (electech6/ORB_SLAM3_detailed_comments) ships no tests and cannot be built as a whole in this
+// image (no OpenCV C++ / Eigen).  Pins: (1) the OpenCV-backed stages against the real cv2 4.13 build (tests/test_oracle_vs_cv2.py)
+// and glibc sinf / cosf / logf exhaustively; (2) the reference's OWN SOURCE where it compiles from its files (oracle/_ref, DESIGN.md
+// section 2): ORBextractor.cc unmodified; every function of ORBmatcher.cc, the Frame / KeyFrame grid, isInFrustum,
+// ComputeStereoMatches, the MapPoint routines and Pinhole's projection / epipolar test cut out at build time and compiled verbatim
+// over skeleton classes; Thirdparty/DBoW2 unmodified on the reference's ORBvoc.txt.  (3) The g2o Levenberg loops
+// (PoseOptimization, LocalBundleAdjustment, LocalInertialBA) are Eigen expressions and stay "parity unpinned by the reference
+// source": their pins are finite differences, the objective restated in numpy, stationarity and planted-solution recovery.
 #pragma once
 #include <cstddef>
 #include <cstdint>
