@@ -34,6 +34,29 @@ ORB_HD int st_popc(uint32_t v) {
 #endif
 }
 
+// bytes [sh/8 .. sh/8 + 3] of the 8-byte little-endian pair (lo, hi); sh = 0, 8, 16, 24
+ORB_HD uint32_t st_funnel(uint32_t lo, uint32_t hi, uint32_t sh) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
+#endif
+}
+// acc + sum of |a_i - b_i| over the four bytes (VABSDIFF4.U8 with accumulate: one instruction on sm_100a)
+ORB_HD uint32_t st_sad4(uint32_t a, uint32_t b, uint32_t acc) {
+#if defined(__CUDA_ARCH__)
+    uint32_t d;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc));
+    return d;
+#else
+    for (int i = 0; i < 4; ++i) {
+        const int x = (int)((a >> (8 * i)) & 0xffu) - (int)((b >> (8 * i)) & 0xffu);
+        acc += (uint32_t)(x < 0 ? -x : x);
+    }
+    return acc;
+#endif
+}
+
 ORB_HD int st_row_bucket(float y, int H) {
     int b = (int)floorf(y);
     return b < 0 ? 0 : (b >= H ? H - 1 : b);
@@ -79,24 +102,38 @@ ORB_HD void stereo_match_one(float uL, float vL, int octL, const uint32_t* dl /*
     const float iniu = scaleduR0, endu = fadd(scaleduR0, 11.0f);   // scaleduR0 + L - w, scaleduR0 + L + w + 1  (w = 5, L = 5)
     if (iniu < 0 || endu >= (float)G.wR) return;
     const int cy = (int)scaledvL, cxL = (int)scaleduL, cxR = (int)scaleduR0;
-    int dist[11];
-    for (int s = 0; s < 11; ++s) dist[s] = 0;
+    // 11 x 11 SAD at 11 shifts, four pixels per instruction: a row of the left patch is three words (11 bytes, the twelfth masked),
+    // the 21 bytes of the right row six; the window of shift s is three funnel shifts of those.  (Round 2 until here: 1331 scalar
+    // |l - r| per keypoint, 61 % of the kernel's instructions.)  The rows are read as aligned words around the patch: the patch is
+    // >= 9 columns inside the level (keypoints keep EDGE_THRESHOLD = 19 px from the border), so the <= 3 extra bytes exist.
+    uint32_t dist[11];
+    for (int s = 0; s < 11; ++s) dist[s] = 0u;
     for (int row = 0; row < 11; ++row) {
         const int y = cy + row - 5;
         const uint8_t* pl = G.L + (size_t)y * G.pitchL + (cxL - 5);
         const uint8_t* pr = G.R + (size_t)y * G.pitchR + (cxR - 10);
-        int l[11], r[21];
-        for (int k = 0; k < 11; ++k) l[k] = pl[k];
-        for (int k = 0; k < 21; ++k) r[k] = pr[k];
-        for (int s = 0; s < 11; ++s) {
-            int acc = 0;
-            for (int k = 0; k < 11; ++k) { const int df = l[k] - r[s + k]; acc += df < 0 ? -df : df; }
-            dist[s] += acc;
+        const uint32_t al = (uint32_t)(reinterpret_cast<uintptr_t>(pl) & 3u), ar = (uint32_t)(reinterpret_cast<uintptr_t>(pr) & 3u);
+        const uint32_t* wl = reinterpret_cast<const uint32_t*>(pl - al);
+        const uint32_t* wr = reinterpret_cast<const uint32_t*>(pr - ar);
+        const uint32_t a0 = wl[0], a1 = wl[1], a2 = wl[2], a3 = wl[3];
+        const uint32_t L0 = st_funnel(a0, a1, 8u * al), L1 = st_funnel(a1, a2, 8u * al), L2 = st_funnel(a2, a3, 8u * al) & 0x00ffffffu;
+        uint32_t b[7], Rw[6];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) b[k] = wr[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) Rw[k] = st_funnel(b[k], b[k + 1], 8u * ar);
+#pragma unroll
+        for (int s = 0; s < 11; ++s) {   // s is a compile-time constant after unrolling: Rw[] stays in registers, the shifts are immediates
+            const int q = s >> 2;
+            const uint32_t sh = 8u * (uint32_t)(s & 3);
+            const uint32_t w0 = st_funnel(Rw[q], Rw[q + 1], sh), w1 = st_funnel(Rw[q + 1], Rw[q + 2], sh),
+                           w2 = st_funnel(Rw[q + 2], Rw[q + 3], sh) & 0x00ffffffu;
+            dist[s] = st_sad4(L2, w2, st_sad4(L1, w1, st_sad4(L0, w0, dist[s])));
         }
     }
     int bestSad = 0x7fffffff, bestinc = 0;
     for (int s = 0; s < 11; ++s)
-        if (dist[s] < bestSad) { bestSad = dist[s]; bestinc = s - 5; }
+        if ((int)dist[s] < bestSad) { bestSad = (int)dist[s]; bestinc = s - 5; }
     if (bestinc == -5 || bestinc == 5) return;
     const float d1 = (float)dist[5 + bestinc - 1], d2 = (float)dist[5 + bestinc], d3 = (float)dist[5 + bestinc + 1];
     const float deltaR = fdiv(fsub(d1, d3), fmul(2.0f, fsub(fadd(d1, d3), fmul(2.0f, d2))));
