@@ -16,3 +16,6 @@ print("chain", d["chained_flow"].get("e2e_frames_per_s"), "latency", d["latency_
 PY
 timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none --graph-profiling node -c 2500 --csv --log-file gpurun_out/r02_launches_final.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --e2e-repeats 1 --latency-frames 5 > gpurun_out/r02_launches_final.log 2>&1
 echo "launches rc=$?"; wc -l gpurun_out/r02_launches_final.csv
+# the side kernels (LocalBundleAdjustment, LocalInertialBA, brute-force 2-NN, isInFrustum, the chained-flow glue, the keyframe packer)
+timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none --graph-profiling node -k regex:"k_lba|k_liba|k_hamming|k_in_frustum|k_chain|k_pack|k_bow|k_pose_edges" -c 400 --csv --log-file gpurun_out/r02_launches_side.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --e2e-repeats 1 --latency-frames 2 > gpurun_out/r02_launches_side.log 2>&1
+echo "side rc=$?"; wc -l gpurun_out/r02_launches_side.csv
