@@ -621,7 +621,8 @@ __global__ void __launch_bounds__(256, 4) k_blur(const __grid_constant__ Extract
     uint8_t* __restrict__ dst = G.blur + (int64_t)img * G.blur_stride;
     const int mode = (x0 + 8 <= G.w) ? (x0 >= 4 ? 0 : 1) : 2;
     const int colA = x0 - 3, kr = G.w - colA, colB = 2 * G.w - 2 - colA;   // mode 2: window column colA + k, mirrored from k == kr on
-    // horizontal results of the last 7 rows, unpacked to one 32-bit value per pixel (Q8.8 <= 65280)
+    // horizontal results of the last 7 rows, unpacked to one 32-bit value per pixel (Q8.8 <= 65280).  (Measured and dropped: the vertical
+    // pass by IDP.2A on (h[r-1] | h[r] << 16) pairs -- 5 instead of 10 instructions per pixel by count, 0.295 instead of 0.264 ms.)
     uint32_t hwin[7][4];
     const int rows = min(BLUR_ROWS, G.h - y0);
     // 7 rows per trip: the window slot r % 7 == j is then a compile-time register index, and the body (1/5 of the fully
