@@ -64,19 +64,8 @@ static void build_tables(orbx_handle* h) {
     }
 }
 
-// cv::resize INTER_LINEAR tap table: {source index, c0 | c1 << 16}
-static void linear_taps(int ssize, int dsize, int2* out) {
-    const double scale = (double)ssize / dsize;
-    for (int d = 0; d < dsize; ++d) {
-        float f = (float)((d + 0.5) * scale - 0.5);
-        int s = (int)floorf(f);
-        f -= (float)s;
-        if (s < 0) { s = 0; f = 0.f; }
-        if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
-        const int c0 = (int)lrintf((1.f - f) * 2048.f), c1 = (int)lrintf(f * 2048.f);
-        out[d] = make_int2(s, (c0 & 0xffff) | (c1 << 16));
-    }
-}
+// cv::resize INTER_LINEAR tap table: resize_core.cuh (shared with the host emulation of k_resize_v3)
+static void linear_taps(int ssize, int dsize, int2* out) { orbdev::rs_linear_taps(ssize, dsize, reinterpret_cast<int*>(out)); }
 
 // geometry for images of (w,h); (re)allocates nothing -- buffers are sized for max_width/max_height
 static orb_status plan_geometry(orbx_handle* h, int w, int hh) {
@@ -461,7 +450,13 @@ static orb_status run_pipeline(orbx_handle* h, int batch, int lap0, int lap1) {
     if (prof) cudaEventRecord(h->ev[1], st);
     ORB_CUDA(cudaMemsetAsync(h->d_cand_cnt, 0, sizeof(int) * batch * g.nlevels, st));
     for (int l = 1; l < g.nlevels; ++l) {
-        if (h->resize_variant >= 1 && !g.lv[l].area2x) {   // 4 px x 4 (or 8) rows per thread, source-row interpolations shared between rows
+        if (h->resize_variant == 3 && !g.lv[l].area2x) {   // as variant 1, source rows by word loads + PRMT + IDP.2A
+            const LevelGeom& S = g.lv[l - 1];
+            const uint8_t* src_end = S.base + (int64_t)(batch - 1) * S.img_stride + (int64_t)(S.h - 1) * S.pitch + S.w;   // a caller-owned level 0 ends here
+            if (S.base >= h->d_pyr && S.base < h->d_pyr + h->pyr_bytes) src_end = h->d_pyr + h->pyr_bytes;               // own levels: the allocation has slack
+            dim3 grid((g.lv[l].w + 127) / 128, (g.lv[l].h + 31) / 32, batch);
+            k_resize_v3<<<grid, 256, 0, st>>>(g, l, h->d_taps, src_end);
+        } else if (h->resize_variant >= 1 && !g.lv[l].area2x) {   // 4 px x 4 (or 8) rows per thread, source-row interpolations shared between rows
             const int rows = h->resize_variant == 2 ? 8 : 4;
             dim3 grid((g.lv[l].w + 127) / 128, (g.lv[l].h + 8 * rows - 1) / (8 * rows), batch);
             if (rows == 8) k_resize_v2<8><<<grid, 256, 0, st>>>(g, l, h->d_taps);

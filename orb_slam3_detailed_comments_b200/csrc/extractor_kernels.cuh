@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "devmath.cuh"
 #include "quadtree_core.cuh"
+#include "resize_core.cuh"
 
 namespace orb {
 using namespace orbdev;
@@ -115,6 +116,18 @@ __global__ void __launch_bounds__(256) k_resize_v2(const __grid_constant__ Extra
         if (dx4 + 4 > D.w) packed &= 0xffffffffu >> (8 * (dx4 + 4 - D.w));   // as k_resize: zero past the width
         *reinterpret_cast<uint32_t*>(dst + (int64_t)(dy0 + k) * D.pitch) = packed;
     }
+}
+
+// k_resize_v3: k_resize_v2's work split, the source rows by aligned word loads + PRMT + IDP.2A (resize_core.cuh).
+__global__ void __launch_bounds__(256) k_resize_v3(const __grid_constant__ ExtractGeom g, int l, const int2* __restrict__ taps, const uint8_t* src_end) {
+    const LevelGeom& D = g.lv[l];
+    const LevelGeom& S = g.lv[l - 1];
+    const int dx4 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
+    const int dy0 = (blockIdx.y * 8 + (threadIdx.x >> 5)) * 4;
+    if (dx4 >= D.w || dy0 >= D.h) return;
+    const int* t2 = reinterpret_cast<const int*>(taps + D.tapOff);
+    rs_thread<4>(S.base + (int64_t)blockIdx.z * S.img_stride, S.w, S.h, S.pitch, src_end, D.base + (int64_t)blockIdx.z * D.img_stride, D.w, D.h,
+                 D.pitch, t2, t2 + 2 * D.w, dx4, dy0);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -282,3 +282,16 @@ extern "C" void emul_stereo_v1(const orbx_keypoint* kL, const uint8_t* dL, int n
         stereo_match_one(kL[i].x, kL[i].y, kL[i].octave, reinterpret_cast<const uint32_t*>(dL + 32 * (size_t)i), R, dR, lv.data(), bf, b,
                          &out_u[i], &out_d[i], &out_sad[i]);
 }
+
+// ---- ComputePyramid, one level transition: csrc/resize_core.cuh (the body of k_resize_v3's threads) on the host ------------------------
+#include "../../orb_slam3_detailed_comments_b200/csrc/resize_core.cuh"
+
+// src: sh rows of spitch bytes (src_avail readable bytes from src: the word loads stop there); dst: dh rows of dpitch bytes.
+extern "C" void emul_resize_v3(const uint8_t* src, int sw, int sh, int spitch, long src_avail, uint8_t* dst, int dw, int dh, int dpitch) {
+    std::vector<int> tx(2 * dw), ty(2 * dh);
+    rs_linear_taps(sw, dw, tx.data());
+    rs_linear_taps(sh, dh, ty.data());
+    for (int dy0 = 0; dy0 < dh; dy0 += 4)
+        for (int dx4 = 0; dx4 < dw; dx4 += 4)
+            rs_thread<4>(src, sw, sh, spitch, src + src_avail, dst, dw, dh, dpitch, tx.data(), ty.data(), dx4, dy0);
+}

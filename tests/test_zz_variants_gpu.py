@@ -1,7 +1,7 @@
 """GPU tier (runs last): the selectable kernel variants of the per-frame path give the results of the defaults.
   ORB_PROJ_LANES   lanes per query of the two per-frame searches (default 4 / 8; 16; 32 = the warp-per-query kernel), read at every search
   ORB_PROJ_QPB     queries per CTA of the grouped candidate kernel
-  ORB_RESIZE_VARIANT / ORB_BLUR_VARIANT   read by orbx_create: k_resize (0), k_resize_v2<4> (1, default), <8> (2); k_blur<false> (0)
+  ORB_RESIZE_VARIANT / ORB_BLUR_VARIANT   read by orbx_create: k_resize (0), k_resize_v2<4> (1, default), <8> (2), k_resize_v3 (3); k_blur<false> (0)
 Each case reruns the oracle comparison of the default-variant tests."""
 import numpy as np
 import pytest
@@ -25,7 +25,7 @@ def test_per_frame_searches_with_other_lane_groupings(monkeypatch, scene, lanes,
     tm.test_search_last_frame_matches_oracle(scene)
 
 
-@pytest.mark.parametrize("resize,blur", [("0", "0"), ("2", "1"), ("1", "0")])
+@pytest.mark.parametrize("resize,blur", [("0", "0"), ("2", "1"), ("1", "0"), ("3", "1")])
 @pytest.mark.parametrize("w,h,seed,nf", [(640, 480, 1, 1200), (500, 377, 8, 1500), (1280, 720, 5, 2000)])
 def test_extractor_with_other_resize_and_blur_kernels(monkeypatch, resize, blur, w, h, seed, nf):
     monkeypatch.setenv("ORB_RESIZE_VARIANT", resize)
