@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <functional>
 #include <vector>
 
 namespace {
@@ -206,35 +207,128 @@ inline bool inv3(const double* M, double* Mi) {
 
 }  // namespace
 
-extern "C" {
+// ONE restatement of g2o's Levenberg-Marquardt control flow for every optimiser of this file: SparseOptimizer::optimize(maxIters)
+// (sparse_optimizer.cpp:354-416) around OptimizationAlgorithmLevenberg::solve (optimization_algorithm_levenberg.cpp:61-172, with
+// ORB-SLAM3's nBad stop), computeLambdaInit (:174-188, tau = 1e-5) and computeScale (:190-197).  oracle/_ref part 4 compiles those
+// functions of the reference verbatim and runs them over LbaEngine: tests/test_oracle_vs_ref_g2o.py holds this template to them.
+// Ops: compute_errors() -> robust chi2 (computeActiveErrors + activeRobustChi2), build_system(), solve(lambda) -> bool (setLambda +
+// solve + restoreDiagonal), apply_update() (SparseOptimizer::update(solver->x())), push() / pop() / discard_top(), max_diagonal(),
+// scale(lambda) = sum_j x_j (lambda x_j + b_j).
+struct LmOutcome {
+    int iters = 0, trials = 0;
+    double lambda = -1, currentChi = 0, iniChi0 = 0, lastChi = 0;
+};
+template <class Ops>
+static LmOutcome lm_optimize(Ops& E, int maxIters, double userLambdaInit, const volatile int* stop_flag) {
+    LmOutcome R;
+    double lambda = userLambdaInit > 0 ? userLambdaInit : -1, ni = 2;
+    int nBad = 0;
+    bool ok = true;
+    for (int it = 0; it < maxIters && ok && !(stop_flag && *stop_flag); ++it) {
+        double currentChi = E.compute_errors();
+        R.lastChi = currentChi;
+        if (it == 0) R.iniChi0 = currentChi;
+        double tempChi = currentChi;
+        const double iniChi = currentChi;
+        E.build_system();
+        if (it == 0) {
+            if (!(userLambdaInit > 0)) lambda = 1e-5 * E.max_diagonal();
+            ni = 2;
+            nBad = 0;
+        }
+        double rho = 0;
+        int qmax = 0;
+        do {
+            E.push();
+            const bool ok2 = E.solve(lambda);
+            E.apply_update();
+            tempChi = E.compute_errors();
+            R.lastChi = tempChi;
+            if (!ok2) tempChi = std::numeric_limits<double>::max();
+            rho = currentChi - tempChi;
+            double scale = E.scale(lambda);
+            scale += 1e-3;
+            rho /= scale;
+            if (rho > 0 && std::isfinite(tempChi)) {
+                double alpha = 1. - std::pow((2 * rho - 1), 3);
+                alpha = std::min(alpha, 2. / 3.);
+                const double sf = std::max(1. / 3., alpha);
+                lambda *= sf;
+                ni = 2;
+                currentChi = tempChi;
+                E.discard_top();
+            } else {
+                lambda *= ni;
+                ni *= 2;
+                E.pop();
+            }
+            ++qmax;
+            ++R.trials;
+        } while (rho < 0 && qmax < 10 && !(stop_flag && *stop_flag));
+        ++R.iters;
+        R.currentChi = currentChi;
+        R.lambda = lambda;
+        if (qmax == 10 || rho == 0) { ok = false; break; }
+        if ((iniChi - currentChi) * 1e3 < iniChi) ++nBad; else nBad = 0;
+        if (nBad >= 3) { ok = false; break; }
+    }
+    R.lambda = lambda;
+    return R;
+}
 
-// pose: nKF x 7 (qx qy qz qw tx ty tz), in/out.  fixed: nKF.  point: nMP x 3, in/out.  obs: nE x 3 (ur < 0 =>
-// monocular edge).  invs2: nE (information = invSigma2 * I).  cam5: fx fy cx cy bf (float members promoted).
-// stop_flag: polled like pbStopFlag.  Outputs: edge_chi2[nE] = e->chi2() as left by the LAST computeActiveErrors,
-// edge_depth_pos[nE] at the final estimate, stats[0..] = {outer iterations, final lambda, final robust chi2,
-// total LM trials, initial robust chi2}.  Returns number of outer iterations run.
-int orc_lba(int nKF, int nMP, int nE, double* pose, const uint8_t* fixed, double* point, const int* ekf, const int* emp,
-            const double* obs, const double* invs2, const double* cam5, double lambdaInit, int maxIters,
-            const volatile int* stop_flag, double* edge_chi2, uint8_t* edge_depth_pos, double* stats) {
+struct LmFnOps {   // the same interface from closures (PoseOptimization and LocalInertialBA keep their state in locals)
+    std::function<double()> errors_, max_diagonal_;
+    std::function<void()> build_, update_, push_, pop_, discard_;
+    std::function<bool(double)> solve_;
+    std::function<double(double)> scale_;
+    double compute_errors() { return errors_(); }
+    void build_system() { build_(); }
+    bool solve(double lambda) { return solve_(lambda); }
+    void apply_update() { update_(); }
+    void push() { push_(); }
+    void pop() { pop_(); }
+    void discard_top() { discard_(); }
+    double max_diagonal() { return max_diagonal_(); }
+    double scale(double lambda) { return scale_(lambda); }
+};
+
+// The numeric engine of LocalBundleAdjustment as g2o splits it between SparseOptimizer (errors, robust chi2, update, push / pop) and
+// BlockSolver<6,3> + LinearSolverEigen (buildSystem, setLambda + solve + restoreDiagonal).  orc_lba drives it with the restated
+// Levenberg loop below; oracle/_ref part 4 drives the SAME engine with g2o's own OptimizationAlgorithmLevenberg::solve and
+// SparseOptimizer::optimize compiled verbatim (tests/test_oracle_vs_ref_g2o.py), which pins the loop.
+struct LbaEngine {
     Problem P;
-    P.nKF = nKF; P.nMP = nMP; P.nE = nE;
-    P.pose.assign(pose, pose + 7 * (size_t)nKF);
-    P.point.assign(point, point + 3 * (size_t)nMP);
-    P.fixed = fixed; P.ekf = ekf; P.emp = emp; P.obs = obs; P.invs2 = invs2;
-    P.cam = {cam5[0], cam5[1], cam5[2], cam5[3], cam5[4]};
-    P.deltaMono = (double)(float)std::sqrt(5.991);   // Optimizer.cc:1957-1958 (const float)
-    P.deltaStereo = (double)(float)std::sqrt(7.815);
-    P.dsqrMono = (double)(float)(P.deltaMono * P.deltaMono);        // RobustKernelHuber::dsqr is a float
-    P.dsqrStereo = (double)(float)(P.deltaStereo * P.deltaStereo);
+    int nKF, nMP, nE, nP, sp, sl;
+    const int *ekf, *emp;
+    const double* invs2;
+    std::vector<int> pidx;
+    std::vector<double> Hpp, Hll, Hpl, b, x, err;
+    std::vector<std::vector<int>> byMp;   // edges grouped by landmark for the Schur complement
+    std::vector<std::vector<double>> stackPose, stackPoint;   // SparseOptimizer::push / pop / discardTop
 
-    std::vector<int> pidx(nKF, -1);
-    int nP = 0;
-    for (int k = 0; k < nKF; ++k) if (!fixed[k]) pidx[k] = nP++;
-    const int sp = 6 * nP, sl = 3 * nMP;
-    std::vector<double> Hpp((size_t)nP * 36), Hll((size_t)nMP * 9), Hpl((size_t)nE * 18), b(sp + sl), x(sp + sl);
-    std::vector<double> err(nE, 0.0);
+    LbaEngine(int nKF_, int nMP_, int nE_, const double* pose, const uint8_t* fixed, const double* point, const int* ekf_, const int* emp_,
+              const double* obs, const double* invs2_, const double* cam5)
+        : nKF(nKF_), nMP(nMP_), nE(nE_), ekf(ekf_), emp(emp_), invs2(invs2_) {
+        P.nKF = nKF; P.nMP = nMP; P.nE = nE;
+        P.pose.assign(pose, pose + 7 * (size_t)nKF);
+        P.point.assign(point, point + 3 * (size_t)nMP);
+        P.fixed = fixed; P.ekf = ekf; P.emp = emp; P.obs = obs; P.invs2 = invs2;
+        P.cam = {cam5[0], cam5[1], cam5[2], cam5[3], cam5[4]};
+        P.deltaMono = (double)(float)std::sqrt(5.991);   // Optimizer.cc:1957-1958 (const float)
+        P.deltaStereo = (double)(float)std::sqrt(7.815);
+        P.dsqrMono = (double)(float)(P.deltaMono * P.deltaMono);        // RobustKernelHuber::dsqr is a float
+        P.dsqrStereo = (double)(float)(P.deltaStereo * P.deltaStereo);
+        pidx.assign(nKF, -1);
+        nP = 0;
+        for (int k = 0; k < nKF; ++k) if (!fixed[k]) pidx[k] = nP++;
+        sp = 6 * nP; sl = 3 * nMP;
+        Hpp.assign((size_t)nP * 36, 0.0); Hll.assign((size_t)nMP * 9, 0.0); Hpl.assign((size_t)nE * 18, 0.0);
+        b.assign(sp + sl, 0.0); x.assign(sp + sl, 0.0); err.assign(nE, 0.0);
+        byMp.resize(nMP);
+        for (int e = 0; e < nE; ++e) byMp[emp[e]].push_back(e);
+    }
 
-    auto compute_errors = [&]() -> double {  // computeActiveErrors + activeRobustChi2
+    double compute_errors() {  // computeActiveErrors + activeRobustChi2
         double chi = 0;
         for (int e = 0; e < nE; ++e) {
             double r[3], Xc[3];
@@ -245,9 +339,9 @@ int orc_lba(int nKF, int nMP, int nE, double* pose, const uint8_t* fixed, double
             chi += huber_rho(c, D == 2 ? P.deltaMono : P.deltaStereo, D == 2 ? P.dsqrMono : P.dsqrStereo, &w);
         }
         return chi;
-    };
+    }
 
-    auto build_system = [&]() {  // BlockSolver::buildSystem (linearizeOplus + constructQuadraticForm)
+    void build_system() {  // BlockSolver::buildSystem (linearizeOplus + constructQuadraticForm)
         std::fill(Hpp.begin(), Hpp.end(), 0.0);
         std::fill(Hll.begin(), Hll.end(), 0.0);
         std::fill(Hpl.begin(), Hpl.end(), 0.0);
@@ -295,13 +389,9 @@ int orc_lba(int nKF, int nMP, int nE, double* pose, const uint8_t* fixed, double
                 }
             }
         }
-    };
+    }
 
-    // edges grouped by landmark for the Schur complement
-    std::vector<std::vector<int>> byMp(nMP);
-    for (int e = 0; e < nE; ++e) byMp[emp[e]].push_back(e);
-
-    auto solve = [&](double lambda) -> bool {  // setLambda + BlockSolver::solve + restoreDiagonal
+    bool solve(double lambda) {  // setLambda + BlockSolver::solve + restoreDiagonal
         const int n = sp;
         std::vector<double> Hs((size_t)n * n, 0.0), bs(b.begin(), b.begin() + n), Dinv((size_t)nMP * 9);
         for (int p = 0; p < nP; ++p)
@@ -347,77 +437,90 @@ int orc_lba(int nKF, int nMP, int nE, double* pose, const uint8_t* fixed, double
             for (int i = 0; i < 3; ++i) x[sp + 3 * l + i] = Di[3 * i] * c[0] + Di[3 * i + 1] * c[1] + Di[3 * i + 2] * c[2];
         }
         return true;
-    };
+    }
 
-    double lambda = -1, ni = 2;
-    int nBad = 0, iters = 0, trials = 0;
-    double currentChi = 0, iniChi0 = 0;
-    bool ok = true;
-    for (int it = 0; it < maxIters && ok && !(stop_flag && *stop_flag); ++it) {
-        currentChi = compute_errors();
-        if (it == 0) iniChi0 = currentChi;
-        double tempChi = currentChi;
-        const double iniChi = currentChi;
-        build_system();
-        if (it == 0) {
-            if (lambdaInit > 0) lambda = lambdaInit;
-            else {
-                double md = 0;
-                for (int p = 0; p < nP; ++p) for (int j = 0; j < 6; ++j) md = std::max(std::fabs(Hpp[36 * (size_t)p + 7 * j]), md);
-                for (int l = 0; l < nMP; ++l) for (int j = 0; j < 3; ++j) md = std::max(std::fabs(Hll[9 * (size_t)l + 4 * j]), md);
-                lambda = 1e-5 * md;
-            }
-            ni = 2;
-            nBad = 0;
+    void update(const double* u) {  // SparseOptimizer::update: VertexSE3Expmap::oplusImpl / VertexSBAPointXYZ::oplusImpl
+        for (int k = 0; k < nKF; ++k) if (pidx[k] >= 0) pose_oplus(&P.pose[7 * k], &u[6 * pidx[k]]);
+        for (int l = 0; l < nMP; ++l) for (int i = 0; i < 3; ++i) P.point[3 * l + i] += u[sp + 3 * l + i];
+    }
+    void apply_update() { update(x.data()); }
+    double scale(double lambda) const {
+        double sc = 0;
+        for (int j = 0; j < sp + sl; ++j) sc += x[j] * (lambda * x[j] + b[j]);
+        return sc;
+    }
+    void push() { stackPose.push_back(P.pose); stackPoint.push_back(P.point); }
+    void pop() { P.pose = stackPose.back(); P.point = stackPoint.back(); stackPose.pop_back(); stackPoint.pop_back(); }
+    void discard_top() { stackPose.pop_back(); stackPoint.pop_back(); }
+    double max_diagonal() const {  // OptimizationAlgorithmLevenberg::computeLambdaInit's scan over the vertices' Hessian diagonals
+        double md = 0;
+        for (int p = 0; p < nP; ++p) for (int j = 0; j < 6; ++j) md = std::max(std::fabs(Hpp[36 * (size_t)p + 7 * j]), md);
+        for (int l = 0; l < nMP; ++l) for (int j = 0; j < 3; ++j) md = std::max(std::fabs(Hll[9 * (size_t)l + 4 * j]), md);
+        return md;
+    }
+    // post-processing inputs, Optimizer.cc:2107-2150; stats as orc_lba documents them
+    void finish(double* pose, double* point, double* edge_chi2, uint8_t* edge_depth_pos) {
+        for (int e = 0; e < nE; ++e) {
+            edge_chi2[e] = err[e];
+            double Xc[3];
+            se3_map(&P.pose[7 * ekf[e]], &P.point[3 * emp[e]], Xc);
+            edge_depth_pos[e] = Xc[2] > 0.0 ? 1 : 0;
         }
-        double rho = 0;
-        int qmax = 0;
-        do {
-            const std::vector<double> savedPose = P.pose, savedPoint = P.point;  // push
-            const bool ok2 = solve(lambda);
-            for (int k = 0; k < nKF; ++k) if (pidx[k] >= 0) pose_oplus(&P.pose[7 * k], &x[6 * pidx[k]]);
-            for (int l = 0; l < nMP; ++l) for (int i = 0; i < 3; ++i) P.point[3 * l + i] += x[sp + 3 * l + i];
-            tempChi = compute_errors();
-            if (!ok2) tempChi = std::numeric_limits<double>::max();
-            rho = currentChi - tempChi;
-            double scale = 0;
-            for (int j = 0; j < sp + sl; ++j) scale += x[j] * (lambda * x[j] + b[j]);
-            scale += 1e-3;
-            rho /= scale;
-            if (rho > 0 && std::isfinite(tempChi)) {
-                double alpha = 1. - std::pow((2 * rho - 1), 3);
-                alpha = std::min(alpha, 2. / 3.);
-                const double sf = std::max(1. / 3., alpha);
-                lambda *= sf;
-                ni = 2;
-                currentChi = tempChi;
-            } else {
-                lambda *= ni;
-                ni *= 2;
-                P.pose = savedPose;   // pop
-                P.point = savedPoint;
-            }
-            ++qmax;
-            ++trials;
-        } while (rho < 0 && qmax < 10 && !(stop_flag && *stop_flag));
-        ++iters;
-        if (qmax == 10 || rho == 0) { ok = false; break; }
-        if ((iniChi - currentChi) * 1e3 < iniChi) ++nBad; else nBad = 0;
-        if (nBad >= 3) { ok = false; break; }
+        memcpy(pose, P.pose.data(), sizeof(double) * 7 * (size_t)nKF);
+        memcpy(point, P.point.data(), sizeof(double) * 3 * (size_t)nMP);
     }
-    // post-processing inputs, Optimizer.cc:2107-2150
-    for (int e = 0; e < nE; ++e) {
-        edge_chi2[e] = err[e];
-        double Xc[3];
-        se3_map(&P.pose[7 * ekf[e]], &P.point[3 * emp[e]], Xc);
-        edge_depth_pos[e] = Xc[2] > 0.0 ? 1 : 0;
-    }
-    memcpy(pose, P.pose.data(), sizeof(double) * 7 * (size_t)nKF);
-    memcpy(point, P.point.data(), sizeof(double) * 3 * (size_t)nMP);
+};
+
+extern "C" {
+
+// pose: nKF x 7 (qx qy qz qw tx ty tz), in/out.  fixed: nKF.  point: nMP x 3, in/out.  obs: nE x 3 (ur < 0 =>
+// monocular edge).  invs2: nE (information = invSigma2 * I).  cam5: fx fy cx cy bf (float members promoted).
+// stop_flag: polled like pbStopFlag.  Outputs: edge_chi2[nE] = e->chi2() as left by the LAST computeActiveErrors,
+// edge_depth_pos[nE] at the final estimate, stats[0..] = {outer iterations, final lambda, final robust chi2,
+// total LM trials, initial robust chi2}.  Returns number of outer iterations run.
+int orc_lba(int nKF, int nMP, int nE, double* pose, const uint8_t* fixed, double* point, const int* ekf, const int* emp,
+            const double* obs, const double* invs2, const double* cam5, double lambdaInit, int maxIters,
+            const volatile int* stop_flag, double* edge_chi2, uint8_t* edge_depth_pos, double* stats) {
+    LbaEngine E(nKF, nMP, nE, pose, fixed, point, ekf, emp, obs, invs2, cam5);
+    const LmOutcome R = lm_optimize(E, maxIters, lambdaInit, stop_flag);
+    E.finish(pose, point, edge_chi2, edge_depth_pos);
     if (stats) {
-        stats[0] = iters; stats[1] = lambda; stats[2] = currentChi; stats[3] = trials; stats[4] = iniChi0;
+        stats[0] = R.iters; stats[1] = R.lambda; stats[2] = R.currentChi; stats[3] = R.trials; stats[4] = R.iniChi0;
     }
-    return iters;
+    return R.iters;
+}
+
+// ---- the engine behind a C interface, for oracle/_ref part 4 (g2o's own Levenberg loop drives it) ---------------------------------
+void* orc_lba_engine_create(int nKF, int nMP, int nE, const double* pose, const uint8_t* fixed, const double* point, const int* ekf, const int* emp,
+                            const double* obs, const double* invs2, const double* cam5) {
+    return new LbaEngine(nKF, nMP, nE, pose, fixed, point, ekf, emp, obs, invs2, cam5);
+}
+void orc_lba_engine_destroy(void* h) { delete (LbaEngine*)h; }
+double orc_lba_engine_errors(void* h) { return ((LbaEngine*)h)->compute_errors(); }
+void orc_lba_engine_build(void* h) { ((LbaEngine*)h)->build_system(); }
+int orc_lba_engine_solve(void* h, double lambda) { return ((LbaEngine*)h)->solve(lambda) ? 1 : 0; }
+void orc_lba_engine_update(void* h, const double* u) { ((LbaEngine*)h)->update(u); }
+void orc_lba_engine_push(void* h) { ((LbaEngine*)h)->push(); }
+void orc_lba_engine_pop(void* h) { ((LbaEngine*)h)->pop(); }
+void orc_lba_engine_discard_top(void* h) { ((LbaEngine*)h)->discard_top(); }
+double orc_lba_engine_max_diagonal(void* h) { return ((LbaEngine*)h)->max_diagonal(); }
+int orc_lba_engine_vector_size(void* h) { return ((LbaEngine*)h)->sp + ((LbaEngine*)h)->sl; }
+const double* orc_lba_engine_x(void* h) { return ((LbaEngine*)h)->x.data(); }
+const double* orc_lba_engine_b(void* h) { return ((LbaEngine*)h)->b.data(); }
+// the optimisable vertices as g2o indexes them for computeLambdaInit: free poses (dimension 6), then points (dimension 3)
+int orc_lba_engine_vertices(void* h) { return ((LbaEngine*)h)->nP + ((LbaEngine*)h)->nMP; }
+int orc_lba_engine_vertex_dim(void* h, int k) { return k < ((LbaEngine*)h)->nP ? 6 : 3; }
+double orc_lba_engine_hessian_diag(void* h, int k, int j) {
+    LbaEngine* E = (LbaEngine*)h;
+    return k < E->nP ? E->Hpp[36 * (size_t)k + 7 * j] : E->Hll[9 * (size_t)(k - E->nP) + 4 * j];
+}
+void orc_lba_engine_finish(void* h, double* pose, double* point, double* edge_chi2, uint8_t* edge_depth_pos) {
+    ((LbaEngine*)h)->finish(pose, point, edge_chi2, edge_depth_pos);
+}
+// RobustKernelHuber::robustify as the engine applies it: rho[0] and rho[1] for squared error e and delta = sqrt(chi2 threshold) as float
+void orc_huber(double e, float delta_f, double* rho2) {
+    const double delta = (double)delta_f, dsqr = (double)(float)(delta * delta);
+    rho2[0] = huber_rho(e, delta, dsqr, &rho2[1]);
 }
 }
 
@@ -528,55 +631,25 @@ extern "C" int orc_pose_optimization(int n, const double* Xw, const double* obs,
         int nActive = 0;
         for (int e = 0; e < n; ++e) nActive += level[e] == 0;
         if (nActive > 0) {                                   // optimize(10): initializeOptimization(0) found the vertex
-            double ni = 2, currentChi = 0;
-            int nBadIt = 0;
-            bool ok = true;
-            for (int iter = 0; iter < 10 && ok; ++iter) {
-                currentChi = compute_errors();
-                double tempChi = currentChi;
-                const double iniChi = currentChi;
-                build_system();
-                if (iter == 0) {
-                    double md = 0;
-                    for (int j = 0; j < 6; ++j) md = std::max(std::fabs(H[7 * j]), md);
-                    lambda = 1e-5 * md;
-                    ni = 2;
-                    nBadIt = 0;
-                }
-                double rho = 0;
-                int qmax = 0;
-                do {
-                    const std::vector<double> saved = P.pose;    // push
-                    std::vector<double> Hl(H, H + 36);
-                    for (int j = 0; j < 6; ++j) Hl[7 * j] += lambda;
-                    const bool ok2 = ldlt_solve(Hl, 6, b, x);
-                    pose_oplus(P.pose.data(), x);
-                    tempChi = compute_errors();
-                    if (!ok2) tempChi = std::numeric_limits<double>::max();
-                    rho = currentChi - tempChi;
-                    double scale = 0;
-                    for (int j = 0; j < 6; ++j) scale += x[j] * (lambda * x[j] + b[j]);
-                    scale += 1e-3;
-                    rho /= scale;
-                    if (rho > 0 && std::isfinite(tempChi)) {
-                        double alpha = 1. - std::pow((2 * rho - 1), 3);
-                        alpha = std::min(alpha, 2. / 3.);
-                        lambda *= std::max(1. / 3., alpha);
-                        ni = 2;
-                        currentChi = tempChi;
-                    } else {
-                        lambda *= ni;
-                        ni *= 2;
-                        P.pose = saved;                          // pop
-                    }
-                    ++qmax;
-                    ++totalTrials;
-                } while (rho < 0 && qmax < 10);
-                ++totalIters;
-                if (qmax == 10 || rho == 0) { ok = false; break; }
-                if ((iniChi - currentChi) * 1e3 < iniChi) ++nBadIt; else nBadIt = 0;
-                if (nBadIt >= 3) { ok = false; break; }
-            }
+            std::vector<std::vector<double>> stack;
+            LmFnOps ops;
+            ops.errors_ = [&]() { return compute_errors(); };
+            ops.build_ = [&]() { build_system(); };
+            ops.solve_ = [&](double lam) {
+                std::vector<double> Hl(H, H + 36);
+                for (int j = 0; j < 6; ++j) Hl[7 * j] += lam;
+                return ldlt_solve(Hl, 6, b, x);
+            };
+            ops.update_ = [&]() { pose_oplus(P.pose.data(), x); };
+            ops.push_ = [&]() { stack.push_back(P.pose); };
+            ops.pop_ = [&]() { P.pose = stack.back(); stack.pop_back(); };
+            ops.discard_ = [&]() { stack.pop_back(); };
+            ops.max_diagonal_ = [&]() { double md = 0; for (int j = 0; j < 6; ++j) md = std::max(std::fabs(H[7 * j]), md); return md; };
+            ops.scale_ = [&](double lam) { double sc = 0; for (int j = 0; j < 6; ++j) sc += x[j] * (lam * x[j] + b[j]); return sc; };
+            const LmOutcome R = lm_optimize(ops, 10, 0.0, nullptr);
+            lambda = R.lambda;
+            totalIters += R.iters;
+            totalTrials += R.trials;
         }
         nBadEdges = 0;
         for (int e = 0; e < n; ++e) {
@@ -993,62 +1066,29 @@ int orc_liba(int nKF, int nMP, int nE, int nL, double* state, const uint8_t* fix
         return true;
     };
 
-    double lambda = lambdaInit, ni = 2;
-    int nBad = 0, iters = 0, trials = 0;
-    double currentChi = 0, iniChi0 = 0, lastChi = 0;
-    for (int it = 0; it < maxIters; ++it) {
-        currentChi = compute_errors();
-        lastChi = currentChi;
-        if (it == 0) iniChi0 = currentChi;
-        double tempChi = currentChi;
-        const double iniChi = currentChi;
-        build_system();
-        if (it == 0) {
-            if (!(lambdaInit > 0)) {
-                double md = 0;
-                for (int j = 0; j < sp; ++j) md = std::max(std::fabs(Hpp[(size_t)j * sp + j]), md);
-                for (int l = 0; l < nMP; ++l) for (int j = 0; j < 3; ++j) md = std::max(std::fabs(Hll[9 * (size_t)l + 4 * j]), md);
-                lambda = 1e-5 * md;
-            }
-            ni = 2;
-            nBad = 0;
-        }
-        double rho = 0;
-        int qmax = 0;
-        do {
-            const std::vector<KfState> savedKf = P.kf;
-            const std::vector<double> savedPoint = P.point;
-            const bool ok2 = solve(lambda);
-            for (int k = 0; k < nKF; ++k) if (pidx[k] >= 0) kf_oplus(P.kf[k], &x[15 * pidx[k]]);
-            for (int l = 0; l < nMP; ++l) for (int i = 0; i < 3; ++i) P.point[3 * l + i] += x[sp + 3 * l + i];
-            tempChi = compute_errors();
-            lastChi = tempChi;
-            if (!ok2) tempChi = std::numeric_limits<double>::max();
-            rho = currentChi - tempChi;
-            double scale = 0;
-            for (int j = 0; j < sp + sl; ++j) scale += x[j] * (lambda * x[j] + b[j]);
-            scale += 1e-3;
-            rho /= scale;
-            if (rho > 0 && std::isfinite(tempChi)) {
-                double alpha = 1. - std::pow((2 * rho - 1), 3);
-                alpha = std::min(alpha, 2. / 3.);
-                lambda *= std::max(1. / 3., alpha);
-                ni = 2;
-                currentChi = tempChi;
-            } else {
-                lambda *= ni;
-                ni *= 2;
-                P.kf = savedKf;
-                P.point = savedPoint;
-            }
-            ++qmax;
-            ++trials;
-        } while (rho < 0 && qmax < 10);
-        ++iters;
-        if (qmax == 10 || rho == 0) break;
-        if ((iniChi - currentChi) * 1e3 < iniChi) ++nBad; else nBad = 0;
-        if (nBad >= 3) break;
-    }
+    std::vector<std::vector<KfState>> stackKf;
+    std::vector<std::vector<double>> stackPoint;
+    LmFnOps ops;
+    ops.errors_ = [&]() { return compute_errors(); };
+    ops.build_ = [&]() { build_system(); };
+    ops.solve_ = [&](double lam) { return solve(lam); };
+    ops.update_ = [&]() {
+        for (int k = 0; k < nKF; ++k) if (pidx[k] >= 0) kf_oplus(P.kf[k], &x[15 * pidx[k]]);
+        for (int l = 0; l < nMP; ++l) for (int i = 0; i < 3; ++i) P.point[3 * l + i] += x[sp + 3 * l + i];
+    };
+    ops.push_ = [&]() { stackKf.push_back(P.kf); stackPoint.push_back(P.point); };
+    ops.pop_ = [&]() { P.kf = stackKf.back(); P.point = stackPoint.back(); stackKf.pop_back(); stackPoint.pop_back(); };
+    ops.discard_ = [&]() { stackKf.pop_back(); stackPoint.pop_back(); };
+    ops.max_diagonal_ = [&]() {
+        double md = 0;
+        for (int j = 0; j < sp; ++j) md = std::max(std::fabs(Hpp[(size_t)j * sp + j]), md);
+        for (int l = 0; l < nMP; ++l) for (int j = 0; j < 3; ++j) md = std::max(std::fabs(Hll[9 * (size_t)l + 4 * j]), md);
+        return md;
+    };
+    ops.scale_ = [&](double lam) { double sc = 0; for (int j = 0; j < sp + sl; ++j) sc += x[j] * (lam * x[j] + b[j]); return sc; };
+    const LmOutcome R = lm_optimize(ops, maxIters, lambdaInit, nullptr);
+    const int iters = R.iters, trials = R.trials;
+    const double lambda = R.lambda, currentChi = R.currentChi, iniChi0 = R.iniChi0, lastChi = R.lastChi;
     for (int e = 0; e < nE; ++e) if (edge_chi2) edge_chi2[e] = err[e];
     for (int l = 0; l < 3 * nL; ++l) if (link_chi2) link_chi2[l] = lerr[l];
     for (int k = 0; k < nKF; ++k) {

@@ -9,9 +9,10 @@
 // and glibc sinf / cosf / logf exhaustively; (2) the reference's OWN SOURCE where it compiles from its files (oracle/_ref, DESIGN.md
 // section 2): ORBextractor.cc unmodified; every function of ORBmatcher.cc, the Frame / KeyFrame grid, isInFrustum,
 // ComputeStereoMatches, the MapPoint routines and Pinhole's projection / epipolar test cut out at build time and compiled verbatim
-// over skeleton classes; Thirdparty/DBoW2 unmodified on the reference's ORBvoc.txt.  (3) The g2o Levenberg loops
-// (PoseOptimization, LocalBundleAdjustment, LocalInertialBA) are Eigen expressions and stay "parity unpinned by the reference
-// source": their pins are finite differences, the objective restated in numpy, stationarity and planted-solution recovery.
+// over skeleton classes; Thirdparty/DBoW2 unmodified on the reference's ORBvoc.txt; g2o's Levenberg control flow and Huber kernel
+// verbatim, driving this oracle's bundle-adjustment engine.  (3) The Eigen-expressed numerics under the optimisers (edge errors and
+// Jacobians, Schur complement, LDL^T) stay "parity unpinned by the reference source": their pins are finite differences, the
+// objective restated in numpy, stationarity and planted-solution recovery.
 #pragma once
 #include <cstddef>
 #include <cstdint>

@@ -980,3 +980,59 @@ class RefVocabulary:
 def ref3_forb_distance(a, b):
     a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
     return int(ref3_lib().ref3_forb_distance(_p(a), _p(b)))
+
+
+# ---- oracle/_ref part 4: g2o's own Levenberg control flow + Huber kernel over the oracle's LbaEngine (oracle/Makefile target ref4) ------
+_REF4_SO = os.path.join(_HERE, "_ref", "liborb_ref4.so")
+_ref4_lib = None
+
+
+def build_ref4(force=False):
+    if os.path.exists(os.path.join(REFERENCE_ROOT, "Thirdparty", "g2o", "g2o", "core", "optimization_algorithm_levenberg.cpp")):
+        build()
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref4", f"REF={REFERENCE_ROOT}"] + (["-B"] if force else []))
+    return _REF4_SO if os.path.exists(_REF4_SO) else None
+
+
+def ref4_lib():
+    global _ref4_lib
+    if _ref4_lib is None:
+        if build_ref4() is None:
+            raise RuntimeError("oracle/_ref/liborb_ref4.so is not built and /root/reference is not present")
+        lib()                                   # liborb_oracle.so first: ref4 resolves the LbaEngine entry points against it
+        L = _ref4_lib = C.CDLL(_REF4_SO)
+        L.ref4_lba.restype = C.c_int
+        L.ref4_lba.argtypes = [C.c_int] * 3 + [C.c_void_p] * 8 + [C.c_double, C.c_int] + [C.c_void_p] * 3
+        L.ref4_huber.argtypes = [C.c_double, C.c_float, C.c_void_p]
+    return _ref4_lib
+
+
+def ref4_lba(pose, fixed, point, edge_kf, edge_mp, obs, inv_sigma2, cam5, lambda_init=0.0, max_iters=10):
+    """lba() with g2o's own OptimizationAlgorithmLevenberg::solve / SparseOptimizer::optimize deciding every step."""
+    L = ref4_lib()
+    pose = np.ascontiguousarray(pose, np.float64).copy()
+    point = np.ascontiguousarray(point, np.float64).copy()
+    fixed = np.ascontiguousarray(fixed, np.uint8)
+    ekf, emp = np.ascontiguousarray(edge_kf, np.int32), np.ascontiguousarray(edge_mp, np.int32)
+    obs, w = np.ascontiguousarray(obs, np.float64), np.ascontiguousarray(inv_sigma2, np.float64)
+    cam5 = np.ascontiguousarray(cam5, np.float64)
+    nE = len(ekf)
+    chi, dpos, stats = np.zeros(nE, np.float64), np.zeros(nE, np.uint8), np.zeros(8, np.float64)
+    it = L.ref4_lba(len(pose), len(point), nE, _p(pose), _p(fixed), _p(point), _p(ekf), _p(emp), _p(obs), _p(w), _p(cam5),
+                    float(lambda_init), int(max_iters), _p(chi), _p(dpos), _p(stats))
+    return dict(pose=pose, point=point, edge_chi2=chi, edge_depth_pos=dpos, iterations=it, lambda_=stats[1], chi2=stats[2], trials=int(stats[3]))
+
+
+def ref4_huber(e, delta):
+    out = np.zeros(3, np.float64)
+    ref4_lib().ref4_huber(float(e), float(np.float32(delta)), _p(out))
+    return out
+
+
+def huber(e, delta):
+    """The oracle's Huber weight as every optimiser of oracle/lba_oracle.cpp applies it: (rho, rho')."""
+    L = lib()
+    L.orc_huber.argtypes = [C.c_double, C.c_float, C.c_void_p]
+    out = np.zeros(2, np.float64)
+    L.orc_huber(float(e), float(np.float32(delta)), _p(out))
+    return out
