@@ -14,6 +14,8 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <vector>
 
@@ -558,34 +560,36 @@ void orc_edge_jacobians(const double* pose7, const double* X, int D, const doubl
 //   Xw[n][3], obs[n][3] (obs[2] < 0 => monocular edge), invs2[n], cam5 = fx fy cx cy bf.
 //   pose7 in: frame pose (qx qy qz qw tx ty tz), out: SE3quat_recov.  outlier[n] out: pFrame->mvbOutlier.
 //   stats: {rounds run, total LM iterations, total LM trials, final lambda}.  Returns nInitialCorrespondences - nBad.
-extern "C" int orc_pose_optimization(int n, const double* Xw, const double* obs, const double* invs2, const double* cam5,
-                                     double* pose7, uint8_t* outlier, double* stats) {
-    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
-    if (n < 3) return 0;                                    // Optimizer.cc:292-293
+struct PoseEngine {   // the one-vertex problem of PoseOptimization as g2o splits it (see LbaEngine)
     Problem P;
-    P.nKF = 1; P.nMP = n; P.nE = n;
-    P.pose.assign(pose7, pose7 + 7);
-    P.point.assign(Xw, Xw + 3 * (size_t)n);
-    std::vector<int> ekf(n, 0), emp(n);
-    for (int i = 0; i < n; ++i) emp[i] = i;
-    P.fixed = nullptr; P.ekf = ekf.data(); P.emp = emp.data(); P.obs = obs; P.invs2 = invs2;
-    P.cam = {cam5[0], cam5[1], cam5[2], cam5[3], cam5[4]};
-    P.deltaMono = (double)(float)std::sqrt(5.991);          // Optimizer.cc:101-102 (const float)
-    P.deltaStereo = (double)(float)std::sqrt(7.815);
-    P.dsqrMono = (double)(float)(P.deltaMono * P.deltaMono);
-    P.dsqrStereo = (double)(float)(P.deltaStereo * P.deltaStereo);
-    std::vector<double> pose0(pose7, pose7 + 7), err(n, 0.0);
-    std::vector<uint8_t> level(n, 0);
-    bool robust = true;
-    for (int i = 0; i < n; ++i) outlier[i] = 0;
+    int n;
+    std::vector<int> ekf, emp;
+    const double *obs, *invs2;
+    std::vector<double> err;
+    std::vector<uint8_t> level, robust;
     double H[36], b[6], x[6];
+    std::vector<std::vector<double>> stack;
 
-    auto edge_chi2 = [&](int e) {
+    PoseEngine(int n_, const double* Xw, const double* obs_, const double* invs2_, const double* cam5, const double* pose7)
+        : n(n_), ekf(n_, 0), emp(n_), obs(obs_), invs2(invs2_), err(n_, 0.0), level(n_, 0), robust(n_, 1) {
+        P.nKF = 1; P.nMP = n; P.nE = n;
+        P.pose.assign(pose7, pose7 + 7);
+        P.point.assign(Xw, Xw + 3 * (size_t)n);
+        for (int i = 0; i < n; ++i) emp[i] = i;
+        P.fixed = nullptr; P.ekf = ekf.data(); P.emp = emp.data(); P.obs = obs; P.invs2 = invs2;
+        P.cam = {cam5[0], cam5[1], cam5[2], cam5[3], cam5[4]};
+        P.deltaMono = (double)(float)std::sqrt(5.991);          // Optimizer.cc:101-102 (const float)
+        P.deltaStereo = (double)(float)std::sqrt(7.815);
+        P.dsqrMono = (double)(float)(P.deltaMono * P.deltaMono);
+        P.dsqrStereo = (double)(float)(P.deltaStereo * P.deltaStereo);
+        std::fill(H, H + 36, 0.0); std::fill(b, b + 6, 0.0); std::fill(x, x + 6, 0.0);
+    }
+    double edge_chi2(int e) {
         double r[3], Xc[3];
         edge_error(P, e, r, Xc);
         return invs2[e] * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
-    };
-    auto compute_errors = [&]() -> double {                  // computeActiveErrors + activeRobustChi2
+    }
+    double compute_errors() {                  // computeActiveErrors + activeRobustChi2
         double chi = 0;
         for (int e = 0; e < n; ++e) {
             if (level[e]) continue;
@@ -593,11 +597,11 @@ extern "C" int orc_pose_optimization(int n, const double* Xw, const double* obs,
             err[e] = c;
             const bool mono = obs[3 * e + 2] < 0;
             double w;
-            chi += robust ? huber_rho(c, mono ? P.deltaMono : P.deltaStereo, mono ? P.dsqrMono : P.dsqrStereo, &w) : c;
+            chi += robust[e] ? huber_rho(c, mono ? P.deltaMono : P.deltaStereo, mono ? P.dsqrMono : P.dsqrStereo, &w) : c;
         }
         return chi;
-    };
-    auto build_system = [&]() {
+    }
+    void build_system() {
         std::fill(H, H + 36, 0.0);
         std::fill(b, b + 6, 0.0);
         double R[9];
@@ -609,7 +613,7 @@ extern "C" int orc_pose_optimization(int n, const double* Xw, const double* obs,
             edge_jacobians(P.cam, D, R, Xc, A, B);
             const double c2 = invs2[e] * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
             double w = 1.0;
-            if (robust) huber_rho(c2, D == 2 ? P.deltaMono : P.deltaStereo, D == 2 ? P.dsqrMono : P.dsqrStereo, &w);
+            if (robust[e]) huber_rho(c2, D == 2 ? P.deltaMono : P.deltaStereo, D == 2 ? P.dsqrMono : P.dsqrStereo, &w);
             const double om = w * invs2[e];
             for (int i = 0; i < 6; ++i) {
                 for (int j = 0; j < 6; ++j) {
@@ -622,50 +626,78 @@ extern "C" int orc_pose_optimization(int n, const double* Xw, const double* obs,
                 b[i] += -om * s;
             }
         }
-    };
+    }
+    bool solve(double lambda) {
+        std::vector<double> Hl(H, H + 36);
+        for (int j = 0; j < 6; ++j) Hl[7 * j] += lambda;
+        return ldlt_solve(Hl, 6, b, x);
+    }
+    void apply_update() { pose_oplus(P.pose.data(), x); }
+    void push() { stack.push_back(P.pose); }
+    void pop() { P.pose = stack.back(); stack.pop_back(); }
+    void discard_top() { stack.pop_back(); }
+    double max_diagonal() const { double md = 0; for (int j = 0; j < 6; ++j) md = std::max(std::fabs(H[7 * j]), md); return md; }
+    double scale(double lambda) const { double sc = 0; for (int j = 0; j < 6; ++j) sc += x[j] * (lambda * x[j] + b[j]); return sc; }
+    int active() const { int a = 0; for (int e = 0; e < n; ++e) a += level[e] == 0; return a; }
+};
 
+extern "C" int orc_pose_optimization(int n, const double* Xw, const double* obs, const double* invs2, const double* cam5,
+                                     double* pose7, uint8_t* outlier, double* stats) {
+    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    if (n < 3) return 0;                                    // Optimizer.cc:292-293
+    PoseEngine E(n, Xw, obs, invs2, cam5, pose7);
+    const std::vector<double> pose0(pose7, pose7 + 7);
+    for (int i = 0; i < n; ++i) outlier[i] = 0;
     int nBadEdges = 0, rounds = 0, totalIters = 0, totalTrials = 0;
     double lambda = -1;
     for (int it = 0; it < 4; ++it) {
-        P.pose = pose0;                                      // vSE3->setEstimate(pFrame->GetPose())
-        int nActive = 0;
-        for (int e = 0; e < n; ++e) nActive += level[e] == 0;
-        if (nActive > 0) {                                   // optimize(10): initializeOptimization(0) found the vertex
-            std::vector<std::vector<double>> stack;
-            LmFnOps ops;
-            ops.errors_ = [&]() { return compute_errors(); };
-            ops.build_ = [&]() { build_system(); };
-            ops.solve_ = [&](double lam) {
-                std::vector<double> Hl(H, H + 36);
-                for (int j = 0; j < 6; ++j) Hl[7 * j] += lam;
-                return ldlt_solve(Hl, 6, b, x);
-            };
-            ops.update_ = [&]() { pose_oplus(P.pose.data(), x); };
-            ops.push_ = [&]() { stack.push_back(P.pose); };
-            ops.pop_ = [&]() { P.pose = stack.back(); stack.pop_back(); };
-            ops.discard_ = [&]() { stack.pop_back(); };
-            ops.max_diagonal_ = [&]() { double md = 0; for (int j = 0; j < 6; ++j) md = std::max(std::fabs(H[7 * j]), md); return md; };
-            ops.scale_ = [&](double lam) { double sc = 0; for (int j = 0; j < 6; ++j) sc += x[j] * (lam * x[j] + b[j]); return sc; };
-            const LmOutcome R = lm_optimize(ops, 10, 0.0, nullptr);
+        E.P.pose = pose0;                                    // vSE3->setEstimate(pFrame->GetPose())
+        if (E.active() > 0) {                                // optimize(10): initializeOptimization(0) found the vertex
+            const LmOutcome R = lm_optimize(E, 10, 0.0, nullptr);
             lambda = R.lambda;
             totalIters += R.iters;
             totalTrials += R.trials;
         }
         nBadEdges = 0;
         for (int e = 0; e < n; ++e) {
-            if (outlier[e]) err[e] = edge_chi2(e);            // e->computeError() for the edges the optimiser did not touch
-            const float chi2 = (float)err[e];
+            if (outlier[e]) E.err[e] = E.edge_chi2(e);        // e->computeError() for the edges the optimiser did not touch
+            const float chi2 = (float)E.err[e];
             const float th = obs[3 * e + 2] < 0 ? 5.991f : 7.815f;
-            if (chi2 > th) { outlier[e] = 1; level[e] = 1; ++nBadEdges; }
-            else { outlier[e] = 0; level[e] = 0; }
+            if (chi2 > th) { outlier[e] = 1; E.level[e] = 1; ++nBadEdges; }
+            else { outlier[e] = 0; E.level[e] = 0; }
+            if (it == 2) E.robust[e] = 0;                    // e->setRobustKernel(0)
         }
-        if (it == 2) robust = false;
         ++rounds;
         if (n < 10) break;                                   // optimizer.edges().size() < 10
     }
-    memcpy(pose7, P.pose.data(), sizeof(double) * 7);
+    memcpy(pose7, E.P.pose.data(), sizeof(double) * 7);
     if (stats) { stats[0] = rounds; stats[1] = totalIters; stats[2] = totalTrials; stats[3] = lambda; }
     return n - nBadEdges;
+}
+
+// ---- PoseEngine behind a C interface, for oracle/_ref part 4 (the reference's own Optimizer::PoseOptimization drives it) ------------------
+extern "C" {
+void* orc_po_engine_create(int n, const double* Xw, const double* obs, const double* invs2, const double* cam5, const double* pose7) {
+    return new PoseEngine(n, Xw, obs, invs2, cam5, pose7);
+}
+void orc_po_engine_destroy(void* h) { delete (PoseEngine*)h; }
+void orc_po_engine_set_estimate(void* h, const double* pose7) { ((PoseEngine*)h)->P.pose.assign(pose7, pose7 + 7); }
+void orc_po_engine_get_estimate(void* h, double* pose7) { memcpy(pose7, ((PoseEngine*)h)->P.pose.data(), sizeof(double) * 7); }
+void orc_po_engine_set_level(void* h, int e, int level) { ((PoseEngine*)h)->level[e] = (uint8_t)level; }
+void orc_po_engine_set_robust(void* h, int e, int on) { ((PoseEngine*)h)->robust[e] = on ? 1 : 0; }
+void orc_po_engine_compute_error(void* h, int e) { PoseEngine* E = (PoseEngine*)h; E->err[e] = E->edge_chi2(e); }
+double orc_po_engine_chi2(void* h, int e) { return ((PoseEngine*)h)->err[e]; }
+int orc_po_engine_active(void* h) { return ((PoseEngine*)h)->active(); }
+double orc_po_engine_errors(void* h) { return ((PoseEngine*)h)->compute_errors(); }
+void orc_po_engine_build(void* h) { ((PoseEngine*)h)->build_system(); }
+int orc_po_engine_solve(void* h, double lambda) { return ((PoseEngine*)h)->solve(lambda) ? 1 : 0; }
+void orc_po_engine_update(void* h) { ((PoseEngine*)h)->apply_update(); }
+void orc_po_engine_push(void* h) { ((PoseEngine*)h)->push(); }
+void orc_po_engine_pop(void* h) { ((PoseEngine*)h)->pop(); }
+void orc_po_engine_discard_top(void* h) { ((PoseEngine*)h)->discard_top(); }
+double orc_po_engine_hessian_diag(void* h, int j) { return ((PoseEngine*)h)->H[7 * j]; }
+const double* orc_po_engine_x(void* h) { return ((PoseEngine*)h)->x; }
+const double* orc_po_engine_b(void* h) { return ((PoseEngine*)h)->b; }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1036,3 +1036,36 @@ def huber(e, delta):
     out = np.zeros(2, np.float64)
     L.orc_huber(float(e), float(np.float32(delta)), _p(out))
     return out
+
+
+# ---- oracle/_ref part 5: the reference's own Optimizer::PoseOptimization over the oracle's PoseEngine (oracle/Makefile target ref5) ----
+_REF5_SO = os.path.join(_HERE, "_ref", "liborb_ref5.so")
+_ref5_lib = None
+
+
+def build_ref5(force=False):
+    if os.path.exists(os.path.join(REFERENCE_ROOT, "src", "Optimizer.cc")):
+        build()
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref5", f"REF={REFERENCE_ROOT}"] + (["-B"] if force else []))
+    return _REF5_SO if os.path.exists(_REF5_SO) else None
+
+
+def ref5_pose_optimization(pose7, has_mp, world_pos, kp_xy, octave, uright, inv_level_sigma2, cam5):
+    """Optimizer::PoseOptimization of the reference on a frame given as flat arrays (all float32 like the Frame's members).
+    Returns dict(pose (float32), outlier[N], inliers)."""
+    global _ref5_lib
+    if _ref5_lib is None:
+        if build_ref5() is None:
+            raise RuntimeError("oracle/_ref/liborb_ref5.so is not built and /root/reference is not present")
+        lib()
+        _ref5_lib = C.CDLL(_REF5_SO)
+        _ref5_lib.ref5_pose_optimization.restype = C.c_int
+        _ref5_lib.ref5_pose_optimization.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 3
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    pose = f32(pose7).copy()
+    hm, xw, xy = np.ascontiguousarray(has_mp, np.uint8), f32(world_pos), f32(kp_xy)
+    oc, ur, isg, c5 = np.ascontiguousarray(octave, np.int32), f32(uright), f32(inv_level_sigma2), f32(cam5)
+    N = len(hm)
+    out = np.zeros(max(N, 1), np.uint8)
+    inl = _ref5_lib.ref5_pose_optimization(N, _p(hm), _p(xw), _p(xy), _p(oc), _p(ur), _p(isg), len(isg), _p(c5), _p(pose), _p(out))
+    return dict(pose=pose, outlier=out[:N], inliers=inl)

@@ -79,3 +79,57 @@ def test_huber_kernel_with_its_float_member():
         for e in np.concatenate([rng.uniform(0, 30, 200), [float(np.float32(d * d)), float(np.float64(d) * np.float64(d)), 5.991, 7.815, 0.0]]):
             r, o = po.ref4_huber(e, d), po.huber(e, d)
             assert np.float64(r[0]).view(np.uint64) == np.float64(o[0]).view(np.uint64) and np.float64(r[1]).view(np.uint64) == np.float64(o[1]).view(np.uint64)
+
+
+# ---- Optimizer::PoseOptimization: the reference's own function (graph construction, four rounds, float chi2 classification, levels,
+# kernel removal, return value) over the oracle's PoseEngine, against orc_pose_optimization ------------------------------------------------
+def _quat(axis, ang):
+    a = np.asarray(axis, float)
+    a /= np.linalg.norm(a)
+    return np.concatenate([a * np.sin(ang / 2), [np.cos(ang / 2)]])
+
+
+def _qR(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+FX, FY, CX, CY, BF = 435.2, 435.2, 320.0, 240.0, 47.9
+
+
+def _frame(seed, N, mp_frac, mono_frac, outlier_frac, motion=1.0, noise=0.7):
+    rng = np.random.default_rng(seed)
+    Xc = np.stack([rng.uniform(-3, 3, N), rng.uniform(-2, 2, N), rng.uniform(2, 12, N)], 1)
+    qt, tt = _quat(rng.normal(size=3), 0.03 * motion), rng.normal(0, 0.05 * motion, 3)
+    Xw = ((Xc - tt) @ _qR(qt)).astype(np.float32)
+    u, v = FX * Xc[:, 0] / Xc[:, 2] + CX, FY * Xc[:, 1] / Xc[:, 2] + CY
+    xy = (np.stack([u, v], 1) + rng.normal(0, noise, (N, 2))).astype(np.float32)
+    ur = (u - BF / Xc[:, 2] + rng.normal(0, noise, N)).astype(np.float32)
+    ur[rng.random(N) < mono_frac] = -1
+    bad = rng.random(N) < outlier_frac
+    xy[bad] += rng.normal(0, 30, (int(bad.sum()), 2)).astype(np.float32)
+    octave = rng.integers(0, 8, N).astype(np.int32)
+    has_mp = (rng.random(N) < mp_frac).astype(np.uint8)
+    isg = (1.0 / (np.float32(1.2) ** np.arange(8, dtype=np.float32)) ** 2).astype(np.float32)
+    return dict(pose=np.array([0, 0, 0, 1, 0, 0, 0], np.float32), has_mp=has_mp, world_pos=Xw, kp_xy=xy, octave=octave, uright=ur, isg=isg)
+
+
+@pytest.mark.skipif(po.build_ref5() is None, reason="oracle/_ref part 5 not built and /root/reference absent")
+@pytest.mark.parametrize("seed,N,mp_frac,mono_frac,outlier_frac,motion", [(1, 1200, 0.5, 0.3, 0.15, 1.0), (2, 600, 0.9, 0.0, 0.05, 0.5), (3, 800, 0.4, 1.0, 0.2, 1.0),
+                                                                          (4, 60, 0.5, 0.2, 0.3, 2.0), (5, 30, 0.3, 0.5, 0.1, 1.0), (6, 12, 0.2, 0.5, 0.0, 1.0),
+                                                                          (7, 1500, 0.6, 0.3, 0.45, 3.0)])
+def test_pose_optimization_against_the_reference_function(seed, N, mp_frac, mono_frac, outlier_frac, motion):
+    f = _frame(seed, N, mp_frac, mono_frac, outlier_frac, motion)
+    cam5 = np.array([FX, FY, CX, CY, BF], np.float32)
+    r = po.ref5_pose_optimization(f["pose"], f["has_mp"], f["world_pos"], f["kp_xy"], f["octave"], f["uright"], f["isg"], cam5)
+    sel = np.nonzero(f["has_mp"])[0]                      # the oracle takes the correspondences: features with a map point, in order
+    obs = np.concatenate([f["kp_xy"][sel], f["uright"][sel, None]], 1)
+    o = po.pose_optimization(f["pose"], f["world_pos"][sel], obs, f["isg"][f["octave"][sel]], cam5)
+    assert r["inliers"] == o["inliers"]
+    assert (r["outlier"][sel] == o["outlier"]).all() and not r["outlier"][f["has_mp"] == 0].any()
+    if len(sel) >= 3:                                     # fewer: the function returns before it touches the pose
+        assert (r["pose"].view(np.uint32) == o["pose"].astype(np.float32).view(np.uint32)).all()   # SetPose takes the estimate as float
+    else:
+        assert r["inliers"] == 0
