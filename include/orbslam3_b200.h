@@ -565,8 +565,8 @@ orb_status orbp_update_normal_and_depth(orbx_handle* h, int32_t n_points, const 
  * VertexPose / VertexVelocity / VertexGyroBias / VertexAccBias per keyframe, marginalised VertexSBAPointXYZ, EdgeMono /
  * EdgeStereo (Huber sqrt(5.991) / sqrt(7.815)), EdgeInertial (+ optional Huber sqrt(16.92)), EdgeGyroRW, EdgeAccRW.
  *
- * STATUS: host-emulation-validated against the oracle (tests/test_liba_emul.py); NOT yet run on a GPU (round-1 GPU budget
- * was spent before this row).  The shim builds the window (Optimizer.cc:2217-2340) and fills these arrays:
+ * Device parity: tests/test_liba_gpu.py (same LM iterations / trials as the fp64 oracle, states to 1e-13); host emulation of the
+ * same source: tests/test_liba_emul.py.  The shim builds the window (Optimizer.cc:2217-2340) and fills these arrays:
  *   state[k]   Rwb (9, row-major) twb v bg ba of keyframe k  (ImuCamPose of VertexPose + the three additive vertices)
  *   fixed[k]   1 for the N+1-th keyframe and the covisible lFixedKeyFrames (all four vertices setFixed)
  *   links      one per consecutive pair with mpImuPreintegrated: float members of IMU::Preintegrated (dR dV dP JRg JVg JVa

@@ -118,6 +118,8 @@ class KeyFrame {
     const std::vector<float> mvInvLevelSigma2;
     GeometricCamera* mpCamera, *mpCamera2;
     const int NLeft, NRight;
+    Sophus::SE3f GetRelativePoseTrl();
+    const std::vector<cv::KeyPoint> mvKeysRight;
 //@end
     // mock state (tests/host only)
     Sophus::SE3f mock_Tcw;
@@ -130,7 +132,7 @@ class KeyFrame {
              const std::vector<float>& uRight, const std::vector<float>& invSigma2)
         : mnId(id), mnBALocalForKF(0), mnBAFixedForKF(0), fx(fx_), fy(fy_), cx(cx_), cy(cy_), invfx(1.f / fx_), invfy(1.f / fy_), mbf(bf_),
           mb(b_), mThDepth(0), mvKeys(keysUn), mvKeysUn(keysUn), mvuRight(uRight), mDescriptors(), mvInvLevelSigma2(invSigma2),
-          mpCamera(nullptr), mpCamera2(nullptr), NLeft(-1), NRight(-1) {}
+          mpCamera(nullptr), mpCamera2(nullptr), NLeft(-1), NRight(-1), mvKeysRight() {}
 };
 
 class Frame {

@@ -31,6 +31,7 @@ void KeyFrame::EraseMapPointMatch(MapPoint* pMP) {
 }
 std::vector<MapPoint*> KeyFrame::GetMapPointMatches() { return mock_matches; }
 bool KeyFrame::isBad() { return mock_bad; }
+Sophus::SE3f KeyFrame::GetRelativePoseTrl() { return Sophus::SE3f(); }   // two-camera rigs: not exercised
 Map* KeyFrame::GetMap() { return mock_map; }
 
 }  // namespace ORB_SLAM3
