@@ -53,6 +53,23 @@ def config_dict(cid, B, bps):
 
 
 # algorithmic bytes per IMAGE: read each input once, write each output once
+def issue_table(stage_ms, nimg, sm_mhz, counts):
+    """Second roofline of the extractor stages: executed warp instructions per clock per SM (counts from the committed ncu captures,
+    stage times and SM clock of THIS run) against the 4 per clock an SM can issue -- and against the 2.0 at which the multiply /
+    byte-permute instructions these kernels are made of issue (profiles/r02_idp_rate.txt).  Pure function: unit-tested on the CPU."""
+    out = {}
+    scale = nimg / float(counts["images_per_launch"])
+    for k, n in counts["warp_instructions_per_launch"].items():
+        ms = stage_ms.get(k)
+        if not ms or not sm_mhz:
+            continue
+        ipc = n * scale / (ms * 1e-3 * sm_mhz * 1e6 * counts["n_sms"])
+        out[k] = {"warp_inst_per_clk_per_sm": ipc, "frac_of_issue_peak_4": ipc / 4.0}
+    return {"stages": out, "peak_warp_inst_per_clk_per_sm": 4.0, "half_rate_pipe": 2.0,
+            "note": "IMAD / IDP / PRMT / SHF / VIMNMX3 issue at 2.0 per clock per SM, IADD3 and two-input packed min / max at 3.9 (measured)",
+            "source": counts.get("source")}
+
+
 def algorithmic_bytes(n_kp, n_cand, level_px):
     p_all = sum(level_px)
     pyramid = (p_all - level_px[-1]) + (p_all - level_px[0])
@@ -1026,6 +1043,11 @@ def main():
                     "note": "stage times from a serial eager pass (one stream) right after the timed region; the timed region itself replays "
                             "one graph per batch on the handles' streams.  FAST is bound by integer issue and shared-memory latency (profiles/), "
                             "not by HBM; see DESIGN.md"}
+        try:        # the integer-pipe roofline (see issue_table); never allowed to break the line
+            cnt = json.load(open(os.path.join(ROOT, "profiles", "r02_inst_counts.json")))
+            roofline["integer_issue"] = issue_table(ext, nimg, (clocks or {}).get("sm_mhz"), cnt)
+        except Exception:
+            roofline["integer_issue"] = None
         if isinstance(natural, dict) and "w" in natural:
             abn, extn, stn, gbn, frn = stage_table(natural["stage"], natural["serial"], natural["n_kp"], natural["n_cand"])
             roofline["real_texture_like_input"] = {

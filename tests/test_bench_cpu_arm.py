@@ -32,3 +32,15 @@ def test_threaded_drivers_run():
     r1, _ = bench.cpu_oracle_frames(pairs, 4)
     r2, _ = bench.cpu_reference_frames(pairs, 4)
     assert r1 > 0 and r2 > 0
+
+
+def test_issue_table_is_the_ratio_it_claims():
+    import json
+    cnt = json.load(open(os.path.join(ROOT, "profiles", "r02_inst_counts.json")))
+    t = bench.issue_table({"fast": 0.423, "blur": 0.264, "pyramid": 0.188, "orient_desc": 0.153, "quadtree": 0.25}, 128, 1965, cnt)
+    f = t["stages"]["fast"]["warp_inst_per_clk_per_sm"]
+    assert abs(f - 371081902 / (0.423e-3 * 1965e6 * 148)) < 1e-9 and 2.9 < f < 3.1
+    assert 1.9 < t["stages"]["blur"]["warp_inst_per_clk_per_sm"] < 2.1            # at the half-rate pipe's limit
+    assert "quadtree" not in t["stages"] and bench.issue_table({"fast": 0.4}, 128, None, cnt)["stages"] == {}
+    half = bench.issue_table({"fast": 0.423}, 64, 1965, cnt)["stages"]["fast"]["warp_inst_per_clk_per_sm"]
+    assert abs(half - f / 2) < 1e-9                                                # counts scale with the images of a launch
