@@ -470,7 +470,7 @@ ORB_HD uint64_t qt_order_key(int x, int y, const QtGeom& g) {
 // when the workspace capacity would be exceeded.
 // ---------------------------------------------------------------------------------------------
 // VARIANT 0: the ordered phase's std::sort by one thread (GPU-validated in round 1).  VARIANT 1: the same moves spread over the
-// CTA (quadtree_sort_par.cuh; CPU-validated, opt-in until its first device run).
+// CTA (quadtree_sort_par.cuh; host-emulated in tests/test_quadtree_emul.py; the default since its round-2 device run).
 template <int VARIANT>
 ORB_HD int qt_distribute_v(const uint32_t* arr, int n, const QtGeom& g, QtWork& w, uint32_t* out) {
     // roots (ORBextractor.cc:718-786): non-empty ones, in order

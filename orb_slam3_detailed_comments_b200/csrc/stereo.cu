@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(const __grid_con
     }
 }
 
-// Variant 1 (ORB_STEREO_VARIANT=1; CPU-validated through tests/host_emul, first device run pending): one THREAD per left keypoint,
+// Variant 1 (the default; ORB_STEREO_VARIANT=0 selects k_stereo_match; host-emulated in tests/host_emul, device parity in tests/test_zz_stereo_v1_gpu.py): one THREAD per left keypoint,
 // the right keypoints bucketed by image row once per CTA -- see stereo_core.cuh.  k_stereo_match above keeps its round-1 machine code.
 #define ST1_THREADS 128
 
