@@ -11,8 +11,14 @@ from orb_slam3_detailed_comments_b200 import synth
 
 pytestmark = pytest.mark.skipif(po.build_ref2() is None, reason="oracle/_ref part 2 not built and /root/reference absent")
 
-W, H = 640, 480
-FX, FY, CX, CY, BF, B = 435.2, 435.2, 320.0, 240.0, 47.9, 0.11
+import os
+
+if os.environ.get("ORB_PIN_GEOMETRY") == "720p":      # tests/test_oracle_vs_ref_matcher2_720p.py re-runs this file at BASELINE config 5's geometry
+    W, H, NFEAT = 1280, 720, 2000
+    FX, FY, CX, CY, BF, B = 870.4, 870.4, 640.0, 360.0, 95.7, 0.11
+else:
+    W, H, NFEAT = 640, 480, 1200
+    FX, FY, CX, CY, BF, B = 435.2, 435.2, 320.0, 240.0, 47.9, 0.11
 CAM6 = np.array([FX, FY, CX, CY, BF, B], np.float32)
 BOUNDS = np.array([0, W, 0, H], np.float32)
 
@@ -27,7 +33,7 @@ def two_frames():
     l, r, _ = synth.stereo_pair(W, H, seed=510)
     out = []
     for k in range(2):
-        eL, eR = po.OracleExtractor(1200, 1.2, 8, 20, 7), po.OracleExtractor(1200, 1.2, 8, 20, 7)
+        eL, eR = po.OracleExtractor(NFEAT, 1.2, 8, 20, 7), po.OracleExtractor(NFEAT, 1.2, 8, 20, 7)
         if k == 1:
             noise = rng.integers(-3, 4, (H, W))
             l = np.clip(np.roll(l, (4, 1), (1, 0)).astype(int) + noise, 0, 255).astype(np.uint8)
