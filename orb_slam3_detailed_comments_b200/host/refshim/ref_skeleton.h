@@ -118,9 +118,13 @@ class KeyFrame {
     const std::vector<float> mvInvLevelSigma2;
     GeometricCamera* mpCamera, *mpCamera2;
     const int NLeft, NRight;
+//@end
+#ifdef ORB_REFSHIM_REF_LBA   // only when the REFERENCE's own LocalBundleAdjustment is compiled over this skeleton (tests/host/build_lba_cpu.sh)
+//@ref KeyFrame.h
     Sophus::SE3f GetRelativePoseTrl();
     const std::vector<cv::KeyPoint> mvKeysRight;
 //@end
+#endif
     // mock state (tests/host only)
     Sophus::SE3f mock_Tcw;
     std::vector<KeyFrame*> mock_covisible;
@@ -132,7 +136,11 @@ class KeyFrame {
              const std::vector<float>& uRight, const std::vector<float>& invSigma2)
         : mnId(id), mnBALocalForKF(0), mnBAFixedForKF(0), fx(fx_), fy(fy_), cx(cx_), cy(cy_), invfx(1.f / fx_), invfy(1.f / fy_), mbf(bf_),
           mb(b_), mThDepth(0), mvKeys(keysUn), mvKeysUn(keysUn), mvuRight(uRight), mDescriptors(), mvInvLevelSigma2(invSigma2),
-          mpCamera(nullptr), mpCamera2(nullptr), NLeft(-1), NRight(-1), mvKeysRight() {}
+          mpCamera(nullptr), mpCamera2(nullptr), NLeft(-1), NRight(-1)
+#ifdef ORB_REFSHIM_REF_LBA
+          , mvKeysRight()
+#endif
+    {}
 };
 
 class Frame {

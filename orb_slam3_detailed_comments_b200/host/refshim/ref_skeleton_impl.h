@@ -31,7 +31,9 @@ void KeyFrame::EraseMapPointMatch(MapPoint* pMP) {
 }
 std::vector<MapPoint*> KeyFrame::GetMapPointMatches() { return mock_matches; }
 bool KeyFrame::isBad() { return mock_bad; }
+#ifdef ORB_REFSHIM_REF_LBA
 Sophus::SE3f KeyFrame::GetRelativePoseTrl() { return Sophus::SE3f(); }   // two-camera rigs: not exercised
+#endif
 Map* KeyFrame::GetMap() { return mock_map; }
 
 }  // namespace ORB_SLAM3

@@ -20,7 +20,7 @@ python3 "$X" "$G2O/optimization_algorithm_levenberg.cpp" "$T/_gen/g1.inc" "Optim
 python3 "$X" "$G2O/sparse_optimizer.cpp" "$T/_gen/g2.inc" "int SparseOptimizer::optimize(int iterations, bool online)"
 python3 "$X" "$G2O/robust_kernel_impl.cpp" "$T/_gen/g3.inc" "void RobustKernelHuber::setDelta(double delta)"
 cat "$T/_gen/g1.inc" "$T/_gen/g2.inc" "$T/_gen/g3.inc" > "$T/_gen/lba_g2o.inc"
-CXXF="-std=c++14 -O1 -Wall -Wno-unused-function -Wno-comment -Wno-unused-variable -Wno-unused-but-set-variable -include $H/refshim/ref_skeleton.h -I $H/refshim -I $REF/include -I $REF -I $ROOT/include -I $H -I $T"
+CXXF="-std=c++14 -O1 -DORB_REFSHIM_REF_LBA -Wall -Wno-unused-function -Wno-comment -Wno-unused-variable -Wno-unused-but-set-variable -include $H/refshim/ref_skeleton.h -I $H/refshim -I $REF/include -I $REF -I $ROOT/include -I $H -I $T"
 LD="-L $ROOT/oracle/_build -lorb_oracle -Wl,-rpath,$ROOT/oracle/_build -lpthread"
 g++ $CXXF "$T/lba_cpu.cc" "$H/Optimizer_lba_b200.cc" "$T/lba_stub.cc" $LD -o "$T/lba_cpu_mine"
 g++ $CXXF "$T/lba_cpu.cc" "$T/lba_ref.cc" $LD -o "$T/lba_cpu_ref"
