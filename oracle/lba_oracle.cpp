@@ -113,8 +113,16 @@ struct Problem {
     double deltaMono, deltaStereo, dsqrMono, dsqrStereo;
 };
 
-// residual of edge e at the current estimate; returns dimension (2 mono, 3 stereo)
-inline int edge_error(const Problem& P, int e, double r[3], double Xc[3]) {
+// The stereo projections divide as `const float invz = 1.0f/trans_xyz[2]` (types_six_dof_expmap.cpp:191, :340): the float literal is
+// promoted, the division is a DOUBLE division and its quotient is rounded to float.  The binary edge of LocalBundleAdjustment then
+// multiplies `bf*invz` with bf a `const float&` parameter -- a FLOAT product (:196) -- while the pose-only edge uses its double member
+// (:345), a double product.  g_stereo_form = 1 reproduces what the device kernels compute instead (float(z) first, a float division,
+// double products everywhere; csrc/lba.cu:105, csrc/poseopt.cu:62), so that the tests can bound what that costs
+// (tests/test_oracle_vs_ref_g2o.py::test_device_stereo_form_*).  Pinned against the reference source by oracle/_ref part 7.
+int g_stereo_form = 0;
+
+// residual of edge e at the current estimate; returns dimension (2 mono, 3 stereo).  unary: the pose-only edges of PoseOptimization
+inline int edge_error(const Problem& P, int e, double r[3], double Xc[3], bool unary = false) {
     se3_map(&P.pose[7 * P.ekf[e]], &P.point[3 * P.emp[e]], Xc);
     const double* z = &P.obs[3 * e];
     if (z[2] < 0) {  // mono: EdgeSE3ProjectXYZ::computeError, Pinhole::project(Vector3d)
@@ -123,11 +131,13 @@ inline int edge_error(const Problem& P, int e, double r[3], double Xc[3]) {
         r[2] = 0;
         return 2;
     }
-    const double invz = (double)(1.0f / (float)Xc[2]);  // `const float invz = 1.0f/trans_xyz[2]` (.cpp:191)
+    const float invzf = g_stereo_form ? 1.0f / (float)Xc[2] : (float)(1.0 / Xc[2]);
+    const double invz = (double)invzf;
     const double u = Xc[0] * invz * P.cam.fx + P.cam.cx;
     r[0] = z[0] - u;
     r[1] = z[1] - (Xc[1] * invz * P.cam.fy + P.cam.cy);
-    r[2] = z[2] - (u - P.cam.bf * invz);
+    const double disp = (unary || g_stereo_form) ? P.cam.bf * invz : (double)((float)P.cam.bf * invzf);
+    r[2] = z[2] - (u - disp);
     return 3;
 }
 
@@ -165,6 +175,22 @@ inline void edge_jacobians(const Cam& cam, int D, const double R[9], const doubl
             B[6 + c] = J[3] * S[c] + J[4] * S[6 + c] + J[5] * S[12 + c];
         }
     }
+}
+
+// the pose-only edges' Jacobian B = d r / d (omega, upsilon).  The stereo one is written with reciprocals
+// (EdgeStereoSE3ProjectXYZOnlyPose::linearizeOplus, types_six_dof_expmap.cpp:352-404: invz = 1.0/z, invz_2 = invz*invz), unlike the
+// binary edge's quotients; the monocular one is the binary edge's (OptimizableTypes.cpp:58-73).
+inline void pose_edge_jacobian(const Cam& cam, int D, const double R[9], const double Xc[3], double B[18]) {
+    if (D == 2 || g_stereo_form) {
+        double A[9];
+        edge_jacobians(cam, D, R, Xc, A, B);
+        return;
+    }
+    const double fx = cam.fx, fy = cam.fy, bf = cam.bf;
+    const double x = Xc[0], y = Xc[1], invz = 1.0 / Xc[2], invz_2 = invz * invz;
+    B[0] = x * y * invz_2 * fx; B[1] = -(1 + (x * x * invz_2)) * fx; B[2] = y * invz * fx; B[3] = -invz * fx; B[4] = 0; B[5] = x * invz_2 * fx;
+    B[6] = (1 + y * y * invz_2) * fy; B[7] = -x * y * invz_2 * fy; B[8] = -x * invz * fy; B[9] = 0; B[10] = -invz * fy; B[11] = y * invz_2 * fy;
+    B[12] = B[0] - bf * y * invz_2; B[13] = B[1] + bf * x * invz_2; B[14] = B[2]; B[15] = B[3]; B[16] = 0; B[17] = B[5] - bf * invz_2;
 }
 
 // dense LDL^T (no pivoting) of an n x n symmetric matrix given by its upper triangle (row-major full
@@ -539,6 +565,22 @@ int orc_edge_residual(const double* pose7, const double* X, const double* obs3, 
     double Xc[3];
     return edge_error(P, 0, r, Xc);
 }
+// the same for a pose-only edge (PoseOptimization), with its Jacobian B (D x 6)
+int orc_pose_edge(const double* pose7, const double* Xw, const double* obs3, const double* cam5, double* B18, double* r) {
+    Problem P;
+    P.pose.assign(pose7, pose7 + 7);
+    P.point.assign(Xw, Xw + 3);
+    static const int zero = 0;
+    P.ekf = &zero; P.emp = &zero; P.obs = obs3;
+    P.cam = {cam5[0], cam5[1], cam5[2], cam5[3], cam5[4]};
+    double Xc[3], R[9];
+    const int D = edge_error(P, 0, r, Xc, true);
+    quat_to_R(pose7, R);
+    for (int i = 0; i < 18; ++i) B18[i] = 0;
+    pose_edge_jacobian(P.cam, D, R, Xc, B18);
+    return D;
+}
+int orc_set_stereo_form(int device_form) { const int prev = g_stereo_form; g_stereo_form = device_form; return prev; }
 void orc_pose_oplus(double* pose7, const double* upd6) { pose_oplus(pose7, upd6); }
 void orc_edge_jacobians(const double* pose7, const double* X, int D, const double* cam5, double* A9, double* B18) {
     Cam cam = {cam5[0], cam5[1], cam5[2], cam5[3], cam5[4]};
@@ -586,7 +628,7 @@ struct PoseEngine {   // the one-vertex problem of PoseOptimization as g2o split
     }
     double edge_chi2(int e) {
         double r[3], Xc[3];
-        edge_error(P, e, r, Xc);
+        edge_error(P, e, r, Xc, true);
         return invs2[e] * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
     }
     double compute_errors() {                  // computeActiveErrors + activeRobustChi2
@@ -608,9 +650,9 @@ struct PoseEngine {   // the one-vertex problem of PoseOptimization as g2o split
         quat_to_R(P.pose.data(), R);
         for (int e = 0; e < n; ++e) {
             if (level[e]) continue;
-            double r[3], Xc[3], A[9] = {0}, B[18] = {0};
-            const int D = edge_error(P, e, r, Xc);
-            edge_jacobians(P.cam, D, R, Xc, A, B);
+            double r[3], Xc[3], B[18] = {0};
+            const int D = edge_error(P, e, r, Xc, true);
+            pose_edge_jacobian(P.cam, D, R, Xc, B);
             const double c2 = invs2[e] * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
             double w = 1.0;
             if (robust[e]) huber_rho(c2, D == 2 ? P.deltaMono : P.deltaStereo, D == 2 ? P.dsqrMono : P.dsqrStereo, &w);

@@ -382,6 +382,26 @@ def pose_optimization(pose7, Xw, obs, inv_sigma2, cam5):
                 lambda_=float(stats[3]))
 
 
+def set_stereo_form(device_form):
+    """0 (default): the stereo projections of the optimisers exactly as the reference's edges compute them (pinned bitwise against the
+    reference source, oracle/_ref part 7).  1: as the device kernels compute them (float(z) before a float division, double bf * invz,
+    the binary edge's quotient Jacobian for the pose-only edge) -- see oracle/lba_oracle.cpp g_stereo_form.  Returns the previous form."""
+    L = lib()
+    L.orc_set_stereo_form.restype = C.c_int
+    return int(L.orc_set_stereo_form(int(device_form)))
+
+
+def pose_edge(pose7, Xw, obs3, cam5):
+    """One pose-only edge (PoseOptimization): (D, B[D][6], r[D])."""
+    L = lib()
+    L.orc_pose_edge.restype = C.c_int
+    c = lambda a: np.ascontiguousarray(a, np.float64)
+    pose7, Xw, obs3, cam5 = c(pose7), c(Xw), c(obs3), c(cam5)
+    B, r = np.zeros(18), np.zeros(3)
+    D = L.orc_pose_edge(_p(pose7), _p(Xw), _p(obs3), _p(cam5), _p(B), _p(r))
+    return D, B.reshape(3, 6)[:D], r[:D]
+
+
 def is_in_frustum(Rcw, tcw, Ow, bounds, cam6, n_levels, log_scale_factor, xw, normal, max_dist, min_dist, viewing_cos_limit=0.5):
     """Frame::isInFrustum restated (Frame.cc:667-720).  Returns dict(in_view, proj_x, proj_y, proj_xr, level, view_cos, depth)."""
     L = lib()
@@ -1041,6 +1061,51 @@ def huber(e, delta):
 # ---- oracle/_ref part 5: the reference's own Optimizer::PoseOptimization over the oracle's PoseEngine (oracle/Makefile target ref5) ----
 _REF5_SO = os.path.join(_HERE, "_ref", "liborb_ref5.so")
 _ref5_lib = None
+
+
+_REF7_SO = os.path.join(_HERE, "_ref", "liborb_ref7.so")
+_ref7_lib = None
+
+
+def build_ref7(force=False):
+    """oracle/_ref part 7: the reprojection edges' own linearizeOplus / cam_project and Pinhole::projectJac / project, compiled verbatim."""
+    if os.path.exists(os.path.join(REFERENCE_ROOT, "src", "OptimizableTypes.cpp")):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref7", f"REF={REFERENCE_ROOT}"] + (["-B"] if force else []))
+    return _REF7_SO if os.path.exists(_REF7_SO) else None
+
+
+def ref7_edge(pose7, X, obs3, cam5, unary):
+    """The reference's own edge of LocalBundleAdjustment (unary False: EdgeSE3ProjectXYZ / EdgeStereoSE3ProjectXYZ) or PoseOptimization
+    (unary True: the ...OnlyPose edges); obs3[2] < 0 selects the monocular edge.  cam5 as float32, like the KeyFrame / Frame members the
+    Optimizer copies into the edge.  Returns (A[D][3] or None, B[D][6], r[D])."""
+    global _ref7_lib
+    if _ref7_lib is None:
+        if build_ref7() is None:
+            raise RuntimeError("oracle/_ref/liborb_ref7.so is not built and /root/reference is not present")
+        _ref7_lib = C.CDLL(_REF7_SO)
+    c = lambda a: np.ascontiguousarray(a, np.float64)
+    pose7, X, obs3 = c(pose7), c(X), c(obs3)
+    cam = np.ascontiguousarray(cam5, np.float32)
+    stereo = int(obs3[2] >= 0)
+    D = 3 if stereo else 2
+    A, B, r = np.zeros(9), np.zeros(18), np.zeros(3)
+    if unary:
+        _ref7_lib.ref7_pose_edge(_p(pose7), _p(X), _p(obs3), _p(cam), stereo, _p(B), _p(r))
+        return None, B[:6 * D].reshape(D, 6), r[:D]
+    _ref7_lib.ref7_edge(_p(pose7), _p(X), _p(obs3), _p(cam), stereo, _p(A), _p(B), _p(r))
+    return A[:3 * D].reshape(D, 3), B[:6 * D].reshape(D, 6), r[:D]
+
+
+def edge(pose7, X, obs3, cam5):
+    """The oracle's binary edge (LocalBundleAdjustment): (A[D][3], B[D][6], r[D])."""
+    L = lib()
+    L.orc_edge_residual.restype = C.c_int
+    c = lambda a: np.ascontiguousarray(a, np.float64)
+    pose7, X, obs3, cam5 = c(pose7), c(X), c(obs3), c(cam5)
+    A, B, r = np.zeros(9), np.zeros(18), np.zeros(3)
+    D = L.orc_edge_residual(_p(pose7), _p(X), _p(obs3), _p(cam5), _p(r))
+    L.orc_edge_jacobians(_p(pose7), _p(X), D, _p(cam5), _p(A), _p(B))
+    return A.reshape(3, 3)[:D], B.reshape(3, 6)[:D], r[:D]
 
 
 def build_ref5(force=False):

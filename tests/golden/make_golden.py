@@ -57,6 +57,12 @@ def main():
         out["lba_in_" + key] = pr[key]
     out["lba_pose"], out["lba_point"] = res["pose"], res["point"]
     out["lba_stats"] = np.array([res["iterations"], res["trials"], res["chi2_init"], res["chi2"], res["lambda_"]])
+    # the same problem with the stereo projection evaluated as the device kernels do (oracle/lba_oracle.cpp g_stereo_form): the vectors
+    # this file held before the oracle was pinned against the reference's own edges (tests/test_oracle_vs_ref_edges.py)
+    prev = po.set_stereo_form(1)
+    res = po.lba(pr["pose"], pr["fixed"], pr["point"], pr["edge_kf"], pr["edge_mp"], pr["obs"], pr["inv_sigma2"], pr["cam5"], 0.0, 10)
+    po.set_stereo_form(prev)
+    out["lba_pose_devform"], out["lba_point_devform"] = res["pose"], res["point"]
     # known-answer values derived independently of the oracle
     out["kat_umax"] = np.array([15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3], np.int32)
     out["kat_quota_1000"] = np.array([217, 181, 151, 126, 105, 87, 73, 60], np.int32)
