@@ -42,6 +42,44 @@ class Map;
 class Frame;
 class GeometricCamera;
 
+#ifdef ORB_REFSHIM_LIBA   // host/Optimizer_liba_b200.cc (LocalInertialBA) and the reference's own function next to it (tests/host/build_liba_cpu.sh)
+namespace IMU {
+class Bias {
+   public:
+//@ref ImuTypes.h
+    Bias():bax(0),bay(0),baz(0),bwx(0),bwy(0),bwz(0){}
+    Bias(const float &b_acc_x, const float &b_acc_y, const float &b_acc_z,
+            const float &b_ang_vel_x, const float &b_ang_vel_y, const float &b_ang_vel_z):
+            bax(b_acc_x), bay(b_acc_y), baz(b_acc_z), bwx(b_ang_vel_x), bwy(b_ang_vel_y), bwz(b_ang_vel_z){}
+    float bax, bay, baz;
+    float bwx, bwy, bwz;
+//@end
+};
+class Calib {
+   public:
+//@ref ImuTypes.h
+    Sophus::SE3<float> mTcb;
+    Sophus::SE3<float> mTbc;
+//@end
+};
+class Preintegrated {
+   public:
+//@ref ImuTypes.h
+    void SetNewBias(const Bias &bu_);
+    float dT;
+    Eigen::Matrix<float,15,15> C;
+    Bias b;
+    Eigen::Matrix3f dR;
+    Eigen::Vector3f dV, dP;
+    Eigen::Matrix3f JRg, JVg, JVa, JPg, JPa;
+//@end
+    // mock state (tests/host only)
+    Bias mock_bu;
+    int mock_bias_sets = 0;
+};
+}  // namespace IMU
+#endif
+
 class LoopClosing {
    public:
     typedef std::map<KeyFrame*, g2o::Sim3*> KeyFrameAndPose;   // placeholder: Optimizer.h names the type in signatures we do not implement
@@ -57,6 +95,12 @@ class Map {
     std::set<long unsigned int> msOptKFs;
     std::set<long unsigned int> msFixedKFs;
 //@end
+#ifdef ORB_REFSHIM_LIBA
+//@ref Map.h
+    long unsigned  KeyFramesInMap();
+//@end
+    long unsigned mock_n_keyframes = 0;
+#endif
     // mock state (tests/host only)
     long unsigned int mock_init_kf_id = 0;
     bool mock_inertial = false;
@@ -125,6 +169,28 @@ class KeyFrame {
     const std::vector<cv::KeyPoint> mvKeysRight;
 //@end
 #endif
+#ifdef ORB_REFSHIM_LIBA
+//@ref KeyFrame.h
+    void SetVelocity(const Eigen::Vector3f &Vw_);
+    Eigen::Vector3f GetImuPosition();
+    Eigen::Matrix3f GetImuRotation();
+    Eigen::Matrix3f GetRotation();
+    Eigen::Vector3f GetTranslation();
+    Eigen::Vector3f GetVelocity();
+    void SetNewBias(const IMU::Bias &b);
+    Eigen::Vector3f GetGyroBias();
+    Eigen::Vector3f GetAccBias();
+    IMU::Bias GetImuBias();
+    bool bImu;
+    KeyFrame* mPrevKF;
+    IMU::Preintegrated* mpImuPreintegrated;
+    IMU::Calib mImuCalib;
+//@end
+    // mock state (tests/host only): the body pose is kept next to the camera pose, as the reference keyframe does (SetPose updates both)
+    Eigen::Vector3f mock_vel;
+    IMU::Bias mock_bias;
+    int mock_vel_sets = 0, mock_bias_sets = 0;
+#endif
     // mock state (tests/host only)
     Sophus::SE3f mock_Tcw;
     std::vector<KeyFrame*> mock_covisible;
@@ -139,6 +205,9 @@ class KeyFrame {
           mpCamera(nullptr), mpCamera2(nullptr), NLeft(-1), NRight(-1)
 #ifdef ORB_REFSHIM_REF_LBA
           , mvKeysRight()
+#endif
+#ifdef ORB_REFSHIM_LIBA
+          , bImu(false), mPrevKF(nullptr), mpImuPreintegrated(nullptr)
 #endif
     {}
 };

@@ -35,5 +35,20 @@ bool KeyFrame::isBad() { return mock_bad; }
 Sophus::SE3f KeyFrame::GetRelativePoseTrl() { return Sophus::SE3f(); }   // two-camera rigs: not exercised
 #endif
 Map* KeyFrame::GetMap() { return mock_map; }
+#ifdef ORB_REFSHIM_LIBA
+long unsigned Map::KeyFramesInMap() { return mock_n_keyframes; }
+void IMU::Preintegrated::SetNewBias(const Bias& bu_) { mock_bu = bu_; ++mock_bias_sets; }
+void KeyFrame::SetVelocity(const Eigen::Vector3f& Vw_) { mock_vel = Vw_; ++mock_vel_sets; }
+Eigen::Matrix3f KeyFrame::GetRotation() { return mock_Tcw.rotationMatrix(); }
+Eigen::Vector3f KeyFrame::GetTranslation() { return mock_Tcw.translation(); }
+// KeyFrame::GetImuRotation / GetImuPosition (KeyFrame.cc:157-167): the rotation and translation of Twb = mTwc * mImuCalib.mTcb
+Eigen::Matrix3f KeyFrame::GetImuRotation() { return (mock_Tcw.inverse() * mImuCalib.mTcb).rotationMatrix(); }
+Eigen::Vector3f KeyFrame::GetImuPosition() { return (mock_Tcw.inverse() * mImuCalib.mTcb).translation(); }
+Eigen::Vector3f KeyFrame::GetVelocity() { return mock_vel; }
+void KeyFrame::SetNewBias(const IMU::Bias& b) { mock_bias = b; ++mock_bias_sets; }
+Eigen::Vector3f KeyFrame::GetGyroBias() { return Eigen::Vector3f(mock_bias.bwx, mock_bias.bwy, mock_bias.bwz); }
+Eigen::Vector3f KeyFrame::GetAccBias() { return Eigen::Vector3f(mock_bias.bax, mock_bias.bay, mock_bias.baz); }
+IMU::Bias KeyFrame::GetImuBias() { return mock_bias; }
+#endif
 
 }  // namespace ORB_SLAM3

@@ -232,7 +232,7 @@ def preintegrate(acc, gyr, dt, bias6=None, ng=1.7e-4, na=2.0e-3, ngw=1.9393e-5, 
     return dict(dR=dR, dV=dV, dP=dP, JRg=JRg, JVg=JVg, JVa=JVa, JPg=JPg, JPa=JPa, C=C, dT=float(dT), bias=b)
 
 
-def inertial_window(n_opt=10, n_cov_fixed=3, n_mp=2000, seed=0, noise=0.5, perturb=True, dt=0.25):
+def inertial_window(n_opt=10, n_cov_fixed=3, n_mp=2000, seed=0, noise=0.5, perturb=True, dt=0.25, keep_pre=False):
     """A synthetic Optimizer::LocalInertialBA window (Optimizer.cc:2217-2340): a temporal chain of n_opt optimisable keyframes
     plus the fixed keyframe before them (index 0), joined by inertial links preintegrated from synthetic 200 Hz IMU samples
     (preintegrate(), information matrices through liba_link_information), then n_cov_fixed fixed covisible keyframes without links; stereo / mono observations of n_mp points.  Returns the dict orb_slam3_detailed_comments_b200.InertialOptimizer takes
@@ -242,7 +242,7 @@ def inertial_window(n_opt=10, n_cov_fixed=3, n_mp=2000, seed=0, noise=0.5, pertu
     rng = np.random.default_rng(seed)
     G = np.array([0, 0, -float(np.float32(9.81))])
     n_chain = n_opt + 1
-    states, links = [], np.zeros(n_chain - 1, LIBA_LINK)
+    states, links, pres = [], np.zeros(n_chain - 1, LIBA_LINK), []
     R, p, v = _expm(rng.normal(0, 0.2, 3)), rng.normal(0, 1, 3), rng.normal(0, 0.3, 3)
     for k in range(n_chain):
         states.append(np.concatenate([R.reshape(-1), p, v, np.zeros(6)]))
@@ -257,6 +257,7 @@ def inertial_window(n_opt=10, n_cov_fixed=3, n_mp=2000, seed=0, noise=0.5, pertu
         gyr = w0 * (1 - tt) + w1 * tt
         acc = a0 * (1 - tt) + a1 * tt - (R.T @ G) * 0.97
         pre = preintegrate(acc, gyr, dt / n_s)
+        pres.append(pre)
         dT = pre["dT"]
         dR = pre["dR"].astype(np.float64)
         v2 = v + G * dT + R @ pre["dV"].astype(np.float64)
@@ -309,5 +310,8 @@ def inertial_window(n_opt=10, n_cov_fixed=3, n_mp=2000, seed=0, noise=0.5, pertu
             states[k, 15:18] += rng.normal(0, 1e-3, 3)
             states[k, 18:21] += rng.normal(0, 1e-2, 3)
         point += rng.normal(0, 0.03, point.shape)
-    return dict(state=states, fixed=fixed, point=point, edge_kf=ekf.astype(np.int32), edge_mp=emp.astype(np.int32), obs=obs,
-                inv_sigma2=inv_sigma2, links=links, Tcb=np.concatenate([Rcb.reshape(-1), tcb]), cam5=[FX, FY, CX, CY, BF])
+    out = dict(state=states, fixed=fixed, point=point, edge_kf=ekf.astype(np.int32), edge_mp=emp.astype(np.int32), obs=obs,
+               inv_sigma2=inv_sigma2, links=links, Tcb=np.concatenate([Rcb.reshape(-1), tcb]), cam5=[FX, FY, CX, CY, BF])
+    if keep_pre:
+        out["pre"] = pres       # the IMU::Preintegrated members behind links[k] (tests/test_host_liba_vs_ref.py builds a mock map from them)
+    return out
