@@ -130,6 +130,11 @@ class MapPoint {
     float mTrackViewCos, mTrackViewCosR;
     long unsigned int mnBALocalForKF;
 //@end
+#ifdef ORB_REFSHIM_POSE   // host/Optimizer_pose_b200.cc (PoseOptimization)
+//@ref MapPoint.h
+    static std::mutex mGlobalMutex;
+//@end
+#endif
     // mock state (tests/host only)
     Eigen::Vector3f mock_pos, mock_normal;
     std::map<KeyFrame*, std::tuple<int, int>> mock_obs;
@@ -242,6 +247,13 @@ class Frame {
     int Nleft, Nright;
     Sophus::SE3<float> mTcw;
 //@end
+#ifdef ORB_REFSHIM_POSE
+//@ref Frame.h
+    void SetPose(const Sophus::SE3<float> &Tcw);
+    vector<float> mvInvLevelSigma2;
+//@end
+    int mock_pose_sets = 0;
+#endif
     Frame() : mpORBextractorLeft(nullptr), mpORBextractorRight(nullptr), mbf(0), mb(0), N(0), mpCamera(nullptr), mpCamera2(nullptr), Nleft(-1), Nright(-1) {}
 };
 

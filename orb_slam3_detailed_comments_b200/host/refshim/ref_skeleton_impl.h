@@ -35,6 +35,10 @@ bool KeyFrame::isBad() { return mock_bad; }
 Sophus::SE3f KeyFrame::GetRelativePoseTrl() { return Sophus::SE3f(); }   // two-camera rigs: not exercised
 #endif
 Map* KeyFrame::GetMap() { return mock_map; }
+#ifdef ORB_REFSHIM_POSE
+std::mutex MapPoint::mGlobalMutex;
+void Frame::SetPose(const Sophus::SE3<float>& Tcw) { mTcw = Tcw; ++mock_pose_sets; }
+#endif
 #ifdef ORB_REFSHIM_LIBA
 long unsigned Map::KeyFramesInMap() { return mock_n_keyframes; }
 void IMU::Preintegrated::SetNewBias(const Bias& bu_) { mock_bu = bu_; ++mock_bias_sets; }
