@@ -31,6 +31,12 @@
 #include "ORBextractor.h"   // the reference's own header (it needs nothing but <opencv2/opencv.hpp>)
 
 namespace g2o { class Sim3; }
+#ifdef ORB_REFSHIM_BOW   // host/ORBmatcher_bow_b200.cc: Thirdparty/DBoW2/DBoW2/FeatureVector.h:23-27 is `class FeatureVector: public std::map<NodeId, std::vector<unsigned int> >`
+namespace DBoW2 {
+typedef unsigned int NodeId;
+class FeatureVector : public std::map<NodeId, std::vector<unsigned int> > {};
+}
+#endif
 
 using namespace std;   // the reference headers rely on it (ORBmatcher.h:64 `vector<pair<size_t, size_t> >`, Optimizer.h:64 `map<...>`)
 
@@ -174,6 +180,11 @@ class KeyFrame {
     const std::vector<cv::KeyPoint> mvKeysRight;
 //@end
 #endif
+#ifdef ORB_REFSHIM_BOW
+//@ref KeyFrame.h
+    DBoW2::FeatureVector mFeatVec;
+//@end
+#endif
 #ifdef ORB_REFSHIM_LIBA
 //@ref KeyFrame.h
     void SetVelocity(const Eigen::Vector3f &Vw_);
@@ -247,6 +258,11 @@ class Frame {
     int Nleft, Nright;
     Sophus::SE3<float> mTcw;
 //@end
+#ifdef ORB_REFSHIM_BOW
+//@ref Frame.h
+    DBoW2::FeatureVector mFeatVec;
+//@end
+#endif
 #ifdef ORB_REFSHIM_POSE
 //@ref Frame.h
     void SetPose(const Sophus::SE3<float> &Tcw);

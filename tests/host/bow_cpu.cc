@@ -1,0 +1,90 @@
+// tests/host/bow_cpu.cc -- TEST INFRASTRUCTURE (CPU tier): both ORBmatcher::SearchByBoW overloads (host/ORBmatcher_bow_b200.cc, the searches
+// answered by the oracle: bow_stub.cc) over a mock keyframe pair / frame read from raw arrays; tests/test_host_bow_vs_ref.py compares the
+// match vectors with those of the reference's own functions (oracle/_ref part 2).
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "ref_skeleton_impl.h"
+#include "ORBmatcher.h"
+#include "orbslam3_b200.h"
+
+using namespace ORB_SLAM3;
+extern "C" void bow_stub_set_frame(const orbx_keypoint* kps, const uint8_t* desc, int n);
+
+static std::string g_dir;
+template <typename T>
+static std::vector<T> rd(const std::string& name) {
+    std::ifstream f(g_dir + "/" + name, std::ios::binary);
+    if (!f) { std::fprintf(stderr, "missing input %s\n", name.c_str()); std::exit(2); }
+    f.seekg(0, std::ios::end);
+    const size_t n = (size_t)f.tellg();
+    f.seekg(0);
+    std::vector<T> v(n / sizeof(T));
+    f.read((char*)v.data(), (std::streamsize)(v.size() * sizeof(T)));
+    return v;
+}
+template <typename T>
+static void wr(const std::string& name, const std::vector<T>& v) {
+    std::ofstream f(g_dir + "/" + name, std::ios::binary);
+    f.write((const char*)v.data(), (std::streamsize)(v.size() * sizeof(T)));
+}
+static std::vector<cv::KeyPoint> keys_of(const std::vector<orbx_keypoint>& k) {
+    std::vector<cv::KeyPoint> o(k.size());
+    for (size_t i = 0; i < k.size(); ++i) { o[i].pt.x = k[i].x; o[i].pt.y = k[i].y; o[i].size = k[i].size; o[i].angle = k[i].angle; o[i].response = k[i].response; o[i].octave = k[i].octave; o[i].class_id = k[i].class_id; }
+    return o;
+}
+static void fill_featvec(DBoW2::FeatureVector& fv, const std::vector<int>& node) {
+    for (size_t i = 0; i < node.size(); ++i) if (node[i] >= 0) fv[(DBoW2::NodeId)node[i]].push_back((unsigned int)i);
+}
+
+struct MockKF {
+    std::vector<MapPoint> mps;
+    KeyFrame* kf;
+    MockKF(int id, const std::vector<orbx_keypoint>& k, const std::vector<uint8_t>& d, const std::vector<int>& node, const std::vector<uint8_t>& has, const std::vector<uint8_t>& bad)
+        : mps(k.size()) {
+        const int n = (int)k.size();
+        kf = new KeyFrame(id, 1, 1, 0, 0, 0, 0, keys_of(k), std::vector<float>(n, -1.f), std::vector<float>(8, 1.f));
+        cv::Mat D(n, 32, CV_8UC1);
+        std::memcpy(D.ptr(0), d.data(), (size_t)n * 32);
+        const_cast<cv::Mat&>(kf->mDescriptors) = D;
+        fill_featvec(kf->mFeatVec, node);
+        kf->mock_matches.assign(n, nullptr);
+        for (int i = 0; i < n; ++i) if (has[i]) { mps[i].mock_bad = bad[i] != 0; mps[i].mnId = 1000 * id + i; kf->mock_matches[i] = &mps[i]; }
+    }
+    int index_of(MapPoint* p) const { return p ? (int)(p - mps.data()) : -1; }
+};
+
+int main(int argc, char** argv) {
+    if (argc < 2) { std::fprintf(stderr, "usage: bow_cpu <dir>\n"); return 2; }
+    g_dir = argv[1];
+    auto k1 = rd<orbx_keypoint>("k1.kp"), k2 = rd<orbx_keypoint>("k2.kp");
+    auto d1 = rd<uint8_t>("d1.u8"), d2 = rd<uint8_t>("d2.u8");
+    auto n1 = rd<int>("node1.i32"), n2 = rd<int>("node2.i32");
+    auto has1 = rd<uint8_t>("has1.u8"), bad1 = rd<uint8_t>("bad1.u8"), has2 = rd<uint8_t>("has2.u8"), bad2 = rd<uint8_t>("bad2.u8");
+    auto par = rd<float>("params.f32");   // nnratio, check orientation
+    MockKF K1(1, k1, d1, n1, has1, bad1), K2(2, k2, d2, n2, has2, bad2);
+    ORBmatcher matcher(par[0], par[1] != 0);
+    // (a) keyframe 1 against the FRAME made of the second feature set
+    Frame F;
+    F.N = (int)k2.size();
+    int dummy_extractor = 0;
+    F.mpORBextractorLeft = reinterpret_cast<ORBextractor*>(&dummy_extractor);
+    F.mvKeys = keys_of(k2); F.mvKeysUn = F.mvKeys;
+    fill_featvec(F.mFeatVec, n2);
+    bow_stub_set_frame(k2.data(), d2.data(), (int)k2.size());
+    std::vector<MapPoint*> vpMatches(3, nullptr);     // the function resizes it
+    const int ra = matcher.SearchByBoW(K1.kf, F, vpMatches);
+    std::vector<int> fa(vpMatches.size());
+    for (size_t i = 0; i < vpMatches.size(); ++i) fa[i] = K1.index_of(vpMatches[i]);
+    // (b) keyframe 1 against keyframe 2
+    std::vector<MapPoint*> vp12;
+    const int rb = matcher.SearchByBoW(K1.kf, K2.kf, vp12);
+    std::vector<int> fb(vp12.size());
+    for (size_t i = 0; i < vp12.size(); ++i) fb[i] = K2.index_of(vp12[i]);
+    wr("out_frame_match.i32", fa); wr("out_kf_match.i32", fb); wr("out_ret.i32", std::vector<int>{ra, rb});
+    std::printf("bow_cpu ok\n");
+    return 0;
+}

@@ -61,6 +61,13 @@ def test_inertial_ba_unit(tmp_path):
     assert "U liba_solve" in syms and "U liba_link_information" in syms and "g2o" not in syms and "abort" not in syms
 
 
+def test_bow_search_unit(tmp_path):
+    syms = _compile(tmp_path, "ORBmatcher_bow_b200", "-DORB_REFSHIM_BOW")
+    assert re.search(r"T ORB_SLAM3::ORBmatcher::SearchByBoW\(ORB_SLAM3::KeyFrame\*, ORB_SLAM3::Frame&, std::vector<ORB_SLAM3::MapPoint\*.*>&\)", syms)
+    assert re.search(r"T ORB_SLAM3::ORBmatcher::SearchByBoW\(ORB_SLAM3::KeyFrame\*, ORB_SLAM3::KeyFrame\*, std::vector<ORB_SLAM3::MapPoint\*.*>&\)", syms)
+    assert "U orbm_search_bow" in syms and "U orbm_search_bow_keyframes" in syms and "abort" not in syms
+
+
 def test_pose_optimization_unit(tmp_path):
     syms = _compile(tmp_path, "Optimizer_pose_b200", "-DORB_REFSHIM_POSE")
     assert "T ORB_SLAM3::Optimizer::PoseOptimization(ORB_SLAM3::Frame*)" in syms
@@ -88,4 +95,4 @@ def test_skeleton_members_are_the_reference_declarations():
         if cur and _norm(line):
             assert _norm(line) in cache[cur], f"{cur}: no such declaration: {line.strip()}"
             checked += 1
-    assert checked >= 98
+    assert checked >= 100
