@@ -19,6 +19,7 @@
 // (any live extractor handle of the process), or on the one the frame overload saw last.
 static orbx_handle* g_keyframe_search_handle = nullptr;
 extern "C" void orb_b200_use_handle_for_keyframe_searches(orbx_handle* h) { g_keyframe_search_handle = h; }
+extern "C" orbx_handle* orb_b200_keyframe_search_handle(void) { return g_keyframe_search_handle; }   // SearchForTriangulation uses the same one
 
 namespace ORB_SLAM3 {
 

@@ -185,6 +185,12 @@ class KeyFrame {
     DBoW2::FeatureVector mFeatVec;
 //@end
 #endif
+#ifdef ORB_REFSHIM_TRI   // host/ORBmatcher_triangulation_b200.cc
+//@ref KeyFrame.h
+    Sophus::SE3f GetPoseInverse();
+    Eigen::Vector3f GetCameraCenter();
+//@end
+#endif
 #ifdef ORB_REFSHIM_LIBA
 //@ref KeyFrame.h
     void SetVelocity(const Eigen::Vector3f &Vw_);

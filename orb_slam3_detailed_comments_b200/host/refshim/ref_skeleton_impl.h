@@ -35,6 +35,10 @@ bool KeyFrame::isBad() { return mock_bad; }
 Sophus::SE3f KeyFrame::GetRelativePoseTrl() { return Sophus::SE3f(); }   // two-camera rigs: not exercised
 #endif
 Map* KeyFrame::GetMap() { return mock_map; }
+#ifdef ORB_REFSHIM_TRI
+Sophus::SE3f KeyFrame::GetPoseInverse() { return mock_Tcw.inverse(); }
+Eigen::Vector3f KeyFrame::GetCameraCenter() { return mock_Tcw.inverse().translation(); }
+#endif
 #ifdef ORB_REFSHIM_POSE
 std::mutex MapPoint::mGlobalMutex;
 void Frame::SetPose(const Sophus::SE3<float>& Tcw) { mTcw = Tcw; ++mock_pose_sets; }

@@ -37,6 +37,17 @@ class SE3 {
     Eigen::Quaternion<T> q_;
     Eigen::Matrix<T, 3, 1> t_;
 };
+#ifdef ORB_REFSHIM_TRI
+template <typename T>
+struct SO3 {
+    static Eigen::Matrix<T, 3, 3> hat(const Eigen::Matrix<T, 3, 1>& w) {   // so3.hpp: [0 -c b; c 0 -a; -b a 0]
+        Eigen::Matrix<T, 3, 3> m;
+        m(0, 1) = -w(2); m(0, 2) = w(1); m(1, 0) = w(2); m(1, 2) = -w(0); m(2, 0) = -w(1); m(2, 1) = w(0);
+        return m;
+    }
+};
+typedef SO3<float> SO3f;
+#endif
 typedef SE3<float> SE3f;
 typedef SE3<double> SE3d;
 

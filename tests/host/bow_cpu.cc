@@ -43,10 +43,12 @@ static void fill_featvec(DBoW2::FeatureVector& fv, const std::vector<int>& node)
 struct MockKF {
     std::vector<MapPoint> mps;
     KeyFrame* kf;
-    MockKF(int id, const std::vector<orbx_keypoint>& k, const std::vector<uint8_t>& d, const std::vector<int>& node, const std::vector<uint8_t>& has, const std::vector<uint8_t>& bad)
+    MockKF(int id, const std::vector<orbx_keypoint>& k, const std::vector<uint8_t>& d, const std::vector<int>& node, const std::vector<uint8_t>& has, const std::vector<uint8_t>& bad,
+           const std::vector<float>& ur, const std::vector<float>& cam4, const float* T7)
         : mps(k.size()) {
         const int n = (int)k.size();
-        kf = new KeyFrame(id, 1, 1, 0, 0, 0, 0, keys_of(k), std::vector<float>(n, -1.f), std::vector<float>(8, 1.f));
+        kf = new KeyFrame(id, cam4[0], cam4[1], cam4[2], cam4[3], 0, 0, keys_of(k), ur, std::vector<float>(8, 1.f));
+        kf->mock_Tcw = Sophus::SE3f(Eigen::Quaternionf(T7[3], T7[0], T7[1], T7[2]), Eigen::Vector3f(T7[4], T7[5], T7[6]));
         cv::Mat D(n, 32, CV_8UC1);
         std::memcpy(D.ptr(0), d.data(), (size_t)n * 32);
         const_cast<cv::Mat&>(kf->mDescriptors) = D;
@@ -64,8 +66,10 @@ int main(int argc, char** argv) {
     auto d1 = rd<uint8_t>("d1.u8"), d2 = rd<uint8_t>("d2.u8");
     auto n1 = rd<int>("node1.i32"), n2 = rd<int>("node2.i32");
     auto has1 = rd<uint8_t>("has1.u8"), bad1 = rd<uint8_t>("bad1.u8"), has2 = rd<uint8_t>("has2.u8"), bad2 = rd<uint8_t>("bad2.u8");
-    auto par = rd<float>("params.f32");   // nnratio, check orientation
-    MockKF K1(1, k1, d1, n1, has1, bad1), K2(2, k2, d2, n2, has2, bad2);
+    auto par = rd<float>("params.f32");   // nnratio, check orientation, only stereo, coarse, cam4, T1w (7), T2w (7)
+    auto u1 = rd<float>("ur1.f32"), u2 = rd<float>("ur2.f32");
+    const std::vector<float> cam4(par.begin() + 4, par.begin() + 8);
+    MockKF K1(1, k1, d1, n1, has1, bad1, u1, cam4, &par[8]), K2(2, k2, d2, n2, has2, bad2, u2, cam4, &par[15]);
     ORBmatcher matcher(par[0], par[1] != 0);
     // (a) keyframe 1 against the FRAME made of the second feature set
     Frame F;
@@ -84,6 +88,18 @@ int main(int argc, char** argv) {
     const int rb = matcher.SearchByBoW(K1.kf, K2.kf, vp12);
     std::vector<int> fb(vp12.size());
     for (size_t i = 0; i < vp12.size(); ++i) fb[i] = K2.index_of(vp12[i]);
+    // (c) SearchForTriangulation between the two keyframes, with its own sets of features that already hold a map point
+    {
+        auto th1 = rd<uint8_t>("tri_has1.u8"), th2 = rd<uint8_t>("tri_has2.u8");
+        for (size_t i = 0; i < th1.size(); ++i) K1.kf->mock_matches[i] = th1[i] ? &K1.mps[i] : nullptr;
+        for (size_t i = 0; i < th2.size(); ++i) K2.kf->mock_matches[i] = th2[i] ? &K2.mps[i] : nullptr;
+    }
+    std::vector<std::pair<size_t, size_t> > pairs(2, std::make_pair((size_t)7, (size_t)7));   // the function clears it
+    const int rc = matcher.SearchForTriangulation(K1.kf, K2.kf, pairs, par[2] != 0, par[3] != 0);
+    std::vector<int> fc;
+    for (size_t i = 0; i < pairs.size(); ++i) { fc.push_back((int)pairs[i].first); fc.push_back((int)pairs[i].second); }
+    fc.push_back(rc);
+    wr("out_tri_pairs.i32", fc);
     wr("out_frame_match.i32", fa); wr("out_kf_match.i32", fb); wr("out_ret.i32", std::vector<int>{ra, rb});
     std::printf("bow_cpu ok\n");
     return 0;

@@ -12,6 +12,10 @@ extern "C" int orc_search_bow(const orbx_keypoint* kps, const uint8_t* desc, con
 extern "C" int orc_search_bow_kf(const orbx_keypoint* kp2, const uint8_t* desc2, const int* node2, const uint8_t* valid2, int n2, int nq, const int* qnode,
                                  const float* qangle, const uint8_t* desc1, float nnratio, int checkOri, int* match12);
 
+extern "C" int orc_search_triangulation(int nq, const orbx_keypoint* kp1, const uint8_t* desc1, const int* node1, const uint8_t* stereo1, int N2,
+                                        const orbx_keypoint* kp2, const uint8_t* desc2, const int* node2, const uint8_t* valid2, const uint8_t* stereo2,
+                                        const float* F12, const float* ep2, const float* scaleFactors, const float* sigma2, int bCoarse, int checkOri, int* match12);
+
 static std::vector<orbx_keypoint> g_kps;
 static std::vector<uint8_t> g_desc;
 
@@ -25,6 +29,14 @@ orb_status orbm_search_bow(orbx_handle*, const orbm_bow_queries* q, float nnrati
     if (q->n_frames != 1 || q->on_device || q->frame_image[0] != 0) return ORB_ERR_INVALID;
     const int nq = q->query_offset[1] - q->query_offset[0];
     nm[0] = orc_search_bow(g_kps.data(), g_desc.data(), q->feature_node, (int)g_kps.size(), nq, q->query_node, q->query_angle, q->desc, nnratio, check, fm);
+    return ORB_OK;
+}
+orb_status orbm_search_triangulation(orbx_handle*, const orbm_triangulation* t, int32_t* m12, int32_t* nm) {
+    float sf[8], s2[8];                    // the handle's level tables: scaleFactor 1.2, 8 levels (ORBextractor.cc:484-494)
+    sf[0] = 1.0f; s2[0] = 1.0f;
+    for (int i = 1; i < 8; ++i) { sf[i] = (float)(sf[i - 1] * 1.2f); s2[i] = sf[i] * sf[i]; }
+    nm[0] = orc_search_triangulation(t->n_queries, t->kp1, t->desc1, t->node1, t->stereo1, t->n2, t->kp2, t->desc2, t->node2, t->valid2, t->stereo2, t->F12,
+                                     t->epipole2, sf, s2, t->coarse, t->check_orientation, m12);
     return ORB_OK;
 }
 orb_status orbm_search_bow_keyframes(orbx_handle*, const orbm_bow_kf_queries* q, float nnratio, int32_t check, int32_t* m12, int32_t* nm) {

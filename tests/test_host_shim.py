@@ -68,6 +68,12 @@ def test_bow_search_unit(tmp_path):
     assert "U orbm_search_bow" in syms and "U orbm_search_bow_keyframes" in syms and "abort" not in syms
 
 
+def test_triangulation_search_unit(tmp_path):
+    syms = _compile(tmp_path, "ORBmatcher_triangulation_b200", "-DORB_REFSHIM_BOW", "-DORB_REFSHIM_TRI")
+    assert re.search(r"T ORB_SLAM3::ORBmatcher::SearchForTriangulation\(ORB_SLAM3::KeyFrame\*, ORB_SLAM3::KeyFrame\*, std::vector<std::pair<unsigned long, unsigned long>.*>&, bool, bool\)", syms)
+    assert "U orbm_search_triangulation" in syms and "abort" not in syms
+
+
 def test_pose_optimization_unit(tmp_path):
     syms = _compile(tmp_path, "Optimizer_pose_b200", "-DORB_REFSHIM_POSE")
     assert "T ORB_SLAM3::Optimizer::PoseOptimization(ORB_SLAM3::Frame*)" in syms
@@ -95,4 +101,4 @@ def test_skeleton_members_are_the_reference_declarations():
         if cur and _norm(line):
             assert _norm(line) in cache[cur], f"{cur}: no such declaration: {line.strip()}"
             checked += 1
-    assert checked >= 100
+    assert checked >= 102
