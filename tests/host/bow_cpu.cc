@@ -100,6 +100,28 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < pairs.size(); ++i) { fc.push_back((int)pairs[i].first); fc.push_back((int)pairs[i].second); }
     fc.push_back(rc);
     wr("out_tri_pairs.i32", fc);
+    // (d) SearchForInitialization: the first feature set as the reference frame, the second as the current frame -- once resident
+    //     (the registered frame), once from its own arrays (another frame is "on the device")
+    auto bounds = rd<float>("bounds.f32");
+    Frame::mnMinX = bounds[0]; Frame::mnMaxX = bounds[1]; Frame::mnMinY = bounds[2]; Frame::mnMaxY = bounds[3];
+    Frame F1;
+    F1.N = (int)k1.size(); F1.mvKeys = keys_of(k1); F1.mvKeysUn = F1.mvKeys;
+    cv::Mat D1((int)k1.size(), 32, CV_8UC1), D2((int)k2.size(), 32, CV_8UC1);
+    std::memcpy(D1.ptr(0), d1.data(), d1.size()); std::memcpy(D2.ptr(0), d2.data(), d2.size());
+    F1.mDescriptors = D1; F.mDescriptors = D2;
+    std::vector<int> init_out;
+    std::vector<float> prev_out;
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) bow_stub_set_frame(k1.data(), d1.data(), 7);        // something else is resident now
+        std::vector<cv::Point2f> prev(k1.size());
+        for (size_t i = 0; i < k1.size(); ++i) prev[i] = F1.mvKeysUn[i].pt;
+        std::vector<int> m12;
+        const int rd_ = matcher.SearchForInitialization(F1, F, prev, m12, (int)par[22]);
+        init_out.insert(init_out.end(), m12.begin(), m12.end());
+        init_out.push_back(rd_);
+        for (size_t i = 0; i < prev.size(); ++i) { prev_out.push_back(prev[i].x); prev_out.push_back(prev[i].y); }
+    }
+    wr("out_init.i32", init_out); wr("out_init_prev.f32", prev_out);
     wr("out_frame_match.i32", fa); wr("out_kf_match.i32", fb); wr("out_ret.i32", std::vector<int>{ra, rb});
     std::printf("bow_cpu ok\n");
     return 0;

@@ -16,6 +16,9 @@ extern "C" int orc_search_triangulation(int nq, const orbx_keypoint* kp1, const 
                                         const orbx_keypoint* kp2, const uint8_t* desc2, const int* node2, const uint8_t* valid2, const uint8_t* stereo2,
                                         const float* F12, const float* ep2, const float* scaleFactors, const float* sigma2, int bCoarse, int checkOri, int* match12);
 
+extern "C" int orc_search_initialization(const orbx_keypoint* kp1, const uint8_t* desc1, int n1, const float* prevMatched, const orbx_keypoint* kp2,
+                                         const uint8_t* desc2, int n2, const float* bounds4, int windowSize, float nnratio, int checkOri, int* matches12);
+
 static std::vector<orbx_keypoint> g_kps;
 static std::vector<uint8_t> g_desc;
 
@@ -29,6 +32,15 @@ orb_status orbm_search_bow(orbx_handle*, const orbm_bow_queries* q, float nnrati
     if (q->n_frames != 1 || q->on_device || q->frame_image[0] != 0) return ORB_ERR_INVALID;
     const int nq = q->query_offset[1] - q->query_offset[0];
     nm[0] = orc_search_bow(g_kps.data(), g_desc.data(), q->feature_node, (int)g_kps.size(), nq, q->query_node, q->query_angle, q->desc, nnratio, check, fm);
+    return ORB_OK;
+}
+orb_status orbm_search_initialization(orbx_handle*, const orbm_camera* cam, const orbm_init_queries* q, int32_t window, float nnratio, int32_t check, int32_t* m12,
+                                      int32_t* nm) {
+    const float bounds[4] = {cam->min_x, cam->max_x, cam->min_y, cam->max_y};
+    const bool resident = q->kp2 == nullptr;      // the registered frame plays the image on the device
+    if (resident && q->target_image != 0) return ORB_ERR_INVALID;
+    nm[0] = orc_search_initialization(q->kp1, q->desc1, q->n1, q->prev_matched, resident ? g_kps.data() : q->kp2, resident ? g_desc.data() : q->desc2,
+                                      resident ? (int)g_kps.size() : q->n2, bounds, window, nnratio, check, m12);
     return ORB_OK;
 }
 orb_status orbm_search_triangulation(orbx_handle*, const orbm_triangulation* t, int32_t* m12, int32_t* nm) {

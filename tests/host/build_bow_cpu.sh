@@ -10,5 +10,5 @@ T="$ROOT/tests/host"
 [ -f "$REF/include/ORBmatcher.h" ] || { echo "reference checkout not present: $REF" >&2; exit 3; }
 make -C "$ROOT/oracle" -s
 g++ -std=c++14 -O1 -DORB_REFSHIM_BOW -DORB_REFSHIM_TRI -Wall -Wno-unused-function -Wno-comment -include "$H/refshim/ref_skeleton.h" -I "$H/refshim" -I "$REF/include" -I "$REF" \
-    -I "$ROOT/include" -I "$H" "$T/bow_cpu.cc" "$H/ORBmatcher_bow_b200.cc" "$H/ORBmatcher_triangulation_b200.cc" "$T/bow_stub.cc" "$T/bow_ctor.cc" -L "$ROOT/oracle/_build" -lorb_oracle \
+    -I "$ROOT/include" -I "$H" "$T/bow_cpu.cc" "$H/ORBmatcher_bow_b200.cc" "$H/ORBmatcher_triangulation_b200.cc" "$H/ORBmatcher_init_b200.cc" "$T/bow_stub.cc" "$T/bow_ctor.cc" -L "$ROOT/oracle/_build" -lorb_oracle \
     -Wl,-rpath,"$ROOT/oracle/_build" -lpthread -o "$T/bow_cpu_mine"

@@ -49,7 +49,8 @@ def test_both_overloads_equal_the_reference_functions(tmp_path, two_frames, nnra
     only_stereo, coarse = seed == 2, seed == 3
     T1, T2 = _m._quat_pose(0.0, [0, 0, 0]), _m._quat_pose(0.4, [-0.03, -0.002, -0.01])
     ur1, ur2 = (u1, u2) if seed != 1 else (np.full(len(k1), -1, np.float32), np.full(len(k2), -1, np.float32))
-    np.concatenate([np.float32([nnratio, 1.0 if check else 0.0, float(only_stereo), float(coarse)]), _m.CAM6[:4], np.float32(T1), np.float32(T2)]).astype(np.float32).tofile(os.path.join(d, "params.f32"))
+    np.concatenate([np.float32([nnratio, 1.0 if check else 0.0, float(only_stereo), float(coarse)]), _m.CAM6[:4], np.float32(T1), np.float32(T2), np.float32([100 if seed != 2 else 30])]).astype(np.float32).tofile(os.path.join(d, "params.f32"))
+    _m.BOUNDS.astype(np.float32).tofile(os.path.join(d, "bounds.f32"))
     tri1, tri2 = rng.random(len(k1)) < 0.4, rng.random(len(k2)) < 0.3
     tri1.astype(np.uint8).tofile(os.path.join(d, "tri_has1.u8")); tri2.astype(np.uint8).tofile(os.path.join(d, "tri_has2.u8"))
     np.ascontiguousarray(ur1, np.float32).tofile(os.path.join(d, "ur1.f32")); np.ascontiguousarray(ur2, np.float32).tofile(os.path.join(d, "ur2.f32"))
@@ -75,3 +76,13 @@ def test_both_overloads_equal_the_reference_functions(tmp_path, two_frames, nnra
     want = np.stack([np.nonzero(wm >= 0)[0], wm[wm >= 0]], 1)
     assert rc == wn and pairs.shape == want.shape and (pairs == want).all()
     assert wn > (3 if not coarse else 40)
+    # SearchForInitialization, the current frame once resident on the "device", once uploaded from its own arrays
+    window = 100 if seed != 2 else 30
+    F1i, F2i = po.RefFrame(k1, d1, None, _m.BOUNDS, sf, _m.CAM6), po.RefFrame(k2, d2, None, _m.BOUNDS, sf, _m.CAM6)
+    prev0 = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    im, inn, iprev = po.ref2_search_initialization(F1i, F2i, prev0, window, nnratio, check)
+    got = np.fromfile(os.path.join(d, "out_init.i32"), np.int32).reshape(2, len(k1) + 1)
+    gprev = np.fromfile(os.path.join(d, "out_init_prev.f32"), np.float32).reshape(2, len(k1), 2)
+    for p in range(2):
+        assert got[p, -1] == inn and (got[p, :-1] == im).all() and (gprev[p] == iprev).all()
+    assert inn > 50

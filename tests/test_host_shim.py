@@ -74,6 +74,12 @@ def test_triangulation_search_unit(tmp_path):
     assert "U orbm_search_triangulation" in syms and "abort" not in syms
 
 
+def test_initialization_search_unit(tmp_path):
+    syms = _compile(tmp_path, "ORBmatcher_init_b200")
+    assert re.search(r"T ORB_SLAM3::ORBmatcher::SearchForInitialization\(ORB_SLAM3::Frame&, ORB_SLAM3::Frame&, std::vector<cv::Point_<float>.*>&, std::vector<int.*>&, int\)", syms)
+    assert "U orbm_search_initialization" in syms and "abort" not in syms
+
+
 def test_pose_optimization_unit(tmp_path):
     syms = _compile(tmp_path, "Optimizer_pose_b200", "-DORB_REFSHIM_POSE")
     assert "T ORB_SLAM3::Optimizer::PoseOptimization(ORB_SLAM3::Frame*)" in syms
