@@ -75,6 +75,13 @@ def cases():
     r = po.pose_optimization(np.array([0, 0, 0, 1, 0, 0, 0], np.float32), pts, obs, isg[kL["octave"][sel]], np.float32([FX, FY, CX, CY, BF]))
     out["po_pose"], out["po_outlier"], out["po_stats"] = r["pose"], r["outlier"], np.int32([r["inliers"], r["rounds"], r["iterations"], r["trials"]])
     out["po_obs"] = obs
+    # the same frame with the stereo projection evaluated as the device kernels do (oracle/lba_oracle.cpp g_stereo_form): what this file held
+    # before the oracle was pinned against the reference's own edges (tests/test_oracle_vs_ref_edges.py)
+    prev = po.set_stereo_form(1)
+    r = po.pose_optimization(np.array([0, 0, 0, 1, 0, 0, 0], np.float32), pts, obs, isg[kL["octave"][sel]], np.float32([FX, FY, CX, CY, BF]))
+    po.set_stereo_form(prev)
+    out["po_pose_devform"], out["po_outlier_devform"] = r["pose"], r["outlier"]
+    out["po_stats_devform"] = np.int32([r["inliers"], r["rounds"], r["iterations"], r["trials"]])
     f = po.is_in_frustum(np.eye(3, dtype=np.float32), T[4:], Ow, bounds, cam6, 8, logsf, pts, nrm, maxd, mind)
     for k, v in f.items():
         out["fr_" + k] = v

@@ -79,6 +79,10 @@ def test_device_form_is_the_round_1_oracle():
         po.set_stereo_form(prev)
     assert (_bits(r["pose"]) == _bits(G["lba_pose_devform"])).all() and (_bits(r["point"]) == _bits(G["lba_point_devform"])).all()
     assert prev == 0 and po.set_stereo_form(0) == 0
+    G2 = np.load(os.path.join(HERE, "golden", "golden_v2.npz"))          # ... and the pose optimisation of golden_v2 likewise
+    assert not (_bits(G2["po_pose"]) == _bits(G2["po_pose_devform"])).all()
+    assert (G2["po_outlier"] == G2["po_outlier_devform"]).all() and (G2["po_stats"][:2] == G2["po_stats_devform"][:2]).all()
+    assert np.abs(G2["po_pose"] - G2["po_pose_devform"]).max() < 2e-6
 
 
 def _both_forms(fn):
