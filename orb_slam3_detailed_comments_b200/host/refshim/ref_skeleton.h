@@ -31,11 +31,47 @@
 #include "ORBextractor.h"   // the reference's own header (it needs nothing but <opencv2/opencv.hpp>)
 
 namespace g2o { class Sim3; }
+#ifdef ORB_REFSHIM_VOC   // host/Frame_bow_b200.cc: what Thirdparty/DBoW2/DBoW2/{BowVector.h, FeatureVector.h, TemplatedVocabulary.h} declare, as far as
+#define ORB_REFSHIM_BOW   // Frame::ComputeBoW and the flattening of the vocabulary touch it (the nodes are PROTECTED members there too)
+namespace DBoW2 {
+typedef unsigned int WordId;
+typedef double WordValue;
+class BowVector : public std::map<WordId, WordValue> {};
+}
+#endif
 #ifdef ORB_REFSHIM_BOW   // host/ORBmatcher_bow_b200.cc: Thirdparty/DBoW2/DBoW2/FeatureVector.h:23-27 is `class FeatureVector: public std::map<NodeId, std::vector<unsigned int> >`
 namespace DBoW2 {
 typedef unsigned int NodeId;
-class FeatureVector : public std::map<NodeId, std::vector<unsigned int> > {};
+class FeatureVector : public std::map<NodeId, std::vector<unsigned int> > {
+   public:
+    void addFeature(NodeId id, unsigned int i_feature) { (*this)[id].push_back(i_feature); }   // FeatureVector.cpp:27-41
+};
 }
+#endif
+#ifdef ORB_REFSHIM_VOC
+namespace DBoW2 {
+template <class TDescriptor, class F>
+class TemplatedVocabulary {   // TemplatedVocabulary.h:297-329 (Node), :408-427 (the protected members)
+   public:
+    struct Node {
+        NodeId id;
+        WordValue weight;
+        std::vector<NodeId> children;
+        NodeId parent;
+        TDescriptor descriptor;
+        WordId word_id;
+        Node() : id(0), weight(0), parent(0), word_id(0) {}
+        inline bool isLeaf() const { return children.empty(); }
+    };
+    void mock_set(int L, const std::vector<Node>& nodes) { m_L = L; m_nodes = nodes; }
+   protected:
+    int m_k = 0;
+    int m_L = 0;
+    std::vector<Node> m_nodes;
+};
+struct FORB { typedef cv::Mat TDescriptor; };
+}
+namespace ORB_SLAM3 { typedef DBoW2::TemplatedVocabulary<DBoW2::FORB::TDescriptor, DBoW2::FORB> ORBVocabulary; }   // include/ORBVocabulary.h:30-31
 #endif
 
 using namespace std;   // the reference headers rely on it (ORBmatcher.h:64 `vector<pair<size_t, size_t> >`, Optimizer.h:64 `map<...>`)
@@ -267,6 +303,13 @@ class Frame {
 #ifdef ORB_REFSHIM_BOW
 //@ref Frame.h
     DBoW2::FeatureVector mFeatVec;
+//@end
+#endif
+#ifdef ORB_REFSHIM_VOC
+//@ref Frame.h
+    void ComputeBoW();
+    ORBVocabulary* mpORBvocabulary;
+    DBoW2::BowVector mBowVec;
 //@end
 #endif
 #ifdef ORB_REFSHIM_POSE

@@ -80,6 +80,17 @@ def test_initialization_search_unit(tmp_path):
     assert "U orbm_search_initialization" in syms and "abort" not in syms
 
 
+def test_compute_bow_unit_and_its_vocabulary_access(tmp_path):
+    """Frame_bow_b200.cc against the skeleton (with a mock vocabulary whose nodes are protected, as in DBoW2), and the same access pattern
+    against the reference's REAL DBoW2 headers (over the boost / OpenCV miniatures of oracle/ref_shim)."""
+    syms = _compile(tmp_path, "Frame_bow_b200", "-DORB_REFSHIM_VOC")
+    assert "T ORB_SLAM3::Frame::ComputeBoW()" in syms and "U orbv_transform" in syms and "U orbv_create" in syms and "abort" not in syms
+    dbow = os.path.join(REF, "Thirdparty", "DBoW2")
+    shim = os.path.join(ROOT, "oracle", "ref_shim")
+    subprocess.check_call(["g++", "-std=c++14", "-Wall", "-Wno-comment", "-Wno-sign-compare", "-Wno-unused-variable", "-c", os.path.join(ROOT, "tests", "host", "voc_access_probe.cc"),
+                           "-I", os.path.join(shim, "dbow"), "-I", shim, "-I", dbow, "-I", os.path.join(dbow, "DBoW2"), "-o", str(tmp_path / "probe.o")])
+
+
 def test_pose_optimization_unit(tmp_path):
     syms = _compile(tmp_path, "Optimizer_pose_b200", "-DORB_REFSHIM_POSE")
     assert "T ORB_SLAM3::Optimizer::PoseOptimization(ORB_SLAM3::Frame*)" in syms
@@ -107,4 +118,4 @@ def test_skeleton_members_are_the_reference_declarations():
         if cur and _norm(line):
             assert _norm(line) in cache[cur], f"{cur}: no such declaration: {line.strip()}"
             checked += 1
-    assert checked >= 102
+    assert checked >= 105
