@@ -31,6 +31,9 @@
 #include "ORBextractor.h"   // the reference's own header (it needs nothing but <opencv2/opencv.hpp>)
 
 namespace g2o { class Sim3; }
+#ifdef ORB_REFSHIM_FUSE  // host/ORBmatcher_fuse_b200.cc
+#define ORB_REFSHIM_TRI
+#endif
 #ifdef ORB_REFSHIM_VOC   // host/Frame_bow_b200.cc: what Thirdparty/DBoW2/DBoW2/{BowVector.h, FeatureVector.h, TemplatedVocabulary.h} declare, as far as
 #define ORB_REFSHIM_BOW   // Frame::ComputeBoW and the flattening of the vocabulary touch it (the nodes are PROTECTED members there too)
 namespace DBoW2 {
@@ -177,6 +180,21 @@ class MapPoint {
     static std::mutex mGlobalMutex;
 //@end
 #endif
+#ifdef ORB_REFSHIM_FUSE
+//@ref MapPoint.h
+    void AddObservation(KeyFrame* pKF,int idx);
+    bool IsInKeyFrame(KeyFrame* pKF);
+    void Replace(MapPoint* pMP);
+//@end
+    void mock_set_distances(float mn, float mx) { mfMinDistance = mn; mfMaxDistance = mx; }
+    int mock_id = -1;
+   protected:
+//@ref MapPoint.h
+     float mfMinDistance;
+     float mfMaxDistance;
+//@end
+   public:
+#endif
     // mock state (tests/host only)
     Eigen::Vector3f mock_pos, mock_normal;
     std::map<KeyFrame*, std::tuple<int, int>> mock_obs;
@@ -227,6 +245,16 @@ class KeyFrame {
     Eigen::Vector3f GetCameraCenter();
 //@end
 #endif
+#ifdef ORB_REFSHIM_FUSE
+//@ref KeyFrame.h
+    void AddMapPoint(MapPoint* pMP, const size_t &idx);
+    MapPoint* GetMapPoint(const size_t &idx);
+    const int mnMinX;
+    const int mnMinY;
+    const int mnMaxX;
+    const int mnMaxY;
+//@end
+#endif
 #ifdef ORB_REFSHIM_LIBA
 //@ref KeyFrame.h
     void SetVelocity(const Eigen::Vector3f &Vw_);
@@ -263,6 +291,9 @@ class KeyFrame {
           mpCamera(nullptr), mpCamera2(nullptr), NLeft(-1), NRight(-1)
 #ifdef ORB_REFSHIM_REF_LBA
           , mvKeysRight()
+#endif
+#ifdef ORB_REFSHIM_FUSE
+          , mnMinX(0), mnMinY(0), mnMaxX(0), mnMaxY(0)
 #endif
 #ifdef ORB_REFSHIM_LIBA
           , bImu(false), mPrevKF(nullptr), mpImuPreintegrated(nullptr)

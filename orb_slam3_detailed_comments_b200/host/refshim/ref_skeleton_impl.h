@@ -35,6 +35,14 @@ bool KeyFrame::isBad() { return mock_bad; }
 Sophus::SE3f KeyFrame::GetRelativePoseTrl() { return Sophus::SE3f(); }   // two-camera rigs: not exercised
 #endif
 Map* KeyFrame::GetMap() { return mock_map; }
+#ifdef ORB_REFSHIM_FUSE
+std::vector<int> g_fuse_log;   // (op, acting point, other point or -1, keyframe feature or -1) per mutation, in call order
+void MapPoint::AddObservation(KeyFrame* pKF, int idx) { mock_obs[pKF] = std::make_tuple(idx, -1); g_fuse_log.insert(g_fuse_log.end(), {3, mock_id, -1, idx}); }
+bool MapPoint::IsInKeyFrame(KeyFrame* pKF) { return mock_obs.count(pKF) != 0; }
+void MapPoint::Replace(MapPoint* pMP) { mock_bad = true; g_fuse_log.insert(g_fuse_log.end(), {1, mock_id, pMP->mock_id, -1}); }   // MapPoint.cc:323-384 marks this point bad
+void KeyFrame::AddMapPoint(MapPoint* pMP, const size_t& idx) { mock_matches[idx] = pMP; }
+MapPoint* KeyFrame::GetMapPoint(const size_t& idx) { return mock_matches[idx]; }
+#endif
 #ifdef ORB_REFSHIM_TRI
 Sophus::SE3f KeyFrame::GetPoseInverse() { return mock_Tcw.inverse(); }
 Eigen::Vector3f KeyFrame::GetCameraCenter() { return mock_Tcw.inverse().translation(); }

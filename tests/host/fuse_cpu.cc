@@ -1,0 +1,79 @@
+// tests/host/fuse_cpu.cc -- TEST INFRASTRUCTURE (CPU tier): ORBmatcher::Fuse(pKF, vpMapPoints, th) (host/ORBmatcher_fuse_b200.cc, the search answered
+// by the oracle: fuse_stub.cc) over a mock keyframe and map points read from raw arrays; tests/test_host_fuse_vs_ref.py compares the
+// mutation log with the best features the reference's own function finds (oracle/_ref part 2).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "ref_skeleton_impl.h"
+#include "ORBmatcher.h"
+#include "orbslam3_b200.h"
+
+using namespace ORB_SLAM3;
+extern "C" void fuse_stub_set_log_scale_factor(float v);
+namespace ORB_SLAM3 { extern std::vector<int> g_fuse_log; }
+
+static std::string g_dir;
+template <typename T>
+static std::vector<T> rd(const std::string& name) {
+    std::ifstream f(g_dir + "/" + name, std::ios::binary);
+    if (!f) { std::fprintf(stderr, "missing input %s\n", name.c_str()); std::exit(2); }
+    f.seekg(0, std::ios::end);
+    const size_t n = (size_t)f.tellg();
+    f.seekg(0);
+    std::vector<T> v(n / sizeof(T));
+    f.read((char*)v.data(), (std::streamsize)(v.size() * sizeof(T)));
+    return v;
+}
+template <typename T>
+static void wr(const std::string& name, const std::vector<T>& v) {
+    std::ofstream f(g_dir + "/" + name, std::ios::binary);
+    f.write((const char*)v.data(), (std::streamsize)(v.size() * sizeof(T)));
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2) { std::fprintf(stderr, "usage: fuse_cpu <dir>\n"); return 2; }
+    g_dir = argv[1];
+    auto k2 = rd<orbx_keypoint>("kf.kp");
+    auto d2 = rd<uint8_t>("kf_desc.u8"), has = rd<uint8_t>("kf_has_mp.u8");
+    auto u2 = rd<float>("kf_uright.f32"), par = rd<float>("params.f32");   // fx fy cx cy bf b | minx maxx miny maxy | T (7) | th | logsf
+    auto kfobs = rd<int>("kf_mp_obs.i32");                                 // Observations() of the keyframe's own map points
+    auto xw = rd<float>("q_xw.f32"), nr = rd<float>("q_normal.f32"), mx = rd<float>("q_max.f32"), mn = rd<float>("q_min.f32");
+    auto qd = rd<uint8_t>("q_desc.u8"), qbad = rd<uint8_t>("q_bad.u8"), qin = rd<uint8_t>("q_in_kf.u8");
+    auto qobs = rd<int>("q_obs.i32"), qslot = rd<int>("q_slot.i32");       // Observations() of every query; slot: which MapPoint object a vpMapPoints entry points at (-1: NULL)
+    fuse_stub_set_log_scale_factor(par[18]);
+    const int N = (int)k2.size(), nq = (int)qslot.size(), nobj = (int)(xw.size() / 3);
+    std::vector<cv::KeyPoint> keys(N);
+    for (int i = 0; i < N; ++i) { keys[i].pt.x = k2[i].x; keys[i].pt.y = k2[i].y; keys[i].size = k2[i].size; keys[i].angle = k2[i].angle; keys[i].response = k2[i].response; keys[i].octave = k2[i].octave; keys[i].class_id = k2[i].class_id; }
+    KeyFrame K(7, par[0], par[1], par[2], par[3], par[4], par[5], keys, u2, std::vector<float>(8, 1.f));
+    const_cast<int&>(K.mnMinX) = (int)par[6]; const_cast<int&>(K.mnMaxX) = (int)par[7]; const_cast<int&>(K.mnMinY) = (int)par[8]; const_cast<int&>(K.mnMaxY) = (int)par[9];
+    K.mock_Tcw = Sophus::SE3f(Eigen::Quaternionf(par[13], par[10], par[11], par[12]), Eigen::Vector3f(par[14], par[15], par[16]));
+    cv::Mat D(N, 32, CV_8UC1);
+    std::memcpy(D.ptr(0), d2.data(), (size_t)N * 32);
+    const_cast<cv::Mat&>(K.mDescriptors) = D;
+    std::vector<KeyFrame*> others;                                         // stand-ins for the observers that make up Observations()
+    auto observers = [&](MapPoint& p, int n) { for (int k = 0; k < n; ++k) { while ((int)others.size() <= k) others.push_back((KeyFrame*)(0x1000 + 64 * others.size())); p.mock_obs[others[k]] = std::make_tuple(0, -1); } };
+    std::vector<MapPoint> kfmp(N), obj(nobj);
+    K.mock_matches.assign(N, nullptr);
+    for (int i = 0; i < N; ++i) if (has[i]) { kfmp[i].mock_id = 100000 + i; observers(kfmp[i], kfobs[i]); kfmp[i].mock_obs[&K] = std::make_tuple(i, -1); K.mock_matches[i] = &kfmp[i]; }
+    for (int j = 0; j < nobj; ++j) {
+        obj[j].mock_id = j; obj[j].mock_pos = Eigen::Vector3f(xw[3 * j], xw[3 * j + 1], xw[3 * j + 2]); obj[j].mock_normal = Eigen::Vector3f(nr[3 * j], nr[3 * j + 1], nr[3 * j + 2]);
+        obj[j].mock_set_distances(mn[j], mx[j]);
+        obj[j].mock_desc.create(1, 32, CV_8UC1); std::memcpy(obj[j].mock_desc.ptr(0), &qd[(size_t)j * 32], 32);
+        obj[j].mock_bad = qbad[j] != 0;
+        observers(obj[j], qobs[j]);
+        if (qin[j]) obj[j].mock_obs[&K] = std::make_tuple(0, -1);
+    }
+    std::vector<MapPoint*> vp(nq);
+    for (int i = 0; i < nq; ++i) vp[i] = qslot[i] < 0 ? nullptr : &obj[qslot[i]];
+    ORBmatcher matcher(0.6f, true);
+    const int ret = matcher.Fuse(&K, vp, par[17], false);
+    std::vector<int> out = g_fuse_log;
+    out.push_back(ret);
+    wr("out_log.i32", out);
+    std::printf("fuse_cpu ok\n");
+    return 0;
+}

@@ -91,6 +91,12 @@ def test_compute_bow_unit_and_its_vocabulary_access(tmp_path):
                            "-I", os.path.join(shim, "dbow"), "-I", shim, "-I", dbow, "-I", os.path.join(dbow, "DBoW2"), "-o", str(tmp_path / "probe.o")])
 
 
+def test_fuse_unit(tmp_path):
+    syms = _compile(tmp_path, "ORBmatcher_fuse_b200", "-DORB_REFSHIM_FUSE", "-Wno-reorder")
+    assert re.search(r"T ORB_SLAM3::ORBmatcher::Fuse\(ORB_SLAM3::KeyFrame\*, std::vector<ORB_SLAM3::MapPoint\*.*> const&, float, bool\)", syms)
+    assert "U orbm_search_keyframe" in syms and "abort" not in syms
+
+
 def test_pose_optimization_unit(tmp_path):
     syms = _compile(tmp_path, "Optimizer_pose_b200", "-DORB_REFSHIM_POSE")
     assert "T ORB_SLAM3::Optimizer::PoseOptimization(ORB_SLAM3::Frame*)" in syms
@@ -118,4 +124,4 @@ def test_skeleton_members_are_the_reference_declarations():
         if cur and _norm(line):
             assert _norm(line) in cache[cur], f"{cur}: no such declaration: {line.strip()}"
             checked += 1
-    assert checked >= 105
+    assert checked >= 115
