@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -14,6 +15,7 @@
 
 using namespace ORB_SLAM3;
 extern "C" void fuse_stub_set_log_scale_factor(float v);
+extern "C" void fuse_stub_set_frame(const orbx_keypoint* kps, const uint8_t* desc, const float* ur, int n);
 namespace ORB_SLAM3 { extern std::vector<int> g_fuse_log; }
 
 static std::string g_dir;
@@ -74,6 +76,47 @@ int main(int argc, char** argv) {
     std::vector<int> out = g_fuse_log;
     out.push_back(ret);
     wr("out_log.i32", out);
+    // (b) relocalisation: SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist).  The keyframe is made of the query objects
+    //     (feature i holds object i where r_has[i]); the frame is the feature set above, resident on the "device".
+    {
+        auto rk = rd<orbx_keypoint>("r_kf.kp");
+        auto rhas = rd<uint8_t>("r_has.u8"), rbad = rd<uint8_t>("r_bad.u8"), ralready = rd<uint8_t>("r_already.u8"), rclaimed = rd<uint8_t>("r_claimed.u8");
+        auto rxw = rd<float>("r_xw.f32"), rmx = rd<float>("r_max.f32"), rmn = rd<float>("r_min.f32"), rpar = rd<float>("r_params.f32");   // th, ORBdist, check
+        auto rdesc = rd<uint8_t>("r_desc.u8");
+        const int n1 = (int)rk.size();
+        std::vector<cv::KeyPoint> rkeys(n1);
+        for (int i = 0; i < n1; ++i) { rkeys[i].pt.x = rk[i].x; rkeys[i].pt.y = rk[i].y; rkeys[i].angle = rk[i].angle; rkeys[i].octave = rk[i].octave; }
+        KeyFrame K1(9, par[0], par[1], par[2], par[3], par[4], par[5], rkeys, std::vector<float>(n1, -1.f), std::vector<float>(8, 1.f));
+        std::vector<MapPoint> mp1(n1);
+        K1.mock_matches.assign(n1, nullptr);
+        std::set<MapPoint*> found;
+        for (int i = 0; i < n1; ++i) {
+            if (!rhas[i]) continue;
+            mp1[i].mock_id = i; mp1[i].mock_pos = Eigen::Vector3f(rxw[3 * i], rxw[3 * i + 1], rxw[3 * i + 2]); mp1[i].mock_set_distances(rmn[i], rmx[i]);
+            mp1[i].mock_desc.create(1, 32, CV_8UC1); std::memcpy(mp1[i].mock_desc.ptr(0), &rdesc[(size_t)i * 32], 32);
+            mp1[i].mock_bad = rbad[i] != 0;
+            K1.mock_matches[i] = &mp1[i];
+            if (ralready[i]) found.insert(&mp1[i]);
+        }
+        Frame F;
+        F.N = N; F.mbf = par[4]; F.mb = par[5];
+        Frame::fx = par[0]; Frame::fy = par[1]; Frame::cx = par[2]; Frame::cy = par[3];
+        Frame::mnMinX = par[6]; Frame::mnMaxX = par[7]; Frame::mnMinY = par[8]; Frame::mnMaxY = par[9];
+        int dummy_extractor = 0;
+        F.mpORBextractorLeft = reinterpret_cast<ORBextractor*>(&dummy_extractor);
+        F.mTcw = K.mock_Tcw;
+        F.mvKeysUn = keys;
+        MapPoint occupied;
+        F.mvpMapPoints.assign(N, nullptr);
+        for (int i = 0; i < N; ++i) if (rclaimed[i]) F.mvpMapPoints[i] = &occupied;
+        fuse_stub_set_frame(k2.data(), d2.data(), u2.data(), N);
+        ORBmatcher m2(0.9f, rpar[2] != 0);
+        const int r2 = m2.SearchByProjection(F, &K1, found, rpar[0], (int)rpar[1]);
+        std::vector<int> fm(N, -1);
+        for (int i = 0; i < N; ++i) if (F.mvpMapPoints[i] && F.mvpMapPoints[i] != &occupied) fm[i] = F.mvpMapPoints[i]->mock_id;
+        fm.push_back(r2);
+        wr("out_reloc.i32", fm);
+    }
     std::printf("fuse_cpu ok\n");
     return 0;
 }

@@ -56,6 +56,20 @@ def test_fuse_equals_the_reference_function(tmp_path, two_frames, kf_target, th)
     for name, a in dict(kf_mp_obs=kfobs, q_obs=qobs, q_slot=slot).items():
         np.ascontiguousarray(a, np.int32).tofile(os.path.join(d, name + ".i32"))
     np.concatenate([_m.CAM6, _m.BOUNDS, np.float32(T), np.float32([th, kf_target["logsf"]])]).astype(np.float32).tofile(os.path.join(d, "params.f32"))
+    # inputs of the relocalisation search (second half of the driver): keyframe 1 with its own map points as queries
+    orb_dist, check = (100, True) if th < 5 else (64, False)
+    has1 = dep1 > 0
+    bad1 = has1 & (rng.random(len(k1)) < 0.04)
+    pts1 = _m._unproject(k1, np.where(has1, dep1, 1.0))
+    dist1 = np.linalg.norm(pts1, axis=1).astype(np.float32)
+    maxd1 = (dist1 * sf[k1["octave"]]).astype(np.float32)
+    mind1 = (maxd1 / sf[7]).astype(np.float32)
+    already, claimed = (rng.random(len(k1)) < 0.1).astype(np.uint8), (rng.random(len(k2)) < 0.1).astype(np.uint8)
+    np.ascontiguousarray(k1).tofile(os.path.join(d, "r_kf.kp"))
+    for name, a in dict(r_has=has1, r_bad=bad1, r_already=already, r_claimed=claimed, r_desc=d1).items():
+        np.ascontiguousarray(a, np.uint8).tofile(os.path.join(d, name + ".u8"))
+    for name, a in dict(r_xw=pts1, r_max=maxd1, r_min=mind1, r_params=np.float32([10.0 if th < 5 else 3.0, orb_dist, float(check)])).items():
+        np.ascontiguousarray(a, np.float32).tofile(os.path.join(d, name + ".f32"))
     r = subprocess.run([MINE, d], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "fuse_cpu ok" in r.stdout, (r.returncode, r.stdout[-1000:], r.stderr[-1000:])
     out = np.fromfile(os.path.join(d, "out_log.i32"), np.int32)
@@ -79,3 +93,9 @@ def test_fuse_equals_the_reference_function(tmp_path, two_frames, kf_target, th)
         fused += 1
     assert ret == rn == fused and log == want
     assert rn > 100 and sum(1 for w in want if w[0] == 1) > 10 and sum(1 for w in want if w[0] == 3) > 50
+    # relocalisation search against the reference's own function
+    K1 = po.RefKeyFrame(k1, d1, u1, None, has1, bad1, sf, sf * sf, _m.CAM6[:4])
+    po.ref2_kf_set_mappoints(K1, pts1, maxd1, mind1, d1)
+    wfm, wn = po.ref2_search_frame_kf(F, T, K1, already, claimed, 10.0 if th < 5 else 3.0, orb_dist, check)
+    got = np.fromfile(os.path.join(d, "out_reloc.i32"), np.int32)
+    assert got[-1] == wn and (got[:-1] == wfm).all() and wn > 30

@@ -97,6 +97,12 @@ def test_fuse_unit(tmp_path):
     assert "U orbm_search_keyframe" in syms and "abort" not in syms
 
 
+def test_relocalisation_search_unit(tmp_path):
+    syms = _compile(tmp_path, "ORBmatcher_reloc_b200", "-DORB_REFSHIM_FUSE", "-Wno-reorder")
+    assert re.search(r"T ORB_SLAM3::ORBmatcher::SearchByProjection\(ORB_SLAM3::Frame&, ORB_SLAM3::KeyFrame\*, std::set<ORB_SLAM3::MapPoint\*.*> const&, float, int\)", syms)
+    assert "U orbm_search_keyframe" in syms and "abort" not in syms
+
+
 def test_pose_optimization_unit(tmp_path):
     syms = _compile(tmp_path, "Optimizer_pose_b200", "-DORB_REFSHIM_POSE")
     assert "T ORB_SLAM3::Optimizer::PoseOptimization(ORB_SLAM3::Frame*)" in syms
