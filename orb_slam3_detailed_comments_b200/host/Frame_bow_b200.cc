@@ -12,6 +12,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "Frame.h"             // the reference's header (here: the skeleton that stands in for it)

@@ -17,6 +17,7 @@
 //    observations of two-camera rigs (EdgeMono(1), :2622-2657) -- such a window is refused with an exception.
 //  * GeometricCamera::uncertainty2 (:2583, :2609) is 1.0f in both camera models of the tree (Pinhole.h, KannalaBrandt8.h); x / 1.0f == x.
 //  * `assert(mit->second >= 3)` (:2664) is compiled out of the reference's Release build; it is not evaluated here.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
