@@ -249,6 +249,7 @@ class KeyFrame {
 //@ref KeyFrame.h
     void AddMapPoint(MapPoint* pMP, const size_t &idx);
     MapPoint* GetMapPoint(const size_t &idx);
+    std::set<MapPoint*> GetMapPoints();
     const int mnMinX;
     const int mnMinY;
     const int mnMaxX;

@@ -42,6 +42,7 @@ bool MapPoint::IsInKeyFrame(KeyFrame* pKF) { return mock_obs.count(pKF) != 0; }
 void MapPoint::Replace(MapPoint* pMP) { mock_bad = true; g_fuse_log.insert(g_fuse_log.end(), {1, mock_id, pMP->mock_id, -1}); }   // MapPoint.cc:323-384 marks this point bad
 void KeyFrame::AddMapPoint(MapPoint* pMP, const size_t& idx) { mock_matches[idx] = pMP; }
 MapPoint* KeyFrame::GetMapPoint(const size_t& idx) { return mock_matches[idx]; }
+std::set<MapPoint*> KeyFrame::GetMapPoints() { std::set<MapPoint*> s; for (MapPoint* p : mock_matches) if (p && !p->isBad()) s.insert(p); return s; }   // KeyFrame.cc:370-385: the non-NULL, non-bad entries of mvpMapPoints
 #endif
 #ifdef ORB_REFSHIM_TRI
 Sophus::SE3f KeyFrame::GetPoseInverse() { return mock_Tcw.inverse(); }

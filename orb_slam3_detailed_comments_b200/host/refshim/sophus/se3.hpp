@@ -10,7 +10,7 @@ class SE3 {
    public:
     SE3() {}
     SE3(const Eigen::Quaternion<T>& q, const Eigen::Matrix<T, 3, 1>& t) : q_(q), t_(t) { q_.normalize(); }   // SO3(quat) normalises
-#ifdef ORB_REFSHIM_LIBA
+#if defined(ORB_REFSHIM_LIBA) || defined(ORB_REFSHIM_FUSE)
     SE3(const Eigen::Matrix<T, 3, 3>& R, const Eigen::Matrix<T, 3, 1>& t) : q_(Eigen::Quaternion<T>(R)), t_(t) { q_.normalize(); }
 #endif
     const Eigen::Quaternion<T>& unit_quaternion() const { return q_; }

@@ -1,6 +1,7 @@
 // tests/host/fuse_cpu.cc -- TEST INFRASTRUCTURE (CPU tier): ORBmatcher::Fuse(pKF, vpMapPoints, th) (host/ORBmatcher_fuse_b200.cc, the search answered
 // by the oracle: fuse_stub.cc) over a mock keyframe and map points read from raw arrays; tests/test_host_fuse_vs_ref.py compares the
 // mutation log with the best features the reference's own function finds (oracle/_ref part 2).
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -76,6 +77,49 @@ int main(int argc, char** argv) {
     std::vector<int> out = g_fuse_log;
     out.push_back(ret);
     wr("out_log.i32", out);
+    // (c) the Sim3 searches on a fresh copy of the keyframe and of the query objects
+    {
+        auto sp = rd<float>("s_params.f32");          // S8 (non-unit quaternion, translation, scale), th, ratioHamming
+        auto sclaimed = rd<uint8_t>("s_claimed.u8");
+        const float ss = sp[0] * sp[0] + sp[1] * sp[1] + sp[2] * sp[2] + sp[3] * sp[3], nn = std::sqrt(ss);
+        Sophus::Sim3f Scw(ss, Eigen::Quaternionf(sp[3] / nn, sp[0] / nn, sp[1] / nn, sp[2] / nn), Eigen::Vector3f(sp[4], sp[5], sp[6]));
+        std::vector<int> sout;
+        for (int which = 0; which < 2; ++which) {
+            KeyFrame K3(11 + which, par[0], par[1], par[2], par[3], par[4], par[5], keys, u2, std::vector<float>(8, 1.f));
+            const_cast<int&>(K3.mnMinX) = (int)par[6]; const_cast<int&>(K3.mnMaxX) = (int)par[7]; const_cast<int&>(K3.mnMinY) = (int)par[8]; const_cast<int&>(K3.mnMaxY) = (int)par[9];
+            const_cast<cv::Mat&>(K3.mDescriptors) = D;
+            std::vector<MapPoint> kfmp3(N), obj3(nobj);
+            K3.mock_matches.assign(N, nullptr);
+            for (int i = 0; i < N; ++i) if (has[i]) { kfmp3[i].mock_id = 100000 + i; K3.mock_matches[i] = &kfmp3[i]; }
+            std::vector<MapPoint*> vp3(nobj);
+            for (int j = 0; j < nobj; ++j) {
+                obj3[j].mock_id = j; obj3[j].mock_pos = Eigen::Vector3f(xw[3 * j], xw[3 * j + 1], xw[3 * j + 2]); obj3[j].mock_normal = Eigen::Vector3f(nr[3 * j], nr[3 * j + 1], nr[3 * j + 2]);
+                obj3[j].mock_set_distances(mn[j], mx[j]);
+                obj3[j].mock_desc.create(1, 32, CV_8UC1); std::memcpy(obj3[j].mock_desc.ptr(0), &qd[(size_t)j * 32], 32);
+                obj3[j].mock_bad = qbad[j] != 0;
+                vp3[j] = &obj3[j];
+            }
+            ORBmatcher m3(0.75f, true);
+            g_fuse_log.clear();
+            if (which == 0) {
+                MapPoint occupied;
+                occupied.mock_id = -2;
+                std::vector<MapPoint*> vpMatched(N, nullptr);
+                for (int i = 0; i < N; ++i) if (sclaimed[i]) vpMatched[i] = &occupied;
+                const int r3 = m3.SearchByProjection(&K3, Scw, vp3, vpMatched, (int)sp[8], sp[9]);
+                for (int i = 0; i < N; ++i) sout.push_back(vpMatched[i] ? vpMatched[i]->mock_id : -1);
+                sout.push_back(r3);
+            } else {
+                std::vector<MapPoint*> repl(nobj, nullptr);
+                const int r3 = m3.Fuse(&K3, Scw, vp3, sp[8], repl);
+                for (int j = 0; j < nobj; ++j) sout.push_back(repl[j] ? repl[j]->mock_id : -1);
+                sout.push_back(r3);
+                sout.push_back((int)g_fuse_log.size() / 4);
+                sout.insert(sout.end(), g_fuse_log.begin(), g_fuse_log.end());
+            }
+        }
+        wr("out_sim3.i32", sout);
+    }
     // (b) relocalisation: SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist).  The keyframe is made of the query objects
     //     (feature i holds object i where r_has[i]); the frame is the feature set above, resident on the "device".
     {

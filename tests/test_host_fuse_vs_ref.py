@@ -70,6 +70,13 @@ def test_fuse_equals_the_reference_function(tmp_path, two_frames, kf_target, th)
         np.ascontiguousarray(a, np.uint8).tofile(os.path.join(d, name + ".u8"))
     for name, a in dict(r_xw=pts1, r_max=maxd1, r_min=mind1, r_params=np.float32([10.0 if th < 5 else 3.0, orb_dist, float(check)])).items():
         np.ascontiguousarray(a, np.float32).tofile(os.path.join(d, name + ".f32"))
+    # inputs of the two Sim3 searches (third part of the driver)
+    sc = 1.03
+    S = _m._sim3(T[:4], T[4:].astype(np.float64) * sc, sc)
+    ratio = 1.0 if th < 5 else 0.8
+    sclaimed = (rng.random(len(k2)) < 0.2).astype(np.uint8)
+    np.concatenate([S, np.float32([th, ratio])]).astype(np.float32).tofile(os.path.join(d, "s_params.f32"))
+    sclaimed.tofile(os.path.join(d, "s_claimed.u8"))
     r = subprocess.run([MINE, d], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "fuse_cpu ok" in r.stdout, (r.returncode, r.stdout[-1000:], r.stderr[-1000:])
     out = np.fromfile(os.path.join(d, "out_log.i32"), np.int32)
@@ -93,6 +100,31 @@ def test_fuse_equals_the_reference_function(tmp_path, two_frames, kf_target, th)
         fused += 1
     assert ret == rn == fused and log == want
     assert rn > 100 and sum(1 for w in want if w[0] == 1) > 10 and sum(1 for w in want if w[0] == 3) > 50
+    # the Sim3 searches against the reference's own functions (a fresh keyframe: no bad points, nothing fused yet)
+    so = np.fromfile(os.path.join(d, "out_sim3.i32"), np.int32).tolist()
+    N2 = len(k2)
+    K3 = po.RefKeyFrame(k2, d2, u2, None, has_mp, None, sf, sf * sf, _m.CAM6[:4], T)
+    po.ref2_kf_set_geometry(K3, F, isg, _m.BF)
+    wm, wn, _, _ = po.ref2_search_kf_sim3(K3, S, q, sclaimed, int(th), ratio)
+    matched, r3 = np.array(so[:N2]), so[N2]
+    exp = np.where(sclaimed != 0, -2, -1)
+    for j in np.nonzero(wm >= 0)[0]:
+        exp[wm[j]] = j
+    assert r3 == wn and (matched == exp).all() and wn > 100
+    wf, wfn, _, _ = po.ref2_fuse_sim3(K3, S, q, th)
+    repl, r4, nlog = np.array(so[N2 + 1:N2 + 1 + nobj]), so[N2 + 1 + nobj], so[N2 + 2 + nobj]
+    flog = np.array(so[N2 + 3 + nobj:]).reshape(nlog, 4).tolist()
+    holder = {int(i): 100000 + int(i) for i in np.nonzero(has_mp)[0]}
+    erepl, elog = np.full(nobj, -1), []
+    for j in range(nobj):
+        if q["bad"][j] or wf[j] < 0:
+            continue
+        b = int(wf[j])
+        if b in holder:
+            erepl[j] = holder[b]
+        else:
+            elog.append([3, j, -1, b]); holder[b] = j
+    assert r4 == wfn and (repl == erepl).all() and flog == elog and wfn > 100
     # relocalisation search against the reference's own function
     K1 = po.RefKeyFrame(k1, d1, u1, None, has1, bad1, sf, sf * sf, _m.CAM6[:4])
     po.ref2_kf_set_mappoints(K1, pts1, maxd1, mind1, d1)

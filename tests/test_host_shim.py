@@ -103,6 +103,13 @@ def test_relocalisation_search_unit(tmp_path):
     assert "U orbm_search_keyframe" in syms and "abort" not in syms
 
 
+def test_sim3_searches_unit(tmp_path):
+    syms = _compile(tmp_path, "ORBmatcher_sim3_b200", "-DORB_REFSHIM_FUSE", "-Wno-reorder")
+    assert re.search(r"T ORB_SLAM3::ORBmatcher::SearchByProjection\(ORB_SLAM3::KeyFrame\*, Sophus::Sim3<float>&, std::vector<ORB_SLAM3::MapPoint\*.*> const&, std::vector<ORB_SLAM3::MapPoint\*.*>&, int, float\)", syms)
+    assert re.search(r"T ORB_SLAM3::ORBmatcher::Fuse\(ORB_SLAM3::KeyFrame\*, Sophus::Sim3<float>&, std::vector<ORB_SLAM3::MapPoint\*.*> const&, float, std::vector<ORB_SLAM3::MapPoint\*.*>&\)", syms)
+    assert "U orbm_search_keyframe" in syms and "abort" not in syms
+
+
 def test_pose_optimization_unit(tmp_path):
     syms = _compile(tmp_path, "Optimizer_pose_b200", "-DORB_REFSHIM_POSE")
     assert "T ORB_SLAM3::Optimizer::PoseOptimization(ORB_SLAM3::Frame*)" in syms
@@ -130,4 +137,4 @@ def test_skeleton_members_are_the_reference_declarations():
         if cur and _norm(line):
             assert _norm(line) in cache[cur], f"{cur}: no such declaration: {line.strip()}"
             checked += 1
-    assert checked >= 115
+    assert checked >= 116
