@@ -1,6 +1,7 @@
-// ORBmatcher_sim3_b200.cc -- the two loop-closing / map-merging searches that project map points into a keyframe through a Sim3 pose
+// ORBmatcher_sim3_b200.cc -- the loop-closing / map-merging searches that project map points into a keyframe through a Sim3 pose
 // (/root/reference/src/ORBmatcher.cc) on the B200:
 //   SearchByProjection(KeyFrame* pKF, Sophus::Sim3f& Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched, int th, float ratioHamming)   :495-618
+//   the overload with vpPointsKFs / vpMatchedKF                                                                                                        :620-732
 //   Fuse(KeyFrame* pKF, Sophus::Sim3f& Scw, const vector<MapPoint*>& vpPoints, float th, vector<MapPoint*>& vpReplacePoint)                               :1546-1687
 // Compiled against the reference's UNMODIFIED include/ORBmatcher.h.  On the host: Tcw = SE3f(Scw.rotationMatrix(), Scw.translation() /
 // Scw.scale()) and the camera centre in the caller's own Sophus, the skips (isBad(), already matched / already in the keyframe), the query
@@ -94,6 +95,23 @@ int ORBmatcher::SearchByProjection(KeyFrame* pKF, Sophus::Sim3f& Scw, const std:
                                 "ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched)");
     for (size_t k = 0; k < R.src.size(); ++k)
         if (R.best[k] >= 0) vpMatched[R.best[k]] = vpPoints[R.src[k]];                        // :609-613
+    return R.nmatches;
+}
+
+// ORBmatcher.cc:620-732: the same search; the keyframe each point came from is recorded next to it
+int ORBmatcher::SearchByProjection(KeyFrame* pKF, Sophus::Sim3<float>& Scw, const std::vector<MapPoint*>& vpPoints, const std::vector<KeyFrame*>& vpPointsKFs,
+                                   std::vector<MapPoint*>& vpMatched, std::vector<KeyFrame*>& vpMatchedKF, int th, float ratioHamming) {
+    std::set<MapPoint*> spAlreadyFound(vpMatched.begin(), vpMatched.end());
+    spAlreadyFound.erase(static_cast<MapPoint*>(NULL));
+    std::vector<uint8_t> claimed(vpMatched.size());
+    for (size_t i = 0; i < vpMatched.size(); ++i) claimed[i] = vpMatched[i] ? 1 : 0;
+    const Sim3Search R = search(pKF, Scw, vpPoints, spAlreadyFound, claimed.data(), ORBM_KF_PROJ_SIM3, (float)th, (float)TH_LOW * ratioHamming, mbCheckOrientation,
+                                "ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpPointsKFs, vpMatched, vpMatchedKF)");
+    for (size_t k = 0; k < R.src.size(); ++k)
+        if (R.best[k] >= 0) {                                                                 // :724-728
+            vpMatched[R.best[k]] = vpPoints[R.src[k]];
+            vpMatchedKF[R.best[k]] = vpPointsKFs[R.src[k]];
+        }
     return R.nmatches;
 }
 

@@ -106,9 +106,22 @@ int main(int argc, char** argv) {
                 occupied.mock_id = -2;
                 std::vector<MapPoint*> vpMatched(N, nullptr);
                 for (int i = 0; i < N; ++i) if (sclaimed[i]) vpMatched[i] = &occupied;
+                std::vector<MapPoint*> vpMatchedB = vpMatched;
                 const int r3 = m3.SearchByProjection(&K3, Scw, vp3, vpMatched, (int)sp[8], sp[9]);
                 for (int i = 0; i < N; ++i) sout.push_back(vpMatched[i] ? vpMatched[i]->mock_id : -1);
                 sout.push_back(r3);
+                // the overload that also records the keyframe of every point: point j "comes from" the fake keyframe address 0x100000 + 64 j
+                std::vector<KeyFrame*> fromKF(nobj), vpMatchedKF(N, nullptr);
+                for (int j = 0; j < nobj; ++j) fromKF[j] = (KeyFrame*)(size_t)(0x100000 + 64 * j);
+                const int r3b = m3.SearchByProjection(&K3, Scw, vp3, fromKF, vpMatchedB, vpMatchedKF, (int)sp[8], sp[9]);
+                int same = r3b == r3 ? 1 : 0;
+                for (int i = 0; i < N; ++i) {
+                    if (vpMatchedB[i] != vpMatched[i]) same = 0;
+                    const bool fresh = vpMatched[i] && vpMatched[i] != &occupied;
+                    if (fresh != (vpMatchedKF[i] != nullptr)) same = 0;
+                    if (fresh && vpMatchedKF[i] != fromKF[vpMatched[i]->mock_id]) same = 0;
+                }
+                sout.push_back(same);
             } else {
                 std::vector<MapPoint*> repl(nobj, nullptr);
                 const int r3 = m3.Fuse(&K3, Scw, vp3, sp[8], repl);

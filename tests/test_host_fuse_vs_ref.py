@@ -106,7 +106,10 @@ def test_fuse_equals_the_reference_function(tmp_path, two_frames, kf_target, th)
     K3 = po.RefKeyFrame(k2, d2, u2, None, has_mp, None, sf, sf * sf, _m.CAM6[:4], T)
     po.ref2_kf_set_geometry(K3, F, isg, _m.BF)
     wm, wn, _, _ = po.ref2_search_kf_sim3(K3, S, q, sclaimed, int(th), ratio)
-    matched, r3 = np.array(so[:N2]), so[N2]
+    matched, r3, kfs_overload_agrees = np.array(so[:N2]), so[N2], so[N2 + 1]
+    so = so[:N2 + 1] + so[N2 + 2:]
+    wm2, wn2, _, _ = po.ref2_search_kf_sim3(K3, S, q, sclaimed, int(th), ratio, with_kfs=True)        # the reference's vpPointsKFs overload: the same matches
+    assert kfs_overload_agrees == 1 and wn2 == wn and (wm2 == wm).all()
     exp = np.where(sclaimed != 0, -2, -1)
     for j in np.nonzero(wm >= 0)[0]:
         exp[wm[j]] = j

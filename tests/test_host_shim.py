@@ -107,6 +107,7 @@ def test_sim3_searches_unit(tmp_path):
     syms = _compile(tmp_path, "ORBmatcher_sim3_b200", "-DORB_REFSHIM_FUSE", "-Wno-reorder")
     assert re.search(r"T ORB_SLAM3::ORBmatcher::SearchByProjection\(ORB_SLAM3::KeyFrame\*, Sophus::Sim3<float>&, std::vector<ORB_SLAM3::MapPoint\*.*> const&, std::vector<ORB_SLAM3::MapPoint\*.*>&, int, float\)", syms)
     assert re.search(r"T ORB_SLAM3::ORBmatcher::Fuse\(ORB_SLAM3::KeyFrame\*, Sophus::Sim3<float>&, std::vector<ORB_SLAM3::MapPoint\*.*> const&, float, std::vector<ORB_SLAM3::MapPoint\*.*>&\)", syms)
+    assert re.search(r"T ORB_SLAM3::ORBmatcher::SearchByProjection\(ORB_SLAM3::KeyFrame\*, Sophus::Sim3<float>&, std::vector<ORB_SLAM3::MapPoint\*.*> const&, std::vector<ORB_SLAM3::KeyFrame\*.*> const&, std::vector<ORB_SLAM3::MapPoint\*.*>&, std::vector<ORB_SLAM3::KeyFrame\*.*>&, int, float\)", syms)
     assert "U orbm_search_keyframe" in syms and "abort" not in syms
 
 
